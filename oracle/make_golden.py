@@ -1,0 +1,144 @@
+"""Extract the reference's own golden vectors for the hot path into small JSON fixtures.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+Sources (read-only, never executed as code):
+  * /root/reference/test/reference_results/all_models_reference.pkl.gz
+    (generator: test/reference_results/generate_all_model_ref_data.py:53-143; checked by
+    test/test_all_models_regression.py:75 at rtol 1e-5 / atol 1e-12)
+  * /root/reference/test/reference_results/tophat_redback_ref_data.ecsv
+    (generator: test/reference_results/make_afterglow_ref_data.py:14-26; checked by
+    test/test_on_ref_results.py:57-69 with np.allclose defaults)
+
+The pickle is read with a restricted Unpickler: only numpy array reconstruction is allowed and
+astropy Quantity objects are mapped onto a plain ndarray subclass, so nothing from the pickle runs.
+"""
+import gzip
+import io
+import json
+import os
+import pickle
+import sys
+
+import numpy as np
+
+REF = "/root/reference/test/reference_results"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+class _Quantity(np.ndarray):
+    def __setstate__(self, state):
+        nd_state, _own = state
+        super().__setstate__(nd_state)
+
+
+class _Inert:
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return self
+
+    def __setstate__(self, state):
+        pass
+
+
+class _Restricted(pickle.Unpickler):
+    _ALLOWED = {
+        ("numpy._core.multiarray", "_reconstruct"),
+        ("numpy.core.multiarray", "_reconstruct"),
+        ("numpy", "dtype"),
+        ("numpy", "ndarray"),
+        ("numpy._core.numeric", "_frombuffer"),
+        ("numpy._core.multiarray", "scalar"),
+        ("numpy.core.multiarray", "scalar"),
+    }
+
+    def find_class(self, module, name):
+        if (module, name) in self._ALLOWED:
+            mod = __import__(module, fromlist=[name])
+            return getattr(mod, name)
+        if module.startswith("astropy.units.quantity") and name == "Quantity":
+            return _Quantity
+        if module.startswith("astropy"):
+            return _Inert
+        raise pickle.UnpicklingError(f"blocked {module}.{name}")
+
+
+KEEP = [
+    "supernova.arnett_bolometric", "supernova.arnett",
+    "supernova.basic_magnetar_powered_bolometric", "supernova.basic_magnetar_powered",
+    "supernova.slsn_bolometric", "supernova.slsn", "supernova.type_1a",
+    "supernova.magnetar_nickel",
+    "kilonova.one_component_kilonova_model", "kilonova.metzger_kilonova_model",
+    "magnetar.basic_magnetar",
+]
+
+
+def _tolist(x):
+    arr = np.asarray(x, dtype=float)
+    return [None if not np.isfinite(v) and np.isnan(v) else (repr(float(v)) if not np.isfinite(v) else float(v))
+            for v in arr.ravel()]
+
+
+def dump_pkl():
+    with gzip.open(os.path.join(REF, "all_models_reference.pkl.gz"), "rb") as fh:
+        data = _Restricted(io.BytesIO(fh.read())).load()
+    keys = sorted(data.keys())
+    print(len(keys), "keys in pickle")
+    out = {}
+    for k in keys:
+        if k not in KEEP:
+            continue
+        entry = data[k]
+        md = entry["metadata"]
+        out[k] = {
+            "time": [float(v) for v in np.asarray(md["time_array"], dtype=float)],
+            "eval_kwargs": {kk: (float(vv) if isinstance(vv, (int, float, np.floating)) else vv)
+                            for kk, vv in md["eval_kwargs"].items()},
+            "params": [{pk: float(pv) for pk, pv in p.items()} for p in entry["params"]],
+            "results": [_tolist(r) for r in entry["results"]],
+        }
+        print(k, list(entry["params"][0].keys()))
+    with open(os.path.join(OUT, "all_models_subset.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
+def dump_ecsv():
+    rows = []
+    header = None
+    with open(os.path.join(REF, "tophat_redback_ref_data.ecsv")) as fh:
+        for line in fh:
+            if line.startswith("#"):
+                continue
+            if header is None:
+                header = line.split()
+                continue
+            rows.append(line.rstrip("\n"))
+    out = []
+    for r in rows:
+        cells = r.split(" ")
+        rec = {}
+        for name, cell in zip(header, cells):
+            if cell.startswith("["):
+                rec[name] = json.loads(cell)
+            else:
+                try:
+                    rec[name] = float(cell)
+                except ValueError:
+                    rec[name] = cell
+        out.append(rec)
+    time = out[0]["time"]
+    assert all(o["time"] == time for o in out)
+    doc = {"time": time, "rows": [{k: v for k, v in o.items() if k != "time"} for o in out]}
+    with open(os.path.join(OUT, "tophat_redback_ref.json"), "w") as fh:
+        json.dump(doc, fh)
+    print("ecsv rows:", len(out), "epochs:", len(time))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    dump_pkl()
+    dump_ecsv()

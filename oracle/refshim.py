@@ -1,0 +1,96 @@
+"""Import selected reference source files *verbatim, where they lie* under /root/reference.
+
+TEST INFRASTRUCTURE ONLY, and only usable in the build container (the GPU box has no
+/root/reference).  `import redback` fails here because astropy / bilby / sncosmo are not installed,
+but `redback/interaction_processes.py`, `redback/photosphere.py` and
+`redback/transient_models/afterglow_models/base_models.py` only need a handful of names, which are
+provided as stub modules in sys.modules.  Nothing is copied; the files are executed from their
+original location.  Used to validate oracle/restated.py and to generate tests/golden/ fixtures.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_ROOT = "/root/reference"
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "redback"))
+
+
+def _stub(name, **attrs):
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    sys.modules[name] = mod
+    return mod
+
+
+def _load(modname, relpath):
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(REFERENCE_ROOT, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load():
+    """Return a namespace with the reference's own Diffusion / TemperatureFloor / afterglow code."""
+    if not available():
+        raise RuntimeError("reference tree not present")
+    from . import restated as r
+    if "redback" not in sys.modules or not hasattr(sys.modules["redback"], "_oracle_stub"):
+        pkg = _stub("redback", _oracle_stub=True, __path__=[])
+        const = _stub(
+            "redback.constants",
+            speed_of_light=r.speed_of_light, planck=r.planck, boltzmann_constant=r.boltzmann_constant,
+            sigma_sb=r.sigma_sb, solar_mass=r.solar_mass, proton_mass=r.proton_mass,
+            electron_mass=r.electron_mass, sigma_T=r.sigma_T, km_cgs=r.km_cgs, day_to_s=r.day_to_s,
+            angstrom_cgs=r.angstrom_cgs, speed_of_light_si=r.speed_of_light_si,
+            radiation_constant=r.sigma_sb * 4 / r.speed_of_light, ev_to_erg=1.60218e-12,
+            qe=4.80320425e-10, au_cgs=14959787070000.0, solar_radius=69570000000.0,
+            graviational_constant=6.674299999999999e-08, mev_cgs=1.602176634e-06,
+            ang_to_hz=2.9979245799999995e+18, jansky=1e-26)
+        const.__all__ = [k for k in const.__dict__ if not k.startswith("_")]
+        pkg.constants = const
+    ns = types.SimpleNamespace()
+    ns.interaction_processes = _load("redback.interaction_processes", "redback/interaction_processes.py")
+    ns.photosphere = _load("redback.photosphere", "redback/photosphere.py")
+    return ns
+
+
+def load_afterglow():
+    """Import afterglow_models/base_models.py verbatim (numba kernels + RedbackAfterglows)."""
+    load()
+    import logging
+    from . import restated as r
+
+    def citation_wrapper(_):
+        def deco(f):
+            return f
+        return deco
+
+    _stub("redback.utils", logger=logging.getLogger("redback-oracle"), citation_wrapper=citation_wrapper)
+    _stub("redback.sed")
+    _load("redback.wrappers", "redback/wrappers.py")
+
+    class _Val:
+        def __init__(self, v):
+            self.value = v
+
+        @property
+        def cgs(self):
+            return self
+
+    class _Cosmo:
+        def luminosity_distance(self, z):
+            return _Val(r.cosmo.luminosity_distance_cm(z))
+
+    _stub("astropy")
+    _stub("astropy.cosmology", Planck18=_Cosmo())
+    _stub("astropy.units")
+    sys.modules["astropy"].units = sys.modules["astropy.units"]
+    _stub("redback.transient_models", __path__=[])
+    _stub("redback.transient_models.afterglow_models", __path__=[])
+    return _load("redback.transient_models.afterglow_models.base_models",
+                 "redback/transient_models/afterglow_models/base_models.py")

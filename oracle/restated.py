@@ -1,0 +1,341 @@
+"""CPU oracle: numpy restatement of redback's light-curve + Gaussian-likelihood hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``redback_b200/`` may import this module; it exists so that
+``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` have an independent statement of what the reference computes.
+
+Every function cites the reference file:line it follows (paths relative to /root/reference).  The
+arithmetic is float64 numpy/scipy, one parameter sample per call, exactly like the reference.
+
+Pinning (see tests/test_oracle_golden.py):
+  * supernova / kilonova / magnetar models are checked against the reference's own golden vectors
+    test/reference_results/all_models_reference.pkl.gz (extracted to tests/golden/ by
+    oracle/make_golden.py) at the reference's tolerance and much tighter;
+  * Diffusion / TemperatureFloor are additionally checked against the reference's *own source files*
+    imported verbatim through stub modules (oracle/refshim.py) when /root/reference is present;
+  * GaussianLikelihood closed forms from test/likelihood_test.py:63-69,148-153;
+  * TemperatureFloor known answer from test/photosphere_test.py:24-29.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+from scipy.integrate import quad
+from scipy.interpolate import interp1d
+
+# --------------------------------------------------------------------------------------------------
+# constants  (redback/constants.py:1-23 -> astropy CODATA-2018 cgs values)
+# --------------------------------------------------------------------------------------------------
+speed_of_light = 29979245800.0
+planck = 6.62607015e-27
+boltzmann_constant = 1.380649e-16
+sigma_sb = 5.6703744191844314e-05
+solar_mass = 1.988409870698051e33
+proton_mass = 1.67262192369e-24
+electron_mass = 9.1093837015e-28
+sigma_T = 6.6524587321e-25
+km_cgs = 100000.0
+day_to_s = 86400
+angstrom_cgs = 1e-08
+speed_of_light_si = 299792458.0
+
+# --------------------------------------------------------------------------------------------------
+# cosmology: astropy Planck18 = FlatLambdaCDM(H0=67.66, Om0=0.30966, Tcmb0=2.7255, Neff=3.046,
+# m_nu=[0,0,0.06] eV).  astropy is not installed here, so this restates its published algorithm
+# (astropy/cosmology/flrw/base.py: nu_relative_density, inv_efunc; flrw/lambdacdm.py FlatLambdaCDM)
+# and is anchored by every flux_density golden vector (d_L enters as d_L**-2).
+# Call site: supernova_models.py:997 `cosmology.luminosity_distance(redshift).cgs.value`.
+# --------------------------------------------------------------------------------------------------
+_MPC_CM = 3.0856775814913674e24
+_G_SI = 6.6743e-11
+_KB_EV_K = 8.617333262145179e-05
+
+
+class Planck18:
+    H0 = 67.66
+    Om0 = 0.30966
+    Tcmb0 = 2.7255
+    Neff = 3.046
+    m_nu = (0.0, 0.0, 0.06)
+
+    def __init__(self):
+        H0_s = self.H0 * 1e5 / _MPC_CM                      # 1/s
+        rho_crit = 3.0 * H0_s ** 2 / (8.0 * math.pi * _G_SI) * 1e-3   # g/cm^3 (G in SI -> kg/m^3 -> g/cm^3)
+        a_B_c2 = 4.0 * (sigma_sb * 1e-3) / (speed_of_light_si ** 3) * 1e-3  # g/cm^3/K^4
+        self.Ogamma0 = a_B_c2 * self.Tcmb0 ** 4 / rho_crit
+        self.Tnu0 = 0.7137658555036082 * self.Tcmb0
+        nnu = int(math.floor(self.Neff))
+        self.neff_per_nu = self.Neff / nnu
+        massive = [m for m in self.m_nu if m > 0]
+        self.nmassless = nnu - len(massive)
+        self.nu_y = np.array(massive) / (_KB_EV_K * self.Tnu0)
+        self.Onu0 = self.Ogamma0 * self.nu_relative_density(0.0)
+        self.Ode0 = 1.0 - self.Om0 - self.Ogamma0 - self.Onu0
+        self.hubble_distance_mpc = speed_of_light_si / 1e3 / self.H0
+
+    def nu_relative_density(self, z):
+        prefac = 0.22710731766
+        p, invp, k = 1.83, 0.54644808743, 0.3173
+        curr = self.nu_y / (1.0 + z)
+        rel = (1.0 + (k * curr) ** p) ** invp
+        return prefac * self.neff_per_nu * (rel.sum() + self.nmassless)
+
+    def inv_efunc(self, z):
+        zp1 = 1.0 + z
+        Or = self.Ogamma0 * (1.0 + self.nu_relative_density(z))
+        return (zp1 ** 3 * (Or * zp1 + self.Om0) + self.Ode0) ** -0.5
+
+    def luminosity_distance_cm(self, z):
+        integral = quad(self.inv_efunc, 0.0, float(z), epsabs=0.0, epsrel=1e-13, limit=200)[0]
+        return (1.0 + z) * self.hubble_distance_mpc * integral * _MPC_CM
+
+
+cosmo = Planck18()
+
+
+# --------------------------------------------------------------------------------------------------
+# utilities (redback/utils.py)
+# --------------------------------------------------------------------------------------------------
+def calc_kcorrected_properties(frequency, redshift, time):
+    """utils.py:373-384"""
+    return frequency * (1 + redshift), time / (1 + redshift)
+
+
+def lambda_to_nu(wavelength):
+    """utils.py:357-362"""
+    return speed_of_light_si / (wavelength * 1.e-10)
+
+
+def nu_to_lambda(frequency):
+    """utils.py:365-370"""
+    return 1.e10 * (speed_of_light_si / frequency)
+
+
+# --------------------------------------------------------------------------------------------------
+# engines
+# --------------------------------------------------------------------------------------------------
+def nickelcobalt_engine(time, f_nickel, mej):
+    """supernova_models.py:564-579"""
+    return f_nickel * mej * (6.45e43 * np.exp(-time / 8.8) + 1.45e43 * np.exp(-time / 111.3))
+
+
+def basic_magnetar(time, p0, bp, mass_ns, theta_pb):
+    """magnetar_models.py:171-185 (time in seconds)"""
+    with np.errstate(all="ignore"):
+        erot = 2.6e52 * (mass_ns / 1.4) ** (3. / 2.) * p0 ** (-2)
+        tp = 1.3e5 * bp ** (-2) * p0 ** 2 * (mass_ns / 1.4) ** (3. / 2.) * (np.sin(theta_pb)) ** (-2)
+        return 2. * erot / tp / (1. + 2. * time / tp) ** 2
+
+
+# --------------------------------------------------------------------------------------------------
+# interaction process: Arnett diffusion  (interaction_processes.py:33-65)
+# --------------------------------------------------------------------------------------------------
+def diffusion(time, dense_times, luminosity, kappa, kappa_gamma, mej, vej):
+    """Return (tau_diff [days], L_bol[E]).  Follows interaction_processes.py:33-65 step by step."""
+    time = np.asarray(time, dtype=float)
+    with np.errstate(all="ignore"):
+        diffusion_constant = 2.0 * solar_mass / (13.7 * speed_of_light * km_cgs)          # :36
+        trapping_constant = 3.0 * solar_mass / (4 * np.pi * km_cgs ** 2)                   # :37
+        tau_diff = np.sqrt(diffusion_constant * kappa * mej / vej) / day_to_s              # :39
+        trap_coeff = (trapping_constant * kappa_gamma * mej / (vej ** 2)) / day_to_s ** 2  # :40
+        t_end = dense_times[-1]
+        tb = max(0.0, np.min(dense_times))                                                  # :42-43
+        interp = interp1d(dense_times, luminosity, copy=False, assume_sorted=True)         # :44
+        uniq = np.unique(time[(time >= tb) & (time <= t_end)])                              # :46
+        lu = len(uniq)
+        lsp = np.logspace(np.log10(tau_diff / t_end) - 3, 0, 50)                            # :49-50
+        xm = np.unique(np.concatenate((lsp, 1 - lsp)))                                      # :51
+        nodes = np.clip(tb + (uniq.reshape(lu, 1) - tb) * xm, tb, t_end)                    # :53
+        te2 = nodes[:, -1] ** 2                                                             # :55
+        lum = interp(nodes)                                                                 # :56
+        integrand = lum * nodes * np.exp((nodes ** 2 - te2.reshape(lu, 1)) / tau_diff ** 2)  # :57
+        integrand[np.isnan(integrand)] = 0.                                                 # :58
+        out = np.trapezoid(integrand, nodes, axis=1)                                        # :60
+        out *= -2.0 * np.expm1(-trap_coeff / te2) / tau_diff ** 2                           # :61
+        return tau_diff, out[np.searchsorted(uniq, time)]                                   # :63
+
+
+# --------------------------------------------------------------------------------------------------
+# photosphere  (photosphere.py:56-111)
+# --------------------------------------------------------------------------------------------------
+def temperature_floor(time, luminosity, vej, temperature_floor):
+    """Return (T_phot[E], R_phot[E]).  photosphere.py:87-111"""
+    with np.errstate(all="ignore"):
+        radius_constant = km_cgs * day_to_s
+        stef_constant = 4 * np.pi * sigma_sb
+        r2 = (radius_constant * vej * time) ** 2
+        rec2 = luminosity / (stef_constant * temperature_floor ** 4)
+        mask = r2 <= rec2
+        r = rec2 ** 0.5
+        r[mask] = r2[mask] ** 0.5
+        temp = np.zeros(len(time))
+        temp[mask] = (luminosity[mask] / (stef_constant * r2[mask])) ** 0.25
+        temp[~mask] = temperature_floor
+        return temp, r
+
+
+# --------------------------------------------------------------------------------------------------
+# SEDs  (sed.py)
+# --------------------------------------------------------------------------------------------------
+_ERG_S_CM2_HZ_TO_MJY = 1e26
+
+
+def blackbody_to_flux_density(temperature, r_photosphere, dl, frequency):
+    """sed.py:199-222; returns erg/s/Hz/cm^2 (plain floats instead of astropy Quantity)."""
+    with np.errstate(all="ignore"):
+        num = 2 * np.pi * planck * frequency ** 3 * r_photosphere ** 2
+        denom = dl ** 2 * speed_of_light ** 2
+        frac = 1. / np.expm1((planck * frequency) / (boltzmann_constant * temperature))
+        return num / denom * frac
+
+
+def cutoff_blackbody_mjy(time, temperature, luminosity, r_photosphere, frequency, dl,
+                         cutoff_wavelength=3000., absorption_index=1.0):
+    """sed.py:301-426 + _SED.flux_density (sed.py:225-251).  `frequency` is [E] (or scalar) for the
+    flux_density branch, or [N_lambda, 1] for the spectral-grid branch.  Returns mJy."""
+    from scipy.special import gammainc, gammaincc, gamma as gamma_func
+    time = np.asarray(time, dtype=float)
+    X_CONST = planck * speed_of_light / boltzmann_constant
+    FLUX_CONST = 4 * np.pi * 2 * np.pi * planck * speed_of_light ** 2 * angstrom_cgs
+    if isinstance(frequency, (float, int)):
+        frequency = np.array([frequency] * len(time))                                      # :233-234
+    uniq = np.unique(time)
+    uniq_is = np.searchsorted(time, uniq, sorter=np.argsort(time))                         # :329-331
+    lam_c = cutoff_wavelength * angstrom_cgs
+    alpha = absorption_index
+    if alpha >= 4.0:
+        raise ValueError("absorption_index >= 4 is not supported")                         # :396-400
+    with np.errstate(all="ignore"):
+        # _set_norm, :386-421
+        norms = luminosity[uniq_is] / (FLUX_CONST / angstrom_cgs * r_photosphere[uniq_is] ** 2
+                                       * temperature[uniq_is])
+        tp = temperature[uniq_is]
+        kT_over_hc = tp / X_CONST
+        n_arr = np.arange(1, 11, dtype=float)
+        x_c = 1.0 / (lam_c * kT_over_hc)
+        n_x_c = np.outer(x_c, n_arr)
+        above = kT_over_hc ** 4 * gamma_func(4.0) * np.sum(gammainc(4.0, n_x_c) / n_arr ** 4, axis=1)
+        s = 4.0 - alpha
+        below = (1.0 / lam_c ** alpha) * kT_over_hc ** s * gamma_func(s) * \
+            np.sum(gammaincc(s, n_x_c) / n_arr ** s, axis=1)
+        norms = norms / ((above + below) / tp)
+        # wavelength property, :345-352
+        if len(frequency) == 1:
+            frequency = np.ones(len(time)) * frequency
+        wavelength = nu_to_lambda(frequency) * angstrom_cgs
+        if len(wavelength) != len(time):
+            wavelength = np.tile(wavelength.T, (len(time), 1)).T
+        mask = wavelength < lam_c
+        # _set_sed, :362-384
+        if np.size(wavelength) != np.size(time):
+            R = np.tile(r_photosphere, (len(frequency), 1))
+            T = np.tile(temperature, (len(frequency), 1))
+        else:
+            R, T = r_photosphere, temperature
+        sed = np.where(mask,
+                       FLUX_CONST * (R ** 2 * (wavelength / lam_c) ** alpha / wavelength ** 5)
+                       / np.expm1(X_CONST / wavelength / T),
+                       FLUX_CONST * (R ** 2 / wavelength ** 5) / np.expm1(X_CONST / wavelength / T))
+        sed = sed * norms[np.searchsorted(uniq, time)]
+        # _SED.flux_density, :239-251
+        fd = sed / (4 * np.pi * dl ** 2)
+        fd = fd * nu_to_lambda(frequency)
+        fd = fd / frequency
+        return fd * _ERG_S_CM2_HZ_TO_MJY
+
+
+# --------------------------------------------------------------------------------------------------
+# supernova models (supernova_models.py)
+# --------------------------------------------------------------------------------------------------
+def arnett_bolometric(time, f_nickel, mej, *, vej, kappa, kappa_gamma, dense_resolution=1000, **_):
+    """supernova_models.py:949-969 with the default interaction_process=Diffusion."""
+    time = np.asarray(time, dtype=float)
+    dense_times = np.linspace(0, time[-1] + 100, dense_resolution)
+    dense_lbols = nickelcobalt_engine(dense_times, f_nickel, mej)
+    return diffusion(time, dense_times, dense_lbols, kappa, kappa_gamma, mej, vej)[1]
+
+
+def basic_magnetar_powered_bolometric(time, p0, bp, mass_ns, theta_pb, *, mej, vej, kappa, kappa_gamma,
+                                      dense_resolution=1000, **_):
+    """supernova_models.py:1447-1469 (slsn_bolometric :1532-1549 is the same function)."""
+    time = np.asarray(time, dtype=float)
+    dense_times = np.linspace(0, time[-1] + 100, dense_resolution)
+    dense_lbols = basic_magnetar(dense_times * day_to_s, p0, bp, mass_ns, theta_pb)
+    return diffusion(time, dense_times, dense_lbols, kappa, kappa_gamma, mej, vej)[1]
+
+
+slsn_bolometric = basic_magnetar_powered_bolometric
+
+
+def _sn_flux_density(time, redshift, bolometric, sed, *, frequency, vej, temperature_floor, dl=None,
+                     cutoff_wavelength=3000., absorption_index=1.0):
+    """flux_density branch shared by arnett (:999-1007), basic_magnetar_powered (:1501-1509) and
+    slsn (:1587-1597).  Returns mJy[E]."""
+    time = np.asarray(time, dtype=float)
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    frequency, time = calc_kcorrected_properties(np.asarray(frequency, dtype=float), redshift, time)
+    lbol = bolometric(time)
+    temp, rad = globals()["temperature_floor"](time, lbol, vej, temperature_floor)
+    with np.errstate(all="ignore"):
+        if sed == "blackbody":
+            fd = blackbody_to_flux_density(temp, rad, dl, frequency) * _ERG_S_CM2_HZ_TO_MJY
+        elif sed == "cutoff_blackbody":
+            freq = frequency if np.ndim(frequency) else float(frequency)
+            fd = cutoff_blackbody_mjy(time, temp, lbol, rad, freq, dl, cutoff_wavelength, absorption_index)
+        else:
+            raise ValueError(sed)
+        return fd * (1 + redshift)
+
+
+def arnett(time, redshift, f_nickel, mej, *, frequency, vej, kappa, kappa_gamma, temperature_floor,
+           dl=None, **kw):
+    """supernova_models.py:971-1007 (flux_density branch)."""
+    return _sn_flux_density(
+        time, redshift,
+        lambda t: arnett_bolometric(t, f_nickel, mej, vej=vej, kappa=kappa, kappa_gamma=kappa_gamma, **kw),
+        "blackbody", frequency=frequency, vej=vej, temperature_floor=temperature_floor, dl=dl)
+
+
+def basic_magnetar_powered(time, redshift, p0, bp, mass_ns, theta_pb, *, frequency, mej, vej, kappa,
+                           kappa_gamma, temperature_floor, dl=None, **kw):
+    """supernova_models.py:1471-1509 (flux_density branch)."""
+    return _sn_flux_density(
+        time, redshift,
+        lambda t: basic_magnetar_powered_bolometric(t, p0, bp, mass_ns, theta_pb, mej=mej, vej=vej,
+                                                    kappa=kappa, kappa_gamma=kappa_gamma, **kw),
+        "blackbody", frequency=frequency, vej=vej, temperature_floor=temperature_floor, dl=dl)
+
+
+def slsn(time, redshift, p0, bp, mass_ns, theta_pb, *, frequency, mej, vej, kappa, kappa_gamma,
+         temperature_floor, dl=None, sed="cutoff_blackbody", cutoff_wavelength=3000.,
+         absorption_index=1.0, **kw):
+    """supernova_models.py:1552-1597 (flux_density branch; default sed = CutoffBlackbody)."""
+    return _sn_flux_density(
+        time, redshift,
+        lambda t: basic_magnetar_powered_bolometric(t, p0, bp, mass_ns, theta_pb, mej=mej, vej=vej,
+                                                    kappa=kappa, kappa_gamma=kappa_gamma, **kw),
+        sed, frequency=frequency, vej=vej, temperature_floor=temperature_floor, dl=dl,
+        cutoff_wavelength=cutoff_wavelength, absorption_index=absorption_index)
+
+
+# --------------------------------------------------------------------------------------------------
+# likelihoods (likelihoods.py)
+# --------------------------------------------------------------------------------------------------
+def gaussian_log_likelihood(res, sigma):
+    """likelihoods.py:229-231"""
+    with np.errstate(all="ignore"):
+        return np.sum(- (res / sigma) ** 2 / 2 - np.log(2 * np.pi * sigma ** 2) / 2)
+
+
+def gaussian_likelihood(y, model, sigma):
+    """GaussianLikelihood.log_likelihood, likelihoods.py:221-227 (incl. np.nan_to_num)."""
+    return float(np.nan_to_num(gaussian_log_likelihood(np.asarray(y) - model, sigma)))
+
+
+def gaussian_likelihood_quadrature(y, model, sigma_i, sigma):
+    """GaussianLikelihoodQuadratureNoise.log_likelihood, likelihoods.py:767-790."""
+    with np.errstate(all="ignore"):
+        full = np.sqrt(np.asarray(sigma_i) ** 2. + sigma ** 2.)
+    return float(np.nan_to_num(gaussian_log_likelihood(np.asarray(y) - model, full)))
