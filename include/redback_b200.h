@@ -1,0 +1,154 @@
+/*
+ * redback_b200 -- C ABI of the B200-native batched light-curve + Gaussian-likelihood engine.
+ *
+ * This is the drop-in boundary for redback's per-sample Python hot path.  The
+ * reference has no native boundary of its own (it is pure Python); each entry point below names
+ * the reference Python interface it replaces (paths relative to the redback source tree).
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch / numpy types;
+ *   - `*_f64` entry points take DEVICE pointers and are stream-ordered (`stream` is a cudaStream_t
+ *     passed as void*; NULL = default stream); they never synchronise;
+ *   - `*_host` entry points take HOST pointers, do H2D, launch, D2H and synchronise;
+ *   - per-sample parameters are struct-of-arrays: params[row * N + sample];
+ *   - return 0 on success or a negative rb_status; rb_last_error() gives a message;
+ *   - there is no CPU fallback: without a usable CUDA device every compute call fails with
+ *     RB_ERR_CUDA.
+ */
+#ifndef REDBACK_B200_H
+#define REDBACK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RB_OK = 0,
+  RB_ERR_INVALID = -1,      /* bad argument (maps to Python ValueError)            */
+  RB_ERR_UNSUPPORTED = -2,  /* valid in the reference, not implemented on device   */
+  RB_ERR_CUDA = -3          /* CUDA runtime error / no device                      */
+} rb_status;
+
+/* ---- luminosity engines: redback/transient_models/supernova_models.py:564-579 (_nickelcobalt_engine),
+ *      redback/transient_models/magnetar_models.py:171-185 (basic_magnetar) ---------------------- */
+enum { RB_ENGINE_NICKEL = 0, RB_ENGINE_MAGNETAR = 1 };
+
+/* ---- output stage: bolometric models return L_bol; flux_density models go through
+ *      photosphere.TemperatureFloor (photosphere.py:56-111) and sed.Blackbody (sed.py:475-502) or
+ *      sed.CutoffBlackbody (sed.py:301-426) ------------------------------------------------------ */
+enum { RB_SED_BOLOMETRIC = 0, RB_SED_BLACKBODY = 1, RB_SED_CUTOFF_BLACKBODY = 2 };
+
+/* ---- noise model of the fused likelihood reduction ------------------------------------------- */
+enum {
+  RB_SIGMA_FIXED = 0,      /* GaussianLikelihood(sigma=array|float)   likelihoods.py:146-231        */
+  RB_SIGMA_SAMPLED = 1,    /* GaussianLikelihood(sigma=None): `sigma` is a sampled parameter :179-185 */
+  RB_SIGMA_QUADRATURE = 2  /* GaussianLikelihoodQuadratureNoise: sqrt(sigma_i^2 + sigma^2) :738-790 */
+};
+
+/* Row indices of the SoA parameter block of the supernova path (rows not used by the chosen
+ * engine / sed are ignored and may hold anything). */
+enum {
+  RB_SN_REDSHIFT = 0,          /* ignored (0) for RB_SED_BOLOMETRIC */
+  RB_SN_F_NICKEL = 1,          /* nickel engine */
+  RB_SN_P0 = 1,                /* magnetar engine: p0 [ms] */
+  RB_SN_BP = 2,                /*   bp [1e14 G]            */
+  RB_SN_MASS_NS = 3,           /*   mass_ns [Msun]         */
+  RB_SN_THETA_PB = 4,          /*   theta_pb [rad]         */
+  RB_SN_MEJ = 5,               /* [Msun] */
+  RB_SN_VEJ = 6,               /* [km/s] */
+  RB_SN_KAPPA = 7,
+  RB_SN_KAPPA_GAMMA = 8,
+  RB_SN_TEMPERATURE_FLOOR = 9, /* [K]; unused for RB_SED_BOLOMETRIC */
+  RB_SN_NPARAM = 10
+};
+
+/* Flat LambdaCDM with massive neutrinos, the subset of astropy's FlatLambdaCDM that
+ * `cosmology.luminosity_distance(redshift).cgs.value` (supernova_models.py:997) needs. */
+typedef struct {
+  double hubble_distance_cm;
+  double Om0, Ogamma0, Ode0;
+  double neff_per_nu;
+  double nu_y[3];      /* m_nu / (k_B T_nu0) of the massive species */
+  int n_massive;
+  int n_massless;
+} rb_cosmology;
+
+/* Fill `out` from (H0 [km/s/Mpc], Om0, Tcmb0 [K], Neff, m_nu[3] [eV]). */
+int rb_cosmology_flat_lcdm(double H0, double Om0, double Tcmb0, double Neff, const double m_nu[3],
+                           rb_cosmology* out);
+/* astropy.cosmology.Planck18 (redback's default `cosmo`, supernova_models.py:996). */
+int rb_cosmology_planck18(rb_cosmology* out);
+
+typedef struct {
+  int engine;               /* RB_ENGINE_*  */
+  int sed;                  /* RB_SED_*     */
+  int sigma_mode;           /* RB_SIGMA_*   */
+  int dense_resolution;     /* kwargs 'dense_resolution', default 1000 (supernova_models.py:964) */
+  double cutoff_wavelength; /* Angstrom, default 3000 (supernova_models.py:1582)                 */
+  double absorption_index;  /* default 1.0; 4 - index must be a positive integer on device       */
+  rb_cosmology cosmology;   /* used only when dl_cm == NULL                                      */
+} rb_sn_config;
+
+/* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */
+int rb_sn_config_default(rb_sn_config* cfg);
+
+/*
+ * Fused supernova light curve (+ optional Gaussian log-likelihood) for N parameter samples x E epochs.
+ *
+ * Replaces, per sample, the reference call chain
+ *   GaussianLikelihood.log_likelihood            redback/likelihoods.py:221-231
+ *     -> arnett | basic_magnetar_powered | slsn  redback/transient_models/supernova_models.py:971-1007, 1471-1509, 1552-1597
+ *        (or the *_bolometric functions :949-969, :1447-1469, :1532-1549)
+ *        -> Diffusion.convert_input_luminosity   redback/interaction_processes.py:33-65
+ *        -> TemperatureFloor                     redback/photosphere.py:56-111
+ *        -> Blackbody | CutoffBlackbody          redback/sed.py:199-222, 301-426
+ *
+ *   params      [RB_SN_NPARAM][N]  device, SoA
+ *   t_obs       [E]  observer-frame days (source-frame for RB_SED_BOLOMETRIC); must be >= 0 and
+ *                    max(t_obs) <= t_obs[E-1] + 100  (outside that the reference indexes out of range)
+ *   freq_obs    [E]  observer-frame Hz (ignored for RB_SED_BOLOMETRIC; may be NULL then)
+ *   dl_cm       [N]  luminosity distance in cm, or NULL to integrate cfg->cosmology on device
+ *   y, sigma    [E]  data and (fixed or sigma_i) noise; y == NULL skips the likelihood
+ *   sigma_param [N]  sampled `sigma` for RB_SIGMA_SAMPLED / RB_SIGMA_QUADRATURE, else NULL
+ *   out_model   [N][E] row-major model output (erg/s bolometric, mJy otherwise) or NULL
+ *   out_logl    [N]  np.nan_to_num(log L) or NULL
+ */
+int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* params,
+                   const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
+                   const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
+                   void* stream);
+
+/* Same computation with HOST buffers (H2D + kernel + D2H + sync inside the call). */
+int rb_sn_eval_f64_host(const rb_sn_config* cfg, int64_t N, int64_t E, const double* params,
+                        const double* t_obs, const double* freq_obs, const double* dl_cm,
+                        const double* y, const double* sigma, const double* sigma_param,
+                        double* out_model, double* out_logl);
+
+/* Luminosity distance [cm] for N redshifts on device (same quadrature the fused kernels use). */
+int rb_luminosity_distance_f64(const rb_cosmology* cosmo, int64_t N, const double* redshift,
+                               double* out_dl_cm, void* stream);
+
+/*
+ * Stand-alone Gaussian log-likelihood reduction over a precomputed model matrix:
+ * GaussianLikelihood._gaussian_log_likelihood + np.nan_to_num (likelihoods.py:221-231, 767-790).
+ *   model [N][E], y [E], sigma [E], sigma_param [N] or NULL, out_logl [N]
+ */
+int rb_gaussian_logl_f64(int sigma_mode, int64_t N, int64_t E, const double* model, const double* y,
+                         const double* sigma, const double* sigma_param, double* out_logl, void* stream);
+
+/* FP64 FMA micro-benchmark: runs `iters` dependent-chain DFMAs per thread on a full grid and
+ * returns the achieved TFLOP/s (2 flop per FMA) in *out_tflops.  Used as the roofline denominator. */
+int rb_measure_fp64_peak(int iters, double* out_tflops, double* out_ms);
+
+/* Number of kernel launches issued by this library in the current process. */
+int64_t rb_launch_count(void);
+
+const char* rb_last_error(void);
+const char* rb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REDBACK_B200_H */

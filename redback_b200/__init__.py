@@ -1,0 +1,14 @@
+"""redback_b200: B200-native batched light-curve + Gaussian-likelihood engine behind redback's model /
+likelihood API.  The CUDA library is the only compute path; importing the package does
+not need a GPU, calling it does."""
+from . import _capi, engine, likelihoods, supernova_models  # noqa: F401
+from .likelihoods import GaussianLikelihood, GaussianLikelihoodQuadratureNoise  # noqa: F401
+
+__version__ = "0.1.0"
+
+# redback.model_library.all_models_dict equivalent (model_library.py:20-34) for the fused models
+all_models_dict = {
+    name: getattr(supernova_models, name)
+    for name in ("arnett_bolometric", "arnett", "basic_magnetar_powered_bolometric", "basic_magnetar_powered",
+                 "slsn_bolometric", "slsn")
+}

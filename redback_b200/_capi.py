@@ -1,0 +1,100 @@
+"""ctypes binding of the C ABI in include/redback_b200.h.
+
+The shared library is the product; there is no CPU fallback.  If it is missing it is built in-tree
+with nvcc; if that is impossible, importing any compute entry point raises.
+"""
+import ctypes as C
+import os
+
+from . import _build
+
+RB_OK, RB_ERR_INVALID, RB_ERR_UNSUPPORTED, RB_ERR_CUDA = 0, -1, -2, -3
+ENGINE_NICKEL, ENGINE_MAGNETAR = 0, 1
+SED_BOLOMETRIC, SED_BLACKBODY, SED_CUTOFF_BLACKBODY = 0, 1, 2
+SIGMA_FIXED, SIGMA_SAMPLED, SIGMA_QUADRATURE = 0, 1, 2
+
+SN_ROWS = dict(redshift=0, f_nickel=1, p0=1, bp=2, mass_ns=3, theta_pb=4, mej=5, vej=6, kappa=7,
+               kappa_gamma=8, temperature_floor=9)
+SN_NPARAM = 10
+
+
+class Cosmology(C.Structure):
+    _fields_ = [("hubble_distance_cm", C.c_double), ("Om0", C.c_double), ("Ogamma0", C.c_double),
+                ("Ode0", C.c_double), ("neff_per_nu", C.c_double), ("nu_y", C.c_double * 3),
+                ("n_massive", C.c_int), ("n_massless", C.c_int)]
+
+
+class SnConfig(C.Structure):
+    _fields_ = [("engine", C.c_int), ("sed", C.c_int), ("sigma_mode", C.c_int), ("dense_resolution", C.c_int),
+                ("cutoff_wavelength", C.c_double), ("absorption_index", C.c_double), ("cosmology", Cosmology)]
+
+
+class RedbackB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+_dp = C.c_void_p  # device or host pointer to double
+
+EXPORTS = {
+    "rb_last_error": (C.c_char_p, []),
+    "rb_version": (C.c_char_p, []),
+    "rb_launch_count": (C.c_int64, []),
+    "rb_cosmology_flat_lcdm": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double,
+                                         C.POINTER(C.c_double), C.POINTER(Cosmology)]),
+    "rb_cosmology_planck18": (C.c_int, [C.POINTER(Cosmology)]),
+    "rb_sn_config_default": (C.c_int, [C.POINTER(SnConfig)]),
+    "rb_sn_eval_f64": (C.c_int, [C.POINTER(SnConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
+    "rb_sn_eval_f64_host": (C.c_int, [C.POINTER(SnConfig), C.c_int64, C.c_int64] + [_dp] * 9),
+    "rb_luminosity_distance_f64": (C.c_int, [C.POINTER(Cosmology), C.c_int64, _dp, _dp, C.c_void_p]),
+    "rb_gaussian_logl_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 5 + [C.c_void_p]),
+    "rb_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+
+def lib():
+    """Load (building if necessary) libredback_b200.so and declare its signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build()
+    handle = C.CDLL(path)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(handle, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc == RB_OK:
+        return
+    msg = lib().rb_last_error().decode()
+    if rc == RB_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == RB_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RedbackB200Error(msg)
+
+
+def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
+              absorption_index=1.0, cosmology=None):
+    cfg = SnConfig()
+    check(lib().rb_sn_config_default(C.byref(cfg)))
+    cfg.engine, cfg.sed, cfg.sigma_mode = engine, sed, sigma_mode
+    cfg.dense_resolution = int(dense_resolution)
+    cfg.cutoff_wavelength = float(cutoff_wavelength)
+    cfg.absorption_index = float(absorption_index)
+    if cosmology is not None:
+        cfg.cosmology = cosmology
+    return cfg
+
+
+def flat_lcdm(H0, Om0, Tcmb0=2.7255, Neff=3.046, m_nu=(0.06, 0.0, 0.0)):
+    out = Cosmology()
+    arr = (C.c_double * 3)(*[float(m) for m in m_nu])
+    check(lib().rb_cosmology_flat_lcdm(float(H0), float(Om0), float(Tcmb0), float(Neff), arr, C.byref(out)))
+    return out

@@ -1,0 +1,269 @@
+// redback_b200 -- C ABI (include/redback_b200.h): argument checking, launches, host-buffer variants.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "sn_kernel.cu"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t>* launch_counter() {
+  static std::atomic<int64_t> c{0};
+  return &c;
+}
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(RB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define RB_CUDA(call)                                        \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
+  } while (0)
+
+size_t sn_smem_bytes(int D) { return sizeof(double) * (size_t)(2 * D + rb::kNodes + rb::kNodesHalf + 32 + 36); }
+
+int sn_block_threads(int64_t E) {
+  int b = (int)((E + 31) / 32) * 32;
+  if (b < 128) b = 128;
+  if (b > 512) b = 512;
+  return b;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rb_last_error(void) { return g_err.c_str(); }
+const char* rb_version(void) { return "redback_b200 0.1 (sm_100a)"; }
+int64_t rb_launch_count(void) { return launch_counter()->load(); }
+
+int rb_cosmology_flat_lcdm(double H0, double Om0, double Tcmb0, double Neff, const double m_nu[3],
+                           rb_cosmology* out) {
+  if (!out || !(H0 > 0)) return fail(RB_ERR_INVALID, "rb_cosmology_flat_lcdm: bad arguments");
+  const double mpc_cm = 3.0856775814913674e24, G_si = 6.6743e-11, kb_ev_k = 8.617333262145179e-05;
+  const double H0_s = H0 * 1e5 / mpc_cm;
+  const double rho_crit = 3.0 * H0_s * H0_s / (8.0 * M_PI * G_si) * 1e-3;
+  const double a_B_c2 = 4.0 * (rb::kSigmaSB * 1e-3) / (rb::kCSI * rb::kCSI * rb::kCSI) * 1e-3;
+  std::memset(out, 0, sizeof(*out));
+  out->Om0 = Om0;
+  out->Ogamma0 = a_B_c2 * std::pow(Tcmb0, 4) / rho_crit;
+  const double Tnu0 = 0.7137658555036082 * Tcmb0;
+  const int nnu = (int)std::floor(Neff);
+  out->neff_per_nu = nnu > 0 ? Neff / nnu : 0.0;
+  int nm = 0;
+  for (int i = 0; i < 3 && i < nnu; ++i)
+    if (m_nu && m_nu[i] > 0) out->nu_y[nm++] = m_nu[i] / (kb_ev_k * Tnu0);
+  out->n_massive = nm;
+  out->n_massless = nnu - nm;
+  double rel = out->n_massless;
+  for (int i = 0; i < nm; ++i) rel += std::pow(1.0 + std::pow(0.3173 * out->nu_y[i], 1.83), 0.54644808743);
+  const double Onu0 = out->Ogamma0 * 0.22710731766 * out->neff_per_nu * rel;
+  out->Ode0 = 1.0 - Om0 - out->Ogamma0 - Onu0;
+  out->hubble_distance_cm = rb::kCSI / 1e3 / H0 * mpc_cm;
+  return RB_OK;
+}
+
+int rb_cosmology_planck18(rb_cosmology* out) {
+  const double m_nu[3] = {0.06, 0.0, 0.0};
+  return rb_cosmology_flat_lcdm(67.66, 0.30966, 2.7255, 3.046, m_nu, out);
+}
+
+int rb_sn_config_default(rb_sn_config* cfg) {
+  if (!cfg) return fail(RB_ERR_INVALID, "rb_sn_config_default: null config");
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->engine = RB_ENGINE_NICKEL;
+  cfg->sed = RB_SED_BLACKBODY;
+  cfg->sigma_mode = RB_SIGMA_FIXED;
+  cfg->dense_resolution = 1000;
+  cfg->cutoff_wavelength = 3000.0;
+  cfg->absorption_index = 1.0;
+  return rb_cosmology_planck18(&cfg->cosmology);
+}
+
+static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* params, const void* t_obs,
+                    const void* freq_obs, const void* y, const void* sigma, const void* sigma_param,
+                    const void* out_model, const void* out_logl) {
+  if (!cfg) return fail(RB_ERR_INVALID, "rb_sn_eval: null config");
+  if (N < 0 || E <= 0 || E > (1 << 24)) return fail(RB_ERR_INVALID, "rb_sn_eval: need N >= 0 and 0 < E <= 2^24");
+  if (cfg->engine != RB_ENGINE_NICKEL && cfg->engine != RB_ENGINE_MAGNETAR)
+    return fail(RB_ERR_INVALID, "rb_sn_eval: unknown engine");
+  if (cfg->sed < RB_SED_BOLOMETRIC || cfg->sed > RB_SED_CUTOFF_BLACKBODY)
+    return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sed");
+  if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_QUADRATURE)
+    return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sigma_mode");
+  if (cfg->dense_resolution < 2 || cfg->dense_resolution > 12000)
+    return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution must be in [2, 12000]");
+  if (!params || !t_obs) return fail(RB_ERR_INVALID, "rb_sn_eval: params and t_obs are required");
+  if (cfg->sed != RB_SED_BOLOMETRIC && !freq_obs)
+    return fail(RB_ERR_INVALID, "rb_sn_eval: freq_obs is required for flux_density output");
+  if (cfg->sed == RB_SED_CUTOFF_BLACKBODY) {
+    // sed.py:396-400: absorption_index >= 4 raises ValueError in the reference
+    if (cfg->absorption_index >= 4.0)
+      return fail(RB_ERR_INVALID, "absorption_index >= 4 is not supported: the integral below the cutoff diverges");
+    const double s = 4.0 - cfg->absorption_index;
+    if (s != std::floor(s) || s < 1.0)
+      return fail(RB_ERR_UNSUPPORTED, "CutoffBlackbody on device needs integer 4 - absorption_index in {1,2,3,4}");
+    if (!(cfg->cutoff_wavelength > 0)) return fail(RB_ERR_INVALID, "cutoff_wavelength must be positive");
+  }
+  if (y) {
+    if (!out_logl) return fail(RB_ERR_INVALID, "rb_sn_eval: y given but out_logl is null");
+    if (cfg->sigma_mode != RB_SIGMA_SAMPLED && !sigma)
+      return fail(RB_ERR_INVALID, "rb_sn_eval: sigma is required for this sigma_mode");
+    if (cfg->sigma_mode != RB_SIGMA_FIXED && !sigma_param)
+      return fail(RB_ERR_INVALID, "rb_sn_eval: sigma_param is required for this sigma_mode");
+  } else if (out_logl) {
+    return fail(RB_ERR_INVALID, "rb_sn_eval: out_logl requested without data y");
+  }
+  if (!out_model && !out_logl) return fail(RB_ERR_INVALID, "rb_sn_eval: nothing to compute");
+  return RB_OK;
+}
+
+int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* params,
+                   const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
+                   const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
+                   void* stream) {
+  int rc = sn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  rb::SnArgs a;
+  a.cfg = *cfg;
+  a.N = N;
+  a.E = (int)E;
+  a.params = params;
+  a.t_obs = t_obs;
+  a.freq_obs = freq_obs;
+  a.dl_cm = dl_cm;
+  a.y = y;
+  a.sigma = (cfg->sigma_mode == RB_SIGMA_SAMPLED && !sigma) ? t_obs : sigma;  // never dereferenced meaningfully
+  a.sigma_param = sigma_param;
+  a.out_model = out_model;
+  a.out_logl = y ? out_logl : nullptr;
+  const size_t smem = sn_smem_bytes(cfg->dense_resolution);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(rb::sn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sn_kernel)");
+  const int threads = sn_block_threads(E);
+  const int64_t grid = N < 2147483647LL ? N : 2147483647LL;
+  rb::sn_kernel<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(a);
+  launch_counter()->fetch_add(1);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
+int rb_luminosity_distance_f64(const rb_cosmology* cosmo, int64_t N, const double* redshift,
+                               double* out_dl_cm, void* stream) {
+  if (!cosmo || !redshift || !out_dl_cm || N < 0) return fail(RB_ERR_INVALID, "rb_luminosity_distance: bad arguments");
+  if (N == 0) return RB_OK;
+  const int threads = 256, wpb = threads / 32;
+  rb::dl_kernel<<<(unsigned)((N + wpb - 1) / wpb), threads, 0, (cudaStream_t)stream>>>(*cosmo, N, redshift, out_dl_cm);
+  launch_counter()->fetch_add(1);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
+int rb_gaussian_logl_f64(int sigma_mode, int64_t N, int64_t E, const double* model, const double* y,
+                         const double* sigma, const double* sigma_param, double* out_logl, void* stream) {
+  if (!model || !y || !out_logl || N < 0 || E <= 0) return fail(RB_ERR_INVALID, "rb_gaussian_logl: bad arguments");
+  if (sigma_mode < RB_SIGMA_FIXED || sigma_mode > RB_SIGMA_QUADRATURE)
+    return fail(RB_ERR_INVALID, "rb_gaussian_logl: unknown sigma_mode");
+  if (sigma_mode != RB_SIGMA_SAMPLED && !sigma) return fail(RB_ERR_INVALID, "rb_gaussian_logl: sigma required");
+  if (sigma_mode != RB_SIGMA_FIXED && !sigma_param) return fail(RB_ERR_INVALID, "rb_gaussian_logl: sigma_param required");
+  if (N == 0) return RB_OK;
+  const int threads = E >= 256 ? 256 : (E >= 128 ? 128 : 64);
+  const int64_t grid = N < 1048576 ? N : 1048576;
+  rb::logl_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(sigma_mode, N, (int)E, model, y,
+                                                                         sigma ? sigma : y, sigma_param, out_logl);
+  launch_counter()->fetch_add(1);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
+namespace {
+struct DevBuf {
+  double* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n * sizeof(double) : sizeof(double)); }
+};
+}  // namespace
+
+int rb_sn_eval_f64_host(const rb_sn_config* cfg, int64_t N, int64_t E, const double* params,
+                        const double* t_obs, const double* freq_obs, const double* dl_cm,
+                        const double* y, const double* sigma, const double* sigma_param,
+                        double* out_model, double* out_logl) {
+  int rc = sn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
+  const size_t nN = (size_t)N, nE = (size_t)E;
+  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
+    if (!h) return cudaSuccess;
+    cudaError_t e = b.alloc(n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  RB_CUDA(up(d_par, params, (size_t)RB_SN_NPARAM * nN));
+  RB_CUDA(up(d_t, t_obs, nE));
+  RB_CUDA(up(d_f, freq_obs, nE));
+  RB_CUDA(up(d_dl, dl_cm, nN));
+  RB_CUDA(up(d_y, y, nE));
+  RB_CUDA(up(d_s, sigma, nE));
+  RB_CUDA(up(d_sp, sigma_param, nN));
+  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
+  if (out_logl) RB_CUDA(d_l.alloc(nN));
+  rc = rb_sn_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
+  if (rc != RB_OK) return rc;
+  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
+  RB_CUDA(cudaDeviceSynchronize());
+  return RB_OK;
+}
+
+int rb_measure_fp64_peak(int iters, double* out_tflops, double* out_ms) {
+  if (iters <= 0 || !out_tflops) return fail(RB_ERR_INVALID, "rb_measure_fp64_peak: bad arguments");
+  int dev = 0, sms = 0;
+  RB_CUDA(cudaGetDevice(&dev));
+  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* d = nullptr;
+  RB_CUDA(cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t e0, e1;
+  RB_CUDA(cudaEventCreate(&e0));
+  RB_CUDA(cudaEventCreate(&e1));
+  const int threads = 512, blocks = sms * 4;
+  rb::dfma_kernel<<<blocks, threads>>>(iters / 8 + 1, d);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    rb::dfma_kernel<<<blocks, threads>>>(iters, d);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  launch_counter()->fetch_add(6);
+  cudaError_t e = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "dfma_kernel");
+  const double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+  *out_tflops = flops / (best * 1e-3) / 1e12;
+  if (out_ms) *out_ms = best;
+  return RB_OK;
+}
+
+}  // extern "C"

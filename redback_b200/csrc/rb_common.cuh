@@ -1,0 +1,109 @@
+// redback_b200 -- shared device helpers (constants, exp, reductions, cosmology quadrature).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "redback_b200.h"
+
+namespace rb {
+
+// ---- constants: redback/constants.py:1-23 (astropy CODATA-2018 cgs), SURVEY.md §8 a20 ----------
+constexpr double kC = 29979245800.0;
+constexpr double kCSI = 299792458.0;
+constexpr double kH = 6.62607015e-27;
+constexpr double kKB = 1.380649e-16;
+constexpr double kSigmaSB = 5.6703744191844314e-05;
+constexpr double kMsun = 1.988409870698051e33;
+constexpr double kKm = 100000.0;
+constexpr double kDay = 86400.0;
+constexpr double kAngstrom = 1e-08;
+constexpr double kPi = 3.141592653589793;
+
+// interaction_processes.py:36-37
+constexpr double kDiffusionConst = 2.0 * kMsun / (13.7 * kC * kKm);
+constexpr double kTrappingConst = 3.0 * kMsun / (4 * kPi * (kKm * kKm));
+// photosphere.py:58-59
+constexpr double kRadiusConst = kKm * kDay;
+constexpr double kStefConst = 4 * kPi * kSigmaSB;
+// sed.py:303-304
+constexpr double kXConst = kH * kC / kKB;
+constexpr double kFluxConst = 4 * kPi * 2 * kPi * kH * (kC * kC) * kAngstrom;
+// erg s^-1 cm^-2 Hz^-1 -> mJy
+constexpr double kToMJy = 1e26;
+
+// ---- table-driven exp -------------------------------------------------------------------------
+// exp(x) = 2^m * 2^(j/32) * exp(r), k = rint(x*32/ln2) = 32 m + j, |r| <= ln2/64.
+// Degree-6 Taylor for expm1(r) (truncation < 4e-18).  Valid for -708 < x < 709 (no denormal /
+// overflow handling: callers clamp).  `tab` points at 2^(j/32), j=0..31 (shared memory copy of
+// RB_EXP2_32).  PRECISE adds the low word of ln2/32 to the reduction (abs. error of the reduced
+// argument < 1e-18 instead of |x| * 8e-17).
+constexpr double kExpMagic = 6755399441055744.0;  // 1.5 * 2^52
+constexpr double k32OverLn2 = 46.16624130844683;
+constexpr double kLn2Over32Hi = 0.02166084939249829;
+constexpr double kLn2Over32Lo = 7.250602028496811e-19;
+
+template <bool PRECISE>
+__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
+  double v = fma(x, k32OverLn2, kExpMagic);
+  int k = __double2loint(v);
+  double kd = v - kExpMagic;
+  double r = fma(kd, -kLn2Over32Hi, x);
+  if (PRECISE) r = fma(kd, -kLn2Over32Lo, r);
+  double q = fma(r, 0.001388888888888889, 0.008333333333333333);
+  q = fma(r, q, 0.041666666666666664);
+  q = fma(r, q, 0.16666666666666666);
+  q = fma(r, q, 0.5);
+  q = fma(r, q, 1.0);
+  double p = r * q;
+  double t = tab[k & 31];
+  double res = fma(t, p, t);
+  int hi = __double2hiint(res) + ((k >> 5) << 20);
+  return __hiloint2double(hi, __double2loint(res));
+}
+
+// ---- reductions -------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block; result valid in every thread.  `scratch` has >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double s = (lane < nw) ? scratch[lane] : 0.0;
+    s = warp_sum(s);
+    if (lane == 0) scratch[32] = s;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+// np.nan_to_num for a float64 scalar (likelihoods.py:227)
+__device__ __forceinline__ double nan_to_num(double v) {
+  if (isnan(v)) return 0.0;
+  if (isinf(v)) return v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+  return v;
+}
+
+// ---- cosmology --------------------------------------------------------------------------------
+// 1/E(z) of flat LambdaCDM with massive neutrinos (astropy FLRW.nu_relative_density / inv_efunc).
+__device__ __forceinline__ double inv_efunc(const rb_cosmology& c, double z) {
+  const double zp1 = 1.0 + z;
+  double rel = (double)c.n_massless;
+  for (int i = 0; i < c.n_massive; ++i) {
+    double cur = c.nu_y[i] / zp1;
+    rel += pow(1.0 + pow(0.3173 * cur, 1.83), 0.54644808743);
+  }
+  const double nu = 0.22710731766 * c.neff_per_nu * rel;
+  const double Or = c.Ogamma0 * (1.0 + nu);
+  return rsqrt(zp1 * zp1 * zp1 * (Or * zp1 + c.Om0) + c.Ode0);
+}
+
+}  // namespace rb

@@ -1,0 +1,339 @@
+// redback_b200 -- fused supernova light-curve + Gaussian log-likelihood kernel (FP64, sm_100a).
+//
+// One thread block owns one parameter sample at a time (grid-stride over samples); inside the block
+// one thread owns one epoch.  Per sample the block stages in shared memory
+//   * the engine luminosity on the reference's dense grid linspace(0, t[-1]+100, D) together with
+//     the per-interval slopes of scipy's linear interp1d          (interaction_processes.py:44,56)
+//   * the merged quadrature abscissae xm = unique(lsp U 1-lsp)     (interaction_processes.py:49-51)
+// and every thread then walks the <=100 abscissae of its epoch sequentially, accumulating the
+// trapezoid in registers (interaction_processes.py:53-61).  Photosphere (photosphere.py:87-111),
+// SED (sed.py:199-222 / 301-426) and the Gaussian log-likelihood term (likelihoods.py:229-231) are
+// applied in the same thread and the likelihood is reduced across the block.
+//
+// The roofline that bounds this kernel is the FP64 pipe: ~24 FP64 instructions per abscissa
+// (DESIGN.md §4); HBM traffic is 8*P bytes in and 8 (+8E) bytes out per sample.
+#include "rb_common.cuh"
+#include "rb_tables.inc"
+
+namespace rb {
+
+constexpr int kNodesHalf = 50;            // int(round(timesteps / 2.0)), interaction_processes.py:34,49
+constexpr int kNodes = 2 * kNodesHalf;    // merged abscissae, duplicates kept (zero-width intervals)
+constexpr double kExpSkip = -690.0;       // exp() arguments below this contribute < 1e-299: skipped
+
+struct SnArgs {
+  rb_sn_config cfg;
+  int64_t N;
+  int E;
+  const double* params;
+  const double* t_obs;
+  const double* freq_obs;
+  const double* dl_cm;
+  const double* y;
+  const double* sigma;
+  const double* sigma_param;
+  double* out_model;
+  double* out_logl;
+};
+
+// regularised incomplete gammas for the CutoffBlackbody normalisation (sed.py:386-421); integer order
+__device__ __forceinline__ double gammaincc_int(int s, double x, double emx) {
+  // Q(s, x) = e^-x sum_{k<s} x^k / k!
+  double term = 1.0, sum = 1.0;
+  for (int k = 1; k < s; ++k) {
+    term *= x / k;
+    sum += term;
+  }
+  return emx * sum;
+}
+
+__device__ __forceinline__ double gammainc4(double x, double emx) {
+  // P(4, x); series e^-x sum_{k>=4} x^k/k! below 1.5 (no cancellation), 1 - Q(4, x) above
+  if (x < 1.5) {
+    double term = x * x * x * x * (1.0 / 24.0), sum = term;
+    for (int k = 5; k < 30; ++k) {
+      term *= x / k;
+      sum += term;
+    }
+    return emx * sum;
+  }
+  return 1.0 - gammaincc_int(4, x, emx);
+}
+
+__global__ void __launch_bounds__(512) sn_kernel(const SnArgs a) {
+  extern __shared__ double smem[];
+  const int D = a.cfg.dense_resolution;
+  double* ylo = smem;                 // [D]   engine luminosity on the dense grid
+  double* slope = ylo + D;            // [D]   slope[k] of interval (k-1, k)
+  double* xm = slope + D;             // [kNodes]
+  double* lsp = xm + kNodes;          // [kNodesHalf]
+  double* tab = lsp + kNodesHalf;     // [32]  2^(j/32)
+  double* scratch = tab + 32;         // [36]  reductions + d_L
+
+  const int tid = threadIdx.x;
+  const int E = a.E;
+  const int sed = a.cfg.sed;
+  if (tid < 32) tab[tid] = RB_EXP2_32[tid];
+
+  for (int64_t n = blockIdx.x; n < a.N; n += gridDim.x) {
+    const double* P = a.params + n;
+    const int64_t N = a.N;
+    // ---- per-sample scalars (every thread; uniform) -------------------------------------------
+    const double z = (sed == RB_SED_BOLOMETRIC) ? 0.0 : P[RB_SN_REDSHIFT * N];
+    const double opz = 1.0 + z;
+    const double mej = P[RB_SN_MEJ * N], vej = P[RB_SN_VEJ * N];
+    const double kappa = P[RB_SN_KAPPA * N], kappa_gamma = P[RB_SN_KAPPA_GAMMA * N];
+    const double t_end = a.t_obs[E - 1] / opz + 100.0;                       // supernova_models.py:965
+    const double tau = sqrt(kDiffusionConst * kappa * mej / vej) / kDay;      // interaction_processes.py:39
+    const double trap = (kTrappingConst * kappa_gamma * mej / (vej * vej)) / (kDay * kDay);  // :40
+    const double tau2 = tau * tau;
+    const double inv_tau2 = 1.0 / tau2;
+    const double step = t_end / (double)(D - 1);                              // np.linspace step
+    // slightly shrunk so that ceil(t * inv_step) never exceeds D-1 and t == x_k lands in (k-1, k]
+    const double inv_step_exact = 1.0 / step;
+    const double inv_step = inv_step_exact * (1.0 - 0x1p-50);
+
+    __syncthreads();  // previous sample's epilogue is done with smem
+    // ---- engine on the dense grid --------------------------------------------------------------
+    if (a.cfg.engine == RB_ENGINE_NICKEL) {
+      const double nickel_mass = P[RB_SN_F_NICKEL * N] * mej;                 // supernova_models.py:577
+      for (int k = tid; k < D; k += blockDim.x) {
+        const double x = (k == D - 1) ? t_end : (double)k * step;
+        ylo[k] = nickel_mass * (6.45e43 * exp_tab<true>(fmax(-x / 8.8, -708.0), tab) +
+                                1.45e43 * exp_tab<true>(fmax(-x / 111.3, -708.0), tab));
+      }
+    } else {
+      // magnetar_models.py:181-184 with time in seconds (supernova_models.py:1466)
+      const double p0 = P[RB_SN_P0 * N], bp = P[RB_SN_BP * N];
+      const double mns = P[RB_SN_MASS_NS * N], theta = P[RB_SN_THETA_PB * N];
+      const double m15 = pow(mns / 1.4, 1.5);
+      const double sn = sin(theta);
+      const double erot = 2.6e52 * m15 * (1.0 / (p0 * p0));
+      const double tp = 1.3e5 * (1.0 / (bp * bp)) * (p0 * p0) * m15 * (1.0 / (sn * sn));
+      const double l0 = 2.0 * erot / tp;
+      for (int k = tid; k < D; k += blockDim.x) {
+        const double x = ((k == D - 1) ? t_end : (double)k * step) * kDay;
+        const double den = 1.0 + 2.0 * x / tp;
+        ylo[k] = l0 / (den * den);
+      }
+    }
+    // ---- quadrature abscissae: lsp = logspace(log10(tau/t_end) - 3, 0, 50) ----------------------
+    if (tid < kNodesHalf) {
+      const double a0 = log10(tau / t_end) - 3.0;
+      const double da = (0.0 - a0) / (double)(kNodesHalf - 1);
+      const double yv = (tid == kNodesHalf - 1) ? 0.0 : (double)tid * da + a0;
+      lsp[tid] = pow(10.0, yv);
+    }
+    // ---- luminosity distance -------------------------------------------------------------------
+    double dl = 1.0;
+    if (sed != RB_SED_BOLOMETRIC) {
+      if (a.dl_cm != nullptr) {
+        dl = a.dl_cm[n];
+      } else {
+        if (tid >= 64 && tid < 128) {  // warps 2,3: 64-point Gauss-Legendre on [0, z]
+          const int i = tid - 64;
+          const double zi = 0.5 * z * (RB_GL64_X[i] + 1.0);
+          double w = RB_GL64_W[i] * inv_efunc(a.cfg.cosmology, zi);
+          w = warp_sum(w);
+          if ((tid & 31) == 0) scratch[33 + (i >> 5)] = w;  // scratch[33], scratch[34]
+        }
+      }
+    }
+    __syncthreads();
+    if (sed != RB_SED_BOLOMETRIC && a.dl_cm == nullptr)
+      dl = opz * a.cfg.cosmology.hubble_distance_cm * (0.5 * z * (scratch[33] + scratch[34]));
+    // slopes of interp1d (interaction_processes.py:44): (y_hi - y_lo) / (x_hi - x_lo)
+    for (int k = tid; k < D; k += blockDim.x) slope[k] = (k == 0) ? 0.0 : (ylo[k] - ylo[k - 1]) * inv_step_exact;
+    // merge lsp (ascending) with 1 - lsp (descending): rank by counting, np.unique order
+    if (tid < kNodes) {
+      int rank;
+      double v;
+      if (tid < kNodesHalf) {
+        v = lsp[tid];
+        int c = 0;
+        for (int j = 0; j < kNodesHalf; ++j) c += ((1.0 - lsp[j]) < v);
+        rank = tid + c;
+      } else {
+        const int j0 = tid - kNodesHalf;
+        v = 1.0 - lsp[j0];
+        int c = 0;
+        for (int j = 0; j < kNodesHalf; ++j) c += (lsp[j] <= v);
+        rank = (kNodesHalf - 1 - j0) + c;
+      }
+      xm[rank] = v;
+    }
+    __syncthreads();
+
+    // ---- per-epoch work ------------------------------------------------------------------------
+    double logl_part = 0.0;
+    for (int e = tid; e < E; e += blockDim.x) {
+      const double te = a.t_obs[e] / opz;                                     // utils.py:382
+      const double te2 = te * te;                                             // interaction_processes.py:55
+      // first abscissa whose exponent can exceed kExpSkip: xm^2 >= 1 + kExpSkip * tau^2 / te^2
+      int m0 = 0;
+      {
+        const double x02 = 1.0 + (kExpSkip - 1.0) * tau2 / te2;
+        if (x02 > 0.0) {
+          const double x0 = sqrt(x02) * (1.0 - 1e-12);
+          int lo = 0, hi = kNodes;  // lower_bound
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (xm[mid] < x0) lo = mid + 1; else hi = mid;
+          }
+          m0 = lo;
+        }
+      }
+      const int ms = max(m0, 1);  // xm[0] = 1 - lsp[49] = 0 -> integrand 0 there
+      double t_prev = te * xm[ms - 1];
+      double f_prev = 0.0;
+      double acc = 0.0;
+#pragma unroll 2
+      for (int m = ms; m < kNodes; ++m) {
+        const double t = te * xm[m];                                          // :53
+        // searchsorted(dense_times, t) via round-up FMA: v = 2^52 + ceil(t / step)
+        const double v = __fma_ru(t, inv_step, 4503599627370496.0);
+        int k = __double2loint(v);
+        const double kdm1 = v - 4503599627370497.0;                           // ceil(t/step) - 1
+        k = min(max(k, 1), D - 1);
+        const double dx = fma(-kdm1, step, t);                                // t - x_lo
+        const double lum = fma(slope[k], dx, ylo[k - 1]);                     // scipy _call_linear
+        const double d = __dsub_rn(__dmul_rn(t, t), te2);                     // t_i^2 - t_e^2 (unfused, :57)
+        const double arg = fmax(d * inv_tau2, -700.0);
+        const double ex = exp_tab<false>(arg, tab);
+        double f = lum * t * ex;
+        if (isnan(f)) f = 0.0;                                                // :58
+        acc = fma(t - t_prev, f + f_prev, acc);                               // np.trapezoid, :60
+        t_prev = t;
+        f_prev = f;
+      }
+      double lbol = (0.5 * acc) * (-2.0 * expm1(-trap / te2) / tau2);         // :61
+
+      double model;
+      if (sed == RB_SED_BOLOMETRIC) {
+        model = lbol;
+      } else {
+        // ---- photosphere.TemperatureFloor (photosphere.py:87-111) ----
+        const double tfloor = P[RB_SN_TEMPERATURE_FLOOR * N];
+        const double rr = kRadiusConst * vej * te;
+        const double r2 = rr * rr;
+        const double tf2 = tfloor * tfloor;
+        const double rec2 = lbol / (kStefConst * (tf2 * tf2));
+        const bool mask = r2 <= rec2;
+        const double rph = sqrt(mask ? r2 : rec2);
+        const double tph = mask ? sqrt(sqrt(lbol / (kStefConst * r2))) : tfloor;
+        const double nu = a.freq_obs[e] * opz;                                // utils.py:383
+        if (sed == RB_SED_BLACKBODY) {
+          // sed.py:199-222
+          const double num = 2 * kPi * kH * (nu * nu * nu) * (rph * rph);
+          const double den = (dl * dl) * (kC * kC);
+          const double frac = 1.0 / expm1((kH * nu) / (kKB * tph));
+          model = num / den * frac * kToMJy * opz;                            // supernova_models.py:1007
+        } else {
+          // sed.CutoffBlackbody (sed.py:301-426), integer s = 4 - absorption_index
+          const double alpha = a.cfg.absorption_index;
+          const int s = (int)(4.0 - alpha + 0.5);
+          const double lam_c = a.cfg.cutoff_wavelength * kAngstrom;
+          double norm = lbol / (kFluxConst / kAngstrom * (rph * rph) * tph);  // :388-390
+          const double kt_hc = tph / kXConst;
+          const double x_c = 1.0 / (lam_c * kt_hc);
+          const double e1 = exp(-x_c);
+          double en = 1.0, above = 0.0, below = 0.0;
+          for (int i = 1; i <= 10; ++i) {
+            en *= e1;  // e^{-i x_c}
+            const double xi = x_c * (double)i;
+            const double di = (double)i;
+            const double emx = (i == 1) ? e1 : ((xi > 700.0) ? 0.0 : en);
+            double ns = di;
+            for (int q = 1; q < s; ++q) ns *= di;
+            above += gammainc4(xi, emx) / (di * di * di * di);
+            below += gammaincc_int(s, xi, emx) / ns;
+          }
+          const double kt2 = kt_hc * kt_hc;
+          double kts = kt_hc, gam = 1.0;  // kT_over_hc^s, Gamma(s) = (s-1)!
+          for (int q = 1; q < s; ++q) { kts *= kt_hc; gam *= (double)q; }
+          above = kt2 * kt2 * 6.0 * above;
+          below = (1.0 / pow(lam_c, alpha)) * kts * gam * below;
+          norm /= ((above + below) / tph);
+          const double lam_A = 1.e10 * (kCSI / nu);                           // utils.py:365-370
+          const double lam = lam_A * kAngstrom;
+          const double l2 = lam * lam;
+          const double l5 = l2 * l2 * lam;
+          const double em = expm1(kXConst / lam / tph);
+          double sedv;
+          if (lam < lam_c)
+            sedv = kFluxConst * ((rph * rph) * pow(lam / lam_c, alpha) / l5) / em;
+          else
+            sedv = kFluxConst * ((rph * rph) / l5) / em;
+          sedv *= norm;
+          double fd = sedv / (4 * kPi * (dl * dl));                           // sed.py:239-251
+          fd *= lam_A;
+          fd /= nu;
+          model = fd * kToMJy * opz;                                          // supernova_models.py:1597
+        }
+      }
+      if (a.out_model != nullptr) a.out_model[n * (int64_t)E + e] = model;
+      if (a.y != nullptr) {
+        double sg = a.sigma[e];
+        if (a.cfg.sigma_mode == RB_SIGMA_SAMPLED) sg = a.sigma_param[n];
+        else if (a.cfg.sigma_mode == RB_SIGMA_QUADRATURE) {
+          const double sp = a.sigma_param[n];
+          sg = sqrt(sg * sg + sp * sp);                                       // likelihoods.py:767
+        }
+        const double rs = (a.y[e] - model) / sg;
+        logl_part += -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;           // likelihoods.py:231
+      }
+    }
+    if (a.out_logl != nullptr) {
+      const double total = block_sum(logl_part, scratch);
+      if (tid == 0) a.out_logl[n] = nan_to_num(total);
+    }
+  }
+}
+
+// ---- luminosity distance only ---------------------------------------------------------------------
+__global__ void dl_kernel(const rb_cosmology c, int64_t N, const double* __restrict__ z_in,
+                          double* __restrict__ out) {
+  // one warp per redshift, 2 Gauss-Legendre nodes per lane
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= N) return;
+  const double z = z_in[w];
+  double s = 0.0;
+  for (int i = lane; i < 64; i += 32) s += RB_GL64_W[i] * inv_efunc(c, 0.5 * z * (RB_GL64_X[i] + 1.0));
+  s = warp_sum(s);
+  if (lane == 0) out[w] = (1.0 + z) * c.hubble_distance_cm * (0.5 * z * s);
+}
+
+// ---- stand-alone likelihood reduction -----------------------------------------------------------
+__global__ void logl_kernel(int sigma_mode, int64_t N, int E, const double* __restrict__ model,
+                            const double* __restrict__ y, const double* __restrict__ sigma,
+                            const double* __restrict__ sigma_param, double* __restrict__ out) {
+  __shared__ double scratch[34];
+  for (int64_t n = blockIdx.x; n < N; n += gridDim.x) {
+    double part = 0.0;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      double sg = sigma[e];
+      if (sigma_mode == RB_SIGMA_SAMPLED) sg = sigma_param[n];
+      else if (sigma_mode == RB_SIGMA_QUADRATURE) sg = sqrt(sg * sg + sigma_param[n] * sigma_param[n]);
+      const double rs = (y[e] - model[n * (int64_t)E + e]) / sg;
+      part += -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;
+    }
+    const double total = block_sum(part, scratch);
+    if (threadIdx.x == 0) out[n] = nan_to_num(total);
+  }
+}
+
+// ---- FP64 peak micro-benchmark ------------------------------------------------------------------
+__global__ void dfma_kernel(int iters, double* out) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace rb

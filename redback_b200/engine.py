@@ -1,0 +1,168 @@
+"""Device-resident evaluation paths: epochs / frequencies / data are uploaded once, parameter batches
+stream through the fused kernels.  torch is used for device memory and streams only."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+
+_F64 = torch.float64
+
+
+def _device(device=None):
+    if not torch.cuda.is_available():
+        raise _capi.RedbackB200Error(
+            "redback_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def as_device_f64(x, device):
+    """1-D float64 contiguous device tensor from a python scalar / sequence / ndarray / tensor."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=_F64).contiguous()
+    arr = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    return torch.from_numpy(arr).to(device)
+
+
+def batch_size(params):
+    n = None
+    for k, v in params.items():
+        if isinstance(v, torch.Tensor):
+            m = v.numel() if v.dim() > 0 else None
+        elif np.ndim(v) > 0:
+            m = int(np.size(v))
+        else:
+            m = None
+        if m is not None:
+            if n is not None and m != n:
+                raise ValueError(f"params_batch entries have different lengths ({n} vs {m} for '{k}')")
+            n = m
+    return n
+
+
+class SupernovaPath:
+    """Fused Diffusion -> TemperatureFloor -> Blackbody|CutoffBlackbody -> Gaussian log L.
+
+    Mirrors the reference call chain GaussianLikelihood.log_likelihood -> arnett / slsn / ... ->
+    Diffusion (redback/interaction_processes.py:33-65) -> TemperatureFloor (redback/photosphere.py:56-111)
+    -> Blackbody / CutoffBlackbody (redback/sed.py:199-222, 301-426), for N samples at once.
+    """
+
+    def __init__(self, engine, sed, time, frequency=None, y=None, sigma=None,
+                 sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
+                 absorption_index=1.0, cosmology=None, device=None):
+        self.device = _device(device)
+        self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength,
+                                   absorption_index, cosmology)
+        t = np.atleast_1d(np.asarray(time.detach().cpu().numpy() if isinstance(time, torch.Tensor) else time,
+                                     dtype=np.float64))
+        if t.ndim != 1 or t.size == 0:
+            raise ValueError("time must be a non-empty 1-D array")
+        if np.any(t < 0):
+            raise NotImplementedError("negative times are not supported on device (the reference maps them "
+                                      "to the first valid epoch)")
+        if np.max(t) > t[-1] + 100:
+            # interaction_processes.py:63 would index past uniq_lums here
+            raise IndexError("max(time) exceeds time[-1] + 100: outside the reference's dense grid")
+        self.E = int(t.size)
+        self.time = torch.from_numpy(np.ascontiguousarray(t)).to(self.device)
+        self.frequency = None
+        if sed != _capi.SED_BOLOMETRIC:
+            if frequency is None:
+                raise KeyError("frequency")  # the reference does kwargs['frequency']
+            f = np.asarray(frequency.detach().cpu().numpy() if isinstance(frequency, torch.Tensor) else frequency,
+                           dtype=np.float64)
+            if f.ndim == 0:
+                f = np.full(self.E, float(f))
+            if f.shape != (self.E,):
+                raise ValueError("frequency must be a single number or the same length as time")
+            self.frequency = torch.from_numpy(np.ascontiguousarray(f)).to(self.device)
+        self.y = self.sigma = None
+        if y is not None:
+            self.y = as_device_f64(y, self.device)
+            if self.y.shape != (self.E,):
+                raise ValueError("y must have the same length as time")
+            if sigma is not None:
+                s = np.asarray(sigma, dtype=np.float64) if not isinstance(sigma, torch.Tensor) else sigma
+                if np.ndim(s) == 0:
+                    s = np.full(self.E, float(s))
+                self.sigma = as_device_f64(s, self.device)
+                if self.sigma.shape != (self.E,):
+                    raise ValueError('Sigma must be either float or array-like x.')
+
+    def pack(self, params, N):
+        """SoA [RB_SN_NPARAM, N] device tensor from {name: scalar | array[N] | tensor[N]}."""
+        out = torch.zeros((_capi.SN_NPARAM, N), dtype=_F64, device=self.device)
+        host_rows, host_idx = [], []
+        for name, val in params.items():
+            if name not in _capi.SN_ROWS:
+                continue
+            row = _capi.SN_ROWS[name]
+            if isinstance(val, torch.Tensor):
+                out[row] = val.to(device=self.device, dtype=_F64).reshape(-1).expand(N) if val.numel() == 1 \
+                    else val.to(device=self.device, dtype=_F64).reshape(N)
+            elif np.ndim(val) == 0:
+                out[row].fill_(float(val))
+            else:
+                host_rows.append(np.asarray(val, dtype=np.float64).reshape(N))
+                host_idx.append(row)
+        if host_rows:
+            block = torch.from_numpy(np.ascontiguousarray(np.stack(host_rows)))
+            out[torch.tensor(host_idx, device=self.device)] = block.to(self.device, non_blocking=False)
+        return out
+
+    def evaluate(self, params_dev, dl=None, sigma_param=None, want_model=True, want_logl=False):
+        """Launch the fused kernel on the current stream.  Returns (model[N,E] | None, logl[N] | None)."""
+        if params_dev.dtype != _F64 or params_dev.dim() != 2 or params_dev.shape[0] != _capi.SN_NPARAM:
+            raise ValueError("params_dev must be float64 [RB_SN_NPARAM, N]")
+        params_dev = params_dev.contiguous()
+        N = params_dev.shape[1]
+        model = torch.empty((N, self.E), dtype=_F64, device=self.device) if want_model else None
+        logl = torch.empty((N,), dtype=_F64, device=self.device) if want_logl else None
+        if want_logl and self.y is None:
+            raise ValueError("log-likelihood requested but no data were given")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = _capi.lib().rb_sn_eval_f64(
+                C.byref(self.cfg), N, self.E, _ptr(params_dev), _ptr(self.time), _ptr(self.frequency),
+                _ptr(dl), _ptr(self.y if want_logl else None), _ptr(self.sigma if want_logl else None),
+                _ptr(sigma_param if want_logl else None), _ptr(model), _ptr(logl), C.c_void_p(stream))
+        _capi.check(rc)
+        return model, logl
+
+
+def luminosity_distance(redshift, cosmology=None, device=None):
+    """Planck18 (default) luminosity distance in cm for an array of redshifts, on device."""
+    dev = _device(device)
+    z = as_device_f64(np.atleast_1d(redshift) if not isinstance(redshift, torch.Tensor) else redshift, dev)
+    out = torch.empty_like(z)
+    cosmo = cosmology
+    if cosmo is None:
+        cosmo = _capi.Cosmology()
+        _capi.check(_capi.lib().rb_cosmology_planck18(C.byref(cosmo)))
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().rb_luminosity_distance_f64(
+            C.byref(cosmo), z.numel(), _ptr(z), _ptr(out), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
+
+
+def gaussian_logl(model, y, sigma, sigma_param=None, sigma_mode=_capi.SIGMA_FIXED):
+    """Stand-alone reduction over a device model matrix [N, E] (likelihoods.py:221-231, 767-790)."""
+    dev = model.device
+    N, E = model.shape
+    y = as_device_f64(y, dev)
+    if sigma is not None and not isinstance(sigma, torch.Tensor) and np.ndim(sigma) == 0:
+        sigma = np.full(E, float(sigma))
+    sigma = as_device_f64(sigma, dev) if sigma is not None else None
+    sp = as_device_f64(sigma_param, dev) if sigma_param is not None else None
+    out = torch.empty((N,), dtype=_F64, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().rb_gaussian_logl_f64(
+            sigma_mode, N, E, _ptr(model.contiguous()), _ptr(y), _ptr(sigma), _ptr(sp), _ptr(out),
+            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out

@@ -1,0 +1,235 @@
+"""Batched drop-ins for redback.likelihoods.GaussianLikelihood / GaussianLikelihoodQuadratureNoise.
+
+Same constructor, `.parameters`, `.log_likelihood(parameters=None)`, `.noise_log_likelihood()` as
+redback/likelihoods.py:22-231 and :738-790, plus `log_likelihood_batch(params_batch) -> ndarray[N]`.
+bilby is not a dependency: the two things the reference takes from `bilby.Likelihood` (the `parameters`
+dict inferred from the model signature and `log_likelihood_ratio`) are provided here, so instances can be
+handed to bilby samplers (which only call those methods) when bilby is installed.
+"""
+import inspect
+
+import numpy as np
+import torch
+
+from . import _capi
+from . import supernova_models as _sn
+from .engine import SupernovaPath, batch_size, gaussian_logl
+
+
+def infer_parameters_from_function(func):
+    """bilby.core.utils.introspection.infer_parameters_from_function: all positional-or-keyword argument
+    names after the first one; *args / **kwargs are ignored (likelihoods.py:50)."""
+    sig = inspect.signature(func)
+    names = [n for n, p in sig.parameters.items()
+             if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+    return [n for n in names[1:] if n != "params_batch"]
+
+
+class _RedbackLikelihood:
+    """redback/likelihoods.py:22-143"""
+
+    def __init__(self, x, y, function, kwargs=None, priors=None, fiducial_parameters=None):
+        self.x = x
+        self.y = y
+        self.function = function
+        self.kwargs = kwargs
+        self.priors = priors
+        self.fiducial_parameters = fiducial_parameters
+        self.parameters = dict.fromkeys(infer_parameters_from_function(function))
+        self._marginalized_parameters = []
+
+    def _update_parameters(self, parameters=None):
+        if parameters is not None:
+            self.parameters.update(parameters)
+
+    @property
+    def kwargs(self):
+        return self._kwargs
+
+    @kwargs.setter
+    def kwargs(self, kwargs):
+        self._kwargs = dict() if kwargs is None else kwargs
+
+    @property
+    def n(self):
+        return len(self.x)
+
+    def log_likelihood_ratio(self):
+        return self.log_likelihood() - self.noise_log_likelihood()
+
+
+class GaussianLikelihood(_RedbackLikelihood):
+    """redback/likelihoods.py:146-231 with a vectorised `log_likelihood_batch`."""
+
+    _sigma_mode_sampled = _capi.SIGMA_SAMPLED
+
+    def __init__(self, x, y, sigma, function, kwargs=None, priors=None, fiducial_parameters=None):
+        self._noise_log_likelihood = None
+        self._path = None
+        super().__init__(x=x, y=y, function=function, kwargs=kwargs, priors=priors,
+                         fiducial_parameters=fiducial_parameters)
+        self.sigma = sigma
+        if self.sigma is None:
+            self.parameters['sigma'] = None
+
+    @property
+    def sigma(self):
+        return self.parameters.get('sigma', self._sigma)
+
+    @sigma.setter
+    def sigma(self, sigma):
+        if sigma is None:
+            self._sigma = sigma
+        elif isinstance(sigma, float) or isinstance(sigma, int):
+            self._sigma = sigma
+        elif len(sigma) == self.n:
+            self._sigma = sigma
+        elif sigma.shape == ((2, len(self.x))):
+            self._sigma = sigma
+        else:
+            raise ValueError('Sigma must be either float or array-like x.')
+
+    @property
+    def model_output(self):
+        return self.function(self.x, **self.parameters, **self.kwargs)
+
+    @property
+    def residual(self):
+        return self.y - self.model_output
+
+    # ---- single-sample API (what bilby samplers call) -------------------------------------------
+    def noise_log_likelihood(self):
+        if self._noise_log_likelihood is None:
+            self._noise_log_likelihood = self._gaussian_log_likelihood(res=self.y, sigma=self._noise_sigma())
+        return self._noise_log_likelihood
+
+    def _noise_sigma(self):
+        return self.sigma
+
+    def log_likelihood(self, parameters=None):
+        self._update_parameters(parameters)
+        if self.function in _sn.FUSED:
+            batch = {k: np.array([v], dtype=np.float64) for k, v in self.parameters.items() if v is not None}
+            return float(self.log_likelihood_batch(batch)[0])
+        return float(np.nan_to_num(self._gaussian_log_likelihood(res=self.residual, sigma=self._full_sigma())))
+
+    def _full_sigma(self):
+        return self.sigma
+
+    def _gaussian_log_likelihood(self, res, sigma):
+        """likelihoods.py:229-231 -- evaluated by the device reduction kernel (one 'sample')."""
+        res = np.asarray(res, dtype=np.float64)
+        model = torch.zeros((1, res.size), dtype=torch.float64, device=self._dev())
+        sig = np.broadcast_to(np.asarray(sigma, dtype=np.float64), res.shape)
+        out = gaussian_logl(model, res, sig, sigma_mode=_capi.SIGMA_FIXED)
+        # the kernel applies nan_to_num; the reference does not inside this helper but every caller does
+        return float(out[0].item())
+
+    def _dev(self):
+        return torch.device(self.kwargs.get("device") or f"cuda:{torch.cuda.current_device()}") \
+            if torch.cuda.is_available() else _raise_no_cuda()
+
+    # ---- batched API ----------------------------------------------------------------------------
+    def _sigma_mode(self, batch):
+        if self._sigma is None:
+            return _capi.SIGMA_SAMPLED
+        return _capi.SIGMA_FIXED
+
+    def _split_sigma_param(self, batch, N):
+        """Return the per-sample `sigma` parameter array (or None) for the chosen noise mode."""
+        mode = self._sigma_mode(batch)
+        if mode == _capi.SIGMA_FIXED:
+            return mode, None
+        sp = batch.get('sigma', self.parameters.get('sigma'))
+        if sp is None:
+            raise KeyError('sigma')
+        return mode, sp
+
+    def log_likelihood_batch(self, params_batch, device_output=False):
+        """np.nan_to_num(log L) for every sample of `params_batch` ({name: array[N]}); parameters not in the
+        batch are taken from `self.parameters` / `self.kwargs`.  Shape (N,)."""
+        batch = dict(params_batch)
+        merged = {k: v for k, v in self.parameters.items() if v is not None}
+        merged.update(batch)
+        N = batch_size(merged)
+        if N is None:
+            raise ValueError("params_batch must contain at least one array")
+        mode, sp = self._split_sigma_param(merged, N)
+        if self.function in _sn.FUSED:
+            logl = self._fused(merged, N, mode, sp)
+        else:
+            kw = dict(self.kwargs)
+            kw["device_output"] = True
+            fn_params = {k: v for k, v in merged.items() if k != 'sigma' or 'sigma' in
+                         inspect.signature(self.function).parameters}
+            try:
+                model = self.function(self.x, params_batch=fn_params, **kw)
+            except TypeError as exc:
+                raise NotImplementedError(
+                    "log_likelihood_batch needs a model function with a params_batch entry point") from exc
+            if not isinstance(model, torch.Tensor):
+                model = torch.as_tensor(np.asarray(model, dtype=np.float64), device=self._dev())
+            sp_dev = None
+            if sp is not None:
+                sp_dev = sp if isinstance(sp, torch.Tensor) else np.broadcast_to(np.asarray(sp, dtype=np.float64), (N,))
+            logl = gaussian_logl(model, self.y, self._sigma, sp_dev, sigma_mode=mode)
+        return logl if device_output else logl.cpu().numpy()
+
+    def _fused(self, merged, N, mode, sp):
+        engine, engine_params, needs_z, default_sed = _sn.FUSED[self.function]
+        kw = self.kwargs
+        sed_id = _capi.SED_BOLOMETRIC
+        if needs_z:
+            _sn._flux_density_only(kw, self.function.__name__)
+            _sn._operator_name("photosphere", kw.get("photosphere"), "TemperatureFloor")
+            sed_id = _sn._SED_IDS[_sn._operator_name("sed", kw.get("sed"), default_sed)]
+        _sn._operator_name("interaction_process", kw.get("interaction_process", "Diffusion"), "Diffusion")
+        key = (engine, sed_id, mode, kw.get("dense_resolution", 1000), kw.get("cutoff_wavelength", 3000),
+               kw.get("absorption_index", 1.0), id(kw.get("cosmology")))
+        if self._path is None or self._path[0] != key:
+            path = SupernovaPath(engine, sed_id, self.x, frequency=kw.get("frequency") if needs_z else None,
+                                 y=self.y, sigma=self._sigma, sigma_mode=mode,
+                                 dense_resolution=kw.get("dense_resolution", 1000),
+                                 cutoff_wavelength=kw.get("cutoff_wavelength", 3000),
+                                 absorption_index=kw.get("absorption_index", 1.0),
+                                 cosmology=_sn._cosmology(kw), device=kw.get("device"))
+            self._path = (key, path)
+        path = self._path[1]
+        needed = list(engine_params) + list(_sn._DIFFUSION)
+        if needs_z:
+            needed = ["redshift"] + needed + ["temperature_floor"]
+        params, _ = _sn._collect(merged, kw, None, needed)
+        dev = path.pack(params, N)
+        sp_dev = None
+        if sp is not None:
+            sp_dev = sp.to(device=path.device, dtype=torch.float64).reshape(-1).expand(N).contiguous() \
+                if isinstance(sp, torch.Tensor) else \
+                torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(sp, dtype=np.float64), (N,)))).to(path.device)
+        _, logl = path.evaluate(dev, dl=_sn._dl(kw, path, N), sigma_param=sp_dev, want_model=False, want_logl=True)
+        return logl
+
+
+def _raise_no_cuda():
+    raise _capi.RedbackB200Error("redback_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+class GaussianLikelihoodQuadratureNoise(GaussianLikelihood):
+    """redback/likelihoods.py:738-790: sigma_full = sqrt(sigma_i^2 + sigma^2), `sigma` sampled."""
+
+    def __init__(self, x, y, sigma_i, function, kwargs=None, priors=None, fiducial_parameters=None):
+        self.sigma_i = sigma_i
+        super().__init__(x=x, y=y, sigma=sigma_i, function=function, kwargs=kwargs, priors=priors,
+                         fiducial_parameters=fiducial_parameters)
+
+    @property
+    def full_sigma(self):
+        return np.sqrt(self.sigma_i ** 2. + self.sigma ** 2.)
+
+    def _noise_sigma(self):
+        return self.full_sigma
+
+    def _full_sigma(self):
+        return self.full_sigma
+
+    def _sigma_mode(self, batch):
+        return _capi.SIGMA_QUADRATURE

@@ -1,0 +1,75 @@
+"""CPU: the oracle against the reference's own golden vectors and known-answer tests."""
+import numpy as np
+import pytest
+
+from oracle import refshim
+from oracle import restated as r
+from helpers import golden_array
+
+RTOL = 1e-12  # reference tolerance is 1e-5 (test/test_all_models_regression.py:75); the oracle does far better
+
+CASES = {
+    "supernova.arnett_bolometric": lambda t, p, kw: r.arnett_bolometric(t, **p),
+    "supernova.slsn_bolometric": lambda t, p, kw: r.slsn_bolometric(t, **p),
+    "supernova.basic_magnetar_powered_bolometric": lambda t, p, kw: r.basic_magnetar_powered_bolometric(t, **p),
+    "supernova.arnett": lambda t, p, kw: r.arnett(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "supernova.basic_magnetar_powered":
+        lambda t, p, kw: r.basic_magnetar_powered(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "supernova.slsn": lambda t, p, kw: r.slsn(t, kw["redshift"], frequency=kw["frequency"], **p),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_golden(golden, name):
+    entry = golden[name]
+    t = np.array(entry["time"])
+    for params, res in zip(entry["params"], entry["results"]):
+        expected = golden_array(res)
+        out = CASES[name](t, params, entry["eval_kwargs"])
+        assert np.array_equal(np.isnan(out), np.isnan(expected))
+        ok = ~np.isnan(expected)
+        np.testing.assert_allclose(out[ok], expected[ok], rtol=RTOL, atol=0)
+
+
+def test_planck18_luminosity_distance():
+    # astropy Planck18.luminosity_distance(0.1) = 475.822 Mpc, (0.01) = 44.647 Mpc
+    mpc = 3.0856775814913674e24
+    assert abs(r.cosmo.luminosity_distance_cm(0.1) / mpc - 475.822) < 1e-3
+    assert abs(r.cosmo.luminosity_distance_cm(0.01) / mpc - 44.647) < 1e-3
+
+
+def test_temperature_floor_known_answer():
+    # test/photosphere_test.py:24-29
+    T, R = r.temperature_floor(np.array([1., 2., 3.]), np.array([1., 2., 3.]) * 2e17, np.array([1., 2., 3.]), 1)
+    assert np.allclose(T, [1.39250008, 1., 1.])
+    assert np.allclose(R, [8640000000.0, 2.36929531e10, 29017822836.350456])
+
+
+def test_gaussian_likelihood_closed_forms():
+    # test/likelihood_test.py:63-69 and :148-153
+    x = np.array([0., 1., 2.])
+    sigma = 1.0
+    assert r.gaussian_likelihood(x, x, sigma) == -3 * np.log(2 * np.pi * sigma ** 2) / 2
+    assert r.gaussian_log_likelihood(x, sigma) == np.sum(-(x / sigma) ** 2 / 2 - np.log(2 * np.pi * sigma ** 2) / 2)
+    assert r.gaussian_likelihood_quadrature(x, x, 1, 1) == -3 * np.log(2 * np.pi * np.sqrt(2) ** 2) / 2
+    assert r.gaussian_likelihood(x, np.array([np.nan, 1, 2]), 1.0) == 0.0  # np.nan_to_num, likelihoods.py:227
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+def test_oracle_matches_verbatim_reference_sources():
+    ns = refshim.load()
+    rng = np.random.default_rng(1)
+    t = np.sort(rng.uniform(1, 300, 60))
+    dense = np.linspace(0, t[-1] + 100, 1000)
+    for _ in range(20):
+        f, m, v = 10 ** rng.uniform(-3, 0), 10 ** rng.uniform(-2, 2), 10 ** rng.uniform(3, 5)
+        k, kg = rng.uniform(.05, 2), 10 ** rng.uniform(-4, 4)
+        lum = r.nickelcobalt_engine(dense, f, m)
+        ref = ns.interaction_processes.Diffusion(t, dense, lum, k, kg, m, v)
+        tau, out = r.diffusion(t, dense, lum, k, kg, m, v)
+        assert tau == ref.tau_d
+        np.testing.assert_array_equal(out, ref.new_luminosity)
+        ph = ns.photosphere.TemperatureFloor(t, out, v, 3000.)
+        T, R = r.temperature_floor(t, out, v, 3000.)
+        np.testing.assert_array_equal(T, ph.photosphere_temperature)
+        np.testing.assert_array_equal(R, ph.r_photosphere)
