@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark: sample x epoch model+likelihood evaluations per second (BASELINE.json).
+
+Workload (BASELINE.json configs[1]): magnetar-powered SLSN (`slsn`) multiband
+flux_density with TemperatureFloor + blackbody SED, ZTF g/r/i x 100 epochs (E = 300), 10^7 prior draws
+per GPU, fused with the Gaussian log-likelihood.  One step = one pass over the whole batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--samples S] [--sed blackbody|cutoff]
+    python bench.py --impl reference ...      # the reference algorithm (CPU oracle port) on host cores
+
+Prints ONE JSON line (rank 0).  `value` is timed with CUDA events with inputs resident in HBM; `e2e` is the
+same metric through the host-buffer entry (pinned host params -> H2D -> kernel -> D2H of log L).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sample_x_epoch_likelihood_evals_per_sec"
+UNIT = "sample*epoch/s"
+ZTF_NU = (6.272e14, 4.675e14, 3.813e14)  # redback/tables/filters.csv:65-67 (ztfg, ztfr, ztfi)
+# algorithmic work per sample x epoch in flop-eq = F + 20 T
+FLOP_EQ = {"blackbody": 3.8e3, "cutoff": 4.1e3}
+TRUTH = dict(redshift=0.1, p0=2.0, bp=1.0, mass_ns=1.4, theta_pb=0.5, mej=5.0, vej=8000.0, kappa=0.1,
+             kappa_gamma=0.1, temperature_floor=5000.0)
+
+
+def epochs(seed=0):
+    rng = np.random.default_rng(seed)
+    t = np.concatenate([rng.uniform(1, 300, 100) for _ in ZTF_NU])
+    nu = np.concatenate([np.full(100, v) for v in ZTF_NU])
+    order = np.argsort(t, kind="stable")
+    return t[order], nu[order]
+
+
+def prior_rows_numpy(rng, n):
+    """priors/slsn.prior as SoA rows in C-ABI order (include/redback_b200.h RB_SN_*)."""
+    lu = lambda lo, hi: np.exp(rng.uniform(np.log(lo), np.log(hi), n))
+    return np.stack([rng.uniform(1e-6, 3, n), rng.uniform(1, 10, n), lu(0.1, 10), rng.uniform(1.1, 2.2, n),
+                     rng.uniform(0, 1.57, n), lu(0.1, 100), lu(1e3, 1e5), rng.uniform(0.05, 2, n), lu(1e-4, 1e4),
+                     lu(1e3, 1e5)])
+
+
+def prior_rows_torch(n, device, seed):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    u = lambda lo, hi: lo + (hi - lo) * torch.rand(n, dtype=torch.float64, device=device, generator=g)
+    lu = lambda lo, hi: torch.exp(u(np.log(lo), np.log(hi)))
+    return torch.stack([u(1e-6, 3), u(1, 10), lu(0.1, 10), u(1.1, 2.2), u(0, 1.57), lu(0.1, 100), lu(1e3, 1e5),
+                        u(0.05, 2), lu(1e-4, 1e4), lu(1e3, 1e5)]).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port of the reference algorithm on the host cores (only place oracle/ is executed)
+# ----------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    rows, t, nu, y, sigma, sed = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import restated as r
+    names = ["p0", "bp", "mass_ns", "theta_pb", "mej", "vej", "kappa", "kappa_gamma", "temperature_floor"]
+    t0 = time.perf_counter()
+    acc = 0.0
+    for i in range(rows.shape[1]):
+        kw = dict(zip(names, rows[1:, i]))
+        model = r.slsn(t, rows[0, i], frequency=nu, sed=sed, **kw)
+        acc += r.gaussian_likelihood(y, model, sigma)
+    return time.perf_counter() - t0, acc
+
+
+def cpu_reference_rate(sed, per_core, seed, cores=None):
+    """Units/s of the oracle port on `cores` processes (one per core), `per_core` samples each."""
+    import multiprocessing as mp
+    from oracle import restated as r
+    cores = cores or os.cpu_count() or 1
+    t, nu = epochs()
+    osed = "blackbody" if sed == "blackbody" else "cutoff_blackbody"
+    truth = dict(TRUTH)
+    z = truth.pop("redshift")
+    y = r.slsn(t, z, frequency=nu, sed=osed, **truth)
+    sigma = 0.1 * np.abs(y) + 1e-9
+    rng = np.random.default_rng(seed)
+    jobs = [(prior_rows_numpy(rng, per_core), t, nu, y, sigma, osed) for _ in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(j[0][:, :2],) + j[1:] for j in jobs])  # warm import / caches
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, jobs)
+        wall = time.perf_counter() - t0
+    units = cores * per_core * t.size
+    return units / wall, cores, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_core = max(8, args.cpu_samples_per_core)
+    for _ in range(args.warmup):
+        cpu_reference_rate(args.sed, 4, 1, cores)
+    walls, rates = [], []
+    for s in range(args.steps):
+        rate, cores, wall = cpu_reference_rate(args.sed, per_core, 100 + s, cores)
+        rates.append(rate)
+        walls.append(wall)
+    value = statistics.mean(rates)
+    sample = f"{cores * per_core} prior draws x 300 epochs per step ({per_core} per core), same priors/epochs as the GPU arm"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(walls), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, cores * per_core),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, samples):
+    return {"workload": f"slsn multiband flux_density (ZTF g/r/i x 100 epochs), TemperatureFloor + "
+                        f"{'Blackbody' if args.sed == 'blackbody' else 'CutoffBlackbody'} SED, fused GaussianLikelihood",
+            "samples_per_gpu": samples, "epochs": 300, "bands": ["ztfg", "ztfr", "ztfi"],
+            "priors": "priors/slsn.prior incl. redshift U(1e-6,3); d_L integrated on device",
+            "l2": "inputs_exceed_l2" if samples * 80 > 126e6 else "small_inputs", "sharding": "samples"}
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons, power = [], [], set(), []
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import redback_b200 as rb
+    from redback_b200 import _capi
+    from redback_b200.engine import SupernovaPath
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- redback_b200 has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _capi.lib()
+    n = args.samples
+    t, nu = epochs()
+    E = t.size
+    sed_id = _capi.SED_BLACKBODY if args.sed == "blackbody" else _capi.SED_CUTOFF_BLACKBODY
+
+    # data: our own model at a fixed truth + 10 % noise
+    mk = SupernovaPath(_capi.ENGINE_MAGNETAR, sed_id, t, frequency=nu, device=dev)
+    y_model, _ = mk.evaluate(mk.pack(TRUTH, 1))
+    y_model = y_model[0].cpu().numpy()
+    rng = np.random.default_rng(0)
+    y = y_model + rng.normal(0, 0.1 * np.abs(y_model))
+    sigma = 0.1 * np.abs(y_model) + 1e-12
+    path = SupernovaPath(_capi.ENGINE_MAGNETAR, sed_id, t, frequency=nu, y=y, sigma=sigma, device=dev)
+
+    params = prior_rows_torch(n, dev, seed=1000 + rank)     # resident in HBM before the timed region
+    logl = torch.empty(n, dtype=torch.float64, device=dev)
+    gathered = torch.empty(n * world, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        path.evaluate(params, want_model=False, want_logl=True, out_logl=logl)
+        if world > 1:  # the path's only exchange: all-gather of per-sample log L
+            dist.all_gather_into_tensor(gathered, logl)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.rb_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev[0].record()
+    for i in range(args.steps):
+        kev[i][0].record()
+        path.evaluate(params, want_model=False, want_logl=True, out_logl=logl)
+        kev[i][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, logl)
+        ev[i + 1].record()
+    barrier()
+    launches = lib.rb_launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    clocks = sampler.stop() if rank == 0 else None
+    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms = float(tm.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n * E / (ms_per_step * 1e-3)
+    finite = bool(torch.isfinite(logl).all().item())
+
+    # ---- end to end through the host-buffer entry: pinned host params -> H2D -> kernel -> D2H log L ----
+    host_params = torch.empty(params.shape, dtype=torch.float64, pin_memory=True)
+    host_params.copy_(params)
+    host_out = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    path.log_likelihood_host(host_params, host_out)  # warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(1, min(args.steps, 3))
+    e0.record()
+    for _ in range(e2e_steps):
+        path.log_likelihood_host(host_params, host_out)
+    e1.record()
+    barrier()
+    em = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(em, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * E / (float(em.item()) / e2e_steps * 1e-3)
+    same = bool(torch.equal(host_out.to(dev), logl))
+
+    if rank == 0:
+        import ctypes as C
+        peak, pms = C.c_double(0), C.c_double(0)
+        _capi.check(lib.rb_measure_fp64_peak(1 << 16, C.byref(peak), C.byref(pms)))
+        flop_eq = FLOP_EQ[args.sed]
+        achieved = n * E * flop_eq / (kernel_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except OSError:
+            pass
+        hbm_bytes = n * (10 * 8 + 8)
+        roofline = {
+            "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+            "frac": achieved / peak.value if peak.value else None, "traffic": None,
+            "kernel": "rb::sn_kernel", "kernel_ms": kernel_ms,
+            "flop_eq_per_unit": flop_eq,
+            "peak_source": "DFMA micro-benchmark measured live in this run (rb_measure_fp64_peak); nominal 37.2",
+            "hbm": {"achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs", 6650.0),
+                    "peak_source": "measured" if peaks else "fallback", "algorithmic_bytes_per_launch": hbm_bytes},
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            rate, cores, wall = cpu_reference_rate(args.sed, args.cpu_samples_per_core, 7)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{cores * args.cpu_samples_per_core} prior draws x {E} epochs, one process per core, "
+                             f"{wall:.1f} s wall"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, n), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_params.numel() * 8),
+                    "d2h_bytes_per_step": int(n * 8), "matches_resident_run": same},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "all_logl_finite": finite,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--samples", type=int, default=10_000_000, help="prior draws per GPU")
+    ap.add_argument("--sed", choices=["blackbody", "cutoff"], default="blackbody")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--cpu-samples-per-core", type=int, default=8000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

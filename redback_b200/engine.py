@@ -116,14 +116,18 @@ class SupernovaPath:
             out[torch.tensor(host_idx, device=self.device)] = block.to(self.device, non_blocking=False)
         return out
 
-    def evaluate(self, params_dev, dl=None, sigma_param=None, want_model=True, want_logl=False):
+    def evaluate(self, params_dev, dl=None, sigma_param=None, want_model=True, want_logl=False, out_logl=None):
         """Launch the fused kernel on the current stream.  Returns (model[N,E] | None, logl[N] | None)."""
         if params_dev.dtype != _F64 or params_dev.dim() != 2 or params_dev.shape[0] != _capi.SN_NPARAM:
             raise ValueError("params_dev must be float64 [RB_SN_NPARAM, N]")
         params_dev = params_dev.contiguous()
         N = params_dev.shape[1]
         model = torch.empty((N, self.E), dtype=_F64, device=self.device) if want_model else None
-        logl = torch.empty((N,), dtype=_F64, device=self.device) if want_logl else None
+        logl = None
+        if want_logl:
+            logl = out_logl if out_logl is not None else torch.empty((N,), dtype=_F64, device=self.device)
+            if logl.shape != (N,) or logl.dtype != _F64 or not logl.is_contiguous():
+                raise ValueError("out_logl must be a contiguous float64 [N] device tensor")
         if want_logl and self.y is None:
             raise ValueError("log-likelihood requested but no data were given")
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -134,6 +138,44 @@ class SupernovaPath:
                 _ptr(sigma_param if want_logl else None), _ptr(model), _ptr(logl), C.c_void_p(stream))
         _capi.check(rc)
         return model, logl
+
+
+    def log_likelihood_host(self, params_host, out_host=None, chunk=1 << 21):
+        """End-to-end entry for host-resident batches: `params_host` is a (pinned) CPU float64 tensor
+        [RB_SN_NPARAM, N]; chunks are copied H2D, evaluated and the log-likelihoods copied back D2H on
+        two alternating streams so that copies overlap compute.  Returns a pinned CPU tensor [N]."""
+        if params_host.dtype != _F64 or params_host.dim() != 2 or params_host.shape[0] != _capi.SN_NPARAM:
+            raise ValueError("params_host must be float64 [RB_SN_NPARAM, N]")
+        N = params_host.shape[1]
+        if out_host is None:
+            out_host = torch.empty((N,), dtype=_F64, pin_memory=True)
+        chunk = max(1, min(int(chunk), N))
+        if getattr(self, "_slots", None) is None or self._slots[0][0].shape[1] != chunk:
+            self._slots = [(torch.empty((_capi.SN_NPARAM, chunk), dtype=_F64, device=self.device),
+                            torch.empty((chunk,), dtype=_F64, device=self.device),
+                            torch.cuda.Stream(self.device)) for _ in range(2)]
+        cur = torch.cuda.current_stream(self.device)
+        for _, _, st in self._slots:
+            st.wait_stream(cur)
+        for i, a in enumerate(range(0, N, chunk)):
+            b = min(a + chunk, N)
+            dbuf, lbuf, st = self._slots[i % 2]
+            with torch.cuda.stream(st):
+                if b - a == chunk:
+                    view = dbuf
+                    for r in range(_capi.SN_NPARAM):
+                        dbuf[r].copy_(params_host[r, a:b], non_blocking=True)
+                else:
+                    view = torch.empty((_capi.SN_NPARAM, b - a), dtype=_F64, device=self.device)
+                    for r in range(_capi.SN_NPARAM):
+                        view[r].copy_(params_host[r, a:b], non_blocking=True)
+                _, logl = self.evaluate(view, want_model=False, want_logl=True,
+                                        out_logl=lbuf[: b - a] if b - a == chunk else None)
+                out_host[a:b].copy_(logl, non_blocking=True)
+        for _, _, st in self._slots:
+            cur.wait_stream(st)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_host
 
 
 def luminosity_distance(redshift, cosmology=None, device=None):
