@@ -31,7 +31,9 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
   } while (0)
 
-size_t sn_smem_bytes(int D) { return sizeof(double) * (size_t)(2 * D + rb::kNodes + rb::kNodesHalf + 32 + 36); }
+size_t sn_smem_bytes(int D) {
+  return sizeof(double) * (size_t)(2 * D + 2 * rb::kNodes + D + rb::kNodesHalf + rb::kNodes + 256 + 8 + 36);
+}
 
 int sn_block_threads(int64_t E) {
   int b = (int)((E + 31) / 32) * 32;
@@ -102,8 +104,8 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sed");
   if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_QUADRATURE)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sigma_mode");
-  if (cfg->dense_resolution < 2 || cfg->dense_resolution > 12000)
-    return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution must be in [2, 12000]");
+  if (cfg->dense_resolution < 2 || cfg->dense_resolution > 8000)
+    return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution must be in [2, 8000]");
   if (!params || !t_obs) return fail(RB_ERR_INVALID, "rb_sn_eval: params and t_obs are required");
   if (cfg->sed != RB_SED_BOLOMETRIC && !freq_obs)
     return fail(RB_ERR_INVALID, "rb_sn_eval: freq_obs is required for flux_density output");

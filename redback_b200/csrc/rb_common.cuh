@@ -33,33 +33,30 @@ constexpr double kFluxConst = 4 * kPi * 2 * kPi * kH * (kC * kC) * kAngstrom;
 constexpr double kToMJy = 1e26;
 
 // ---- table-driven exp -------------------------------------------------------------------------
-// exp(x) = 2^m * 2^(j/32) * exp(r), k = rint(x*32/ln2) = 32 m + j, |r| <= ln2/64.
-// Degree-6 Taylor for expm1(r) (truncation < 4e-18).  Valid for -708 < x < 709 (no denormal /
-// overflow handling: callers clamp).  `tab` points at 2^(j/32), j=0..31 (shared memory copy of
-// RB_EXP2_32).  PRECISE adds the low word of ln2/32 to the reduction (abs. error of the reduced
-// argument < 1e-18 instead of |x| * 8e-17).
+// exp(x) = 2^m * 2^(j/256) * exp(r), k = rint(x*256/ln2) = 256 m + j, |r| <= ln2/512 = 1.36e-3.
+// `tab` points at a shared-memory copy of RB_EXP2_256.  Valid for -708 < x < 709 (no denormal /
+// overflow handling: callers clamp).
+//   exp_tab  : degree-4 expm1 polynomial (truncation 4e-17) + two-word ln2/256: ~1 ulp, used for the
+//              engine luminosities and anywhere full accuracy matters.
+//   The diffusion hot loop inlines a cheaper variant (degree 3, error 1.4e-13; see sn_kernel.cu).
 constexpr double kExpMagic = 6755399441055744.0;  // 1.5 * 2^52
-constexpr double k32OverLn2 = 46.16624130844683;
-constexpr double kLn2Over32Hi = 0.02166084939249829;
-constexpr double kLn2Over32Lo = 7.250602028496811e-19;
+constexpr double k256OverLn2 = 369.3299304675746;
+constexpr double kLn2Over256Hi = 0.0027076061740622863;
+constexpr double kLn2Over256Lo = 9.063252535621014e-20;
 
-template <bool PRECISE>
 __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
-  double v = fma(x, k32OverLn2, kExpMagic);
-  int k = __double2loint(v);
-  double kd = v - kExpMagic;
-  double r = fma(kd, -kLn2Over32Hi, x);
-  if (PRECISE) r = fma(kd, -kLn2Over32Lo, r);
-  double q = fma(r, 0.001388888888888889, 0.008333333333333333);
-  q = fma(r, q, 0.041666666666666664);
-  q = fma(r, q, 0.16666666666666666);
+  const double v = fma(x, k256OverLn2, kExpMagic);
+  const int k = __double2loint(v);
+  const double kd = v - kExpMagic;
+  double r = fma(kd, -kLn2Over256Hi, x);
+  r = fma(kd, -kLn2Over256Lo, r);
+  double q = fma(r, 0.041666666666666664, 0.16666666666666666);
   q = fma(r, q, 0.5);
   q = fma(r, q, 1.0);
-  double p = r * q;
-  double t = tab[k & 31];
-  double res = fma(t, p, t);
-  int hi = __double2hiint(res) + ((k >> 5) << 20);
-  return __hiloint2double(hi, __double2loint(res));
+  const double p = r * q;
+  const double t = tab[k & 255];
+  const double res = fma(t, p, t);
+  return __hiloint2double(__double2hiint(res) + ((k >> 8) << 20), __double2loint(res));
 }
 
 // ---- reductions -------------------------------------------------------------------------------

@@ -60,20 +60,107 @@ __device__ __forceinline__ double gammainc4(double x, double emx) {
   return 1.0 - gammaincc_int(4, x, emx);
 }
 
-__global__ void __launch_bounds__(512) sn_kernel(const SnArgs a) {
-  extern __shared__ double smem[];
+// sed.CutoffBlackbody (sed.py:301-426) + _SED.flux_density (sed.py:239-251) for one (epoch, frequency);
+// integer s = 4 - absorption_index.  Returns mJy (before the (1+z) factor of supernova_models.py:1597).
+__device__ __noinline__ double cutoff_blackbody_mjy(const rb_sn_config& cfg, double lbol, double rph, double tph,
+                                                    double nu, double dl) {
+  const double alpha = cfg.absorption_index;
+  const int s = (int)(4.0 - alpha + 0.5);
+  const double lam_c = cfg.cutoff_wavelength * kAngstrom;
+  double norm = lbol / (kFluxConst / kAngstrom * (rph * rph) * tph);          // :388-390
+  const double kt_hc = tph / kXConst;
+  const double x_c = 1.0 / (lam_c * kt_hc);
+  const double e1 = exp(-x_c);
+  double en = 1.0, above = 0.0, below = 0.0;
+  for (int i = 1; i <= 10; ++i) {
+    en *= e1;  // e^{-i x_c}
+    const double di = (double)i;
+    const double xi = x_c * di;
+    double ns = di;
+    for (int q = 1; q < s; ++q) ns *= di;
+    above += gammainc4(xi, en) / (di * di * di * di);
+    below += gammaincc_int(s, xi, en) / ns;
+  }
+  const double kt2 = kt_hc * kt_hc;
+  double kts = kt_hc, gam = 1.0;  // kT_over_hc^s, Gamma(s) = (s-1)!
+  for (int q = 1; q < s; ++q) { kts *= kt_hc; gam *= (double)q; }
+  above = kt2 * kt2 * 6.0 * above;
+  below = (1.0 / pow(lam_c, alpha)) * kts * gam * below;
+  norm /= ((above + below) / tph);
+  const double lam_A = 1.e10 * (kCSI / nu);                                   // utils.py:365-370
+  const double lam = lam_A * kAngstrom;
+  const double l2 = lam * lam;
+  const double l5 = l2 * l2 * lam;
+  const double em = expm1(kXConst / lam / tph);
+  double sedv;
+  if (lam < lam_c)
+    sedv = kFluxConst * ((rph * rph) * pow(lam / lam_c, alpha) / l5) / em;
+  else
+    sedv = kFluxConst * ((rph * rph) / l5) / em;
+  sedv *= norm;
+  double fd = sedv / (4 * kPi * (dl * dl));                                   // sed.py:239-251
+  fd *= lam_A;
+  fd /= nu;
+  return fd * kToMJy;
+}
+
+// scalars staged in shared memory per sample so that they do not occupy registers across the hot loop
+enum { SC_OPZ = 0, SC_VEJ, SC_TRAP, SC_TAU2, SC_DL, SC_TFLOOR, SC_COUNT };
+
+// Hot-loop exp(x), x in [-700, 0]: k = rint(x * 256/ln2), r' = x * 256/ln2 - k in [-0.5, 0.5],
+// exp = 2^(k>>8) * tab[k&255] * (1 + r'(A1 + r'(A2 + r' A3))), A_i = (ln2/256)^i / i!.
+// Truncation (ln2/512)^4/24 = 1.4e-13, argument-scaling error |x| * 256/ln2 * 2^-52 * ln2/256 < 1.6e-13.
+constexpr double kA1 = 0.0027076061740622863;
+constexpr double kA2 = 3.6655655969101062e-06;
+constexpr double kA3 = 3.3083026805413713e-09;
+
+template <bool GUARD>
+__device__ __forceinline__ double diffusion_sum(const double2* __restrict__ nodes, const double2* __restrict__ seg,
+                                                const double* __restrict__ tab, int ms, int Dm1, double te,
+                                                double te2, double te_is, double c1) {
+  double acc = 0.0;
+#pragma unroll 4
+  for (int m = ms; m < kNodes; ++m) {
+    const double2 nd = nodes[m];                                            // (xm, xm * dw)
+    const double t = te * nd.x;                                             // interaction_processes.py:53
+    // searchsorted(dense_times, t): v = 2^52 + ceil(t / step) with a round-up FMA
+    const double v = __fma_ru(nd.x, te_is, 4503599627370496.0);
+    const unsigned k = min((unsigned)__double2loint(v), (unsigned)Dm1);
+    const double2 sg = seg[k];                                              // L(t) = a_k + b_k t on (x_{k-1}, x_k]
+    const double lum = fma(sg.y, t, sg.x);                                  // scipy interp1d, :56
+    const double d = __dsub_rn(__dmul_rn(t, t), te2);                       // t_i^2 - t_e^2, unfused as in :57
+    const double vv = fma(d, c1, kExpMagic);
+    const int kk = __double2loint(vv);
+    const double r = fma(d, c1, -(vv - kExpMagic));
+    double q = fma(r, kA3, kA2);
+    q = fma(r, q, kA1);
+    const double pp = r * q;
+    const double tb = tab[kk & 255];
+    const double res = fma(tb, pp, tb);
+    const double ex = __hiloint2double(__double2hiint(res) + ((kk >> 8) << 20), __double2loint(res));
+    double g = lum * ex;
+    if (GUARD) { if (isnan(g * t)) g = 0.0; }                              // :58 (NaN integrand -> 0)
+    acc = fma(g, nd.y, acc);                                                // trapezoid, regrouped
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
+  extern __shared__ double2 smem2[];
   const int D = a.cfg.dense_resolution;
-  double* ylo = smem;                 // [D]   engine luminosity on the dense grid
-  double* slope = ylo + D;            // [D]   slope[k] of interval (k-1, k)
-  double* xm = slope + D;             // [kNodes]
-  double* lsp = xm + kNodes;          // [kNodesHalf]
-  double* tab = lsp + kNodesHalf;     // [32]  2^(j/32)
-  double* scratch = tab + 32;         // [36]  reductions + d_L
+  double2* seg = smem2;                                  // [D]      (a_k, b_k)
+  double2* nodes = seg + D;                              // [kNodes] (xm, xm * dw)
+  double* ytmp = reinterpret_cast<double*>(nodes + kNodes);  // [D]  engine luminosity on the dense grid
+  double* lsp = ytmp + D;                                // [kNodesHalf]
+  double* xms = lsp + kNodesHalf;                        // [kNodes] merged abscissae
+  double* tab = xms + kNodes;                            // [256]    2^(j/256)
+  double* sc = tab + 256;                                // [SC_COUNT]
+  double* scratch = sc + 8;                              // [36]     reductions + d_L partial sums
 
   const int tid = threadIdx.x;
   const int E = a.E;
   const int sed = a.cfg.sed;
-  if (tid < 32) tab[tid] = RB_EXP2_32[tid];
+  for (int i = tid; i < 256; i += blockDim.x) tab[i] = RB_EXP2_256[i];
 
   for (int64_t n = blockIdx.x; n < a.N; n += gridDim.x) {
     const double* P = a.params + n;
@@ -82,25 +169,23 @@ __global__ void __launch_bounds__(512) sn_kernel(const SnArgs a) {
     const double z = (sed == RB_SED_BOLOMETRIC) ? 0.0 : P[RB_SN_REDSHIFT * N];
     const double opz = 1.0 + z;
     const double mej = P[RB_SN_MEJ * N], vej = P[RB_SN_VEJ * N];
-    const double kappa = P[RB_SN_KAPPA * N], kappa_gamma = P[RB_SN_KAPPA_GAMMA * N];
     const double t_end = a.t_obs[E - 1] / opz + 100.0;                       // supernova_models.py:965
-    const double tau = sqrt(kDiffusionConst * kappa * mej / vej) / kDay;      // interaction_processes.py:39
-    const double trap = (kTrappingConst * kappa_gamma * mej / (vej * vej)) / (kDay * kDay);  // :40
+    const double tau = sqrt(kDiffusionConst * P[RB_SN_KAPPA * N] * mej / vej) / kDay;  // interaction_processes.py:39
     const double tau2 = tau * tau;
-    const double inv_tau2 = 1.0 / tau2;
     const double step = t_end / (double)(D - 1);                              // np.linspace step
-    // slightly shrunk so that ceil(t * inv_step) never exceeds D-1 and t == x_k lands in (k-1, k]
-    const double inv_step_exact = 1.0 / step;
-    const double inv_step = inv_step_exact * (1.0 - 0x1p-50);
+    const double inv_step = 1.0 / step;
 
-    __syncthreads();  // previous sample's epilogue is done with smem
+    __syncthreads();  // previous sample's epilogue is done with shared memory
     // ---- engine on the dense grid --------------------------------------------------------------
+    bool bad = false;
     if (a.cfg.engine == RB_ENGINE_NICKEL) {
       const double nickel_mass = P[RB_SN_F_NICKEL * N] * mej;                 // supernova_models.py:577
       for (int k = tid; k < D; k += blockDim.x) {
         const double x = (k == D - 1) ? t_end : (double)k * step;
-        ylo[k] = nickel_mass * (6.45e43 * exp_tab<true>(fmax(-x / 8.8, -708.0), tab) +
-                                1.45e43 * exp_tab<true>(fmax(-x / 111.3, -708.0), tab));
+        const double y = nickel_mass * (6.45e43 * exp_tab(fmax(-x / 8.8, -708.0), tab) +
+                                        1.45e43 * exp_tab(fmax(-x / 111.3, -708.0), tab));
+        ytmp[k] = y;
+        bad |= !isfinite(y);
       }
     } else {
       // magnetar_models.py:181-184 with time in seconds (supernova_models.py:1466)
@@ -114,7 +199,9 @@ __global__ void __launch_bounds__(512) sn_kernel(const SnArgs a) {
       for (int k = tid; k < D; k += blockDim.x) {
         const double x = ((k == D - 1) ? t_end : (double)k * step) * kDay;
         const double den = 1.0 + 2.0 * x / tp;
-        ylo[k] = l0 / (den * den);
+        const double y = l0 / (den * den);
+        ytmp[k] = y;
+        bad |= !isfinite(y);
       }
     }
     // ---- quadrature abscissae: lsp = logspace(log10(tau/t_end) - 3, 0, 50) ----------------------
@@ -124,26 +211,36 @@ __global__ void __launch_bounds__(512) sn_kernel(const SnArgs a) {
       const double yv = (tid == kNodesHalf - 1) ? 0.0 : (double)tid * da + a0;
       lsp[tid] = pow(10.0, yv);
     }
-    // ---- luminosity distance -------------------------------------------------------------------
-    double dl = 1.0;
-    if (sed != RB_SED_BOLOMETRIC) {
-      if (a.dl_cm != nullptr) {
-        dl = a.dl_cm[n];
-      } else {
-        if (tid >= 64 && tid < 128) {  // warps 2,3: 64-point Gauss-Legendre on [0, z]
-          const int i = tid - 64;
-          const double zi = 0.5 * z * (RB_GL64_X[i] + 1.0);
-          double w = RB_GL64_W[i] * inv_efunc(a.cfg.cosmology, zi);
-          w = warp_sum(w);
-          if ((tid & 31) == 0) scratch[33 + (i >> 5)] = w;  // scratch[33], scratch[34]
-        }
-      }
+    // ---- luminosity distance (warps 2,3: 64-point Gauss-Legendre on [0, z]) ---------------------
+    if (sed != RB_SED_BOLOMETRIC && a.dl_cm == nullptr && tid >= 64 && tid < 128) {
+      const int i = tid - 64;
+      double w = RB_GL64_W[i] * inv_efunc(a.cfg.cosmology, 0.5 * z * (RB_GL64_X[i] + 1.0));
+      w = warp_sum(w);
+      if ((tid & 31) == 0) scratch[33 + (i >> 5)] = w;  // scratch[33], scratch[34]
     }
-    __syncthreads();
-    if (sed != RB_SED_BOLOMETRIC && a.dl_cm == nullptr)
-      dl = opz * a.cfg.cosmology.hubble_distance_cm * (0.5 * z * (scratch[33] + scratch[34]));
-    // slopes of interp1d (interaction_processes.py:44): (y_hi - y_lo) / (x_hi - x_lo)
-    for (int k = tid; k < D; k += blockDim.x) slope[k] = (k == 0) ? 0.0 : (ylo[k] - ylo[k - 1]) * inv_step_exact;
+    const bool any_bad = __syncthreads_or(bad);
+    if (tid == 0) {
+      double dl = 1.0;
+      if (sed != RB_SED_BOLOMETRIC)
+        dl = (a.dl_cm != nullptr) ? a.dl_cm[n]
+                                  : opz * a.cfg.cosmology.hubble_distance_cm * (0.5 * z * (scratch[33] + scratch[34]));
+      sc[SC_OPZ] = opz;
+      sc[SC_VEJ] = vej;
+      sc[SC_TRAP] = (kTrappingConst * P[RB_SN_KAPPA_GAMMA * N] * mej / (vej * vej)) / (kDay * kDay);  // :40
+      sc[SC_TAU2] = tau2;
+      sc[SC_DL] = dl;
+      sc[SC_TFLOOR] = (sed != RB_SED_BOLOMETRIC) ? P[RB_SN_TEMPERATURE_FLOOR * N] : 0.0;
+    }
+    // interp1d segments (interaction_processes.py:44): L(t) = y_{k-1} + s_k (t - x_{k-1}) = a_k + s_k t
+    for (int k = tid; k < D; k += blockDim.x) {
+      double2 sg = make_double2(0.0, 0.0);
+      if (k > 0) {
+        const double y0 = ytmp[k - 1];
+        const double sk = (ytmp[k] - y0) * inv_step;
+        sg = make_double2(fma(-sk, (double)(k - 1) * step, y0), sk);
+      }
+      seg[k] = sg;
+    }
     // merge lsp (ascending) with 1 - lsp (descending): rank by counting, np.unique order
     if (tid < kNodes) {
       int rank;
@@ -160,7 +257,15 @@ __global__ void __launch_bounds__(512) sn_kernel(const SnArgs a) {
         for (int j = 0; j < kNodesHalf; ++j) c += (lsp[j] <= v);
         rank = (kNodesHalf - 1 - j0) + c;
       }
-      xm[rank] = v;
+      xms[rank] = v;
+    }
+    __syncthreads();
+    // trapezoid regrouped by node: sum_i (t_i - t_{i-1})(f_i + f_{i-1}) = te^2 sum_i L_i e_i xm_i dw_i with
+    // dw_i = xm_{i+1} - xm_{i-1} (dw_last = xm_last - xm_{last-1}); f_0 = 0 because xm_0 = 0.
+    if (tid < kNodes) {
+      const double x = xms[tid];
+      const double dw = (tid == kNodes - 1) ? (x - xms[tid - 1]) : (xms[tid + 1] - xms[max(tid - 1, 0)]);
+      nodes[tid] = make_double2(x, x * dw);
     }
     __syncthreads();
 
@@ -178,97 +283,43 @@ __global__ void __launch_bounds__(512) sn_kernel(const SnArgs a) {
           int lo = 0, hi = kNodes;  // lower_bound
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (xm[mid] < x0) lo = mid + 1; else hi = mid;
+            if (nodes[mid].x < x0) lo = mid + 1; else hi = mid;
           }
           m0 = lo;
         }
       }
       const int ms = max(m0, 1);  // xm[0] = 1 - lsp[49] = 0 -> integrand 0 there
-      double t_prev = te * xm[ms - 1];
-      double f_prev = 0.0;
-      double acc = 0.0;
-#pragma unroll 2
-      for (int m = ms; m < kNodes; ++m) {
-        const double t = te * xm[m];                                          // :53
-        // searchsorted(dense_times, t) via round-up FMA: v = 2^52 + ceil(t / step)
-        const double v = __fma_ru(t, inv_step, 4503599627370496.0);
-        int k = __double2loint(v);
-        const double kdm1 = v - 4503599627370497.0;                           // ceil(t/step) - 1
-        k = min(max(k, 1), D - 1);
-        const double dx = fma(-kdm1, step, t);                                // t - x_lo
-        const double lum = fma(slope[k], dx, ylo[k - 1]);                     // scipy _call_linear
-        const double d = __dsub_rn(__dmul_rn(t, t), te2);                     // t_i^2 - t_e^2 (unfused, :57)
-        const double arg = fmax(d * inv_tau2, -700.0);
-        const double ex = exp_tab<false>(arg, tab);
-        double f = lum * t * ex;
-        if (isnan(f)) f = 0.0;                                                // :58
-        acc = fma(t - t_prev, f + f_prev, acc);                               // np.trapezoid, :60
-        t_prev = t;
-        f_prev = f;
-      }
-      double lbol = (0.5 * acc) * (-2.0 * expm1(-trap / te2) / tau2);         // :61
+      // shrunk by 2^-50 so that ceil() never exceeds D-1 and t == x_k lands in (k-1, k]
+      const double te_is = te * inv_step * (1.0 - 0x1p-50);
+      const double c1 = k256OverLn2 / tau2;
+      const double acc = any_bad ? diffusion_sum<true>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1)
+                                 : diffusion_sum<false>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
+      const double tau2s = sc[SC_TAU2];
+      const double lbol = (0.5 * (te2 * acc)) * (-2.0 * expm1(-sc[SC_TRAP] / te2) / tau2s);  // :60-61
 
       double model;
       if (sed == RB_SED_BOLOMETRIC) {
         model = lbol;
       } else {
         // ---- photosphere.TemperatureFloor (photosphere.py:87-111) ----
-        const double tfloor = P[RB_SN_TEMPERATURE_FLOOR * N];
-        const double rr = kRadiusConst * vej * te;
+        const double opzs = sc[SC_OPZ], dl = sc[SC_DL];
+        const double tfloor = sc[SC_TFLOOR];
+        const double rr = kRadiusConst * sc[SC_VEJ] * te;
         const double r2 = rr * rr;
         const double tf2 = tfloor * tfloor;
         const double rec2 = lbol / (kStefConst * (tf2 * tf2));
         const bool mask = r2 <= rec2;
         const double rph = sqrt(mask ? r2 : rec2);
         const double tph = mask ? sqrt(sqrt(lbol / (kStefConst * r2))) : tfloor;
-        const double nu = a.freq_obs[e] * opz;                                // utils.py:383
+        const double nu = a.freq_obs[e] * opzs;                               // utils.py:383
         if (sed == RB_SED_BLACKBODY) {
           // sed.py:199-222
           const double num = 2 * kPi * kH * (nu * nu * nu) * (rph * rph);
           const double den = (dl * dl) * (kC * kC);
           const double frac = 1.0 / expm1((kH * nu) / (kKB * tph));
-          model = num / den * frac * kToMJy * opz;                            // supernova_models.py:1007
+          model = num / den * frac * kToMJy * opzs;                           // supernova_models.py:1007
         } else {
-          // sed.CutoffBlackbody (sed.py:301-426), integer s = 4 - absorption_index
-          const double alpha = a.cfg.absorption_index;
-          const int s = (int)(4.0 - alpha + 0.5);
-          const double lam_c = a.cfg.cutoff_wavelength * kAngstrom;
-          double norm = lbol / (kFluxConst / kAngstrom * (rph * rph) * tph);  // :388-390
-          const double kt_hc = tph / kXConst;
-          const double x_c = 1.0 / (lam_c * kt_hc);
-          const double e1 = exp(-x_c);
-          double en = 1.0, above = 0.0, below = 0.0;
-          for (int i = 1; i <= 10; ++i) {
-            en *= e1;  // e^{-i x_c}
-            const double xi = x_c * (double)i;
-            const double di = (double)i;
-            const double emx = (i == 1) ? e1 : ((xi > 700.0) ? 0.0 : en);
-            double ns = di;
-            for (int q = 1; q < s; ++q) ns *= di;
-            above += gammainc4(xi, emx) / (di * di * di * di);
-            below += gammaincc_int(s, xi, emx) / ns;
-          }
-          const double kt2 = kt_hc * kt_hc;
-          double kts = kt_hc, gam = 1.0;  // kT_over_hc^s, Gamma(s) = (s-1)!
-          for (int q = 1; q < s; ++q) { kts *= kt_hc; gam *= (double)q; }
-          above = kt2 * kt2 * 6.0 * above;
-          below = (1.0 / pow(lam_c, alpha)) * kts * gam * below;
-          norm /= ((above + below) / tph);
-          const double lam_A = 1.e10 * (kCSI / nu);                           // utils.py:365-370
-          const double lam = lam_A * kAngstrom;
-          const double l2 = lam * lam;
-          const double l5 = l2 * l2 * lam;
-          const double em = expm1(kXConst / lam / tph);
-          double sedv;
-          if (lam < lam_c)
-            sedv = kFluxConst * ((rph * rph) * pow(lam / lam_c, alpha) / l5) / em;
-          else
-            sedv = kFluxConst * ((rph * rph) / l5) / em;
-          sedv *= norm;
-          double fd = sedv / (4 * kPi * (dl * dl));                           // sed.py:239-251
-          fd *= lam_A;
-          fd /= nu;
-          model = fd * kToMJy * opz;                                          // supernova_models.py:1597
+          model = cutoff_blackbody_mjy(a.cfg, lbol, rph, tph, nu, dl) * opzs;  // supernova_models.py:1597
         }
       }
       if (a.out_model != nullptr) a.out_model[n * (int64_t)E + e] = model;
