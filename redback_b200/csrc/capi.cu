@@ -31,8 +31,10 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
   } while (0)
 
-size_t sn_smem_bytes(int D) {
-  return sizeof(double) * (size_t)(2 * D + 2 * rb::kNodes + D + rb::kNodesHalf + rb::kNodes + 256 + 8 + 36);
+size_t sn_smem_bytes(int D, int64_t E, bool epochs_in_smem) {
+  size_t n = (size_t)(2 * D + 2 * rb::kNodes + D + rb::kNodesHalf + rb::kNodes + 256 + 2 * rb::kScalars + 16);
+  if (epochs_in_smem) n += (size_t)rb::kEpochCols * (size_t)E;
+  return sizeof(double) * n;
 }
 
 int sn_block_threads(int64_t E) {
@@ -138,31 +140,59 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   int rc = sn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  RB_CUDA(cudaGetDevice(&dev));
+  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(rb::sn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sn_kernel)");
+
+  // workspace: per-launch epoch table [kEpochCols][E] + per-sample scalar records [N][kScalars]
+  const size_t ws_doubles = (size_t)rb::kEpochCols * (size_t)E + (size_t)rb::kScalars * (size_t)N;
+  double* ws = nullptr;
+  RB_CUDA(cudaMallocAsync(&ws, ws_doubles * sizeof(double), st));
+  double* epoch_tab = ws;
+  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
+                                                                    y ? sigma : nullptr, epoch_tab);
   rb::SnArgs a;
   a.cfg = *cfg;
   a.N = N;
   a.E = (int)E;
   a.params = params;
-  a.t_obs = t_obs;
-  a.freq_obs = freq_obs;
   a.dl_cm = dl_cm;
-  a.y = y;
-  a.sigma = (cfg->sigma_mode == RB_SIGMA_SAMPLED && !sigma) ? t_obs : sigma;  // never dereferenced meaningfully
   a.sigma_param = sigma_param;
   a.out_model = out_model;
   a.out_logl = y ? out_logl : nullptr;
-  const size_t smem = sn_smem_bytes(cfg->dense_resolution);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::sn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  });
-  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sn_kernel)");
+  a.want_logl = y ? 1 : 0;
+  a.epoch_tab = epoch_tab;
+  a.scalars = ws + (size_t)rb::kEpochCols * (size_t)E;
+  rb::sn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
   const int threads = sn_block_threads(E);
-  const int64_t grid = N < 2147483647LL ? N : 2147483647LL;
-  rb::sn_kernel<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(a);
-  launch_counter()->fetch_add(1);
-  RB_CUDA(cudaGetLastError());
+  a.epochs_in_smem = (sn_smem_bytes(cfg->dense_resolution, E, true) <= 64 * 1024) ? 1 : 0;
+  const size_t smem = sn_smem_bytes(cfg->dense_resolution, E, a.epochs_in_smem != 0);
+  if (smem > 220 * 1024) {
+    cudaFreeAsync(ws, st);
+    return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution too large for shared memory");
+  }
+  int occ = 0;
+  cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::sn_kernel, threads, smem);
+  if (oe != cudaSuccess) {
+    cudaFreeAsync(ws, st);
+    return cuda_fail(oe, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  }
+  if (occ < 1) occ = 1;
+  // persistent blocks, grid-stride over samples; 4 waves' worth of blocks for load balance at mid-size N
+  int64_t grid = (int64_t)sms * occ * 4;
+  if (grid > N) grid = N;
+  rb::sn_kernel<<<(unsigned)grid, threads, smem, st>>>(a);
+  launch_counter()->fetch_add(3);
+  cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(ws, st);
+  if (le != cudaSuccess) return cuda_fail(le, "sn_kernel launch");
   return RB_OK;
 }
 
