@@ -328,12 +328,14 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       }
     }
     // ---- quadrature abscissae: lsp = logspace(log10(tau/t_end) - 3, 0, 50) ----------------------
-    if (tid < kNodesHalf) {
+    // (done by the block's last threads, which have one fewer dense-grid iteration than the first ones)
+    const int rt = (int)blockDim.x - 1 - tid;
+    if (rt < kNodesHalf) {
       const double a0 = sc[SC_A0];
       const double da = (0.0 - a0) / (double)(kNodesHalf - 1);
-      const double yv = (tid == kNodesHalf - 1) ? 0.0 : (double)tid * da + a0;
+      const double yv = (rt == kNodesHalf - 1) ? 0.0 : (double)rt * da + a0;
       // 10**y; a last-bit difference to numpy's pow is immaterial here
-      lsp[tid] = (yv > -300.0) ? exp_tab(yv * 2.302585092994046, tab) : pow(10.0, yv);
+      lsp[rt] = (yv > -300.0) ? exp_tab(yv * 2.302585092994046, tab) : pow(10.0, yv);
     }
     const bool any_bad = __syncthreads_or(bad);
     // interp1d segments (interaction_processes.py:44): L(t) = y_{k-1} + s_k (t - x_{k-1}) = a_k + s_k t
@@ -348,19 +350,19 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
     }
     // merge lsp (ascending) with 1 - lsp (non-increasing) in np.unique order: rank = own index + number of
     // elements of the other list that sort before it (binary search on the monotone other list)
-    if (tid < kNodes) {
+    if (rt < kNodes) {
       int rank;
       double v;
-      if (tid < kNodesHalf) {
-        v = lsp[tid];
+      if (rt < kNodesHalf) {
+        v = lsp[rt];
         int lo = 0, hi = kNodesHalf;  // first j with (1 - lsp[j]) < v; the set is a suffix
         while (lo < hi) {
           const int mid = (lo + hi) >> 1;
           if ((1.0 - lsp[mid]) < v) hi = mid; else lo = mid + 1;
         }
-        rank = tid + (kNodesHalf - lo);
+        rank = rt + (kNodesHalf - lo);
       } else {
-        const int j0 = tid - kNodesHalf;
+        const int j0 = rt - kNodesHalf;
         v = 1.0 - lsp[j0];
         int lo = 0, hi = kNodesHalf;  // number of j with lsp[j] <= v; the set is a prefix
         while (lo < hi) {
@@ -374,10 +376,10 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
     __syncthreads();
     // trapezoid regrouped by node: sum_i (t_i - t_{i-1})(f_i + f_{i-1}) = te^2 sum_i L_i e_i xm_i dw_i with
     // dw_i = xm_{i+1} - xm_{i-1} (dw_last = xm_last - xm_{last-1}); f_0 = 0 because xm_0 = 0.
-    if (tid < kNodes) {
-      const double x = xms[tid];
-      const double dw = (tid == kNodes - 1) ? (x - xms[tid - 1]) : (xms[tid + 1] - xms[max(tid - 1, 0)]);
-      nodes[tid] = make_double2(x, x * dw);
+    if (rt < kNodes) {
+      const double x = xms[rt];
+      const double dw = (rt == kNodes - 1) ? (x - xms[rt - 1]) : (xms[rt + 1] - xms[max(rt - 1, 0)]);
+      nodes[rt] = make_double2(x, x * dw);
     }
     __syncthreads();
 
