@@ -126,6 +126,43 @@ int rb_sn_eval_f64_host(const rb_sn_config* cfg, int64_t N, int64_t E, const dou
                         const double* y, const double* sigma, const double* sigma_param,
                         double* out_model, double* out_logl);
 
+/* ---- kilonova path ----------------------------------------------------------------------------------
+ * one_component_kilonova_model   redback/transient_models/kilonova_models.py:1537-1603 (+ :1853-1893)
+ * metzger_kilonova_model         redback/transient_models/kilonova_models.py:1895-1962 (+ :1965-2068)
+ * both in output_format='flux_density', on the reference's adaptive grid
+ * get_optimal_time_array(1e-2, 7e6, dense_resolution, user_times) (redback/utils.py:42-80). */
+enum { RB_KN_ONE_COMPONENT = 0, RB_KN_METZGER = 1 };
+enum {
+  RB_KN_REDSHIFT = 0,
+  RB_KN_MEJ = 1,               /* [Msun]                      */
+  RB_KN_VEJ = 2,               /* [c]                         */
+  RB_KN_KAPPA = 3,
+  RB_KN_TEMPERATURE_FLOOR = 4, /* one-component: [K]          */
+  RB_KN_BETA = 4,              /* Metzger: velocity power law */
+  RB_KN_NPARAM = 5
+};
+
+typedef struct {
+  int model;                    /* RB_KN_*                                                       */
+  int sigma_mode;               /* RB_SIGMA_*                                                    */
+  int dense_resolution;         /* kwargs 'dense_resolution', default 500 (kilonova_models.py:1558) */
+  int neutron_precursor_switch; /* Metzger only, default 1 (kilonova_models.py:1977)             */
+  double vmax;                  /* Metzger only, default 0.7 (kilonova_models.py:1997)           */
+  rb_cosmology cosmology;       /* used only when dl_cm == NULL                                  */
+} rb_kn_config;
+
+int rb_kn_config_default(rb_kn_config* cfg);
+
+/* Same argument conventions as rb_sn_eval_f64; params is [RB_KN_NPARAM][N]; t_obs in observer-frame days
+ * (> 0); epochs whose source-frame time falls outside the model grid [1e-2 s, 7e6 s] (where scipy's
+ * interp1d raises ValueError in the reference) come back as NaN. */
+int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, const double* params, const double* t_obs,
+                   const double* freq_obs, const double* dl_cm, const double* y, const double* sigma,
+                   const double* sigma_param, double* out_model, double* out_logl, void* stream);
+int rb_kn_eval_f64_host(const rb_kn_config* cfg, int64_t N, int64_t E, const double* params,
+                        const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
+                        const double* sigma, const double* sigma_param, double* out_model, double* out_logl);
+
 /* Luminosity distance [cm] for N redshifts on device (same quadrature the fused kernels use). */
 int rb_luminosity_distance_f64(const rb_cosmology* cosmo, int64_t N, const double* redshift,
                                double* out_dl_cm, void* stream);

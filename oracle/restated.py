@@ -339,3 +339,191 @@ def gaussian_likelihood_quadrature(y, model, sigma_i, sigma):
     with np.errstate(all="ignore"):
         full = np.sqrt(np.asarray(sigma_i) ** 2. + sigma ** 2.)
     return float(np.nan_to_num(gaussian_log_likelihood(np.asarray(y) - model, full)))
+
+
+# --------------------------------------------------------------------------------------------------
+# kilonova: one-component model (kilonova_models.py:1537-1603, 1853-1893)
+# --------------------------------------------------------------------------------------------------
+def get_optimal_time_array(t_min, t_max, resolution, user_times=None):
+    """utils.py:42-145 (the lru_cache is irrelevant for the values)."""
+    if user_times is not None:
+        user_times = np.atleast_1d(user_times)
+        user_min, user_max = np.min(user_times), np.max(user_times)
+        eval_min = max(t_min, user_min * 0.5)
+        eval_max = min(t_max, user_max * 2.0)
+        n_before = int(resolution * 0.15)
+        n_user = int(resolution * 0.70)
+        n_after = resolution - n_before - n_user
+        if eval_min > t_min:
+            segment_before = np.geomspace(t_min, eval_min, n_before)
+        else:
+            segment_before = np.array([t_min])
+            n_user += n_before
+        segment_user = np.geomspace(eval_min, eval_max, n_user)
+        if eval_max < t_max:
+            segment_after = np.geomspace(eval_max, t_max, n_after)
+        else:
+            segment_after = np.array([t_max])
+            n_user += n_after
+            segment_user = np.geomspace(eval_min, eval_max, n_user)
+        return np.unique(np.concatenate([segment_before, segment_user, segment_after]))
+    log_range = np.log10(t_max) - np.log10(t_min)
+    if log_range > 6:
+        n_early = int(resolution * 0.25)
+        n_mid = int(resolution * 0.50)
+        n_late = resolution - n_early - n_mid
+        trans1 = t_min * (t_max / t_min) ** 0.25
+        trans2 = t_min * (t_max / t_min) ** 0.75
+        return np.unique(np.concatenate([np.geomspace(t_min, trans1, n_early), np.geomspace(trans1, trans2, n_mid),
+                                         np.geomspace(trans2, t_max, n_late)]))
+    return np.geomspace(t_min, t_max, resolution)
+
+
+_BK_V = np.asarray([0.1, 0.2, 0.3, 0.4])
+_BK_M = np.asarray([1.e-3, 5.e-3, 1.e-2, 5.e-2, 1.e-1])
+_BK_A = np.asarray([[2.01, 4.52, 8.16, 16.3], [0.81, 1.9, 3.2, 5.0], [0.56, 1.31, 2.19, 3.0],
+                    [.27, .55, .95, 2.0], [0.20, 0.39, 0.65, 0.9]])
+_BK_B = np.asarray([[0.28, 0.62, 1.19, 2.4], [0.19, 0.28, 0.45, 0.65], [0.17, 0.21, 0.31, 0.45],
+                    [0.10, 0.13, 0.15, 0.17], [0.06, 0.11, 0.12, 0.12]])
+_BK_D = np.asarray([[1.12, 1.39, 1.52, 1.65], [0.86, 1.21, 1.39, 1.5], [0.74, 1.13, 1.32, 1.4],
+                    [0.6, 0.9, 1.13, 1.25], [0.63, 0.79, 1.04, 1.5]])
+
+
+def barnes_kasen_thermalisation(mej, vej):
+    """utils.py:1161-1187: three bilinear RegularGridInterpolators with linear extrapolation."""
+    from scipy.interpolate import RegularGridInterpolator
+    out = []
+    for arr in (_BK_A, _BK_B, _BK_D):
+        f = RegularGridInterpolator((_BK_M, _BK_V), arr, bounds_error=False, fill_value=None)
+        out.append(f([mej, vej])[0])
+    return tuple(out)
+
+
+def one_component_kilonova_internal(time, mej, vej, kappa, temperature_floor=4000):
+    """kilonova_models.py:1853-1893.  time: source-frame seconds.  Returns (L_bol, T, R)."""
+    from scipy.integrate import cumulative_trapezoid
+    with np.errstate(all="ignore"):
+        tdays = time / day_to_s
+        av, bv, dv = barnes_kasen_thermalisation(mej, vej)
+        e_th = 0.36 * (np.exp(-av * tdays) + np.log1p(2.0 * bv * tdays ** dv) / (2.0 * bv * tdays ** dv))
+        t0, sig, beta = 1.3, 0.11, 13.7
+        v0 = vej * speed_of_light
+        m0 = mej * solar_mass
+        tdiff = np.sqrt(2.0 * kappa * (m0) / (beta * v0 * speed_of_light))
+        lum_in = 4.0e18 * (m0) * (0.5 - np.arctan((time - t0) / sig) / np.pi) ** 1.3
+        integrand = lum_in * e_th * (time / tdiff) * np.exp(time ** 2 / tdiff ** 2)
+        lbol = np.zeros(len(time))
+        lbol[1:] = cumulative_trapezoid(integrand, time)
+        lbol[0] = lbol[1]
+        lbol = lbol * np.exp(-time ** 2 / tdiff ** 2) / tdiff
+        temperature = (lbol / (4.0 * np.pi * sigma_sb * v0 ** 2 * time ** 2)) ** 0.25
+        r_photosphere = (lbol / (4.0 * np.pi * sigma_sb * temperature_floor ** 4)) ** 0.5
+        mask = temperature <= temperature_floor
+        temperature[mask] = temperature_floor
+        mask = np.logical_not(mask)
+        r_photosphere[mask] = v0 * time[mask]
+        return lbol, temperature, r_photosphere
+
+
+def one_component_kilonova_model(time, redshift, mej, vej, kappa, *, frequency, temperature_floor=4000,
+                                 dense_resolution=500, dl=None, **_):
+    """kilonova_models.py:1537-1577 (flux_density branch).  time: observer-frame days.  Returns mJy[E]."""
+    time = np.asarray(time, dtype=float)
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    t_src_s = time * day_to_s / (1. + redshift)
+    time_temp = get_optimal_time_array(1e-2, 7e6, dense_resolution, user_times=t_src_s)
+    _, temperature, r_photosphere = one_component_kilonova_internal(time_temp, mej, vej, kappa, temperature_floor)
+    with np.errstate(all="ignore"):
+        t = time * day_to_s
+        temp_func = interp1d(time_temp, y=temperature)
+        rad_func = interp1d(time_temp, y=r_photosphere)
+        frequency, t = calc_kcorrected_properties(np.asarray(frequency, dtype=float), redshift, t)
+        fd = blackbody_to_flux_density(temp_func(t), rad_func(t), dl, frequency)
+        return fd * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)
+
+
+# --------------------------------------------------------------------------------------------------
+# kilonova: Metzger (2017) shell model (kilonova_models.py:1895-1962, 1965-2068)
+# --------------------------------------------------------------------------------------------------
+def electron_fraction_from_kappa(kappa):
+    """utils.py:1479-1491"""
+    kappa_array = np.array([35, 32.2, 22.3, 5.60, 5.36, 3.30, 0.96, 0.5])
+    ye_array = np.array([0.10, 0.15, 0.2, 0.25, 0.30, 0.35, 0.4, 0.5])
+    return interp1d(kappa_array, y=ye_array, fill_value='extrapolate')(kappa)
+
+
+def metzger_kilonova_internal(time, mej, vej, beta, kappa, neutron_precursor_switch=True, vmax=0.7):
+    """kilonova_models.py:1965-2068.  time: source-frame seconds.  Returns (L_bol, T, R)."""
+    with np.errstate(all="ignore"):
+        tdays = time / day_to_s
+        time_len = len(time)
+        mass_len = 200
+        av, bv, dv = barnes_kasen_thermalisation(mej, vej)
+        e_th = 0.36 * (np.exp(-av * tdays) + np.log1p(2.0 * bv * tdays ** dv) / (2.0 * bv * tdays ** dv))
+        electron_fraction = electron_fraction_from_kappa(kappa)
+        t0, sig, tau_neutron = 1.3, 0.11, 900
+        vel = np.linspace(vej, vmax, mass_len)
+        m_array = mej * (vel / vej) ** (-beta)
+        v_m = vel * speed_of_light
+        time_array = np.tile(time, (mass_len, 1))
+        e_th_array = np.tile(e_th, (mass_len, 1))
+        edotr = np.zeros((mass_len, time_len))
+        time_mask = time > t0
+        time_1 = time_array[:, time_mask]
+        time_2 = time_array[:, ~time_mask]
+        edotr[:, time_mask] = 2.1e10 * e_th_array[:, time_mask] * ((time_1 / (3600. * 24.)) ** (-1.3))
+        edotr[:, ~time_mask] = 4.0e18 * (0.5 - (1. / np.pi) * np.arctan((time_2 - t0) / sig)) ** (1.3) * \
+            e_th_array[:, ~time_mask]
+        energy_v = np.zeros((mass_len, time_len))
+        lum_rad = np.zeros((mass_len, time_len))
+        td_v = np.zeros((mass_len, time_len))
+        tau = np.zeros((mass_len, time_len))
+        v_photosphere = np.zeros(time_len)
+        r_photosphere = np.zeros(time_len)
+        if neutron_precursor_switch:
+            neutron_mass = 1e-4 * solar_mass
+            xn0 = (2.0 / np.pi) * (1.0 - electron_fraction) * np.arctan(neutron_mass / m_array / solar_mass)
+            xr = 1.0 - xn0
+            xn0_arr = np.tile(xn0, (time_len, 1)).T
+            xr_arr = np.tile(xr, (time_len, 1)).T
+            xn_arr = xn0_arr * np.exp(-time_array / tau_neutron)
+            edotr = 3.2e14 * xn_arr + edotr
+            kappa = 0.4 * (1.0 - xn_arr - xr_arr) + kappa * xr_arr
+        dt = np.diff(time)
+        dm = np.abs(np.diff(m_array))
+        energy_v[:, 0] = 0.5 * m_array * v_m ** 2
+        for ii in range(time_len - 1):
+            kap = kappa[:-1, ii] if neutron_precursor_switch else kappa
+            td_v[:-1, ii] = (kap * m_array[:-1] * solar_mass * 3) / (4 * np.pi * v_m[:-1] * speed_of_light * time[ii] * beta)
+            tau[:-1, ii] = (m_array[:-1] * solar_mass * kap / (4 * np.pi * (time[ii] * v_m[:-1]) ** 2))
+            lum_rad[:-1, ii] = energy_v[:-1, ii] / (td_v[:-1, ii] + time[ii] * (v_m[:-1] / speed_of_light))
+            energy_v[:-1, ii + 1] = (edotr[:-1, ii] - (energy_v[:-1, ii] / time[ii]) - lum_rad[:-1, ii]) * dt[ii] \
+                + energy_v[:-1, ii]
+            lum_rad[:-1, ii] = lum_rad[:-1, ii] * dm * solar_mass
+            tau[mass_len - 1, ii] = tau[mass_len - 2, ii]
+            photosphere_index = np.argmin(np.abs(tau[:, ii] - 1))
+            v_photosphere[ii] = v_m[photosphere_index]
+            r_photosphere[ii] = v_photosphere[ii] * time[ii]
+        lbol = np.sum(lum_rad, axis=0)
+        temperature = (lbol / (4.0 * np.pi * (r_photosphere) ** (2.0) * sigma_sb)) ** (0.25)
+        return lbol, temperature, r_photosphere
+
+
+def metzger_kilonova_model(time, redshift, mej, vej, beta, kappa, *, frequency, dense_resolution=500, dl=None,
+                           neutron_precursor_switch=True, vmax=0.7, **_):
+    """kilonova_models.py:1895-1935 (flux_density branch).  Returns mJy[E]."""
+    time = np.asarray(time, dtype=float)
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    t_src_s = time * day_to_s / (1. + redshift)
+    time_temp = get_optimal_time_array(1e-2, 7e6, dense_resolution, user_times=t_src_s)
+    _, temperature, r_photosphere = metzger_kilonova_internal(time_temp, mej, vej, beta, kappa,
+                                                              neutron_precursor_switch, vmax)
+    with np.errstate(all="ignore"):
+        t = time * day_to_s
+        temp_func = interp1d(time_temp, y=temperature)
+        rad_func = interp1d(time_temp, y=r_photosphere)
+        frequency, t = calc_kcorrected_properties(np.asarray(frequency, dtype=float), redshift, t)
+        fd = blackbody_to_flux_density(temp_func(t), rad_func(t), dl, frequency)
+        return fd * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)

@@ -29,6 +29,16 @@ class SnConfig(C.Structure):
                 ("cutoff_wavelength", C.c_double), ("absorption_index", C.c_double), ("cosmology", Cosmology)]
 
 
+KN_ONE_COMPONENT, KN_METZGER = 0, 1
+KN_ROWS = dict(redshift=0, mej=1, vej=2, kappa=3, temperature_floor=4, beta=4)
+KN_NPARAM = 5
+
+
+class KnConfig(C.Structure):
+    _fields_ = [("model", C.c_int), ("sigma_mode", C.c_int), ("dense_resolution", C.c_int),
+                ("neutron_precursor_switch", C.c_int), ("vmax", C.c_double), ("cosmology", Cosmology)]
+
+
 class RedbackB200Error(RuntimeError):
     pass
 
@@ -46,6 +56,9 @@ EXPORTS = {
     "rb_sn_config_default": (C.c_int, [C.POINTER(SnConfig)]),
     "rb_sn_eval_f64": (C.c_int, [C.POINTER(SnConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
     "rb_sn_eval_f64_host": (C.c_int, [C.POINTER(SnConfig), C.c_int64, C.c_int64] + [_dp] * 9),
+    "rb_kn_config_default": (C.c_int, [C.POINTER(KnConfig)]),
+    "rb_kn_eval_f64": (C.c_int, [C.POINTER(KnConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
+    "rb_kn_eval_f64_host": (C.c_int, [C.POINTER(KnConfig), C.c_int64, C.c_int64] + [_dp] * 9),
     "rb_luminosity_distance_f64": (C.c_int, [C.POINTER(Cosmology), C.c_int64, _dp, _dp, C.c_void_p]),
     "rb_gaussian_logl_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 5 + [C.c_void_p]),
     "rb_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -88,6 +101,19 @@ def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff
     cfg.dense_resolution = int(dense_resolution)
     cfg.cutoff_wavelength = float(cutoff_wavelength)
     cfg.absorption_index = float(absorption_index)
+    if cosmology is not None:
+        cfg.cosmology = cosmology
+    return cfg
+
+
+def kn_config(model, sigma_mode=SIGMA_FIXED, dense_resolution=500, neutron_precursor_switch=True, vmax=0.7,
+              cosmology=None):
+    cfg = KnConfig()
+    check(lib().rb_kn_config_default(C.byref(cfg)))
+    cfg.model, cfg.sigma_mode = model, sigma_mode
+    cfg.dense_resolution = int(dense_resolution)
+    cfg.neutron_precursor_switch = 1 if neutron_precursor_switch else 0
+    cfg.vmax = float(vmax)
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg

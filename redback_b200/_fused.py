@@ -1,0 +1,100 @@
+"""Glue shared by the model modules and the likelihoods: how a redback-style model function maps onto a
+fused device path (which parameters it needs, how to build the path from kwargs)."""
+import numpy as np
+import torch
+
+from . import _capi
+from .engine import batch_size
+
+
+class FusedSpec:
+    def __init__(self, name, needed, build, validate=None):
+        self.name = name
+        self.needed = tuple(needed)          # parameter names, in any order
+        self._build = build                  # (time, kwargs, y, sigma, sigma_mode) -> path
+        self._validate = validate            # kwargs -> None (raises like the reference)
+
+    def validate(self, kwargs):
+        if self._validate is not None:
+            self._validate(kwargs)
+
+    def build(self, time, kwargs, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED):
+        self.validate(kwargs)
+        return self._build(time, kwargs, y, sigma, sigma_mode)
+
+    def cache_key(self, kwargs):
+        items = []
+        for k in sorted(kwargs):
+            v = kwargs[k]
+            if k in ("frequency", "bands"):
+                continue
+            items.append((k, v if isinstance(v, (int, float, str, bool, type(None))) else id(v)))
+        return (self.name, tuple(items))
+
+
+def collect(named, kwargs, params_batch, needed):
+    """Merge positional/kwargs scalars and params_batch arrays into {name: value} for `needed`."""
+    params = {}
+    batch = dict(params_batch) if params_batch is not None else {}
+    for name in needed:
+        if name in batch:
+            params[name] = batch[name]
+        elif named.get(name) is not None:
+            params[name] = named[name]
+        elif name in kwargs:
+            params[name] = kwargs[name]
+        else:
+            raise KeyError(name)  # same failure mode as the reference (missing kwarg)
+    return params, batch_size(params)
+
+
+def finish(model, N, kwargs):
+    if kwargs.get("device_output", False):
+        return model if N is not None else model[0]
+    out = model.cpu().numpy()
+    return out if N is not None else out[0]
+
+
+def cosmology_from_kwargs(kwargs):
+    cosmo = kwargs.get("cosmology")
+    if cosmo is None or isinstance(cosmo, _capi.Cosmology):
+        return cosmo
+    try:  # astropy-like FlatLambdaCDM object
+        H0 = getattr(cosmo.H0, "value", cosmo.H0)
+        Tcmb0 = getattr(cosmo.Tcmb0, "value", cosmo.Tcmb0)
+        m_nu = [float(getattr(m, "value", m)) for m in np.atleast_1d(getattr(cosmo.m_nu, "value", cosmo.m_nu))]
+        m_nu = sorted(m_nu, reverse=True)[:3] + [0.0] * (3 - len(m_nu))
+        return _capi.flat_lcdm(float(H0), float(cosmo.Om0), float(Tcmb0), float(cosmo.Neff), m_nu)
+    except AttributeError as exc:
+        raise NotImplementedError("cosmology must be a flat LambdaCDM-like object") from exc
+
+
+def dl_from_kwargs(kwargs, path, N):
+    """Optional precomputed luminosity distance [cm] (kwarg 'dl', scalar or array[N]); default: integrate
+    the cosmology on device from the sampled redshift."""
+    dl = kwargs.get("dl")
+    if dl is None:
+        return None
+    n = N if N is not None else 1
+    if isinstance(dl, torch.Tensor):
+        return dl.to(device=path.device, dtype=torch.float64).reshape(-1).expand(n).contiguous()
+    arr = np.array(np.broadcast_to(np.asarray(dl, dtype=np.float64), (n,)))
+    return torch.from_numpy(arr).to(path.device)
+
+
+def flux_density_only(kwargs, name):
+    fmt = kwargs.get("output_format")
+    if fmt is None:
+        raise KeyError("output_format")
+    if fmt != "flux_density":
+        if fmt in ("magnitude", "flux", "spectra", "sncosmo_source"):
+            raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device yet")
+        raise ValueError("Output format must be 'flux', 'magnitude', 'sncosmo_source', or 'flux_density'")
+
+
+def run(spec, time, named, kwargs, params_batch):
+    params, N = collect(named, kwargs, params_batch, spec.needed)
+    path = spec.build(time, kwargs)
+    dev = path.pack(params, N if N is not None else 1)
+    model, _ = path.evaluate(dev, dl=dl_from_kwargs(kwargs, path, N))
+    return finish(model, N, kwargs)

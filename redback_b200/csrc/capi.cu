@@ -7,6 +7,7 @@
 #include <string>
 
 #include "sn_kernel.cu"
+#include "kn_kernel.cu"
 
 namespace {
 
@@ -305,3 +306,176 @@ int rb_measure_fp64_peak(int iters, double* out_tflops, double* out_ms) {
 }
 
 }  // extern "C"
+
+// ---- kilonova path ------------------------------------------------------------------------------------
+namespace {
+size_t kn_smem_bytes(const rb_kn_config* cfg, int64_t E) {
+  const size_t R = (size_t)cfg->dense_resolution;
+  size_t bytes = sizeof(double) * (5 * R + 256 + rb::kKnScalars + 34 + (size_t)rb::kEpochCols * (size_t)E);
+  if (cfg->model == RB_KN_METZGER) bytes += sizeof(double) * 2 * rb::kShellWarps * R + sizeof(int) * rb::kShellWarps * R;
+  return bytes;
+}
+
+__global__ void minmax_kernel(int E, const double* __restrict__ t, double* __restrict__ out) {
+  // single block: min / max of the epochs (tiny E)
+  __shared__ double smin[32], smax[32];
+  double mn = INFINITY, mx = -INFINITY;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) { mn = fmin(mn, t[e]); mx = fmax(mx, t[e]); }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mn = fmin(mn, smin[w]); mx = fmax(mx, smax[w]); }
+    out[0] = mn;
+    out[1] = mx;
+  }
+}
+}  // namespace
+
+extern "C" int rb_kn_config_default(rb_kn_config* cfg) {
+  if (!cfg) return fail(RB_ERR_INVALID, "rb_kn_config_default: null config");
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->model = RB_KN_ONE_COMPONENT;
+  cfg->sigma_mode = RB_SIGMA_FIXED;
+  cfg->dense_resolution = 500;
+  cfg->neutron_precursor_switch = 1;
+  cfg->vmax = 0.7;
+  return rb_cosmology_planck18(&cfg->cosmology);
+}
+
+static int kn_check(const rb_kn_config* cfg, int64_t N, int64_t E, const void* params, const void* t_obs,
+                    const void* freq_obs, const void* y, const void* sigma, const void* sigma_param,
+                    const void* out_model, const void* out_logl) {
+  if (!cfg) return fail(RB_ERR_INVALID, "rb_kn_eval: null config");
+  if (N < 0 || E <= 0) return fail(RB_ERR_INVALID, "rb_kn_eval: need N >= 0 and E > 0");
+  if (cfg->model != RB_KN_ONE_COMPONENT && cfg->model != RB_KN_METZGER)
+    return fail(RB_ERR_INVALID, "rb_kn_eval: unknown model");
+  if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_QUADRATURE)
+    return fail(RB_ERR_INVALID, "rb_kn_eval: unknown sigma_mode");
+  if (cfg->dense_resolution < 20 || cfg->dense_resolution > 2000)
+    return fail(RB_ERR_INVALID, "rb_kn_eval: dense_resolution must be in [20, 2000]");
+  if (!params || !t_obs || !freq_obs) return fail(RB_ERR_INVALID, "rb_kn_eval: params, t_obs and freq_obs are required");
+  if (cfg->model == RB_KN_METZGER && !(cfg->vmax > 0)) return fail(RB_ERR_INVALID, "rb_kn_eval: vmax must be positive");
+  if (y) {
+    if (!out_logl) return fail(RB_ERR_INVALID, "rb_kn_eval: y given but out_logl is null");
+    if (cfg->sigma_mode != RB_SIGMA_SAMPLED && !sigma) return fail(RB_ERR_INVALID, "rb_kn_eval: sigma is required");
+    if (cfg->sigma_mode != RB_SIGMA_FIXED && !sigma_param) return fail(RB_ERR_INVALID, "rb_kn_eval: sigma_param is required");
+  } else if (out_logl) {
+    return fail(RB_ERR_INVALID, "rb_kn_eval: out_logl requested without data y");
+  }
+  if (!out_model && !out_logl) return fail(RB_ERR_INVALID, "rb_kn_eval: nothing to compute");
+  if (kn_smem_bytes(cfg, E) > 220 * 1024)
+    return fail(RB_ERR_UNSUPPORTED, "rb_kn_eval: dense_resolution / number of epochs exceed shared memory");
+  return RB_OK;
+}
+
+extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, const double* params,
+                              const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
+                              const double* sigma, const double* sigma_param, double* out_model,
+                              double* out_logl, void* stream) {
+  int rc = kn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  RB_CUDA(cudaGetDevice(&dev));
+  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [dev] {
+    attr_err = cudaFuncSetAttribute(rb::kn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(kn_kernel)");
+  const size_t ws_doubles = (size_t)rb::kEpochCols * (size_t)E + (size_t)rb::kKnScalars * (size_t)N + 2;
+  double* ws = nullptr;
+  RB_CUDA(cudaMallocAsync(&ws, ws_doubles * sizeof(double), st));
+  double* epoch_tab = ws;
+  double* scal = ws + (size_t)rb::kEpochCols * (size_t)E;
+  double* mm = scal + (size_t)rb::kKnScalars * (size_t)N;
+  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
+                                                                    y ? sigma : nullptr, epoch_tab);
+  minmax_kernel<<<1, 256, 0, st>>>((int)E, t_obs, mm);
+  double h_mm[2];
+  cudaError_t ce = cudaMemcpyAsync(h_mm, mm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);  // two doubles; needed to size the time grid
+  if (ce != cudaSuccess) {
+    cudaFreeAsync(ws, st);
+    return cuda_fail(ce, "epoch min/max");
+  }
+  if (!(h_mm[0] > 0.0)) {
+    cudaFreeAsync(ws, st);
+    return fail(RB_ERR_INVALID, "rb_kn_eval: epochs must be strictly positive (days)");
+  }
+  rb::KnArgs a;
+  a.cfg = *cfg;
+  a.N = N;
+  a.E = (int)E;
+  a.params = params;
+  a.dl_cm = dl_cm;
+  a.sigma_param = sigma_param;
+  a.out_model = out_model;
+  a.out_logl = y ? out_logl : nullptr;
+  a.want_logl = y ? 1 : 0;
+  a.epoch_tab = epoch_tab;
+  a.scalars = scal;
+  a.tmin_obs = h_mm[0];
+  a.tmax_obs = h_mm[1];
+  rb::kn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
+  const size_t smem = kn_smem_bytes(cfg, E);
+  const int threads = 512;
+  int occ = 0;
+  cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::kn_kernel, threads, smem);
+  if (oe != cudaSuccess) {
+    cudaFreeAsync(ws, st);
+    return cuda_fail(oe, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  }
+  if (occ < 1) occ = 1;
+  int64_t grid = (int64_t)sms * occ * 4;
+  if (grid > N) grid = N;
+  rb::kn_kernel<<<(unsigned)grid, threads, smem, st>>>(a);
+  launch_counter()->fetch_add(4);
+  cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(ws, st);
+  if (le != cudaSuccess) return cuda_fail(le, "kn_kernel launch");
+  return RB_OK;
+}
+
+extern "C" int rb_kn_eval_f64_host(const rb_kn_config* cfg, int64_t N, int64_t E, const double* params,
+                                   const double* t_obs, const double* freq_obs, const double* dl_cm,
+                                   const double* y, const double* sigma, const double* sigma_param,
+                                   double* out_model, double* out_logl) {
+  int rc = kn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
+  const size_t nN = (size_t)N, nE = (size_t)E;
+  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
+    if (!h) return cudaSuccess;
+    cudaError_t e = b.alloc(n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  RB_CUDA(up(d_par, params, (size_t)RB_KN_NPARAM * nN));
+  RB_CUDA(up(d_t, t_obs, nE));
+  RB_CUDA(up(d_f, freq_obs, nE));
+  RB_CUDA(up(d_dl, dl_cm, nN));
+  RB_CUDA(up(d_y, y, nE));
+  RB_CUDA(up(d_s, sigma, nE));
+  RB_CUDA(up(d_sp, sigma_param, nN));
+  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
+  if (out_logl) RB_CUDA(d_l.alloc(nN));
+  rc = rb_kn_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
+  if (rc != RB_OK) return rc;
+  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
+  RB_CUDA(cudaDeviceSynchronize());
+  return RB_OK;
+}

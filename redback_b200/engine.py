@@ -45,34 +45,31 @@ def batch_size(params):
     return n
 
 
-class SupernovaPath:
-    """Fused Diffusion -> TemperatureFloor -> Blackbody|CutoffBlackbody -> Gaussian log L.
+class _FusedPath:
+    """Common host side of a fused model+likelihood path: epochs / frequencies / data resident on device,
+    SoA packing of parameter batches, stream-ordered launch through the C ABI."""
 
-    Mirrors the reference call chain GaussianLikelihood.log_likelihood -> arnett / slsn / ... ->
-    Diffusion (redback/interaction_processes.py:33-65) -> TemperatureFloor (redback/photosphere.py:56-111)
-    -> Blackbody / CutoffBlackbody (redback/sed.py:199-222, 301-426), for N samples at once.
-    """
+    ROWS = {}
+    NPARAM = 0
+    NEEDS_FREQUENCY = True
 
-    def __init__(self, engine, sed, time, frequency=None, y=None, sigma=None,
-                 sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
-                 absorption_index=1.0, cosmology=None, device=None):
+    def _eval_fn(self):
+        raise NotImplementedError
+
+    def _check_time(self, t):
+        pass
+
+    def _setup(self, time, frequency, y, sigma, device):
         self.device = _device(device)
-        self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength,
-                                   absorption_index, cosmology)
         t = np.atleast_1d(np.asarray(time.detach().cpu().numpy() if isinstance(time, torch.Tensor) else time,
                                      dtype=np.float64))
         if t.ndim != 1 or t.size == 0:
             raise ValueError("time must be a non-empty 1-D array")
-        if np.any(t < 0):
-            raise NotImplementedError("negative times are not supported on device (the reference maps them "
-                                      "to the first valid epoch)")
-        if np.max(t) > t[-1] + 100:
-            # interaction_processes.py:63 would index past uniq_lums here
-            raise IndexError("max(time) exceeds time[-1] + 100: outside the reference's dense grid")
+        self._check_time(t)
         self.E = int(t.size)
         self.time = torch.from_numpy(np.ascontiguousarray(t)).to(self.device)
         self.frequency = None
-        if sed != _capi.SED_BOLOMETRIC:
+        if self.NEEDS_FREQUENCY:
             if frequency is None:
                 raise KeyError("frequency")  # the reference does kwargs['frequency']
             f = np.asarray(frequency.detach().cpu().numpy() if isinstance(frequency, torch.Tensor) else frequency,
@@ -97,12 +94,12 @@ class SupernovaPath:
 
     def pack(self, params, N):
         """SoA [RB_SN_NPARAM, N] device tensor from {name: scalar | array[N] | tensor[N]}."""
-        out = torch.zeros((_capi.SN_NPARAM, N), dtype=_F64, device=self.device)
+        out = torch.zeros((self.NPARAM, N), dtype=_F64, device=self.device)
         host_rows, host_idx = [], []
         for name, val in params.items():
-            if name not in _capi.SN_ROWS:
+            if name not in self.ROWS:
                 continue
-            row = _capi.SN_ROWS[name]
+            row = self.ROWS[name]
             if isinstance(val, torch.Tensor):
                 out[row] = val.to(device=self.device, dtype=_F64).reshape(-1).expand(N) if val.numel() == 1 \
                     else val.to(device=self.device, dtype=_F64).reshape(N)
@@ -118,8 +115,8 @@ class SupernovaPath:
 
     def evaluate(self, params_dev, dl=None, sigma_param=None, want_model=True, want_logl=False, out_logl=None):
         """Launch the fused kernel on the current stream.  Returns (model[N,E] | None, logl[N] | None)."""
-        if params_dev.dtype != _F64 or params_dev.dim() != 2 or params_dev.shape[0] != _capi.SN_NPARAM:
-            raise ValueError("params_dev must be float64 [RB_SN_NPARAM, N]")
+        if params_dev.dtype != _F64 or params_dev.dim() != 2 or params_dev.shape[0] != self.NPARAM:
+            raise ValueError(f"params_dev must be float64 [{self.NPARAM}, N]")
         params_dev = params_dev.contiguous()
         N = params_dev.shape[1]
         model = torch.empty((N, self.E), dtype=_F64, device=self.device) if want_model else None
@@ -132,7 +129,7 @@ class SupernovaPath:
             raise ValueError("log-likelihood requested but no data were given")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            rc = _capi.lib().rb_sn_eval_f64(
+            rc = self._eval_fn()(
                 C.byref(self.cfg), N, self.E, _ptr(params_dev), _ptr(self.time), _ptr(self.frequency),
                 _ptr(dl), _ptr(self.y if want_logl else None), _ptr(self.sigma if want_logl else None),
                 _ptr(sigma_param if want_logl else None), _ptr(model), _ptr(logl), C.c_void_p(stream))
@@ -144,14 +141,14 @@ class SupernovaPath:
         """End-to-end entry for host-resident batches: `params_host` is a (pinned) CPU float64 tensor
         [RB_SN_NPARAM, N]; chunks are copied H2D, evaluated and the log-likelihoods copied back D2H on
         two alternating streams so that copies overlap compute.  Returns a pinned CPU tensor [N]."""
-        if params_host.dtype != _F64 or params_host.dim() != 2 or params_host.shape[0] != _capi.SN_NPARAM:
-            raise ValueError("params_host must be float64 [RB_SN_NPARAM, N]")
+        if params_host.dtype != _F64 or params_host.dim() != 2 or params_host.shape[0] != self.NPARAM:
+            raise ValueError(f"params_host must be float64 [{self.NPARAM}, N]")
         N = params_host.shape[1]
         if out_host is None:
             out_host = torch.empty((N,), dtype=_F64, pin_memory=True)
         chunk = max(1, min(int(chunk), N))
         if getattr(self, "_slots", None) is None or self._slots[0][0].shape[1] != chunk:
-            self._slots = [(torch.empty((_capi.SN_NPARAM, chunk), dtype=_F64, device=self.device),
+            self._slots = [(torch.empty((self.NPARAM, chunk), dtype=_F64, device=self.device),
                             torch.empty((chunk,), dtype=_F64, device=self.device),
                             torch.cuda.Stream(self.device)) for _ in range(2)]
         cur = torch.cuda.current_stream(self.device)
@@ -163,11 +160,11 @@ class SupernovaPath:
             with torch.cuda.stream(st):
                 if b - a == chunk:
                     view = dbuf
-                    for r in range(_capi.SN_NPARAM):
+                    for r in range(self.NPARAM):
                         dbuf[r].copy_(params_host[r, a:b], non_blocking=True)
                 else:
-                    view = torch.empty((_capi.SN_NPARAM, b - a), dtype=_F64, device=self.device)
-                    for r in range(_capi.SN_NPARAM):
+                    view = torch.empty((self.NPARAM, b - a), dtype=_F64, device=self.device)
+                    for r in range(self.NPARAM):
                         view[r].copy_(params_host[r, a:b], non_blocking=True)
                 _, logl = self.evaluate(view, want_model=False, want_logl=True,
                                         out_logl=lbuf[: b - a] if b - a == chunk else None)
@@ -176,6 +173,57 @@ class SupernovaPath:
             cur.wait_stream(st)
         torch.cuda.current_stream(self.device).synchronize()
         return out_host
+
+
+class SupernovaPath(_FusedPath):
+    """Fused Diffusion -> TemperatureFloor -> Blackbody|CutoffBlackbody -> Gaussian log L.
+
+    Mirrors the reference call chain GaussianLikelihood.log_likelihood -> arnett / slsn / ... ->
+    Diffusion (redback/interaction_processes.py:33-65) -> TemperatureFloor (redback/photosphere.py:56-111)
+    -> Blackbody / CutoffBlackbody (redback/sed.py:199-222, 301-426), for N samples at once.
+    """
+
+    ROWS = _capi.SN_ROWS
+    NPARAM = _capi.SN_NPARAM
+
+    def __init__(self, engine, sed, time, frequency=None, y=None, sigma=None,
+                 sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
+                 absorption_index=1.0, cosmology=None, device=None):
+        self.NEEDS_FREQUENCY = sed != _capi.SED_BOLOMETRIC
+        self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength,
+                                   absorption_index, cosmology)
+        self._setup(time, frequency, y, sigma, device)
+
+    def _eval_fn(self):
+        return _capi.lib().rb_sn_eval_f64
+
+    def _check_time(self, t):
+        if np.any(t < 0):
+            raise NotImplementedError("negative times are not supported on device (the reference maps them "
+                                      "to the first valid epoch)")
+        if np.max(t) > t[-1] + 100:
+            # interaction_processes.py:63 would index past uniq_lums here
+            raise IndexError("max(time) exceeds time[-1] + 100: outside the reference's dense grid")
+
+
+class KilonovaPath(_FusedPath):
+    """Fused one-component / Metzger kilonova -> interp1d -> blackbody -> Gaussian log L
+    (redback/transient_models/kilonova_models.py:1537-1603, 1853-2068)."""
+
+    ROWS = _capi.KN_ROWS
+    NPARAM = _capi.KN_NPARAM
+
+    def __init__(self, model, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED,
+                 dense_resolution=500, neutron_precursor_switch=True, vmax=0.7, cosmology=None, device=None):
+        self.cfg = _capi.kn_config(model, sigma_mode, dense_resolution, neutron_precursor_switch, vmax, cosmology)
+        self._setup(time, frequency, y, sigma, device)
+
+    def _eval_fn(self):
+        return _capi.lib().rb_kn_eval_f64
+
+    def _check_time(self, t):
+        if np.any(t <= 0):
+            raise ValueError("A value in x_new is below the interpolation range.")  # scipy interp1d's error
 
 
 def luminosity_distance(redshift, cosmology=None, device=None):

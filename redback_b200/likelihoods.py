@@ -11,9 +11,14 @@ import inspect
 import numpy as np
 import torch
 
-from . import _capi
+from . import _capi, _fused
+from . import kilonova_models as _kn
 from . import supernova_models as _sn
-from .engine import SupernovaPath, batch_size, gaussian_logl
+from .engine import batch_size, gaussian_logl
+
+FUSED = {}
+FUSED.update(_sn.FUSED)
+FUSED.update(_kn.FUSED)
 
 
 def infer_parameters_from_function(func):
@@ -108,7 +113,7 @@ class GaussianLikelihood(_RedbackLikelihood):
 
     def log_likelihood(self, parameters=None):
         self._update_parameters(parameters)
-        if self.function in _sn.FUSED:
+        if self.function in FUSED:
             batch = {k: np.array([v], dtype=np.float64) for k, v in self.parameters.items() if v is not None}
             return float(self.log_likelihood_batch(batch)[0])
         return float(np.nan_to_num(self._gaussian_log_likelihood(res=self.residual, sigma=self._full_sigma())))
@@ -155,7 +160,7 @@ class GaussianLikelihood(_RedbackLikelihood):
         if N is None:
             raise ValueError("params_batch must contain at least one array")
         mode, sp = self._split_sigma_param(merged, N)
-        if self.function in _sn.FUSED:
+        if self.function in FUSED:
             logl = self._fused(merged, N, mode, sp)
         else:
             kw = dict(self.kwargs)
@@ -176,36 +181,24 @@ class GaussianLikelihood(_RedbackLikelihood):
         return logl if device_output else logl.cpu().numpy()
 
     def _fused(self, merged, N, mode, sp):
-        engine, engine_params, needs_z, default_sed = _sn.FUSED[self.function]
-        kw = self.kwargs
-        sed_id = _capi.SED_BOLOMETRIC
-        if needs_z:
-            _sn._flux_density_only(kw, self.function.__name__)
-            _sn._operator_name("photosphere", kw.get("photosphere"), "TemperatureFloor")
-            sed_id = _sn._SED_IDS[_sn._operator_name("sed", kw.get("sed"), default_sed)]
-        _sn._operator_name("interaction_process", kw.get("interaction_process", "Diffusion"), "Diffusion")
-        key = (engine, sed_id, mode, kw.get("dense_resolution", 1000), kw.get("cutoff_wavelength", 3000),
-               kw.get("absorption_index", 1.0), id(kw.get("cosmology")))
+        spec = FUSED[self.function]
+        kw = dict(self.kwargs)
+        if self.function is _kn.one_component_kilonova_model:
+            kw.setdefault("temperature_floor", 4000)
+        key = (spec.cache_key(kw), mode)
         if self._path is None or self._path[0] != key:
-            path = SupernovaPath(engine, sed_id, self.x, frequency=kw.get("frequency") if needs_z else None,
-                                 y=self.y, sigma=self._sigma, sigma_mode=mode,
-                                 dense_resolution=kw.get("dense_resolution", 1000),
-                                 cutoff_wavelength=kw.get("cutoff_wavelength", 3000),
-                                 absorption_index=kw.get("absorption_index", 1.0),
-                                 cosmology=_sn._cosmology(kw), device=kw.get("device"))
-            self._path = (key, path)
+            self._path = (key, spec.build(self.x, kw, y=self.y, sigma=self._sigma, sigma_mode=mode))
         path = self._path[1]
-        needed = list(engine_params) + list(_sn._DIFFUSION)
-        if needs_z:
-            needed = ["redshift"] + needed + ["temperature_floor"]
-        params, _ = _sn._collect(merged, kw, None, needed)
+        params, _ = _fused.collect(merged, kw, None, spec.needed)
         dev = path.pack(params, N)
         sp_dev = None
         if sp is not None:
-            sp_dev = sp.to(device=path.device, dtype=torch.float64).reshape(-1).expand(N).contiguous() \
-                if isinstance(sp, torch.Tensor) else \
-                torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(sp, dtype=np.float64), (N,)))).to(path.device)
-        _, logl = path.evaluate(dev, dl=_sn._dl(kw, path, N), sigma_param=sp_dev, want_model=False, want_logl=True)
+            if isinstance(sp, torch.Tensor):
+                sp_dev = sp.to(device=path.device, dtype=torch.float64).reshape(-1).expand(N).contiguous()
+            else:
+                sp_dev = torch.from_numpy(np.array(np.broadcast_to(np.asarray(sp, dtype=np.float64), (N,)))).to(path.device)
+        _, logl = path.evaluate(dev, dl=_fused.dl_from_kwargs(kw, path, N), sigma_param=sp_dev, want_model=False,
+                                want_logl=True)
         return logl
 
 

@@ -66,3 +66,35 @@ def assert_close(actual, expected, rtol, extra_rtol=0.0, what=""):
         i = np.argmax(np.where(bad, diff / np.maximum(np.abs(expected), 1e-300), 0))
         raise AssertionError(f"{what}: {bad.sum()} / {bad.size} outside rtol={rtol}; worst idx {i}: "
                              f"{actual.flat[i]!r} vs {expected.flat[i]!r}")
+
+
+LSST_NU = dict(lsstu=8.152e14, lsstg=6.273e14, lsstr=4.825e14, lssti=3.983e14, lsstz=3.454e14, lssty=3.083e14)
+
+
+def config3_epochs(n=200):
+    """t = geomspace(0.1, 30 d, 200) cycling LSST u,g,r,i,z,y
+    (effective frequencies from redback/tables/filters.csv:54-59)."""
+    t = np.geomspace(0.1, 30, n)
+    nus = list(LSST_NU.values())
+    nu = np.array([nus[i % 6] for i in range(n)])
+    return t, nu
+
+
+def one_component_prior(rng, n):
+    """priors/one_component_kilonova_model.prior"""
+    return dict(redshift=rng.uniform(1e-6, 0.1, n), mej=rng.uniform(0.01, 0.05, n), vej=rng.uniform(0.1, 0.5, n),
+                kappa=rng.uniform(1, 30, n), temperature_floor=loguniform(rng, 100, 6000, n))
+
+
+def metzger_prior(rng, n):
+    """priors/metzger_kilonova_model.prior"""
+    return dict(redshift=rng.uniform(1e-3, 0.1, n), mej=rng.uniform(0.01, 0.05, n), vej=rng.uniform(0.1, 0.5, n),
+                beta=rng.uniform(3, 5, n), kappa=rng.uniform(1, 30, n))
+
+
+def engine_atan_condition(t_src_seconds):
+    """Noise floor of the reference's own kilonova engine term (0.5 - arctan((t-1.3)/0.11)/pi)**1.3
+    (kilonova_models.py:1878): one ulp of arctan near pi/2 (2.2e-16) is a relative error
+    1.3 * 2.2e-16 * pi * x of the luminosity, x = (t-1.3)/0.11."""
+    x = np.maximum((np.asarray(t_src_seconds) - 1.3) / 0.11, 1.0)
+    return 1.3 * 2.2e-16 * np.pi * x

@@ -1,0 +1,85 @@
+"""GPU parity: fused kilonova kernels vs the CPU oracle (one-component and Metzger models).
+
+Tolerance: rtol 1e-9 on flux densities, widened by the documented conditioning of the reference's own
+engine term (helpers.engine_atan_condition) times the blackbody's temperature sensitivity; |d logL| < 1e-6
+or 1e-9 relative."""
+import numpy as np
+import pytest
+
+import helpers as h
+from oracle import restated as r
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import redback_b200
+    return redback_b200
+
+
+def _tol_extra(t_obs, z, nu, temp_floor=100.0):
+    # d ln F / d ln L <= 0.5 + (h nu / k T)/4 with T >= a few 1e3 K at these epochs; bound it generously
+    amp = 0.5 + 0.25 * (6.626e-27 * nu * (1 + z)) / (1.381e-16 * 1500.0)
+    return amp * h.engine_atan_condition(t_obs * 86400 / (1 + z))
+
+
+def test_golden_vectors(rb, golden):
+    for name, fn in [("one_component_kilonova_model", rb.kilonova_models.one_component_kilonova_model),
+                     ("metzger_kilonova_model", rb.kilonova_models.metzger_kilonova_model)]:
+        e = golden["kilonova." + name]
+        t = np.array(e["time"])
+        for params, res in zip(e["params"], e["results"]):
+            out = fn(t, **dict(params, **e["eval_kwargs"]))
+            h.assert_close(out, h.golden_array(res), RTOL, what=name)
+
+
+def test_config3_one_component_flux_density(rb):
+    """BASELINE configs[2] shape (flux_density branch): 200 epochs cycling LSST ugrizy, prior draws."""
+    t, nu = h.config3_epochs()
+    rng = np.random.default_rng(3)
+    N = 200
+    p = h.one_component_prior(rng, N)
+    fn = rb.kilonova_models.one_component_kilonova_model
+    out = fn(t, params_batch=p, frequency=nu, output_format="flux_density")
+    assert out.shape == (N, t.size)
+    y = r.one_component_kilonova_model(t, 0.05, 0.03, 0.3, 10.0, frequency=nu, temperature_floor=2000.0)
+    sigma = 0.1 * np.abs(y) + 1e-9
+    like = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=dict(frequency=nu, output_format="flux_density"))
+    logl = like.log_likelihood_batch(p)
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.one_component_kilonova_model(t, z, frequency=nu, **kw)
+        h.assert_close(out[i], ref, RTOL, _tol_extra(t, z, nu), what=f"sample {i}")
+        ref_l = r.gaussian_likelihood(y, ref, sigma)
+        assert abs(logl[i] - ref_l) <= 1e-6 + 1e-8 * abs(ref_l), (i, logl[i], ref_l)
+
+
+def test_metzger_flux_density(rb):
+    t, nu = h.config3_epochs(60)
+    rng = np.random.default_rng(4)
+    N = 48
+    p = h.metzger_prior(rng, N)
+    fn = rb.kilonova_models.metzger_kilonova_model
+    out = fn(t, params_batch=p, frequency=nu, output_format="flux_density")
+    out_noprec = fn(t, params_batch=p, frequency=nu, output_format="flux_density", neutron_precursor_switch=False)
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.metzger_kilonova_model(t, z, frequency=nu, **kw)
+        h.assert_close(out[i], ref, RTOL, _tol_extra(t, z, nu), what=f"sample {i}")
+        ref2 = r.metzger_kilonova_model(t, z, frequency=nu, neutron_precursor_switch=False, **kw)
+        h.assert_close(out_noprec[i], ref2, RTOL, _tol_extra(t, z, nu), what=f"no-precursor sample {i}")
+
+
+def test_scalar_call_and_small_resolution(rb):
+    t = np.array([0.5, 1.0, 2.0, 4.0, 8.0])
+    kw = dict(frequency=4.8e14, output_format="flux_density", temperature_floor=3000.0, dense_resolution=120)
+    out = rb.kilonova_models.one_component_kilonova_model(t, 0.02, 0.02, 0.2, 5.0, **kw)
+    ref = r.one_component_kilonova_model(t, 0.02, 0.02, 0.2, 5.0, frequency=np.full(5, 4.8e14),
+                                         temperature_floor=3000.0, dense_resolution=120)
+    h.assert_close(out, ref, RTOL, 1e-9)
+    with pytest.raises(ValueError):
+        rb.kilonova_models.one_component_kilonova_model(np.array([0.0, 1.0]), 0.02, 0.02, 0.2, 5.0, **kw)
