@@ -65,13 +65,18 @@ def load_afterglow():
     import logging
     from . import restated as r
 
+    def _unavailable(*a, **k):
+        raise RuntimeError("not available in the oracle shim")
+
     def citation_wrapper(_):
         def deco(f):
             return f
         return deco
 
-    _stub("redback.utils", logger=logging.getLogger("redback-oracle"), citation_wrapper=citation_wrapper)
-    _stub("redback.sed")
+    _stub("redback.utils", logger=logging.getLogger("redback-oracle"), citation_wrapper=citation_wrapper,
+          calc_ABmag_from_flux_density=_unavailable, lambda_to_nu=r.lambda_to_nu, bands_to_frequency=_unavailable,
+          calc_kcorrected_properties=r.calc_kcorrected_properties, nu_to_lambda=r.nu_to_lambda)
+    _stub("redback.sed", get_correct_output_format_from_spectra=_unavailable)
     _load("redback.wrappers", "redback/wrappers.py")
 
     class _Val:

@@ -527,3 +527,222 @@ def metzger_kilonova_model(time, redshift, mej, vej, beta, kappa, *, frequency, 
         frequency, t = calc_kcorrected_properties(np.asarray(frequency, dtype=float), redshift, t)
         fd = blackbody_to_flux_density(temp_func(t), rad_func(t), dl, frequency)
         return fd * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)
+
+
+# --------------------------------------------------------------------------------------------------
+# redback-native structured-jet afterglow (afterglow_models/base_models.py:32-483, 486-640, 885-1010)
+# Restated with numpy vectorised over steps / cells; arithmetic order follows the reference.
+# --------------------------------------------------------------------------------------------------
+AG_MP = 1.6726231e-24
+AG_ME = 9.1093897e-28
+AG_CC = 2.99792453e10
+AG_QE = 4.8032068e-10
+AG_C2 = AG_CC * AG_CC
+AG_SIGT = (AG_QE * AG_QE / (AG_ME * AG_C2)) ** 2 * (8 * np.pi / 3)
+AG_FOURPI = 4 * np.pi
+_AG_PXF = np.array([[1.0, 3.0, 0.41], [1.2, 1.4, 0.44], [1.4, 1.1, 0.48], [1.6, 0.86, 0.53], [1.8, 0.725, 0.56],
+                    [2.0, 0.637, 0.59], [2.2, 0.579, 0.612], [2.5, 0.520, 0.630], [2.7, 0.487, 0.641],
+                    [3.0, 0.451, 0.659], [3.2, 0.434, 0.660], [3.4, 0.420, 0.675]])
+
+
+def ag_segments(thj, res):
+    """get_segments_numba, base_models.py:43-64"""
+    latstep = thj / res
+    rotstep = 2.0 * np.pi / res
+    nlat = int(res)
+    nrot = int(2 * np.pi / rotstep)
+    phi = np.linspace(rotstep, nrot * rotstep, nrot)
+    i = np.arange(nlat)
+    omi = ((phi - (phi - rotstep))[None, :] * (np.cos(i * latstep) - np.cos((i + 1) * latstep))[:, None]).ravel()
+    thi = np.linspace(latstep - latstep / 2., nlat * latstep - latstep / 2., nlat)
+    phii = np.linspace(rotstep - rotstep / 2., nrot * rotstep - rotstep / 2., nrot)
+    return omi, thi, phii, rotstep, latstep
+
+
+def ag_erf(x):
+    """erf_approximation_numba (A&S 7.1.26), base_models.py:67-89"""
+    a1, a2, a3, a4, a5, p = 0.254829592, -0.284496736, 1.421413741, -1.453152027, 1.061405429, 0.3275911
+    sign = np.where(x >= 0, 1.0, -1.0)
+    xa = np.abs(x)
+    t = 1.0 / (1.0 + p * xa)
+    y = 1.0 - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * np.exp(-xa * xa)
+    return sign * y
+
+
+def ag_structure(gamma, en, thi, thc, method_id, thj):
+    """get_structure_numba for the tophat (1) and Gaussian (2) jets, base_models.py:92-148"""
+    gs = np.full(thi.shape[0], float(gamma))
+    ei = np.full(thi.shape[0], float(en))
+    if method_id == 1:
+        fac = ag_erf(-(thi - min(thc, thj)) * 1000.0) * 0.5 + 0.5
+    elif method_id == 2:
+        fac = np.exp(-0.5 * (thi / thc) ** 2)
+    else:
+        raise NotImplementedError(method_id)
+    return (gs - 1) * fac + 1.0000000000001, ei * fac
+
+
+def _ag_rk4(ghat, dm, g, m, fac, therm):
+    """RK4_step_numba, base_models.py:182-192"""
+    ghatm1 = ghat - 1.0
+    dm10 = 10.0 ** dm
+    g2 = g * g
+    return fac * dm10 * (ghat * (g2 - 1.0) - ghatm1 * (g - 1.0 / g)) / \
+        (m + dm10 * (therm + (1.0 - therm) * (2.0 * ghat * g - ghatm1 * (1 + 1.0 / g2))))
+
+
+def ag_gamma(g0, eps, therm, steps, n0, k):
+    """get_gamma_numba, base_models.py:195-249.  Returns G, dm (= 10**state_dm), ghat with shape [ring, step]."""
+    steps = int(steps)
+    nmin = (AG_FOURPI / (3.0 - k)) * n0 * 1e10 ** (3.0 - k)
+    nmax = (AG_FOURPI / (3.0 - k)) * n0 * 1e24 ** (3.0 - k)
+    dlogm = np.log10(nmin * AG_MP)
+    h = np.log10(nmax / nmin) / float(steps)
+    fac = -h * np.log(10.0)
+    m = eps / (g0 * AG_C2)
+    sg = np.zeros((steps, g0.shape[0]))
+    sdm = np.zeros((steps, g0.shape[0]))
+    sgh = np.zeros((steps, g0.shape[0]))
+    g = g0.astype(np.float64).copy()
+    dm = np.full(g0.shape[0], dlogm)
+    for i in range(steps):
+        sg[i] = g
+        sdm[i] = dm
+        g2m1 = g * g - 1.0
+        root = np.sqrt(g2m1)
+        theta = root * (root + 1.07 * g2m1) / (3.0 * (1 + root + 1.07 * g2m1))
+        z = theta / (0.24 + theta)
+        ghat = ((((((1.07136 * z - 2.39332) * z + 2.32513) * z - 0.96583) * z + 0.18203) * z - 1.21937) * z + 5.0) / 3.0
+        sgh[i] = ghat
+        f1 = _ag_rk4(ghat, dm, g, m, fac, therm)
+        f2 = _ag_rk4(ghat, dm + 0.5 * h, g + 0.5 * f1, m, fac, therm)
+        f3 = _ag_rk4(ghat, dm + 0.5 * h, g + 0.5 * f2, m, fac, therm)
+        f4 = _ag_rk4(ghat, dm + h, g + f3, m, fac, therm)
+        g = g + (f1 + 2.0 * (f2 + f3) + f4) / 6.0 + 1e-15
+        dm = dm + h
+    return sg.T, (10.0 ** sdm).T, sgh.T
+
+
+def ag_step1(g, dm, p, xp, fx, eb, ee, n, k, thi, ghat, rotstep, latstep, xin, is_expansion, a1, res):
+    """calc_afterglow_step1_numba for one ring, base_models.py:252-322"""
+    gm1 = g - 1.0
+    g2 = g * g
+    beta = np.sqrt(1 - 1.0 / g2)
+    ne = dm / AG_MP
+    cs = np.sqrt(AG_C2 * ghat * (ghat - 1) * gm1 / (1 + ghat * gm1))
+    te = np.arcsin(cs / (AG_CC * np.sqrt(g2 - 1.0)))
+    fac = 0.5 * latstep
+    if is_expansion:
+        ex = te / g ** (a1 + 1)
+        omg = rotstep * (np.cos(thi - fac) - np.cos(ex / res + thi + fac))
+    else:
+        ex = np.ones(g.shape[0])
+        omg = np.full(g.shape[0], rotstep * (np.cos(thi - fac) - np.cos(thi + fac)))
+    exponent = np.ones(g.shape[0])
+    exponent[1:] = ((1 - np.cos(latstep + ex[0])) / (1 - np.cos(latstep + ex[1:]))) ** (1.0 / 2.0)
+    r = ((3.0 - k) * ne / (AG_FOURPI * n)) ** (1.0 / (3.0 - k))
+    r[1:] = np.diff(r) * exponent[1:] ** (1.0 / (3.0 - k))
+    r = np.cumsum(r)
+    n0 = n * r ** (-k)
+    b = np.sqrt(2 * AG_FOURPI * eb * n0 * AG_MP * AG_C2 * ((ghat * g + 1.0) / (ghat - 1.0)) * gm1)
+    gmm = np.sqrt(1.5 * AG_FOURPI * AG_QE / (AG_SIGT * b))
+    if p > 2:
+        gm = ((p - 2) / (p - 1)) * (ee / xin) * gm1 * (AG_MP / AG_ME)
+    elif p == 2:
+        gm = (1 / np.log(gmm / ((ee / xin) * gm1 * (AG_MP / AG_ME)))) * (ee / xin) * gm1 * (AG_MP / AG_ME)
+    else:
+        gm = ((2 - p) / (p - 1) * (AG_MP / AG_ME) * (ee / xin) * gm1 * gmm ** (p - 2)) ** (1 / (p - 1))
+    nump = 3.0 * xp * gm * gm * AG_QE * b / (AG_FOURPI * AG_ME * AG_CC)
+    pp = xin * fx * AG_ME * AG_C2 * AG_SIGT * b / (3.0 * AG_QE)
+    kt = gm * AG_ME * AG_C2
+    return beta, ne, omg, r, b, gm, nump, pp, kt
+
+
+def ag_step2(dl, om0, rotstep, obsa, beta, ne, omg, r, b, nump, pp, kt, g, is_expansion):
+    """calc_afterglow_step2_numba for one cell, base_models.py:325-370"""
+    dl2 = dl * dl
+    no = om0 * ne / AG_FOURPI
+    cosa = np.cos(obsa)
+    om = np.maximum(om0, omg) if is_expansion else omg
+    thii = np.arccos(1.0 - om / rotstep)
+    rdiff = np.diff(r, prepend=0)
+    tobs = np.cumsum(rdiff * (1.0 / beta - cosa) / AG_CC)
+    tobso = np.cumsum(rdiff * (1.0 / beta - 1.0) / AG_CC)
+    dop = 1.0 / (g * (1.0 - beta * cosa))
+    gc = 6.0 * np.pi * AG_ME * AG_CC / (g * AG_SIGT * b * b * tobso)
+    nucp = 0.286 * 3.0 * gc * gc * AG_QE * b / (AG_FOURPI * AG_ME * AG_CC)
+    num = dop * nump
+    nuc = dop * nucp
+    fmax = no * pp * dop * dop * dop / (AG_FOURPI * dl2)
+    fbb = 2 * om * np.cos(thii) * dop * kt * r * r / (AG_C2 * dl2)
+    return fbb, fmax, nuc, num, tobs
+
+
+def ag_flux(fbb, nuc, num, nu1, fmax, p):
+    """get_ag_numba (overlapping if-chain: later conditions overwrite), base_models.py:373-399"""
+    with np.errstate(all="ignore"):
+        f = np.zeros(num.shape[0])
+        c = (nuc < num) & (nu1 < nuc); f[c] = (fmax * (nu1 / nuc) ** (1.0 / 3.0))[c]
+        c = (nuc < nu1) & (nuc < num); f[c] = (fmax * (nu1 / nuc) ** (-1.0 / 2.0))[c]
+        c = (num < nu1) & (nuc < num); f[c] = (fmax * (num / nuc) ** (-1.0 / 2.0) * (nu1 / num) ** (-p / 2.0))[c]
+        c = (num < nuc) & (nu1 < num); f[c] = (fmax * (nu1 / num) ** (1.0 / 3.0))[c]
+        c = (num < nu1) & (num < nuc); f[c] = (fmax * (nu1 / num) ** (-(p - 1.0) / 2.0))[c]
+        c = (nuc < nu1) & (num < nuc); f[c] = (fmax * (nuc / num) ** (-(p - 1.0) / 2.0) * (nu1 / nuc) ** (-p / 2.0))[c]
+        fbb_adj = fbb * nu1 ** 2.0 * np.maximum(1.0, (nu1 / num) ** 0.5)
+        return np.minimum(fbb_adj, f)
+
+
+def ag_default_res(thv, thc, g0):
+    """tophat_redback / gaussian_redback resolution rule, base_models.py:932-935"""
+    sep = max(thv - thc, 0)
+    order = min(int((2 - 10 * sep) * thc * g0), 100)
+    return max(10, order)
+
+
+def redback_afterglow(time, redshift, thv, loge0, thc, logn0, p, logepse, logepsb, g0, xiN, *, frequency,
+                      method_id=1, thj=None, res=None, steps=250, k=0, a1=1, expansion=1, dl=None, **_):
+    """tophat_redback (method_id=1, base_models.py:885-946) / gaussian_redback (method_id=2, :948-1010) through
+    RedbackAfterglows.get_lightcurve (:573-640), output_format='flux_density'.  time: observer days.  mJy[E]."""
+    time = np.asarray(time, dtype=float) * 86400.0
+    frequency = np.asarray(frequency, dtype=float)
+    if frequency.ndim == 0:
+        frequency = np.ones(len(time)) * float(frequency)
+    if k not in (0, 2):
+        raise ValueError("k must either be 0 or 2")
+    if (p < 1.2) or (p > 3.4):
+        raise ValueError("p is out of range, 1.2 < p < 3.4")
+    epse, epsb, nism, e0 = 10 ** logepse, 10 ** logepsb, 10 ** logn0, 10 ** loge0
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    if thj is None:
+        thj = thc
+    if res is None:
+        res = ag_default_res(thv, thc, g0)
+    n = float(nism) if k == 0 else float(nism * 3e35)
+    res = float(res)
+    with np.errstate(all="ignore"):
+        xp = np.interp(p, _AG_PXF[:, 0], _AG_PXF[:, 1])
+        fx = np.interp(p, _AG_PXF[:, 0], _AG_PXF[:, 2])
+        nu0 = np.unique(frequency)
+        nu = nu0 * (1 + redshift)
+        omi, thi, phii, rotstep, latstep = ag_segments(thj, res)
+        gs, ei = ag_structure(g0, e0, thi, thc, method_id, thj)
+        G, SM, ghat = ag_gamma(gs, ei, 0.0, steps, n, float(k))
+        sin_thi, cos_thi = np.sin(thi), np.cos(thi)
+        ang = (np.cos(thv) * cos_thi[:, None] + np.cos(0.0) * np.sin(thv) * np.cos(phii)[None, :] * sin_thi[:, None]
+               + np.sin(0.0) * np.sin(thv) * np.sin(phii)[None, :] * sin_thi[:, None])
+        obsa = np.arccos(np.clip(ang, -1.0, 1.0)).ravel()                      # get_obsangle_numba :151-179
+        lc = np.zeros(frequency.size)
+        kk = 0
+        for i in range(thi.size):
+            beta, ne, omg, r, b, gm, nump, pp, kt = ag_step1(G[i], SM[i], p, xp, fx, epsb, epse, n, float(k), thi[i],
+                                                             ghat[i], rotstep, latstep, xiN, bool(expansion),
+                                                             float(a1), res)
+            for _j in range(phii.size):
+                fbb, fmax, nuc, num, tobs = ag_step2(dl, omi[kk], rotstep, obsa[kk], beta, ne, omg, r, b, nump, pp,
+                                                     kt, G[i], bool(expansion))
+                for hh in range(nu.size):
+                    sel = frequency == nu0[hh]
+                    lc[sel] += np.interp(time[sel] / (1 + redshift), tobs, ag_flux(fbb, nuc, num, nu[hh], fmax, p))
+                kk += 1
+        return lc * (1 + redshift) / 1e-26
