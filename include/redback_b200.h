@@ -163,6 +163,42 @@ int rb_kn_eval_f64_host(const rb_kn_config* cfg, int64_t N, int64_t E, const dou
                         const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
                         const double* sigma, const double* sigma_param, double* out_model, double* out_logl);
 
+/* ---- redback-native afterglow path --------------------------------------------------------------------
+ * tophat_redback    redback/transient_models/afterglow_models/base_models.py:885-946
+ * gaussian_redback  redback/transient_models/afterglow_models/base_models.py:948-1010
+ * through RedbackAfterglows.get_lightcurve (:573-640) and the numba kernels (:43-400),
+ * output_format='flux_density'. */
+enum { RB_AG_TOPHAT = 1, RB_AG_GAUSSIAN = 2 };  /* RedbackAfterglows._method_to_id (:567-571) */
+enum {
+  RB_AG_REDSHIFT = 0, RB_AG_THV = 1, RB_AG_LOGE0 = 2, RB_AG_THC = 3,
+  RB_AG_THJ = 4,      /* Gaussian jet only (tophat uses thj = thc, :937) */
+  RB_AG_LOGN0 = 5, RB_AG_P = 6, RB_AG_LOGEPSE = 7, RB_AG_LOGEPSB = 8, RB_AG_G0 = 9, RB_AG_XIN = 10,
+  RB_AG_NPARAM = 11
+};
+
+typedef struct {
+  int jet;            /* RB_AG_*                                                              */
+  int sigma_mode;     /* RB_SIGMA_*                                                           */
+  int steps;          /* kwargs 'steps', default 250 (:936)                                   */
+  int res;            /* kwargs 'res'; 0 = the reference's rule max(10, min(int((2-10*max(thv-thc,0))*thc*g0), 100)) (:932-935) */
+  int k;              /* 0 (ISM) or 2 (wind), kwargs 'k' (:918)                               */
+  int expansion;      /* kwargs 'expansion', default 1 (:920)                                 */
+  double a1;          /* kwargs 'a1', default 1 (:919)                                        */
+  rb_cosmology cosmology;
+} rb_ag_config;
+
+int rb_ag_config_default(rb_ag_config* cfg);
+
+/* Argument conventions as rb_sn_eval_f64; params is [RB_AG_NPARAM][N]; t_obs in observer-frame days;
+ * at most 4 distinct values in freq_obs.  Samples with p outside [1.2, 3.4] (ValueError in the reference,
+ * :576-577) come back as NaN. */
+int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, const double* params, const double* t_obs,
+                   const double* freq_obs, const double* dl_cm, const double* y, const double* sigma,
+                   const double* sigma_param, double* out_model, double* out_logl, void* stream);
+int rb_ag_eval_f64_host(const rb_ag_config* cfg, int64_t N, int64_t E, const double* params,
+                        const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
+                        const double* sigma, const double* sigma_param, double* out_model, double* out_logl);
+
 /* Luminosity distance [cm] for N redshifts on device (same quadrature the fused kernels use). */
 int rb_luminosity_distance_f64(const rb_cosmology* cosmo, int64_t N, const double* redshift,
                                double* out_dl_cm, void* stream);

@@ -1,7 +1,7 @@
 """redback_b200: B200-native batched light-curve + Gaussian-likelihood engine behind redback's model /
 likelihood API.  The CUDA library is the only compute path; importing the package does
 not need a GPU, calling it does."""
-from . import _capi, engine, kilonova_models, likelihoods, supernova_models  # noqa: F401
+from . import _capi, afterglow_models, engine, kilonova_models, likelihoods, supernova_models  # noqa: F401
 from .likelihoods import GaussianLikelihood, GaussianLikelihoodQuadratureNoise  # noqa: F401
 
 __version__ = "0.1.0"
@@ -14,3 +14,4 @@ all_models_dict = {
 }
 all_models_dict.update({name: getattr(kilonova_models, name)
                         for name in ("one_component_kilonova_model", "metzger_kilonova_model")})
+all_models_dict.update({name: getattr(afterglow_models, name) for name in ("tophat_redback", "gaussian_redback")})

@@ -39,6 +39,16 @@ class KnConfig(C.Structure):
                 ("neutron_precursor_switch", C.c_int), ("vmax", C.c_double), ("cosmology", Cosmology)]
 
 
+AG_TOPHAT, AG_GAUSSIAN = 1, 2
+AG_ROWS = dict(redshift=0, thv=1, loge0=2, thc=3, thj=4, logn0=5, p=6, logepse=7, logepsb=8, g0=9, xiN=10)
+AG_NPARAM = 11
+
+
+class AgConfig(C.Structure):
+    _fields_ = [("jet", C.c_int), ("sigma_mode", C.c_int), ("steps", C.c_int), ("res", C.c_int), ("k", C.c_int),
+                ("expansion", C.c_int), ("a1", C.c_double), ("cosmology", Cosmology)]
+
+
 class RedbackB200Error(RuntimeError):
     pass
 
@@ -59,6 +69,9 @@ EXPORTS = {
     "rb_kn_config_default": (C.c_int, [C.POINTER(KnConfig)]),
     "rb_kn_eval_f64": (C.c_int, [C.POINTER(KnConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
     "rb_kn_eval_f64_host": (C.c_int, [C.POINTER(KnConfig), C.c_int64, C.c_int64] + [_dp] * 9),
+    "rb_ag_config_default": (C.c_int, [C.POINTER(AgConfig)]),
+    "rb_ag_eval_f64": (C.c_int, [C.POINTER(AgConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
+    "rb_ag_eval_f64_host": (C.c_int, [C.POINTER(AgConfig), C.c_int64, C.c_int64] + [_dp] * 9),
     "rb_luminosity_distance_f64": (C.c_int, [C.POINTER(Cosmology), C.c_int64, _dp, _dp, C.c_void_p]),
     "rb_gaussian_logl_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 5 + [C.c_void_p]),
     "rb_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -114,6 +127,18 @@ def kn_config(model, sigma_mode=SIGMA_FIXED, dense_resolution=500, neutron_precu
     cfg.dense_resolution = int(dense_resolution)
     cfg.neutron_precursor_switch = 1 if neutron_precursor_switch else 0
     cfg.vmax = float(vmax)
+    if cosmology is not None:
+        cfg.cosmology = cosmology
+    return cfg
+
+
+def ag_config(jet, sigma_mode=SIGMA_FIXED, steps=250, res=0, k=0, expansion=1, a1=1.0, cosmology=None):
+    cfg = AgConfig()
+    check(lib().rb_ag_config_default(C.byref(cfg)))
+    cfg.jet, cfg.sigma_mode = jet, sigma_mode
+    cfg.steps, cfg.res, cfg.k = int(steps), int(res), int(k)
+    cfg.expansion = 1 if expansion else 0
+    cfg.a1 = float(a1)
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg

@@ -1,0 +1,490 @@
+// redback_b200 -- redback-native structured-jet afterglow (tophat / Gaussian) + Gaussian log-likelihood.
+//
+// Reference: redback/transient_models/afterglow_models/base_models.py
+//   constants :32-39 (the module's own, not astropy's)        get_segments_numba :43-64
+//   erf_approximation_numba :67-89   get_structure_numba :92-148   get_obsangle_numba :151-179
+//   RK4_step_numba :182-192          get_gamma_numba :195-249
+//   calc_afterglow_step1_numba :252-322   calc_afterglow_step2_numba :325-370   get_ag_numba :373-399
+//   RedbackAfterglows.get_lightcurve / calc_afterglow_numba / calc_lightcurve :573-640
+//   tophat_redback :885-946   gaussian_redback :948-1010
+//
+// The jet is discretised into `res` rings x N_rot cells; work per sample is data dependent (res in
+// [10, 100]).  Samples are processed in chunks; per chunk:
+//   ag_prep_kernel   one warp per sample: d_L (32-point Gauss-Legendre), derived scalars, res -> ring count
+//   ag_scan_kernel   exclusive scan of ring counts -> ring offsets (one block)
+//   ag_ring_kernel   one THREAD per (sample, ring): RK4 of Gamma(log m) over `steps` steps in registers and
+//                    the ring's synchrotron parameters (step1) streamed to a ring-major scratch buffer
+//   ag_cell_kernel   one BLOCK per sample, one WARP per cell: each lane owns a contiguous run of steps; the
+//                    observer-time cumsums are warp-shuffle scans; per-step spectra go to shared memory and
+//                    the lanes then interpolate them at the epochs (np.interp) into per-warp accumulators
+//                    (deterministic summation order: cells within a warp in sequence, then warps in order).
+#include "rb_common.cuh"
+
+namespace rb {
+
+// base_models.py:32-39
+constexpr double AG_MP = 1.6726231e-24;
+constexpr double AG_ME = 9.1093897e-28;
+constexpr double AG_CC = 2.99792453e10;
+constexpr double AG_QE = 4.8032068e-10;
+constexpr double AG_C2 = AG_CC * AG_CC;
+constexpr double AG_FOURPI = 4 * kPi;
+// SIGT = (QE*QE/(ME*C2))**2 * (8*pi/3): the square is a Python float pow; value computed on the host
+// with the same operations (see ag_sigt()) and passed in AgConst.
+
+constexpr int kAgMaxNu = 4;      // unique frequencies per call
+constexpr int kAgWarps = 5;      // warps per block in ag_cell_kernel
+enum { RA_BETA = 0, RA_NE, RA_OMG, RA_R, RA_B, RA_NUMP, RA_PP, RA_KT, RA_G, kRingArrays };
+
+enum {
+  AS_OPZ = 0, AS_DL, AS_THV, AS_N, AS_EB, AS_EE, AS_P, AS_XP, AS_FX, AS_XIN, AS_G0, AS_EK, AS_THC, AS_THJ,
+  AS_LATSTEP, AS_ROTSTEP, AS_RES, AS_NROT, AS_SIGMA, AS_PAD, kAgScalars  // = 20
+};
+
+struct AgArgs {
+  rb_ag_config cfg;
+  int64_t N;            // samples in this chunk
+  int64_t n_base;       // index of the chunk's first sample in the full batch
+  int64_t N_total;
+  int E;
+  const double* params; // [RB_AG_NPARAM][N_total]
+  const double* dl_cm;
+  const double* sigma_param;
+  double* out_model;
+  double* out_logl;
+  const double* epoch_tab;   // [kEpochCols][E]
+  const int* nu_index;       // [E] index into nu_unique
+  double nu_unique[kAgMaxNu];
+  int n_nu;
+  double* scalars;           // [N][kAgScalars]
+  int* ring_count;           // [N]
+  int64_t* ring_off;         // [N + 1]
+  double* ring_scratch;      // [rings][kRingArrays][steps]
+  double sigt;
+  int want_logl;
+};
+
+__device__ const double kPxfP[12] = {1.0, 1.2, 1.4, 1.6, 1.8, 2.0, 2.2, 2.5, 2.7, 3.0, 3.2, 3.4};
+__device__ const double kPxfX[12] = {3.0, 1.4, 1.1, 0.86, 0.725, 0.637, 0.579, 0.520, 0.487, 0.451, 0.434, 0.420};
+__device__ const double kPxfF[12] = {0.41, 0.44, 0.48, 0.53, 0.56, 0.59, 0.612, 0.630, 0.641, 0.659, 0.660, 0.675};
+
+// np.interp(p, xp, fp) for p inside the table (base_models.py:584-585)
+__device__ __forceinline__ double pxf_interp(const double* fp, double p) {
+  if (p <= kPxfP[0]) return fp[0];
+  if (p >= kPxfP[11]) return fp[11];
+  int j = 0;
+  while (j < 10 && kPxfP[j + 1] <= p) ++j;
+  const double slope = (fp[j + 1] - fp[j]) / (kPxfP[j + 1] - kPxfP[j]);
+  return slope * (p - kPxfP[j]) + fp[j];
+}
+
+// ---- per-sample scalars -----------------------------------------------------------------------------------
+__global__ void ag_prep_kernel(const AgArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= a.N) return;
+  const int64_t NT = a.N_total;
+  const double* P = a.params + a.n_base + n;
+  const double z = P[RB_AG_REDSHIFT * NT];
+  const double opz = 1.0 + z;
+  double dl;
+  if (a.dl_cm != nullptr) {
+    dl = a.dl_cm[a.n_base + n];
+  } else {
+    double s = RB_GL32_W[lane] * inv_efunc(a.cfg.cosmology, 0.5 * z * (RB_GL32_X[lane] + 1.0));
+    s = warp_sum(s);
+    dl = opz * a.cfg.cosmology.hubble_distance_cm * (0.5 * z * s);
+  }
+  if (lane != 0) return;
+  const double thv = P[RB_AG_THV * NT], thc = P[RB_AG_THC * NT], g0 = P[RB_AG_G0 * NT];
+  const double thj = (a.cfg.jet == RB_AG_GAUSSIAN) ? P[RB_AG_THJ * NT] : thc;     // tophat: thj = thc (:937)
+  const double p = P[RB_AG_P * NT];
+  double nism = pow(10.0, P[RB_AG_LOGN0 * NT]);
+  if (a.cfg.k == 2) nism = nism * 3e35;                                            // :540-541
+  // resolution rule (:932-935)
+  int res = a.cfg.res;
+  if (res <= 0) {
+    const double sep = fmax(thv - thc, 0.0);
+    const double ord = (2 - 10 * sep) * thc * g0;
+    int order = (ord >= 2147483647.0) ? 2147483647 : (ord <= -2147483648.0 ? -2147483647 - 1 : (int)ord);
+    order = min(order, 100);
+    res = max(10, order);
+  }
+  const double resd = (double)res;
+  const double latstep = thj / resd;                                               // :46-49
+  const double rotstep = 2.0 * kPi / resd;
+  const int nrot = (int)(2 * kPi / rotstep);
+  double* S = a.scalars + n * kAgScalars;
+  S[AS_OPZ] = opz;
+  S[AS_DL] = dl;
+  S[AS_THV] = thv;
+  S[AS_N] = nism;
+  S[AS_EB] = pow(10.0, P[RB_AG_LOGEPSB * NT]);
+  S[AS_EE] = pow(10.0, P[RB_AG_LOGEPSE * NT]);
+  S[AS_P] = p;
+  S[AS_XP] = pxf_interp(kPxfX, p);
+  S[AS_FX] = pxf_interp(kPxfF, p);
+  S[AS_XIN] = P[RB_AG_XIN * NT];
+  S[AS_G0] = g0;
+  S[AS_EK] = pow(10.0, P[RB_AG_LOGE0 * NT]);
+  S[AS_THC] = thc;
+  S[AS_THJ] = thj;
+  S[AS_LATSTEP] = latstep;
+  S[AS_ROTSTEP] = rotstep;
+  S[AS_RES] = resd;
+  S[AS_NROT] = (double)nrot;
+  S[AS_SIGMA] = (a.cfg.sigma_mode != RB_SIGMA_FIXED && a.want_logl) ? a.sigma_param[a.n_base + n] : 0.0;
+  S[AS_PAD] = 0.0;
+  // p outside (1.2, 3.4) raises ValueError in the reference (:576-577): flagged by zero rings -> NaN output
+  a.ring_count[n] = (p < 1.2 || p > 3.4 || !(p == p)) ? 0 : res;
+}
+
+// exclusive scan of ring_count[0..N) -> ring_off[0..N]; single block
+__global__ void ag_scan_kernel(int64_t N, const int* __restrict__ cnt, int64_t* __restrict__ off) {
+  __shared__ int64_t wsum[33];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int64_t base = 0; base < N; base += blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    int64_t v = (i < N) ? cnt[i] : 0;
+    const int64_t own = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = (lane < nw) ? wsum[lane] : 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t u = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += u;
+      }
+      if (lane < nw) wsum[lane] = w;
+    }
+    __syncthreads();
+    const int64_t incl = carry + (warp > 0 ? wsum[warp - 1] : 0) + v;
+    if (i < N) off[i] = incl - own;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[N] = carry;
+}
+
+// RK4_step_numba (:182-192)
+__device__ __forceinline__ double ag_rk4(double ghat, double dm, double g, double m, double fac, double therm) {
+  const double ghatm1 = ghat - 1.0;
+  const double dm10 = pow(10.0, dm);
+  const double g2 = g * g;
+  const double ig = 1.0 / g;
+  return fac * dm10 * (ghat * (g2 - 1.0) - ghatm1 * (g - ig)) /
+         (m + dm10 * (therm + (1.0 - therm) * (2.0 * ghat * g - ghatm1 * (1 + 1.0 / g2))));
+}
+
+// ---- one thread per ring: structure, RK4 dynamics, step1 ----------------------------------------------------
+__global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t total_rings) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= total_rings) return;
+  // ring -> sample: last n with ring_off[n] <= r
+  int64_t lo = 0, hi = a.N;
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a.ring_off[mid] <= r) lo = mid; else hi = mid;
+  }
+  const int64_t n = lo;
+  const int i = (int)(r - a.ring_off[n]);
+  const double* S = a.scalars + n * kAgScalars;
+  const int steps = a.cfg.steps;
+  const double kk = (double)a.cfg.k;
+  const double latstep = S[AS_LATSTEP], rotstep = S[AS_ROTSTEP], resd = S[AS_RES];
+  const int nlat = (int)resd;
+  // thi = linspace(latstep - latstep/2, nlat*latstep - latstep/2, nlat)[i]  (:61)
+  const double th_lo = latstep - latstep / 2., th_hi = (double)nlat * latstep - latstep / 2.;
+  double thi;
+  if (nlat == 1) thi = th_lo;
+  else if (i == nlat - 1) thi = th_hi;
+  else thi = (double)i * ((th_hi - th_lo) / (double)(nlat - 1)) + th_lo;
+  // jet structure (:92-112)
+  const double g0 = S[AS_G0], ek = S[AS_EK], thc = S[AS_THC], thj = S[AS_THJ];
+  double fac_s;
+  if (a.cfg.jet == RB_AG_TOPHAT) {
+    const double x = -(thi - fmin(thc, thj)) * 1000.0;
+    const double sign = (x >= 0) ? 1.0 : -1.0;
+    const double xa = fabs(x);
+    const double t = 1.0 / (1.0 + 0.3275911 * xa);
+    const double yv = 1.0 - (((((1.061405429 * t + -1.453152027) * t) + 1.421413741) * t + -0.284496736) * t +
+                             0.254829592) * t * exp(-xa * xa);
+    fac_s = (sign * yv) * 0.5 + 0.5;
+  } else {
+    const double q = thi / thc;
+    fac_s = exp(-0.5 * (q * q));
+  }
+  const double Gs = (g0 - 1) * fac_s + 1.0000000000001;
+  const double Ei = ek * fac_s;
+  // get_gamma_numba (:195-249), therm = 0
+  const double n_amb = S[AS_N];
+  const double Nmin = (AG_FOURPI / (3.0 - kk)) * n_amb * pow(1e10, 3.0 - kk);
+  const double Nmax = (AG_FOURPI / (3.0 - kk)) * n_amb * pow(1e24, 3.0 - kk);
+  const double dlogm = log10(Nmin * AG_MP);
+  const double h = log10(Nmax / Nmin) / (double)steps;
+  const double fac = -h * log(10.0);
+  const double M = Ei / (Gs * AG_C2);
+  // step1 constants
+  const double p = S[AS_P], xp = S[AS_XP], Fx = S[AS_FX], EB = S[AS_EB], Ee = S[AS_EE], xiN = S[AS_XIN];
+  const bool expansion = a.cfg.expansion != 0;
+  const double a1 = a.cfg.a1;
+  const double hfac = 0.5 * latstep;
+  const double cos_lo = cos(thi - hfac);
+  const double omg_noexp = rotstep * (cos_lo - cos(thi + hfac));
+  const double inv3k = 1.0 / (3.0 - kk);
+  const double sigt = a.sigt;
+  double* out = a.ring_scratch + (size_t)r * kRingArrays * steps;
+
+  double G = Gs, dm = dlogm;
+  double ex0 = 1.0, r_prev_orig = 0.0, r_cum = 0.0;
+  for (int s = 0; s < steps; ++s) {
+    const double g2m1 = G * G - 1.0;
+    const double root = sqrt(g2m1);
+    const double theta = root * (root + 1.07 * g2m1) / (3.0 * (1 + root + 1.07 * g2m1));
+    const double zz = theta / (0.24 + theta);
+    const double ghat = ((((((1.07136 * zz - 2.39332) * zz + 2.32513) * zz - 0.96583) * zz + 0.18203) * zz - 1.21937) * zz + 5.0) / 3.0;
+    // ---- step1 at this step (uses the state before the RK4 update) ----
+    {
+      const double Gm1 = G - 1.0, G2 = G * G;
+      const double beta = sqrt(1 - 1.0 / G2);
+      const double Ne = pow(10.0, dm) / AG_MP;
+      const double cs = sqrt(AG_C2 * ghat * (ghat - 1) * Gm1 / (1 + ghat * Gm1));
+      const double te = asin(cs / (AG_CC * sqrt(G2 - 1.0)));
+      double ex = 1.0, omg = omg_noexp;
+      if (expansion) {
+        ex = te / pow(G, a1 + 1);
+        omg = rotstep * (cos_lo - cos(ex / resd + thi + hfac));
+      }
+      if (s == 0) ex0 = ex;
+      const double r_orig = pow((3.0 - kk) * Ne / (AG_FOURPI * n_amb), inv3k);
+      double r_inc = r_orig;
+      if (s > 0) {
+        const double expo = sqrt((1 - cos(latstep + ex0)) / (1 - cos(latstep + ex)));
+        r_inc = (r_orig - r_prev_orig) * pow(expo, inv3k);
+      }
+      r_prev_orig = r_orig;
+      r_cum = (s == 0) ? r_inc : r_cum + r_inc;
+      const double n0 = n_amb * pow(r_cum, -kk);
+      const double B = sqrt(2 * AG_FOURPI * EB * n0 * AG_MP * AG_C2 * ((ghat * G + 1.0) / (ghat - 1.0)) * Gm1);
+      double gm;
+      if (p > 2) {
+        gm = ((p - 2) / (p - 1)) * (Ee / xiN) * Gm1 * (AG_MP / AG_ME);
+      } else {
+        const double gmm = sqrt(1.5 * AG_FOURPI * AG_QE / (sigt * B));
+        if (p == 2) gm = (1 / log(gmm / ((Ee / xiN) * Gm1 * (AG_MP / AG_ME)))) * (Ee / xiN) * Gm1 * (AG_MP / AG_ME);
+        else gm = pow((2 - p) / (p - 1) * (AG_MP / AG_ME) * (Ee / xiN) * Gm1 * pow(gmm, p - 2), 1 / (p - 1));
+      }
+      out[RA_BETA * steps + s] = beta;
+      out[RA_NE * steps + s] = Ne;
+      out[RA_OMG * steps + s] = omg;
+      out[RA_R * steps + s] = r_cum;
+      out[RA_B * steps + s] = B;
+      out[RA_NUMP * steps + s] = 3.0 * xp * gm * gm * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);
+      out[RA_PP * steps + s] = xiN * Fx * AG_ME * AG_C2 * sigt * B / (3.0 * AG_QE);
+      out[RA_KT * steps + s] = gm * AG_ME * AG_C2;
+      out[RA_G * steps + s] = G;
+    }
+    // ---- RK4 (:238-246) ----
+    const double F1 = ag_rk4(ghat, dm, G, M, fac, 0.0);
+    const double F2 = ag_rk4(ghat, dm + 0.5 * h, G + 0.5 * F1, M, fac, 0.0);
+    const double F3 = ag_rk4(ghat, dm + 0.5 * h, G + 0.5 * F2, M, fac, 0.0);
+    const double F4 = ag_rk4(ghat, dm + h, G + F3, M, fac, 0.0);
+    G = G + (F1 + 2.0 * (F2 + F3) + F4) / 6.0 + 1e-15;
+    dm = dm + h;
+  }
+}
+
+// get_ag_numba (:373-399): the overlapping if-chain reduces to the last matching condition
+__device__ __forceinline__ double ag_flux(double fbb, double nuc, double num, double nu1, double fmax, double p) {
+  double f = 0.0;
+  if (nuc < num) {
+    if (num < nu1) f = fmax * (1.0 / sqrt(num / nuc)) * pow(nu1 / num, -p / 2.0);
+    else if (nuc < nu1) f = fmax * (1.0 / sqrt(nu1 / nuc));
+    else if (nu1 < nuc) f = fmax * cbrt(nu1 / nuc);
+  } else if (num < nuc) {
+    if (nuc < nu1) f = fmax * pow(nuc / num, -(p - 1.0) / 2.0) * pow(nu1 / nuc, -p / 2.0);
+    else if (num < nu1) f = fmax * pow(nu1 / num, -(p - 1.0) / 2.0);
+    else if (nu1 < num) f = fmax * cbrt(nu1 / num);
+  }
+  const double adj = fbb * (nu1 * nu1) * fmax_nan(1.0, sqrt(nu1 / num));
+  return (f < adj) ? f : adj;  // min(FBB_adj, Fluxt): first argument unless the second is smaller
+}
+
+// ---- one block per sample, one warp per cell ------------------------------------------------------------------
+__global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a) {
+  extern __shared__ double asm_[];
+  const int steps = a.cfg.steps, E = a.E, n_nu = a.n_nu;
+  const int spl = (steps + 31) / 32;          // steps per lane
+  double* ring = asm_;                         // [kRingArrays][steps]
+  double* et = ring + kRingArrays * steps;     // [E] epochs in source-frame-ready seconds (t * 86400)
+  double* wbuf = et + E;                       // per warp: tobs[steps] + flux[n_nu][steps]
+  double* acc = wbuf + (size_t)kAgWarps * (1 + n_nu) * steps;   // [kAgWarps][E]
+  double* sc = acc + (size_t)kAgWarps * E;     // [kAgScalars]
+  int* nuidx = reinterpret_cast<int*>(sc + kAgScalars);         // [E]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < E; e += blockDim.x) {
+    et[e] = a.epoch_tab[EP_T * E + e] * kDay;                    // :923  time * day_to_s
+    nuidx[e] = a.nu_index[e];
+  }
+  double* my_tobs = wbuf + (size_t)warp * (1 + n_nu) * steps;
+  double* my_flux = my_tobs + steps;
+  double* my_acc = acc + (size_t)warp * E;
+
+  for (int64_t n = blockIdx.x; n < a.N; n += gridDim.x) {
+    __syncthreads();
+    if (tid < kAgScalars) sc[tid] = a.scalars[n * kAgScalars + tid];
+    for (int e = tid; e < kAgWarps * E; e += blockDim.x) acc[e] = 0.0;
+    __syncthreads();
+    const int rings = a.ring_count[n];
+    const int nrot = (int)sc[AS_NROT];
+    const double opz = sc[AS_OPZ], dl = sc[AS_DL], rotstep = sc[AS_ROTSTEP], latstep = sc[AS_LATSTEP];
+    const double thv = sc[AS_THV], p = sc[AS_P];
+    const double dl2 = dl * dl;
+    const bool expansion = a.cfg.expansion != 0;
+    const double sin_tho = sin(thv), cos_tho = cos(thv);
+    const int nlat = (int)sc[AS_RES];
+    const double th_lo = latstep - latstep / 2., th_hi = (double)nlat * latstep - latstep / 2.;
+    const double ph_lo = rotstep - rotstep / 2., ph_hi = (double)nrot * rotstep - rotstep / 2.;
+
+    for (int i = 0; i < rings; ++i) {
+      __syncthreads();  // previous ring's cells are done with `ring`
+      const double* src = a.ring_scratch + (size_t)(a.ring_off[n] + i) * kRingArrays * steps;
+      for (int q = tid; q < kRingArrays * steps; q += blockDim.x) ring[q] = src[q];
+      __syncthreads();
+      double thi;
+      if (nlat == 1) thi = th_lo;
+      else if (i == nlat - 1) thi = th_hi;
+      else thi = (double)i * ((th_hi - th_lo) / (double)(nlat - 1)) + th_lo;
+      const double sin_thi = sin(thi), cos_thi = cos(thi);
+      // Omi row factor (:57): (cos(i*latstep) - cos((i+1)*latstep))
+      const double dcos = cos((double)i * latstep) - cos((double)(i + 1) * latstep);
+
+      for (int j = warp; j < nrot; j += kAgWarps) {
+        // phi = linspace(rotstep, nrot*rotstep, nrot)[j]; phii = linspace(rotstep/2, ...)[j]   (:53,62)
+        double phi, phii;
+        if (nrot == 1) { phi = rotstep; phii = ph_lo; }
+        else {
+          const double phi_hi = (double)nrot * rotstep;
+          phi = (j == nrot - 1) ? phi_hi : (double)j * ((phi_hi - rotstep) / (double)(nrot - 1)) + rotstep;
+          phii = (j == nrot - 1) ? ph_hi : (double)j * ((ph_hi - ph_lo) / (double)(nrot - 1)) + ph_lo;
+        }
+        const double Om0 = (phi - (phi - rotstep)) * dcos;
+        // get_obsangle_numba (:151-179) with phi = 0
+        const double f1 = 0.0 * sin_tho * sin(phii) * sin_thi;
+        const double f2 = 1.0 * sin_tho * cos(phii) * sin_thi;
+        double ang = cos_tho * cos_thi + f2 + f1;
+        ang = (ang > 1.0) ? 1.0 : ((ang < -1.0) ? -1.0 : ang);
+        const double obsa = acos(ang);
+        const double cosa = cos(obsa);
+        // ---- step2 (:325-370): this lane's steps [s0, s1) ----
+        const int s0 = min(lane * spl, steps), s1 = min(s0 + spl, steps);
+        double sum_dt = 0.0, sum_dto = 0.0;
+        for (int s = s0; s < s1; ++s) {
+          const double rd = ring[RA_R * steps + s] - (s > 0 ? ring[RA_R * steps + s - 1] : 0.0);
+          const double ib = 1.0 / ring[RA_BETA * steps + s];
+          sum_dt += rd * (ib - cosa) / AG_CC;
+          sum_dto += rd * (ib - 1.0) / AG_CC;
+        }
+        double pre_dt = sum_dt, pre_dto = sum_dto;   // inclusive scan over lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double u = __shfl_up_sync(0xffffffffu, pre_dt, o);
+          const double w = __shfl_up_sync(0xffffffffu, pre_dto, o);
+          if (lane >= o) { pre_dt += u; pre_dto += w; }
+        }
+        double tobs = pre_dt - sum_dt, tobso = pre_dto - sum_dto;   // exclusive prefix
+        for (int s = s0; s < s1; ++s) {
+          const double G = ring[RA_G * steps + s], beta = ring[RA_BETA * steps + s], B = ring[RA_B * steps + s];
+          const double R = ring[RA_R * steps + s];
+          const double rd = R - (s > 0 ? ring[RA_R * steps + s - 1] : 0.0);
+          const double ib = 1.0 / beta;
+          tobs += rd * (ib - cosa) / AG_CC;
+          tobso += rd * (ib - 1.0) / AG_CC;
+          const double omg = ring[RA_OMG * steps + s];
+          const double Om = expansion ? fmax_nan(Om0, omg) : omg;
+          const double thii = acos(1.0 - Om / rotstep);
+          const double NO = Om0 * ring[RA_NE * steps + s] / AG_FOURPI;
+          const double dop = 1.0 / (G * (1.0 - beta * cosa));
+          const double gc = 6.0 * kPi * AG_ME * AG_CC / (G * a.sigt * B * B * tobso);
+          const double nucp = 0.286 * 3.0 * gc * gc * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);
+          const double num = dop * ring[RA_NUMP * steps + s];
+          const double nuc = dop * nucp;
+          const double Fmax = NO * ring[RA_PP * steps + s] * dop * dop * dop / (AG_FOURPI * dl2);
+          const double FBB = 2 * Om * cos(thii) * dop * ring[RA_KT * steps + s] * R * R / (AG_C2 * dl2);
+          my_tobs[s] = tobs;
+          for (int h = 0; h < n_nu; ++h)
+            my_flux[h * steps + s] = ag_flux(FBB, nuc, num, a.nu_unique[h] * opz, Fmax, p);   // nu = nu0*(1+z) :587
+        }
+        __syncwarp();
+        // ---- calc_lightcurve (:632-640): np.interp(t/(1+z), tobs, Flux[h]) summed over cells ----
+        const double x_first = my_tobs[0], x_last = my_tobs[steps - 1];
+        for (int e = lane; e < E; e += 32) {
+          const double x = et[e] / opz;
+          const double* fp = my_flux + nuidx[e] * steps;
+          double v;
+          if (!(x == x)) v = x;
+          else if (x <= x_first) v = fp[0];           // numpy: x < xp[0] -> left; x == xp[0] -> fp[0]
+          else if (x >= x_last) v = fp[steps - 1];
+          else {
+            int lo = 0, hi = steps - 1;   // largest j with tobs[j] <= x
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              if (my_tobs[mid] <= x) lo = mid; else hi = mid;
+            }
+            const double slope = (fp[lo + 1] - fp[lo]) / (my_tobs[lo + 1] - my_tobs[lo]);
+            v = slope * (x - my_tobs[lo]) + fp[lo];
+          }
+          my_acc[e] += v;
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- finish: (1+z) / 1e-26 -> mJy, likelihood ----
+    double logl_part = 0.0;
+    for (int e = tid; e < E; e += blockDim.x) {
+      double lc = 0.0;
+      for (int w = 0; w < kAgWarps; ++w) lc += acc[w * E + e];
+      double model_v = (rings > 0) ? lc * opz / 1e-26 : NAN;                     // :640, :942
+      if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = model_v;
+      if (a.want_logl) {
+        const double res = a.epoch_tab[EP_Y * E + e] - model_v;
+        if (a.cfg.sigma_mode == RB_SIGMA_FIXED) {
+          const double rs = res * a.epoch_tab[EP_ISIG * E + e];
+          logl_part += -(rs * rs) / 2 - a.epoch_tab[EP_LOGT * E + e];
+        } else {
+          const double sp = sc[AS_SIGMA];
+          double sg = sp;
+          if (a.cfg.sigma_mode == RB_SIGMA_QUADRATURE) {
+            const double si = a.epoch_tab[EP_ISIG * E + e];
+            sg = sqrt(si * si + sp * sp);
+          }
+          const double rs = res / sg;
+          logl_part += -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;
+        }
+      }
+    }
+    if (a.want_logl) {
+      logl_part = warp_sum(logl_part);
+      __syncthreads();
+      if (lane == 0) acc[warp] = logl_part;   // acc is free again
+      __syncthreads();
+      if (tid == 0) {
+        double total = 0.0;
+        for (int w = 0; w < kAgWarps; ++w) total += acc[w];
+        a.out_logl[a.n_base + n] = nan_to_num(total);
+      }
+    }
+  }
+}
+
+}  // namespace rb

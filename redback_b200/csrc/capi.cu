@@ -8,6 +8,9 @@
 
 #include "sn_kernel.cu"
 #include "kn_kernel.cu"
+#include "ag_kernel.cu"
+#include <algorithm>
+#include <vector>
 
 namespace {
 
@@ -473,6 +476,205 @@ extern "C" int rb_kn_eval_f64_host(const rb_kn_config* cfg, int64_t N, int64_t E
   if (out_model) RB_CUDA(d_m.alloc(nN * nE));
   if (out_logl) RB_CUDA(d_l.alloc(nN));
   rc = rb_kn_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
+  if (rc != RB_OK) return rc;
+  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
+  RB_CUDA(cudaDeviceSynchronize());
+  return RB_OK;
+}
+
+// ---- afterglow path ---------------------------------------------------------------------------------------
+extern "C" int rb_ag_config_default(rb_ag_config* cfg) {
+  if (!cfg) return fail(RB_ERR_INVALID, "rb_ag_config_default: null config");
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->jet = RB_AG_TOPHAT;
+  cfg->sigma_mode = RB_SIGMA_FIXED;
+  cfg->steps = 250;
+  cfg->res = 0;
+  cfg->k = 0;
+  cfg->expansion = 1;
+  cfg->a1 = 1.0;
+  return rb_cosmology_planck18(&cfg->cosmology);
+}
+
+static int ag_check(const rb_ag_config* cfg, int64_t N, int64_t E, const void* params, const void* t_obs,
+                    const void* freq_obs, const void* y, const void* sigma, const void* sigma_param,
+                    const void* out_model, const void* out_logl) {
+  if (!cfg) return fail(RB_ERR_INVALID, "rb_ag_eval: null config");
+  if (N < 0 || E <= 0) return fail(RB_ERR_INVALID, "rb_ag_eval: need N >= 0 and E > 0");
+  if (cfg->jet != RB_AG_TOPHAT && cfg->jet != RB_AG_GAUSSIAN)
+    return fail(RB_ERR_UNSUPPORTED, "rb_ag_eval: only the tophat ('TH') and Gaussian ('GJ') jets are on device");
+  if (cfg->k != 0 && cfg->k != 2) return fail(RB_ERR_INVALID, "k must either be 0 or 2");  // base_models.py:574-575
+  if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_QUADRATURE)
+    return fail(RB_ERR_INVALID, "rb_ag_eval: unknown sigma_mode");
+  if (cfg->steps < 2 || cfg->steps > 1000) return fail(RB_ERR_INVALID, "rb_ag_eval: steps must be in [2, 1000]");
+  if (cfg->res < 0 || cfg->res > 400) return fail(RB_ERR_INVALID, "rb_ag_eval: res must be in [1, 400] (0 = default rule)");
+  if (!params || !t_obs || !freq_obs) return fail(RB_ERR_INVALID, "rb_ag_eval: params, t_obs and freq_obs are required");
+  if (y) {
+    if (!out_logl) return fail(RB_ERR_INVALID, "rb_ag_eval: y given but out_logl is null");
+    if (cfg->sigma_mode != RB_SIGMA_SAMPLED && !sigma) return fail(RB_ERR_INVALID, "rb_ag_eval: sigma is required");
+    if (cfg->sigma_mode != RB_SIGMA_FIXED && !sigma_param) return fail(RB_ERR_INVALID, "rb_ag_eval: sigma_param is required");
+  } else if (out_logl) {
+    return fail(RB_ERR_INVALID, "rb_ag_eval: out_logl requested without data y");
+  }
+  if (!out_model && !out_logl) return fail(RB_ERR_INVALID, "rb_ag_eval: nothing to compute");
+  return RB_OK;
+}
+
+extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, const double* params,
+                              const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
+                              const double* sigma, const double* sigma_param, double* out_model,
+                              double* out_logl, void* stream) {
+  int rc = ag_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  RB_CUDA(cudaGetDevice(&dev));
+  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [dev] {
+    attr_err = cudaFuncSetAttribute(rb::ag_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(ag_cell_kernel)");
+
+  // unique frequencies (np.unique(self.freq), base_models.py:586): E doubles to the host once per call
+  std::vector<double> h_freq((size_t)E);
+  RB_CUDA(cudaMemcpyAsync(h_freq.data(), freq_obs, (size_t)E * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  std::vector<double> uniq(h_freq);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  if ((int)uniq.size() > rb::kAgMaxNu)
+    return fail(RB_ERR_UNSUPPORTED, "rb_ag_eval: more than 4 distinct frequencies in one call");
+  std::vector<int> h_idx((size_t)E);
+  for (int64_t e = 0; e < E; ++e)
+    h_idx[(size_t)e] = (int)(std::lower_bound(uniq.begin(), uniq.end(), h_freq[(size_t)e]) - uniq.begin());
+
+  const int steps = cfg->steps, n_nu = (int)uniq.size();
+  const size_t cell_smem = sizeof(double) * ((size_t)rb::kRingArrays * steps + (size_t)E +
+                                             (size_t)rb::kAgWarps * (1 + n_nu) * steps + (size_t)rb::kAgWarps * E +
+                                             rb::kAgScalars) + sizeof(int) * (size_t)E;
+  if (cell_smem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_ag_eval: steps / epochs exceed shared memory");
+
+  const int64_t chunk_max = 8192;
+  const size_t fixed_doubles = (size_t)rb::kEpochCols * (size_t)E;
+  double* d_epoch = nullptr;
+  int* d_idx = nullptr;
+  RB_CUDA(cudaMallocAsync(&d_epoch, fixed_doubles * sizeof(double), st));
+  RB_CUDA(cudaMallocAsync(&d_idx, (size_t)E * sizeof(int), st));
+  RB_CUDA(cudaMemcpyAsync(d_idx, h_idx.data(), (size_t)E * sizeof(int), cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaStreamSynchronize(st));  // h_idx is pageable host memory
+  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
+                                                                    y ? sigma : nullptr, d_epoch);
+  launch_counter()->fetch_add(1);
+
+  const double q = rb::AG_QE * rb::AG_QE / (rb::AG_ME * rb::AG_C2);
+  const double sigt = (q * q) * (8 * M_PI / 3);   // base_models.py:37
+  double* d_scal = nullptr;
+  int* d_cnt = nullptr;
+  int64_t* d_off = nullptr;
+  RB_CUDA(cudaMallocAsync(&d_scal, (size_t)chunk_max * rb::kAgScalars * sizeof(double), st));
+  RB_CUDA(cudaMallocAsync(&d_cnt, (size_t)chunk_max * sizeof(int), st));
+  RB_CUDA(cudaMallocAsync(&d_off, (size_t)(chunk_max + 1) * sizeof(int64_t), st));
+  int occ = 0;
+  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::ag_cell_kernel, rb::kAgWarps * 32, cell_smem));
+  if (occ < 1) occ = 1;
+
+  int status = RB_OK;
+  const size_t ring_bytes = (size_t)rb::kRingArrays * steps * sizeof(double);
+  const size_t scratch_cap = (size_t)6 << 30;   // bound the ring scratch at 6 GiB per chunk
+  int64_t n0 = 0;
+  int64_t chunk = chunk_max;
+  while (n0 < N && status == RB_OK) {
+    const int64_t nc = std::min<int64_t>(chunk, N - n0);
+    rb::AgArgs a;
+    a.cfg = *cfg;
+    a.N = nc;
+    a.n_base = n0;
+    a.N_total = N;
+    a.E = (int)E;
+    a.params = params;
+    a.dl_cm = dl_cm;
+    a.sigma_param = sigma_param;
+    a.out_model = out_model;
+    a.out_logl = y ? out_logl : nullptr;
+    a.want_logl = y ? 1 : 0;
+    a.epoch_tab = d_epoch;
+    a.nu_index = d_idx;
+    for (int h = 0; h < rb::kAgMaxNu; ++h) a.nu_unique[h] = h < n_nu ? uniq[(size_t)h] : 0.0;
+    a.n_nu = n_nu;
+    a.scalars = d_scal;
+    a.ring_count = d_cnt;
+    a.ring_off = d_off;
+    a.ring_scratch = nullptr;
+    a.sigt = sigt;
+    rb::ag_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
+    rb::ag_scan_kernel<<<1, 1024, 0, st>>>(nc, d_cnt, d_off);
+    int64_t total = 0;
+    cudaError_t ce = cudaMemcpyAsync(&total, d_off + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    launch_counter()->fetch_add(2);
+    if (ce != cudaSuccess) { status = cuda_fail(ce, "ring count"); break; }
+    if ((size_t)total * ring_bytes > scratch_cap && nc > 64) {
+      chunk = std::max<int64_t>(64, nc / 2);   // too many rings (large res): retry with a smaller chunk
+      continue;
+    }
+    double* d_ring = nullptr;
+    ce = cudaMallocAsync(&d_ring, std::max<size_t>((size_t)total, 1) * ring_bytes, st);
+    if (ce != cudaSuccess) { status = cuda_fail(ce, "ring scratch allocation"); break; }
+    a.ring_scratch = d_ring;
+    if (total > 0) {
+      rb::ag_ring_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, total);
+      launch_counter()->fetch_add(1);
+    }
+    int64_t grid = std::min<int64_t>(nc, (int64_t)sms * occ * 2);
+    rb::ag_cell_kernel<<<(unsigned)grid, rb::kAgWarps * 32, cell_smem, st>>>(a);
+    launch_counter()->fetch_add(1);
+    ce = cudaGetLastError();
+    cudaFreeAsync(d_ring, st);
+    if (ce != cudaSuccess) { status = cuda_fail(ce, "afterglow kernels"); break; }
+    n0 += nc;
+  }
+  cudaFreeAsync(d_off, st);
+  cudaFreeAsync(d_cnt, st);
+  cudaFreeAsync(d_scal, st);
+  cudaFreeAsync(d_idx, st);
+  cudaFreeAsync(d_epoch, st);
+  return status;
+}
+
+extern "C" int rb_ag_eval_f64_host(const rb_ag_config* cfg, int64_t N, int64_t E, const double* params,
+                                   const double* t_obs, const double* freq_obs, const double* dl_cm,
+                                   const double* y, const double* sigma, const double* sigma_param,
+                                   double* out_model, double* out_logl) {
+  int rc = ag_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
+  const size_t nN = (size_t)N, nE = (size_t)E;
+  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
+    if (!h) return cudaSuccess;
+    cudaError_t e = b.alloc(n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  RB_CUDA(up(d_par, params, (size_t)RB_AG_NPARAM * nN));
+  RB_CUDA(up(d_t, t_obs, nE));
+  RB_CUDA(up(d_f, freq_obs, nE));
+  RB_CUDA(up(d_dl, dl_cm, nN));
+  RB_CUDA(up(d_y, y, nE));
+  RB_CUDA(up(d_s, sigma, nE));
+  RB_CUDA(up(d_sp, sigma_param, nN));
+  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
+  if (out_logl) RB_CUDA(d_l.alloc(nN));
+  rc = rb_ag_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
   if (rc != RB_OK) return rc;
   if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
   if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));

@@ -82,6 +82,13 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
   return scratch[32];
 }
 
+// np.maximum / Python max(a, b) on floats: NaN-propagating maximum
+__device__ __forceinline__ double fmax_nan(double a, double b) {
+  if (a != a) return a;
+  if (b != b) return b;
+  return (b > a) ? b : a;
+}
+
 // np.nan_to_num for a float64 scalar (likelihoods.py:227)
 __device__ __forceinline__ double nan_to_num(double v) {
   if (isnan(v)) return 0.0;

@@ -226,6 +226,24 @@ class KilonovaPath(_FusedPath):
             raise ValueError("A value in x_new is below the interpolation range.")  # scipy interp1d's error
 
 
+class AfterglowPath(_FusedPath):
+    """redback-native tophat / Gaussian afterglow -> Gaussian log L
+    (redback/transient_models/afterglow_models/base_models.py:43-640, 885-1010)."""
+
+    ROWS = _capi.AG_ROWS
+    NPARAM = _capi.AG_NPARAM
+
+    def __init__(self, jet, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED, steps=250,
+                 res=None, k=0, expansion=1, a1=1, cosmology=None, device=None):
+        if k not in (0, 2):
+            raise ValueError("k must either be 0 or 2")
+        self.cfg = _capi.ag_config(jet, sigma_mode, steps, 0 if res is None else int(res), k, expansion, a1, cosmology)
+        self._setup(time, frequency, y, sigma, device)
+
+    def _eval_fn(self):
+        return _capi.lib().rb_ag_eval_f64
+
+
 def luminosity_distance(redshift, cosmology=None, device=None):
     """Planck18 (default) luminosity distance in cm for an array of redshifts, on device."""
     dev = _device(device)

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import _capi, _fused
+from . import afterglow_models as _ag
 from . import kilonova_models as _kn
 from . import supernova_models as _sn
 from .engine import batch_size, gaussian_logl
@@ -19,6 +20,7 @@ from .engine import batch_size, gaussian_logl
 FUSED = {}
 FUSED.update(_sn.FUSED)
 FUSED.update(_kn.FUSED)
+FUSED.update(_ag.FUSED)
 
 
 def infer_parameters_from_function(func):

@@ -98,3 +98,19 @@ def engine_atan_condition(t_src_seconds):
     1.3 * 2.2e-16 * pi * x of the luminosity, x = (t-1.3)/0.11."""
     x = np.maximum((np.asarray(t_src_seconds) - 1.3) / 0.11, 1.0)
     return 1.3 * 2.2e-16 * np.pi * x
+
+
+def tophat_prior(rng, n):
+    """priors/tophat_redback.prior."""
+    return dict(redshift=rng.uniform(0.01, 3, n), thv=np.arccos(rng.uniform(0, 1, n)), loge0=rng.uniform(44, 54, n),
+                thc=rng.uniform(0.01, 0.1, n), logn0=rng.uniform(-5, 2, n), p=rng.uniform(2, 3, n),
+                logepse=rng.uniform(-5, 0, n), logepsb=rng.uniform(-5, 0, n), g0=rng.uniform(100, 2000, n),
+                xiN=rng.uniform(0, 1, n))
+
+
+def config4_epochs(n_per=250):
+    """radio + X-ray, 250 epochs each, t = geomspace(0.1, 300 d)."""
+    t = np.concatenate([np.geomspace(0.1, 300, n_per)] * 2)
+    nu = np.concatenate([np.full(n_per, 5e9), np.full(n_per, 2e17)])
+    order = np.argsort(t, kind="stable")
+    return t[order], nu[order]
