@@ -34,6 +34,7 @@ constexpr double AG_FOURPI = 4 * kPi;
 
 constexpr int kAgMaxNu = 4;      // unique frequencies per call
 constexpr int kAgWarps = 5;      // warps per block in ag_cell_kernel
+constexpr int kAgRingsPerUnit = 10;  // rings handled by one block of ag_cell_kernel (load balance for res up to 100+)
 enum { RA_BETA = 0, RA_NE, RA_OMG, RA_R, RA_B, RA_NUMP, RA_PP, RA_KT, RA_G, kRingArrays };
 
 enum {
@@ -60,6 +61,9 @@ struct AgArgs {
   int* ring_count;           // [N]
   int64_t* ring_off;         // [N + 1]
   double* ring_scratch;      // [rings][kRingArrays][steps]
+  int* unit_count;           // [N]   work units (groups of <= kAgRingsPerUnit rings) per sample
+  int64_t* unit_off;         // [N + 1]
+  double* partial;           // [units][E] per-unit light-curve partial sums
   double sigt;
   int want_logl;
 };
@@ -136,7 +140,9 @@ __global__ void ag_prep_kernel(const AgArgs a) {
   S[AS_SIGMA] = (a.cfg.sigma_mode != RB_SIGMA_FIXED && a.want_logl) ? a.sigma_param[a.n_base + n] : 0.0;
   S[AS_PAD] = 0.0;
   // p outside (1.2, 3.4) raises ValueError in the reference (:576-577): flagged by zero rings -> NaN output
-  a.ring_count[n] = (p < 1.2 || p > 3.4 || !(p == p)) ? 0 : res;
+  const int rings = (p < 1.2 || p > 3.4 || !(p == p)) ? 0 : res;
+  a.ring_count[n] = rings;
+  a.unit_count[n] = (rings + kAgRingsPerUnit - 1) / kAgRingsPerUnit;
 }
 
 // exclusive scan of ring_count[0..N) -> ring_off[0..N]; single block
@@ -318,19 +324,31 @@ __device__ __forceinline__ double ag_flux(double fbb, double nuc, double num, do
   return (f < adj) ? f : adj;  // min(FBB_adj, Fluxt): first argument unless the second is smaller
 }
 
-// ---- one block per sample, one warp per cell ------------------------------------------------------------------
-__global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a) {
+// ---- one block per work unit (<= kAgRingsPerUnit rings of one sample), one warp per cell -------------------------
+__global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, int64_t total_units) {
   extern __shared__ double asm_[];
   const int steps = a.cfg.steps, E = a.E, n_nu = a.n_nu;
   const int spl = (steps + 31) / 32;          // steps per lane
   double* ring = asm_;                         // [kRingArrays][steps]
-  double* et = ring + kRingArrays * steps;     // [E] epochs in source-frame-ready seconds (t * 86400)
+  double* et = ring + kRingArrays * steps;     // [E] epochs in seconds (t * 86400)
   double* wbuf = et + E;                       // per warp: tobs[steps] + flux[n_nu][steps]
   double* acc = wbuf + (size_t)kAgWarps * (1 + n_nu) * steps;   // [kAgWarps][E]
   double* sc = acc + (size_t)kAgWarps * E;     // [kAgScalars]
   int* nuidx = reinterpret_cast<int*>(sc + kAgScalars);         // [E]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t u = blockIdx.x;
+  if (u >= total_units) return;
+  // unit -> sample: last n with unit_off[n] <= u
+  int64_t lo_n = 0, hi_n = a.N;
+  while (hi_n - lo_n > 1) {
+    const int64_t mid = (lo_n + hi_n) >> 1;
+    if (a.unit_off[mid] <= u) lo_n = mid; else hi_n = mid;
+  }
+  const int64_t n = lo_n;
+  const int ring_begin = (int)(u - a.unit_off[n]) * kAgRingsPerUnit;
+  const int ring_end = min(ring_begin + kAgRingsPerUnit, a.ring_count[n]);
+
   for (int e = tid; e < E; e += blockDim.x) {
     et[e] = a.epoch_tab[EP_T * E + e] * kDay;                    // :923  time * day_to_s
     nuidx[e] = a.nu_index[e];
@@ -338,13 +356,10 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a) 
   double* my_tobs = wbuf + (size_t)warp * (1 + n_nu) * steps;
   double* my_flux = my_tobs + steps;
   double* my_acc = acc + (size_t)warp * E;
-
-  for (int64_t n = blockIdx.x; n < a.N; n += gridDim.x) {
-    __syncthreads();
-    if (tid < kAgScalars) sc[tid] = a.scalars[n * kAgScalars + tid];
-    for (int e = tid; e < kAgWarps * E; e += blockDim.x) acc[e] = 0.0;
-    __syncthreads();
-    const int rings = a.ring_count[n];
+  if (tid < kAgScalars) sc[tid] = a.scalars[n * kAgScalars + tid];
+  for (int e = tid; e < kAgWarps * E; e += blockDim.x) acc[e] = 0.0;
+  __syncthreads();
+  {
     const int nrot = (int)sc[AS_NROT];
     const double opz = sc[AS_OPZ], dl = sc[AS_DL], rotstep = sc[AS_ROTSTEP], latstep = sc[AS_LATSTEP];
     const double thv = sc[AS_THV], p = sc[AS_P];
@@ -355,7 +370,7 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a) 
     const double th_lo = latstep - latstep / 2., th_hi = (double)nlat * latstep - latstep / 2.;
     const double ph_lo = rotstep - rotstep / 2., ph_hi = (double)nrot * rotstep - rotstep / 2.;
 
-    for (int i = 0; i < rings; ++i) {
+    for (int i = ring_begin; i < ring_end; ++i) {
       __syncthreads();  // previous ring's cells are done with `ring`
       const double* src = a.ring_scratch + (size_t)(a.ring_off[n] + i) * kRingArrays * steps;
       for (int q = tid; q < kRingArrays * steps; q += blockDim.x) ring[q] = src[q];
@@ -449,12 +464,28 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a) 
       }
     }
     __syncthreads();
-    // ---- finish: (1+z) / 1e-26 -> mJy, likelihood ----
-    double logl_part = 0.0;
+    // per-unit partial light curve (deterministic: warps summed in order)
     for (int e = tid; e < E; e += blockDim.x) {
       double lc = 0.0;
       for (int w = 0; w < kAgWarps; ++w) lc += acc[w * E + e];
-      double model_v = (rings > 0) ? lc * opz / 1e-26 : NAN;                     // :640, :942
+      a.partial[u * (int64_t)E + e] = lc;
+    }
+  }
+}
+
+// ---- one block per sample: sum the sample's unit partials in order, (1+z)/1e-26 -> mJy, likelihood ------------
+__global__ void __launch_bounds__(128) ag_finish_kernel(const AgArgs a) {
+  __shared__ double wsum[4];
+  const int E = a.E, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t n = blockIdx.x; n < a.N; n += gridDim.x) {
+    const int64_t u0 = a.unit_off[n], u1 = a.unit_off[n + 1];
+    const double opz = a.scalars[n * kAgScalars + AS_OPZ];
+    const double sp = a.scalars[n * kAgScalars + AS_SIGMA];
+    double logl_part = 0.0;
+    for (int e = tid; e < E; e += blockDim.x) {
+      double lc = 0.0;
+      for (int64_t u = u0; u < u1; ++u) lc += a.partial[u * (int64_t)E + e];
+      const double model_v = (u1 > u0) ? lc * opz / 1e-26 : NAN;                   // :640, :942
       if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = model_v;
       if (a.want_logl) {
         const double res = a.epoch_tab[EP_Y * E + e] - model_v;
@@ -462,7 +493,6 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a) 
           const double rs = res * a.epoch_tab[EP_ISIG * E + e];
           logl_part += -(rs * rs) / 2 - a.epoch_tab[EP_LOGT * E + e];
         } else {
-          const double sp = sc[AS_SIGMA];
           double sg = sp;
           if (a.cfg.sigma_mode == RB_SIGMA_QUADRATURE) {
             const double si = a.epoch_tab[EP_ISIG * E + e];
@@ -476,13 +506,9 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a) 
     if (a.want_logl) {
       logl_part = warp_sum(logl_part);
       __syncthreads();
-      if (lane == 0) acc[warp] = logl_part;   // acc is free again
+      if (lane == 0) wsum[warp] = logl_part;
       __syncthreads();
-      if (tid == 0) {
-        double total = 0.0;
-        for (int w = 0; w < kAgWarps; ++w) total += acc[w];
-        a.out_logl[a.n_base + n] = nan_to_num(total);
-      }
+      if (tid == 0) a.out_logl[a.n_base + n] = nan_to_num(wsum[0] + wsum[1] + wsum[2] + wsum[3]);
     }
   }
 }

@@ -580,12 +580,13 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
   double* d_scal = nullptr;
   int* d_cnt = nullptr;
   int64_t* d_off = nullptr;
+  int* d_ucnt = nullptr;
+  int64_t* d_uoff = nullptr;
   RB_CUDA(cudaMallocAsync(&d_scal, (size_t)chunk_max * rb::kAgScalars * sizeof(double), st));
   RB_CUDA(cudaMallocAsync(&d_cnt, (size_t)chunk_max * sizeof(int), st));
   RB_CUDA(cudaMallocAsync(&d_off, (size_t)(chunk_max + 1) * sizeof(int64_t), st));
-  int occ = 0;
-  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::ag_cell_kernel, rb::kAgWarps * 32, cell_smem));
-  if (occ < 1) occ = 1;
+  RB_CUDA(cudaMallocAsync(&d_ucnt, (size_t)chunk_max * sizeof(int), st));
+  RB_CUDA(cudaMallocAsync(&d_uoff, (size_t)(chunk_max + 1) * sizeof(int64_t), st));
 
   int status = RB_OK;
   const size_t ring_bytes = (size_t)rb::kRingArrays * steps * sizeof(double);
@@ -614,13 +615,18 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
     a.ring_count = d_cnt;
     a.ring_off = d_off;
     a.ring_scratch = nullptr;
+    a.unit_count = d_ucnt;
+    a.unit_off = d_uoff;
+    a.partial = nullptr;
     a.sigt = sigt;
     rb::ag_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
     rb::ag_scan_kernel<<<1, 1024, 0, st>>>(nc, d_cnt, d_off);
-    int64_t total = 0;
+    rb::ag_scan_kernel<<<1, 1024, 0, st>>>(nc, d_ucnt, d_uoff);
+    int64_t total = 0, total_units = 0;
     cudaError_t ce = cudaMemcpyAsync(&total, d_off + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&total_units, d_uoff + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    launch_counter()->fetch_add(2);
+    launch_counter()->fetch_add(3);
     if (ce != cudaSuccess) { status = cuda_fail(ce, "ring count"); break; }
     if ((size_t)total * ring_bytes > scratch_cap && nc > 64) {
       chunk = std::max<int64_t>(64, nc / 2);   // too many rings (large res): retry with a smaller chunk
@@ -630,18 +636,25 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
     ce = cudaMallocAsync(&d_ring, std::max<size_t>((size_t)total, 1) * ring_bytes, st);
     if (ce != cudaSuccess) { status = cuda_fail(ce, "ring scratch allocation"); break; }
     a.ring_scratch = d_ring;
+    double* d_part = nullptr;
+    ce = cudaMallocAsync(&d_part, std::max<size_t>((size_t)total_units, 1) * (size_t)E * sizeof(double), st);
+    if (ce != cudaSuccess) { cudaFreeAsync(d_ring, st); status = cuda_fail(ce, "partial sums allocation"); break; }
+    a.partial = d_part;
     if (total > 0) {
       rb::ag_ring_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, total);
-      launch_counter()->fetch_add(1);
+      rb::ag_cell_kernel<<<(unsigned)total_units, rb::kAgWarps * 32, cell_smem, st>>>(a, total_units);
+      launch_counter()->fetch_add(2);
     }
-    int64_t grid = std::min<int64_t>(nc, (int64_t)sms * occ * 2);
-    rb::ag_cell_kernel<<<(unsigned)grid, rb::kAgWarps * 32, cell_smem, st>>>(a);
+    rb::ag_finish_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * 16), 128, 0, st>>>(a);
     launch_counter()->fetch_add(1);
     ce = cudaGetLastError();
+    cudaFreeAsync(d_part, st);
     cudaFreeAsync(d_ring, st);
     if (ce != cudaSuccess) { status = cuda_fail(ce, "afterglow kernels"); break; }
     n0 += nc;
   }
+  cudaFreeAsync(d_uoff, st);
+  cudaFreeAsync(d_ucnt, st);
   cudaFreeAsync(d_off, st);
   cudaFreeAsync(d_cnt, st);
   cudaFreeAsync(d_scal, st);
