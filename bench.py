@@ -50,6 +50,13 @@ def prior_rows_numpy(rng, n):
                      lu(1e3, 1e5)])
 
 
+def shard_bounds(n_total, rank, world):
+    """Contiguous shard [lo, hi) of `n_total` samples owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 def prior_rows_torch(n, device, seed):
     import torch
     g = torch.Generator(device=device)
