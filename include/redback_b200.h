@@ -199,6 +199,42 @@ int rb_ag_eval_f64_host(const rb_ag_config* cfg, int64_t N, int64_t E, const dou
                         const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
                         const double* sigma, const double* sigma_param, double* out_model, double* out_logl);
 
+/* ---- magnitude / bandpass branch (output_format = 'magnitude' | 'flux') ---------------------------------
+ * get_correct_output_format_from_spectra -> RedbackTimeSeriesSource.bandmag -> _bandflux_single_redback
+ * (redback/sed.py:971-1009, 120-195, 10-118) and bandpass_magnitude_to_flux (redback/utils.py:707-718).
+ * Everything in rb_photometry is a HOST pointer: small per-call tables the library uploads itself.
+ * The caller prepares, per band b (what sncosmo does on the host in the reference):
+ *   - the integration grid  wave = arange(minwave + d/2, maxwave, d), d = range / ceil(range / 5 A)
+ *   - int_wt = wave * transmission(wave), band_scale = d / HC_ERG_AA, band_zp = AB zero-point band flux. */
+enum { RB_OUT_MAGNITUDE = 0, RB_OUT_FLUX = 1 };
+typedef struct {
+  int output;                   /* RB_OUT_*                                                         */
+  int n_lambda;
+  const double* lambda_obs;     /* [n_lambda] kwargs 'lambda_array': observer-frame Angstrom grid   */
+  int n_tgrid;                  /* supernova path only: the model time grid                          */
+  const double* tgrid;          /* [n_tgrid] get_optimal_time_array(0.1, 3000, 300) in days          */
+  int n_bands;
+  const int* band_of_epoch;     /* [E]                                                               */
+  const int64_t* band_off;      /* [n_bands + 1] offsets into int_wave / int_wt                      */
+  const double* int_wave;       /* [band_off[n_bands]]                                               */
+  const double* int_wt;
+  const double* band_scale;     /* [n_bands]                                                         */
+  const double* band_zp;        /* [n_bands]                                                         */
+  const double* band_ref_flux;  /* [n_bands] tables/filters.csv reference_flux (RB_OUT_FLUX) or NULL */
+} rb_photometry;
+
+/* Magnitude-branch twins of rb_sn_eval_f64 / rb_kn_eval_f64: same device arguments minus freq_obs
+ * (supernova_models.py:1008-1028, 1510-1530, 1599-1624; kilonova_models.py:1579-1603, 1937-1962).
+ * cfg->sed selects Blackbody / CutoffBlackbody for the supernova path; RB_SED_BOLOMETRIC is invalid. */
+int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
+                       const double* params, const double* t_obs, const double* dl_cm, const double* y,
+                       const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
+                       void* stream);
+int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
+                       const double* params, const double* t_obs, const double* dl_cm, const double* y,
+                       const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
+                       void* stream);
+
 /* Luminosity distance [cm] for N redshifts on device (same quadrature the fused kernels use). */
 int rb_luminosity_distance_f64(const rb_cosmology* cosmo, int64_t N, const double* redshift,
                                double* out_dl_cm, void* stream);

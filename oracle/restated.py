@@ -746,3 +746,153 @@ def redback_afterglow(time, redshift, thv, loge0, thc, logn0, p, logepse, logeps
                     lc[sel] += np.interp(time[sel] / (1 + redshift), tobs, ag_flux(fbb, nuc, num, nu[hh], fmax, p))
                 kk += 1
         return lc * (1 + redshift) / 1e-26
+
+
+# --------------------------------------------------------------------------------------------------
+# magnitude / bandpass branch (sed.py:10-118, 120-195, 911-1009; supernova_models.py:1008-1028 etc.)
+#
+# PARITY UNPINNED: sncosmo (TimeSeriesSource, Bandpass, integration_grid, ABMagSystem) is a third-party
+# dependency that is neither vendored in the reference nor installable here, the reference's tests mock it
+# (test/sed_test.py:436-490) and the golden pickle covers flux_density only.  What follows restates the
+# published sncosmo 2.10 algorithm on top of the same scipy RectBivariateSpline sncosmo uses.
+# --------------------------------------------------------------------------------------------------
+HC_ERG_AA = 1.9864458571489284e-08       # sed.py:19
+MODEL_BANDFLUX_SPACING = 5.0             # sed.py:20
+_C_AA_PER_S = 2.99792458e18
+
+
+class Bandpass:
+    """sncosmo.Bandpass restricted to what the path uses: tabulated transmission, linear interpolation,
+    zero outside [minwave, maxwave]."""
+
+    def __init__(self, name, wave, trans):
+        self.name = name
+        self.wave = np.asarray(wave, dtype=float)
+        self.trans = np.asarray(trans, dtype=float)
+
+    def minwave(self):
+        return self.wave[0]
+
+    def maxwave(self):
+        return self.wave[-1]
+
+    def __call__(self, wave):
+        return np.interp(wave, self.wave, self.trans, left=0.0, right=0.0)
+
+    def zpbandflux_ab(self):
+        """sncosmo ABMagSystem._refspectrum_bandflux: sum(3631e-23 / h / nu * trans * gradient(nu))."""
+        nu = _C_AA_PER_S / self.wave
+        tr = self.trans
+        if nu[0] > nu[-1]:
+            nu, tr = nu[::-1], tr[::-1]
+        f = 3631.e-23 / planck / nu
+        return np.sum(f * tr * np.gradient(nu))
+
+
+def integration_grid(low, high, target_spacing):
+    """sncosmo.utils.integration_grid"""
+    range_diff = high - low
+    spacing = range_diff / int(math.ceil(range_diff / target_spacing))
+    grid = np.arange(low + spacing / 2., high, spacing)
+    return grid, spacing
+
+
+def flux_density_to_spectrum(flux_density_cgs, redshift, lambda_observer_frame):
+    """sed.py:911-934: erg/s/Hz/cm^2 -> (x (1+z)) mJy -> erg/cm^2/s/Angstrom (astropy spectral_density)."""
+    mjy = flux_density_cgs * (1 + redshift) * _ERG_S_CM2_HZ_TO_MJY
+    return mjy * 1e-26 * _C_AA_PER_S / lambda_observer_frame ** 2
+
+
+def clean_spectra(values):
+    """sed.py:985-992"""
+    with np.errstate(all="ignore"):
+        valid = np.isfinite(values) & (values != 0)
+        mean_value = np.nanmean(np.where(valid, values, np.nan)) if valid.any() else np.nan
+    if not np.isfinite(mean_value) or mean_value == 0:
+        mean_value = 1.0
+    return np.where(valid, values, 1e-30 * mean_value)
+
+
+def bandmag_from_spectra(time, time_eval, spectra, lambda_array, bands, bandpasses, time_spline_degree=3):
+    """get_correct_output_format_from_spectra (sed.py:971-1009, output_format='magnitude') ->
+    RedbackTimeSeriesSource.bandmag -> _bandmag_redback -> _bandflux_redback -> _bandflux_single_redback.
+    `bands`: array of band names per epoch; `bandpasses`: {name: Bandpass}."""
+    from scipy.interpolate import RectBivariateSpline
+    spectra = clean_spectra(np.asarray(spectra, dtype=float))
+    if len(time_eval) < 4:
+        time_spline_degree = max(1, min(time_spline_degree, len(time_eval) - 1))
+    spline = RectBivariateSpline(time_eval, lambda_array, spectra, kx=time_spline_degree, ky=3)
+    time = np.atleast_1d(np.asarray(time, dtype=float))
+    bands = np.broadcast_to(np.asarray(bands), time.shape)
+    bandflux = np.zeros(time.shape)
+    for name in set(bands.tolist()):
+        mask = bands == name
+        b = bandpasses[name]
+        if b.minwave() < lambda_array[0] or b.maxwave() > lambda_array[-1]:
+            raise ValueError(f"bandpass {name!r} outside spectral range")              # sed.py:22-28
+        wave, dwave = integration_grid(b.minwave(), b.maxwave(), MODEL_BANDFLUX_SPACING)
+        trans = b(wave)
+        f = np.abs(spline(time[mask], wave))                                           # sed.py:35-36
+        bandflux[mask] = np.sum(wave * trans * f, axis=1) * dwave / HC_ERG_AA          # sed.py:37
+    with np.errstate(all="ignore"):
+        zp = np.array([bandpasses[n].zpbandflux_ab() for n in bands.tolist()])
+        return -2.5 * np.log10(bandflux / zp)                                          # sed.py:111-114
+
+
+def bandpass_magnitude_to_flux(magnitude, reference_flux):
+    """utils.py:707-718 with the per-band reference flux looked up by the caller (tables/filters.csv)."""
+    return 10.0 ** (magnitude / (-2.5)) * reference_flux
+
+
+def sn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, **params):
+    """Magnitude branch of arnett / basic_magnetar_powered / slsn (supernova_models.py:1008-1028, 1510-1530,
+    1599-1624).  `model` in {'arnett', 'basic_magnetar_powered', 'slsn'}."""
+    time_obs = np.asarray(time, dtype=float)
+    lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=float)
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    time_temp = get_optimal_time_array(0.1, 3000, 300)
+    time_observer_frame = time_temp * (1. + redshift)
+    frequency, t = calc_kcorrected_properties(lambda_to_nu(lam), redshift, time_observer_frame)
+    dkw = dict(vej=params["vej"], kappa=params["kappa"], kappa_gamma=params["kappa_gamma"])
+    if model == "arnett":
+        lbol = arnett_bolometric(t, params["f_nickel"], params["mej"], **dkw)
+    else:
+        lbol = basic_magnetar_powered_bolometric(t, params["p0"], params["bp"], params["mass_ns"],
+                                                 params["theta_pb"], mej=params["mej"], **dkw)
+    temp, rad = temperature_floor(t, lbol, params["vej"], params["temperature_floor"])
+    with np.errstate(all="ignore"):
+        if model == "slsn":
+            full = cutoff_blackbody_mjy(t, temp, lbol, rad, frequency[:, None], dl,
+                                        params.get("cutoff_wavelength", 3000.), params.get("absorption_index", 1.0)).T
+            full = full * (1 + redshift)
+            spectra = full * 1e-26 * _C_AA_PER_S / lam ** 2                      # :1613-1616
+        else:
+            fd = blackbody_to_flux_density(temp, rad, dl, frequency[:, None]).T
+            spectra = flux_density_to_spectrum(fd, redshift, lam)
+    return bandmag_from_spectra(time_obs, time_observer_frame, spectra, lam, bands, bandpasses)
+
+
+def kn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, dense_resolution=500,
+                 **params):
+    """Magnitude branch of one_component_kilonova_model / metzger_kilonova_model
+    (kilonova_models.py:1579-1603, 1937-1962)."""
+    time_obs = np.asarray(time, dtype=float)
+    lam = np.geomspace(100, 60000, 200) if lambda_array is None else np.asarray(lambda_array, dtype=float)
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    t_src_s = time_obs * day_to_s / (1. + redshift)
+    time_temp = get_optimal_time_array(1e-2, 7e6, dense_resolution, user_times=t_src_s)
+    if model == "one_component":
+        _, temp, rad = one_component_kilonova_internal(time_temp, params["mej"], params["vej"], params["kappa"],
+                                                       params.get("temperature_floor", 4000))
+    else:
+        _, temp, rad = metzger_kilonova_internal(time_temp, params["mej"], params["vej"], params["beta"],
+                                                 params["kappa"], params.get("neutron_precursor_switch", True),
+                                                 params.get("vmax", 0.7))
+    time_observer_frame = time_temp * (1. + redshift)
+    frequency, _t = calc_kcorrected_properties(lambda_to_nu(lam), redshift, time_observer_frame)
+    with np.errstate(all="ignore"):
+        fd = blackbody_to_flux_density(temp, rad, dl, frequency[:, None]).T
+        spectra = flux_density_to_spectrum(fd, redshift, lam)
+    return bandmag_from_spectra(time_obs, time_observer_frame / day_to_s, spectra, lam, bands, bandpasses)

@@ -26,8 +26,10 @@ class FusedSpec:
         items = []
         for k in sorted(kwargs):
             v = kwargs[k]
-            if k in ("frequency", "bands"):
+            if k == "frequency":
                 continue
+            if k == "bands":
+                v = tuple(np.atleast_1d(np.asarray(v)).tolist())
             items.append((k, v if isinstance(v, (int, float, str, bool, type(None))) else id(v)))
         return (self.name, tuple(items))
 
@@ -82,14 +84,27 @@ def dl_from_kwargs(kwargs, path, N):
     return torch.from_numpy(arr).to(path.device)
 
 
-def flux_density_only(kwargs, name):
+def output_mode(kwargs, name, photometric=True):
+    """kwargs['output_format'] -> 'flux_density' | 'magnitude' | 'flux' (sed.py:971-1009).  'spectra' and
+    'sncosmo_source' return Python objects in the reference and are not fused on device."""
     fmt = kwargs.get("output_format")
     if fmt is None:
         raise KeyError("output_format")
-    if fmt != "flux_density":
-        if fmt in ("magnitude", "flux", "spectra", "sncosmo_source"):
-            raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device yet")
-        raise ValueError("Output format must be 'flux', 'magnitude', 'sncosmo_source', or 'flux_density'")
+    if fmt == "flux_density":
+        return fmt
+    if fmt in ("magnitude", "flux"):
+        if not photometric:
+            raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device")
+        if "bands" not in kwargs:
+            raise KeyError("bands")
+        return fmt
+    if fmt in ("spectra", "sncosmo_source"):
+        raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device")
+    raise ValueError("Output format must be 'flux', 'magnitude', 'sncosmo_source', or 'flux_density'")
+
+
+def flux_density_only(kwargs, name):
+    output_mode(kwargs, name, photometric=False)
 
 
 def run(spec, time, named, kwargs, params_batch):

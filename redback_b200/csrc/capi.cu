@@ -9,6 +9,7 @@
 #include "sn_kernel.cu"
 #include "kn_kernel.cu"
 #include "ag_kernel.cu"
+#include "phot_kernel.cu"
 #include <algorithm>
 #include <vector>
 
@@ -168,7 +169,7 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   double* epoch_tab = ws;
   rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
                                                                     y ? sigma : nullptr, epoch_tab);
-  rb::SnArgs a;
+  rb::SnArgs a{};
   a.cfg = *cfg;
   a.N = N;
   a.E = (int)E;
@@ -180,6 +181,7 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   a.want_logl = y ? 1 : 0;
   a.epoch_tab = epoch_tab;
   a.scalars = ws + (size_t)rb::kEpochCols * (size_t)E;
+  a.param_stride = N;
   rb::sn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
   const int threads = sn_block_threads(E);
   a.epochs_in_smem = (sn_smem_bytes(cfg->dense_resolution, E, true) <= 64 * 1024) ? 1 : 0;
@@ -417,7 +419,7 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
     cudaFreeAsync(ws, st);
     return fail(RB_ERR_INVALID, "rb_kn_eval: epochs must be strictly positive (days)");
   }
-  rb::KnArgs a;
+  rb::KnArgs a{};
   a.cfg = *cfg;
   a.N = N;
   a.E = (int)E;
@@ -429,6 +431,7 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   a.want_logl = y ? 1 : 0;
   a.epoch_tab = epoch_tab;
   a.scalars = scal;
+  a.param_stride = N;
   a.tmin_obs = h_mm[0];
   a.tmax_obs = h_mm[1];
   rb::kn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
@@ -595,7 +598,7 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
   int64_t chunk = chunk_max;
   while (n0 < N && status == RB_OK) {
     const int64_t nc = std::min<int64_t>(chunk, N - n0);
-    rb::AgArgs a;
+    rb::AgArgs a{};
     a.cfg = *cfg;
     a.N = nc;
     a.n_base = n0;
@@ -693,4 +696,420 @@ extern "C" int rb_ag_eval_f64_host(const rb_ag_config* cfg, int64_t N, int64_t E
   if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
   RB_CUDA(cudaDeviceSynchronize());
   return RB_OK;
+}
+
+// ---- magnitude / bandpass branch ---------------------------------------------------------------------------
+namespace {
+
+// FITPACK fpbspl (k = 3) on the host; same arithmetic as the device version
+void host_fpbspl3(const double* t, int l, double x, double h[4]) {
+  double hh[3];
+  h[0] = 1.0;
+  for (int j = 1; j <= 3; ++j) {
+    for (int i = 0; i < j; ++i) hh[i] = h[i];
+    h[0] = 0.0;
+    for (int i = 1; i <= j; ++i) {
+      const int li = l + i, lj = li - j;
+      const double f = hh[i - 1] / (t[li] - t[lj]);
+      h[i - 1] = h[i - 1] + f * (t[li] - x);
+      h[i] = f * (x - t[lj]);
+    }
+  }
+}
+
+std::vector<double> nak_knots(const double* x, int n) {
+  std::vector<double> t((size_t)n + 4);
+  for (int i = 0; i < n + 4; ++i) t[(size_t)i] = (i < 4) ? x[0] : (i >= n ? x[n - 1] : x[i - 2]);
+  return t;
+}
+
+// banded LU (l2, l1, d, u1, u2 per row) of the not-a-knot cubic B-spline collocation matrix on sites x[0..n)
+std::vector<double> collocation_lu(const double* x, int n) {
+  std::vector<double> t = nak_knots(x, n);
+  std::vector<double> lu((size_t)5 * n, 0.0);
+  for (int i = 0; i < n; ++i) {
+    double* row = &lu[(size_t)5 * i];
+    if (i == 0 || i == n - 1) { row[2] = 1.0; continue; }
+    const int l = (i == 1) ? 3 : ((i >= n - 2) ? n - 1 : i + 2);
+    double h[4];
+    host_fpbspl3(t.data(), l, x[i], h);
+    for (int q = 0; q < 4; ++q) {
+      const int off = (l - 3 + q) - i + 2;
+      if (off >= 0 && off < 5) row[off] = h[q];
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    double* r = &lu[(size_t)5 * i];
+    double l2 = 0.0, l1 = 0.0, am1 = r[1], d = r[2], u1 = r[3];
+    if (i >= 2) {
+      const double* r2 = &lu[(size_t)5 * (i - 2)];
+      l2 = r[0] / r2[2];
+      am1 -= l2 * r2[3];
+      d -= l2 * r2[4];
+    }
+    if (i >= 1) {
+      const double* r1 = &lu[(size_t)5 * (i - 1)];
+      l1 = am1 / r1[2];
+      d -= l1 * r1[3];
+      u1 -= l1 * r1[4];
+    }
+    r[0] = l2; r[1] = l1; r[2] = d; r[3] = u1;
+  }
+  return lu;
+}
+
+struct PhotDevice {
+  // device copies of the per-call tables; freed stream-ordered by release()
+  std::vector<void*> allocs;
+  cudaStream_t st;
+  template <typename T>
+  cudaError_t upload(const std::vector<T>& h, const T** out) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(h.size(), 1) * sizeof(T), st);
+    if (e != cudaSuccess) return e;
+    allocs.push_back(p);
+    if (!h.empty()) e = cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    *out = (const T*)p;
+    return e;
+  }
+  void release() {
+    for (void* p : allocs) cudaFreeAsync(p, st);
+    allocs.clear();
+  }
+};
+
+int phot_check(const rb_photometry* ph, int64_t E, bool need_tgrid) {
+  if (!ph) return fail(RB_ERR_INVALID, "rb_*_mag_eval: null photometry");
+  if (ph->output != RB_OUT_MAGNITUDE && ph->output != RB_OUT_FLUX)
+    return fail(RB_ERR_INVALID, "Output format must be 'flux', 'magnitude', 'sncosmo_source', or 'flux_density'");
+  if (ph->n_lambda < 8 || ph->n_lambda > 1024 || !ph->lambda_obs)
+    return fail(RB_ERR_INVALID, "rb_*_mag_eval: lambda_array needs 8..1024 points");
+  if (need_tgrid && (ph->n_tgrid < 8 || ph->n_tgrid > 2000 || !ph->tgrid))
+    return fail(RB_ERR_INVALID, "rb_sn_mag_eval: time grid needs 8..2000 points");
+  if (ph->n_bands < 1 || !ph->band_of_epoch || !ph->band_off || !ph->int_wave || !ph->int_wt || !ph->band_scale ||
+      !ph->band_zp)
+    return fail(RB_ERR_INVALID, "rb_*_mag_eval: incomplete band tables");
+  if (ph->output == RB_OUT_FLUX && !ph->band_ref_flux)
+    return fail(RB_ERR_INVALID, "rb_*_mag_eval: band_ref_flux is required for flux output");
+  for (int64_t e = 0; e < E; ++e)
+    if (ph->band_of_epoch[e] < 0 || ph->band_of_epoch[e] >= ph->n_bands)
+      return fail(RB_ERR_INVALID, "rb_*_mag_eval: band_of_epoch out of range");
+  for (int i = 1; i < ph->n_lambda; ++i)
+    if (!(ph->lambda_obs[i] > ph->lambda_obs[i - 1]))
+      return fail(RB_ERR_INVALID, "rb_*_mag_eval: lambda_array must be strictly increasing");
+  return RB_OK;
+}
+
+// Build and upload everything phot_kernel needs that does not depend on the sample.
+int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotArgs& pa) {
+  const int NL = ph->n_lambda;
+  std::vector<double> lam(ph->lambda_obs, ph->lambda_obs + NL);
+  std::vector<double> lu_l = collocation_lu(lam.data(), NL);
+  std::vector<double> tk = nak_knots(lam.data(), NL);
+  const int64_t total = ph->band_off[ph->n_bands];
+  std::vector<int> ly((size_t)total), boff((size_t)ph->n_bands + 1), jlo((size_t)ph->n_bands), span((size_t)ph->n_bands);
+  std::vector<double> wy((size_t)total * 4), wt(ph->int_wt, ph->int_wt + total);
+  for (int b = 0; b <= ph->n_bands; ++b) boff[(size_t)b] = (int)ph->band_off[b];
+  for (int b = 0; b < ph->n_bands; ++b) {
+    int lo = NL, hi = -1;
+    if (ph->band_off[b + 1] <= ph->band_off[b]) return fail(RB_ERR_INVALID, "rb_*_mag_eval: empty band");
+    for (int64_t w = ph->band_off[b]; w < ph->band_off[b + 1]; ++w) {
+      double x = ph->int_wave[w];
+      if (x < lam[0] || x > lam[(size_t)NL - 1])   // sed.py:22-28
+        return fail(RB_ERR_INVALID, "bandpass outside spectral range of lambda_array");
+      int l = 3;
+      for (int lo2 = 4, hi2 = NL - 1; lo2 <= hi2;) {
+        const int mid = (lo2 + hi2) >> 1;
+        if (lam[(size_t)mid - 2] <= x) { l = mid; lo2 = mid + 1; } else hi2 = mid - 1;
+      }
+      double h[4];
+      host_fpbspl3(tk.data(), l, x, h);
+      ly[(size_t)w] = l - 3;
+      for (int q = 0; q < 4; ++q) wy[(size_t)w * 4 + q] = h[q];
+      lo = std::min(lo, l - 3);
+      hi = std::max(hi, l);
+    }
+    jlo[(size_t)b] = lo;
+    span[(size_t)b] = hi - lo + 1;
+    if (span[(size_t)b] > rb::kPhotMaxSpan)
+      return fail(RB_ERR_UNSUPPORTED, "rb_*_mag_eval: a band overlaps too many wavelength-grid points");
+  }
+  std::vector<int> boe(ph->band_of_epoch, ph->band_of_epoch + E);
+  std::vector<double> scale(ph->band_scale, ph->band_scale + ph->n_bands), zp(ph->band_zp, ph->band_zp + ph->n_bands);
+  std::vector<double> ref;
+  if (ph->band_ref_flux) ref.assign(ph->band_ref_flux, ph->band_ref_flux + ph->n_bands);
+  cudaError_t e = dev.upload(lam, &pa.lambda_obs);
+  if (e == cudaSuccess) e = dev.upload(lu_l, &pa.lu_lambda);
+  if (e == cudaSuccess) e = dev.upload(boe, &pa.band_of_epoch);
+  if (e == cudaSuccess) e = dev.upload(boff, &pa.band_off);
+  if (e == cudaSuccess) e = dev.upload(jlo, &pa.band_jlo);
+  if (e == cudaSuccess) e = dev.upload(span, &pa.band_span);
+  if (e == cudaSuccess) e = dev.upload(scale, &pa.band_scale);
+  if (e == cudaSuccess) e = dev.upload(zp, &pa.band_zp);
+  if (e == cudaSuccess) e = dev.upload(ref, &pa.band_ref);
+  if (e == cudaSuccess) e = dev.upload(wt, &pa.int_wt);
+  if (e == cudaSuccess) e = dev.upload(ly, &pa.int_ly);
+  if (e == cudaSuccess) e = dev.upload(wy, &pa.int_wy);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(dev.st);   // host vectors go out of scope
+  if (e != cudaSuccess) return cuda_fail(e, "photometry table upload");
+  pa.n_lambda = NL;
+  pa.output = ph->output;
+  return RB_OK;
+}
+
+size_t phot_smem_bytes(int NT, int NL) {
+  return sizeof(double) * ((size_t)7 * NT + 5 * (size_t)NL + (size_t)rb::kPhotTileRows * (NL + 1) + 40 + 256);
+}
+
+}  // namespace
+
+extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
+                                  const double* params, const double* t_obs, const double* dl_cm, const double* y,
+                                  const double* sigma, const double* sigma_param, double* out_model,
+                                  double* out_logl, void* stream) {
+  static const double dummy = 0.0;
+  int rc = sn_check(cfg, N, E, params, t_obs, &dummy, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (cfg->sed == RB_SED_BOLOMETRIC) return fail(RB_ERR_INVALID, "rb_sn_mag_eval: bolometric models have no magnitude output");
+  rc = phot_check(phot, E, true);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev_id = 0, sms = 0;
+  RB_CUDA(cudaGetDevice(&dev_id));
+  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(rb::sn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute");
+  const int NT = phot->n_tgrid, NL = phot->n_lambda;
+  const size_t psmem = phot_smem_bytes(NT, NL);
+  if (psmem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_sn_mag_eval: grids exceed shared memory");
+
+  PhotDevice pd;
+  pd.st = st;
+  rb::PhotArgs pa{};
+  rc = phot_prepare(phot, E, pd, pa);
+  if (rc != RB_OK) { pd.release(); return rc; }
+  std::vector<double> tg(phot->tgrid, phot->tgrid + NT);
+  std::vector<double> lu_t = collocation_lu(tg.data(), NT);
+  const double* d_tgrid = nullptr;
+  cudaError_t ce = pd.upload(tg, &d_tgrid);
+  if (ce == cudaSuccess) ce = pd.upload(lu_t, &pa.lu_time);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "time grid upload"); }
+
+  // epoch tables: one for the model grid (sn_kernel in grid mode), one for the observed epochs (phot_kernel)
+  double *d_ep_grid = nullptr, *d_ep_obs = nullptr;
+  ce = cudaMallocAsync(&d_ep_grid, (size_t)rb::kEpochCols * NT * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_ep_obs, (size_t)rb::kEpochCols * E * sizeof(double), st);
+  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "epoch tables"); }
+  rb::epoch_table_kernel<<<(unsigned)((NT + 255) / 256), 256, 0, st>>>(NT, RB_SIGMA_FIXED, d_tgrid, nullptr, nullptr,
+                                                                     nullptr, d_ep_grid);
+  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, nullptr, y,
+                                                                    y ? sigma : nullptr, d_ep_obs);
+  launch_counter()->fetch_add(2);
+
+  const int64_t chunk_max = 32768;
+  const int sn_threads = sn_block_threads(NT);
+  const int ep_in_smem = (sn_smem_bytes(cfg->dense_resolution, NT, true) <= 64 * 1024) ? 1 : 0;
+  const size_t sn_smem = sn_smem_bytes(cfg->dense_resolution, NT, ep_in_smem != 0);
+  int occ_sn = 1, occ_ph = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sn, rb::sn_kernel, sn_threads, sn_smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
+  if (occ_sn < 1) occ_sn = 1;
+  if (occ_ph < 1) occ_ph = 1;
+  const int64_t ph_grid_max = (int64_t)sms * occ_ph;
+  double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_scal = nullptr, *d_scratch = nullptr;
+  const int64_t nc_max = std::min<int64_t>(chunk_max, N);
+  ce = cudaMallocAsync(&d_grid, (size_t)nc_max * 4 * NT * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_opz, (size_t)nc_max * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dl, (size_t)nc_max * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_scal, (size_t)nc_max * rb::kScalars * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_scratch, (size_t)std::min<int64_t>(ph_grid_max, nc_max) * NT * NL * sizeof(double), st);
+  int status = RB_OK;
+  if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude workspace");
+  for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
+    const int64_t nc = std::min<int64_t>(chunk_max, N - n0);
+    rb::SnArgs a{};
+    a.cfg = *cfg;
+    a.N = nc;
+    a.E = NT;
+    a.params = params + n0;          // SoA rows are N_total apart: handled through the stride below
+    a.dl_cm = dl_cm ? dl_cm + n0 : nullptr;
+    a.sigma_param = nullptr;
+    a.out_model = nullptr;
+    a.out_logl = nullptr;
+    a.want_logl = 0;
+    a.epoch_tab = d_ep_grid;
+    a.scalars = d_scal;
+    a.grid_mode = 1;
+    a.grid_out = d_grid;
+    a.opz_out = d_opz;
+    a.dl_out = d_dl;
+    a.param_stride = N;
+    a.epochs_in_smem = ep_in_smem;
+    rb::sn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
+    rb::sn_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_sn * 4), sn_threads, sn_smem, st>>>(a);
+    pa.N = nc;
+    pa.n_base = n0;
+    pa.E = (int)E;
+    pa.n_t_max = NT;
+    pa.sed = (cfg->sed == RB_SED_CUTOFF_BLACKBODY) ? rb::PH_SED_CUTOFF : rb::PH_SED_BLACKBODY;
+    pa.sigma_mode = cfg->sigma_mode;
+    pa.want_logl = y ? 1 : 0;
+    pa.common_time_lu = 1;
+    pa.cutoff_wavelength = cfg->cutoff_wavelength;
+    pa.absorption_index = cfg->absorption_index;
+    pa.grid = d_grid;
+    pa.grid_len = nullptr;
+    pa.opz = d_opz;
+    pa.dl = d_dl;
+    pa.sigma_param_s = sigma_param ? sigma_param + n0 : nullptr;
+    pa.epoch_tab = d_ep_obs;
+    pa.scratch = d_scratch;
+    pa.out_model = out_model;
+    pa.out_logl = y ? out_logl : nullptr;
+    rb::phot_kernel<<<(unsigned)std::min<int64_t>(ph_grid_max, nc), rb::kPhotThreads, psmem, st>>>(pa);
+    launch_counter()->fetch_add(3);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude kernels");
+  }
+  cudaFreeAsync(d_scratch, st);
+  cudaFreeAsync(d_scal, st);
+  cudaFreeAsync(d_dl, st);
+  cudaFreeAsync(d_opz, st);
+  cudaFreeAsync(d_grid, st);
+  cudaFreeAsync(d_ep_obs, st);
+  cudaFreeAsync(d_ep_grid, st);
+  pd.release();
+  return status;
+}
+
+extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
+                                  const double* params, const double* t_obs, const double* dl_cm, const double* y,
+                                  const double* sigma, const double* sigma_param, double* out_model,
+                                  double* out_logl, void* stream) {
+  static const double dummy = 0.0;
+  int rc = kn_check(cfg, N, E, params, t_obs, &dummy, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  rc = phot_check(phot, E, false);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev_id = 0, sms = 0;
+  RB_CUDA(cudaGetDevice(&dev_id));
+  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(rb::kn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute");
+  const int NT = cfg->dense_resolution, NL = phot->n_lambda;
+  const size_t psmem = phot_smem_bytes(NT, NL);
+  if (psmem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_kn_mag_eval: grids exceed shared memory");
+  PhotDevice pd;
+  pd.st = st;
+  rb::PhotArgs pa{};
+  rc = phot_prepare(phot, E, pd, pa);
+  if (rc != RB_OK) { pd.release(); return rc; }
+
+  double *d_ep_obs = nullptr, *d_mm = nullptr;
+  cudaError_t ce = cudaMallocAsync(&d_ep_obs, (size_t)rb::kEpochCols * E * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_mm, 2 * sizeof(double), st);
+  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "epoch tables"); }
+  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, nullptr, y,
+                                                                    y ? sigma : nullptr, d_ep_obs);
+  minmax_kernel<<<1, 256, 0, st>>>((int)E, t_obs, d_mm);
+  double h_mm[2];
+  ce = cudaMemcpyAsync(h_mm, d_mm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  launch_counter()->fetch_add(2);
+  int status = RB_OK;
+  if (ce != cudaSuccess) status = cuda_fail(ce, "epoch min/max");
+  else if (!(h_mm[0] > 0.0)) status = fail(RB_ERR_INVALID, "rb_kn_mag_eval: epochs must be strictly positive (days)");
+
+  const int64_t chunk_max = 32768;
+  rb_kn_config kcfg = *cfg;
+  const size_t ksmem = kn_smem_bytes(&kcfg, 1);
+  int occ_kn = 1, occ_ph = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_kn, rb::kn_kernel, 512, ksmem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
+  if (occ_kn < 1) occ_kn = 1;
+  if (occ_ph < 1) occ_ph = 1;
+  const int64_t ph_grid_max = (int64_t)sms * occ_ph;
+  const int64_t nc_max = std::min<int64_t>(chunk_max, N);
+  double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_scal = nullptr, *d_scratch = nullptr, *d_ep1 = nullptr;
+  int* d_len = nullptr;
+  if (status == RB_OK) {
+    ce = cudaMallocAsync(&d_grid, (size_t)nc_max * 4 * NT * sizeof(double), st);
+    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_opz, (size_t)nc_max * sizeof(double), st);
+    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dl, (size_t)nc_max * sizeof(double), st);
+    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_len, (size_t)nc_max * sizeof(int), st);
+    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_scal, (size_t)nc_max * rb::kKnScalars * sizeof(double), st);
+    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_ep1, (size_t)rb::kEpochCols * sizeof(double), st);
+    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_scratch, (size_t)std::min<int64_t>(ph_grid_max, nc_max) * NT * NL * sizeof(double), st);
+    if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude workspace");
+  }
+  for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
+    const int64_t nc = std::min<int64_t>(chunk_max, N - n0);
+    rb::KnArgs a{};
+    a.cfg = *cfg;
+    a.N = nc;
+    a.E = 1;                       // the kernel only stages the epoch table; unused in grid mode
+    a.params = params + n0;
+    a.param_stride = N;
+    a.dl_cm = dl_cm ? dl_cm + n0 : nullptr;
+    a.want_logl = 0;
+    a.epoch_tab = d_ep1;
+    a.scalars = d_scal;
+    a.tmin_obs = h_mm[0];
+    a.tmax_obs = h_mm[1];
+    a.grid_mode = 1;
+    a.grid_out = d_grid;
+    a.grid_len = d_len;
+    a.opz_out = d_opz;
+    a.dl_out = d_dl;
+    rb::kn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
+    rb::kn_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_kn * 4), 512, ksmem, st>>>(a);
+    pa.N = nc;
+    pa.n_base = n0;
+    pa.E = (int)E;
+    pa.n_t_max = NT;
+    pa.sed = rb::PH_SED_BLACKBODY;
+    pa.sigma_mode = cfg->sigma_mode;
+    pa.want_logl = y ? 1 : 0;
+    pa.common_time_lu = 0;
+    pa.grid = d_grid;
+    pa.grid_len = d_len;
+    pa.opz = d_opz;
+    pa.dl = d_dl;
+    pa.sigma_param_s = sigma_param ? sigma_param + n0 : nullptr;
+    pa.epoch_tab = d_ep_obs;
+    pa.scratch = d_scratch;
+    pa.out_model = out_model;
+    pa.out_logl = y ? out_logl : nullptr;
+    rb::phot_kernel<<<(unsigned)std::min<int64_t>(ph_grid_max, nc), rb::kPhotThreads, psmem, st>>>(pa);
+    launch_counter()->fetch_add(3);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude kernels");
+  }
+  cudaFreeAsync(d_scratch, st);
+  cudaFreeAsync(d_ep1, st);
+  cudaFreeAsync(d_scal, st);
+  cudaFreeAsync(d_len, st);
+  cudaFreeAsync(d_dl, st);
+  cudaFreeAsync(d_opz, st);
+  cudaFreeAsync(d_grid, st);
+  cudaFreeAsync(d_mm, st);
+  cudaFreeAsync(d_ep_obs, st);
+  pd.release();
+  return status;
 }

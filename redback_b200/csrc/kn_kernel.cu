@@ -46,6 +46,14 @@ struct KnArgs {
   double* scalars;
   double tmin_obs, tmax_obs;  // min / max of the observer-frame epochs [days]
   int want_logl;
+  // grid mode (magnitude branch, kilonova_models.py:1579-1603): write T, R and the observer-frame phase
+  // (time_temp*(1+z))/86400 on the model grid for phot_kernel instead of evaluating the epochs
+  int64_t param_stride;  // distance between SoA rows of `params` (= total batch size)
+  int grid_mode;
+  double* grid_out;   // [N][4][dense_resolution]
+  int* grid_len;      // [N]
+  double* opz_out;    // [N]
+  double* dl_out;     // [N]
 };
 
 // ---- correctly rounded atan for large arguments ------------------------------------------------------
@@ -104,7 +112,7 @@ __global__ void kn_prep_kernel(const KnArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= a.N) return;
-  const int64_t N = a.N;
+  const int64_t N = a.param_stride;
   const double* P = a.params + n;
   const double z = P[RB_KN_REDSHIFT * N];
   const double opz = 1.0 + z;
@@ -360,9 +368,21 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
     }
     __syncthreads();
 
+    const double opz = sc[KS_OPZ];
+    if (a.grid_mode) {
+      double* go = a.grid_out + (size_t)n * 4 * R;
+      for (int k = tid; k < G; k += blockDim.x) {
+        go[0 * R + k] = Tg[k];
+        go[1 * R + k] = Rg[k];
+        go[2 * R + k] = 0.0;
+        go[3 * R + k] = (tg[k] * opz) / kDay;                                  // :1580, :1600
+      }
+      if (tid == 0) { a.grid_len[n] = G; a.opz_out[n] = opz; a.dl_out[n] = sc[KS_DL]; }
+      __syncthreads();
+      continue;
+    }
     // ---- phase B: epochs -----------------------------------------------------------------------
     double logl_part = 0.0;
-    const double opz = sc[KS_OPZ];
     for (int e = tid; e < E; e += blockDim.x) {
       const double t = (ep[EP_T * E + e] * kDay) / opz;                        // :1563, utils.py:382
       const double nu = ep[EP_NU * E + e] * opz;

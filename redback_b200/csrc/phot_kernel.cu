@@ -1,0 +1,365 @@
+// redback_b200 -- spectral grid -> bicubic spline -> bandpass synthetic photometry -> magnitudes (+ log L).
+//
+// Reference path (output_format = 'magnitude' | 'flux'):
+//   blackbody_to_spectrum / flux_density_to_spectrum             redback/sed.py:911-968
+//   get_correct_output_format_from_spectra                       redback/sed.py:971-1009
+//   RedbackTimeSeriesSource (sncosmo.TimeSeriesSource: scipy RectBivariateSpline(phase, wave, flux, kx=3, ky=3),
+//     i.e. FITPACK regrid with s = 0: the interpolating not-a-knot bicubic tensor spline)   redback/sed.py:120-195
+//   _bandflux_single_redback / _bandflux_redback / _bandmag_redback                        redback/sed.py:10-118
+//   bandpass_magnitude_to_flux                                   redback/utils.py:707-718
+//
+// One persistent block per sample works on a private N_t x N_lambda scratch tile in global memory (L2):
+//   1. spectra S[k][j] from the model's (T_k, R_k[, L_k]) on its time grid         (all threads, elementwise)
+//   2. clean: non-finite / zero -> 1e-30 * mean(valid)                              (block reduction)
+//   3. spline coefficients C = A_t^-1 S A_lambda^-T: banded (pentadiagonal) LU of the B-spline collocation
+//      matrices, no pivoting (totally positive); time axis: one thread per wavelength column; wavelength
+//      axis: one thread per time row, staged through shared-memory tiles
+//   4. one thread per epoch: FITPACK fpbspl time basis, contraction over time, then the band's 5-Angstrom
+//      integration grid with host-precomputed wavelength bases; |f| is summed as the reference does
+//   5. magnitude / flux, Gaussian log-likelihood term, block reduction.
+#include "rb_common.cuh"
+
+namespace rb {
+
+constexpr int kPhotThreads = 256;
+constexpr int kPhotMaxSpan = 96;     // max B-spline coefficients (along wavelength) overlapped by one band
+constexpr int kPhotTileRows = 32;    // rows per shared-memory tile in the wavelength-axis solve
+
+enum { PH_SED_BLACKBODY = 1, PH_SED_CUTOFF = 2 };
+enum { PH_T = 0, PH_R, PH_L, PH_X, kPhotGridCols };   // per-sample model grid: temperature, radius, L_bol, phase
+
+struct PhotArgs {
+  int64_t N;
+  int64_t n_base;
+  int E;
+  int n_t_max;            // allocated grid length per sample
+  int n_lambda;
+  int sed;                // PH_SED_*
+  int output;             // RB_OUT_MAGNITUDE | RB_OUT_FLUX
+  int sigma_mode;
+  int want_logl;
+  int common_time_lu;     // 1: time-axis LU supplied (grid identical up to scaling for all samples)
+  double cutoff_wavelength, absorption_index;
+  const double* grid;     // [N][kPhotGridCols][n_t_max]   (written by the model kernels in grid mode)
+  const int* grid_len;    // [N] or nullptr (= n_t_max)
+  const double* opz;      // [N] 1 + z
+  const double* dl;       // [N]
+  const double* sigma_param_s;  // [N] sampled sigma (already sliced to the chunk) or nullptr
+  const double* lambda_obs;     // [n_lambda]
+  const double* lu_lambda;      // [n_lambda][5]: l2, l1, d, u1, u2
+  const double* lu_time;        // [n_t_max][5] when common_time_lu
+  const double* epoch_tab;      // [kEpochCols][E] (EP_T = observer-frame days)
+  const int* band_of_epoch;     // [E]
+  const int* band_off;          // [n_bands + 1] into the integration-grid arrays
+  const int* band_jlo;          // [n_bands] first wavelength coefficient used by the band
+  const int* band_span;         // [n_bands] number of coefficients used
+  const double* band_scale;     // [n_bands] dwave / HC_ERG_AA
+  const double* band_zp;        // [n_bands]
+  const double* band_ref;       // [n_bands] reference flux ('flux' output) or nullptr
+  const double* int_wt;         // [total] wave * trans
+  const int* int_ly;            // [total] first coefficient of the 4 non-zero wavelength B-splines
+  const double* int_wy;         // [total][4] their values
+  double* scratch;              // [gridDim][n_t_max][n_lambda]
+  double* out_model;
+  double* out_logl;
+};
+
+// FITPACK fpbspl for k = 3: the four non-zero cubic B-splines at x, t[l] <= x < t[l+1] (0-based l)
+__device__ __forceinline__ void fpbspl3(const double* __restrict__ t, int l, double x, double h[4]) {
+  double hh[3];
+  h[0] = 1.0;
+#pragma unroll
+  for (int j = 1; j <= 3; ++j) {
+#pragma unroll
+    for (int i = 0; i < j; ++i) hh[i] = h[i];
+    h[0] = 0.0;
+#pragma unroll
+    for (int i = 1; i <= j; ++i) {
+      const int li = l + i, lj = li - j;
+      const double f = hh[i - 1] / (t[li] - t[lj]);
+      h[i - 1] = h[i - 1] + f * (t[li] - x);
+      h[i] = f * (x - t[lj]);
+    }
+  }
+}
+
+// knot vector of the interpolating (not-a-knot) cubic spline through x[0..n): t[0..3] = x0, t[4..n-1] = x[2..n-3],
+// t[n..n+3] = x[n-1]   (FITPACK fpregr/fpgrre with s = 0)
+__device__ __forceinline__ double nak_knot(const double* __restrict__ x, int n, int i) {
+  if (i < 4) return x[0];
+  if (i >= n) return x[n - 1];
+  return x[i - 2];
+}
+
+// CutoffBlackbody normalisation for one time (sed.py:386-421); mirrors cutoff_blackbody_mjy in sn_kernel.cu
+__device__ double cutoff_norm(double lbol, double rph, double tph, double lam_c, double alpha) {
+  const int s = (int)(4.0 - alpha + 0.5);
+  double norm = lbol / (kFluxConst / kAngstrom * (rph * rph) * tph);
+  const double kt_hc = tph / kXConst;
+  const double x_c = 1.0 / (lam_c * kt_hc);
+  const double e1 = exp(-x_c);
+  double en = 1.0, above = 0.0, below = 0.0;
+  for (int i = 1; i <= 10; ++i) {
+    en *= e1;
+    const double di = (double)i;
+    const double xi = x_c * di;
+    double ns = di;
+    for (int q = 1; q < s; ++q) ns *= di;
+    above += gammainc4(xi, en) / (di * di * di * di);
+    below += gammaincc_int(s, xi, en) / ns;
+  }
+  const double kt2 = kt_hc * kt_hc;
+  double kts = kt_hc, gam = 1.0;
+  for (int q = 1; q < s; ++q) { kts *= kt_hc; gam *= (double)q; }
+  above = kt2 * kt2 * 6.0 * above;
+  below = (1.0 / pow(lam_c, alpha)) * kts * gam * below;
+  return norm / ((above + below) / tph);
+}
+
+__global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
+  extern __shared__ double psm[];
+  const int NT = a.n_t_max, NL = a.n_lambda, E = a.E;
+  double* xk = psm;                       // [NT]      time-axis data sites (observer-frame phase, days)
+  double* lut = xk + NT;                  // [NT][5]   time-axis banded LU
+  double* lul = lut + 5 * NT;             // [NL][5]   wavelength-axis banded LU
+  double* aux = lul + 5 * NL;             // [NT]      per-time scalar (cutoff norm)
+  double* tile = aux + NT;                // [kPhotTileRows][NL + 1]
+  double* red = tile + kPhotTileRows * (NL + 1);   // [40]
+  double* tab = red + 40;                 // [256]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 256; i += blockDim.x) tab[i] = RB_EXP2_256[i];
+  for (int i = tid; i < 5 * NL; i += blockDim.x) lul[i] = a.lu_lambda[i];
+  double* S = a.scratch + (size_t)blockIdx.x * NT * NL;
+  __syncthreads();
+
+  for (int64_t n = blockIdx.x; n < a.N; n += gridDim.x) {
+    const int G = a.grid_len ? a.grid_len[n] : NT;
+    const double* gT = a.grid + (size_t)n * kPhotGridCols * NT + PH_T * NT;
+    const double* gR = a.grid + (size_t)n * kPhotGridCols * NT + PH_R * NT;
+    const double* gL = a.grid + (size_t)n * kPhotGridCols * NT + PH_L * NT;
+    const double* gX = a.grid + (size_t)n * kPhotGridCols * NT + PH_X * NT;
+    const double opz = a.opz[n], dl = a.dl[n];
+    const double lam_c = a.cutoff_wavelength * kAngstrom;
+    for (int k = tid; k < G; k += blockDim.x) {
+      xk[k] = gX[k];
+      if (a.sed == PH_SED_CUTOFF) aux[k] = cutoff_norm(gL[k], gR[k], gT[k], lam_c, a.absorption_index);
+    }
+    if (a.common_time_lu) for (int i = tid; i < 5 * G; i += blockDim.x) lut[i] = a.lu_time[i];
+    __syncthreads();
+
+    // ---- 1. spectra + statistics for the clean-up -------------------------------------------------------
+    double vsum = 0.0, vcnt = 0.0;
+    const double inv_den = 1.0 / ((dl * dl) * (kC * kC));
+    for (int idx = tid; idx < G * NL; idx += blockDim.x) {
+      const int k = idx / NL, j = idx - k * NL;
+      const double lam_obs = a.lambda_obs[j];
+      const double nu = (kCSI / (lam_obs * 1.e-10)) * opz;                       // utils.py:357-362, 383
+      const double T = gT[k], R = gR[k];
+      double mjy;
+      if (a.sed == PH_SED_BLACKBODY) {
+        const double num = 2 * kPi * kH * (nu * nu * nu) * (R * R);             // sed.py:216
+        const double frac = 1.0 / expm1_fast((kH * nu) / (kKB * T), tab);
+        mjy = num * inv_den * frac * opz * kToMJy;                               // sed.py:929
+      } else {
+        const double lam_A = 1.e10 * (kCSI / nu);
+        const double lam = lam_A * kAngstrom;
+        const double l2 = lam * lam, l5 = l2 * l2 * lam;
+        const double em = expm1_fast(kXConst / lam / T, tab);
+        double sedv = (lam < lam_c) ? kFluxConst * ((R * R) * pow(lam / lam_c, a.absorption_index) / l5) / em
+                                    : kFluxConst * ((R * R) / l5) / em;          // sed.py:362-384
+        sedv *= aux[k];
+        double fd = sedv / (4 * kPi * (dl * dl));
+        fd *= lam_A;
+        fd /= nu;
+        mjy = fd * kToMJy * opz;                                                 // supernova_models.py:1611-1612
+      }
+      const double v = mjy * 1e-26 * 2.99792458e18 / (lam_obs * lam_obs);       // mJy -> erg/cm^2/s/Angstrom
+      S[idx] = v;
+      if (isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
+    }
+    // ---- 2. clean-up value (sed.py:985-992) ---------------------------------------------------------------
+    vsum = warp_sum(vsum);
+    vcnt = warp_sum(vcnt);
+    if (lane == 0) { red[warp] = vsum; red[8 + warp] = vcnt; }
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0, c = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s += red[w]; c += red[8 + w]; }
+      double mean = (c > 0) ? s / c : NAN;
+      if (!isfinite(mean) || mean == 0.0) mean = 1.0;
+      red[32] = 1e-30 * mean;
+    }
+    // ---- 3a. time-axis collocation + LU when the grid is per-sample ----------------------------------------
+    if (!a.common_time_lu) {
+      for (int i = tid; i < G; i += blockDim.x) {
+        // row i of B_j(x_i): interval l with t[l] <= x_i < t[l+1]; non-zero columns l-3..l
+        double row[5] = {0, 0, 0, 0, 0};   // columns i-2..i+2
+        if (i == 0) row[2] = 1.0;
+        else if (i == G - 1) row[2] = 1.0;
+        else {
+          int l;
+          if (i == 1) l = 3;
+          else if (i >= G - 2) l = G - 1;
+          else l = i + 2;
+          double tl[8];
+          for (int q = 0; q < 8; ++q) tl[q] = nak_knot(xk, G, l - 3 + q);
+          double h[4];
+          fpbspl3(tl, 3, xk[i], h);
+          for (int q = 0; q < 4; ++q) {
+            const int col = l - 3 + q, off = col - i + 2;
+            if (off >= 0 && off < 5) row[off] = h[q];
+          }
+        }
+        for (int q = 0; q < 5; ++q) lut[5 * i + q] = row[q];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        // banded LU without pivoting, in place: row -> (l2, l1, d, u1, u2)
+        for (int i = 0; i < G; ++i) {
+          double l2 = 0.0, l1 = 0.0;
+          double am1 = lut[5 * i + 1], d = lut[5 * i + 2], u1 = lut[5 * i + 3];
+          if (i >= 2) {
+            l2 = lut[5 * i + 0] / lut[5 * (i - 2) + 2];
+            am1 -= l2 * lut[5 * (i - 2) + 3];
+            d -= l2 * lut[5 * (i - 2) + 4];
+          }
+          if (i >= 1) {
+            l1 = am1 / lut[5 * (i - 1) + 2];
+            d -= l1 * lut[5 * (i - 1) + 3];
+            u1 -= l1 * lut[5 * (i - 1) + 4];
+          }
+          lut[5 * i + 0] = l2;
+          lut[5 * i + 1] = l1;
+          lut[5 * i + 2] = d;
+          lut[5 * i + 3] = u1;
+        }
+      }
+    }
+    __syncthreads();
+    const double repl = red[32];
+
+    // ---- 3b. time-axis solve: one thread per wavelength column (coalesced across columns) ------------------
+    for (int j = tid; j < NL; j += blockDim.x) {
+      double y1 = 0.0, y2 = 0.0;   // y[i-1], y[i-2]
+      for (int i = 0; i < G; ++i) {
+        double b = S[i * NL + j];
+        if (!(isfinite(b) && b != 0.0)) b = repl;
+        const double y = b - lut[5 * i + 1] * y1 - lut[5 * i + 0] * y2;
+        S[i * NL + j] = y;
+        y2 = y1;
+        y1 = y;
+      }
+      double x1 = 0.0, x2 = 0.0;   // x[i+1], x[i+2]
+      for (int i = G - 1; i >= 0; --i) {
+        const double x = (S[i * NL + j] - lut[5 * i + 3] * x1 - lut[5 * i + 4] * x2) / lut[5 * i + 2];
+        S[i * NL + j] = x;
+        x2 = x1;
+        x1 = x;
+      }
+    }
+    __syncthreads();
+    // ---- 3c. wavelength-axis solve: tiles of rows through shared memory ------------------------------------
+    for (int r0 = 0; r0 < G; r0 += kPhotTileRows) {
+      const int rows = min(kPhotTileRows, G - r0);
+      for (int idx = tid; idx < rows * NL; idx += blockDim.x) {
+        const int r = idx / NL, j = idx - r * NL;
+        tile[r * (NL + 1) + j] = S[(r0 + r) * NL + j];
+      }
+      __syncthreads();
+      if (tid < rows) {
+        double* row = tile + tid * (NL + 1);
+        double y1 = 0.0, y2 = 0.0;
+        for (int j = 0; j < NL; ++j) {
+          const double y = row[j] - lul[5 * j + 1] * y1 - lul[5 * j + 0] * y2;
+          row[j] = y;
+          y2 = y1;
+          y1 = y;
+        }
+        double x1 = 0.0, x2 = 0.0;
+        for (int j = NL - 1; j >= 0; --j) {
+          const double x = (row[j] - lul[5 * j + 3] * x1 - lul[5 * j + 4] * x2) / lul[5 * j + 2];
+          row[j] = x;
+          x2 = x1;
+          x1 = x;
+        }
+      }
+      __syncthreads();
+      for (int idx = tid; idx < rows * NL; idx += blockDim.x) {
+        const int r = idx / NL, j = idx - r * NL;
+        S[(r0 + r) * NL + j] = tile[r * (NL + 1) + j];
+      }
+      __syncthreads();
+    }
+
+    // ---- 4./5. epochs: bispev at (t_e, band grid), band flux, magnitude, likelihood -------------------------
+    double logl_part = 0.0;
+    for (int e = tid; e < E; e += blockDim.x) {
+      double x = a.epoch_tab[EP_T * E + e];
+      if (x < xk[0]) x = xk[0];                                                   // fpbisp clamps to [tb, te]
+      if (x > xk[G - 1]) x = xk[G - 1];
+      // knot interval: largest l in [3, G-1] with t[l] <= x  (t[l] = x[l-2] for 4 <= l <= G-1)
+      int l = 3;
+      {
+        int lo = 4, hi = G - 1;   // find count of knots t[4..G-1] = xk[2..G-3] that are <= x
+        while (lo <= hi) {
+          const int mid = (lo + hi) >> 1;
+          if (xk[mid - 2] <= x) { l = mid; lo = mid + 1; } else hi = mid - 1;
+        }
+      }
+      double tl[8], h[4];
+      for (int q = 0; q < 8; ++q) tl[q] = nak_knot(xk, G, l - 3 + q);
+      fpbspl3(tl, 3, x, h);
+      const int lx = l - 3;
+      const int b = a.band_of_epoch[e];
+      const int jlo = a.band_jlo[b], span = a.band_span[b];
+      double d[kPhotMaxSpan];
+      for (int q = 0; q < span; ++q) {
+        const int j = jlo + q;
+        d[q] = h[0] * S[(lx + 0) * NL + j] + h[1] * S[(lx + 1) * NL + j] + h[2] * S[(lx + 2) * NL + j] +
+               h[3] * S[(lx + 3) * NL + j];
+      }
+      double acc = 0.0;
+      for (int w = a.band_off[b]; w < a.band_off[b + 1]; ++w) {
+        const int q = a.int_ly[w] - jlo;
+        const double* wy = a.int_wy + 4 * (size_t)w;
+        const double f = wy[0] * d[q] + wy[1] * d[q + 1] + wy[2] * d[q + 2] + wy[3] * d[q + 3];
+        acc += a.int_wt[w] * fabs(f);                                             // sed.py:36-37
+      }
+      const double bandflux = acc * a.band_scale[b];
+      double model_v = -2.5 * log10(bandflux / a.band_zp[b]);                     // sed.py:114
+      if (a.output == RB_OUT_FLUX) model_v = pow(10.0, model_v / (-2.5)) * a.band_ref[b];   // utils.py:716-718
+      if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = model_v;
+      if (a.want_logl) {
+        const double res = a.epoch_tab[EP_Y * E + e] - model_v;
+        if (a.sigma_mode == RB_SIGMA_FIXED) {
+          const double rs = res * a.epoch_tab[EP_ISIG * E + e];
+          logl_part += -(rs * rs) / 2 - a.epoch_tab[EP_LOGT * E + e];
+        } else {
+          const double sp = a.sigma_param_s[n];
+          double sg = sp;
+          if (a.sigma_mode == RB_SIGMA_QUADRATURE) {
+            const double si = a.epoch_tab[EP_ISIG * E + e];
+            sg = sqrt(si * si + sp * sp);
+          }
+          const double rs = res / sg;
+          logl_part += -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;
+        }
+      }
+    }
+    if (a.want_logl) {
+      logl_part = warp_sum(logl_part);
+      __syncthreads();
+      if (lane == 0) red[warp] = logl_part;
+      __syncthreads();
+      if (tid == 0) {
+        double total = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total += red[w];
+        a.out_logl[a.n_base + n] = nan_to_num(total);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace rb

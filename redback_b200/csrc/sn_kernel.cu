@@ -63,6 +63,14 @@ struct SnArgs {
   double* scalars;          // [N][kScalars]   built by sn_prep_kernel
   int epochs_in_smem;       // copy epoch_tab into shared memory (fits) or read it from global/L2
   int want_logl;
+  // grid mode (magnitude branch, supernova_models.py:1008-1028): the "epochs" are the model's own time grid
+  // t_temp (source frame: (t_temp*(1+z))/(1+z)); instead of flux densities the kernel writes T, R, L_bol and the
+  // observer-frame phase t_temp*(1+z) per grid point for phot_kernel
+  int64_t param_stride;     // distance between SoA rows of `params` (= total batch size)
+  int grid_mode;
+  double* grid_out;         // [N][4][E]
+  double* opz_out;          // [N]
+  double* dl_out;           // [N]
 };
 
 // ---- 1. per-launch epoch table ----------------------------------------------------------------------
@@ -95,7 +103,7 @@ __global__ void sn_prep_kernel(const SnArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= a.N) return;
-  const int64_t N = a.N;
+  const int64_t N = a.param_stride;
   const double* P = a.params + n;
   const int sed = a.cfg.sed;
   const double z = (sed == RB_SED_BOLOMETRIC) ? 0.0 : P[RB_SN_REDSHIFT * N];
@@ -113,9 +121,11 @@ __global__ void sn_prep_kernel(const SnArgs a) {
   }
   if (lane != 0) return;
   const double mej = P[RB_SN_MEJ * N], vej = P[RB_SN_VEJ * N];
-  const double t_end = a.epoch_tab[EP_T * a.E + a.E - 1] / opz + 100.0;
+  const double t_last = a.epoch_tab[EP_T * a.E + a.E - 1];
+  const double t_end = (a.grid_mode ? (t_last * opz) / opz : t_last / opz) + 100.0;
   const double tau = sqrt(kDiffusionConst * P[RB_SN_KAPPA * N] * mej / vej) / kDay;
   const double tau2 = tau * tau;
+  if (a.grid_mode) { a.opz_out[n] = opz; a.dl_out[n] = dl; }
   double* S = a.scalars + n * kScalars;
   S[SC_OPZ] = opz;
   S[SC_TEND] = t_end;
@@ -386,7 +396,8 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
     // ---- per-epoch work ------------------------------------------------------------------------
     double logl_part = 0.0;
     for (int e = tid; e < E; e += blockDim.x) {
-      const double te = ep[EP_T * E + e] / sc[SC_OPZ];                        // utils.py:382
+      const double t_in = ep[EP_T * E + e];
+      const double te = a.grid_mode ? (t_in * sc[SC_OPZ]) / sc[SC_OPZ] : t_in / sc[SC_OPZ];   // utils.py:382 (:1012-1014)
       const double te2 = te * te;                                             // interaction_processes.py:55
       // first abscissa whose exponent can exceed kExpSkip: xm^2 >= 1 + kExpSkip * tau^2 / te^2
       int m0 = 0;
@@ -424,6 +435,14 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
         const bool mask = r2 <= rec2;
         const double rph = sqrt(mask ? r2 : rec2);
         const double tph = mask ? sqrt(sqrt(lbol / (kStefConst * r2))) : tfloor;
+        if (a.grid_mode) {
+          double* go = a.grid_out + (size_t)n * 4 * E;
+          go[0 * E + e] = tph;
+          go[1 * E + e] = rph;
+          go[2 * E + e] = lbol;
+          go[3 * E + e] = t_in * opz;                                          // time_observer_frame (:1011)
+          continue;
+        }
         const double nu = ep[EP_NU * E + e] * opz;                            // utils.py:383
         if (sed == RB_SED_BLACKBODY) {
           // sed.py:199-222

@@ -59,6 +59,15 @@ class _FusedPath:
     def _check_time(self, t):
         pass
 
+    def _launch(self, N, params_dev, dl, y, sigma, sigma_param, model, logl, stream):
+        return self._eval_fn()(C.byref(self.cfg), N, self.E, _ptr(params_dev), _ptr(self.time), _ptr(self.frequency),
+                               _ptr(dl), _ptr(y), _ptr(sigma), _ptr(sigma_param), _ptr(model), _ptr(logl),
+                               C.c_void_p(stream))
+
+    def _launch_mag(self, fn, N, params_dev, dl, y, sigma, sigma_param, model, logl, stream):
+        return fn(C.byref(self.cfg), C.addressof(self.phot), N, self.E, _ptr(params_dev), _ptr(self.time), _ptr(dl),
+                  _ptr(y), _ptr(sigma), _ptr(sigma_param), _ptr(model), _ptr(logl), C.c_void_p(stream))
+
     def _setup(self, time, frequency, y, sigma, device):
         self.device = _device(device)
         t = np.atleast_1d(np.asarray(time.detach().cpu().numpy() if isinstance(time, torch.Tensor) else time,
@@ -129,10 +138,8 @@ class _FusedPath:
             raise ValueError("log-likelihood requested but no data were given")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            rc = self._eval_fn()(
-                C.byref(self.cfg), N, self.E, _ptr(params_dev), _ptr(self.time), _ptr(self.frequency),
-                _ptr(dl), _ptr(self.y if want_logl else None), _ptr(self.sigma if want_logl else None),
-                _ptr(sigma_param if want_logl else None), _ptr(model), _ptr(logl), C.c_void_p(stream))
+            rc = self._launch(N, params_dev, dl, self.y if want_logl else None, self.sigma if want_logl else None,
+                              sigma_param if want_logl else None, model, logl, stream)
         _capi.check(rc)
         return model, logl
 
@@ -224,6 +231,48 @@ class KilonovaPath(_FusedPath):
     def _check_time(self, t):
         if np.any(t <= 0):
             raise ValueError("A value in x_new is below the interpolation range.")  # scipy interp1d's error
+
+
+class SupernovaMagPath(SupernovaPath):
+    """Magnitude / bandpass-flux branch of arnett / basic_magnetar_powered / slsn
+    (supernova_models.py:1008-1028, 1510-1530, 1599-1624): model on get_optimal_time_array(0.1, 3000, 300) x
+    lambda_array, bicubic spline, band integrals -- all on device (csrc/phot_kernel.cu)."""
+
+    def __init__(self, engine, sed, time, bands, output="magnitude", lambda_array=None, y=None, sigma=None,
+                 sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0, absorption_index=1.0,
+                 cosmology=None, device=None):
+        from . import bands as _bands
+        if sed == _capi.SED_BOLOMETRIC:
+            raise ValueError("bolometric models have no magnitude output")
+        self.NEEDS_FREQUENCY = False
+        self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength, absorption_index,
+                                   cosmology)
+        self._setup(time, None, y, sigma, device)
+        lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
+        tgrid = np.geomspace(0.1, 3000, 300)     # get_optimal_time_array(0.1, 3000, 300), utils.py:108
+        self.phot, self._keep = _bands.build_photometry(bands, self.E, lam, output, tgrid=tgrid)
+
+    def _launch(self, *args):
+        return self._launch_mag(_capi.lib().rb_sn_mag_eval_f64, *args)
+
+
+class KilonovaMagPath(KilonovaPath):
+    """Magnitude / bandpass-flux branch of one_component_kilonova_model / metzger_kilonova_model
+    (kilonova_models.py:1579-1603, 1937-1962)."""
+
+    NEEDS_FREQUENCY = False
+
+    def __init__(self, model, time, bands, output="magnitude", lambda_array=None, y=None, sigma=None,
+                 sigma_mode=_capi.SIGMA_FIXED, dense_resolution=500, neutron_precursor_switch=True, vmax=0.7,
+                 cosmology=None, device=None):
+        from . import bands as _bands
+        self.cfg = _capi.kn_config(model, sigma_mode, dense_resolution, neutron_precursor_switch, vmax, cosmology)
+        self._setup(time, None, y, sigma, device)
+        lam = np.geomspace(100, 60000, 200) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
+        self.phot, self._keep = _bands.build_photometry(bands, self.E, lam, output)
+
+    def _launch(self, *args):
+        return self._launch_mag(_capi.lib().rb_kn_mag_eval_f64, *args)
 
 
 class AfterglowPath(_FusedPath):

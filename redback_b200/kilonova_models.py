@@ -2,15 +2,23 @@
 (redback/transient_models/kilonova_models.py:1537-1603 and :1895-1962), output_format='flux_density'.
 Same signatures as the reference plus `params_batch` (see supernova_models.py)."""
 from . import _capi
-from ._fused import FusedSpec, cosmology_from_kwargs, flux_density_only, run
-from .engine import KilonovaPath
+from ._fused import FusedSpec, cosmology_from_kwargs, output_mode, run
+from .engine import KilonovaMagPath, KilonovaPath
 
 
 def _spec(name, model, needed):
     def validate(kwargs):
-        flux_density_only(kwargs, name)
+        output_mode(kwargs, name)
 
     def build(time, kwargs, y, sigma, sigma_mode):
+        mode = output_mode(kwargs, name)
+        if mode != "flux_density":
+            return KilonovaMagPath(model, time, kwargs["bands"], output=mode, lambda_array=kwargs.get("lambda_array"),
+                                   y=y, sigma=sigma, sigma_mode=sigma_mode,
+                                   dense_resolution=kwargs.get("dense_resolution", 500),
+                                   neutron_precursor_switch=kwargs.get("neutron_precursor_switch", True),
+                                   vmax=kwargs.get("vmax", 0.7), cosmology=cosmology_from_kwargs(kwargs),
+                                   device=kwargs.get("device"))
         return KilonovaPath(model, time, frequency=kwargs.get("frequency"), y=y, sigma=sigma, sigma_mode=sigma_mode,
                             dense_resolution=kwargs.get("dense_resolution", 500),
                             neutron_precursor_switch=kwargs.get("neutron_precursor_switch", True),

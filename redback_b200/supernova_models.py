@@ -8,8 +8,8 @@ parameter that is not in `params_batch` is taken from the call (positional / kwa
 With `params_batch` the result has shape (N, E); without it the scalar call returns (E,), as in redback.
 """
 from . import _capi
-from ._fused import FusedSpec, cosmology_from_kwargs, flux_density_only, run
-from .engine import SupernovaPath
+from ._fused import FusedSpec, cosmology_from_kwargs, output_mode, run
+from .engine import SupernovaMagPath, SupernovaPath
 
 _ALLOWED_OPERATORS = {
     "interaction_process": ("Diffusion",),
@@ -42,7 +42,7 @@ def _spec(name, engine, engine_params, flux_density, default_sed):
     def validate(kwargs):
         _operator_name("interaction_process", kwargs.get("interaction_process", "Diffusion"), "Diffusion")
         if flux_density:
-            flux_density_only(kwargs, name)
+            output_mode(kwargs, name)
             _operator_name("photosphere", kwargs.get("photosphere"), "TemperatureFloor")
             _operator_name("sed", kwargs.get("sed"), default_sed)
 
@@ -50,6 +50,14 @@ def _spec(name, engine, engine_params, flux_density, default_sed):
         sed_id = _capi.SED_BOLOMETRIC
         if flux_density:
             sed_id = _SED_IDS[_operator_name("sed", kwargs.get("sed"), default_sed)]
+            mode = output_mode(kwargs, name)
+            if mode != "flux_density":
+                return SupernovaMagPath(engine, sed_id, time, kwargs["bands"], output=mode,
+                                        lambda_array=kwargs.get("lambda_array"), y=y, sigma=sigma,
+                                        sigma_mode=sigma_mode, dense_resolution=kwargs.get("dense_resolution", 1000),
+                                        cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000),
+                                        absorption_index=kwargs.get("absorption_index", 1.0),
+                                        cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"))
         return SupernovaPath(engine, sed_id, time, frequency=kwargs.get("frequency") if flux_density else None,
                              y=y, sigma=sigma, sigma_mode=sigma_mode,
                              dense_resolution=kwargs.get("dense_resolution", 1000),
