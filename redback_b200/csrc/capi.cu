@@ -37,7 +37,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 size_t sn_smem_bytes(int D, int64_t E, bool epochs_in_smem) {
-  size_t n = (size_t)(2 * D + 2 * rb::kNodes + D + rb::kNodesHalf + rb::kNodes + 256 + 2 * rb::kScalars + 16);
+  size_t n = (size_t)(2 * D + 2 * rb::kNodes + D + rb::kNodesHalf + rb::kNodes + rb::kNodes + rb::kExpTabSize + 2 * rb::kScalars + 16);  // incl. omx2
   if (epochs_in_smem) n += (size_t)rb::kEpochCols * (size_t)E;
   return sizeof(double) * n;
 }
@@ -316,7 +316,7 @@ int rb_measure_fp64_peak(int iters, double* out_tflops, double* out_ms) {
 namespace {
 size_t kn_smem_bytes(const rb_kn_config* cfg, int64_t E) {
   const size_t R = (size_t)cfg->dense_resolution;
-  size_t bytes = sizeof(double) * (5 * R + 256 + rb::kKnScalars + 34 + (size_t)rb::kEpochCols * (size_t)E);
+  size_t bytes = sizeof(double) * (5 * R + rb::kExpTabSize + rb::kKnScalars + 34 + (size_t)rb::kEpochCols * (size_t)E);
   if (cfg->model == RB_KN_METZGER) bytes += sizeof(double) * 2 * rb::kShellWarps * R + sizeof(int) * rb::kShellWarps * R;
   return bytes;
 }
@@ -858,7 +858,7 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
 }
 
 size_t phot_smem_bytes(int NT, int NL) {
-  return sizeof(double) * ((size_t)7 * NT + 5 * (size_t)NL + (size_t)rb::kPhotTileRows * (NL + 1) + 40 + 256);
+  return sizeof(double) * ((size_t)7 * NT + 5 * (size_t)NL + (size_t)rb::kPhotTileRows * (NL + 1) + 40 + rb::kExpTabSize);
 }
 
 }  // namespace

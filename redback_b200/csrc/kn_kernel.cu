@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
   double* Rg = Tg + R;              // [R] photospheric radius on the grid
   double* w1 = Rg + R;              // [R] work: integrand | edot_base
   double* w2 = w1 + R;              // [R] work: L | exp(-t/900)
-  double* tab = w2 + R;             // [256]
-  double* sc = tab + 256;           // [kKnScalars]
+  double* tab = w2 + R;             // [1024]
+  double* sc = tab + kExpTabSize;           // [kKnScalars]
   double* wsum = sc + kKnScalars;   // [34] scan / reduction scratch (+ carry at [33])
   double* ep = wsum + 34;           // [kEpochCols][E]
   double* lpart = ep + kEpochCols * E;                 // Metzger: [kShellWarps][R] partial luminosities
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int model = a.cfg.model, sigma_mode = a.cfg.sigma_mode;
   const bool want_logl = a.want_logl != 0;
-  for (int i = tid; i < 256; i += blockDim.x) tab[i] = RB_EXP2_256[i];
+  for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
   for (int i = tid; i < kEpochCols * E; i += blockDim.x) ep[i] = a.epoch_tab[i];
   __syncthreads();
 

@@ -125,10 +125,10 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
   double* aux = lul + 5 * NL;             // [NT]      per-time scalar (cutoff norm)
   double* tile = aux + NT;                // [kPhotTileRows][NL + 1]
   double* red = tile + kPhotTileRows * (NL + 1);   // [40]
-  double* tab = red + 40;                 // [256]
+  double* tab = red + 40;                 // [1024]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 256; i += blockDim.x) tab[i] = RB_EXP2_256[i];
+  for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
   for (int i = tid; i < 5 * NL; i += blockDim.x) lul[i] = a.lu_lambda[i];
   double* S = a.scratch + (size_t)blockIdx.x * NT * NL;
   __syncthreads();

@@ -33,30 +33,30 @@ constexpr double kFluxConst = 4 * kPi * 2 * kPi * kH * (kC * kC) * kAngstrom;
 constexpr double kToMJy = 1e26;
 
 // ---- table-driven exp -------------------------------------------------------------------------
-// exp(x) = 2^m * 2^(j/256) * exp(r), k = rint(x*256/ln2) = 256 m + j, |r| <= ln2/512 = 1.36e-3.
-// `tab` points at a shared-memory copy of RB_EXP2_256.  Valid for -708 < x < 709 (no denormal /
+// exp(x) = 2^m * 2^(j/1024) * exp(r), k = rint(x*1024/ln2) = 1024 m + j, |r| <= ln2/2048 = 3.4e-4.
+// `tab` points at a shared-memory copy of RB_EXP2_1024 (8 KB).  Valid for -708 < x < 709 (no denormal /
 // overflow handling: callers clamp).
-//   exp_tab  : degree-4 expm1 polynomial (truncation 4e-17) + two-word ln2/256: ~1 ulp, used for the
+//   exp_tab  : degree-3 expm1 polynomial (truncation 5.5e-16) + two-word ln2/1024: ~1 ulp, used for the
 //              engine luminosities and anywhere full accuracy matters.
-//   The diffusion hot loop inlines a cheaper variant (degree 3, error 1.4e-13; see sn_kernel.cu).
+//   The diffusion hot loop inlines a cheaper variant (degree 2, error 6.5e-12; see sn_kernel.cu).
+constexpr int kExpTabSize = 1024;
 constexpr double kExpMagic = 6755399441055744.0;  // 1.5 * 2^52
-constexpr double k256OverLn2 = 369.3299304675746;
-constexpr double kLn2Over256Hi = 0.0027076061740622863;
-constexpr double kLn2Over256Lo = 9.063252535621014e-20;
+constexpr double kTabOverLn2 = 1477.3197218702985;   // 1024 / ln 2
+constexpr double kLn2OverTabHi = 0.0006769015435155716;
+constexpr double kLn2OverTabLo = 2.2658131339052534e-20;
 
 __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
-  const double v = fma(x, k256OverLn2, kExpMagic);
+  const double v = fma(x, kTabOverLn2, kExpMagic);
   const int k = __double2loint(v);
   const double kd = v - kExpMagic;
-  double r = fma(kd, -kLn2Over256Hi, x);
-  r = fma(kd, -kLn2Over256Lo, r);
-  double q = fma(r, 0.041666666666666664, 0.16666666666666666);
-  q = fma(r, q, 0.5);
+  double r = fma(kd, -kLn2OverTabHi, x);
+  r = fma(kd, -kLn2OverTabLo, r);
+  double q = fma(r, 0.16666666666666666, 0.5);
   q = fma(r, q, 1.0);
   const double p = r * q;
-  const double t = tab[k & 255];
+  const double t = tab[k & 1023];
   const double res = fma(t, p, t);
-  return __hiloint2double(__double2hiint(res) + ((k >> 8) << 20), __double2loint(res));
+  return __hiloint2double(__double2hiint(res) + ((k >> 10) << 20), __double2loint(res));
 }
 
 // ---- reductions -------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ enum {
   SC_OPZ = 0,    // 1 + z
   SC_TEND,       // dense_times[-1] = t[-1]/(1+z) + 100                       supernova_models.py:965
   SC_TAU2,       // tau_diff^2 [day^2]                                          interaction_processes.py:39
-  SC_C1,         // (256/ln2) / tau_diff^2
+  SC_C1,         // (1024/ln2) / tau_diff^2
   SC_TRAP,       // trap_coeff [day^2]                                          interaction_processes.py:40
   SC_A0,         // log10(tau_diff / dense_times[-1]) - 3                       interaction_processes.py:50
   SC_ENG_A,      // nickel: f_nickel*mej ; magnetar: 2 E_rot / t_p
@@ -130,7 +130,7 @@ __global__ void sn_prep_kernel(const SnArgs a) {
   S[SC_OPZ] = opz;
   S[SC_TEND] = t_end;
   S[SC_TAU2] = tau2;
-  S[SC_C1] = k256OverLn2 / tau2;
+  S[SC_C1] = kTabOverLn2 / tau2;
   S[SC_INV_TAU2] = 1.0 / tau2;
   S[SC_TRAP] = (kTrappingConst * P[RB_SN_KAPPA_GAMMA * N] * mej / (vej * vej)) / (kDay * kDay);
   S[SC_A0] = log10(tau / t_end) - 3.0;
@@ -238,14 +238,18 @@ __device__ __forceinline__ double expm1_fast(double x, const double* __restrict_
 }
 
 // ---- 3. the diffusion quadrature ----------------------------------------------------------------------
-// Hot-loop exp(x), x in [-700, 0]: k = rint(x * 256/ln2), r' = x * 256/ln2 - k in [-0.5, 0.5],
-// exp = 2^(k>>8) * tab[k&255] * (1 + r'(A1 + r'(A2 + r' A3))), A_i = (ln2/256)^i / i!.
-// Truncation (ln2/512)^4/24 = 1.4e-13, argument-scaling error |x| * 2^-52 < 1.6e-13.
-constexpr double kA1 = 0.0027076061740622863;
-constexpr double kA2 = 3.6655655969101062e-06;
-constexpr double kA3 = 3.3083026805413713e-09;
+// Hot-loop exp(x), x in [-700, 0]: k = rint(x * 1024/ln2), r' = x * 1024/ln2 - k in [-0.5, 0.5],
+// exp = 2^(k>>10) * tab[k&1023] * (1 + r'(A1 + r' A2)), A_i = (ln2/1024)^i / i!.
+// Truncation (ln2/2048)^3/6 = 6.5e-12, argument-scaling error |x| * 2^-52 < 1.6e-13.
+constexpr double kA1 = 0.0006769015435155716;
+constexpr double kA2 = 2.2909784980688164e-07;
 
-template <bool GUARD>
+// GUARD: apply the NaN -> 0 replacement of interaction_processes.py:58 (only needed when the dense luminosity
+//        contains non-finite values).
+// FUSED: evaluate t_i^2 - t_e^2 with one FMA instead of the reference's rounded square + subtraction.  The two
+//        differ by the rounding of t_i^2, i.e. by eps/2 * (t_e/tau_d)^2 relative in the integrand -- the
+//        reference's own noise floor.  Selected per sample only where that is < 2e-11.
+template <bool GUARD, bool FUSED>
 __device__ __forceinline__ double diffusion_sum(const double2* __restrict__ nodes, const double2* __restrict__ seg,
                                                 const double* __restrict__ tab, int ms, int Dm1, double te,
                                                 double te2, double te_is, double c1) {
@@ -259,16 +263,15 @@ __device__ __forceinline__ double diffusion_sum(const double2* __restrict__ node
     const unsigned k = min((unsigned)__double2loint(v), (unsigned)Dm1);
     const double2 sg = seg[k];                                              // L(t) = a_k + b_k t on (x_{k-1}, x_k]
     const double lum = fma(sg.y, t, sg.x);                                  // scipy interp1d, :56
-    const double d = __dsub_rn(__dmul_rn(t, t), te2);                       // t_i^2 - t_e^2, unfused as in :57
+    const double d = FUSED ? fma(t, t, -te2) : __dsub_rn(__dmul_rn(t, t), te2);   // t_i^2 - t_e^2, :57
     const double vv = fma(d, c1, kExpMagic);
     const int kk = __double2loint(vv);
     const double r = fma(d, c1, -(vv - kExpMagic));
-    double q = fma(r, kA3, kA2);
-    q = fma(r, q, kA1);
+    const double q = fma(r, kA2, kA1);
     const double pp = r * q;
-    const double tb = tab[kk & 255];
+    const double tb = tab[kk & 1023];
     const double res = fma(tb, pp, tb);
-    const double ex = __hiloint2double(__double2hiint(res) + ((kk >> 8) << 20), __double2loint(res));
+    const double ex = __hiloint2double(__double2hiint(res) + ((kk >> 10) << 20), __double2loint(res));
     double g = lum * ex;
     if (GUARD) { if (isnan(g * t)) g = 0.0; }                              // :58 (NaN integrand -> 0)
     acc = fma(g, nd.y, acc);                                                // trapezoid, regrouped
@@ -284,8 +287,9 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
   double* ytmp = reinterpret_cast<double*>(nodes + kNodes);  // [D]  engine luminosity on the dense grid
   double* lsp = ytmp + D;                                // [kNodesHalf]
   double* xms = lsp + kNodesHalf;                        // [kNodes] merged abscissae
-  double* tab = xms + kNodes;                            // [256]    2^(j/256)
-  double* scb = tab + 256;                               // [2][kScalars] per-sample scalars, double-buffered
+  double* omx2 = xms + kNodes;                           // [kNodes] 1 - xm^2 (skip search)
+  double* tab = omx2 + kNodes;                           // [1024]   2^(j/1024)
+  double* scb = tab + kExpTabSize;                               // [2][kScalars] per-sample scalars, double-buffered
   double* scratch = scb + 2 * kScalars;                  // [16]     per-warp partial sums
   double* ep_s = scratch + 16;                           // [kEpochCols][E] when epochs_in_smem
 
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
   const int sed = a.cfg.sed;
   const int sigma_mode = a.cfg.sigma_mode;
   const bool want_logl = a.want_logl != 0;
-  for (int i = tid; i < 256; i += blockDim.x) tab[i] = RB_EXP2_256[i];
+  for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
   const double* ep = a.epoch_tab;
   if (a.epochs_in_smem) {
     for (int i = tid; i < kEpochCols * E; i += blockDim.x) ep_s[i] = a.epoch_tab[i];
@@ -348,6 +352,8 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       lsp[rt] = (yv > -300.0) ? exp_tab(yv * 2.302585092994046, tab) : pow(10.0, yv);
     }
     const bool any_bad = __syncthreads_or(bad);
+    // (t_end / tau_d)^2 * eps/2 < 2e-11: the fused t^2 - te^2 is indistinguishable from the reference's
+    const bool fused_ok = t_end * t_end < 3.6e5 * sc[SC_TAU2];
     // interp1d segments (interaction_processes.py:44): L(t) = y_{k-1} + s_k (t - x_{k-1}) = a_k + s_k t
     for (int k = tid; k < D; k += blockDim.x) {
       double2 sg = make_double2(0.0, 0.0);
@@ -390,6 +396,7 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       const double x = xms[rt];
       const double dw = (rt == kNodes - 1) ? (x - xms[rt - 1]) : (xms[rt + 1] - xms[max(rt - 1, 0)]);
       nodes[rt] = make_double2(x, x * dw);
+      omx2[rt] = (1.0 - x) * (1.0 + x);
     }
     __syncthreads();
 
@@ -399,26 +406,27 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       const double t_in = ep[EP_T * E + e];
       const double te = a.grid_mode ? (t_in * sc[SC_OPZ]) / sc[SC_OPZ] : t_in / sc[SC_OPZ];   // utils.py:382 (:1012-1014)
       const double te2 = te * te;                                             // interaction_processes.py:55
-      // first abscissa whose exponent can exceed kExpSkip: xm^2 >= 1 + kExpSkip * tau^2 / te^2
+      // first abscissa whose exponent can exceed kExpSkip: te^2 (1 - xm^2) <= -(kExpSkip - 1) tau^2
       int m0 = 0;
       {
-        const double x02 = 1.0 + (kExpSkip - 1.0) * sc[SC_TAU2] / te2;
-        if (x02 > 0.0) {
-          const double x0 = sqrt(x02) * (1.0 - 1e-12);
-          int lo = 0, hi = kNodes;  // lower_bound
+        const double lim = -(kExpSkip - 1.0) * sc[SC_TAU2];
+        if (te2 > lim) {                 // 1 - xm^2 <= 1: nothing to skip otherwise
+          int lo = 0, hi = kNodes;       // first m with te2 * omx2[m] <= lim (omx2 decreases with m)
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (nodes[mid].x < x0) lo = mid + 1; else hi = mid;
+            if (te2 * omx2[mid] > lim) lo = mid + 1; else hi = mid;
           }
-          m0 = lo;
+          m0 = lo;   // every abscissa kept has exponent >= kExpSkip - 1 > -708 (the table exp's domain)
         }
       }
       const int ms = max(m0, 1);  // xm[0] = 1 - lsp[49] = 0 -> integrand 0 there
       // shrunk by 2^-50 so that ceil() never exceeds D-1 and t == x_k lands in (k-1, k]
       const double te_is = te * inv_step * (1.0 - 0x1p-50);
       const double c1 = sc[SC_C1];
-      const double acc = any_bad ? diffusion_sum<true>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1)
-                                 : diffusion_sum<false>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
+      double acc;
+      if (any_bad) acc = diffusion_sum<true, false>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
+      else if (fused_ok) acc = diffusion_sum<false, true>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
+      else acc = diffusion_sum<false, false>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
       const double lbol = (0.5 * (te2 * acc)) *
                           (-2.0 * expm1_fast(-sc[SC_TRAP] / te2, tab) * sc[SC_INV_TAU2]);       // :60-61
 

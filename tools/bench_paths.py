@@ -16,7 +16,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import helpers as h  # noqa: E402
 from redback_b200 import _capi  # noqa: E402
-from redback_b200.engine import AfterglowPath, KilonovaPath, SupernovaPath  # noqa: E402
+from redback_b200 import bands as rb_bands  # noqa: E402
+from redback_b200.engine import (AfterglowPath, KilonovaMagPath, KilonovaPath, SupernovaMagPath,  # noqa: E402
+                                 SupernovaPath)
 
 
 def timed(path, params, steps=3, warmup=3):
@@ -61,6 +63,18 @@ def main():
     jobs.append(("tophat_redback radio+X-ray E=500 (config 4 shape)", int(200_000 * scale),
                  lambda n: AfterglowPath(_capi.AG_TOPHAT, t4, frequency=nu4, y=np.full(500, 1e-3), sigma=1e-4),
                  lambda n: h.tophat_prior(rng, n), None))
+    rb_bands.register_synthetic_lsst()
+    names6 = list(h.LSST_NU)
+    b3 = np.array([names6[i % 6] for i in range(200)])
+    jobs.append(("one_component_kilonova_model LSST ugrizy magnitudes E=200 (config 3)", int(100_000 * scale),
+                 lambda n: KilonovaMagPath(_capi.KN_ONE_COMPONENT, t3, b3, y=np.full(200, 22.0), sigma=0.1),
+                 lambda n: h.one_component_prior(rng, n), 4.0e4))
+    t5 = np.arange(1.0, 151.0, 0.5)     # LSST-like cadence over 150 d, E = 300 (config 5 shape)
+    b5 = np.array([names6[i % 6] for i in range(300)])
+    jobs.append(("arnett LSST ugrizy magnitudes E=300 (config 5 shape, no noise model)", int(200_000 * scale),
+                 lambda n: SupernovaMagPath(_capi.ENGINE_NICKEL, _capi.SED_BLACKBODY, t5, b5, y=np.full(300, 22.0),
+                                            sigma=0.1),
+                 lambda n: h.arnett_prior(rng, n, zmax=0.5), 2.0e4))
     for name, n, mk, prior, flop_eq in jobs:
         if args.only and args.only not in name:
             continue
