@@ -38,7 +38,9 @@ enum { RB_ENGINE_NICKEL = 0, RB_ENGINE_MAGNETAR = 1 };
 /* ---- output stage: bolometric models return L_bol; flux_density models go through
  *      photosphere.TemperatureFloor (photosphere.py:56-111) and sed.Blackbody (sed.py:475-502) or
  *      sed.CutoffBlackbody (sed.py:301-426) ------------------------------------------------------ */
-enum { RB_SED_BOLOMETRIC = 0, RB_SED_BLACKBODY = 1, RB_SED_CUTOFF_BLACKBODY = 2 };
+/* RB_SED_CUTOFF_LINE = CutoffBlackbody modified by sed.Line (sed.py:753-909): redback's `type_1a`
+ * (supernova_models.py:2229-2314) with the nickel engine. */
+enum { RB_SED_BOLOMETRIC = 0, RB_SED_BLACKBODY = 1, RB_SED_CUTOFF_BLACKBODY = 2, RB_SED_CUTOFF_LINE = 3 };
 
 /* ---- noise model of the fused likelihood reduction ------------------------------------------- */
 enum {
@@ -89,6 +91,12 @@ typedef struct {
   double cutoff_wavelength; /* Angstrom, default 3000 (supernova_models.py:1582)                 */
   double absorption_index;  /* default 1.0; 4 - index must be a positive integer on device       */
   rb_cosmology cosmology;   /* used only when dl_cm == NULL                                      */
+  /* sed.Line parameters (RB_SED_CUTOFF_LINE), kwargs of type_1a (supernova_models.py:2255-2259) */
+  double line_wavelength;   /* Angstrom, default 7.5e3 */
+  double line_width;        /* Angstrom, default 500   */
+  double line_time;         /* days, default 50        */
+  double line_duration;     /* days, default 25        */
+  double line_amplitude;    /* default 0.3             */
 } rb_sn_config;
 
 /* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */

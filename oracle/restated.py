@@ -320,6 +320,43 @@ def slsn(time, redshift, p0, bp, mass_ns, theta_pb, *, frequency, mej, vej, kapp
         cutoff_wavelength=cutoff_wavelength, absorption_index=absorption_index)
 
 
+def line_sed_cgs(time, luminosity, frequency, base_flux_cgs, dl, line_wavelength=7.5e3, line_width=500,
+                 line_time=50, line_duration=25, line_amplitude=0.3):
+    """sed.Line._set_sed (sed.py:859-909).  `frequency`: (1, n_freq) row for the flux_density branch or (n_freq, 1)
+    column for the grid branch; base flux density in erg/s/cm^2/Hz, broadcastable."""
+    time_vals = np.atleast_1d(time).reshape(-1, 1).T
+    lum_vals = np.atleast_1d(luminosity).reshape(-1, 1).T
+    with np.errstate(all="ignore"):
+        amplitude_time = line_amplitude * np.exp(-0.5 * ((time_vals - line_time) / line_duration) ** 2)
+        flux_modified = base_flux_cgs * (1 - amplitude_time)
+        amplitude_scaled = amplitude_time * lum_vals / (4 * np.pi * dl ** 2)
+        amplitude_scaled = amplitude_scaled / (line_width * np.sqrt(2 * np.pi))
+        wavelength = nu_to_lambda(frequency)
+        line_profile = np.exp(-0.5 * ((wavelength - line_wavelength) / line_width) ** 2)
+        wavelength_cm = wavelength * angstrom_cgs
+        return flux_modified + amplitude_scaled * line_profile * (wavelength_cm ** 2) / speed_of_light
+
+
+def type_1a(time, redshift, f_nickel, mej, *, frequency, vej, kappa, kappa_gamma, temperature_floor, dl=None,
+            cutoff_wavelength=3000, absorption_index=1.0, line_wavelength=7.5e3, line_width=500, line_time=50,
+            line_duration=25, line_amplitude=0.3, **kw):
+    """supernova_models.py:2229-2278 (flux_density branch).  Returns mJy[E]."""
+    time = np.asarray(time, dtype=float)
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    frequency = np.asarray(frequency, dtype=float)
+    if frequency.ndim == 0:
+        frequency = np.full(time.shape, float(frequency))
+    frequency, t = calc_kcorrected_properties(frequency, redshift, time)
+    lbol = arnett_bolometric(t, f_nickel, mej, vej=vej, kappa=kappa, kappa_gamma=kappa_gamma, **kw)
+    temp, rad = globals()["temperature_floor"](t, lbol, vej, temperature_floor)
+    with np.errstate(all="ignore"):
+        base = cutoff_blackbody_mjy(t, temp, lbol, rad, frequency, dl, cutoff_wavelength, absorption_index) * 1e-26
+        fd = line_sed_cgs(t, lbol, frequency.reshape(1, -1), base, dl, line_wavelength, line_width, line_time,
+                          line_duration, line_amplitude).flatten()
+        return fd * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)
+
+
 # --------------------------------------------------------------------------------------------------
 # likelihoods (likelihoods.py)
 # --------------------------------------------------------------------------------------------------
@@ -855,18 +892,22 @@ def sn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None,
     time_observer_frame = time_temp * (1. + redshift)
     frequency, t = calc_kcorrected_properties(lambda_to_nu(lam), redshift, time_observer_frame)
     dkw = dict(vej=params["vej"], kappa=params["kappa"], kappa_gamma=params["kappa_gamma"])
-    if model == "arnett":
+    if model in ("arnett", "type_1a"):
         lbol = arnett_bolometric(t, params["f_nickel"], params["mej"], **dkw)
     else:
         lbol = basic_magnetar_powered_bolometric(t, params["p0"], params["bp"], params["mass_ns"],
                                                  params["theta_pb"], mej=params["mej"], **dkw)
     temp, rad = temperature_floor(t, lbol, params["vej"], params["temperature_floor"])
     with np.errstate(all="ignore"):
-        if model == "slsn":
+        if model in ("slsn", "type_1a"):
             full = cutoff_blackbody_mjy(t, temp, lbol, rad, frequency[:, None], dl,
-                                        params.get("cutoff_wavelength", 3000.), params.get("absorption_index", 1.0)).T
-            full = full * (1 + redshift)
-            spectra = full * 1e-26 * _C_AA_PER_S / lam ** 2                      # :1613-1616
+                                        params.get("cutoff_wavelength", 3000.), params.get("absorption_index", 1.0))
+            if model == "type_1a":                                               # :2295-2304
+                lk = {k: params[k] for k in ("line_wavelength", "line_width", "line_time", "line_duration",
+                                             "line_amplitude") if k in params}
+                full = line_sed_cgs(t, lbol, frequency[:, None], full * 1e-26, dl, **lk) * _ERG_S_CM2_HZ_TO_MJY
+            full = full.T * (1 + redshift)
+            spectra = full * 1e-26 * _C_AA_PER_S / lam ** 2                      # :1613-1616, :2305-2309
         else:
             fd = blackbody_to_flux_density(temp, rad, dl, frequency[:, None]).T
             spectra = flux_density_to_spectrum(fd, redshift, lam)

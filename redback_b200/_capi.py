@@ -10,7 +10,7 @@ from . import _build
 
 RB_OK, RB_ERR_INVALID, RB_ERR_UNSUPPORTED, RB_ERR_CUDA = 0, -1, -2, -3
 ENGINE_NICKEL, ENGINE_MAGNETAR = 0, 1
-SED_BOLOMETRIC, SED_BLACKBODY, SED_CUTOFF_BLACKBODY = 0, 1, 2
+SED_BOLOMETRIC, SED_BLACKBODY, SED_CUTOFF_BLACKBODY, SED_CUTOFF_LINE = 0, 1, 2, 3
 SIGMA_FIXED, SIGMA_SAMPLED, SIGMA_QUADRATURE = 0, 1, 2
 
 SN_ROWS = dict(redshift=0, f_nickel=1, p0=1, bp=2, mass_ns=3, theta_pb=4, mej=5, vej=6, kappa=7,
@@ -26,7 +26,9 @@ class Cosmology(C.Structure):
 
 class SnConfig(C.Structure):
     _fields_ = [("engine", C.c_int), ("sed", C.c_int), ("sigma_mode", C.c_int), ("dense_resolution", C.c_int),
-                ("cutoff_wavelength", C.c_double), ("absorption_index", C.c_double), ("cosmology", Cosmology)]
+                ("cutoff_wavelength", C.c_double), ("absorption_index", C.c_double), ("cosmology", Cosmology),
+                ("line_wavelength", C.c_double), ("line_width", C.c_double), ("line_time", C.c_double),
+                ("line_duration", C.c_double), ("line_amplitude", C.c_double)]
 
 
 KN_ONE_COMPONENT, KN_METZGER = 0, 1
@@ -109,7 +111,7 @@ def check(rc):
 
 
 def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
-              absorption_index=1.0, cosmology=None):
+              absorption_index=1.0, cosmology=None, line=None):
     cfg = SnConfig()
     check(lib().rb_sn_config_default(C.byref(cfg)))
     cfg.engine, cfg.sed, cfg.sigma_mode = engine, sed, sigma_mode
@@ -118,6 +120,9 @@ def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff
     cfg.absorption_index = float(absorption_index)
     if cosmology is not None:
         cfg.cosmology = cosmology
+    if line is not None:
+        for key, val in line.items():
+            setattr(cfg, key, float(val))
     return cfg
 
 

@@ -97,6 +97,11 @@ int rb_sn_config_default(rb_sn_config* cfg) {
   cfg->dense_resolution = 1000;
   cfg->cutoff_wavelength = 3000.0;
   cfg->absorption_index = 1.0;
+  cfg->line_wavelength = 7.5e3;
+  cfg->line_width = 500.0;
+  cfg->line_time = 50.0;
+  cfg->line_duration = 25.0;
+  cfg->line_amplitude = 0.3;
   return rb_cosmology_planck18(&cfg->cosmology);
 }
 
@@ -107,7 +112,7 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
   if (N < 0 || E <= 0 || E > (1 << 24)) return fail(RB_ERR_INVALID, "rb_sn_eval: need N >= 0 and 0 < E <= 2^24");
   if (cfg->engine != RB_ENGINE_NICKEL && cfg->engine != RB_ENGINE_MAGNETAR)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown engine");
-  if (cfg->sed < RB_SED_BOLOMETRIC || cfg->sed > RB_SED_CUTOFF_BLACKBODY)
+  if (cfg->sed < RB_SED_BOLOMETRIC || cfg->sed > RB_SED_CUTOFF_LINE)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sed");
   if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_QUADRATURE)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sigma_mode");
@@ -116,7 +121,7 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
   if (!params || !t_obs) return fail(RB_ERR_INVALID, "rb_sn_eval: params and t_obs are required");
   if (cfg->sed != RB_SED_BOLOMETRIC && !freq_obs)
     return fail(RB_ERR_INVALID, "rb_sn_eval: freq_obs is required for flux_density output");
-  if (cfg->sed == RB_SED_CUTOFF_BLACKBODY) {
+  if (cfg->sed == RB_SED_CUTOFF_BLACKBODY || cfg->sed == RB_SED_CUTOFF_LINE) {
     // sed.py:396-400: absorption_index >= 4 raises ValueError in the reference
     if (cfg->absorption_index >= 4.0)
       return fail(RB_ERR_INVALID, "absorption_index >= 4 is not supported: the integral below the cutoff diverges");
@@ -959,7 +964,13 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
     pa.n_base = n0;
     pa.E = (int)E;
     pa.n_t_max = NT;
-    pa.sed = (cfg->sed == RB_SED_CUTOFF_BLACKBODY) ? rb::PH_SED_CUTOFF : rb::PH_SED_BLACKBODY;
+    pa.sed = (cfg->sed == RB_SED_CUTOFF_BLACKBODY) ? rb::PH_SED_CUTOFF
+             : (cfg->sed == RB_SED_CUTOFF_LINE ? rb::PH_SED_CUTOFF_LINE : rb::PH_SED_BLACKBODY);
+    pa.line_wavelength = cfg->line_wavelength;
+    pa.line_width = cfg->line_width;
+    pa.line_time = cfg->line_time;
+    pa.line_duration = cfg->line_duration;
+    pa.line_amplitude = cfg->line_amplitude;
     pa.sigma_mode = cfg->sigma_mode;
     pa.want_logl = y ? 1 : 0;
     pa.common_time_lu = 1;

@@ -25,7 +25,7 @@ constexpr int kPhotThreads = 256;
 constexpr int kPhotMaxSpan = 96;     // max B-spline coefficients (along wavelength) overlapped by one band
 constexpr int kPhotTileRows = 32;    // rows per shared-memory tile in the wavelength-axis solve
 
-enum { PH_SED_BLACKBODY = 1, PH_SED_CUTOFF = 2 };
+enum { PH_SED_BLACKBODY = 1, PH_SED_CUTOFF = 2, PH_SED_CUTOFF_LINE = 3 };
 enum { PH_T = 0, PH_R, PH_L, PH_X, kPhotGridCols };   // per-sample model grid: temperature, radius, L_bol, phase
 
 struct PhotArgs {
@@ -40,6 +40,7 @@ struct PhotArgs {
   int want_logl;
   int common_time_lu;     // 1: time-axis LU supplied (grid identical up to scaling for all samples)
   double cutoff_wavelength, absorption_index;
+  double line_wavelength, line_width, line_time, line_duration, line_amplitude;   // sed.Line (type_1a)
   const double* grid;     // [N][kPhotGridCols][n_t_max]   (written by the model kernels in grid mode)
   const int* grid_len;    // [N] or nullptr (= n_t_max)
   const double* opz;      // [N] 1 + z
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
     const double lam_c = a.cutoff_wavelength * kAngstrom;
     for (int k = tid; k < G; k += blockDim.x) {
       xk[k] = gX[k];
-      if (a.sed == PH_SED_CUTOFF) aux[k] = cutoff_norm(gL[k], gR[k], gT[k], lam_c, a.absorption_index);
+      if (a.sed != PH_SED_BLACKBODY) aux[k] = cutoff_norm(gL[k], gR[k], gT[k], lam_c, a.absorption_index);
     }
     if (a.common_time_lu) for (int i = tid; i < 5 * G; i += blockDim.x) lut[i] = a.lu_time[i];
     __syncthreads();
@@ -172,7 +173,20 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
         double fd = sedv / (4 * kPi * (dl * dl));
         fd *= lam_A;
         fd /= nu;
-        mjy = fd * kToMJy * opz;                                                 // supernova_models.py:1611-1612
+        double base = fd * kToMJy;
+        if (a.sed == PH_SED_CUTOFF_LINE) {
+          // sed.Line on the (N_lambda, N_t) grid (sed.py:859-909; supernova_models.py:2295-2303); time is source frame
+          const double te = xk[k] / opz;
+          const double q = (te - a.line_time) / a.line_duration;
+          const double amp = a.line_amplitude * exp(-0.5 * (q * q));
+          double flux = (base * 1e-26) * (1 - amp);
+          double amp_scaled = amp * gL[k] / (4 * kPi * (dl * dl));
+          amp_scaled /= (a.line_width * sqrt(2 * kPi));
+          const double u = (lam_A - a.line_wavelength) / a.line_width;
+          flux += amp_scaled * exp(-0.5 * (u * u)) * (lam * lam) / kC;
+          base = flux * kToMJy;
+        }
+        mjy = base * opz;                                                        // supernova_models.py:1611-1612, 2304-2305
       }
       const double v = mjy * 1e-26 * 2.99792458e18 / (lam_obs * lam_obs);       // mJy -> erg/cm^2/s/Angstrom
       S[idx] = v;

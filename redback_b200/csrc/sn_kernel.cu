@@ -231,6 +231,23 @@ __device__ __noinline__ double cutoff_blackbody_mjy(const rb_sn_config& cfg, dou
   return fd * kToMJy;
 }
 
+// sed.Line._set_sed (sed.py:859-909) for one (time, frequency): attenuate the base SED by the time-dependent line
+// amplitude and add the Gaussian line emission scaled by L_bol.  `base_mjy` is the CutoffBlackbody flux density.
+__device__ __forceinline__ double line_sed_mjy(const rb_sn_config& cfg, double base_mjy, double lbol, double te,
+                                               double nu, double dl) {
+  const double q = (te - cfg.line_time) / cfg.line_duration;
+  const double amp = cfg.line_amplitude * exp(-0.5 * (q * q));                // :871-873
+  double flux = (base_mjy * 1e-26) * (1 - amp);                               // :880-886 (mJy -> erg/s/cm^2/Hz)
+  double amp_scaled = amp * lbol / (4 * kPi * (dl * dl));                     // :893
+  amp_scaled /= (cfg.line_width * sqrt(2 * kPi));                             // :894
+  const double lam_A = 1.e10 * (kCSI / nu);                                   // utils.py:365-370
+  const double u = (lam_A - cfg.line_wavelength) / cfg.line_width;
+  const double profile = exp(-0.5 * (u * u));                                 // :897
+  const double lam_cm = lam_A * kAngstrom;
+  flux += amp_scaled * profile * (lam_cm * lam_cm) / kC;                      // :906
+  return flux * kToMJy;
+}
+
 // expm1 with the table-driven exp where there is no cancellation (|x| >= 0.5), libm otherwise
 __device__ __forceinline__ double expm1_fast(double x, const double* __restrict__ tab) {
   if (fabs(x) >= 0.5 && x > -700.0 && x < 700.0) return exp_tab(x, tab) - 1.0;
@@ -458,7 +475,9 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
           const double em = expm1_fast((kH * nu) / (kKB * tph), tab);
           model = num * sc[SC_INV_DEN] / em * kToMJy * opz;                   // supernova_models.py:1007
         } else {
-          model = cutoff_blackbody_mjy(a.cfg, lbol, rph, tph, nu, sc[SC_DL]) * opz;  // supernova_models.py:1597
+          double mjy = cutoff_blackbody_mjy(a.cfg, lbol, rph, tph, nu, sc[SC_DL]);
+          if (sed == RB_SED_CUTOFF_LINE) mjy = line_sed_mjy(a.cfg, mjy, lbol, te, nu, sc[SC_DL]);   // sed.py:859-909
+          model = mjy * opz;                                                  // supernova_models.py:1597, 2278
         }
       }
       if (a.out_model != nullptr) a.out_model[n * (int64_t)E + e] = model;

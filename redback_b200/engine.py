@@ -195,10 +195,10 @@ class SupernovaPath(_FusedPath):
 
     def __init__(self, engine, sed, time, frequency=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
-                 absorption_index=1.0, cosmology=None, device=None):
+                 absorption_index=1.0, cosmology=None, device=None, line=None):
         self.NEEDS_FREQUENCY = sed != _capi.SED_BOLOMETRIC
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength,
-                                   absorption_index, cosmology)
+                                   absorption_index, cosmology, line)
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):
@@ -240,13 +240,13 @@ class SupernovaMagPath(SupernovaPath):
 
     def __init__(self, engine, sed, time, bands, output="magnitude", lambda_array=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0, absorption_index=1.0,
-                 cosmology=None, device=None):
+                 cosmology=None, device=None, line=None):
         from . import bands as _bands
         if sed == _capi.SED_BOLOMETRIC:
             raise ValueError("bolometric models have no magnitude output")
         self.NEEDS_FREQUENCY = False
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength, absorption_index,
-                                   cosmology)
+                                   cosmology, line)
         self._setup(time, None, y, sigma, device)
         lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
         tgrid = np.geomspace(0.1, 3000, 300)     # get_optimal_time_array(0.1, 3000, 300), utils.py:108

@@ -34,7 +34,22 @@ def _operator_name(kind, value, default):
     return name
 
 
-def _spec(name, engine, engine_params, flux_density, default_sed):
+_LINE_DEFAULTS = dict(line_wavelength=7.5e3, line_width=500, line_time=50, line_duration=25, line_amplitude=0.3)
+
+
+def _line_kwargs(kwargs):
+    """sed.Line parameters of type_1a (supernova_models.py:2255-2259): per-call scalars on device."""
+    import numpy as np
+    out = {}
+    for key, default in _LINE_DEFAULTS.items():
+        val = kwargs.get(key, default)
+        if np.ndim(val) != 0:
+            raise NotImplementedError(f"{key} must be a scalar in the fused B200 path")
+        out[key] = float(val)
+    return out
+
+
+def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None):
     needed = list(engine_params) + list(_DIFFUSION)
     if flux_density:
         needed = ["redshift"] + needed + ["temperature_floor"]
@@ -44,12 +59,17 @@ def _spec(name, engine, engine_params, flux_density, default_sed):
         if flux_density:
             output_mode(kwargs, name)
             _operator_name("photosphere", kwargs.get("photosphere"), "TemperatureFloor")
-            _operator_name("sed", kwargs.get("sed"), default_sed)
+            if fixed_sed is None:
+                _operator_name("sed", kwargs.get("sed"), default_sed)
 
     def build(time, kwargs, y, sigma, sigma_mode):
         sed_id = _capi.SED_BOLOMETRIC
+        line = None
         if flux_density:
-            sed_id = _SED_IDS[_operator_name("sed", kwargs.get("sed"), default_sed)]
+            if fixed_sed is not None:     # type_1a hard-wires CutoffBlackbody + Line (supernova_models.py:2268-2275)
+                sed_id, line = fixed_sed, _line_kwargs(kwargs)
+            else:
+                sed_id = _SED_IDS[_operator_name("sed", kwargs.get("sed"), default_sed)]
             mode = output_mode(kwargs, name)
             if mode != "flux_density":
                 return SupernovaMagPath(engine, sed_id, time, kwargs["bands"], output=mode,
@@ -57,13 +77,14 @@ def _spec(name, engine, engine_params, flux_density, default_sed):
                                         sigma_mode=sigma_mode, dense_resolution=kwargs.get("dense_resolution", 1000),
                                         cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000),
                                         absorption_index=kwargs.get("absorption_index", 1.0),
-                                        cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"))
+                                        cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"),
+                                        line=line)
         return SupernovaPath(engine, sed_id, time, frequency=kwargs.get("frequency") if flux_density else None,
                              y=y, sigma=sigma, sigma_mode=sigma_mode,
                              dense_resolution=kwargs.get("dense_resolution", 1000),
                              cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000),
                              absorption_index=kwargs.get("absorption_index", 1.0),
-                             cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"))
+                             cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"), line=line)
 
     return FusedSpec(name, needed, build, validate)
 
@@ -73,6 +94,7 @@ _ARNETT = _spec("arnett", _capi.ENGINE_NICKEL, ("f_nickel",), True, "Blackbody")
 _MAGNETAR_BOLO = _spec("basic_magnetar_powered_bolometric", _capi.ENGINE_MAGNETAR, _MAGNETAR, False, None)
 _MAGNETAR_BB = _spec("basic_magnetar_powered", _capi.ENGINE_MAGNETAR, _MAGNETAR, True, "Blackbody")
 _SLSN = _spec("slsn", _capi.ENGINE_MAGNETAR, _MAGNETAR, True, "CutoffBlackbody")
+_TYPE_1A = _spec("type_1a", _capi.ENGINE_NICKEL, ("f_nickel",), True, None, fixed_sed=_capi.SED_CUTOFF_LINE)
 
 
 def arnett_bolometric(time, f_nickel=None, mej=None, params_batch=None, **kwargs):
@@ -109,10 +131,16 @@ def slsn(time, redshift=None, p0=None, bp=None, mass_ns=None, theta_pb=None, par
                kwargs, params_batch)
 
 
+def type_1a(time, redshift=None, f_nickel=None, mej=None, params_batch=None, **kwargs):
+    """redback supernova_models.type_1a (:2229-2314): nickel engine, CutoffBlackbody + absorption/emission
+    Line; kwargs line_wavelength, line_width, line_time, line_duration, line_amplitude (scalars); mJy / mag."""
+    return run(_TYPE_1A, time, dict(redshift=redshift, f_nickel=f_nickel, mej=mej), kwargs, params_batch)
+
+
 # model function -> FusedSpec: lets GaussianLikelihood.log_likelihood_batch route through the fused kernel
 # without materialising the (N, E) model matrix.
 FUSED = {
     arnett_bolometric: _ARNETT_BOLO, arnett: _ARNETT,
     basic_magnetar_powered_bolometric: _MAGNETAR_BOLO, slsn_bolometric: _MAGNETAR_BOLO,
-    basic_magnetar_powered: _MAGNETAR_BB, slsn: _SLSN,
+    basic_magnetar_powered: _MAGNETAR_BB, slsn: _SLSN, type_1a: _TYPE_1A,
 }

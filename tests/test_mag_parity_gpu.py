@@ -53,15 +53,15 @@ def test_host_band_tables_match_oracle(rb, obands):
         assert np.array_equal(b(w), ob(w))
 
 
-@pytest.mark.parametrize("model", ["arnett", "basic_magnetar_powered", "slsn"])
+@pytest.mark.parametrize("model", ["arnett", "basic_magnetar_powered", "slsn", "type_1a"])
 def test_supernova_magnitudes(rb, obands, model):
     rng = np.random.default_rng(21)
     t = np.sort(rng.uniform(3, 150, 48))
     names = np.array(list(h.LSST_NU)[:6] * 8)
     N = 24
-    if model == "arnett":
+    if model in ("arnett", "type_1a"):
         p = h.arnett_prior(rng, N, zmax=0.5)
-        fn = rb.supernova_models.arnett
+        fn = getattr(rb.supernova_models, model)
     else:
         p = h.slsn_prior(rng, N, zmax=0.5)
         fn = getattr(rb.supernova_models, model)

@@ -33,7 +33,8 @@ def test_golden_vectors(rb, golden):
     sn = rb.supernova_models
     for name, fn in [("arnett_bolometric", sn.arnett_bolometric), ("slsn_bolometric", sn.slsn_bolometric),
                      ("basic_magnetar_powered_bolometric", sn.basic_magnetar_powered_bolometric),
-                     ("arnett", sn.arnett), ("basic_magnetar_powered", sn.basic_magnetar_powered), ("slsn", sn.slsn)]:
+                     ("arnett", sn.arnett), ("basic_magnetar_powered", sn.basic_magnetar_powered), ("slsn", sn.slsn),
+                     ("type_1a", sn.type_1a)]:
         e = golden["supernova." + name]
         t = np.array(e["time"])
         for params, res in zip(e["params"], e["results"]):
@@ -119,6 +120,22 @@ def test_arnett_flux_density_and_noise_modes(rb):
         b = r.gaussian_likelihood_quadrature(y, ref, sig_i, sig_s[i])
         assert abs(l_sampled[i] - a) <= 1e-6 + 1e-9 * abs(a)
         assert abs(l_quad[i] - b) <= 1e-6 + 1e-9 * abs(b)
+
+
+def test_type_1a_prior_draws(rb):
+    """type_1a = nickel engine + CutoffBlackbody + sed.Line (supernova_models.py:2229-2278)."""
+    rng = np.random.default_rng(31)
+    t = np.sort(rng.uniform(2, 150, 60))
+    nu = rng.choice([8.152e14, 6.273e14, 4.825e14, 3.983e14], 60)
+    N = 64
+    p = h.arnett_prior(rng, N)
+    line = dict(line_wavelength=6.5e3, line_width=500, line_amplitude=0.3)
+    out = rb.supernova_models.type_1a(t, params_batch=p, frequency=nu, output_format="flux_density", **line)
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.type_1a(t, z, frequency=nu, **kw, **line)
+        h.assert_close(out[i], ref, RTOL, h.diffusion_condition(t / (1 + z), _tau(p, i)), what=f"type_1a sample {i}")
 
 
 def test_device_luminosity_distance(rb):
