@@ -214,7 +214,8 @@ def run_gpu(args):
     rng = np.random.default_rng(0)
     y = y_model + rng.normal(0, 0.1 * np.abs(y_model))
     sigma = 0.1 * np.abs(y_model) + 1e-12
-    path = SupernovaPath(_capi.ENGINE_MAGNETAR, sed_id, t, frequency=nu, y=y, sigma=sigma, device=dev)
+    path = SupernovaPath(_capi.ENGINE_MAGNETAR, sed_id, t, frequency=nu, y=y, sigma=sigma, device=dev,
+                         dtype=args.dtype)
 
     params = prior_rows_torch(n, dev, seed=1000 + rank)     # resident in HBM before the timed region
     logl = torch.empty(n, dtype=torch.float64, device=dev)
@@ -310,7 +311,8 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, n), "clocks": clocks,
+            "dtype": "f64" if args.dtype == "float64" else "f32-quadrature/f64-epilogue", "data": "synthetic",
+            "config": workload_config(args, n), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_params.numel() * 8),
                     "d2h_bytes_per_step": int(n * 8), "matches_resident_run": same},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
@@ -328,6 +330,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--samples", type=int, default=10_000_000, help="prior draws per GPU")
     ap.add_argument("--sed", choices=["blackbody", "cutoff"], default="blackbody")
+    ap.add_argument("--dtype", choices=["float64", "float32"], default="float64",
+                    help="float32: FP32 diffusion quadrature (RB_PREC_F32); the headline number is float64")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--cpu-samples-per-core", type=int, default=8000)
     ap.add_argument("--no-cpu-baseline", action="store_true")

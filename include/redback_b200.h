@@ -34,6 +34,7 @@ typedef enum {
 /* ---- luminosity engines: redback/transient_models/supernova_models.py:564-579 (_nickelcobalt_engine),
  *      redback/transient_models/magnetar_models.py:171-185 (basic_magnetar) ---------------------- */
 enum { RB_ENGINE_NICKEL = 0, RB_ENGINE_MAGNETAR = 1 };
+enum { RB_PREC_F64 = 0, RB_PREC_F32 = 1 };
 
 /* ---- output stage: bolometric models return L_bol; flux_density models go through
  *      photosphere.TemperatureFloor (photosphere.py:56-111) and sed.Blackbody (sed.py:475-502) or
@@ -97,6 +98,10 @@ typedef struct {
   double line_time;         /* days, default 50        */
   double line_duration;     /* days, default 25        */
   double line_amplitude;    /* default 0.3             */
+  /* RB_PREC_F32: the diffusion quadrature (the hot loop) runs in FP32 with MUFU exponentials on a
+   * cancellation-free form of the exponent; engine tables, photosphere, SED and the likelihood reduction stay
+   * FP64.  Target: rtol 1e-5 on model outputs (north_star).  Inputs / outputs remain float64. */
+  int precision;            /* RB_PREC_F64 (default) | RB_PREC_F32 */
 } rb_sn_config;
 
 /* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */

@@ -10,6 +10,7 @@ from . import _build
 
 RB_OK, RB_ERR_INVALID, RB_ERR_UNSUPPORTED, RB_ERR_CUDA = 0, -1, -2, -3
 ENGINE_NICKEL, ENGINE_MAGNETAR = 0, 1
+PREC_F64, PREC_F32 = 0, 1
 SED_BOLOMETRIC, SED_BLACKBODY, SED_CUTOFF_BLACKBODY, SED_CUTOFF_LINE = 0, 1, 2, 3
 SIGMA_FIXED, SIGMA_SAMPLED, SIGMA_QUADRATURE = 0, 1, 2
 
@@ -28,7 +29,7 @@ class SnConfig(C.Structure):
     _fields_ = [("engine", C.c_int), ("sed", C.c_int), ("sigma_mode", C.c_int), ("dense_resolution", C.c_int),
                 ("cutoff_wavelength", C.c_double), ("absorption_index", C.c_double), ("cosmology", Cosmology),
                 ("line_wavelength", C.c_double), ("line_width", C.c_double), ("line_time", C.c_double),
-                ("line_duration", C.c_double), ("line_amplitude", C.c_double)]
+                ("line_duration", C.c_double), ("line_amplitude", C.c_double), ("precision", C.c_int)]
 
 
 KN_ONE_COMPONENT, KN_METZGER = 0, 1
@@ -111,7 +112,7 @@ def check(rc):
 
 
 def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
-              absorption_index=1.0, cosmology=None, line=None):
+              absorption_index=1.0, cosmology=None, line=None, precision=0):
     cfg = SnConfig()
     check(lib().rb_sn_config_default(C.byref(cfg)))
     cfg.engine, cfg.sed, cfg.sigma_mode = engine, sed, sigma_mode
@@ -123,6 +124,7 @@ def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff
     if line is not None:
         for key, val in line.items():
             setattr(cfg, key, float(val))
+    cfg.precision = int(precision)
     return cfg
 
 

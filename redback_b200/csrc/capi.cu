@@ -37,7 +37,8 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 size_t sn_smem_bytes(int D, int64_t E, bool epochs_in_smem) {
-  size_t n = (size_t)(2 * D + 2 * rb::kNodes + D + rb::kNodesHalf + rb::kNodes + rb::kNodes + rb::kExpTabSize + 2 * rb::kScalars + 16);  // incl. omx2
+  size_t n = (size_t)(2 * D + 2 * rb::kNodes + D + rb::kNodesHalf + rb::kNodes + rb::kNodes + rb::kExpTabSize + 2 * rb::kScalars + 16)  // incl. omx2
+             + (size_t)(2 * rb::kNodes + (D + 1) / 2 * 2);   // FP32 copies: float4 nodes, float2 segments
   if (epochs_in_smem) n += (size_t)rb::kEpochCols * (size_t)E;
   return sizeof(double) * n;
 }
@@ -116,6 +117,8 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sed");
   if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_QUADRATURE)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sigma_mode");
+  if (cfg->precision != RB_PREC_F64 && cfg->precision != RB_PREC_F32)
+    return fail(RB_ERR_INVALID, "rb_sn_eval: unknown precision");
   if (cfg->dense_resolution < 2 || cfg->dense_resolution > 8000)
     return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution must be in [2, 8000]");
   if (!params || !t_obs) return fail(RB_ERR_INVALID, "rb_sn_eval: params and t_obs are required");

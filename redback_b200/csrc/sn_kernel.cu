@@ -296,6 +296,30 @@ __device__ __forceinline__ double diffusion_sum(const double2* __restrict__ node
   return acc;
 }
 
+// FP32 variant of the quadrature (cfg.precision == RB_PREC_F32).  Differences to the FP64 loop:
+//  * the exponent is evaluated as -(te/tau)^2 * (1 - xm^2) with (1 - xm^2) tabulated from FP64 -- algebraically
+//    the reference's (t_i^2 - t_e^2)/tau^2 but without its catastrophic cancellation (fatal in FP32);
+//  * exp() is MUFU.EX2 (__expf), relative error ~2e-7 + |arg| * 1e-7;
+//  * luminosities are scaled by 1 / L(0) so that they fit the FP32 range; slope form of the interpolation.
+__device__ __forceinline__ float diffusion_sum_f32(const float4* __restrict__ nodesf, const float2* __restrict__ segf,
+                                                   int ms, int Dm1, float te, float te_is, float stepf, float cf) {
+  float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 4
+  for (int m = ms; m < kNodes; ++m) {
+    const float4 nd = nodesf[m];                                   // (xm, xm * dw, 1 - xm^2, -)
+    const float t = te * nd.x;
+    const float v = __fmaf_ru(nd.x, te_is, 8388608.0f);            // 2^23 + ceil(t / step)
+    const unsigned k = min((unsigned)(__float_as_int(v) & 0x7fffff), (unsigned)Dm1);
+    const float2 sg = segf[k];                                     // (y_{k-1}, s_k) / L(0)
+    const float dx = fmaf(-(v - 8388609.0f), stepf, t);            // t - x_{k-1}
+    const float lum = fmaf(sg.y, dx, sg.x);
+    const float ex = __expf(cf * nd.z);
+    const float g = lum * ex;
+    if (m & 1) acc1 = fmaf(g, nd.y, acc1); else acc0 = fmaf(g, nd.y, acc0);
+  }
+  return acc0 + acc1;
+}
+
 __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
   extern __shared__ double2 smem2[];
   const int D = a.cfg.dense_resolution;
@@ -308,13 +332,16 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
   double* tab = omx2 + kNodes;                           // [1024]   2^(j/1024)
   double* scb = tab + kExpTabSize;                               // [2][kScalars] per-sample scalars, double-buffered
   double* scratch = scb + 2 * kScalars;                  // [16]     per-warp partial sums
-  double* ep_s = scratch + 16;                           // [kEpochCols][E] when epochs_in_smem
+  float4* nodesf = reinterpret_cast<float4*>(scratch + 16);          // [kNodes]  FP32 copies (RB_PREC_F32)
+  float2* segf = reinterpret_cast<float2*>(nodesf + kNodes);         // [D]
+  double* ep_s = reinterpret_cast<double*>(segf + D + (D & 1));      // [kEpochCols][E] when epochs_in_smem
 
   const int tid = threadIdx.x;
   const int E = a.E;
   const int sed = a.cfg.sed;
   const int sigma_mode = a.cfg.sigma_mode;
   const bool want_logl = a.want_logl != 0;
+  const bool fp32 = a.cfg.precision == RB_PREC_F32;
   for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
   const double* ep = a.epoch_tab;
   if (a.epochs_in_smem) {
@@ -380,6 +407,11 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
         sg = make_double2(fma(-sk, (double)(k - 1) * step, y0), sk);
       }
       seg[k] = sg;
+      if (fp32) {
+        const double sc0 = 1.0 / ytmp[0];                                     // engines decrease monotonically
+        segf[k] = (k > 0) ? make_float2((float)(ytmp[k - 1] * sc0), (float)((ytmp[k] - ytmp[k - 1]) * inv_step * sc0))
+                          : make_float2(0.0f, 0.0f);
+      }
     }
     // merge lsp (ascending) with 1 - lsp (non-increasing) in np.unique order: rank = own index + number of
     // elements of the other list that sort before it (binary search on the monotone other list)
@@ -414,6 +446,7 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       const double dw = (rt == kNodes - 1) ? (x - xms[rt - 1]) : (xms[rt + 1] - xms[max(rt - 1, 0)]);
       nodes[rt] = make_double2(x, x * dw);
       omx2[rt] = (1.0 - x) * (1.0 + x);
+      if (fp32) nodesf[rt] = make_float4((float)x, (float)(x * dw), (float)((1.0 - x) * (1.0 + x)), 0.0f);
     }
     __syncthreads();
 
@@ -441,7 +474,23 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       const double te_is = te * inv_step * (1.0 - 0x1p-50);
       const double c1 = sc[SC_C1];
       double acc;
-      if (any_bad) acc = diffusion_sum<true, false>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
+      const double l0 = ytmp[0];
+      if (fp32 && !any_bad && l0 > 0.0) {
+        // FP32 skip: exponents below -87 underflow in FP32
+        int mf = ms;
+        const double limf = 87.0 * sc[SC_TAU2];
+        if (te2 > limf) {
+          int lo = 0, hi = kNodes;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (te2 * omx2[mid] > limf) lo = mid + 1; else hi = mid;
+          }
+          mf = max(lo, 1);
+        }
+        const float accf = diffusion_sum_f32(nodesf, segf, mf, D - 1, (float)te, (float)te_is, (float)step,
+                                             (float)(-te2 * sc[SC_INV_TAU2]));
+        acc = (double)accf * l0;
+      } else if (any_bad) acc = diffusion_sum<true, false>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
       else if (fused_ok) acc = diffusion_sum<false, true>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
       else acc = diffusion_sum<false, false>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
       const double lbol = (0.5 * (te2 * acc)) *

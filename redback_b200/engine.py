@@ -29,6 +29,15 @@ def as_device_f64(x, device):
     return torch.from_numpy(arr).to(device)
 
 
+def _precision(dtype):
+    name = str(dtype).replace("torch.", "").replace("numpy.", "")
+    if name in ("float64", "f64", "double", "<class 'float'>"):
+        return _capi.PREC_F64
+    if name in ("float32", "f32", "single"):
+        return _capi.PREC_F32
+    raise ValueError(f"dtype must be float64 or float32, got {dtype!r}")
+
+
 def batch_size(params):
     n = None
     for k, v in params.items():
@@ -195,10 +204,10 @@ class SupernovaPath(_FusedPath):
 
     def __init__(self, engine, sed, time, frequency=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
-                 absorption_index=1.0, cosmology=None, device=None, line=None):
+                 absorption_index=1.0, cosmology=None, device=None, line=None, dtype="float64"):
         self.NEEDS_FREQUENCY = sed != _capi.SED_BOLOMETRIC
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength,
-                                   absorption_index, cosmology, line)
+                                   absorption_index, cosmology, line, _precision(dtype))
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):

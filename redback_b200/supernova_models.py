@@ -84,7 +84,8 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
                              dense_resolution=kwargs.get("dense_resolution", 1000),
                              cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000),
                              absorption_index=kwargs.get("absorption_index", 1.0),
-                             cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"), line=line)
+                             cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"), line=line,
+                             dtype=kwargs.get("dtype", "float64"))
 
     return FusedSpec(name, needed, build, validate)
 

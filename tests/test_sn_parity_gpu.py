@@ -138,6 +138,36 @@ def test_type_1a_prior_draws(rb):
         h.assert_close(out[i], ref, RTOL, h.diffusion_condition(t / (1 + z), _tau(p, i)), what=f"type_1a sample {i}")
 
 
+def test_fp32_quadrature_path(rb):
+    """dtype='float32': the diffusion quadrature in FP32 (MUFU exp, cancellation-free exponent).  north_star
+    tolerance for the FP32 path: rtol 1e-5 on model outputs."""
+    rng = np.random.default_rng(41)
+    t, nu = h.config2_epochs(rng)
+    N = 200
+    p = h.slsn_prior(rng, N)
+    out = rb.supernova_models.slsn(t, params_batch=p, frequency=nu, output_format="flux_density", sed="Blackbody",
+                                   dtype="float32")
+    out64 = rb.supernova_models.slsn(t, params_batch=p, frequency=nu, output_format="flux_density", sed="Blackbody")
+    pb = h.arnett_bolometric_prior(rng, N)
+    tb = h.config1_time()
+    bol = rb.supernova_models.arnett_bolometric(tb, params_batch=pb, dtype="float32")
+    worst = 0.0
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.slsn(t, z, frequency=nu, sed="blackbody", **kw)
+        ok = np.isfinite(ref) & (ref != 0)
+        assert np.array_equal(np.isnan(out[i]), np.isnan(ref))
+        # the blackbody's Wien tail amplifies a relative error of L_bol by up to (h nu / k T) / 4
+        rel = np.abs(out[i][ok] - ref[ok]) / np.abs(ref[ok])
+        worst = max(worst, float(rel.max()) if rel.size else 0.0)
+        refb = r.arnett_bolometric(tb, **{k: v[i] for k, v in pb.items()})
+        np.testing.assert_allclose(bol[i], refb, rtol=1e-5)
+    assert worst < 5e-5, worst
+    ok = np.isfinite(out64) & (out64 != 0)
+    assert np.median(np.abs(out[ok] - out64[ok]) / np.abs(out64[ok])) < 1e-6
+
+
 def test_device_luminosity_distance(rb):
     z = np.array([1e-6, 0.01, 0.1, 0.5, 1.0, 2.0, 3.0, 8.0])
     out = rb.engine.luminosity_distance(z).cpu().numpy()
