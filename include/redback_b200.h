@@ -248,6 +248,17 @@ int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* phot, int64
                        const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
                        void* stream);
 
+/* ---- observation noise + SNR cut for simulated optical light curves ------------------------------------
+ * SimulateTransientWithCadence._evaluate_optical_model / _add_optical_noise_and_cuts
+ * (redback/simulate_transients.py:412-431, 457-527).  model_mag, z and all outputs are [N][E] (device);
+ * ref_flux / limiting_mag are [E]; z holds standard-normal variates (the reference draws rng.normal).
+ * obs_flux / flux_err may be NULL (they are NaN for the two Gaussian noise types). */
+enum { RB_NOISE_LIMITING_MAG = 0, RB_NOISE_GAUSSIAN = 1, RB_NOISE_GAUSSIANMODEL = 2 };
+int rb_optical_noise_f64(int noise_type, int64_t N, int64_t E, const double* model_mag, const double* ref_flux,
+                         const double* limiting_mag, const double* z, double snr_threshold, int apply_snr_cut,
+                         double* obs_mag, double* mag_err, double* obs_flux, double* flux_err, double* snr,
+                         unsigned char* detected, void* stream);
+
 /* Luminosity distance [cm] for N redshifts on device (same quadrature the fused kernels use). */
 int rb_luminosity_distance_f64(const rb_cosmology* cosmo, int64_t N, const double* redshift,
                                double* out_dl_cm, void* stream);

@@ -937,3 +937,35 @@ def kn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None,
         fd = blackbody_to_flux_density(temp, rad, dl, frequency[:, None]).T
         spectra = flux_density_to_spectrum(fd, redshift, lam)
     return bandmag_from_spectra(time_obs, time_observer_frame / day_to_s, spectra, lam, bands, bandpasses)
+
+
+# --------------------------------------------------------------------------------------------------
+# simulate_transients.SimulateTransientWithCadence noise model (simulate_transients.py:457-527)
+# --------------------------------------------------------------------------------------------------
+def optical_noise_and_cuts(model_mag, ref_flux, limiting_mag, z, noise_type="limiting_mag", snr_threshold=5.0):
+    """z: standard-normal draws with the shape of model_mag (the reference calls rng.normal(0, sigma, n_obs),
+    which equals sigma * standard_normal for numpy's Generator)."""
+    model_mag = np.asarray(model_mag, dtype=float)
+    out = {}
+    with np.errstate(all="ignore"):
+        if noise_type == "limiting_mag":
+            model_flux = bandpass_magnitude_to_flux(model_mag, ref_flux)
+            flux_error = bandpass_magnitude_to_flux(np.asarray(limiting_mag, dtype=float), ref_flux) / 5.0
+            observed_flux = model_flux + z * flux_error
+            snr = model_flux / flux_error
+            observed_mag = -2.5 * np.log10(observed_flux / ref_flux)                    # utils.py:834-845
+            mag_error = np.abs((2.5 / np.log(10)) * (flux_error / observed_flux))      # utils.py:829
+            mag_error[np.isnan(observed_flux) | (np.abs(observed_flux) <= 1.0e-20)] = np.nan
+            out.update(flux=observed_flux, flux_error=np.broadcast_to(flux_error, model_mag.shape))
+        elif noise_type == "gaussian":
+            mag_error = np.ones(model_mag.shape) * 0.1
+            observed_mag = model_mag + z * 0.1
+            snr = 1.0 / mag_error
+        elif noise_type == "gaussianmodel":
+            mag_error = 0.05 * np.abs(model_mag)
+            observed_mag = model_mag + z * mag_error
+            snr = np.full(model_mag.shape, 1.0 / 0.05)
+        else:
+            raise ValueError(noise_type)
+    out.update(magnitude=observed_mag, magnitude_error=mag_error, snr=snr, detected=snr >= snr_threshold)
+    return out

@@ -1,7 +1,7 @@
 """redback_b200: B200-native batched light-curve + Gaussian-likelihood engine behind redback's model /
 likelihood API.  The CUDA library is the only compute path; importing the package does
 not need a GPU, calling it does."""
-from . import _capi, afterglow_models, bands, engine, kilonova_models, likelihoods, supernova_models  # noqa: F401
+from . import _capi, afterglow_models, bands, engine, simulate, kilonova_models, likelihoods, supernova_models  # noqa: F401
 from .likelihoods import GaussianLikelihood, GaussianLikelihoodQuadratureNoise  # noqa: F401
 
 __version__ = "0.1.0"

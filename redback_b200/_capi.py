@@ -11,6 +11,7 @@ from . import _build
 RB_OK, RB_ERR_INVALID, RB_ERR_UNSUPPORTED, RB_ERR_CUDA = 0, -1, -2, -3
 ENGINE_NICKEL, ENGINE_MAGNETAR = 0, 1
 PREC_F64, PREC_F32 = 0, 1
+NOISE_TYPES = dict(limiting_mag=0, gaussian=1, gaussianmodel=2)
 SED_BOLOMETRIC, SED_BLACKBODY, SED_CUTOFF_BLACKBODY, SED_CUTOFF_LINE = 0, 1, 2, 3
 SIGMA_FIXED, SIGMA_SAMPLED, SIGMA_QUADRATURE = 0, 1, 2
 
@@ -77,6 +78,8 @@ EXPORTS = {
     "rb_ag_eval_f64_host": (C.c_int, [C.POINTER(AgConfig), C.c_int64, C.c_int64] + [_dp] * 9),
     "rb_sn_mag_eval_f64": (C.c_int, [C.POINTER(SnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_kn_mag_eval_f64": (C.c_int, [C.POINTER(KnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
+    "rb_optical_noise_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 4 + [C.c_double, C.c_int] + [_dp] * 6
+                             + [C.c_void_p]),
     "rb_luminosity_distance_f64": (C.c_int, [C.POINTER(Cosmology), C.c_int64, _dp, _dp, C.c_void_p]),
     "rb_gaussian_logl_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 5 + [C.c_void_p]),
     "rb_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

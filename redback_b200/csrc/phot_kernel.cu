@@ -24,6 +24,7 @@ namespace rb {
 constexpr int kPhotThreads = 256;
 constexpr int kPhotMaxSpan = 96;     // max B-spline coefficients (along wavelength) overlapped by one band
 constexpr int kPhotTileRows = 32;    // rows per shared-memory tile in the wavelength-axis solve
+constexpr int kPhotBatch = 8;        // rows of the scratch tile loaded ahead of the time-axis recurrence
 
 enum { PH_SED_BLACKBODY = 1, PH_SED_CUTOFF = 2, PH_SED_CUTOFF_LINE = 3 };
 enum { PH_T = 0, PH_R, PH_L, PH_X, kPhotGridCols };   // per-sample model grid: temperature, radius, L_bol, phase
@@ -253,23 +254,42 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
     __syncthreads();
     const double repl = red[32];
 
-    // ---- 3b. time-axis solve: one thread per wavelength column (coalesced across columns) ------------------
+    // ---- 3b. time-axis solve: one thread per wavelength column (coalesced across columns).  The scratch tile
+    // lives in global memory / L2: loads are issued kPhotBatch rows ahead of the recurrence to hide latency.
     for (int j = tid; j < NL; j += blockDim.x) {
       double y1 = 0.0, y2 = 0.0;   // y[i-1], y[i-2]
-      for (int i = 0; i < G; ++i) {
-        double b = S[i * NL + j];
-        if (!(isfinite(b) && b != 0.0)) b = repl;
-        const double y = b - lut[5 * i + 1] * y1 - lut[5 * i + 0] * y2;
-        S[i * NL + j] = y;
-        y2 = y1;
-        y1 = y;
+      for (int i0 = 0; i0 < G; i0 += kPhotBatch) {
+        double b[kPhotBatch];
+#pragma unroll
+        for (int u = 0; u < kPhotBatch; ++u) b[u] = (i0 + u < G) ? S[(i0 + u) * NL + j] : 0.0;
+#pragma unroll
+        for (int u = 0; u < kPhotBatch; ++u) {
+          const int i = i0 + u;
+          if (i < G) {
+            double v = b[u];
+            if (!(isfinite(v) && v != 0.0)) v = repl;
+            const double y = v - lut[5 * i + 1] * y1 - lut[5 * i + 0] * y2;
+            S[i * NL + j] = y;
+            y2 = y1;
+            y1 = y;
+          }
+        }
       }
       double x1 = 0.0, x2 = 0.0;   // x[i+1], x[i+2]
-      for (int i = G - 1; i >= 0; --i) {
-        const double x = (S[i * NL + j] - lut[5 * i + 3] * x1 - lut[5 * i + 4] * x2) / lut[5 * i + 2];
-        S[i * NL + j] = x;
-        x2 = x1;
-        x1 = x;
+      for (int i0 = G - 1; i0 >= 0; i0 -= kPhotBatch) {
+        double b[kPhotBatch];
+#pragma unroll
+        for (int u = 0; u < kPhotBatch; ++u) b[u] = (i0 - u >= 0) ? S[(i0 - u) * NL + j] : 0.0;
+#pragma unroll
+        for (int u = 0; u < kPhotBatch; ++u) {
+          const int i = i0 - u;
+          if (i >= 0) {
+            const double x = (b[u] - lut[5 * i + 3] * x1 - lut[5 * i + 4] * x2) / lut[5 * i + 2];
+            S[i * NL + j] = x;
+            x2 = x1;
+            x1 = x;
+          }
+        }
       }
     }
     __syncthreads();
