@@ -181,10 +181,14 @@ int rb_kn_eval_f64_host(const rb_kn_config* cfg, int64_t N, int64_t E, const dou
  * gaussian_redback  redback/transient_models/afterglow_models/base_models.py:948-1010
  * through RedbackAfterglows.get_lightcurve (:573-640) and the numba kernels (:43-400),
  * output_format='flux_density'. */
-enum { RB_AG_TOPHAT = 1, RB_AG_GAUSSIAN = 2 };  /* RedbackAfterglows._method_to_id (:567-571) */
+/* RedbackAfterglows._method_to_id (:567-571): 'TH', 'GJ', 'PL', 'PL2', '2C', 'DG' =
+ * tophat_redback, gaussian_redback, powerlaw_redback (:1081), alternativepowerlaw_redback (:1150),
+ * twocomponent_redback (:1013), doublegaussian_redback (:1218) */
+enum { RB_AG_TOPHAT = 1, RB_AG_GAUSSIAN = 2, RB_AG_POWERLAW = 3, RB_AG_POWERLAW_ALT = 4, RB_AG_TWO_COMPONENT = 5,
+       RB_AG_DOUBLE_GAUSSIAN = 6 };
 enum {
   RB_AG_REDSHIFT = 0, RB_AG_THV = 1, RB_AG_LOGE0 = 2, RB_AG_THC = 3,
-  RB_AG_THJ = 4,      /* Gaussian jet only (tophat uses thj = thc, :937) */
+  RB_AG_THJ = 4,      /* every jet except the tophat (which uses thj = thc, :937) */
   RB_AG_LOGN0 = 5, RB_AG_P = 6, RB_AG_LOGEPSE = 7, RB_AG_LOGEPSB = 8, RB_AG_G0 = 9, RB_AG_XIN = 10,
   RB_AG_NPARAM = 11
 };
@@ -198,6 +202,7 @@ typedef struct {
   int expansion;      /* kwargs 'expansion', default 1 (:920)                                 */
   double a1;          /* kwargs 'a1', default 1 (:919)                                        */
   rb_cosmology cosmology;
+  double ss, aa;      /* kwargs 'ss', 'aa': extra structure parameters of the PL / PL2 / 2C / DG jets */
 } rb_ag_config;
 
 int rb_ag_config_default(rb_ag_config* cfg);

@@ -606,17 +606,37 @@ def ag_erf(x):
     return sign * y
 
 
-def ag_structure(gamma, en, thi, thc, method_id, thj):
-    """get_structure_numba for the tophat (1) and Gaussian (2) jets, base_models.py:92-148"""
+def ag_structure(gamma, en, thi, thc, method_id, thj, s=0.01, a=0.5):
+    """get_structure_numba, base_models.py:92-148 (1 tophat, 2 Gaussian, 3 power law, 4 alternative power law,
+    5 two-component, 6 double Gaussian)"""
     gs = np.full(thi.shape[0], float(gamma))
     ei = np.full(thi.shape[0], float(en))
-    if method_id == 1:
-        fac = ag_erf(-(thi - min(thc, thj)) * 1000.0) * 0.5 + 0.5
-    elif method_id == 2:
-        fac = np.exp(-0.5 * (thi / thc) ** 2)
-    else:
-        raise NotImplementedError(method_id)
-    return (gs - 1) * fac + 1.0000000000001, ei * fac
+    with np.errstate(all="ignore"):
+        if method_id == 1:
+            fac = ag_erf(-(thi - min(thc, thj)) * 1000.0) * 0.5 + 0.5
+            return (gs - 1) * fac + 1.0000000000001, ei * fac
+        if method_id == 2:
+            fac = np.exp(-0.5 * (thi / thc) ** 2)
+            return (gs - 1.0) * fac + 1.0000000000001, ei * fac
+        if method_id == 3:
+            m = thi >= thc
+            ei[m] = ei[m] * (thc / thi[m]) ** s
+            gs[m] = (gs[m] - 1.0) * (thc / thi[m]) ** a + 1.000000000000001
+            return gs, ei
+        if method_id == 4:
+            fac = (1 + (thi / thc) ** 2) ** 0.5
+            return 1.000000000001 + (gs - 1.0) * fac ** (-a), ei * fac ** (-s)
+        if method_id == 5:
+            m = thi > thc
+            gs[m] = a
+            ei[m] = ei[m] * s
+            return gs, ei
+        if method_id == 6:
+            ec, ej = np.exp(-0.5 * (thi / thc) ** 2), np.exp(-0.5 * (thi / thj) ** 2)
+            eo = ei * ((1.0 - s) * ec + s * ej)
+            temp = ((1.0 - s) * ec + s * ej) / ((1.0 - s / a) * ec + (s / a) * ej)
+            return np.where(np.isfinite(temp), (gs - 1.0) * temp + 1.0000000000001, a), eo
+    raise NotImplementedError(method_id)
 
 
 def _ag_rk4(ghat, dm, g, m, fac, therm):
@@ -737,7 +757,8 @@ def ag_default_res(thv, thc, g0):
 
 
 def redback_afterglow(time, redshift, thv, loge0, thc, logn0, p, logepse, logepsb, g0, xiN, *, frequency,
-                      method_id=1, thj=None, res=None, steps=250, k=0, a1=1, expansion=1, dl=None, **_):
+                      method_id=1, thj=None, res=None, steps=250, k=0, a1=1, expansion=1, dl=None, ss=0.01, aa=0.5,
+                      **_):
     """tophat_redback (method_id=1, base_models.py:885-946) / gaussian_redback (method_id=2, :948-1010) through
     RedbackAfterglows.get_lightcurve (:573-640), output_format='flux_density'.  time: observer days.  mJy[E]."""
     time = np.asarray(time, dtype=float) * 86400.0
@@ -763,7 +784,7 @@ def redback_afterglow(time, redshift, thv, loge0, thc, logn0, p, logepse, logeps
         nu0 = np.unique(frequency)
         nu = nu0 * (1 + redshift)
         omi, thi, phii, rotstep, latstep = ag_segments(thj, res)
-        gs, ei = ag_structure(g0, e0, thi, thc, method_id, thj)
+        gs, ei = ag_structure(g0, e0, thi, thc, method_id, thj, ss, aa)
         G, SM, ghat = ag_gamma(gs, ei, 0.0, steps, n, float(k))
         sin_thi, cos_thi = np.sin(thi), np.cos(thi)
         ang = (np.cos(thv) * cos_thi[:, None] + np.cos(0.0) * np.sin(thv) * np.cos(phii)[None, :] * sin_thi[:, None]

@@ -14,4 +14,4 @@ all_models_dict = {
 }
 all_models_dict.update({name: getattr(kilonova_models, name)
                         for name in ("one_component_kilonova_model", "metzger_kilonova_model")})
-all_models_dict.update({name: getattr(afterglow_models, name) for name in ("tophat_redback", "gaussian_redback")})
+all_models_dict.update({fn.__name__: fn for fn in afterglow_models.FUSED})

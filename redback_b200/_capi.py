@@ -43,14 +43,15 @@ class KnConfig(C.Structure):
                 ("neutron_precursor_switch", C.c_int), ("vmax", C.c_double), ("cosmology", Cosmology)]
 
 
-AG_TOPHAT, AG_GAUSSIAN = 1, 2
+AG_TOPHAT, AG_GAUSSIAN, AG_POWERLAW, AG_POWERLAW_ALT, AG_TWO_COMPONENT, AG_DOUBLE_GAUSSIAN = 1, 2, 3, 4, 5, 6
 AG_ROWS = dict(redshift=0, thv=1, loge0=2, thc=3, thj=4, logn0=5, p=6, logepse=7, logepsb=8, g0=9, xiN=10)
 AG_NPARAM = 11
 
 
 class AgConfig(C.Structure):
     _fields_ = [("jet", C.c_int), ("sigma_mode", C.c_int), ("steps", C.c_int), ("res", C.c_int), ("k", C.c_int),
-                ("expansion", C.c_int), ("a1", C.c_double), ("cosmology", Cosmology)]
+                ("expansion", C.c_int), ("a1", C.c_double), ("cosmology", Cosmology), ("ss", C.c_double),
+                ("aa", C.c_double)]
 
 
 class RedbackB200Error(RuntimeError):
@@ -144,13 +145,15 @@ def kn_config(model, sigma_mode=SIGMA_FIXED, dense_resolution=500, neutron_precu
     return cfg
 
 
-def ag_config(jet, sigma_mode=SIGMA_FIXED, steps=250, res=0, k=0, expansion=1, a1=1.0, cosmology=None):
+def ag_config(jet, sigma_mode=SIGMA_FIXED, steps=250, res=0, k=0, expansion=1, a1=1.0, cosmology=None, ss=0.01,
+              aa=0.5):
     cfg = AgConfig()
     check(lib().rb_ag_config_default(C.byref(cfg)))
     cfg.jet, cfg.sigma_mode = jet, sigma_mode
     cfg.steps, cfg.res, cfg.k = int(steps), int(res), int(k)
     cfg.expansion = 1 if expansion else 0
     cfg.a1 = float(a1)
+    cfg.ss, cfg.aa = float(ss), float(aa)
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg

@@ -8,7 +8,7 @@ from .engine import AfterglowPath
 _COMMON = ("redshift", "thv", "loge0", "thc", "logn0", "p", "logepse", "logepsb", "g0", "xiN")
 
 
-def _spec(name, jet, needed):
+def _spec(name, jet, needed, ss=0.01, aa=0.5):
     def validate(kwargs):
         flux_density_only(kwargs, name)
 
@@ -16,7 +16,8 @@ def _spec(name, jet, needed):
         return AfterglowPath(jet, time, frequency=kwargs.get("frequency"), y=y, sigma=sigma, sigma_mode=sigma_mode,
                              steps=kwargs.get("steps", 250), res=kwargs.get("res"), k=kwargs.get("k", 0),
                              expansion=kwargs.get("expansion", 1), a1=kwargs.get("a1", 1),
-                             cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"))
+                             cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"),
+                             ss=kwargs.get("ss", ss), aa=kwargs.get("aa", aa))
 
     return FusedSpec(name, needed, build, validate)
 
@@ -42,4 +43,34 @@ def gaussian_redback(time, redshift=None, thv=None, loge0=None, thc=None, thj=No
     return run(_GAUSSIAN, time, named, kwargs, params_batch)
 
 
-FUSED = {tophat_redback: _TOPHAT, gaussian_redback: _GAUSSIAN}
+_WITH_THJ = _COMMON[:4] + ("thj",) + _COMMON[4:]
+# defaults of the extra structure parameters: base_models.py:1060-1061, 1129-1130, 1197-1198, 1265-1266
+_TWO_COMPONENT = _spec("twocomponent_redback", _capi.AG_TWO_COMPONENT, _WITH_THJ, ss=0.01, aa=4)
+_POWERLAW = _spec("powerlaw_redback", _capi.AG_POWERLAW, _WITH_THJ, ss=3, aa=-3)
+_POWERLAW_ALT = _spec("alternativepowerlaw_redback", _capi.AG_POWERLAW_ALT, _WITH_THJ, ss=3, aa=3)
+_DOUBLE_GAUSSIAN = _spec("doublegaussian_redback", _capi.AG_DOUBLE_GAUSSIAN, _WITH_THJ, ss=0.1, aa=0.5)
+
+
+def _with_thj(spec, doc):
+    def model(time, redshift=None, thv=None, loge0=None, thc=None, thj=None, logn0=None, p=None, logepse=None,
+              logepsb=None, g0=None, xiN=None, params_batch=None, **kwargs):
+        named = dict(redshift=redshift, thv=thv, loge0=loge0, thc=thc, thj=thj, logn0=logn0, p=p, logepse=logepse,
+                     logepsb=logepsb, g0=g0, xiN=xiN)
+        return run(spec, time, named, kwargs, params_batch)
+    model.__name__ = model.__qualname__ = spec.name
+    model.__doc__ = doc
+    return model
+
+
+twocomponent_redback = _with_thj(_TWO_COMPONENT, "redback afterglow_models.twocomponent_redback (:1013-1078); "
+                                                 "kwargs ss (0.01), aa (4); returns mJy.")
+powerlaw_redback = _with_thj(_POWERLAW, "redback afterglow_models.powerlaw_redback (:1081-1147); kwargs ss (3), "
+                                        "aa (-3); returns mJy.")
+alternativepowerlaw_redback = _with_thj(_POWERLAW_ALT, "redback afterglow_models.alternativepowerlaw_redback "
+                                                       "(:1150-1215); kwargs ss (3), aa (3); returns mJy.")
+doublegaussian_redback = _with_thj(_DOUBLE_GAUSSIAN, "redback afterglow_models.doublegaussian_redback (:1218-1283); "
+                                                     "kwargs ss (0.1), aa (0.5); returns mJy.")
+
+FUSED = {tophat_redback: _TOPHAT, gaussian_redback: _GAUSSIAN, twocomponent_redback: _TWO_COMPONENT,
+         powerlaw_redback: _POWERLAW, alternativepowerlaw_redback: _POWERLAW_ALT,
+         doublegaussian_redback: _DOUBLE_GAUSSIAN}

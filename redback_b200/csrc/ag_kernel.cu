@@ -101,7 +101,7 @@ __global__ void ag_prep_kernel(const AgArgs a) {
   }
   if (lane != 0) return;
   const double thv = P[RB_AG_THV * NT], thc = P[RB_AG_THC * NT], g0 = P[RB_AG_G0 * NT];
-  const double thj = (a.cfg.jet == RB_AG_GAUSSIAN) ? P[RB_AG_THJ * NT] : thc;     // tophat: thj = thc (:937)
+  const double thj = (a.cfg.jet != RB_AG_TOPHAT) ? P[RB_AG_THJ * NT] : thc;       // tophat: thj = thc (:937)
   const double p = P[RB_AG_P * NT];
   double nism = pow(10.0, P[RB_AG_LOGN0 * NT]);
   if (a.cfg.k == 2) nism = nism * 3e35;                                            // :540-541
@@ -228,8 +228,32 @@ __global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t to
     const double q = thi / thc;
     fac_s = exp(-0.5 * (q * q));
   }
-  const double Gs = (g0 - 1) * fac_s + 1.0000000000001;
-  const double Ei = ek * fac_s;
+  double Gs = (g0 - 1) * fac_s + 1.0000000000001;
+  double Ei = ek * fac_s;
+  const double ss = a.cfg.ss, aa = a.cfg.aa;
+  if (a.cfg.jet == RB_AG_POWERLAW) {                         // :114-120
+    Gs = g0;
+    Ei = ek;
+    if (thi >= thc) {
+      Ei = ek * pow(thc / thi, ss);
+      Gs = (g0 - 1.0) * pow(thc / thi, aa) + 1.000000000000001;
+    }
+  } else if (a.cfg.jet == RB_AG_POWERLAW_ALT) {              // :122-125
+    const double q = thi / thc;
+    const double fac = sqrt(1 + q * q);
+    Gs = 1.000000000001 + (g0 - 1.0) * pow(fac, -aa);
+    Ei = ek * pow(fac, -ss);
+  } else if (a.cfg.jet == RB_AG_TWO_COMPONENT) {             // :127-131
+    Gs = g0;
+    Ei = ek;
+    if (thi > thc) { Gs = aa; Ei = ek * ss; }
+  } else if (a.cfg.jet == RB_AG_DOUBLE_GAUSSIAN) {           // :133-146
+    const double qc = thi / thc, qj = thi / thj;
+    const double ec = exp(-0.5 * (qc * qc)), ej = exp(-0.5 * (qj * qj));
+    Ei = ek * ((1.0 - ss) * ec + ss * ej);
+    const double temp = ((1.0 - ss) * ec + ss * ej) / ((1.0 - ss / aa) * ec + (ss / aa) * ej);
+    Gs = isfinite(temp) ? (g0 - 1.0) * temp + 1.0000000000001 : aa;
+  }
   // get_gamma_numba (:195-249), therm = 0
   const double n_amb = S[AS_N];
   const double Nmin = (AG_FOURPI / (3.0 - kk)) * n_amb * pow(1e10, 3.0 - kk);

@@ -506,6 +506,8 @@ extern "C" int rb_ag_config_default(rb_ag_config* cfg) {
   cfg->k = 0;
   cfg->expansion = 1;
   cfg->a1 = 1.0;
+  cfg->ss = 0.01;
+  cfg->aa = 0.5;
   return rb_cosmology_planck18(&cfg->cosmology);
 }
 
@@ -514,8 +516,7 @@ static int ag_check(const rb_ag_config* cfg, int64_t N, int64_t E, const void* p
                     const void* out_model, const void* out_logl) {
   if (!cfg) return fail(RB_ERR_INVALID, "rb_ag_eval: null config");
   if (N < 0 || E <= 0) return fail(RB_ERR_INVALID, "rb_ag_eval: need N >= 0 and E > 0");
-  if (cfg->jet != RB_AG_TOPHAT && cfg->jet != RB_AG_GAUSSIAN)
-    return fail(RB_ERR_UNSUPPORTED, "rb_ag_eval: only the tophat ('TH') and Gaussian ('GJ') jets are on device");
+  if (cfg->jet < RB_AG_TOPHAT || cfg->jet > RB_AG_DOUBLE_GAUSSIAN) return fail(RB_ERR_INVALID, "rb_ag_eval: unknown jet");
   if (cfg->k != 0 && cfg->k != 2) return fail(RB_ERR_INVALID, "k must either be 0 or 2");  // base_models.py:574-575
   if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_QUADRATURE)
     return fail(RB_ERR_INVALID, "rb_ag_eval: unknown sigma_mode");

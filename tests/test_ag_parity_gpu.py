@@ -78,6 +78,26 @@ def test_variants(rb, k, pval, expansion):
     h.assert_close(outg, refg, RTOL, what=f"gaussian k={k} p={pval}")
 
 
+@pytest.mark.parametrize("name,method_id,ss,aa", [("twocomponent_redback", 5, 0.01, 4), ("powerlaw_redback", 3, 3, -3),
+                                                  ("alternativepowerlaw_redback", 4, 3, 3),
+                                                  ("doublegaussian_redback", 6, 0.1, 0.5)])
+def test_other_jet_structures(rb, name, method_id, ss, aa):
+    """get_structure_numba methods 3-6 (base_models.py:114-146) through their *_redback model functions."""
+    t = np.geomspace(0.1, 300, 24)
+    nu = np.where(np.arange(24) % 2 == 0, 5e9, 2e17)
+    rng = np.random.default_rng(17)
+    N = 12
+    p = h.tophat_prior(rng, N)
+    p["thj"] = p["thc"] * rng.uniform(1.5, 4.0, N)
+    p["thv"][:4] = p["thc"][:4] * rng.uniform(0, 1.5, 4)
+    out = getattr(rb.afterglow_models, name)(t, params_batch=p, frequency=nu, output_format="flux_density")
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.redback_afterglow(t, z, frequency=nu, method_id=method_id, ss=ss, aa=aa, **kw)
+        h.assert_close(out[i], ref, RTOL, what=f"{name} sample {i}")
+
+
 def test_errors(rb):
     t = np.array([1., 2.])
     kw = dict(thv=0.2, loge0=52., thc=0.08, logn0=-1., p=2.2, logepse=-1., logepsb=-2., g0=300., xiN=0.5)
