@@ -129,9 +129,6 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
     // sed.py:396-400: absorption_index >= 4 raises ValueError in the reference
     if (cfg->absorption_index >= 4.0)
       return fail(RB_ERR_INVALID, "absorption_index >= 4 is not supported: the integral below the cutoff diverges");
-    const double s = 4.0 - cfg->absorption_index;
-    if (s != std::floor(s) || s < 1.0)
-      return fail(RB_ERR_UNSUPPORTED, "CutoffBlackbody on device needs integer 4 - absorption_index in {1,2,3,4}");
     if (!(cfg->cutoff_wavelength > 0)) return fail(RB_ERR_INVALID, "cutoff_wavelength must be positive");
   }
   if (y) {

@@ -93,31 +93,6 @@ __device__ __forceinline__ double nak_knot(const double* __restrict__ x, int n, 
   return x[i - 2];
 }
 
-// CutoffBlackbody normalisation for one time (sed.py:386-421); mirrors cutoff_blackbody_mjy in sn_kernel.cu
-__device__ double cutoff_norm(double lbol, double rph, double tph, double lam_c, double alpha) {
-  const int s = (int)(4.0 - alpha + 0.5);
-  double norm = lbol / (kFluxConst / kAngstrom * (rph * rph) * tph);
-  const double kt_hc = tph / kXConst;
-  const double x_c = 1.0 / (lam_c * kt_hc);
-  const double e1 = exp(-x_c);
-  double en = 1.0, above = 0.0, below = 0.0;
-  for (int i = 1; i <= 10; ++i) {
-    en *= e1;
-    const double di = (double)i;
-    const double xi = x_c * di;
-    double ns = di;
-    for (int q = 1; q < s; ++q) ns *= di;
-    above += gammainc4(xi, en) / (di * di * di * di);
-    below += gammaincc_int(s, xi, en) / ns;
-  }
-  const double kt2 = kt_hc * kt_hc;
-  double kts = kt_hc, gam = 1.0;
-  for (int q = 1; q < s; ++q) { kts *= kt_hc; gam *= (double)q; }
-  above = kt2 * kt2 * 6.0 * above;
-  below = (1.0 / pow(lam_c, alpha)) * kts * gam * below;
-  return norm / ((above + below) / tph);
-}
-
 __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
   extern __shared__ double psm[];
   const int NT = a.n_t_max, NL = a.n_lambda, E = a.E;

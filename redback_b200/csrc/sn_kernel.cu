@@ -174,6 +174,38 @@ __device__ __forceinline__ double gammaincc_int(int s, double x, double emx) {
   return emx * sum;
 }
 
+// Q(s, x) for real s > 0 (non-integer absorption_index): series for P below x < s + 1, modified Lentz continued
+// fraction for Q above (both converge to ~1e-15; scipy.special.gammaincc is accurate to the same level)
+__device__ double gammaincc_real(double s, double x) {
+  if (!(x > 0.0)) return 1.0;
+  const double lead = exp(s * log(x) - x - lgamma(s));   // x^s e^-x / Gamma(s)
+  if (x < s + 1.0) {
+    double ap = s, del = 1.0 / s, sum = del;
+    for (int n = 0; n < 500; ++n) {
+      ap += 1.0;
+      del *= x / ap;
+      sum += del;
+      if (fabs(del) < fabs(sum) * 1e-17) break;
+    }
+    return 1.0 - sum * lead;
+  }
+  const double tiny = 1e-300;
+  double b = x + 1.0 - s, c = 1.0 / tiny, d = 1.0 / b, h = d;
+  for (int i = 1; i < 500; ++i) {
+    const double an = -(double)i * ((double)i - s);
+    b += 2.0;
+    d = an * d + b;
+    if (fabs(d) < tiny) d = tiny;
+    c = b + an / c;
+    if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < 1e-16) break;
+  }
+  return lead * h;
+}
+
 __device__ __forceinline__ double gammainc4(double x, double emx) {
   // P(4, x); series e^-x sum_{k>=4} x^k/k! below 1.5 (no cancellation), 1 - Q(4, x) above
   if (x < 1.5) {
@@ -187,14 +219,14 @@ __device__ __forceinline__ double gammainc4(double x, double emx) {
   return 1.0 - gammaincc_int(4, x, emx);
 }
 
-// sed.CutoffBlackbody (sed.py:301-426) + _SED.flux_density (sed.py:239-251) for one (epoch, frequency);
-// integer s = 4 - absorption_index.  Returns mJy (before the (1+z) factor of supernova_models.py:1597).
-__device__ __noinline__ double cutoff_blackbody_mjy(const rb_sn_config& cfg, double lbol, double rph, double tph,
-                                                    double nu, double dl) {
-  const double alpha = cfg.absorption_index;
-  const int s = (int)(4.0 - alpha + 0.5);
-  const double lam_c = cfg.cutoff_wavelength * kAngstrom;
-  double norm = lbol / (kFluxConst / kAngstrom * (rph * rph) * tph);          // :388-390
+// CutoffBlackbody normalisation for one time (sed.py:386-421): norms = L / (FLUX_CONST/A R^2 T) / ((above+below)/T)
+// with above = (kT/hc)^4 Gamma(4) sum_n P(4, n x_c)/n^4, below = lam_c^-alpha (kT/hc)^s Gamma(s) sum_n Q(s, n x_c)/n^s,
+// s = 4 - alpha.  Integer s uses the closed forms, real s the series / continued fraction.
+__device__ double cutoff_norm(double lbol, double rph, double tph, double lam_c, double alpha) {
+  const double sr = 4.0 - alpha;
+  const int s = (int)(sr + 0.5);
+  const bool s_int = (sr == (double)s);
+  double norm = lbol / (kFluxConst / kAngstrom * (rph * rph) * tph);
   const double kt_hc = tph / kXConst;
   const double x_c = 1.0 / (lam_c * kt_hc);
   const double e1 = exp(-x_c);
@@ -203,17 +235,37 @@ __device__ __noinline__ double cutoff_blackbody_mjy(const rb_sn_config& cfg, dou
     en *= e1;  // e^{-i x_c}
     const double di = (double)i;
     const double xi = x_c * di;
-    double ns = di;
-    for (int q = 1; q < s; ++q) ns *= di;
     above += gammainc4(xi, en) / (di * di * di * di);
-    below += gammaincc_int(s, xi, en) / ns;
+    if (s_int) {
+      double ns = di;
+      for (int q = 1; q < s; ++q) ns *= di;
+      below += gammaincc_int(s, xi, en) / ns;
+    } else {
+      below += gammaincc_real(sr, xi) / pow(di, sr);
+    }
   }
   const double kt2 = kt_hc * kt_hc;
-  double kts = kt_hc, gam = 1.0;  // kT_over_hc^s, Gamma(s) = (s-1)!
-  for (int q = 1; q < s; ++q) { kts *= kt_hc; gam *= (double)q; }
+  double kts, gam;
+  if (s_int) {
+    kts = kt_hc;
+    gam = 1.0;  // kT_over_hc^s, Gamma(s) = (s-1)!
+    for (int q = 1; q < s; ++q) { kts *= kt_hc; gam *= (double)q; }
+  } else {
+    kts = pow(kt_hc, sr);
+    gam = tgamma(sr);
+  }
   above = kt2 * kt2 * 6.0 * above;
   below = (1.0 / pow(lam_c, alpha)) * kts * gam * below;
-  norm /= ((above + below) / tph);
+  return norm / ((above + below) / tph);
+}
+
+// sed.CutoffBlackbody (sed.py:301-426) + _SED.flux_density (sed.py:239-251) for one (epoch, frequency);
+// Returns mJy (before the (1+z) factor of supernova_models.py:1597).
+__device__ __noinline__ double cutoff_blackbody_mjy(const rb_sn_config& cfg, double lbol, double rph, double tph,
+                                                    double nu, double dl) {
+  const double alpha = cfg.absorption_index;
+  const double lam_c = cfg.cutoff_wavelength * kAngstrom;
+  const double norm = cutoff_norm(lbol, rph, tph, lam_c, alpha);              // :386-421
   const double lam_A = 1.e10 * (kCSI / nu);                                   // utils.py:365-370
   const double lam = lam_A * kAngstrom;
   const double l2 = lam * lam;

@@ -40,9 +40,6 @@ def test_host_side_calls_without_gpu():
     assert lib.rb_sn_eval_f64(ctypes.byref(cfg), 1, 3, one, one, one, None, None, None, None, one, None, None) \
         == _capi.RB_ERR_INVALID
     assert b"absorption_index" in lib.rb_last_error()
-    cfg.absorption_index = 0.5
-    assert lib.rb_sn_eval_f64(ctypes.byref(cfg), 1, 3, one, one, one, None, None, None, None, one, None, None) \
-        == _capi.RB_ERR_UNSUPPORTED
 
 
 def test_library_is_in_tree():

@@ -168,6 +168,25 @@ def test_fp32_quadrature_path(rb):
     assert np.median(np.abs(out[ok] - out64[ok]) / np.abs(out64[ok])) < 1e-6
 
 
+@pytest.mark.parametrize("alpha", [0.0, 0.5, 1.7, 2.0, 3.2])
+def test_cutoff_blackbody_absorption_index(rb, alpha):
+    """CutoffBlackbody with integer (closed-form) and non-integer (series / continued-fraction incomplete gamma)
+    absorption_index (sed.py:386-421)."""
+    rng = np.random.default_rng(51)
+    t = np.sort(rng.uniform(2, 250, 40))
+    nu = rng.choice([1.2e15, 8.152e14, 6.273e14, 4.825e14], 40)
+    N = 40
+    p = h.slsn_prior(rng, N, zmax=1.0)
+    out = rb.supernova_models.slsn(t, params_batch=p, frequency=nu, output_format="flux_density",
+                                   absorption_index=alpha, cutoff_wavelength=3500.0)
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.slsn(t, z, frequency=nu, absorption_index=alpha, cutoff_wavelength=3500.0, **kw)
+        h.assert_close(out[i], ref, RTOL, 1e-12 + h.diffusion_condition(t / (1 + z), _tau(p, i)),
+                       what=f"alpha={alpha} sample {i}")
+
+
 def test_device_luminosity_distance(rb):
     z = np.array([1e-6, 0.01, 0.1, 0.5, 1.0, 2.0, 3.0, 8.0])
     out = rb.engine.luminosity_distance(z).cpu().numpy()
