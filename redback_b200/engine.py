@@ -145,6 +145,8 @@ class _FusedPath:
                 raise ValueError("out_logl must be a contiguous float64 [N] device tensor")
         if want_logl and self.y is None:
             raise ValueError("log-likelihood requested but no data were given")
+        if N == 0:      # empty batch: nothing to launch
+            return model, logl
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             rc = self._launch(N, params_dev, dl, self.y if want_logl else None, self.sigma if want_logl else None,

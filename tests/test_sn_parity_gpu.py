@@ -262,3 +262,23 @@ def test_full_size_properties(rb):
     pb2 = dict(pb, f_nickel=pb["f_nickel"] * 2.0)
     b = rb.supernova_models.arnett_bolometric(tb, params_batch=pb2)
     np.testing.assert_allclose(b, 2.0 * a, rtol=1e-14)
+
+
+def test_edge_shapes(rb):
+    """Single epoch (test/interaction_processes_test.py:321), duplicate and unsorted epochs, empty batch."""
+    sn = rb.supernova_models
+    kw = dict(vej=5e3, kappa=0.1, kappa_gamma=0.1)
+    one = sn.arnett_bolometric(np.array([2.0]), 0.1, 1.0, **kw)
+    h.assert_close(one, r.arnett_bolometric(np.array([2.0]), 0.1, 1.0, **kw), RTOL)
+    t = np.array([5.0, 1.0, 3.0, 3.0, 40.0, 2.0, 7.5])   # unsorted with a duplicate; time[-1] + 100 is the grid end
+    out = sn.arnett_bolometric(t, 0.1, 1.0, **kw)
+    h.assert_close(out, r.arnett_bolometric(t, 0.1, 1.0, **kw), RTOL)
+    empty = {k: np.zeros(0) for k in ("f_nickel", "mej", "vej", "kappa", "kappa_gamma")}
+    res = sn.arnett_bolometric(t, params_batch=empty)
+    assert res.shape == (0, t.size)
+    like = rb.GaussianLikelihood(t, out, 0.1 * out, sn.arnett_bolometric)
+    assert like.log_likelihood_batch(empty).shape == (0,)
+    with pytest.raises(NotImplementedError):
+        sn.arnett_bolometric(np.array([-1.0, 2.0]), 0.1, 1.0, **kw)
+    with pytest.raises(IndexError):
+        sn.arnett_bolometric(np.array([500.0, 2.0]), 0.1, 1.0, **kw)   # max(t) > t[-1] + 100
