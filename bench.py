@@ -295,7 +295,11 @@ def run_gpu(args):
         hbm_bytes = n * (10 * 8 + 8)
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-            "frac": achieved / peak.value if peak.value else None, "traffic": None,
+            "frac": achieved / peak.value if peak.value else None,
+            # dram__bytes_read+write of rb::sn_kernel from the committed ncu --set full capture
+            # (profiles/r1_final_sn_kernel_ncu_summary.txt: 27.1 MB for 200000 samples), scaled to this launch
+            "traffic": 135.5 * n, "traffic_source": "ncu capture at 200000 samples, scaled per sample",
+            "limiter": "shared-memory data pipe 88 % of peak, FP64 pipe 50 % (ncu, profiles/r1_final_*)",
             "kernel": "rb::sn_kernel", "kernel_ms": kernel_ms,
             "flop_eq_per_unit": flop_eq,
             "peak_source": "DFMA micro-benchmark measured live in this run (rb_measure_fp64_peak); nominal 37.2",
