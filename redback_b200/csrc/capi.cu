@@ -37,6 +37,21 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
   } while (0)
 
+// stream-ordered device allocation released (cudaFreeAsync) when it goes out of scope, on every return path
+struct StreamAlloc {
+  void* p = nullptr;
+  cudaStream_t st = nullptr;
+  StreamAlloc() = default;
+  StreamAlloc(const StreamAlloc&) = delete;
+  StreamAlloc& operator=(const StreamAlloc&) = delete;
+  ~StreamAlloc() { if (p) cudaFreeAsync(p, st); }
+  cudaError_t alloc(size_t bytes, cudaStream_t s) {
+    st = s;
+    return cudaMallocAsync(&p, bytes ? bytes : 8, s);
+  }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
 size_t sn_smem_bytes(int D, int64_t E, bool epochs_in_smem) {
   size_t n = (size_t)(2 * D + 2 * rb::kNodes + D + rb::kNodesHalf + rb::kNodes + rb::kNodes + rb::kExpTabSize + 2 * rb::kScalars + 16)  // incl. omx2
              + (size_t)(2 * rb::kNodes + (D + 1) / 2 * 2);   // FP32 copies: float4 nodes, float2 segments
@@ -170,8 +185,9 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
 
   // workspace: per-launch epoch table [kEpochCols][E] + per-sample scalar records [N][kScalars]
   const size_t ws_doubles = (size_t)rb::kEpochCols * (size_t)E + (size_t)rb::kScalars * (size_t)N;
-  double* ws = nullptr;
-  RB_CUDA(cudaMallocAsync(&ws, ws_doubles * sizeof(double), st));
+  StreamAlloc ws_buf;
+  RB_CUDA(ws_buf.alloc(ws_doubles * sizeof(double), st));
+  double* ws = ws_buf.as<double>();
   double* epoch_tab = ws;
   rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
                                                                     y ? sigma : nullptr, epoch_tab);
@@ -192,25 +208,16 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   const int threads = sn_block_threads(E);
   a.epochs_in_smem = (sn_smem_bytes(cfg->dense_resolution, E, true) <= 64 * 1024) ? 1 : 0;
   const size_t smem = sn_smem_bytes(cfg->dense_resolution, E, a.epochs_in_smem != 0);
-  if (smem > 220 * 1024) {
-    cudaFreeAsync(ws, st);
-    return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution too large for shared memory");
-  }
+  if (smem > 220 * 1024) return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution too large for shared memory");
   int occ = 0;
-  cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::sn_kernel, threads, smem);
-  if (oe != cudaSuccess) {
-    cudaFreeAsync(ws, st);
-    return cuda_fail(oe, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-  }
+  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::sn_kernel, threads, smem));
   if (occ < 1) occ = 1;
   // persistent blocks, grid-stride over samples; 4 waves' worth of blocks for load balance at mid-size N
   int64_t grid = (int64_t)sms * occ * 4;
   if (grid > N) grid = N;
   rb::sn_kernel<<<(unsigned)grid, threads, smem, st>>>(a);
   launch_counter()->fetch_add(3);
-  cudaError_t le = cudaGetLastError();
-  cudaFreeAsync(ws, st);
-  if (le != cudaSuccess) return cuda_fail(le, "sn_kernel launch");
+  RB_CUDA(cudaGetLastError());
   return RB_OK;
 }
 
@@ -406,8 +413,9 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(kn_kernel)");
   const size_t ws_doubles = (size_t)rb::kEpochCols * (size_t)E + (size_t)rb::kKnScalars * (size_t)N + 2;
-  double* ws = nullptr;
-  RB_CUDA(cudaMallocAsync(&ws, ws_doubles * sizeof(double), st));
+  StreamAlloc ws_buf;
+  RB_CUDA(ws_buf.alloc(ws_doubles * sizeof(double), st));
+  double* ws = ws_buf.as<double>();
   double* epoch_tab = ws;
   double* scal = ws + (size_t)rb::kEpochCols * (size_t)E;
   double* mm = scal + (size_t)rb::kKnScalars * (size_t)N;
@@ -417,14 +425,8 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   double h_mm[2];
   cudaError_t ce = cudaMemcpyAsync(h_mm, mm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);  // two doubles; needed to size the time grid
-  if (ce != cudaSuccess) {
-    cudaFreeAsync(ws, st);
-    return cuda_fail(ce, "epoch min/max");
-  }
-  if (!(h_mm[0] > 0.0)) {
-    cudaFreeAsync(ws, st);
-    return fail(RB_ERR_INVALID, "rb_kn_eval: epochs must be strictly positive (days)");
-  }
+  if (ce != cudaSuccess) return cuda_fail(ce, "epoch min/max");
+  if (!(h_mm[0] > 0.0)) return fail(RB_ERR_INVALID, "rb_kn_eval: epochs must be strictly positive (days)");
   rb::KnArgs a{};
   a.cfg = *cfg;
   a.N = N;
@@ -444,19 +446,13 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   const size_t smem = kn_smem_bytes(cfg, E);
   const int threads = 512;
   int occ = 0;
-  cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::kn_kernel, threads, smem);
-  if (oe != cudaSuccess) {
-    cudaFreeAsync(ws, st);
-    return cuda_fail(oe, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-  }
+  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::kn_kernel, threads, smem));
   if (occ < 1) occ = 1;
   int64_t grid = (int64_t)sms * occ * 4;
   if (grid > N) grid = N;
   rb::kn_kernel<<<(unsigned)grid, threads, smem, st>>>(a);
   launch_counter()->fetch_add(4);
-  cudaError_t le = cudaGetLastError();
-  cudaFreeAsync(ws, st);
-  if (le != cudaSuccess) return cuda_fail(le, "kn_kernel launch");
+  RB_CUDA(cudaGetLastError());
   return RB_OK;
 }
 
@@ -574,11 +570,11 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
   if (cell_smem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_ag_eval: steps / epochs exceed shared memory");
 
   const int64_t chunk_max = 8192;
-  const size_t fixed_doubles = (size_t)rb::kEpochCols * (size_t)E;
-  double* d_epoch = nullptr;
-  int* d_idx = nullptr;
-  RB_CUDA(cudaMallocAsync(&d_epoch, fixed_doubles * sizeof(double), st));
-  RB_CUDA(cudaMallocAsync(&d_idx, (size_t)E * sizeof(int), st));
+  StreamAlloc b_epoch, b_idx, b_scal, b_cnt, b_off, b_ucnt, b_uoff;
+  RB_CUDA(b_epoch.alloc((size_t)rb::kEpochCols * (size_t)E * sizeof(double), st));
+  RB_CUDA(b_idx.alloc((size_t)E * sizeof(int), st));
+  double* d_epoch = b_epoch.as<double>();
+  int* d_idx = b_idx.as<int>();
   RB_CUDA(cudaMemcpyAsync(d_idx, h_idx.data(), (size_t)E * sizeof(int), cudaMemcpyHostToDevice, st));
   RB_CUDA(cudaStreamSynchronize(st));  // h_idx is pageable host memory
   rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
@@ -587,23 +583,21 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
 
   const double q = rb::AG_QE * rb::AG_QE / (rb::AG_ME * rb::AG_C2);
   const double sigt = (q * q) * (8 * M_PI / 3);   // base_models.py:37
-  double* d_scal = nullptr;
-  int* d_cnt = nullptr;
-  int64_t* d_off = nullptr;
-  int* d_ucnt = nullptr;
-  int64_t* d_uoff = nullptr;
-  RB_CUDA(cudaMallocAsync(&d_scal, (size_t)chunk_max * rb::kAgScalars * sizeof(double), st));
-  RB_CUDA(cudaMallocAsync(&d_cnt, (size_t)chunk_max * sizeof(int), st));
-  RB_CUDA(cudaMallocAsync(&d_off, (size_t)(chunk_max + 1) * sizeof(int64_t), st));
-  RB_CUDA(cudaMallocAsync(&d_ucnt, (size_t)chunk_max * sizeof(int), st));
-  RB_CUDA(cudaMallocAsync(&d_uoff, (size_t)(chunk_max + 1) * sizeof(int64_t), st));
+  RB_CUDA(b_scal.alloc((size_t)chunk_max * rb::kAgScalars * sizeof(double), st));
+  RB_CUDA(b_cnt.alloc((size_t)chunk_max * sizeof(int), st));
+  RB_CUDA(b_off.alloc((size_t)(chunk_max + 1) * sizeof(int64_t), st));
+  RB_CUDA(b_ucnt.alloc((size_t)chunk_max * sizeof(int), st));
+  RB_CUDA(b_uoff.alloc((size_t)(chunk_max + 1) * sizeof(int64_t), st));
+  int* d_cnt = b_cnt.as<int>();
+  int64_t* d_off = b_off.as<int64_t>();
+  int* d_ucnt = b_ucnt.as<int>();
+  int64_t* d_uoff = b_uoff.as<int64_t>();
 
-  int status = RB_OK;
   const size_t ring_bytes = (size_t)rb::kRingArrays * steps * sizeof(double);
   const size_t scratch_cap = (size_t)6 << 30;   // bound the ring scratch at 6 GiB per chunk
   int64_t n0 = 0;
   int64_t chunk = chunk_max;
-  while (n0 < N && status == RB_OK) {
+  while (n0 < N) {
     const int64_t nc = std::min<int64_t>(chunk, N - n0);
     rb::AgArgs a{};
     a.cfg = *cfg;
@@ -621,35 +615,29 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
     a.nu_index = d_idx;
     for (int h = 0; h < rb::kAgMaxNu; ++h) a.nu_unique[h] = h < n_nu ? uniq[(size_t)h] : 0.0;
     a.n_nu = n_nu;
-    a.scalars = d_scal;
+    a.scalars = b_scal.as<double>();
     a.ring_count = d_cnt;
     a.ring_off = d_off;
-    a.ring_scratch = nullptr;
     a.unit_count = d_ucnt;
     a.unit_off = d_uoff;
-    a.partial = nullptr;
     a.sigt = sigt;
     rb::ag_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
     rb::ag_scan_kernel<<<1, 1024, 0, st>>>(nc, d_cnt, d_off);
     rb::ag_scan_kernel<<<1, 1024, 0, st>>>(nc, d_ucnt, d_uoff);
     int64_t total = 0, total_units = 0;
-    cudaError_t ce = cudaMemcpyAsync(&total, d_off + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&total_units, d_uoff + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    RB_CUDA(cudaMemcpyAsync(&total, d_off + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaMemcpyAsync(&total_units, d_uoff + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    RB_CUDA(cudaStreamSynchronize(st));
     launch_counter()->fetch_add(3);
-    if (ce != cudaSuccess) { status = cuda_fail(ce, "ring count"); break; }
     if ((size_t)total * ring_bytes > scratch_cap && nc > 64) {
       chunk = std::max<int64_t>(64, nc / 2);   // too many rings (large res): retry with a smaller chunk
       continue;
     }
-    double* d_ring = nullptr;
-    ce = cudaMallocAsync(&d_ring, std::max<size_t>((size_t)total, 1) * ring_bytes, st);
-    if (ce != cudaSuccess) { status = cuda_fail(ce, "ring scratch allocation"); break; }
-    a.ring_scratch = d_ring;
-    double* d_part = nullptr;
-    ce = cudaMallocAsync(&d_part, std::max<size_t>((size_t)total_units, 1) * (size_t)E * sizeof(double), st);
-    if (ce != cudaSuccess) { cudaFreeAsync(d_ring, st); status = cuda_fail(ce, "partial sums allocation"); break; }
-    a.partial = d_part;
+    StreamAlloc b_ring, b_part;
+    RB_CUDA(b_ring.alloc(std::max<size_t>((size_t)total, 1) * ring_bytes, st));
+    RB_CUDA(b_part.alloc(std::max<size_t>((size_t)total_units, 1) * (size_t)E * sizeof(double), st));
+    a.ring_scratch = b_ring.as<double>();
+    a.partial = b_part.as<double>();
     if (total > 0) {
       rb::ag_ring_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, total);
       rb::ag_cell_kernel<<<(unsigned)total_units, rb::kAgWarps * 32, cell_smem, st>>>(a, total_units);
@@ -657,20 +645,10 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
     }
     rb::ag_finish_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * 16), 128, 0, st>>>(a);
     launch_counter()->fetch_add(1);
-    ce = cudaGetLastError();
-    cudaFreeAsync(d_part, st);
-    cudaFreeAsync(d_ring, st);
-    if (ce != cudaSuccess) { status = cuda_fail(ce, "afterglow kernels"); break; }
+    RB_CUDA(cudaGetLastError());
     n0 += nc;
   }
-  cudaFreeAsync(d_uoff, st);
-  cudaFreeAsync(d_ucnt, st);
-  cudaFreeAsync(d_off, st);
-  cudaFreeAsync(d_cnt, st);
-  cudaFreeAsync(d_scal, st);
-  cudaFreeAsync(d_idx, st);
-  cudaFreeAsync(d_epoch, st);
-  return status;
+  return RB_OK;
 }
 
 extern "C" int rb_ag_eval_f64_host(const rb_ag_config* cfg, int64_t N, int64_t E, const double* params,
