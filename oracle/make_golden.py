@@ -138,7 +138,66 @@ def dump_ecsv():
     print("ecsv rows:", len(out), "epochs:", len(time))
 
 
+def dump_verbatim():
+    """Outputs of the reference's OWN source files, imported verbatim through oracle/refshim.py (numba JIT
+    disabled = the pure-Python path the reference's CI tests, .github/workflows/python-app.yml:88), on seeded
+    prior draws: interaction_processes.Diffusion + photosphere.TemperatureFloor, and the redback-native afterglows."""
+    os.environ["NUMBA_DISABLE_JIT"] = "1"
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import warnings
+    warnings.simplefilter("ignore")
+    from oracle import refshim, restated as r
+    ns = refshim.load()
+    bm = refshim.load_afterglow()
+    rng = np.random.default_rng(2024)
+    doc = {"diffusion": [], "afterglow": []}
+    t = np.sort(rng.uniform(0.5, 300, 40))
+    for i in range(16):
+        prm = dict(mej=float(10 ** rng.uniform(-1, 2)), vej=float(10 ** rng.uniform(3, 5)),
+                   kappa=float(rng.uniform(0.05, 2)), kappa_gamma=float(10 ** rng.uniform(-4, 4)))
+        dense = np.linspace(0, t[-1] + 100, 1000)
+        if i % 2 == 0:
+            eng = dict(engine="nickel", f_nickel=float(10 ** rng.uniform(-3, 0)))
+            lum = r.nickelcobalt_engine(dense, eng["f_nickel"], prm["mej"])
+        else:
+            eng = dict(engine="magnetar", p0=float(rng.uniform(1, 10)), bp=float(10 ** rng.uniform(-1, 1)),
+                       mass_ns=float(rng.uniform(1.1, 2.2)), theta_pb=float(rng.uniform(0, 1.57)))
+            lum = r.basic_magnetar(dense * 86400, eng["p0"], eng["bp"], eng["mass_ns"], eng["theta_pb"])
+        d = ns.interaction_processes.Diffusion(t, dense, lum, prm["kappa"], prm["kappa_gamma"], prm["mej"], prm["vej"])
+        tfl = float(10 ** rng.uniform(3, 4.5))
+        ph = ns.photosphere.TemperatureFloor(t, d.new_luminosity, prm["vej"], tfl)
+        doc["diffusion"].append(dict(params=dict(prm, temperature_floor=tfl, **eng), tau_d=float(d.tau_d),
+                                     lbol=[float(v) for v in d.new_luminosity],
+                                     temperature=[float(v) for v in ph.photosphere_temperature],
+                                     radius=[float(v) for v in ph.r_photosphere]))
+    doc["diffusion_time"] = [float(v) for v in t]
+    ta = np.geomspace(0.1, 300, 24)
+    fr = np.where(np.arange(24) % 2 == 0, 5e9, 2e17)
+    models = [("tophat_redback", {}), ("gaussian_redback", {}), ("twocomponent_redback", {}), ("powerlaw_redback", {}),
+              ("alternativepowerlaw_redback", {}), ("doublegaussian_redback", {})]
+    for j in range(12):
+        name, _ = models[j % len(models)]
+        kw = dict(thv=float(np.arccos(rng.uniform(0.6, 1))), loge0=float(rng.uniform(48, 53)),
+                  thc=float(rng.uniform(0.03, 0.1)), logn0=float(rng.uniform(-3, 1)), p=float(rng.uniform(1.6, 3)),
+                  logepse=float(rng.uniform(-3, -0.5)), logepsb=float(rng.uniform(-4, -1)), g0=float(rng.uniform(100, 600)),
+                  xiN=float(rng.uniform(0.1, 1)))
+        if j < 3:
+            kw["thv"] = kw["thc"] * float(rng.uniform(0, 1.2))     # on-axis: resolution above 10
+        if name != "tophat_redback":
+            kw["thj"] = kw["thc"] * float(rng.uniform(1.5, 3))
+        z = float(rng.uniform(0.05, 2))
+        k = 2 if j % 4 == 3 else 0
+        out = getattr(bm, name)(ta, z, frequency=fr, output_format="flux_density", k=k, **kw)
+        doc["afterglow"].append(dict(model=name, redshift=z, k=k, params=kw, results=[float(v) for v in out]))
+    doc["afterglow_time"] = [float(v) for v in ta]
+    doc["afterglow_frequency"] = [float(v) for v in fr]
+    with open(os.path.join(OUT, "verbatim_reference_draws.json"), "w") as fh:
+        json.dump(doc, fh)
+    print("verbatim fixtures:", len(doc["diffusion"]), "diffusion,", len(doc["afterglow"]), "afterglow")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     dump_pkl()
     dump_ecsv()
+    dump_verbatim()

@@ -1,0 +1,63 @@
+"""Fixtures produced by the reference's OWN source files (imported verbatim in the build container by
+oracle/make_golden.py::dump_verbatim): interaction_processes.Diffusion + photosphere.TemperatureFloor and the six
+redback-native afterglow models on seeded prior draws.  CPU: the oracle reproduces them; GPU: so does the device."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers as h
+from oracle import restated as r
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+METHOD = dict(tophat_redback=1, gaussian_redback=2, powerlaw_redback=3, alternativepowerlaw_redback=4,
+              twocomponent_redback=5, doublegaussian_redback=6)
+EXTRA = dict(tophat_redback=(0.01, 0.5), gaussian_redback=(0.01, 0.5), twocomponent_redback=(0.01, 4),
+             powerlaw_redback=(3, -3), alternativepowerlaw_redback=(3, 3), doublegaussian_redback=(0.1, 0.5))
+
+
+@pytest.fixture(scope="module")
+def fx():
+    with open(os.path.join(ROOT, "tests", "golden", "verbatim_reference_draws.json")) as fh:
+        return json.load(fh)
+
+
+def _bolometric(kind, t, p):
+    common = dict(mej=p["mej"], vej=p["vej"], kappa=p["kappa"], kappa_gamma=p["kappa_gamma"])
+    if kind == "nickel":
+        return ("arnett_bolometric", dict(f_nickel=p["f_nickel"], **common))
+    return ("basic_magnetar_powered_bolometric", dict(p0=p["p0"], bp=p["bp"], mass_ns=p["mass_ns"],
+                                                      theta_pb=p["theta_pb"], **common))
+
+
+def test_oracle_reproduces_verbatim_reference(fx):
+    t = np.array(fx["diffusion_time"])
+    for row in fx["diffusion"]:
+        name, kw = _bolometric(row["params"]["engine"], t, row["params"])
+        out = getattr(r, name)(t, **kw)
+        np.testing.assert_allclose(out, row["lbol"], rtol=1e-14)
+        T, R = r.temperature_floor(t, out, row["params"]["vej"], row["params"]["temperature_floor"])
+        np.testing.assert_allclose(T, row["temperature"], rtol=1e-13)
+        np.testing.assert_allclose(R, row["radius"], rtol=1e-13)
+    ta, fr = np.array(fx["afterglow_time"]), np.array(fx["afterglow_frequency"])
+    for row in fx["afterglow"][:6]:
+        ss, aa = EXTRA[row["model"]]
+        out = r.redback_afterglow(ta, row["redshift"], frequency=fr, method_id=METHOD[row["model"]], k=row["k"],
+                                  ss=ss, aa=aa, **row["params"])
+        np.testing.assert_allclose(out, row["results"], rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_device_reproduces_verbatim_reference(fx):
+    import redback_b200 as rb
+    t = np.array(fx["diffusion_time"])
+    for row in fx["diffusion"]:
+        name, kw = _bolometric(row["params"]["engine"], t, row["params"])
+        out = getattr(rb.supernova_models, name)(t, **kw)
+        h.assert_close(out, np.array(row["lbol"]), 1e-9, h.diffusion_condition(t, row["tau_d"]), what=name)
+    ta, fr = np.array(fx["afterglow_time"]), np.array(fx["afterglow_frequency"])
+    for row in fx["afterglow"]:
+        out = getattr(rb.afterglow_models, row["model"])(ta, row["redshift"], frequency=fr,
+                                                          output_format="flux_density", k=row["k"], **row["params"])
+        h.assert_close(out, np.array(row["results"]), 1e-9, what=row["model"])
