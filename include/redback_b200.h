@@ -47,7 +47,9 @@ enum { RB_SED_BOLOMETRIC = 0, RB_SED_BLACKBODY = 1, RB_SED_CUTOFF_BLACKBODY = 2,
 enum {
   RB_SIGMA_FIXED = 0,      /* GaussianLikelihood(sigma=array|float)   likelihoods.py:146-231        */
   RB_SIGMA_SAMPLED = 1,    /* GaussianLikelihood(sigma=None): `sigma` is a sampled parameter :179-185 */
-  RB_SIGMA_QUADRATURE = 2  /* GaussianLikelihoodQuadratureNoise: sqrt(sigma_i^2 + sigma^2) :738-790 */
+  RB_SIGMA_QUADRATURE = 2, /* GaussianLikelihoodQuadratureNoise: sqrt(sigma_i^2 + sigma^2) :738-790 */
+  RB_SIGMA_FRACTIONAL = 3, /* GaussianLikelihoodWithFractionalNoise: sqrt(sigma_i^2 model^2) :792-851 (no sampled sigma) */
+  RB_SIGMA_SYSTEMATIC = 4  /* GaussianLikelihoodWithSystematicNoise: sqrt(sigma_i^2 + model^2 sigma^2) :853-913 */
 };
 
 /* Row indices of the SoA parameter block of the supernova path (rows not used by the chosen

@@ -320,6 +320,20 @@ def slsn(time, redshift, p0, bp, mass_ns, theta_pb, *, frequency, mej, vej, kapp
         cutoff_wavelength=cutoff_wavelength, absorption_index=absorption_index)
 
 
+def gaussian_likelihood_fractional(y, model, sigma_i):
+    """GaussianLikelihoodWithFractionalNoise.log_likelihood, likelihoods.py:821-851."""
+    with np.errstate(all="ignore"):
+        full = np.sqrt(np.asarray(sigma_i) ** 2. * np.asarray(model) ** 2)
+    return float(np.nan_to_num(gaussian_log_likelihood(np.asarray(y) - model, full)))
+
+
+def gaussian_likelihood_systematic(y, model, sigma_i, sigma):
+    """GaussianLikelihoodWithSystematicNoise.log_likelihood, likelihoods.py:883-913."""
+    with np.errstate(all="ignore"):
+        full = np.sqrt(np.asarray(sigma_i) ** 2. + np.asarray(model) ** 2 * sigma ** 2.)
+    return float(np.nan_to_num(gaussian_log_likelihood(np.asarray(y) - model, full)))
+
+
 def line_sed_cgs(time, luminosity, frequency, base_flux_cgs, dl, line_wavelength=7.5e3, line_width=500,
                  line_time=50, line_duration=25, line_amplitude=0.3):
     """sed.Line._set_sed (sed.py:859-909).  `frequency`: (1, n_freq) row for the flux_density branch or (n_freq, 1)

@@ -13,7 +13,7 @@ ENGINE_NICKEL, ENGINE_MAGNETAR = 0, 1
 PREC_F64, PREC_F32 = 0, 1
 NOISE_TYPES = dict(limiting_mag=0, gaussian=1, gaussianmodel=2)
 SED_BOLOMETRIC, SED_BLACKBODY, SED_CUTOFF_BLACKBODY, SED_CUTOFF_LINE = 0, 1, 2, 3
-SIGMA_FIXED, SIGMA_SAMPLED, SIGMA_QUADRATURE = 0, 1, 2
+SIGMA_FIXED, SIGMA_SAMPLED, SIGMA_QUADRATURE, SIGMA_FRACTIONAL, SIGMA_SYSTEMATIC = 0, 1, 2, 3, 4
 
 SN_ROWS = dict(redshift=0, f_nickel=1, p0=1, bp=2, mass_ns=3, theta_pb=4, mej=5, vej=6, kappa=7,
                kappa_gamma=8, temperature_floor=9)

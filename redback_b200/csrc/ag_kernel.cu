@@ -137,7 +137,7 @@ __global__ void ag_prep_kernel(const AgArgs a) {
   S[AS_ROTSTEP] = rotstep;
   S[AS_RES] = resd;
   S[AS_NROT] = (double)nrot;
-  S[AS_SIGMA] = (a.cfg.sigma_mode != RB_SIGMA_FIXED && a.want_logl) ? a.sigma_param[a.n_base + n] : 0.0;
+  S[AS_SIGMA] = (a.sigma_param != nullptr && a.want_logl) ? a.sigma_param[a.n_base + n] : 0.0;
   S[AS_PAD] = 0.0;
   // p outside (1.2, 3.4) raises ValueError in the reference (:576-577): flagged by zero rings -> NaN output
   const int rings = (p < 1.2 || p > 3.4 || !(p == p)) ? 0 : res;
@@ -512,19 +512,8 @@ __global__ void __launch_bounds__(128) ag_finish_kernel(const AgArgs a) {
       const double model_v = (u1 > u0) ? lc * opz / 1e-26 : NAN;                   // :640, :942
       if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = model_v;
       if (a.want_logl) {
-        const double res = a.epoch_tab[EP_Y * E + e] - model_v;
-        if (a.cfg.sigma_mode == RB_SIGMA_FIXED) {
-          const double rs = res * a.epoch_tab[EP_ISIG * E + e];
-          logl_part += -(rs * rs) / 2 - a.epoch_tab[EP_LOGT * E + e];
-        } else {
-          double sg = sp;
-          if (a.cfg.sigma_mode == RB_SIGMA_QUADRATURE) {
-            const double si = a.epoch_tab[EP_ISIG * E + e];
-            sg = sqrt(si * si + sp * sp);
-          }
-          const double rs = res / sg;
-          logl_part += -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;
-        }
+        logl_part += logl_term(a.cfg.sigma_mode, a.epoch_tab[EP_Y * E + e], model_v, a.epoch_tab[EP_ISIG * E + e],
+                               a.epoch_tab[EP_LOGT * E + e], sp);
       }
     }
     if (a.want_logl) {

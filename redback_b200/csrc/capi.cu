@@ -131,7 +131,7 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown engine");
   if (cfg->sed < RB_SED_BOLOMETRIC || cfg->sed > RB_SED_CUTOFF_LINE)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sed");
-  if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_QUADRATURE)
+  if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_SYSTEMATIC)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sigma_mode");
   if (cfg->precision != RB_PREC_F64 && cfg->precision != RB_PREC_F32)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown precision");
@@ -150,7 +150,7 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
     if (!out_logl) return fail(RB_ERR_INVALID, "rb_sn_eval: y given but out_logl is null");
     if (cfg->sigma_mode != RB_SIGMA_SAMPLED && !sigma)
       return fail(RB_ERR_INVALID, "rb_sn_eval: sigma is required for this sigma_mode");
-    if (cfg->sigma_mode != RB_SIGMA_FIXED && !sigma_param)
+    if (cfg->sigma_mode != RB_SIGMA_FIXED && cfg->sigma_mode != RB_SIGMA_FRACTIONAL && !sigma_param)
       return fail(RB_ERR_INVALID, "rb_sn_eval: sigma_param is required for this sigma_mode");
   } else if (out_logl) {
     return fail(RB_ERR_INVALID, "rb_sn_eval: out_logl requested without data y");
@@ -235,10 +235,11 @@ int rb_luminosity_distance_f64(const rb_cosmology* cosmo, int64_t N, const doubl
 int rb_gaussian_logl_f64(int sigma_mode, int64_t N, int64_t E, const double* model, const double* y,
                          const double* sigma, const double* sigma_param, double* out_logl, void* stream) {
   if (!model || !y || !out_logl || N < 0 || E <= 0) return fail(RB_ERR_INVALID, "rb_gaussian_logl: bad arguments");
-  if (sigma_mode < RB_SIGMA_FIXED || sigma_mode > RB_SIGMA_QUADRATURE)
+  if (sigma_mode < RB_SIGMA_FIXED || sigma_mode > RB_SIGMA_SYSTEMATIC)
     return fail(RB_ERR_INVALID, "rb_gaussian_logl: unknown sigma_mode");
   if (sigma_mode != RB_SIGMA_SAMPLED && !sigma) return fail(RB_ERR_INVALID, "rb_gaussian_logl: sigma required");
-  if (sigma_mode != RB_SIGMA_FIXED && !sigma_param) return fail(RB_ERR_INVALID, "rb_gaussian_logl: sigma_param required");
+  if (sigma_mode != RB_SIGMA_FIXED && sigma_mode != RB_SIGMA_FRACTIONAL && !sigma_param)
+    return fail(RB_ERR_INVALID, "rb_gaussian_logl: sigma_param required");
   if (N == 0) return RB_OK;
   const int threads = E >= 256 ? 256 : (E >= 128 ? 128 : 64);
   const int64_t grid = N < 1048576 ? N : 1048576;
@@ -371,7 +372,7 @@ static int kn_check(const rb_kn_config* cfg, int64_t N, int64_t E, const void* p
   if (N < 0 || E <= 0) return fail(RB_ERR_INVALID, "rb_kn_eval: need N >= 0 and E > 0");
   if (cfg->model != RB_KN_ONE_COMPONENT && cfg->model != RB_KN_METZGER)
     return fail(RB_ERR_INVALID, "rb_kn_eval: unknown model");
-  if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_QUADRATURE)
+  if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_SYSTEMATIC)
     return fail(RB_ERR_INVALID, "rb_kn_eval: unknown sigma_mode");
   if (cfg->dense_resolution < 20 || cfg->dense_resolution > 2000)
     return fail(RB_ERR_INVALID, "rb_kn_eval: dense_resolution must be in [20, 2000]");
@@ -380,7 +381,7 @@ static int kn_check(const rb_kn_config* cfg, int64_t N, int64_t E, const void* p
   if (y) {
     if (!out_logl) return fail(RB_ERR_INVALID, "rb_kn_eval: y given but out_logl is null");
     if (cfg->sigma_mode != RB_SIGMA_SAMPLED && !sigma) return fail(RB_ERR_INVALID, "rb_kn_eval: sigma is required");
-    if (cfg->sigma_mode != RB_SIGMA_FIXED && !sigma_param) return fail(RB_ERR_INVALID, "rb_kn_eval: sigma_param is required");
+    if (cfg->sigma_mode != RB_SIGMA_FIXED && cfg->sigma_mode != RB_SIGMA_FRACTIONAL && !sigma_param) return fail(RB_ERR_INVALID, "rb_kn_eval: sigma_param is required");
   } else if (out_logl) {
     return fail(RB_ERR_INVALID, "rb_kn_eval: out_logl requested without data y");
   }
@@ -511,7 +512,7 @@ static int ag_check(const rb_ag_config* cfg, int64_t N, int64_t E, const void* p
   if (N < 0 || E <= 0) return fail(RB_ERR_INVALID, "rb_ag_eval: need N >= 0 and E > 0");
   if (cfg->jet < RB_AG_TOPHAT || cfg->jet > RB_AG_DOUBLE_GAUSSIAN) return fail(RB_ERR_INVALID, "rb_ag_eval: unknown jet");
   if (cfg->k != 0 && cfg->k != 2) return fail(RB_ERR_INVALID, "k must either be 0 or 2");  // base_models.py:574-575
-  if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_QUADRATURE)
+  if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_SYSTEMATIC)
     return fail(RB_ERR_INVALID, "rb_ag_eval: unknown sigma_mode");
   if (cfg->steps < 2 || cfg->steps > 1000) return fail(RB_ERR_INVALID, "rb_ag_eval: steps must be in [2, 1000]");
   if (cfg->res < 0 || cfg->res > 400) return fail(RB_ERR_INVALID, "rb_ag_eval: res must be in [1, 400] (0 = default rule)");
@@ -519,7 +520,7 @@ static int ag_check(const rb_ag_config* cfg, int64_t N, int64_t E, const void* p
   if (y) {
     if (!out_logl) return fail(RB_ERR_INVALID, "rb_ag_eval: y given but out_logl is null");
     if (cfg->sigma_mode != RB_SIGMA_SAMPLED && !sigma) return fail(RB_ERR_INVALID, "rb_ag_eval: sigma is required");
-    if (cfg->sigma_mode != RB_SIGMA_FIXED && !sigma_param) return fail(RB_ERR_INVALID, "rb_ag_eval: sigma_param is required");
+    if (cfg->sigma_mode != RB_SIGMA_FIXED && cfg->sigma_mode != RB_SIGMA_FRACTIONAL && !sigma_param) return fail(RB_ERR_INVALID, "rb_ag_eval: sigma_param is required");
   } else if (out_logl) {
     return fail(RB_ERR_INVALID, "rb_ag_eval: out_logl requested without data y");
   }

@@ -138,7 +138,7 @@ __global__ void kn_prep_kernel(const KnArgs a) {
   S[KS_V0] = v0;
   S[KS_TDIFF] = sqrt(2.0 * kappa * m0 / (13.7 * v0 * kC));                      // kilonova_models.py:1877
   S[KS_TFLOOR] = (a.cfg.model == KN_ONE_COMPONENT) ? P[RB_KN_TEMPERATURE_FLOOR * N] : 0.0;
-  S[KS_SIGMA] = (a.cfg.sigma_mode != RB_SIGMA_FIXED && a.want_logl) ? a.sigma_param[n] : 0.0;
+  S[KS_SIGMA] = (a.sigma_param != nullptr && a.want_logl) ? a.sigma_param[n] : 0.0;
   // get_optimal_time_array(1e-2, 7e6, R, user_times = t_obs * 86400 / (1+z))  (utils.py:50-80)
   const double t_min = 1e-2, t_max = 7e6;
   const double user_min = a.tmin_obs * kDay / opz, user_max = a.tmax_obs * kDay / opz;
@@ -405,20 +405,8 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
       }
       if (a.out_model != nullptr) a.out_model[n * (int64_t)E + e] = model_v;
       if (want_logl) {
-        const double res = ep[EP_Y * E + e] - model_v;
-        if (sigma_mode == RB_SIGMA_FIXED) {
-          const double rs = res * ep[EP_ISIG * E + e];
-          logl_part += -(rs * rs) / 2 - ep[EP_LOGT * E + e];
-        } else {
-          const double sp = sc[KS_SIGMA];
-          double sg = sp;
-          if (sigma_mode == RB_SIGMA_QUADRATURE) {
-            const double si = ep[EP_ISIG * E + e];
-            sg = sqrt(si * si + sp * sp);
-          }
-          const double rs = res / sg;
-          logl_part += -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;
-        }
+        logl_part += logl_term(sigma_mode, ep[EP_Y * E + e], model_v, ep[EP_ISIG * E + e], ep[EP_LOGT * E + e],
+                               sc[KS_SIGMA]);
       }
     }
     if (want_logl) {

@@ -340,20 +340,8 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
       if (a.output == RB_OUT_FLUX) model_v = pow(10.0, model_v / (-2.5)) * a.band_ref[b];   // utils.py:716-718
       if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = model_v;
       if (a.want_logl) {
-        const double res = a.epoch_tab[EP_Y * E + e] - model_v;
-        if (a.sigma_mode == RB_SIGMA_FIXED) {
-          const double rs = res * a.epoch_tab[EP_ISIG * E + e];
-          logl_part += -(rs * rs) / 2 - a.epoch_tab[EP_LOGT * E + e];
-        } else {
-          const double sp = a.sigma_param_s[n];
-          double sg = sp;
-          if (a.sigma_mode == RB_SIGMA_QUADRATURE) {
-            const double si = a.epoch_tab[EP_ISIG * E + e];
-            sg = sqrt(si * si + sp * sp);
-          }
-          const double rs = res / sg;
-          logl_part += -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;
-        }
+        logl_part += logl_term(a.sigma_mode, a.epoch_tab[EP_Y * E + e], model_v, a.epoch_tab[EP_ISIG * E + e],
+                               a.epoch_tab[EP_LOGT * E + e], a.sigma_param_s ? a.sigma_param_s[n] : 0.0);
       }
     }
     if (a.want_logl) {

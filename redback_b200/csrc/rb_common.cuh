@@ -96,6 +96,27 @@ __device__ __forceinline__ double nan_to_num(double v) {
   return v;
 }
 
+// ---- Gaussian log-likelihood term of one datum (likelihoods.py:229-231) for every noise model -----------------
+//   RB_SIGMA_FIXED       sigma given: `isig` = 1/sigma, `logt` = log(2 pi sigma^2)/2 precomputed per epoch
+//   RB_SIGMA_SAMPLED     sigma = sampled parameter `sp`                                   (likelihoods.py:179-185)
+//   RB_SIGMA_QUADRATURE  sqrt(sigma_i^2 + sp^2)                                           (likelihoods.py:767)
+//   RB_SIGMA_FRACTIONAL  sqrt(sigma_i^2 * model^2)                                        (likelihoods.py:826)
+//   RB_SIGMA_SYSTEMATIC  sqrt(sigma_i^2 + model^2 * sp^2)                                 (likelihoods.py:888)
+// For the modes other than FIXED `isig` carries sigma_i itself.
+__device__ __forceinline__ double logl_term(int mode, double y, double model, double isig, double logt, double sp) {
+  const double res = y - model;
+  if (mode == RB_SIGMA_FIXED) {
+    const double rs = res * isig;
+    return -(rs * rs) / 2 - logt;
+  }
+  double sg = sp;
+  if (mode == RB_SIGMA_QUADRATURE) sg = sqrt(isig * isig + sp * sp);
+  else if (mode == RB_SIGMA_FRACTIONAL) sg = sqrt((isig * isig) * (model * model));
+  else if (mode == RB_SIGMA_SYSTEMATIC) sg = sqrt(isig * isig + (model * model) * (sp * sp));
+  const double rs = res / sg;
+  return -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;
+}
+
 // ---- cosmology --------------------------------------------------------------------------------
 // 1/E(z) of flat LambdaCDM with massive neutrinos (astropy FLRW.nu_relative_density / inv_efunc).
 __device__ __forceinline__ double inv_efunc(const rb_cosmology& c, double z) {

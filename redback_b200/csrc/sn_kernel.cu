@@ -158,7 +158,7 @@ __global__ void sn_prep_kernel(const SnArgs a) {
   S[SC_INV_REC] = inv_rec;
   S[SC_INV_DEN] = 1.0 / ((dl * dl) * (kC * kC));
   S[SC_DL] = dl;
-  S[SC_SIGMA] = (a.cfg.sigma_mode != RB_SIGMA_FIXED && a.want_logl) ? a.sigma_param[n] : 0.0;
+  S[SC_SIGMA] = (a.sigma_param != nullptr && a.want_logl) ? a.sigma_param[n] : 0.0;
   S[SC_SPARE] = 0.0;
 }
 
@@ -583,20 +583,8 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       }
       if (a.out_model != nullptr) a.out_model[n * (int64_t)E + e] = model;
       if (want_logl) {
-        const double res = ep[EP_Y * E + e] - model;
-        if (sigma_mode == RB_SIGMA_FIXED) {
-          const double rs = res * ep[EP_ISIG * E + e];
-          logl_part += -(rs * rs) / 2 - ep[EP_LOGT * E + e];                  // likelihoods.py:231
-        } else {
-          const double sp = sc[SC_SIGMA];
-          double sg = sp;
-          if (sigma_mode == RB_SIGMA_QUADRATURE) {
-            const double si = ep[EP_ISIG * E + e];
-            sg = sqrt(si * si + sp * sp);                                     // likelihoods.py:767
-          }
-          const double rs = res / sg;
-          logl_part += -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;
-        }
+        logl_part += logl_term(sigma_mode, ep[EP_Y * E + e], model, ep[EP_ISIG * E + e], ep[EP_LOGT * E + e],
+                               sc[SC_SIGMA]);                                 // likelihoods.py:231
       }
     }
     if (want_logl) {
@@ -636,11 +624,14 @@ __global__ void logl_kernel(int sigma_mode, int64_t N, int E, const double* __re
   for (int64_t n = blockIdx.x; n < N; n += gridDim.x) {
     double part = 0.0;
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
-      double sg = sigma[e];
-      if (sigma_mode == RB_SIGMA_SAMPLED) sg = sigma_param[n];
-      else if (sigma_mode == RB_SIGMA_QUADRATURE) sg = sqrt(sg * sg + sigma_param[n] * sigma_param[n]);
-      const double rs = (y[e] - model[n * (int64_t)E + e]) / sg;
-      part += -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;
+      const double sg = sigma ? sigma[e] : 0.0;
+      const double sp = sigma_param ? sigma_param[n] : 0.0;
+      if (sigma_mode == RB_SIGMA_FIXED) {
+        const double rs = (y[e] - model[n * (int64_t)E + e]) / sg;
+        part += -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;
+      } else {
+        part += logl_term(sigma_mode, y[e], model[n * (int64_t)E + e], sg, 0.0, sp);
+      }
     }
     const double total = block_sum(part, scratch);
     if (threadIdx.x == 0) out[n] = nan_to_num(total);

@@ -25,7 +25,7 @@ def as_device_f64(x, device):
     """1-D float64 contiguous device tensor from a python scalar / sequence / ndarray / tensor."""
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=_F64).contiguous()
-    arr = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    arr = np.array(x, dtype=np.float64, order="C", copy=True)   # own, writable buffer (inputs may be read-only views)
     return torch.from_numpy(arr).to(device)
 
 

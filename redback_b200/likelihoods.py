@@ -145,7 +145,7 @@ class GaussianLikelihood(_RedbackLikelihood):
     def _split_sigma_param(self, batch, N):
         """Return the per-sample `sigma` parameter array (or None) for the chosen noise mode."""
         mode = self._sigma_mode(batch)
-        if mode == _capi.SIGMA_FIXED:
+        if mode in (_capi.SIGMA_FIXED, _capi.SIGMA_FRACTIONAL):
             return mode, None
         sp = batch.get('sigma', self.parameters.get('sigma'))
         if sp is None:
@@ -228,3 +228,49 @@ class GaussianLikelihoodQuadratureNoise(GaussianLikelihood):
 
     def _sigma_mode(self, batch):
         return _capi.SIGMA_QUADRATURE
+
+
+class GaussianLikelihoodWithFractionalNoise(GaussianLikelihood):
+    """redback/likelihoods.py:792-851: sigma = sqrt(sigma_i^2 * model^2) (noise proportional to the model)."""
+
+    def __init__(self, x, y, sigma_i, function, kwargs=None, priors=None, fiducial_parameters=None):
+        self.sigma_i = sigma_i
+        super().__init__(x=x, y=y, sigma=sigma_i, function=function, kwargs=kwargs, priors=priors,
+                         fiducial_parameters=fiducial_parameters)
+
+    @property
+    def full_sigma(self):
+        model_y = self.model_output
+        return np.sqrt(self.sigma_i ** 2. * model_y ** 2)
+
+    def _noise_sigma(self):
+        return self.sigma_i
+
+    def _full_sigma(self):
+        return self.full_sigma
+
+    def _sigma_mode(self, batch):
+        return _capi.SIGMA_FRACTIONAL
+
+
+class GaussianLikelihoodWithSystematicNoise(GaussianLikelihood):
+    """redback/likelihoods.py:853-913: sigma = sqrt(sigma_i^2 + model^2 * sigma^2), `sigma` sampled."""
+
+    def __init__(self, x, y, sigma_i, function, kwargs=None, priors=None, fiducial_parameters=None):
+        self.sigma_i = sigma_i
+        super().__init__(x=x, y=y, sigma=sigma_i, function=function, kwargs=kwargs, priors=priors,
+                         fiducial_parameters=fiducial_parameters)
+
+    @property
+    def full_sigma(self):
+        model_y = self.model_output
+        return np.sqrt(self.sigma_i ** 2. + model_y ** 2 * self.sigma ** 2.)
+
+    def _noise_sigma(self):
+        return self.sigma_i
+
+    def _full_sigma(self):
+        return self.full_sigma
+
+    def _sigma_mode(self, batch):
+        return _capi.SIGMA_SYSTEMATIC

@@ -187,6 +187,39 @@ def test_cutoff_blackbody_absorption_index(rb, alpha):
                        what=f"alpha={alpha} sample {i}")
 
 
+def test_fractional_and_systematic_noise_likelihoods(rb):
+    """GaussianLikelihoodWithFractionalNoise / WithSystematicNoise (likelihoods.py:792-913), fused and generic."""
+    rng = np.random.default_rng(61)
+    t = np.sort(rng.uniform(1, 200, 45))
+    nu = np.full(t.size, 4.675e14)
+    N = 70
+    p = h.arnett_prior(rng, N)
+    fn = rb.supernova_models.arnett
+    kw = dict(frequency=nu, output_format="flux_density")
+    out = fn(t, params_batch=p, **kw)
+    y = out[3] * 1.1
+    sig_i = 0.1
+    sig_s = h.loguniform(rng, 1e-3, 0.5, N)
+    lf = rb.GaussianLikelihoodWithFractionalNoise(t, y, sig_i, fn, kwargs=kw).log_likelihood_batch(p)
+    sig_arr = 0.05 * np.abs(y) + 1e-9
+    ls = rb.GaussianLikelihoodWithSystematicNoise(t, y, sig_arr, fn, kwargs=kw).log_likelihood_batch(dict(p, sigma=sig_s))
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        z = kwi.pop("redshift")
+        ref = r.arnett(t, z, frequency=nu, **kwi)
+        a = r.gaussian_likelihood_fractional(y, ref, sig_i)
+        b = r.gaussian_likelihood_systematic(y, ref, sig_arr, sig_s[i])
+        assert abs(lf[i] - a) <= 1e-6 + 1e-8 * abs(a), (i, lf[i], a)
+        assert abs(ls[i] - b) <= 1e-6 + 1e-8 * abs(b), (i, ls[i], b)
+
+    def plain(x, a_par, b_par, **kwargs):      # generic (non-fused) function without params_batch: single-sample API
+        return a_par * x + b_par
+    like = rb.GaussianLikelihoodWithFractionalNoise(t, 2 * t + 1, 0.1, plain)
+    like.parameters.update(a_par=2.0, b_par=0.5)
+    exp = r.gaussian_likelihood_fractional(2 * t + 1, 2.0 * t + 0.5, 0.1)
+    assert abs(like.log_likelihood() - exp) < 1e-9
+
+
 def test_device_luminosity_distance(rb):
     z = np.array([1e-6, 0.01, 0.1, 0.5, 1.0, 2.0, 3.0, 8.0])
     out = rb.engine.luminosity_distance(z).cpu().numpy()
