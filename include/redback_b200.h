@@ -52,6 +52,15 @@ enum {
   RB_SIGMA_SYSTEMATIC = 4  /* GaussianLikelihoodWithSystematicNoise: sqrt(sigma_i^2 + model^2 sigma^2) :853-913 */
 };
 
+/* Upper limits (GaussianLikelihoodWithUpperLimits, likelihoods.py:234-489): epochs with sigma_level[e] > 0 are
+ * non-detections at that many sigma; they contribute log(clip(Phi((y - model)/sigma_meas))) with
+ * sigma_meas = y / level (flux-like data) or (2.5/ln 10)/level and the survival function (magnitudes, :392-412)
+ * instead of the Gaussian term.  sigma_level is a DEVICE pointer [E] or NULL (all detections). */
+typedef struct {
+  const double* sigma_level;
+  int magnitude_mode;   /* data_mode == 'magnitude' */
+} rb_upper_limits;
+
 /* Row indices of the SoA parameter block of the supernova path (rows not used by the chosen
  * engine / sed are ignored and may hold anything). */
 enum {
@@ -104,6 +113,7 @@ typedef struct {
    * cancellation-free form of the exponent; engine tables, photosphere, SED and the likelihood reduction stay
    * FP64.  Target: rtol 1e-5 on model outputs (north_star).  Inputs / outputs remain float64. */
   int precision;            /* RB_PREC_F64 (default) | RB_PREC_F32 */
+  rb_upper_limits upper_limits;
 } rb_sn_config;
 
 /* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */
@@ -164,6 +174,7 @@ typedef struct {
   int neutron_precursor_switch; /* Metzger only, default 1 (kilonova_models.py:1977)             */
   double vmax;                  /* Metzger only, default 0.7 (kilonova_models.py:1997)           */
   rb_cosmology cosmology;       /* used only when dl_cm == NULL                                  */
+  rb_upper_limits upper_limits;
 } rb_kn_config;
 
 int rb_kn_config_default(rb_kn_config* cfg);
@@ -205,6 +216,7 @@ typedef struct {
   double a1;          /* kwargs 'a1', default 1 (:919)                                        */
   rb_cosmology cosmology;
   double ss, aa;      /* kwargs 'ss', 'aa': extra structure parameters of the PL / PL2 / 2C / DG jets */
+  rb_upper_limits upper_limits;
 } rb_ag_config;
 
 int rb_ag_config_default(rb_ag_config* cfg);
@@ -273,10 +285,11 @@ int rb_luminosity_distance_f64(const rb_cosmology* cosmo, int64_t N, const doubl
 /*
  * Stand-alone Gaussian log-likelihood reduction over a precomputed model matrix:
  * GaussianLikelihood._gaussian_log_likelihood + np.nan_to_num (likelihoods.py:221-231, 767-790).
- *   model [N][E], y [E], sigma [E], sigma_param [N] or NULL, out_logl [N]
+ *   model [N][E], y [E], sigma [E], sigma_param [N] or NULL, upper_limits or NULL, out_logl [N]
  */
 int rb_gaussian_logl_f64(int sigma_mode, int64_t N, int64_t E, const double* model, const double* y,
-                         const double* sigma, const double* sigma_param, double* out_logl, void* stream);
+                         const double* sigma, const double* sigma_param, const rb_upper_limits* upper_limits,
+                         double* out_logl, void* stream);
 
 /* FP64 FMA micro-benchmark: runs `iters` dependent-chain DFMAs per thread on a full grid and
  * returns the achieved TFLOP/s (2 flop per FMA) in *out_tflops.  Used as the roofline denominator. */

@@ -385,6 +385,45 @@ def gaussian_likelihood(y, model, sigma):
     return float(np.nan_to_num(gaussian_log_likelihood(np.asarray(y) - model, sigma)))
 
 
+def normal_cdf(x):
+    """GaussianLikelihoodWithUpperLimits._normal_cdf, likelihoods.py:366-375."""
+    from scipy.special import erf
+    return 0.5 * (1.0 + erf(x / np.sqrt(2)))
+
+
+def upper_limit_log_likelihood(observed_ul, model_ul, ul_sigma_levels, data_mode="flux"):
+    """GaussianLikelihoodWithUpperLimits._upper_limit_log_likelihood, likelihoods.py:377-419, on the upper-limit
+    points only."""
+    observed_ul = np.asarray(observed_ul, dtype=float)
+    model_ul = np.asarray(model_ul, dtype=float)
+    if observed_ul.size == 0:
+        return 0.0
+    if data_mode == "magnitude":
+        sigma_measurement = (2.5 / np.log(10.0)) / ul_sigma_levels
+        cdf_values = 1.0 - normal_cdf((observed_ul - model_ul) / sigma_measurement)
+    else:
+        sigma_measurement = observed_ul / ul_sigma_levels
+        cdf_values = normal_cdf((observed_ul - model_ul) / sigma_measurement)
+    epsilon = 1e-30
+    cdf_values = np.clip(cdf_values, epsilon, 1.0 - epsilon)
+    return np.sum(np.log(cdf_values))
+
+
+def gaussian_likelihood_upper_limits(y, model, sigma, detections, upper_limit_sigma=3.0, data_mode="flux"):
+    """GaussianLikelihoodWithUpperLimits.log_likelihood, likelihoods.py:448-468."""
+    y, model = np.asarray(y, dtype=float), np.asarray(model, dtype=float)
+    det = np.asarray(detections, dtype=bool)
+    levels = np.broadcast_to(np.asarray(upper_limit_sigma, dtype=float), y.shape)[~det] \
+        if np.ndim(upper_limit_sigma) == 0 or len(upper_limit_sigma) == len(y) else np.asarray(upper_limit_sigma)
+    det_ll = 0.0
+    if np.any(det):
+        sig = sigma if np.isscalar(sigma) else np.asarray(sigma)[det]
+        det_ll = gaussian_log_likelihood((y - model)[det], sig)
+    with np.errstate(all="ignore"):
+        ul_ll = upper_limit_log_likelihood(y[~det], model[~det], levels, data_mode)
+    return float(np.nan_to_num(det_ll + ul_ll))
+
+
 def gaussian_likelihood_quadrature(y, model, sigma_i, sigma):
     """GaussianLikelihoodQuadratureNoise.log_likelihood, likelihoods.py:767-790."""
     with np.errstate(all="ignore"):

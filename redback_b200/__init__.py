@@ -3,7 +3,8 @@ likelihood API.  The CUDA library is the only compute path; impo
 not need a GPU, calling it does."""
 from . import _capi, afterglow_models, bands, engine, simulate, kilonova_models, likelihoods, supernova_models  # noqa: F401
 from .likelihoods import (GaussianLikelihood, GaussianLikelihoodQuadratureNoise,  # noqa: F401
-                          GaussianLikelihoodWithFractionalNoise, GaussianLikelihoodWithSystematicNoise)
+                          GaussianLikelihoodWithFractionalNoise, GaussianLikelihoodWithSystematicNoise,
+                          GaussianLikelihoodWithUpperLimits)
 
 __version__ = "0.1.0"
 

@@ -26,11 +26,16 @@ class Cosmology(C.Structure):
                 ("n_massive", C.c_int), ("n_massless", C.c_int)]
 
 
+class UpperLimits(C.Structure):
+    _fields_ = [("sigma_level", C.c_void_p), ("magnitude_mode", C.c_int)]
+
+
 class SnConfig(C.Structure):
     _fields_ = [("engine", C.c_int), ("sed", C.c_int), ("sigma_mode", C.c_int), ("dense_resolution", C.c_int),
                 ("cutoff_wavelength", C.c_double), ("absorption_index", C.c_double), ("cosmology", Cosmology),
                 ("line_wavelength", C.c_double), ("line_width", C.c_double), ("line_time", C.c_double),
-                ("line_duration", C.c_double), ("line_amplitude", C.c_double), ("precision", C.c_int)]
+                ("line_duration", C.c_double), ("line_amplitude", C.c_double), ("precision", C.c_int),
+                ("upper_limits", UpperLimits)]
 
 
 KN_ONE_COMPONENT, KN_METZGER = 0, 1
@@ -40,7 +45,8 @@ KN_NPARAM = 5
 
 class KnConfig(C.Structure):
     _fields_ = [("model", C.c_int), ("sigma_mode", C.c_int), ("dense_resolution", C.c_int),
-                ("neutron_precursor_switch", C.c_int), ("vmax", C.c_double), ("cosmology", Cosmology)]
+                ("neutron_precursor_switch", C.c_int), ("vmax", C.c_double), ("cosmology", Cosmology),
+                ("upper_limits", UpperLimits)]
 
 
 AG_TOPHAT, AG_GAUSSIAN, AG_POWERLAW, AG_POWERLAW_ALT, AG_TWO_COMPONENT, AG_DOUBLE_GAUSSIAN = 1, 2, 3, 4, 5, 6
@@ -51,7 +57,7 @@ AG_NPARAM = 11
 class AgConfig(C.Structure):
     _fields_ = [("jet", C.c_int), ("sigma_mode", C.c_int), ("steps", C.c_int), ("res", C.c_int), ("k", C.c_int),
                 ("expansion", C.c_int), ("a1", C.c_double), ("cosmology", Cosmology), ("ss", C.c_double),
-                ("aa", C.c_double)]
+                ("aa", C.c_double), ("upper_limits", UpperLimits)]
 
 
 class RedbackB200Error(RuntimeError):
@@ -82,7 +88,8 @@ EXPORTS = {
     "rb_optical_noise_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 4 + [C.c_double, C.c_int] + [_dp] * 6
                              + [C.c_void_p]),
     "rb_luminosity_distance_f64": (C.c_int, [C.POINTER(Cosmology), C.c_int64, _dp, _dp, C.c_void_p]),
-    "rb_gaussian_logl_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 5 + [C.c_void_p]),
+    "rb_gaussian_logl_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 4 + [C.POINTER(UpperLimits), _dp,
+                                       C.c_void_p]),
     "rb_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -512,7 +512,8 @@ __global__ void __launch_bounds__(128) ag_finish_kernel(const AgArgs a) {
       const double model_v = (u1 > u0) ? lc * opz / 1e-26 : NAN;                   // :640, :942
       if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = model_v;
       if (a.want_logl) {
-        logl_part += logl_term(a.cfg.sigma_mode, a.epoch_tab[EP_Y * E + e], model_v, a.epoch_tab[EP_ISIG * E + e],
+        logl_part += logl_term(a.cfg.sigma_mode, a.epoch_tab[EP_KIND * E + e], a.epoch_tab[EP_Y * E + e], model_v,
+                               a.epoch_tab[EP_ISIG * E + e],
                                a.epoch_tab[EP_LOGT * E + e], sp);
       }
     }

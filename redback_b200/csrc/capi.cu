@@ -190,7 +190,7 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   double* ws = ws_buf.as<double>();
   double* epoch_tab = ws;
   rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
-                                                                    y ? sigma : nullptr, epoch_tab);
+                                                                    y ? sigma : nullptr, cfg->upper_limits, epoch_tab);
   rb::SnArgs a{};
   a.cfg = *cfg;
   a.N = N;
@@ -233,7 +233,8 @@ int rb_luminosity_distance_f64(const rb_cosmology* cosmo, int64_t N, const doubl
 }
 
 int rb_gaussian_logl_f64(int sigma_mode, int64_t N, int64_t E, const double* model, const double* y,
-                         const double* sigma, const double* sigma_param, double* out_logl, void* stream) {
+                         const double* sigma, const double* sigma_param, const rb_upper_limits* upper_limits,
+                         double* out_logl, void* stream) {
   if (!model || !y || !out_logl || N < 0 || E <= 0) return fail(RB_ERR_INVALID, "rb_gaussian_logl: bad arguments");
   if (sigma_mode < RB_SIGMA_FIXED || sigma_mode > RB_SIGMA_SYSTEMATIC)
     return fail(RB_ERR_INVALID, "rb_gaussian_logl: unknown sigma_mode");
@@ -244,7 +245,8 @@ int rb_gaussian_logl_f64(int sigma_mode, int64_t N, int64_t E, const double* mod
   const int threads = E >= 256 ? 256 : (E >= 128 ? 128 : 64);
   const int64_t grid = N < 1048576 ? N : 1048576;
   rb::logl_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(sigma_mode, N, (int)E, model, y,
-                                                                         sigma ? sigma : y, sigma_param, out_logl);
+                                                                         sigma ? sigma : y, sigma_param,
+                                                                         upper_limits ? *upper_limits : rb_upper_limits{nullptr, 0}, out_logl);
   launch_counter()->fetch_add(1);
   RB_CUDA(cudaGetLastError());
   return RB_OK;
@@ -421,7 +423,7 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   double* scal = ws + (size_t)rb::kEpochCols * (size_t)E;
   double* mm = scal + (size_t)rb::kKnScalars * (size_t)N;
   rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
-                                                                    y ? sigma : nullptr, epoch_tab);
+                                                                    y ? sigma : nullptr, cfg->upper_limits, epoch_tab);
   minmax_kernel<<<1, 256, 0, st>>>((int)E, t_obs, mm);
   double h_mm[2];
   cudaError_t ce = cudaMemcpyAsync(h_mm, mm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
@@ -579,7 +581,7 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
   RB_CUDA(cudaMemcpyAsync(d_idx, h_idx.data(), (size_t)E * sizeof(int), cudaMemcpyHostToDevice, st));
   RB_CUDA(cudaStreamSynchronize(st));  // h_idx is pageable host memory
   rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
-                                                                    y ? sigma : nullptr, d_epoch);
+                                                                    y ? sigma : nullptr, cfg->upper_limits, d_epoch);
   launch_counter()->fetch_add(1);
 
   const double q = rb::AG_QE * rb::AG_QE / (rb::AG_ME * rb::AG_C2);
@@ -895,9 +897,9 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
   if (ce == cudaSuccess) ce = cudaMallocAsync(&d_ep_obs, (size_t)rb::kEpochCols * E * sizeof(double), st);
   if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "epoch tables"); }
   rb::epoch_table_kernel<<<(unsigned)((NT + 255) / 256), 256, 0, st>>>(NT, RB_SIGMA_FIXED, d_tgrid, nullptr, nullptr,
-                                                                     nullptr, d_ep_grid);
+                                                                     nullptr, rb_upper_limits{nullptr, 0}, d_ep_grid);
   rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, nullptr, y,
-                                                                    y ? sigma : nullptr, d_ep_obs);
+                                                                    y ? sigma : nullptr, cfg->upper_limits, d_ep_obs);
   launch_counter()->fetch_add(2);
 
   const int64_t chunk_max = 32768;
@@ -1018,7 +1020,7 @@ extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* 
   if (ce == cudaSuccess) ce = cudaMallocAsync(&d_mm, 2 * sizeof(double), st);
   if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "epoch tables"); }
   rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, nullptr, y,
-                                                                    y ? sigma : nullptr, d_ep_obs);
+                                                                    y ? sigma : nullptr, cfg->upper_limits, d_ep_obs);
   minmax_kernel<<<1, 256, 0, st>>>((int)E, t_obs, d_mm);
   double h_mm[2];
   ce = cudaMemcpyAsync(h_mm, d_mm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);

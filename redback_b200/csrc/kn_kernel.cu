@@ -405,7 +405,8 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
       }
       if (a.out_model != nullptr) a.out_model[n * (int64_t)E + e] = model_v;
       if (want_logl) {
-        logl_part += logl_term(sigma_mode, ep[EP_Y * E + e], model_v, ep[EP_ISIG * E + e], ep[EP_LOGT * E + e],
+        logl_part += logl_term(sigma_mode, ep[EP_KIND * E + e], ep[EP_Y * E + e], model_v, ep[EP_ISIG * E + e],
+                               ep[EP_LOGT * E + e],
                                sc[KS_SIGMA]);
       }
     }

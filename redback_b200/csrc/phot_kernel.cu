@@ -340,7 +340,8 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
       if (a.output == RB_OUT_FLUX) model_v = pow(10.0, model_v / (-2.5)) * a.band_ref[b];   // utils.py:716-718
       if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = model_v;
       if (a.want_logl) {
-        logl_part += logl_term(a.sigma_mode, a.epoch_tab[EP_Y * E + e], model_v, a.epoch_tab[EP_ISIG * E + e],
+        logl_part += logl_term(a.sigma_mode, a.epoch_tab[EP_KIND * E + e], a.epoch_tab[EP_Y * E + e], model_v,
+                               a.epoch_tab[EP_ISIG * E + e],
                                a.epoch_tab[EP_LOGT * E + e], a.sigma_param_s ? a.sigma_param_s[n] : 0.0);
       }
     }

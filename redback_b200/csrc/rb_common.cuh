@@ -103,8 +103,17 @@ __device__ __forceinline__ double nan_to_num(double v) {
 //   RB_SIGMA_FRACTIONAL  sqrt(sigma_i^2 * model^2)                                        (likelihoods.py:826)
 //   RB_SIGMA_SYSTEMATIC  sqrt(sigma_i^2 + model^2 * sp^2)                                 (likelihoods.py:888)
 // For the modes other than FIXED `isig` carries sigma_i itself.
-__device__ __forceinline__ double logl_term(int mode, double y, double model, double isig, double logt, double sp) {
+// kind != 0: the datum is an upper limit (GaussianLikelihoodWithUpperLimits._upper_limit_log_likelihood,
+// likelihoods.py:377-419): `isig` = 1/sigma_measurement; kind 1 = "true value < limit" (flux-like), 2 = magnitudes.
+__device__ __forceinline__ double logl_term(int mode, double kind, double y, double model, double isig, double logt,
+                                            double sp) {
   const double res = y - model;
+  if (kind != 0.0) {
+    double cdf = 0.5 * (1.0 + erf((res * isig) / 1.4142135623730951));
+    if (kind == 2.0) cdf = 1.0 - cdf;
+    cdf = fmin(fmax(cdf, 1e-30), 1.0 - 1e-30);   // np.clip(cdf, eps, 1 - eps), NaN propagates
+    return log(cdf);
+  }
   if (mode == RB_SIGMA_FIXED) {
     const double rs = res * isig;
     return -(rs * rs) / 2 - logt;

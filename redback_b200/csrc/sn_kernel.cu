@@ -27,7 +27,7 @@ constexpr int kNodesHalf = 50;            // int(round(timesteps / 2.0)), intera
 constexpr int kNodes = 2 * kNodesHalf;    // merged abscissae, duplicates kept (zero-width intervals)
 constexpr double kExpSkip = -690.0;       // exp() arguments below this contribute < 1e-299: skipped
 
-enum { EP_T = 0, EP_NU, EP_Y, EP_ISIG, EP_LOGT, kEpochCols };
+enum { EP_T = 0, EP_NU, EP_Y, EP_ISIG, EP_LOGT, EP_KIND, kEpochCols };
 
 // per-sample scalar record written by sn_prep_kernel
 enum {
@@ -78,9 +78,11 @@ struct SnArgs {
 // of once per sample x epoch; other modes keep sigma_i itself in the EP_ISIG column.
 __global__ void epoch_table_kernel(int E, int sigma_mode, const double* __restrict__ t_obs,
                                    const double* __restrict__ freq_obs, const double* __restrict__ y,
-                                   const double* __restrict__ sigma, double* __restrict__ tab) {
+                                   const double* __restrict__ sigma, rb_upper_limits ul,
+                                   double* __restrict__ tab) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
+  double kind = 0.0;
   tab[EP_T * E + e] = t_obs[e];
   tab[EP_NU * E + e] = freq_obs ? freq_obs[e] : 0.0;
   tab[EP_Y * E + e] = y ? y[e] : 0.0;
@@ -94,8 +96,16 @@ __global__ void epoch_table_kernel(int E, int sigma_mode, const double* __restri
       isig = sg;  // sigma_i, combined with the sampled sigma per sample
     }
   }
+  if (y && ul.sigma_level != nullptr && ul.sigma_level[e] > 0.0) {
+    // likelihoods.py:392-398: sigma_measurement = y / N (flux-like) or (2.5 / ln 10) / N (magnitudes)
+    const double level = ul.sigma_level[e];
+    kind = ul.magnitude_mode ? 2.0 : 1.0;
+    isig = ul.magnitude_mode ? level / (2.5 / log(10.0)) : level / y[e];
+    logt = 0.0;
+  }
   tab[EP_ISIG * E + e] = isig;
   tab[EP_LOGT * E + e] = logt;
+  tab[EP_KIND * E + e] = kind;
 }
 
 // ---- 2. per-sample scalars --------------------------------------------------------------------------
@@ -583,7 +593,8 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       }
       if (a.out_model != nullptr) a.out_model[n * (int64_t)E + e] = model;
       if (want_logl) {
-        logl_part += logl_term(sigma_mode, ep[EP_Y * E + e], model, ep[EP_ISIG * E + e], ep[EP_LOGT * E + e],
+        logl_part += logl_term(sigma_mode, ep[EP_KIND * E + e], ep[EP_Y * E + e], model, ep[EP_ISIG * E + e],
+                               ep[EP_LOGT * E + e],
                                sc[SC_SIGMA]);                                 // likelihoods.py:231
       }
     }
@@ -619,18 +630,22 @@ __global__ void dl_kernel(const rb_cosmology c, int64_t N, const double* __restr
 // ---- stand-alone likelihood reduction -----------------------------------------------------------
 __global__ void logl_kernel(int sigma_mode, int64_t N, int E, const double* __restrict__ model,
                             const double* __restrict__ y, const double* __restrict__ sigma,
-                            const double* __restrict__ sigma_param, double* __restrict__ out) {
+                            const double* __restrict__ sigma_param, rb_upper_limits ul, double* __restrict__ out) {
   __shared__ double scratch[34];
   for (int64_t n = blockIdx.x; n < N; n += gridDim.x) {
     double part = 0.0;
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
       const double sg = sigma ? sigma[e] : 0.0;
       const double sp = sigma_param ? sigma_param[n] : 0.0;
-      if (sigma_mode == RB_SIGMA_FIXED) {
+      if (ul.sigma_level != nullptr && ul.sigma_level[e] > 0.0) {
+        const double level = ul.sigma_level[e];
+        const double isig = ul.magnitude_mode ? level / (2.5 / log(10.0)) : level / y[e];
+        part += logl_term(sigma_mode, ul.magnitude_mode ? 2.0 : 1.0, y[e], model[n * (int64_t)E + e], isig, 0.0, sp);
+      } else if (sigma_mode == RB_SIGMA_FIXED) {
         const double rs = (y[e] - model[n * (int64_t)E + e]) / sg;
         part += -(rs * rs) / 2 - log(2 * kPi * (sg * sg)) / 2;
       } else {
-        part += logl_term(sigma_mode, y[e], model[n * (int64_t)E + e], sg, 0.0, sp);
+        part += logl_term(sigma_mode, 0.0, y[e], model[n * (int64_t)E + e], sg, 0.0, sp);
       }
     }
     const double total = block_sum(part, scratch);

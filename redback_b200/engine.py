@@ -110,6 +110,20 @@ class _FusedPath:
                 if self.sigma.shape != (self.E,):
                     raise ValueError('Sigma must be either float or array-like x.')
 
+    def set_upper_limits(self, sigma_level, magnitude_mode=False):
+        """Mark epochs with sigma_level[e] > 0 as upper limits at that many sigma
+        (GaussianLikelihoodWithUpperLimits, likelihoods.py:234-489); None clears them."""
+        if sigma_level is None:
+            self._ul_level = None
+            self.cfg.upper_limits.sigma_level = None
+            self.cfg.upper_limits.magnitude_mode = 0
+            return
+        self._ul_level = as_device_f64(sigma_level, self.device)   # kept alive by the path
+        if self._ul_level.shape != (self.E,):
+            raise ValueError("upper-limit sigma levels must have the same length as time")
+        self.cfg.upper_limits.sigma_level = self._ul_level.data_ptr()
+        self.cfg.upper_limits.magnitude_mode = int(bool(magnitude_mode))
+
     def pack(self, params, N):
         """SoA [RB_SN_NPARAM, N] device tensor from {name: scalar | array[N] | tensor[N]}."""
         out = torch.zeros((self.NPARAM, N), dtype=_F64, device=self.device)
@@ -320,8 +334,10 @@ def luminosity_distance(redshift, cosmology=None, device=None):
     return out
 
 
-def gaussian_logl(model, y, sigma, sigma_param=None, sigma_mode=_capi.SIGMA_FIXED):
-    """Stand-alone reduction over a device model matrix [N, E] (likelihoods.py:221-231, 767-790)."""
+def gaussian_logl(model, y, sigma, sigma_param=None, sigma_mode=_capi.SIGMA_FIXED, ul_level=None,
+                  ul_magnitude=False):
+    """Stand-alone reduction over a device model matrix [N, E] (likelihoods.py:221-231, 767-790); epochs with
+    ul_level[e] > 0 are upper limits (likelihoods.py:377-419)."""
     dev = model.device
     N, E = model.shape
     y = as_device_f64(y, dev)
@@ -330,8 +346,15 @@ def gaussian_logl(model, y, sigma, sigma_param=None, sigma_mode=_capi.SIGMA_FIXE
     sigma = as_device_f64(sigma, dev) if sigma is not None else None
     sp = as_device_f64(sigma_param, dev) if sigma_param is not None else None
     out = torch.empty((N,), dtype=_F64, device=dev)
+    ul = None
+    if ul_level is not None:
+        level = as_device_f64(ul_level, dev)
+        if level.shape != (E,):
+            raise ValueError("upper-limit sigma levels must have the same length as y")
+        ul = _capi.UpperLimits(level.data_ptr(), int(bool(ul_magnitude)))
     with torch.cuda.device(dev):
         _capi.check(_capi.lib().rb_gaussian_logl_f64(
-            sigma_mode, N, E, _ptr(model.contiguous()), _ptr(y), _ptr(sigma), _ptr(sp), _ptr(out),
+            sigma_mode, N, E, _ptr(model.contiguous()), _ptr(y), _ptr(sigma), _ptr(sp),
+            C.byref(ul) if ul is not None else None, _ptr(out),
             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     return out

@@ -179,8 +179,14 @@ class GaussianLikelihood(_RedbackLikelihood):
             sp_dev = None
             if sp is not None:
                 sp_dev = sp if isinstance(sp, torch.Tensor) else np.broadcast_to(np.asarray(sp, dtype=np.float64), (N,))
-            logl = gaussian_logl(model, self.y, self._sigma, sp_dev, sigma_mode=mode)
+            level, ul_mag = self._upper_limit_levels()
+            logl = gaussian_logl(model, self.y, self._sigma, sp_dev, sigma_mode=mode, ul_level=level,
+                                 ul_magnitude=ul_mag)
         return logl if device_output else logl.cpu().numpy()
+
+    def _upper_limit_levels(self):
+        """(per-epoch sigma level with 0 = detection, magnitude mode) or (None, False): no upper limits."""
+        return None, False
 
     def _fused(self, merged, N, mode, sp):
         spec = FUSED[self.function]
@@ -190,6 +196,9 @@ class GaussianLikelihood(_RedbackLikelihood):
         key = (spec.cache_key(kw), mode)
         if self._path is None or self._path[0] != key:
             self._path = (key, spec.build(self.x, kw, y=self.y, sigma=self._sigma, sigma_mode=mode))
+            level, ul_mag = self._upper_limit_levels()
+            if level is not None:
+                self._path[1].set_upper_limits(level, ul_mag)
         path = self._path[1]
         params, _ = _fused.collect(merged, kw, None, spec.needed)
         dev = path.pack(params, N)
@@ -206,6 +215,125 @@ class GaussianLikelihood(_RedbackLikelihood):
 
 def _raise_no_cuda():
     raise _capi.RedbackB200Error("redback_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+class GaussianLikelihoodWithUpperLimits(GaussianLikelihood):
+    """redback/likelihoods.py:234-489: non-detections contribute log Phi((limit - model)/sigma_meas) (flux-like
+    data) or the survival function (magnitudes); detections keep the Gaussian term.  The per-epoch split is done
+    inside the fused kernels (an extra epoch-table column), so a batch costs the same as without upper limits."""
+
+    def __init__(self, x, y, sigma, function, kwargs=None, priors=None, fiducial_parameters=None, detections=None,
+                 upper_limit_sigma=3.0, data_mode='flux'):
+        super().__init__(x=x, y=y, sigma=sigma, function=function, kwargs=kwargs, priors=priors,
+                         fiducial_parameters=fiducial_parameters)
+        self.detections = detections
+        self.upper_limit_sigma = upper_limit_sigma
+        self.data_mode = data_mode
+        if not np.all(self._detections):
+            nan_ul = np.isnan(np.asarray(self.y, dtype=np.float64)[~self._detections])
+            if np.any(nan_ul):
+                raise ValueError(
+                    f"{int(np.sum(nan_ul))} upper limit(s) have NaN y-values. Upper limits require a finite "
+                    f"value (e.g. the limiting magnitude or flux) to compute likelihood. "
+                    f"Replace NaN values with the upper limit value, or remove those data points.")
+
+    @property
+    def detections(self):
+        return self._detections
+
+    @detections.setter
+    def detections(self, detections):
+        if detections is None:
+            self._detections = np.ones(len(self.x), dtype=bool)
+        elif len(detections) == len(self.x):
+            self._detections = np.array(detections, dtype=bool)
+        else:
+            raise ValueError('detections must have the same length as x.')
+        self._path = None
+
+    @property
+    def upper_limits(self):
+        return ~self._detections
+
+    @property
+    def upper_limit_sigma(self):
+        return self._upper_limit_sigma
+
+    @upper_limit_sigma.setter
+    def upper_limit_sigma(self, upper_limit_sigma):
+        if isinstance(upper_limit_sigma, (float, int)):
+            self._upper_limit_sigma = float(upper_limit_sigma)
+        elif isinstance(upper_limit_sigma, np.ndarray):
+            if len(upper_limit_sigma) == len(self.x) or \
+                    (hasattr(self, '_detections') and len(upper_limit_sigma) == np.sum(~self._detections)):
+                self._upper_limit_sigma = upper_limit_sigma
+            else:
+                raise ValueError('upper_limit_sigma array must have length equal to x or to number of upper limits.')
+        else:
+            raise ValueError('upper_limit_sigma must be a float or array.')
+        self._path = None
+
+    @property
+    def data_mode(self):
+        return self._data_mode
+
+    @data_mode.setter
+    def data_mode(self, data_mode):
+        if data_mode.lower() not in ['flux', 'flux_density', 'luminosity', 'magnitude', 'mag']:
+            raise ValueError("data_mode must be 'flux', 'flux_density', 'luminosity', or 'magnitude' (or 'mag')")
+        self._data_mode = 'magnitude' if data_mode.lower() == 'mag' else data_mode.lower()
+        self._path = None
+
+    def get_upper_limit_sigma_values(self):
+        if not np.any(self.upper_limits):
+            return np.array([])
+        if isinstance(self.upper_limit_sigma, (float, int)):
+            return np.full(np.sum(self.upper_limits), self.upper_limit_sigma)
+        if len(self.upper_limit_sigma) == len(self.x):
+            return self.upper_limit_sigma[self.upper_limits]
+        return self.upper_limit_sigma
+
+    def _upper_limit_levels(self):
+        if not np.any(self.upper_limits):
+            return None, False
+        level = np.zeros(len(self.x), dtype=np.float64)
+        level[self.upper_limits] = self.get_upper_limit_sigma_values()
+        if np.any(~(level[self.upper_limits] > 0)):
+            raise ValueError('upper_limit_sigma must be positive for every upper limit.')
+        return level, self.data_mode == 'magnitude'
+
+    def _device_logl(self, model_row):
+        """detections + upper limits for one model vector through the device reduction (likelihoods.py:421-468)."""
+        model = torch.as_tensor(np.asarray(model_row, dtype=np.float64).reshape(1, -1), device=self._dev())
+        level, ul_mag = self._upper_limit_levels()
+        sig = self.sigma
+        if sig is None:
+            raise KeyError('sigma')
+        sig = np.array(np.broadcast_to(np.asarray(sig, dtype=np.float64), (len(self.x),)))
+        sig[self.upper_limits] = 1.0    # never read for upper limits; keeps NaN placeholders out of the table
+        out = gaussian_logl(model, self.y, sig, sigma_mode=_capi.SIGMA_FIXED, ul_level=level, ul_magnitude=ul_mag)
+        return float(out[0].item())
+
+    def noise_log_likelihood(self):
+        if self._noise_log_likelihood is None:
+            fill = 60.0 if self.data_mode == 'magnitude' else 0.0
+            # model = 0 at detections makes the residual y itself (:432-435); 0 / 60 mag at the limits (:440-445)
+            noise_model = np.where(self.detections, 0.0, fill)
+            self._noise_log_likelihood = self._device_logl(noise_model)
+        return self._noise_log_likelihood
+
+    def log_likelihood(self, parameters=None):
+        self._update_parameters(parameters)
+        if self.function in FUSED:
+            batch = {k: np.array([v], dtype=np.float64) for k, v in self.parameters.items() if v is not None}
+            return float(self.log_likelihood_batch(batch)[0])
+        return self._device_logl(self.model_output)
+
+    def summary(self):
+        n_upper_limits = np.sum(self.upper_limits)
+        return {'total_data_points': len(self.x), 'detections': np.sum(self.detections),
+                'upper_limits': n_upper_limits, 'data_mode': self.data_mode,
+                'upper_limit_sigma_levels': self.get_upper_limit_sigma_values() if n_upper_limits > 0 else None}
 
 
 class GaussianLikelihoodQuadratureNoise(GaussianLikelihood):

@@ -78,3 +78,17 @@ def test_oracle_matches_verbatim_reference_sources():
         T, R = r.temperature_floor(t, out, v, 3000.)
         np.testing.assert_array_equal(T, ph.photosphere_temperature)
         np.testing.assert_array_equal(R, ph.r_photosphere)
+
+
+def test_upper_limit_likelihood_known_answers():
+    # test/likelihood_test.py:440-462: sigma_m = (2.5 / ln 10) / N and the survival function for magnitudes
+    expected = np.log(1.0 - r.normal_cdf((22.0 - 22.2) / ((2.5 / np.log(10.0)) / 5.0)))
+    got = r.upper_limit_log_likelihood(np.array([22.0]), np.array([22.2]), np.array([5.0]), "magnitude")
+    assert abs(got - expected) < 1e-15
+    # likelihoods.py:448-468: detections keep the Gaussian term, limits add log Phi((y - m) N / y)
+    y = np.array([0.5, 1.2, 2.1, 3.5, 4.8])
+    det = np.array([True, True, True, False, False])
+    model = 1.1 * np.arange(5.0)
+    want = r.gaussian_log_likelihood((y - model)[:3], 0.1) + np.sum(np.log(r.normal_cdf((y - model)[3:] * 2.0 / y[3:])))
+    assert abs(r.gaussian_likelihood_upper_limits(y, model, np.full(5, 0.1), det, 2.0) - want) < 1e-13
+    assert r.gaussian_likelihood_upper_limits(y, model, 0.1, np.ones(5, bool)) == r.gaussian_likelihood(y, model, 0.1)

@@ -315,3 +315,127 @@ def test_edge_shapes(rb):
         sn.arnett_bolometric(np.array([-1.0, 2.0]), 0.1, 1.0, **kw)
     with pytest.raises(IndexError):
         sn.arnett_bolometric(np.array([500.0, 2.0]), 0.1, 1.0, **kw)   # max(t) > t[-1] + 100
+
+
+def _narrow(rng, fiducial, N, width=0.05):
+    return {k: float(v) * (1.0 + width * rng.uniform(-1, 1, N)) for k, v in fiducial.items()}
+
+
+@pytest.mark.gpu
+def test_upper_limit_likelihood(rb):
+    """GaussianLikelihoodWithUpperLimits (likelihoods.py:234-489): fused flux-density path, fused magnitude path and
+    the generic single-sample path.  The batch is drawn narrowly around a fiducial so that the standardised
+    residuals stay where 0.5 (1 + erf) is well conditioned (|z| < 6); two far-away samples exercise the 1e-30 clip."""
+    rng = np.random.default_rng(67)
+    t = np.sort(rng.uniform(5, 150, 40))
+    nu = np.full(t.size, 4.675e14)
+    fid = dict(redshift=0.05, f_nickel=0.3, mej=3.0, vej=8000.0, kappa=0.1, kappa_gamma=1.0, temperature_floor=4000.0)
+    N = 48
+    p = _narrow(rng, fid, N)
+    p["f_nickel"][-2:] = [0.999, 0.998]
+    p["mej"][-2:] = [40.0, 45.0]           # ~100x brighter than the limits: Phi underflows -> clip
+    fn = rb.supernova_models.arnett
+    kw = dict(frequency=nu, output_format="flux_density")
+    zf = fid.copy()
+    z0 = zf.pop("redshift")
+    base = r.arnett(t, z0, frequency=nu, **zf)
+    det = np.ones(t.size, bool)
+    det[rng.choice(t.size, 12, replace=False)] = False
+    y = base * (1 + 0.05 * rng.standard_normal(t.size))
+    y[~det] = base[~det] * rng.uniform(1.2, 2.0, (~det).sum())
+    sig = 0.05 * base
+    sig[~det] = np.nan                      # never read for upper limits
+    levels = np.where(det, 0.0, rng.choice([2.0, 3.0, 5.0], t.size))
+    like = rb.GaussianLikelihoodWithUpperLimits(t, y, sig, fn, kwargs=kw, detections=det,
+                                                upper_limit_sigma=levels, data_mode="flux_density")
+    got = like.log_likelihood_batch(p)
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        z = kwi.pop("redshift")
+        ref = r.arnett(t, z, frequency=nu, **kwi)
+        want = r.gaussian_likelihood_upper_limits(y, ref, sig, det, levels, "flux_density")
+        assert abs(got[i] - want) <= 1e-6 + 1e-8 * abs(want), (i, got[i], want)
+    assert got[-1] < -12 * 69.0              # every limit clipped at log(1e-30)
+    # single-sample API, scalar sigma level, and the noise likelihood
+    like3 = rb.GaussianLikelihoodWithUpperLimits(t, y, sig, fn, kwargs=kw, detections=det.astype(int),
+                                                 upper_limit_sigma=3.0)
+    like3.parameters.update(fid)
+    want = r.gaussian_likelihood_upper_limits(y, base, sig, det, 3.0, "flux")
+    assert abs(like3.log_likelihood() - want) <= 1e-6 + 1e-8 * abs(want)
+    noise = r.gaussian_likelihood_upper_limits(y, np.zeros_like(y), sig, det, 3.0, "flux")
+    assert abs(like3.noise_log_likelihood() - noise) <= 1e-6 + 1e-8 * abs(noise)
+    assert like3.summary()["upper_limits"] == 12
+
+    # magnitudes through the fused photometry path: limits use the survival function and sigma_m = 1.0857 / N
+    bands = np.array(["lsstg", "lsstr", "lssti"])[rng.integers(0, 3, t.size)]
+    kwm = dict(bands=bands, output_format="magnitude")
+    mags = fn(t, **fid, **kwm)
+    ym = mags + 0.05 * rng.standard_normal(t.size)
+    ym[~det] = mags[~det] - rng.uniform(0.0, 0.6, (~det).sum())   # limits slightly brighter than the source
+    likem = rb.GaussianLikelihoodWithUpperLimits(t, ym, 0.05, fn, kwargs=kwm, detections=det,
+                                                 upper_limit_sigma=5.0, data_mode="mag")
+    pm = {k: v[:8] for k, v in p.items()}
+    gotm = likem.log_likelihood_batch(pm)
+    model = fn(t, params_batch=pm, **kwm)
+    for i in range(8):
+        want = r.gaussian_likelihood_upper_limits(ym, model[i], 0.05, det, 5.0, "magnitude")
+        assert abs(gotm[i] - want) <= 1e-6 + 1e-8 * abs(want), (i, gotm[i], want)
+    noise = r.gaussian_likelihood_upper_limits(ym, np.full_like(ym, 60.0), 0.05, det, 5.0, "magnitude")
+    got_noise = likem.noise_log_likelihood()
+    # detections' residual is y itself in the noise hypothesis (likelihoods.py:432-435)
+    noise_det = r.gaussian_log_likelihood(ym[det], 0.05) + r.upper_limit_log_likelihood(
+        ym[~det], np.full((~det).sum(), 60.0), np.full((~det).sum(), 5.0), "magnitude")
+    assert abs(got_noise - noise_det) <= 1e-6 + 1e-9 * abs(noise_det), (got_noise, noise_det, noise)
+
+    # generic function (reference test fixture, test/likelihood_test.py:360-375)
+    def func(x, param_1, **kwargs):
+        return x * param_1
+    x = np.array([0, 1, 2, 3, 4])
+    yy = np.array([0.5, 1.2, 2.1, 3.5, 4.8])
+    dd = np.array([True, True, True, False, False])
+    lg = rb.GaussianLikelihoodWithUpperLimits(x, yy, np.full(5, 0.1), func, detections=dd, upper_limit_sigma=2.0)
+    lg.parameters["param_1"] = 1.1
+    want = r.gaussian_likelihood_upper_limits(yy, 1.1 * x, np.full(5, 0.1), dd, 2.0)
+    assert abs(lg.log_likelihood() - want) < 1e-9
+    with pytest.raises(ValueError):
+        lg.detections = np.array([True, False])
+    with pytest.raises(ValueError):
+        lg.upper_limit_sigma = np.array([1.0, 2.0, 3.0])
+    with pytest.raises(ValueError):
+        rb.GaussianLikelihoodWithUpperLimits(x, np.array([0.5, 1.2, 2.1, np.nan, np.nan]), np.full(5, 0.1), func,
+                                             detections=dd)
+
+
+@pytest.mark.gpu
+def test_upper_limits_in_every_fused_kernel(rb):
+    """The kilonova, Metzger, afterglow and photometry kernels share logl_term: their fused upper-limit log L must
+    equal the stand-alone reduction (checked against the oracle above) applied to their own model matrices."""
+    from redback_b200.engine import gaussian_logl
+    import torch
+    rng = np.random.default_rng(71)
+    t = np.sort(rng.uniform(0.5, 20, 30))
+    nu = np.full(t.size, 4.675e14)
+    det = rng.uniform(size=t.size) > 0.3
+    cases = [
+        (rb.kilonova_models.one_component_kilonova_model, h.one_component_prior(rng, 16),
+         dict(frequency=nu, output_format="flux_density")),
+        (rb.kilonova_models.metzger_kilonova_model, h.metzger_prior(rng, 8),
+         dict(frequency=nu, output_format="flux_density")),
+        (rb.afterglow_models.tophat_redback, h.tophat_prior(rng, 8), dict(frequency=nu, output_format="flux_density")),
+        (rb.kilonova_models.one_component_kilonova_model, h.one_component_prior(rng, 8),
+         dict(bands=np.array(["lsstr"] * t.size), output_format="magnitude")),
+    ]
+    for fn, p, kw in cases:
+        mag = kw["output_format"] == "magnitude"
+        model = np.asarray(fn(t, params_batch=p, **kw))
+        y = np.median(model, axis=0) * (1.0 if not mag else 1.0) + (0.0 if not mag else -0.2)
+        sig = 0.2 * np.abs(y) if not mag else np.full(t.size, 0.1)
+        like = rb.GaussianLikelihoodWithUpperLimits(t, y, sig, fn, kwargs=kw, detections=det, upper_limit_sigma=3.0,
+                                                    data_mode="magnitude" if mag else "flux")
+        fused = like.log_likelihood_batch(p)
+        level = np.where(det, 0.0, 3.0)
+        alone = gaussian_logl(torch.as_tensor(model, device="cuda"), y, sig, ul_level=level,
+                              ul_magnitude=mag).cpu().numpy()
+        np.testing.assert_allclose(fused, alone, rtol=1e-9, atol=1e-6, err_msg=fn.__name__)
+        plain = rb.GaussianLikelihood(t, y, sig, fn, kwargs=kw).log_likelihood_batch(p)
+        assert np.any(np.abs(plain - fused) > 1e-3)
