@@ -33,7 +33,7 @@ typedef enum {
 
 /* ---- luminosity engines: redback/transient_models/supernova_models.py:564-579 (_nickelcobalt_engine),
  *      redback/transient_models/magnetar_models.py:171-185 (basic_magnetar) ---------------------- */
-enum { RB_ENGINE_NICKEL = 0, RB_ENGINE_MAGNETAR = 1 };
+enum { RB_ENGINE_NICKEL = 0, RB_ENGINE_MAGNETAR = 1, RB_ENGINE_CSM = 2 };
 enum { RB_PREC_F64 = 0, RB_PREC_F32 = 1 };
 
 /* ---- output stage: bolometric models return L_bol; flux_density models go through
@@ -70,6 +70,10 @@ enum {
   RB_SN_BP = 2,                /*   bp [1e14 G]            */
   RB_SN_MASS_NS = 3,           /*   mass_ns [Msun]         */
   RB_SN_THETA_PB = 4,          /*   theta_pb [rad]         */
+  RB_SN_CSM_MASS = 1,          /* CSM engine (supernova_models.py:1910-1997): csm_mass [Msun] */
+  RB_SN_ETA = 2,               /*   eta: CSM density profile exponent, table range [0, 2]     */
+  RB_SN_RHO = 3,               /*   rho: CSM density amplitude [g cm^-3]                      */
+  RB_SN_R0 = 4,                /*   r0: inner CSM radius [AU]                                 */
   RB_SN_MEJ = 5,               /* [Msun] */
   RB_SN_VEJ = 6,               /* [km/s] */
   RB_SN_KAPPA = 7,
@@ -114,6 +118,10 @@ typedef struct {
    * FP64.  Target: rtol 1e-5 on model outputs (north_star).  Inputs / outputs remain float64. */
   int precision;            /* RB_PREC_F64 (default) | RB_PREC_F32 */
   rb_upper_limits upper_limits;
+  /* RB_ENGINE_CSM only: kwargs nn (12), delta (1), efficiency (0.5) of _csm_engine (supernova_models.py:1934-1936);
+     interaction process = CSMDiffusion, method "cumulative" (interaction_processes.py:176-197); dense grid =
+     get_optimal_time_array(min(0.1, min t), max t + 100, dense_resolution, user_times = t) (:2026-2030) */
+  double csm_nn, csm_delta, csm_efficiency;
 } rb_sn_config;
 
 /* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */
@@ -217,6 +225,8 @@ typedef struct {
   rb_cosmology cosmology;
   double ss, aa;      /* kwargs 'ss', 'aa': extra structure parameters of the PL / PL2 / 2C / DG jets */
   rb_upper_limits upper_limits;
+  int ab_magnitude;   /* output_format='magnitude': monochromatic AB magnitude of the mJy flux density
+                         (utils.calc_ABmag_from_flux_density, utils.py:481-488; base_models.py:944-946) */
 } rb_ag_config;
 
 int rb_ag_config_default(rb_ag_config* cfg);

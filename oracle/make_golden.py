@@ -196,8 +196,41 @@ def dump_verbatim():
     print("verbatim fixtures:", len(doc["diffusion"]), "diffusion,", len(doc["afterglow"]), "afterglow")
 
 
+def dump_csm():
+    """_csm_engine + CSMDiffusion (+ TemperatureFloor) of the reference's own sources on seeded prior draws
+    (priors/csm_interaction.prior ranges)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import warnings
+    warnings.simplefilter("ignore")
+    from oracle import refshim
+    ns = refshim.load_csm()
+    rng = np.random.default_rng(2025)
+    t = np.sort(np.concatenate([rng.uniform(0.03, 5, 6), rng.uniform(5, 400, 34)]))
+    doc = {"time": [float(v) for v in t], "draws": []}
+    for i in range(16):
+        prm = dict(mej=float(10 ** rng.uniform(0, 2)), csm_mass=float(10 ** rng.uniform(0, 2)),
+                   vej=float(10 ** rng.uniform(3, 5)), eta=float(rng.uniform(0, 2)),
+                   rho=float(10 ** rng.uniform(-14, -12)), kappa=float(rng.uniform(0.05, 2)),
+                   r0=float(rng.uniform(50, 700)))
+        tt = t if i % 4 else t[6:]          # with and without epochs below the 0.1 d default grid start
+        lbol = ns.csm_interaction_bolometric(tt, **prm)
+        eng = ns._csm_engine(time=tt, **prm)
+        tfl = float(10 ** rng.uniform(2, 4))
+        ph = ns.photosphere.TemperatureFloor(tt, lbol, prm["vej"], tfl)
+        doc["draws"].append(dict(params=dict(prm, temperature_floor=tfl), skip=0 if i % 4 else 6,
+                                 r_photosphere=float(eng.r_photosphere),
+                                 mass_csm_threshold=float(eng.mass_csm_threshold),
+                                 engine_lbol=[float(v) for v in eng.lbol], lbol=[float(v) for v in lbol],
+                                 temperature=[float(v) for v in ph.photosphere_temperature],
+                                 radius=[float(v) for v in ph.r_photosphere]))
+    with open(os.path.join(OUT, "csm_reference_draws.json"), "w") as fh:
+        json.dump(doc, fh)
+    print("csm fixtures:", len(doc["draws"]))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     dump_pkl()
     dump_ecsv()
     dump_verbatim()
+    dump_csm()

@@ -99,3 +99,42 @@ def load_afterglow():
     _stub("redback.transient_models.afterglow_models", __path__=[])
     return _load("redback.transient_models.afterglow_models.base_models",
                  "redback/transient_models/afterglow_models/base_models.py")
+
+
+def load_functions(relpath, names, namespace):
+    """Compile the named top-level functions of a reference source file *from where it lies* (decorators dropped)
+    and define them in `namespace`.  For functions whose module cannot be imported as a whole here
+    (utils.py / supernova_models.py need astropy, sncosmo, ...)."""
+    import ast
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    with open(path) as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    picked = [node for node in tree.body if isinstance(node, ast.FunctionDef) and node.name in names]
+    missing = set(names) - {node.name for node in picked}
+    if missing:
+        raise RuntimeError(f"{relpath}: no top-level function(s) {sorted(missing)}")
+    for node in picked:
+        node.decorator_list = []
+    exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), namespace)
+    return namespace
+
+
+def load_csm():
+    """The reference's own _csm_engine / csm_interaction_bolometric / get_csm_properties /
+    get_optimal_time_array (lru_cache dropped) + CSMDiffusion, executed from /root/reference."""
+    from collections import namedtuple
+    import numpy as np
+    from scipy.interpolate import RegularGridInterpolator
+    from . import restated as r
+    ns = load()
+    glb = dict(np=np, namedtuple=namedtuple, RegularGridInterpolator=RegularGridInterpolator,
+               dirname=os.path.join(REFERENCE_ROOT, "redback"), solar_mass=r.solar_mass, au_cgs=r.au_cgs,
+               km_cgs=r.km_cgs, day_to_s=r.day_to_s, ip=ns.interaction_processes)
+    load_functions("redback/utils.py", ["get_csm_properties", "get_optimal_time_array",
+                                         "_get_optimal_time_array_cached"], glb)
+    load_functions("redback/transient_models/supernova_models.py", ["_csm_engine", "csm_interaction_bolometric"], glb)
+    out = types.SimpleNamespace(**{k: glb[k] for k in ("get_csm_properties", "get_optimal_time_array", "_csm_engine",
+                                                       "csm_interaction_bolometric")})
+    out.photosphere = ns.photosphere
+    out.interaction_processes = ns.interaction_processes
+    return out

@@ -469,6 +469,109 @@ def get_optimal_time_array(t_min, t_max, resolution, user_times=None):
     return np.geomspace(t_min, t_max, resolution)
 
 
+# --------------------------------------------------------------------------------------------------
+# CSM interaction: _csm_engine (supernova_models.py:1910-1997), CSMDiffusion
+# (interaction_processes.py:133-229), csm_interaction(_bolometric) (supernova_models.py:2001-2111)
+# --------------------------------------------------------------------------------------------------
+au_cgs = 14959787070000.0
+_CSM_TABLE = None
+
+
+def _csm_table():
+    """redback/tables/csm_table.txt as committed by tools/gen_csm_table.py (tests/golden/csm_table.json)."""
+    global _CSM_TABLE
+    if _CSM_TABLE is None:
+        import json
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "csm_table.json")
+        with open(path) as fh:
+            doc = json.load(fh)
+        _CSM_TABLE = {k: np.asarray(v) for k, v in doc.items()}
+    return _CSM_TABLE
+
+
+def get_csm_properties(nn, eta):
+    """utils.get_csm_properties (utils.py:288-315): bilinear RegularGridInterpolator on (n, s); out-of-range raises."""
+    from scipy.interpolate import RegularGridInterpolator
+    tab = _csm_table()
+    out = {}
+    for key in ("aa", "bf", "br"):
+        out[key] = RegularGridInterpolator((tab["n"], tab["s"]), tab[key])([nn, eta])[0]
+    return out["aa"], out["bf"], out["br"]
+
+
+def csm_engine(time, mej, csm_mass, vej, eta, rho, kappa, r0, *, delta=1, nn=12, efficiency=0.5):
+    """_csm_engine (supernova_models.py:1910-1997).  time: source-frame days.  Returns (lbol, r_photosphere,
+    mass_csm_threshold) in cgs."""
+    time = np.asarray(time, dtype=float)
+    m_ej = mej * solar_mass
+    m_csm = csm_mass * solar_mass
+    r_in = r0 * au_cgs
+    v = vej * km_cgs
+    e_sn = 3. * v ** 2 * m_ej / 10.
+    t_i = 1.
+    a_c, b_f, b_r = get_csm_properties(nn, eta)
+    with np.errstate(all="ignore"):
+        q = rho * r_in ** eta                                                                       # :1942
+        r_csm = ((3.0 - eta) / (4.0 * np.pi * q) * m_csm + r_in ** (3.0 - eta)) ** (1.0 / (3.0 - eta))
+        r_ph = abs((-2.0 * (1.0 - eta) / (3.0 * kappa * q) + r_csm ** (1.0 - eta)) ** (1.0 / (1.0 - eta)))
+        m_th = np.abs(4.0 * np.pi * q / (3.0 - eta) * (r_ph ** (3.0 - eta) - r_in ** (3.0 - eta)))   # :1949-1950
+        g_n = (1.0 / (4.0 * np.pi * (nn - delta)) * (2.0 * (5.0 - delta) * (nn - 5.0) * e_sn) ** ((nn - 3.) / 2.0)
+               / ((3.0 - delta) * (nn - 3.0) * m_ej) ** ((nn - 5.0) / 2.0))                         # :1953-1955
+        pw = (nn - eta) / ((nn - 3.0) * (3.0 - eta))
+        t_fs = (abs((3.0 - eta) * q ** ((3.0 - nn) / (nn - eta)) * (a_c * g_n) ** ((eta - 3.0) / (nn - eta))
+                    / (4.0 * np.pi * b_f ** (3.0 - eta))) ** pw * m_th ** pw)                        # :1958-1962
+        t_rs = (v / (b_r * (a_c * g_n / q) ** (1.0 / (nn - eta)))
+                * (1.0 - (3.0 - nn) * m_ej / (4.0 * np.pi * v ** (3.0 - nn) * g_n)) ** (1.0 / (3.0 - nn))
+                ) ** ((nn - eta) / (eta - 3.0))                                                     # :1965-1970
+        ts = time * day_to_s
+        alpha = (2.0 * nn + 6.0 * eta - nn * eta - 15.) / (nn - eta)
+        l_fs = (2.0 * np.pi / (nn - eta) ** 3 * g_n ** ((5.0 - eta) / (nn - eta)) * q ** ((nn - 5.0) / (nn - eta))
+                * (nn - 3.0) ** 2 * (nn - 5.0) * b_f ** (5.0 - eta) * a_c ** ((5.0 - eta) / (nn - eta))
+                * (ts + t_i) ** alpha)                                                              # :1975-1977
+        l_rs = (2.0 * np.pi * (a_c * g_n / q) ** ((5.0 - nn) / (nn - eta)) * b_r ** (5.0 - nn) * g_n
+                * ((3.0 - eta) / (nn - eta)) ** 3 * (ts + t_i) ** alpha)                            # :1979-1980
+        l_fs = np.where(t_fs - ts > 0, l_fs, 0.0)
+        l_rs = np.where(t_rs - ts > 0, l_rs, 0.0)
+    return efficiency * (l_fs + l_rs), r_ph, m_th
+
+
+def csm_diffusion(time, dense_times, luminosity, kappa, r_photosphere, mass_csm_threshold):
+    """CSMDiffusion._convert_input_luminosity_cumulative (interaction_processes.py:176-197, the default method)."""
+    time = np.asarray(time, dtype=float)
+    dense_times = np.asarray(dense_times, dtype=float)
+    t0 = kappa * mass_csm_threshold / (4. * np.pi ** 3. / 9. * speed_of_light * r_photosphere) / day_to_s   # :171-173
+    inside = time[(time >= dense_times[0]) & (time <= dense_times[-1])]
+    knots = np.unique(np.concatenate((dense_times, inside)))
+    lum = np.interp(knots, dense_times, luminosity)
+    out = np.zeros_like(knots)
+    with np.errstate(all="ignore"):
+        dt = np.diff(knots)
+        slope = np.diff(lum) / dt
+        decay = np.exp(-dt / t0)
+        fill = -np.expm1(-dt / t0)
+        for i in range(dt.size):                                                                   # :190-195
+            out[i + 1] = out[i] * decay[i] + lum[i] * fill[i] + slope[i] * (dt[i] - t0 * fill[i])
+    return np.interp(time, knots, out)
+
+
+def csm_interaction_bolometric(time, mej, csm_mass, vej, eta, rho, kappa, r0, *, dense_resolution=1000, **kw):
+    """supernova_models.py:2001-2050 with the default interaction process."""
+    time = np.atleast_1d(np.asarray(time, dtype=float))
+    dense = get_optimal_time_array(min(0.1, np.min(time)), np.max(time) + 100, dense_resolution, user_times=time)
+    lbol, r_ph, m_th = csm_engine(dense, mej, csm_mass, vej, eta, rho, kappa, r0, **kw)
+    return csm_diffusion(time, dense, lbol, kappa, r_ph, m_th)
+
+
+def csm_interaction(time, redshift, mej, csm_mass, vej, eta, rho, kappa, r0, *, frequency, temperature_floor,
+                    dl=None, **kw):
+    """supernova_models.py:2054-2092 (flux_density, TemperatureFloor + Blackbody defaults), mJy."""
+    return _sn_flux_density(
+        time, redshift,
+        lambda t: csm_interaction_bolometric(t, mej, csm_mass, vej, eta, rho, kappa, r0, **kw),
+        "blackbody", frequency=frequency, vej=vej, temperature_floor=temperature_floor, dl=dl)
+
+
 _BK_V = np.asarray([0.1, 0.2, 0.3, 0.4])
 _BK_M = np.asarray([1.e-3, 5.e-3, 1.e-2, 5.e-2, 1.e-1])
 _BK_A = np.asarray([[2.01, 4.52, 8.16, 16.3], [0.81, 1.9, 3.2, 5.0], [0.56, 1.31, 2.19, 3.0],
@@ -802,6 +905,14 @@ def ag_flux(fbb, nuc, num, nu1, fmax, p):
         return np.minimum(fbb_adj, f)
 
 
+def calc_ABmag_from_flux_density(fluxdensity_mjy):
+    """utils.calc_ABmag_from_flux_density (utils.py:481-488): `(f * mJy).to(ABmag)`.  astropy (absent here) defines
+    AB = 10**(48.6 / -2.5) erg s^-1 cm^-2 Hz^-1 (astropy/units/photometric.py) and ABmag = -2.5 log10(f / AB);
+    restated from that published definition."""
+    with np.errstate(all="ignore"):
+        return -2.5 * np.log10(np.asarray(fluxdensity_mjy, dtype=float) * (1e-26 / 10 ** (48.6 / -2.5)))
+
+
 def ag_default_res(thv, thc, g0):
     """tophat_redback / gaussian_redback resolution rule, base_models.py:932-935"""
     sep = max(thv - thc, 0)
@@ -957,16 +1068,20 @@ def bandpass_magnitude_to_flux(magnitude, reference_flux):
 
 def sn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, **params):
     """Magnitude branch of arnett / basic_magnetar_powered / slsn (supernova_models.py:1008-1028, 1510-1530,
-    1599-1624).  `model` in {'arnett', 'basic_magnetar_powered', 'slsn'}."""
+    1599-1624; csm_interaction :2093-2111).  `model` in {'arnett', 'basic_magnetar_powered', 'slsn', 'type_1a',
+    'csm_interaction'}."""
     time_obs = np.asarray(time, dtype=float)
     lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=float)
     if dl is None:
         dl = cosmo.luminosity_distance_cm(redshift)
-    time_temp = get_optimal_time_array(0.1, 3000, 300)
+    time_temp = get_optimal_time_array(0.1, 500 if model == "csm_interaction" else 3000, 300)   # :1010, :2095
     time_observer_frame = time_temp * (1. + redshift)
     frequency, t = calc_kcorrected_properties(lambda_to_nu(lam), redshift, time_observer_frame)
-    dkw = dict(vej=params["vej"], kappa=params["kappa"], kappa_gamma=params["kappa_gamma"])
-    if model in ("arnett", "type_1a"):
+    dkw = dict(vej=params["vej"], kappa=params["kappa"], kappa_gamma=params.get("kappa_gamma"))
+    if model == "csm_interaction":                                                             # :2099-2100
+        lbol = csm_interaction_bolometric(t, params["mej"], params["csm_mass"], params["vej"], params["eta"],
+                                          params["rho"], params["kappa"], params["r0"])
+    elif model in ("arnett", "type_1a"):
         lbol = arnett_bolometric(t, params["f_nickel"], params["mej"], **dkw)
     else:
         lbol = basic_magnetar_powered_bolometric(t, params["p0"], params["bp"], params["mass_ns"],

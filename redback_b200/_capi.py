@@ -9,14 +9,15 @@ import os
 from . import _build
 
 RB_OK, RB_ERR_INVALID, RB_ERR_UNSUPPORTED, RB_ERR_CUDA = 0, -1, -2, -3
-ENGINE_NICKEL, ENGINE_MAGNETAR = 0, 1
+ENGINE_NICKEL, ENGINE_MAGNETAR, ENGINE_CSM = 0, 1, 2
 PREC_F64, PREC_F32 = 0, 1
 NOISE_TYPES = dict(limiting_mag=0, gaussian=1, gaussianmodel=2)
 SED_BOLOMETRIC, SED_BLACKBODY, SED_CUTOFF_BLACKBODY, SED_CUTOFF_LINE = 0, 1, 2, 3
 SIGMA_FIXED, SIGMA_SAMPLED, SIGMA_QUADRATURE, SIGMA_FRACTIONAL, SIGMA_SYSTEMATIC = 0, 1, 2, 3, 4
 
 SN_ROWS = dict(redshift=0, f_nickel=1, p0=1, bp=2, mass_ns=3, theta_pb=4, mej=5, vej=6, kappa=7,
-               kappa_gamma=8, temperature_floor=9)
+               kappa_gamma=8, temperature_floor=9,
+               csm_mass=1, eta=2, rho=3, r0=4)     # RB_ENGINE_CSM reuses the engine rows
 SN_NPARAM = 10
 
 
@@ -35,7 +36,8 @@ class SnConfig(C.Structure):
                 ("cutoff_wavelength", C.c_double), ("absorption_index", C.c_double), ("cosmology", Cosmology),
                 ("line_wavelength", C.c_double), ("line_width", C.c_double), ("line_time", C.c_double),
                 ("line_duration", C.c_double), ("line_amplitude", C.c_double), ("precision", C.c_int),
-                ("upper_limits", UpperLimits)]
+                ("upper_limits", UpperLimits), ("csm_nn", C.c_double), ("csm_delta", C.c_double),
+                ("csm_efficiency", C.c_double)]
 
 
 KN_ONE_COMPONENT, KN_METZGER = 0, 1
@@ -57,7 +59,7 @@ AG_NPARAM = 11
 class AgConfig(C.Structure):
     _fields_ = [("jet", C.c_int), ("sigma_mode", C.c_int), ("steps", C.c_int), ("res", C.c_int), ("k", C.c_int),
                 ("expansion", C.c_int), ("a1", C.c_double), ("cosmology", Cosmology), ("ss", C.c_double),
-                ("aa", C.c_double), ("upper_limits", UpperLimits)]
+                ("aa", C.c_double), ("upper_limits", UpperLimits), ("ab_magnitude", C.c_int)]
 
 
 class RedbackB200Error(RuntimeError):
@@ -123,7 +125,7 @@ def check(rc):
 
 
 def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
-              absorption_index=1.0, cosmology=None, line=None, precision=0):
+              absorption_index=1.0, cosmology=None, line=None, precision=0, csm=None):
     cfg = SnConfig()
     check(lib().rb_sn_config_default(C.byref(cfg)))
     cfg.engine, cfg.sed, cfg.sigma_mode = engine, sed, sigma_mode
@@ -136,6 +138,8 @@ def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff
         for key, val in line.items():
             setattr(cfg, key, float(val))
     cfg.precision = int(precision)
+    if csm is not None:
+        cfg.csm_nn, cfg.csm_delta, cfg.csm_efficiency = (float(csm[k]) for k in ("nn", "delta", "efficiency"))
     return cfg
 
 
@@ -153,7 +157,7 @@ def kn_config(model, sigma_mode=SIGMA_FIXED, dense_resolution=500, neutron_precu
 
 
 def ag_config(jet, sigma_mode=SIGMA_FIXED, steps=250, res=0, k=0, expansion=1, a1=1.0, cosmology=None, ss=0.01,
-              aa=0.5):
+              aa=0.5, ab_magnitude=False):
     cfg = AgConfig()
     check(lib().rb_ag_config_default(C.byref(cfg)))
     cfg.jet, cfg.sigma_mode = jet, sigma_mode
@@ -161,6 +165,7 @@ def ag_config(jet, sigma_mode=SIGMA_FIXED, steps=250, res=0, k=0, expansion=1, a
     cfg.expansion = 1 if expansion else 0
     cfg.a1 = float(a1)
     cfg.ss, cfg.aa = float(ss), float(aa)
+    cfg.ab_magnitude = int(bool(ab_magnitude))
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg

@@ -1,8 +1,8 @@
 """Batched drop-ins for redback's native structured-jet afterglows
 (redback/transient_models/afterglow_models/base_models.py: tophat_redback :885-946, gaussian_redback :948-1010),
-output_format='flux_density'.  Same signatures as the reference plus `params_batch`."""
+output_format='flux_density' | 'magnitude'.  Same signatures as the reference plus `params_batch`."""
 from . import _capi
-from ._fused import FusedSpec, cosmology_from_kwargs, flux_density_only, run
+from ._fused import FusedSpec, cosmology_from_kwargs, run
 from .engine import AfterglowPath
 
 _COMMON = ("redshift", "thv", "loge0", "thc", "logn0", "p", "logepse", "logepsb", "g0", "xiN")
@@ -10,14 +10,20 @@ _COMMON = ("redshift", "thv", "loge0", "thc", "logn0", "p", "logepse", "logepsb"
 
 def _spec(name, jet, needed, ss=0.01, aa=0.5):
     def validate(kwargs):
-        flux_density_only(kwargs, name)
+        # base_models.py:942-946: 'flux_density' (mJy) or 'magnitude' (monochromatic AB); anything else -> None there
+        fmt = kwargs.get("output_format")
+        if fmt is None:
+            raise KeyError("output_format")
+        if fmt not in ("flux_density", "magnitude"):
+            raise NotImplementedError(f"{name}: output_format='{fmt}' is not defined for this model")
 
     def build(time, kwargs, y, sigma, sigma_mode):
         return AfterglowPath(jet, time, frequency=kwargs.get("frequency"), y=y, sigma=sigma, sigma_mode=sigma_mode,
                              steps=kwargs.get("steps", 250), res=kwargs.get("res"), k=kwargs.get("k", 0),
                              expansion=kwargs.get("expansion", 1), a1=kwargs.get("a1", 1),
                              cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"),
-                             ss=kwargs.get("ss", ss), aa=kwargs.get("aa", aa))
+                             ss=kwargs.get("ss", ss), aa=kwargs.get("aa", aa),
+                             ab_magnitude=kwargs["output_format"] == "magnitude")
 
     return FusedSpec(name, needed, build, validate)
 

@@ -509,7 +509,9 @@ __global__ void __launch_bounds__(128) ag_finish_kernel(const AgArgs a) {
     for (int e = tid; e < E; e += blockDim.x) {
       double lc = 0.0;
       for (int64_t u = u0; u < u1; ++u) lc += a.partial[u * (int64_t)E + e];
-      const double model_v = (u1 > u0) ? lc * opz / 1e-26 : NAN;                   // :640, :942
+      double model_v = (u1 > u0) ? lc * opz / 1e-26 : NAN;                         // :640, :942
+      // astropy: (f * mJy).to(ABmag) = -2.5 log10(f * 1e-26 / AB), AB = 10^(48.6 / -2.5) erg s^-1 cm^-2 Hz^-1
+      if (a.cfg.ab_magnitude) model_v = -2.5 * log10(model_v * 2.754228703338175e-07);
       if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = model_v;
       if (a.want_logl) {
         logl_part += logl_term(a.cfg.sigma_mode, a.epoch_tab[EP_KIND * E + e], a.epoch_tab[EP_Y * E + e], model_v,

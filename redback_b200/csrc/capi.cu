@@ -8,6 +8,7 @@
 
 #include "sn_kernel.cu"
 #include "kn_kernel.cu"
+#include "csm_kernel.cu"
 #include "ag_kernel.cu"
 #include "phot_kernel.cu"
 #include "noise_kernel.cu"
@@ -57,6 +58,48 @@ size_t sn_smem_bytes(int D, int64_t E, bool epochs_in_smem) {
              + (size_t)(2 * rb::kNodes + (D + 1) / 2 * 2);   // FP32 copies: float4 nodes, float2 segments
   if (epochs_in_smem) n += (size_t)rb::kEpochCols * (size_t)E;
   return sizeof(double) * n;
+}
+
+size_t csm_smem_bytes(int D, int64_t E) {
+  const size_t M = (size_t)D + (size_t)E;
+  return sizeof(double) * ((size_t)rb::kExpTabSize + 2 * (size_t)D + 4 * M + (size_t)E + 96) + sizeof(int) * (size_t)E;
+}
+
+// CSM engine (RB_ENGINE_CSM): unique epochs -> per-sample scalars -> one block per sample.  `t_dev` are the E
+// observer-frame epochs (or the model's own time grid in grid mode) that a.epoch_tab was built from.
+int launch_csm(rb::SnArgs a, const double* t_dev, cudaStream_t st, int sms) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(rb::csm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(csm_kernel)");
+  const int E = a.E;
+  const size_t smem = csm_smem_bytes(a.cfg.dense_resolution, E);
+  if (smem > 220 * 1024)
+    return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval (CSM): dense_resolution + number of epochs exceed shared memory");
+  StreamAlloc b_ut, b_ui, b_sc;
+  RB_CUDA(b_ut.alloc((size_t)E * sizeof(double), st));
+  RB_CUDA(b_ui.alloc(((size_t)E + 1) * sizeof(int), st));
+  RB_CUDA(b_sc.alloc((size_t)a.N * rb::kCsmScalars * sizeof(double), st));
+  rb::CsmArgs c{};
+  c.s = a;
+  c.utime = b_ut.as<double>();
+  c.uidx = b_ui.as<int>();
+  c.n_unique = b_ui.as<int>() + E;
+  c.cscal = b_sc.as<double>();
+  rb::unique_times_kernel<<<1, 1024, (size_t)E * sizeof(int), st>>>(E, t_dev, b_ut.as<double>(), b_ui.as<int>(),
+                                                                   b_ui.as<int>() + E);
+  rb::csm_prep_kernel<<<(unsigned)((a.N + 7) / 8), 256, 0, st>>>(c);
+  int occ = 0;
+  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::csm_kernel, rb::kCsmThreads, smem));
+  if (occ < 1) occ = 1;
+  int64_t grid = (int64_t)sms * occ * 4;
+  if (grid > a.N) grid = a.N;
+  rb::csm_kernel<<<(unsigned)grid, rb::kCsmThreads, smem, st>>>(c);
+  launch_counter()->fetch_add(3);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
 }
 
 int sn_block_threads(int64_t E) {
@@ -119,6 +162,9 @@ int rb_sn_config_default(rb_sn_config* cfg) {
   cfg->line_time = 50.0;
   cfg->line_duration = 25.0;
   cfg->line_amplitude = 0.3;
+  cfg->csm_nn = 12.0;
+  cfg->csm_delta = 1.0;
+  cfg->csm_efficiency = 0.5;
   return rb_cosmology_planck18(&cfg->cosmology);
 }
 
@@ -127,8 +173,15 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
                     const void* out_model, const void* out_logl) {
   if (!cfg) return fail(RB_ERR_INVALID, "rb_sn_eval: null config");
   if (N < 0 || E <= 0 || E > (1 << 24)) return fail(RB_ERR_INVALID, "rb_sn_eval: need N >= 0 and 0 < E <= 2^24");
-  if (cfg->engine != RB_ENGINE_NICKEL && cfg->engine != RB_ENGINE_MAGNETAR)
+  if (cfg->engine != RB_ENGINE_NICKEL && cfg->engine != RB_ENGINE_MAGNETAR && cfg->engine != RB_ENGINE_CSM)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown engine");
+  if (cfg->engine == RB_ENGINE_CSM) {
+    // utils.py:304-310: RegularGridInterpolator raises outside the tabulated range of n
+    if (!(cfg->csm_nn >= 6.0 && cfg->csm_nn <= 14.0))
+      return fail(RB_ERR_INVALID, "One of the requested xi is out of bounds in dimension 0 (nn must be in [6, 14])");
+    if (cfg->precision != RB_PREC_F64) return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: the CSM path is FP64 only");
+    if (cfg->dense_resolution < 20) return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution must be >= 20 (CSM)");
+  }
   if (cfg->sed < RB_SED_BOLOMETRIC || cfg->sed > RB_SED_CUTOFF_LINE)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sed");
   if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_SYSTEMATIC)
@@ -204,6 +257,10 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   a.epoch_tab = epoch_tab;
   a.scalars = ws + (size_t)rb::kEpochCols * (size_t)E;
   a.param_stride = N;
+  if (cfg->engine == RB_ENGINE_CSM) {
+    launch_counter()->fetch_add(1);
+    return launch_csm(a, t_obs, st, sms);
+  }
   rb::sn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
   const int threads = sn_block_threads(E);
   a.epochs_in_smem = (sn_smem_bytes(cfg->dense_resolution, E, true) <= 64 * 1024) ? 1 : 0;
@@ -941,8 +998,13 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
     a.dl_out = d_dl;
     a.param_stride = N;
     a.epochs_in_smem = ep_in_smem;
-    rb::sn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
-    rb::sn_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_sn * 4), sn_threads, sn_smem, st>>>(a);
+    if (cfg->engine == RB_ENGINE_CSM) {
+      status = launch_csm(a, d_tgrid, st, sms);
+      if (status != RB_OK) break;
+    } else {
+      rb::sn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
+      rb::sn_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_sn * 4), sn_threads, sn_smem, st>>>(a);
+    }
     pa.N = nc;
     pa.n_base = n0;
     pa.E = (int)E;

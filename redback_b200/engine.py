@@ -220,16 +220,21 @@ class SupernovaPath(_FusedPath):
 
     def __init__(self, engine, sed, time, frequency=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
-                 absorption_index=1.0, cosmology=None, device=None, line=None, dtype="float64"):
+                 absorption_index=1.0, cosmology=None, device=None, line=None, dtype="float64", csm=None):
         self.NEEDS_FREQUENCY = sed != _capi.SED_BOLOMETRIC
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength,
-                                   absorption_index, cosmology, line, _precision(dtype))
+                                   absorption_index, cosmology, line, _precision(dtype), csm)
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):
         return _capi.lib().rb_sn_eval_f64
 
     def _check_time(self, t):
+        if self.cfg.engine == _capi.ENGINE_CSM:
+            # the dense grid is np.geomspace(min(0.1, min(time)), ...) (supernova_models.py:2026-2030)
+            if np.any(~(t > 0)):
+                raise ValueError("Geometric sequence cannot include zero: csm_interaction needs time > 0")
+            return
         if np.any(t < 0):
             raise NotImplementedError("negative times are not supported on device (the reference maps them "
                                       "to the first valid epoch)")
@@ -265,16 +270,17 @@ class SupernovaMagPath(SupernovaPath):
 
     def __init__(self, engine, sed, time, bands, output="magnitude", lambda_array=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0, absorption_index=1.0,
-                 cosmology=None, device=None, line=None):
+                 cosmology=None, device=None, line=None, csm=None):
         from . import bands as _bands
         if sed == _capi.SED_BOLOMETRIC:
             raise ValueError("bolometric models have no magnitude output")
         self.NEEDS_FREQUENCY = False
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength, absorption_index,
-                                   cosmology, line)
+                                   cosmology, line, 0, csm)
         self._setup(time, None, y, sigma, device)
         lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
-        tgrid = np.geomspace(0.1, 3000, 300)     # get_optimal_time_array(0.1, 3000, 300), utils.py:108
+        # get_optimal_time_array(0.1, 3000, 300) (utils.py:108); csm_interaction: (0.1, 500, 300) (:2095)
+        tgrid = np.geomspace(0.1, 500 if engine == _capi.ENGINE_CSM else 3000, 300)
         self.phot, self._keep = _bands.build_photometry(bands, self.E, lam, output, tgrid=tgrid)
 
     def _launch(self, *args):
@@ -308,11 +314,12 @@ class AfterglowPath(_FusedPath):
     NPARAM = _capi.AG_NPARAM
 
     def __init__(self, jet, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED, steps=250,
-                 res=None, k=0, expansion=1, a1=1, cosmology=None, device=None, ss=0.01, aa=0.5):
+                 res=None, k=0, expansion=1, a1=1, cosmology=None, device=None, ss=0.01, aa=0.5,
+                 ab_magnitude=False):
         if k not in (0, 2):
             raise ValueError("k must either be 0 or 2")
         self.cfg = _capi.ag_config(jet, sigma_mode, steps, 0 if res is None else int(res), k, expansion, a1, cosmology,
-                                   ss, aa)
+                                   ss, aa, ab_magnitude)
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):

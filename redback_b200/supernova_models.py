@@ -12,7 +12,7 @@ from ._fused import FusedSpec, cosmology_from_kwargs, output_mode, run
 from .engine import SupernovaMagPath, SupernovaPath
 
 _ALLOWED_OPERATORS = {
-    "interaction_process": ("Diffusion",),
+    "interaction_process": ("Diffusion", "CSMDiffusion"),
     "photosphere": ("TemperatureFloor",),
     "sed": ("Blackbody", "CutoffBlackbody"),
 }
@@ -49,13 +49,32 @@ def _line_kwargs(kwargs):
     return out
 
 
+def _csm_kwargs(kwargs):
+    """_csm_engine / CSMDiffusion keyword arguments (supernova_models.py:1934-1936, interaction_processes.py:154-155)."""
+    method = kwargs.get("csm_diffusion_method", "cumulative")
+    if method != "cumulative":
+        if method in ("quadrature", "legacy"):
+            raise NotImplementedError("csm_diffusion_method='quadrature' is not fused on device (default: 'cumulative')")
+        raise ValueError("csm_diffusion_method must be 'cumulative' or 'quadrature'")
+    if "dense_time_min" in kwargs or "stop_time" in kwargs:
+        raise NotImplementedError("dense_time_min / stop_time overrides are not fused on device")
+    return dict(nn=kwargs.get("nn", 12), delta=kwargs.get("delta", 1), efficiency=kwargs.get("efficiency", 0.5))
+
+
 def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None):
+    is_csm = engine == _capi.ENGINE_CSM
+    default_ip = "CSMDiffusion" if is_csm else "Diffusion"
     needed = list(engine_params) + list(_DIFFUSION)
+    if is_csm:
+        needed = list(engine_params)
     if flux_density:
         needed = ["redshift"] + needed + ["temperature_floor"]
 
     def validate(kwargs):
-        _operator_name("interaction_process", kwargs.get("interaction_process", "Diffusion"), "Diffusion")
+        if _operator_name("interaction_process", kwargs.get("interaction_process", default_ip), default_ip) != default_ip:
+            raise NotImplementedError(f"{name}: only interaction_process={default_ip} is fused on device")
+        if is_csm:
+            _csm_kwargs(kwargs)
         if flux_density:
             output_mode(kwargs, name)
             _operator_name("photosphere", kwargs.get("photosphere"), "TemperatureFloor")
@@ -65,6 +84,7 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
     def build(time, kwargs, y, sigma, sigma_mode):
         sed_id = _capi.SED_BOLOMETRIC
         line = None
+        csm = _csm_kwargs(kwargs) if is_csm else None
         if flux_density:
             if fixed_sed is not None:     # type_1a hard-wires CutoffBlackbody + Line (supernova_models.py:2268-2275)
                 sed_id, line = fixed_sed, _line_kwargs(kwargs)
@@ -78,14 +98,14 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
                                         cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000),
                                         absorption_index=kwargs.get("absorption_index", 1.0),
                                         cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"),
-                                        line=line)
+                                        line=line, csm=csm)
         return SupernovaPath(engine, sed_id, time, frequency=kwargs.get("frequency") if flux_density else None,
                              y=y, sigma=sigma, sigma_mode=sigma_mode,
                              dense_resolution=kwargs.get("dense_resolution", 1000),
                              cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000),
                              absorption_index=kwargs.get("absorption_index", 1.0),
                              cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"), line=line,
-                             dtype=kwargs.get("dtype", "float64"))
+                             dtype=kwargs.get("dtype", "float64"), csm=csm)
 
     return FusedSpec(name, needed, build, validate)
 
@@ -96,6 +116,26 @@ _MAGNETAR_BOLO = _spec("basic_magnetar_powered_bolometric", _capi.ENGINE_MAGNETA
 _MAGNETAR_BB = _spec("basic_magnetar_powered", _capi.ENGINE_MAGNETAR, _MAGNETAR, True, "Blackbody")
 _SLSN = _spec("slsn", _capi.ENGINE_MAGNETAR, _MAGNETAR, True, "CutoffBlackbody")
 _TYPE_1A = _spec("type_1a", _capi.ENGINE_NICKEL, ("f_nickel",), True, None, fixed_sed=_capi.SED_CUTOFF_LINE)
+
+
+_CSM = ("mej", "csm_mass", "vej", "eta", "rho", "kappa", "r0")
+_CSM_BOLO = _spec("csm_interaction_bolometric", _capi.ENGINE_CSM, _CSM, False, None)
+_CSM_BB = _spec("csm_interaction", _capi.ENGINE_CSM, _CSM, True, "Blackbody")
+
+
+def csm_interaction_bolometric(time, mej=None, csm_mass=None, vej=None, eta=None, rho=None, kappa=None, r0=None,
+                               params_batch=None, **kwargs):
+    """redback supernova_models.csm_interaction_bolometric (:2001-2050): _csm_engine on the adaptive dense grid +
+    CSMDiffusion (cumulative); kwargs nn, delta, efficiency, dense_resolution; returns erg/s."""
+    named = dict(mej=mej, csm_mass=csm_mass, vej=vej, eta=eta, rho=rho, kappa=kappa, r0=r0)
+    return run(_CSM_BOLO, time, named, kwargs, params_batch)
+
+
+def csm_interaction(time, redshift=None, mej=None, csm_mass=None, vej=None, eta=None, rho=None, kappa=None, r0=None,
+                    params_batch=None, **kwargs):
+    """redback supernova_models.csm_interaction (:2054-2111); TemperatureFloor + Blackbody by default; mJy / mag."""
+    named = dict(redshift=redshift, mej=mej, csm_mass=csm_mass, vej=vej, eta=eta, rho=rho, kappa=kappa, r0=r0)
+    return run(_CSM_BB, time, named, kwargs, params_batch)
 
 
 def arnett_bolometric(time, f_nickel=None, mej=None, params_batch=None, **kwargs):
@@ -144,4 +184,5 @@ FUSED = {
     arnett_bolometric: _ARNETT_BOLO, arnett: _ARNETT,
     basic_magnetar_powered_bolometric: _MAGNETAR_BOLO, slsn_bolometric: _MAGNETAR_BOLO,
     basic_magnetar_powered: _MAGNETAR_BB, slsn: _SLSN, type_1a: _TYPE_1A,
+    csm_interaction_bolometric: _CSM_BOLO, csm_interaction: _CSM_BB,
 }

@@ -114,3 +114,11 @@ def config4_epochs(n_per=250):
     nu = np.concatenate([np.full(n_per, 5e9), np.full(n_per, 2e17)])
     order = np.argsort(t, kind="stable")
     return t[order], nu[order]
+
+
+def csm_prior(rng, n, zmax=1.0):
+    """priors/csm_interaction.prior"""
+    return dict(redshift=rng.uniform(1e-3, zmax, n), mej=loguniform(rng, 1, 100, n),
+                csm_mass=loguniform(rng, 1, 100, n), vej=loguniform(rng, 1e3, 1e5, n), eta=rng.uniform(0, 2, n),
+                rho=loguniform(rng, 1e-14, 1e-12, n), kappa=rng.uniform(0.05, 2, n), r0=rng.uniform(50, 700, n),
+                temperature_floor=loguniform(rng, 100, 1e4, n))

@@ -98,6 +98,30 @@ def test_other_jet_structures(rb, name, method_id, ss, aa):
         h.assert_close(out[i], ref, RTOL, what=f"{name} sample {i}")
 
 
+def test_monochromatic_ab_magnitude(rb):
+    """output_format='magnitude' (base_models.py:944-946): AB magnitude of the mJy flux density, also inside the
+    fused likelihood."""
+    t = np.geomspace(0.1, 100, 20)
+    nu = np.full(20, 4.6e14)
+    rng = np.random.default_rng(23)
+    N = 6
+    p = h.tophat_prior(rng, N)
+    out = rb.afterglow_models.tophat_redback(t, params_batch=p, frequency=nu, output_format="magnitude")
+    y = out[2] + 0.1
+    logl = rb.GaussianLikelihood(t, y, 0.2, rb.afterglow_models.tophat_redback,
+                                 kwargs=dict(frequency=nu, output_format="magnitude")).log_likelihood_batch(p)
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.calc_ABmag_from_flux_density(r.redback_afterglow(t, z, frequency=nu, **kw))
+        np.testing.assert_allclose(out[i], ref, rtol=0, atol=2.5 / np.log(10) * RTOL)
+        ref_l = r.gaussian_likelihood(y, ref, 0.2)
+        assert abs(logl[i] - ref_l) <= 1e-6 + 1e-9 * abs(ref_l)
+    assert abs(r.calc_ABmag_from_flux_density(3631e3) - 0.0) < 1e-4     # 3631 Jy is AB = 0 to 1e-4 mag
+    with pytest.raises(NotImplementedError):
+        rb.afterglow_models.tophat_redback(t, params_batch=p, frequency=nu, output_format="flux")
+
+
 def test_errors(rb):
     t = np.array([1., 2.])
     kw = dict(thv=0.2, loge0=52., thc=0.08, logn0=-1., p=2.2, logepse=-1., logepsb=-2., g0=300., xiN=0.5)

@@ -76,6 +76,22 @@ def test_supernova_magnitudes(rb, obands, model):
         _check(out[i], ref, f"{model} sample {i}", floor_mag=np.nanmin(ref))
 
 
+def test_csm_interaction_magnitudes(rb, obands):
+    """csm_interaction magnitude branch (supernova_models.py:2093-2111): grid get_optimal_time_array(0.1, 500, 300)."""
+    rng = np.random.default_rng(27)
+    t = np.sort(rng.uniform(3, 150, 36))
+    names = np.array(list(h.LSST_NU)[:6] * 6)
+    N = 10
+    p = h.csm_prior(rng, N, zmax=0.5)
+    p["temperature_floor"] = h.loguniform(rng, 3e3, 1.2e4, N)
+    out = rb.supernova_models.csm_interaction(t, params_batch=p, bands=names, output_format="magnitude")
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.sn_magnitude("csm_interaction", t, z, bands=names, bandpasses=obands, **kw)
+        _check(out[i], ref, f"csm_interaction sample {i}", floor_mag=np.nanmin(ref))
+
+
 def test_kilonova_magnitudes_config3(rb, obands):
     """BASELINE configs[2]: one_component_kilonova_model in LSST ugrizy magnitudes."""
     t = np.geomspace(0.3, 20, 36)

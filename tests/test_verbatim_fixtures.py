@@ -61,3 +61,26 @@ def test_device_reproduces_verbatim_reference(fx):
         out = getattr(rb.afterglow_models, row["model"])(ta, row["redshift"], frequency=fr,
                                                           output_format="flux_density", k=row["k"], **row["params"])
         h.assert_close(out, np.array(row["results"]), 1e-9, what=row["model"])
+
+
+@pytest.fixture(scope="module")
+def csm_fx():
+    with open(os.path.join(ROOT, "tests", "golden", "csm_reference_draws.json")) as fh:
+        return json.load(fh)
+
+
+def test_oracle_reproduces_reference_csm(csm_fx):
+    """_csm_engine + CSMDiffusion + TemperatureFloor of the reference's own sources (make_golden.py::dump_csm)."""
+    t_all = np.array(csm_fx["time"])
+    for row in csm_fx["draws"]:
+        t = t_all[row["skip"]:]
+        p = dict(row["params"])
+        tfl = p.pop("temperature_floor")
+        eng, r_ph, m_th = r.csm_engine(t, **p)
+        np.testing.assert_allclose(eng, row["engine_lbol"], rtol=1e-14)
+        assert abs(r_ph / row["r_photosphere"] - 1) < 1e-14 and abs(m_th / row["mass_csm_threshold"] - 1) < 1e-14
+        out = r.csm_interaction_bolometric(t, **p)
+        np.testing.assert_allclose(out, row["lbol"], rtol=1e-14)
+        T, R = r.temperature_floor(t, out, p["vej"], tfl)
+        np.testing.assert_allclose(T, row["temperature"], rtol=1e-13)
+        np.testing.assert_allclose(R, row["radius"], rtol=1e-13)
