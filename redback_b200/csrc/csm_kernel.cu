@@ -195,7 +195,7 @@ __device__ __forceinline__ double sed_mjy(const rb_sn_config& cfg, double lbol, 
 
 constexpr int kCsmThreads = 512;
 
-__global__ void __launch_bounds__(kCsmThreads) csm_kernel(const CsmArgs c) {
+__global__ void __launch_bounds__(kCsmThreads, 2) csm_kernel(const CsmArgs c) {
   extern __shared__ double csm_smem[];
   const SnArgs& a = c.s;
   const int D = a.cfg.dense_resolution, E = a.E;
@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(kCsmThreads) csm_kernel(const CsmArgs c) {
         if (na == 1 && k == G - 1) t = sc[CS_TMAX];
         tg[k] = t;
         const double ts = t * kDay;
-        const double pw = pow(ts + 1.0, alpha);
+        // (ts + ti)^alpha, |alpha ln x| < 40: 1e-15 relative through the table exp
+        const double pw = exp_tab(alpha * log(ts + 1.0), tab);
         const double lfs = (tfs - ts > 0) ? cfs * pw : 0.0;
         const double lrs = (trs - ts > 0) ? crs * pw : 0.0;
         ld[k] = sc[CS_EFF] * (lfs + lrs);
@@ -285,8 +286,8 @@ __global__ void __launch_bounds__(kCsmThreads) csm_kernel(const CsmArgs c) {
         if (dt != 0.0) {
           const double slope = (ml[i + 1] - ml[i]) / dt;
           const double sdt = dt / t0;
-          av = exp(-sdt);
-          const double om = -expm1(-sdt);
+          av = (sdt < 700.0) ? exp_tab(-sdt, tab) : exp(-sdt);
+          const double om = -expm1_fast(-sdt, tab);
           bv = ml[i] * om + slope * (dt - t0 * om);
         }
         ca[i] = av;

@@ -52,6 +52,11 @@ def main():
                  lambda n: SupernovaPath(_capi.ENGINE_MAGNETAR, _capi.SED_CUTOFF_BLACKBODY, t2, frequency=nu2,
                                          y=np.full(300, 1e-3), sigma=1e-4),
                  lambda n: h.slsn_prior(rng, n), 4.1e3))
+    jobs.append(("csm_interaction Blackbody multiband E=300 (config 2 epochs)", int(2_000_000 * scale),
+                 lambda n: SupernovaPath(_capi.ENGINE_CSM, _capi.SED_BLACKBODY, t2, frequency=nu2,
+                                         y=np.full(300, 1e-3), sigma=1e-4,
+                                         csm=dict(nn=12, delta=1, efficiency=0.5)),
+                 lambda n: h.csm_prior(rng, n, zmax=3.0), None))
     t3, nu3 = h.config3_epochs()
     jobs.append(("one_component_kilonova_model flux_density E=200 (config 3 epochs)", int(1_000_000 * scale),
                  lambda n: KilonovaPath(_capi.KN_ONE_COMPONENT, t3, frequency=nu3, y=np.full(200, 1e-3), sigma=1e-4),
