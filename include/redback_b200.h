@@ -241,6 +241,57 @@ int rb_ag_eval_f64_host(const rb_ag_config* cfg, int64_t N, int64_t E, const dou
                         const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
                         const double* sigma, const double* sigma_param, double* out_model, double* out_logl);
 
+/* ---- magnetar-driven relativistic ejecta ("mergernova") path ---------------------------------------------
+ * basic_mergernova / general_mergernova / general_mergernova_thermalisation
+ * (redback/transient_models/magnetar_driven_ejecta_models.py:275-419): magnetar luminosity on
+ * get_optimal_time_array(1e-4, 1e8, 500) [s, source frame] -> _ejecta_dynamics_and_interaction (:14-151, explicit
+ * Euler of Lorentz factor, radius, comoving volume and internal energy) -> interp1d of comoving temperature,
+ * radius and Doppler factor at the epochs -> _comoving_blackbody_to_flux_density (:153-174) -> mJy (1+z)^2
+ * (:262, :272) -> Gaussian log-likelihood. */
+enum { RB_MN_BASIC_MAGNETAR = 0,   /* basic_magnetar(p0, bp, mass_ns, theta_pb)  (magnetar_models.py:171-185) */
+       RB_MN_MAGNETAR_ONLY = 1 };  /* magnetar_only(l0, tau_sd, nn)              (magnetar_models.py:134-144) */
+enum {
+  RB_MN_REDSHIFT = 0,
+  RB_MN_MEJ = 1,            /* [Msun] */
+  RB_MN_BETA = 2,           /* initial ejecta velocity [c] */
+  RB_MN_EJECTA_RADIUS = 3,  /* [cm] */
+  RB_MN_KAPPA = 4,
+  RB_MN_N_ISM = 5,          /* [cm^-3] */
+  RB_MN_P0 = 6, RB_MN_L0 = 6,
+  RB_MN_BP = 7, RB_MN_TAU_SD = 7,
+  RB_MN_MASS_NS = 8, RB_MN_NN = 8,
+  RB_MN_THETA_PB = 9,
+  RB_MN_THERMALISATION_EFFICIENCY = 10, RB_MN_KAPPA_GAMMA = 10,   /* by use_gamma_ray_opacity */
+  RB_MN_NPARAM = 11
+};
+
+typedef struct {
+  int engine;                  /* RB_MN_BASIC_MAGNETAR | RB_MN_MAGNETAR_ONLY */
+  int sigma_mode;              /* RB_SIGMA_* */
+  int use_gamma_ray_opacity;   /* general_mergernova_thermalisation (:405-410): row 10 is kappa_gamma */
+  int pair_cascade_switch;     /* kwargs 'pair_cascade_switch' (:131-135); default 0 basic, 1 general */
+  double ejecta_albedo;        /* kwargs 'ejecta_albedo', default 0.5 */
+  double pair_cascade_fraction;/* kwargs 'pair_cascade_fraction', default 0.05 */
+  int resolution;              /* points requested from get_optimal_time_array(1e-4, 1e8, .), 500 (:301) */
+  rb_cosmology cosmology;
+  rb_upper_limits upper_limits;
+} rb_mn_config;
+
+int rb_mn_config_default(rb_mn_config* cfg);
+
+/* Same argument conventions as rb_sn_eval_f64; params is [RB_MN_NPARAM][N]; t_obs in observer-frame days.  Epochs
+ * whose source-frame time falls outside the grid [1e-4 s, 1e8 s] (scipy's interp1d raises there) come back NaN. */
+int rb_mn_eval_f64(const rb_mn_config* cfg, int64_t N, int64_t E, const double* params, const double* t_obs,
+                   const double* freq_obs, const double* dl_cm, const double* y, const double* sigma,
+                   const double* sigma_param, double* out_model, double* out_logl, void* stream);
+int rb_mn_eval_f64_host(const rb_mn_config* cfg, int64_t N, int64_t E, const double* params,
+                        const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
+                        const double* sigma, const double* sigma_param, double* out_model, double* out_logl);
+
+/* utils.get_optimal_time_array(t_min, t_max, resolution) without user times (utils.py:79-93), HOST function:
+ * writes at most `resolution` ascending points to out (host memory) and their count to *n_out. */
+int rb_optimal_time_array(double t_min, double t_max, int resolution, double* out, int* n_out);
+
 /* ---- magnitude / bandpass branch (output_format = 'magnitude' | 'flux') ---------------------------------
  * get_correct_output_format_from_spectra -> RedbackTimeSeriesSource.bandmag -> _bandflux_single_redback
  * (redback/sed.py:971-1009, 120-195, 10-118) and bandpass_magnitude_to_flux (redback/utils.py:707-718).

@@ -228,9 +228,50 @@ def dump_csm():
     print("csm fixtures:", len(doc["draws"]))
 
 
+def dump_mergernova():
+    """_ejecta_dynamics_and_interaction of the reference's own source on seeded prior draws
+    (priors/basic_mergernova.prior, general_mergernova(_thermalisation).prior); every 7th grid point is stored."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import warnings
+    warnings.simplefilter("ignore")
+    from oracle import refshim
+    ns = refshim.load_mergernova()
+    rng = np.random.default_rng(2026)
+    tg = ns.get_optimal_time_array(1e-4, 1e8, 500)
+    doc = {"stride": 7, "n_grid": int(tg.size), "draws": []}
+    for i in range(12):
+        ej = dict(mej=float(rng.uniform(1e-4, 0.1)), beta=float(rng.uniform(0.1, 0.7)),
+                  ejecta_radius=float(10 ** rng.uniform(9, 10)), kappa=float(rng.uniform(1, 30)),
+                  n_ism=float(10 ** rng.uniform(-4, 0)))
+        kind = ("basic", "general", "thermalisation")[i % 3]
+        if kind == "basic":
+            eng = dict(p0=float(10 ** rng.uniform(np.log10(0.7), 4)), bp=float(10 ** rng.uniform(-4, 4)),
+                       mass_ns=float(rng.uniform(1.1, 2.2)), theta_pb=float(rng.uniform(0.05, 1.57)))
+            lum = ns.basic_magnetar(tg, **eng)
+        else:
+            eng = dict(l0=float(10 ** rng.uniform(40, 50)), tau_sd=float(10 ** rng.uniform(1, 5)),
+                       nn=float(rng.uniform(2, 7)))
+            lum = ns.magnetar_only(tg, eng["l0"], eng["tau_sd"], eng["nn"])
+        extra = dict(kappa_gamma=float(10 ** rng.uniform(-4, 4))) if kind == "thermalisation" else \
+            dict(thermalisation_efficiency=float(rng.uniform(0.1, 1)))
+        pcs = bool(i % 2)
+        out = ns._ejecta_dynamics_and_interaction(time=tg, magnetar_luminosity=lum, pair_cascade_switch=pcs,
+                                                  use_gamma_ray_opacity=kind == "thermalisation", **ej, **extra)
+        pick = slice(None, None, 7)
+        doc["draws"].append(dict(kind=kind, ejecta=ej, engine=eng, extra=extra, pair_cascade_switch=pcs,
+                                 bolometric_luminosity=[float(v) for v in out.bolometric_luminosity[pick]],
+                                 comoving_temperature=[float(v) for v in out.comoving_temperature[pick]],
+                                 radius=[float(v) for v in out.radius[pick]],
+                                 doppler_factor=[float(v) for v in out.doppler_factor[pick]]))
+    with open(os.path.join(OUT, "mergernova_reference_draws.json"), "w") as fh:
+        json.dump(doc, fh)
+    print("mergernova fixtures:", len(doc["draws"]))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     dump_pkl()
     dump_ecsv()
     dump_verbatim()
     dump_csm()
+    dump_mergernova()

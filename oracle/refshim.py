@@ -138,3 +138,20 @@ def load_csm():
     out.photosphere = ns.photosphere
     out.interaction_processes = ns.interaction_processes
     return out
+
+
+def load_mergernova():
+    """The reference's own _ejecta_dynamics_and_interaction, basic_magnetar, magnetar_only,
+    velocity_from_lorentz_factor and get_optimal_time_array, executed from /root/reference."""
+    from collections import namedtuple
+    import numpy as np
+    from . import restated as r
+    load()
+    glb = dict(np=np, namedtuple=namedtuple, solar_mass=r.solar_mass, speed_of_light=r.speed_of_light,
+               proton_mass=r.proton_mass, radiation_constant=r.sigma_sb * 4 / r.speed_of_light, sigma_sb=r.sigma_sb)
+    load_functions("redback/utils.py", ["velocity_from_lorentz_factor", "get_optimal_time_array",
+                                         "_get_optimal_time_array_cached"], glb)
+    load_functions("redback/transient_models/magnetar_models.py", ["basic_magnetar", "magnetar_only"], glb)
+    load_functions("redback/transient_models/magnetar_driven_ejecta_models.py", ["_ejecta_dynamics_and_interaction"], glb)
+    return types.SimpleNamespace(**{k: glb[k] for k in ("_ejecta_dynamics_and_interaction", "basic_magnetar",
+                                                       "magnetar_only", "get_optimal_time_array")})

@@ -572,6 +572,130 @@ def csm_interaction(time, redshift, mej, csm_mass, vej, eta, rho, kappa, r0, *, 
         "blackbody", frequency=frequency, vej=vej, temperature_floor=temperature_floor, dl=dl)
 
 
+# --------------------------------------------------------------------------------------------------
+# Magnetar-driven relativistic ejecta: _ejecta_dynamics_and_interaction
+# (magnetar_driven_ejecta_models.py:14-151), _comoving_blackbody_to_flux_density (:153-174),
+# _process_flux_density (:240-272), basic_mergernova / general_mergernova(_thermalisation) (:275-420)
+# --------------------------------------------------------------------------------------------------
+radiation_constant = sigma_sb * 4 / speed_of_light       # constants.py:14
+
+
+def magnetar_only(time, l0, tau, nn):
+    """magnetar_models.magnetar_only (:134-144)."""
+    return l0 * (1. + time / tau) ** ((1. + nn) / (1. - nn))
+
+
+def ejecta_dynamics_and_interaction(time, mej, beta, ejecta_radius, kappa, n_ism, magnetar_luminosity,
+                                    pair_cascade_switch, use_gamma_ray_opacity, *, thermalisation_efficiency=None,
+                                    kappa_gamma=None, ejecta_albedo=0.5, pair_cascade_fraction=0.05):
+    """_ejecta_dynamics_and_interaction (magnetar_driven_ejecta_models.py:14-151), r-process heating branch.
+    time: source-frame seconds.  Returns (bolometric_luminosity, comoving_temperature, radius, doppler_factor)."""
+    m = mej * solar_mass
+    n = len(time)
+    out_l, out_t, out_r, out_d, out_g = (np.zeros(n) for _ in range(5))
+    e_int = 0.5 * beta ** 2 * m * speed_of_light ** 2
+    vol = (4 / 3) * np.pi * ejecta_radius ** 3
+    gam = 1 / np.sqrt(1 - beta ** 2)
+    rad = ejecta_radius
+    d_gam = d_rad = d_vol = d_e = 0.0
+    with np.errstate(all="ignore"):
+        for i in range(n):
+            beta = np.sqrt(1 - 1 / gam ** 2)                                                   # :65
+            dop = 1 / (gam * (1 - beta))
+            if i > 0:
+                dt = time[i] - time[i - 1]
+                gam = gam + d_gam * dt
+                rad = rad + d_rad * dt
+                vol = vol + d_vol * dt
+                e_int = e_int + d_e * dt
+            swept = (4 / 3) * np.pi * rad ** 3 * n_ism * proton_mass
+            pressure = e_int / (3 * vol)
+            t_com = dop * time[i]
+            dvdt_com = 4 * np.pi * rad ** 2 * beta * speed_of_light
+            denom = (1 / 2) - (1 / 3.141592654) * np.arctan((t_com - 1.3) / 0.11)              # :78
+            l_rad = (4 * 10 ** 49 * (m / (2 * 10 ** 33) * 10 ** 2) * denom ** 1.3)              # :80
+            tau = kappa * (m / vol) * (rad / gam)
+            if tau <= 1:
+                l_emit = (e_int * speed_of_light) / (rad / gam)
+                temp = (e_int / (radiation_constant * vol)) ** (1. / 4.)
+            else:
+                l_emit = (e_int * speed_of_light) / (tau * rad / gam)
+                temp = (e_int / (radiation_constant * vol * tau)) ** (1. / 4.)
+            vej = speed_of_light * np.sqrt(1 - 1 / gam ** 2)                                   # utils.py:1524
+            if use_gamma_ray_opacity:
+                eff = 1 - np.exp(-(3 * kappa_gamma * m / (4 * np.pi * vej ** 2)) * time[i] ** -2)   # :102-104
+            else:
+                eff = thermalisation_efficiency
+            d_rad = (beta * speed_of_light) / (1 - beta)
+            d_swept = 4 * np.pi * rad ** 2 * n_ism * proton_mass * d_rad
+            dedt = eff * magnetar_luminosity[i] + dop ** 2 * l_rad - dop ** 2 * l_emit
+            de_com = eff * dop ** (-2) * magnetar_luminosity[i] + l_rad - l_emit - pressure * dvdt_com
+            d_vol = dvdt_com * dop
+            d_e = de_com * dop
+            d_gam = (dedt - gam * dop * de_com - (gam ** 2 - 1) * speed_of_light ** 2 * d_swept) / (
+                m * speed_of_light ** 2 + e_int + 2 * gam * swept * speed_of_light ** 2)
+            out_g[i], out_l[i], out_t[i], out_r[i], out_d[i] = gam, l_emit * dop ** 2, temp, rad, dop
+        if pair_cascade_switch:                                                                # :131-135
+            v0 = ((1 / out_g) ** 2 + 1) ** 0.5 * speed_of_light
+            tlife = ((0.6 / (1 - ejecta_albedo)) * (pair_cascade_fraction / 0.1) ** 0.5
+                     * (magnetar_luminosity / 1.0e45) ** 0.5 * (v0 / (0.3 * speed_of_light)) ** (0.5)
+                     * (time / 86400) ** (-0.5))
+            out_l = out_l / (1.0 + tlife)
+            out_t = (out_l / (4.0 * np.pi * out_r ** (2.0) * sigma_sb)) ** (0.25)
+    return out_l, out_t, out_r, out_d
+
+
+def mergernova_flux_density(time, redshift, dynamics, *, frequency, dl=None):
+    """_process_flux_density (:240-263) with use_relativistic_blackbody=True + _comoving_blackbody_to_flux_density
+    (:153-174); `dynamics` = (time_temp, comoving_temperature, radius, doppler_factor).  mJy."""
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    t_grid, temp_g, rad_g, dop_g = dynamics
+    frequency, t = calc_kcorrected_properties(np.asarray(frequency, dtype=float), redshift,
+                                              np.asarray(time, dtype=float) * day_to_s)
+    temp = interp1d(t_grid, temp_g)(t)
+    rad = interp1d(t_grid, rad_g)(t)
+    dop = interp1d(t_grid, dop_g)(t)
+    with np.errstate(all="ignore"):
+        num = 2 * np.pi * planck * frequency ** 3 * rad ** 2
+        den = dl ** 2 * speed_of_light ** 2 * dop ** 2
+        frac = 1. / (np.exp((planck * frequency) / (boltzmann_constant * temp * dop)) - 1)
+        fd = num / den * frac * (1 + redshift)                                                   # :262
+        return fd * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)                                        # :272
+
+
+def _mergernova(time, redshift, mag_lum_fn, mej, beta, ejecta_radius, kappa, n_ism, *, frequency, pair_cascade_switch,
+                dl=None, **dyn):
+    t_grid = get_optimal_time_array(1e-4, 1e8, 500)
+    lum, temp, rad, dop = ejecta_dynamics_and_interaction(t_grid, mej, beta, ejecta_radius, kappa, n_ism,
+                                                          mag_lum_fn(t_grid), pair_cascade_switch, **dyn)
+    return mergernova_flux_density(time, redshift, (t_grid, temp, rad, dop), frequency=frequency, dl=dl)
+
+
+def basic_mergernova(time, redshift, mej, beta, ejecta_radius, kappa, n_ism, p0, bp, mass_ns, theta_pb,
+                     thermalisation_efficiency, *, frequency, pair_cascade_switch=False, dl=None, **kw):
+    """magnetar_driven_ejecta_models.basic_mergernova (:275-321), flux_density."""
+    return _mergernova(time, redshift, lambda t: basic_magnetar(t, p0, bp, mass_ns, theta_pb), mej, beta,
+                       ejecta_radius, kappa, n_ism, frequency=frequency, pair_cascade_switch=pair_cascade_switch,
+                       dl=dl, use_gamma_ray_opacity=False, thermalisation_efficiency=thermalisation_efficiency, **kw)
+
+
+def general_mergernova(time, redshift, mej, beta, ejecta_radius, kappa, n_ism, l0, tau_sd, nn,
+                       thermalisation_efficiency, *, frequency, pair_cascade_switch=True, dl=None, **kw):
+    """general_mergernova (:324-371), flux_density."""
+    return _mergernova(time, redshift, lambda t: magnetar_only(t, l0, tau_sd, nn), mej, beta, ejecta_radius, kappa,
+                       n_ism, frequency=frequency, pair_cascade_switch=pair_cascade_switch, dl=dl,
+                       use_gamma_ray_opacity=False, thermalisation_efficiency=thermalisation_efficiency, **kw)
+
+
+def general_mergernova_thermalisation(time, redshift, mej, beta, ejecta_radius, kappa, n_ism, l0, tau_sd, nn,
+                                      kappa_gamma, *, frequency, pair_cascade_switch=True, dl=None, **kw):
+    """general_mergernova_thermalisation (:374-419), flux_density."""
+    return _mergernova(time, redshift, lambda t: magnetar_only(t, l0, tau_sd, nn), mej, beta, ejecta_radius, kappa,
+                       n_ism, frequency=frequency, pair_cascade_switch=pair_cascade_switch, dl=dl,
+                       use_gamma_ray_opacity=True, kappa_gamma=kappa_gamma, **kw)
+
+
 _BK_V = np.asarray([0.1, 0.2, 0.3, 0.4])
 _BK_M = np.asarray([1.e-3, 5.e-3, 1.e-2, 5.e-2, 1.e-1])
 _BK_A = np.asarray([[2.01, 4.52, 8.16, 16.3], [0.81, 1.9, 3.2, 5.0], [0.56, 1.31, 2.19, 3.0],

@@ -1,7 +1,8 @@
 """redback_b200: B200-native batched light-curve + Gaussian-likelihood engine behind redback's model /
 likelihood API.  The CUDA library is the only compute path; importing the package does
 not need a GPU, calling it does."""
-from . import _capi, afterglow_models, bands, engine, simulate, kilonova_models, likelihoods, supernova_models  # noqa: F401
+from . import (_capi, afterglow_models, bands, engine, kilonova_models, likelihoods,  # noqa: F401
+               magnetar_driven_ejecta_models, simulate, supernova_models)
 from .likelihoods import (GaussianLikelihood, GaussianLikelihoodQuadratureNoise,  # noqa: F401
                           GaussianLikelihoodWithFractionalNoise, GaussianLikelihoodWithSystematicNoise,
                           GaussianLikelihoodWithUpperLimits)
@@ -12,8 +13,9 @@ __version__ = "0.1.0"
 all_models_dict = {
     name: getattr(supernova_models, name)
     for name in ("arnett_bolometric", "arnett", "basic_magnetar_powered_bolometric", "basic_magnetar_powered",
-                 "slsn_bolometric", "slsn", "type_1a")
+                 "slsn_bolometric", "slsn", "type_1a", "csm_interaction_bolometric", "csm_interaction")
 }
 all_models_dict.update({name: getattr(kilonova_models, name)
                         for name in ("one_component_kilonova_model", "metzger_kilonova_model")})
 all_models_dict.update({fn.__name__: fn for fn in afterglow_models.FUSED})
+all_models_dict.update({fn.__name__: fn for fn in magnetar_driven_ejecta_models.FUSED})

@@ -62,6 +62,18 @@ class AgConfig(C.Structure):
                 ("aa", C.c_double), ("upper_limits", UpperLimits), ("ab_magnitude", C.c_int)]
 
 
+MN_BASIC_MAGNETAR, MN_MAGNETAR_ONLY = 0, 1
+MN_ROWS = dict(redshift=0, mej=1, beta=2, ejecta_radius=3, kappa=4, n_ism=5, p0=6, l0=6, bp=7, tau_sd=7, mass_ns=8,
+               nn=8, theta_pb=9, thermalisation_efficiency=10, kappa_gamma=10)
+MN_NPARAM = 11
+
+
+class MnConfig(C.Structure):
+    _fields_ = [("engine", C.c_int), ("sigma_mode", C.c_int), ("use_gamma_ray_opacity", C.c_int),
+                ("pair_cascade_switch", C.c_int), ("ejecta_albedo", C.c_double), ("pair_cascade_fraction", C.c_double),
+                ("resolution", C.c_int), ("cosmology", Cosmology), ("upper_limits", UpperLimits)]
+
+
 class RedbackB200Error(RuntimeError):
     pass
 
@@ -85,6 +97,10 @@ EXPORTS = {
     "rb_ag_config_default": (C.c_int, [C.POINTER(AgConfig)]),
     "rb_ag_eval_f64": (C.c_int, [C.POINTER(AgConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
     "rb_ag_eval_f64_host": (C.c_int, [C.POINTER(AgConfig), C.c_int64, C.c_int64] + [_dp] * 9),
+    "rb_mn_config_default": (C.c_int, [C.POINTER(MnConfig)]),
+    "rb_mn_eval_f64": (C.c_int, [C.POINTER(MnConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
+    "rb_mn_eval_f64_host": (C.c_int, [C.POINTER(MnConfig), C.c_int64, C.c_int64] + [_dp] * 9),
+    "rb_optimal_time_array": (C.c_int, [C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "rb_sn_mag_eval_f64": (C.c_int, [C.POINTER(SnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_kn_mag_eval_f64": (C.c_int, [C.POINTER(KnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_optical_noise_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 4 + [C.c_double, C.c_int] + [_dp] * 6
@@ -169,6 +185,28 @@ def ag_config(jet, sigma_mode=SIGMA_FIXED, steps=250, res=0, k=0, expansion=1, a
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg
+
+
+def mn_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_cascade_switch=False,
+              ejecta_albedo=0.5, pair_cascade_fraction=0.05, cosmology=None):
+    cfg = MnConfig()
+    check(lib().rb_mn_config_default(C.byref(cfg)))
+    cfg.engine, cfg.sigma_mode = engine, sigma_mode
+    cfg.use_gamma_ray_opacity = int(bool(use_gamma_ray_opacity))
+    cfg.pair_cascade_switch = int(bool(pair_cascade_switch))
+    cfg.ejecta_albedo, cfg.pair_cascade_fraction = float(ejecta_albedo), float(pair_cascade_fraction)
+    if cosmology is not None:
+        cfg.cosmology = cosmology
+    return cfg
+
+
+def optimal_time_array(t_min, t_max, resolution):
+    """utils.get_optimal_time_array without user times, through the library's host function."""
+    import numpy as np
+    out = (C.c_double * int(resolution))()
+    n = C.c_int(0)
+    check(lib().rb_optimal_time_array(float(t_min), float(t_max), int(resolution), out, C.byref(n)))
+    return np.array(out[:n.value])
 
 
 def flat_lcdm(H0, Om0, Tcmb0=2.7255, Neff=3.046, m_nu=(0.06, 0.0, 0.0)):

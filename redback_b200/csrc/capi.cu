@@ -9,6 +9,7 @@
 #include "sn_kernel.cu"
 #include "kn_kernel.cu"
 #include "csm_kernel.cu"
+#include "mn_kernel.cu"
 #include "ag_kernel.cu"
 #include "phot_kernel.cu"
 #include "noise_kernel.cu"
@@ -541,6 +542,162 @@ extern "C" int rb_kn_eval_f64_host(const rb_kn_config* cfg, int64_t N, int64_t E
   if (out_model) RB_CUDA(d_m.alloc(nN * nE));
   if (out_logl) RB_CUDA(d_l.alloc(nN));
   rc = rb_kn_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
+  if (rc != RB_OK) return rc;
+  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
+  RB_CUDA(cudaDeviceSynchronize());
+  return RB_OK;
+}
+
+// ---- magnetar-driven ejecta (mergernova) path ---------------------------------------------------------------
+namespace {
+// numpy.geomspace(a, b, n) for 0 < a < b (numpy/_core/function_base.py): 10 ** linspace(log10 a, log10 b, n), end
+// points set exactly
+void host_geomspace(double a, double b, int n, std::vector<double>& out) {
+  const double la = std::log10(a), lb = std::log10(b);
+  const double step = n > 1 ? (lb - la) / (double)(n - 1) : 0.0;
+  for (int i = 0; i < n; ++i) {
+    double v = std::pow(10.0, (double)i * step + la);
+    if (i == 0) v = a;
+    if (i == n - 1 && n > 1) v = b;
+    out.push_back(v);
+  }
+}
+
+int mn_check(const rb_mn_config* cfg, int64_t N, int64_t E, const void* params, const void* t_obs,
+             const void* freq_obs, const void* y, const void* sigma, const void* sigma_param, const void* out_model,
+             const void* out_logl) {
+  if (!cfg) return fail(RB_ERR_INVALID, "rb_mn_eval: null config");
+  if (N < 0 || E <= 0) return fail(RB_ERR_INVALID, "rb_mn_eval: need N >= 0 and E > 0");
+  if (cfg->engine != RB_MN_BASIC_MAGNETAR && cfg->engine != RB_MN_MAGNETAR_ONLY)
+    return fail(RB_ERR_INVALID, "rb_mn_eval: unknown engine");
+  if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_SYSTEMATIC)
+    return fail(RB_ERR_INVALID, "rb_mn_eval: unknown sigma_mode");
+  if (cfg->resolution < 8 || cfg->resolution > 4096)
+    return fail(RB_ERR_INVALID, "rb_mn_eval: resolution must be in [8, 4096]");
+  if (!params || !t_obs || !freq_obs) return fail(RB_ERR_INVALID, "rb_mn_eval: params, t_obs and freq_obs are required");
+  if (y) {
+    if (!out_logl) return fail(RB_ERR_INVALID, "rb_mn_eval: y given but out_logl is null");
+    if (cfg->sigma_mode != RB_SIGMA_SAMPLED && !sigma) return fail(RB_ERR_INVALID, "rb_mn_eval: sigma is required");
+    if (cfg->sigma_mode != RB_SIGMA_FIXED && cfg->sigma_mode != RB_SIGMA_FRACTIONAL && !sigma_param)
+      return fail(RB_ERR_INVALID, "rb_mn_eval: sigma_param is required");
+  } else if (out_logl) {
+    return fail(RB_ERR_INVALID, "rb_mn_eval: out_logl requested without data y");
+  }
+  if (!out_model && !out_logl) return fail(RB_ERR_INVALID, "rb_mn_eval: nothing to compute");
+  return RB_OK;
+}
+}  // namespace
+
+extern "C" int rb_optimal_time_array(double t_min, double t_max, int resolution, double* out, int* n_out) {
+  if (!out || !n_out || resolution < 2 || !(t_min > 0.0) || !(t_max > t_min))
+    return fail(RB_ERR_INVALID, "rb_optimal_time_array: need 0 < t_min < t_max, resolution >= 2");
+  std::vector<double> v;
+  const double log_range = std::log10(t_max) - std::log10(t_min);          // utils.py:80
+  if (log_range > 6) {
+    const int n_early = (int)(resolution * 0.25), n_mid = (int)(resolution * 0.50);
+    const int n_late = resolution - n_early - n_mid;
+    const double trans1 = t_min * std::pow(t_max / t_min, 0.25), trans2 = t_min * std::pow(t_max / t_min, 0.75);
+    host_geomspace(t_min, trans1, n_early, v);
+    host_geomspace(trans1, trans2, n_mid, v);
+    host_geomspace(trans2, t_max, n_late, v);
+    std::sort(v.begin(), v.end());                                         // np.unique
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+  } else {
+    host_geomspace(t_min, t_max, resolution, v);
+  }
+  for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+  *n_out = (int)v.size();
+  return RB_OK;
+}
+
+extern "C" int rb_mn_config_default(rb_mn_config* cfg) {
+  if (!cfg) return fail(RB_ERR_INVALID, "rb_mn_config_default: null config");
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->engine = RB_MN_BASIC_MAGNETAR;
+  cfg->sigma_mode = RB_SIGMA_FIXED;
+  cfg->ejecta_albedo = 0.5;
+  cfg->pair_cascade_fraction = 0.05;
+  cfg->resolution = 500;
+  return rb_cosmology_planck18(&cfg->cosmology);
+}
+
+extern "C" int rb_mn_eval_f64(const rb_mn_config* cfg, int64_t N, int64_t E, const double* params,
+                              const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
+                              const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
+                              void* stream) {
+  int rc = mn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<double> tg((size_t)cfg->resolution);
+  int G = 0;
+  rc = rb_optimal_time_array(1e-4, 1e8, cfg->resolution, tg.data(), &G);   // magnetar_driven_ejecta_models.py:301
+  if (rc != RB_OK) return rc;
+  StreamAlloc b_tg, b_ep, b_sorted, b_dl;
+  RB_CUDA(b_tg.alloc((size_t)G * sizeof(double), st));
+  RB_CUDA(cudaMemcpyAsync(b_tg.p, tg.data(), (size_t)G * sizeof(double), cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaStreamSynchronize(st));   // tg is a stack-owned staging buffer
+  RB_CUDA(b_ep.alloc((size_t)rb::kEpochCols * (size_t)E * sizeof(double), st));
+  RB_CUDA(b_sorted.alloc((size_t)rb::kMnEpochCols * (size_t)E * sizeof(double), st));
+  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
+                                                                    y ? sigma : nullptr, cfg->upper_limits,
+                                                                    b_ep.as<double>());
+  rb::mn_sort_epochs_kernel<<<1, 1024, 0, st>>>((int)E, b_ep.as<double>(), b_sorted.as<double>());
+  launch_counter()->fetch_add(2);
+  const double* dl = dl_cm;
+  if (!dl) {
+    RB_CUDA(b_dl.alloc((size_t)N * sizeof(double), st));
+    rb::dl_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(cfg->cosmology, N, params + (size_t)RB_MN_REDSHIFT * N,
+                                                          b_dl.as<double>());
+    launch_counter()->fetch_add(1);
+    dl = b_dl.as<double>();
+  }
+  rb::MnArgs a{};
+  a.cfg = *cfg;
+  a.N = N;
+  a.E = (int)E;
+  a.G = G;
+  a.params = params;
+  a.param_stride = N;
+  a.dl_cm = dl;
+  a.sigma_param = sigma_param;
+  a.tgrid = b_tg.as<double>();
+  a.sorted_ep = b_sorted.as<double>();
+  a.out_model = out_model;
+  a.out_logl = y ? out_logl : nullptr;
+  a.want_logl = y ? 1 : 0;
+  rb::mn_kernel<<<(unsigned)((N + 127) / 128), 128, (size_t)G * sizeof(double), st>>>(a);
+  launch_counter()->fetch_add(1);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
+extern "C" int rb_mn_eval_f64_host(const rb_mn_config* cfg, int64_t N, int64_t E, const double* params,
+                                   const double* t_obs, const double* freq_obs, const double* dl_cm,
+                                   const double* y, const double* sigma, const double* sigma_param,
+                                   double* out_model, double* out_logl) {
+  int rc = mn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
+  const size_t nN = (size_t)N, nE = (size_t)E;
+  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
+    if (!h) return cudaSuccess;
+    cudaError_t e = b.alloc(n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  RB_CUDA(up(d_par, params, (size_t)RB_MN_NPARAM * nN));
+  RB_CUDA(up(d_t, t_obs, nE));
+  RB_CUDA(up(d_f, freq_obs, nE));
+  RB_CUDA(up(d_dl, dl_cm, nN));
+  RB_CUDA(up(d_y, y, nE));
+  RB_CUDA(up(d_s, sigma, nE));
+  RB_CUDA(up(d_sp, sigma_param, nN));
+  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
+  if (out_logl) RB_CUDA(d_l.alloc(nN));
+  rc = rb_mn_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
   if (rc != RB_OK) return rc;
   if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
   if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));

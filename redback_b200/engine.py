@@ -326,6 +326,29 @@ class AfterglowPath(_FusedPath):
         return _capi.lib().rb_ag_eval_f64
 
 
+class MergernovaPath(_FusedPath):
+    """Magnetar-driven relativistic ejecta -> relativistic blackbody -> Gaussian log L
+    (redback/transient_models/magnetar_driven_ejecta_models.py:14-151, 240-419)."""
+
+    ROWS = _capi.MN_ROWS
+    NPARAM = _capi.MN_NPARAM
+
+    def __init__(self, engine, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED,
+                 use_gamma_ray_opacity=False, pair_cascade_switch=False, ejecta_albedo=0.5,
+                 pair_cascade_fraction=0.05, cosmology=None, device=None):
+        self.cfg = _capi.mn_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
+                                   pair_cascade_fraction, cosmology)
+        self._setup(time, frequency, y, sigma, device)
+
+    def _eval_fn(self):
+        return _capi.lib().rb_mn_eval_f64
+
+    def _check_time(self, t):
+        if np.any(~(t > 0)):
+            # scipy's interp1d raises below the model grid (starts at 1e-4 s, source frame)
+            raise ValueError("A value in x_new is below the interpolation range: mergernova models need time > 0")
+
+
 def luminosity_distance(redshift, cosmology=None, device=None):
     """Planck18 (default) luminosity distance in cm for an array of redshifts, on device."""
     dev = _device(device)

@@ -14,6 +14,7 @@ import torch
 from . import _capi, _fused
 from . import afterglow_models as _ag
 from . import kilonova_models as _kn
+from . import magnetar_driven_ejecta_models as _mn
 from . import supernova_models as _sn
 from .engine import batch_size, gaussian_logl
 
@@ -21,6 +22,7 @@ FUSED = {}
 FUSED.update(_sn.FUSED)
 FUSED.update(_kn.FUSED)
 FUSED.update(_ag.FUSED)
+FUSED.update(_mn.FUSED)
 
 
 def infer_parameters_from_function(func):

@@ -1,0 +1,71 @@
+"""Batched drop-ins for redback's magnetar-driven relativistic-ejecta ("mergernova") models
+(redback/transient_models/magnetar_driven_ejecta_models.py: basic_mergernova :275-321, general_mergernova :324-371,
+general_mergernova_thermalisation :374-419), output_format='flux_density'.  Same signatures as the reference plus
+`params_batch` (see supernova_models.py)."""
+from . import _capi
+from ._fused import FusedSpec, cosmology_from_kwargs, run
+from .engine import MergernovaPath
+
+_EJECTA = ("redshift", "mej", "beta", "ejecta_radius", "kappa", "n_ism")
+
+
+def _spec(name, engine, engine_params, last, pair_cascade_default, gamma_ray):
+    needed = _EJECTA + tuple(engine_params) + (last,)
+
+    def validate(kwargs):
+        fmt = kwargs.get("output_format")
+        if fmt is None:
+            raise KeyError("output_format")
+        if fmt != "flux_density":
+            raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device")
+        if not kwargs.get("use_r_process", True):
+            raise NotImplementedError(f"{name}: use_r_process=False (nickel heating) is not fused on device")
+
+    def build(time, kwargs, y, sigma, sigma_mode):
+        return MergernovaPath(engine, time, frequency=kwargs.get("frequency"), y=y, sigma=sigma, sigma_mode=sigma_mode,
+                              use_gamma_ray_opacity=gamma_ray,
+                              pair_cascade_switch=kwargs.get("pair_cascade_switch", pair_cascade_default),
+                              ejecta_albedo=kwargs.get("ejecta_albedo", 0.5),
+                              pair_cascade_fraction=kwargs.get("pair_cascade_fraction", 0.05),
+                              cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"))
+
+    return FusedSpec(name, needed, build, validate)
+
+
+_BASIC = _spec("basic_mergernova", _capi.MN_BASIC_MAGNETAR, ("p0", "bp", "mass_ns", "theta_pb"),
+               "thermalisation_efficiency", False, False)
+_GENERAL = _spec("general_mergernova", _capi.MN_MAGNETAR_ONLY, ("l0", "tau_sd", "nn"),
+                 "thermalisation_efficiency", True, False)
+_GENERAL_TH = _spec("general_mergernova_thermalisation", _capi.MN_MAGNETAR_ONLY, ("l0", "tau_sd", "nn"),
+                    "kappa_gamma", True, True)
+
+
+def basic_mergernova(time, redshift=None, mej=None, beta=None, ejecta_radius=None, kappa=None, n_ism=None, p0=None,
+                     bp=None, mass_ns=None, theta_pb=None, thermalisation_efficiency=None, params_batch=None,
+                     **kwargs):
+    """redback magnetar_driven_ejecta_models.basic_mergernova (:275-321); kwargs pair_cascade_switch (False),
+    ejecta_albedo, pair_cascade_fraction, frequency; returns mJy."""
+    named = dict(redshift=redshift, mej=mej, beta=beta, ejecta_radius=ejecta_radius, kappa=kappa, n_ism=n_ism, p0=p0,
+                 bp=bp, mass_ns=mass_ns, theta_pb=theta_pb, thermalisation_efficiency=thermalisation_efficiency)
+    return run(_BASIC, time, named, kwargs, params_batch)
+
+
+def general_mergernova(time, redshift=None, mej=None, beta=None, ejecta_radius=None, kappa=None, n_ism=None, l0=None,
+                       tau_sd=None, nn=None, thermalisation_efficiency=None, params_batch=None, **kwargs):
+    """redback magnetar_driven_ejecta_models.general_mergernova (:324-371); pair_cascade_switch defaults to True."""
+    named = dict(redshift=redshift, mej=mej, beta=beta, ejecta_radius=ejecta_radius, kappa=kappa, n_ism=n_ism, l0=l0,
+                 tau_sd=tau_sd, nn=nn, thermalisation_efficiency=thermalisation_efficiency)
+    return run(_GENERAL, time, named, kwargs, params_batch)
+
+
+def general_mergernova_thermalisation(time, redshift=None, mej=None, beta=None, ejecta_radius=None, kappa=None,
+                                      n_ism=None, l0=None, tau_sd=None, nn=None, kappa_gamma=None, params_batch=None,
+                                      **kwargs):
+    """redback magnetar_driven_ejecta_models.general_mergernova_thermalisation (:374-419): thermalisation efficiency
+    1 - exp(-3 kappa_gamma M / (4 pi v^2 t^2)) per step."""
+    named = dict(redshift=redshift, mej=mej, beta=beta, ejecta_radius=ejecta_radius, kappa=kappa, n_ism=n_ism, l0=l0,
+                 tau_sd=tau_sd, nn=nn, kappa_gamma=kappa_gamma)
+    return run(_GENERAL_TH, time, named, kwargs, params_batch)
+
+
+FUSED = {basic_mergernova: _BASIC, general_mergernova: _GENERAL, general_mergernova_thermalisation: _GENERAL_TH}

@@ -122,3 +122,20 @@ def csm_prior(rng, n, zmax=1.0):
                 csm_mass=loguniform(rng, 1, 100, n), vej=loguniform(rng, 1e3, 1e5, n), eta=rng.uniform(0, 2, n),
                 rho=loguniform(rng, 1e-14, 1e-12, n), kappa=rng.uniform(0.05, 2, n), r0=rng.uniform(50, 700, n),
                 temperature_floor=loguniform(rng, 100, 1e4, n))
+
+
+def mergernova_prior(rng, n, kind="basic"):
+    """priors/basic_mergernova.prior, general_mergernova.prior, general_mergernova_thermalisation.prior"""
+    p = dict(redshift=rng.uniform(1e-6, 0.1, n), mej=rng.uniform(1e-4, 0.1, n), beta=rng.uniform(0.1, 0.7, n),
+             ejecta_radius=loguniform(rng, 1e9, 1e10, n), kappa=rng.uniform(1, 30, n),
+             n_ism=loguniform(rng, 1e-4, 1, n))
+    if kind == "basic":
+        p.update(p0=loguniform(rng, 0.7, 1e4, n), bp=loguniform(rng, 1e-4, 1e4, n), mass_ns=rng.uniform(1.1, 2.2, n),
+                 theta_pb=rng.uniform(0.01, 1.57, n))
+    else:
+        p.update(l0=loguniform(rng, 1e40, 1e50, n), tau_sd=loguniform(rng, 10, 1e5, n), nn=rng.uniform(2, 7, n))
+    if kind == "thermalisation":
+        p["kappa_gamma"] = loguniform(rng, 1e-4, 1e4, n)
+    else:
+        p["thermalisation_efficiency"] = rng.uniform(0.1, 1, n)
+    return p

@@ -1,0 +1,85 @@
+"""Magnetar-driven relativistic ejecta: basic_mergernova, general_mergernova,
+general_mergernova_thermalisation -- device vs the oracle (which reproduces the reference's own
+_ejecta_dynamics_and_interaction bit for bit, tests/test_verbatim_fixtures.py)."""
+import numpy as np
+import pytest
+
+import helpers as h
+from oracle import restated as r
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import redback_b200
+    return redback_b200
+
+
+def _exp_condition(t, z, nu, dyn):
+    """The reference evaluates exp(x) - 1 (magnetar_driven_ejecta_models.py:172): one rounding of exp(x) is a relative
+    error eps / x of the flux for small x = h nu / (k T' D)."""
+    from scipy.interpolate import interp1d
+    t_grid, temp_g, _, dop_g = dyn
+    ts = t * 86400 / (1 + z)
+    x = r.planck * nu * (1 + z) / (r.boltzmann_constant * interp1d(t_grid, temp_g)(ts) * interp1d(t_grid, dop_g)(ts))
+    return 4 * 2.3e-16 / np.minimum(x, 1.0)
+
+
+@pytest.mark.parametrize("kind", ["basic", "general", "thermalisation"])
+def test_prior_draws(rb, kind):
+    rng = np.random.default_rng({"basic": 91, "general": 92, "thermalisation": 93}[kind])
+    t = np.concatenate([np.geomspace(0.01, 300, 40), np.geomspace(0.02, 200, 30)])     # unsorted on purpose
+    nu = np.concatenate([np.full(40, 4.6e14), np.where(np.arange(30) % 2 == 0, 5e9, 2.4e17)])
+    N = 40
+    p = h.mergernova_prior(rng, N, kind)
+    name = dict(basic="basic_mergernova", general="general_mergernova",
+                thermalisation="general_mergernova_thermalisation")[kind]
+    fn = getattr(rb.magnetar_driven_ejecta_models, name)
+    kw = dict(frequency=nu, output_format="flux_density")
+    if kind == "general":
+        kw["pair_cascade_switch"] = False           # non-default value
+    out = fn(t, params_batch=p, **kw)
+    y = out[7] * 1.05
+    sigma = 0.1 * np.abs(out[7]) + 1e-30
+    logl = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=kw).log_likelihood_batch(p)
+    tg = r.get_optimal_time_array(1e-4, 1e8, 500)
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        z = kwi.pop("redshift")
+        okw = dict(frequency=nu)
+        if kind == "general":
+            okw["pair_cascade_switch"] = False
+        ref = getattr(r, name)(t, z, **kwi, **okw)
+        lum_fn = (lambda tt: r.basic_magnetar(tt, kwi["p0"], kwi["bp"], kwi["mass_ns"], kwi["theta_pb"])) \
+            if kind == "basic" else (lambda tt: r.magnetar_only(tt, kwi["l0"], kwi["tau_sd"], kwi["nn"]))
+        dyn = r.ejecta_dynamics_and_interaction(
+            tg, kwi["mej"], kwi["beta"], kwi["ejecta_radius"], kwi["kappa"], kwi["n_ism"], lum_fn(tg),
+            kind != "basic" and kind != "general", kind == "thermalisation",
+            thermalisation_efficiency=kwi.get("thermalisation_efficiency"), kappa_gamma=kwi.get("kappa_gamma"))
+        extra = _exp_condition(t, z, nu, (tg, dyn[1], dyn[2], dyn[3]))
+        h.assert_close(out[i], ref, RTOL, extra, what=f"{name} sample {i}")
+        ref_l = r.gaussian_likelihood(y, ref, sigma)
+        assert abs(logl[i] - ref_l) <= 1e-6 + 1e-8 * abs(ref_l), (i, logl[i], ref_l)
+
+
+def test_scalar_call_kwargs_and_errors(rb):
+    t = np.geomspace(0.05, 100, 12)
+    kw = dict(mej=0.02, beta=0.3, ejecta_radius=3e9, kappa=5.0, n_ism=1e-2, l0=1e47, tau_sd=1e3, nn=3.0,
+              thermalisation_efficiency=0.4)
+    out = rb.magnetar_driven_ejecta_models.general_mergernova(t, 0.05, frequency=4.6e14, output_format="flux_density",
+                                                              ejecta_albedo=0.3, pair_cascade_fraction=0.2, **kw)
+    ref = r.general_mergernova(t, 0.05, frequency=np.full(12, 4.6e14), ejecta_albedo=0.3, pair_cascade_fraction=0.2,
+                               **kw)
+    h.assert_close(out, ref, RTOL, what="general_mergernova kwargs")
+    with pytest.raises(ValueError):
+        rb.magnetar_driven_ejecta_models.general_mergernova(np.array([0.0, 1.0]), 0.05, frequency=4.6e14,
+                                                            output_format="flux_density", **kw)
+    with pytest.raises(NotImplementedError):
+        rb.magnetar_driven_ejecta_models.general_mergernova(t, 0.05, bands="lsstr", output_format="magnitude", **kw)
+    with pytest.raises(KeyError):
+        rb.magnetar_driven_ejecta_models.general_mergernova(t, 0.05, output_format="flux_density", **kw)
+    far = rb.magnetar_driven_ejecta_models.general_mergernova(np.array([10.0, 2000.0]), 0.05, frequency=4.6e14,
+                                                              output_format="flux_density", **kw)
+    assert np.isfinite(far[0]) and np.isnan(far[1])          # 2000 d > 1e8 s: interp1d raises in the reference

@@ -84,3 +84,23 @@ def test_oracle_reproduces_reference_csm(csm_fx):
         T, R = r.temperature_floor(t, out, p["vej"], tfl)
         np.testing.assert_allclose(T, row["temperature"], rtol=1e-13)
         np.testing.assert_allclose(R, row["radius"], rtol=1e-13)
+
+
+def test_oracle_reproduces_reference_mergernova():
+    """_ejecta_dynamics_and_interaction of the reference's own source (make_golden.py::dump_mergernova)."""
+    with open(os.path.join(ROOT, "tests", "golden", "mergernova_reference_draws.json")) as fh:
+        fx = json.load(fh)
+    tg = r.get_optimal_time_array(1e-4, 1e8, 500)
+    assert tg.size == fx["n_grid"]
+    pick = slice(None, None, fx["stride"])
+    for row in fx["draws"]:
+        if row["kind"] == "basic":
+            lum = r.basic_magnetar(tg, **row["engine"])
+        else:
+            lum = r.magnetar_only(tg, row["engine"]["l0"], row["engine"]["tau_sd"], row["engine"]["nn"])
+        out = r.ejecta_dynamics_and_interaction(tg, magnetar_luminosity=lum,
+                                                pair_cascade_switch=row["pair_cascade_switch"],
+                                                use_gamma_ray_opacity=row["kind"] == "thermalisation",
+                                                **row["ejecta"], **row["extra"])
+        for got, key in zip(out, ("bolometric_luminosity", "comoving_temperature", "radius", "doppler_factor")):
+            np.testing.assert_allclose(got[pick], row[key], rtol=1e-14, err_msg=key)
