@@ -352,6 +352,12 @@ int rb_gaussian_logl_f64(int sigma_mode, int64_t N, int64_t E, const double* mod
                          const double* sigma, const double* sigma_param, const rb_upper_limits* upper_limits,
                          double* out_logl, void* stream);
 
+/* MixtureGaussianLikelihood.log_likelihood (redback/likelihoods.py:542-617) on a device model matrix [N][E]:
+ * sum_e logaddexp(log alpha + log N(y - m | sigma_e), log(1 - alpha) + log N(y - m | sigma_out)), alpha [N] and
+ * sigma_out [N] per sample, sigma [E].  No nan_to_num (the reference returns the raw sum). */
+int rb_mixture_logl_f64(int64_t N, int64_t E, const double* model, const double* y, const double* sigma,
+                        const double* alpha, const double* sigma_out, double* out_logl, void* stream);
+
 /* FP64 FMA micro-benchmark: runs `iters` dependent-chain DFMAs per thread on a full grid and
  * returns the achieved TFLOP/s (2 flop per FMA) in *out_tflops.  Used as the roofline denominator. */
 int rb_measure_fp64_peak(int iters, double* out_tflops, double* out_ms);

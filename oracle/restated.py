@@ -424,6 +424,25 @@ def gaussian_likelihood_upper_limits(y, model, sigma, detections, upper_limit_si
     return float(np.nan_to_num(det_ll + ul_ll))
 
 
+def mixture_gaussian_likelihood(y, model, sigma, sigma_out, alpha):
+    """MixtureGaussianLikelihood.log_likelihood, likelihoods.py:542-617."""
+    res = np.asarray(y, dtype=float) - model
+    with np.errstate(all="ignore"):
+        logp_in = -0.5 * np.log(2 * np.pi) - np.log(sigma) - 0.5 * (res / sigma) ** 2
+        logp_out = -0.5 * np.log(2 * np.pi) - np.log(sigma_out) - 0.5 * (res / sigma_out) ** 2
+        return float(np.sum(np.logaddexp(np.log(alpha) + logp_in, np.log(1 - alpha) + logp_out)))
+
+
+def mixture_outlier_posteriors(y, model, sigma, sigma_out, alpha):
+    """MixtureGaussianLikelihood.calculate_outlier_posteriors, likelihoods.py:637-665."""
+    r_ = np.asarray(y, dtype=float) - model
+    pin = (1 / (np.sqrt(2 * np.pi) * sigma)) * np.exp(-0.5 * (r_ / sigma) ** 2)
+    pout = (1 / (np.sqrt(2 * np.pi) * sigma_out)) * np.exp(-0.5 * (r_ / sigma_out) ** 2)
+    den = alpha * pin + (1 - alpha) * pout
+    with np.errstate(all="ignore"):
+        return np.where(den > 0, (1 - alpha) * pout / den, 0.0)
+
+
 def gaussian_likelihood_quadrature(y, model, sigma_i, sigma):
     """GaussianLikelihoodQuadratureNoise.log_likelihood, likelihoods.py:767-790."""
     with np.errstate(all="ignore"):

@@ -5,7 +5,7 @@ from . import (_capi, afterglow_models, bands, engine, kilonova_models, likeliho
                magnetar_driven_ejecta_models, simulate, supernova_models)
 from .likelihoods import (GaussianLikelihood, GaussianLikelihoodQuadratureNoise,  # noqa: F401
                           GaussianLikelihoodWithFractionalNoise, GaussianLikelihoodWithSystematicNoise,
-                          GaussianLikelihoodWithUpperLimits)
+                          GaussianLikelihoodWithUpperLimits, MixtureGaussianLikelihood)
 
 __version__ = "0.1.0"
 

@@ -310,6 +310,20 @@ int rb_gaussian_logl_f64(int sigma_mode, int64_t N, int64_t E, const double* mod
   return RB_OK;
 }
 
+int rb_mixture_logl_f64(int64_t N, int64_t E, const double* model, const double* y, const double* sigma,
+                        const double* alpha, const double* sigma_out, double* out_logl, void* stream) {
+  if (!model || !y || !sigma || !alpha || !sigma_out || !out_logl || N < 0 || E <= 0)
+    return fail(RB_ERR_INVALID, "rb_mixture_logl: bad arguments");
+  if (N == 0) return RB_OK;
+  const int threads = E >= 256 ? 256 : (E >= 128 ? 128 : 64);
+  const int64_t grid = N < 1048576 ? N : 1048576;
+  rb::mixture_logl_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(N, (int)E, model, y, sigma, alpha,
+                                                                                 sigma_out, out_logl);
+  launch_counter()->fetch_add(1);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
 namespace {
 struct DevBuf {
   double* p = nullptr;

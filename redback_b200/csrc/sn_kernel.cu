@@ -666,4 +666,32 @@ __global__ void dfma_kernel(int iters, double* out) {
   if (s == 12345.678) out[0] = s;
 }
 
+// MixtureGaussianLikelihood._mixture_gaussian_log_likelihood (likelihoods.py:542-577): per datum
+// logaddexp(log alpha + log N(r | sigma), log(1 - alpha) + log N(r | sigma_out)); alpha and sigma_out per sample.
+__global__ void mixture_logl_kernel(int64_t N, int E, const double* __restrict__ model, const double* __restrict__ y,
+                                    const double* __restrict__ sigma, const double* __restrict__ alpha,
+                                    const double* __restrict__ sigma_out, double* __restrict__ out) {
+  __shared__ double scratch[34];
+  const double half_log_2pi = 0.5 * log(2 * kPi);
+  for (int64_t n = blockIdx.x; n < N; n += gridDim.x) {
+    const double al = alpha[n], so = sigma_out[n];
+    const double la = log(al), lb = log(1 - al), lso = log(so);
+    double part = 0.0;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const double res = y[e] - model[n * (int64_t)E + e];
+      const double sg = sigma[e];
+      const double zi = res / sg, zo = res / so;
+      const double ti = la + (-half_log_2pi - log(sg) - 0.5 * (zi * zi));
+      const double to = lb + (-half_log_2pi - lso - 0.5 * (zo * zo));
+      // np.logaddexp: max + log1p(exp(-|d|)); NaN propagates, equal infinities return themselves
+      const double hi = fmax(ti, to), d = -fabs(ti - to);
+      part += (ti == to) ? ti + 0.6931471805599453 : ((isnan(ti) || isnan(to)) ? NAN : hi + log1p(exp(d)));
+    }
+    const double total = block_sum(part, scratch);
+    if (threadIdx.x == 0) out[n] = total;
+    __syncthreads();
+  }
+}
+
+
 }  // namespace rb

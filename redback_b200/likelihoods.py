@@ -338,6 +338,104 @@ class GaussianLikelihoodWithUpperLimits(GaussianLikelihood):
                 'upper_limit_sigma_levels': self.get_upper_limit_sigma_values() if n_upper_limits > 0 else None}
 
 
+class MixtureGaussianLikelihood(GaussianLikelihood):
+    """redback/likelihoods.py:492-665: every datum is alpha * N(r | sigma) + (1 - alpha) * N(r | sigma_out); `alpha`
+    and `sigma_out` are parameters (sampled or fixed).  The batch path evaluates the model matrix on device in
+    chunks and reduces it with the mixture kernel (the two extra per-sample parameters are not part of the fused
+    kernels' single noise-parameter slot)."""
+
+    _CHUNK_BYTES = 1 << 28
+
+    def __init__(self, x, y, sigma, function, kwargs=None, priors=None, fiducial_parameters=None):
+        super().__init__(x=x, y=y, sigma=sigma, function=function, kwargs=kwargs, priors=priors,
+                         fiducial_parameters=fiducial_parameters)
+        if 'alpha' not in self.parameters:
+            self.parameters['alpha'] = 0.9
+        if 'sigma_out' not in self.parameters:
+            self.parameters['sigma_out'] = sigma * 10 if sigma is not None and isinstance(sigma, (int, float)) \
+                else 10.0
+        self._noise_log_likelihood = None
+
+    def _mixture(self, model, alpha, sigma_out):
+        """model: device tensor [N, E]; alpha, sigma_out: [N] arrays -> device tensor [N]."""
+        import ctypes as C
+        if self._sigma is None:
+            raise NotImplementedError("MixtureGaussianLikelihood with a sampled inlier sigma is not available on device")
+        dev = model.device
+        N, E = model.shape
+        from .engine import as_device_f64, _ptr
+        y = as_device_f64(self.y, dev)
+        sig = as_device_f64(np.broadcast_to(np.asarray(self._sigma, dtype=np.float64), (E,)), dev)
+        al = as_device_f64(np.broadcast_to(np.asarray(alpha, dtype=np.float64), (N,)), dev)
+        so = as_device_f64(np.broadcast_to(np.asarray(sigma_out, dtype=np.float64), (N,)), dev)
+        out = torch.empty((N,), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().rb_mixture_logl_f64(
+                N, E, _ptr(model.contiguous()), _ptr(y), _ptr(sig), _ptr(al), _ptr(so), _ptr(out),
+                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        return out
+
+    def log_likelihood(self, parameters=None):
+        self._update_parameters(parameters)
+        fn_params = {k: v for k, v in self.parameters.items() if k not in ('alpha', 'sigma_out', 'sigma')
+                     and v is not None}
+        model = np.asarray(self.function(self.x, **fn_params, **self.kwargs), dtype=np.float64)
+        dev_model = torch.as_tensor(model.reshape(1, -1), device=self._dev())
+        return float(self._mixture(dev_model, self.parameters['alpha'], self.parameters['sigma_out'])[0].item())
+
+    def log_likelihood_batch(self, params_batch, device_output=False):
+        merged = {k: v for k, v in self.parameters.items() if v is not None}
+        merged.update(params_batch)
+        N = batch_size(merged)
+        if N is None:
+            raise ValueError("params_batch must contain at least one array")
+        alpha = np.broadcast_to(np.asarray(merged.pop('alpha'), dtype=np.float64), (N,))
+        sigma_out = np.broadcast_to(np.asarray(merged.pop('sigma_out'), dtype=np.float64), (N,))
+        merged.pop('sigma', None)
+        kw = dict(self.kwargs)
+        kw["device_output"] = True
+        step = max(1, self._CHUNK_BYTES // (8 * len(self.x)))
+        parts = []
+        for n0 in range(0, N, step):
+            sl = slice(n0, min(N, n0 + step))
+            chunk = {k: (v[sl] if np.ndim(v) > 0 and len(v) == N else v) for k, v in merged.items()}
+            chunk = {k: (np.full(sl.stop - sl.start, float(v)) if np.ndim(v) == 0 else v) for k, v in chunk.items()}
+            try:
+                model = self.function(self.x, params_batch=chunk, **kw)
+            except TypeError as exc:
+                raise NotImplementedError(
+                    "log_likelihood_batch needs a model function with a params_batch entry point") from exc
+            if not isinstance(model, torch.Tensor):
+                model = torch.as_tensor(np.asarray(model, dtype=np.float64), device=self._dev())
+            parts.append(self._mixture(model, alpha[sl], sigma_out[sl]))
+        logl = torch.cat(parts)
+        return logl if device_output else logl.cpu().numpy()
+
+    def _density(self, r, sigma):
+        dev = self._dev()
+        r = torch.as_tensor(np.asarray(r, dtype=np.float64), device=dev)
+        sigma = torch.as_tensor(np.asarray(sigma, dtype=np.float64), device=dev)
+        return (1 / (float(np.sqrt(2 * np.pi)) * sigma)) * torch.exp(-0.5 * (r / sigma) ** 2)
+
+    def p_in(self, r):
+        """likelihoods.py:579-593"""
+        return self._density(r, self.sigma).cpu().numpy()
+
+    def p_out(self, r):
+        """likelihoods.py:595-609"""
+        return self._density(r, self.parameters.get('sigma_out')).cpu().numpy()
+
+    def calculate_outlier_posteriors(self, model_prediction):
+        """likelihoods.py:637-665 (a per-fit diagnostic on one model vector; elementwise on device)."""
+        r = np.asarray(self.y, dtype=np.float64) - np.asarray(model_prediction, dtype=np.float64)
+        alpha = float(self.parameters.get('alpha'))
+        pin = self._density(r, self.sigma)
+        pout = self._density(r, self.parameters.get('sigma_out'))
+        numerator = (1 - alpha) * pout
+        denominator = alpha * pin + (1 - alpha) * pout
+        return torch.where(denominator > 0, numerator / denominator, torch.zeros_like(denominator)).cpu().numpy()
+
+
 class GaussianLikelihoodQuadratureNoise(GaussianLikelihood):
     """redback/likelihoods.py:738-790: sigma_full = sqrt(sigma_i^2 + sigma^2), `sigma` sampled."""
 

@@ -367,6 +367,7 @@ def test_upper_limit_likelihood(rb):
     assert like3.summary()["upper_limits"] == 12
 
     # magnitudes through the fused photometry path: limits use the survival function and sigma_m = 1.0857 / N
+    rb.bands.register_synthetic_lsst()
     bands = np.array(["lsstg", "lsstr", "lssti"])[rng.integers(0, 3, t.size)]
     kwm = dict(bands=bands, output_format="magnitude")
     mags = fn(t, **fid, **kwm)
@@ -412,6 +413,7 @@ def test_upper_limits_in_every_fused_kernel(rb):
     equal the stand-alone reduction (checked against the oracle above) applied to their own model matrices."""
     from redback_b200.engine import gaussian_logl
     import torch
+    rb.bands.register_synthetic_lsst()
     rng = np.random.default_rng(71)
     t = np.sort(rng.uniform(0.5, 20, 30))
     nu = np.full(t.size, 4.675e14)
@@ -439,3 +441,50 @@ def test_upper_limits_in_every_fused_kernel(rb):
         np.testing.assert_allclose(fused, alone, rtol=1e-9, atol=1e-6, err_msg=fn.__name__)
         plain = rb.GaussianLikelihood(t, y, sig, fn, kwargs=kw).log_likelihood_batch(p)
         assert np.any(np.abs(plain - fused) > 1e-3)
+
+
+@pytest.mark.gpu
+def test_mixture_gaussian_likelihood(rb):
+    """MixtureGaussianLikelihood (likelihoods.py:492-665): batch path (model matrix + mixture reduction kernel),
+    single-sample path with a generic function, outlier posteriors."""
+    rng = np.random.default_rng(73)
+    t = np.sort(rng.uniform(5, 150, 35))
+    nu = np.full(t.size, 4.675e14)
+    N = 50
+    p = h.arnett_prior(rng, N)
+    fn = rb.supernova_models.arnett
+    kw = dict(frequency=nu, output_format="flux_density")
+    model = fn(t, params_batch=p, **kw)
+    y = model[4] * (1 + 0.05 * rng.standard_normal(t.size))
+    y[::7] *= 3.0                                            # outliers
+    sig = 0.05 * np.abs(model[4]) + 1e-12
+    alpha = rng.uniform(0.5, 0.99, N)
+    sigma_out = h.loguniform(rng, 1e-3, 1e2, N) * np.median(sig)
+    like = rb.MixtureGaussianLikelihood(t, y, sig, fn, kwargs=kw)
+    like._CHUNK_BYTES = 8 * t.size * 16                      # force several chunks
+    got = like.log_likelihood_batch(dict(p, alpha=alpha, sigma_out=sigma_out))
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        z = kwi.pop("redshift")
+        ref = r.arnett(t, z, frequency=nu, **kwi)
+        want = r.mixture_gaussian_likelihood(y, ref, sig, sigma_out[i], alpha[i])
+        assert abs(got[i] - want) <= 1e-6 + 1e-8 * abs(want), (i, got[i], want)
+    # defaults alpha = 0.9, sigma_out = 10 (array sigma) / 10 sigma (scalar sigma): likelihoods.py:533-540
+    d = rb.MixtureGaussianLikelihood(t, y, sig, fn, kwargs=kw).log_likelihood_batch({k: v[:3] for k, v in p.items()})
+    want = r.mixture_gaussian_likelihood(y, r.arnett(t, p["redshift"][0], frequency=nu,
+                                                    **{k: v[0] for k, v in p.items() if k != "redshift"}), sig, 10.0, 0.9)
+    assert abs(d[0] - want) <= 1e-6 + 1e-8 * abs(want)
+
+    def line(x, slope, **kwargs):
+        return slope * x
+    x = np.arange(10.0)
+    yy = 2.0 * x + np.array([0.1, -0.2, 0.05, 5.0, -0.1, 0.0, 0.15, -6.0, 0.1, -0.05])
+    lg = rb.MixtureGaussianLikelihood(x, yy, 0.2, line)
+    assert lg.parameters["alpha"] == 0.9 and lg.parameters["sigma_out"] == 2.0
+    lg.parameters["slope"] = 2.0
+    want = r.mixture_gaussian_likelihood(yy, 2.0 * x, 0.2, 2.0, 0.9)
+    assert abs(lg.log_likelihood() - want) < 1e-9
+    post = lg.calculate_outlier_posteriors(2.0 * x)
+    np.testing.assert_allclose(post, r.mixture_outlier_posteriors(yy, 2.0 * x, 0.2, 2.0, 0.9), rtol=1e-12, atol=1e-300)
+    assert post[3] > 0.99 and post[7] > 0.99 and post[0] < 0.1
+    assert hasattr(lg, "p_in") and hasattr(lg, "p_out")
