@@ -118,11 +118,15 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path):
-        path = _build.build()
+    path = os.environ.get("REDBACK_B200_LIB")   # alternate build of the same ABI (kernel experiments)
+    if not path:
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            path = _build.build()
     handle = C.CDLL(path)
     for name, (res, args) in EXPORTS.items():
+        if not hasattr(handle, name) and os.environ.get("REDBACK_B200_LIB"):
+            continue                # an older experimental build may lack newer entry points
         fn = getattr(handle, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
