@@ -327,6 +327,13 @@ int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* phot, int64
                        const double* params, const double* t_obs, const double* dl_cm, const double* y,
                        const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
                        void* stream);
+/* Magnitude branch of the mergernova models (_processing_other_formats, magnetar_driven_ejecta_models.py:198-238,
+ * use_relativistic_blackbody = True): spectra on (get_optimal_time_array(1e-4, 1e8, 500) x lambda_array), phases
+ * time_temp (1+z) / 86400 d.  phot->tgrid is not used (the library builds the grid itself). */
+int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
+                       const double* params, const double* t_obs, const double* dl_cm, const double* y,
+                       const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
+                       void* stream);
 
 /* ---- observation noise + SNR cut for simulated optical light curves ------------------------------------
  * SimulateTransientWithCadence._evaluate_optical_model / _add_optical_noise_and_cuts

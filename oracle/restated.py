@@ -1246,6 +1246,36 @@ def sn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None,
     return bandmag_from_spectra(time_obs, time_observer_frame, spectra, lam, bands, bandpasses)
 
 
+def mergernova_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, **params):
+    """_processing_other_formats (magnetar_driven_ejecta_models.py:198-238) with use_relativistic_blackbody=True for
+    `model` in {'basic_mergernova', 'general_mergernova', 'general_mergernova_thermalisation'}."""
+    time_obs = np.asarray(time, dtype=float)
+    lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=float)
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    t_grid = get_optimal_time_array(1e-4, 1e8, 500)
+    ej = [params[k] for k in ("mej", "beta", "ejecta_radius", "kappa", "n_ism")]
+    if model == "basic_mergernova":
+        lum = basic_magnetar(t_grid, params["p0"], params["bp"], params["mass_ns"], params["theta_pb"])
+        pcs = params.get("pair_cascade_switch", False)
+    else:
+        lum = magnetar_only(t_grid, params["l0"], params["tau_sd"], params["nn"])
+        pcs = params.get("pair_cascade_switch", True)
+    gamma_ray = model == "general_mergernova_thermalisation"
+    _, temp, rad, dop = ejecta_dynamics_and_interaction(
+        t_grid, *ej, lum, pcs, gamma_ray, thermalisation_efficiency=params.get("thermalisation_efficiency"),
+        kappa_gamma=params.get("kappa_gamma"))
+    time_observer_frame = t_grid * (1. + redshift)
+    frequency, _ = calc_kcorrected_properties(lambda_to_nu(lam), redshift, time_observer_frame)
+    with np.errstate(all="ignore"):
+        nu = frequency[:, None]
+        num = 2 * np.pi * planck * nu ** 3 * rad ** 2
+        den = dl ** 2 * speed_of_light ** 2 * dop ** 2
+        fd = (num / den * (1. / (np.exp((planck * nu) / (boltzmann_constant * temp * dop)) - 1))).T   # :164-173
+        spectra = flux_density_to_spectrum(fd, redshift, lam)
+    return bandmag_from_spectra(time_obs, time_observer_frame / day_to_s, spectra, lam, bands, bandpasses)
+
+
 def kn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, dense_resolution=500,
                  **params):
     """Magnitude branch of one_component_kilonova_model / metzger_kilonova_model

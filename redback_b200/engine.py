@@ -349,6 +349,26 @@ class MergernovaPath(_FusedPath):
             raise ValueError("A value in x_new is below the interpolation range: mergernova models need time > 0")
 
 
+class MergernovaMagPath(MergernovaPath):
+    """Magnitude / bandpass-flux branch of the mergernova models (_processing_other_formats,
+    magnetar_driven_ejecta_models.py:198-238)."""
+
+    NEEDS_FREQUENCY = False
+
+    def __init__(self, engine, time, bands, output="magnitude", lambda_array=None, y=None, sigma=None,
+                 sigma_mode=_capi.SIGMA_FIXED, use_gamma_ray_opacity=False, pair_cascade_switch=False,
+                 ejecta_albedo=0.5, pair_cascade_fraction=0.05, cosmology=None, device=None):
+        from . import bands as _bands
+        self.cfg = _capi.mn_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
+                                   pair_cascade_fraction, cosmology)
+        self._setup(time, None, y, sigma, device)
+        lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
+        self.phot, self._keep = _bands.build_photometry(bands, self.E, lam, output)
+
+    def _launch(self, *args):
+        return self._launch_mag(_capi.lib().rb_mn_mag_eval_f64, *args)
+
+
 def luminosity_distance(redshift, cosmology=None, device=None):
     """Planck18 (default) luminosity distance in cm for an array of redshifts, on device."""
     dev = _device(device)

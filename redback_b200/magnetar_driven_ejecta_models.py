@@ -1,10 +1,10 @@
 """Batched drop-ins for redback's magnetar-driven relativistic-ejecta ("mergernova") models
 (redback/transient_models/magnetar_driven_ejecta_models.py: basic_mergernova :275-321, general_mergernova :324-371,
-general_mergernova_thermalisation :374-419), output_format='flux_density'.  Same signatures as the reference plus
+general_mergernova_thermalisation :374-419), output_format='flux_density' | 'magnitude' | 'flux'.  Same signatures as the reference plus
 `params_batch` (see supernova_models.py)."""
 from . import _capi
-from ._fused import FusedSpec, cosmology_from_kwargs, run
-from .engine import MergernovaPath
+from ._fused import FusedSpec, cosmology_from_kwargs, output_mode, run
+from .engine import MergernovaMagPath, MergernovaPath
 
 _EJECTA = ("redshift", "mej", "beta", "ejecta_radius", "kappa", "n_ism")
 
@@ -13,15 +13,20 @@ def _spec(name, engine, engine_params, last, pair_cascade_default, gamma_ray):
     needed = _EJECTA + tuple(engine_params) + (last,)
 
     def validate(kwargs):
-        fmt = kwargs.get("output_format")
-        if fmt is None:
-            raise KeyError("output_format")
-        if fmt != "flux_density":
-            raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device")
+        output_mode(kwargs, name)
         if not kwargs.get("use_r_process", True):
             raise NotImplementedError(f"{name}: use_r_process=False (nickel heating) is not fused on device")
 
     def build(time, kwargs, y, sigma, sigma_mode):
+        mode = output_mode(kwargs, name)
+        if mode != "flux_density":
+            return MergernovaMagPath(engine, time, kwargs["bands"], output=mode,
+                                     lambda_array=kwargs.get("lambda_array"), y=y, sigma=sigma, sigma_mode=sigma_mode,
+                                     use_gamma_ray_opacity=gamma_ray,
+                                     pair_cascade_switch=kwargs.get("pair_cascade_switch", pair_cascade_default),
+                                     ejecta_albedo=kwargs.get("ejecta_albedo", 0.5),
+                                     pair_cascade_fraction=kwargs.get("pair_cascade_fraction", 0.05),
+                                     cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"))
         return MergernovaPath(engine, time, frequency=kwargs.get("frequency"), y=y, sigma=sigma, sigma_mode=sigma_mode,
                               use_gamma_ray_opacity=gamma_ray,
                               pair_cascade_switch=kwargs.get("pair_cascade_switch", pair_cascade_default),

@@ -92,6 +92,24 @@ def test_csm_interaction_magnitudes(rb, obands):
         _check(out[i], ref, f"csm_interaction sample {i}", floor_mag=np.nanmin(ref))
 
 
+@pytest.mark.parametrize("kind", ["basic", "thermalisation"])
+def test_mergernova_magnitudes(rb, obands, kind):
+    """_processing_other_formats of the mergernova models (magnetar_driven_ejecta_models.py:198-238)."""
+    rng = np.random.default_rng(29)
+    t = np.geomspace(0.3, 40, 30)
+    names = np.array(list(h.LSST_NU)[:6] * 5)
+    N = 8
+    p = h.mergernova_prior(rng, N, kind)
+    name = "basic_mergernova" if kind == "basic" else "general_mergernova_thermalisation"
+    out = getattr(rb.magnetar_driven_ejecta_models, name)(t, params_batch=p, bands=names, output_format="magnitude")
+    assert out.shape == (N, t.size)
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.mergernova_magnitude(name, t, z, bands=names, bandpasses=obands, **kw)
+        _check(out[i], ref, f"{name} sample {i}", atol=2e-8, floor_mag=np.nanmin(ref))
+
+
 def test_kilonova_magnitudes_config3(rb, obands):
     """BASELINE configs[2]: one_component_kilonova_model in LSST ugrizy magnitudes."""
     t = np.geomspace(0.3, 20, 36)

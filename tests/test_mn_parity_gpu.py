@@ -76,8 +76,8 @@ def test_scalar_call_kwargs_and_errors(rb):
     with pytest.raises(ValueError):
         rb.magnetar_driven_ejecta_models.general_mergernova(np.array([0.0, 1.0]), 0.05, frequency=4.6e14,
                                                             output_format="flux_density", **kw)
-    with pytest.raises(NotImplementedError):
-        rb.magnetar_driven_ejecta_models.general_mergernova(t, 0.05, bands="lsstr", output_format="magnitude", **kw)
+    with pytest.raises(KeyError):
+        rb.magnetar_driven_ejecta_models.general_mergernova(t, 0.05, output_format="magnitude", **kw)     # no bands
     with pytest.raises(KeyError):
         rb.magnetar_driven_ejecta_models.general_mergernova(t, 0.05, output_format="flux_density", **kw)
     far = rb.magnetar_driven_ejecta_models.general_mergernova(np.array([10.0, 2000.0]), 0.05, frequency=4.6e14,
