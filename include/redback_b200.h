@@ -122,6 +122,11 @@ typedef struct {
      interaction process = CSMDiffusion, method "cumulative" (interaction_processes.py:176-197); dense grid =
      get_optimal_time_array(min(0.1, min t), max t + 100, dense_resolution, user_times = t) (:2026-2030) */
   double csm_nn, csm_delta, csm_efficiency;
+  /* phase_models.t0_base_model (redback/transient_models/phase_models.py:19-59): per-sample explosion epoch, DEVICE
+     pointer [N] or NULL.  The model is evaluated at t_obs - t0[n]; epochs before t0 return 0 (flux density, flux,
+     luminosity) or 1000 (magnitude), and the dense grid ends 100 d after the last epoch with t_obs >= t0
+     (RB_ENGINE_NICKEL / RB_ENGINE_MAGNETAR only). */
+  const double* t0;
 } rb_sn_config;
 
 /* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */

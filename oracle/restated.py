@@ -320,6 +320,21 @@ def slsn(time, redshift, p0, bp, mass_ns, theta_pb, *, frequency, mej, vej, kapp
         cutoff_wavelength=cutoff_wavelength, absorption_index=absorption_index)
 
 
+def t0_base_model(time, t0, base, output_format="flux_density", **kw):
+    """phase_models.t0_base_model (phase_models.py:19-59): `base(transient_time, frequency=..., bands=...)` is one of
+    the restated models; astropy's `(Time(time, 'mjd') - Time(t0, 'mjd')).to(day)` is the double-double difference of
+    the two MJDs, i.e. time - t0 rounded once."""
+    time = np.asarray(time, dtype=float) - t0
+    good = time >= 0.0
+    kw = dict(kw)
+    for key in ("frequency", "bands"):
+        if key in kw and isinstance(kw[key], np.ndarray):
+            kw[key] = kw[key][good]
+    real = base(time[good], **kw)
+    fake = np.zeros(int((~good).sum())) + (1000 if output_format == "magnitude" else 0)
+    return np.concatenate((fake, real))
+
+
 def gaussian_likelihood_fractional(y, model, sigma_i):
     """GaussianLikelihoodWithFractionalNoise.log_likelihood, likelihoods.py:821-851."""
     with np.errstate(all="ignore"):

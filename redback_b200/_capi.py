@@ -37,7 +37,7 @@ class SnConfig(C.Structure):
                 ("line_wavelength", C.c_double), ("line_width", C.c_double), ("line_time", C.c_double),
                 ("line_duration", C.c_double), ("line_amplitude", C.c_double), ("precision", C.c_int),
                 ("upper_limits", UpperLimits), ("csm_nn", C.c_double), ("csm_delta", C.c_double),
-                ("csm_efficiency", C.c_double)]
+                ("csm_efficiency", C.c_double), ("t0", C.c_void_p)]
 
 
 KN_ONE_COMPONENT, KN_METZGER = 0, 1

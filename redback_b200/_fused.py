@@ -107,9 +107,20 @@ def flux_density_only(kwargs, name):
     output_mode(kwargs, name, photometric=False)
 
 
+def t0_tensor(params, path, N):
+    """Per-sample explosion epoch (phase_models.t0_base_model) as a device tensor [N], or None."""
+    if "t0" not in params:
+        return None
+    n = N if N is not None else 1
+    t0 = params["t0"]
+    if isinstance(t0, torch.Tensor):
+        return t0.to(device=path.device, dtype=torch.float64).reshape(-1).expand(n).contiguous()
+    return torch.from_numpy(np.array(np.broadcast_to(np.asarray(t0, dtype=np.float64), (n,)))).to(path.device)
+
+
 def run(spec, time, named, kwargs, params_batch):
     params, N = collect(named, kwargs, params_batch, spec.needed)
     path = spec.build(time, kwargs)
     dev = path.pack(params, N if N is not None else 1)
-    model, _ = path.evaluate(dev, dl=dl_from_kwargs(kwargs, path, N))
+    model, _ = path.evaluate(dev, dl=dl_from_kwargs(kwargs, path, N), t0=t0_tensor(params, path, N))
     return finish(model, N, kwargs)

@@ -182,6 +182,7 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
       return fail(RB_ERR_INVALID, "One of the requested xi is out of bounds in dimension 0 (nn must be in [6, 14])");
     if (cfg->precision != RB_PREC_F64) return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: the CSM path is FP64 only");
     if (cfg->dense_resolution < 20) return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution must be >= 20 (CSM)");
+    if (cfg->t0 != nullptr) return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: t0 is not available for the CSM engine");
   }
   if (cfg->sed < RB_SED_BOLOMETRIC || cfg->sed > RB_SED_CUTOFF_LINE)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sed");
@@ -227,7 +228,9 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [dev] {
-    attr_err = cudaFuncSetAttribute(rb::sn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_err = cudaFuncSetAttribute(rb::sn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rb::sn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     // keep the stream-ordered workspace pool resident across synchronisations (default trims it to 0)
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -268,12 +271,13 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   const size_t smem = sn_smem_bytes(cfg->dense_resolution, E, a.epochs_in_smem != 0);
   if (smem > 220 * 1024) return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution too large for shared memory");
   int occ = 0;
-  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::sn_kernel, threads, smem));
+  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::sn_kernel<false>, threads, smem));
   if (occ < 1) occ = 1;
   // persistent blocks, grid-stride over samples; 4 waves' worth of blocks for load balance at mid-size N
   int64_t grid = (int64_t)sms * occ * 4;
   if (grid > N) grid = N;
-  rb::sn_kernel<<<(unsigned)grid, threads, smem, st>>>(a);
+  if (cfg->t0 != nullptr) rb::sn_kernel<true><<<(unsigned)grid, threads, smem, st>>>(a);
+  else rb::sn_kernel<false><<<(unsigned)grid, threads, smem, st>>>(a);
   launch_counter()->fetch_add(3);
   RB_CUDA(cudaGetLastError());
   return RB_OK;
@@ -1097,7 +1101,7 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::sn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_err = cudaFuncSetAttribute(rb::sn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   });
@@ -1135,7 +1139,7 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
   const int ep_in_smem = (sn_smem_bytes(cfg->dense_resolution, NT, true) <= 64 * 1024) ? 1 : 0;
   const size_t sn_smem = sn_smem_bytes(cfg->dense_resolution, NT, ep_in_smem != 0);
   int occ_sn = 1, occ_ph = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sn, rb::sn_kernel, sn_threads, sn_smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sn, rb::sn_kernel<false>, sn_threads, sn_smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
   if (occ_sn < 1) occ_sn = 1;
   if (occ_ph < 1) occ_ph = 1;
@@ -1174,7 +1178,7 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
       if (status != RB_OK) break;
     } else {
       rb::sn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
-      rb::sn_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_sn * 4), sn_threads, sn_smem, st>>>(a);
+      rb::sn_kernel<false><<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_sn * 4), sn_threads, sn_smem, st>>>(a);
     }
     pa.N = nc;
     pa.n_base = n0;
@@ -1197,6 +1201,7 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
     pa.opz = d_opz;
     pa.dl = d_dl;
     pa.sigma_param_s = sigma_param ? sigma_param + n0 : nullptr;
+    pa.t0_s = (cfg->t0 && cfg->engine != RB_ENGINE_CSM) ? cfg->t0 + n0 : nullptr;
     pa.epoch_tab = d_ep_obs;
     pa.scratch = d_scratch;
     pa.out_model = out_model;

@@ -47,6 +47,7 @@ struct PhotArgs {
   const double* opz;      // [N] 1 + z
   const double* dl;       // [N]
   const double* sigma_param_s;  // [N] sampled sigma (already sliced to the chunk) or nullptr
+  const double* t0_s;           // [N] explosion epochs of t0_base_model (sliced to the chunk) or nullptr
   const double* lambda_obs;     // [n_lambda]
   const double* lu_lambda;      // [n_lambda][5]: l2, l1, d, u1, u2
   const double* lu_time;        // [n_t_max][5] when common_time_lu
@@ -305,6 +306,18 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
     double logl_part = 0.0;
     for (int e = tid; e < E; e += blockDim.x) {
       double x = a.epoch_tab[EP_T * E + e];
+      if (a.t0_s != nullptr) {                                                    // phase_models.py:33-58
+        x -= a.t0_s[n];
+        if (x < 0.0) {
+          const double fake = (a.output == RB_OUT_FLUX) ? 0.0 : 1000.0;
+          if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = fake;
+          if (a.want_logl)
+            logl_part += logl_term(a.sigma_mode, a.epoch_tab[EP_KIND * E + e], a.epoch_tab[EP_Y * E + e], fake,
+                                   a.epoch_tab[EP_ISIG * E + e], a.epoch_tab[EP_LOGT * E + e],
+                                   a.sigma_param_s ? a.sigma_param_s[n] : 0.0);
+          continue;
+        }
+      }
       if (x < xk[0]) x = xk[0];                                                   // fpbisp clamps to [tb, te]
       if (x > xk[G - 1]) x = xk[G - 1];
       // knot interval: largest l in [3, G-1] with t[l] <= x  (t[l] = x[l-2] for 4 <= l <= G-1)

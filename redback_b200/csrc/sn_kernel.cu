@@ -46,7 +46,7 @@ enum {
   SC_DL,         // luminosity distance [cm]
   SC_SIGMA,      // sampled sigma (RB_SIGMA_SAMPLED / RB_SIGMA_QUADRATURE)
   SC_INV_TAU2,   // 1 / tau_diff^2
-  SC_SPARE,
+  SC_T0,         // explosion epoch t0 (phase_models.t0_base_model) or 0
   kScalars       // = 16
 };
 
@@ -131,7 +131,15 @@ __global__ void sn_prep_kernel(const SnArgs a) {
   }
   if (lane != 0) return;
   const double mej = P[RB_SN_MEJ * N], vej = P[RB_SN_VEJ * N];
-  const double t_last = a.epoch_tab[EP_T * a.E + a.E - 1];
+  double t_last = a.epoch_tab[EP_T * a.E + a.E - 1];
+  double t0 = 0.0;
+  if (a.cfg.t0 != nullptr && !a.grid_mode) {
+    // phase_models.py:33-48: the base model only sees the epochs with t - t0 >= 0; its time[-1] is the last of them
+    t0 = a.cfg.t0[n];
+    int e = a.E - 1;
+    while (e >= 0 && !(a.epoch_tab[EP_T * a.E + e] - t0 >= 0.0)) --e;
+    t_last = (e >= 0) ? a.epoch_tab[EP_T * a.E + e] - t0 : 0.0;
+  }
   const double t_end = (a.grid_mode ? (t_last * opz) / opz : t_last / opz) + 100.0;
   const double tau = sqrt(kDiffusionConst * P[RB_SN_KAPPA * N] * mej / vej) / kDay;
   const double tau2 = tau * tau;
@@ -169,7 +177,7 @@ __global__ void sn_prep_kernel(const SnArgs a) {
   S[SC_INV_DEN] = 1.0 / ((dl * dl) * (kC * kC));
   S[SC_DL] = dl;
   S[SC_SIGMA] = (a.sigma_param != nullptr && a.want_logl) ? a.sigma_param[n] : 0.0;
-  S[SC_SPARE] = 0.0;
+  S[SC_T0] = t0;
 }
 
 // ---- CutoffBlackbody --------------------------------------------------------------------------------
@@ -382,6 +390,9 @@ __device__ __forceinline__ float diffusion_sum_f32(const float4* __restrict__ no
   return acc0 + acc1;
 }
 
+// HAS_T0: per-sample explosion epoch (phase_models.t0_base_model); a separate instantiation so that the plain path
+// keeps its register allocation.
+template <bool HAS_T0>
 __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
   extern __shared__ double2 smem2[];
   const int D = a.cfg.dense_resolution;
@@ -515,7 +526,14 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
     // ---- per-epoch work ------------------------------------------------------------------------
     double logl_part = 0.0;
     for (int e = tid; e < E; e += blockDim.x) {
-      const double t_in = ep[EP_T * E + e];
+      const double t_in = HAS_T0 ? ep[EP_T * E + e] - sc[SC_T0] : ep[EP_T * E + e];
+      if (HAS_T0 && t_in < 0.0) {                                             // phase_models.py:54-58: before t0
+        if (a.out_model != nullptr) a.out_model[n * (int64_t)E + e] = 0.0;
+        if (want_logl)
+          logl_part += logl_term(sigma_mode, ep[EP_KIND * E + e], ep[EP_Y * E + e], 0.0, ep[EP_ISIG * E + e],
+                                 ep[EP_LOGT * E + e], sc[SC_SIGMA]);
+        continue;
+      }
       const double te = a.grid_mode ? (t_in * sc[SC_OPZ]) / sc[SC_OPZ] : t_in / sc[SC_OPZ];   // utils.py:382 (:1012-1014)
       const double te2 = te * te;                                             // interaction_processes.py:55
       // first abscissa whose exponent can exceed kExpSkip: te^2 (1 - xm^2) <= -(kExpSkip - 1) tau^2

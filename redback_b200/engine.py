@@ -145,8 +145,10 @@ class _FusedPath:
             out[torch.tensor(host_idx, device=self.device)] = block.to(self.device, non_blocking=False)
         return out
 
-    def evaluate(self, params_dev, dl=None, sigma_param=None, want_model=True, want_logl=False, out_logl=None):
-        """Launch the fused kernel on the current stream.  Returns (model[N,E] | None, logl[N] | None)."""
+    def evaluate(self, params_dev, dl=None, sigma_param=None, want_model=True, want_logl=False, out_logl=None,
+                 t0=None):
+        """Launch the fused kernel on the current stream.  Returns (model[N,E] | None, logl[N] | None).
+        `t0`: optional device tensor [N] of explosion epochs (phase_models.t0_base_model; supernova paths only)."""
         if params_dev.dtype != _F64 or params_dev.dim() != 2 or params_dev.shape[0] != self.NPARAM:
             raise ValueError(f"params_dev must be float64 [{self.NPARAM}, N]")
         params_dev = params_dev.contiguous()
@@ -162,9 +164,20 @@ class _FusedPath:
         if N == 0:      # empty batch: nothing to launch
             return model, logl
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        with torch.cuda.device(self.device):
-            rc = self._launch(N, params_dev, dl, self.y if want_logl else None, self.sigma if want_logl else None,
-                              sigma_param if want_logl else None, model, logl, stream)
+        if t0 is not None:
+            if not hasattr(self.cfg, "t0"):
+                raise NotImplementedError("a per-sample t0 is only available on the supernova paths")
+            if t0.dtype != _F64 or t0.shape != (N,) or not t0.is_contiguous():
+                raise ValueError("t0 must be a contiguous float64 [N] device tensor")
+            self.cfg.t0 = t0.data_ptr()
+        try:
+            with torch.cuda.device(self.device):
+                rc = self._launch(N, params_dev, dl, self.y if want_logl else None,
+                                  self.sigma if want_logl else None, sigma_param if want_logl else None, model, logl,
+                                  stream)
+        finally:
+            if t0 is not None:
+                self.cfg.t0 = None
         _capi.check(rc)
         return model, logl
 

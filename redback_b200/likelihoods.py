@@ -15,6 +15,7 @@ from . import _capi, _fused
 from . import afterglow_models as _ag
 from . import kilonova_models as _kn
 from . import magnetar_driven_ejecta_models as _mn
+from . import phase_models as _ph
 from . import supernova_models as _sn
 from .engine import batch_size, gaussian_logl
 
@@ -23,6 +24,7 @@ FUSED.update(_sn.FUSED)
 FUSED.update(_kn.FUSED)
 FUSED.update(_ag.FUSED)
 FUSED.update(_mn.FUSED)
+FUSED.update(_ph.FUSED)
 
 
 def infer_parameters_from_function(func):
@@ -192,6 +194,8 @@ class GaussianLikelihood(_RedbackLikelihood):
 
     def _fused(self, merged, N, mode, sp):
         spec = FUSED[self.function]
+        if hasattr(spec, "for_kwargs"):          # wrappers (t0_base_model) resolve their base model from kwargs
+            spec = spec.for_kwargs(self.kwargs)
         kw = dict(self.kwargs)
         if self.function is _kn.one_component_kilonova_model:
             kw.setdefault("temperature_floor", 4000)
@@ -211,7 +215,7 @@ class GaussianLikelihood(_RedbackLikelihood):
             else:
                 sp_dev = torch.from_numpy(np.array(np.broadcast_to(np.asarray(sp, dtype=np.float64), (N,)))).to(path.device)
         _, logl = path.evaluate(dev, dl=_fused.dl_from_kwargs(kw, path, N), sigma_param=sp_dev, want_model=False,
-                                want_logl=True)
+                                want_logl=True, t0=_fused.t0_tensor(params, path, N))
         return logl
 
 

@@ -488,3 +488,62 @@ def test_mixture_gaussian_likelihood(rb):
     np.testing.assert_allclose(post, r.mixture_outlier_posteriors(yy, 2.0 * x, 0.2, 2.0, 0.9), rtol=1e-12, atol=1e-300)
     assert post[3] > 0.99 and post[7] > 0.99 and post[0] < 0.1
     assert hasattr(lg, "p_in") and hasattr(lg, "p_out")
+
+
+@pytest.mark.gpu
+def test_t0_base_model(rb):
+    """phase_models.t0_base_model (phase_models.py:19-59): per-sample explosion epochs in one launch; epochs before
+    t0 return 0 (1000 mag); the dense grid of each sample ends 100 d after ITS last valid epoch."""
+    rng = np.random.default_rng(79)
+    mjd0 = 59000.0
+    t = mjd0 + np.sort(rng.uniform(0, 120, 45))
+    nu = np.where(np.arange(t.size) % 2 == 0, 6.3e14, 4.7e14)
+    N = 30
+    p = h.arnett_prior(rng, N)
+    p["t0"] = mjd0 + rng.uniform(-30, 60, N)
+    p["t0"][0] = t[10]                                    # an epoch exactly at t0: time 0 is kept (>= 0)
+    p["t0"][1] = t[-1] - 1e-3                             # only the last epoch is valid
+    fn = rb.phase_models.t0_base_model
+    kw = dict(base_model="arnett", frequency=nu, output_format="flux_density")
+    out = fn(t, params_batch=p, **kw)
+    y = out[5] + 1e-3 * np.abs(out[5]).max()
+    sigma = 0.1 * np.abs(y) + 1e-9
+    like = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=kw)
+    assert list(like.parameters) == ["t0"]
+    logl = like.log_likelihood_batch(p)
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        t0 = kwi.pop("t0")
+        z = kwi.pop("redshift")
+        ref = r.t0_base_model(t, t0, lambda tt, frequency: r.arnett(tt, z, frequency=frequency, **kwi), frequency=nu)
+        assert np.all(out[i][t - t0 < 0] == 0.0)
+        with np.errstate(all="ignore"):
+            cond = h.diffusion_condition(np.maximum(t - t0, 0) / (1 + z),
+                                         np.sqrt(2 * kwi["kappa"] * kwi["mej"] * r.solar_mass
+                                                 / (13.7 * r.speed_of_light * kwi["vej"] * r.km_cgs)) / r.day_to_s)
+        h.assert_close(out[i], ref, 1e-9, cond, what=f"t0_base_model(arnett) sample {i}")
+        ref_l = r.gaussian_likelihood(y, ref, sigma)
+        assert abs(logl[i] - ref_l) <= 1e-6 + 1e-9 * abs(ref_l), (i, logl[i], ref_l)
+    # scalar call, bolometric base model
+    kb = dict(f_nickel=0.2, mej=2.0, vej=9000.0, kappa=0.1, kappa_gamma=10.0)
+    one = fn(t, mjd0 + 20.0, base_model="arnett_bolometric", **kb)
+    ref = r.t0_base_model(t, mjd0 + 20.0, lambda tt: r.arnett_bolometric(tt, **kb), output_format="luminosity")
+    h.assert_close(one, ref, 1e-9, what="t0_base_model(arnett_bolometric)")
+    # magnitudes: 1000 before t0
+    rb.bands.register_synthetic_lsst()
+    bands = np.array(["lsstg", "lsstr", "lssti"])[np.arange(t.size) % 3]
+    pm = {k: v[:4] for k, v in p.items()}
+    mags = fn(t, params_batch=pm, base_model="arnett", bands=bands, output_format="magnitude")
+    plain = rb.supernova_models.arnett
+    for i in range(4):
+        kwi = {k: v[i] for k, v in pm.items()}
+        t0 = kwi.pop("t0")
+        good = t - t0 >= 0
+        assert np.all(mags[i][~good] == 1000.0)
+        want = plain(t[good] - t0, bands=bands[good], output_format="magnitude", **kwi)
+        np.testing.assert_allclose(mags[i][good], want, rtol=0, atol=1e-9)
+    with pytest.raises(NotImplementedError):
+        fn(t[::-1], mjd0, base_model="arnett", frequency=nu, output_format="flux_density",
+           **{k: float(v[0]) for k, v in p.items() if k != "t0"})
+    with pytest.raises(NotImplementedError):
+        fn(t, mjd0, base_model="tophat_redback", frequency=nu, output_format="flux_density")
