@@ -33,7 +33,9 @@ typedef enum {
 
 /* ---- luminosity engines: redback/transient_models/supernova_models.py:564-579 (_nickelcobalt_engine),
  *      redback/transient_models/magnetar_models.py:171-185 (basic_magnetar) ---------------------- */
-enum { RB_ENGINE_NICKEL = 0, RB_ENGINE_MAGNETAR = 1, RB_ENGINE_CSM = 2 };
+enum { RB_ENGINE_NICKEL = 0, RB_ENGINE_MAGNETAR = 1, RB_ENGINE_CSM = 2,
+       RB_ENGINE_MAGNETAR_NICKEL = 3 /* magnetar_nickel (supernova_models.py:1628-1681): both engines summed; the
+                                        magnetar rows as for RB_ENGINE_MAGNETAR, f_nickel through cfg.f_nickel */ };
 enum { RB_PREC_F64 = 0, RB_PREC_F32 = 1 };
 
 /* ---- output stage: bolometric models return L_bol; flux_density models go through
@@ -127,6 +129,8 @@ typedef struct {
      luminosity) or 1000 (magnitude), and the dense grid ends 100 d after the last epoch with t_obs >= t0
      (RB_ENGINE_NICKEL / RB_ENGINE_MAGNETAR only). */
   const double* t0;
+  /* RB_ENGINE_MAGNETAR_NICKEL only: per-sample nickel fraction, DEVICE pointer [N] (row 1 holds p0 there). */
+  const double* f_nickel;
 } rb_sn_config;
 
 /* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */

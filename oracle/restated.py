@@ -335,6 +335,18 @@ def t0_base_model(time, t0, base, output_format="flux_density", **kw):
     return np.concatenate((fake, real))
 
 
+def magnetar_nickel(time, redshift, f_nickel, mej, p0, bp, mass_ns, theta_pb, *, frequency, vej, kappa, kappa_gamma,
+                    temperature_floor, dl=None, dense_resolution=1000, **_):
+    """supernova_models.magnetar_nickel (:1628-1681), flux_density: nickel + magnetar engines through one Diffusion."""
+    def bolometric(t):
+        dense = np.linspace(0, t[-1] + 100, dense_resolution)
+        lum = nickelcobalt_engine(dense, f_nickel, mej)
+        lum += basic_magnetar(dense * day_to_s, p0, bp, mass_ns, theta_pb)                     # :1669-1670
+        return diffusion(t, dense, lum, kappa, kappa_gamma, mej, vej)[1]
+    return _sn_flux_density(time, redshift, bolometric, "blackbody", frequency=frequency, vej=vej,
+                            temperature_floor=temperature_floor, dl=dl)
+
+
 def gaussian_likelihood_fractional(y, model, sigma_i):
     """GaussianLikelihoodWithFractionalNoise.log_likelihood, likelihoods.py:821-851."""
     with np.errstate(all="ignore"):

@@ -13,7 +13,8 @@ __version__ = "0.1.0"
 all_models_dict = {
     name: getattr(supernova_models, name)
     for name in ("arnett_bolometric", "arnett", "basic_magnetar_powered_bolometric", "basic_magnetar_powered",
-                 "slsn_bolometric", "slsn", "type_1a", "csm_interaction_bolometric", "csm_interaction")
+                 "slsn_bolometric", "slsn", "type_1a", "magnetar_nickel", "csm_interaction_bolometric",
+                 "csm_interaction")
 }
 all_models_dict.update({name: getattr(kilonova_models, name)
                         for name in ("one_component_kilonova_model", "metzger_kilonova_model")})

@@ -9,7 +9,7 @@ import os
 from . import _build
 
 RB_OK, RB_ERR_INVALID, RB_ERR_UNSUPPORTED, RB_ERR_CUDA = 0, -1, -2, -3
-ENGINE_NICKEL, ENGINE_MAGNETAR, ENGINE_CSM = 0, 1, 2
+ENGINE_NICKEL, ENGINE_MAGNETAR, ENGINE_CSM, ENGINE_MAGNETAR_NICKEL = 0, 1, 2, 3
 PREC_F64, PREC_F32 = 0, 1
 NOISE_TYPES = dict(limiting_mag=0, gaussian=1, gaussianmodel=2)
 SED_BOLOMETRIC, SED_BLACKBODY, SED_CUTOFF_BLACKBODY, SED_CUTOFF_LINE = 0, 1, 2, 3
@@ -37,7 +37,7 @@ class SnConfig(C.Structure):
                 ("line_wavelength", C.c_double), ("line_width", C.c_double), ("line_time", C.c_double),
                 ("line_duration", C.c_double), ("line_amplitude", C.c_double), ("precision", C.c_int),
                 ("upper_limits", UpperLimits), ("csm_nn", C.c_double), ("csm_delta", C.c_double),
-                ("csm_efficiency", C.c_double), ("t0", C.c_void_p)]
+                ("csm_efficiency", C.c_double), ("t0", C.c_void_p), ("f_nickel", C.c_void_p)]
 
 
 KN_ONE_COMPONENT, KN_METZGER = 0, 1

@@ -118,9 +118,18 @@ def t0_tensor(params, path, N):
     return torch.from_numpy(np.array(np.broadcast_to(np.asarray(t0, dtype=np.float64), (n,)))).to(path.device)
 
 
+def aux_tensor(params, path, N):
+    """The path's extra per-sample parameter (AUX_PARAM, e.g. f_nickel of magnetar_nickel) as a device tensor [N]."""
+    name = getattr(path, "AUX_PARAM", None)
+    if name is None:
+        return None
+    return t0_tensor({"t0": params[name]}, path, N)
+
+
 def run(spec, time, named, kwargs, params_batch):
     params, N = collect(named, kwargs, params_batch, spec.needed)
     path = spec.build(time, kwargs)
     dev = path.pack(params, N if N is not None else 1)
-    model, _ = path.evaluate(dev, dl=dl_from_kwargs(kwargs, path, N), t0=t0_tensor(params, path, N))
+    model, _ = path.evaluate(dev, dl=dl_from_kwargs(kwargs, path, N), t0=t0_tensor(params, path, N),
+                             aux=aux_tensor(params, path, N))
     return finish(model, N, kwargs)

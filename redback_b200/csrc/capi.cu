@@ -103,6 +103,23 @@ int launch_csm(rb::SnArgs a, const double* t_dev, cudaStream_t st, int sms) {
   return RB_OK;
 }
 
+typedef void (*SnKernelFn)(const rb::SnArgs);
+SnKernelFn sn_kernel_fn(int engine, bool has_t0) {
+  if (engine == RB_ENGINE_MAGNETAR_NICKEL)
+    return has_t0 ? rb::sn_kernel<true, RB_ENGINE_MAGNETAR_NICKEL> : rb::sn_kernel<false, RB_ENGINE_MAGNETAR_NICKEL>;
+  return has_t0 ? rb::sn_kernel<true, 0> : rb::sn_kernel<false, 0>;
+}
+
+cudaError_t sn_kernel_attributes() {
+  cudaError_t err = cudaSuccess;
+  const int engines[2] = {RB_ENGINE_NICKEL, RB_ENGINE_MAGNETAR_NICKEL};
+  for (int e = 0; e < 2 && err == cudaSuccess; ++e)
+    for (int t = 0; t < 2 && err == cudaSuccess; ++t)
+      err = cudaFuncSetAttribute(sn_kernel_fn(engines[e], t != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 220 * 1024);
+  return err;
+}
+
 int sn_block_threads(int64_t E) {
   int b = (int)((E + 31) / 32) * 32;
   if (b < 128) b = 128;
@@ -174,8 +191,10 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
                     const void* out_model, const void* out_logl) {
   if (!cfg) return fail(RB_ERR_INVALID, "rb_sn_eval: null config");
   if (N < 0 || E <= 0 || E > (1 << 24)) return fail(RB_ERR_INVALID, "rb_sn_eval: need N >= 0 and 0 < E <= 2^24");
-  if (cfg->engine != RB_ENGINE_NICKEL && cfg->engine != RB_ENGINE_MAGNETAR && cfg->engine != RB_ENGINE_CSM)
+  if (cfg->engine < RB_ENGINE_NICKEL || cfg->engine > RB_ENGINE_MAGNETAR_NICKEL)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown engine");
+  if (cfg->engine == RB_ENGINE_MAGNETAR_NICKEL && !cfg->f_nickel)
+    return fail(RB_ERR_INVALID, "rb_sn_eval: cfg.f_nickel is required for RB_ENGINE_MAGNETAR_NICKEL");
   if (cfg->engine == RB_ENGINE_CSM) {
     // utils.py:304-310: RegularGridInterpolator raises outside the tabulated range of n
     if (!(cfg->csm_nn >= 6.0 && cfg->csm_nn <= 14.0))
@@ -228,9 +247,7 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [dev] {
-    attr_err = cudaFuncSetAttribute(rb::sn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(rb::sn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_err = sn_kernel_attributes();
     // keep the stream-ordered workspace pool resident across synchronisations (default trims it to 0)
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -271,13 +288,13 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   const size_t smem = sn_smem_bytes(cfg->dense_resolution, E, a.epochs_in_smem != 0);
   if (smem > 220 * 1024) return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution too large for shared memory");
   int occ = 0;
-  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::sn_kernel<false>, threads, smem));
+  const SnKernelFn kern = sn_kernel_fn(cfg->engine, cfg->t0 != nullptr);
+  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (occ < 1) occ = 1;
   // persistent blocks, grid-stride over samples; 4 waves' worth of blocks for load balance at mid-size N
   int64_t grid = (int64_t)sms * occ * 4;
   if (grid > N) grid = N;
-  if (cfg->t0 != nullptr) rb::sn_kernel<true><<<(unsigned)grid, threads, smem, st>>>(a);
-  else rb::sn_kernel<false><<<(unsigned)grid, threads, smem, st>>>(a);
+  kern<<<(unsigned)grid, threads, smem, st>>>(a);
   launch_counter()->fetch_add(3);
   RB_CUDA(cudaGetLastError());
   return RB_OK;
@@ -1101,7 +1118,7 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::sn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_err = sn_kernel_attributes();
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   });
@@ -1139,7 +1156,8 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
   const int ep_in_smem = (sn_smem_bytes(cfg->dense_resolution, NT, true) <= 64 * 1024) ? 1 : 0;
   const size_t sn_smem = sn_smem_bytes(cfg->dense_resolution, NT, ep_in_smem != 0);
   int occ_sn = 1, occ_ph = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sn, rb::sn_kernel<false>, sn_threads, sn_smem);
+  const SnKernelFn sn_kern = sn_kernel_fn(cfg->engine, false);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sn, sn_kern, sn_threads, sn_smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
   if (occ_sn < 1) occ_sn = 1;
   if (occ_ph < 1) occ_ph = 1;
@@ -1160,6 +1178,7 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
     a.N = nc;
     a.E = NT;
     a.params = params + n0;          // SoA rows are N_total apart: handled through the stride below
+    if (cfg->f_nickel) a.cfg.f_nickel = cfg->f_nickel + n0;
     a.dl_cm = dl_cm ? dl_cm + n0 : nullptr;
     a.sigma_param = nullptr;
     a.out_model = nullptr;
@@ -1178,7 +1197,7 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
       if (status != RB_OK) break;
     } else {
       rb::sn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
-      rb::sn_kernel<false><<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_sn * 4), sn_threads, sn_smem, st>>>(a);
+      sn_kern<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_sn * 4), sn_threads, sn_smem, st>>>(a);
     }
     pa.N = nc;
     pa.n_base = n0;

@@ -392,7 +392,10 @@ __device__ __forceinline__ float diffusion_sum_f32(const float4* __restrict__ no
 
 // HAS_T0: per-sample explosion epoch (phase_models.t0_base_model); a separate instantiation so that the plain path
 // keeps its register allocation.
-template <bool HAS_T0>
+// ENGINE: 0 = nickel or magnetar chosen at run time (cfg.engine); RB_ENGINE_MAGNETAR_NICKEL = its own instantiation.
+// (ptxas' register allocation of the hot loop is sensitive to the surrounding code: adding the third engine to the
+// run-time branch cost 4 %, resolving nickel / magnetar at compile time cost the magnetar variant 30 % more spills.)
+template <bool HAS_T0, int ENGINE>
 __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
   extern __shared__ double2 smem2[];
   const int D = a.cfg.dense_resolution;
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
     bool bad = false;
     {
       const double ea = sc[SC_ENG_A], eb = sc[SC_ENG_B];
-      if (a.cfg.engine == RB_ENGINE_NICKEL) {
+      if (ENGINE != RB_ENGINE_MAGNETAR_NICKEL && a.cfg.engine == RB_ENGINE_NICKEL) {
         for (int k = tid; k < D; k += blockDim.x) {                           // supernova_models.py:564-579
           const double x = (k == D - 1) ? t_end : (double)k * step;
           const double y = ea * (6.45e43 * exp_tab(fmax(-x / 8.8, -708.0), tab) +
@@ -448,11 +451,23 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
           ytmp[k] = y;
           bad |= !isfinite(y);
         }
-      } else {
+      } else if (ENGINE != RB_ENGINE_MAGNETAR_NICKEL) {
         for (int k = tid; k < D; k += blockDim.x) {                           // magnetar_models.py:184
           const double x = (k == D - 1) ? t_end : (double)k * step;
           const double den = fma(x, eb, 1.0);
           const double y = ea / (den * den);
+          ytmp[k] = y;
+          bad |= !isfinite(y);
+        }
+      } else {                                                                // magnetar_nickel, :1669-1670
+        // f_nickel * mej (:1669); read here rather than through a 17th scalar slot: the record layout feeds the hot
+        // loop's register allocation
+        const double ec = a.cfg.f_nickel[n] * a.params[RB_SN_MEJ * a.param_stride + n];
+        for (int k = tid; k < D; k += blockDim.x) {
+          const double x = (k == D - 1) ? t_end : (double)k * step;
+          const double den = fma(x, eb, 1.0);
+          const double y = ec * (6.45e43 * exp_tab(fmax(-x / 8.8, -708.0), tab) +
+                                 1.45e43 * exp_tab(fmax(-x / 111.3, -708.0), tab)) + ea / (den * den);
           ytmp[k] = y;
           bad |= !isfinite(y);
         }

@@ -146,9 +146,10 @@ class _FusedPath:
         return out
 
     def evaluate(self, params_dev, dl=None, sigma_param=None, want_model=True, want_logl=False, out_logl=None,
-                 t0=None):
+                 t0=None, aux=None):
         """Launch the fused kernel on the current stream.  Returns (model[N,E] | None, logl[N] | None).
-        `t0`: optional device tensor [N] of explosion epochs (phase_models.t0_base_model; supernova paths only)."""
+        `t0`: optional device tensor [N] of explosion epochs (phase_models.t0_base_model; supernova paths only).
+        `aux`: device tensor [N] of the path's extra per-sample parameter `AUX_PARAM` (f_nickel of magnetar_nickel)."""
         if params_dev.dtype != _F64 or params_dev.dim() != 2 or params_dev.shape[0] != self.NPARAM:
             raise ValueError(f"params_dev must be float64 [{self.NPARAM}, N]")
         params_dev = params_dev.contiguous()
@@ -170,6 +171,11 @@ class _FusedPath:
             if t0.dtype != _F64 or t0.shape != (N,) or not t0.is_contiguous():
                 raise ValueError("t0 must be a contiguous float64 [N] device tensor")
             self.cfg.t0 = t0.data_ptr()
+        aux_name = getattr(self, "AUX_PARAM", None)
+        if aux_name is not None:
+            if aux is None or aux.dtype != _F64 or aux.shape != (N,) or not aux.is_contiguous():
+                raise ValueError(f"this path needs aux = contiguous float64 [N] device tensor of '{aux_name}'")
+            setattr(self.cfg, aux_name, aux.data_ptr())
         try:
             with torch.cuda.device(self.device):
                 rc = self._launch(N, params_dev, dl, self.y if want_logl else None,
@@ -178,6 +184,8 @@ class _FusedPath:
         finally:
             if t0 is not None:
                 self.cfg.t0 = None
+            if aux_name is not None:
+                setattr(self.cfg, aux_name, None)
         _capi.check(rc)
         return model, logl
 
@@ -237,10 +245,17 @@ class SupernovaPath(_FusedPath):
         self.NEEDS_FREQUENCY = sed != _capi.SED_BOLOMETRIC
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength,
                                    absorption_index, cosmology, line, _precision(dtype), csm)
+        self._engine_rows(engine)
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):
         return _capi.lib().rb_sn_eval_f64
+
+    def _engine_rows(self, engine):
+        if engine == _capi.ENGINE_MAGNETAR_NICKEL:
+            # f_nickel and p0 share row 1 of the parameter block: f_nickel travels through cfg.f_nickel instead
+            self.ROWS = {k: v for k, v in _capi.SN_ROWS.items() if k != "f_nickel"}
+            self.AUX_PARAM = "f_nickel"
 
     def _check_time(self, t):
         if self.cfg.engine == _capi.ENGINE_CSM:
@@ -290,6 +305,7 @@ class SupernovaMagPath(SupernovaPath):
         self.NEEDS_FREQUENCY = False
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength, absorption_index,
                                    cosmology, line, 0, csm)
+        self._engine_rows(engine)
         self._setup(time, None, y, sigma, device)
         lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
         # get_optimal_time_array(0.1, 3000, 300) (utils.py:108); csm_interaction: (0.1, 500, 300) (:2095)

@@ -215,7 +215,8 @@ class GaussianLikelihood(_RedbackLikelihood):
             else:
                 sp_dev = torch.from_numpy(np.array(np.broadcast_to(np.asarray(sp, dtype=np.float64), (N,)))).to(path.device)
         _, logl = path.evaluate(dev, dl=_fused.dl_from_kwargs(kw, path, N), sigma_param=sp_dev, want_model=False,
-                                want_logl=True, t0=_fused.t0_tensor(params, path, N))
+                                want_logl=True, t0=_fused.t0_tensor(params, path, N),
+                                aux=_fused.aux_tensor(params, path, N))
         return logl
 
 

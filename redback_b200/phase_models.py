@@ -11,7 +11,8 @@ from . import supernova_models as _sn
 from ._fused import FusedSpec, run
 
 _BASE = {name: getattr(_sn, name) for name in ("arnett_bolometric", "arnett", "basic_magnetar_powered_bolometric",
-                                               "basic_magnetar_powered", "slsn_bolometric", "slsn", "type_1a")}
+                                               "basic_magnetar_powered", "slsn_bolometric", "slsn", "type_1a",
+                                               "magnetar_nickel")}
 
 
 def _check_sorted(time):

@@ -115,6 +115,7 @@ _ARNETT = _spec("arnett", _capi.ENGINE_NICKEL, ("f_nickel",), True, "Blackbody")
 _MAGNETAR_BOLO = _spec("basic_magnetar_powered_bolometric", _capi.ENGINE_MAGNETAR, _MAGNETAR, False, None)
 _MAGNETAR_BB = _spec("basic_magnetar_powered", _capi.ENGINE_MAGNETAR, _MAGNETAR, True, "Blackbody")
 _SLSN = _spec("slsn", _capi.ENGINE_MAGNETAR, _MAGNETAR, True, "CutoffBlackbody")
+_MAGNETAR_NICKEL = _spec("magnetar_nickel", _capi.ENGINE_MAGNETAR_NICKEL, ("f_nickel",) + _MAGNETAR, True, "Blackbody")
 _TYPE_1A = _spec("type_1a", _capi.ENGINE_NICKEL, ("f_nickel",), True, None, fixed_sed=_capi.SED_CUTOFF_LINE)
 
 
@@ -172,6 +173,14 @@ def slsn(time, redshift=None, p0=None, bp=None, mass_ns=None, theta_pb=None, par
                kwargs, params_batch)
 
 
+def magnetar_nickel(time, redshift=None, f_nickel=None, mej=None, p0=None, bp=None, mass_ns=None, theta_pb=None,
+                    params_batch=None, **kwargs):
+    """redback supernova_models.magnetar_nickel (:1628-1711): nickel-cobalt decay + magnetar spin-down through one
+    Diffusion; default sed = Blackbody; mJy / mag."""
+    named = dict(redshift=redshift, f_nickel=f_nickel, mej=mej, p0=p0, bp=bp, mass_ns=mass_ns, theta_pb=theta_pb)
+    return run(_MAGNETAR_NICKEL, time, named, kwargs, params_batch)
+
+
 def type_1a(time, redshift=None, f_nickel=None, mej=None, params_batch=None, **kwargs):
     """redback supernova_models.type_1a (:2229-2314): nickel engine, CutoffBlackbody + absorption/emission
     Line; kwargs line_wavelength, line_width, line_time, line_duration, line_amplitude (scalars); mJy / mag."""
@@ -184,5 +193,5 @@ FUSED = {
     arnett_bolometric: _ARNETT_BOLO, arnett: _ARNETT,
     basic_magnetar_powered_bolometric: _MAGNETAR_BOLO, slsn_bolometric: _MAGNETAR_BOLO,
     basic_magnetar_powered: _MAGNETAR_BB, slsn: _SLSN, type_1a: _TYPE_1A,
-    csm_interaction_bolometric: _CSM_BOLO, csm_interaction: _CSM_BB,
+    csm_interaction_bolometric: _CSM_BOLO, csm_interaction: _CSM_BB, magnetar_nickel: _MAGNETAR_NICKEL,
 }

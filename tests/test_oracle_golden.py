@@ -16,6 +16,8 @@ CASES = {
     "supernova.basic_magnetar_powered":
         lambda t, p, kw: r.basic_magnetar_powered(t, kw["redshift"], frequency=kw["frequency"], **p),
     "supernova.slsn": lambda t, p, kw: r.slsn(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "supernova.magnetar_nickel":
+        lambda t, p, kw: r.magnetar_nickel(t, kw["redshift"], frequency=kw["frequency"], **p),
     "supernova.type_1a": lambda t, p, kw: r.type_1a(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.one_component_kilonova_model":
         lambda t, p, kw: r.one_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),

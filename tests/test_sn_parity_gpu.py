@@ -34,7 +34,7 @@ def test_golden_vectors(rb, golden):
     for name, fn in [("arnett_bolometric", sn.arnett_bolometric), ("slsn_bolometric", sn.slsn_bolometric),
                      ("basic_magnetar_powered_bolometric", sn.basic_magnetar_powered_bolometric),
                      ("arnett", sn.arnett), ("basic_magnetar_powered", sn.basic_magnetar_powered), ("slsn", sn.slsn),
-                     ("type_1a", sn.type_1a)]:
+                     ("type_1a", sn.type_1a), ("magnetar_nickel", sn.magnetar_nickel)]:
         e = golden["supernova." + name]
         t = np.array(e["time"])
         for params, res in zip(e["params"], e["results"]):
@@ -547,3 +547,41 @@ def test_t0_base_model(rb):
            **{k: float(v[0]) for k, v in p.items() if k != "t0"})
     with pytest.raises(NotImplementedError):
         fn(t, mjd0, base_model="tophat_redback", frequency=nu, output_format="flux_density")
+
+
+@pytest.mark.gpu
+def test_magnetar_nickel_prior_draws(rb):
+    """supernova_models.magnetar_nickel (:1628-1681): batch, fused likelihood, magnitudes == scalar calls."""
+    rng = np.random.default_rng(97)
+    t = np.sort(rng.uniform(1, 250, 40))
+    nu = np.where(np.arange(t.size) % 2 == 0, 6.3e14, 4.7e14)
+    N = 24
+    p = h.slsn_prior(rng, N, zmax=1.0)
+    p["f_nickel"] = h.loguniform(rng, 1e-3, 1, N)
+    fn = rb.supernova_models.magnetar_nickel
+    kw = dict(frequency=nu, output_format="flux_density")
+    out = fn(t, params_batch=p, **kw)
+    y = out[2] * 1.02
+    sigma = 0.05 * np.abs(out[2]) + 1e-12
+    logl = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=kw).log_likelihood_batch(p)
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        z = kwi.pop("redshift")
+        ref = r.magnetar_nickel(t, z, frequency=nu, **kwi)
+        tau = np.sqrt(2 * kwi["kappa"] * kwi["mej"] * r.solar_mass / (13.7 * r.speed_of_light * kwi["vej"] * r.km_cgs)) \
+            / r.day_to_s
+        h.assert_close(out[i], ref, 1e-9, h.diffusion_condition(t / (1 + z), tau), what=f"magnetar_nickel sample {i}")
+        ref_l = r.gaussian_likelihood(y, ref, sigma)
+        assert abs(logl[i] - ref_l) <= 1e-6 + 1e-9 * abs(ref_l), (i, logl[i], ref_l)
+    rb.bands.register_synthetic_lsst()
+    bands = np.array(["lsstg", "lsstr", "lssti"])[np.arange(t.size) % 3]
+    pm = {k: v[:3] for k, v in p.items()}
+    mags = fn(t, params_batch=pm, bands=bands, output_format="magnitude")
+    for i in range(3):
+        one = fn(t, bands=bands, output_format="magnitude", **{k: float(v[i]) for k, v in pm.items()})
+        np.testing.assert_array_equal(mags[i], one)
+    # with the nickel switched off the model is basic_magnetar_powered
+    p0 = dict(pm, f_nickel=np.zeros(3))
+    a = fn(t, params_batch=p0, **kw)
+    b = rb.supernova_models.basic_magnetar_powered(t, params_batch={k: v for k, v in pm.items() if k != "f_nickel"}, **kw)
+    np.testing.assert_allclose(a, b, rtol=1e-12)
