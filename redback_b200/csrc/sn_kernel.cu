@@ -341,7 +341,7 @@ __device__ __forceinline__ double diffusion_sum(const double2* __restrict__ node
                                                 const double* __restrict__ tab, int ms, int Dm1, double te,
                                                 double te2, double te_is, double c1) {
   double acc = 0.0;
-#pragma unroll 4
+#pragma unroll 6   // A/B-measured (tools/bench_variants.py): 2: -1.1 %, 3: +0.1 %, 4: base, 6: +0.6 %, 8: +0.2 %
   for (int m = ms; m < kNodes; ++m) {
     const double2 nd = nodes[m];                                            // (xm, xm * dw)
     const double t = te * nd.x;                                             // interaction_processes.py:53
