@@ -34,8 +34,15 @@ typedef enum {
 /* ---- luminosity engines: redback/transient_models/supernova_models.py:564-579 (_nickelcobalt_engine),
  *      redback/transient_models/magnetar_models.py:171-185 (basic_magnetar) ---------------------- */
 enum { RB_ENGINE_NICKEL = 0, RB_ENGINE_MAGNETAR = 1, RB_ENGINE_CSM = 2,
-       RB_ENGINE_MAGNETAR_NICKEL = 3 /* magnetar_nickel (supernova_models.py:1628-1681): both engines summed; the
-                                        magnetar rows as for RB_ENGINE_MAGNETAR, f_nickel through cfg.f_nickel */ };
+       RB_ENGINE_MAGNETAR_NICKEL = 3, /* magnetar_nickel (supernova_models.py:1628-1681): both engines summed; the
+                                         magnetar rows as for RB_ENGINE_MAGNETAR, f_nickel through cfg.f_nickel */
+       RB_ENGINE_MAGNETAR_ONLY = 4,   /* general_magnetar_slsn (:2379-2440): l0 (1 + t/tsd)^((1+nn)/(1-nn));
+                                         rows 1-3 = l0 [erg/s], tsd [d], nn */
+       RB_ENGINE_EXP_POWERLAW = 5,    /* sn_exponential_powerlaw (:357-381, :501-560; phenomenological_models.py:743-754):
+                                         lbol_0 (1 - e^(-t/tp))^a1 (t/tp)^(-a2); rows 1-4 = lbol_0, alpha_1, alpha_2,
+                                         tpeak_d */
+       RB_ENGINE_TDE_FALLBACK = 6     /* tde_analytical (tde_models.py:16-27, 682-760): l0 / (max(t, t0) 86400 s)^(5/3);
+                                         rows 1-2 = l0, t_0_turn [d] */ };
 enum { RB_PREC_F64 = 0, RB_PREC_F32 = 1 };
 
 /* ---- output stage: bolometric models return L_bol; flux_density models go through

@@ -74,6 +74,11 @@ KEEP = [
     "supernova.magnetar_nickel",
     "kilonova.one_component_kilonova_model", "kilonova.metzger_kilonova_model",
     "magnetar.basic_magnetar",
+    "magnetar.basic_mergernova", "magnetar.general_mergernova", "magnetar.general_mergernova_thermalisation",
+    "magnetar.trapped_magnetar", "magnetar.magnetar_only",
+    "supernova.general_magnetar_slsn", "supernova.sn_exponential_powerlaw", "supernova.exponential_powerlaw_bolometric",
+    "supernova.sn_fallback", "supernova.sn_nickel_fallback", "supernova.homologous_expansion_supernova",
+    "supernova.thin_shell_supernova", "tde.tde_analytical", "tde.tde_analytical_bolometric",
 ]
 
 

@@ -320,6 +320,85 @@ def slsn(time, redshift, p0, bp, mass_ns, theta_pb, *, frequency, mej, vej, kapp
         cutoff_wavelength=cutoff_wavelength, absorption_index=absorption_index)
 
 
+def _diffused(engine, time, *, mej, vej, kappa, kappa_gamma, dense_resolution=1000):
+    """engine(dense_times) -> Diffusion on np.linspace(0, time[-1] + 100, dense_resolution) (the pattern of
+    supernova_models.py:373-379, 2392-2400, tde_models.py:693-700)."""
+    dense = np.linspace(0, time[-1] + 100, dense_resolution)
+    with np.errstate(all="ignore"):
+        lum = engine(dense)
+    return diffusion(time, dense, lum, kappa, kappa_gamma, mej, vej)[1]
+
+
+def exponential_powerlaw(time, a_1, alpha_1, alpha_2, tpeak):
+    """phenomenological_models.exponential_powerlaw (:743-754)."""
+    return a_1 * (1 - np.exp(-time / tpeak)) ** alpha_1 * (time / tpeak) ** (-alpha_2)
+
+
+def analytic_fallback(time, l0, t_0):
+    """tde_models._analytic_fallback (:16-27)."""
+    mask = time - t_0 > 0.
+    lbol = np.zeros(len(time))
+    lbol[mask] = l0 / (time[mask] * 86400) ** (5. / 3.)
+    lbol[~mask] = l0 / (t_0 * 86400) ** (5. / 3.)
+    return lbol
+
+
+def general_magnetar_slsn_bolometric(time, l0, tsd, nn, **dkw):
+    """supernova_models.general_magnetar_slsn_bolometric (:2379-2401)."""
+    return _diffused(lambda d: magnetar_only(d * day_to_s, l0, tsd * day_to_s, nn), np.asarray(time, dtype=float), **dkw)
+
+
+def exponential_powerlaw_bolometric(time, lbol_0, alpha_1, alpha_2, tpeak_d, **dkw):
+    """supernova_models.exponential_powerlaw_bolometric (:357-381)."""
+    return _diffused(lambda d: exponential_powerlaw(d, lbol_0, alpha_1, alpha_2, tpeak_d),
+                     np.asarray(time, dtype=float), **dkw)
+
+
+def tde_analytical_bolometric(time, l0, t_0_turn, **dkw):
+    """tde_models.tde_analytical_bolometric (:682-701)."""
+    return _diffused(lambda d: analytic_fallback(d, l0, t_0_turn), np.asarray(time, dtype=float), **dkw)
+
+
+def _diffused_flux_density(bolometric, sed, time, redshift, *, frequency, mej, vej, kappa, kappa_gamma,
+                           temperature_floor, dl=None, dense_resolution=1000, **sed_kw):
+    return _sn_flux_density(
+        time, redshift,
+        lambda t: bolometric(t, mej=mej, vej=vej, kappa=kappa, kappa_gamma=kappa_gamma, dense_resolution=dense_resolution),
+        sed, frequency=frequency, vej=vej, temperature_floor=temperature_floor, dl=dl, **sed_kw)
+
+
+def general_magnetar_slsn(time, redshift, l0, tsd, nn, **kw):
+    """supernova_models.general_magnetar_slsn (:2404-2440), flux_density, Blackbody."""
+    return _diffused_flux_density(lambda t, **d: general_magnetar_slsn_bolometric(t, l0, tsd, nn, **d), "blackbody",
+                                  time, redshift, **kw)
+
+
+def sn_exponential_powerlaw(time, redshift, lbol_0, alpha_1, alpha_2, tpeak_d, **kw):
+    """supernova_models.sn_exponential_powerlaw (:501-560), flux_density, Blackbody."""
+    return _diffused_flux_density(
+        lambda t, **d: exponential_powerlaw_bolometric(t, lbol_0, alpha_1, alpha_2, tpeak_d, **d), "blackbody", time,
+        redshift, **kw)
+
+
+def tde_analytical(time, redshift, l0, t_0_turn, **kw):
+    """tde_models.tde_analytical (:704-760), flux_density, CutoffBlackbody (cutoff_wavelength 3000 A by default)."""
+    return _diffused_flux_density(lambda t, **d: tde_analytical_bolometric(t, l0, t_0_turn, **d), "cutoff_blackbody",
+                                  time, redshift, **kw)
+
+
+def velocity_from_kinetic_energy(mej, ek, thin_shell=False):
+    """supernova_models.py:1727 (homologous expansion) / :1763 (thin shell), km/s."""
+    if thin_shell:
+        return np.sqrt(2.0 * ek / (mej * solar_mass)) / km_cgs
+    return np.sqrt(10.0 * ek / (3.0 * mej * solar_mass)) / km_cgs
+
+
+def homologous_expansion_supernova(time, redshift, mej, ek, *, thin_shell=False, **kw):
+    """supernova_models.homologous_expansion_supernova (:1782-1844) / thin_shell_supernova (:1847-1905) with the
+    default base model arnett_bolometric."""
+    return arnett(time, redshift, kw.pop("f_nickel"), mej, vej=velocity_from_kinetic_energy(mej, ek, thin_shell), **kw)
+
+
 def t0_base_model(time, t0, base, output_format="flux_density", **kw):
     """phase_models.t0_base_model (phase_models.py:19-59): `base(transient_time, frequency=..., bands=...)` is one of
     the restated models; astropy's `(Time(time, 'mjd') - Time(t0, 'mjd')).to(day)` is the double-double difference of

@@ -2,7 +2,7 @@
 likelihood API.  The CUDA library is the only compute path; importing the package does
 not need a GPU, calling it does."""
 from . import (_capi, afterglow_models, bands, engine, kilonova_models, likelihoods,  # noqa: F401
-               magnetar_driven_ejecta_models, phase_models, simulate, supernova_models)
+               magnetar_driven_ejecta_models, phase_models, simulate, supernova_models, tde_models)
 from .likelihoods import (GaussianLikelihood, GaussianLikelihoodQuadratureNoise,  # noqa: F401
                           GaussianLikelihoodWithFractionalNoise, GaussianLikelihoodWithSystematicNoise,
                           GaussianLikelihoodWithUpperLimits, MixtureGaussianLikelihood)
@@ -14,10 +14,14 @@ all_models_dict = {
     name: getattr(supernova_models, name)
     for name in ("arnett_bolometric", "arnett", "basic_magnetar_powered_bolometric", "basic_magnetar_powered",
                  "slsn_bolometric", "slsn", "type_1a", "magnetar_nickel", "csm_interaction_bolometric",
-                 "csm_interaction")
+                 "csm_interaction", "general_magnetar_slsn_bolometric", "general_magnetar_slsn",
+                 "exponential_powerlaw_bolometric", "sn_exponential_powerlaw",
+                 "homologous_expansion_supernova_model_bolometric", "homologous_expansion_supernova",
+                 "thin_shell_supernova_model_bolometric", "thin_shell_supernova")
 }
 all_models_dict.update({name: getattr(kilonova_models, name)
                         for name in ("one_component_kilonova_model", "metzger_kilonova_model")})
 all_models_dict.update({fn.__name__: fn for fn in afterglow_models.FUSED})
 all_models_dict.update({fn.__name__: fn for fn in magnetar_driven_ejecta_models.FUSED})
+all_models_dict.update({fn.__name__: fn for fn in tde_models.FUSED})
 all_models_dict["t0_base_model"] = phase_models.t0_base_model

@@ -10,6 +10,7 @@ from . import _build
 
 RB_OK, RB_ERR_INVALID, RB_ERR_UNSUPPORTED, RB_ERR_CUDA = 0, -1, -2, -3
 ENGINE_NICKEL, ENGINE_MAGNETAR, ENGINE_CSM, ENGINE_MAGNETAR_NICKEL = 0, 1, 2, 3
+ENGINE_MAGNETAR_ONLY, ENGINE_EXP_POWERLAW, ENGINE_TDE_FALLBACK = 4, 5, 6
 PREC_F64, PREC_F32 = 0, 1
 NOISE_TYPES = dict(limiting_mag=0, gaussian=1, gaussianmodel=2)
 SED_BOLOMETRIC, SED_BLACKBODY, SED_CUTOFF_BLACKBODY, SED_CUTOFF_LINE = 0, 1, 2, 3
@@ -17,7 +18,10 @@ SIGMA_FIXED, SIGMA_SAMPLED, SIGMA_QUADRATURE, SIGMA_FRACTIONAL, SIGMA_SYSTEMATIC
 
 SN_ROWS = dict(redshift=0, f_nickel=1, p0=1, bp=2, mass_ns=3, theta_pb=4, mej=5, vej=6, kappa=7,
                kappa_gamma=8, temperature_floor=9,
-               csm_mass=1, eta=2, rho=3, r0=4)     # RB_ENGINE_CSM reuses the engine rows
+               csm_mass=1, eta=2, rho=3, r0=4,     # RB_ENGINE_CSM reuses the engine rows
+               l0=1, tsd=2, nn=3,                  # RB_ENGINE_MAGNETAR_ONLY
+               lbol_0=1, alpha_1=2, alpha_2=3, tpeak_d=4,   # RB_ENGINE_EXP_POWERLAW
+               t_0_turn=2)                         # RB_ENGINE_TDE_FALLBACK (l0 in row 1)
 SN_NPARAM = 10
 
 

@@ -8,11 +8,15 @@ from .engine import batch_size
 
 
 class FusedSpec:
-    def __init__(self, name, needed, build, validate=None):
+    def __init__(self, name, needed, build, validate=None, transform=None):
         self.name = name
         self.needed = tuple(needed)          # parameter names, in any order
         self._build = build                  # (time, kwargs, y, sigma, sigma_mode) -> path
         self._validate = validate            # kwargs -> None (raises like the reference)
+        self._transform = transform          # {name: value} -> {name: value}: derived parameters (e.g. ek -> vej)
+
+    def transform(self, params):
+        return params if self._transform is None else self._transform(params)
 
     def validate(self, kwargs):
         if self._validate is not None:
@@ -128,6 +132,7 @@ def aux_tensor(params, path, N):
 
 def run(spec, time, named, kwargs, params_batch):
     params, N = collect(named, kwargs, params_batch, spec.needed)
+    params = spec.transform(params)
     path = spec.build(time, kwargs)
     dev = path.pack(params, N if N is not None else 1)
     model, _ = path.evaluate(dev, dl=dl_from_kwargs(kwargs, path, N), t0=t0_tensor(params, path, N),

@@ -105,15 +105,25 @@ int launch_csm(rb::SnArgs a, const double* t_dev, cudaStream_t st, int sms) {
 
 typedef void (*SnKernelFn)(const rb::SnArgs);
 SnKernelFn sn_kernel_fn(int engine, bool has_t0) {
-  if (engine == RB_ENGINE_MAGNETAR_NICKEL)
-    return has_t0 ? rb::sn_kernel<true, RB_ENGINE_MAGNETAR_NICKEL> : rb::sn_kernel<false, RB_ENGINE_MAGNETAR_NICKEL>;
-  return has_t0 ? rb::sn_kernel<true, 0> : rb::sn_kernel<false, 0>;
+  switch (engine) {
+    case RB_ENGINE_MAGNETAR_NICKEL:
+      return has_t0 ? rb::sn_kernel<true, RB_ENGINE_MAGNETAR_NICKEL> : rb::sn_kernel<false, RB_ENGINE_MAGNETAR_NICKEL>;
+    case RB_ENGINE_MAGNETAR_ONLY:
+      return has_t0 ? rb::sn_kernel<true, RB_ENGINE_MAGNETAR_ONLY> : rb::sn_kernel<false, RB_ENGINE_MAGNETAR_ONLY>;
+    case RB_ENGINE_EXP_POWERLAW:
+      return has_t0 ? rb::sn_kernel<true, RB_ENGINE_EXP_POWERLAW> : rb::sn_kernel<false, RB_ENGINE_EXP_POWERLAW>;
+    case RB_ENGINE_TDE_FALLBACK:
+      return has_t0 ? rb::sn_kernel<true, RB_ENGINE_TDE_FALLBACK> : rb::sn_kernel<false, RB_ENGINE_TDE_FALLBACK>;
+    default:
+      return has_t0 ? rb::sn_kernel<true, 0> : rb::sn_kernel<false, 0>;
+  }
 }
 
 cudaError_t sn_kernel_attributes() {
   cudaError_t err = cudaSuccess;
-  const int engines[2] = {RB_ENGINE_NICKEL, RB_ENGINE_MAGNETAR_NICKEL};
-  for (int e = 0; e < 2 && err == cudaSuccess; ++e)
+  const int engines[5] = {RB_ENGINE_NICKEL, RB_ENGINE_MAGNETAR_NICKEL, RB_ENGINE_MAGNETAR_ONLY, RB_ENGINE_EXP_POWERLAW,
+                          RB_ENGINE_TDE_FALLBACK};
+  for (int e = 0; e < 5 && err == cudaSuccess; ++e)
     for (int t = 0; t < 2 && err == cudaSuccess; ++t)
       err = cudaFuncSetAttribute(sn_kernel_fn(engines[e], t != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  220 * 1024);
@@ -191,7 +201,7 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
                     const void* out_model, const void* out_logl) {
   if (!cfg) return fail(RB_ERR_INVALID, "rb_sn_eval: null config");
   if (N < 0 || E <= 0 || E > (1 << 24)) return fail(RB_ERR_INVALID, "rb_sn_eval: need N >= 0 and 0 < E <= 2^24");
-  if (cfg->engine < RB_ENGINE_NICKEL || cfg->engine > RB_ENGINE_MAGNETAR_NICKEL)
+  if (cfg->engine < RB_ENGINE_NICKEL || cfg->engine > RB_ENGINE_TDE_FALLBACK)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown engine");
   if (cfg->engine == RB_ENGINE_MAGNETAR_NICKEL && !cfg->f_nickel)
     return fail(RB_ERR_INVALID, "rb_sn_eval: cfg.f_nickel is required for RB_ENGINE_MAGNETAR_NICKEL");
@@ -209,6 +219,8 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sigma_mode");
   if (cfg->precision != RB_PREC_F64 && cfg->precision != RB_PREC_F32)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown precision");
+  if (cfg->precision == RB_PREC_F32 && cfg->engine >= RB_ENGINE_EXP_POWERLAW)
+    return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: the FP32 quadrature needs a monotonically decreasing engine");
   if (cfg->dense_resolution < 2 || cfg->dense_resolution > 8000)
     return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution must be in [2, 8000]");
   if (!params || !t_obs) return fail(RB_ERR_INVALID, "rb_sn_eval: params and t_obs are required");

@@ -155,6 +155,9 @@ __global__ void sn_prep_kernel(const SnArgs a) {
   if (a.cfg.engine == RB_ENGINE_NICKEL) {
     S[SC_ENG_A] = P[RB_SN_F_NICKEL * N] * mej;                                 // supernova_models.py:577
     S[SC_ENG_B] = 0.0;
+  } else if (a.cfg.engine >= RB_ENGINE_MAGNETAR_ONLY) {
+    S[SC_ENG_A] = 0.0;                 // these engines read their parameter rows inside the kernel
+    S[SC_ENG_B] = 0.0;
   } else {
     // magnetar_models.py:181-184 with time in seconds (supernova_models.py:1466)
     const double p0 = P[RB_SN_P0 * N], bp = P[RB_SN_BP * N];
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
     bool bad = false;
     {
       const double ea = sc[SC_ENG_A], eb = sc[SC_ENG_B];
-      if (ENGINE != RB_ENGINE_MAGNETAR_NICKEL && a.cfg.engine == RB_ENGINE_NICKEL) {
+      if (ENGINE == 0 && a.cfg.engine == RB_ENGINE_NICKEL) {
         for (int k = tid; k < D; k += blockDim.x) {                           // supernova_models.py:564-579
           const double x = (k == D - 1) ? t_end : (double)k * step;
           const double y = ea * (6.45e43 * exp_tab(fmax(-x / 8.8, -708.0), tab) +
@@ -451,11 +454,38 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
           ytmp[k] = y;
           bad |= !isfinite(y);
         }
-      } else if (ENGINE != RB_ENGINE_MAGNETAR_NICKEL) {
+      } else if (ENGINE == 0) {
         for (int k = tid; k < D; k += blockDim.x) {                           // magnetar_models.py:184
           const double x = (k == D - 1) ? t_end : (double)k * step;
           const double den = fma(x, eb, 1.0);
           const double y = ea / (den * den);
+          ytmp[k] = y;
+          bad |= !isfinite(y);
+        }
+      } else if (ENGINE == RB_ENGINE_MAGNETAR_ONLY) {                         // magnetar_models.py:143, :2391
+        const double l0 = a.params[1 * a.param_stride + n], tsd = a.params[2 * a.param_stride + n];
+        const double nn = a.params[3 * a.param_stride + n];
+        const double pw = (1. + nn) / (1. - nn), tau_s = tsd * kDay;
+        for (int k = tid; k < D; k += blockDim.x) {
+          const double x = (k == D - 1) ? t_end : (double)k * step;
+          const double y = l0 * pow(1. + (x * kDay) / tau_s, pw);
+          ytmp[k] = y;
+          bad |= !isfinite(y);
+        }
+      } else if (ENGINE == RB_ENGINE_EXP_POWERLAW) {                          // phenomenological_models.py:753
+        const double a1 = a.params[1 * a.param_stride + n], al1 = a.params[2 * a.param_stride + n];
+        const double al2 = a.params[3 * a.param_stride + n], tp = a.params[4 * a.param_stride + n];
+        for (int k = tid; k < D; k += blockDim.x) {
+          const double x = (k == D - 1) ? t_end : (double)k * step;
+          const double y = a1 * pow(1 - exp(-x / tp), al1) * pow(x / tp, -al2);    // NaN at t = 0, as in the reference
+          ytmp[k] = y;
+          bad |= !isfinite(y);
+        }
+      } else if (ENGINE == RB_ENGINE_TDE_FALLBACK) {                          // tde_models.py:23-26
+        const double l0 = a.params[1 * a.param_stride + n], tt = a.params[2 * a.param_stride + n];
+        for (int k = tid; k < D; k += blockDim.x) {
+          const double x = (k == D - 1) ? t_end : (double)k * step;
+          const double y = (x - tt > 0.) ? l0 / pow(x * 86400, 5. / 3.) : l0 / pow(tt * 86400, 5. / 3.);
           ytmp[k] = y;
           bad |= !isfinite(y);
         }

@@ -17,6 +17,7 @@ from . import kilonova_models as _kn
 from . import magnetar_driven_ejecta_models as _mn
 from . import phase_models as _ph
 from . import supernova_models as _sn
+from . import tde_models as _tde
 from .engine import batch_size, gaussian_logl
 
 FUSED = {}
@@ -25,6 +26,7 @@ FUSED.update(_kn.FUSED)
 FUSED.update(_ag.FUSED)
 FUSED.update(_mn.FUSED)
 FUSED.update(_ph.FUSED)
+FUSED.update(_tde.FUSED)
 
 
 def infer_parameters_from_function(func):
@@ -207,6 +209,7 @@ class GaussianLikelihood(_RedbackLikelihood):
                 self._path[1].set_upper_limits(level, ul_mag)
         path = self._path[1]
         params, _ = _fused.collect(merged, kw, None, spec.needed)
+        params = spec.transform(params)
         dev = path.pack(params, N)
         sp_dev = None
         if sp is not None:

@@ -173,6 +173,37 @@ def slsn(time, redshift=None, p0=None, bp=None, mass_ns=None, theta_pb=None, par
                kwargs, params_batch)
 
 
+_MAGNETAR_ONLY_BOLO = _spec("general_magnetar_slsn_bolometric", _capi.ENGINE_MAGNETAR_ONLY, ("l0", "tsd", "nn"), False, None)
+_MAGNETAR_ONLY = _spec("general_magnetar_slsn", _capi.ENGINE_MAGNETAR_ONLY, ("l0", "tsd", "nn"), True, "Blackbody")
+_EXP_PL = ("lbol_0", "alpha_1", "alpha_2", "tpeak_d")
+_EXP_PL_BOLO = _spec("exponential_powerlaw_bolometric", _capi.ENGINE_EXP_POWERLAW, _EXP_PL, False, None)
+_EXP_PL_BB = _spec("sn_exponential_powerlaw", _capi.ENGINE_EXP_POWERLAW, _EXP_PL, True, "Blackbody")
+
+
+def general_magnetar_slsn_bolometric(time, l0=None, tsd=None, nn=None, params_batch=None, **kwargs):
+    """redback supernova_models.general_magnetar_slsn_bolometric (:2379-2401): magnetar_only engine + Diffusion."""
+    return run(_MAGNETAR_ONLY_BOLO, time, dict(l0=l0, tsd=tsd, nn=nn), kwargs, params_batch)
+
+
+def general_magnetar_slsn(time, redshift=None, l0=None, tsd=None, nn=None, params_batch=None, **kwargs):
+    """redback supernova_models.general_magnetar_slsn (:2404-2460); default sed = Blackbody; mJy / mag."""
+    return run(_MAGNETAR_ONLY, time, dict(redshift=redshift, l0=l0, tsd=tsd, nn=nn), kwargs, params_batch)
+
+
+def exponential_powerlaw_bolometric(time, lbol_0=None, alpha_1=None, alpha_2=None, tpeak_d=None, params_batch=None,
+                                    **kwargs):
+    """redback supernova_models.exponential_powerlaw_bolometric (:357-381)."""
+    named = dict(lbol_0=lbol_0, alpha_1=alpha_1, alpha_2=alpha_2, tpeak_d=tpeak_d)
+    return run(_EXP_PL_BOLO, time, named, kwargs, params_batch)
+
+
+def sn_exponential_powerlaw(time, redshift=None, lbol_0=None, alpha_1=None, alpha_2=None, tpeak_d=None,
+                            params_batch=None, **kwargs):
+    """redback supernova_models.sn_exponential_powerlaw (:501-560); default sed = Blackbody."""
+    named = dict(redshift=redshift, lbol_0=lbol_0, alpha_1=alpha_1, alpha_2=alpha_2, tpeak_d=tpeak_d)
+    return run(_EXP_PL_BB, time, named, kwargs, params_batch)
+
+
 def magnetar_nickel(time, redshift=None, f_nickel=None, mej=None, p0=None, bp=None, mass_ns=None, theta_pb=None,
                     params_batch=None, **kwargs):
     """redback supernova_models.magnetar_nickel (:1628-1711): nickel-cobalt decay + magnetar spin-down through one
@@ -194,4 +225,85 @@ FUSED = {
     basic_magnetar_powered_bolometric: _MAGNETAR_BOLO, slsn_bolometric: _MAGNETAR_BOLO,
     basic_magnetar_powered: _MAGNETAR_BB, slsn: _SLSN, type_1a: _TYPE_1A,
     csm_interaction_bolometric: _CSM_BOLO, csm_interaction: _CSM_BB, magnetar_nickel: _MAGNETAR_NICKEL,
+    general_magnetar_slsn_bolometric: _MAGNETAR_ONLY_BOLO, general_magnetar_slsn: _MAGNETAR_ONLY,
+    exponential_powerlaw_bolometric: _EXP_PL_BOLO, sn_exponential_powerlaw: _EXP_PL_BB,
 }
+
+
+# ---- kinetic-energy parameterisations (supernova_models.py:1708-1905): vej derived from ek and mej ---------------
+_SOLAR_MASS, _KM = 1.988409870698051e33, 100000.0
+_EK_BASES = {"arnett_bolometric": (arnett_bolometric, arnett),
+             "basic_magnetar_powered_bolometric": (basic_magnetar_powered_bolometric, basic_magnetar_powered),
+             "slsn_bolometric": (slsn_bolometric, basic_magnetar_powered),    # the wrapper's default sed is Blackbody
+             "general_magnetar_slsn_bolometric": (general_magnetar_slsn_bolometric, general_magnetar_slsn),
+             "exponential_powerlaw_bolometric": (exponential_powerlaw_bolometric, sn_exponential_powerlaw)}
+
+
+def _velocity_from_ek(factor):
+    def transform(params):
+        import numpy as np
+        import torch
+        params = dict(params)
+        ek, mej = params.pop("ek"), params["mej"]
+        if isinstance(ek, torch.Tensor) or isinstance(mej, torch.Tensor):
+            ek, mej = torch.as_tensor(ek, dtype=torch.float64), torch.as_tensor(mej, dtype=torch.float64)
+            params["vej"] = torch.sqrt(factor[0] * ek / (factor[1] * mej * _SOLAR_MASS)) / _KM
+        else:
+            params["vej"] = np.sqrt(factor[0] * np.asarray(ek, dtype=np.float64)
+                                    / (factor[1] * np.asarray(mej, dtype=np.float64) * _SOLAR_MASS)) / _KM
+        return params
+    return transform
+
+
+class _EkSpec:
+    """FusedSpec of the base model with `vej` replaced by `ek` (resolved from kwargs['base_model'])."""
+
+    def __init__(self, name, factor, full):
+        self.name, self.factor, self.full = name, factor, full
+
+    def for_kwargs(self, kwargs):
+        base_model = kwargs.get("base_model", "arnett_bolometric")
+        key = base_model if isinstance(base_model, str) else getattr(base_model, "__name__", None)
+        if key not in _EK_BASES:
+            raise ValueError("Please choose a different base model")     # supernova_models.py:1724-1726
+        base = FUSED[_EK_BASES[key][1 if self.full else 0]]
+        needed = tuple(n for n in base.needed if n != "vej") + ("ek",)
+
+        def strip(kw):
+            return {k: v for k, v in kw.items() if k != "base_model"}
+        return FusedSpec(f"{self.name}:{key}", needed,
+                         lambda time, kw, y, sigma, sigma_mode: base.build(time, strip(kw), y=y, sigma=sigma,
+                                                                           sigma_mode=sigma_mode),
+                         lambda kw: base.validate(strip(kw)), _velocity_from_ek(self.factor))
+
+
+_HOMOLOGOUS_BOLO = _EkSpec("homologous_expansion_supernova_model_bolometric", (10.0, 3.0), False)
+_HOMOLOGOUS = _EkSpec("homologous_expansion_supernova", (10.0, 3.0), True)
+_THIN_SHELL_BOLO = _EkSpec("thin_shell_supernova_model_bolometric", (2.0, 1.0), False)
+_THIN_SHELL = _EkSpec("thin_shell_supernova", (2.0, 1.0), True)
+
+
+def homologous_expansion_supernova_model_bolometric(time, mej=None, ek=None, params_batch=None, **kwargs):
+    """redback supernova_models.homologous_expansion_supernova_model_bolometric (:1708-1741):
+    vej = sqrt(10 ek / (3 mej)); kwargs base_model (default 'arnett_bolometric') + its parameters."""
+    return run(_HOMOLOGOUS_BOLO.for_kwargs(kwargs), time, dict(mej=mej, ek=ek), kwargs, params_batch)
+
+
+def thin_shell_supernova_model_bolometric(time, mej=None, ek=None, params_batch=None, **kwargs):
+    """redback supernova_models.thin_shell_supernova_model_bolometric (:1744-1779): vej = sqrt(2 ek / mej)."""
+    return run(_THIN_SHELL_BOLO.for_kwargs(kwargs), time, dict(mej=mej, ek=ek), kwargs, params_batch)
+
+
+def homologous_expansion_supernova(time, redshift=None, mej=None, ek=None, params_batch=None, **kwargs):
+    """redback supernova_models.homologous_expansion_supernova (:1782-1844); default sed = Blackbody."""
+    return run(_HOMOLOGOUS.for_kwargs(kwargs), time, dict(redshift=redshift, mej=mej, ek=ek), kwargs, params_batch)
+
+
+def thin_shell_supernova(time, redshift=None, mej=None, ek=None, params_batch=None, **kwargs):
+    """redback supernova_models.thin_shell_supernova (:1847-1905); default sed = Blackbody."""
+    return run(_THIN_SHELL.for_kwargs(kwargs), time, dict(redshift=redshift, mej=mej, ek=ek), kwargs, params_batch)
+
+
+FUSED.update({homologous_expansion_supernova_model_bolometric: _HOMOLOGOUS_BOLO,
+              homologous_expansion_supernova: _HOMOLOGOUS,
+              thin_shell_supernova_model_bolometric: _THIN_SHELL_BOLO, thin_shell_supernova: _THIN_SHELL})

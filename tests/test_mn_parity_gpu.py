@@ -64,6 +64,23 @@ def test_prior_draws(rb, kind):
         assert abs(logl[i] - ref_l) <= 1e-6 + 1e-8 * abs(ref_l), (i, logl[i], ref_l)
 
 
+def test_reference_golden_vectors(rb):
+    """The reference's own regression vectors (test/reference_results/all_models_reference.pkl.gz) for the three
+    mergernova models, through the drop-in functions."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "all_models_subset.json")) as fh:
+        golden = json.load(fh)
+    for name in ("basic_mergernova", "general_mergernova", "general_mergernova_thermalisation"):
+        e = golden["magnetar." + name]
+        t = np.array(e["time"])
+        for params, res in zip(e["params"], e["results"]):
+            out = getattr(rb.magnetar_driven_ejecta_models, name)(t, **params, **e["eval_kwargs"])
+            # exp(x) - 1 of the reference is ill-conditioned for small x (see _exp_condition): x > 1e-3 here
+            h.assert_close(out, h.golden_array(res), 1e-9, 1e-12, what=name)
+
+
 def test_scalar_call_kwargs_and_errors(rb):
     t = np.geomspace(0.05, 100, 12)
     kw = dict(mej=0.02, beta=0.3, ejecta_radius=3e9, kappa=5.0, n_ism=1e-2, l0=1e47, tau_sd=1e3, nn=3.0,

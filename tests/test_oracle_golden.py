@@ -19,6 +19,26 @@ CASES = {
     "supernova.magnetar_nickel":
         lambda t, p, kw: r.magnetar_nickel(t, kw["redshift"], frequency=kw["frequency"], **p),
     "supernova.type_1a": lambda t, p, kw: r.type_1a(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "magnetar.basic_mergernova":
+        lambda t, p, kw: r.basic_mergernova(t, kw["redshift"], frequency=np.full(t.size, kw["frequency"]), **p),
+    "magnetar.general_mergernova":
+        lambda t, p, kw: r.general_mergernova(t, kw["redshift"], frequency=np.full(t.size, kw["frequency"]), **p),
+    "magnetar.general_mergernova_thermalisation":
+        lambda t, p, kw: r.general_mergernova_thermalisation(t, kw["redshift"],
+                                                             frequency=np.full(t.size, kw["frequency"]), **p),
+    "supernova.general_magnetar_slsn":
+        lambda t, p, kw: r.general_magnetar_slsn(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "supernova.sn_exponential_powerlaw":
+        lambda t, p, kw: r.sn_exponential_powerlaw(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "supernova.exponential_powerlaw_bolometric": lambda t, p, kw: r.exponential_powerlaw_bolometric(t, **p),
+    "supernova.homologous_expansion_supernova":
+        lambda t, p, kw: r.homologous_expansion_supernova(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "supernova.thin_shell_supernova":
+        lambda t, p, kw: r.homologous_expansion_supernova(t, kw["redshift"], frequency=kw["frequency"],
+                                                          thin_shell=True, **p),
+    "tde.tde_analytical": lambda t, p, kw: r.tde_analytical(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "tde.tde_analytical_bolometric": lambda t, p, kw: r.tde_analytical_bolometric(
+        t, **{k: v for k, v in p.items() if k != "temperature_floor"}),
     "kilonova.one_component_kilonova_model":
         lambda t, p, kw: r.one_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.metzger_kilonova_model":

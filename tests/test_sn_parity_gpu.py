@@ -34,8 +34,15 @@ def test_golden_vectors(rb, golden):
     for name, fn in [("arnett_bolometric", sn.arnett_bolometric), ("slsn_bolometric", sn.slsn_bolometric),
                      ("basic_magnetar_powered_bolometric", sn.basic_magnetar_powered_bolometric),
                      ("arnett", sn.arnett), ("basic_magnetar_powered", sn.basic_magnetar_powered), ("slsn", sn.slsn),
-                     ("type_1a", sn.type_1a), ("magnetar_nickel", sn.magnetar_nickel)]:
-        e = golden["supernova." + name]
+                     ("type_1a", sn.type_1a), ("magnetar_nickel", sn.magnetar_nickel),
+                     ("general_magnetar_slsn", sn.general_magnetar_slsn),
+                     ("sn_exponential_powerlaw", sn.sn_exponential_powerlaw),
+                     ("exponential_powerlaw_bolometric", sn.exponential_powerlaw_bolometric),
+                     ("homologous_expansion_supernova", sn.homologous_expansion_supernova),
+                     ("thin_shell_supernova", sn.thin_shell_supernova),
+                     ("tde.tde_analytical", rb.tde_models.tde_analytical),
+                     ("tde.tde_analytical_bolometric", rb.tde_models.tde_analytical_bolometric)]:
+        e = golden[name if "." in name else "supernova." + name]
         t = np.array(e["time"])
         for params, res in zip(e["params"], e["results"]):
             kw = dict(params)
@@ -585,3 +592,61 @@ def test_magnetar_nickel_prior_draws(rb):
     a = fn(t, params_batch=p0, **kw)
     b = rb.supernova_models.basic_magnetar_powered(t, params_batch={k: v for k, v in pm.items() if k != "f_nickel"}, **kw)
     np.testing.assert_allclose(a, b, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_extra_engines_batches(rb):
+    """general_magnetar_slsn / sn_exponential_powerlaw / tde_analytical / kinetic-energy wrappers on batches: rows of
+    a batch equal the oracle, and the fused likelihood equals the oracle's."""
+    rng = np.random.default_rng(101)
+    t = np.sort(rng.uniform(2, 200, 30))
+    nu = np.where(np.arange(t.size) % 2 == 0, 6.3e14, 4.7e14)
+    N = 12
+    diff = dict(mej=h.loguniform(rng, 0.5, 30, N), vej=h.loguniform(rng, 3e3, 3e4, N), kappa=rng.uniform(0.05, 0.5, N),
+                kappa_gamma=h.loguniform(rng, 1e-2, 1e2, N), temperature_floor=h.loguniform(rng, 2e3, 1e4, N))
+    z = rng.uniform(0.01, 0.5, N)
+    cases = [
+        (rb.supernova_models.general_magnetar_slsn, r.general_magnetar_slsn,
+         dict(l0=h.loguniform(rng, 1e43, 1e47, N), tsd=h.loguniform(rng, 1, 100, N), nn=rng.uniform(2.2, 6, N))),
+        (rb.supernova_models.sn_exponential_powerlaw, r.sn_exponential_powerlaw,
+         dict(lbol_0=h.loguniform(rng, 1e42, 1e45, N), alpha_1=rng.uniform(0.5, 3, N), alpha_2=rng.uniform(0.5, 3, N),
+              tpeak_d=rng.uniform(5, 60, N))),
+        (rb.tde_models.tde_analytical, r.tde_analytical,
+         dict(l0=h.loguniform(rng, 1e52, 1e56, N), t_0_turn=rng.uniform(1, 80, N))),
+    ]
+    kw = dict(frequency=nu, output_format="flux_density")
+    for fn, ofn, eng in cases:
+        p = dict(redshift=z, **eng, **diff)
+        out = fn(t, params_batch=p, **kw)
+        y = out[1] * 1.03
+        sigma = 0.1 * np.abs(out[1]) + 1e-12
+        logl = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=kw).log_likelihood_batch(p)
+        for i in range(N):
+            kwi = {k: v[i] for k, v in p.items()}
+            zi = kwi.pop("redshift")
+            ref = ofn(t, zi, frequency=nu, **kwi)
+            tau = np.sqrt(2 * kwi["kappa"] * kwi["mej"] * r.solar_mass
+                          / (13.7 * r.speed_of_light * kwi["vej"] * r.km_cgs)) / r.day_to_s
+            h.assert_close(out[i], ref, 1e-9, h.diffusion_condition(t / (1 + zi), tau), what=f"{fn.__name__} {i}")
+            ref_l = r.gaussian_likelihood(y, ref, sigma)
+            assert abs(logl[i] - ref_l) <= 1e-6 + 1e-9 * abs(ref_l), (fn.__name__, i, logl[i], ref_l)
+    # kinetic-energy wrappers: vej is derived per sample
+    pe = dict(redshift=z, f_nickel=h.loguniform(rng, 1e-2, 1, N), mej=diff["mej"], ek=h.loguniform(rng, 1e50, 1e52, N),
+              kappa=diff["kappa"], kappa_gamma=diff["kappa_gamma"], temperature_floor=diff["temperature_floor"])
+    for fn, thin in ((rb.supernova_models.homologous_expansion_supernova, False),
+                     (rb.supernova_models.thin_shell_supernova, True)):
+        out = fn(t, params_batch=pe, **kw)
+        like = rb.GaussianLikelihood(t, out[0] * 1.01, 0.1 * np.abs(out[0]) + 1e-12, fn, kwargs=kw)
+        logl = like.log_likelihood_batch(pe)
+        for i in range(N):
+            kwi = {k: v[i] for k, v in pe.items()}
+            zi = kwi.pop("redshift")
+            ref = r.homologous_expansion_supernova(t, zi, frequency=nu, thin_shell=thin, **kwi)
+            vej = r.velocity_from_kinetic_energy(kwi["mej"], kwi["ek"], thin)
+            tau = np.sqrt(2 * kwi["kappa"] * kwi["mej"] * r.solar_mass
+                          / (13.7 * r.speed_of_light * vej * r.km_cgs)) / r.day_to_s
+            h.assert_close(out[i], ref, 1e-9, h.diffusion_condition(t / (1 + zi), tau), what=f"{fn.__name__} {i}")
+            ref_l = r.gaussian_likelihood(out[0] * 1.01, ref, 0.1 * np.abs(out[0]) + 1e-12)
+            assert abs(logl[i] - ref_l) <= 1e-6 + 1e-9 * abs(ref_l)
+    with pytest.raises(ValueError):
+        rb.supernova_models.homologous_expansion_supernova(t, params_batch=pe, base_model="type_1c_bolometric", **kw)
