@@ -199,6 +199,8 @@ typedef struct {
   double vmax;                  /* Metzger only, default 0.7 (kilonova_models.py:1997)           */
   rb_cosmology cosmology;       /* used only when dl_cm == NULL                                  */
   rb_upper_limits upper_limits;
+  double grid_t_max;            /* end of the model time grid [s]: 7e6 (kilonova_models.py:1561, default); the
+                                   two-component model uses 86400*6 (:1241)                       */
 } rb_kn_config;
 
 int rb_kn_config_default(rb_kn_config* cfg);

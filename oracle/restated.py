@@ -885,6 +885,40 @@ def one_component_kilonova_model(time, redshift, mej, vej, kappa, *, frequency, 
         return fd * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)
 
 
+def multi_component_kilonova_model(time, redshift, components, *, frequency, dense_resolution, grid_t_max, dl=None):
+    """two_component_kilonova_model (kilonova_models.py:1214-1260: grid end 86400*6 s, 500 points) and
+    three_component_kilonova_model (:1113-1165: 7e6 s, 300 points), flux_density branch: the components'
+    blackbody flux densities are summed.  components: [(mej, vej, kappa, temperature_floor), ...]."""
+    time = np.asarray(time, dtype=float)
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    time_temp = get_optimal_time_array(1e-2, grid_t_max, dense_resolution, user_times=time * day_to_s / (1. + redshift))
+    frequency, t = calc_kcorrected_properties(np.asarray(frequency, dtype=float), redshift, time * day_to_s)
+    ff = np.zeros(len(time))
+    with np.errstate(all="ignore"):
+        for mej, vej, kappa, tfloor in components:
+            _, temperature, r_photosphere = one_component_kilonova_internal(time_temp, mej, vej, kappa, tfloor)
+            ff += blackbody_to_flux_density(interp1d(time_temp, y=temperature)(t), interp1d(time_temp, y=r_photosphere)(t),
+                                            dl, frequency)
+        return ff * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)
+
+
+def two_component_kilonova_model(time, redshift, mej_1, vej_1, temperature_floor_1, kappa_1, mej_2, vej_2,
+                                 temperature_floor_2, kappa_2, *, frequency, dense_resolution=500, dl=None, **_):
+    comps = [(mej_1, vej_1, kappa_1, temperature_floor_1), (mej_2, vej_2, kappa_2, temperature_floor_2)]
+    return multi_component_kilonova_model(time, redshift, comps, frequency=frequency,
+                                          dense_resolution=dense_resolution, grid_t_max=86400 * 6, dl=dl)
+
+
+def three_component_kilonova_model(time, redshift, mej_1, vej_1, temperature_floor_1, kappa_1, mej_2, vej_2,
+                                   temperature_floor_2, kappa_2, mej_3, vej_3, temperature_floor_3, kappa_3, *,
+                                   frequency, dense_resolution=300, dl=None, **_):
+    comps = [(mej_1, vej_1, kappa_1, temperature_floor_1), (mej_2, vej_2, kappa_2, temperature_floor_2),
+             (mej_3, vej_3, kappa_3, temperature_floor_3)]
+    return multi_component_kilonova_model(time, redshift, comps, frequency=frequency,
+                                          dense_resolution=dense_resolution, grid_t_max=7e6, dl=dl)
+
+
 # --------------------------------------------------------------------------------------------------
 # kilonova: Metzger (2017) shell model (kilonova_models.py:1895-1962, 1965-2068)
 # --------------------------------------------------------------------------------------------------

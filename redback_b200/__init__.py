@@ -20,7 +20,8 @@ all_models_dict = {
                  "thin_shell_supernova_model_bolometric", "thin_shell_supernova")
 }
 all_models_dict.update({name: getattr(kilonova_models, name)
-                        for name in ("one_component_kilonova_model", "metzger_kilonova_model")})
+                        for name in ("one_component_kilonova_model", "metzger_kilonova_model",
+                                     "two_component_kilonova_model", "three_component_kilonova_model")})
 all_models_dict.update({fn.__name__: fn for fn in afterglow_models.FUSED})
 all_models_dict.update({fn.__name__: fn for fn in magnetar_driven_ejecta_models.FUSED})
 all_models_dict.update({fn.__name__: fn for fn in tde_models.FUSED})

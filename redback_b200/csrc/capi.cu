@@ -469,6 +469,7 @@ extern "C" int rb_kn_config_default(rb_kn_config* cfg) {
   cfg->dense_resolution = 500;
   cfg->neutron_precursor_switch = 1;
   cfg->vmax = 0.7;
+  cfg->grid_t_max = 7e6;
   return rb_cosmology_planck18(&cfg->cosmology);
 }
 
@@ -485,6 +486,8 @@ static int kn_check(const rb_kn_config* cfg, int64_t N, int64_t E, const void* p
     return fail(RB_ERR_INVALID, "rb_kn_eval: dense_resolution must be in [20, 2000]");
   if (!params || !t_obs || !freq_obs) return fail(RB_ERR_INVALID, "rb_kn_eval: params, t_obs and freq_obs are required");
   if (cfg->model == RB_KN_METZGER && !(cfg->vmax > 0)) return fail(RB_ERR_INVALID, "rb_kn_eval: vmax must be positive");
+  if (!(cfg->grid_t_max > 1.0 && cfg->grid_t_max <= 1e9))
+    return fail(RB_ERR_INVALID, "rb_kn_eval: grid_t_max must be in (1, 1e9] seconds");
   if (y) {
     if (!out_logl) return fail(RB_ERR_INVALID, "rb_kn_eval: y given but out_logl is null");
     if (cfg->sigma_mode != RB_SIGMA_SAMPLED && !sigma) return fail(RB_ERR_INVALID, "rb_kn_eval: sigma is required");

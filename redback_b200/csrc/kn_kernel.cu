@@ -140,7 +140,7 @@ __global__ void kn_prep_kernel(const KnArgs a) {
   S[KS_TFLOOR] = (a.cfg.model == KN_ONE_COMPONENT) ? P[RB_KN_TEMPERATURE_FLOOR * N] : 0.0;
   S[KS_SIGMA] = (a.sigma_param != nullptr && a.want_logl) ? a.sigma_param[n] : 0.0;
   // get_optimal_time_array(1e-2, 7e6, R, user_times = t_obs * 86400 / (1+z))  (utils.py:50-80)
-  const double t_min = 1e-2, t_max = 7e6;
+  const double t_min = 1e-2, t_max = a.cfg.grid_t_max;
   const double user_min = a.tmin_obs * kDay / opz, user_max = a.tmax_obs * kDay / opz;
   const double eval_min = fmax(t_min, user_min * 0.5);
   const double eval_max = fmin(t_max, user_max * 2.0);
@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int model = a.cfg.model, sigma_mode = a.cfg.sigma_mode;
   const bool want_logl = a.want_logl != 0;
+  const double grid_t_max = a.cfg.grid_t_max, log_grid_t_max = log10(a.cfg.grid_t_max);
   for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
   for (int i = tid; i < kEpochCols * E; i += blockDim.x) ep[i] = a.epoch_tab[i];
   __syncthreads();
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
       double t;
       if (k < nb) t = geom_point(1e-2, sc[KS_EMIN], -2.0, sc[KS_LOG_EMIN], nb, k, tab);
       else if (k < nb + nu - 1) t = geom_point(sc[KS_EMIN], sc[KS_EMAX], sc[KS_LOG_EMIN], sc[KS_LOG_EMAX], nu, k - nb + 1, tab);
-      else t = geom_point(sc[KS_EMAX], 7e6, sc[KS_LOG_EMAX], 6.845098040014257, na, k - nb - nu + 2, tab);
+      else t = geom_point(sc[KS_EMAX], grid_t_max, sc[KS_LOG_EMAX], log_grid_t_max, na, k - nb - nu + 2, tab);
       if (nb == 1 && k == 0) t = 1e-2;
       tg[k] = t;
       const double tdays = t / kDay;

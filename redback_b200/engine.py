@@ -279,8 +279,10 @@ class KilonovaPath(_FusedPath):
     NPARAM = _capi.KN_NPARAM
 
     def __init__(self, model, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED,
-                 dense_resolution=500, neutron_precursor_switch=True, vmax=0.7, cosmology=None, device=None):
-        self.cfg = _capi.kn_config(model, sigma_mode, dense_resolution, neutron_precursor_switch, vmax, cosmology)
+                 dense_resolution=500, neutron_precursor_switch=True, vmax=0.7, cosmology=None, device=None,
+                 grid_t_max=7e6):
+        self.cfg = _capi.kn_config(model, sigma_mode, dense_resolution, neutron_precursor_switch, vmax, cosmology,
+                                   grid_t_max)
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):

@@ -48,4 +48,51 @@ def metzger_kilonova_model(time, redshift=None, mej=None, vej=None, beta=None, k
                params_batch)
 
 
+def _multi_component(name, time, redshift, components, params_batch, kwargs, dense_resolution, grid_t_max):
+    """Sum of one-component models on a shared time grid (kilonova_models.py:1113-1260, flux_density branch): one
+    launch of the one-component kernel per component, the flux densities are added on device."""
+    import numpy as np
+    from ._fused import collect, dl_from_kwargs, finish
+    if kwargs.get("output_format") is None:
+        raise KeyError("output_format")
+    if kwargs["output_format"] != "flux_density":
+        raise NotImplementedError(f"{name}: output_format='{kwargs['output_format']}' is not fused on device")
+    names = ["redshift"] + [f"{k}_{c}" for c in range(1, len(components) + 1)
+                            for k in ("mej", "vej", "kappa", "temperature_floor")]
+    named = dict(redshift=redshift)
+    for c, comp in enumerate(components, start=1):
+        named.update({f"{k}_{c}": v for k, v in zip(("mej", "vej", "temperature_floor", "kappa"), comp)})
+    params, N = collect(named, kwargs, params_batch, names)
+    path = KilonovaPath(_capi.KN_ONE_COMPONENT, time, frequency=kwargs.get("frequency"),
+                        dense_resolution=kwargs.get("dense_resolution", dense_resolution),
+                        cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"), grid_t_max=grid_t_max)
+    dl = dl_from_kwargs(kwargs, path, N)
+    total = None
+    for c in range(1, len(components) + 1):
+        comp = dict(redshift=params["redshift"], mej=params[f"mej_{c}"], vej=params[f"vej_{c}"],
+                    kappa=params[f"kappa_{c}"], temperature_floor=params[f"temperature_floor_{c}"])
+        model, _ = path.evaluate(path.pack(comp, N if N is not None else 1), dl=dl)
+        total = model if total is None else total.add_(model)
+    return finish(total, N, kwargs)
+
+
+def two_component_kilonova_model(time, redshift=None, mej_1=None, vej_1=None, temperature_floor_1=None, kappa_1=None,
+                                 mej_2=None, vej_2=None, temperature_floor_2=None, kappa_2=None, params_batch=None,
+                                 **kwargs):
+    """redback kilonova_models.two_component_kilonova_model (:1214-1260), flux_density; grid end 86400*6 s, 500 points
+    by default.  (Not fused with the likelihood: log_likelihood_batch reduces the summed model matrix.)"""
+    comps = [(mej_1, vej_1, temperature_floor_1, kappa_1), (mej_2, vej_2, temperature_floor_2, kappa_2)]
+    return _multi_component("two_component_kilonova_model", time, redshift, comps, params_batch, kwargs, 500,
+                            86400 * 6)
+
+
+def three_component_kilonova_model(time, redshift=None, mej_1=None, vej_1=None, temperature_floor_1=None, kappa_1=None,
+                                   mej_2=None, vej_2=None, temperature_floor_2=None, kappa_2=None, mej_3=None,
+                                   vej_3=None, temperature_floor_3=None, kappa_3=None, params_batch=None, **kwargs):
+    """redback kilonova_models.three_component_kilonova_model (:1113-1165), flux_density; 300 grid points by default."""
+    comps = [(mej_1, vej_1, temperature_floor_1, kappa_1), (mej_2, vej_2, temperature_floor_2, kappa_2),
+             (mej_3, vej_3, temperature_floor_3, kappa_3)]
+    return _multi_component("three_component_kilonova_model", time, redshift, comps, params_batch, kwargs, 300, 7e6)
+
+
 FUSED = {one_component_kilonova_model: _ONE, metzger_kilonova_model: _METZGER}

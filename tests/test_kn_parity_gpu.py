@@ -27,7 +27,9 @@ def _tol_extra(t_obs, z, nu, temp_floor=100.0):
 
 def test_golden_vectors(rb, golden):
     for name, fn in [("one_component_kilonova_model", rb.kilonova_models.one_component_kilonova_model),
-                     ("metzger_kilonova_model", rb.kilonova_models.metzger_kilonova_model)]:
+                     ("metzger_kilonova_model", rb.kilonova_models.metzger_kilonova_model),
+                     ("two_component_kilonova_model", rb.kilonova_models.two_component_kilonova_model),
+                     ("three_component_kilonova_model", rb.kilonova_models.three_component_kilonova_model)]:
         e = golden["kilonova." + name]
         t = np.array(e["time"])
         for params, res in zip(e["params"], e["results"]):
@@ -83,3 +85,36 @@ def test_scalar_call_and_small_resolution(rb):
     h.assert_close(out, ref, RTOL, 1e-9)
     with pytest.raises(ValueError):
         rb.kilonova_models.one_component_kilonova_model(np.array([0.0, 1.0]), 0.02, 0.02, 0.2, 5.0, **kw)
+
+
+def test_multi_component_batches(rb):
+    """two / three_component_kilonova_model (kilonova_models.py:1113-1260): components summed on device, likelihood
+    through the stand-alone reduction."""
+    rng = np.random.default_rng(57)
+    t = np.geomspace(0.2, 5.0, 25)                    # the two-component grid ends at 6 d (source frame)
+    nu = np.array(list(h.LSST_NU.values()))[np.arange(t.size) % 6]
+    N = 10
+    p = dict(redshift=rng.uniform(0.005, 0.1, N))
+    for c in (1, 2, 3):
+        one = h.one_component_prior(rng, N)
+        for k in ("mej", "vej", "kappa", "temperature_floor"):
+            p[f"{k}_{c}"] = one[k]
+    for fn, ofn, ncomp in ((rb.kilonova_models.two_component_kilonova_model, r.two_component_kilonova_model, 2),
+                           (rb.kilonova_models.three_component_kilonova_model, r.three_component_kilonova_model, 3)):
+        pc = {k: v for k, v in p.items() if k == "redshift" or int(k[-1]) <= ncomp}
+        kw = dict(frequency=nu, output_format="flux_density")
+        out = fn(t, params_batch=pc, **kw)
+        y = out[0] * 1.02
+        sigma = 0.1 * np.abs(out[0]) + 1e-12
+        logl = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=kw).log_likelihood_batch(pc)
+        for i in range(N):
+            kwi = {k: v[i] for k, v in pc.items()}
+            z = kwi.pop("redshift")
+            ref = ofn(t, z, frequency=nu, **kwi)
+            h.assert_close(out[i], ref, RTOL, _tol_extra(t, z, nu), what=f"{fn.__name__} sample {i}")
+            ref_l = r.gaussian_likelihood(y, ref, sigma)
+            assert abs(logl[i] - ref_l) <= 1e-6 + 1e-8 * abs(ref_l), (i, logl[i], ref_l)
+    late = rb.kilonova_models.two_component_kilonova_model(
+        np.array([1.0, 9.0]), **{k: float(v[0]) for k, v in p.items() if k == "redshift" or int(k[-1]) <= 2},
+        frequency=4e14, output_format="flux_density")
+    assert np.isfinite(late[0]) and np.isnan(late[1])        # 9 d is beyond the 6 d grid: interp1d raises in the reference

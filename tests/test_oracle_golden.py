@@ -39,6 +39,10 @@ CASES = {
     "tde.tde_analytical": lambda t, p, kw: r.tde_analytical(t, kw["redshift"], frequency=kw["frequency"], **p),
     "tde.tde_analytical_bolometric": lambda t, p, kw: r.tde_analytical_bolometric(
         t, **{k: v for k, v in p.items() if k != "temperature_floor"}),
+    "kilonova.two_component_kilonova_model":
+        lambda t, p, kw: r.two_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "kilonova.three_component_kilonova_model":
+        lambda t, p, kw: r.three_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.one_component_kilonova_model":
         lambda t, p, kw: r.one_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.metzger_kilonova_model":
