@@ -41,8 +41,11 @@ enum { RB_ENGINE_NICKEL = 0, RB_ENGINE_MAGNETAR = 1, RB_ENGINE_CSM = 2,
        RB_ENGINE_EXP_POWERLAW = 5,    /* sn_exponential_powerlaw (:357-381, :501-560; phenomenological_models.py:743-754):
                                          lbol_0 (1 - e^(-t/tp))^a1 (t/tp)^(-a2); rows 1-4 = lbol_0, alpha_1, alpha_2,
                                          tpeak_d */
-       RB_ENGINE_TDE_FALLBACK = 6     /* tde_analytical (tde_models.py:16-27, 682-760): l0 / (max(t, t0) 86400 s)^(5/3);
-                                         rows 1-2 = l0, t_0_turn [d] */ };
+       RB_ENGINE_TDE_FALLBACK = 6,    /* tde_analytical (tde_models.py:16-27, 682-760): l0 / (max(t, t0) 86400 s)^(5/3);
+                                         rows 1-2 = l0, t_0_turn [d] */
+       RB_ENGINE_FALLBACK = 7,        /* sn_fallback (supernova_models.py:383-438; phenomenological_models.py:690-702):
+                                         rows 1-2 = logl1, tr [d]; never diffused (no_interaction implied) */
+       RB_ENGINE_FALLBACK_NICKEL = 8  /* sn_nickel_fallback (:441-498): + nickel-cobalt decay; row 3 = f_nickel */ };
 enum { RB_PREC_F64 = 0, RB_PREC_F32 = 1 };
 
 /* ---- output stage: bolometric models return L_bol; flux_density models go through
@@ -138,6 +141,9 @@ typedef struct {
   const double* t0;
   /* RB_ENGINE_MAGNETAR_NICKEL only: per-sample nickel fraction, DEVICE pointer [N] (row 1 holds p0 there). */
   const double* f_nickel;
+  /* interaction_process=None (supernova_models.py:961-968 and the like): the engine luminosity at the epochs goes
+     straight to the photosphere / SED; mej, kappa, kappa_gamma are then unused. */
+  int no_interaction;
 } rb_sn_config;
 
 /* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */

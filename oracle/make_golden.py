@@ -80,6 +80,7 @@ KEEP = [
     "supernova.sn_fallback", "supernova.sn_nickel_fallback", "supernova.homologous_expansion_supernova",
     "supernova.thin_shell_supernova", "tde.tde_analytical", "tde.tde_analytical_bolometric",
     "kilonova.two_component_kilonova_model", "kilonova.three_component_kilonova_model",
+    "supernova.sn_fallback", "supernova.sn_nickel_fallback",
 ]
 
 

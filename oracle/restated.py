@@ -386,6 +386,35 @@ def tde_analytical(time, redshift, l0, t_0_turn, **kw):
                                   time, redshift, **kw)
 
 
+def fallback_lbol(time, logl1, tr):
+    """phenomenological_models.fallback_lbol (:690-702)."""
+    l1 = 10 ** logl1
+    time = np.asarray(time, dtype=float) * 86400
+    tr = tr * 86400
+    lbol = l1 * time ** (-5. / 3.)
+    lbol[time < tr] = l1 * tr ** (-5. / 3.)
+    return lbol
+
+
+def sn_fallback(time, redshift, logl1, tr, *, frequency, vej, temperature_floor, dl=None, **_):
+    """supernova_models.sn_fallback (:383-412): no interaction process."""
+    return _sn_flux_density(time, redshift, lambda t: fallback_lbol(t, logl1, tr), "blackbody", frequency=frequency,
+                            vej=vej, temperature_floor=temperature_floor, dl=dl)
+
+
+def sn_nickel_fallback(time, redshift, mej, f_nickel, logl1, tr, *, frequency, vej, temperature_floor, dl=None, **_):
+    """supernova_models.sn_nickel_fallback (:441-470)."""
+    return _sn_flux_density(time, redshift,
+                            lambda t: fallback_lbol(t, logl1, tr) + nickelcobalt_engine(t, f_nickel, mej), "blackbody",
+                            frequency=frequency, vej=vej, temperature_floor=temperature_floor, dl=dl)
+
+
+def arnett_no_interaction(time, redshift, f_nickel, mej, *, frequency, vej, temperature_floor, dl=None, **_):
+    """supernova_models.arnett with interaction_process=None (:961-968, 999-1007): the raw engine luminosity."""
+    return _sn_flux_density(time, redshift, lambda t: nickelcobalt_engine(t, f_nickel, mej), "blackbody",
+                            frequency=frequency, vej=vej, temperature_floor=temperature_floor, dl=dl)
+
+
 def velocity_from_kinetic_energy(mej, ek, thin_shell=False):
     """supernova_models.py:1727 (homologous expansion) / :1763 (thin shell), km/s."""
     if thin_shell:

@@ -10,7 +10,7 @@ from . import _build
 
 RB_OK, RB_ERR_INVALID, RB_ERR_UNSUPPORTED, RB_ERR_CUDA = 0, -1, -2, -3
 ENGINE_NICKEL, ENGINE_MAGNETAR, ENGINE_CSM, ENGINE_MAGNETAR_NICKEL = 0, 1, 2, 3
-ENGINE_MAGNETAR_ONLY, ENGINE_EXP_POWERLAW, ENGINE_TDE_FALLBACK = 4, 5, 6
+ENGINE_MAGNETAR_ONLY, ENGINE_EXP_POWERLAW, ENGINE_TDE_FALLBACK, ENGINE_FALLBACK, ENGINE_FALLBACK_NICKEL = 4, 5, 6, 7, 8
 PREC_F64, PREC_F32 = 0, 1
 NOISE_TYPES = dict(limiting_mag=0, gaussian=1, gaussianmodel=2)
 SED_BOLOMETRIC, SED_BLACKBODY, SED_CUTOFF_BLACKBODY, SED_CUTOFF_LINE = 0, 1, 2, 3
@@ -21,7 +21,8 @@ SN_ROWS = dict(redshift=0, f_nickel=1, p0=1, bp=2, mass_ns=3, theta_pb=4, mej=5,
                csm_mass=1, eta=2, rho=3, r0=4,     # RB_ENGINE_CSM reuses the engine rows
                l0=1, tsd=2, nn=3,                  # RB_ENGINE_MAGNETAR_ONLY
                lbol_0=1, alpha_1=2, alpha_2=3, tpeak_d=4,   # RB_ENGINE_EXP_POWERLAW
-               t_0_turn=2)                         # RB_ENGINE_TDE_FALLBACK (l0 in row 1)
+               t_0_turn=2,                         # RB_ENGINE_TDE_FALLBACK (l0 in row 1)
+               logl1=1, tr=2)                      # RB_ENGINE_FALLBACK(_NICKEL); f_nickel of the latter: SN_ROWS_FALLBACK
 SN_NPARAM = 10
 
 
@@ -41,7 +42,8 @@ class SnConfig(C.Structure):
                 ("line_wavelength", C.c_double), ("line_width", C.c_double), ("line_time", C.c_double),
                 ("line_duration", C.c_double), ("line_amplitude", C.c_double), ("precision", C.c_int),
                 ("upper_limits", UpperLimits), ("csm_nn", C.c_double), ("csm_delta", C.c_double),
-                ("csm_efficiency", C.c_double), ("t0", C.c_void_p), ("f_nickel", C.c_void_p)]
+                ("csm_efficiency", C.c_double), ("t0", C.c_void_p), ("f_nickel", C.c_void_p),
+                ("no_interaction", C.c_int)]
 
 
 KN_ONE_COMPONENT, KN_METZGER = 0, 1
@@ -151,7 +153,7 @@ def check(rc):
 
 
 def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
-              absorption_index=1.0, cosmology=None, line=None, precision=0, csm=None):
+              absorption_index=1.0, cosmology=None, line=None, precision=0, csm=None, no_interaction=False):
     cfg = SnConfig()
     check(lib().rb_sn_config_default(C.byref(cfg)))
     cfg.engine, cfg.sed, cfg.sigma_mode = engine, sed, sigma_mode
@@ -164,6 +166,7 @@ def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff
         for key, val in line.items():
             setattr(cfg, key, float(val))
     cfg.precision = int(precision)
+    cfg.no_interaction = int(bool(no_interaction))
     if csm is not None:
         cfg.csm_nn, cfg.csm_delta, cfg.csm_efficiency = (float(csm[k]) for k in ("nn", "delta", "efficiency"))
     return cfg

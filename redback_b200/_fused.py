@@ -8,12 +8,17 @@ from .engine import batch_size
 
 
 class FusedSpec:
-    def __init__(self, name, needed, build, validate=None, transform=None):
+    def __init__(self, name, needed, build, validate=None, transform=None, resolver=None):
+        self._resolver = resolver            # kwargs -> FusedSpec | None: a variant selected by kwargs
         self.name = name
         self.needed = tuple(needed)          # parameter names, in any order
         self._build = build                  # (time, kwargs, y, sigma, sigma_mode) -> path
         self._validate = validate            # kwargs -> None (raises like the reference)
         self._transform = transform          # {name: value} -> {name: value}: derived parameters (e.g. ek -> vej)
+
+    def for_kwargs(self, kwargs):
+        alt = self._resolver(kwargs) if self._resolver is not None else None
+        return self if alt is None else alt
 
     def transform(self, params):
         return params if self._transform is None else self._transform(params)
@@ -131,6 +136,7 @@ def aux_tensor(params, path, N):
 
 
 def run(spec, time, named, kwargs, params_batch):
+    spec = spec.for_kwargs(kwargs)
     params, N = collect(named, kwargs, params_batch, spec.needed)
     params = spec.transform(params)
     path = spec.build(time, kwargs)

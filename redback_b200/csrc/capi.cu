@@ -10,6 +10,7 @@
 #include "kn_kernel.cu"
 #include "csm_kernel.cu"
 #include "mn_kernel.cu"
+#include "direct_kernel.cu"
 #include "ag_kernel.cu"
 #include "phot_kernel.cu"
 #include "noise_kernel.cu"
@@ -201,7 +202,7 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
                     const void* out_model, const void* out_logl) {
   if (!cfg) return fail(RB_ERR_INVALID, "rb_sn_eval: null config");
   if (N < 0 || E <= 0 || E > (1 << 24)) return fail(RB_ERR_INVALID, "rb_sn_eval: need N >= 0 and 0 < E <= 2^24");
-  if (cfg->engine < RB_ENGINE_NICKEL || cfg->engine > RB_ENGINE_TDE_FALLBACK)
+  if (cfg->engine < RB_ENGINE_NICKEL || cfg->engine > RB_ENGINE_FALLBACK_NICKEL)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown engine");
   if (cfg->engine == RB_ENGINE_MAGNETAR_NICKEL && !cfg->f_nickel)
     return fail(RB_ERR_INVALID, "rb_sn_eval: cfg.f_nickel is required for RB_ENGINE_MAGNETAR_NICKEL");
@@ -219,6 +220,8 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sigma_mode");
   if (cfg->precision != RB_PREC_F64 && cfg->precision != RB_PREC_F32)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown precision");
+  if (cfg->precision == RB_PREC_F32 && (cfg->no_interaction || cfg->engine >= RB_ENGINE_FALLBACK))
+    return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: FP32 applies to the diffusion quadrature only");
   if (cfg->precision == RB_PREC_F32 && cfg->engine >= RB_ENGINE_EXP_POWERLAW)
     return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: the FP32 quadrature needs a monotonically decreasing engine");
   if (cfg->dense_resolution < 2 || cfg->dense_resolution > 8000)
@@ -293,6 +296,13 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   if (cfg->engine == RB_ENGINE_CSM) {
     launch_counter()->fetch_add(1);
     return launch_csm(a, t_obs, st, sms);
+  }
+  if (cfg->no_interaction || cfg->engine >= RB_ENGINE_FALLBACK) {
+    rb::sn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
+    rb::sn_direct_kernel<<<(unsigned)std::min<int64_t>(N, (int64_t)sms * 32), 256, 0, st>>>(a);
+    launch_counter()->fetch_add(3);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
   }
   rb::sn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
   const int threads = sn_block_threads(E);
@@ -1210,6 +1220,9 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
     if (cfg->engine == RB_ENGINE_CSM) {
       status = launch_csm(a, d_tgrid, st, sms);
       if (status != RB_OK) break;
+    } else if (cfg->no_interaction || cfg->engine >= RB_ENGINE_FALLBACK) {
+      rb::sn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
+      rb::sn_direct_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * 32), 256, 0, st>>>(a);
     } else {
       rb::sn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
       sn_kern<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_sn * 4), sn_threads, sn_smem, st>>>(a);

@@ -241,10 +241,11 @@ class SupernovaPath(_FusedPath):
 
     def __init__(self, engine, sed, time, frequency=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
-                 absorption_index=1.0, cosmology=None, device=None, line=None, dtype="float64", csm=None):
+                 absorption_index=1.0, cosmology=None, device=None, line=None, dtype="float64", csm=None,
+                 no_interaction=False):
         self.NEEDS_FREQUENCY = sed != _capi.SED_BOLOMETRIC
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength,
-                                   absorption_index, cosmology, line, _precision(dtype), csm)
+                                   absorption_index, cosmology, line, _precision(dtype), csm, no_interaction)
         self._engine_rows(engine)
         self._setup(time, frequency, y, sigma, device)
 
@@ -256,6 +257,8 @@ class SupernovaPath(_FusedPath):
             # f_nickel and p0 share row 1 of the parameter block: f_nickel travels through cfg.f_nickel instead
             self.ROWS = {k: v for k, v in _capi.SN_ROWS.items() if k != "f_nickel"}
             self.AUX_PARAM = "f_nickel"
+        elif engine == _capi.ENGINE_FALLBACK_NICKEL:
+            self.ROWS = dict(_capi.SN_ROWS, f_nickel=3)      # rows 1-3 = logl1, tr, f_nickel
 
     def _check_time(self, t):
         if self.cfg.engine == _capi.ENGINE_CSM:
@@ -266,6 +269,8 @@ class SupernovaPath(_FusedPath):
         if np.any(t < 0):
             raise NotImplementedError("negative times are not supported on device (the reference maps them "
                                       "to the first valid epoch)")
+        if self.cfg.no_interaction or self.cfg.engine >= _capi.ENGINE_FALLBACK:
+            return
         if np.max(t) > t[-1] + 100:
             # interaction_processes.py:63 would index past uniq_lums here
             raise IndexError("max(time) exceeds time[-1] + 100: outside the reference's dense grid")
@@ -300,13 +305,13 @@ class SupernovaMagPath(SupernovaPath):
 
     def __init__(self, engine, sed, time, bands, output="magnitude", lambda_array=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0, absorption_index=1.0,
-                 cosmology=None, device=None, line=None, csm=None):
+                 cosmology=None, device=None, line=None, csm=None, no_interaction=False):
         from . import bands as _bands
         if sed == _capi.SED_BOLOMETRIC:
             raise ValueError("bolometric models have no magnitude output")
         self.NEEDS_FREQUENCY = False
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength, absorption_index,
-                                   cosmology, line, 0, csm)
+                                   cosmology, line, 0, csm, no_interaction)
         self._engine_rows(engine)
         self._setup(time, None, y, sigma, device)
         lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)

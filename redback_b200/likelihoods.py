@@ -196,8 +196,7 @@ class GaussianLikelihood(_RedbackLikelihood):
 
     def _fused(self, merged, N, mode, sp):
         spec = FUSED[self.function]
-        if hasattr(spec, "for_kwargs"):          # wrappers (t0_base_model) resolve their base model from kwargs
-            spec = spec.for_kwargs(self.kwargs)
+        spec = spec.for_kwargs(self.kwargs)      # wrappers / kwargs-selected variants (base_model, interaction_process)
         kw = dict(self.kwargs)
         if self.function is _kn.one_component_kilonova_model:
             kw.setdefault("temperature_floor", 4000)

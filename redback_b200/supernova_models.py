@@ -61,18 +61,27 @@ def _csm_kwargs(kwargs):
     return dict(nn=kwargs.get("nn", 12), delta=kwargs.get("delta", 1), efficiency=kwargs.get("efficiency", 0.5))
 
 
-def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None):
+_USES_MEJ = (_capi.ENGINE_NICKEL, _capi.ENGINE_MAGNETAR_NICKEL, _capi.ENGINE_FALLBACK_NICKEL)
+
+
+def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None, direct=False, _variant=False):
+    """direct: the model has no interaction process at all (sn_fallback); otherwise `interaction_process=None`
+    selects the direct variant of the same spec (engine luminosity -> photosphere -> SED, :961-968)."""
     is_csm = engine == _capi.ENGINE_CSM
     default_ip = "CSMDiffusion" if is_csm else "Diffusion"
     needed = list(engine_params) + list(_DIFFUSION)
     if is_csm:
         needed = list(engine_params)
+    if direct or _variant:
+        needed = list(engine_params) + (["mej"] if engine in _USES_MEJ and "mej" not in engine_params else []) + ["vej"]
     if flux_density:
         needed = ["redshift"] + needed + ["temperature_floor"]
 
     def validate(kwargs):
-        if _operator_name("interaction_process", kwargs.get("interaction_process", default_ip), default_ip) != default_ip:
-            raise NotImplementedError(f"{name}: only interaction_process={default_ip} is fused on device")
+        if not (direct or _variant):
+            ip_name = _operator_name("interaction_process", kwargs.get("interaction_process", default_ip), default_ip)
+            if ip_name != default_ip:
+                raise NotImplementedError(f"{name}: only interaction_process={default_ip} is fused on device")
         if is_csm:
             _csm_kwargs(kwargs)
         if flux_density:
@@ -85,6 +94,7 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
         sed_id = _capi.SED_BOLOMETRIC
         line = None
         csm = _csm_kwargs(kwargs) if is_csm else None
+        no_ip = direct or _variant
         if flux_density:
             if fixed_sed is not None:     # type_1a hard-wires CutoffBlackbody + Line (supernova_models.py:2268-2275)
                 sed_id, line = fixed_sed, _line_kwargs(kwargs)
@@ -98,16 +108,23 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
                                         cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000),
                                         absorption_index=kwargs.get("absorption_index", 1.0),
                                         cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"),
-                                        line=line, csm=csm)
+                                        line=line, csm=csm, no_interaction=no_ip)
         return SupernovaPath(engine, sed_id, time, frequency=kwargs.get("frequency") if flux_density else None,
                              y=y, sigma=sigma, sigma_mode=sigma_mode,
                              dense_resolution=kwargs.get("dense_resolution", 1000),
                              cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000),
                              absorption_index=kwargs.get("absorption_index", 1.0),
                              cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"), line=line,
-                             dtype=kwargs.get("dtype", "float64"), csm=csm)
+                             dtype=kwargs.get("dtype", "float64"), csm=csm, no_interaction=no_ip)
 
-    return FusedSpec(name, needed, build, validate)
+    resolver = None
+    if not (direct or _variant or is_csm):
+        variant = _spec(name + "[no interaction]", engine, engine_params, flux_density, default_sed, fixed_sed,
+                        _variant=True)
+
+        def resolver(kwargs):
+            return variant if "interaction_process" in kwargs and kwargs["interaction_process"] is None else None
+    return FusedSpec(name, needed, build, validate, resolver=resolver)
 
 
 _ARNETT_BOLO = _spec("arnett_bolometric", _capi.ENGINE_NICKEL, ("f_nickel",), False, None)
@@ -204,6 +221,23 @@ def sn_exponential_powerlaw(time, redshift=None, lbol_0=None, alpha_1=None, alph
     return run(_EXP_PL_BB, time, named, kwargs, params_batch)
 
 
+_FALLBACK = _spec("sn_fallback", _capi.ENGINE_FALLBACK, ("logl1", "tr"), True, "Blackbody", direct=True)
+_FALLBACK_NI = _spec("sn_nickel_fallback", _capi.ENGINE_FALLBACK_NICKEL, ("mej", "f_nickel", "logl1", "tr"), True,
+                     "Blackbody", direct=True)
+
+
+def sn_fallback(time, redshift=None, logl1=None, tr=None, params_batch=None, **kwargs):
+    """redback supernova_models.sn_fallback (:383-438): fallback luminosity l1 t^(-5/3) (flat before tr) ->
+    TemperatureFloor -> Blackbody, no interaction process; kwargs vej, temperature_floor."""
+    return run(_FALLBACK, time, dict(redshift=redshift, logl1=logl1, tr=tr), kwargs, params_batch)
+
+
+def sn_nickel_fallback(time, redshift=None, mej=None, f_nickel=None, logl1=None, tr=None, params_batch=None, **kwargs):
+    """redback supernova_models.sn_nickel_fallback (:441-498): fallback + nickel-cobalt decay, no interaction process."""
+    named = dict(redshift=redshift, mej=mej, f_nickel=f_nickel, logl1=logl1, tr=tr)
+    return run(_FALLBACK_NI, time, named, kwargs, params_batch)
+
+
 def magnetar_nickel(time, redshift=None, f_nickel=None, mej=None, p0=None, bp=None, mass_ns=None, theta_pb=None,
                     params_batch=None, **kwargs):
     """redback supernova_models.magnetar_nickel (:1628-1711): nickel-cobalt decay + magnetar spin-down through one
@@ -227,6 +261,7 @@ FUSED = {
     csm_interaction_bolometric: _CSM_BOLO, csm_interaction: _CSM_BB, magnetar_nickel: _MAGNETAR_NICKEL,
     general_magnetar_slsn_bolometric: _MAGNETAR_ONLY_BOLO, general_magnetar_slsn: _MAGNETAR_ONLY,
     exponential_powerlaw_bolometric: _EXP_PL_BOLO, sn_exponential_powerlaw: _EXP_PL_BB,
+    sn_fallback: _FALLBACK, sn_nickel_fallback: _FALLBACK_NI,
 }
 
 

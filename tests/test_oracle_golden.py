@@ -43,6 +43,9 @@ CASES = {
         lambda t, p, kw: r.two_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.three_component_kilonova_model":
         lambda t, p, kw: r.three_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "supernova.sn_fallback": lambda t, p, kw: r.sn_fallback(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "supernova.sn_nickel_fallback":
+        lambda t, p, kw: r.sn_nickel_fallback(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.one_component_kilonova_model":
         lambda t, p, kw: r.one_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.metzger_kilonova_model":

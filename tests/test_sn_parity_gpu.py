@@ -40,6 +40,7 @@ def test_golden_vectors(rb, golden):
                      ("exponential_powerlaw_bolometric", sn.exponential_powerlaw_bolometric),
                      ("homologous_expansion_supernova", sn.homologous_expansion_supernova),
                      ("thin_shell_supernova", sn.thin_shell_supernova),
+                     ("sn_fallback", sn.sn_fallback), ("sn_nickel_fallback", sn.sn_nickel_fallback),
                      ("tde.tde_analytical", rb.tde_models.tde_analytical),
                      ("tde.tde_analytical_bolometric", rb.tde_models.tde_analytical_bolometric)]:
         e = golden[name if "." in name else "supernova." + name]
@@ -650,3 +651,47 @@ def test_extra_engines_batches(rb):
             assert abs(logl[i] - ref_l) <= 1e-6 + 1e-9 * abs(ref_l)
     with pytest.raises(ValueError):
         rb.supernova_models.homologous_expansion_supernova(t, params_batch=pe, base_model="type_1c_bolometric", **kw)
+
+
+@pytest.mark.gpu
+def test_no_interaction_process(rb):
+    """sn_fallback / sn_nickel_fallback (no interaction process at all, supernova_models.py:383-498) and
+    interaction_process=None of the diffusion models (:961-968): engine -> TemperatureFloor -> SED, element-wise."""
+    rng = np.random.default_rng(103)
+    t = np.sort(rng.uniform(1, 300, 40))
+    nu = np.where(np.arange(t.size) % 2 == 0, 6.3e14, 4.7e14)
+    N = 20
+    z = rng.uniform(0.01, 1.0, N)
+    common = dict(vej=h.loguniform(rng, 1e3, 3e4, N), temperature_floor=h.loguniform(rng, 1e3, 1e4, N))
+    kw = dict(frequency=nu, output_format="flux_density")
+    cases = [
+        (rb.supernova_models.sn_fallback, r.sn_fallback, dict(logl1=rng.uniform(50, 56, N), tr=rng.uniform(5, 60, N)), {}),
+        (rb.supernova_models.sn_nickel_fallback, r.sn_nickel_fallback,
+         dict(mej=h.loguniform(rng, 0.5, 20, N), f_nickel=h.loguniform(rng, 1e-2, 1, N), logl1=rng.uniform(50, 56, N),
+              tr=rng.uniform(5, 60, N)), {}),
+        (rb.supernova_models.arnett, r.arnett_no_interaction,
+         dict(f_nickel=h.loguniform(rng, 1e-2, 1, N), mej=h.loguniform(rng, 0.5, 20, N)), dict(interaction_process=None)),
+    ]
+    for fn, ofn, eng, extra in cases:
+        p = dict(redshift=z, **eng, **common)
+        out = fn(t, params_batch=p, **kw, **extra)
+        y = out[3] * 0.97
+        sigma = 0.1 * np.abs(out[3]) + 1e-12
+        logl = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=dict(kw, **extra)).log_likelihood_batch(p)
+        for i in range(N):
+            kwi = {k: v[i] for k, v in p.items()}
+            zi = kwi.pop("redshift")
+            ref = ofn(t, zi, frequency=nu, **kwi)
+            h.assert_close(out[i], ref, 1e-9, what=f"{fn.__name__} sample {i}")
+            ref_l = r.gaussian_likelihood(y, ref, sigma)
+            assert abs(logl[i] - ref_l) <= 1e-6 + 1e-9 * abs(ref_l), (fn.__name__, i, logl[i], ref_l)
+    # scalar == batch row; magnitudes run through the same direct kernel in grid mode
+    rb.bands.register_synthetic_lsst()
+    bands = np.array(["lsstg", "lsstr", "lssti"])[np.arange(t.size) % 3]
+    p = dict(redshift=z[:3], logl1=cases[0][2]["logl1"][:3], tr=cases[0][2]["tr"][:3], vej=common["vej"][:3],
+             temperature_floor=np.full(3, 5e3))
+    mags = rb.supernova_models.sn_fallback(t, params_batch=p, bands=bands, output_format="magnitude")
+    one = rb.supernova_models.sn_fallback(t, bands=bands, output_format="magnitude",
+                                          **{k: float(v[1]) for k, v in p.items()})
+    np.testing.assert_array_equal(mags[1], one)
+    assert np.all(np.isfinite(mags))
