@@ -18,7 +18,8 @@ KEEP = [
     'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
     'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
-    'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+    'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+    'l1tex__data_pipe_lsu_wavefronts.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
     'smsp__thread_inst_executed_per_inst_executed.ratio',
     'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum', 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum',
     'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum',
