@@ -299,7 +299,14 @@ typedef struct {
   int resolution;              /* points requested from get_optimal_time_array(1e-4, 1e8, .), 500 (:301) */
   rb_cosmology cosmology;
   rb_upper_limits upper_limits;
+  /* RB_MN_OUT_FLUX_DENSITY (default): mJy at t_obs [days].  trapped_magnetar (:477-573), t_obs in SECONDS, engine
+     RB_MN_MAGNETAR_ONLY, no pair cascade: RB_MN_OUT_TRAPPED_LUMINOSITY = exp(-tau) L_sd + comoving-blackbody
+     luminosity at freq_obs [erg/s/Hz -> as the reference returns it]; RB_MN_OUT_TRAPPED_FLUX = that luminosity at
+     the k-corrected time / frequency over 4 pi d_L^2 (1+z)^(photon_index - 2). */
+  int output;
+  double photon_index;
 } rb_mn_config;
+enum { RB_MN_OUT_FLUX_DENSITY = 0, RB_MN_OUT_TRAPPED_LUMINOSITY = 1, RB_MN_OUT_TRAPPED_FLUX = 2 };
 
 int rb_mn_config_default(rb_mn_config* cfg);
 

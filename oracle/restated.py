@@ -818,6 +818,75 @@ def mergernova_flux_density(time, redshift, dynamics, *, frequency, dl=None):
         return fd * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)                                        # :272
 
 
+def trapped_magnetar(time, redshift, mej, beta, ejecta_radius, kappa, n_ism, l0, tau_sd, nn,
+                     thermalisation_efficiency, *, frequency, output_format="flux", photon_index=2.0, dl=None):
+    """magnetar_driven_ejecta_models.trapped_magnetar (:477-573).  time: seconds."""
+    time = np.asarray(time, dtype=float)
+    frequency = np.asarray(frequency, dtype=float)
+    if output_format == "flux":
+        frequency, time = calc_kcorrected_properties(frequency, redshift, time)                  # :537
+    t_grid = get_optimal_time_array(1e-4, 1e8, 500)
+    m = mej * solar_mass
+    # optical depth series (:85): recomputed from the dynamics outputs is not possible, so march again with tau kept
+    lum_g = magnetar_only(t_grid, l0, tau_sd, nn)
+    _, temp_g, rad_g, dop_g = ejecta_dynamics_and_interaction(
+        t_grid, mej, beta, ejecta_radius, kappa, n_ism, lum_g, False, False,
+        thermalisation_efficiency=thermalisation_efficiency)
+    tau_g = _ejecta_optical_depth(t_grid, mej, beta, ejecta_radius, kappa, n_ism, lum_g, thermalisation_efficiency)
+    temp, rad, dop = (interp1d(t_grid, y=v)(time) for v in (temp_g, rad_g, dop_g))
+    optical_depth = interp1d(t_grid, y=tau_g)(time)
+    with np.errstate(all="ignore"):
+        num = 8 * np.pi ** 2 * planck * frequency ** 4 * rad ** 2                               # :190-195
+        den = speed_of_light ** 2 * dop ** 2
+        l_ej = num / den * (1. / (np.exp((planck * frequency) / (boltzmann_constant * temp * dop)) - 1))
+        lum = np.exp(-optical_depth) * magnetar_only(time, l0, tau_sd, nn) + l_ej                 # :509-511
+    if output_format == "luminosity":
+        return lum
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    return lum / (4 * np.pi * dl ** 2 * (1. + redshift) ** (photon_index - 2))                    # :544-545
+
+
+def _ejecta_optical_depth(time, mej, beta, ejecta_radius, kappa, n_ism, magnetar_luminosity, thermalisation_efficiency):
+    """The `tau` series of _ejecta_dynamics_and_interaction (:85, :124): the same march as
+    ejecta_dynamics_and_interaction, returning kappa (m / V') (R / gamma) per step."""
+    m = mej * solar_mass
+    n = len(time)
+    out = np.zeros(n)
+    e_int = 0.5 * beta ** 2 * m * speed_of_light ** 2
+    vol = (4 / 3) * np.pi * ejecta_radius ** 3
+    gam = 1 / np.sqrt(1 - beta ** 2)
+    rad = ejecta_radius
+    d_gam = d_rad = d_vol = d_e = 0.0
+    with np.errstate(all="ignore"):
+        for i in range(n):
+            beta = np.sqrt(1 - 1 / gam ** 2)
+            dop = 1 / (gam * (1 - beta))
+            if i > 0:
+                dt = time[i] - time[i - 1]
+                gam, rad, vol, e_int = gam + d_gam * dt, rad + d_rad * dt, vol + d_vol * dt, e_int + d_e * dt
+            swept = (4 / 3) * np.pi * rad ** 3 * n_ism * proton_mass
+            pressure = e_int / (3 * vol)
+            t_com = dop * time[i]
+            dvdt_com = 4 * np.pi * rad ** 2 * beta * speed_of_light
+            denom = (1 / 2) - (1 / 3.141592654) * np.arctan((t_com - 1.3) / 0.11)
+            l_rad = (4 * 10 ** 49 * (m / (2 * 10 ** 33) * 10 ** 2) * denom ** 1.3)
+            tau = kappa * (m / vol) * (rad / gam)
+            l_emit = (e_int * speed_of_light) / (rad / gam) if tau <= 1 else \
+                (e_int * speed_of_light) / (tau * rad / gam)
+            eff = thermalisation_efficiency
+            d_rad = (beta * speed_of_light) / (1 - beta)
+            d_swept = 4 * np.pi * rad ** 2 * n_ism * proton_mass * d_rad
+            dedt = eff * magnetar_luminosity[i] + dop ** 2 * l_rad - dop ** 2 * l_emit
+            de_com = eff * dop ** (-2) * magnetar_luminosity[i] + l_rad - l_emit - pressure * dvdt_com
+            d_vol = dvdt_com * dop
+            d_e = de_com * dop
+            d_gam = (dedt - gam * dop * de_com - (gam ** 2 - 1) * speed_of_light ** 2 * d_swept) / (
+                m * speed_of_light ** 2 + e_int + 2 * gam * swept * speed_of_light ** 2)
+            out[i] = tau
+    return out
+
+
 def _mergernova(time, redshift, mag_lum_fn, mej, beta, ejecta_radius, kappa, n_ism, *, frequency, pair_cascade_switch,
                 dl=None, **dyn):
     t_grid = get_optimal_time_array(1e-4, 1e8, 500)

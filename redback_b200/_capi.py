@@ -69,6 +69,7 @@ class AgConfig(C.Structure):
 
 
 MN_BASIC_MAGNETAR, MN_MAGNETAR_ONLY = 0, 1
+MN_OUT_FLUX_DENSITY, MN_OUT_TRAPPED_LUMINOSITY, MN_OUT_TRAPPED_FLUX = 0, 1, 2
 MN_ROWS = dict(redshift=0, mej=1, beta=2, ejecta_radius=3, kappa=4, n_ism=5, p0=6, l0=6, bp=7, tau_sd=7, mass_ns=8,
                nn=8, theta_pb=9, thermalisation_efficiency=10, kappa_gamma=10)
 MN_NPARAM = 11
@@ -77,7 +78,8 @@ MN_NPARAM = 11
 class MnConfig(C.Structure):
     _fields_ = [("engine", C.c_int), ("sigma_mode", C.c_int), ("use_gamma_ray_opacity", C.c_int),
                 ("pair_cascade_switch", C.c_int), ("ejecta_albedo", C.c_double), ("pair_cascade_fraction", C.c_double),
-                ("resolution", C.c_int), ("cosmology", Cosmology), ("upper_limits", UpperLimits)]
+                ("resolution", C.c_int), ("cosmology", Cosmology), ("upper_limits", UpperLimits), ("output", C.c_int),
+                ("photon_index", C.c_double)]
 
 
 class RedbackB200Error(RuntimeError):
@@ -202,13 +204,14 @@ def ag_config(jet, sigma_mode=SIGMA_FIXED, steps=250, res=0, k=0, expansion=1, a
 
 
 def mn_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_cascade_switch=False,
-              ejecta_albedo=0.5, pair_cascade_fraction=0.05, cosmology=None):
+              ejecta_albedo=0.5, pair_cascade_fraction=0.05, cosmology=None, output=0, photon_index=2.0):
     cfg = MnConfig()
     check(lib().rb_mn_config_default(C.byref(cfg)))
     cfg.engine, cfg.sigma_mode = engine, sigma_mode
     cfg.use_gamma_ray_opacity = int(bool(use_gamma_ray_opacity))
     cfg.pair_cascade_switch = int(bool(pair_cascade_switch))
     cfg.ejecta_albedo, cfg.pair_cascade_fraction = float(ejecta_albedo), float(pair_cascade_fraction)
+    cfg.output, cfg.photon_index = int(output), float(photon_index)
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg

@@ -635,6 +635,12 @@ int mn_check(const rb_mn_config* cfg, int64_t N, int64_t E, const void* params, 
     return fail(RB_ERR_INVALID, "rb_mn_eval: unknown sigma_mode");
   if (cfg->resolution < 8 || cfg->resolution > 4096)
     return fail(RB_ERR_INVALID, "rb_mn_eval: resolution must be in [8, 4096]");
+  if (cfg->output < RB_MN_OUT_FLUX_DENSITY || cfg->output > RB_MN_OUT_TRAPPED_FLUX)
+    return fail(RB_ERR_INVALID, "rb_mn_eval: unknown output");
+  if (cfg->output != RB_MN_OUT_FLUX_DENSITY &&
+      (cfg->engine != RB_MN_MAGNETAR_ONLY || cfg->pair_cascade_switch || cfg->use_gamma_ray_opacity))
+    return fail(RB_ERR_INVALID, "rb_mn_eval: the trapped-magnetar outputs need the magnetar_only engine without pair "
+                                "cascade / gamma-ray opacity");
   if (!params || !t_obs || !freq_obs) return fail(RB_ERR_INVALID, "rb_mn_eval: params, t_obs and freq_obs are required");
   if (y) {
     if (!out_logl) return fail(RB_ERR_INVALID, "rb_mn_eval: y given but out_logl is null");
@@ -679,6 +685,8 @@ extern "C" int rb_mn_config_default(rb_mn_config* cfg) {
   cfg->ejecta_albedo = 0.5;
   cfg->pair_cascade_fraction = 0.05;
   cfg->resolution = 500;
+  cfg->output = RB_MN_OUT_FLUX_DENSITY;
+  cfg->photon_index = 2.0;
   return rb_cosmology_planck18(&cfg->cosmology);
 }
 

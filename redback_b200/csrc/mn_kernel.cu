@@ -101,12 +101,14 @@ __global__ void __launch_bounds__(128) mn_kernel(const MnArgs a) {
   const double inv_den = 1.0 / ((dl * dl) * (kC * kC));
   const double* ep = a.sorted_ep;
   const double t0g = mn_tg[0], t1g = mn_tg[G - 1];
+  const bool trapped = a.cfg.output != RB_MN_OUT_FLUX_DENSITY;      // trapped_magnetar: epochs in seconds (:477-573)
+  const double kcorr = pow(opz, a.cfg.photon_index - 2.0);          // :544
 
   int ei = 0;
   double logl = 0.0;
   // epochs before the grid: interp1d raises in the reference -> NaN
   while (ei < E) {
-    const double ts = (ep[MS_T * E + ei] * kDay) / opz;                        // :252-254
+    const double ts = trapped ? ep[MS_T * E + ei] / opz : (ep[MS_T * E + ei] * kDay) / opz;   // :252-254, :537
     if (ts >= t0g) break;
     if (!a.grid_mode) {
       if (a.out_model != nullptr) a.out_model[n * (int64_t)E + (int)ep[MS_ORIG * E + ei]] = NAN;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(128) mn_kernel(const MnArgs a) {
     }
     ++ei;
   }
-  double pt = 0.0, ptemp = 0.0, prad = 0.0, pdop = 0.0;
+  double pt = 0.0, ptemp = 0.0, prad = 0.0, pdop = 0.0, ptau = 0.0;
   for (int i = 0; i < G; ++i) {
     const double t = mn_tg[i];
     const double beta = sqrt(1.0 - 1.0 / (gam * gam));                         // :65
@@ -180,16 +182,27 @@ __global__ void __launch_bounds__(128) mn_kernel(const MnArgs a) {
     } else if (i > 0) {
       // epochs in (t_{i-1}, t_i]: interp1d (:256-261) + _comoving_blackbody_to_flux_density (:164-173)
       while (ei < E) {
-        const double ts = (ep[MS_T * E + ei] * kDay) / opz;
+        const double ts = trapped ? ep[MS_T * E + ei] / opz : (ep[MS_T * E + ei] * kDay) / opz;
         if (!(ts <= t)) break;
         const double w = ts - pt, inv = 1.0 / (t - pt);
         const double te = (temp - ptemp) * inv * w + ptemp;
         const double re = (rad - prad) * inv * w + prad;
         const double de = (dop - pdop) * inv * w + pdop;
         const double nu = ep[MS_NU * E + ei] * opz;
-        const double num = 2 * kPi * kH * (nu * nu * nu) * (re * re);
         const double frac = 1.0 / (exp((kH * nu) / (kKB * te * de)) - 1.0);   // the reference's exp(x) - 1 (:172)
-        const double model = num * (inv_den / (de * de)) * frac * opz * kToMJy * opz;             // :262, :272
+        double model;
+        if (!trapped) {
+          const double num = 2 * kPi * kH * (nu * nu * nu) * (re * re);
+          model = num * (inv_den / (de * de)) * frac * opz * kToMJy * opz;                        // :262, :272
+        } else {
+          // _comoving_blackbody_to_luminosity (:177-196) + the leaking spin-down luminosity (:509-511)
+          const double optical_depth = (tau - ptau) * inv * w + ptau;
+          const double num = 8 * (kPi * kPi) * kH * ((nu * nu) * (nu * nu)) * (re * re);
+          const double l_ej = num / ((kC * kC) * (de * de)) * frac;
+          const double lsd = eng_a * pow(1.0 + ts / eng_b, eng_c);
+          model = exp(-optical_depth) * lsd + l_ej;
+          if (a.cfg.output == RB_MN_OUT_TRAPPED_FLUX) model = model / (4 * kPi * (dl * dl) * kcorr);   // :545
+        }
         if (a.out_model != nullptr) a.out_model[n * (int64_t)E + (int)ep[MS_ORIG * E + ei]] = model;
         if (a.want_logl)
           logl += logl_term(a.cfg.sigma_mode, ep[MS_KIND * E + ei], ep[MS_Y * E + ei], model, ep[MS_ISIG * E + ei],
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(128) mn_kernel(const MnArgs a) {
         ++ei;
       }
     }
-    pt = t; ptemp = temp; prad = rad; pdop = dop;
+    pt = t; ptemp = temp; prad = rad; pdop = dop; ptau = tau;
   }
   if (!a.grid_mode) {
     for (; ei < E; ++ei) {               // beyond the grid (t_src > 1e8 s or NaN)

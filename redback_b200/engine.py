@@ -371,9 +371,9 @@ class MergernovaPath(_FusedPath):
 
     def __init__(self, engine, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED,
                  use_gamma_ray_opacity=False, pair_cascade_switch=False, ejecta_albedo=0.5,
-                 pair_cascade_fraction=0.05, cosmology=None, device=None):
+                 pair_cascade_fraction=0.05, cosmology=None, device=None, output=0, photon_index=2.0):
         self.cfg = _capi.mn_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
-                                   pair_cascade_fraction, cosmology)
+                                   pair_cascade_fraction, cosmology, output, photon_index)
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):

@@ -73,4 +73,46 @@ def general_mergernova_thermalisation(time, redshift=None, mej=None, beta=None, 
     return run(_GENERAL_TH, time, named, kwargs, params_batch)
 
 
-FUSED = {basic_mergernova: _BASIC, general_mergernova: _GENERAL, general_mergernova_thermalisation: _GENERAL_TH}
+def _trapped_spec(output):
+    needed = (("redshift",) if output == _capi.MN_OUT_TRAPPED_FLUX else ()) + _EJECTA[1:] + \
+        ("l0", "tau_sd", "nn", "thermalisation_efficiency")
+
+    def build(time, kwargs, y, sigma, sigma_mode):
+        return MergernovaPath(_capi.MN_MAGNETAR_ONLY, time, frequency=kwargs.get("frequency"), y=y, sigma=sigma,
+                              sigma_mode=sigma_mode, cosmology=cosmology_from_kwargs(kwargs),
+                              device=kwargs.get("device"), output=output,
+                              photon_index=kwargs.get("photon_index", 2.0) if output == _capi.MN_OUT_TRAPPED_FLUX
+                              else 2.0)
+
+    return FusedSpec("trapped_magnetar", needed, build)
+
+
+_TRAPPED_LUM = _trapped_spec(_capi.MN_OUT_TRAPPED_LUMINOSITY)
+_TRAPPED_FLUX = _trapped_spec(_capi.MN_OUT_TRAPPED_FLUX)
+
+
+class _TrappedSpec:
+    def for_kwargs(self, kwargs):
+        fmt = kwargs["output_format"]                           # KeyError like the reference (:568)
+        if fmt == "luminosity":
+            return _TRAPPED_LUM
+        if fmt == "flux":
+            if "photon_index" not in kwargs:
+                raise KeyError("photon_index")                  # positional argument of _trapped_magnetar_flux (:518)
+            return _TRAPPED_FLUX
+        raise ValueError("trapped_magnetar: output_format must be 'luminosity' or 'flux'")
+
+
+_TRAPPED = _TrappedSpec()
+
+
+def trapped_magnetar(time, redshift=None, mej=None, beta=None, ejecta_radius=None, kappa=None, n_ism=None, l0=None,
+                     tau_sd=None, nn=None, thermalisation_efficiency=None, params_batch=None, **kwargs):
+    """redback magnetar_driven_ejecta_models.trapped_magnetar (:549-573): `time` in SECONDS; output_format
+    'luminosity' (source frame, redshift unused) or 'flux' (needs kwargs frequency, photon_index)."""
+    named = dict(redshift=redshift, mej=mej, beta=beta, ejecta_radius=ejecta_radius, kappa=kappa, n_ism=n_ism, l0=l0,
+                 tau_sd=tau_sd, nn=nn, thermalisation_efficiency=thermalisation_efficiency)
+    return run(_TRAPPED.for_kwargs(kwargs), time, named, kwargs, params_batch)
+
+
+FUSED = {trapped_magnetar: _TRAPPED, basic_mergernova: _BASIC, general_mergernova: _GENERAL, general_mergernova_thermalisation: _GENERAL_TH}

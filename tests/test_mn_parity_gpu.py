@@ -81,6 +81,45 @@ def test_reference_golden_vectors(rb):
             h.assert_close(out, h.golden_array(res), 1e-9, 1e-12, what=name)
 
 
+def test_trapped_magnetar(rb):
+    """trapped_magnetar (magnetar_driven_ejecta_models.py:477-573): time in seconds, 'flux' and 'luminosity' outputs;
+    the reference's golden vectors and prior draws against the oracle."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "all_models_subset.json")) as fh:
+        e = json.load(fh)["magnetar.trapped_magnetar"]
+    t = np.array(e["time"])
+    fn = rb.magnetar_driven_ejecta_models.trapped_magnetar
+    for params, res in zip(e["params"], e["results"]):
+        out = fn(t, **params, **e["eval_kwargs"])
+        h.assert_close(out, h.golden_array(res), 1e-9, 1e-12, what="trapped_magnetar golden")
+    rng = np.random.default_rng(95)
+    ts = np.geomspace(10.0, 1e6, 30)                      # seconds
+    nu = np.full(30, 2.4e17)
+    N = 16
+    p = h.mergernova_prior(rng, N, "general")
+    flux = fn(ts, params_batch=p, frequency=nu, output_format="flux", photon_index=1.8)
+    lum = fn(ts, params_batch={k: v for k, v in p.items() if k != "redshift"}, frequency=nu, output_format="luminosity")
+    y = flux[2] * 1.1
+    sigma = 0.2 * np.abs(flux[2]) + 1e-30
+    kw = dict(frequency=nu, output_format="flux", photon_index=1.8)
+    logl = rb.GaussianLikelihood(ts, y, sigma, fn, kwargs=kw).log_likelihood_batch(p)
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        z = kwi.pop("redshift")
+        ref_f = r.trapped_magnetar(ts, z, frequency=nu, output_format="flux", photon_index=1.8, **kwi)
+        ref_l = r.trapped_magnetar(ts, 0.0, frequency=nu, output_format="luminosity", **kwi)
+        h.assert_close(flux[i], ref_f, 1e-9, 1e-11, what=f"trapped flux {i}")
+        h.assert_close(lum[i], ref_l, 1e-9, 1e-11, what=f"trapped luminosity {i}")
+        want = r.gaussian_likelihood(y, ref_f, sigma)
+        assert abs(logl[i] - want) <= 1e-6 + 1e-8 * abs(want)
+    with pytest.raises(KeyError):
+        fn(ts, params_batch=p, frequency=nu, output_format="flux")          # photon_index is required (:518)
+    with pytest.raises(ValueError):
+        fn(ts, params_batch=p, frequency=nu, output_format="flux_density")
+
+
 def test_scalar_call_kwargs_and_errors(rb):
     t = np.geomspace(0.05, 100, 12)
     kw = dict(mej=0.02, beta=0.3, ejecta_radius=3e9, kappa=5.0, n_ism=1e-2, l0=1e47, tau_sd=1e3, nn=3.0,

@@ -39,6 +39,9 @@ CASES = {
     "tde.tde_analytical": lambda t, p, kw: r.tde_analytical(t, kw["redshift"], frequency=kw["frequency"], **p),
     "tde.tde_analytical_bolometric": lambda t, p, kw: r.tde_analytical_bolometric(
         t, **{k: v for k, v in p.items() if k != "temperature_floor"}),
+    "magnetar.trapped_magnetar":
+        lambda t, p, kw: r.trapped_magnetar(t, kw["redshift"], frequency=np.full(t.size, kw["frequency"]),
+                                            output_format=kw["output_format"], photon_index=kw["photon_index"], **p),
     "kilonova.two_component_kilonova_model":
         lambda t, p, kw: r.two_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.three_component_kilonova_model":
