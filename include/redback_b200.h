@@ -323,6 +323,47 @@ int rb_mn_eval_f64_host(const rb_mn_config* cfg, int64_t N, int64_t E, const dou
  * writes at most `resolution` ascending points to out (host memory) and their count to *n_out. */
 int rb_optimal_time_array(double t_min, double t_max, int resolution, double* out, int* n_out);
 
+/* ---- magnetar-driven Metzger shell model ------------------------------------------------------------------
+ * metzger_magnetar_driven_kilonova_model / general_metzger_magnetar_driven / ..._thermalisation
+ * (magnetar_driven_ejecta_models.py:760-905) -> _general_metzger_magnetar_driven_kilonova_model (:576-757,
+ * magnetar_heating='first_layer') on get_optimal_time_array(1e-4, 1e7, 300) -> interp1d of T and R_photosphere ->
+ * blackbody (:263-272) -> Gaussian log-likelihood.  The engine ids are RB_MN_BASIC_MAGNETAR / RB_MN_MAGNETAR_ONLY. */
+enum {
+  RB_MK_REDSHIFT = 0,
+  RB_MK_MEJ = 1,       /* [Msun] */
+  RB_MK_VEJ = 2,       /* minimum ejecta velocity [c] */
+  RB_MK_BETA = 3,      /* velocity power-law slope of the mass profile */
+  RB_MK_KAPPA_R = 4,
+  RB_MK_P0 = 5, RB_MK_L0 = 5,
+  RB_MK_BP = 6, RB_MK_TAU_SD = 6,
+  RB_MK_MASS_NS = 7, RB_MK_NN = 7,
+  RB_MK_THETA_PB = 8,
+  RB_MK_THERMALISATION_EFFICIENCY = 9, RB_MK_KAPPA_GAMMA = 9,
+  RB_MK_NPARAM = 10
+};
+
+typedef struct {
+  int engine;
+  int sigma_mode;
+  int use_gamma_ray_opacity;     /* ..._thermalisation: row 9 is kappa_gamma (:674-676) */
+  int pair_cascade_switch;       /* default 1 (:590) */
+  double ejecta_albedo;          /* 0.5 */
+  double pair_cascade_fraction;  /* 0.01 (:592) */
+  int neutron_precursor_switch;  /* default 1 (:593) */
+  double vmax;                   /* 0.7 (:595) */
+  int resolution;                /* get_optimal_time_array(1e-4, 1e7, 300) (:777) */
+  rb_cosmology cosmology;
+  rb_upper_limits upper_limits;
+} rb_mk_config;
+
+int rb_mk_config_default(rb_mk_config* cfg);
+int rb_mk_eval_f64(const rb_mk_config* cfg, int64_t N, int64_t E, const double* params, const double* t_obs,
+                   const double* freq_obs, const double* dl_cm, const double* y, const double* sigma,
+                   const double* sigma_param, double* out_model, double* out_logl, void* stream);
+int rb_mk_eval_f64_host(const rb_mk_config* cfg, int64_t N, int64_t E, const double* params,
+                        const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
+                        const double* sigma, const double* sigma_param, double* out_model, double* out_logl);
+
 /* ---- magnitude / bandpass branch (output_format = 'magnitude' | 'flux') ---------------------------------
  * get_correct_output_format_from_spectra -> RedbackTimeSeriesSource.bandmag -> _bandflux_single_redback
  * (redback/sed.py:971-1009, 120-195, 10-118) and bandpass_magnitude_to_flux (redback/utils.py:707-718).

@@ -81,6 +81,8 @@ KEEP = [
     "supernova.thin_shell_supernova", "tde.tde_analytical", "tde.tde_analytical_bolometric",
     "kilonova.two_component_kilonova_model", "kilonova.three_component_kilonova_model",
     "supernova.sn_fallback", "supernova.sn_nickel_fallback",
+    "magnetar.metzger_magnetar_driven_kilonova_model", "magnetar.general_metzger_magnetar_driven",
+    "magnetar.general_metzger_magnetar_driven_thermalisation",
 ]
 
 

@@ -1084,6 +1084,115 @@ def metzger_kilonova_internal(time, mej, vej, beta, kappa, neutron_precursor_swi
         return lbol, temperature, r_photosphere
 
 
+def metzger_magnetar_driven_internal(time, mej, vej, beta, kappa, magnetar_luminosity, use_gamma_ray_opacity, *,
+                                     thermalisation_efficiency=None, kappa_gamma=None, pair_cascade_switch=True,
+                                     ejecta_albedo=0.5, pair_cascade_fraction=0.01, neutron_precursor_switch=True,
+                                     vmax=0.7):
+    """_general_metzger_magnetar_driven_kilonova_model (magnetar_driven_ejecta_models.py:576-757) with
+    magnetar_heating='first_layer' (the default).  time: source-frame seconds.  Returns (L_bol, T, R_photosphere)."""
+    with np.errstate(all="ignore"):
+        tdays = time / day_to_s
+        time_len, mass_len = len(time), 200
+        av, bv, dv = barnes_kasen_thermalisation(mej, vej)
+        e_th = 0.36 * (np.exp(-av * tdays) + np.log1p(2.0 * bv * tdays ** dv) / (2.0 * bv * tdays ** dv))
+        electron_fraction = electron_fraction_from_kappa(kappa)
+        t0, sig, tau_neutron = 1.3, 0.11, 900
+        m0 = mej * solar_mass
+        v0 = vej * speed_of_light
+        kinetic_energy = 0.5 * m0 * v0 ** 2
+        vel = np.linspace(vej, vmax, mass_len)
+        m_array = mej * (vel / vej) ** (-beta)
+        m_array = m_array * (mej / np.sum(m_array))                                     # :617-619
+        v_m = vel * speed_of_light
+        time_array = np.tile(time, (mass_len, 1))
+        e_th_array = np.tile(e_th, (mass_len, 1))
+        edotr = np.zeros((mass_len, time_len))
+        mask = time > t0
+        edotr[:, mask] = 2.1e10 * e_th_array[:, mask] * ((time_array[:, mask] / (3600. * 24.)) ** (-1.3))
+        edotr[:, ~mask] = 4.0e18 * (0.5 - (1. / np.pi) * np.arctan((time_array[:, ~mask] - t0) / sig)) ** (1.3) * \
+            e_th_array[:, ~mask]
+        lsd = magnetar_luminosity
+        energy_v = np.zeros((mass_len, time_len))
+        lum_rad = np.zeros((mass_len, time_len))
+        td_v = np.zeros((mass_len, time_len))
+        tau = np.zeros((mass_len, time_len))
+        r_photosphere = np.zeros(time_len)
+        if neutron_precursor_switch:
+            xn0 = (2.0 / np.pi) * (1.0 - electron_fraction) * np.arctan(1e-4 * solar_mass / m_array / solar_mass)
+            xr = 1.0 - xn0
+            xn_arr = np.tile(xn0, (time_len, 1)).T * np.exp(-time_array / tau_neutron)
+            xr_arr = np.tile(xr, (time_len, 1)).T
+            edotr = 3.2e14 * xn_arr + edotr
+            kappa = 0.4 * (1.0 - xn_arr - xr_arr) + kappa * xr_arr
+        dt = np.diff(time)
+        dm = np.abs(np.diff(m_array))
+        energy_v[:, 0] = 0.5 * m_array * v_m ** 2
+        for ii in range(time_len - 1):
+            kinetic_energy = kinetic_energy + (energy_v[0, ii] / time[ii]) * dt[ii]            # :667
+            v0 = (2 * kinetic_energy / m0) ** 0.5
+            v_m = v0 * (m_array / mej) ** (-1 / beta)
+            v_m[v_m > 3e10] = speed_of_light
+            if use_gamma_ray_opacity:
+                eff = 1 - np.exp(-(3 * kappa_gamma * mej / (4 * np.pi * vej ** 2)) * time[ii] ** -2)   # :674-676
+            else:
+                eff = thermalisation_efficiency
+            qdot = eff * lsd[ii]
+            kap = kappa[:-1, ii] if neutron_precursor_switch else kappa
+            td_v[:-1, ii] = (kap * m_array[:-1] * solar_mass * 3) / (4 * np.pi * v_m[:-1] * speed_of_light * time[ii] * beta)
+            lum_rad[:-1, ii] = energy_v[:-1, ii] / (td_v[:-1, ii] + time[ii] * (v_m[:-1] / speed_of_light))
+            energy_v[0, ii + 1] = (qdot + edotr[0, ii] * dm[0] * solar_mass - (energy_v[0, ii] / time[ii])
+                                   - lum_rad[0, ii]) * dt[ii] + energy_v[0, ii]                 # :707
+            energy_v[1:-1, ii + 1] = (edotr[1:-1, ii] * dm[1:] * solar_mass - (energy_v[1:-1, ii] / time[ii])
+                                      - lum_rad[1:-1, ii]) * dt[ii] + energy_v[1:-1, ii]        # :710
+            tau[:-1, ii] = (m_array[:-1] * solar_mass * kap / (4 * np.pi * (time[ii] * v_m[:-1]) ** 2))
+            tau[mass_len - 1, ii] = tau[mass_len - 2, ii]
+            r_photosphere[ii] = v_m[np.argmin(np.abs(tau[:, ii] - 1))] * time[ii]
+        lbol = np.sum(lum_rad, axis=0)
+        if pair_cascade_switch:                                                                # :725-728
+            tlife = ((0.6 / (1 - ejecta_albedo)) * (pair_cascade_fraction / 0.1) ** 0.5 * (lsd / 1.0e45) ** 0.5
+                     * (v0 / (0.3 * speed_of_light)) ** (0.5) * (time / day_to_s) ** (-0.5))
+            lbol = lbol / (1.0 + tlife)
+        temperature = (lbol / (4.0 * np.pi * (r_photosphere) ** (2.0) * sigma_sb)) ** (0.25)
+        return lbol, temperature, r_photosphere
+
+
+def _metzger_magnetar_driven(time, redshift, lum_fn, mej, vej, beta, kappa_r, use_gamma_ray_opacity, *, frequency,
+                             dl=None, **dyn):
+    """metzger_magnetar_driven_kilonova_model & co. (:760-905) + _process_flux_density (:240-272) with
+    use_relativistic_blackbody=False."""
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    t_grid = get_optimal_time_array(1e-4, 1e7, 300)
+    _, temperature, r_photosphere = metzger_magnetar_driven_internal(t_grid, mej, vej, beta, kappa_r, lum_fn(t_grid),
+                                                                     use_gamma_ray_opacity, **dyn)
+    frequency, t = calc_kcorrected_properties(np.asarray(frequency, dtype=float), redshift,
+                                              np.asarray(time, dtype=float) * day_to_s)
+    with np.errstate(all="ignore"):
+        fd = blackbody_to_flux_density(interp1d(t_grid, y=temperature)(t), interp1d(t_grid, y=r_photosphere)(t), dl,
+                                       frequency)
+        return fd * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)
+
+
+def metzger_magnetar_driven_kilonova_model(time, redshift, mej, vej, beta, kappa_r, p0, bp, mass_ns, theta_pb,
+                                           thermalisation_efficiency, *, frequency, **kw):
+    return _metzger_magnetar_driven(time, redshift, lambda t: basic_magnetar(t, p0, bp, mass_ns, theta_pb), mej, vej,
+                                    beta, kappa_r, False, frequency=frequency,
+                                    thermalisation_efficiency=thermalisation_efficiency, **kw)
+
+
+def general_metzger_magnetar_driven(time, redshift, mej, vej, beta, kappa_r, l0, tau_sd, nn,
+                                    thermalisation_efficiency, *, frequency, **kw):
+    return _metzger_magnetar_driven(time, redshift, lambda t: magnetar_only(t, l0, tau_sd, nn), mej, vej, beta,
+                                    kappa_r, False, frequency=frequency,
+                                    thermalisation_efficiency=thermalisation_efficiency, **kw)
+
+
+def general_metzger_magnetar_driven_thermalisation(time, redshift, mej, vej, beta, kappa_r, l0, tau_sd, nn,
+                                                   kappa_gamma, *, frequency, **kw):
+    return _metzger_magnetar_driven(time, redshift, lambda t: magnetar_only(t, l0, tau_sd, nn), mej, vej, beta,
+                                    kappa_r, True, frequency=frequency, kappa_gamma=kappa_gamma, **kw)
+
+
 def metzger_kilonova_model(time, redshift, mej, vej, beta, kappa, *, frequency, dense_resolution=500, dl=None,
                            neutron_precursor_switch=True, vmax=0.7, **_):
     """kilonova_models.py:1895-1935 (flux_density branch).  Returns mJy[E]."""

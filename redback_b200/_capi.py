@@ -82,6 +82,18 @@ class MnConfig(C.Structure):
                 ("photon_index", C.c_double)]
 
 
+MK_ROWS = dict(redshift=0, mej=1, vej=2, beta=3, kappa_r=4, p0=5, l0=5, bp=6, tau_sd=6, mass_ns=7, nn=7, theta_pb=8,
+               thermalisation_efficiency=9, kappa_gamma=9)
+MK_NPARAM = 10
+
+
+class MkConfig(C.Structure):
+    _fields_ = [("engine", C.c_int), ("sigma_mode", C.c_int), ("use_gamma_ray_opacity", C.c_int),
+                ("pair_cascade_switch", C.c_int), ("ejecta_albedo", C.c_double), ("pair_cascade_fraction", C.c_double),
+                ("neutron_precursor_switch", C.c_int), ("vmax", C.c_double), ("resolution", C.c_int),
+                ("cosmology", Cosmology), ("upper_limits", UpperLimits)]
+
+
 class RedbackB200Error(RuntimeError):
     pass
 
@@ -109,6 +121,9 @@ EXPORTS = {
     "rb_mn_eval_f64": (C.c_int, [C.POINTER(MnConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
     "rb_mn_eval_f64_host": (C.c_int, [C.POINTER(MnConfig), C.c_int64, C.c_int64] + [_dp] * 9),
     "rb_optimal_time_array": (C.c_int, [C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "rb_mk_config_default": (C.c_int, [C.POINTER(MkConfig)]),
+    "rb_mk_eval_f64": (C.c_int, [C.POINTER(MkConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
+    "rb_mk_eval_f64_host": (C.c_int, [C.POINTER(MkConfig), C.c_int64, C.c_int64] + [_dp] * 9),
     "rb_sn_mag_eval_f64": (C.c_int, [C.POINTER(SnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_kn_mag_eval_f64": (C.c_int, [C.POINTER(KnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_mn_mag_eval_f64": (C.c_int, [C.POINTER(MnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
@@ -212,6 +227,21 @@ def mn_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_
     cfg.pair_cascade_switch = int(bool(pair_cascade_switch))
     cfg.ejecta_albedo, cfg.pair_cascade_fraction = float(ejecta_albedo), float(pair_cascade_fraction)
     cfg.output, cfg.photon_index = int(output), float(photon_index)
+    if cosmology is not None:
+        cfg.cosmology = cosmology
+    return cfg
+
+
+def mk_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_cascade_switch=True,
+              ejecta_albedo=0.5, pair_cascade_fraction=0.01, neutron_precursor_switch=True, vmax=0.7, cosmology=None):
+    cfg = MkConfig()
+    check(lib().rb_mk_config_default(C.byref(cfg)))
+    cfg.engine, cfg.sigma_mode = engine, sigma_mode
+    cfg.use_gamma_ray_opacity = int(bool(use_gamma_ray_opacity))
+    cfg.pair_cascade_switch = int(bool(pair_cascade_switch))
+    cfg.ejecta_albedo, cfg.pair_cascade_fraction = float(ejecta_albedo), float(pair_cascade_fraction)
+    cfg.neutron_precursor_switch = int(bool(neutron_precursor_switch))
+    cfg.vmax = float(vmax)
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg

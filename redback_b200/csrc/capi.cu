@@ -11,6 +11,7 @@
 #include "csm_kernel.cu"
 #include "mn_kernel.cu"
 #include "direct_kernel.cu"
+#include "mk_kernel.cu"
 #include "ag_kernel.cu"
 #include "phot_kernel.cu"
 #include "noise_kernel.cu"
@@ -766,6 +767,144 @@ extern "C" int rb_mn_eval_f64_host(const rb_mn_config* cfg, int64_t N, int64_t E
   if (out_model) RB_CUDA(d_m.alloc(nN * nE));
   if (out_logl) RB_CUDA(d_l.alloc(nN));
   rc = rb_mn_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
+  if (rc != RB_OK) return rc;
+  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
+  RB_CUDA(cudaDeviceSynchronize());
+  return RB_OK;
+}
+
+// ---- magnetar-driven Metzger shell model ----------------------------------------------------------------------
+namespace {
+int mk_check(const rb_mk_config* cfg, int64_t N, int64_t E, const void* params, const void* t_obs,
+             const void* freq_obs, const void* y, const void* sigma, const void* sigma_param, const void* out_model,
+             const void* out_logl) {
+  if (!cfg) return fail(RB_ERR_INVALID, "rb_mk_eval: null config");
+  if (N < 0 || E <= 0) return fail(RB_ERR_INVALID, "rb_mk_eval: need N >= 0 and E > 0");
+  if (cfg->engine != RB_MN_BASIC_MAGNETAR && cfg->engine != RB_MN_MAGNETAR_ONLY)
+    return fail(RB_ERR_INVALID, "rb_mk_eval: unknown engine");
+  if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_SYSTEMATIC)
+    return fail(RB_ERR_INVALID, "rb_mk_eval: unknown sigma_mode");
+  if (cfg->resolution < 8 || cfg->resolution > 1024)
+    return fail(RB_ERR_INVALID, "rb_mk_eval: resolution must be in [8, 1024]");
+  if (!(cfg->vmax > 0)) return fail(RB_ERR_INVALID, "rb_mk_eval: vmax must be positive");
+  if (!params || !t_obs || !freq_obs) return fail(RB_ERR_INVALID, "rb_mk_eval: params, t_obs and freq_obs are required");
+  if (y) {
+    if (!out_logl) return fail(RB_ERR_INVALID, "rb_mk_eval: y given but out_logl is null");
+    if (cfg->sigma_mode != RB_SIGMA_SAMPLED && !sigma) return fail(RB_ERR_INVALID, "rb_mk_eval: sigma is required");
+    if (cfg->sigma_mode != RB_SIGMA_FIXED && cfg->sigma_mode != RB_SIGMA_FRACTIONAL && !sigma_param)
+      return fail(RB_ERR_INVALID, "rb_mk_eval: sigma_param is required");
+  } else if (out_logl) {
+    return fail(RB_ERR_INVALID, "rb_mk_eval: out_logl requested without data y");
+  }
+  if (!out_model && !out_logl) return fail(RB_ERR_INVALID, "rb_mk_eval: nothing to compute");
+  return RB_OK;
+}
+}  // namespace
+
+extern "C" int rb_mk_config_default(rb_mk_config* cfg) {
+  if (!cfg) return fail(RB_ERR_INVALID, "rb_mk_config_default: null config");
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->engine = RB_MN_BASIC_MAGNETAR;
+  cfg->sigma_mode = RB_SIGMA_FIXED;
+  cfg->pair_cascade_switch = 1;
+  cfg->ejecta_albedo = 0.5;
+  cfg->pair_cascade_fraction = 0.01;
+  cfg->neutron_precursor_switch = 1;
+  cfg->vmax = 0.7;
+  cfg->resolution = 300;
+  return rb_cosmology_planck18(&cfg->cosmology);
+}
+
+extern "C" int rb_mk_eval_f64(const rb_mk_config* cfg, int64_t N, int64_t E, const double* params,
+                              const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
+                              const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
+                              void* stream) {
+  int rc = mk_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  RB_CUDA(cudaGetDevice(&dev));
+  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(rb::mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(mk_kernel)");
+  std::vector<double> tg((size_t)cfg->resolution);
+  int G = 0;
+  rc = rb_optimal_time_array(1e-4, 1e7, cfg->resolution, tg.data(), &G);   // magnetar_driven_ejecta_models.py:777
+  if (rc != RB_OK) return rc;
+  const size_t smem = sizeof(double) * ((size_t)7 * G + 2 * (size_t)rb::kShellWarps * G + 2 * rb::kShells + 40) +
+                      sizeof(int) * (size_t)rb::kShellWarps * G;
+  if (smem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_mk_eval: resolution exceeds shared memory");
+  StreamAlloc b_tg, b_ep, b_dl;
+  RB_CUDA(b_tg.alloc((size_t)G * sizeof(double), st));
+  RB_CUDA(cudaMemcpyAsync(b_tg.p, tg.data(), (size_t)G * sizeof(double), cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  RB_CUDA(b_ep.alloc((size_t)rb::kEpochCols * (size_t)E * sizeof(double), st));
+  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
+                                                                    y ? sigma : nullptr, cfg->upper_limits,
+                                                                    b_ep.as<double>());
+  launch_counter()->fetch_add(1);
+  const double* dl = dl_cm;
+  if (!dl) {
+    RB_CUDA(b_dl.alloc((size_t)N * sizeof(double), st));
+    rb::dl_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(cfg->cosmology, N, params + (size_t)RB_MK_REDSHIFT * N,
+                                                          b_dl.as<double>());
+    launch_counter()->fetch_add(1);
+    dl = b_dl.as<double>();
+  }
+  rb::MkArgs a{};
+  a.cfg = *cfg;
+  a.N = N;
+  a.E = (int)E;
+  a.G = G;
+  a.params = params;
+  a.param_stride = N;
+  a.dl_cm = dl;
+  a.sigma_param = sigma_param;
+  a.tgrid = b_tg.as<double>();
+  a.epoch_tab = b_ep.as<double>();
+  a.out_model = out_model;
+  a.out_logl = y ? out_logl : nullptr;
+  a.want_logl = y ? 1 : 0;
+  int occ = 0;
+  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::mk_kernel, rb::kMkThreads, smem));
+  if (occ < 1) occ = 1;
+  rb::mk_kernel<<<(unsigned)std::min<int64_t>(N, (int64_t)sms * occ * 4), rb::kMkThreads, smem, st>>>(a);
+  launch_counter()->fetch_add(1);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
+extern "C" int rb_mk_eval_f64_host(const rb_mk_config* cfg, int64_t N, int64_t E, const double* params,
+                                   const double* t_obs, const double* freq_obs, const double* dl_cm,
+                                   const double* y, const double* sigma, const double* sigma_param,
+                                   double* out_model, double* out_logl) {
+  int rc = mk_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
+  const size_t nN = (size_t)N, nE = (size_t)E;
+  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
+    if (!h) return cudaSuccess;
+    cudaError_t e = b.alloc(n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  RB_CUDA(up(d_par, params, (size_t)RB_MK_NPARAM * nN));
+  RB_CUDA(up(d_t, t_obs, nE));
+  RB_CUDA(up(d_f, freq_obs, nE));
+  RB_CUDA(up(d_dl, dl_cm, nN));
+  RB_CUDA(up(d_y, y, nE));
+  RB_CUDA(up(d_s, sigma, nE));
+  RB_CUDA(up(d_sp, sigma_param, nN));
+  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
+  if (out_logl) RB_CUDA(d_l.alloc(nN));
+  rc = rb_mk_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
   if (rc != RB_OK) return rc;
   if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
   if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));

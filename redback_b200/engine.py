@@ -385,6 +385,28 @@ class MergernovaPath(_FusedPath):
             raise ValueError("A value in x_new is below the interpolation range: mergernova models need time > 0")
 
 
+class MetzgerMagnetarPath(_FusedPath):
+    """Magnetar-driven Metzger shell model -> blackbody -> Gaussian log L
+    (redback/transient_models/magnetar_driven_ejecta_models.py:576-905)."""
+
+    ROWS = _capi.MK_ROWS
+    NPARAM = _capi.MK_NPARAM
+
+    def __init__(self, engine, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED,
+                 use_gamma_ray_opacity=False, pair_cascade_switch=True, ejecta_albedo=0.5, pair_cascade_fraction=0.01,
+                 neutron_precursor_switch=True, vmax=0.7, cosmology=None, device=None):
+        self.cfg = _capi.mk_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
+                                   pair_cascade_fraction, neutron_precursor_switch, vmax, cosmology)
+        self._setup(time, frequency, y, sigma, device)
+
+    def _eval_fn(self):
+        return _capi.lib().rb_mk_eval_f64
+
+    def _check_time(self, t):
+        if np.any(~(t > 0)):
+            raise ValueError("A value in x_new is below the interpolation range: these models need time > 0")
+
+
 class MergernovaMagPath(MergernovaPath):
     """Magnitude / bandpass-flux branch of the mergernova models (_processing_other_formats,
     magnetar_driven_ejecta_models.py:198-238)."""

@@ -4,7 +4,7 @@ general_mergernova_thermalisation :374-419), output_format='flux_density' | 'mag
 `params_batch` (see supernova_models.py)."""
 from . import _capi
 from ._fused import FusedSpec, cosmology_from_kwargs, output_mode, run
-from .engine import MergernovaMagPath, MergernovaPath
+from .engine import MergernovaMagPath, MergernovaPath, MetzgerMagnetarPath
 
 _EJECTA = ("redshift", "mej", "beta", "ejecta_radius", "kappa", "n_ism")
 
@@ -73,6 +73,70 @@ def general_mergernova_thermalisation(time, redshift=None, mej=None, beta=None, 
     return run(_GENERAL_TH, time, named, kwargs, params_batch)
 
 
+_SHELLS = ("redshift", "mej", "vej", "beta", "kappa_r")
+
+
+def _metzger_spec(name, engine, engine_params, last, gamma_ray):
+    needed = _SHELLS + tuple(engine_params) + (last,)
+
+    def validate(kwargs):
+        fmt = kwargs.get("output_format")
+        if fmt is None:
+            raise KeyError("output_format")
+        if fmt != "flux_density":
+            raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device")
+        if kwargs.get("magnetar_heating", "first_layer") != "first_layer":
+            raise NotImplementedError(f"{name}: magnetar_heating='all_layers' is not fused on device")
+
+    def build(time, kwargs, y, sigma, sigma_mode):
+        return MetzgerMagnetarPath(engine, time, frequency=kwargs.get("frequency"), y=y, sigma=sigma,
+                                   sigma_mode=sigma_mode, use_gamma_ray_opacity=gamma_ray,
+                                   pair_cascade_switch=kwargs.get("pair_cascade_switch", True),
+                                   ejecta_albedo=kwargs.get("ejecta_albedo", 0.5),
+                                   pair_cascade_fraction=kwargs.get("pair_cascade_fraction", 0.01),
+                                   neutron_precursor_switch=kwargs.get("neutron_precursor_switch", True),
+                                   vmax=kwargs.get("vmax", 0.7), cosmology=cosmology_from_kwargs(kwargs),
+                                   device=kwargs.get("device"))
+
+    return FusedSpec(name, needed, build, validate)
+
+
+_MK_BASIC = _metzger_spec("metzger_magnetar_driven_kilonova_model", _capi.MN_BASIC_MAGNETAR,
+                          ("p0", "bp", "mass_ns", "theta_pb"), "thermalisation_efficiency", False)
+_MK_GENERAL = _metzger_spec("general_metzger_magnetar_driven", _capi.MN_MAGNETAR_ONLY, ("l0", "tau_sd", "nn"),
+                            "thermalisation_efficiency", False)
+_MK_GENERAL_TH = _metzger_spec("general_metzger_magnetar_driven_thermalisation", _capi.MN_MAGNETAR_ONLY,
+                               ("l0", "tau_sd", "nn"), "kappa_gamma", True)
+
+
+def metzger_magnetar_driven_kilonova_model(time, redshift=None, mej=None, vej=None, beta=None, kappa_r=None, p0=None,
+                                           bp=None, mass_ns=None, theta_pb=None, thermalisation_efficiency=None,
+                                           params_batch=None, **kwargs):
+    """redback magnetar_driven_ejecta_models.metzger_magnetar_driven_kilonova_model (:760-806): Metzger (2017) shell
+    model with a basic_magnetar heating the innermost shell; kwargs pair_cascade_switch (True), ejecta_albedo,
+    pair_cascade_fraction (0.01), neutron_precursor_switch, vmax; mJy."""
+    named = dict(redshift=redshift, mej=mej, vej=vej, beta=beta, kappa_r=kappa_r, p0=p0, bp=bp, mass_ns=mass_ns,
+                 theta_pb=theta_pb, thermalisation_efficiency=thermalisation_efficiency)
+    return run(_MK_BASIC, time, named, kwargs, params_batch)
+
+
+def general_metzger_magnetar_driven(time, redshift=None, mej=None, vej=None, beta=None, kappa_r=None, l0=None,
+                                    tau_sd=None, nn=None, thermalisation_efficiency=None, params_batch=None, **kwargs):
+    """redback magnetar_driven_ejecta_models.general_metzger_magnetar_driven (:809-856)."""
+    named = dict(redshift=redshift, mej=mej, vej=vej, beta=beta, kappa_r=kappa_r, l0=l0, tau_sd=tau_sd, nn=nn,
+                 thermalisation_efficiency=thermalisation_efficiency)
+    return run(_MK_GENERAL, time, named, kwargs, params_batch)
+
+
+def general_metzger_magnetar_driven_thermalisation(time, redshift=None, mej=None, vej=None, beta=None, kappa_r=None,
+                                                   l0=None, tau_sd=None, nn=None, kappa_gamma=None, params_batch=None,
+                                                   **kwargs):
+    """redback magnetar_driven_ejecta_models.general_metzger_magnetar_driven_thermalisation (:859-905)."""
+    named = dict(redshift=redshift, mej=mej, vej=vej, beta=beta, kappa_r=kappa_r, l0=l0, tau_sd=tau_sd, nn=nn,
+                 kappa_gamma=kappa_gamma)
+    return run(_MK_GENERAL_TH, time, named, kwargs, params_batch)
+
+
 def _trapped_spec(output):
     needed = (("redshift",) if output == _capi.MN_OUT_TRAPPED_FLUX else ()) + _EJECTA[1:] + \
         ("l0", "tau_sd", "nn", "thermalisation_efficiency")
@@ -115,4 +179,6 @@ def trapped_magnetar(time, redshift=None, mej=None, beta=None, ejecta_radius=Non
     return run(_TRAPPED.for_kwargs(kwargs), time, named, kwargs, params_batch)
 
 
-FUSED = {trapped_magnetar: _TRAPPED, basic_mergernova: _BASIC, general_mergernova: _GENERAL, general_mergernova_thermalisation: _GENERAL_TH}
+FUSED = {trapped_magnetar: _TRAPPED, metzger_magnetar_driven_kilonova_model: _MK_BASIC,
+         general_metzger_magnetar_driven: _MK_GENERAL, general_metzger_magnetar_driven_thermalisation: _MK_GENERAL_TH,
+         basic_mergernova: _BASIC, general_mergernova: _GENERAL, general_mergernova_thermalisation: _GENERAL_TH}

@@ -139,3 +139,19 @@ def mergernova_prior(rng, n, kind="basic"):
     else:
         p["thermalisation_efficiency"] = rng.uniform(0.1, 1, n)
     return p
+
+
+def metzger_magnetar_prior(rng, n, kind="basic"):
+    """priors/metzger_magnetar_driven_kilonova_model.prior, general_metzger_magnetar_driven(_thermalisation).prior"""
+    p = dict(redshift=rng.uniform(1e-6, 0.1, n), mej=rng.uniform(1e-2, 0.05, n), vej=rng.uniform(0.05, 0.3, n),
+             beta=rng.uniform(1.5, 8, n), kappa_r=rng.uniform(1, 30, n))
+    if kind == "basic":
+        p.update(p0=loguniform(rng, 0.7, 1e2, n), bp=loguniform(rng, 1e-2, 1e2, n), mass_ns=rng.uniform(1.1, 2.2, n),
+                 theta_pb=rng.uniform(0.01, 1.57, n))
+    else:
+        p.update(l0=loguniform(rng, 1e40, 1e48, n), tau_sd=loguniform(rng, 10, 1e5, n), nn=rng.uniform(2, 7, n))
+    if kind == "thermalisation":
+        p["kappa_gamma"] = loguniform(rng, 1e-4, 1e4, n)
+    else:
+        p["thermalisation_efficiency"] = rng.uniform(0.1, 1, n)
+    return p

@@ -120,6 +120,47 @@ def test_trapped_magnetar(rb):
         fn(ts, params_batch=p, frequency=nu, output_format="flux_density")
 
 
+@pytest.mark.parametrize("kind", ["basic", "general", "thermalisation"])
+def test_metzger_magnetar_driven(rb, kind):
+    """metzger_magnetar_driven_kilonova_model / general_metzger_magnetar_driven(_thermalisation)
+    (magnetar_driven_ejecta_models.py:576-905): the reference's golden vectors and prior draws against the oracle.
+    The thermalisation variant's efficiency 1 - exp(-x), x ~ 1e-15, is quantised in units of 1.1e-16 in the reference
+    itself (see tests/test_oracle_golden.py): it is compared at the reference's own 1e-5."""
+    import json
+    import os
+    name = dict(basic="metzger_magnetar_driven_kilonova_model", general="general_metzger_magnetar_driven",
+                thermalisation="general_metzger_magnetar_driven_thermalisation")[kind]
+    rtol = 1e-5 if kind == "thermalisation" else 1e-9
+    fn = getattr(rb.magnetar_driven_ejecta_models, name)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "all_models_subset.json")) as fh:
+        e = json.load(fh)["magnetar." + name]
+    t = np.array(e["time"])
+    for params, res in zip(e["params"], e["results"]):
+        out = fn(t, **params, **e["eval_kwargs"])
+        h.assert_close(out, h.golden_array(res), max(rtol, 2e-7), what=name + " golden")   # Wien-tail values x 200
+    rng = np.random.default_rng({"basic": 111, "general": 112, "thermalisation": 113}[kind])
+    t = np.geomspace(0.05, 60, 30)
+    nu = np.where(np.arange(30) % 3 == 0, 3e14, 6e14)
+    N = 12
+    p = h.metzger_magnetar_prior(rng, N, kind)
+    kw = dict(frequency=nu, output_format="flux_density")
+    out = fn(t, params_batch=p, **kw)
+    y = out[1] * 1.04
+    sigma = 0.1 * np.abs(out[1]) + 1e-30
+    logl = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=kw).log_likelihood_batch(p)
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        z = kwi.pop("redshift")
+        ref = getattr(r, name)(t, z, frequency=nu, **kwi)
+        # h nu / k T amplifies the ~1e-15 agreement of the temperatures in the Wien tail
+        with np.errstate(all="ignore"):
+            amp = 1e-13 * np.maximum(1.0, -np.log(np.maximum(np.abs(ref), 1e-300) / np.nanmax(np.abs(ref))))
+        h.assert_close(out[i], ref, rtol, amp, what=f"{name} sample {i}")
+        ref_l = r.gaussian_likelihood(y, ref, sigma)
+        assert abs(logl[i] - ref_l) <= 1e-6 + max(rtol, 1e-8) * abs(ref_l), (i, logl[i], ref_l)
+
+
 def test_scalar_call_kwargs_and_errors(rb):
     t = np.geomspace(0.05, 100, 12)
     kw = dict(mej=0.02, beta=0.3, ejecta_radius=3e9, kappa=5.0, n_ism=1e-2, l0=1e47, tau_sd=1e3, nn=3.0,

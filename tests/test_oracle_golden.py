@@ -42,6 +42,15 @@ CASES = {
     "magnetar.trapped_magnetar":
         lambda t, p, kw: r.trapped_magnetar(t, kw["redshift"], frequency=np.full(t.size, kw["frequency"]),
                                             output_format=kw["output_format"], photon_index=kw["photon_index"], **p),
+    "magnetar.metzger_magnetar_driven_kilonova_model":
+        lambda t, p, kw: r.metzger_magnetar_driven_kilonova_model(t, kw["redshift"],
+                                                                  frequency=np.full(t.size, kw["frequency"]), **p),
+    "magnetar.general_metzger_magnetar_driven":
+        lambda t, p, kw: r.general_metzger_magnetar_driven(t, kw["redshift"],
+                                                           frequency=np.full(t.size, kw["frequency"]), **p),
+    "magnetar.general_metzger_magnetar_driven_thermalisation":
+        lambda t, p, kw: r.general_metzger_magnetar_driven_thermalisation(
+            t, kw["redshift"], frequency=np.full(t.size, kw["frequency"]), **p),
     "kilonova.two_component_kilonova_model":
         lambda t, p, kw: r.two_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.three_component_kilonova_model":
@@ -56,6 +65,14 @@ CASES = {
 }
 
 
+# The thermalisation variant evaluates 1 - exp(-x) with x = 3 kappa_gamma mej / (4 pi vej^2) / t^2 in (Msun, c, s) units
+# (magnetar_driven_ejecta_models.py:674-676): x ~ 1e-15 at late times, so the reference's own efficiency is quantised
+# in steps of 1.1e-16 and depends on the last bit of exp().  The pickle (another platform) and this machine differ by
+# 1e-8 in the late-time temperature, times h nu / k T ~ 200 in the stored Wien-tail values (1e-82, 1e-106 mJy).  The
+# reference checks these vectors at 1e-5.
+RTOL_BY_CASE = {"magnetar.general_metzger_magnetar_driven_thermalisation": 1e-5}
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_oracle_matches_reference_golden(golden, name):
     entry = golden[name]
@@ -65,7 +82,7 @@ def test_oracle_matches_reference_golden(golden, name):
         out = CASES[name](t, params, entry["eval_kwargs"])
         assert np.array_equal(np.isnan(out), np.isnan(expected))
         ok = ~np.isnan(expected)
-        np.testing.assert_allclose(out[ok], expected[ok], rtol=RTOL, atol=0)
+        np.testing.assert_allclose(out[ok], expected[ok], rtol=RTOL_BY_CASE.get(name, RTOL), atol=0)
 
 
 def test_planck18_luminosity_distance():

@@ -18,7 +18,7 @@ import helpers as h  # noqa: E402
 from redback_b200 import _capi  # noqa: E402
 from redback_b200 import bands as rb_bands  # noqa: E402
 from redback_b200.engine import (AfterglowPath, KilonovaMagPath, KilonovaPath, MergernovaPath,  # noqa: E402
-                                 SupernovaMagPath, SupernovaPath)
+                                 MetzgerMagnetarPath, SupernovaMagPath, SupernovaPath)
 
 
 def timed(path, params, steps=3, warmup=3):
@@ -68,6 +68,10 @@ def main():
                  lambda n: MergernovaPath(_capi.MN_MAGNETAR_ONLY, t3, frequency=nu3, y=np.full(200, 1e-3), sigma=1e-4,
                                           pair_cascade_switch=True),
                  lambda n: h.mergernova_prior(rng, n, "general"), None))
+    jobs.append(("general_metzger_magnetar_driven flux_density E=200 (config 3 epochs)", int(200_000 * scale),
+                 lambda n: MetzgerMagnetarPath(_capi.MN_MAGNETAR_ONLY, t3, frequency=nu3, y=np.full(200, 1e-3),
+                                               sigma=1e-4),
+                 lambda n: h.metzger_magnetar_prior(rng, n, "general"), None))
     t4, nu4 = h.config4_epochs()
     jobs.append(("tophat_redback radio+X-ray E=500 (config 4 shape)", int(200_000 * scale),
                  lambda n: AfterglowPath(_capi.AG_TOPHAT, t4, frequency=nu4, y=np.full(500, 1e-3), sigma=1e-4),
