@@ -75,3 +75,22 @@ def simulate_population_with_cadence(model, params_batch, times, bands, limiting
     out = add_optical_noise_and_cuts(mags, bands, limiting_mag, noise_type, snr_threshold, apply_snr_cut, seed)
     out["model_magnitude"] = mags
     return out
+
+
+def population_light_curves(model, parameters, times=None, model_kwargs=None, device_output=False):
+    """The light-curve loop of PopulationSynthesizer.simulate_population (simulate_transients.py:2027-2036) as one
+    batched call: `parameters` is the population table ({name: array[N]} or a pandas DataFrame as returned by
+    generate_population), `times` defaults to np.linspace(0, 100, 100) like the reference.  Columns that are not
+    parameters of `model` (sky position, event time, ...) are ignored.  Returns {'times': [E], 'flux': [N, E]}."""
+    times = np.linspace(0, 100, 100) if times is None else np.asarray(times, dtype=np.float64)
+    table = parameters.to_dict("list") if hasattr(parameters, "to_dict") else dict(parameters)
+    batch = {}
+    for k, v in table.items():          # the model picks the columns it needs; non-numeric ones cannot be parameters
+        try:
+            batch[k] = np.asarray(v, dtype=np.float64)
+        except (TypeError, ValueError):
+            continue
+    kw = dict(model_kwargs or {})
+    if device_output:
+        kw["device_output"] = True
+    return {"times": times, "flux": model(times, params_batch=batch, **kw)}

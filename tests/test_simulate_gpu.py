@@ -63,3 +63,23 @@ def test_population_with_cadence(rb):
     assert abs(pull.mean()) < 0.05 and abs(pull.std() - 1) < 0.05
     again = rb.simulate.simulate_population_with_cadence(rb.supernova_models.arnett, p, t, names, lim, seed=3)
     assert torch.equal(again["flux"].nan_to_num(0.0), out["flux"].nan_to_num(0.0))   # seeded => reproducible
+
+
+def test_population_light_curves(rb):
+    """PopulationSynthesizer.simulate_population's per-event light-curve loop (simulate_transients.py:2027-2036) as
+    one batched call; non-model columns of the population table are ignored."""
+    import numpy as np
+    import helpers as h
+    from oracle import restated as r
+    rng = np.random.default_rng(5)
+    N = 9
+    p = h.arnett_prior(rng, N, zmax=0.3)
+    table = dict(p, ra=rng.uniform(0, 360, N), dec=rng.uniform(-90, 90, N), t0_mjd_transient=rng.uniform(6e4, 6.1e4, N))
+    times = np.linspace(1, 100, 40)
+    out = rb.simulate.population_light_curves(rb.supernova_models.arnett, table, times,
+                                              model_kwargs=dict(frequency=4.7e14, output_format="flux_density"))
+    assert out["flux"].shape == (N, 40) and np.array_equal(out["times"], times)
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        h.assert_close(out["flux"][i], r.arnett(times, z, frequency=np.full(40, 4.7e14), **kw), 1e-9, what=f"event {i}")
