@@ -437,6 +437,11 @@ int rb_gaussian_logl_f64(int sigma_mode, int64_t N, int64_t E, const double* mod
 int rb_mixture_logl_f64(int64_t N, int64_t E, const double* model, const double* y, const double* sigma,
                         const double* alpha, const double* sigma_out, double* out_logl, void* stream);
 
+/* sizeof() of the ABI structs, so that a foreign-language binding can check its own layout before the first call:
+ * which = 0 rb_cosmology, 1 rb_upper_limits, 2 rb_sn_config, 3 rb_kn_config, 4 rb_ag_config, 5 rb_mn_config,
+ * 6 rb_mk_config, 7 rb_photometry; -1 for anything else. */
+int64_t rb_sizeof(int which);
+
 /* FP64 FMA micro-benchmark: runs `iters` dependent-chain DFMAs per thread on a full grid and
  * returns the achieved TFLOP/s (2 flop per FMA) in *out_tflops.  Used as the roofline denominator. */
 int rb_measure_fp64_peak(int iters, double* out_tflops, double* out_ms);

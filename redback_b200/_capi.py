@@ -133,6 +133,7 @@ EXPORTS = {
     "rb_gaussian_logl_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 4 + [C.POINTER(UpperLimits), _dp,
                                        C.c_void_p]),
     "rb_mixture_logl_f64": (C.c_int, [C.c_int64, C.c_int64] + [_dp] * 6 + [C.c_void_p]),
+    "rb_sizeof": (C.c_int64, [C.c_int]),
     "rb_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -408,6 +408,20 @@ int rb_sn_eval_f64_host(const rb_sn_config* cfg, int64_t N, int64_t E, const dou
   return RB_OK;
 }
 
+int64_t rb_sizeof(int which) {
+  switch (which) {
+    case 0: return (int64_t)sizeof(rb_cosmology);
+    case 1: return (int64_t)sizeof(rb_upper_limits);
+    case 2: return (int64_t)sizeof(rb_sn_config);
+    case 3: return (int64_t)sizeof(rb_kn_config);
+    case 4: return (int64_t)sizeof(rb_ag_config);
+    case 5: return (int64_t)sizeof(rb_mn_config);
+    case 6: return (int64_t)sizeof(rb_mk_config);
+    case 7: return (int64_t)sizeof(rb_photometry);
+    default: return -1;
+  }
+}
+
 int rb_measure_fp64_peak(int iters, double* out_tflops, double* out_ms) {
   if (iters <= 0 || !out_tflops) return fail(RB_ERR_INVALID, "rb_measure_fp64_peak: bad arguments");
   int dev = 0, sms = 0;

@@ -44,3 +44,25 @@ def test_host_side_calls_without_gpu():
 
 def test_library_is_in_tree():
     assert _build.LIB_PATH.startswith(ROOT)
+
+
+def test_ctypes_struct_layouts_match_the_library():
+    """The ctypes mirrors must have the C structs' sizes (a config_default memset would overrun a short mirror), and the
+    defaults must land in the right fields (offsets)."""
+    from redback_b200 import bands
+    lib = _capi.lib()
+    mirrors = [_capi.Cosmology, _capi.UpperLimits, _capi.SnConfig, _capi.KnConfig, _capi.AgConfig, _capi.MnConfig,
+               _capi.MkConfig, bands.Photometry]
+    for which, cls in enumerate(mirrors):
+        assert lib.rb_sizeof(which) == ctypes.sizeof(cls), (cls.__name__, lib.rb_sizeof(which), ctypes.sizeof(cls))
+    assert lib.rb_sizeof(99) == -1
+    sn = _capi.sn_config(_capi.ENGINE_NICKEL, _capi.SED_BLACKBODY)
+    assert (sn.csm_nn, sn.csm_delta, sn.csm_efficiency, sn.line_amplitude, sn.no_interaction) == (12.0, 1.0, 0.5, 0.3, 0)
+    kn = _capi.kn_config(_capi.KN_ONE_COMPONENT)
+    assert kn.grid_t_max == 7e6 and kn.vmax == 0.7
+    mn = _capi.mn_config(_capi.MN_BASIC_MAGNETAR)
+    assert (mn.resolution, mn.photon_index, mn.ejecta_albedo) == (500, 2.0, 0.5)
+    mk = _capi.mk_config(_capi.MN_BASIC_MAGNETAR)
+    assert (mk.resolution, mk.pair_cascade_fraction, mk.vmax, mk.pair_cascade_switch) == (300, 0.01, 0.7, 1)
+    ag = _capi.ag_config(_capi.AG_TOPHAT)
+    assert (ag.steps, ag.ab_magnitude) == (250, 0)
