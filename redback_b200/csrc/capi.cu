@@ -580,7 +580,9 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   a.tmax_obs = h_mm[1];
   rb::kn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
   const size_t smem = kn_smem_bytes(cfg, E);
-  const int threads = 512;
+  // measured (tools/bench_paths.py): one-component 512 threads 45.4 ms, 256: 35.1, 128: 29.8; Metzger (needs 224 shell
+  // threads) 512: 404 ms, 256: 241 -- smaller blocks, more of them per SM hide the per-sample barriers
+  const int threads = (cfg->model == RB_KN_METZGER) ? 256 : 128;
   int occ = 0;
   RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::kn_kernel, threads, smem));
   if (occ < 1) occ = 1;
@@ -1480,7 +1482,8 @@ extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* 
   rb_kn_config kcfg = *cfg;
   const size_t ksmem = kn_smem_bytes(&kcfg, 1);
   int occ_kn = 1, occ_ph = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_kn, rb::kn_kernel, 512, ksmem);
+  const int kn_threads = (cfg->model == RB_KN_METZGER) ? 256 : 512;   // grid mode: 512 measured faster than 128 (457 vs 537 ms)
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_kn, rb::kn_kernel, kn_threads, ksmem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
   if (occ_kn < 1) occ_kn = 1;
   if (occ_ph < 1) occ_ph = 1;
@@ -1518,7 +1521,7 @@ extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* 
     a.opz_out = d_opz;
     a.dl_out = d_dl;
     rb::kn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
-    rb::kn_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_kn * 4), 512, ksmem, st>>>(a);
+    rb::kn_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_kn * 4), kn_threads, ksmem, st>>>(a);
     pa.N = nc;
     pa.n_base = n0;
     pa.E = (int)E;
