@@ -56,10 +56,10 @@ struct StreamAlloc {
   template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
-size_t sn_smem_bytes(int D, int64_t E, bool epochs_in_smem) {
-  size_t n = (size_t)(2 * D + 2 * rb::kNodes + D + rb::kNodesHalf + rb::kNodes + rb::kNodes + rb::kExpTabSize + 2 * rb::kScalars + 16)  // incl. omx2
-             + (size_t)(2 * rb::kNodes + (D + 1) / 2 * 2);   // FP32 copies: float4 nodes, float2 segments
+size_t sn_smem_bytes(int D, int64_t E, bool epochs_in_smem, bool fp32 = false) {
+  size_t n = (size_t)(2 * D + 2 * rb::kNodes + D + rb::kNodesHalf + rb::kNodes + rb::kNodes + rb::kExpTabSize + 2 * rb::kScalars + 16);  // incl. omx2
   if (epochs_in_smem) n += (size_t)rb::kEpochCols * (size_t)E;
+  if (fp32) n += (size_t)(2 * rb::kNodes + (D + 1) / 2 * 2);   // FP32 copies: float4 nodes, float2 segments
   return sizeof(double) * n;
 }
 
@@ -307,8 +307,9 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   }
   rb::sn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
   const int threads = sn_block_threads(E);
-  a.epochs_in_smem = (sn_smem_bytes(cfg->dense_resolution, E, true) <= 64 * 1024) ? 1 : 0;
-  const size_t smem = sn_smem_bytes(cfg->dense_resolution, E, a.epochs_in_smem != 0);
+  const bool fp32 = cfg->precision == RB_PREC_F32;
+  a.epochs_in_smem = (sn_smem_bytes(cfg->dense_resolution, E, true, true) <= 64 * 1024) ? 1 : 0;
+  const size_t smem = sn_smem_bytes(cfg->dense_resolution, E, a.epochs_in_smem != 0, fp32);
   if (smem > 220 * 1024) return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution too large for shared memory");
   int occ = 0;
   const SnKernelFn kern = sn_kernel_fn(cfg->engine, cfg->t0 != nullptr);

@@ -411,9 +411,11 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
   double* tab = omx2 + kNodes;                           // [1024]   2^(j/1024)
   double* scb = tab + kExpTabSize;                               // [2][kScalars] per-sample scalars, double-buffered
   double* scratch = scb + 2 * kScalars;                  // [16]     per-warp partial sums
-  float4* nodesf = reinterpret_cast<float4*>(scratch + 16);          // [kNodes]  FP32 copies (RB_PREC_F32)
+  // FP32 copies only for RB_PREC_F32: the FP64 path does not pay their 10 KB per block (one more resident block per SM
+  // at small E); [kEpochCols][E] follows when epochs_in_smem
+  float4* nodesf = reinterpret_cast<float4*>(scratch + 16);          // [kNodes]
   float2* segf = reinterpret_cast<float2*>(nodesf + kNodes);         // [D]
-  double* ep_s = reinterpret_cast<double*>(segf + D + (D & 1));      // [kEpochCols][E] when epochs_in_smem
+  double* ep_s = (a.cfg.precision == RB_PREC_F32) ? reinterpret_cast<double*>(segf + D + (D & 1)) : scratch + 16;
 
   const int tid = threadIdx.x;
   const int E = a.E;
