@@ -273,7 +273,11 @@ int rb_ag_eval_f64_host(const rb_ag_config* cfg, int64_t N, int64_t E, const dou
  * radius and Doppler factor at the epochs -> _comoving_blackbody_to_flux_density (:153-174) -> mJy (1+z)^2
  * (:262, :272) -> Gaussian log-likelihood. */
 enum { RB_MN_BASIC_MAGNETAR = 0,   /* basic_magnetar(p0, bp, mass_ns, theta_pb)  (magnetar_models.py:171-185) */
-       RB_MN_MAGNETAR_ONLY = 1 };  /* magnetar_only(l0, tau_sd, nn)              (magnetar_models.py:134-144) */
+       RB_MN_MAGNETAR_ONLY = 1,    /* magnetar_only(l0, tau_sd, nn)              (magnetar_models.py:134-144) */
+       RB_MN_EVOLVING = 2 };       /* _evolving_gw_and_em_magnetar(bint, bext, p0 [s], chi0, radius, moi)
+                                      (magnetar_models.py:187-224): explicit Euler of the spin frequency under EM + GW
+                                      torques on the model grid, L = Edot_d; general_mergernova_evolution (:422-474) and
+                                      general_metzger_magnetar_driven_evolution (:908-956), both with gamma-ray opacity */
 enum {
   RB_MN_REDSHIFT = 0,
   RB_MN_MEJ = 1,            /* [Msun] */
@@ -286,7 +290,11 @@ enum {
   RB_MN_MASS_NS = 8, RB_MN_NN = 8,
   RB_MN_THETA_PB = 9,
   RB_MN_THERMALISATION_EFFICIENCY = 10, RB_MN_KAPPA_GAMMA = 10,   /* by use_gamma_ray_opacity */
-  RB_MN_NPARAM = 11
+  /* RB_MN_EVOLVING: rows 6-9 = logbint, logbext, p0 [s], chi0; row 10 = kappa_gamma; then */
+  RB_MN_LOGBINT = 6, RB_MN_LOGBEXT = 7, RB_MN_EV_P0 = 8, RB_MN_CHI0 = 9,
+  RB_MN_NS_RADIUS = 11,     /* [km] */
+  RB_MN_LOGMOI = 12,
+  RB_MN_NPARAM = 13
 };
 
 typedef struct {
@@ -339,7 +347,11 @@ enum {
   RB_MK_MASS_NS = 7, RB_MK_NN = 7,
   RB_MK_THETA_PB = 8,
   RB_MK_THERMALISATION_EFFICIENCY = 9, RB_MK_KAPPA_GAMMA = 9,
-  RB_MK_NPARAM = 10
+  /* RB_MN_EVOLVING: rows 5-8 = logbint, logbext, p0 [s], chi0; row 9 = kappa_gamma; then */
+  RB_MK_LOGBINT = 5, RB_MK_LOGBEXT = 6, RB_MK_EV_P0 = 7, RB_MK_CHI0 = 8,
+  RB_MK_NS_RADIUS = 10,     /* [km] */
+  RB_MK_LOGMOI = 11,
+  RB_MK_NPARAM = 12
 };
 
 typedef struct {
@@ -351,7 +363,7 @@ typedef struct {
   double pair_cascade_fraction;  /* 0.01 (:592) */
   int neutron_precursor_switch;  /* default 1 (:593) */
   double vmax;                   /* 0.7 (:595) */
-  int resolution;                /* get_optimal_time_array(1e-4, 1e7, 300) (:777) */
+  int resolution;                /* get_optimal_time_array(1e-4, 1e7, 300) (:777); 500 for ..._evolution (:917) */
   rb_cosmology cosmology;
   rb_upper_limits upper_limits;
 } rb_mk_config;

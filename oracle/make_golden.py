@@ -83,6 +83,7 @@ KEEP = [
     "supernova.sn_fallback", "supernova.sn_nickel_fallback",
     "magnetar.metzger_magnetar_driven_kilonova_model", "magnetar.general_metzger_magnetar_driven",
     "magnetar.general_metzger_magnetar_driven_thermalisation",
+    "magnetar.general_mergernova_evolution", "magnetar.general_metzger_magnetar_driven_evolution",
 ]
 
 

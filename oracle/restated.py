@@ -818,6 +818,37 @@ def mergernova_flux_density(time, redshift, dynamics, *, frequency, dl=None):
         return fd * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)                                        # :272
 
 
+graviational_constant = 6.674299999999999e-08     # constants.py:20 (astropy G in cgs)
+
+
+def evolving_gw_and_em_magnetar(time, bint, bext, p0, chi0, radius, moi):
+    """magnetar_models._evolving_gw_and_em_magnetar (:187-224): Edot_d on `time` (explicit Euler of omega)."""
+    epsilon_b = -3e-4 * (bint / bext) ** 2 * (bext / 1e16) ** 2
+    omega_0 = 2.0 * np.pi / p0
+    dt = time[1:] - time[:-1]
+    omega = np.zeros_like(time)
+    chi = chi0
+    omega[0] = omega_0
+    for i in range(len(time) - 1):
+        omega[i + 1] = omega[i] + dt[i] * (
+            -(bext ** 2 * radius ** 6 / (moi * speed_of_light ** 3)) * omega[i] ** 3 * (1. + np.sin(chi)) - (
+                2.0 * graviational_constant * moi * epsilon_b ** 2 / (5.0 * speed_of_light ** 5)) * omega[i] ** 5
+            * np.sin(chi) ** 2 * (1.0 + 15.0 * np.sin(chi) ** 2))
+    return (bext ** 2 * radius ** 6 / (4 * speed_of_light ** 3)) * omega ** 4 * (1.0 + np.sin(chi) ** 2)
+
+
+def _evolving(logbint, logbext, p0, chi0, radius, logmoi):
+    return lambda t: evolving_gw_and_em_magnetar(t, 10 ** logbint, 10 ** logbext, p0, chi0, radius * km_cgs, 10 ** logmoi)
+
+
+def general_mergernova_evolution(time, redshift, mej, beta, ejecta_radius, kappa, n_ism, logbint, logbext, p0, chi0,
+                                 radius, logmoi, kappa_gamma, *, frequency, pair_cascade_switch=True, dl=None, **kw):
+    """general_mergernova_evolution (:422-474), flux_density."""
+    return _mergernova(time, redshift, _evolving(logbint, logbext, p0, chi0, radius, logmoi), mej, beta, ejecta_radius,
+                       kappa, n_ism, frequency=frequency, pair_cascade_switch=pair_cascade_switch, dl=dl,
+                       use_gamma_ray_opacity=True, kappa_gamma=kappa_gamma, **kw)
+
+
 def trapped_magnetar(time, redshift, mej, beta, ejecta_radius, kappa, n_ism, l0, tau_sd, nn,
                      thermalisation_efficiency, *, frequency, output_format="flux", photon_index=2.0, dl=None):
     """magnetar_driven_ejecta_models.trapped_magnetar (:477-573).  time: seconds."""
@@ -1157,12 +1188,12 @@ def metzger_magnetar_driven_internal(time, mej, vej, beta, kappa, magnetar_lumin
 
 
 def _metzger_magnetar_driven(time, redshift, lum_fn, mej, vej, beta, kappa_r, use_gamma_ray_opacity, *, frequency,
-                             dl=None, **dyn):
+                             dl=None, resolution=300, **dyn):
     """metzger_magnetar_driven_kilonova_model & co. (:760-905) + _process_flux_density (:240-272) with
     use_relativistic_blackbody=False."""
     if dl is None:
         dl = cosmo.luminosity_distance_cm(redshift)
-    t_grid = get_optimal_time_array(1e-4, 1e7, 300)
+    t_grid = get_optimal_time_array(1e-4, 1e7, resolution)
     _, temperature, r_photosphere = metzger_magnetar_driven_internal(t_grid, mej, vej, beta, kappa_r, lum_fn(t_grid),
                                                                      use_gamma_ray_opacity, **dyn)
     frequency, t = calc_kcorrected_properties(np.asarray(frequency, dtype=float), redshift,
@@ -1171,6 +1202,14 @@ def _metzger_magnetar_driven(time, redshift, lum_fn, mej, vej, beta, kappa_r, us
         fd = blackbody_to_flux_density(interp1d(t_grid, y=temperature)(t), interp1d(t_grid, y=r_photosphere)(t), dl,
                                        frequency)
         return fd * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)
+
+
+def general_metzger_magnetar_driven_evolution(time, redshift, mej, vej, beta, kappa_r, logbint, logbext, p0, chi0,
+                                              radius, logmoi, kappa_gamma, *, frequency, **kw):
+    """general_metzger_magnetar_driven_evolution (:908-956): 500-point grid request (:917)."""
+    return _metzger_magnetar_driven(time, redshift, _evolving(logbint, logbext, p0, chi0, radius, logmoi), mej, vej,
+                                    beta, kappa_r, True, frequency=frequency, kappa_gamma=kappa_gamma, resolution=500,
+                                    **kw)
 
 
 def metzger_magnetar_driven_kilonova_model(time, redshift, mej, vej, beta, kappa_r, p0, bp, mass_ns, theta_pb,

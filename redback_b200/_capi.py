@@ -68,11 +68,14 @@ class AgConfig(C.Structure):
                 ("aa", C.c_double), ("upper_limits", UpperLimits), ("ab_magnitude", C.c_int)]
 
 
-MN_BASIC_MAGNETAR, MN_MAGNETAR_ONLY = 0, 1
+MN_BASIC_MAGNETAR, MN_MAGNETAR_ONLY, MN_EVOLVING = 0, 1, 2
 MN_OUT_FLUX_DENSITY, MN_OUT_TRAPPED_LUMINOSITY, MN_OUT_TRAPPED_FLUX = 0, 1, 2
 MN_ROWS = dict(redshift=0, mej=1, beta=2, ejecta_radius=3, kappa=4, n_ism=5, p0=6, l0=6, bp=7, tau_sd=7, mass_ns=8,
                nn=8, theta_pb=9, thermalisation_efficiency=10, kappa_gamma=10)
-MN_NPARAM = 11
+MN_NPARAM = 13
+# RB_MN_EVOLVING reuses rows 6-9 and adds two
+MN_ROWS_EVOLVING = dict(redshift=0, mej=1, beta=2, ejecta_radius=3, kappa=4, n_ism=5, logbint=6, logbext=7, p0=8, chi0=9,
+                        kappa_gamma=10, radius=11, logmoi=12)
 
 
 class MnConfig(C.Structure):
@@ -84,7 +87,9 @@ class MnConfig(C.Structure):
 
 MK_ROWS = dict(redshift=0, mej=1, vej=2, beta=3, kappa_r=4, p0=5, l0=5, bp=6, tau_sd=6, mass_ns=7, nn=7, theta_pb=8,
                thermalisation_efficiency=9, kappa_gamma=9)
-MK_NPARAM = 10
+MK_NPARAM = 12
+MK_ROWS_EVOLVING = dict(redshift=0, mej=1, vej=2, beta=3, kappa_r=4, logbint=5, logbext=6, p0=7, chi0=8, kappa_gamma=9,
+                        radius=10, logmoi=11)
 
 
 class MkConfig(C.Structure):
@@ -234,7 +239,8 @@ def mn_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_
 
 
 def mk_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_cascade_switch=True,
-              ejecta_albedo=0.5, pair_cascade_fraction=0.01, neutron_precursor_switch=True, vmax=0.7, cosmology=None):
+              ejecta_albedo=0.5, pair_cascade_fraction=0.01, neutron_precursor_switch=True, vmax=0.7, cosmology=None,
+              resolution=300):
     cfg = MkConfig()
     check(lib().rb_mk_config_default(C.byref(cfg)))
     cfg.engine, cfg.sigma_mode = engine, sigma_mode
@@ -243,6 +249,7 @@ def mk_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_
     cfg.ejecta_albedo, cfg.pair_cascade_fraction = float(ejecta_albedo), float(pair_cascade_fraction)
     cfg.neutron_precursor_switch = int(bool(neutron_precursor_switch))
     cfg.vmax = float(vmax)
+    cfg.resolution = int(resolution)
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg

@@ -72,11 +72,22 @@ __global__ void __launch_bounds__(kMkThreads) mk_kernel(const MkArgs a) {
       const double tp = 1.3e5 * (1.0 / (bp * bp)) * (p0 * p0) * m15 * (1.0 / (sn * sn));
       eng_a = 2.0 * erot / tp;
       eng_b = tp;
-    } else {
+    } else if (a.cfg.engine == RB_MN_MAGNETAR_ONLY) {
       eng_a = P[RB_MK_L0 * S];
       eng_b = P[RB_MK_TAU_SD * S];
       const double nn = P[RB_MK_NN * S];
       eng_c = (1.0 + nn) / (1.0 - nn);
+    } else {
+      eng_a = eng_b = 0.0;
+      if (tid == 0) {                                   // sequential spin-down ODE over the grid (magnetar_models.py:200-205)
+        EvolvingMagnetar ev;
+        ev.init(P[RB_MK_LOGBINT * S], P[RB_MK_LOGBEXT * S], P[RB_MK_EV_P0 * S], P[RB_MK_CHI0 * S],
+                P[RB_MK_NS_RADIUS * S], P[RB_MK_LOGMOI * S]);
+        for (int k = 0; k < G; ++k) {
+          lsd[k] = ev.luminosity();
+          if (k + 1 < G) ev.step(tg[k + 1] - tg[k]);
+        }
+      }
     }
     // ---- grid quantities (:596-631) -------------------------------------------------------------------------------
     {
@@ -92,7 +103,7 @@ __global__ void __launch_bounds__(kMkThreads) mk_kernel(const MkArgs a) {
         if (a.cfg.engine == RB_MN_BASIC_MAGNETAR) {
           const double den = 1.0 + 2.0 * t / eng_b;
           lsd[k] = eng_a / (den * den);
-        } else {
+        } else if (a.cfg.engine == RB_MN_MAGNETAR_ONLY) {
           lsd[k] = eng_a * pow(1.0 + t / eng_b, eng_c);
         }
       }

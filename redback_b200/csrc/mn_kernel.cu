@@ -14,6 +14,31 @@ namespace rb {
 constexpr double kProtonMass = 1.67262192369e-24;      // constants.proton_mass
 constexpr double kRadiationConst = kSigmaSB * 4 / kC;  // constants.py:14
 
+constexpr double kGravConst = 6.674299999999999e-08;    // constants.graviational_constant (astropy G, cgs)
+
+// _evolving_gw_and_em_magnetar (magnetar_models.py:187-211): coefficients of the spin-down ODE and of Edot_d
+struct EvolvingMagnetar {
+  double c_em, c_gw, c_lum, omega;     // d omega/dt = -c_em omega^3 - c_gw omega^5;  L = c_lum omega^4
+  __device__ __forceinline__ void init(double logbint, double logbext, double p0, double chi0, double radius_km,
+                                       double logmoi) {
+    const double bint = pow(10.0, logbint), bext = pow(10.0, logbext), radius = radius_km * kKm, moi = pow(10.0, logmoi);
+    const double rb = bint / bext, b16 = bext / 1e16;
+    const double eps = -3e-4 * (rb * rb) * (b16 * b16);                                          // :192
+    const double sn = sin(chi0), sn2 = sn * sn;
+    const double r6 = (radius * radius * radius) * (radius * radius * radius);
+    const double c3 = kC * kC * kC, c5 = c3 * kC * kC;
+    c_em = (bext * bext * r6 / (moi * c3)) * (1. + sn);                                          // :202
+    c_gw = (2.0 * kGravConst * moi * (eps * eps) / (5.0 * c5)) * sn2 * (1.0 + 15.0 * sn2);       // :203
+    c_lum = (bext * bext * r6 / (4 * c3)) * (1.0 + sn2);                                         // :205
+    omega = 2.0 * kPi / p0;                                                                      // :193
+  }
+  __device__ __forceinline__ double luminosity() const { const double o2 = omega * omega; return c_lum * (o2 * o2); }
+  __device__ __forceinline__ void step(double dt) {                                              // :200-203
+    const double o2 = omega * omega, o3 = o2 * omega;
+    omega = omega + dt * (-c_em * o3 - c_gw * (o3 * o2));
+  }
+};
+
 // sorted epoch table columns
 enum { MS_T = 0, MS_NU, MS_Y, MS_ISIG, MS_LOGT, MS_KIND, MS_ORIG, kMnEpochCols };
 
@@ -87,12 +112,19 @@ __global__ void __launch_bounds__(128) mn_kernel(const MnArgs a) {
     const double tp = 1.3e5 * (1.0 / (bp * bp)) * (p0 * p0) * m15 * (1.0 / (sn * sn));
     eng_a = 2.0 * erot / tp;
     eng_b = tp;
-  } else {                                                                     // magnetar_models.py:143
+  } else if (a.cfg.engine == RB_MN_MAGNETAR_ONLY) {                            // magnetar_models.py:143
     eng_a = P[RB_MN_L0 * S];
     eng_b = P[RB_MN_TAU_SD * S];
     const double nn = P[RB_MN_NN * S];
     eng_c = (1.0 + nn) / (1.0 - nn);
+  } else {
+    eng_a = eng_b = 0.0;
   }
+  EvolvingMagnetar ev;
+  ev.c_em = ev.c_gw = ev.c_lum = ev.omega = 0.0;
+  if (a.cfg.engine == RB_MN_EVOLVING)
+    ev.init(P[RB_MN_LOGBINT * S], P[RB_MN_LOGBEXT * S], P[RB_MN_EV_P0 * S], P[RB_MN_CHI0 * S], P[RB_MN_NS_RADIUS * S],
+            P[RB_MN_LOGMOI * S]);
   const double row10 = P[RB_MN_THERMALISATION_EFFICIENCY * S];
   const double gprefac = 3.0 * row10 * m / (4.0 * kPi);                        // :103 (kappa_gamma variant), / vej^2 below
   const double lrad_coef = 4e49 * (m / 2e33 * 100.0);                          // :80
@@ -149,8 +181,11 @@ __global__ void __launch_bounds__(128) mn_kernel(const MnArgs a) {
     if (a.cfg.engine == RB_MN_BASIC_MAGNETAR) {
       const double den = 1.0 + 2.0 * t / eng_b;
       mag_lum = eng_a / (den * den);
-    } else {
+    } else if (a.cfg.engine == RB_MN_MAGNETAR_ONLY) {
       mag_lum = eng_a * pow(1.0 + t / eng_b, eng_c);
+    } else {
+      mag_lum = ev.luminosity();                       // Edot_d at grid point i; omega advances to i + 1 below
+      if (i + 1 < G) ev.step(mn_tg[i + 1] - t);
     }
     double eff = row10;
     if (a.cfg.use_gamma_ray_opacity) {

@@ -374,6 +374,8 @@ class MergernovaPath(_FusedPath):
                  pair_cascade_fraction=0.05, cosmology=None, device=None, output=0, photon_index=2.0):
         self.cfg = _capi.mn_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
                                    pair_cascade_fraction, cosmology, output, photon_index)
+        if engine == _capi.MN_EVOLVING:
+            self.ROWS = _capi.MN_ROWS_EVOLVING
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):
@@ -394,9 +396,11 @@ class MetzgerMagnetarPath(_FusedPath):
 
     def __init__(self, engine, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED,
                  use_gamma_ray_opacity=False, pair_cascade_switch=True, ejecta_albedo=0.5, pair_cascade_fraction=0.01,
-                 neutron_precursor_switch=True, vmax=0.7, cosmology=None, device=None):
+                 neutron_precursor_switch=True, vmax=0.7, cosmology=None, device=None, resolution=300):
         self.cfg = _capi.mk_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
-                                   pair_cascade_fraction, neutron_precursor_switch, vmax, cosmology)
+                                   pair_cascade_fraction, neutron_precursor_switch, vmax, cosmology, resolution)
+        if engine == _capi.MN_EVOLVING:
+            self.ROWS = _capi.MK_ROWS_EVOLVING
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):
@@ -419,6 +423,8 @@ class MergernovaMagPath(MergernovaPath):
         from . import bands as _bands
         self.cfg = _capi.mn_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
                                    pair_cascade_fraction, cosmology)
+        if engine == _capi.MN_EVOLVING:
+            self.ROWS = _capi.MN_ROWS_EVOLVING
         self._setup(time, None, y, sigma, device)
         lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
         self.phot, self._keep = _bands.build_photometry(bands, self.E, lam, output)

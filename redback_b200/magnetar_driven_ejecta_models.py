@@ -43,6 +43,8 @@ _GENERAL = _spec("general_mergernova", _capi.MN_MAGNETAR_ONLY, ("l0", "tau_sd", 
                  "thermalisation_efficiency", True, False)
 _GENERAL_TH = _spec("general_mergernova_thermalisation", _capi.MN_MAGNETAR_ONLY, ("l0", "tau_sd", "nn"),
                     "kappa_gamma", True, True)
+_GENERAL_EV = _spec("general_mergernova_evolution", _capi.MN_EVOLVING,
+                    ("logbint", "logbext", "p0", "chi0", "radius", "logmoi"), "kappa_gamma", True, True)
 
 
 def basic_mergernova(time, redshift=None, mej=None, beta=None, ejecta_radius=None, kappa=None, n_ism=None, p0=None,
@@ -76,7 +78,7 @@ def general_mergernova_thermalisation(time, redshift=None, mej=None, beta=None, 
 _SHELLS = ("redshift", "mej", "vej", "beta", "kappa_r")
 
 
-def _metzger_spec(name, engine, engine_params, last, gamma_ray):
+def _metzger_spec(name, engine, engine_params, last, gamma_ray, resolution=300):
     needed = _SHELLS + tuple(engine_params) + (last,)
 
     def validate(kwargs):
@@ -96,17 +98,32 @@ def _metzger_spec(name, engine, engine_params, last, gamma_ray):
                                    pair_cascade_fraction=kwargs.get("pair_cascade_fraction", 0.01),
                                    neutron_precursor_switch=kwargs.get("neutron_precursor_switch", True),
                                    vmax=kwargs.get("vmax", 0.7), cosmology=cosmology_from_kwargs(kwargs),
-                                   device=kwargs.get("device"))
+                                   device=kwargs.get("device"), resolution=resolution)
 
     return FusedSpec(name, needed, build, validate)
 
 
+_EVOLVING = ("logbint", "logbext", "p0", "chi0", "radius", "logmoi")
 _MK_BASIC = _metzger_spec("metzger_magnetar_driven_kilonova_model", _capi.MN_BASIC_MAGNETAR,
                           ("p0", "bp", "mass_ns", "theta_pb"), "thermalisation_efficiency", False)
 _MK_GENERAL = _metzger_spec("general_metzger_magnetar_driven", _capi.MN_MAGNETAR_ONLY, ("l0", "tau_sd", "nn"),
                             "thermalisation_efficiency", False)
 _MK_GENERAL_TH = _metzger_spec("general_metzger_magnetar_driven_thermalisation", _capi.MN_MAGNETAR_ONLY,
                                ("l0", "tau_sd", "nn"), "kappa_gamma", True)
+
+
+_MK_EVOLUTION = _metzger_spec("general_metzger_magnetar_driven_evolution", _capi.MN_EVOLVING, _EVOLVING, "kappa_gamma",
+                              True, resolution=500)
+
+
+def general_metzger_magnetar_driven_evolution(time, redshift=None, mej=None, vej=None, beta=None, kappa_r=None,
+                                              logbint=None, logbext=None, p0=None, chi0=None, radius=None, logmoi=None,
+                                              kappa_gamma=None, params_batch=None, **kwargs):
+    """redback magnetar_driven_ejecta_models.general_metzger_magnetar_driven_evolution (:908-956): the magnetar spins
+    down under EM + GW torques (magnetar_models._evolving_gw_and_em_magnetar); p0 in seconds, radius in km."""
+    named = dict(redshift=redshift, mej=mej, vej=vej, beta=beta, kappa_r=kappa_r, logbint=logbint, logbext=logbext,
+                 p0=p0, chi0=chi0, radius=radius, logmoi=logmoi, kappa_gamma=kappa_gamma)
+    return run(_MK_EVOLUTION, time, named, kwargs, params_batch)
 
 
 def metzger_magnetar_driven_kilonova_model(time, redshift=None, mej=None, vej=None, beta=None, kappa_r=None, p0=None,
@@ -135,6 +152,16 @@ def general_metzger_magnetar_driven_thermalisation(time, redshift=None, mej=None
     named = dict(redshift=redshift, mej=mej, vej=vej, beta=beta, kappa_r=kappa_r, l0=l0, tau_sd=tau_sd, nn=nn,
                  kappa_gamma=kappa_gamma)
     return run(_MK_GENERAL_TH, time, named, kwargs, params_batch)
+
+
+def general_mergernova_evolution(time, redshift=None, mej=None, beta=None, ejecta_radius=None, kappa=None, n_ism=None,
+                                 logbint=None, logbext=None, p0=None, chi0=None, radius=None, logmoi=None,
+                                 kappa_gamma=None, params_batch=None, **kwargs):
+    """redback magnetar_driven_ejecta_models.general_mergernova_evolution (:422-474): evolving GW + EM magnetar."""
+    named = dict(redshift=redshift, mej=mej, beta=beta, ejecta_radius=ejecta_radius, kappa=kappa, n_ism=n_ism,
+                 logbint=logbint, logbext=logbext, p0=p0, chi0=chi0, radius=radius, logmoi=logmoi,
+                 kappa_gamma=kappa_gamma)
+    return run(_GENERAL_EV, time, named, kwargs, params_batch)
 
 
 def _trapped_spec(output):
@@ -181,4 +208,5 @@ def trapped_magnetar(time, redshift=None, mej=None, beta=None, ejecta_radius=Non
 
 FUSED = {trapped_magnetar: _TRAPPED, metzger_magnetar_driven_kilonova_model: _MK_BASIC,
          general_metzger_magnetar_driven: _MK_GENERAL, general_metzger_magnetar_driven_thermalisation: _MK_GENERAL_TH,
+         general_metzger_magnetar_driven_evolution: _MK_EVOLUTION, general_mergernova_evolution: _GENERAL_EV,
          basic_mergernova: _BASIC, general_mergernova: _GENERAL, general_mergernova_thermalisation: _GENERAL_TH}

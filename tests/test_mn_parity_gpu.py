@@ -161,6 +161,45 @@ def test_metzger_magnetar_driven(rb, kind):
         assert abs(logl[i] - ref_l) <= 1e-6 + max(rtol, 1e-8) * abs(ref_l), (i, logl[i], ref_l)
 
 
+def test_evolving_magnetar_variants(rb):
+    """general_mergernova_evolution (:422-474) and general_metzger_magnetar_driven_evolution (:908-956): the spin-down
+    ODE of magnetar_models._evolving_gw_and_em_magnetar runs on device; golden vectors + a small batch."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "all_models_subset.json")) as fh:
+        golden = json.load(fh)
+    mod = rb.magnetar_driven_ejecta_models
+    for name, rtol in (("general_mergernova_evolution", 1e-9), ("general_metzger_magnetar_driven_evolution", 1e-5)):
+        e = golden["magnetar." + name]
+        t = np.array(e["time"])
+        for params, res in zip(e["params"], e["results"]):
+            out = getattr(mod, name)(t, **params, **e["eval_kwargs"])
+            h.assert_close(out, h.golden_array(res), rtol, 1e-9, what=name + " golden")
+    rng = np.random.default_rng(121)
+    N = 8
+    ev = dict(logbint=rng.uniform(14, 17, N), logbext=rng.uniform(13.5, 16, N), p0=h.loguniform(rng, 7e-4, 1e-2, N),
+              chi0=rng.uniform(0, 1.5, N), radius=rng.uniform(10, 13, N), logmoi=rng.uniform(44.5, 45.5, N),
+              kappa_gamma=h.loguniform(rng, 1e-2, 1e3, N))
+    t = np.geomspace(0.05, 40, 24)
+    nu = np.where(np.arange(24) % 2 == 0, 3e14, 6e14)
+    base = h.mergernova_prior(rng, N, "general")
+    p = dict({k: base[k] for k in ("redshift", "mej", "beta", "ejecta_radius", "kappa", "n_ism")}, **ev)
+    out = mod.general_mergernova_evolution(t, params_batch=p, frequency=nu, output_format="flux_density")
+    mk = h.metzger_magnetar_prior(rng, N, "general")
+    q = dict({k: mk[k] for k in ("redshift", "mej", "vej", "beta", "kappa_r")}, **ev)
+    out2 = mod.general_metzger_magnetar_driven_evolution(t, params_batch=q, frequency=nu, output_format="flux_density")
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        z = kwi.pop("redshift")
+        ref = r.general_mergernova_evolution(t, z, frequency=nu, **kwi)
+        h.assert_close(out[i], ref, 1e-9, 1e-9, what=f"general_mergernova_evolution sample {i}")
+        kwi = {k: v[i] for k, v in q.items()}
+        z = kwi.pop("redshift")
+        ref = r.general_metzger_magnetar_driven_evolution(t, z, frequency=nu, **kwi)
+        h.assert_close(out2[i], ref, 1e-5, what=f"general_metzger_magnetar_driven_evolution sample {i}")
+
+
 def test_scalar_call_kwargs_and_errors(rb):
     t = np.geomspace(0.05, 100, 12)
     kw = dict(mej=0.02, beta=0.3, ejecta_radius=3e9, kappa=5.0, n_ism=1e-2, l0=1e47, tau_sd=1e3, nn=3.0,

@@ -51,6 +51,12 @@ CASES = {
     "magnetar.general_metzger_magnetar_driven_thermalisation":
         lambda t, p, kw: r.general_metzger_magnetar_driven_thermalisation(
             t, kw["redshift"], frequency=np.full(t.size, kw["frequency"]), **p),
+    "magnetar.general_mergernova_evolution":
+        lambda t, p, kw: r.general_mergernova_evolution(t, kw["redshift"], frequency=np.full(t.size, kw["frequency"]),
+                                                        **p),
+    "magnetar.general_metzger_magnetar_driven_evolution":
+        lambda t, p, kw: r.general_metzger_magnetar_driven_evolution(
+            t, kw["redshift"], frequency=np.full(t.size, kw["frequency"]), **p),
     "kilonova.two_component_kilonova_model":
         lambda t, p, kw: r.two_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.three_component_kilonova_model":
@@ -70,7 +76,10 @@ CASES = {
 # in steps of 1.1e-16 and depends on the last bit of exp().  The pickle (another platform) and this machine differ by
 # 1e-8 in the late-time temperature, times h nu / k T ~ 200 in the stored Wien-tail values (1e-82, 1e-106 mJy).  The
 # reference checks these vectors at 1e-5.
-RTOL_BY_CASE = {"magnetar.general_metzger_magnetar_driven_thermalisation": 1e-5}
+RTOL_BY_CASE = {"magnetar.general_metzger_magnetar_driven_thermalisation": 1e-5,
+                "magnetar.general_metzger_magnetar_driven_evolution": 1e-5,
+                # 1.7e-12 on a 4e-68 mJy Wien-tail value (pow / exp of another platform, times h nu / k T = 150)
+                "magnetar.general_mergernova_evolution": 1e-10}
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
