@@ -305,6 +305,35 @@ def test_full_size_properties(rb):
     np.testing.assert_allclose(b, 2.0 * a, rtol=1e-14)
 
 
+def test_baseline_full_size(rb):
+    """BASELINE configs[1] at its full size (N = 1e7 prior draws x 300 epochs) through the host-buffer entry point:
+    duplication invariance (the second half of the batch repeats the first), a checksum of checksums against chunked
+    evaluation, and a subset against the unfused model matrix."""
+    import torch
+    rng = np.random.default_rng(13)
+    t, nu = h.config2_epochs(rng)
+    half = 5_000_000
+    p = h.slsn_prior(rng, half)
+    path = rb.engine.SupernovaPath(rb._capi.ENGINE_MAGNETAR, rb._capi.SED_BLACKBODY, t, frequency=nu,
+                                   y=np.full(t.size, 1e-3), sigma=np.full(t.size, 1e-4))
+    host = torch.empty((rb._capi.SN_NPARAM, 2 * half), dtype=torch.float64, pin_memory=True)
+    for name, row in rb._capi.SN_ROWS.items():
+        if name in p:
+            host[row, :half] = torch.from_numpy(p[name])
+            host[row, half:] = torch.from_numpy(p[name])
+    logl = path.log_likelihood_host(host)                       # pinned host -> chunked H2D -> kernels -> D2H
+    assert logl.shape == (2 * half,) and bool(torch.isfinite(logl).all())
+    assert torch.equal(logl[:half], logl[half:])
+    # checksum of checksums: resident evaluation in 10 chunks of 5e5 must give the same per-chunk sums
+    for c in range(0, half, 500_000):
+        dev = host[:, c:c + 500_000].cuda()
+        _, part = path.evaluate(dev, want_model=False, want_logl=True)
+        assert float(part.sum()) == float(logl[c:c + 500_000].cuda().sum())
+    model, ll = path.evaluate(host[:, :20000].cuda(), want_model=True, want_logl=True)
+    ref = rb.engine.gaussian_logl(model, np.full(t.size, 1e-3), np.full(t.size, 1e-4))
+    assert bool(((ll - ref).abs() <= 1e-6 + 1e-12 * ref.abs()).all())
+
+
 def test_edge_shapes(rb):
     """Single epoch (test/interaction_processes_test.py:321), duplicate and unsorted epochs, empty batch."""
     sn = rb.supernova_models
