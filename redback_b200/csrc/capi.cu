@@ -647,6 +647,7 @@ int mn_check(const rb_mn_config* cfg, int64_t N, int64_t E, const void* params, 
              const void* out_logl) {
   if (!cfg) return fail(RB_ERR_INVALID, "rb_mn_eval: null config");
   if (N < 0 || E <= 0) return fail(RB_ERR_INVALID, "rb_mn_eval: need N >= 0 and E > 0");
+  if (E > 65536) return fail(RB_ERR_UNSUPPORTED, "rb_mn_eval: at most 65536 epochs (the per-launch epoch sort is O(E^2))");
   if (cfg->engine < RB_MN_BASIC_MAGNETAR || cfg->engine > RB_MN_EVOLVING)
     return fail(RB_ERR_INVALID, "rb_mn_eval: unknown engine");
   if (cfg->sigma_mode < RB_SIGMA_FIXED || cfg->sigma_mode > RB_SIGMA_SYSTEMATIC)
