@@ -144,6 +144,11 @@ typedef struct {
   /* interaction_process=None (supernova_models.py:961-968 and the like): the engine luminosity at the epochs goes
      straight to the photosphere / SED; mej, kappa, kappa_gamma are then unused. */
   int no_interaction;
+  /* interaction_process=AsphericalDiffusion (interaction_processes.py:66-131): Diffusion times
+     1 + 1.4 (2 + u) / (1 + e^u) (area_projection / area_reference - 1), u = t / tau_d / 0.59; nickel / magnetar
+     engines, no t0.  area_ratio = area_projection / area_reference (kwargs, per-call scalars). */
+  int aspherical;
+  double area_ratio;
 } rb_sn_config;
 
 /* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */

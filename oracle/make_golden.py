@@ -206,6 +206,31 @@ def dump_verbatim():
     print("verbatim fixtures:", len(doc["diffusion"]), "diffusion,", len(doc["afterglow"]), "afterglow")
 
 
+def dump_aspherical():
+    """interaction_processes.AsphericalDiffusion of the reference's own source on seeded draws."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import warnings
+    warnings.simplefilter("ignore")
+    from oracle import refshim, restated as r
+    ns = refshim.load()
+    rng = np.random.default_rng(2027)
+    t = np.sort(rng.uniform(0.5, 250, 30))
+    doc = {"time": [float(v) for v in t], "draws": []}
+    for i in range(8):
+        prm = dict(mej=float(10 ** rng.uniform(-1, 1.5)), vej=float(10 ** rng.uniform(3.3, 4.5)),
+                   kappa=float(rng.uniform(0.05, 1)), kappa_gamma=float(10 ** rng.uniform(-2, 2)),
+                   f_nickel=float(10 ** rng.uniform(-2, 0)), area_projection=float(rng.uniform(0.3, 2.0)),
+                   area_reference=float(rng.uniform(0.5, 1.5)))
+        dense = np.linspace(0, t[-1] + 100, 1000)
+        lum = r.nickelcobalt_engine(dense, prm["f_nickel"], prm["mej"])
+        d = ns.interaction_processes.AsphericalDiffusion(t, dense, lum, prm["kappa"], prm["kappa_gamma"], prm["mej"],
+                                                         prm["vej"], prm["area_projection"], prm["area_reference"])
+        doc["draws"].append(dict(params=prm, tau_d=float(d.tau_d), lbol=[float(v) for v in d.new_luminosity]))
+    with open(os.path.join(OUT, "aspherical_reference_draws.json"), "w") as fh:
+        json.dump(doc, fh)
+    print("aspherical fixtures:", len(doc["draws"]))
+
+
 def dump_csm():
     """_csm_engine + CSMDiffusion (+ TemperatureFloor) of the reference's own sources on seeded prior draws
     (priors/csm_interaction.prior ranges)."""
@@ -283,5 +308,6 @@ if __name__ == "__main__":
     dump_pkl()
     dump_ecsv()
     dump_verbatim()
+    dump_aspherical()
     dump_csm()
     dump_mergernova()

@@ -159,6 +159,17 @@ def diffusion(time, dense_times, luminosity, kappa, kappa_gamma, mej, vej):
 # --------------------------------------------------------------------------------------------------
 # photosphere  (photosphere.py:56-111)
 # --------------------------------------------------------------------------------------------------
+def aspherical_diffusion(time, dense_times, luminosity, kappa, kappa_gamma, mej, vej, area_projection, area_reference):
+    """interaction_processes.AsphericalDiffusion (:66-131): Diffusion's quadrature times the viewing-angle factor
+    (:124-125).  Returns (tau_diff, new_luminosity)."""
+    tau_diff, lum = diffusion(time, dense_times, luminosity, kappa, kappa_gamma, mej, vej)
+    time = np.asarray(time, dtype=float)
+    with np.errstate(all="ignore"):
+        lum = lum * (1 + 1.4 * (2 + time / tau_diff / 0.59) / (1 + np.exp(time / tau_diff / 0.59))
+                     * (area_projection / area_reference - 1))
+    return tau_diff, lum
+
+
 def temperature_floor(time, luminosity, vej, temperature_floor):
     """Return (T_phot[E], R_phot[E]).  photosphere.py:87-111"""
     with np.errstate(all="ignore"):

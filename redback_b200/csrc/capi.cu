@@ -106,7 +106,8 @@ int launch_csm(rb::SnArgs a, const double* t_dev, cudaStream_t st, int sms) {
 }
 
 typedef void (*SnKernelFn)(const rb::SnArgs);
-SnKernelFn sn_kernel_fn(int engine, bool has_t0) {
+SnKernelFn sn_kernel_fn(int engine, bool has_t0, bool aspherical = false) {
+  if (aspherical) return rb::sn_kernel<false, 0, true>;
   switch (engine) {
     case RB_ENGINE_MAGNETAR_NICKEL:
       return has_t0 ? rb::sn_kernel<true, RB_ENGINE_MAGNETAR_NICKEL> : rb::sn_kernel<false, RB_ENGINE_MAGNETAR_NICKEL>;
@@ -129,6 +130,8 @@ cudaError_t sn_kernel_attributes() {
     for (int t = 0; t < 2 && err == cudaSuccess; ++t)
       err = cudaFuncSetAttribute(sn_kernel_fn(engines[e], t != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  220 * 1024);
+  if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(sn_kernel_fn(0, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   return err;
 }
 
@@ -205,6 +208,9 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
   if (N < 0 || E <= 0 || E > (1 << 24)) return fail(RB_ERR_INVALID, "rb_sn_eval: need N >= 0 and 0 < E <= 2^24");
   if (cfg->engine < RB_ENGINE_NICKEL || cfg->engine > RB_ENGINE_FALLBACK_NICKEL)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown engine");
+  if (cfg->aspherical && (cfg->engine > RB_ENGINE_MAGNETAR || cfg->t0 != nullptr || cfg->no_interaction))
+    return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: AsphericalDiffusion is available for the nickel / magnetar engines "
+                                    "without t0");
   if (cfg->engine == RB_ENGINE_MAGNETAR_NICKEL && !cfg->f_nickel)
     return fail(RB_ERR_INVALID, "rb_sn_eval: cfg.f_nickel is required for RB_ENGINE_MAGNETAR_NICKEL");
   if (cfg->engine == RB_ENGINE_CSM) {
@@ -312,7 +318,7 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   const size_t smem = sn_smem_bytes(cfg->dense_resolution, E, a.epochs_in_smem != 0, fp32);
   if (smem > 220 * 1024) return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution too large for shared memory");
   int occ = 0;
-  const SnKernelFn kern = sn_kernel_fn(cfg->engine, cfg->t0 != nullptr);
+  const SnKernelFn kern = sn_kernel_fn(cfg->engine, cfg->t0 != nullptr, cfg->aspherical != 0);
   RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (occ < 1) occ = 1;
   // persistent blocks, grid-stride over samples; 4 waves' worth of blocks for load balance at mid-size N
@@ -1346,7 +1352,7 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
   const int ep_in_smem = (sn_smem_bytes(cfg->dense_resolution, NT, true) <= 64 * 1024) ? 1 : 0;
   const size_t sn_smem = sn_smem_bytes(cfg->dense_resolution, NT, ep_in_smem != 0);
   int occ_sn = 1, occ_ph = 1;
-  const SnKernelFn sn_kern = sn_kernel_fn(cfg->engine, false);
+  const SnKernelFn sn_kern = sn_kernel_fn(cfg->engine, false, cfg->aspherical != 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sn, sn_kern, sn_threads, sn_smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
   if (occ_sn < 1) occ_sn = 1;

@@ -398,7 +398,8 @@ __device__ __forceinline__ float diffusion_sum_f32(const float4* __restrict__ no
 // ENGINE: 0 = nickel or magnetar chosen at run time (cfg.engine); RB_ENGINE_MAGNETAR_NICKEL = its own instantiation.
 // (ptxas' register allocation of the hot loop is sensitive to the surrounding code: adding the third engine to the
 // run-time branch cost 4 %, resolving nickel / magnetar at compile time cost the magnetar variant 30 % more spills.)
-template <bool HAS_T0, int ENGINE>
+// ASPH: AsphericalDiffusion's viewing-angle factor on the diffused luminosity (interaction_processes.py:124-125).
+template <bool HAS_T0, int ENGINE, bool ASPH = false>
 __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
   extern __shared__ double2 smem2[];
   const int D = a.cfg.dense_resolution;
@@ -620,8 +621,12 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       } else if (any_bad) acc = diffusion_sum<true, false>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
       else if (fused_ok) acc = diffusion_sum<false, true>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
       else acc = diffusion_sum<false, false>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
-      const double lbol = (0.5 * (te2 * acc)) *
-                          (-2.0 * expm1_fast(-sc[SC_TRAP] / te2, tab) * sc[SC_INV_TAU2]);       // :60-61
+      double lbol = (0.5 * (te2 * acc)) *
+                    (-2.0 * expm1_fast(-sc[SC_TRAP] / te2, tab) * sc[SC_INV_TAU2]);             // :60-61
+      if (ASPH) {                                                                               // :124-125
+        const double u = te / sqrt(sc[SC_TAU2]) / 0.59;
+        lbol *= (1 + 1.4 * (2 + u) / (1 + exp(u)) * (a.cfg.area_ratio - 1));
+      }
 
       double model;
       if (sed == RB_SED_BOLOMETRIC) {

@@ -242,10 +242,11 @@ class SupernovaPath(_FusedPath):
     def __init__(self, engine, sed, time, frequency=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
                  absorption_index=1.0, cosmology=None, device=None, line=None, dtype="float64", csm=None,
-                 no_interaction=False):
+                 no_interaction=False, area_ratio=None):
         self.NEEDS_FREQUENCY = sed != _capi.SED_BOLOMETRIC
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength,
-                                   absorption_index, cosmology, line, _precision(dtype), csm, no_interaction)
+                                   absorption_index, cosmology, line, _precision(dtype), csm, no_interaction,
+                                   area_ratio)
         self._engine_rows(engine)
         self._setup(time, frequency, y, sigma, device)
 
@@ -305,13 +306,13 @@ class SupernovaMagPath(SupernovaPath):
 
     def __init__(self, engine, sed, time, bands, output="magnitude", lambda_array=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0, absorption_index=1.0,
-                 cosmology=None, device=None, line=None, csm=None, no_interaction=False):
+                 cosmology=None, device=None, line=None, csm=None, no_interaction=False, area_ratio=None):
         from . import bands as _bands
         if sed == _capi.SED_BOLOMETRIC:
             raise ValueError("bolometric models have no magnitude output")
         self.NEEDS_FREQUENCY = False
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength, absorption_index,
-                                   cosmology, line, 0, csm, no_interaction)
+                                   cosmology, line, 0, csm, no_interaction, area_ratio)
         self._engine_rows(engine)
         self._setup(time, None, y, sigma, device)
         lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)

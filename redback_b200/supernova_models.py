@@ -12,7 +12,7 @@ from ._fused import FusedSpec, cosmology_from_kwargs, output_mode, run
 from .engine import SupernovaMagPath, SupernovaPath
 
 _ALLOWED_OPERATORS = {
-    "interaction_process": ("Diffusion", "CSMDiffusion"),
+    "interaction_process": ("Diffusion", "CSMDiffusion", "AsphericalDiffusion"),
     "photosphere": ("TemperatureFloor",),
     "sed": ("Blackbody", "CutoffBlackbody"),
 }
@@ -61,6 +61,20 @@ def _csm_kwargs(kwargs):
     return dict(nn=kwargs.get("nn", 12), delta=kwargs.get("delta", 1), efficiency=kwargs.get("efficiency", 0.5))
 
 
+def _area_ratio(kwargs):
+    """interaction_process=AsphericalDiffusion (interaction_processes.py:66-131): area_projection / area_reference from
+    the kwargs (per-call scalars), None for the plain Diffusion."""
+    import numpy as np
+    value = kwargs.get("interaction_process")
+    name = value if isinstance(value, str) else getattr(value, "__name__", None)
+    if name != "AsphericalDiffusion":
+        return None
+    proj, ref = kwargs["area_projection"], kwargs["area_reference"]      # KeyError like the reference's constructor
+    if np.ndim(proj) != 0 or np.ndim(ref) != 0:
+        raise NotImplementedError("area_projection / area_reference must be scalars in the fused B200 path")
+    return float(proj) / float(ref)
+
+
 _USES_MEJ = (_capi.ENGINE_NICKEL, _capi.ENGINE_MAGNETAR_NICKEL, _capi.ENGINE_FALLBACK_NICKEL)
 
 
@@ -80,7 +94,9 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
     def validate(kwargs):
         if not (direct or _variant):
             ip_name = _operator_name("interaction_process", kwargs.get("interaction_process", default_ip), default_ip)
-            if ip_name != default_ip:
+            if ip_name == "AsphericalDiffusion" and not is_csm:
+                _area_ratio(kwargs)
+            elif ip_name != default_ip:
                 raise NotImplementedError(f"{name}: only interaction_process={default_ip} is fused on device")
         if is_csm:
             _csm_kwargs(kwargs)
@@ -95,6 +111,7 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
         line = None
         csm = _csm_kwargs(kwargs) if is_csm else None
         no_ip = direct or _variant
+        area_ratio = None if no_ip or is_csm else _area_ratio(kwargs)
         if flux_density:
             if fixed_sed is not None:     # type_1a hard-wires CutoffBlackbody + Line (supernova_models.py:2268-2275)
                 sed_id, line = fixed_sed, _line_kwargs(kwargs)
@@ -108,14 +125,15 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
                                         cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000),
                                         absorption_index=kwargs.get("absorption_index", 1.0),
                                         cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"),
-                                        line=line, csm=csm, no_interaction=no_ip)
+                                        line=line, csm=csm, no_interaction=no_ip, area_ratio=area_ratio)
         return SupernovaPath(engine, sed_id, time, frequency=kwargs.get("frequency") if flux_density else None,
                              y=y, sigma=sigma, sigma_mode=sigma_mode,
                              dense_resolution=kwargs.get("dense_resolution", 1000),
                              cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000),
                              absorption_index=kwargs.get("absorption_index", 1.0),
                              cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"), line=line,
-                             dtype=kwargs.get("dtype", "float64"), csm=csm, no_interaction=no_ip)
+                             dtype=kwargs.get("dtype", "float64"), csm=csm, no_interaction=no_ip,
+                             area_ratio=area_ratio)
 
     resolver = None
     if not (direct or _variant or is_csm):

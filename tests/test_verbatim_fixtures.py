@@ -104,3 +104,49 @@ def test_oracle_reproduces_reference_mergernova():
                                                 **row["ejecta"], **row["extra"])
         for got, key in zip(out, ("bolometric_luminosity", "comoving_temperature", "radius", "doppler_factor")):
             np.testing.assert_allclose(got[pick], row[key], rtol=1e-14, err_msg=key)
+
+
+@pytest.fixture(scope="module")
+def asph_fx():
+    with open(os.path.join(ROOT, "tests", "golden", "aspherical_reference_draws.json")) as fh:
+        return json.load(fh)
+
+
+def test_oracle_reproduces_reference_aspherical_diffusion(asph_fx):
+    t = np.array(asph_fx["time"])
+    for row in asph_fx["draws"]:
+        p = row["params"]
+        dense = np.linspace(0, t[-1] + 100, 1000)
+        lum = r.nickelcobalt_engine(dense, p["f_nickel"], p["mej"])
+        tau, out = r.aspherical_diffusion(t, dense, lum, p["kappa"], p["kappa_gamma"], p["mej"], p["vej"],
+                                          p["area_projection"], p["area_reference"])
+        assert abs(tau / row["tau_d"] - 1) < 1e-15
+        np.testing.assert_allclose(out, row["lbol"], rtol=1e-14)
+
+
+@pytest.mark.gpu
+def test_device_reproduces_reference_aspherical_diffusion(asph_fx):
+    """interaction_process='AsphericalDiffusion' (interaction_processes.py:66-131) through arnett_bolometric, and the
+    same factor inside the flux-density path and the fused likelihood."""
+    import redback_b200 as rb
+    t = np.array(asph_fx["time"])
+    for row in asph_fx["draws"]:
+        p = dict(row["params"])
+        out = rb.supernova_models.arnett_bolometric(t, interaction_process="AsphericalDiffusion", **p)
+        h.assert_close(out, np.array(row["lbol"]), 1e-9, h.diffusion_condition(t, row["tau_d"]), what="aspherical")
+    p = dict(asph_fx["draws"][0]["params"])
+    nu = np.full(t.size, 4.7e14)
+    kw = dict(frequency=nu, output_format="flux_density", interaction_process="AsphericalDiffusion",
+              area_projection=p.pop("area_projection"), area_reference=p.pop("area_reference"))
+    batch = {k: np.array([v, v * 1.1]) for k, v in p.items()}
+    batch.update(redshift=np.array([0.05, 0.1]), temperature_floor=np.array([4000.0, 5000.0]))
+    flux = rb.supernova_models.arnett(t, params_batch=batch, **kw)
+    plain = rb.supernova_models.arnett(t, params_batch=batch, frequency=nu, output_format="flux_density")
+    assert np.all(np.isfinite(flux)) and not np.allclose(flux, plain)
+    like = rb.GaussianLikelihood(t, flux[0], 0.1 * flux[0], rb.supernova_models.arnett, kwargs=kw)
+    ll = like.log_likelihood_batch(batch)
+    want = float(np.sum(-np.log(2 * np.pi * (0.1 * flux[0]) ** 2) / 2))
+    assert abs(ll[0] - want) <= 1e-6 + 1e-9 * abs(want)
+    with pytest.raises(KeyError):
+        rb.supernova_models.arnett_bolometric(t, interaction_process="AsphericalDiffusion",
+                                              **{k: v for k, v in row["params"].items() if k != "area_reference"})
