@@ -318,8 +318,20 @@ typedef struct {
      the k-corrected time / frequency over 4 pi d_L^2 (1+z)^(photon_index - 2). */
   int output;
   double photon_index;
+  /* general_magnetar_driven_supernova(_bolometric) (supernova_models.py:2464-2584): the same dynamics with nickel
+     heating (use_r_process = 0, f_nickel in row RB_MN_F_NICKEL), gamma-ray opacity, grid
+     get_optimal_time_array(1e0, 1e8, 2000); RB_MN_OUT_SUPERNOVA: TemperatureFloor on the grid with the time-dependent
+     ejecta velocity (temperature floor in row RB_MN_TEMPERATURE_FLOOR), T / R / L interpolated at the epochs [days],
+     then `sed` (RB_SED_BLACKBODY | RB_SED_CUTOFF_BLACKBODY) -> mJy (1+z); RB_MN_OUT_LBOL: L_bol(t) [erg/s] at source-
+     frame days (the bolometric variant; redshift row ignored). */
+  int use_r_process;           /* default 1 */
+  double grid_t_min, grid_t_max;   /* [s], defaults 1e-4, 1e8 */
+  int sed;
+  double cutoff_wavelength, absorption_index;
 } rb_mn_config;
-enum { RB_MN_OUT_FLUX_DENSITY = 0, RB_MN_OUT_TRAPPED_LUMINOSITY = 1, RB_MN_OUT_TRAPPED_FLUX = 2 };
+enum { RB_MN_OUT_FLUX_DENSITY = 0, RB_MN_OUT_TRAPPED_LUMINOSITY = 1, RB_MN_OUT_TRAPPED_FLUX = 2,
+       RB_MN_OUT_SUPERNOVA = 3, RB_MN_OUT_LBOL = 4 };
+enum { RB_MN_F_NICKEL = 9, RB_MN_TEMPERATURE_FLOOR = 11 };
 
 int rb_mn_config_default(rb_mn_config* cfg);
 

@@ -84,6 +84,7 @@ KEEP = [
     "magnetar.metzger_magnetar_driven_kilonova_model", "magnetar.general_metzger_magnetar_driven",
     "magnetar.general_metzger_magnetar_driven_thermalisation",
     "magnetar.general_mergernova_evolution", "magnetar.general_metzger_magnetar_driven_evolution",
+    "supernova.general_magnetar_driven_supernova", "supernova.general_magnetar_driven_supernova_bolometric",
 ]
 
 

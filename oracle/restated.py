@@ -752,9 +752,11 @@ def magnetar_only(time, l0, tau, nn):
 
 def ejecta_dynamics_and_interaction(time, mej, beta, ejecta_radius, kappa, n_ism, magnetar_luminosity,
                                     pair_cascade_switch, use_gamma_ray_opacity, *, thermalisation_efficiency=None,
-                                    kappa_gamma=None, ejecta_albedo=0.5, pair_cascade_fraction=0.05):
-    """_ejecta_dynamics_and_interaction (magnetar_driven_ejecta_models.py:14-151), r-process heating branch.
-    time: source-frame seconds.  Returns (bolometric_luminosity, comoving_temperature, radius, doppler_factor)."""
+                                    kappa_gamma=None, ejecta_albedo=0.5, pair_cascade_fraction=0.05,
+                                    use_r_process=True, f_nickel=0, return_lorentz_factor=False):
+    """_ejecta_dynamics_and_interaction (magnetar_driven_ejecta_models.py:14-151).
+    time: source-frame seconds.  Returns (bolometric_luminosity, comoving_temperature, radius, doppler_factor)
+    [+ lorentz_factor]."""
     m = mej * solar_mass
     n = len(time)
     out_l, out_t, out_r, out_d, out_g = (np.zeros(n) for _ in range(5))
@@ -778,7 +780,11 @@ def ejecta_dynamics_and_interaction(time, mej, beta, ejecta_radius, kappa, n_ism
             t_com = dop * time[i]
             dvdt_com = 4 * np.pi * rad ** 2 * beta * speed_of_light
             denom = (1 / 2) - (1 / 3.141592654) * np.arctan((t_com - 1.3) / 0.11)              # :78
-            l_rad = (4 * 10 ** 49 * (m / (2 * 10 ** 33) * 10 ** 2) * denom ** 1.3)              # :80
+            if use_r_process:
+                l_rad = (4 * 10 ** 49 * (m / (2 * 10 ** 33) * 10 ** 2) * denom ** 1.3)          # :80
+            else:                                                                              # :82-84
+                nickel_mass = f_nickel * m / solar_mass
+                l_rad = nickel_mass * (6.45e43 * np.exp(-t_com / (8.8 * 86400)) + 1.45e43 * np.exp(-t_com / (111.3 * 86400)))
             tau = kappa * (m / vol) * (rad / gam)
             if tau <= 1:
                 l_emit = (e_int * speed_of_light) / (rad / gam)
@@ -807,6 +813,8 @@ def ejecta_dynamics_and_interaction(time, mej, beta, ejecta_radius, kappa, n_ism
                      * (time / 86400) ** (-0.5))
             out_l = out_l / (1.0 + tlife)
             out_t = (out_l / (4.0 * np.pi * out_r ** (2.0) * sigma_sb)) ** (0.25)
+    if return_lorentz_factor:
+        return out_l, out_t, out_r, out_d, out_g
     return out_l, out_t, out_r, out_d
 
 
@@ -858,6 +866,45 @@ def general_mergernova_evolution(time, redshift, mej, beta, ejecta_radius, kappa
     return _mergernova(time, redshift, _evolving(logbint, logbext, p0, chi0, radius, logmoi), mej, beta, ejecta_radius,
                        kappa, n_ism, frequency=frequency, pair_cascade_switch=pair_cascade_switch, dl=dl,
                        use_gamma_ray_opacity=True, kappa_gamma=kappa_gamma, **kw)
+
+
+def _magnetar_driven_supernova_dynamics(mej, E_sn, kappa, l0, tau_sd, nn, kappa_gamma, f_nickel, pair_cascade_switch):
+    """Shared part of general_magnetar_driven_supernova(_bolometric) (supernova_models.py:2476-2488, 2560-2570)."""
+    t_grid = get_optimal_time_array(1e0, 1e8, 2000)
+    beta = np.sqrt(E_sn / (0.5 * mej * solar_mass)) / speed_of_light
+    lbol, _, _, _, gam = ejecta_dynamics_and_interaction(
+        t_grid, mej, beta, 1.0e11, kappa, 1.0e-5, magnetar_only(t_grid, l0, tau_sd, nn), pair_cascade_switch, True,
+        kappa_gamma=kappa_gamma, use_r_process=False, f_nickel=f_nickel, return_lorentz_factor=True)
+    with np.errstate(all="ignore"):
+        vej = speed_of_light * np.sqrt(1 - 1 / gam ** 2) / km_cgs                                # utils.py:1524
+    return t_grid, lbol, vej
+
+
+def general_magnetar_driven_supernova_bolometric(time, mej, E_sn, kappa, l0, tau_sd, nn, kappa_gamma, *, f_nickel=0,
+                                                 pair_cascade_switch=False, **_):
+    """supernova_models.general_magnetar_driven_supernova_bolometric (:2464-2507): erg/s at source-frame days."""
+    t_grid, lbol, _ = _magnetar_driven_supernova_dynamics(mej, E_sn, kappa, l0, tau_sd, nn, kappa_gamma, f_nickel,
+                                                          pair_cascade_switch)
+    return interp1d(t_grid, y=lbol)(np.asarray(time, dtype=float) * day_to_s)
+
+
+def general_magnetar_driven_supernova(time, redshift, mej, E_sn, kappa, l0, tau_sd, nn, kappa_gamma, *, frequency,
+                                      temperature_floor, f_nickel=0, pair_cascade_switch=False,
+                                      cutoff_wavelength=3000, absorption_index=1.0, dl=None, **_):
+    """supernova_models.general_magnetar_driven_supernova (:2510-2584), flux_density, CutoffBlackbody: the photosphere
+    is evaluated on the dynamics grid with the time-dependent ejecta velocity, then T, R, L are interpolated."""
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    frequency, t = calc_kcorrected_properties(np.asarray(frequency, dtype=float), redshift, np.asarray(time, dtype=float))
+    t_grid, lbol_g, vej = _magnetar_driven_supernova_dynamics(mej, E_sn, kappa, l0, tau_sd, nn, kappa_gamma, f_nickel,
+                                                              pair_cascade_switch)
+    days = t_grid / day_to_s
+    with np.errstate(all="ignore"):
+        temp_g, rad_g = temperature_floor_grid = globals()["temperature_floor"](days, lbol_g, vej, temperature_floor)
+        temp, rad, lbol = (interp1d(days, y=v)(t) for v in (temp_g, rad_g, lbol_g))
+        freq = frequency if np.ndim(frequency) else float(frequency)
+        fd = cutoff_blackbody_mjy(t, temp, lbol, rad, freq, dl, cutoff_wavelength, absorption_index)
+    return fd * (1 + redshift)
 
 
 def trapped_magnetar(time, redshift, mej, beta, ejecta_radius, kappa, n_ism, l0, tau_sd, nn,

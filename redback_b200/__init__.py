@@ -17,7 +17,8 @@ all_models_dict = {
                  "csm_interaction", "general_magnetar_slsn_bolometric", "general_magnetar_slsn",
                  "exponential_powerlaw_bolometric", "sn_exponential_powerlaw", "sn_fallback", "sn_nickel_fallback",
                  "homologous_expansion_supernova_model_bolometric", "homologous_expansion_supernova",
-                 "thin_shell_supernova_model_bolometric", "thin_shell_supernova")
+                 "thin_shell_supernova_model_bolometric", "thin_shell_supernova",
+                 "general_magnetar_driven_supernova_bolometric", "general_magnetar_driven_supernova")
 }
 all_models_dict.update({name: getattr(kilonova_models, name)
                         for name in ("one_component_kilonova_model", "metzger_kilonova_model",

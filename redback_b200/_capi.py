@@ -69,11 +69,14 @@ class AgConfig(C.Structure):
 
 
 MN_BASIC_MAGNETAR, MN_MAGNETAR_ONLY, MN_EVOLVING = 0, 1, 2
-MN_OUT_FLUX_DENSITY, MN_OUT_TRAPPED_LUMINOSITY, MN_OUT_TRAPPED_FLUX = 0, 1, 2
+MN_OUT_FLUX_DENSITY, MN_OUT_TRAPPED_LUMINOSITY, MN_OUT_TRAPPED_FLUX, MN_OUT_SUPERNOVA, MN_OUT_LBOL = 0, 1, 2, 3, 4
 MN_ROWS = dict(redshift=0, mej=1, beta=2, ejecta_radius=3, kappa=4, n_ism=5, p0=6, l0=6, bp=7, tau_sd=7, mass_ns=8,
                nn=8, theta_pb=9, thermalisation_efficiency=10, kappa_gamma=10)
 MN_NPARAM = 13
 # RB_MN_EVOLVING reuses rows 6-9 and adds two
+# general_magnetar_driven_supernova: magnetar_only rows + f_nickel / temperature_floor (RB_MN_F_NICKEL, ..._FLOOR)
+MN_ROWS_SUPERNOVA = dict(redshift=0, mej=1, beta=2, ejecta_radius=3, kappa=4, n_ism=5, l0=6, tau_sd=7, nn=8, f_nickel=9,
+                         kappa_gamma=10, temperature_floor=11)
 MN_ROWS_EVOLVING = dict(redshift=0, mej=1, beta=2, ejecta_radius=3, kappa=4, n_ism=5, logbint=6, logbext=7, p0=8, chi0=9,
                         kappa_gamma=10, radius=11, logmoi=12)
 
@@ -82,7 +85,9 @@ class MnConfig(C.Structure):
     _fields_ = [("engine", C.c_int), ("sigma_mode", C.c_int), ("use_gamma_ray_opacity", C.c_int),
                 ("pair_cascade_switch", C.c_int), ("ejecta_albedo", C.c_double), ("pair_cascade_fraction", C.c_double),
                 ("resolution", C.c_int), ("cosmology", Cosmology), ("upper_limits", UpperLimits), ("output", C.c_int),
-                ("photon_index", C.c_double)]
+                ("photon_index", C.c_double), ("use_r_process", C.c_int), ("grid_t_min", C.c_double),
+                ("grid_t_max", C.c_double), ("sed", C.c_int), ("cutoff_wavelength", C.c_double),
+                ("absorption_index", C.c_double)]
 
 
 MK_ROWS = dict(redshift=0, mej=1, vej=2, beta=3, kappa_r=4, p0=5, l0=5, bp=6, tau_sd=6, mass_ns=7, nn=7, theta_pb=8,
@@ -228,7 +233,10 @@ def ag_config(jet, sigma_mode=SIGMA_FIXED, steps=250, res=0, k=0, expansion=1, a
 
 
 def mn_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_cascade_switch=False,
-              ejecta_albedo=0.5, pair_cascade_fraction=0.05, cosmology=None, output=0, photon_index=2.0):
+              ejecta_albedo=0.5, pair_cascade_fraction=0.05, cosmology=None, output=0, photon_index=2.0,
+              supernova=None):
+    """supernova: dict(sed, cutoff_wavelength, absorption_index) selects the general_magnetar_driven_supernova set-up
+    (nickel heating, grid 1e0..1e8 s with 2000 points requested)."""
     cfg = MnConfig()
     check(lib().rb_mn_config_default(C.byref(cfg)))
     cfg.engine, cfg.sigma_mode = engine, sigma_mode
@@ -236,6 +244,11 @@ def mn_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_
     cfg.pair_cascade_switch = int(bool(pair_cascade_switch))
     cfg.ejecta_albedo, cfg.pair_cascade_fraction = float(ejecta_albedo), float(pair_cascade_fraction)
     cfg.output, cfg.photon_index = int(output), float(photon_index)
+    if supernova is not None:
+        cfg.use_r_process, cfg.grid_t_min, cfg.grid_t_max, cfg.resolution = 0, 1e0, 1e8, 2000
+        cfg.sed = int(supernova.get("sed", SED_CUTOFF_BLACKBODY))
+        cfg.cutoff_wavelength = float(supernova.get("cutoff_wavelength", 3000.0))
+        cfg.absorption_index = float(supernova.get("absorption_index", 1.0))
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg

@@ -8,7 +8,8 @@ from .engine import batch_size
 
 
 class FusedSpec:
-    def __init__(self, name, needed, build, validate=None, transform=None, resolver=None):
+    def __init__(self, name, needed, build, validate=None, transform=None, resolver=None, defaults=None):
+        self.defaults = dict(defaults or {})  # parameters that are optional kwargs in the reference
         self._resolver = resolver            # kwargs -> FusedSpec | None: a variant selected by kwargs
         self.name = name
         self.needed = tuple(needed)          # parameter names, in any order
@@ -43,7 +44,7 @@ class FusedSpec:
         return (self.name, tuple(items))
 
 
-def collect(named, kwargs, params_batch, needed):
+def collect(named, kwargs, params_batch, needed, defaults=None):
     """Merge positional/kwargs scalars and params_batch arrays into {name: value} for `needed`."""
     params = {}
     batch = dict(params_batch) if params_batch is not None else {}
@@ -54,6 +55,8 @@ def collect(named, kwargs, params_batch, needed):
             params[name] = named[name]
         elif name in kwargs:
             params[name] = kwargs[name]
+        elif defaults is not None and name in defaults:
+            params[name] = defaults[name]
         else:
             raise KeyError(name)  # same failure mode as the reference (missing kwarg)
     return params, batch_size(params)
@@ -137,7 +140,7 @@ def aux_tensor(params, path, N):
 
 def run(spec, time, named, kwargs, params_batch):
     spec = spec.for_kwargs(kwargs)
-    params, N = collect(named, kwargs, params_batch, spec.needed)
+    params, N = collect(named, kwargs, params_batch, spec.needed, spec.defaults)
     params = spec.transform(params)
     path = spec.build(time, kwargs)
     dev = path.pack(params, N if N is not None else 1)

@@ -660,13 +660,20 @@ int mn_check(const rb_mn_config* cfg, int64_t N, int64_t E, const void* params, 
     return fail(RB_ERR_INVALID, "rb_mn_eval: unknown sigma_mode");
   if (cfg->resolution < 8 || cfg->resolution > 4096)
     return fail(RB_ERR_INVALID, "rb_mn_eval: resolution must be in [8, 4096]");
-  if (cfg->output < RB_MN_OUT_FLUX_DENSITY || cfg->output > RB_MN_OUT_TRAPPED_FLUX)
+  if (cfg->output < RB_MN_OUT_FLUX_DENSITY || cfg->output > RB_MN_OUT_LBOL)
     return fail(RB_ERR_INVALID, "rb_mn_eval: unknown output");
-  if (cfg->output != RB_MN_OUT_FLUX_DENSITY &&
+  if (!(cfg->grid_t_min > 0.0 && cfg->grid_t_max > cfg->grid_t_min))
+    return fail(RB_ERR_INVALID, "rb_mn_eval: need 0 < grid_t_min < grid_t_max");
+  if (cfg->output == RB_MN_OUT_SUPERNOVA && cfg->sed != RB_SED_BLACKBODY && cfg->sed != RB_SED_CUTOFF_BLACKBODY)
+    return fail(RB_ERR_INVALID, "rb_mn_eval: sed must be RB_SED_BLACKBODY or RB_SED_CUTOFF_BLACKBODY");
+  if (cfg->output == RB_MN_OUT_SUPERNOVA && cfg->sed == RB_SED_CUTOFF_BLACKBODY && cfg->absorption_index >= 4.0)
+    return fail(RB_ERR_INVALID, "absorption_index >= 4 is not supported: the integral below the cutoff diverges");
+  if ((cfg->output == RB_MN_OUT_TRAPPED_LUMINOSITY || cfg->output == RB_MN_OUT_TRAPPED_FLUX) &&
       (cfg->engine != RB_MN_MAGNETAR_ONLY || cfg->pair_cascade_switch || cfg->use_gamma_ray_opacity))
     return fail(RB_ERR_INVALID, "rb_mn_eval: the trapped-magnetar outputs need the magnetar_only engine without pair "
                                 "cascade / gamma-ray opacity");
-  if (!params || !t_obs || !freq_obs) return fail(RB_ERR_INVALID, "rb_mn_eval: params, t_obs and freq_obs are required");
+  if (!params || !t_obs || (!freq_obs && cfg->output != RB_MN_OUT_LBOL))
+    return fail(RB_ERR_INVALID, "rb_mn_eval: params, t_obs and freq_obs are required");
   if (y) {
     if (!out_logl) return fail(RB_ERR_INVALID, "rb_mn_eval: y given but out_logl is null");
     if (cfg->sigma_mode != RB_SIGMA_SAMPLED && !sigma) return fail(RB_ERR_INVALID, "rb_mn_eval: sigma is required");
@@ -712,6 +719,12 @@ extern "C" int rb_mn_config_default(rb_mn_config* cfg) {
   cfg->resolution = 500;
   cfg->output = RB_MN_OUT_FLUX_DENSITY;
   cfg->photon_index = 2.0;
+  cfg->use_r_process = 1;
+  cfg->grid_t_min = 1e-4;
+  cfg->grid_t_max = 1e8;
+  cfg->sed = RB_SED_BLACKBODY;
+  cfg->cutoff_wavelength = 3000.0;
+  cfg->absorption_index = 1.0;
   return rb_cosmology_planck18(&cfg->cosmology);
 }
 
@@ -725,7 +738,7 @@ extern "C" int rb_mn_eval_f64(const rb_mn_config* cfg, int64_t N, int64_t E, con
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<double> tg((size_t)cfg->resolution);
   int G = 0;
-  rc = rb_optimal_time_array(1e-4, 1e8, cfg->resolution, tg.data(), &G);   // magnetar_driven_ejecta_models.py:301
+  rc = rb_optimal_time_array(cfg->grid_t_min, cfg->grid_t_max, cfg->resolution, tg.data(), &G);   // :301, supernova_models.py:2476
   if (rc != RB_OK) return rc;
   StreamAlloc b_tg, b_ep, b_sorted, b_dl;
   RB_CUDA(b_tg.alloc((size_t)G * sizeof(double), st));
@@ -742,7 +755,7 @@ extern "C" int rb_mn_eval_f64(const rb_mn_config* cfg, int64_t N, int64_t E, con
   if (!dl) {
     RB_CUDA(b_dl.alloc((size_t)N * sizeof(double), st));
     rb::dl_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(cfg->cosmology, N, params + (size_t)RB_MN_REDSHIFT * N,
-                                                          b_dl.as<double>());
+                                                          b_dl.as<double>());   // z = 0 -> d_L = 0 (unused: RB_MN_OUT_LBOL)
     launch_counter()->fetch_add(1);
     dl = b_dl.as<double>();
   }
@@ -760,7 +773,10 @@ extern "C" int rb_mn_eval_f64(const rb_mn_config* cfg, int64_t N, int64_t E, con
   a.out_model = out_model;
   a.out_logl = y ? out_logl : nullptr;
   a.want_logl = y ? 1 : 0;
-  rb::mn_kernel<<<(unsigned)((N + 127) / 128), 128, (size_t)G * sizeof(double), st>>>(a);
+  if (cfg->output >= RB_MN_OUT_SUPERNOVA || !cfg->use_r_process)
+    rb::mn_kernel<true><<<(unsigned)((N + 127) / 128), 128, (size_t)G * sizeof(double), st>>>(a);
+  else
+    rb::mn_kernel<false><<<(unsigned)((N + 127) / 128), 128, (size_t)G * sizeof(double), st>>>(a);
   launch_counter()->fetch_add(1);
   RB_CUDA(cudaGetLastError());
   return RB_OK;
@@ -1587,7 +1603,7 @@ extern "C" int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* 
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute");
   std::vector<double> tg((size_t)cfg->resolution);
   int G = 0;
-  rc = rb_optimal_time_array(1e-4, 1e8, cfg->resolution, tg.data(), &G);
+  rc = rb_optimal_time_array(cfg->grid_t_min, cfg->grid_t_max, cfg->resolution, tg.data(), &G);
   if (rc != RB_OK) return rc;
   tg.resize((size_t)G);
   const int NT = G, NL = phot->n_lambda;
@@ -1651,7 +1667,7 @@ extern "C" int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* 
     a.grid_out = d_grid;
     a.opz_out = d_opz;
     a.dl_out = d_dl;
-    rb::mn_kernel<<<(unsigned)((nc + 127) / 128), 128, (size_t)G * sizeof(double), st>>>(a);
+    rb::mn_kernel<false><<<(unsigned)((nc + 127) / 128), 128, (size_t)G * sizeof(double), st>>>(a);
     pa.N = nc;
     pa.n_base = n0;
     pa.E = (int)E;

@@ -81,7 +81,10 @@ __global__ void mn_sort_epochs_kernel(int E, const double* __restrict__ ep, doub
   }
 }
 
-__global__ void __launch_bounds__(128) mn_kernel(const MnArgs a) {
+// SN: the general_magnetar_driven_supernova outputs (RB_MN_OUT_SUPERNOVA / RB_MN_OUT_LBOL) as a separate instantiation, so
+// that the mergernova outputs keep their register budget (96 vs 168 registers).
+template <bool SN>
+__global__ void __launch_bounds__(128, SN ? 3 : 5) mn_kernel(const MnArgs a) {
   extern __shared__ double mn_tg[];     // [G] time grid
   const int G = a.G, E = a.E;
   for (int i = threadIdx.x; i < G; i += blockDim.x) mn_tg[i] = a.tgrid[i];
@@ -128,27 +131,47 @@ __global__ void __launch_bounds__(128) mn_kernel(const MnArgs a) {
   const double row10 = P[RB_MN_THERMALISATION_EFFICIENCY * S];
   const double gprefac = 3.0 * row10 * m / (4.0 * kPi);                        // :103 (kappa_gamma variant), / vej^2 below
   const double lrad_coef = 4e49 * (m / 2e33 * 100.0);                          // :80
+  const double nickel_mass = a.cfg.use_r_process ? 0.0 : P[RB_MN_F_NICKEL * S] * m / kMsun;   // :83
   const double pc_coef = (0.6 / (1.0 - a.cfg.ejecta_albedo)) * sqrt(a.cfg.pair_cascade_fraction / 0.1);   // :132
   const double sp = (a.sigma_param != nullptr && a.want_logl) ? a.sigma_param[n] : 0.0;
   const double inv_den = 1.0 / ((dl * dl) * (kC * kC));
   const double* ep = a.sorted_ep;
   const double t0g = mn_tg[0], t1g = mn_tg[G - 1];
-  const bool trapped = a.cfg.output != RB_MN_OUT_FLUX_DENSITY;      // trapped_magnetar: epochs in seconds (:477-573)
+  const int out_mode = a.cfg.output;
+  const bool trapped = out_mode == RB_MN_OUT_TRAPPED_LUMINOSITY || out_mode == RB_MN_OUT_TRAPPED_FLUX;   // seconds (:477-573)
+  const bool sn_mode = SN && out_mode == RB_MN_OUT_SUPERNOVA;       // interpolation axis in days (supernova_models.py:2573)
+  const bool lbol_mode = SN && out_mode == RB_MN_OUT_LBOL;          // seconds, no redshift (:2484-2487)
   const double kcorr = pow(opz, a.cfg.photon_index - 2.0);          // :544
+  double tfloor = 0.0, inv_rec = 0.0;
+  rb_sn_config sed_cfg;                                             // only the cut-off parameters are read
+  sed_cfg.cutoff_wavelength = a.cfg.cutoff_wavelength;
+  sed_cfg.absorption_index = a.cfg.absorption_index;
+  if (sn_mode) {
+    tfloor = P[RB_MN_TEMPERATURE_FLOOR * S];
+    const double tf2 = tfloor * tfloor;
+    inv_rec = 1.0 / (kStefConst * (tf2 * tf2));
+  }
+  // epoch coordinate on the interpolation axis of the mode
+  auto epoch_x = [&](int e) -> double {
+    const double t_obs = ep[MS_T * E + e];
+    if (trapped || sn_mode) return t_obs / opz;                     // :537 / supernova_models.py:2561
+    if (lbol_mode) return t_obs * kDay;                             // :2484
+    return (t_obs * kDay) / opz;                                    // :252-254
+  };
 
   int ei = 0;
   double logl = 0.0;
   // epochs before the grid: interp1d raises in the reference -> NaN
   while (ei < E) {
-    const double ts = trapped ? ep[MS_T * E + ei] / opz : (ep[MS_T * E + ei] * kDay) / opz;   // :252-254, :537
-    if (ts >= t0g) break;
+    const double ts = epoch_x(ei);
+    if (ts >= (sn_mode ? t0g / kDay : t0g)) break;
     if (!a.grid_mode) {
       if (a.out_model != nullptr) a.out_model[n * (int64_t)E + (int)ep[MS_ORIG * E + ei]] = NAN;
       logl = NAN;
     }
     ++ei;
   }
-  double pt = 0.0, ptemp = 0.0, prad = 0.0, pdop = 0.0, ptau = 0.0;
+  double pt = 0.0, ptemp = 0.0, prad = 0.0, pdop = 0.0, ptau = 0.0, plb = 0.0;
   for (int i = 0; i < G; ++i) {
     const double t = mn_tg[i];
     const double beta = sqrt(1.0 - 1.0 / (gam * gam));                         // :65
@@ -167,7 +190,12 @@ __global__ void __launch_bounds__(128) mn_kernel(const MnArgs a) {
     // :78 -- product and difference rounded separately as in the reference: at late times the difference is ~1e-9,
     // a fused multiply-subtract (no rounding of the ~0.5 product) would move it by up to 1.5e-8 relative
     const double denom = __dsub_rn(0.5, __dmul_rn(1.0 / 3.141592654, atan_cr((t_com - 1.3) / 0.11)));
-    const double l_rad = lrad_coef * pow(denom, 1.3);                                             // :80
+    double l_rad;
+    if (!SN || a.cfg.use_r_process) {
+      l_rad = lrad_coef * pow(denom, 1.3);                                                        // :80
+    } else {                                                                                      // :82-84
+      l_rad = nickel_mass * (6.45e43 * exp(-t_com / (8.8 * 86400)) + 1.45e43 * exp(-t_com / (111.3 * 86400)));
+    }
     const double tau = kappa * (m / vol) * (rad / gam);                                           // :85
     double l_emit, temp;
     if (tau <= 1.0) {
@@ -214,36 +242,61 @@ __global__ void __launch_bounds__(128) mn_kernel(const MnArgs a) {
       go[1 * G + i] = rad / dop;         // ... and radius R / D (:164-172)
       go[2 * G + i] = lbol;
       go[3 * G + i] = (t * opz) / kDay;  // time_observer_frame / day_to_s (:236)
-    } else if (i > 0) {
-      // epochs in (t_{i-1}, t_i]: interp1d (:256-261) + _comoving_blackbody_to_flux_density (:164-173)
-      while (ei < E) {
-        const double ts = trapped ? ep[MS_T * E + ei] / opz : (ep[MS_T * E + ei] * kDay) / opz;
-        if (!(ts <= t)) break;
-        const double w = ts - pt, inv = 1.0 / (t - pt);
-        const double te = (temp - ptemp) * inv * w + ptemp;
-        const double re = (rad - prad) * inv * w + prad;
-        const double de = (dop - pdop) * inv * w + pdop;
-        const double nu = ep[MS_NU * E + ei] * opz;
-        const double frac = 1.0 / (exp((kH * nu) / (kKB * te * de)) - 1.0);   // the reference's exp(x) - 1 (:172)
-        double model;
-        if (!trapped) {
-          const double num = 2 * kPi * kH * (nu * nu * nu) * (re * re);
-          model = num * (inv_den / (de * de)) * frac * opz * kToMJy * opz;                        // :262, :272
-        } else {
-          // _comoving_blackbody_to_luminosity (:177-196) + the leaking spin-down luminosity (:509-511)
-          const double optical_depth = (tau - ptau) * inv * w + ptau;
-          const double num = 8 * (kPi * kPi) * kH * ((nu * nu) * (nu * nu)) * (re * re);
-          const double l_ej = num / ((kC * kC) * (de * de)) * frac;
-          const double lsd = eng_a * pow(1.0 + ts / eng_b, eng_c);
-          model = exp(-optical_depth) * lsd + l_ej;
-          if (a.cfg.output == RB_MN_OUT_TRAPPED_FLUX) model = model / (4 * kPi * (dl * dl) * kcorr);   // :545
-        }
-        if (a.out_model != nullptr) a.out_model[n * (int64_t)E + (int)ep[MS_ORIG * E + ei]] = model;
-        if (a.want_logl)
-          logl += logl_term(a.cfg.sigma_mode, ep[MS_KIND * E + ei], ep[MS_Y * E + ei], model, ep[MS_ISIG * E + ei],
-                            ep[MS_LOGT * E + ei], sp);
-        ++ei;
+    } else {
+      // quantities interpolated by the mode: (T', R, D, tau) of the ejecta, or (T_ph, R_ph, L) of the photosphere
+      double q_temp = temp, q_rad = rad;
+      const double xg = sn_mode ? t / kDay : t;                               // supernova_models.py:2573
+      if (sn_mode) {                                                          // :2570-2572: TemperatureFloor on the grid
+        const double vej_km = kC * sqrt(1.0 - 1.0 / (gam * gam)) / kKm;       // utils.py:1524
+        temperature_floor_dev(lbol, xg, kRadiusConst * vej_km, tfloor, inv_rec, q_temp, q_rad);
       }
+      if (i > 0) {
+        // epochs in (x_{i-1}, x_i]: interp1d (:256-261) + the mode's emission law
+        while (ei < E) {
+          const double ts = epoch_x(ei);
+          if (!(ts <= xg)) break;
+          const double w = ts - pt, inv = 1.0 / (xg - pt);
+          const double te = (q_temp - ptemp) * inv * w + ptemp;
+          const double re = (q_rad - prad) * inv * w + prad;
+          const double nu = ep[MS_NU * E + ei] * opz;
+          double model;
+          if (SN && lbol_mode) {
+            model = (lbol - plb) * inv * w + plb;                             // :2481-2485
+          } else if (SN && sn_mode) {
+            const double lb = (lbol - plb) * inv * w + plb;
+            if (a.cfg.sed == RB_SED_BLACKBODY) {
+              const double num = 2 * kPi * kH * (nu * nu * nu) * (re * re);
+              model = num * inv_den / expm1((kH * nu) / (kKB * te)) * kToMJy * opz;
+            } else {
+              model = cutoff_blackbody_mjy(sed_cfg, lb, re, te, nu, dl) * opz;     // :2577-2581
+            }
+          } else if (!SN) {
+            const double de = (dop - pdop) * inv * w + pdop;
+            const double frac = 1.0 / (exp((kH * nu) / (kKB * te * de)) - 1.0);   // the reference's exp(x) - 1 (:172)
+            if (!trapped) {
+              const double num = 2 * kPi * kH * (nu * nu * nu) * (re * re);
+              model = num * (inv_den / (de * de)) * frac * opz * kToMJy * opz;                    // :262, :272
+            } else {
+              // _comoving_blackbody_to_luminosity (:177-196) + the leaking spin-down luminosity (:509-511)
+              const double optical_depth = (tau - ptau) * inv * w + ptau;
+              const double num = 8 * (kPi * kPi) * kH * ((nu * nu) * (nu * nu)) * (re * re);
+              const double l_ej = num / ((kC * kC) * (de * de)) * frac;
+              const double lsd = eng_a * pow(1.0 + ts / eng_b, eng_c);
+              model = exp(-optical_depth) * lsd + l_ej;
+              if (out_mode == RB_MN_OUT_TRAPPED_FLUX) model = model / (4 * kPi * (dl * dl) * kcorr);   // :545
+            }
+          } else {
+            model = NAN;
+          }
+          if (a.out_model != nullptr) a.out_model[n * (int64_t)E + (int)ep[MS_ORIG * E + ei]] = model;
+          if (a.want_logl)
+            logl += logl_term(a.cfg.sigma_mode, ep[MS_KIND * E + ei], ep[MS_Y * E + ei], model, ep[MS_ISIG * E + ei],
+                              ep[MS_LOGT * E + ei], sp);
+          ++ei;
+        }
+      }
+      pt = xg; ptemp = q_temp; prad = q_rad; pdop = dop; ptau = tau; plb = lbol;
+      continue;
     }
     pt = t; ptemp = temp; prad = rad; pdop = dop; ptau = tau;
   }

@@ -372,11 +372,15 @@ class MergernovaPath(_FusedPath):
 
     def __init__(self, engine, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED,
                  use_gamma_ray_opacity=False, pair_cascade_switch=False, ejecta_albedo=0.5,
-                 pair_cascade_fraction=0.05, cosmology=None, device=None, output=0, photon_index=2.0):
+                 pair_cascade_fraction=0.05, cosmology=None, device=None, output=0, photon_index=2.0,
+                 supernova=None):
         self.cfg = _capi.mn_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
-                                   pair_cascade_fraction, cosmology, output, photon_index)
+                                   pair_cascade_fraction, cosmology, output, photon_index, supernova)
         if engine == _capi.MN_EVOLVING:
             self.ROWS = _capi.MN_ROWS_EVOLVING
+        if supernova is not None:
+            self.ROWS = _capi.MN_ROWS_SUPERNOVA
+        self.NEEDS_FREQUENCY = output != _capi.MN_OUT_LBOL
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):

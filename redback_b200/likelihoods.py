@@ -207,7 +207,7 @@ class GaussianLikelihood(_RedbackLikelihood):
             if level is not None:
                 self._path[1].set_upper_limits(level, ul_mag)
         path = self._path[1]
-        params, _ = _fused.collect(merged, kw, None, spec.needed)
+        params, _ = _fused.collect(merged, kw, None, spec.needed, spec.defaults)
         params = spec.transform(params)
         dev = path.pack(params, N)
         sp_dev = None

@@ -360,3 +360,75 @@ def thin_shell_supernova(time, redshift=None, mej=None, ek=None, params_batch=No
 FUSED.update({homologous_expansion_supernova_model_bolometric: _HOMOLOGOUS_BOLO,
               homologous_expansion_supernova: _HOMOLOGOUS,
               thin_shell_supernova_model_bolometric: _THIN_SHELL_BOLO, thin_shell_supernova: _THIN_SHELL})
+
+
+# ---- general_magnetar_driven_supernova (supernova_models.py:2464-2638): relativistic ejecta dynamics -------------------
+def _gmds_spec(name, flux_density):
+    from .engine import MergernovaPath
+    needed = (("redshift",) if flux_density else ()) + ("mej", "E_sn", "kappa", "l0", "tau_sd", "nn", "kappa_gamma",
+                                                         "f_nickel") + (("temperature_floor",) if flux_density else ())
+
+    def validate(kwargs):
+        if flux_density:
+            fmt = kwargs.get("output_format")
+            if fmt is None:
+                raise KeyError("output_format")
+            if fmt != "flux_density":
+                raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device")
+            _operator_name("photosphere", kwargs.get("photosphere"), "TemperatureFloor")
+            _operator_name("sed", kwargs.get("sed"), "CutoffBlackbody")
+        elif kwargs.get("output_format") == "dynamics_output":
+            raise NotImplementedError(f"{name}: output_format='dynamics_output' returns Python objects in the reference")
+
+    def build(time, kwargs, y, sigma, sigma_mode):
+        sn = dict(sed=_SED_IDS[_operator_name("sed", kwargs.get("sed"), "CutoffBlackbody")] if flux_density
+                  else _capi.SED_BLACKBODY,
+                  cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000), absorption_index=kwargs.get("absorption_index", 1.0))
+        return MergernovaPath(_capi.MN_MAGNETAR_ONLY, time, frequency=kwargs.get("frequency") if flux_density else None,
+                              y=y, sigma=sigma, sigma_mode=sigma_mode, use_gamma_ray_opacity=True,
+                              pair_cascade_switch=kwargs.get("pair_cascade_switch", False),
+                              ejecta_albedo=kwargs.get("ejecta_albedo", 0.5),
+                              pair_cascade_fraction=kwargs.get("pair_cascade_fraction", 0.05),
+                              cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"),
+                              output=_capi.MN_OUT_SUPERNOVA if flux_density else _capi.MN_OUT_LBOL, supernova=sn)
+
+    def transform(params):
+        import numpy as np
+        import torch
+        params = dict(params)
+        e_sn, mej = params.pop("E_sn"), params["mej"]
+        if isinstance(e_sn, torch.Tensor) or isinstance(mej, torch.Tensor):
+            e_sn, mej = torch.as_tensor(e_sn, dtype=torch.float64), torch.as_tensor(mej, dtype=torch.float64)
+            params["beta"] = torch.sqrt(e_sn / (0.5 * mej * _SOLAR_MASS)) / 29979245800.0
+        else:
+            params["beta"] = np.sqrt(np.asarray(e_sn, dtype=np.float64)
+                                     / (0.5 * np.asarray(mej, dtype=np.float64) * _SOLAR_MASS)) / 29979245800.0   # :2478
+        params["ejecta_radius"] = 1.0e11                                                                            # :2479
+        params["n_ism"] = 1.0e-5
+        return params
+
+    return FusedSpec(name, needed, build, validate, transform, defaults={"f_nickel": 0})   # :82 of the dynamics
+
+
+_GMDS_BOLO = _gmds_spec("general_magnetar_driven_supernova_bolometric", False)
+_GMDS = _gmds_spec("general_magnetar_driven_supernova", True)
+
+
+def general_magnetar_driven_supernova_bolometric(time, mej=None, E_sn=None, kappa=None, l0=None, tau_sd=None, nn=None,
+                                                 kappa_gamma=None, params_batch=None, **kwargs):
+    """redback supernova_models.general_magnetar_driven_supernova_bolometric (:2464-2507): relativistic ejecta dynamics
+    (nickel heating, gamma-ray leakage) driven by a magnetar; kwargs f_nickel, pair_cascade_switch; erg/s."""
+    named = dict(mej=mej, E_sn=E_sn, kappa=kappa, l0=l0, tau_sd=tau_sd, nn=nn, kappa_gamma=kappa_gamma)
+    return run(_GMDS_BOLO, time, named, kwargs, params_batch)
+
+
+def general_magnetar_driven_supernova(time, redshift=None, mej=None, E_sn=None, kappa=None, l0=None, tau_sd=None,
+                                      nn=None, kappa_gamma=None, params_batch=None, **kwargs):
+    """redback supernova_models.general_magnetar_driven_supernova (:2510-2584), flux_density: TemperatureFloor on the
+    dynamics grid with the time-dependent ejecta velocity, CutoffBlackbody by default; mJy."""
+    named = dict(redshift=redshift, mej=mej, E_sn=E_sn, kappa=kappa, l0=l0, tau_sd=tau_sd, nn=nn,
+                 kappa_gamma=kappa_gamma)
+    return run(_GMDS, time, named, kwargs, params_batch)
+
+
+FUSED.update({general_magnetar_driven_supernova_bolometric: _GMDS_BOLO, general_magnetar_driven_supernova: _GMDS})

@@ -57,6 +57,10 @@ CASES = {
     "magnetar.general_metzger_magnetar_driven_evolution":
         lambda t, p, kw: r.general_metzger_magnetar_driven_evolution(
             t, kw["redshift"], frequency=np.full(t.size, kw["frequency"]), **p),
+    "supernova.general_magnetar_driven_supernova":
+        lambda t, p, kw: r.general_magnetar_driven_supernova(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "supernova.general_magnetar_driven_supernova_bolometric":
+        lambda t, p, kw: r.general_magnetar_driven_supernova_bolometric(t, **p),
     "kilonova.two_component_kilonova_model":
         lambda t, p, kw: r.two_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.three_component_kilonova_model":

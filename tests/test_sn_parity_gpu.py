@@ -41,6 +41,8 @@ def test_golden_vectors(rb, golden):
                      ("homologous_expansion_supernova", sn.homologous_expansion_supernova),
                      ("thin_shell_supernova", sn.thin_shell_supernova),
                      ("sn_fallback", sn.sn_fallback), ("sn_nickel_fallback", sn.sn_nickel_fallback),
+                     ("general_magnetar_driven_supernova", sn.general_magnetar_driven_supernova),
+                     ("general_magnetar_driven_supernova_bolometric", sn.general_magnetar_driven_supernova_bolometric),
                      ("tde.tde_analytical", rb.tde_models.tde_analytical),
                      ("tde.tde_analytical_bolometric", rb.tde_models.tde_analytical_bolometric)]:
         e = golden[name if "." in name else "supernova." + name]
@@ -724,3 +726,41 @@ def test_no_interaction_process(rb):
                                           **{k: float(v[1]) for k, v in p.items()})
     np.testing.assert_array_equal(mags[1], one)
     assert np.all(np.isfinite(mags))
+
+
+@pytest.mark.gpu
+def test_general_magnetar_driven_supernova_batches(rb):
+    """general_magnetar_driven_supernova(_bolometric) (supernova_models.py:2464-2584): relativistic dynamics with
+    nickel heating on the 1998-point grid, photosphere on the grid, CutoffBlackbody; batch rows and the fused
+    likelihood against the oracle."""
+    rng = np.random.default_rng(131)
+    t = np.sort(rng.uniform(1, 300, 30))
+    nu = np.where(np.arange(t.size) % 2 == 0, 6.3e14, 4.7e14)
+    N = 8
+    p = dict(redshift=rng.uniform(0.01, 0.5, N), mej=h.loguniform(rng, 1, 30, N), E_sn=h.loguniform(rng, 1e50, 3e51, N),
+             kappa=rng.uniform(0.05, 0.3, N), l0=h.loguniform(rng, 1e44, 1e48, N), tau_sd=h.loguniform(rng, 1e4, 1e7, N),
+             nn=rng.uniform(2.2, 6, N), kappa_gamma=h.loguniform(rng, 1e-2, 1e2, N), f_nickel=rng.uniform(0, 0.3, N),
+             temperature_floor=h.loguniform(rng, 3e3, 1e4, N))
+    fn = rb.supernova_models.general_magnetar_driven_supernova
+    kw = dict(frequency=nu, output_format="flux_density")
+    out = fn(t, params_batch=p, **kw)
+    y = out[0] * 1.05
+    sigma = 0.1 * np.abs(out[0]) + 1e-12
+    logl = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=kw).log_likelihood_batch(p)
+    pb = {k: v for k, v in p.items() if k not in ("redshift", "temperature_floor")}
+    lbol = rb.supernova_models.general_magnetar_driven_supernova_bolometric(t, params_batch=pb)
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        z = kwi.pop("redshift")
+        ref = r.general_magnetar_driven_supernova(t, z, frequency=nu, **kwi)
+        h.assert_close(out[i], ref, 1e-9, 1e-11, what=f"general_magnetar_driven_supernova sample {i}")
+        ref_l = r.gaussian_likelihood(y, ref, sigma)
+        assert abs(logl[i] - ref_l) <= 1e-6 + 1e-9 * abs(ref_l), (i, logl[i], ref_l)
+        kwb = {k: v[i] for k, v in pb.items()}
+        h.assert_close(lbol[i], r.general_magnetar_driven_supernova_bolometric(t, **kwb), 1e-9, 1e-12,
+                       what=f"general_magnetar_driven_supernova_bolometric sample {i}")
+    # f_nickel is an optional kwarg of the reference (default 0)
+    nop = {k: v for k, v in p.items() if k != "f_nickel"}
+    a = fn(t, params_batch=nop, **kw)
+    b = fn(t, params_batch=dict(nop, f_nickel=np.zeros(N)), **kw)
+    np.testing.assert_array_equal(a, b)
