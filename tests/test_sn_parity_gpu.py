@@ -764,3 +764,63 @@ def test_general_magnetar_driven_supernova_batches(rb):
     a = fn(t, params_batch=nop, **kw)
     b = fn(t, params_batch=dict(nop, f_nickel=np.zeros(N)), **kw)
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_noise_models_in_every_fused_kernel(rb):
+    """Every fused kernel x every Gaussian noise model: the fused log L must equal the stand-alone reduction (checked
+    against the oracle elsewhere) applied to the kernel's own model matrix."""
+    import torch
+    from redback_b200.engine import gaussian_logl
+    from redback_b200 import _capi
+    rb.bands.register_synthetic_lsst()
+    rng = np.random.default_rng(141)
+    t = np.sort(rng.uniform(1.0, 40.0, 24))
+    nu = np.where(np.arange(t.size) % 2 == 0, 6.3e14, 4.7e14)
+    fd = dict(frequency=nu, output_format="flux_density")
+    N = 6
+    sn_common = dict(mej=h.loguniform(rng, 1, 10, N), vej=h.loguniform(rng, 5e3, 2e4, N), kappa=rng.uniform(0.05, 0.3, N),
+                     kappa_gamma=h.loguniform(rng, 0.1, 10, N), temperature_floor=h.loguniform(rng, 3e3, 8e3, N))
+    z = rng.uniform(0.01, 0.2, N)
+    cases = [
+        (rb.supernova_models.arnett, dict(redshift=z, f_nickel=rng.uniform(0.05, 0.5, N), **sn_common), fd),
+        (rb.supernova_models.csm_interaction, h.csm_prior(rng, N, zmax=0.2), fd),
+        (rb.supernova_models.sn_fallback, dict(redshift=z, logl1=rng.uniform(52, 55, N), tr=rng.uniform(2, 20, N),
+                                                vej=sn_common["vej"], temperature_floor=sn_common["temperature_floor"]), fd),
+        (rb.supernova_models.general_magnetar_driven_supernova,
+         dict(redshift=z, mej=sn_common["mej"], E_sn=h.loguniform(rng, 1e50, 1e51, N), kappa=sn_common["kappa"],
+              l0=h.loguniform(rng, 1e44, 1e47, N), tau_sd=h.loguniform(rng, 1e4, 1e6, N), nn=rng.uniform(2.5, 5, N),
+              kappa_gamma=sn_common["kappa_gamma"], temperature_floor=sn_common["temperature_floor"]), fd),
+        (rb.kilonova_models.one_component_kilonova_model, h.one_component_prior(rng, N), fd),
+        (rb.kilonova_models.metzger_kilonova_model, h.metzger_prior(rng, N), fd),
+        (rb.magnetar_driven_ejecta_models.general_mergernova, h.mergernova_prior(rng, N, "general"), fd),
+        (rb.magnetar_driven_ejecta_models.general_metzger_magnetar_driven, h.metzger_magnetar_prior(rng, N, "general"), fd),
+        (rb.afterglow_models.tophat_redback, h.tophat_prior(rng, N), fd),
+        (rb.supernova_models.arnett, dict(redshift=z, f_nickel=rng.uniform(0.05, 0.5, N), **sn_common),
+         dict(bands=np.array(["lsstg", "lsstr", "lssti"])[np.arange(t.size) % 3], output_format="magnitude")),
+    ]
+    LIKES = [
+        (rb.GaussianLikelihood, _capi.SIGMA_FIXED, False),
+        (rb.GaussianLikelihood, _capi.SIGMA_SAMPLED, True),                       # sigma=None: sampled
+        (rb.GaussianLikelihoodQuadratureNoise, _capi.SIGMA_QUADRATURE, True),
+        (rb.GaussianLikelihoodWithFractionalNoise, _capi.SIGMA_FRACTIONAL, False),
+        (rb.GaussianLikelihoodWithSystematicNoise, _capi.SIGMA_SYSTEMATIC, True),
+    ]
+    for fn, p, kw in cases:
+        model = np.asarray(fn(t, params_batch=p, **kw))
+        good = np.isfinite(model).all(axis=1)
+        assert good.sum() >= 3, fn.__name__
+        y = np.nanmedian(model[good], axis=0) * 1.01
+        sig_i = 0.15 * np.abs(y) + 1e-30
+        for cls, mode, sampled in LIKES:
+            sp = h.loguniform(rng, 0.05, 0.5, N) * (np.abs(y).mean() if mode != _capi.SIGMA_SYSTEMATIC else 1.0)
+            sigma_arg = None if mode == _capi.SIGMA_SAMPLED else (0.2 if mode == _capi.SIGMA_FRACTIONAL else sig_i)
+            like = cls(t, y, sigma_arg, fn, kwargs=kw)
+            batch = dict(p, sigma=sp) if sampled else p
+            fused = like.log_likelihood_batch(batch)
+            dev_model = torch.as_tensor(model, device="cuda")
+            alone = gaussian_logl(dev_model, y, 0.2 if mode == _capi.SIGMA_FRACTIONAL else
+                                  (None if mode == _capi.SIGMA_SAMPLED else sig_i),
+                                  sp if sampled else None, sigma_mode=mode).cpu().numpy()
+            np.testing.assert_allclose(fused[good], alone[good], rtol=1e-9, atol=1e-6,
+                                       err_msg=f"{fn.__name__} {cls.__name__} mode {mode}")
