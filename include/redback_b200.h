@@ -435,6 +435,11 @@ int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* phot, int64
                        const double* params, const double* t_obs, const double* dl_cm, const double* y,
                        const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
                        void* stream);
+/* The same for the magnetar-driven Metzger shell models (plain blackbody of T and R_photosphere on the model grid). */
+int rb_mk_mag_eval_f64(const rb_mk_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
+                       const double* params, const double* t_obs, const double* dl_cm, const double* y,
+                       const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
+                       void* stream);
 
 /* ---- observation noise + SNR cut for simulated optical light curves ------------------------------------
  * SimulateTransientWithCadence._evaluate_optical_model / _add_optical_noise_and_cuts

@@ -1720,6 +1720,31 @@ def mergernova_magnitude(model, time, redshift, *, bands, bandpasses, lambda_arr
     return bandmag_from_spectra(time_obs, time_observer_frame / day_to_s, spectra, lam, bands, bandpasses)
 
 
+def metzger_magnetar_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, **params):
+    """_processing_other_formats (magnetar_driven_ejecta_models.py:198-238) with use_relativistic_blackbody=False for
+    `model` in {'metzger_magnetar_driven_kilonova_model', 'general_metzger_magnetar_driven',
+    'general_metzger_magnetar_driven_thermalisation'}."""
+    time_obs = np.asarray(time, dtype=float)
+    lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=float)
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    t_grid = get_optimal_time_array(1e-4, 1e7, 300)
+    if model == "metzger_magnetar_driven_kilonova_model":
+        lum = basic_magnetar(t_grid, params["p0"], params["bp"], params["mass_ns"], params["theta_pb"])
+    else:
+        lum = magnetar_only(t_grid, params["l0"], params["tau_sd"], params["nn"])
+    gamma_ray = model == "general_metzger_magnetar_driven_thermalisation"
+    _, temp, rad = metzger_magnetar_driven_internal(
+        t_grid, params["mej"], params["vej"], params["beta"], params["kappa_r"], lum, gamma_ray,
+        thermalisation_efficiency=params.get("thermalisation_efficiency"), kappa_gamma=params.get("kappa_gamma"))
+    time_observer_frame = t_grid * (1. + redshift)
+    frequency, _ = calc_kcorrected_properties(lambda_to_nu(lam), redshift, time_observer_frame)
+    with np.errstate(all="ignore"):
+        fd = blackbody_to_flux_density(temp, rad, dl, frequency[:, None]).T                      # sed.py:954-963
+        spectra = flux_density_to_spectrum(fd, redshift, lam)
+    return bandmag_from_spectra(time_obs, time_observer_frame / day_to_s, spectra, lam, bands, bandpasses)
+
+
 def kn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, dense_resolution=500,
                  **params):
     """Magnitude branch of one_component_kilonova_model / metzger_kilonova_model

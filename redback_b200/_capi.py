@@ -137,6 +137,7 @@ EXPORTS = {
     "rb_sn_mag_eval_f64": (C.c_int, [C.POINTER(SnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_kn_mag_eval_f64": (C.c_int, [C.POINTER(KnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_mn_mag_eval_f64": (C.c_int, [C.POINTER(MnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
+    "rb_mk_mag_eval_f64": (C.c_int, [C.POINTER(MkConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_optical_noise_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 4 + [C.c_double, C.c_int] + [_dp] * 6
                              + [C.c_void_p]),
     "rb_luminosity_distance_f64": (C.c_int, [C.POINTER(Cosmology), C.c_int64, _dp, _dp, C.c_void_p]),

@@ -1700,6 +1700,129 @@ extern "C" int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* 
   return status;
 }
 
+extern "C" int rb_mk_mag_eval_f64(const rb_mk_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
+                                  const double* params, const double* t_obs, const double* dl_cm, const double* y,
+                                  const double* sigma, const double* sigma_param, double* out_model,
+                                  double* out_logl, void* stream) {
+  static const double dummy = 0.0;
+  int rc = mk_check(cfg, N, E, params, t_obs, &dummy, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  rc = phot_check(phot, E, false);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev_id = 0, sms = 0;
+  RB_CUDA(cudaGetDevice(&dev_id));
+  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rb::mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute");
+  std::vector<double> tg((size_t)cfg->resolution);
+  int G = 0;
+  rc = rb_optimal_time_array(1e-4, 1e7, cfg->resolution, tg.data(), &G);
+  if (rc != RB_OK) return rc;
+  tg.resize((size_t)G);
+  const int NT = G, NL = phot->n_lambda;
+  const size_t psmem = phot_smem_bytes(NT, NL);
+  const size_t mk_smem = sizeof(double) * ((size_t)7 * G + 2 * (size_t)rb::kShellWarps * G + 2 * rb::kShells + 40) +
+                         sizeof(int) * (size_t)rb::kShellWarps * G;
+  if (psmem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_mk_mag_eval: grids exceed shared memory");
+
+  PhotDevice pd;
+  pd.st = st;
+  rb::PhotArgs pa{};
+  rc = phot_prepare(phot, E, pd, pa);
+  if (rc != RB_OK) { pd.release(); return rc; }
+  std::vector<double> tdays((size_t)G);
+  for (int i = 0; i < G; ++i) tdays[(size_t)i] = tg[(size_t)i] / 86400.0;     // time_eval (:236), up to the (1+z) scale
+  std::vector<double> lu_t = collocation_lu(tdays.data(), NT);
+  const double* d_tgrid = nullptr;
+  cudaError_t ce = pd.upload(tg, &d_tgrid);
+  if (ce == cudaSuccess) ce = pd.upload(lu_t, &pa.lu_time);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "time grid upload"); }
+
+  double* d_ep_obs = nullptr;
+  ce = cudaMallocAsync(&d_ep_obs, (size_t)rb::kEpochCols * E * sizeof(double), st);
+  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "epoch table"); }
+  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, nullptr, y,
+                                                                    y ? sigma : nullptr, cfg->upper_limits, d_ep_obs);
+  launch_counter()->fetch_add(1);
+
+  const int64_t chunk_max = 32768;
+  int occ_ph = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
+  if (occ_ph < 1) occ_ph = 1;
+  const int64_t ph_grid_max = (int64_t)sms * occ_ph;
+  const int64_t nc_max = std::min<int64_t>(chunk_max, N);
+  double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_dlc = nullptr, *d_scratch = nullptr;
+  ce = cudaMallocAsync(&d_grid, (size_t)nc_max * 4 * NT * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_opz, (size_t)nc_max * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dl, (size_t)nc_max * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dlc, (size_t)nc_max * sizeof(double), st);
+  if (ce == cudaSuccess)
+    ce = cudaMallocAsync(&d_scratch, (size_t)std::min<int64_t>(ph_grid_max, nc_max) * NT * NL * sizeof(double), st);
+  int status = RB_OK;
+  if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude workspace");
+  for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
+    const int64_t nc = std::min<int64_t>(chunk_max, N - n0);
+    const double* dl = dl_cm ? dl_cm + n0 : d_dlc;
+    if (!dl_cm) {
+      rb::dl_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(cfg->cosmology, nc,
+                                                            params + (size_t)RB_MK_REDSHIFT * N + n0, d_dlc);
+      launch_counter()->fetch_add(1);
+    }
+    rb::MkArgs a{};
+    a.cfg = *cfg;
+    a.N = nc;
+    a.E = 0;
+    a.G = G;
+    a.params = params + n0;
+    a.param_stride = N;
+    a.dl_cm = dl;
+    a.tgrid = d_tgrid;
+    a.grid_mode = 1;
+    a.grid_out = d_grid;
+    a.opz_out = d_opz;
+    a.dl_out = d_dl;
+    rb::mk_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * 8), rb::kMkThreads, mk_smem, st>>>(a);
+    pa.N = nc;
+    pa.n_base = n0;
+    pa.E = (int)E;
+    pa.n_t_max = NT;
+    pa.sed = rb::PH_SED_BLACKBODY;
+    pa.sigma_mode = cfg->sigma_mode;
+    pa.want_logl = y ? 1 : 0;
+    pa.common_time_lu = 1;
+    pa.grid = d_grid;
+    pa.grid_len = nullptr;
+    pa.opz = d_opz;
+    pa.dl = d_dl;
+    pa.sigma_param_s = sigma_param ? sigma_param + n0 : nullptr;
+    pa.epoch_tab = d_ep_obs;
+    pa.scratch = d_scratch;
+    pa.out_model = out_model;
+    pa.out_logl = y ? out_logl : nullptr;
+    rb::phot_kernel<<<(unsigned)std::min<int64_t>(ph_grid_max, nc), rb::kPhotThreads, psmem, st>>>(pa);
+    launch_counter()->fetch_add(2);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude kernels");
+  }
+  cudaFreeAsync(d_scratch, st);
+  cudaFreeAsync(d_dlc, st);
+  cudaFreeAsync(d_dl, st);
+  cudaFreeAsync(d_opz, st);
+  cudaFreeAsync(d_grid, st);
+  cudaFreeAsync(d_ep_obs, st);
+  pd.release();
+  return status;
+}
+
 extern "C" int rb_optical_noise_f64(int noise_type, int64_t N, int64_t E, const double* model_mag,
                                     const double* ref_flux, const double* limiting_mag, const double* z,
                                     double snr_threshold, int apply_snr_cut, double* obs_mag, double* mag_err,

@@ -29,6 +29,10 @@ struct MkArgs {
   double* out_model;
   double* out_logl;
   int want_logl;
+  int grid_mode;             // magnitude branch: write (T, R_photosphere, L, phase [d]) per grid point for phot_kernel
+  double* grid_out;          // [N][4][G]
+  double* opz_out;
+  double* dl_out;
 };
 
 __global__ void __launch_bounds__(kMkThreads) mk_kernel(const MkArgs a) {
@@ -227,6 +231,17 @@ __global__ void __launch_bounds__(kMkThreads) mk_kernel(const MkArgs a) {
       }
     }
     __syncthreads();
+    if (a.grid_mode) {                       // _processing_other_formats (:198-238), use_relativistic_blackbody = False
+      double* go = a.grid_out + (size_t)n * 4 * G;
+      for (int k = tid; k < G; k += blockDim.x) {
+        go[0 * G + k] = Tg[k];
+        go[1 * G + k] = Rg[k];
+        go[2 * G + k] = 0.0;
+        go[3 * G + k] = (tg[k] * opz) / kDay;                                   // time_observer_frame / day_to_s (:236)
+      }
+      if (tid == 0) { a.opz_out[n] = opz; a.dl_out[n] = dl; }
+      continue;
+    }
     // ---- epochs: interp1d + blackbody (:263-272) + likelihood ------------------------------------------------------------
     const double inv_den = 1.0 / ((dl * dl) * (kC * kC));
     const double sp = (a.sigma_param != nullptr && a.want_logl) ? a.sigma_param[n] : 0.0;

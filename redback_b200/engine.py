@@ -416,6 +416,29 @@ class MetzgerMagnetarPath(_FusedPath):
             raise ValueError("A value in x_new is below the interpolation range: these models need time > 0")
 
 
+class MetzgerMagnetarMagPath(MetzgerMagnetarPath):
+    """Magnitude / bandpass-flux branch of the magnetar-driven Metzger shell models (_processing_other_formats,
+    magnetar_driven_ejecta_models.py:198-238, plain blackbody)."""
+
+    NEEDS_FREQUENCY = False
+
+    def __init__(self, engine, time, bands, output="magnitude", lambda_array=None, y=None, sigma=None,
+                 sigma_mode=_capi.SIGMA_FIXED, use_gamma_ray_opacity=False, pair_cascade_switch=True, ejecta_albedo=0.5,
+                 pair_cascade_fraction=0.01, neutron_precursor_switch=True, vmax=0.7, cosmology=None, device=None,
+                 resolution=300):
+        from . import bands as _bands
+        self.cfg = _capi.mk_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
+                                   pair_cascade_fraction, neutron_precursor_switch, vmax, cosmology, resolution)
+        if engine == _capi.MN_EVOLVING:
+            self.ROWS = _capi.MK_ROWS_EVOLVING
+        self._setup(time, None, y, sigma, device)
+        lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
+        self.phot, self._keep = _bands.build_photometry(bands, self.E, lam, output)
+
+    def _launch(self, *args):
+        return self._launch_mag(_capi.lib().rb_mk_mag_eval_f64, *args)
+
+
 class MergernovaMagPath(MergernovaPath):
     """Magnitude / bandpass-flux branch of the mergernova models (_processing_other_formats,
     magnetar_driven_ejecta_models.py:198-238)."""

@@ -4,7 +4,7 @@ general_mergernova_thermalisation :374-419), output_format='flux_density' | 'mag
 `params_batch` (see supernova_models.py)."""
 from . import _capi
 from ._fused import FusedSpec, cosmology_from_kwargs, output_mode, run
-from .engine import MergernovaMagPath, MergernovaPath, MetzgerMagnetarPath
+from .engine import MergernovaMagPath, MergernovaPath, MetzgerMagnetarMagPath, MetzgerMagnetarPath
 
 _EJECTA = ("redshift", "mej", "beta", "ejecta_radius", "kappa", "n_ism")
 
@@ -82,15 +82,22 @@ def _metzger_spec(name, engine, engine_params, last, gamma_ray, resolution=300):
     needed = _SHELLS + tuple(engine_params) + (last,)
 
     def validate(kwargs):
-        fmt = kwargs.get("output_format")
-        if fmt is None:
-            raise KeyError("output_format")
-        if fmt != "flux_density":
-            raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device")
+        output_mode(kwargs, name)
         if kwargs.get("magnetar_heating", "first_layer") != "first_layer":
             raise NotImplementedError(f"{name}: magnetar_heating='all_layers' is not fused on device")
 
     def build(time, kwargs, y, sigma, sigma_mode):
+        mode = output_mode(kwargs, name)
+        if mode != "flux_density":
+            return MetzgerMagnetarMagPath(engine, time, kwargs["bands"], output=mode,
+                                          lambda_array=kwargs.get("lambda_array"), y=y, sigma=sigma,
+                                          sigma_mode=sigma_mode, use_gamma_ray_opacity=gamma_ray,
+                                          pair_cascade_switch=kwargs.get("pair_cascade_switch", True),
+                                          ejecta_albedo=kwargs.get("ejecta_albedo", 0.5),
+                                          pair_cascade_fraction=kwargs.get("pair_cascade_fraction", 0.01),
+                                          neutron_precursor_switch=kwargs.get("neutron_precursor_switch", True),
+                                          vmax=kwargs.get("vmax", 0.7), cosmology=cosmology_from_kwargs(kwargs),
+                                          device=kwargs.get("device"), resolution=resolution)
         return MetzgerMagnetarPath(engine, time, frequency=kwargs.get("frequency"), y=y, sigma=sigma,
                                    sigma_mode=sigma_mode, use_gamma_ray_opacity=gamma_ray,
                                    pair_cascade_switch=kwargs.get("pair_cascade_switch", True),

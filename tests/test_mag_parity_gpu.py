@@ -110,6 +110,23 @@ def test_mergernova_magnitudes(rb, obands, kind):
         _check(out[i], ref, f"{name} sample {i}", atol=2e-8, floor_mag=np.nanmin(ref))
 
 
+def test_metzger_magnetar_driven_magnitudes(rb, obands):
+    """Magnitude branch of the magnetar-driven Metzger shell models (_processing_other_formats, plain blackbody); the
+    last grid point of the reference has T = NaN (0/0), which the spectra clean-up replaces -- same on device."""
+    rng = np.random.default_rng(31)
+    t = np.geomspace(0.3, 30, 24)
+    names = np.array(list(h.LSST_NU)[:6] * 4)
+    N = 6
+    p = h.metzger_magnetar_prior(rng, N, "general")
+    name = "general_metzger_magnetar_driven"
+    out = getattr(rb.magnetar_driven_ejecta_models, name)(t, params_batch=p, bands=names, output_format="magnitude")
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.metzger_magnetar_magnitude(name, t, z, bands=names, bandpasses=obands, **kw)
+        _check(out[i], ref, f"{name} sample {i}", atol=2e-8, floor_mag=np.nanmin(ref))
+
+
 def test_kilonova_magnitudes_config3(rb, obands):
     """BASELINE configs[2]: one_component_kilonova_model in LSST ugrizy magnitudes."""
     t = np.geomspace(0.3, 20, 36)
