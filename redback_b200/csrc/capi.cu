@@ -381,6 +381,36 @@ struct DevBuf {
   ~DevBuf() { if (p) cudaFree(p); }
   cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n * sizeof(double) : sizeof(double)); }
 };
+
+// Host-buffer variant of a device entry point: upload, launch on the default stream, download, synchronise.
+extern "C++" template <typename Cfg, typename DeviceEval>
+int eval_host(DeviceEval device_eval, const Cfg* cfg, int nparam, int64_t N, int64_t E, const double* params,
+              const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y, const double* sigma,
+              const double* sigma_param, double* out_model, double* out_logl) {
+  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
+  const size_t nN = (size_t)N, nE = (size_t)E;
+  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
+    if (!h) return cudaSuccess;
+    cudaError_t e = b.alloc(n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  RB_CUDA(up(d_par, params, (size_t)nparam * nN));
+  RB_CUDA(up(d_t, t_obs, nE));
+  RB_CUDA(up(d_f, freq_obs, nE));
+  RB_CUDA(up(d_dl, dl_cm, nN));
+  RB_CUDA(up(d_y, y, nE));
+  RB_CUDA(up(d_s, sigma, nE));
+  RB_CUDA(up(d_sp, sigma_param, nN));
+  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
+  if (out_logl) RB_CUDA(d_l.alloc(nN));
+  const int rc = device_eval(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
+  if (rc != RB_OK) return rc;
+  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
+  RB_CUDA(cudaDeviceSynchronize());
+  return RB_OK;
+}
 }  // namespace
 
 int rb_sn_eval_f64_host(const rb_sn_config* cfg, int64_t N, int64_t E, const double* params,
@@ -390,29 +420,8 @@ int rb_sn_eval_f64_host(const rb_sn_config* cfg, int64_t N, int64_t E, const dou
   int rc = sn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
-  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
-  const size_t nN = (size_t)N, nE = (size_t)E;
-  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
-    if (!h) return cudaSuccess;
-    cudaError_t e = b.alloc(n);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
-  };
-  RB_CUDA(up(d_par, params, (size_t)RB_SN_NPARAM * nN));
-  RB_CUDA(up(d_t, t_obs, nE));
-  RB_CUDA(up(d_f, freq_obs, nE));
-  RB_CUDA(up(d_dl, dl_cm, nN));
-  RB_CUDA(up(d_y, y, nE));
-  RB_CUDA(up(d_s, sigma, nE));
-  RB_CUDA(up(d_sp, sigma_param, nN));
-  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
-  if (out_logl) RB_CUDA(d_l.alloc(nN));
-  rc = rb_sn_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
-  if (rc != RB_OK) return rc;
-  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
-  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
-  RB_CUDA(cudaDeviceSynchronize());
-  return RB_OK;
+  return eval_host(rb_sn_eval_f64, cfg, RB_SN_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
+                   out_model, out_logl);
 }
 
 int64_t rb_sizeof(int which) {
@@ -608,29 +617,8 @@ extern "C" int rb_kn_eval_f64_host(const rb_kn_config* cfg, int64_t N, int64_t E
   int rc = kn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
-  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
-  const size_t nN = (size_t)N, nE = (size_t)E;
-  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
-    if (!h) return cudaSuccess;
-    cudaError_t e = b.alloc(n);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
-  };
-  RB_CUDA(up(d_par, params, (size_t)RB_KN_NPARAM * nN));
-  RB_CUDA(up(d_t, t_obs, nE));
-  RB_CUDA(up(d_f, freq_obs, nE));
-  RB_CUDA(up(d_dl, dl_cm, nN));
-  RB_CUDA(up(d_y, y, nE));
-  RB_CUDA(up(d_s, sigma, nE));
-  RB_CUDA(up(d_sp, sigma_param, nN));
-  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
-  if (out_logl) RB_CUDA(d_l.alloc(nN));
-  rc = rb_kn_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
-  if (rc != RB_OK) return rc;
-  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
-  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
-  RB_CUDA(cudaDeviceSynchronize());
-  return RB_OK;
+  return eval_host(rb_kn_eval_f64, cfg, RB_KN_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
+                   out_model, out_logl);
 }
 
 // ---- magnetar-driven ejecta (mergernova) path ---------------------------------------------------------------
@@ -789,33 +777,17 @@ extern "C" int rb_mn_eval_f64_host(const rb_mn_config* cfg, int64_t N, int64_t E
   int rc = mn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
-  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
-  const size_t nN = (size_t)N, nE = (size_t)E;
-  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
-    if (!h) return cudaSuccess;
-    cudaError_t e = b.alloc(n);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
-  };
-  RB_CUDA(up(d_par, params, (size_t)RB_MN_NPARAM * nN));
-  RB_CUDA(up(d_t, t_obs, nE));
-  RB_CUDA(up(d_f, freq_obs, nE));
-  RB_CUDA(up(d_dl, dl_cm, nN));
-  RB_CUDA(up(d_y, y, nE));
-  RB_CUDA(up(d_s, sigma, nE));
-  RB_CUDA(up(d_sp, sigma_param, nN));
-  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
-  if (out_logl) RB_CUDA(d_l.alloc(nN));
-  rc = rb_mn_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
-  if (rc != RB_OK) return rc;
-  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
-  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
-  RB_CUDA(cudaDeviceSynchronize());
-  return RB_OK;
+  return eval_host(rb_mn_eval_f64, cfg, RB_MN_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
+                   out_model, out_logl);
 }
 
 // ---- magnetar-driven Metzger shell model ----------------------------------------------------------------------
 namespace {
+size_t mk_smem_bytes(int G) {
+  return sizeof(double) * ((size_t)7 * G + 2 * (size_t)rb::kShellWarps * G + 2 * rb::kShells + 40) +
+         sizeof(int) * (size_t)rb::kShellWarps * G;
+}
+
 int mk_check(const rb_mk_config* cfg, int64_t N, int64_t E, const void* params, const void* t_obs,
              const void* freq_obs, const void* y, const void* sigma, const void* sigma_param, const void* out_model,
              const void* out_logl) {
@@ -877,8 +849,7 @@ extern "C" int rb_mk_eval_f64(const rb_mk_config* cfg, int64_t N, int64_t E, con
   int G = 0;
   rc = rb_optimal_time_array(1e-4, 1e7, cfg->resolution, tg.data(), &G);   // magnetar_driven_ejecta_models.py:777
   if (rc != RB_OK) return rc;
-  const size_t smem = sizeof(double) * ((size_t)7 * G + 2 * (size_t)rb::kShellWarps * G + 2 * rb::kShells + 40) +
-                      sizeof(int) * (size_t)rb::kShellWarps * G;
+  const size_t smem = mk_smem_bytes(G);
   if (smem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_mk_eval: resolution exceeds shared memory");
   StreamAlloc b_tg, b_ep, b_dl;
   RB_CUDA(b_tg.alloc((size_t)G * sizeof(double), st));
@@ -927,29 +898,8 @@ extern "C" int rb_mk_eval_f64_host(const rb_mk_config* cfg, int64_t N, int64_t E
   int rc = mk_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
-  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
-  const size_t nN = (size_t)N, nE = (size_t)E;
-  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
-    if (!h) return cudaSuccess;
-    cudaError_t e = b.alloc(n);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
-  };
-  RB_CUDA(up(d_par, params, (size_t)RB_MK_NPARAM * nN));
-  RB_CUDA(up(d_t, t_obs, nE));
-  RB_CUDA(up(d_f, freq_obs, nE));
-  RB_CUDA(up(d_dl, dl_cm, nN));
-  RB_CUDA(up(d_y, y, nE));
-  RB_CUDA(up(d_s, sigma, nE));
-  RB_CUDA(up(d_sp, sigma_param, nN));
-  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
-  if (out_logl) RB_CUDA(d_l.alloc(nN));
-  rc = rb_mk_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
-  if (rc != RB_OK) return rc;
-  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
-  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
-  RB_CUDA(cudaDeviceSynchronize());
-  return RB_OK;
+  return eval_host(rb_mk_eval_f64, cfg, RB_MK_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
+                   out_model, out_logl);
 }
 
 // ---- afterglow path ---------------------------------------------------------------------------------------
@@ -1122,29 +1072,8 @@ extern "C" int rb_ag_eval_f64_host(const rb_ag_config* cfg, int64_t N, int64_t E
   int rc = ag_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
-  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
-  const size_t nN = (size_t)N, nE = (size_t)E;
-  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
-    if (!h) return cudaSuccess;
-    cudaError_t e = b.alloc(n);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
-  };
-  RB_CUDA(up(d_par, params, (size_t)RB_AG_NPARAM * nN));
-  RB_CUDA(up(d_t, t_obs, nE));
-  RB_CUDA(up(d_f, freq_obs, nE));
-  RB_CUDA(up(d_dl, dl_cm, nN));
-  RB_CUDA(up(d_y, y, nE));
-  RB_CUDA(up(d_s, sigma, nE));
-  RB_CUDA(up(d_sp, sigma_param, nN));
-  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
-  if (out_logl) RB_CUDA(d_l.alloc(nN));
-  rc = rb_ag_eval_f64(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
-  if (rc != RB_OK) return rc;
-  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
-  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
-  RB_CUDA(cudaDeviceSynchronize());
-  return RB_OK;
+  return eval_host(rb_ag_eval_f64, cfg, RB_AG_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
+                   out_model, out_logl);
 }
 
 // ---- magnitude / bandpass branch ---------------------------------------------------------------------------
@@ -1310,6 +1239,144 @@ size_t phot_smem_bytes(int NT, int NL) {
   return sizeof(double) * ((size_t)7 * NT + 5 * (size_t)NL + (size_t)rb::kPhotTileRows * (NL + 1) + 40 + rb::kExpTabSize);
 }
 
+
+// ---- shared driver of the magnitude / bandpass branch -------------------------------------------------------------
+// The model kernels run in grid mode and leave (T, R, L, phase) per grid point in a chunk-sized scratch; phot_kernel
+// turns them into spectra, spline coefficients, band integrals, magnitudes and the likelihood.  What differs between
+// the model families is only how a chunk's grids are filled (`fill`) and a few SED / time-axis options.
+struct PhotJob {
+  const char* who;
+  const rb_photometry* phot;
+  int64_t N, E;
+  int NT;                          // grid points per sample (allocated)
+  const double* lu_grid;           // host [NT]: common time axis up to a per-sample scale -> one collocation LU; or
+                                   // nullptr: every sample has its own grid (phot_kernel factorises per sample)
+  bool with_len;                   // per-sample grid lengths
+  int sed = rb::PH_SED_BLACKBODY;
+  double cutoff_wavelength = 3000.0, absorption_index = 1.0;
+  double line_wavelength = 0, line_width = 0, line_time = 0, line_duration = 0, line_amplitude = 0;
+  int sigma_mode;
+  rb_upper_limits upper_limits;
+  const double *t_obs, *y, *sigma, *sigma_param, *t0;
+  double *out_model, *out_logl;
+};
+
+// fill(n0, nc, d_grid, d_opz, d_dl, d_len) -> RB_OK or an error code (already recorded with fail())
+extern "C++" template <typename Fill>
+int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(phot_kernel)");
+  const int NT = j.NT, NL = j.phot->n_lambda;
+  const int64_t N = j.N, E = j.E;
+  const size_t psmem = phot_smem_bytes(NT, NL);
+  if (psmem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, std::string(j.who) + ": grids exceed shared memory");
+  PhotDevice pd;
+  pd.st = st;
+  rb::PhotArgs pa{};
+  int rc = phot_prepare(j.phot, E, pd, pa);
+  if (rc != RB_OK) { pd.release(); return rc; }
+  cudaError_t ce = cudaSuccess;
+  if (j.lu_grid != nullptr) {
+    std::vector<double> lu_t = collocation_lu(j.lu_grid, NT);
+    ce = pd.upload(lu_t, &pa.lu_time);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "time grid upload"); }
+  }
+  double* d_ep_obs = nullptr;
+  ce = cudaMallocAsync(&d_ep_obs, (size_t)rb::kEpochCols * E * sizeof(double), st);
+  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "epoch table"); }
+  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, j.sigma_mode, j.t_obs, nullptr, j.y,
+                                                                    j.y ? j.sigma : nullptr, j.upper_limits, d_ep_obs);
+  launch_counter()->fetch_add(1);
+
+  const int64_t chunk_max = 32768;
+  int occ_ph = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
+  if (occ_ph < 1) occ_ph = 1;
+  const int64_t ph_grid_max = (int64_t)sms * occ_ph;
+  const int64_t nc_max = std::min<int64_t>(chunk_max, N);
+  double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_scratch = nullptr;
+  int* d_len = nullptr;
+  ce = cudaMallocAsync(&d_grid, (size_t)nc_max * 4 * NT * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_opz, (size_t)nc_max * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dl, (size_t)nc_max * sizeof(double), st);
+  if (ce == cudaSuccess && j.with_len) ce = cudaMallocAsync(&d_len, (size_t)nc_max * sizeof(int), st);
+  if (ce == cudaSuccess)
+    ce = cudaMallocAsync(&d_scratch, (size_t)std::min<int64_t>(ph_grid_max, nc_max) * NT * NL * sizeof(double), st);
+  int status = RB_OK;
+  if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude workspace");
+  for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
+    const int64_t nc = std::min<int64_t>(chunk_max, N - n0);
+    status = fill(n0, nc, d_grid, d_opz, d_dl, d_len);
+    if (status != RB_OK) break;
+    pa.N = nc;
+    pa.n_base = n0;
+    pa.E = (int)E;
+    pa.n_t_max = NT;
+    pa.sed = j.sed;
+    pa.cutoff_wavelength = j.cutoff_wavelength;
+    pa.absorption_index = j.absorption_index;
+    pa.line_wavelength = j.line_wavelength;
+    pa.line_width = j.line_width;
+    pa.line_time = j.line_time;
+    pa.line_duration = j.line_duration;
+    pa.line_amplitude = j.line_amplitude;
+    pa.sigma_mode = j.sigma_mode;
+    pa.want_logl = j.y ? 1 : 0;
+    pa.common_time_lu = j.lu_grid != nullptr ? 1 : 0;
+    pa.grid = d_grid;
+    pa.grid_len = d_len;
+    pa.opz = d_opz;
+    pa.dl = d_dl;
+    pa.sigma_param_s = j.sigma_param ? j.sigma_param + n0 : nullptr;
+    pa.t0_s = j.t0 ? j.t0 + n0 : nullptr;
+    pa.epoch_tab = d_ep_obs;
+    pa.scratch = d_scratch;
+    pa.out_model = j.out_model;
+    pa.out_logl = j.y ? j.out_logl : nullptr;
+    rb::phot_kernel<<<(unsigned)std::min<int64_t>(ph_grid_max, nc), rb::kPhotThreads, psmem, st>>>(pa);
+    launch_counter()->fetch_add(1);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude kernels");
+  }
+  cudaFreeAsync(d_scratch, st);
+  if (d_len) cudaFreeAsync(d_len, st);
+  cudaFreeAsync(d_dl, st);
+  cudaFreeAsync(d_opz, st);
+  cudaFreeAsync(d_grid, st);
+  cudaFreeAsync(d_ep_obs, st);
+  pd.release();
+  return status;
+}
+
+// upload a small host array for the lifetime of one call
+struct CallBuffer {
+  double* p = nullptr;
+  cudaStream_t st = nullptr;
+  ~CallBuffer() { if (p) cudaFreeAsync(p, st); }
+  cudaError_t alloc(size_t n, cudaStream_t s) {
+    st = s;
+    return cudaMallocAsync(&p, (n ? n : 1) * sizeof(double), s);
+  }
+  cudaError_t upload(const std::vector<double>& h, cudaStream_t s) {
+    st = s;
+    cudaError_t e = cudaMallocAsync(&p, h.size() * sizeof(double), s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);     // h may be a temporary
+    return e;
+  }
+};
+
+int device_and_sms(int* sms) {
+  int dev = 0;
+  RB_CUDA(cudaGetDevice(&dev));
+  RB_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  return RB_OK;
+}
 }  // namespace
 
 extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
@@ -1317,74 +1384,56 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
                                   const double* sigma, const double* sigma_param, double* out_model,
                                   double* out_logl, void* stream) {
   static const double dummy = 0.0;
-  int rc = sn_check(cfg, N, E, params, t_obs, &dummy, y, sigma, sigma_param, out_model, out_logl);
+  int rc = sn_check(cfg, N, E, params, t_obs, cfg && cfg->sed != RB_SED_BOLOMETRIC ? &dummy : nullptr, y, sigma,
+                    sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (cfg->sed == RB_SED_BOLOMETRIC) return fail(RB_ERR_INVALID, "rb_sn_mag_eval: bolometric models have no magnitude output");
   rc = phot_check(phot, E, true);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int dev_id = 0, sms = 0;
-  RB_CUDA(cudaGetDevice(&dev_id));
-  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+  int sms = 0;
+  rc = device_and_sms(&sms);
+  if (rc != RB_OK) return rc;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = sn_kernel_attributes();
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  });
-  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute");
-  const int NT = phot->n_tgrid, NL = phot->n_lambda;
-  const size_t psmem = phot_smem_bytes(NT, NL);
-  if (psmem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_sn_mag_eval: grids exceed shared memory");
-
-  PhotDevice pd;
-  pd.st = st;
-  rb::PhotArgs pa{};
-  rc = phot_prepare(phot, E, pd, pa);
-  if (rc != RB_OK) { pd.release(); return rc; }
+  std::call_once(once, [] { attr_err = sn_kernel_attributes(); });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sn_kernel)");
+  const int NT = phot->n_tgrid;
   std::vector<double> tg(phot->tgrid, phot->tgrid + NT);
-  std::vector<double> lu_t = collocation_lu(tg.data(), NT);
-  const double* d_tgrid = nullptr;
-  cudaError_t ce = pd.upload(tg, &d_tgrid);
-  if (ce == cudaSuccess) ce = pd.upload(lu_t, &pa.lu_time);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "time grid upload"); }
-
-  // epoch tables: one for the model grid (sn_kernel in grid mode), one for the observed epochs (phot_kernel)
-  double *d_ep_grid = nullptr, *d_ep_obs = nullptr;
-  ce = cudaMallocAsync(&d_ep_grid, (size_t)rb::kEpochCols * NT * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_ep_obs, (size_t)rb::kEpochCols * E * sizeof(double), st);
-  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "epoch tables"); }
-  rb::epoch_table_kernel<<<(unsigned)((NT + 255) / 256), 256, 0, st>>>(NT, RB_SIGMA_FIXED, d_tgrid, nullptr, nullptr,
-                                                                     nullptr, rb_upper_limits{nullptr, 0}, d_ep_grid);
-  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, nullptr, y,
-                                                                    y ? sigma : nullptr, cfg->upper_limits, d_ep_obs);
-  launch_counter()->fetch_add(2);
-
-  const int64_t chunk_max = 32768;
+  CallBuffer b_tgrid, b_ep_grid, b_scal;
+  RB_CUDA(b_tgrid.upload(tg, st));
+  // epoch table of the model grid (the "epochs" of the model kernel in grid mode)
+  RB_CUDA(b_ep_grid.alloc((size_t)rb::kEpochCols * NT, st));
+  rb::epoch_table_kernel<<<(unsigned)((NT + 255) / 256), 256, 0, st>>>(NT, RB_SIGMA_FIXED, b_tgrid.p, nullptr, nullptr,
+                                                                     nullptr, rb_upper_limits{nullptr, 0}, b_ep_grid.p);
+  launch_counter()->fetch_add(1);
+  const int64_t nc_max = std::min<int64_t>(32768, N);
+  RB_CUDA(b_scal.alloc((size_t)nc_max * rb::kScalars, st));
   const int sn_threads = sn_block_threads(NT);
-  const int ep_in_smem = (sn_smem_bytes(cfg->dense_resolution, NT, true) <= 64 * 1024) ? 1 : 0;
+  const int ep_in_smem = (sn_smem_bytes(cfg->dense_resolution, NT, true, true) <= 64 * 1024) ? 1 : 0;
   const size_t sn_smem = sn_smem_bytes(cfg->dense_resolution, NT, ep_in_smem != 0);
-  int occ_sn = 1, occ_ph = 1;
   const SnKernelFn sn_kern = sn_kernel_fn(cfg->engine, false, cfg->aspherical != 0);
+  int occ_sn = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sn, sn_kern, sn_threads, sn_smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
   if (occ_sn < 1) occ_sn = 1;
-  if (occ_ph < 1) occ_ph = 1;
-  const int64_t ph_grid_max = (int64_t)sms * occ_ph;
-  double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_scal = nullptr, *d_scratch = nullptr;
-  const int64_t nc_max = std::min<int64_t>(chunk_max, N);
-  ce = cudaMallocAsync(&d_grid, (size_t)nc_max * 4 * NT * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_opz, (size_t)nc_max * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dl, (size_t)nc_max * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_scal, (size_t)nc_max * rb::kScalars * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_scratch, (size_t)std::min<int64_t>(ph_grid_max, nc_max) * NT * NL * sizeof(double), st);
-  int status = RB_OK;
-  if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude workspace");
-  for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
-    const int64_t nc = std::min<int64_t>(chunk_max, N - n0);
+
+  PhotJob j{};
+  j.who = "rb_sn_mag_eval";
+  j.phot = phot; j.N = N; j.E = E; j.NT = NT;
+  j.lu_grid = tg.data();
+  j.with_len = false;
+  j.sed = (cfg->sed == RB_SED_CUTOFF_BLACKBODY) ? rb::PH_SED_CUTOFF
+          : (cfg->sed == RB_SED_CUTOFF_LINE ? rb::PH_SED_CUTOFF_LINE : rb::PH_SED_BLACKBODY);
+  j.cutoff_wavelength = cfg->cutoff_wavelength;
+  j.absorption_index = cfg->absorption_index;
+  j.line_wavelength = cfg->line_wavelength; j.line_width = cfg->line_width; j.line_time = cfg->line_time;
+  j.line_duration = cfg->line_duration; j.line_amplitude = cfg->line_amplitude;
+  j.sigma_mode = cfg->sigma_mode; j.upper_limits = cfg->upper_limits;
+  j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param;
+  j.t0 = (cfg->t0 && cfg->engine != RB_ENGINE_CSM) ? cfg->t0 : nullptr;
+  j.out_model = out_model; j.out_logl = out_logl;
+  return run_photometry(j, st, sms, [&](int64_t n0, int64_t nc, double* d_grid, double* d_opz, double* d_dl, int*) {
     rb::SnArgs a{};
     a.cfg = *cfg;
     a.N = nc;
@@ -1392,68 +1441,23 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
     a.params = params + n0;          // SoA rows are N_total apart: handled through the stride below
     if (cfg->f_nickel) a.cfg.f_nickel = cfg->f_nickel + n0;
     a.dl_cm = dl_cm ? dl_cm + n0 : nullptr;
-    a.sigma_param = nullptr;
-    a.out_model = nullptr;
-    a.out_logl = nullptr;
-    a.want_logl = 0;
-    a.epoch_tab = d_ep_grid;
-    a.scalars = d_scal;
+    a.epoch_tab = b_ep_grid.p;
+    a.scalars = b_scal.p;
     a.grid_mode = 1;
     a.grid_out = d_grid;
     a.opz_out = d_opz;
     a.dl_out = d_dl;
     a.param_stride = N;
     a.epochs_in_smem = ep_in_smem;
-    if (cfg->engine == RB_ENGINE_CSM) {
-      status = launch_csm(a, d_tgrid, st, sms);
-      if (status != RB_OK) break;
-    } else if (cfg->no_interaction || cfg->engine >= RB_ENGINE_FALLBACK) {
-      rb::sn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
+    if (cfg->engine == RB_ENGINE_CSM) return launch_csm(a, b_tgrid.p, st, sms);
+    rb::sn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
+    if (cfg->no_interaction || cfg->engine >= RB_ENGINE_FALLBACK)
       rb::sn_direct_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * 32), 256, 0, st>>>(a);
-    } else {
-      rb::sn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
+    else
       sn_kern<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_sn * 4), sn_threads, sn_smem, st>>>(a);
-    }
-    pa.N = nc;
-    pa.n_base = n0;
-    pa.E = (int)E;
-    pa.n_t_max = NT;
-    pa.sed = (cfg->sed == RB_SED_CUTOFF_BLACKBODY) ? rb::PH_SED_CUTOFF
-             : (cfg->sed == RB_SED_CUTOFF_LINE ? rb::PH_SED_CUTOFF_LINE : rb::PH_SED_BLACKBODY);
-    pa.line_wavelength = cfg->line_wavelength;
-    pa.line_width = cfg->line_width;
-    pa.line_time = cfg->line_time;
-    pa.line_duration = cfg->line_duration;
-    pa.line_amplitude = cfg->line_amplitude;
-    pa.sigma_mode = cfg->sigma_mode;
-    pa.want_logl = y ? 1 : 0;
-    pa.common_time_lu = 1;
-    pa.cutoff_wavelength = cfg->cutoff_wavelength;
-    pa.absorption_index = cfg->absorption_index;
-    pa.grid = d_grid;
-    pa.grid_len = nullptr;
-    pa.opz = d_opz;
-    pa.dl = d_dl;
-    pa.sigma_param_s = sigma_param ? sigma_param + n0 : nullptr;
-    pa.t0_s = (cfg->t0 && cfg->engine != RB_ENGINE_CSM) ? cfg->t0 + n0 : nullptr;
-    pa.epoch_tab = d_ep_obs;
-    pa.scratch = d_scratch;
-    pa.out_model = out_model;
-    pa.out_logl = y ? out_logl : nullptr;
-    rb::phot_kernel<<<(unsigned)std::min<int64_t>(ph_grid_max, nc), rb::kPhotThreads, psmem, st>>>(pa);
-    launch_counter()->fetch_add(3);
-    ce = cudaGetLastError();
-    if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude kernels");
-  }
-  cudaFreeAsync(d_scratch, st);
-  cudaFreeAsync(d_scal, st);
-  cudaFreeAsync(d_dl, st);
-  cudaFreeAsync(d_opz, st);
-  cudaFreeAsync(d_grid, st);
-  cudaFreeAsync(d_ep_obs, st);
-  cudaFreeAsync(d_ep_grid, st);
-  pd.release();
-  return status;
+    launch_counter()->fetch_add(2);
+    return (int)RB_OK;
+  });
 }
 
 extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
@@ -1467,66 +1471,44 @@ extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* 
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int dev_id = 0, sms = 0;
-  RB_CUDA(cudaGetDevice(&dev_id));
-  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+  int sms = 0;
+  rc = device_and_sms(&sms);
+  if (rc != RB_OK) return rc;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(rb::kn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   });
-  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute");
-  const int NT = cfg->dense_resolution, NL = phot->n_lambda;
-  const size_t psmem = phot_smem_bytes(NT, NL);
-  if (psmem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_kn_mag_eval: grids exceed shared memory");
-  PhotDevice pd;
-  pd.st = st;
-  rb::PhotArgs pa{};
-  rc = phot_prepare(phot, E, pd, pa);
-  if (rc != RB_OK) { pd.release(); return rc; }
-
-  double *d_ep_obs = nullptr, *d_mm = nullptr;
-  cudaError_t ce = cudaMallocAsync(&d_ep_obs, (size_t)rb::kEpochCols * E * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_mm, 2 * sizeof(double), st);
-  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "epoch tables"); }
-  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, nullptr, y,
-                                                                    y ? sigma : nullptr, cfg->upper_limits, d_ep_obs);
-  minmax_kernel<<<1, 256, 0, st>>>((int)E, t_obs, d_mm);
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(kn_kernel)");
+  // epoch range for the adaptive grid (get_optimal_time_array(..., user_times)): one tiny D2H read
+  CallBuffer b_mm, b_ep1, b_scal;
+  RB_CUDA(b_mm.alloc(2, st));
+  minmax_kernel<<<1, 256, 0, st>>>((int)E, t_obs, b_mm.p);
   double h_mm[2];
-  ce = cudaMemcpyAsync(h_mm, d_mm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-  launch_counter()->fetch_add(2);
-  int status = RB_OK;
-  if (ce != cudaSuccess) status = cuda_fail(ce, "epoch min/max");
-  else if (!(h_mm[0] > 0.0)) status = fail(RB_ERR_INVALID, "rb_kn_mag_eval: epochs must be strictly positive (days)");
-
-  const int64_t chunk_max = 32768;
+  RB_CUDA(cudaMemcpyAsync(h_mm, b_mm.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaStreamSynchronize(st));
+  launch_counter()->fetch_add(1);
+  if (!(h_mm[0] > 0.0)) return fail(RB_ERR_INVALID, "rb_kn_mag_eval: epochs must be strictly positive (days)");
+  const int NT = cfg->dense_resolution;
+  const int64_t nc_max = std::min<int64_t>(32768, N);
+  RB_CUDA(b_ep1.alloc((size_t)rb::kEpochCols, st));
+  RB_CUDA(b_scal.alloc((size_t)nc_max * rb::kKnScalars, st));
   rb_kn_config kcfg = *cfg;
   const size_t ksmem = kn_smem_bytes(&kcfg, 1);
-  int occ_kn = 1, occ_ph = 1;
   const int kn_threads = (cfg->model == RB_KN_METZGER) ? 256 : 512;   // grid mode: 512 measured faster than 128 (457 vs 537 ms)
+  int occ_kn = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_kn, rb::kn_kernel, kn_threads, ksmem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
   if (occ_kn < 1) occ_kn = 1;
-  if (occ_ph < 1) occ_ph = 1;
-  const int64_t ph_grid_max = (int64_t)sms * occ_ph;
-  const int64_t nc_max = std::min<int64_t>(chunk_max, N);
-  double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_scal = nullptr, *d_scratch = nullptr, *d_ep1 = nullptr;
-  int* d_len = nullptr;
-  if (status == RB_OK) {
-    ce = cudaMallocAsync(&d_grid, (size_t)nc_max * 4 * NT * sizeof(double), st);
-    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_opz, (size_t)nc_max * sizeof(double), st);
-    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dl, (size_t)nc_max * sizeof(double), st);
-    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_len, (size_t)nc_max * sizeof(int), st);
-    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_scal, (size_t)nc_max * rb::kKnScalars * sizeof(double), st);
-    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_ep1, (size_t)rb::kEpochCols * sizeof(double), st);
-    if (ce == cudaSuccess) ce = cudaMallocAsync(&d_scratch, (size_t)std::min<int64_t>(ph_grid_max, nc_max) * NT * NL * sizeof(double), st);
-    if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude workspace");
-  }
-  for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
-    const int64_t nc = std::min<int64_t>(chunk_max, N - n0);
+
+  PhotJob j{};
+  j.who = "rb_kn_mag_eval";
+  j.phot = phot; j.N = N; j.E = E; j.NT = NT;
+  j.lu_grid = nullptr;             // the grid depends on the sample's redshift
+  j.with_len = true;
+  j.sigma_mode = cfg->sigma_mode; j.upper_limits = cfg->upper_limits;
+  j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param; j.t0 = nullptr;
+  j.out_model = out_model; j.out_logl = out_logl;
+  return run_photometry(j, st, sms, [&](int64_t n0, int64_t nc, double* d_grid, double* d_opz, double* d_dl, int* d_len) {
     rb::KnArgs a{};
     a.cfg = *cfg;
     a.N = nc;
@@ -1534,9 +1516,8 @@ extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* 
     a.params = params + n0;
     a.param_stride = N;
     a.dl_cm = dl_cm ? dl_cm + n0 : nullptr;
-    a.want_logl = 0;
-    a.epoch_tab = d_ep1;
-    a.scalars = d_scal;
+    a.epoch_tab = b_ep1.p;
+    a.scalars = b_scal.p;
     a.tmin_obs = h_mm[0];
     a.tmax_obs = h_mm[1];
     a.grid_mode = 1;
@@ -1546,39 +1527,9 @@ extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* 
     a.dl_out = d_dl;
     rb::kn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
     rb::kn_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_kn * 4), kn_threads, ksmem, st>>>(a);
-    pa.N = nc;
-    pa.n_base = n0;
-    pa.E = (int)E;
-    pa.n_t_max = NT;
-    pa.sed = rb::PH_SED_BLACKBODY;
-    pa.sigma_mode = cfg->sigma_mode;
-    pa.want_logl = y ? 1 : 0;
-    pa.common_time_lu = 0;
-    pa.grid = d_grid;
-    pa.grid_len = d_len;
-    pa.opz = d_opz;
-    pa.dl = d_dl;
-    pa.sigma_param_s = sigma_param ? sigma_param + n0 : nullptr;
-    pa.epoch_tab = d_ep_obs;
-    pa.scratch = d_scratch;
-    pa.out_model = out_model;
-    pa.out_logl = y ? out_logl : nullptr;
-    rb::phot_kernel<<<(unsigned)std::min<int64_t>(ph_grid_max, nc), rb::kPhotThreads, psmem, st>>>(pa);
-    launch_counter()->fetch_add(3);
-    ce = cudaGetLastError();
-    if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude kernels");
-  }
-  cudaFreeAsync(d_scratch, st);
-  cudaFreeAsync(d_ep1, st);
-  cudaFreeAsync(d_scal, st);
-  cudaFreeAsync(d_len, st);
-  cudaFreeAsync(d_dl, st);
-  cudaFreeAsync(d_opz, st);
-  cudaFreeAsync(d_grid, st);
-  cudaFreeAsync(d_mm, st);
-  cudaFreeAsync(d_ep_obs, st);
-  pd.release();
-  return status;
+    launch_counter()->fetch_add(2);
+    return (int)RB_OK;
+  });
 }
 
 extern "C" int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
@@ -1588,70 +1539,39 @@ extern "C" int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* 
   static const double dummy = 0.0;
   int rc = mn_check(cfg, N, E, params, t_obs, &dummy, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
+  if (cfg->output != RB_MN_OUT_FLUX_DENSITY || !cfg->use_r_process)
+    return fail(RB_ERR_UNSUPPORTED, "rb_mn_mag_eval: magnitudes are available for the mergernova flux-density set-up");
   rc = phot_check(phot, E, false);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int dev_id = 0, sms = 0;
-  RB_CUDA(cudaGetDevice(&dev_id));
-  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  });
-  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute");
+  int sms = 0;
+  rc = device_and_sms(&sms);
+  if (rc != RB_OK) return rc;
   std::vector<double> tg((size_t)cfg->resolution);
   int G = 0;
   rc = rb_optimal_time_array(cfg->grid_t_min, cfg->grid_t_max, cfg->resolution, tg.data(), &G);
   if (rc != RB_OK) return rc;
   tg.resize((size_t)G);
-  const int NT = G, NL = phot->n_lambda;
-  const size_t psmem = phot_smem_bytes(NT, NL);
-  if (psmem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_mn_mag_eval: grids exceed shared memory");
-
-  PhotDevice pd;
-  pd.st = st;
-  rb::PhotArgs pa{};
-  rc = phot_prepare(phot, E, pd, pa);
-  if (rc != RB_OK) { pd.release(); return rc; }
   std::vector<double> tdays((size_t)G);
   for (int i = 0; i < G; ++i) tdays[(size_t)i] = tg[(size_t)i] / 86400.0;     // time_eval (:236), up to the (1+z) scale
-  std::vector<double> lu_t = collocation_lu(tdays.data(), NT);
-  const double* d_tgrid = nullptr;
-  cudaError_t ce = pd.upload(tg, &d_tgrid);
-  if (ce == cudaSuccess) ce = pd.upload(lu_t, &pa.lu_time);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "time grid upload"); }
+  CallBuffer b_tgrid, b_dlc;
+  RB_CUDA(b_tgrid.upload(tg, st));
+  if (!dl_cm) RB_CUDA(b_dlc.alloc((size_t)std::min<int64_t>(32768, N), st));
 
-  double* d_ep_obs = nullptr;
-  ce = cudaMallocAsync(&d_ep_obs, (size_t)rb::kEpochCols * E * sizeof(double), st);
-  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "epoch table"); }
-  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, nullptr, y,
-                                                                    y ? sigma : nullptr, cfg->upper_limits, d_ep_obs);
-  launch_counter()->fetch_add(1);
-
-  const int64_t chunk_max = 32768;
-  int occ_ph = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
-  if (occ_ph < 1) occ_ph = 1;
-  const int64_t ph_grid_max = (int64_t)sms * occ_ph;
-  const int64_t nc_max = std::min<int64_t>(chunk_max, N);
-  double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_dlc = nullptr, *d_scratch = nullptr;
-  ce = cudaMallocAsync(&d_grid, (size_t)nc_max * 4 * NT * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_opz, (size_t)nc_max * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dl, (size_t)nc_max * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dlc, (size_t)nc_max * sizeof(double), st);
-  if (ce == cudaSuccess)
-    ce = cudaMallocAsync(&d_scratch, (size_t)std::min<int64_t>(ph_grid_max, nc_max) * NT * NL * sizeof(double), st);
-  int status = RB_OK;
-  if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude workspace");
-  for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
-    const int64_t nc = std::min<int64_t>(chunk_max, N - n0);
-    const double* dl = dl_cm ? dl_cm + n0 : d_dlc;
+  PhotJob j{};
+  j.who = "rb_mn_mag_eval";
+  j.phot = phot; j.N = N; j.E = E; j.NT = G;
+  j.lu_grid = tdays.data();
+  j.with_len = false;
+  j.sigma_mode = cfg->sigma_mode; j.upper_limits = cfg->upper_limits;
+  j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param; j.t0 = nullptr;
+  j.out_model = out_model; j.out_logl = out_logl;
+  return run_photometry(j, st, sms, [&](int64_t n0, int64_t nc, double* d_grid, double* d_opz, double* d_dl, int*) {
+    const double* dl = dl_cm ? dl_cm + n0 : b_dlc.p;
     if (!dl_cm) {
       rb::dl_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(cfg->cosmology, nc,
-                                                            params + (size_t)RB_MN_REDSHIFT * N + n0, d_dlc);
+                                                            params + (size_t)RB_MN_REDSHIFT * N + n0, b_dlc.p);
       launch_counter()->fetch_add(1);
     }
     rb::MnArgs a{};
@@ -1662,42 +1582,15 @@ extern "C" int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* 
     a.params = params + n0;
     a.param_stride = N;
     a.dl_cm = dl;
-    a.tgrid = d_tgrid;
+    a.tgrid = b_tgrid.p;
     a.grid_mode = 1;
     a.grid_out = d_grid;
     a.opz_out = d_opz;
     a.dl_out = d_dl;
     rb::mn_kernel<false><<<(unsigned)((nc + 127) / 128), 128, (size_t)G * sizeof(double), st>>>(a);
-    pa.N = nc;
-    pa.n_base = n0;
-    pa.E = (int)E;
-    pa.n_t_max = NT;
-    pa.sed = rb::PH_SED_BLACKBODY;
-    pa.sigma_mode = cfg->sigma_mode;
-    pa.want_logl = y ? 1 : 0;
-    pa.common_time_lu = 1;
-    pa.grid = d_grid;
-    pa.grid_len = nullptr;
-    pa.opz = d_opz;
-    pa.dl = d_dl;
-    pa.sigma_param_s = sigma_param ? sigma_param + n0 : nullptr;
-    pa.epoch_tab = d_ep_obs;
-    pa.scratch = d_scratch;
-    pa.out_model = out_model;
-    pa.out_logl = y ? out_logl : nullptr;
-    rb::phot_kernel<<<(unsigned)std::min<int64_t>(ph_grid_max, nc), rb::kPhotThreads, psmem, st>>>(pa);
-    launch_counter()->fetch_add(2);
-    ce = cudaGetLastError();
-    if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude kernels");
-  }
-  cudaFreeAsync(d_scratch, st);
-  cudaFreeAsync(d_dlc, st);
-  cudaFreeAsync(d_dl, st);
-  cudaFreeAsync(d_opz, st);
-  cudaFreeAsync(d_grid, st);
-  cudaFreeAsync(d_ep_obs, st);
-  pd.release();
-  return status;
+    launch_counter()->fetch_add(1);
+    return (int)RB_OK;
+  });
 }
 
 extern "C" int rb_mk_mag_eval_f64(const rb_mk_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
@@ -1711,70 +1604,41 @@ extern "C" int rb_mk_mag_eval_f64(const rb_mk_config* cfg, const rb_photometry* 
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int dev_id = 0, sms = 0;
-  RB_CUDA(cudaGetDevice(&dev_id));
-  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+  int sms = 0;
+  rc = device_and_sms(&sms);
+  if (rc != RB_OK) return rc;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(rb::mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_err = cudaFuncSetAttribute(rb::mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   });
-  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute");
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(mk_kernel)");
   std::vector<double> tg((size_t)cfg->resolution);
   int G = 0;
   rc = rb_optimal_time_array(1e-4, 1e7, cfg->resolution, tg.data(), &G);
   if (rc != RB_OK) return rc;
   tg.resize((size_t)G);
-  const int NT = G, NL = phot->n_lambda;
-  const size_t psmem = phot_smem_bytes(NT, NL);
-  const size_t mk_smem = sizeof(double) * ((size_t)7 * G + 2 * (size_t)rb::kShellWarps * G + 2 * rb::kShells + 40) +
-                         sizeof(int) * (size_t)rb::kShellWarps * G;
-  if (psmem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_mk_mag_eval: grids exceed shared memory");
-
-  PhotDevice pd;
-  pd.st = st;
-  rb::PhotArgs pa{};
-  rc = phot_prepare(phot, E, pd, pa);
-  if (rc != RB_OK) { pd.release(); return rc; }
   std::vector<double> tdays((size_t)G);
-  for (int i = 0; i < G; ++i) tdays[(size_t)i] = tg[(size_t)i] / 86400.0;     // time_eval (:236), up to the (1+z) scale
-  std::vector<double> lu_t = collocation_lu(tdays.data(), NT);
-  const double* d_tgrid = nullptr;
-  cudaError_t ce = pd.upload(tg, &d_tgrid);
-  if (ce == cudaSuccess) ce = pd.upload(lu_t, &pa.lu_time);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "time grid upload"); }
+  for (int i = 0; i < G; ++i) tdays[(size_t)i] = tg[(size_t)i] / 86400.0;
+  const size_t mk_smem = mk_smem_bytes(G);
+  if (mk_smem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_mk_mag_eval: resolution exceeds shared memory");
+  CallBuffer b_tgrid, b_dlc;
+  RB_CUDA(b_tgrid.upload(tg, st));
+  if (!dl_cm) RB_CUDA(b_dlc.alloc((size_t)std::min<int64_t>(32768, N), st));
 
-  double* d_ep_obs = nullptr;
-  ce = cudaMallocAsync(&d_ep_obs, (size_t)rb::kEpochCols * E * sizeof(double), st);
-  if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "epoch table"); }
-  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, nullptr, y,
-                                                                    y ? sigma : nullptr, cfg->upper_limits, d_ep_obs);
-  launch_counter()->fetch_add(1);
-
-  const int64_t chunk_max = 32768;
-  int occ_ph = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
-  if (occ_ph < 1) occ_ph = 1;
-  const int64_t ph_grid_max = (int64_t)sms * occ_ph;
-  const int64_t nc_max = std::min<int64_t>(chunk_max, N);
-  double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_dlc = nullptr, *d_scratch = nullptr;
-  ce = cudaMallocAsync(&d_grid, (size_t)nc_max * 4 * NT * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_opz, (size_t)nc_max * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dl, (size_t)nc_max * sizeof(double), st);
-  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dlc, (size_t)nc_max * sizeof(double), st);
-  if (ce == cudaSuccess)
-    ce = cudaMallocAsync(&d_scratch, (size_t)std::min<int64_t>(ph_grid_max, nc_max) * NT * NL * sizeof(double), st);
-  int status = RB_OK;
-  if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude workspace");
-  for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
-    const int64_t nc = std::min<int64_t>(chunk_max, N - n0);
-    const double* dl = dl_cm ? dl_cm + n0 : d_dlc;
+  PhotJob j{};
+  j.who = "rb_mk_mag_eval";
+  j.phot = phot; j.N = N; j.E = E; j.NT = G;
+  j.lu_grid = tdays.data();
+  j.with_len = false;
+  j.sigma_mode = cfg->sigma_mode; j.upper_limits = cfg->upper_limits;
+  j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param; j.t0 = nullptr;
+  j.out_model = out_model; j.out_logl = out_logl;
+  return run_photometry(j, st, sms, [&](int64_t n0, int64_t nc, double* d_grid, double* d_opz, double* d_dl, int*) {
+    const double* dl = dl_cm ? dl_cm + n0 : b_dlc.p;
     if (!dl_cm) {
       rb::dl_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(cfg->cosmology, nc,
-                                                            params + (size_t)RB_MK_REDSHIFT * N + n0, d_dlc);
+                                                            params + (size_t)RB_MK_REDSHIFT * N + n0, b_dlc.p);
       launch_counter()->fetch_add(1);
     }
     rb::MkArgs a{};
@@ -1785,42 +1649,15 @@ extern "C" int rb_mk_mag_eval_f64(const rb_mk_config* cfg, const rb_photometry* 
     a.params = params + n0;
     a.param_stride = N;
     a.dl_cm = dl;
-    a.tgrid = d_tgrid;
+    a.tgrid = b_tgrid.p;
     a.grid_mode = 1;
     a.grid_out = d_grid;
     a.opz_out = d_opz;
     a.dl_out = d_dl;
     rb::mk_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * 8), rb::kMkThreads, mk_smem, st>>>(a);
-    pa.N = nc;
-    pa.n_base = n0;
-    pa.E = (int)E;
-    pa.n_t_max = NT;
-    pa.sed = rb::PH_SED_BLACKBODY;
-    pa.sigma_mode = cfg->sigma_mode;
-    pa.want_logl = y ? 1 : 0;
-    pa.common_time_lu = 1;
-    pa.grid = d_grid;
-    pa.grid_len = nullptr;
-    pa.opz = d_opz;
-    pa.dl = d_dl;
-    pa.sigma_param_s = sigma_param ? sigma_param + n0 : nullptr;
-    pa.epoch_tab = d_ep_obs;
-    pa.scratch = d_scratch;
-    pa.out_model = out_model;
-    pa.out_logl = y ? out_logl : nullptr;
-    rb::phot_kernel<<<(unsigned)std::min<int64_t>(ph_grid_max, nc), rb::kPhotThreads, psmem, st>>>(pa);
-    launch_counter()->fetch_add(2);
-    ce = cudaGetLastError();
-    if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude kernels");
-  }
-  cudaFreeAsync(d_scratch, st);
-  cudaFreeAsync(d_dlc, st);
-  cudaFreeAsync(d_dl, st);
-  cudaFreeAsync(d_opz, st);
-  cudaFreeAsync(d_grid, st);
-  cudaFreeAsync(d_ep_obs, st);
-  pd.release();
-  return status;
+    launch_counter()->fetch_add(1);
+    return (int)RB_OK;
+  });
 }
 
 extern "C" int rb_optical_noise_f64(int noise_type, int64_t N, int64_t E, const double* model_mag,
