@@ -41,6 +41,20 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
   } while (0)
 
+// Keep the stream-ordered workspace pool resident across synchronisations: by default the driver trims it to zero
+// at every sync, and every call would pay for hundreds of MB of fresh allocations (measured: 2x on the photometry path).
+void keep_workspace_pool() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  });
+}
+
 // stream-ordered device allocation released (cudaFreeAsync) when it goes out of scope, on every return path
 struct StreamAlloc {
   void* p = nullptr;
@@ -50,6 +64,7 @@ struct StreamAlloc {
   StreamAlloc& operator=(const StreamAlloc&) = delete;
   ~StreamAlloc() { if (p) cudaFreeAsync(p, st); }
   cudaError_t alloc(size_t bytes, cudaStream_t s) {
+    keep_workspace_pool();
     st = s;
     return cudaMallocAsync(&p, bytes ? bytes : 8, s);
   }
@@ -268,14 +283,8 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [dev] {
+  std::call_once(once, [] {
     attr_err = sn_kernel_attributes();
-    // keep the stream-ordered workspace pool resident across synchronisations (default trims it to 0)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sn_kernel)");
 
@@ -555,13 +564,8 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [dev] {
+  std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(rb::kn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(kn_kernel)");
   const size_t ws_doubles = (size_t)rb::kEpochCols * (size_t)E + (size_t)rb::kKnScalars * (size_t)N + 2;
@@ -954,13 +958,8 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
   RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [dev] {
+  std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(rb::ag_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(ag_cell_kernel)");
 
@@ -1264,6 +1263,7 @@ struct PhotJob {
 // fill(n0, nc, d_grid, d_opz, d_dl, d_len) -> RB_OK or an error code (already recorded with fail())
 extern "C++" template <typename Fill>
 int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
+  keep_workspace_pool();
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -1359,10 +1359,12 @@ struct CallBuffer {
   cudaStream_t st = nullptr;
   ~CallBuffer() { if (p) cudaFreeAsync(p, st); }
   cudaError_t alloc(size_t n, cudaStream_t s) {
+    keep_workspace_pool();
     st = s;
     return cudaMallocAsync(&p, (n ? n : 1) * sizeof(double), s);
   }
   cudaError_t upload(const std::vector<double>& h, cudaStream_t s) {
+    keep_workspace_pool();
     st = s;
     cudaError_t e = cudaMallocAsync(&p, h.size() * sizeof(double), s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, s);
