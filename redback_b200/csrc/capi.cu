@@ -565,7 +565,9 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::kn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_err = cudaFuncSetAttribute(rb::kn_kernel<RB_KN_ONE_COMPONENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rb::kn_kernel<RB_KN_METZGER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(kn_kernel)");
   const size_t ws_doubles = (size_t)rb::kEpochCols * (size_t)E + (size_t)rb::kKnScalars * (size_t)N + 2;
@@ -604,11 +606,12 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   // threads) 512: 404 ms, 256: 241 -- smaller blocks, more of them per SM hide the per-sample barriers
   const int threads = (cfg->model == RB_KN_METZGER) ? 256 : 128;
   int occ = 0;
-  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb::kn_kernel, threads, smem));
+  void (*kn_kern)(const rb::KnArgs) = (cfg->model == RB_KN_METZGER) ? rb::kn_kernel<RB_KN_METZGER> : rb::kn_kernel<RB_KN_ONE_COMPONENT>;
+  RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kn_kern, threads, smem));
   if (occ < 1) occ = 1;
   int64_t grid = (int64_t)sms * occ * 4;
   if (grid > N) grid = N;
-  rb::kn_kernel<<<(unsigned)grid, threads, smem, st>>>(a);
+  kn_kern<<<(unsigned)grid, threads, smem, st>>>(a);
   launch_counter()->fetch_add(4);
   RB_CUDA(cudaGetLastError());
   return RB_OK;
@@ -1479,7 +1482,9 @@ extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::kn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_err = cudaFuncSetAttribute(rb::kn_kernel<RB_KN_ONE_COMPONENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rb::kn_kernel<RB_KN_METZGER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(kn_kernel)");
   // epoch range for the adaptive grid (get_optimal_time_array(..., user_times)): one tiny D2H read
@@ -1499,7 +1504,8 @@ extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* 
   const size_t ksmem = kn_smem_bytes(&kcfg, 1);
   const int kn_threads = (cfg->model == RB_KN_METZGER) ? 256 : 512;   // grid mode: 512 measured faster than 128 (457 vs 537 ms)
   int occ_kn = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_kn, rb::kn_kernel, kn_threads, ksmem);
+  void (*kn_kern)(const rb::KnArgs) = (cfg->model == RB_KN_METZGER) ? rb::kn_kernel<RB_KN_METZGER> : rb::kn_kernel<RB_KN_ONE_COMPONENT>;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_kn, kn_kern, kn_threads, ksmem);
   if (occ_kn < 1) occ_kn = 1;
 
   PhotJob j{};
@@ -1528,7 +1534,7 @@ extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* 
     a.opz_out = d_opz;
     a.dl_out = d_dl;
     rb::kn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
-    rb::kn_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_kn * 4), kn_threads, ksmem, st>>>(a);
+    kn_kern<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_kn * 4), kn_threads, ksmem, st>>>(a);
     launch_counter()->fetch_add(2);
     return (int)RB_OK;
   });

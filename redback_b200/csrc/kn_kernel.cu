@@ -211,6 +211,8 @@ __device__ __forceinline__ double block_scan_inclusive(double v, double* wsum, d
   return out;
 }
 
+// MODEL resolved at compile time: each instantiation carries only its own model's code (instruction cache, registers)
+template <int MODEL>
 __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
   extern __shared__ double ksm[];
   const int R = a.cfg.dense_resolution;
@@ -229,7 +231,8 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
   int* ipart = reinterpret_cast<int*>(tpart + kShellWarps * R);  // Metzger: [kShellWarps][R] argmin shell
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int model = a.cfg.model, sigma_mode = a.cfg.sigma_mode;
+  constexpr int model = MODEL;
+  const int sigma_mode = a.cfg.sigma_mode;
   const bool want_logl = a.want_logl != 0;
   const double grid_t_max = a.cfg.grid_t_max, log_grid_t_max = log10(a.cfg.grid_t_max);
   for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
