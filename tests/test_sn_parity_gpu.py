@@ -465,6 +465,15 @@ def test_upper_limits_in_every_fused_kernel(rb):
         (rb.afterglow_models.tophat_redback, h.tophat_prior(rng, 8), dict(frequency=nu, output_format="flux_density")),
         (rb.kilonova_models.one_component_kilonova_model, h.one_component_prior(rng, 8),
          dict(bands=np.array(["lsstr"] * t.size), output_format="magnitude")),
+        (rb.supernova_models.csm_interaction, h.csm_prior(rng, 8, zmax=0.2), dict(frequency=nu, output_format="flux_density")),
+        (rb.magnetar_driven_ejecta_models.general_mergernova, h.mergernova_prior(rng, 8, "general"),
+         dict(frequency=nu, output_format="flux_density")),
+        (rb.magnetar_driven_ejecta_models.general_metzger_magnetar_driven, h.metzger_magnetar_prior(rng, 8, "general"),
+         dict(frequency=nu, output_format="flux_density")),
+        (rb.supernova_models.sn_fallback,
+         dict(redshift=rng.uniform(0.01, 0.2, 8), logl1=rng.uniform(52, 55, 8), tr=rng.uniform(1, 10, 8),
+              vej=h.loguniform(rng, 3e3, 2e4, 8), temperature_floor=h.loguniform(rng, 3e3, 8e3, 8)),
+         dict(frequency=nu, output_format="flux_density")),
     ]
     for fn, p, kw in cases:
         mag = kw["output_format"] == "magnitude"
