@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
   double* aux = lul + 5 * NL;             // [NT]      per-time scalar (cutoff norm)
   double* tile = aux + NT;                // [kPhotTileRows][NL + 1]
   double* red = tile + kPhotTileRows * (NL + 1);   // [40]
-  double* tab = red + 40;                 // [1024]
+  double* bst = red + 40;                 // [NL][2]   time-axis back-substitution state per wavelength column
+  double* tab = bst + 2 * NL;             // [1024]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
     __syncthreads();
     const double repl = red[32];
 
-    // ---- 3b. time-axis solve: one thread per wavelength column (coalesced across columns).  The scratch tile
+    // ---- 3b. time-axis forward elimination: one thread per wavelength column (coalesced across columns).  The scratch tile
     // lives in global memory / L2: loads are issued kPhotBatch rows ahead of the recurrence to hide latency.
     for (int j = tid; j < NL; j += blockDim.x) {
       double y1 = 0.0, y2 = 0.0;   // y[i-1], y[i-2]
@@ -255,30 +256,33 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
           }
         }
       }
-      double x1 = 0.0, x2 = 0.0;   // x[i+1], x[i+2]
-      for (int i0 = G - 1; i0 >= 0; i0 -= kPhotBatch) {
-        double b[kPhotBatch];
+    }
+    for (int j = tid; j < NL; j += blockDim.x) bst[2 * j] = bst[2 * j + 1] = 0.0;   // x[i+1], x[i+2] per column
+    __syncthreads();
+    // ---- 3c. time-axis back substitution fused with the wavelength-axis solve: the rows come out last-to-first, so
+    // each tile of kPhotTileRows finished rows goes straight into shared memory, is solved along wavelength there and
+    // is written to the scratch once (one read and one write pass fewer than solving the two axes separately)
+    for (int r1 = G; r1 > 0; r1 -= kPhotTileRows) {
+      const int r0 = max(r1 - kPhotTileRows, 0), rows = r1 - r0;
+      for (int j = tid; j < NL; j += blockDim.x) {
+        double x1 = bst[2 * j], x2 = bst[2 * j + 1];
+        for (int i0 = r1 - 1; i0 >= r0; i0 -= kPhotBatch) {
+          double b[kPhotBatch];
 #pragma unroll
-        for (int u = 0; u < kPhotBatch; ++u) b[u] = (i0 - u >= 0) ? S[(i0 - u) * NL + j] : 0.0;
+          for (int u = 0; u < kPhotBatch; ++u) b[u] = (i0 - u >= r0) ? S[(i0 - u) * NL + j] : 0.0;
 #pragma unroll
-        for (int u = 0; u < kPhotBatch; ++u) {
-          const int i = i0 - u;
-          if (i >= 0) {
-            const double x = (b[u] - lut[5 * i + 3] * x1 - lut[5 * i + 4] * x2) * lut[5 * i + 2];
-            S[i * NL + j] = x;
-            x2 = x1;
-            x1 = x;
+          for (int u = 0; u < kPhotBatch; ++u) {
+            const int i = i0 - u;
+            if (i >= r0) {
+              const double x = (b[u] - lut[5 * i + 3] * x1 - lut[5 * i + 4] * x2) * lut[5 * i + 2];
+              tile[(i - r0) * (NL + 1) + j] = x;
+              x2 = x1;
+              x1 = x;
+            }
           }
         }
-      }
-    }
-    __syncthreads();
-    // ---- 3c. wavelength-axis solve: tiles of rows through shared memory ------------------------------------
-    for (int r0 = 0; r0 < G; r0 += kPhotTileRows) {
-      const int rows = min(kPhotTileRows, G - r0);
-      for (int idx = tid; idx < rows * NL; idx += blockDim.x) {
-        const int r = idx / NL, j = idx - r * NL;
-        tile[r * (NL + 1) + j] = S[(r0 + r) * NL + j];
+        bst[2 * j] = x1;
+        bst[2 * j + 1] = x2;
       }
       __syncthreads();
       if (tid < rows) {
