@@ -94,6 +94,32 @@ __device__ __forceinline__ double nak_knot(const double* __restrict__ x, int n, 
   return x[i - 2];
 }
 
+// Banded LU rows (l2, l1, d, u1, u2) are kept in shared memory as (l2, l1, 1/d, u1/d, u2/d): a back-substitution step
+// is then x = b/d - (u1/d) x[i+1] - (u2/d) x[i+2] with a single FMA on the serial dependency chain (b/d and the x[i+2]
+// term do not depend on the previous step), instead of two FMAs and a division.
+__device__ __forceinline__ void load_lu_row(double* __restrict__ dst, const double* __restrict__ src) {
+  const double rd = 1.0 / src[2];
+  dst[0] = src[0];
+  dst[1] = src[1];
+  dst[2] = rd;
+  dst[3] = src[3] * rd;
+  dst[4] = src[4] * rd;
+}
+
+#ifdef RB_PHOT_PROFILE
+// developer aid (tools/phot_phases.sh): block 0 prints the cycles it spent in each phase of its first samples
+#define PHOT_PROF_BEGIN() long long pt_[8]; int pn_ = 0; long long pc_ = clock64();
+#define PHOT_PROF(i) { __syncthreads(); const long long c_ = clock64(); pt_[pn_++] = c_ - pc_; pc_ = c_; }
+#define PHOT_PROF_END()                                                                                             \
+  if (blockIdx.x == 0 && tid == 0 && n < 3 * (int64_t)gridDim.x)                                                      \
+    printf("phot phases [cycles] setup %lld spectra %lld cleanup+lu %lld forward %lld back+lambda %lld epochs %lld\n", \
+           pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[5]);
+#else
+#define PHOT_PROF_BEGIN()
+#define PHOT_PROF(i)
+#define PHOT_PROF_END()
+#endif
+
 __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
   extern __shared__ double psm[];
   const int NT = a.n_t_max, NL = a.n_lambda, E = a.E;
@@ -108,13 +134,12 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
-  // slot 2 of the banded LU rows holds 1 / d: the back substitutions multiply instead of dividing (a division is
-  // ~2/3 of the latency of one step of those sequential recurrences)
-  for (int i = tid; i < 5 * NL; i += blockDim.x) lul[i] = (i % 5 == 2) ? 1.0 / a.lu_lambda[i] : a.lu_lambda[i];
+  for (int j = tid; j < NL; j += blockDim.x) load_lu_row(lul + 5 * j, a.lu_lambda + 5 * j);
   double* S = a.scratch + (size_t)blockIdx.x * NT * NL;
   __syncthreads();
 
   for (int64_t n = blockIdx.x; n < a.N; n += gridDim.x) {
+    PHOT_PROF_BEGIN();
     const int G = a.grid_len ? a.grid_len[n] : NT;
     const double* gT = a.grid + (size_t)n * kPhotGridCols * NT + PH_T * NT;
     const double* gR = a.grid + (size_t)n * kPhotGridCols * NT + PH_R * NT;
@@ -127,9 +152,10 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
       if (a.sed != PH_SED_BLACKBODY) aux[k] = cutoff_norm(gL[k], gR[k], gT[k], lam_c, a.absorption_index);
     }
     if (a.common_time_lu)
-      for (int i = tid; i < 5 * G; i += blockDim.x) lut[i] = (i % 5 == 2) ? 1.0 / a.lu_time[i] : a.lu_time[i];
+      for (int i = tid; i < G; i += blockDim.x) load_lu_row(lut + 5 * i, a.lu_time + 5 * i);
     __syncthreads();
 
+    PHOT_PROF(0);
     // ---- 1. spectra + statistics for the clean-up -------------------------------------------------------
     double vsum = 0.0, vcnt = 0.0;
     const double inv_den = 1.0 / ((dl * dl) * (kC * kC));
@@ -173,6 +199,7 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
       S[idx] = v;
       if (isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
     }
+    PHOT_PROF(1);
     // ---- 2. clean-up value (sed.py:985-992) ---------------------------------------------------------------
     vsum = warp_sum(vsum);
     vcnt = warp_sum(vcnt);
@@ -210,31 +237,35 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
       }
       __syncthreads();
       if (tid == 0) {
-        // banded LU without pivoting, in place: row -> (l2, l1, d, u1, u2)
+        // banded LU without pivoting, in place, stored in the scaled layout of load_lu_row.  The two previous rows
+        // stay in registers and the next row is loaded ahead, so the serial chain per row is multiply, FMA, reciprocal.
+        double rd1 = 0.0, u1_1 = 0.0, u2_1 = 0.0, rd2 = 0.0, u1_2 = 0.0, u2_2 = 0.0;
+        double n0 = lut[0], n1 = lut[1], n2 = lut[2], n3 = lut[3], n4 = lut[4];
         for (int i = 0; i < G; ++i) {
-          double l2 = 0.0, l1 = 0.0;
-          double am1 = lut[5 * i + 1], d = lut[5 * i + 2], u1 = lut[5 * i + 3];
-          if (i >= 2) {
-            l2 = lut[5 * i + 0] / lut[5 * (i - 2) + 2];
-            am1 -= l2 * lut[5 * (i - 2) + 3];
-            d -= l2 * lut[5 * (i - 2) + 4];
-          }
-          if (i >= 1) {
-            l1 = am1 / lut[5 * (i - 1) + 2];
-            d -= l1 * lut[5 * (i - 1) + 3];
-            u1 -= l1 * lut[5 * (i - 1) + 4];
-          }
+          const double a0 = n0, a1 = n1, u2 = n4;
+          double d = n2, u1 = n3;
+          if (i + 1 < G) { n0 = lut[5 * i + 5]; n1 = lut[5 * i + 6]; n2 = lut[5 * i + 7]; n3 = lut[5 * i + 8]; n4 = lut[5 * i + 9]; }
+          const double l2 = a0 * rd2;
+          const double am1 = a1 - l2 * u1_2;
+          d -= l2 * u2_2;
+          const double l1 = am1 * rd1;
+          d -= l1 * u1_1;
+          u1 -= l1 * u2_1;
+          const double rd = 1.0 / d;
           lut[5 * i + 0] = l2;
           lut[5 * i + 1] = l1;
-          lut[5 * i + 2] = d;
-          lut[5 * i + 3] = u1;
+          lut[5 * i + 2] = rd;
+          lut[5 * i + 3] = u1 * rd;
+          lut[5 * i + 4] = u2 * rd;
+          rd2 = rd1; u1_2 = u1_1; u2_2 = u2_1;
+          rd1 = rd; u1_1 = u1; u2_1 = u2;
         }
-        for (int i = 0; i < G; ++i) lut[5 * i + 2] = 1.0 / lut[5 * i + 2];
       }
     }
     __syncthreads();
     const double repl = red[32];
 
+    PHOT_PROF(2);
     // ---- 3b. time-axis forward elimination: one thread per wavelength column (coalesced across columns).  The scratch tile
     // lives in global memory / L2: loads are issued kPhotBatch rows ahead of the recurrence to hide latency.
     for (int j = tid; j < NL; j += blockDim.x) {
@@ -249,7 +280,7 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
           if (i < G) {
             double v = b[u];
             if (!(isfinite(v) && v != 0.0)) v = repl;
-            const double y = v - lut[5 * i + 1] * y1 - lut[5 * i + 0] * y2;
+            const double y = (v - lut[5 * i + 0] * y2) - lut[5 * i + 1] * y1;   // y[i-2] term first: one FMA on the chain
             S[i * NL + j] = y;
             y2 = y1;
             y1 = y;
@@ -259,6 +290,7 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
     }
     for (int j = tid; j < NL; j += blockDim.x) bst[2 * j] = bst[2 * j + 1] = 0.0;   // x[i+1], x[i+2] per column
     __syncthreads();
+    PHOT_PROF(3);
     // ---- 3c. time-axis back substitution fused with the wavelength-axis solve: the rows come out last-to-first, so
     // each tile of kPhotTileRows finished rows goes straight into shared memory, is solved along wavelength there and
     // is written to the scratch once (one read and one write pass fewer than solving the two axes separately)
@@ -274,7 +306,7 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
           for (int u = 0; u < kPhotBatch; ++u) {
             const int i = i0 - u;
             if (i >= r0) {
-              const double x = (b[u] - lut[5 * i + 3] * x1 - lut[5 * i + 4] * x2) * lut[5 * i + 2];
+              const double x = (b[u] * lut[5 * i + 2] - lut[5 * i + 4] * x2) - lut[5 * i + 3] * x1;
               tile[(i - r0) * (NL + 1) + j] = x;
               x2 = x1;
               x1 = x;
@@ -286,20 +318,48 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
       }
       __syncthreads();
       if (tid < rows) {
+        // one thread per row; values and coefficients are loaded a batch ahead of the recurrence (the compiler will
+        // not move the loads across the stores into the same tile on its own)
         double* row = tile + tid * (NL + 1);
         double y1 = 0.0, y2 = 0.0;
-        for (int j = 0; j < NL; ++j) {
-          const double y = row[j] - lul[5 * j + 1] * y1 - lul[5 * j + 0] * y2;
-          row[j] = y;
-          y2 = y1;
-          y1 = y;
+        for (int j0 = 0; j0 < NL; j0 += kPhotBatch) {
+          double b[kPhotBatch], c0[kPhotBatch], c1[kPhotBatch];
+#pragma unroll
+          for (int u = 0; u < kPhotBatch; ++u) {
+            const int j = min(j0 + u, NL - 1);
+            b[u] = row[j];
+            c0[u] = lul[5 * j + 0];
+            c1[u] = lul[5 * j + 1];
+          }
+#pragma unroll
+          for (int u = 0; u < kPhotBatch; ++u) {
+            if (j0 + u < NL) {
+              const double y = (b[u] - c0[u] * y2) - c1[u] * y1;
+              row[j0 + u] = y;
+              y2 = y1;
+              y1 = y;
+            }
+          }
         }
         double x1 = 0.0, x2 = 0.0;
-        for (int j = NL - 1; j >= 0; --j) {
-          const double x = (row[j] - lul[5 * j + 3] * x1 - lul[5 * j + 4] * x2) * lul[5 * j + 2];
-          row[j] = x;
-          x2 = x1;
-          x1 = x;
+        for (int j0 = NL - 1; j0 >= 0; j0 -= kPhotBatch) {
+          double b[kPhotBatch], c3[kPhotBatch], c4[kPhotBatch];
+#pragma unroll
+          for (int u = 0; u < kPhotBatch; ++u) {
+            const int j = max(j0 - u, 0);
+            b[u] = row[j] * lul[5 * j + 2];
+            c3[u] = lul[5 * j + 3];
+            c4[u] = lul[5 * j + 4];
+          }
+#pragma unroll
+          for (int u = 0; u < kPhotBatch; ++u) {
+            if (j0 - u >= 0) {
+              const double x = (b[u] - c4[u] * x2) - c3[u] * x1;
+              row[j0 - u] = x;
+              x2 = x1;
+              x1 = x;
+            }
+          }
         }
       }
       __syncthreads();
@@ -310,6 +370,7 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
       __syncthreads();
     }
 
+    PHOT_PROF(5);
     // ---- 4./5. epochs: bispev at (t_e, band grid), band flux, magnitude, likelihood -------------------------
     double logl_part = 0.0;
     for (int e = tid; e < E; e += blockDim.x) {
@@ -378,6 +439,8 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
       }
     }
     __syncthreads();
+    PHOT_PROF(6);
+    PHOT_PROF_END();
   }
 }
 
