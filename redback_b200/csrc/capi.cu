@@ -1238,7 +1238,7 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
 }
 
 size_t phot_smem_bytes(int NT, int NL) {
-  return sizeof(double) * ((size_t)7 * NT + 7 * (size_t)NL + (size_t)rb::kPhotTileRows * (NL + 1) + 40 + rb::kExpTabSize);
+  return sizeof(double) * ((size_t)6 * NT + 7 * (size_t)NL + (size_t)rb::phot_tile_elems(NT, NL) + 40 + rb::kExpTabSize);
 }
 
 

@@ -26,6 +26,13 @@ constexpr int kPhotMaxSpan = 96;     // max B-spline coefficients (along wavelen
 constexpr int kPhotTileRows = 32;    // rows per shared-memory tile in the wavelength-axis solve
 constexpr int kPhotBatch = 8;        // rows of the scratch tile loaded ahead of the time-axis recurrence
 
+// shared-memory doubles of the tile region: a tile of rows for the wavelength-axis solve, or the 4 per-epoch and 3
+// per-wavelength factor arrays of the spectra phase
+__host__ __device__ inline int phot_tile_elems(int NT, int NL) {
+  const int t = kPhotTileRows * (NL + 1), f = 4 * NT + 3 * NL;
+  return t > f ? t : f;
+}
+
 enum { PH_SED_BLACKBODY = 1, PH_SED_CUTOFF = 2, PH_SED_CUTOFF_LINE = 3 };
 enum { PH_T = 0, PH_R, PH_L, PH_X, kPhotGridCols };   // per-sample model grid: temperature, radius, L_bol, phase
 
@@ -108,15 +115,17 @@ __device__ __forceinline__ void load_lu_row(double* __restrict__ dst, const doub
 
 #ifdef RB_PHOT_PROFILE
 // developer aid (tools/phot_phases.sh): block 0 prints the cycles it spent in each phase of its first samples
-#define PHOT_PROF_BEGIN() long long pt_[8]; int pn_ = 0; long long pc_ = clock64();
+#define PHOT_PROF_BEGIN() long long pt_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; int pn_ = 0; long long pc_ = clock64(), pa_ = pc_;
+#define PHOT_PROF_ACC(i) { __syncthreads(); const long long c_ = clock64(); pt_[i] += c_ - pa_; pa_ = c_; }
 #define PHOT_PROF(i) { __syncthreads(); const long long c_ = clock64(); pt_[pn_++] = c_ - pc_; pc_ = c_; }
 #define PHOT_PROF_END()                                                                                             \
   if (blockIdx.x == 0 && tid == 0 && n < 3 * (int64_t)gridDim.x)                                                      \
-    printf("phot phases [cycles] setup %lld spectra %lld cleanup+lu %lld forward %lld back+lambda %lld epochs %lld\n", \
-           pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[5]);
+    printf("phot phases [cycles] setup %lld spectra %lld cleanup+lu %lld forward %lld back+lambda %lld (back %lld "     \
+           "lambda %lld store %lld) epochs %lld\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[8], pt_[9], pt_[10], pt_[5]);
 #else
 #define PHOT_PROF_BEGIN()
 #define PHOT_PROF(i)
+#define PHOT_PROF_ACC(i)
 #define PHOT_PROF_END()
 #endif
 
@@ -126,9 +135,8 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
   double* xk = psm;                       // [NT]      time-axis data sites (observer-frame phase, days)
   double* lut = xk + NT;                  // [NT][5]   time-axis banded LU
   double* lul = lut + 5 * NT;             // [NL][5]   wavelength-axis banded LU
-  double* aux = lul + 5 * NL;             // [NT]      per-time scalar (cutoff norm)
-  double* tile = aux + NT;                // [kPhotTileRows][NL + 1]
-  double* red = tile + kPhotTileRows * (NL + 1);   // [40]
+  double* tile = lul + 5 * NL;            // [kPhotTileRows][NL + 1]; holds the row / column factors while the spectra are made
+  double* red = tile + phot_tile_elems(NT, NL);    // [40]
   double* bst = red + 40;                 // [NL][2]   time-axis back-substitution state per wavelength column
   double* tab = bst + 2 * NL;             // [1024]
 
@@ -147,9 +155,60 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
     const double* gX = a.grid + (size_t)n * kPhotGridCols * NT + PH_X * NT;
     const double opz = a.opz[n], dl = a.dl[n];
     const double lam_c = a.cutoff_wavelength * kAngstrom;
+    // Every spectrum sample factorises into a per-epoch and a per-wavelength part around the Planck denominator:
+    //   v[k][j] = colB[j] * rowB[k] / expm1(colA[j] * rowA[k])   (+ the sed.Line terms for type Ia),
+    // so the divisions, powers and unit conversions are done once per row / column (they live in the tile region,
+    // which is free until the solves) and a sample costs one expm1, one division and three multiplies.
+    double* rowA = tile;             // [NT]  1 / (k_B T)  or 1 / T
+    double* rowB = rowA + NT;        // [NT]  R^2          or R^2 * cutoff normalisation
+    double* rowC = rowB + NT;        // [NT]  1 - line amplitude
+    double* rowD = rowC + NT;        // [NT]  scaled line amplitude
+    double* colA = rowD + NT;        // [NL]  h nu         or hc / (k_B lambda)
+    double* colB = colA + NL;        // [NL]  everything else that depends on wavelength only
+    double* colC = colB + NL;        // [NL]  line profile in output units
+    const bool line = a.sed == PH_SED_CUTOFF_LINE;
     for (int k = tid; k < G; k += blockDim.x) {
       xk[k] = gX[k];
-      if (a.sed != PH_SED_BLACKBODY) aux[k] = cutoff_norm(gL[k], gR[k], gT[k], lam_c, a.absorption_index);
+      const double T = gT[k], R = gR[k];
+      if (a.sed == PH_SED_BLACKBODY) {
+        rowA[k] = 1.0 / (kKB * T);
+        rowB[k] = R * R;
+      } else {
+        rowA[k] = 1.0 / T;
+        rowB[k] = (R * R) * cutoff_norm(gL[k], R, T, lam_c, a.absorption_index);
+        if (line) {
+          // sed.Line on the (N_lambda, N_t) grid (sed.py:859-909; supernova_models.py:2295-2303); time is source frame
+          const double te = gX[k] / opz;
+          const double q = (te - a.line_time) / a.line_duration;
+          const double amp = a.line_amplitude * exp(-0.5 * (q * q));
+          double amp_scaled = amp * gL[k] / (4 * kPi * (dl * dl));
+          amp_scaled /= (a.line_width * sqrt(2 * kPi));
+          rowC[k] = 1 - amp;
+          rowD[k] = amp_scaled;
+        }
+      }
+    }
+    for (int j = tid; j < NL; j += blockDim.x) {
+      const double lam_obs = a.lambda_obs[j];
+      const double nu = (kCSI / (lam_obs * 1.e-10)) * opz;                       // utils.py:357-362, 383
+      const double to_flam = 1e-26 * 2.99792458e18 / (lam_obs * lam_obs);        // mJy -> erg/cm^2/s/Angstrom
+      if (a.sed == PH_SED_BLACKBODY) {
+        colA[j] = kH * nu;
+        colB[j] = 2 * kPi * kH * (nu * nu * nu) / ((dl * dl) * (kC * kC)) * opz * kToMJy * to_flam;   // sed.py:216, 929
+      } else {
+        const double lam_A = 1.e10 * (kCSI / nu);
+        const double lam = lam_A * kAngstrom;
+        const double l2 = lam * lam, l5 = l2 * l2 * lam;
+        const double absorb = (lam < lam_c) ? pow(lam / lam_c, a.absorption_index) : 1.0;
+        colA[j] = kXConst / lam;
+        double c = kFluxConst * (absorb / l5) / (4 * kPi * (dl * dl)) * lam_A / nu * kToMJy;        // sed.py:362-384
+        if (line) {
+          const double u = (lam_A - a.line_wavelength) / a.line_width;
+          colC[j] = exp(-0.5 * (u * u)) * (lam * lam) / kC * kToMJy * opz * to_flam;
+          c = c * 1e-26 * kToMJy;
+        }
+        colB[j] = c * opz * to_flam;                                              // supernova_models.py:1611-1612, 2304-2305
+      }
     }
     if (a.common_time_lu)
       for (int i = tid; i < G; i += blockDim.x) load_lu_row(lut + 5 * i, a.lu_time + 5 * i);
@@ -158,47 +217,19 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
     PHOT_PROF(0);
     // ---- 1. spectra + statistics for the clean-up -------------------------------------------------------
     double vsum = 0.0, vcnt = 0.0;
-    const double inv_den = 1.0 / ((dl * dl) * (kC * kC));
-    for (int idx = tid; idx < G * NL; idx += blockDim.x) {
-      const int k = idx / NL, j = idx - k * NL;
-      const double lam_obs = a.lambda_obs[j];
-      const double nu = (kCSI / (lam_obs * 1.e-10)) * opz;                       // utils.py:357-362, 383
-      const double T = gT[k], R = gR[k];
-      double mjy;
-      if (a.sed == PH_SED_BLACKBODY) {
-        const double num = 2 * kPi * kH * (nu * nu * nu) * (R * R);             // sed.py:216
-        const double frac = 1.0 / expm1_fast((kH * nu) / (kKB * T), tab);
-        mjy = num * inv_den * frac * opz * kToMJy;                               // sed.py:929
-      } else {
-        const double lam_A = 1.e10 * (kCSI / nu);
-        const double lam = lam_A * kAngstrom;
-        const double l2 = lam * lam, l5 = l2 * l2 * lam;
-        const double em = expm1_fast(kXConst / lam / T, tab);
-        double sedv = (lam < lam_c) ? kFluxConst * ((R * R) * pow(lam / lam_c, a.absorption_index) / l5) / em
-                                    : kFluxConst * ((R * R) / l5) / em;          // sed.py:362-384
-        sedv *= aux[k];
-        double fd = sedv / (4 * kPi * (dl * dl));
-        fd *= lam_A;
-        fd /= nu;
-        double base = fd * kToMJy;
-        if (a.sed == PH_SED_CUTOFF_LINE) {
-          // sed.Line on the (N_lambda, N_t) grid (sed.py:859-909; supernova_models.py:2295-2303); time is source frame
-          const double te = xk[k] / opz;
-          const double q = (te - a.line_time) / a.line_duration;
-          const double amp = a.line_amplitude * exp(-0.5 * (q * q));
-          double flux = (base * 1e-26) * (1 - amp);
-          double amp_scaled = amp * gL[k] / (4 * kPi * (dl * dl));
-          amp_scaled /= (a.line_width * sqrt(2 * kPi));
-          const double u = (lam_A - a.line_wavelength) / a.line_width;
-          flux += amp_scaled * exp(-0.5 * (u * u)) * (lam * lam) / kC;
-          base = flux * kToMJy;
-        }
-        mjy = base * opz;                                                        // supernova_models.py:1611-1612, 2304-2305
+    {
+      int k = tid / NL, j = tid - k * NL;
+      const int dk = (int)blockDim.x / NL, dj = (int)blockDim.x - dk * NL;
+      for (; k < G; k += dk) {
+        double v = colB[j] * rowB[k] / expm1_fast(colA[j] * rowA[k], tab);
+        if (line) v = v * rowC[k] + rowD[k] * colC[j];
+        S[k * NL + j] = v;
+        if (isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
+        j += dj;
+        if (j >= NL) { j -= NL; ++k; }
       }
-      const double v = mjy * 1e-26 * 2.99792458e18 / (lam_obs * lam_obs);       // mJy -> erg/cm^2/s/Angstrom
-      S[idx] = v;
-      if (isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
     }
+    __syncthreads();   // the tile region is reused by the solves below
     PHOT_PROF(1);
     // ---- 2. clean-up value (sed.py:985-992) ---------------------------------------------------------------
     vsum = warp_sum(vsum);
@@ -294,6 +325,7 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
     // ---- 3c. time-axis back substitution fused with the wavelength-axis solve: the rows come out last-to-first, so
     // each tile of kPhotTileRows finished rows goes straight into shared memory, is solved along wavelength there and
     // is written to the scratch once (one read and one write pass fewer than solving the two axes separately)
+    PHOT_PROF_ACC(11);
     for (int r1 = G; r1 > 0; r1 -= kPhotTileRows) {
       const int r0 = max(r1 - kPhotTileRows, 0), rows = r1 - r0;
       for (int j = tid; j < NL; j += blockDim.x) {
@@ -317,6 +349,7 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
         bst[2 * j + 1] = x2;
       }
       __syncthreads();
+      PHOT_PROF_ACC(8);
       if (tid < rows) {
         // one thread per row; values and coefficients are loaded a batch ahead of the recurrence (the compiler will
         // not move the loads across the stores into the same tile on its own)
@@ -363,11 +396,13 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
         }
       }
       __syncthreads();
+      PHOT_PROF_ACC(9);
       for (int idx = tid; idx < rows * NL; idx += blockDim.x) {
         const int r = idx / NL, j = idx - r * NL;
         S[(r0 + r) * NL + j] = tile[r * (NL + 1) + j];
       }
       __syncthreads();
+      PHOT_PROF_ACC(10);
     }
 
     PHOT_PROF(5);
