@@ -27,10 +27,11 @@ constexpr int kPhotTileRows = 32;    // rows per shared-memory tile in the wavel
 constexpr int kPhotBatch = 8;        // rows of the scratch tile loaded ahead of the time-axis recurrence
 
 // shared-memory doubles of the tile region: a tile of rows for the wavelength-axis solve, or the 4 per-epoch and 3
-// per-wavelength factor arrays of the spectra phase
+// per-wavelength factor arrays of the spectra phase, or the per-warp coefficient buffers and per-epoch hand-over arrays
+// of the epoch phase (at least 128 epochs per chunk)
 __host__ __device__ inline int phot_tile_elems(int NT, int NL) {
-  const int t = kPhotTileRows * (NL + 1), f = 4 * NT + 3 * NL;
-  return t > f ? t : f;
+  const int t = kPhotTileRows * (NL + 1), f = 4 * NT + 3 * NL, e = (kPhotThreads / 32) * kPhotMaxSpan + 6 * 128;
+  return max(max(t, f), e);
 }
 
 enum { PH_SED_BLACKBODY = 1, PH_SED_CUTOFF = 2, PH_SED_CUTOFF_LINE = 3 };
@@ -407,60 +408,85 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
 
     PHOT_PROF(5);
     // ---- 4./5. epochs: bispev at (t_e, band grid), band flux, magnitude, likelihood -------------------------
+    // Three sub-phases per chunk of epochs, each with the thread mapping that suits it (the tile region is free again
+    // and holds the per-epoch hand-over arrays):
+    //   a. one thread per epoch: knot interval and the four non-zero B-splines along time (divisions, a search);
+    //   b. one warp per epoch: gather the band's wavelength coefficients from the scratch with coalesced loads into a
+    //      per-warp buffer and split the band-pass integration points between the lanes;
+    //   c. one thread per epoch: magnitude, likelihood term, coalesced store.
     double logl_part = 0.0;
-    for (int e = tid; e < E; e += blockDim.x) {
-      double x = a.epoch_tab[EP_T * E + e];
-      if (a.t0_s != nullptr) {                                                    // phase_models.py:33-58
-        x -= a.t0_s[n];
-        if (x < 0.0) {
-          const double fake = (a.output == RB_OUT_FLUX) ? 0.0 : 1000.0;
-          if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = fake;
-          if (a.want_logl)
-            logl_part += logl_term(a.sigma_mode, a.epoch_tab[EP_KIND * E + e], a.epoch_tab[EP_Y * E + e], fake,
-                                   a.epoch_tab[EP_ISIG * E + e], a.epoch_tab[EP_LOGT * E + e],
-                                   a.sigma_param_s ? a.sigma_param_s[n] : 0.0);
-          continue;
+    const int nwarps = (int)(blockDim.x >> 5);
+    double* dw = tile + warp * kPhotMaxSpan;
+    double* eh = tile + nwarps * kPhotMaxSpan;                 // [chunk][6]: h0..h3, first row (< 0: before t0), band flux
+    const int chunk = (phot_tile_elems(NT, NL) - nwarps * kPhotMaxSpan) / 6;
+    const double sp = a.sigma_param_s ? a.sigma_param_s[n] : 0.0;
+    for (int e0 = 0; e0 < E; e0 += chunk) {
+      const int ne = min(chunk, E - e0);
+      for (int i = tid; i < ne; i += blockDim.x) {
+        const int e = e0 + i;
+        double x = a.epoch_tab[EP_T * E + e];
+        double* o = eh + 6 * i;
+        if (a.t0_s != nullptr) {                                                  // phase_models.py:33-58
+          x -= a.t0_s[n];
+          if (x < 0.0) { o[4] = -1.0; continue; }
         }
-      }
-      if (x < xk[0]) x = xk[0];                                                   // fpbisp clamps to [tb, te]
-      if (x > xk[G - 1]) x = xk[G - 1];
-      // knot interval: largest l in [3, G-1] with t[l] <= x  (t[l] = x[l-2] for 4 <= l <= G-1)
-      int l = 3;
-      {
-        int lo = 4, hi = G - 1;   // find count of knots t[4..G-1] = xk[2..G-3] that are <= x
-        while (lo <= hi) {
-          const int mid = (lo + hi) >> 1;
-          if (xk[mid - 2] <= x) { l = mid; lo = mid + 1; } else hi = mid - 1;
+        if (x < xk[0]) x = xk[0];                                                 // fpbisp clamps to [tb, te]
+        if (x > xk[G - 1]) x = xk[G - 1];
+        // knot interval: largest l in [3, G-1] with t[l] <= x  (t[l] = x[l-2] for 4 <= l <= G-1)
+        int l = 3;
+        {
+          int lo = 4, hi = G - 1;   // find count of knots t[4..G-1] = xk[2..G-3] that are <= x
+          while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            if (xk[mid - 2] <= x) { l = mid; lo = mid + 1; } else hi = mid - 1;
+          }
         }
+        double tl[8], h[4];
+        for (int q = 0; q < 8; ++q) tl[q] = nak_knot(xk, G, l - 3 + q);
+        fpbspl3(tl, 3, x, h);
+        o[0] = h[0]; o[1] = h[1]; o[2] = h[2]; o[3] = h[3];
+        o[4] = (double)(l - 3);
       }
-      double tl[8], h[4];
-      for (int q = 0; q < 8; ++q) tl[q] = nak_knot(xk, G, l - 3 + q);
-      fpbspl3(tl, 3, x, h);
-      const int lx = l - 3;
-      const int b = a.band_of_epoch[e];
-      const int jlo = a.band_jlo[b], span = a.band_span[b];
-      double d[kPhotMaxSpan];
-      for (int q = 0; q < span; ++q) {
-        const int j = jlo + q;
-        d[q] = h[0] * S[(lx + 0) * NL + j] + h[1] * S[(lx + 1) * NL + j] + h[2] * S[(lx + 2) * NL + j] +
-               h[3] * S[(lx + 3) * NL + j];
+      __syncthreads();
+      for (int i = warp; i < ne; i += nwarps) {
+        const double* o = eh + 6 * i;
+        if (o[4] < 0.0) continue;
+        const int b = a.band_of_epoch[e0 + i];
+        const int jlo = a.band_jlo[b], span = a.band_span[b];
+        const double h0 = o[0], h1 = o[1], h2 = o[2], h3 = o[3];
+        const double* Sx = S + (size_t)((int)o[4]) * NL + jlo;
+        for (int q = lane; q < span; q += 32)
+          dw[q] = h0 * Sx[q] + h1 * Sx[NL + q] + h2 * Sx[2 * NL + q] + h3 * Sx[3 * NL + q];
+        __syncwarp();
+        double acc = 0.0;
+        for (int w = a.band_off[b] + lane; w < a.band_off[b + 1]; w += 32) {
+          const int q = a.int_ly[w] - jlo;
+          const double* wy = a.int_wy + 4 * (size_t)w;
+          const double f = wy[0] * dw[q] + wy[1] * dw[q + 1] + wy[2] * dw[q + 2] + wy[3] * dw[q + 3];
+          acc += a.int_wt[w] * fabs(f);                                           // sed.py:36-37
+        }
+        acc = warp_sum(acc);
+        __syncwarp();
+        if (lane == 0) eh[6 * i + 5] = acc;
       }
-      double acc = 0.0;
-      for (int w = a.band_off[b]; w < a.band_off[b + 1]; ++w) {
-        const int q = a.int_ly[w] - jlo;
-        const double* wy = a.int_wy + 4 * (size_t)w;
-        const double f = wy[0] * d[q] + wy[1] * d[q + 1] + wy[2] * d[q + 2] + wy[3] * d[q + 3];
-        acc += a.int_wt[w] * fabs(f);                                             // sed.py:36-37
+      __syncthreads();
+      for (int i = tid; i < ne; i += blockDim.x) {
+        const int e = e0 + i;
+        double model_v;
+        if (eh[6 * i + 4] < 0.0) {
+          model_v = (a.output == RB_OUT_FLUX) ? 0.0 : 1000.0;
+        } else {
+          const int b = a.band_of_epoch[e];
+          const double bandflux = eh[6 * i + 5] * a.band_scale[b];
+          model_v = -2.5 * log10(bandflux / a.band_zp[b]);                        // sed.py:114
+          if (a.output == RB_OUT_FLUX) model_v = pow(10.0, model_v / (-2.5)) * a.band_ref[b];   // utils.py:716-718
+        }
+        if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = model_v;
+        if (a.want_logl)
+          logl_part += logl_term(a.sigma_mode, a.epoch_tab[EP_KIND * E + e], a.epoch_tab[EP_Y * E + e], model_v,
+                                 a.epoch_tab[EP_ISIG * E + e], a.epoch_tab[EP_LOGT * E + e], sp);
       }
-      const double bandflux = acc * a.band_scale[b];
-      double model_v = -2.5 * log10(bandflux / a.band_zp[b]);                     // sed.py:114
-      if (a.output == RB_OUT_FLUX) model_v = pow(10.0, model_v / (-2.5)) * a.band_ref[b];   // utils.py:716-718
-      if (a.out_model != nullptr) a.out_model[(a.n_base + n) * (int64_t)E + e] = model_v;
-      if (a.want_logl) {
-        logl_part += logl_term(a.sigma_mode, a.epoch_tab[EP_KIND * E + e], a.epoch_tab[EP_Y * E + e], model_v,
-                               a.epoch_tab[EP_ISIG * E + e],
-                               a.epoch_tab[EP_LOGT * E + e], a.sigma_param_s ? a.sigma_param_s[n] : 0.0);
-      }
+      __syncthreads();
     }
     if (a.want_logl) {
       logl_part = warp_sum(logl_part);
