@@ -1188,7 +1188,7 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
   std::vector<double> tk = nak_knots(lam.data(), NL);
   const int64_t total = ph->band_off[ph->n_bands];
   std::vector<int> ly((size_t)total), boff((size_t)ph->n_bands + 1), jlo((size_t)ph->n_bands), span((size_t)ph->n_bands);
-  std::vector<double> wy((size_t)total * 4), wt(ph->int_wt, ph->int_wt + total);
+  std::vector<double> rec((size_t)total * 6);   // per integration point: 4 B-spline values, wave * trans, first coefficient
   for (int b = 0; b <= ph->n_bands; ++b) boff[(size_t)b] = (int)ph->band_off[b];
   for (int b = 0; b < ph->n_bands; ++b) {
     int lo = NL, hi = -1;
@@ -1205,16 +1205,23 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
       double h[4];
       host_fpbspl3(tk.data(), l, x, h);
       ly[(size_t)w] = l - 3;
-      for (int q = 0; q < 4; ++q) wy[(size_t)w * 4 + q] = h[q];
+      for (int q = 0; q < 4; ++q) rec[(size_t)w * 6 + q] = h[q];
+      rec[(size_t)w * 6 + 4] = ph->int_wt[w];
       lo = std::min(lo, l - 3);
       hi = std::max(hi, l);
     }
     jlo[(size_t)b] = lo;
     span[(size_t)b] = hi - lo + 1;
+    for (int64_t w = ph->band_off[b]; w < ph->band_off[b + 1]; ++w) rec[(size_t)w * 6 + 5] = (double)(ly[(size_t)w] - lo);
     if (span[(size_t)b] > rb::kPhotMaxSpan)
       return fail(RB_ERR_UNSUPPORTED, "rb_*_mag_eval: a band overlaps too many wavelength-grid points");
   }
   std::vector<int> boe(ph->band_of_epoch, ph->band_of_epoch + E);
+  // epochs grouped by band: the warps of a block then integrate over the same band at the same time and its table of
+  // integration points stays in L1
+  std::vector<int> order((size_t)E);
+  for (int64_t e = 0; e < E; ++e) order[(size_t)e] = (int)e;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return boe[(size_t)x] < boe[(size_t)y]; });
   std::vector<double> scale(ph->band_scale, ph->band_scale + ph->n_bands), zp(ph->band_zp, ph->band_zp + ph->n_bands);
   std::vector<double> ref;
   if (ph->band_ref_flux) ref.assign(ph->band_ref_flux, ph->band_ref_flux + ph->n_bands);
@@ -1227,9 +1234,8 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
   if (e == cudaSuccess) e = dev.upload(scale, &pa.band_scale);
   if (e == cudaSuccess) e = dev.upload(zp, &pa.band_zp);
   if (e == cudaSuccess) e = dev.upload(ref, &pa.band_ref);
-  if (e == cudaSuccess) e = dev.upload(wt, &pa.int_wt);
-  if (e == cudaSuccess) e = dev.upload(ly, &pa.int_ly);
-  if (e == cudaSuccess) e = dev.upload(wy, &pa.int_wy);
+  if (e == cudaSuccess) e = dev.upload(order, &pa.epoch_order);
+  if (e == cudaSuccess) e = dev.upload(rec, &pa.int_rec);
   if (e == cudaSuccess) e = cudaStreamSynchronize(dev.st);   // host vectors go out of scope
   if (e != cudaSuccess) return cuda_fail(e, "photometry table upload");
   pa.n_lambda = NL;

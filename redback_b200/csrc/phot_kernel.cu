@@ -67,9 +67,9 @@ struct PhotArgs {
   const double* band_scale;     // [n_bands] dwave / HC_ERG_AA
   const double* band_zp;        // [n_bands]
   const double* band_ref;       // [n_bands] reference flux ('flux' output) or nullptr
-  const double* int_wt;         // [total] wave * trans
-  const int* int_ly;            // [total] first coefficient of the 4 non-zero wavelength B-splines
-  const double* int_wy;         // [total][4] their values
+  const int* epoch_order;       // [E] epochs grouped by band
+  const double* int_rec;        // [total][6] per integration point: the 4 non-zero wavelength B-splines, wave * trans,
+                                //            index of the first of them relative to the band's first coefficient
   double* scratch;              // [gridDim][n_t_max][n_lambda]
   double* out_model;
   double* out_logl;
@@ -122,7 +122,8 @@ __device__ __forceinline__ void load_lu_row(double* __restrict__ dst, const doub
 #define PHOT_PROF_END()                                                                                             \
   if (blockIdx.x == 0 && tid == 0 && n < 3 * (int64_t)gridDim.x)                                                      \
     printf("phot phases [cycles] setup %lld spectra %lld cleanup+lu %lld forward %lld back+lambda %lld (back %lld "     \
-           "lambda %lld store %lld) epochs %lld\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[8], pt_[9], pt_[10], pt_[5]);
+           "lambda %lld store %lld) epochs %lld (basis %lld integrate %lld)\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[8], \
+           pt_[9], pt_[10], pt_[5], pt_[6], pt_[7]);
 #else
 #define PHOT_PROF_BEGIN()
 #define PHOT_PROF(i)
@@ -420,10 +421,11 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
     double* eh = tile + nwarps * kPhotMaxSpan;                 // [chunk][6]: h0..h3, first row (< 0: before t0), band flux
     const int chunk = (phot_tile_elems(NT, NL) - nwarps * kPhotMaxSpan) / 6;
     const double sp = a.sigma_param_s ? a.sigma_param_s[n] : 0.0;
+    PHOT_PROF_ACC(11);
     for (int e0 = 0; e0 < E; e0 += chunk) {
       const int ne = min(chunk, E - e0);
       for (int i = tid; i < ne; i += blockDim.x) {
-        const int e = e0 + i;
+        const int e = a.epoch_order[e0 + i];
         double x = a.epoch_tab[EP_T * E + e];
         double* o = eh + 6 * i;
         if (a.t0_s != nullptr) {                                                  // phase_models.py:33-58
@@ -448,30 +450,67 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
         o[4] = (double)(l - 3);
       }
       __syncthreads();
+      PHOT_PROF_ACC(6);
       for (int i = warp; i < ne; i += nwarps) {
         const double* o = eh + 6 * i;
         if (o[4] < 0.0) continue;
-        const int b = a.band_of_epoch[e0 + i];
+        const int b = a.band_of_epoch[a.epoch_order[e0 + i]];
         const int jlo = a.band_jlo[b], span = a.band_span[b];
         const double h0 = o[0], h1 = o[1], h2 = o[2], h3 = o[3];
         const double* Sx = S + (size_t)((int)o[4]) * NL + jlo;
-        for (int q = lane; q < span; q += 32)
-          dw[q] = h0 * Sx[q] + h1 * Sx[NL + q] + h2 * Sx[2 * NL + q] + h3 * Sx[3 * NL + q];
+        // all loads of the gather are issued before the first use: the scratch is larger than L2 across the grid, so
+        // each of them may be a DRAM round trip
+        constexpr int kGather = kPhotMaxSpan / 32;
+        double g0[kGather], g1[kGather], g2[kGather], g3[kGather];
+#pragma unroll
+        for (int u = 0; u < kGather; ++u) {
+          const int q = min(lane + 32 * u, span - 1);
+#ifdef RB_PHOT_NOGATHER
+          g0[u] = g1[u] = g2[u] = g3[u] = (double)q;
+#else
+          g0[u] = Sx[q];
+          g1[u] = Sx[NL + q];
+          g2[u] = Sx[2 * NL + q];
+          g3[u] = Sx[3 * NL + q];
+#endif
+        }
+#pragma unroll
+        for (int u = 0; u < kGather; ++u) {
+          const int q = lane + 32 * u;
+          if (q < span) dw[q] = h0 * g0[u] + h1 * g1[u] + h2 * g2[u] + h3 * g3[u];
+        }
         __syncwarp();
         double acc = 0.0;
-        for (int w = a.band_off[b] + lane; w < a.band_off[b + 1]; w += 32) {
-          const int q = a.int_ly[w] - jlo;
-          const double* wy = a.int_wy + 4 * (size_t)w;
-          const double f = wy[0] * dw[q] + wy[1] * dw[q + 1] + wy[2] * dw[q + 2] + wy[3] * dw[q + 3];
-          acc += a.int_wt[w] * fabs(f);                                           // sed.py:36-37
+        // four integration points per lane and trip, indices first, then weights, then coefficients: the loads of a
+        // trip overlap instead of forming one dependent chain per point
+        const int w0 = a.band_off[b], w1 = a.band_off[b + 1];
+        constexpr int kPts = 4;
+        for (int wb = w0 + lane; wb < w1; wb += 32 * kPts) {
+          double2 r0[kPts], r1[kPts], r2[kPts];
+#pragma unroll
+          for (int u = 0; u < kPts; ++u) {
+            const int w = wb + 32 * u;
+            const double2* rec = reinterpret_cast<const double2*>(a.int_rec) + 3 * (size_t)min(w, w1 - 1);
+            r0[u] = __ldg(rec);
+            r1[u] = __ldg(rec + 1);
+            r2[u] = __ldg(rec + 2);
+            if (w >= w1) r2[u].x = 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < kPts; ++u) {
+            const double* dq = dw + (int)r2[u].y;
+            const double f = r0[u].x * dq[0] + r0[u].y * dq[1] + r1[u].x * dq[2] + r1[u].y * dq[3];
+            acc += r2[u].x * fabs(f);                                             // sed.py:36-37
+          }
         }
         acc = warp_sum(acc);
         __syncwarp();
         if (lane == 0) eh[6 * i + 5] = acc;
       }
       __syncthreads();
+      PHOT_PROF_ACC(7);
       for (int i = tid; i < ne; i += blockDim.x) {
-        const int e = e0 + i;
+        const int e = a.epoch_order[e0 + i];
         double model_v;
         if (eh[6 * i + 4] < 0.0) {
           model_v = (a.output == RB_OUT_FLUX) ? 0.0 : 1000.0;
