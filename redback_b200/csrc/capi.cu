@@ -1244,7 +1244,8 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
 }
 
 size_t phot_smem_bytes(int NT, int NL) {
-  return sizeof(double) * ((size_t)6 * NT + 7 * (size_t)NL + (size_t)rb::phot_tile_elems(NT, NL) + 40 + rb::kExpTabSize);
+  return sizeof(double) * ((size_t)6 * NT + 11 * (size_t)NL + (size_t)rb::phot_tile_elems(NT, NL) + 40 +
+                          2 * rb::kPhotTileRows * (rb::kPhotThreads / 32) + rb::kExpTabSize);
 }
 
 

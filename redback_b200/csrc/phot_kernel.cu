@@ -131,7 +131,7 @@ __device__ __forceinline__ void load_lu_row(double* __restrict__ dst, const doub
 #define PHOT_PROF_END()
 #endif
 
-__global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
+__global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a) {
   extern __shared__ double psm[];
   const int NT = a.n_t_max, NL = a.n_lambda, E = a.E;
   double* xk = psm;                       // [NT]      time-axis data sites (observer-frame phase, days)
@@ -140,12 +140,40 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
   double* tile = lul + 5 * NL;            // [kPhotTileRows][NL + 1]; holds the row / column factors while the spectra are made
   double* red = tile + phot_tile_elems(NT, NL);    // [40]
   double* bst = red + 40;                 // [NL][2]   time-axis back-substitution state per wavelength column
-  double* tab = bst + 2 * NL;             // [1024]
+  double* hom = bst + 2 * NL;             // [NL][4]   homogeneous solutions of the partitioned wavelength-axis solve
+  double* bnd = hom + 4 * NL;             // [nwarps][kPhotTileRows][2] boundary states of that solve
+  double* tab = bnd + 2 * kPhotTileRows * (kPhotThreads / 32);   // [1024]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
   for (int j = tid; j < NL; j += blockDim.x) load_lu_row(lul + 5 * j, a.lu_lambda + 5 * j);
   double* S = a.scratch + (size_t)blockIdx.x * NT * NL;
+  __syncthreads();
+  // segments of the partitioned wavelength-axis solve (at least 2 columns each) and their homogeneous solutions:
+  // forward  y[j] = -l2 y[j-2] - l1 y[j-1] from (y[m-1], y[m-2]) = (1, 0) and (0, 1) at the segment start m,
+  // backward x[j] = -u2' x[j+2] - u1' x[j+1] from (x[m'+1], x[m'+2]) = (1, 0) and (0, 1) at the segment end m'
+  const int seg_len = max((NL + (int)(blockDim.x >> 5) - 1) / (int)(blockDim.x >> 5), 2);
+  const int nseg = (NL + seg_len - 1) / seg_len;
+  if (tid < 4 * nseg) {
+    const int k = tid >> 2, which = tid & 3;
+    const int j_lo = k * seg_len, j_hi = min(j_lo + seg_len, NL);
+    double p1 = (which & 1) ? 0.0 : 1.0, p2 = (which & 1) ? 1.0 : 0.0;
+    if (which < 2) {
+      for (int j = j_lo; j < j_hi; ++j) {
+        const double y = -lul[5 * j + 0] * p2 - lul[5 * j + 1] * p1;
+        hom[4 * j + which] = y;
+        p2 = p1;
+        p1 = y;
+      }
+    } else {
+      for (int j = j_hi - 1; j >= j_lo; --j) {
+        const double x = -lul[5 * j + 4] * p2 - lul[5 * j + 3] * p1;
+        hom[4 * j + which] = x;
+        p2 = p1;
+        p1 = x;
+      }
+    }
+  }
   __syncthreads();
 
   for (int64_t n = blockIdx.x; n < a.N; n += gridDim.x) {
@@ -303,10 +331,16 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
     // lives in global memory / L2: loads are issued kPhotBatch rows ahead of the recurrence to hide latency.
     for (int j = tid; j < NL; j += blockDim.x) {
       double y1 = 0.0, y2 = 0.0;   // y[i-1], y[i-2]
+      double nb[kPhotBatch];       // the batch after the one being eliminated: its loads overlap the recurrence
+#pragma unroll
+      for (int u = 0; u < kPhotBatch; ++u) nb[u] = (u < G) ? S[u * NL + j] : 0.0;
       for (int i0 = 0; i0 < G; i0 += kPhotBatch) {
         double b[kPhotBatch];
 #pragma unroll
-        for (int u = 0; u < kPhotBatch; ++u) b[u] = (i0 + u < G) ? S[(i0 + u) * NL + j] : 0.0;
+        for (int u = 0; u < kPhotBatch; ++u) {
+          b[u] = nb[u];
+          nb[u] = (i0 + kPhotBatch + u < G) ? S[(i0 + kPhotBatch + u) * NL + j] : 0.0;
+        }
 #pragma unroll
         for (int u = 0; u < kPhotBatch; ++u) {
           const int i = i0 + u;
@@ -332,10 +366,16 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
       const int r0 = max(r1 - kPhotTileRows, 0), rows = r1 - r0;
       for (int j = tid; j < NL; j += blockDim.x) {
         double x1 = bst[2 * j], x2 = bst[2 * j + 1];
+        double nb[kPhotBatch];
+#pragma unroll
+        for (int u = 0; u < kPhotBatch; ++u) nb[u] = (r1 - 1 - u >= r0) ? S[(r1 - 1 - u) * NL + j] : 0.0;
         for (int i0 = r1 - 1; i0 >= r0; i0 -= kPhotBatch) {
           double b[kPhotBatch];
 #pragma unroll
-          for (int u = 0; u < kPhotBatch; ++u) b[u] = (i0 - u >= r0) ? S[(i0 - u) * NL + j] : 0.0;
+          for (int u = 0; u < kPhotBatch; ++u) {
+            b[u] = nb[u];
+            nb[u] = (i0 - kPhotBatch - u >= r0) ? S[(i0 - kPhotBatch - u) * NL + j] : 0.0;
+          }
 #pragma unroll
           for (int u = 0; u < kPhotBatch; ++u) {
             const int i = i0 - u;
@@ -352,12 +392,17 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
       }
       __syncthreads();
       PHOT_PROF_ACC(8);
-      if (tid < rows) {
-        // one thread per row; values and coefficients are loaded a batch ahead of the recurrence (the compiler will
-        // not move the loads across the stores into the same tile on its own)
-        double* row = tile + tid * (NL + 1);
+      // Wavelength-axis solve of the tile, partitioned: each row is cut into one segment per warp (lane = row), every
+      // segment runs the recurrence from a zero state, and the true solution is that particular solution plus the
+      // segment's two homogeneous solutions (hom, set up once per block) scaled by the true state at the segment
+      // boundary.  The boundary states follow from a short serial pass over the segments; the serial chain per tile
+      // drops from 2 NL steps to 2 NL / nwarps.
+      const int seg = warp, row_i = lane;
+      const int j_lo = min(seg * seg_len, NL), j_hi = min(j_lo + seg_len, NL);
+      double* row = tile + row_i * (NL + 1);
+      if (row_i < rows) {                                      // forward elimination, particular solution
         double y1 = 0.0, y2 = 0.0;
-        for (int j0 = 0; j0 < NL; j0 += kPhotBatch) {
+        for (int j0 = j_lo; j0 < j_hi; j0 += kPhotBatch) {
           double b[kPhotBatch], c0[kPhotBatch], c1[kPhotBatch];
 #pragma unroll
           for (int u = 0; u < kPhotBatch; ++u) {
@@ -368,7 +413,7 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
           }
 #pragma unroll
           for (int u = 0; u < kPhotBatch; ++u) {
-            if (j0 + u < NL) {
+            if (j0 + u < j_hi) {
               const double y = (b[u] - c0[u] * y2) - c1[u] * y1;
               row[j0 + u] = y;
               y2 = y1;
@@ -376,19 +421,37 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
             }
           }
         }
+      }
+      __syncthreads();
+      if (warp == 0 && row_i < rows) {                         // true (y[j-1], y[j-2]) at the start of every segment
+        double Y1 = 0.0, Y2 = 0.0;
+        for (int k = 1; k < nseg; ++k) {
+          const int m = k * seg_len;                           // first column of segment k; segment k-1 is [m - seg_len, m)
+          const double e1 = row[m - 1] + hom[4 * (m - 1) + 0] * Y1 + hom[4 * (m - 1) + 1] * Y2;
+          const double e2 = row[m - 2] + hom[4 * (m - 2) + 0] * Y1 + hom[4 * (m - 2) + 1] * Y2;
+          Y1 = e1;
+          Y2 = e2;
+          bnd[(k * kPhotTileRows + row_i) * 2 + 0] = Y1;
+          bnd[(k * kPhotTileRows + row_i) * 2 + 1] = Y2;
+        }
+      }
+      __syncthreads();
+      if (row_i < rows && j_lo < j_hi) {                       // back substitution, particular solution
+        const double Y1 = seg > 0 ? bnd[(seg * kPhotTileRows + row_i) * 2 + 0] : 0.0;
+        const double Y2 = seg > 0 ? bnd[(seg * kPhotTileRows + row_i) * 2 + 1] : 0.0;
         double x1 = 0.0, x2 = 0.0;
-        for (int j0 = NL - 1; j0 >= 0; j0 -= kPhotBatch) {
+        for (int j0 = j_hi - 1; j0 >= j_lo; j0 -= kPhotBatch) {
           double b[kPhotBatch], c3[kPhotBatch], c4[kPhotBatch];
 #pragma unroll
           for (int u = 0; u < kPhotBatch; ++u) {
             const int j = max(j0 - u, 0);
-            b[u] = row[j] * lul[5 * j + 2];
+            b[u] = (row[j] + hom[4 * j + 0] * Y1 + hom[4 * j + 1] * Y2) * lul[5 * j + 2];   // forward fix-up folded in
             c3[u] = lul[5 * j + 3];
             c4[u] = lul[5 * j + 4];
           }
 #pragma unroll
           for (int u = 0; u < kPhotBatch; ++u) {
-            if (j0 - u >= 0) {
+            if (j0 - u >= j_lo) {
               const double x = (b[u] - c4[u] * x2) - c3[u] * x1;
               row[j0 - u] = x;
               x2 = x1;
@@ -398,10 +461,26 @@ __global__ void __launch_bounds__(kPhotThreads) phot_kernel(const PhotArgs a) {
         }
       }
       __syncthreads();
+      if (warp == 0 && row_i < rows) {                         // true (x[j+1], x[j+2]) at the end of every segment
+        double X1 = 0.0, X2 = 0.0;
+        for (int k = nseg - 2; k >= 0; --k) {
+          const int m = (k + 1) * seg_len;                     // first column of segment k + 1
+          const double s1 = row[m] + hom[4 * m + 2] * X1 + hom[4 * m + 3] * X2;
+          const double s2 = (m + 1 < NL) ? row[m + 1] + hom[4 * (m + 1) + 2] * X1 + hom[4 * (m + 1) + 3] * X2 : 0.0;
+          X1 = s1;
+          X2 = s2;
+          bnd[(k * kPhotTileRows + row_i) * 2 + 0] = X1;
+          bnd[(k * kPhotTileRows + row_i) * 2 + 1] = X2;
+        }
+      }
+      __syncthreads();
       PHOT_PROF_ACC(9);
-      for (int idx = tid; idx < rows * NL; idx += blockDim.x) {
+      for (int idx = tid; idx < rows * NL; idx += blockDim.x) {   // backward fix-up folded into the store
         const int r = idx / NL, j = idx - r * NL;
-        S[(r0 + r) * NL + j] = tile[r * (NL + 1) + j];
+        const int k = j / seg_len;
+        double v = tile[r * (NL + 1) + j];
+        if (k < nseg - 1) v += hom[4 * j + 2] * bnd[(k * kPhotTileRows + r) * 2 + 0] + hom[4 * j + 3] * bnd[(k * kPhotTileRows + r) * 2 + 1];
+        S[(r0 + r) * NL + j] = v;
       }
       __syncthreads();
       PHOT_PROF_ACC(10);
