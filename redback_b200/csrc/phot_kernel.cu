@@ -362,13 +362,21 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
     // each tile of kPhotTileRows finished rows goes straight into shared memory, is solved along wavelength there and
     // is written to the scratch once (one read and one write pass fewer than solving the two axes separately)
     PHOT_PROF_ACC(11);
+    // with one column per thread the first batch of the next tile is loaded before the wavelength-axis solve of the
+    // current one, so no tile starts with an exposed round trip to the scratch
+    const bool one_col = NL <= (int)blockDim.x;
+    double nbx[kPhotBatch];
+#pragma unroll
+    for (int u = 0; u < kPhotBatch; ++u)
+      nbx[u] = (one_col && tid < NL && G - 1 - u >= max(G - kPhotTileRows, 0)) ? S[(G - 1 - u) * NL + tid] : 0.0;
     for (int r1 = G; r1 > 0; r1 -= kPhotTileRows) {
       const int r0 = max(r1 - kPhotTileRows, 0), rows = r1 - r0;
       for (int j = tid; j < NL; j += blockDim.x) {
         double x1 = bst[2 * j], x2 = bst[2 * j + 1];
         double nb[kPhotBatch];
 #pragma unroll
-        for (int u = 0; u < kPhotBatch; ++u) nb[u] = (r1 - 1 - u >= r0) ? S[(r1 - 1 - u) * NL + j] : 0.0;
+        for (int u = 0; u < kPhotBatch; ++u)
+          nb[u] = one_col ? nbx[u] : ((r1 - 1 - u >= r0) ? S[(r1 - 1 - u) * NL + j] : 0.0);
         for (int i0 = r1 - 1; i0 >= r0; i0 -= kPhotBatch) {
           double b[kPhotBatch];
 #pragma unroll
@@ -389,6 +397,11 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
         }
         bst[2 * j] = x1;
         bst[2 * j + 1] = x2;
+        if (one_col) {
+          const int q0 = max(r0 - kPhotTileRows, 0);
+#pragma unroll
+          for (int u = 0; u < kPhotBatch; ++u) nbx[u] = (r0 - 1 - u >= q0) ? S[(r0 - 1 - u) * NL + j] : 0.0;
+        }
       }
       __syncthreads();
       PHOT_PROF_ACC(8);
@@ -475,12 +488,13 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
       }
       __syncthreads();
       PHOT_PROF_ACC(9);
-      for (int idx = tid; idx < rows * NL; idx += blockDim.x) {   // backward fix-up folded into the store
-        const int r = idx / NL, j = idx - r * NL;
+      for (int j = tid; j < NL; j += blockDim.x) {                // backward fix-up folded into the store
         const int k = j / seg_len;
-        double v = tile[r * (NL + 1) + j];
-        if (k < nseg - 1) v += hom[4 * j + 2] * bnd[(k * kPhotTileRows + r) * 2 + 0] + hom[4 * j + 3] * bnd[(k * kPhotTileRows + r) * 2 + 1];
-        S[(r0 + r) * NL + j] = v;
+        const double hA = (k < nseg - 1) ? hom[4 * j + 2] : 0.0, hB = (k < nseg - 1) ? hom[4 * j + 3] : 0.0;
+        const double* bk = bnd + (min(k, nseg - 2 >= 0 ? nseg - 2 : 0) * kPhotTileRows) * 2;
+#pragma unroll 4
+        for (int r = 0; r < rows; ++r)
+          S[(r0 + r) * NL + j] = tile[r * (NL + 1) + j] + hA * bk[2 * r] + hB * bk[2 * r + 1];
       }
       __syncthreads();
       PHOT_PROF_ACC(10);
