@@ -24,13 +24,14 @@ namespace rb {
 constexpr int kPhotThreads = 256;
 constexpr int kPhotMaxSpan = 96;     // max B-spline coefficients (along wavelength) overlapped by one band
 constexpr int kPhotTileRows = 32;    // rows per shared-memory tile in the wavelength-axis solve
+constexpr int kEpRec = 10;           // doubles per epoch in the hand-over array of the epoch phase
 constexpr int kPhotBatch = 8;        // rows of the scratch tile loaded ahead of the time-axis recurrence
 
 // shared-memory doubles of the tile region: a tile of rows for the wavelength-axis solve, or the 4 per-epoch and 3
 // per-wavelength factor arrays of the spectra phase, or the per-warp coefficient buffers and per-epoch hand-over arrays
 // of the epoch phase (at least 128 epochs per chunk)
 __host__ __device__ inline int phot_tile_elems(int NT, int NL) {
-  const int t = kPhotTileRows * (NL + 1), f = 4 * NT + 3 * NL, e = (kPhotThreads / 32) * kPhotMaxSpan + 6 * 128;
+  const int t = kPhotTileRows * (NL + 1), f = 4 * NT + 3 * NL, e = (kPhotThreads / 32) * kPhotMaxSpan + kEpRec * 128;
   return max(max(t, f), e);
 }
 
@@ -511,8 +512,9 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
     double logl_part = 0.0;
     const int nwarps = (int)(blockDim.x >> 5);
     double* dw = tile + warp * kPhotMaxSpan;
-    double* eh = tile + nwarps * kPhotMaxSpan;                 // [chunk][6]: h0..h3, first row (< 0: before t0), band flux
-    const int chunk = (phot_tile_elems(NT, NL) - nwarps * kPhotMaxSpan) / 6;
+    double* eh = tile + nwarps * kPhotMaxSpan;                 // [chunk][kEpRec]: h0..h3, first row (< 0: before t0), band
+                                                               // flux, then the band's jlo, span, first and last point
+    const int chunk = (phot_tile_elems(NT, NL) - nwarps * kPhotMaxSpan) / kEpRec;
     const double sp = a.sigma_param_s ? a.sigma_param_s[n] : 0.0;
     PHOT_PROF_ACC(11);
     for (int e0 = 0; e0 < E; e0 += chunk) {
@@ -520,10 +522,15 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
       for (int i = tid; i < ne; i += blockDim.x) {
         const int e = a.epoch_order[e0 + i];
         double x = a.epoch_tab[EP_T * E + e];
-        double* o = eh + 6 * i;
+        double* o = eh + kEpRec * i;
+        const int b = a.band_of_epoch[e];                      // looked up here so that the warps of sub-phase b do not
+        o[6] = (double)a.band_jlo[b];                          // start each epoch with a chain of dependent global loads
+        o[7] = (double)a.band_span[b];
+        o[8] = (double)a.band_off[b];
+        o[9] = (double)a.band_off[b + 1];
         if (a.t0_s != nullptr) {                                                  // phase_models.py:33-58
           x -= a.t0_s[n];
-          if (x < 0.0) { o[4] = -1.0; continue; }
+          if (x < 0.0) { o[0] = o[1] = o[2] = o[3] = 0.0; o[4] = -1.0; continue; }
         }
         if (x < xk[0]) x = xk[0];                                                 // fpbisp clamps to [tb, te]
         if (x > xk[G - 1]) x = xk[G - 1];
@@ -544,17 +551,15 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
       }
       __syncthreads();
       PHOT_PROF_ACC(6);
-      for (int i = warp; i < ne; i += nwarps) {
-        const double* o = eh + 6 * i;
-        if (o[4] < 0.0) continue;
-        const int b = a.band_of_epoch[a.epoch_order[e0 + i]];
-        const int jlo = a.band_jlo[b], span = a.band_span[b];
-        const double h0 = o[0], h1 = o[1], h2 = o[2], h3 = o[3];
-        const double* Sx = S + (size_t)((int)o[4]) * NL + jlo;
-        // all loads of the gather are issued before the first use: the scratch is larger than L2 across the grid, so
-        // each of them may be a DRAM round trip
-        constexpr int kGather = kPhotMaxSpan / 32;
-        double g0[kGather], g1[kGather], g2[kGather], g3[kGather];
+      // The scratch is larger than L2 across the grid, so every gather may be a DRAM round trip: all its loads are
+      // issued together, and those of the warp's next epoch before the current one is integrated.
+      constexpr int kGather = kPhotMaxSpan / 32;
+      double g0[kGather], g1[kGather], g2[kGather], g3[kGather];
+      auto gather = [&](int i) {
+        if (i >= ne) return;
+        const double* o = eh + kEpRec * i;
+        const int span = (int)o[7];
+        const double* Sx = S + (size_t)max((int)o[4], 0) * NL + (int)o[6];
 #pragma unroll
         for (int u = 0; u < kGather; ++u) {
           const int q = min(lane + 32 * u, span - 1);
@@ -567,16 +572,24 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
           g3[u] = Sx[3 * NL + q];
 #endif
         }
+      };
+      gather(warp);
+      for (int i = warp; i < ne; i += nwarps) {
+        const double* o = eh + kEpRec * i;
+        const int span = (int)o[7];
+        const double h0 = o[0], h1 = o[1], h2 = o[2], h3 = o[3];
 #pragma unroll
         for (int u = 0; u < kGather; ++u) {
           const int q = lane + 32 * u;
           if (q < span) dw[q] = h0 * g0[u] + h1 * g1[u] + h2 * g2[u] + h3 * g3[u];
         }
+        gather(i + nwarps);
+        if (o[4] < 0.0) continue;                              // before t0: no spectrum to integrate
         __syncwarp();
         double acc = 0.0;
         // four integration points per lane and trip, indices first, then weights, then coefficients: the loads of a
         // trip overlap instead of forming one dependent chain per point
-        const int w0 = a.band_off[b], w1 = a.band_off[b + 1];
+        const int w0 = (int)o[8], w1 = (int)o[9];
         constexpr int kPts = 4;
         for (int wb = w0 + lane; wb < w1; wb += 32 * kPts) {
           double2 r0[kPts], r1[kPts], r2[kPts];
@@ -598,18 +611,18 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
         }
         acc = warp_sum(acc);
         __syncwarp();
-        if (lane == 0) eh[6 * i + 5] = acc;
+        if (lane == 0) eh[kEpRec * i + 5] = acc;
       }
       __syncthreads();
       PHOT_PROF_ACC(7);
       for (int i = tid; i < ne; i += blockDim.x) {
         const int e = a.epoch_order[e0 + i];
         double model_v;
-        if (eh[6 * i + 4] < 0.0) {
+        if (eh[kEpRec * i + 4] < 0.0) {
           model_v = (a.output == RB_OUT_FLUX) ? 0.0 : 1000.0;
         } else {
           const int b = a.band_of_epoch[e];
-          const double bandflux = eh[6 * i + 5] * a.band_scale[b];
+          const double bandflux = eh[kEpRec * i + 5] * a.band_scale[b];
           model_v = -2.5 * log10(bandflux / a.band_zp[b]);                        // sed.py:114
           if (a.output == RB_OUT_FLUX) model_v = pow(10.0, model_v / (-2.5)) * a.band_ref[b];   // utils.py:716-718
         }
