@@ -428,6 +428,14 @@ int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* phot, int64
                        const double* params, const double* t_obs, const double* dl_cm, const double* y,
                        const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
                        void* stream);
+/* Magnitude branch of two_component_kilonova_model / three_component_kilonova_model (kilonova_models.py:1166-1211,
+ * 1277-1323): the blackbody spectra of n_components one-component models on the shared time grid are summed before
+ * the spline / band integration.  params is [n_components][RB_KN_NPARAM][N] (each component carries the redshift
+ * row); cfg->model must be RB_KN_ONE_COMPONENT, cfg->grid_t_max the model's grid end. */
+int rb_kn_multi_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* phot, int n_components, int64_t N,
+                             int64_t E, const double* params, const double* t_obs, const double* dl_cm,
+                             const double* y, const double* sigma, const double* sigma_param, double* out_model,
+                             double* out_logl, void* stream);
 /* Magnitude branch of the mergernova models (_processing_other_formats, magnetar_driven_ejecta_models.py:198-238,
  * use_relativistic_blackbody = True): spectra on (get_optimal_time_array(1e-4, 1e8, 500) x lambda_array), phases
  * time_temp (1+z) / 86400 d.  phot->tgrid is not used (the library builds the grid itself). */

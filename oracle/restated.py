@@ -1770,6 +1770,29 @@ def kn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None,
     return bandmag_from_spectra(time_obs, time_observer_frame / day_to_s, spectra, lam, bands, bandpasses)
 
 
+def multi_component_kn_magnitude(time, redshift, components, *, bands, bandpasses, dense_resolution, grid_t_max,
+                                 lambda_array=None, dl=None):
+    """Magnitude branch of two_component_kilonova_model (kilonova_models.py:1277-1323: grid end 86400*6 s, 500
+    points) and three_component_kilonova_model (:1166-1211: 7e6 s, 300 points): blackbody_to_spectrum of every
+    component (sed.py:937-968) summed on the shared grid, then get_correct_output_format_from_spectra.
+    components: [(mej, vej, kappa, temperature_floor), ...]."""
+    time_obs = np.asarray(time, dtype=float)
+    lam = np.geomspace(100, 60000, 200) if lambda_array is None else np.asarray(lambda_array, dtype=float)
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    time_temp = get_optimal_time_array(1e-2, grid_t_max, dense_resolution,
+                                       user_times=time_obs * day_to_s / (1. + redshift))
+    time_observer_frame = time_temp * (1. + redshift)
+    frequency, _t = calc_kcorrected_properties(lambda_to_nu(lam), redshift, time_observer_frame)
+    full_spec = np.zeros((len(time_temp), len(lam)))
+    with np.errstate(all="ignore"):
+        for mej, vej, kappa, tfloor in components:
+            _, temp, rad = one_component_kilonova_internal(time_temp, mej, vej, kappa, tfloor)
+            fd = blackbody_to_flux_density(temp, rad, dl, frequency[:, None]).T
+            full_spec += flux_density_to_spectrum(fd, redshift, lam)
+    return bandmag_from_spectra(time_obs, time_observer_frame / day_to_s, full_spec, lam, bands, bandpasses)
+
+
 # --------------------------------------------------------------------------------------------------
 # simulate_transients.SimulateTransientWithCadence noise model (simulate_transients.py:457-527)
 # --------------------------------------------------------------------------------------------------

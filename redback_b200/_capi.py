@@ -136,6 +136,8 @@ EXPORTS = {
     "rb_mk_eval_f64_host": (C.c_int, [C.POINTER(MkConfig), C.c_int64, C.c_int64] + [_dp] * 9),
     "rb_sn_mag_eval_f64": (C.c_int, [C.POINTER(SnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_kn_mag_eval_f64": (C.c_int, [C.POINTER(KnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
+    "rb_kn_multi_mag_eval_f64": (C.c_int, [C.POINTER(KnConfig), C.c_void_p, C.c_int, C.c_int64, C.c_int64] + [_dp] * 8
+                                 + [C.c_void_p]),
     "rb_mn_mag_eval_f64": (C.c_int, [C.POINTER(MnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_mk_mag_eval_f64": (C.c_int, [C.POINTER(MkConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_optical_noise_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 4 + [C.c_double, C.c_int] + [_dp] * 6

@@ -1243,8 +1243,8 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
   return RB_OK;
 }
 
-size_t phot_smem_bytes(int NT, int NL) {
-  return sizeof(double) * ((size_t)6 * NT + 11 * (size_t)NL + (size_t)rb::phot_tile_elems(NT, NL) + 40 +
+size_t phot_smem_bytes(int NT, int NL, int n_comp) {
+  return sizeof(double) * ((size_t)6 * NT + 11 * (size_t)NL + (size_t)rb::phot_tile_elems(NT, NL, n_comp) + 40 +
                           2 * rb::kPhotTileRows * (rb::kPhotThreads / 32) + rb::kExpTabSize);
 }
 
@@ -1261,6 +1261,8 @@ struct PhotJob {
   const double* lu_grid;           // host [NT]: common time axis up to a per-sample scale -> one collocation LU; or
                                    // nullptr: every sample has its own grid (phot_kernel factorises per sample)
   bool with_len;                   // per-sample grid lengths
+  int n_comp = 1;                  // blackbody components summed per sample; component c's grids start at
+                                   // d_grid + c * (chunk capacity) * 4 * NT
   int sed = rb::PH_SED_BLACKBODY;
   double cutoff_wavelength = 3000.0, absorption_index = 1.0;
   double line_wavelength = 0, line_width = 0, line_time = 0, line_duration = 0, line_amplitude = 0;
@@ -1282,7 +1284,8 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(phot_kernel)");
   const int NT = j.NT, NL = j.phot->n_lambda;
   const int64_t N = j.N, E = j.E;
-  const size_t psmem = phot_smem_bytes(NT, NL);
+  const int n_comp = j.n_comp > 0 ? j.n_comp : 1;
+  const size_t psmem = phot_smem_bytes(NT, NL, n_comp);
   if (psmem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, std::string(j.who) + ": grids exceed shared memory");
   PhotDevice pd;
   pd.st = st;
@@ -1311,7 +1314,7 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   const int64_t nc_max = std::min<int64_t>(chunk_max, N);
   double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_scratch = nullptr;
   int* d_len = nullptr;
-  ce = cudaMallocAsync(&d_grid, (size_t)nc_max * 4 * NT * sizeof(double), st);
+  ce = cudaMallocAsync(&d_grid, (size_t)n_comp * nc_max * 4 * NT * sizeof(double), st);
   if (ce == cudaSuccess) ce = cudaMallocAsync(&d_opz, (size_t)nc_max * sizeof(double), st);
   if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dl, (size_t)nc_max * sizeof(double), st);
   if (ce == cudaSuccess && j.with_len) ce = cudaMallocAsync(&d_len, (size_t)nc_max * sizeof(int), st);
@@ -1338,6 +1341,8 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
     pa.sigma_mode = j.sigma_mode;
     pa.want_logl = j.y ? 1 : 0;
     pa.common_time_lu = j.lu_grid != nullptr ? 1 : 0;
+    pa.n_comp = n_comp;
+    pa.grid_comp_stride = (int64_t)nc_max * 4 * NT;
     pa.grid = d_grid;
     pa.grid_len = d_len;
     pa.opz = d_opz;
@@ -1472,13 +1477,16 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
   });
 }
 
-extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
-                                  const double* params, const double* t_obs, const double* dl_cm, const double* y,
-                                  const double* sigma, const double* sigma_param, double* out_model,
-                                  double* out_logl, void* stream) {
+static int kn_mag_eval(const rb_kn_config* cfg, const rb_photometry* phot, int n_comp, int64_t N, int64_t E,
+                       const double* params, const double* t_obs, const double* dl_cm, const double* y,
+                       const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
+                       void* stream) {
   static const double dummy = 0.0;
   int rc = kn_check(cfg, N, E, params, t_obs, &dummy, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
+  if (n_comp < 1 || n_comp > 4) return fail(RB_ERR_INVALID, "rb_kn_multi_mag_eval: 1..4 components");
+  if (n_comp > 1 && cfg->model != RB_KN_ONE_COMPONENT)
+    return fail(RB_ERR_UNSUPPORTED, "rb_kn_multi_mag_eval: components are one-component kilonova models");
   rc = phot_check(phot, E, false);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
@@ -1504,7 +1512,7 @@ extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* 
   launch_counter()->fetch_add(1);
   if (!(h_mm[0] > 0.0)) return fail(RB_ERR_INVALID, "rb_kn_mag_eval: epochs must be strictly positive (days)");
   const int NT = cfg->dense_resolution;
-  const int64_t nc_max = std::min<int64_t>(32768, N);
+  const int64_t nc_max = std::min<int64_t>(32768, N);   // = run_photometry's chunk capacity
   RB_CUDA(b_ep1.alloc((size_t)rb::kEpochCols, st));
   RB_CUDA(b_scal.alloc((size_t)nc_max * rb::kKnScalars, st));
   rb_kn_config kcfg = *cfg;
@@ -1520,31 +1528,49 @@ extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* 
   j.phot = phot; j.N = N; j.E = E; j.NT = NT;
   j.lu_grid = nullptr;             // the grid depends on the sample's redshift
   j.with_len = true;
+  j.n_comp = n_comp;
   j.sigma_mode = cfg->sigma_mode; j.upper_limits = cfg->upper_limits;
   j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param; j.t0 = nullptr;
   j.out_model = out_model; j.out_logl = out_logl;
   return run_photometry(j, st, sms, [&](int64_t n0, int64_t nc, double* d_grid, double* d_opz, double* d_dl, int* d_len) {
-    rb::KnArgs a{};
-    a.cfg = *cfg;
-    a.N = nc;
-    a.E = 1;                       // the kernel only stages the epoch table; unused in grid mode
-    a.params = params + n0;
-    a.param_stride = N;
-    a.dl_cm = dl_cm ? dl_cm + n0 : nullptr;
-    a.epoch_tab = b_ep1.p;
-    a.scalars = b_scal.p;
-    a.tmin_obs = h_mm[0];
-    a.tmax_obs = h_mm[1];
-    a.grid_mode = 1;
-    a.grid_out = d_grid;
-    a.grid_len = d_len;
-    a.opz_out = d_opz;
-    a.dl_out = d_dl;
-    rb::kn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
-    kn_kern<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_kn * 4), kn_threads, ksmem, st>>>(a);
-    launch_counter()->fetch_add(2);
+    for (int c = 0; c < n_comp; ++c) {   // the components share redshift, grid and epochs; only (T, R) differ
+      rb::KnArgs a{};
+      a.cfg = *cfg;
+      a.N = nc;
+      a.E = 1;                       // the kernel only stages the epoch table; unused in grid mode
+      a.params = params + (size_t)c * RB_KN_NPARAM * N + n0;
+      a.param_stride = N;
+      a.dl_cm = dl_cm ? dl_cm + n0 : nullptr;
+      a.epoch_tab = b_ep1.p;
+      a.scalars = b_scal.p;
+      a.tmin_obs = h_mm[0];
+      a.tmax_obs = h_mm[1];
+      a.grid_mode = 1;
+      a.grid_out = d_grid + (size_t)c * nc_max * 4 * NT;
+      a.grid_len = d_len;
+      a.opz_out = d_opz;
+      a.dl_out = d_dl;
+      rb::kn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
+      kn_kern<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_kn * 4), kn_threads, ksmem, st>>>(a);
+      launch_counter()->fetch_add(2);
+    }
     return (int)RB_OK;
   });
+}
+
+extern "C" int rb_kn_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
+                                  const double* params, const double* t_obs, const double* dl_cm, const double* y,
+                                  const double* sigma, const double* sigma_param, double* out_model,
+                                  double* out_logl, void* stream) {
+  return kn_mag_eval(cfg, phot, 1, N, E, params, t_obs, dl_cm, y, sigma, sigma_param, out_model, out_logl, stream);
+}
+
+extern "C" int rb_kn_multi_mag_eval_f64(const rb_kn_config* cfg, const rb_photometry* phot, int n_components, int64_t N,
+                                        int64_t E, const double* params, const double* t_obs, const double* dl_cm,
+                                        const double* y, const double* sigma, const double* sigma_param,
+                                        double* out_model, double* out_logl, void* stream) {
+  return kn_mag_eval(cfg, phot, n_components, N, E, params, t_obs, dl_cm, y, sigma, sigma_param, out_model, out_logl,
+                     stream);
 }
 
 extern "C" int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,

@@ -27,11 +27,12 @@ constexpr int kPhotTileRows = 32;    // rows per shared-memory tile in the wavel
 constexpr int kEpRec = 10;           // doubles per epoch in the hand-over array of the epoch phase
 constexpr int kPhotBatch = 8;        // rows of the scratch tile loaded ahead of the time-axis recurrence
 
-// shared-memory doubles of the tile region: a tile of rows for the wavelength-axis solve, or the 4 per-epoch and 3
+// shared-memory doubles of the tile region: a tile of rows for the wavelength-axis solve, or the 2 (per component) + 2
+// per-epoch and 3
 // per-wavelength factor arrays of the spectra phase, or the per-warp coefficient buffers and per-epoch hand-over arrays
 // of the epoch phase (at least 128 epochs per chunk)
-__host__ __device__ inline int phot_tile_elems(int NT, int NL) {
-  const int t = kPhotTileRows * (NL + 1), f = 4 * NT + 3 * NL, e = (kPhotThreads / 32) * kPhotMaxSpan + kEpRec * 128;
+__host__ __device__ inline int phot_tile_elems(int NT, int NL, int n_comp) {
+  const int t = kPhotTileRows * (NL + 1), f = (2 * n_comp + 2) * NT + 3 * NL, e = (kPhotThreads / 32) * kPhotMaxSpan + kEpRec * 128;
   return max(max(t, f), e);
 }
 
@@ -49,6 +50,8 @@ struct PhotArgs {
   int sigma_mode;
   int want_logl;
   int common_time_lu;     // 1: time-axis LU supplied (grid identical up to scaling for all samples)
+  int n_comp;             // blackbody components summed into one spectrum (multi-component kilonovae), else 1
+  int64_t grid_comp_stride;   // doubles between the model grids of consecutive components
   double cutoff_wavelength, absorption_index;
   double line_wavelength, line_width, line_time, line_duration, line_amplitude;   // sed.Line (type_1a)
   const double* grid;     // [N][kPhotGridCols][n_t_max]   (written by the model kernels in grid mode)
@@ -134,12 +137,12 @@ __device__ __forceinline__ void load_lu_row(double* __restrict__ dst, const doub
 
 __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a) {
   extern __shared__ double psm[];
-  const int NT = a.n_t_max, NL = a.n_lambda, E = a.E;
+  const int NT = a.n_t_max, NL = a.n_lambda, E = a.E, NC = a.n_comp;
   double* xk = psm;                       // [NT]      time-axis data sites (observer-frame phase, days)
   double* lut = xk + NT;                  // [NT][5]   time-axis banded LU
   double* lul = lut + 5 * NT;             // [NL][5]   wavelength-axis banded LU
   double* tile = lul + 5 * NL;            // [kPhotTileRows][NL + 1]; holds the row / column factors while the spectra are made
-  double* red = tile + phot_tile_elems(NT, NL);    // [40]
+  double* red = tile + phot_tile_elems(NT, NL, NC);    // [40]
   double* bst = red + 40;                 // [NL][2]   time-axis back-substitution state per wavelength column
   double* hom = bst + 2 * NL;             // [NL][4]   homogeneous solutions of the partitioned wavelength-axis solve
   double* bnd = hom + 4 * NL;             // [nwarps][kPhotTileRows][2] boundary states of that solve
@@ -190,9 +193,9 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
     //   v[k][j] = colB[j] * rowB[k] / expm1(colA[j] * rowA[k])   (+ the sed.Line terms for type Ia),
     // so the divisions, powers and unit conversions are done once per row / column (they live in the tile region,
     // which is free until the solves) and a sample costs one expm1, one division and three multiplies.
-    double* rowA = tile;             // [NT]  1 / (k_B T)  or 1 / T
-    double* rowB = rowA + NT;        // [NT]  R^2          or R^2 * cutoff normalisation
-    double* rowC = rowB + NT;        // [NT]  1 - line amplitude
+    double* rowA = tile;             // [NC][NT]  1 / (k_B T)  or 1 / T
+    double* rowB = rowA + NC * NT;   // [NC][NT]  R^2          or R^2 * cutoff normalisation
+    double* rowC = rowB + NC * NT;   // [NT]  1 - line amplitude
     double* rowD = rowC + NT;        // [NT]  scaled line amplitude
     double* colA = rowD + NT;        // [NL]  h nu         or hc / (k_B lambda)
     double* colB = colA + NL;        // [NL]  everything else that depends on wavelength only
@@ -204,6 +207,11 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
       if (a.sed == PH_SED_BLACKBODY) {
         rowA[k] = 1.0 / (kKB * T);
         rowB[k] = R * R;
+        for (int c = 1; c < NC; ++c) {                         // kilonova_models.py:1150-1175, 1278-1300
+          const double Tc = gT[c * a.grid_comp_stride + k], Rc = gR[c * a.grid_comp_stride + k];
+          rowA[c * NT + k] = 1.0 / (kKB * Tc);
+          rowB[c * NT + k] = Rc * Rc;
+        }
       } else {
         rowA[k] = 1.0 / T;
         rowB[k] = (R * R) * cutoff_norm(gL[k], R, T, lam_c, a.absorption_index);
@@ -253,6 +261,7 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
       const int dk = (int)blockDim.x / NL, dj = (int)blockDim.x - dk * NL;
       for (; k < G; k += dk) {
         double v = colB[j] * rowB[k] / expm1_fast(colA[j] * rowA[k], tab);
+        for (int c = 1; c < NC; ++c) v += colB[j] * rowB[c * NT + k] / expm1_fast(colA[j] * rowA[c * NT + k], tab);
         if (line) v = v * rowC[k] + rowD[k] * colC[j];
         S[k * NL + j] = v;
         if (isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
@@ -514,7 +523,7 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
     double* dw = tile + warp * kPhotMaxSpan;
     double* eh = tile + nwarps * kPhotMaxSpan;                 // [chunk][kEpRec]: h0..h3, first row (< 0: before t0), band
                                                                // flux, then the band's jlo, span, first and last point
-    const int chunk = (phot_tile_elems(NT, NL) - nwarps * kPhotMaxSpan) / kEpRec;
+    const int chunk = (phot_tile_elems(NT, NL, NC) - nwarps * kPhotMaxSpan) / kEpRec;
     const double sp = a.sigma_param_s ? a.sigma_param_s[n] : 0.0;
     PHOT_PROF_ACC(11);
     for (int e0 = 0; e0 < E; e0 += chunk) {

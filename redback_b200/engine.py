@@ -343,6 +343,26 @@ class KilonovaMagPath(KilonovaPath):
         return self._launch_mag(_capi.lib().rb_kn_mag_eval_f64, *args)
 
 
+class KilonovaMultiMagPath(KilonovaMagPath):
+    """Magnitude / bandpass-flux branch of two_component_kilonova_model / three_component_kilonova_model
+    (kilonova_models.py:1166-1211, 1277-1323): the components' blackbody spectra are summed on the shared grid.
+    Parameter rows: the one-component rows once per component, named `<row>_<component>` (every `redshift_<c>` row
+    holds the same redshift)."""
+
+    def __init__(self, n_components, time, bands, grid_t_max, **kwargs):
+        super().__init__(_capi.KN_ONE_COMPONENT, time, bands, **kwargs)
+        self.cfg.grid_t_max = float(grid_t_max)
+        self.n_components = int(n_components)
+        self.NPARAM = self.n_components * _capi.KN_NPARAM
+        self.ROWS = {f"{k}_{c + 1}": c * _capi.KN_NPARAM + r for c in range(self.n_components)
+                     for k, r in _capi.KN_ROWS.items() if k != "beta"}
+
+    def _launch(self, N, params_dev, dl, y, sigma, sigma_param, model, logl, stream):
+        return _capi.lib().rb_kn_multi_mag_eval_f64(
+            C.byref(self.cfg), C.addressof(self.phot), self.n_components, N, self.E, _ptr(params_dev), _ptr(self.time),
+            _ptr(dl), _ptr(y), _ptr(sigma), _ptr(sigma_param), _ptr(model), _ptr(logl), C.c_void_p(stream))
+
+
 class AfterglowPath(_FusedPath):
     """redback-native tophat / Gaussian afterglow -> Gaussian log L
     (redback/transient_models/afterglow_models/base_models.py:43-640, 885-1010)."""

@@ -3,7 +3,7 @@
 Same signatures as the reference plus `params_batch` (see supernova_models.py)."""
 from . import _capi
 from ._fused import FusedSpec, cosmology_from_kwargs, output_mode, run
-from .engine import KilonovaMagPath, KilonovaPath
+from .engine import KilonovaMagPath, KilonovaMultiMagPath, KilonovaPath
 
 
 def _spec(name, model, needed):
@@ -55,14 +55,27 @@ def _multi_component(name, time, redshift, components, params_batch, kwargs, den
     from ._fused import collect, dl_from_kwargs, finish
     if kwargs.get("output_format") is None:
         raise KeyError("output_format")
-    if kwargs["output_format"] != "flux_density":
-        raise NotImplementedError(f"{name}: output_format='{kwargs['output_format']}' is not fused on device")
+    mode = output_mode(kwargs, name)
     names = ["redshift"] + [f"{k}_{c}" for c in range(1, len(components) + 1)
                             for k in ("mej", "vej", "kappa", "temperature_floor")]
     named = dict(redshift=redshift)
     for c, comp in enumerate(components, start=1):
         named.update({f"{k}_{c}": v for k, v in zip(("mej", "vej", "temperature_floor", "kappa"), comp)})
     params, N = collect(named, kwargs, params_batch, names)
+    if mode != "flux_density":
+        # kilonova_models.py:1166-1211, 1277-1323: the components' spectra are summed before the band integration
+        path = KilonovaMultiMagPath(len(components), time, kwargs["bands"], grid_t_max, output=mode,
+                                    lambda_array=kwargs.get("lambda_array"),
+                                    dense_resolution=kwargs.get("dense_resolution", dense_resolution),
+                                    cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"))
+        rows = {}
+        for c in range(1, len(components) + 1):
+            rows[f"redshift_{c}"] = params["redshift"]
+            for k in ("mej", "vej", "kappa", "temperature_floor"):
+                rows[f"{k}_{c}"] = params[f"{k}_{c}"]
+        n = N if N is not None else 1
+        model, _ = path.evaluate(path.pack(rows, n), dl=dl_from_kwargs(kwargs, path, N))
+        return finish(model, N, kwargs)
     path = KilonovaPath(_capi.KN_ONE_COMPONENT, time, frequency=kwargs.get("frequency"),
                         dense_resolution=kwargs.get("dense_resolution", dense_resolution),
                         cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"), grid_t_max=grid_t_max)
@@ -79,8 +92,8 @@ def _multi_component(name, time, redshift, components, params_batch, kwargs, den
 def two_component_kilonova_model(time, redshift=None, mej_1=None, vej_1=None, temperature_floor_1=None, kappa_1=None,
                                  mej_2=None, vej_2=None, temperature_floor_2=None, kappa_2=None, params_batch=None,
                                  **kwargs):
-    """redback kilonova_models.two_component_kilonova_model (:1214-1260), flux_density; grid end 86400*6 s, 500 points
-    by default.  (Not fused with the likelihood: log_likelihood_batch reduces the summed model matrix.)"""
+    """redback kilonova_models.two_component_kilonova_model (:1214-1323), flux_density and magnitude / flux; grid end
+    86400*6 s, 500 points by default.  (Not fused with the likelihood: log_likelihood_batch reduces the summed model matrix.)"""
     comps = [(mej_1, vej_1, temperature_floor_1, kappa_1), (mej_2, vej_2, temperature_floor_2, kappa_2)]
     return _multi_component("two_component_kilonova_model", time, redshift, comps, params_batch, kwargs, 500,
                             86400 * 6)
@@ -89,7 +102,8 @@ def two_component_kilonova_model(time, redshift=None, mej_1=None, vej_1=None, te
 def three_component_kilonova_model(time, redshift=None, mej_1=None, vej_1=None, temperature_floor_1=None, kappa_1=None,
                                    mej_2=None, vej_2=None, temperature_floor_2=None, kappa_2=None, mej_3=None,
                                    vej_3=None, temperature_floor_3=None, kappa_3=None, params_batch=None, **kwargs):
-    """redback kilonova_models.three_component_kilonova_model (:1113-1165), flux_density; 300 grid points by default."""
+    """redback kilonova_models.three_component_kilonova_model (:1113-1211), flux_density and magnitude / flux; 300 grid
+    points by default."""
     comps = [(mej_1, vej_1, temperature_floor_1, kappa_1), (mej_2, vej_2, temperature_floor_2, kappa_2),
              (mej_3, vej_3, temperature_floor_3, kappa_3)]
     return _multi_component("three_component_kilonova_model", time, redshift, comps, params_batch, kwargs, 300, 7e6)

@@ -160,6 +160,44 @@ def test_kilonova_magnitudes_config3(rb, obands):
         np.testing.assert_allclose(outf[i], r.bandpass_magnitude_to_flux(ref, ref_flux), rtol=1e-7)
 
 
+def test_multi_component_kilonova_magnitudes(rb, obands):
+    """two_component_kilonova_model / three_component_kilonova_model, magnitude and flux branches
+    (kilonova_models.py:1166-1211, 1277-1323): summed blackbody spectra on the shared grid."""
+    names = np.array(list(h.LSST_NU)[:6] * 5)
+    rng = np.random.default_rng(31)
+    N = 8
+    ref_flux = np.array([rb.bands.REFERENCE_FLUX[n] for n in names])
+    for ncomp, t_hi, res, gmax in ((2, 5.0, 500, 86400 * 6), (3, 20.0, 300, 7e6)):
+        t = np.geomspace(0.3, t_hi, 30)
+        comps = [h.one_component_prior(rng, N) for _ in range(ncomp)]
+        p = dict(redshift=comps[0]["redshift"])
+        for c, comp in enumerate(comps, start=1):
+            for k in ("mej", "vej", "kappa", "temperature_floor"):
+                p[f"{k}_{c}"] = comp[k]
+        fn = getattr(rb.kilonova_models, {2: "two", 3: "three"}[ncomp] + "_component_kilonova_model")
+        out = fn(t, params_batch=p, bands=names, output_format="magnitude")
+        outf = fn(t, params_batch=p, bands=names, output_format="flux")
+        for i in range(N):
+            cl = [(comp["mej"][i], comp["vej"][i], comp["kappa"][i], comp["temperature_floor"][i]) for comp in comps]
+            ref = r.multi_component_kn_magnitude(t, p["redshift"][i], cl, bands=names, bandpasses=obands,
+                                                 dense_resolution=res, grid_t_max=gmax)
+            _check(out[i], ref, f"{ncomp}-component sample {i}", floor_mag=np.nanmin(ref))
+            np.testing.assert_allclose(outf[i], r.bandpass_magnitude_to_flux(ref, ref_flux), rtol=1e-7)
+        # three identical components = the one-component model, 2.5 log10(3) mag brighter (same grid)
+        if ncomp == 3:
+            single = rb.kilonova_models.one_component_kilonova_model(
+                t, params_batch=dict(redshift=p["redshift"], mej=p["mej_1"], vej=p["vej_1"], kappa=p["kappa_1"],
+                                     temperature_floor=p["temperature_floor_1"]),
+                bands=names, output_format="magnitude", dense_resolution=300)
+            same = dict(p)
+            for c in (2, 3):
+                for k in ("mej", "vej", "kappa", "temperature_floor"):
+                    same[f"{k}_{c}"] = p[f"{k}_1"]
+            out3 = fn(t, params_batch=same, bands=names, output_format="magnitude")
+            ok = np.isfinite(single) & (single < 60)
+            assert np.max(np.abs(out3[ok] - (single[ok] - 2.5 * np.log10(3.0)))) < 1e-9
+
+
 def test_errors(rb):
     t = np.array([1., 2., 3.])
     base = dict(f_nickel=0.1, mej=1., vej=5e3, kappa=0.1, kappa_gamma=0.1, temperature_floor=3e3)
