@@ -1690,6 +1690,30 @@ def sn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None,
     return bandmag_from_spectra(time_obs, time_observer_frame, spectra, lam, bands, bandpasses)
 
 
+def general_magnetar_driven_supernova_magnitude(time, redshift, mej, E_sn, kappa, l0, tau_sd, nn, kappa_gamma, *,
+                                                bands, bandpasses, temperature_floor, f_nickel=0,
+                                                pair_cascade_switch=False, cutoff_wavelength=3000,
+                                                absorption_index=1.0, lambda_array=None, dl=None, **_):
+    """Magnitude branch of supernova_models.general_magnetar_driven_supernova (:2585-2637): CutoffBlackbody spectra on
+    (get_optimal_time_array(1e0, 1e8, 2000) x lambda_array), phases time_temp (1 + z) / day_to_s."""
+    time_obs = np.asarray(time, dtype=float)
+    lam = np.geomspace(500, 60000, 200) if lambda_array is None else np.asarray(lambda_array, dtype=float)
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    t_grid, lbol_g, vej = _magnetar_driven_supernova_dynamics(mej, E_sn, kappa, l0, tau_sd, nn, kappa_gamma, f_nickel,
+                                                              pair_cascade_switch)
+    time_observer_frame = t_grid * (1. + redshift)
+    frequency, _t = calc_kcorrected_properties(lambda_to_nu(lam), redshift, time_observer_frame)
+    days = t_grid / day_to_s
+    with np.errstate(all="ignore"):
+        temp_g, rad_g = globals()["temperature_floor"](days, lbol_g, vej, temperature_floor)
+        full = cutoff_blackbody_mjy(days, temp_g, lbol_g, rad_g, frequency[:, None], dl, cutoff_wavelength,
+                                    absorption_index)
+        full = full.T * (1 + redshift)
+        spectra = full * 1e-26 * _C_AA_PER_S / lam ** 2                          # :2628-2629
+    return bandmag_from_spectra(time_obs, time_observer_frame / day_to_s, spectra, lam, bands, bandpasses)
+
+
 def mergernova_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, **params):
     """_processing_other_formats (magnetar_driven_ejecta_models.py:198-238) with use_relativistic_blackbody=True for
     `model` in {'basic_mergernova', 'general_mergernova', 'general_mergernova_thermalisation'}."""

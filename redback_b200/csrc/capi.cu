@@ -1580,8 +1580,10 @@ extern "C" int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* 
   static const double dummy = 0.0;
   int rc = mn_check(cfg, N, E, params, t_obs, &dummy, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
-  if (cfg->output != RB_MN_OUT_FLUX_DENSITY || !cfg->use_r_process)
-    return fail(RB_ERR_UNSUPPORTED, "rb_mn_mag_eval: magnitudes are available for the mergernova flux-density set-up");
+  const bool supernova = cfg->output == RB_MN_OUT_SUPERNOVA && !cfg->use_r_process;   // supernova_models.py:2585-2637
+  if (!supernova && (cfg->output != RB_MN_OUT_FLUX_DENSITY || !cfg->use_r_process))
+    return fail(RB_ERR_UNSUPPORTED, "rb_mn_mag_eval: magnitudes are available for the mergernova flux-density set-up "
+                                    "and for general_magnetar_driven_supernova");
   rc = phot_check(phot, E, false);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
@@ -1605,6 +1607,11 @@ extern "C" int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* 
   j.phot = phot; j.N = N; j.E = E; j.NT = G;
   j.lu_grid = tdays.data();
   j.with_len = false;
+  if (supernova && cfg->sed == RB_SED_CUTOFF_BLACKBODY) {
+    j.sed = rb::PH_SED_CUTOFF;
+    j.cutoff_wavelength = cfg->cutoff_wavelength;
+    j.absorption_index = cfg->absorption_index;
+  }
   j.sigma_mode = cfg->sigma_mode; j.upper_limits = cfg->upper_limits;
   j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param; j.t0 = nullptr;
   j.out_model = out_model; j.out_logl = out_logl;
@@ -1628,7 +1635,10 @@ extern "C" int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* 
     a.grid_out = d_grid;
     a.opz_out = d_opz;
     a.dl_out = d_dl;
-    rb::mn_kernel<false><<<(unsigned)((nc + 127) / 128), 128, (size_t)G * sizeof(double), st>>>(a);
+    if (supernova)
+      rb::mn_kernel<true><<<(unsigned)((nc + 127) / 128), 128, (size_t)G * sizeof(double), st>>>(a);
+    else
+      rb::mn_kernel<false><<<(unsigned)((nc + 127) / 128), 128, (size_t)G * sizeof(double), st>>>(a);
     launch_counter()->fetch_add(1);
     return (int)RB_OK;
   });

@@ -238,8 +238,16 @@ __global__ void __launch_bounds__(128, SN ? 3 : 5) mn_kernel(const MnArgs a) {
     }
     if (a.grid_mode) {
       double* go = a.grid_out + (size_t)n * 4 * G;
-      go[0 * G + i] = temp * dop;        // exp(h nu / (k T' D)): an ordinary blackbody of temperature T' D ...
-      go[1 * G + i] = rad / dop;         // ... and radius R / D (:164-172)
+      if (SN && sn_mode) {               // supernova_models.py:2598-2600, 2622-2626: photosphere on the grid
+        const double vej_km = kC * sqrt(1.0 - 1.0 / (gam * gam)) / kKm;       // utils.py:1524
+        double t_ph, r_ph;
+        temperature_floor_dev(lbol, t / kDay, kRadiusConst * vej_km, tfloor, inv_rec, t_ph, r_ph);
+        go[0 * G + i] = t_ph;
+        go[1 * G + i] = r_ph;
+      } else {
+        go[0 * G + i] = temp * dop;      // exp(h nu / (k T' D)): an ordinary blackbody of temperature T' D ...
+        go[1 * G + i] = rad / dop;       // ... and radius R / D (:164-172)
+      }
       go[2 * G + i] = lbol;
       go[3 * G + i] = (t * opz) / kDay;  // time_observer_frame / day_to_s (:236)
     } else {

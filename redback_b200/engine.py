@@ -467,14 +467,20 @@ class MergernovaMagPath(MergernovaPath):
 
     def __init__(self, engine, time, bands, output="magnitude", lambda_array=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, use_gamma_ray_opacity=False, pair_cascade_switch=False,
-                 ejecta_albedo=0.5, pair_cascade_fraction=0.05, cosmology=None, device=None):
+                 ejecta_albedo=0.5, pair_cascade_fraction=0.05, cosmology=None, device=None, supernova=None):
         from . import bands as _bands
-        self.cfg = _capi.mn_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
-                                   pair_cascade_fraction, cosmology)
+        if supernova is None:
+            self.cfg = _capi.mn_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
+                                       pair_cascade_fraction, cosmology)
+        else:   # general_magnetar_driven_supernova (supernova_models.py:2585-2637): lambda default :2587
+            self.cfg = _capi.mn_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
+                                       pair_cascade_fraction, cosmology, _capi.MN_OUT_SUPERNOVA, 2.0, supernova)
+            self.ROWS = _capi.MN_ROWS_SUPERNOVA
         if engine == _capi.MN_EVOLVING:
             self.ROWS = _capi.MN_ROWS_EVOLVING
         self._setup(time, None, y, sigma, device)
-        lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
+        default_lam = np.geomspace(100, 60000, 100) if supernova is None else np.geomspace(500, 60000, 200)
+        lam = default_lam if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
         self.phot, self._keep = _bands.build_photometry(bands, self.E, lam, output)
 
     def _launch(self, *args):

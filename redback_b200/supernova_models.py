@@ -373,8 +373,9 @@ def _gmds_spec(name, flux_density):
             fmt = kwargs.get("output_format")
             if fmt is None:
                 raise KeyError("output_format")
-            if fmt != "flux_density":
-                raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device")
+            if fmt == "dynamics_output":
+                raise NotImplementedError(f"{name}: output_format='dynamics_output' returns Python objects in the reference")
+            output_mode(kwargs, name)
             _operator_name("photosphere", kwargs.get("photosphere"), "TemperatureFloor")
             _operator_name("sed", kwargs.get("sed"), "CutoffBlackbody")
         elif kwargs.get("output_format") == "dynamics_output":
@@ -384,6 +385,16 @@ def _gmds_spec(name, flux_density):
         sn = dict(sed=_SED_IDS[_operator_name("sed", kwargs.get("sed"), "CutoffBlackbody")] if flux_density
                   else _capi.SED_BLACKBODY,
                   cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000), absorption_index=kwargs.get("absorption_index", 1.0))
+        mode = output_mode(kwargs, name) if flux_density else "flux_density"
+        if mode != "flux_density":                                               # :2585-2637
+            from .engine import MergernovaMagPath
+            return MergernovaMagPath(_capi.MN_MAGNETAR_ONLY, time, kwargs["bands"], output=mode,
+                                     lambda_array=kwargs.get("lambda_array"), y=y, sigma=sigma, sigma_mode=sigma_mode,
+                                     use_gamma_ray_opacity=True,
+                                     pair_cascade_switch=kwargs.get("pair_cascade_switch", False),
+                                     ejecta_albedo=kwargs.get("ejecta_albedo", 0.5),
+                                     pair_cascade_fraction=kwargs.get("pair_cascade_fraction", 0.05),
+                                     cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"), supernova=sn)
         return MergernovaPath(_capi.MN_MAGNETAR_ONLY, time, frequency=kwargs.get("frequency") if flux_density else None,
                               y=y, sigma=sigma, sigma_mode=sigma_mode, use_gamma_ray_opacity=True,
                               pair_cascade_switch=kwargs.get("pair_cascade_switch", False),
@@ -424,8 +435,8 @@ def general_magnetar_driven_supernova_bolometric(time, mej=None, E_sn=None, kapp
 
 def general_magnetar_driven_supernova(time, redshift=None, mej=None, E_sn=None, kappa=None, l0=None, tau_sd=None,
                                       nn=None, kappa_gamma=None, params_batch=None, **kwargs):
-    """redback supernova_models.general_magnetar_driven_supernova (:2510-2584), flux_density: TemperatureFloor on the
-    dynamics grid with the time-dependent ejecta velocity, CutoffBlackbody by default; mJy."""
+    """redback supernova_models.general_magnetar_driven_supernova (:2510-2637), flux_density and magnitude / flux:
+    TemperatureFloor on the dynamics grid with the time-dependent ejecta velocity, CutoffBlackbody by default."""
     named = dict(redshift=redshift, mej=mej, E_sn=E_sn, kappa=kappa, l0=l0, tau_sd=tau_sd, nn=nn,
                  kappa_gamma=kappa_gamma)
     return run(_GMDS, time, named, kwargs, params_batch)

@@ -198,6 +198,33 @@ def test_multi_component_kilonova_magnitudes(rb, obands):
             assert np.max(np.abs(out3[ok] - (single[ok] - 2.5 * np.log10(3.0)))) < 1e-9
 
 
+def test_general_magnetar_driven_supernova_magnitudes(rb, obands):
+    """Magnitude / flux branch of general_magnetar_driven_supernova (supernova_models.py:2585-2637): CutoffBlackbody
+    spectra on the 1998-point dynamics grid."""
+    rng = np.random.default_rng(57)
+    t = np.sort(rng.uniform(2, 200, 24))
+    names = np.array(list(h.LSST_NU)[:6] * 4)
+    N = 4
+    p = dict(redshift=rng.uniform(0.01, 0.4, N), mej=h.loguniform(rng, 1, 30, N), E_sn=h.loguniform(rng, 1e50, 3e51, N),
+             kappa=rng.uniform(0.05, 0.3, N), l0=h.loguniform(rng, 1e44, 1e47, N), tau_sd=h.loguniform(rng, 1e4, 1e7, N),
+             nn=rng.uniform(2.2, 6, N), kappa_gamma=h.loguniform(rng, 1e-2, 1e2, N), f_nickel=rng.uniform(0, 0.3, N),
+             temperature_floor=h.loguniform(rng, 3e3, 1e4, N))
+    fn = rb.supernova_models.general_magnetar_driven_supernova
+    out = fn(t, params_batch=p, bands=names, output_format="magnitude")
+    outf = fn(t, params_batch=p, bands=names, output_format="flux")
+    ref_flux = np.array([rb.bands.REFERENCE_FLUX[n] for n in names])
+    y = out[0] + 0.1
+    logl = rb.GaussianLikelihood(t, y, 0.1, fn, kwargs=dict(bands=names, output_format="magnitude")).log_likelihood_batch(p)
+    for i in range(N):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.general_magnetar_driven_supernova_magnitude(t, z, bands=names, bandpasses=obands, **kw)
+        _check(out[i], ref, f"general_magnetar_driven_supernova sample {i}", atol=2e-8, floor_mag=np.nanmin(ref))
+        np.testing.assert_allclose(outf[i], r.bandpass_magnitude_to_flux(ref, ref_flux), rtol=1e-7)
+        ref_l = r.gaussian_likelihood(y, ref, 0.1)
+        assert abs(logl[i] - ref_l) <= 1e-4 + 1e-7 * abs(ref_l), (i, logl[i], ref_l)
+
+
 def test_errors(rb):
     t = np.array([1., 2., 3.])
     base = dict(f_nickel=0.1, mej=1., vej=5e3, kappa=0.1, kappa_gamma=0.1, temperature_floor=3e3)
