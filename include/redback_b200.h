@@ -383,6 +383,7 @@ typedef struct {
   int resolution;                /* get_optimal_time_array(1e-4, 1e7, 300) (:777); 500 for ..._evolution (:917) */
   rb_cosmology cosmology;
   rb_upper_limits upper_limits;
+  int heat_all_layers;           /* magnetar_heating: 0 'first_layer' (default, :709-721), 1 'all_layers' (:698-704) */
 } rb_mk_config;
 
 int rb_mk_config_default(rb_mk_config* cfg);

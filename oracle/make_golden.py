@@ -304,6 +304,41 @@ def dump_mergernova():
     print("mergernova fixtures:", len(doc["draws"]))
 
 
+def dump_metzger_magnetar():
+    """_general_metzger_magnetar_driven_kilonova_model of the reference's own source with both settings of
+    magnetar_heating on seeded draws (priors/general_metzger_magnetar_driven*.prior ranges); every 5th grid point."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import warnings
+    warnings.simplefilter("ignore")
+    from oracle import refshim
+    ns = refshim.load_metzger_magnetar()
+    rng = np.random.default_rng(2027)
+    tg = ns.get_optimal_time_array(1e-4, 1e7, 300)
+    doc = {"stride": 5, "n_grid": int(tg.size), "draws": []}
+    for i in range(8):
+        ej = dict(mej=float(rng.uniform(1e-3, 0.05)), vej=float(rng.uniform(0.05, 0.3)), beta=float(rng.uniform(1.5, 8)),
+                  kappa=float(rng.uniform(1, 30)))
+        eng = dict(l0=float(10 ** rng.uniform(42, 48)), tau_sd=float(10 ** rng.uniform(2, 5)), nn=float(rng.uniform(2, 6)))
+        gamma = bool(i % 2)
+        extra = dict(kappa_gamma=float(10 ** rng.uniform(-2, 2))) if gamma else \
+            dict(thermalisation_efficiency=float(rng.uniform(0.1, 1)))
+        heating = ("first_layer", "all_layers")[(i // 2) % 2]
+        lum = ns.magnetar_only(tg, eng["l0"], eng["tau_sd"], eng["nn"])
+        out = ns._general_metzger_magnetar_driven_kilonova_model(
+            time=tg, magnetar_luminosity=lum, use_gamma_ray_opacity=gamma, magnetar_heating=heating,
+            neutron_precursor_switch=bool(i % 3), pair_cascade_switch=bool((i + 1) % 2), **ej, **extra)
+        pick = slice(None, None, 5)
+        doc["draws"].append(dict(ejecta=ej, engine=eng, extra=extra, use_gamma_ray_opacity=gamma,
+                                 magnetar_heating=heating, neutron_precursor_switch=bool(i % 3),
+                                 pair_cascade_switch=bool((i + 1) % 2),
+                                 bolometric_luminosity=[float(v) for v in out.bolometric_luminosity[pick]],
+                                 temperature=[float(v) for v in out.temperature[pick]],
+                                 r_photosphere=[float(v) for v in out.r_photosphere[pick]]))
+    with open(os.path.join(OUT, "metzger_magnetar_reference_draws.json"), "w") as fh:
+        json.dump(doc, fh)
+    print("metzger magnetar fixtures:", len(doc["draws"]))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     dump_pkl()
@@ -312,3 +347,4 @@ if __name__ == "__main__":
     dump_aspherical()
     dump_csm()
     dump_mergernova()
+    dump_metzger_magnetar()

@@ -155,3 +155,23 @@ def load_mergernova():
     load_functions("redback/transient_models/magnetar_driven_ejecta_models.py", ["_ejecta_dynamics_and_interaction"], glb)
     return types.SimpleNamespace(**{k: glb[k] for k in ("_ejecta_dynamics_and_interaction", "basic_magnetar",
                                                        "magnetar_only", "get_optimal_time_array")})
+
+
+def load_metzger_magnetar():
+    """The reference's own _general_metzger_magnetar_driven_kilonova_model (with the utils.py helpers it calls),
+    magnetar_only and get_optimal_time_array, executed from /root/reference."""
+    from collections import namedtuple
+    import numpy as np
+    from scipy.interpolate import RegularGridInterpolator, interp1d
+    from . import restated as r
+    load()
+    glb = dict(np=np, namedtuple=namedtuple, RegularGridInterpolator=RegularGridInterpolator, interp1d=interp1d,
+               solar_mass=r.solar_mass, speed_of_light=r.speed_of_light, day_to_s=r.day_to_s, sigma_sb=r.sigma_sb)
+    load_functions("redback/utils.py", ["interpolated_barnes_and_kasen_thermalisation_efficiency",
+                                         "electron_fraction_from_kappa", "get_optimal_time_array",
+                                         "_get_optimal_time_array_cached"], glb)
+    load_functions("redback/transient_models/magnetar_models.py", ["magnetar_only"], glb)
+    load_functions("redback/transient_models/magnetar_driven_ejecta_models.py",
+                   ["_general_metzger_magnetar_driven_kilonova_model"], glb)
+    return types.SimpleNamespace(**{k: glb[k] for k in ("_general_metzger_magnetar_driven_kilonova_model",
+                                                       "magnetar_only", "get_optimal_time_array")})

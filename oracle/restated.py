@@ -1176,9 +1176,12 @@ def metzger_kilonova_internal(time, mej, vej, beta, kappa, neutron_precursor_swi
 def metzger_magnetar_driven_internal(time, mej, vej, beta, kappa, magnetar_luminosity, use_gamma_ray_opacity, *,
                                      thermalisation_efficiency=None, kappa_gamma=None, pair_cascade_switch=True,
                                      ejecta_albedo=0.5, pair_cascade_fraction=0.01, neutron_precursor_switch=True,
-                                     vmax=0.7):
-    """_general_metzger_magnetar_driven_kilonova_model (magnetar_driven_ejecta_models.py:576-757) with
-    magnetar_heating='first_layer' (the default).  time: source-frame seconds.  Returns (L_bol, T, R_photosphere)."""
+                                     vmax=0.7, magnetar_heating="first_layer"):
+    """_general_metzger_magnetar_driven_kilonova_model (magnetar_driven_ejecta_models.py:576-757); magnetar_heating
+    'first_layer' (default: only the innermost shell is heated by the engine) or 'all_layers' (:698-704).
+    time: source-frame seconds.  Returns (L_bol, T, R_photosphere)."""
+    if magnetar_heating not in ("first_layer", "all_layers"):
+        raise ValueError("magnetar_heating must be 'first_layer' or 'all_layers'")
     with np.errstate(all="ignore"):
         tdays = time / day_to_s
         time_len, mass_len = len(time), 200
@@ -1229,10 +1232,14 @@ def metzger_magnetar_driven_internal(time, mej, vej, beta, kappa, magnetar_lumin
             kap = kappa[:-1, ii] if neutron_precursor_switch else kappa
             td_v[:-1, ii] = (kap * m_array[:-1] * solar_mass * 3) / (4 * np.pi * v_m[:-1] * speed_of_light * time[ii] * beta)
             lum_rad[:-1, ii] = energy_v[:-1, ii] / (td_v[:-1, ii] + time[ii] * (v_m[:-1] / speed_of_light))
-            energy_v[0, ii + 1] = (qdot + edotr[0, ii] * dm[0] * solar_mass - (energy_v[0, ii] / time[ii])
-                                   - lum_rad[0, ii]) * dt[ii] + energy_v[0, ii]                 # :707
-            energy_v[1:-1, ii + 1] = (edotr[1:-1, ii] * dm[1:] * solar_mass - (energy_v[1:-1, ii] / time[ii])
-                                      - lum_rad[1:-1, ii]) * dt[ii] + energy_v[1:-1, ii]        # :710
+            if magnetar_heating == "all_layers":
+                energy_v[:-1, ii + 1] = (qdot + edotr[:-1, ii] * dm * solar_mass - (energy_v[:-1, ii] / time[ii])
+                                         - lum_rad[:-1, ii]) * dt[ii] + energy_v[:-1, ii]       # :704
+            else:
+                energy_v[0, ii + 1] = (qdot + edotr[0, ii] * dm[0] * solar_mass - (energy_v[0, ii] / time[ii])
+                                       - lum_rad[0, ii]) * dt[ii] + energy_v[0, ii]             # :707
+                energy_v[1:-1, ii + 1] = (edotr[1:-1, ii] * dm[1:] * solar_mass - (energy_v[1:-1, ii] / time[ii])
+                                          - lum_rad[1:-1, ii]) * dt[ii] + energy_v[1:-1, ii]    # :710
             tau[:-1, ii] = (m_array[:-1] * solar_mass * kap / (4 * np.pi * (time[ii] * v_m[:-1]) ** 2))
             tau[mass_len - 1, ii] = tau[mass_len - 2, ii]
             r_photosphere[ii] = v_m[np.argmin(np.abs(tau[:, ii] - 1))] * time[ii]

@@ -101,7 +101,7 @@ class MkConfig(C.Structure):
     _fields_ = [("engine", C.c_int), ("sigma_mode", C.c_int), ("use_gamma_ray_opacity", C.c_int),
                 ("pair_cascade_switch", C.c_int), ("ejecta_albedo", C.c_double), ("pair_cascade_fraction", C.c_double),
                 ("neutron_precursor_switch", C.c_int), ("vmax", C.c_double), ("resolution", C.c_int),
-                ("cosmology", Cosmology), ("upper_limits", UpperLimits)]
+                ("cosmology", Cosmology), ("upper_limits", UpperLimits), ("heat_all_layers", C.c_int)]
 
 
 class RedbackB200Error(RuntimeError):
@@ -259,7 +259,9 @@ def mn_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_
 
 def mk_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_cascade_switch=True,
               ejecta_albedo=0.5, pair_cascade_fraction=0.01, neutron_precursor_switch=True, vmax=0.7, cosmology=None,
-              resolution=300):
+              resolution=300, magnetar_heating="first_layer"):
+    if magnetar_heating not in ("first_layer", "all_layers"):
+        raise ValueError("magnetar_heating must be 'first_layer' or 'all_layers'")
     cfg = MkConfig()
     check(lib().rb_mk_config_default(C.byref(cfg)))
     cfg.engine, cfg.sigma_mode = engine, sigma_mode
@@ -269,6 +271,7 @@ def mk_config(engine, sigma_mode=SIGMA_FIXED, use_gamma_ray_opacity=False, pair_
     cfg.neutron_precursor_switch = int(bool(neutron_precursor_switch))
     cfg.vmax = float(vmax)
     cfg.resolution = int(resolution)
+    cfg.heat_all_layers = int(magnetar_heating == "all_layers")
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg

@@ -1,5 +1,5 @@
 // Magnetar-driven Metzger shell model: _general_metzger_magnetar_driven_kilonova_model
-// (magnetar_driven_ejecta_models.py:576-757, magnetar_heating = 'first_layer') behind
+// (magnetar_driven_ejecta_models.py:576-757, magnetar_heating = 'first_layer' or 'all_layers') behind
 // metzger_magnetar_driven_kilonova_model / general_metzger_magnetar_driven(_thermalisation) (:760-905), flux density
 // through _process_flux_density (:240-272, plain blackbody) and the Gaussian likelihood.
 //
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kMkThreads) mk_kernel(const MkArgs a) {
         const double td = (kap * ms * kMsun * 3) / (4 * kPi * vm * kC * t * beta);
         const double lum = en / (td + t * (vm / kC));
         if (tid == 0) en = en0;                                                // same arithmetic; keep them identical
+        else if (a.cfg.heat_all_layers) en = (qdot + edot * dm * kMsun - (en / t) - lum) * dt + en;   // :704
         else en = (edot * dm * kMsun - (en / t) - lum) * dt + en;              // :710
         const double tv = t * vm;
         const double tau = (ms * kMsun * kap / (4 * kPi * (tv * tv)));          // :712

@@ -421,9 +421,11 @@ class MetzgerMagnetarPath(_FusedPath):
 
     def __init__(self, engine, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED,
                  use_gamma_ray_opacity=False, pair_cascade_switch=True, ejecta_albedo=0.5, pair_cascade_fraction=0.01,
-                 neutron_precursor_switch=True, vmax=0.7, cosmology=None, device=None, resolution=300):
+                 neutron_precursor_switch=True, vmax=0.7, cosmology=None, device=None, resolution=300,
+                 magnetar_heating="first_layer"):
         self.cfg = _capi.mk_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
-                                   pair_cascade_fraction, neutron_precursor_switch, vmax, cosmology, resolution)
+                                   pair_cascade_fraction, neutron_precursor_switch, vmax, cosmology, resolution,
+                                   magnetar_heating)
         if engine == _capi.MN_EVOLVING:
             self.ROWS = _capi.MK_ROWS_EVOLVING
         self._setup(time, frequency, y, sigma, device)
@@ -445,10 +447,11 @@ class MetzgerMagnetarMagPath(MetzgerMagnetarPath):
     def __init__(self, engine, time, bands, output="magnitude", lambda_array=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, use_gamma_ray_opacity=False, pair_cascade_switch=True, ejecta_albedo=0.5,
                  pair_cascade_fraction=0.01, neutron_precursor_switch=True, vmax=0.7, cosmology=None, device=None,
-                 resolution=300):
+                 resolution=300, magnetar_heating="first_layer"):
         from . import bands as _bands
         self.cfg = _capi.mk_config(engine, sigma_mode, use_gamma_ray_opacity, pair_cascade_switch, ejecta_albedo,
-                                   pair_cascade_fraction, neutron_precursor_switch, vmax, cosmology, resolution)
+                                   pair_cascade_fraction, neutron_precursor_switch, vmax, cosmology, resolution,
+                                   magnetar_heating)
         if engine == _capi.MN_EVOLVING:
             self.ROWS = _capi.MK_ROWS_EVOLVING
         self._setup(time, None, y, sigma, device)

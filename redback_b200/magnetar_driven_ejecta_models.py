@@ -83,8 +83,9 @@ def _metzger_spec(name, engine, engine_params, last, gamma_ray, resolution=300):
 
     def validate(kwargs):
         output_mode(kwargs, name)
-        if kwargs.get("magnetar_heating", "first_layer") != "first_layer":
-            raise NotImplementedError(f"{name}: magnetar_heating='all_layers' is not fused on device")
+        if kwargs.get("magnetar_heating", "first_layer") not in ("first_layer", "all_layers"):
+            # the reference runs neither branch of :698 / :709 for any other value and returns a zero light curve
+            raise ValueError(f"{name}: magnetar_heating must be 'first_layer' or 'all_layers'")
 
     def build(time, kwargs, y, sigma, sigma_mode):
         mode = output_mode(kwargs, name)
@@ -97,7 +98,8 @@ def _metzger_spec(name, engine, engine_params, last, gamma_ray, resolution=300):
                                           pair_cascade_fraction=kwargs.get("pair_cascade_fraction", 0.01),
                                           neutron_precursor_switch=kwargs.get("neutron_precursor_switch", True),
                                           vmax=kwargs.get("vmax", 0.7), cosmology=cosmology_from_kwargs(kwargs),
-                                          device=kwargs.get("device"), resolution=resolution)
+                                          device=kwargs.get("device"), resolution=resolution,
+                                          magnetar_heating=kwargs.get("magnetar_heating", "first_layer"))
         return MetzgerMagnetarPath(engine, time, frequency=kwargs.get("frequency"), y=y, sigma=sigma,
                                    sigma_mode=sigma_mode, use_gamma_ray_opacity=gamma_ray,
                                    pair_cascade_switch=kwargs.get("pair_cascade_switch", True),
@@ -105,7 +107,8 @@ def _metzger_spec(name, engine, engine_params, last, gamma_ray, resolution=300):
                                    pair_cascade_fraction=kwargs.get("pair_cascade_fraction", 0.01),
                                    neutron_precursor_switch=kwargs.get("neutron_precursor_switch", True),
                                    vmax=kwargs.get("vmax", 0.7), cosmology=cosmology_from_kwargs(kwargs),
-                                   device=kwargs.get("device"), resolution=resolution)
+                                   device=kwargs.get("device"), resolution=resolution,
+                                   magnetar_heating=kwargs.get("magnetar_heating", "first_layer"))
 
     return FusedSpec(name, needed, build, validate)
 

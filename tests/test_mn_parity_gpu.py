@@ -161,6 +161,34 @@ def test_metzger_magnetar_driven(rb, kind):
         assert abs(logl[i] - ref_l) <= 1e-6 + max(rtol, 1e-8) * abs(ref_l), (i, logl[i], ref_l)
 
 
+def test_metzger_magnetar_all_layers(rb):
+    """magnetar_heating='all_layers' (magnetar_driven_ejecta_models.py:698-704): every shell is heated by the engine.
+    The oracle's march is pinned to the reference's own source for both settings
+    (tests/golden/metzger_magnetar_reference_draws.json)."""
+    rng = np.random.default_rng(115)
+    t = np.geomspace(0.05, 60, 30)
+    nu = np.where(np.arange(30) % 3 == 0, 3e14, 6e14)
+    N = 8
+    for kind, name in (("general", "general_metzger_magnetar_driven"),
+                       ("thermalisation", "general_metzger_magnetar_driven_thermalisation")):
+        p = h.metzger_magnetar_prior(rng, N, kind)
+        fn = getattr(rb.magnetar_driven_ejecta_models, name)
+        kw = dict(frequency=nu, output_format="flux_density", magnetar_heating="all_layers")
+        out = fn(t, params_batch=p, **kw)
+        first = fn(t, params_batch=p, frequency=nu, output_format="flux_density")
+        assert not np.allclose(out, first, rtol=1e-3, equal_nan=True)
+        rtol = 1e-5 if kind == "thermalisation" else 1e-9
+        for i in range(N):
+            kwi = {k: v[i] for k, v in p.items()}
+            z = kwi.pop("redshift")
+            ref = getattr(r, name)(t, z, frequency=nu, magnetar_heating="all_layers", **kwi)
+            with np.errstate(all="ignore"):
+                amp = 1e-13 * np.maximum(1.0, -np.log(np.maximum(np.abs(ref), 1e-300) / np.nanmax(np.abs(ref))))
+            h.assert_close(out[i], ref, rtol, amp, what=f"{name} all_layers sample {i}")
+    with pytest.raises(ValueError):
+        fn(t, params_batch=p, frequency=nu, output_format="flux_density", magnetar_heating="some_layers")
+
+
 def test_evolving_magnetar_variants(rb):
     """general_mergernova_evolution (:422-474) and general_metzger_magnetar_driven_evolution (:908-956): the spin-down
     ODE of magnetar_models._evolving_gw_and_em_magnetar runs on device; golden vectors + a small batch."""

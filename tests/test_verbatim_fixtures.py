@@ -106,6 +106,27 @@ def test_oracle_reproduces_reference_mergernova():
             np.testing.assert_allclose(got[pick], row[key], rtol=1e-14, err_msg=key)
 
 
+def test_oracle_reproduces_reference_metzger_magnetar_shells():
+    """_general_metzger_magnetar_driven_kilonova_model of the reference's own source, both settings of
+    magnetar_heating (make_golden.py::dump_metzger_magnetar)."""
+    with open(os.path.join(ROOT, "tests", "golden", "metzger_magnetar_reference_draws.json")) as fh:
+        fx = json.load(fh)
+    tg = r.get_optimal_time_array(1e-4, 1e7, 300)
+    assert tg.size == fx["n_grid"]
+    pick = slice(None, None, fx["stride"])
+    assert {row["magnetar_heating"] for row in fx["draws"]} == {"first_layer", "all_layers"}
+    for row in fx["draws"]:
+        e = row["engine"]
+        ej = dict(row["ejecta"])
+        out = r.metzger_magnetar_driven_internal(
+            tg, ej["mej"], ej["vej"], ej["beta"], ej["kappa"], r.magnetar_only(tg, e["l0"], e["tau_sd"], e["nn"]),
+            row["use_gamma_ray_opacity"], magnetar_heating=row["magnetar_heating"],
+            neutron_precursor_switch=row["neutron_precursor_switch"], pair_cascade_switch=row["pair_cascade_switch"],
+            **row["extra"])
+        for got, key in zip(out, ("bolometric_luminosity", "temperature", "r_photosphere")):
+            np.testing.assert_allclose(got[pick], row[key], rtol=1e-13, err_msg=f"{key} {row['magnetar_heating']}")
+
+
 @pytest.fixture(scope="module")
 def asph_fx():
     with open(os.path.join(ROOT, "tests", "golden", "aspherical_reference_draws.json")) as fh:
