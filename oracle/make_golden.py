@@ -80,6 +80,8 @@ KEEP = [
     "supernova.sn_fallback", "supernova.sn_nickel_fallback", "supernova.homologous_expansion_supernova",
     "supernova.thin_shell_supernova", "tde.tde_analytical", "tde.tde_analytical_bolometric",
     "kilonova.two_component_kilonova_model", "kilonova.three_component_kilonova_model",
+    "kilonova.one_component_ejecta_relation", "kilonova.one_component_ejecta_relation_projection",
+    "kilonova.one_component_nsbh_ejecta_relation",
     "supernova.sn_fallback", "supernova.sn_nickel_fallback",
     "magnetar.metzger_magnetar_driven_kilonova_model", "magnetar.general_metzger_magnetar_driven",
     "magnetar.general_metzger_magnetar_driven_thermalisation",

@@ -1072,6 +1072,70 @@ def one_component_kilonova_model(time, redshift, mej, vej, kappa, *, frequency, 
         return fd * _ERG_S_CM2_HZ_TO_MJY * (1 + redshift)
 
 
+def compactness_from_lambda(lam):
+    """ejecta_relations.py:435-444"""
+    return 0.371 - 0.0391 * np.log(lam) + 0.001056 * np.log(lam) ** 2
+
+
+def baryonic_mass(mass, compactness):
+    """ejecta_relations.py:473-482"""
+    return mass * (1 + 0.8857853174243745 * compactness ** 1.2082383572002926)
+
+
+def bns_ejecta_no_projection(mass_1, mass_2, lambda_1, lambda_2):
+    """OneComponentBNSNoProjection (ejecta_relations.py:5-65) -> (mej [Msun], vej [c])."""
+    c1, c2 = compactness_from_lambda(lambda_1), compactness_from_lambda(lambda_2)
+    vej = -0.3090 * (mass_1 / mass_2) * (1 + -1.879 * c1) + -0.3090 * (mass_2 / mass_1) * (1 + -1.879 * c2) + 0.657
+    log10_mej = -0.0719 * (mass_1 * (1 - 2 * c1) / c1 + mass_2 * (1 - 2 * c2) / c2) + 0.2116 * \
+        (mass_1 * (mass_2 / mass_1) ** -2.905 + mass_2 * (mass_1 / mass_2) ** -2.905) + -2.42
+    return 10 ** log10_mej, vej
+
+
+def bns_ejecta_projection(mass_1, mass_2, lambda_1, lambda_2):
+    """OneComponentBNSProjection (ejecta_relations.py:88-147) with calc_vrho / calc_vz (:484-525)."""
+    c1, c2 = compactness_from_lambda(lambda_1), compactness_from_lambda(lambda_2)
+    q12, q21 = mass_1 / mass_2, mass_2 / mass_1
+    vrho = (q12 * (1.0 + -2.67385 * c1) + q21 * (1.0 + -2.67385 * c2)) * -0.219479 + 0.444836
+    vz = (q12 * (1.0 + -1.00757 * c1) + q21 * (1.0 + -1.00757 * c2)) * -0.315585 + 0.63808
+    mb1, mb2 = baryonic_mass(mass_1, c1), baryonic_mass(mass_2, c2)
+    tmp1 = ((mb1 * (q21 ** (1.0 / 3.0)) * (1.0 - 2.0 * c1) / c1) + (mb2 * (q12 ** (1.0 / 3.0)) * (1.0 - 2.0 * c2) / c2)) \
+        * -1.35695
+    tmp2 = (mb1 * (q21 ** -2.5484) + mb2 * (q12 ** -2.5484)) * 6.11252
+    tmp3 = (mb1 * (1.0 - mass_1 / mb1) + mb2 * (1.0 - mass_2 / mb2)) * -49.43355
+    return np.maximum(tmp1 + tmp2 + tmp3 + 16.1144, 0) / 1000.0, (vrho ** 2.0 + vz ** 2.0) ** 0.5
+
+
+def nsbh_ejecta(mass_bh, mass_ns, chi_bh, lambda_ns):
+    """OneComponentNSBH (ejecta_relations.py:380-432)."""
+    q = mass_bh / mass_ns
+    z1 = 1 + ((1 - chi_bh * chi_bh) ** (1 / 3.0)) * (((1 + chi_bh) ** (1 / 3.0)) + (1 - chi_bh) ** (1 / 3.0))
+    z2 = (3 * chi_bh * chi_bh + z1 * z1) ** (1 / 2.0)
+    risco = 3 + z2 - np.sign(chi_bh) * ((3 - z1) * (3 + z1 + 2 * z2)) ** (1 / 2.0)
+    comp = compactness_from_lambda(lambda_ns)
+    mb = baryonic_mass(mass_ns, comp)
+    tmp = risco * (q ** 1.352) * -2.269e-3 + (q ** 0.2497) * (1 - 2 * comp) * 4.464e-2 / comp \
+        + (1 - mass_ns / mb) * 2.431 + -0.4159
+    return mb * np.maximum(tmp, 0), 1.5333330951369120e-2 * q + 0.19066667068621043
+
+
+def one_component_ejecta_relation(time, redshift, mass_1, mass_2, lambda_1, lambda_2, kappa, **kw):
+    """kilonova_models.py:1309-1336"""
+    mej, vej = bns_ejecta_no_projection(mass_1, mass_2, lambda_1, lambda_2)
+    return one_component_kilonova_model(time, redshift, mej, vej, kappa, **kw)
+
+
+def one_component_ejecta_relation_projection(time, redshift, mass_1, mass_2, lambda_1, lambda_2, kappa, **kw):
+    """kilonova_models.py:1339-1366"""
+    mej, vej = bns_ejecta_projection(mass_1, mass_2, lambda_1, lambda_2)
+    return one_component_kilonova_model(time, redshift, mej, vej, kappa, **kw)
+
+
+def one_component_nsbh_ejecta_relation(time, redshift, mass_bh, mass_ns, chi_bh, lambda_ns, kappa, **kw):
+    """kilonova_models.py:1470-1493"""
+    mej, vej = nsbh_ejecta(mass_bh, mass_ns, chi_bh, lambda_ns)
+    return one_component_kilonova_model(time, redshift, mej, vej, kappa, **kw)
+
+
 def multi_component_kilonova_model(time, redshift, components, *, frequency, dense_resolution, grid_t_max, dl=None):
     """two_component_kilonova_model (kilonova_models.py:1214-1260: grid end 86400*6 s, 500 points) and
     three_component_kilonova_model (:1113-1165: 7e6 s, 300 points), flux_density branch: the components'

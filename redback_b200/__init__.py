@@ -1,6 +1,7 @@
 """redback_b200: B200-native batched light-curve + Gaussian-likelihood engine behind redback's model /
 likelihood API.  The CUDA library is the only compute path; importing the package does
 not need a GPU, calling it does."""
+from . import ejecta_relations  # noqa: F401
 from . import (_capi, afterglow_models, bands, engine, kilonova_models, likelihoods,  # noqa: F401
                magnetar_driven_ejecta_models, phase_models, simulate, supernova_models, tde_models)
 from .likelihoods import (GaussianLikelihood, GaussianLikelihoodQuadratureNoise,  # noqa: F401
@@ -22,7 +23,9 @@ all_models_dict = {
 }
 all_models_dict.update({name: getattr(kilonova_models, name)
                         for name in ("one_component_kilonova_model", "metzger_kilonova_model",
-                                     "two_component_kilonova_model", "three_component_kilonova_model")})
+                                     "two_component_kilonova_model", "three_component_kilonova_model",
+                                     "one_component_ejecta_relation", "one_component_ejecta_relation_projection",
+                                     "one_component_nsbh_ejecta_relation")})
 all_models_dict.update({fn.__name__: fn for fn in afterglow_models.FUSED})
 all_models_dict.update({fn.__name__: fn for fn in magnetar_driven_ejecta_models.FUSED})
 all_models_dict.update({fn.__name__: fn for fn in tde_models.FUSED})

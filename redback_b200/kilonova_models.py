@@ -109,4 +109,53 @@ def three_component_kilonova_model(time, redshift=None, mej_1=None, vej_1=None, 
     return _multi_component("three_component_kilonova_model", time, redshift, comps, params_batch, kwargs, 300, 7e6)
 
 
+def _via_ejecta_relation(name, time, redshift, kappa, relation_args, default_relation, params_batch, kwargs):
+    """kilonova_models.py:1309-1366, 1470-1493: (mej, vej) from the ejecta relation of the gravitational-wave source
+    parameters (kwarg `ejecta_relation` replaces the class, as in the reference), then one_component_kilonova_model."""
+    import numpy as np
+    kwargs = dict(kwargs)
+    relation = kwargs.pop("ejecta_relation", default_relation)
+    src = dict(relation_args)
+    if params_batch is not None:
+        missing = [k for k in src if k not in params_batch]
+        if missing:
+            raise KeyError(f"{name}: params_batch lacks {missing}")
+        src = {k: params_batch[k] for k in src}
+        with np.errstate(all="ignore"):        # out-of-range draws give NaN light curves, as in the reference
+            rel = relation(**src)
+        batch = {k: v for k, v in params_batch.items() if k not in src}
+        batch.update(mej=np.asarray(rel.ejecta_mass, dtype=np.float64), vej=np.asarray(rel.ejecta_velocity, dtype=np.float64))
+        return one_component_kilonova_model(time, params_batch=batch, **kwargs)
+    with np.errstate(all="ignore"):
+        rel = relation(**src)
+    return one_component_kilonova_model(time, redshift, float(rel.ejecta_mass), float(rel.ejecta_velocity), kappa, **kwargs)
+
+
+def one_component_ejecta_relation(time, redshift=None, mass_1=None, mass_2=None, lambda_1=None, lambda_2=None,
+                                  kappa=None, params_batch=None, **kwargs):
+    """redback kilonova_models.one_component_ejecta_relation (:1309-1336): Dietrich & Ujevic fits without projection."""
+    from .ejecta_relations import OneComponentBNSNoProjection
+    return _via_ejecta_relation("one_component_ejecta_relation", time, redshift, kappa,
+                                dict(mass_1=mass_1, mass_2=mass_2, lambda_1=lambda_1, lambda_2=lambda_2),
+                                OneComponentBNSNoProjection, params_batch, kwargs)
+
+
+def one_component_ejecta_relation_projection(time, redshift=None, mass_1=None, mass_2=None, lambda_1=None,
+                                             lambda_2=None, kappa=None, params_batch=None, **kwargs):
+    """redback kilonova_models.one_component_ejecta_relation_projection (:1339-1366)."""
+    from .ejecta_relations import OneComponentBNSProjection
+    return _via_ejecta_relation("one_component_ejecta_relation_projection", time, redshift, kappa,
+                                dict(mass_1=mass_1, mass_2=mass_2, lambda_1=lambda_1, lambda_2=lambda_2),
+                                OneComponentBNSProjection, params_batch, kwargs)
+
+
+def one_component_nsbh_ejecta_relation(time, redshift=None, mass_bh=None, mass_ns=None, chi_bh=None, lambda_ns=None,
+                                       kappa=None, params_batch=None, **kwargs):
+    """redback kilonova_models.one_component_nsbh_ejecta_relation (:1470-1493): Kawaguchi et al. fits."""
+    from .ejecta_relations import OneComponentNSBH
+    return _via_ejecta_relation("one_component_nsbh_ejecta_relation", time, redshift, kappa,
+                                dict(mass_bh=mass_bh, mass_ns=mass_ns, chi_bh=chi_bh, lambda_ns=lambda_ns),
+                                OneComponentNSBH, params_batch, kwargs)
+
+
 FUSED = {one_component_kilonova_model: _ONE, metzger_kilonova_model: _METZGER}

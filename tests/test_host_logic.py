@@ -68,6 +68,28 @@ def test_host_reparameterisations_match_the_reference_formulas():
     assert gm["ejecta_radius"] == 1.0e11 and gm["n_ism"] == 1.0e-5
 
 
+def test_ejecta_relations_match_the_reference_formulas():
+    """redback_b200.ejecta_relations (host side of the *_ejecta_relation kilonova models) against the oracle's
+    independent restatement of redback/ejecta_relations.py, vectorised over prior draws."""
+    from redback_b200 import ejecta_relations as ejr
+    rng = np.random.default_rng(4)
+    m1, m2 = rng.uniform(1.3, 2.0, 32), rng.uniform(1.0, 1.3, 32)
+    l1, l2 = rng.uniform(50, 800, 32), rng.uniform(200, 3000, 32)
+    for cls, ref in ((ejr.OneComponentBNSNoProjection, r.bns_ejecta_no_projection),
+                     (ejr.OneComponentBNSProjection, r.bns_ejecta_projection)):
+        rel = cls(m1, m2, l1, l2)
+        mej, vej = ref(m1, m2, l1, l2)
+        np.testing.assert_allclose(rel.ejecta_mass, mej, rtol=1e-14)
+        np.testing.assert_allclose(rel.ejecta_velocity, vej, rtol=1e-14)
+    mbh, mns, chi, lam = rng.uniform(3, 10, 32), rng.uniform(1.1, 1.8, 32), rng.uniform(-0.5, 0.9, 32), rng.uniform(100, 2000, 32)
+    rel = ejr.OneComponentNSBH(mbh, mns, chi, lam)
+    mej, vej = r.nsbh_ejecta(mbh, mns, chi, lam)
+    np.testing.assert_allclose(rel.ejecta_mass, mej, rtol=1e-12, atol=1e-15)   # max(a + b + c, 0) of cancelling terms
+    np.testing.assert_allclose(rel.ejecta_velocity, vej, rtol=1e-14)
+    one = ejr.OneComponentBNSNoProjection(1.4, 1.3, 400.0, 500.0)      # scalars work like the reference's classes
+    assert np.ndim(one.ejecta_mass) == 0 and 0 < float(one.ejecta_mass) < 0.1
+
+
 def test_t0_needs_ascending_times():
     phase_models._check_sorted(np.array([1.0, 2.0, 2.0, 3.0]))
     with pytest.raises(NotImplementedError):

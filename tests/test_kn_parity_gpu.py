@@ -37,6 +37,26 @@ def test_golden_vectors(rb, golden):
             h.assert_close(out, h.golden_array(res), RTOL, what=name)
 
 
+def test_ejecta_relation_models(rb, golden):
+    """one_component_ejecta_relation(_projection) and one_component_nsbh_ejecta_relation (kilonova_models.py:1309-1366,
+    1470-1493): the reference's golden vectors through the scalar call, and a batch through params_batch."""
+    for name in ("one_component_ejecta_relation", "one_component_ejecta_relation_projection",
+                 "one_component_nsbh_ejecta_relation"):
+        e = golden["kilonova." + name]
+        t = np.array(e["time"])
+        fn = getattr(rb.kilonova_models, name)
+        for params, res in zip(e["params"], e["results"]):
+            out = fn(t, **params, **e["eval_kwargs"])
+            h.assert_close(out, h.golden_array(res), RTOL, what=name)
+        batch = {k: np.array([p[k] for p in e["params"]]) for k in e["params"][0]}
+        kw = dict(e["eval_kwargs"])
+        batch["redshift"] = np.full(len(e["params"]), kw.pop("redshift"))
+        outb = fn(t, params_batch=batch, **kw)
+        for i, res in enumerate(e["results"]):
+            h.assert_close(outb[i], h.golden_array(res), RTOL, what=name + " batch")
+        assert name in rb.all_models_dict
+
+
 def test_config3_one_component_flux_density(rb):
     """BASELINE configs[2] shape (flux_density branch): 200 epochs cycling LSST ugrizy, prior draws."""
     t, nu = h.config3_epochs()

@@ -72,6 +72,12 @@ CASES = {
         lambda t, p, kw: r.one_component_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
     "kilonova.metzger_kilonova_model":
         lambda t, p, kw: r.metzger_kilonova_model(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "kilonova.one_component_ejecta_relation":
+        lambda t, p, kw: r.one_component_ejecta_relation(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "kilonova.one_component_ejecta_relation_projection":
+        lambda t, p, kw: r.one_component_ejecta_relation_projection(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "kilonova.one_component_nsbh_ejecta_relation":
+        lambda t, p, kw: r.one_component_nsbh_ejecta_relation(t, kw["redshift"], frequency=kw["frequency"], **p),
 }
 
 
