@@ -70,7 +70,7 @@ class _Restricted(pickle.Unpickler):
 KEEP = [
     "supernova.arnett_bolometric", "supernova.arnett",
     "supernova.basic_magnetar_powered_bolometric", "supernova.basic_magnetar_powered",
-    "supernova.slsn_bolometric", "supernova.slsn", "supernova.type_1a",
+    "supernova.slsn_bolometric", "supernova.slsn", "supernova.type_1a", "supernova.type_1c",
     "supernova.magnetar_nickel",
     "kilonova.one_component_kilonova_model", "kilonova.metzger_kilonova_model",
     "magnetar.basic_magnetar",

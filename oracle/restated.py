@@ -309,6 +309,33 @@ def arnett(time, redshift, f_nickel, mej, *, frequency, vej, kappa, kappa_gamma,
         "blackbody", frequency=frequency, vej=vej, temperature_floor=temperature_floor, dl=dl)
 
 
+def synchrotron_mjy(frequency, dl, pp, nu_max, source_radius=1e13, f0=1e-26):
+    """sed.Synchrotron (sed.py:703-751) through _SED.flux_density (:238-251): mJy at source-frame frequencies."""
+    frequency = np.atleast_1d(np.asarray(frequency, dtype=float))
+    sed = np.zeros(frequency.shape)
+    mask = frequency < nu_max
+    f_max = f0 * source_radius ** 2 * nu_max ** 2.5
+    sed[mask] = f0 * source_radius ** 2 * (frequency[mask] / nu_max) ** 2.5 * angstrom_cgs / speed_of_light \
+        * frequency[mask] ** 2
+    sed[~mask] = f_max * (frequency[~mask] / nu_max) ** (-(pp - 1.) / 2.) * angstrom_cgs / speed_of_light \
+        * frequency[~mask] ** 2
+    fd = sed / (4 * np.pi * dl ** 2)
+    fd = fd * nu_to_lambda(frequency)
+    fd = fd / frequency
+    return fd * _ERG_S_CM2_HZ_TO_MJY
+
+
+def type_1c(time, redshift, f_nickel, mej, pp, *, frequency, nu_max=1e9, f0=1e-26, dl=None, **kw):
+    """supernova_models.type_1c (:2317-2352), flux_density: arnett with Blackbody + Synchrotron."""
+    if dl is None:
+        dl = cosmo.luminosity_distance_cm(redshift)
+    time = np.asarray(time, dtype=float)
+    freq = np.broadcast_to(np.asarray(frequency, dtype=float), time.shape)
+    nu_src, _ = calc_kcorrected_properties(freq, redshift, time)
+    return arnett(time, redshift, f_nickel, mej, frequency=frequency, dl=dl, **kw) \
+        + synchrotron_mjy(nu_src, dl, pp, nu_max, f0=f0) * (1 + redshift)
+
+
 def basic_magnetar_powered(time, redshift, p0, bp, mass_ns, theta_pb, *, frequency, mej, vej, kappa,
                            kappa_gamma, temperature_floor, dl=None, **kw):
     """supernova_models.py:1471-1509 (flux_density branch)."""

@@ -14,7 +14,7 @@ __version__ = "0.1.0"
 all_models_dict = {
     name: getattr(supernova_models, name)
     for name in ("arnett_bolometric", "arnett", "basic_magnetar_powered_bolometric", "basic_magnetar_powered",
-                 "slsn_bolometric", "slsn", "type_1a", "magnetar_nickel", "csm_interaction_bolometric",
+                 "slsn_bolometric", "slsn", "type_1a", "type_1c", "magnetar_nickel", "csm_interaction_bolometric",
                  "csm_interaction", "general_magnetar_slsn_bolometric", "general_magnetar_slsn",
                  "exponential_powerlaw_bolometric", "sn_exponential_powerlaw", "sn_fallback", "sn_nickel_fallback",
                  "homologous_expansion_supernova_model_bolometric", "homologous_expansion_supernova",

@@ -184,6 +184,45 @@ def arnett(time, redshift=None, f_nickel=None, mej=None, params_batch=None, **kw
     return run(_ARNETT, time, dict(redshift=redshift, f_nickel=f_nickel, mej=mej), kwargs, params_batch)
 
 
+def type_1c(time, redshift=None, f_nickel=None, mej=None, pp=None, params_batch=None, **kwargs):
+    """redback supernova_models.type_1c (:2317-2352), output_format='flux_density': arnett with the Blackbody SED plus
+    the epoch-independent Synchrotron SED (sed.py:703-751; kwargs nu_max = 1e9 Hz, f0 = 1e-26, source radius 1e13 cm
+    as in the reference's call).  The synchrotron term is a closed form per (sample, epoch) added to the fused arnett
+    output on device; the likelihood of this model goes through the stand-alone reduction."""
+    import numpy as np
+    import torch
+    from . import engine
+    name = "type_1c"
+    if output_mode(kwargs, name, photometric=False) != "flux_density":
+        raise NotImplementedError(f"{name}: output_format='{kwargs['output_format']}' is not fused on device")
+    if kwargs.get("sed") is not None and _operator_name("sed", kwargs.get("sed"), "Blackbody") != "Blackbody":
+        raise NotImplementedError(f"{name}: the reference always uses sed.Blackbody + sed.Synchrotron")
+    batch = None if params_batch is None else {k: v for k, v in params_batch.items() if k != "pp"}
+    want_device = kwargs.get("device_output", False)
+    inner = dict(kwargs, device_output=True, sed=None)
+    fd = arnett(time, redshift, f_nickel, mej, params_batch=batch, **inner)          # [E] or [N, E], mJy
+    dev = fd.device
+    as_col = (lambda v: torch.as_tensor(np.asarray(v, dtype=np.float64) if not isinstance(v, torch.Tensor) else v,
+                                        dtype=torch.float64, device=dev).reshape(-1, 1))
+    src = params_batch if params_batch is not None else dict(redshift=redshift, pp=pp)
+    if src.get("pp") is None or src.get("redshift") is None:
+        raise TypeError(f"{name}() missing required parameter 'pp' or 'redshift'")
+    z, p = as_col(src["redshift"]), as_col(src["pp"])
+    dl = kwargs.get("dl")
+    dl = engine.luminosity_distance(z.reshape(-1), cosmology_from_kwargs(kwargs), device=dev).reshape(-1, 1) \
+        if dl is None else as_col(dl)
+    nu = torch.as_tensor(np.broadcast_to(np.asarray(kwargs["frequency"], dtype=np.float64), (fd.shape[-1],)).copy(),
+                         device=dev).reshape(1, -1) * (1 + z)                         # utils.py:357-384
+    nu_max, f0, radius = float(kwargs.get("nu_max", 1e9)), float(kwargs.get("f0", 1e-26)), 1e13
+    low = f0 * radius ** 2 * (nu / nu_max) ** 2.5 * 1e-8 / 29979245800.0 * nu ** 2                          # sed.py:742-744
+    high = (f0 * radius ** 2 * nu_max ** 2.5) * (nu / nu_max) ** (-(p - 1.) / 2.) * 1e-8 / 29979245800.0 * nu ** 2   # :745-747
+    sed_2 = torch.where(nu < nu_max, low, high)
+    synch = sed_2 / (4 * np.pi * dl ** 2) * (1.e10 * (299792458.0 / nu)) / nu * 1e26  # sed.py:239-251, mJy
+    out = fd.reshape(-1, fd.shape[-1]) + synch * (1 + z)                              # :2351-2352
+    out = out if params_batch is not None else out[0]
+    return out if want_device else out.cpu().numpy()
+
+
 def basic_magnetar_powered_bolometric(time, p0=None, bp=None, mass_ns=None, theta_pb=None, params_batch=None,
                                       **kwargs):
     """redback supernova_models.basic_magnetar_powered_bolometric (:1447-1469); returns erg/s."""

@@ -19,6 +19,7 @@ CASES = {
     "supernova.magnetar_nickel":
         lambda t, p, kw: r.magnetar_nickel(t, kw["redshift"], frequency=kw["frequency"], **p),
     "supernova.type_1a": lambda t, p, kw: r.type_1a(t, kw["redshift"], frequency=kw["frequency"], **p),
+    "supernova.type_1c": lambda t, p, kw: r.type_1c(t, kw["redshift"], frequency=kw["frequency"], **p),
     "magnetar.basic_mergernova":
         lambda t, p, kw: r.basic_mergernova(t, kw["redshift"], frequency=np.full(t.size, kw["frequency"]), **p),
     "magnetar.general_mergernova":

@@ -34,7 +34,7 @@ def test_golden_vectors(rb, golden):
     for name, fn in [("arnett_bolometric", sn.arnett_bolometric), ("slsn_bolometric", sn.slsn_bolometric),
                      ("basic_magnetar_powered_bolometric", sn.basic_magnetar_powered_bolometric),
                      ("arnett", sn.arnett), ("basic_magnetar_powered", sn.basic_magnetar_powered), ("slsn", sn.slsn),
-                     ("type_1a", sn.type_1a), ("magnetar_nickel", sn.magnetar_nickel),
+                     ("type_1a", sn.type_1a), ("type_1c", sn.type_1c), ("magnetar_nickel", sn.magnetar_nickel),
                      ("general_magnetar_slsn", sn.general_magnetar_slsn),
                      ("sn_exponential_powerlaw", sn.sn_exponential_powerlaw),
                      ("exponential_powerlaw_bolometric", sn.exponential_powerlaw_bolometric),
@@ -53,6 +53,36 @@ def test_golden_vectors(rb, golden):
                 kw.update(e["eval_kwargs"])
             out = fn(t, **kw)
             h.assert_close(out, h.golden_array(res), RTOL, what=name)
+
+
+def test_type_1c_batch_and_likelihood(rb):
+    """type_1c (supernova_models.py:2317-2352): arnett + the Synchrotron SED; radio frequencies below and above nu_max
+    so that both branches of sed.py:742-747 are exercised; likelihood through the stand-alone reduction."""
+    rng = np.random.default_rng(77)
+    t = np.sort(rng.uniform(2, 150, 24))
+    nu = np.where(np.arange(t.size) % 3 == 0, 3e8, np.where(np.arange(t.size) % 3 == 1, 5e9, 5e14))
+    N = 6
+    p = h.arnett_prior(rng, N) if hasattr(h, "arnett_prior") else None
+    if p is None:
+        p = dict(redshift=rng.uniform(0.01, 0.3, N), f_nickel=rng.uniform(0.05, 0.5, N), mej=rng.uniform(1, 10, N),
+                 vej=rng.uniform(5e3, 2e4, N), kappa=rng.uniform(0.05, 0.2, N), kappa_gamma=rng.uniform(0.01, 1, N),
+                 temperature_floor=rng.uniform(3e3, 8e3, N))
+    p["pp"] = rng.uniform(2.1, 3.2, N)
+    fn = rb.supernova_models.type_1c
+    kw = dict(frequency=nu, output_format="flux_density", nu_max=2e9, f0=3e-26)
+    out = fn(t, params_batch=p, **kw)
+    y = out[0] * 1.03
+    sigma = 0.1 * np.abs(out[0]) + 1e-30
+    logl = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=kw).log_likelihood_batch(p)
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        z = kwi.pop("redshift")
+        ref = r.type_1c(t, z, frequency=nu, nu_max=2e9, f0=3e-26, **kwi)
+        h.assert_close(out[i], ref, 1e-9, 1e-300, what=f"type_1c sample {i}")
+        ref_l = r.gaussian_likelihood(y, ref, sigma)
+        assert abs(logl[i] - ref_l) <= 1e-6 + 1e-8 * abs(ref_l), (i, logl[i], ref_l)
+    with pytest.raises(NotImplementedError):
+        fn(t, params_batch=p, bands="lsstg", output_format="magnitude")
 
 
 def test_config1_arnett_bolometric_likelihood(rb):
