@@ -212,6 +212,9 @@ typedef struct {
   rb_upper_limits upper_limits;
   double grid_t_max;            /* end of the model time grid [s]: 7e6 (kilonova_models.py:1561, default); the
                                    two-component model uses 86400*6 (:1241)                       */
+  const double* t0;             /* device [N] or NULL: phase_models.t0_base_model (phase_models.py:19-59) — epochs are
+                                   t_obs - t0[n] (ascending t_obs), those before t0 return 0 (1000 mag), and the
+                                   sample's model grid follows ITS valid epochs                   */
 } rb_kn_config;
 
 int rb_kn_config_default(rb_kn_config* cfg);

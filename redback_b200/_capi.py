@@ -54,7 +54,7 @@ KN_NPARAM = 5
 class KnConfig(C.Structure):
     _fields_ = [("model", C.c_int), ("sigma_mode", C.c_int), ("dense_resolution", C.c_int),
                 ("neutron_precursor_switch", C.c_int), ("vmax", C.c_double), ("cosmology", Cosmology),
-                ("upper_limits", UpperLimits), ("grid_t_max", C.c_double)]
+                ("upper_limits", UpperLimits), ("grid_t_max", C.c_double), ("t0", C.c_void_p)]
 
 
 AG_TOPHAT, AG_GAUSSIAN, AG_POWERLAW, AG_POWERLAW_ALT, AG_TWO_COMPONENT, AG_DOUBLE_GAUSSIAN = 1, 2, 3, 4, 5, 6

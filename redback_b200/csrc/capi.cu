@@ -584,7 +584,7 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   cudaError_t ce = cudaMemcpyAsync(h_mm, mm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);  // two doubles; needed to size the time grid
   if (ce != cudaSuccess) return cuda_fail(ce, "epoch min/max");
-  if (!(h_mm[0] > 0.0)) return fail(RB_ERR_INVALID, "rb_kn_eval: epochs must be strictly positive (days)");
+  if (!cfg->t0 && !(h_mm[0] > 0.0)) return fail(RB_ERR_INVALID, "rb_kn_eval: epochs must be strictly positive (days)");
   rb::KnArgs a{};
   a.cfg = *cfg;
   a.N = N;
@@ -600,6 +600,9 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   a.param_stride = N;
   a.tmin_obs = h_mm[0];
   a.tmax_obs = h_mm[1];
+  a.t0 = cfg->t0;
+  a.t_obs = t_obs;
+  a.n_obs = (int)E;
   rb::kn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
   const size_t smem = kn_smem_bytes(cfg, E);
   // measured (tools/bench_paths.py): one-component 512 threads 45.4 ms, 256: 35.1, 128: 29.8; Metzger (needs 224 shell
@@ -623,6 +626,7 @@ extern "C" int rb_kn_eval_f64_host(const rb_kn_config* cfg, int64_t N, int64_t E
                                    double* out_model, double* out_logl) {
   int rc = kn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
+  if (cfg->t0) return fail(RB_ERR_UNSUPPORTED, "rb_kn_eval_f64_host: cfg->t0 is a device pointer; use rb_kn_eval_f64");
   if (N == 0) return RB_OK;
   return eval_host(rb_kn_eval_f64, cfg, RB_KN_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
                    out_model, out_logl);
@@ -1510,7 +1514,7 @@ static int kn_mag_eval(const rb_kn_config* cfg, const rb_photometry* phot, int n
   RB_CUDA(cudaMemcpyAsync(h_mm, b_mm.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaStreamSynchronize(st));
   launch_counter()->fetch_add(1);
-  if (!(h_mm[0] > 0.0)) return fail(RB_ERR_INVALID, "rb_kn_mag_eval: epochs must be strictly positive (days)");
+  if (!cfg->t0 && !(h_mm[0] > 0.0)) return fail(RB_ERR_INVALID, "rb_kn_mag_eval: epochs must be strictly positive (days)");
   const int NT = cfg->dense_resolution;
   const int64_t nc_max = std::min<int64_t>(32768, N);   // = run_photometry's chunk capacity
   RB_CUDA(b_ep1.alloc((size_t)rb::kEpochCols, st));
@@ -1530,7 +1534,7 @@ static int kn_mag_eval(const rb_kn_config* cfg, const rb_photometry* phot, int n
   j.with_len = true;
   j.n_comp = n_comp;
   j.sigma_mode = cfg->sigma_mode; j.upper_limits = cfg->upper_limits;
-  j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param; j.t0 = nullptr;
+  j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param; j.t0 = cfg->t0;
   j.out_model = out_model; j.out_logl = out_logl;
   return run_photometry(j, st, sms, [&](int64_t n0, int64_t nc, double* d_grid, double* d_opz, double* d_dl, int* d_len) {
     for (int c = 0; c < n_comp; ++c) {   // the components share redshift, grid and epochs; only (T, R) differ
@@ -1545,6 +1549,9 @@ static int kn_mag_eval(const rb_kn_config* cfg, const rb_photometry* phot, int n
       a.scalars = b_scal.p;
       a.tmin_obs = h_mm[0];
       a.tmax_obs = h_mm[1];
+      a.t0 = cfg->t0 ? cfg->t0 + n0 : nullptr;
+      a.t_obs = t_obs;
+      a.n_obs = (int)E;
       a.grid_mode = 1;
       a.grid_out = d_grid + (size_t)c * nc_max * 4 * NT;
       a.grid_len = d_len;

@@ -45,6 +45,9 @@ struct KnArgs {
   const double* epoch_tab;
   double* scalars;
   double tmin_obs, tmax_obs;  // min / max of the observer-frame epochs [days]
+  const double* t0;           // [N] (already offset to this chunk) or nullptr: per-sample explosion epoch
+  const double* t_obs;        // [n_obs] ascending observer-frame epochs, needed with t0
+  int n_obs;
   int want_logl;
   // grid mode (magnitude branch, kilonova_models.py:1579-1603): write T, R and the observer-frame phase
   // (time_temp*(1+z))/86400 on the model grid for phot_kernel instead of evaluating the epochs
@@ -141,7 +144,18 @@ __global__ void kn_prep_kernel(const KnArgs a) {
   S[KS_SIGMA] = (a.sigma_param != nullptr && a.want_logl) ? a.sigma_param[n] : 0.0;
   // get_optimal_time_array(1e-2, 7e6, R, user_times = t_obs * 86400 / (1+z))  (utils.py:50-80)
   const double t_min = 1e-2, t_max = a.cfg.grid_t_max;
-  const double user_min = a.tmin_obs * kDay / opz, user_max = a.tmax_obs * kDay / opz;
+  double first = a.tmin_obs, last = a.tmax_obs, t0 = 0.0;
+  if (a.t0 != nullptr) {                                                         // phase_models.py:33-45
+    t0 = a.t0[n];
+    int lo = 0, hi = a.n_obs;              // first epoch with t_obs - t0 >= 0
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (a.t_obs[mid] - t0 >= 0.0) hi = mid; else lo = mid + 1;
+    }
+    if (lo < a.n_obs) { first = a.t_obs[lo] - t0; last = a.t_obs[a.n_obs - 1] - t0; }
+    else first = last = 1.0;               // no epoch after t0: every output is the placeholder
+  }
+  const double user_min = first * kDay / opz, user_max = last * kDay / opz;
   const double eval_min = fmax(t_min, user_min * 0.5);
   const double eval_max = fmin(t_max, user_max * 2.0);
   const int R = a.cfg.dense_resolution;
@@ -170,7 +184,7 @@ __global__ void kn_prep_kernel(const KnArgs a) {
   }
   S[KS_BETA] = beta;
   S[KS_YE] = ye;
-  S[KS_PAD] = 0.0;
+  S[KS_PAD] = t0;
 }
 
 // np.geomspace(a, b, n)[i] with log10 endpoints la, lb precomputed (numpy function_base.geomspace)
@@ -388,10 +402,13 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
     // ---- phase B: epochs -----------------------------------------------------------------------
     double logl_part = 0.0;
     for (int e = tid; e < E; e += blockDim.x) {
-      const double t = (ep[EP_T * E + e] * kDay) / opz;                        // :1563, utils.py:382
+      const double dt_obs = ep[EP_T * E + e] - sc[KS_PAD];                     // t0_base_model; t0 = 0 otherwise
+      const double t = (dt_obs * kDay) / opz;                                  // :1563, utils.py:382
       const double nu = ep[EP_NU * E + e] * opz;
       double model_v;
-      if (!(t >= tg[0] && t <= tg[G - 1])) {
+      if (dt_obs < 0.0) {
+        model_v = 0.0;                                                         // phase_models.py:52-58
+      } else if (!(t >= tg[0] && t <= tg[G - 1])) {
         model_v = NAN;  // interp1d would raise ValueError (bounds_error): flagged as NaN on device
       } else {
         int lo = 0, hi = G;  // searchsorted(tg, t, 'left')

@@ -1,18 +1,25 @@
 """Batched drop-in for redback.transient_models.phase_models.t0_base_model (phase_models.py:19-59): the explosion
 epoch `t0` (MJD) is a sampled parameter, `time` is in MJD, epochs before t0 return 0 (1000 for magnitudes).
 
-On device the shift is a per-sample offset inside the fused supernova kernels (`rb_sn_config.t0`), so a batch with N
-different explosion epochs is still one launch.  Supported base models: the diffusion-powered supernova family
-(arnett, basic_magnetar_powered, slsn, type_1a and their bolometric variants).
+On device the shift is a per-sample offset inside the fused kernels (`rb_sn_config.t0`, `rb_kn_config.t0`), so a batch
+with N different explosion epochs is still one launch.  Supported base models: the diffusion-powered supernova family
+(arnett, basic_magnetar_powered, slsn, type_1a, magnetar_nickel and their bolometric variants) and the one-component
+and Metzger kilonova models.
 """
 import numpy as np
 
+from . import kilonova_models as _kn
 from . import supernova_models as _sn
 from ._fused import FusedSpec, run
 
 _BASE = {name: getattr(_sn, name) for name in ("arnett_bolometric", "arnett", "basic_magnetar_powered_bolometric",
                                                "basic_magnetar_powered", "slsn_bolometric", "slsn", "type_1a",
                                                "magnetar_nickel")}
+_SPECS = {fn: _sn.FUSED[fn] for fn in _BASE.values()}
+# the one-component and Metzger kilonova models (rb_kn_config.t0): each sample's adaptive grid follows its valid epochs
+for _name in ("one_component_kilonova_model", "metzger_kilonova_model"):
+    _BASE[_name] = getattr(_kn, _name)
+    _SPECS[_BASE[_name]] = _kn.FUSED[_BASE[_name]]
 
 
 def _check_sorted(time):
@@ -33,7 +40,7 @@ class _T0Spec:
         if name not in _BASE:
             raise NotImplementedError(f"t0_base_model: base_model={base_model!r} is not fused on device "
                                       f"(supported: {sorted(_BASE)})")
-        base = _sn.FUSED[_BASE[name]]
+        base = _SPECS[_BASE[name]]
 
         def build(time, kw, y, sigma, sigma_mode):
             kw = {k: v for k, v in kw.items() if k != "base_model"}

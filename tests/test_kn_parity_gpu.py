@@ -57,6 +57,57 @@ def test_ejecta_relation_models(rb, golden):
         assert name in rb.all_models_dict
 
 
+def test_t0_base_model_kilonova(rb):
+    """phase_models.t0_base_model (phase_models.py:19-59) over the kilonova models: per-sample merger epochs in one
+    launch; epochs before t0 return 0 (1000 mag); each sample's adaptive grid follows ITS valid epochs."""
+    rng = np.random.default_rng(91)
+    mjd0 = 59000.0
+    t = mjd0 + np.sort(rng.uniform(0.5, 25, 30))
+    nu = np.where(np.arange(t.size) % 2 == 0, 6.3e14, 4.7e14)
+    N = 8
+    p = h.one_component_prior(rng, N)
+    p["t0"] = mjd0 + rng.uniform(-3, 8, N)
+    p["t0"][1] = t[-1] - 1e-2                              # only the last epoch is valid
+    fn = rb.phase_models.t0_base_model
+    kw = dict(base_model="one_component_kilonova_model", frequency=nu, output_format="flux_density")
+    out = fn(t, params_batch=p, **kw)
+    y = np.where(np.isfinite(out[0]), out[0], 0.0) * 1.02
+    sigma = 0.1 * np.abs(y) + 1e-6
+    logl = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=kw).log_likelihood_batch(p)
+    for i in range(N):
+        kwi = {k: v[i] for k, v in p.items()}
+        z, t0 = kwi.pop("redshift"), kwi.pop("t0")
+        ref = r.t0_base_model(t, t0, lambda tt, frequency: r.one_component_kilonova_model(tt, z, frequency=frequency, **kwi),
+                              frequency=nu)
+        assert np.all(out[i][t - t0 < 0] == 0.0)
+        h.assert_close(out[i], ref, RTOL, _tol_extra(np.maximum(t - t0, 1e-3), z, nu), what=f"t0(one_component) {i}")
+        ref_l = r.gaussian_likelihood(y, ref, sigma)
+        if np.isfinite(ref_l):
+            assert abs(logl[i] - ref_l) <= 1e-6 + 1e-8 * abs(ref_l), (i, logl[i], ref_l)
+    # Metzger model, and the magnitude branch (1000 mag before t0)
+    pm = h.metzger_prior(rng, 4)
+    pm["t0"] = mjd0 + rng.uniform(-2, 5, 4)
+    outm = fn(t, params_batch=pm, base_model="metzger_kilonova_model", frequency=nu, output_format="flux_density")
+    for i in range(4):
+        kwi = {k: v[i] for k, v in pm.items()}
+        z, t0 = kwi.pop("redshift"), kwi.pop("t0")
+        ref = r.t0_base_model(t, t0, lambda tt, frequency: r.metzger_kilonova_model(tt, z, frequency=frequency, **kwi),
+                              frequency=nu)
+        h.assert_close(outm[i], ref, RTOL, _tol_extra(np.maximum(t - t0, 1e-3), z, nu), what=f"t0(metzger) {i}")
+    rb.bands.register_synthetic_lsst()
+    bands = np.array(list(h.LSST_NU)[:6] * 5)
+    mag = fn(t, params_batch=p, base_model="one_component_kilonova_model", bands=bands, output_format="magnitude")
+    plain = rb.kilonova_models.one_component_kilonova_model
+    for i in range(N):
+        kwi = {k: float(v[i]) for k, v in p.items()}
+        t0 = kwi.pop("t0")
+        good = t - t0 >= 0
+        assert np.all(mag[i][~good] == 1000.0)
+        want = plain(t[good] - t0, bands=bands[good], output_format="magnitude", **kwi)
+        ok = np.isfinite(want) & (want < 60)
+        assert np.max(np.abs(mag[i][good][ok] - want[ok])) < 1e-8
+
+
 def test_config3_one_component_flux_density(rb):
     """BASELINE configs[2] shape (flux_density branch): 200 epochs cycling LSST ugrizy, prior draws."""
     t, nu = h.config3_epochs()
