@@ -76,6 +76,26 @@ def test_supernova_magnitudes(rb, obands, model):
         _check(out[i], ref, f"{model} sample {i}", floor_mag=np.nanmin(ref))
 
 
+@pytest.mark.parametrize("n_lambda,n_epochs", [(57, 48), (300, 48), (131, 1500), (200, 7)])
+def test_photometry_kernel_odd_shapes(rb, obands, n_lambda, n_epochs):
+    """Shapes that exercise every branch of the photometry kernel's work split: wavelength grids that are not a
+    multiple of the warp / segment size, more columns than threads (two columns per thread in the time-axis passes),
+    more epochs than one hand-over chunk, fewer epochs than warps."""
+    rng = np.random.default_rng(1000 + n_lambda + n_epochs)
+    t = np.sort(rng.uniform(3, 150, n_epochs))
+    names = np.array((list(h.LSST_NU)[:6] * (n_epochs // 6 + 1))[:n_epochs])
+    lam = np.geomspace(1500, 25000, n_lambda)
+    N = 5
+    p = h.arnett_prior(rng, N, zmax=0.3)
+    p["temperature_floor"] = h.loguniform(rng, 3e3, 1.2e4, N)
+    out = rb.supernova_models.arnett(t, params_batch=p, bands=names, output_format="magnitude", lambda_array=lam)
+    for i in range(N if n_epochs < 1000 else 2):
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.sn_magnitude("arnett", t, z, bands=names, bandpasses=obands, lambda_array=lam, **kw)
+        _check(out[i], ref, f"arnett NL={n_lambda} E={n_epochs} sample {i}", floor_mag=np.nanmin(ref))
+
+
 def test_csm_interaction_magnitudes(rb, obands):
     """csm_interaction magnitude branch (supernova_models.py:2093-2111): grid get_optimal_time_array(0.1, 500, 300)."""
     rng = np.random.default_rng(27)
