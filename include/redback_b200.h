@@ -331,6 +331,8 @@ typedef struct {
   double grid_t_min, grid_t_max;   /* [s], defaults 1e-4, 1e8 */
   int sed;
   double cutoff_wavelength, absorption_index;
+  const double* t0;            /* device [N] or NULL: phase_models.t0_base_model — epochs are t_obs - t0[n] (same unit as
+                                  t_obs), those before t0 return 0 (1000 mag); RB_MN_OUT_FLUX_DENSITY only */
 } rb_mn_config;
 enum { RB_MN_OUT_FLUX_DENSITY = 0, RB_MN_OUT_TRAPPED_LUMINOSITY = 1, RB_MN_OUT_TRAPPED_FLUX = 2,
        RB_MN_OUT_SUPERNOVA = 3, RB_MN_OUT_LBOL = 4 };

@@ -87,7 +87,7 @@ class MnConfig(C.Structure):
                 ("resolution", C.c_int), ("cosmology", Cosmology), ("upper_limits", UpperLimits), ("output", C.c_int),
                 ("photon_index", C.c_double), ("use_r_process", C.c_int), ("grid_t_min", C.c_double),
                 ("grid_t_max", C.c_double), ("sed", C.c_int), ("cutoff_wavelength", C.c_double),
-                ("absorption_index", C.c_double)]
+                ("absorption_index", C.c_double), ("t0", C.c_void_p)]
 
 
 MK_ROWS = dict(redshift=0, mej=1, vej=2, beta=3, kappa_r=4, p0=5, l0=5, bp=6, tau_sd=6, mass_ns=7, nn=7, theta_pb=8,

@@ -663,6 +663,8 @@ int mn_check(const rb_mn_config* cfg, int64_t N, int64_t E, const void* params, 
     return fail(RB_ERR_INVALID, "rb_mn_eval: unknown output");
   if (!(cfg->grid_t_min > 0.0 && cfg->grid_t_max > cfg->grid_t_min))
     return fail(RB_ERR_INVALID, "rb_mn_eval: need 0 < grid_t_min < grid_t_max");
+  if (cfg->t0 && cfg->output != RB_MN_OUT_FLUX_DENSITY)
+    return fail(RB_ERR_UNSUPPORTED, "rb_mn_eval: cfg->t0 is available for RB_MN_OUT_FLUX_DENSITY only");
   if (cfg->output == RB_MN_OUT_SUPERNOVA && cfg->sed != RB_SED_BLACKBODY && cfg->sed != RB_SED_CUTOFF_BLACKBODY)
     return fail(RB_ERR_INVALID, "rb_mn_eval: sed must be RB_SED_BLACKBODY or RB_SED_CUTOFF_BLACKBODY");
   if (cfg->output == RB_MN_OUT_SUPERNOVA && cfg->sed == RB_SED_CUTOFF_BLACKBODY && cfg->absorption_index >= 4.0)
@@ -769,6 +771,7 @@ extern "C" int rb_mn_eval_f64(const rb_mn_config* cfg, int64_t N, int64_t E, con
   a.sigma_param = sigma_param;
   a.tgrid = b_tg.as<double>();
   a.sorted_ep = b_sorted.as<double>();
+  a.t0 = cfg->t0;
   a.out_model = out_model;
   a.out_logl = y ? out_logl : nullptr;
   a.want_logl = y ? 1 : 0;
@@ -788,6 +791,7 @@ extern "C" int rb_mn_eval_f64_host(const rb_mn_config* cfg, int64_t N, int64_t E
   int rc = mn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
+  if (cfg->t0) return fail(RB_ERR_UNSUPPORTED, "rb_mn_eval_f64_host: cfg->t0 is a device pointer; use rb_mn_eval_f64");
   return eval_host(rb_mn_eval_f64, cfg, RB_MN_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
                    out_model, out_logl);
 }
@@ -1620,7 +1624,7 @@ extern "C" int rb_mn_mag_eval_f64(const rb_mn_config* cfg, const rb_photometry* 
     j.absorption_index = cfg->absorption_index;
   }
   j.sigma_mode = cfg->sigma_mode; j.upper_limits = cfg->upper_limits;
-  j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param; j.t0 = nullptr;
+  j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param; j.t0 = cfg->t0;
   j.out_model = out_model; j.out_logl = out_logl;
   return run_photometry(j, st, sms, [&](int64_t n0, int64_t nc, double* d_grid, double* d_opz, double* d_dl, int*) {
     const double* dl = dl_cm ? dl_cm + n0 : b_dlc.p;

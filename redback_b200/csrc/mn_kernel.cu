@@ -53,6 +53,7 @@ struct MnArgs {
   const double* sigma_param;
   const double* tgrid;       // [G] source-frame seconds
   const double* sorted_ep;   // [kMnEpochCols][E], ascending MS_T (observer-frame days)
+  const double* t0;          // [N] (offset to this chunk) or nullptr: per-sample merger epoch (t0_base_model)
   double* out_model;
   double* out_logl;
   int want_logl;
@@ -152,8 +153,9 @@ __global__ void __launch_bounds__(128, SN ? 3 : 5) mn_kernel(const MnArgs a) {
     inv_rec = 1.0 / (kStefConst * (tf2 * tf2));
   }
   // epoch coordinate on the interpolation axis of the mode
+  const double t_zero = a.t0 != nullptr ? a.t0[n] : 0.0;             // phase_models.py:33-45
   auto epoch_x = [&](int e) -> double {
-    const double t_obs = ep[MS_T * E + e];
+    const double t_obs = ep[MS_T * E + e] - t_zero;
     if (trapped || sn_mode) return t_obs / opz;                     // :537 / supernova_models.py:2561
     if (lbol_mode) return t_obs * kDay;                             // :2484
     return (t_obs * kDay) / opz;                                    // :252-254
@@ -161,13 +163,20 @@ __global__ void __launch_bounds__(128, SN ? 3 : 5) mn_kernel(const MnArgs a) {
 
   int ei = 0;
   double logl = 0.0;
-  // epochs before the grid: interp1d raises in the reference -> NaN
+  // epochs before the grid: interp1d raises in the reference -> NaN; epochs before t0 (t0_base_model): 0
   while (ei < E) {
     const double ts = epoch_x(ei);
     if (ts >= (sn_mode ? t0g / kDay : t0g)) break;
     if (!a.grid_mode) {
-      if (a.out_model != nullptr) a.out_model[n * (int64_t)E + (int)ep[MS_ORIG * E + ei]] = NAN;
-      logl = NAN;
+      const double fill = ts < 0.0 ? 0.0 : NAN;                      // ts < 0 only with a per-sample t0
+      if (a.out_model != nullptr) a.out_model[n * (int64_t)E + (int)ep[MS_ORIG * E + ei]] = fill;
+      if (ts < 0.0) {
+        if (a.want_logl)
+          logl += logl_term(a.cfg.sigma_mode, ep[MS_KIND * E + ei], ep[MS_Y * E + ei], 0.0, ep[MS_ISIG * E + ei],
+                            ep[MS_LOGT * E + ei], sp);
+      } else {
+        logl = NAN;
+      }
     }
     ++ei;
   }

@@ -3,12 +3,13 @@ epoch `t0` (MJD) is a sampled parameter, `time` is in MJD, epochs before t0 retu
 
 On device the shift is a per-sample offset inside the fused kernels (`rb_sn_config.t0`, `rb_kn_config.t0`), so a batch
 with N different explosion epochs is still one launch.  Supported base models: the diffusion-powered supernova family
-(arnett, basic_magnetar_powered, slsn, type_1a, magnetar_nickel and their bolometric variants) and the one-component
-and Metzger kilonova models.
+(arnett, basic_magnetar_powered, slsn, type_1a, magnetar_nickel and their bolometric variants) the one-component
+and Metzger kilonova models, and the mergernova models.
 """
 import numpy as np
 
 from . import kilonova_models as _kn
+from . import magnetar_driven_ejecta_models as _mn
 from . import supernova_models as _sn
 from ._fused import FusedSpec, run
 
@@ -20,6 +21,11 @@ _SPECS = {fn: _sn.FUSED[fn] for fn in _BASE.values()}
 for _name in ("one_component_kilonova_model", "metzger_kilonova_model"):
     _BASE[_name] = getattr(_kn, _name)
     _SPECS[_BASE[_name]] = _kn.FUSED[_BASE[_name]]
+# the mergernova models (rb_mn_config.t0; fixed model grid)
+for _name in ("basic_mergernova", "general_mergernova", "general_mergernova_thermalisation",
+              "general_mergernova_evolution"):
+    _BASE[_name] = getattr(_mn, _name)
+    _SPECS[_BASE[_name]] = _mn.FUSED[_BASE[_name]]
 
 
 def _check_sorted(time):
