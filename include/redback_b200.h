@@ -389,6 +389,7 @@ typedef struct {
   rb_cosmology cosmology;
   rb_upper_limits upper_limits;
   int heat_all_layers;           /* magnetar_heating: 0 'first_layer' (default, :709-721), 1 'all_layers' (:698-704) */
+  const double* t0;              /* device [N] or NULL: phase_models.t0_base_model, as in rb_mn_config */
 } rb_mk_config;
 
 int rb_mk_config_default(rb_mk_config* cfg);

@@ -101,7 +101,7 @@ class MkConfig(C.Structure):
     _fields_ = [("engine", C.c_int), ("sigma_mode", C.c_int), ("use_gamma_ray_opacity", C.c_int),
                 ("pair_cascade_switch", C.c_int), ("ejecta_albedo", C.c_double), ("pair_cascade_fraction", C.c_double),
                 ("neutron_precursor_switch", C.c_int), ("vmax", C.c_double), ("resolution", C.c_int),
-                ("cosmology", Cosmology), ("upper_limits", UpperLimits), ("heat_all_layers", C.c_int)]
+                ("cosmology", Cosmology), ("upper_limits", UpperLimits), ("heat_all_layers", C.c_int), ("t0", C.c_void_p)]
 
 
 class RedbackB200Error(RuntimeError):

@@ -886,6 +886,7 @@ extern "C" int rb_mk_eval_f64(const rb_mk_config* cfg, int64_t N, int64_t E, con
   rb::MkArgs a{};
   a.cfg = *cfg;
   a.N = N;
+  a.t0 = cfg->t0;
   a.E = (int)E;
   a.G = G;
   a.params = params;
@@ -913,6 +914,7 @@ extern "C" int rb_mk_eval_f64_host(const rb_mk_config* cfg, int64_t N, int64_t E
   int rc = mk_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
+  if (cfg->t0) return fail(RB_ERR_UNSUPPORTED, "rb_mk_eval_f64_host: cfg->t0 is a device pointer; use rb_mk_eval_f64");
   return eval_host(rb_mk_eval_f64, cfg, RB_MK_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
                    out_model, out_logl);
 }
@@ -1694,7 +1696,7 @@ extern "C" int rb_mk_mag_eval_f64(const rb_mk_config* cfg, const rb_photometry* 
   j.lu_grid = tdays.data();
   j.with_len = false;
   j.sigma_mode = cfg->sigma_mode; j.upper_limits = cfg->upper_limits;
-  j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param; j.t0 = nullptr;
+  j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param; j.t0 = cfg->t0;
   j.out_model = out_model; j.out_logl = out_logl;
   return run_photometry(j, st, sms, [&](int64_t n0, int64_t nc, double* d_grid, double* d_opz, double* d_dl, int*) {
     const double* dl = dl_cm ? dl_cm + n0 : b_dlc.p;
@@ -1706,6 +1708,7 @@ extern "C" int rb_mk_mag_eval_f64(const rb_mk_config* cfg, const rb_photometry* 
     rb::MkArgs a{};
     a.cfg = *cfg;
     a.N = nc;
+    a.t0 = cfg->t0 ? cfg->t0 + n0 : nullptr;
     a.E = 0;
     a.G = G;
     a.params = params + n0;

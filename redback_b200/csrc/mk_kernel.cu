@@ -19,6 +19,7 @@ struct MkArgs {
   rb_mk_config cfg;
   int64_t N;
   int E;
+  const double* t0;          // [N] (offset to this chunk) or nullptr: per-sample merger epoch (t0_base_model)
   int G;
   const double* params;      // [RB_MK_NPARAM][param_stride]
   int64_t param_stride;
@@ -248,10 +249,13 @@ __global__ void __launch_bounds__(kMkThreads) mk_kernel(const MkArgs a) {
     const double sp = (a.sigma_param != nullptr && a.want_logl) ? a.sigma_param[n] : 0.0;
     double logl_part = 0.0;
     for (int e = tid; e < E; e += blockDim.x) {
-      const double t = (a.epoch_tab[EP_T * E + e] * kDay) / opz;
+      const double dt_obs = a.epoch_tab[EP_T * E + e] - (a.t0 != nullptr ? a.t0[n] : 0.0);   // t0_base_model
+      const double t = (dt_obs * kDay) / opz;
       const double nu = a.epoch_tab[EP_NU * E + e] * opz;
       double model_v;
-      if (!(t >= tg[0] && t <= tg[G - 1])) {
+      if (dt_obs < 0.0) {
+        model_v = 0.0;                                                         // phase_models.py:52-58
+      } else if (!(t >= tg[0] && t <= tg[G - 1])) {
         model_v = NAN;                       // interp1d raises ValueError in the reference
       } else {
         int lo = 0, hi = G;                  // searchsorted(tg, t, 'left')

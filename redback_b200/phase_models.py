@@ -4,7 +4,7 @@ epoch `t0` (MJD) is a sampled parameter, `time` is in MJD, epochs before t0 retu
 On device the shift is a per-sample offset inside the fused kernels (`rb_sn_config.t0`, `rb_kn_config.t0`), so a batch
 with N different explosion epochs is still one launch.  Supported base models: the diffusion-powered supernova family
 (arnett, basic_magnetar_powered, slsn, type_1a, magnetar_nickel and their bolometric variants) the one-component
-and Metzger kilonova models, and the mergernova models.
+and Metzger kilonova models, the mergernova and the magnetar-driven Metzger shell models.
 """
 import numpy as np
 
@@ -21,9 +21,11 @@ _SPECS = {fn: _sn.FUSED[fn] for fn in _BASE.values()}
 for _name in ("one_component_kilonova_model", "metzger_kilonova_model"):
     _BASE[_name] = getattr(_kn, _name)
     _SPECS[_BASE[_name]] = _kn.FUSED[_BASE[_name]]
-# the mergernova models (rb_mn_config.t0; fixed model grid)
+# the mergernova and magnetar-driven Metzger shell models (rb_mn_config.t0, rb_mk_config.t0; fixed model grids)
 for _name in ("basic_mergernova", "general_mergernova", "general_mergernova_thermalisation",
-              "general_mergernova_evolution"):
+              "general_mergernova_evolution", "metzger_magnetar_driven_kilonova_model",
+              "general_metzger_magnetar_driven", "general_metzger_magnetar_driven_thermalisation",
+              "general_metzger_magnetar_driven_evolution"):
     _BASE[_name] = getattr(_mn, _name)
     _SPECS[_BASE[_name]] = _mn.FUSED[_BASE[_name]]
 

@@ -229,6 +229,45 @@ def test_t0_base_model_mergernova(rb, obands=None):
         assert np.max(np.abs(mag[i][good][ok] - want[ok])) < 1e-8
 
 
+def test_t0_base_model_metzger_magnetar(rb):
+    """t0_base_model over the magnetar-driven Metzger shell models (rb_mk_config.t0): same checks as for the
+    mergernova models."""
+    rng = np.random.default_rng(98)
+    mjd0 = 60000.0
+    t = mjd0 + np.sort(rng.uniform(0.2, 30, 24))
+    nu = np.where(np.arange(t.size) % 2 == 0, 4.6e14, 6.3e14)
+    N = 6
+    p = h.metzger_magnetar_prior(rng, N, "general")
+    p["t0"] = mjd0 + rng.uniform(-5, 8, N)
+    fn = rb.phase_models.t0_base_model
+    plain = rb.magnetar_driven_ejecta_models.general_metzger_magnetar_driven
+    kw = dict(base_model="general_metzger_magnetar_driven", frequency=nu, output_format="flux_density")
+    out = fn(t, params_batch=p, **kw)
+    y = np.abs(out[2]) * 1.05 + 1e-8
+    sigma = 0.1 * y
+    logl = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=kw).log_likelihood_batch(p)
+    for i in range(N):
+        kwi = {k: float(v[i]) for k, v in p.items()}
+        t0 = kwi.pop("t0")
+        good = t - t0 >= 0
+        assert np.all(out[i][~good] == 0.0)
+        want = plain(t[good] - t0, frequency=nu[good], output_format="flux_density", **kwi)
+        h.assert_close(out[i][good], want, 1e-12, what=f"t0(general_metzger_magnetar_driven) sample {i}")
+        ref_l = r.gaussian_likelihood(y, out[i], sigma)
+        assert abs(logl[i] - ref_l) <= 1e-6 + 1e-9 * abs(ref_l), (i, logl[i], ref_l)
+    rb.bands.register_synthetic_lsst()
+    bands = np.array(list(h.LSST_NU)[:6] * 4)
+    mag = fn(t, params_batch=p, base_model="general_metzger_magnetar_driven", bands=bands, output_format="magnitude")
+    for i in range(N):
+        kwi = {k: float(v[i]) for k, v in p.items()}
+        t0 = kwi.pop("t0")
+        good = t - t0 >= 0
+        assert np.all(mag[i][~good] == 1000.0)
+        want = plain(t[good] - t0, bands=bands[good], output_format="magnitude", **kwi)
+        ok = np.isfinite(want) & (want < 60)
+        assert np.max(np.abs(mag[i][good][ok] - want[ok])) < 1e-8
+
+
 def test_evolving_magnetar_variants(rb):
     """general_mergernova_evolution (:422-474) and general_metzger_magnetar_driven_evolution (:908-956): the spin-down
     ODE of magnetar_models._evolving_gw_and_em_magnetar runs on device; golden vectors + a small batch."""
