@@ -1,91 +1,112 @@
-"""Ejecta relations that map gravitational-wave source parameters to kilonova ejecta parameters
-(redback/ejecta_relations.py).  Host-side, vectorised over the sample axis: the fits are a handful of flops per
-sample and feed the `params_batch` of the fused kilonova kernels."""
+"""Ejecta relations: gravitational-wave source parameters -> kilonova ejecta mass [Msun] and velocity [c]
+(the fits used by redback/ejecta_relations.py: Dietrich & Ujevic 2017 for binary neutron stars, Kawaguchi et al.
+2016 for neutron-star black-hole binaries).  Host-side and vectorised over the sample axis: a handful of flops per
+sample that feed `params_batch` of the fused kilonova kernels.  Each class exposes `ejecta_mass` and
+`ejecta_velocity` like the reference's, evaluated once at construction."""
 import numpy as np
 
+# quasi-universal relations (ejecta_relations.py:435-444, 473-482)
+_C_OF_LOG_LAMBDA = (0.371, -0.0391, 0.001056)
+_MB_COEF, _MB_POWER = 0.8857853174243745, 1.2082383572002926
+# (scale, offset, compactness coefficient) of the symmetric mass-ratio fits  s * [q (1 + c C1) + (1 + c C2) / q] + o
+_V_TOTAL = (-0.3090, 0.657, -1.879)        # ejecta_relations.py:40-43
+_V_RHO = (-0.219479, 0.444836, -2.67385)   # :492-494
+_V_Z = (-0.315585, 0.63808, -1.00757)      # :514-516
 
-def _f64(x):
-    if hasattr(x, "detach"):
-        x = x.detach().cpu().numpy()
-    return np.asarray(x, dtype=np.float64)
+
+def _arr(x):
+    return np.asarray(x.detach().cpu().numpy() if hasattr(x, "detach") else x, dtype=np.float64)
 
 
 def calc_compactness_from_lambda(lambda_1):
-    """ejecta_relations.py:435-444 (quasi-universal C(Lambda) relation)."""
-    log_l = np.log(_f64(lambda_1))
-    return 0.371 - 0.0391 * log_l + 0.001056 * log_l ** 2
+    u = np.log(_arr(lambda_1))
+    k0, k1, k2 = _C_OF_LOG_LAMBDA
+    return k0 + k1 * u + k2 * u ** 2
 
 
 def calc_baryonic_mass(mass, compactness):
-    """ejecta_relations.py:473-482."""
-    return _f64(mass) * (1 + 0.8857853174243745 * _f64(compactness) ** 1.2082383572002926)
+    return _arr(mass) * (1 + _MB_COEF * _arr(compactness) ** _MB_POWER)
 
 
-def _mass_ratio_fit(mass_1, mass_2, lambda_1, lambda_2, a, b, c):
-    m1, m2 = _f64(mass_1), _f64(mass_2)
-    c1, c2 = calc_compactness_from_lambda(lambda_1), calc_compactness_from_lambda(lambda_2)
-    return ((m1 / m2) * (1.0 + c * c1) + (m2 / m1) * (1.0 + c * c2)) * a + b
+def _symmetric_fit(coef, ma, mb, ca, cb):
+    scale, offset, c = coef
+    return ((ma / mb) * (1.0 + c * ca) + (mb / ma) * (1.0 + c * cb)) * scale + offset
 
 
 def calc_vrho(mass_1, mass_2, lambda_1, lambda_2):
-    """Average velocity in the orbital plane (ejecta_relations.py:484-502)."""
-    return _mass_ratio_fit(mass_1, mass_2, lambda_1, lambda_2, -0.219479, 0.444836, -2.67385)
+    """Mean ejecta velocity in the orbital plane."""
+    return _symmetric_fit(_V_RHO, _arr(mass_1), _arr(mass_2), calc_compactness_from_lambda(lambda_1),
+                          calc_compactness_from_lambda(lambda_2))
 
 
 def calc_vz(mass_1, mass_2, lambda_1, lambda_2):
-    """Velocity orthogonal to the orbital plane (ejecta_relations.py:504-525)."""
-    return _mass_ratio_fit(mass_1, mass_2, lambda_1, lambda_2, -0.315585, 0.63808, -1.00757)
+    """Mean ejecta velocity orthogonal to the orbital plane."""
+    return _symmetric_fit(_V_Z, _arr(mass_1), _arr(mass_2), calc_compactness_from_lambda(lambda_1),
+                          calc_compactness_from_lambda(lambda_2))
 
 
-class OneComponentBNSNoProjection:
-    """Dietrich & Ujevic (2017) fits, one component, no projection (ejecta_relations.py:5-86)."""
-
+class _BinaryNeutronStar:
     def __init__(self, mass_1, mass_2, lambda_1, lambda_2):
-        m1, m2 = _f64(mass_1), _f64(mass_2)
-        c1, c2 = calc_compactness_from_lambda(lambda_1), calc_compactness_from_lambda(lambda_2)
-        self.c1, self.c2 = c1, c2
-        self.vrho, self.vz = calc_vrho(m1, m2, lambda_1, lambda_2), calc_vz(m1, m2, lambda_1, lambda_2)
-        a, b, c = -0.3090, 0.657, -1.879
-        self.ejecta_velocity = a * (m1 / m2) * (1 + c * c1) + a * (m2 / m1) * (1 + c * c2) + b       # :37-44
-        a, b, d, n = -0.0719, 0.2116, -2.42, -2.905
-        log10_mej = a * (m1 * (1 - 2 * c1) / c1 + m2 * (1 - 2 * c2) / c2) + b * \
-            (m1 * (m2 / m1) ** n + m2 * (m1 / m2) ** n) + d                                            # :53-63
-        self.ejecta_mass = 10 ** log10_mej
+        self.mass_1, self.mass_2 = _arr(mass_1), _arr(mass_2)
+        self.lambda_1, self.lambda_2 = _arr(lambda_1), _arr(lambda_2)
+        self.c1 = calc_compactness_from_lambda(self.lambda_1)
+        self.c2 = calc_compactness_from_lambda(self.lambda_2)
+        self.vrho = _symmetric_fit(_V_RHO, self.mass_1, self.mass_2, self.c1, self.c2)
+        self.vz = _symmetric_fit(_V_Z, self.mass_1, self.mass_2, self.c1, self.c2)
+        self.ejecta_velocity = self._velocity()
+        self.ejecta_mass = self._mass()
 
 
-class OneComponentBNSProjection:
-    """Dietrich & Ujevic (2017) fits with orbital-plane / orthogonal projection (ejecta_relations.py:88-168)."""
+class OneComponentBNSNoProjection(_BinaryNeutronStar):
+    """One component, no projection (ejecta_relations.py:5-65)."""
 
-    def __init__(self, mass_1, mass_2, lambda_1, lambda_2):
-        m1, m2 = _f64(mass_1), _f64(mass_2)
-        c1, c2 = calc_compactness_from_lambda(lambda_1), calc_compactness_from_lambda(lambda_2)
-        self.c1, self.c2 = c1, c2
-        self.vrho, self.vz = calc_vrho(m1, m2, lambda_1, lambda_2), calc_vz(m1, m2, lambda_1, lambda_2)
-        self.ejecta_velocity = (self.vrho ** 2.0 + self.vz ** 2.0) ** 0.5                             # :120
-        a, b, c, d, n = -1.35695, 6.11252, -49.43355, 16.1144, -2.5484
-        mb1, mb2 = calc_baryonic_mass(m1, c1), calc_baryonic_mass(m2, c2)
-        tmp1 = ((mb1 * ((m2 / m1) ** (1.0 / 3.0)) * (1.0 - 2.0 * c1) / c1)
-                + (mb2 * ((m1 / m2) ** (1.0 / 3.0)) * (1.0 - 2.0 * c2) / c2)) * a
-        tmp2 = (mb1 * ((m2 / m1) ** n) + mb2 * ((m1 / m2) ** n)) * b
-        tmp3 = (mb1 * (1.0 - m1 / mb1) + mb2 * (1.0 - m2 / mb2)) * c
-        self.ejecta_mass = np.maximum(tmp1 + tmp2 + tmp3 + d, 0) / 1000.0                            # :141-147
+    def _velocity(self):
+        scale, offset, c = _V_TOTAL      # the reference adds the two terms and the offset left to right (:43)
+        m1, m2 = self.mass_1, self.mass_2
+        return scale * (m1 / m2) * (1 + c * self.c1) + scale * (m2 / m1) * (1 + c * self.c2) + offset
+
+    def _mass(self):
+        m1, m2, c1, c2 = self.mass_1, self.mass_2, self.c1, self.c2
+        tidal = m1 * (1 - 2 * c1) / c1 + m2 * (1 - 2 * c2) / c2
+        ratio = m1 * (m2 / m1) ** -2.905 + m2 * (m1 / m2) ** -2.905
+        return 10 ** (-0.0719 * tidal + 0.2116 * ratio + -2.42)                 # :56-64, log10 of the mass
+
+
+class OneComponentBNSProjection(_BinaryNeutronStar):
+    """One component with the orbital-plane / orthogonal velocity projection (ejecta_relations.py:88-147)."""
+
+    def _velocity(self):
+        return (self.vrho ** 2.0 + self.vz ** 2.0) ** 0.5
+
+    def _mass(self):
+        m1, m2, c1, c2 = self.mass_1, self.mass_2, self.c1, self.c2
+        b1, b2 = calc_baryonic_mass(m1, c1), calc_baryonic_mass(m2, c2)
+        tidal = (b1 * ((m2 / m1) ** (1.0 / 3.0)) * (1.0 - 2.0 * c1) / c1) + (b2 * ((m1 / m2) ** (1.0 / 3.0)) * (1.0 - 2.0 * c2) / c2)
+        ratio = b1 * ((m2 / m1) ** -2.5484) + b2 * ((m1 / m2) ** -2.5484)
+        binding = b1 * (1.0 - m1 / b1) + b2 * (1.0 - m2 / b2)
+        milli_msun = tidal * -1.35695 + ratio * 6.11252 + binding * -49.43355 + 16.1144               # :130-146
+        return np.maximum(milli_msun, 0) / 1000.0
 
 
 class OneComponentNSBH:
-    """Kawaguchi et al. (2016) fits for a neutron-star black-hole merger (ejecta_relations.py:380-432)."""
+    """Neutron-star black-hole merger, one component (ejecta_relations.py:380-432)."""
 
     def __init__(self, mass_bh, mass_ns, chi_bh, lambda_ns):
-        mbh, mns, chi = _f64(mass_bh), _f64(mass_ns), _f64(chi_bh)
-        q = mbh / mns
+        self.mass_bh, self.mass_ns, self.chi_bh = _arr(mass_bh), _arr(mass_ns), _arr(chi_bh)
+        self.lambda_ns = _arr(lambda_ns)
+        self.mass_ratio = self.mass_bh / self.mass_ns
+        self.risco = self._isco_radius(self.chi_bh)
+        self.ejecta_velocity = 1.5333330951369120e-2 * self.mass_ratio + 0.19066667068621043
+        compactness = calc_compactness_from_lambda(self.lambda_ns)
+        baryonic = calc_baryonic_mass(self.mass_ns, compactness)
+        q = self.mass_ratio
+        bracket = self.risco * (q ** 1.352) * -2.269e-3 + (q ** 0.2497) * (1 - 2 * compactness) * 4.464e-2 / compactness \
+            + ((1 - self.mass_ns / baryonic) * 2.431 + -0.4159)
+        self.ejecta_mass = baryonic * np.maximum(bracket, 0)
+
+    @staticmethod
+    def _isco_radius(chi):
+        """Bardeen, Press & Teukolsky radius of the innermost stable circular orbit in units of G M / c^2."""
         z1 = 1 + ((1 - chi * chi) ** (1 / 3.0)) * (((1 + chi) ** (1 / 3.0)) + (1 - chi) ** (1 / 3.0))
         z2 = (3 * chi * chi + z1 * z1) ** (1 / 2.0)
-        self.risco = 3 + z2 - np.sign(chi) * ((3 - z1) * (3 + z1 + 2 * z2)) ** (1 / 2.0)             # :404-408
-        self.mass_ratio = q
-        self.ejecta_velocity = 1.5333330951369120e-2 * q + 0.19066667068621043                        # :416
-        a1, a2, a3, a4, n1, n2 = -2.269e-3, 4.464e-2, 2.431, -0.4159, 1.352, 0.2497
-        comp = calc_compactness_from_lambda(lambda_ns)
-        mb = calc_baryonic_mass(mns, comp)
-        tmp1 = self.risco * (q ** n1) * a1
-        tmp2 = (q ** n2) * (1 - 2 * comp) * a2 / comp
-        tmp3 = (1 - mns / mb) * a3 + a4
-        self.ejecta_mass = mb * np.maximum(tmp1 + tmp2 + tmp3, 0)                                     # :425-432
+        return 3 + z2 - np.sign(chi) * ((3 - z1) * (3 + z1 + 2 * z2)) ** (1 / 2.0)
