@@ -76,7 +76,7 @@ def test_supernova_magnitudes(rb, obands, model):
         _check(out[i], ref, f"{model} sample {i}", floor_mag=np.nanmin(ref))
 
 
-@pytest.mark.parametrize("n_lambda,n_epochs", [(57, 48), (300, 48), (131, 1500), (200, 7)])
+@pytest.mark.parametrize("n_lambda,n_epochs", [(57, 48), (300, 48), (131, 1500), (200, 7), (9, 12), (16, 12), (33, 12)])
 def test_photometry_kernel_odd_shapes(rb, obands, n_lambda, n_epochs):
     """Shapes that exercise every branch of the photometry kernel's work split: wavelength grids that are not a
     multiple of the warp / segment size, more columns than threads (two columns per thread in the time-axis passes),
