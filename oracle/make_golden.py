@@ -341,6 +341,41 @@ def dump_metzger_magnetar():
     print("metzger magnetar fixtures:", len(doc["draws"]))
 
 
+def dump_ejecta_relations():
+    """The reference's own ejecta-relation classes (redback/ejecta_relations.py) on seeded draws."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import refshim
+    ns = refshim.load_ejecta_relations()
+    rng = np.random.default_rng(2028)
+    n = 24
+    bns = dict(mass_1=rng.uniform(1.3, 2.0, n), mass_2=rng.uniform(1.0, 1.3, n), lambda_1=rng.uniform(50, 800, n),
+               lambda_2=rng.uniform(200, 3000, n))
+    two = dict(mtov=rng.uniform(2.0, 2.4, n), zeta=rng.uniform(0.05, 0.5, n))
+    nsbh = dict(mass_bh=rng.uniform(3, 10, n), mass_ns=rng.uniform(1.1, 1.8, n), chi_bh=rng.uniform(-0.5, 0.9, n),
+                lambda_ns=rng.uniform(100, 2000, n))
+    doc = {"bns": {k: v.tolist() for k, v in bns.items()}, "two": {k: v.tolist() for k, v in two.items()},
+           "nsbh": {k: v.tolist() for k, v in nsbh.items()}, "out": {}}
+    with np.errstate(all="ignore"):
+        for name in ("OneComponentBNSNoProjection", "OneComponentBNSProjection"):
+            rel = getattr(ns, name)(**bns)
+            doc["out"][name] = dict(ejecta_mass=np.asarray(rel.ejecta_mass).tolist(),
+                                    ejecta_velocity=np.asarray(rel.ejecta_velocity).tolist())
+        rel = ns.TwoComponentBNS(**bns, **two)
+        doc["out"]["TwoComponentBNS"] = dict(dynamical_mej=np.asarray(rel.dynamical_mej).tolist(),
+                                             disk_wind_mej=np.asarray(rel.disk_wind_mej).tolist(),
+                                             ejecta_velocity=np.asarray(rel.ejecta_velocity).tolist())
+        rel = ns.TwoComponentNSBH(**nsbh, zeta=two["zeta"])
+        doc["out"]["TwoComponentNSBH"] = dict(dynamical_mej=np.asarray(rel.dynamical_mej).tolist(),
+                                              disk_wind_mej=np.asarray(rel.disk_wind_mej).tolist(),
+                                              ejecta_velocity=np.asarray(rel.ejecta_velocity).tolist())
+        rel = ns.OneComponentNSBH(**nsbh)
+        doc["out"]["OneComponentNSBH"] = dict(ejecta_mass=np.asarray(rel.ejecta_mass).tolist(),
+                                              ejecta_velocity=np.asarray(rel.ejecta_velocity).tolist())
+    with open(os.path.join(OUT, "ejecta_relations_reference_draws.json"), "w") as fh:
+        json.dump(doc, fh)
+    print("ejecta relation fixtures:", n)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     dump_pkl()
@@ -350,3 +385,4 @@ if __name__ == "__main__":
     dump_csm()
     dump_mergernova()
     dump_metzger_magnetar()
+    dump_ejecta_relations()

@@ -102,17 +102,17 @@ def load_afterglow():
 
 
 def load_functions(relpath, names, namespace):
-    """Compile the named top-level functions of a reference source file *from where it lies* (decorators dropped)
+    """Compile the named top-level functions / classes of a reference source file *from where it lies* (decorators dropped)
     and define them in `namespace`.  For functions whose module cannot be imported as a whole here
     (utils.py / supernova_models.py need astropy, sncosmo, ...)."""
     import ast
     path = os.path.join(REFERENCE_ROOT, relpath)
     with open(path) as fh:
         tree = ast.parse(fh.read(), filename=path)
-    picked = [node for node in tree.body if isinstance(node, ast.FunctionDef) and node.name in names]
+    picked = [node for node in tree.body if isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name in names]
     missing = set(names) - {node.name for node in picked}
     if missing:
-        raise RuntimeError(f"{relpath}: no top-level function(s) {sorted(missing)}")
+        raise RuntimeError(f"{relpath}: no top-level function(s) / class(es) {sorted(missing)}")
     for node in picked:
         node.decorator_list = []
     exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), namespace)
@@ -175,3 +175,14 @@ def load_metzger_magnetar():
                    ["_general_metzger_magnetar_driven_kilonova_model"], glb)
     return types.SimpleNamespace(**{k: glb[k] for k in ("_general_metzger_magnetar_driven_kilonova_model",
                                                        "magnetar_only", "get_optimal_time_array")})
+
+
+def load_ejecta_relations():
+    """The reference's own ejecta-relation classes and helper fits (redback/ejecta_relations.py imports astropy at
+    module level; the classes themselves only need numpy), executed from /root/reference."""
+    import numpy as np
+    glb = dict(np=np)
+    names = ["OneComponentBNSNoProjection", "OneComponentBNSProjection", "TwoComponentBNS", "TwoComponentNSBH",
+             "OneComponentNSBH", "calc_compactness_from_lambda", "calc_baryonic_mass", "calc_vrho", "calc_vz"]
+    load_functions("redback/ejecta_relations.py", names, glb)
+    return types.SimpleNamespace(**{k: glb[k] for k in names})

@@ -1145,6 +1145,49 @@ def nsbh_ejecta(mass_bh, mass_ns, chi_bh, lambda_ns):
     return mb * np.maximum(tmp, 0), 1.5333330951369120e-2 * q + 0.19066667068621043
 
 
+def bns_two_component_ejecta(mass_1, mass_2, lambda_1, lambda_2, mtov, zeta):
+    """TwoComponentBNS (ejecta_relations.py:170-267) -> (dynamical mej, disk-wind mej [Msun], vej [c])."""
+    mej_dyn, vej = bns_ejecta_no_projection(mass_1, mass_2, lambda_1, lambda_2)          # same fits (:201-238)
+    q = mass_1 / mass_2
+    lambdatilde = (16.0 / 13.0) * (lambda_2 + lambda_1 * (q ** 5) + 12 * lambda_1 * (q ** 4) + 12 * lambda_2 * q) \
+        / ((q + 1) ** 5)
+    mc = ((mass_1 * mass_2) ** (3. / 5.)) * ((mass_1 + mass_2) ** (-1. / 5.))
+    r16 = mc * (lambdatilde / 0.0042) ** (1.0 / 6.0)
+    mth = (2.38 - 3.606 * mtov / r16) * mtov
+    mdisk = 10 ** (-31.335 * (1 + -0.9760 * np.tanh((1.0474 - (mass_1 + mass_2) / mth) / 0.05957)))
+    return mej_dyn, zeta * mdisk, vej
+
+
+def nsbh_two_component_ejecta(mass_bh, mass_ns, chi_bh, lambda_ns, zeta):
+    """TwoComponentNSBH (ejecta_relations.py:290-378)."""
+    q = mass_bh / mass_ns
+    z1 = 1 + (1 - chi_bh ** 2) ** (1 / 3) * ((1 + chi_bh) ** (1 / 3) + (1 - chi_bh) ** (1 / 3))
+    z2 = np.sqrt(3 * chi_bh ** 2 + z1 ** 2)
+    risco = 3 + z2 - np.sign(chi_bh) * np.sqrt((3 - z1) * (3 + z1 + 2 * z2))
+    comp = compactness_from_lambda(lambda_ns)
+    mb = baryonic_mass(mass_ns, comp)
+    dyn = mb * np.maximum(4.464e-2 * (q ** 0.2497) * (1 - 2 * comp) / comp + -2.269e-3 * (q ** 1.352) * risco
+                          + 2.431 * (1 - mass_ns / mb) + -0.4159, 0)
+    rho = (15 * lambda_ns) ** (-1 / 5)
+    eta = q / (1 + q) ** 2
+    disk = mb * (np.maximum(0.308 * (1 - 2 * rho) / (eta ** (1 / 3)) + -0.124 * risco * rho / eta + 0.283, 0.0)) ** 1.536
+    return dyn, zeta * disk, 1.5333330951369120e-2 * q + 0.19066667068621043
+
+
+def two_component_bns_ejecta_relation(time, redshift, mass_1, mass_2, lambda_1, lambda_2, mtov, zeta, vej_2, kappa_1,
+                                      kappa_2, tf_1, tf_2, **kw):
+    """kilonova_models.py:1369-1397"""
+    mej_1, mej_2, vej_1 = bns_two_component_ejecta(mass_1, mass_2, lambda_1, lambda_2, mtov, zeta)
+    return two_component_kilonova_model(time, redshift, mej_1, vej_1, tf_1, kappa_1, mej_2, vej_2, tf_2, kappa_2, **kw)
+
+
+def two_component_nsbh_ejecta_relation(time, redshift, mass_bh, mass_ns, chi_bh, lambda_ns, zeta, vej_2, kappa_1,
+                                       kappa_2, tf_1, tf_2, **kw):
+    """kilonova_models.py:1496-1527"""
+    mej_1, mej_2, vej_1 = nsbh_two_component_ejecta(mass_bh, mass_ns, chi_bh, lambda_ns, zeta)
+    return two_component_kilonova_model(time, redshift, mej_1, vej_1, tf_1, kappa_1, mej_2, vej_2, tf_2, kappa_2, **kw)
+
+
 def one_component_ejecta_relation(time, redshift, mass_1, mass_2, lambda_1, lambda_2, kappa, **kw):
     """kilonova_models.py:1309-1336"""
     mej, vej = bns_ejecta_no_projection(mass_1, mass_2, lambda_1, lambda_2)

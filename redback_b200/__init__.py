@@ -25,7 +25,8 @@ all_models_dict.update({name: getattr(kilonova_models, name)
                         for name in ("one_component_kilonova_model", "metzger_kilonova_model",
                                      "two_component_kilonova_model", "three_component_kilonova_model",
                                      "one_component_ejecta_relation", "one_component_ejecta_relation_projection",
-                                     "one_component_nsbh_ejecta_relation")})
+                                     "one_component_nsbh_ejecta_relation", "two_component_bns_ejecta_relation",
+                                     "two_component_nsbh_ejecta_relation")})
 all_models_dict.update({fn.__name__: fn for fn in afterglow_models.FUSED})
 all_models_dict.update({fn.__name__: fn for fn in magnetar_driven_ejecta_models.FUSED})
 all_models_dict.update({fn.__name__: fn for fn in tde_models.FUSED})

@@ -88,6 +88,49 @@ class OneComponentBNSProjection(_BinaryNeutronStar):
         return np.maximum(milli_msun, 0) / 1000.0
 
 
+class TwoComponentBNS(OneComponentBNSNoProjection):
+    """Dynamical + disk-wind ejecta of a binary neutron star merger (ejecta_relations.py:170-267, Coughlin et al. 2019):
+    the dynamical component uses the one-component fits, the disk mass follows from the threshold mass for prompt
+    collapse; `zeta` is the fraction of the disk that is unbound."""
+
+    def __init__(self, mass_1, mass_2, lambda_1, lambda_2, mtov, zeta):
+        super().__init__(mass_1, mass_2, lambda_1, lambda_2)
+        self.mtov, self.zeta = _arr(mtov), _arr(zeta)
+        m1, m2, l1, l2 = self.mass_1, self.mass_2, self.lambda_1, self.lambda_2
+        q = m1 / m2
+        lambda_tilde = (16.0 / 13.0) * (l2 + l1 * (q ** 5) + 12 * l1 * (q ** 4) + 12 * l2 * q) / ((q + 1) ** 5)
+        chirp = ((m1 * m2) ** (3. / 5.)) * ((m1 + m2) ** (-1. / 5.))
+        radius_16 = chirp * (lambda_tilde / 0.0042) ** (1.0 / 6.0)
+        threshold = (2.38 - 3.606 * self.mtov / radius_16) * self.mtov
+        log10_disk = -31.335 * (1 + -0.9760 * np.tanh((1.0474 - (m1 + m2) / threshold) / 0.05957))   # :255-262
+        self.dynamical_mej = self.ejecta_mass
+        self.disk_wind_mej = self.zeta * 10 ** log10_disk
+
+
+class TwoComponentNSBH:
+    """Dynamical (Kawaguchi et al. 2016) + disk-wind (Foucart et al. 2018) ejecta of a neutron-star black-hole merger
+    (ejecta_relations.py:290-378)."""
+
+    def __init__(self, mass_bh, mass_ns, chi_bh, lambda_ns, zeta):
+        self.mass_bh, self.mass_ns, self.chi_bh = _arr(mass_bh), _arr(mass_ns), _arr(chi_bh)
+        self.lambda_ns, self.zeta = _arr(lambda_ns), _arr(zeta)
+        q = self.mass_ratio = self.mass_bh / self.mass_ns
+        chi = self.chi_bh
+        z1 = 1 + (1 - chi ** 2) ** (1 / 3) * ((1 + chi) ** (1 / 3) + (1 - chi) ** (1 / 3))
+        z2 = np.sqrt(3 * chi ** 2 + z1 ** 2)
+        self.risco = 3 + z2 - np.sign(chi) * np.sqrt((3 - z1) * (3 + z1 + 2 * z2))                  # :318-328
+        self.ejecta_velocity = 1.5333330951369120e-2 * q + 0.19066667068621043
+        compactness = calc_compactness_from_lambda(self.lambda_ns)
+        baryonic = calc_baryonic_mass(self.mass_ns, compactness)
+        unbound = 4.464e-2 * (q ** 0.2497) * (1 - 2 * compactness) / compactness + -2.269e-3 * (q ** 1.352) * self.risco \
+            + 2.431 * (1 - self.mass_ns / baryonic) + -0.4159                                         # :349-356
+        self.dynamical_mej = baryonic * np.maximum(unbound, 0)
+        rho = (15 * self.lambda_ns) ** (-1 / 5)
+        eta = q / (1 + q) ** 2
+        remnant = 0.308 * (1 - 2 * rho) / (eta ** (1 / 3)) + -0.124 * self.risco * rho / eta + 0.283  # :369-376
+        self.disk_wind_mej = self.zeta * (baryonic * (np.maximum(remnant, 0.0)) ** 1.536)
+
+
 class OneComponentNSBH:
     """Neutron-star black-hole merger, one component (ejecta_relations.py:380-432)."""
 

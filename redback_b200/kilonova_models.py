@@ -158,4 +158,52 @@ def one_component_nsbh_ejecta_relation(time, redshift=None, mass_bh=None, mass_n
                                 OneComponentNSBH, params_batch, kwargs)
 
 
+def _two_component_via_relation(name, time, redshift, relation_args, rest, default_relation, params_batch, kwargs):
+    """kilonova_models.py:1369-1397, 1496-1527: dynamical and disk-wind ejecta masses and the dynamical velocity from
+    the ejecta relation, then two_component_kilonova_model (tf_1 / tf_2 are its temperature floors)."""
+    import numpy as np
+    kwargs = dict(kwargs)
+    relation = kwargs.pop("ejecta_relation", default_relation)
+    src, other = dict(relation_args), dict(rest, redshift=redshift)
+    if params_batch is not None:
+        missing = [k for k in list(src) + list(other) if k not in params_batch]
+        if missing:
+            raise KeyError(f"{name}: params_batch lacks {missing}")
+        src = {k: params_batch[k] for k in src}
+        other = {k: params_batch[k] for k in other}
+    with np.errstate(all="ignore"):                  # out-of-range draws give NaN light curves, as in the reference
+        rel = relation(**src)
+    comp = dict(mej_1=rel.dynamical_mej, vej_1=rel.ejecta_velocity, temperature_floor_1=other["tf_1"],
+                kappa_1=other["kappa_1"], mej_2=rel.disk_wind_mej, vej_2=other["vej_2"],
+                temperature_floor_2=other["tf_2"], kappa_2=other["kappa_2"])
+    if params_batch is not None:
+        batch = {k: np.asarray(v, dtype=np.float64) for k, v in comp.items()}
+        batch["redshift"] = other["redshift"]
+        extra = {k: v for k, v in params_batch.items() if k not in src and k not in other}
+        return two_component_kilonova_model(time, params_batch=dict(extra, **batch), **kwargs)
+    return two_component_kilonova_model(time, other["redshift"], **{k: float(v) for k, v in comp.items()}, **kwargs)
+
+
+def two_component_bns_ejecta_relation(time, redshift=None, mass_1=None, mass_2=None, lambda_1=None, lambda_2=None,
+                                      mtov=None, zeta=None, vej_2=None, kappa_1=None, kappa_2=None, tf_1=None,
+                                      tf_2=None, params_batch=None, **kwargs):
+    """redback kilonova_models.two_component_bns_ejecta_relation (:1369-1397)."""
+    from .ejecta_relations import TwoComponentBNS
+    return _two_component_via_relation(
+        "two_component_bns_ejecta_relation", time, redshift,
+        dict(mass_1=mass_1, mass_2=mass_2, lambda_1=lambda_1, lambda_2=lambda_2, mtov=mtov, zeta=zeta),
+        dict(vej_2=vej_2, kappa_1=kappa_1, kappa_2=kappa_2, tf_1=tf_1, tf_2=tf_2), TwoComponentBNS, params_batch, kwargs)
+
+
+def two_component_nsbh_ejecta_relation(time, redshift=None, mass_bh=None, mass_ns=None, chi_bh=None, lambda_ns=None,
+                                       zeta=None, vej_2=None, kappa_1=None, kappa_2=None, tf_1=None, tf_2=None,
+                                       params_batch=None, **kwargs):
+    """redback kilonova_models.two_component_nsbh_ejecta_relation (:1496-1527)."""
+    from .ejecta_relations import TwoComponentNSBH
+    return _two_component_via_relation(
+        "two_component_nsbh_ejecta_relation", time, redshift,
+        dict(mass_bh=mass_bh, mass_ns=mass_ns, chi_bh=chi_bh, lambda_ns=lambda_ns, zeta=zeta),
+        dict(vej_2=vej_2, kappa_1=kappa_1, kappa_2=kappa_2, tf_1=tf_1, tf_2=tf_2), TwoComponentNSBH, params_batch, kwargs)
+
+
 FUSED = {one_component_kilonova_model: _ONE, metzger_kilonova_model: _METZGER}

@@ -90,6 +90,41 @@ def test_ejecta_relations_match_the_reference_formulas():
     assert np.ndim(one.ejecta_mass) == 0 and 0 < float(one.ejecta_mass) < 0.1
 
 
+def test_ejecta_relations_pinned_to_the_reference_classes():
+    """The oracle's restatement and the product's host module against the reference's own classes executed from their
+    source (tests/golden/ejecta_relations_reference_draws.json, oracle/make_golden.py::dump_ejecta_relations)."""
+    import json
+    import os
+    from redback_b200 import ejecta_relations as ejr
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "ejecta_relations_reference_draws.json")) as fh:
+        fx = json.load(fh)
+    bns = {k: np.array(v) for k, v in fx["bns"].items()}
+    two = {k: np.array(v) for k, v in fx["two"].items()}
+    nsbh = {k: np.array(v) for k, v in fx["nsbh"].items()}
+    close = lambda a, b: np.testing.assert_allclose(a, np.array(b, dtype=float), rtol=1e-12, atol=1e-15)
+    for name, ofn in (("OneComponentBNSNoProjection", r.bns_ejecta_no_projection),
+                      ("OneComponentBNSProjection", r.bns_ejecta_projection)):
+        mej, vej = ofn(**bns)
+        rel = getattr(ejr, name)(**bns)
+        for got_m, got_v in ((mej, vej), (rel.ejecta_mass, rel.ejecta_velocity)):
+            close(got_m, fx["out"][name]["ejecta_mass"])
+            close(got_v, fx["out"][name]["ejecta_velocity"])
+    want = fx["out"]["TwoComponentBNS"]
+    rel = ejr.TwoComponentBNS(**bns, **two)
+    for dyn, wind, vej in (r.bns_two_component_ejecta(**bns, **two), (rel.dynamical_mej, rel.disk_wind_mej, rel.ejecta_velocity)):
+        close(dyn, want["dynamical_mej"]); close(wind, want["disk_wind_mej"]); close(vej, want["ejecta_velocity"])
+    want = fx["out"]["TwoComponentNSBH"]
+    rel = ejr.TwoComponentNSBH(**nsbh, zeta=two["zeta"])
+    for dyn, wind, vej in (r.nsbh_two_component_ejecta(**nsbh, zeta=two["zeta"]),
+                           (rel.dynamical_mej, rel.disk_wind_mej, rel.ejecta_velocity)):
+        close(dyn, want["dynamical_mej"]); close(wind, want["disk_wind_mej"]); close(vej, want["ejecta_velocity"])
+    want = fx["out"]["OneComponentNSBH"]
+    rel = ejr.OneComponentNSBH(**nsbh)
+    for mej, vej in (r.nsbh_ejecta(**nsbh), (rel.ejecta_mass, rel.ejecta_velocity)):
+        close(mej, want["ejecta_mass"]); close(vej, want["ejecta_velocity"])
+
+
 def test_t0_needs_ascending_times():
     phase_models._check_sorted(np.array([1.0, 2.0, 2.0, 3.0]))
     with pytest.raises(NotImplementedError):

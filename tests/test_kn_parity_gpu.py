@@ -57,6 +57,36 @@ def test_ejecta_relation_models(rb, golden):
         assert name in rb.all_models_dict
 
 
+def test_two_component_ejecta_relation_models(rb):
+    """two_component_bns_ejecta_relation / two_component_nsbh_ejecta_relation (kilonova_models.py:1369-1397, 1496-1527):
+    batch and scalar calls against the oracle (whose ejecta relations are pinned to the reference's own classes)."""
+    rng = np.random.default_rng(123)
+    t = np.geomspace(0.3, 5.0, 20)
+    nu = np.where(np.arange(t.size) % 2 == 0, 6.3e14, 4.7e14)
+    N = 6
+    common = dict(redshift=rng.uniform(0.005, 0.1, N), zeta=rng.uniform(0.05, 0.5, N), vej_2=rng.uniform(0.05, 0.2, N),
+                  kappa_1=rng.uniform(1, 10, N), kappa_2=rng.uniform(0.5, 3, N), tf_1=rng.uniform(1e3, 4e3, N),
+                  tf_2=rng.uniform(1e3, 4e3, N))
+    cases = (("two_component_bns_ejecta_relation",
+              dict(mass_1=rng.uniform(1.35, 1.8, N), mass_2=rng.uniform(1.1, 1.35, N), lambda_1=rng.uniform(100, 600, N),
+                   lambda_2=rng.uniform(300, 1500, N), mtov=rng.uniform(2.0, 2.3, N))),
+             ("two_component_nsbh_ejecta_relation",
+              dict(mass_bh=rng.uniform(3, 6, N), mass_ns=rng.uniform(1.2, 1.6, N), chi_bh=rng.uniform(0.2, 0.9, N),
+                   lambda_ns=rng.uniform(300, 1500, N))))
+    for name, own in cases:
+        p = dict(common, **own)
+        fn = getattr(rb.kilonova_models, name)
+        out = fn(t, params_batch=p, frequency=nu, output_format="flux_density")
+        for i in range(N):
+            kwi = {k: float(v[i]) for k, v in p.items()}
+            z = kwi.pop("redshift")
+            ref = getattr(r, name)(t, z, frequency=nu, **kwi)
+            h.assert_close(out[i], ref, RTOL, _tol_extra(t, z, nu), what=f"{name} sample {i}")
+        one = fn(t, frequency=nu, output_format="flux_density", **{k: float(v[0]) for k, v in p.items()})
+        np.testing.assert_allclose(one, out[0], rtol=1e-12)
+        assert name in rb.all_models_dict
+
+
 def test_t0_base_model_kilonova(rb):
     """phase_models.t0_base_model (phase_models.py:19-59) over the kilonova models: per-sample merger epochs in one
     launch; epochs before t0 return 0 (1000 mag); each sample's adaptive grid follows ITS valid epochs."""
