@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
         else eb = 4.0e18 * pow(0.5 - (1. / kPi) * atan_cr((t - 1.3) / 0.11), 1.3) * e_th;      // :2014
         w1[k] = eb;
         w2[k] = exp(-t / 900.0);                                               // :2032
+        Tg[k] = 1.0 / t;             // shared by the 200 shell threads of the march (Tg is filled after it)
       }
     }
     __syncthreads();
@@ -331,20 +332,24 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
         }
         double en = 0.5 * ms * (vm * vm);                                      // :2043
         const bool ode = active && s < kShells - 1;                            // the [:-1] slices
+        // per-shell constants of the step: the four divisions of :2050-2059 collapse into one (1 / t is shared by
+        // all shells and tabulated per grid point)
+        const double c_td = (ms * kMsun * 3) / (4 * kPi * vm * kC * beta);     // t_d = kappa c_td / t        (:2050)
+        const double c_tau = (ms * kMsun) / (4 * kPi * (vm * vm));             // tau = kappa c_tau / t^2     (:2052)
+        const double vmc = vm / kC;
         for (int ii = 0; ii < G - 1; ++ii) {
-          const double t = tg[ii];
+          const double t = tg[ii], it = Tg[ii];
           double kap = kappa, edot = w1[ii];
           if (npre) {
             const double xn = xn0 * w2[ii];
             edot = 3.2e14 * xn + edot;                                         // :2033-2034
             kap = 0.4 * (1.0 - xn - xr) + kappa * xr;                          // :2035-2037
           }
-          const double td = (kap * ms * kMsun * 3) / (4 * kPi * vm * kC * t * beta);   // :2050
-          const double tv = t * vm;
-          const double tau = (ms * kMsun * kap / (4 * kPi * (tv * tv)));        // :2052
-          const double lum = en / (td + t * (vm / kC));                         // :2058
+          const double td = (kap * c_td) * it;
+          const double tau = (kap * c_tau) * (it * it);
+          const double lum = en / (td + t * vmc);                               // :2058
           const double dt = tg[ii + 1] - t;
-          en = (edot - (en / t) - lum) * dt + en;                               // :2059
+          en = (edot - (en * it) - lum) * dt + en;                              // :2059
           double lo = ode ? lum * dm * kMsun : 0.0;                             // :2060
           // shell 199 copies tau of shell 198 (:2062): it can never win the first-minimum argmin
           double dist = ode ? fabs(tau - 1.0) : INFINITY;
