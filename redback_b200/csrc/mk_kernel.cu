@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(kMkThreads) mk_kernel(const MkArgs a) {
         if (t > 1.3) w1[k] = 2.1e10 * e_th * pow(t / (3600. * 24.), -1.3);
         else w1[k] = 4.0e18 * pow(0.5 - (1. / kPi) * atan_cr((t - 1.3) / 0.11), 1.3) * e_th;
         w2[k] = exp(-t / 900.0);
+        Tg[k] = 1.0 / t;               // shared by all shell threads during the march (Tg is filled after it)
         if (a.cfg.engine == RB_MN_BASIC_MAGNETAR) {
           const double den = 1.0 + 2.0 * t / eng_b;
           lsd[k] = eng_a / (den * den);
@@ -154,14 +155,21 @@ __global__ void __launch_bounds__(kMkThreads) mk_kernel(const MkArgs a) {
       double en0 = 0.5 * ms0 * ((vej * kC) * (vej * kC));
       double ke = 0.5 * m0 * ((vej * kC) * (vej * kC));                        // :610
       const double gpref = 3 * row9 * mej / (4 * kPi * (vej * vej));           // :675 (kappa_gamma variant)
+      // Divisions per step: 1 / t is tabulated per grid point, 1 / v_m = (1 / v0) (1 / vf) needs one division for both
+      // shells of the thread; with the two L = E / (t_d + t v / c) that leaves three instead of eight (:667-712)
+      const double ivf = 1.0 / vf, ivf0 = 1.0 / vf0, inv_c = 1.0 / kC;
+      const double c_td = (ms * kMsun * 3) / (4 * kPi * kC * beta), c_td0 = (ms0 * kMsun * 3) / (4 * kPi * kC * beta);
+      const double c_tau = (ms * kMsun) / (4 * kPi);
       for (int ii = 0; ii < G - 1; ++ii) {
-        const double t = tg[ii], dt = tg[ii + 1] - t;
-        ke = ke + (en0 / t) * dt;                                              // :667
+        const double t = tg[ii], dt = tg[ii + 1] - t, it = Tg[ii];
+        ke = ke + (en0 * it) * dt;                                             // :667
         const double v0 = sqrt(2 * ke / m0);
+        const double iv0 = 1.0 / v0;
         if (tid == 0) v0g[ii] = v0;
         double vm = v0 * vf, vm0 = v0 * vf0;                                   // :671-672
-        if (vm > 3e10) vm = kC;
-        if (vm0 > 3e10) vm0 = kC;
+        double ivm = iv0 * ivf, ivm0 = iv0 * ivf0;
+        if (vm > 3e10) { vm = kC; ivm = inv_c; }
+        if (vm0 > 3e10) { vm0 = kC; ivm0 = inv_c; }
         double eff = row9;
         if (a.cfg.use_gamma_ray_opacity) eff = 1 - exp(-gpref * (1.0 / (t * t)));   // :676 (1 - exp, as the reference)
         const double qdot = eff * lsd[ii];
@@ -175,18 +183,18 @@ __global__ void __launch_bounds__(kMkThreads) mk_kernel(const MkArgs a) {
         }
         // shell 0 replica (:697-707)
         {
-          const double td0 = (kap0 * ms0 * kMsun * 3) / (4 * kPi * vm0 * kC * t * beta);
-          const double lum0 = en0 / (td0 + t * (vm0 / kC));
-          en0 = (qdot + edot0 * dm0 * kMsun - (en0 / t) - lum0) * dt + en0;
+          const double td0 = (kap0 * c_td0) * (ivm0 * it);
+          const double lum0 = en0 / (td0 + t * (vm0 * inv_c));
+          en0 = (qdot + edot0 * dm0 * kMsun - (en0 * it) - lum0) * dt + en0;
         }
         // this thread's shell
-        const double td = (kap * ms * kMsun * 3) / (4 * kPi * vm * kC * t * beta);
-        const double lum = en / (td + t * (vm / kC));
+        const double td = (kap * c_td) * (ivm * it);
+        const double lum = en / (td + t * (vm * inv_c));
         if (tid == 0) en = en0;                                                // same arithmetic; keep them identical
-        else if (a.cfg.heat_all_layers) en = (qdot + edot * dm * kMsun - (en / t) - lum) * dt + en;   // :704
-        else en = (edot * dm * kMsun - (en / t) - lum) * dt + en;              // :710
-        const double tv = t * vm;
-        const double tau = (ms * kMsun * kap / (4 * kPi * (tv * tv)));          // :712
+        else if (a.cfg.heat_all_layers) en = (qdot + edot * dm * kMsun - (en * it) - lum) * dt + en;   // :704
+        else en = (edot * dm * kMsun - (en * it) - lum) * dt + en;             // :710
+        const double itv = it * ivm;
+        const double tau = (kap * c_tau) * (itv * itv);                         // :712
         double lo = ode ? lum : 0.0;
         double dist = ode ? fabs(tau - 1.0) : INFINITY;                         // shell 199 copies 198: never first
         if (isnan(dist)) dist = -INFINITY;                                      // np.argmin returns the first NaN
