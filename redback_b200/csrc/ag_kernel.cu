@@ -354,8 +354,9 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
   const int steps = a.cfg.steps, E = a.E, n_nu = a.n_nu;
   const int spl = (steps + 31) / 32;          // steps per lane
   double* ring = asm_;                         // [kRingArrays][steps]
-  double* et = ring + kRingArrays * steps;     // [E] epochs in seconds (t * 86400)
-  double* wbuf = et + E;                       // per warp: tobs[steps] + flux[n_nu][steps]
+  double* ibeta = ring + kRingArrays * steps;  // [steps] 1 / beta                          } per ring and step, shared by
+  double* costh = ibeta + steps;               // [steps] cos(acos(1 - omega / rotstep))    } all cells of the ring
+  double* wbuf = costh + steps;                // per warp: tobs[steps] + flux[n_nu][steps]
   double* acc = wbuf + (size_t)kAgWarps * (1 + n_nu) * steps;   // [kAgWarps][E]
   double* sc = acc + (size_t)kAgWarps * E;     // [kAgScalars]
   int* nuidx = reinterpret_cast<int*>(sc + kAgScalars);         // [E]
@@ -373,10 +374,7 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
   const int ring_begin = (int)(u - a.unit_off[n]) * kAgRingsPerUnit;
   const int ring_end = min(ring_begin + kAgRingsPerUnit, a.ring_count[n]);
 
-  for (int e = tid; e < E; e += blockDim.x) {
-    et[e] = a.epoch_tab[EP_T * E + e] * kDay;                    // :923  time * day_to_s
-    nuidx[e] = a.nu_index[e];
-  }
+  for (int e = tid; e < E; e += blockDim.x) nuidx[e] = a.nu_index[e];
   double* my_tobs = wbuf + (size_t)warp * (1 + n_nu) * steps;
   double* my_flux = my_tobs + steps;
   double* my_acc = acc + (size_t)warp * E;
@@ -398,6 +396,12 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
       __syncthreads();  // previous ring's cells are done with `ring`
       const double* src = a.ring_scratch + (size_t)(a.ring_off[n] + i) * kRingArrays * steps;
       for (int q = tid; q < kRingArrays * steps; q += blockDim.x) ring[q] = src[q];
+      __syncthreads();
+      // quantities of :343-360 that do not depend on the cell's azimuth, with the reference's own expressions
+      for (int q = tid; q < steps; q += blockDim.x) {
+        ibeta[q] = 1.0 / ring[RA_BETA * steps + q];
+        costh[q] = cos(acos(1.0 - ring[RA_OMG * steps + q] / rotstep));
+      }
       __syncthreads();
       double thi;
       if (nlat == 1) thi = th_lo;
@@ -426,12 +430,12 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
         const double cosa = cos(obsa);
         // ---- step2 (:325-370): this lane's steps [s0, s1) ----
         const int s0 = min(lane * spl, steps), s1 = min(s0 + spl, steps);
+        const double cos_th0 = cos(acos(1.0 - Om0 / rotstep));   // the cell's own solid angle (expansion: until the ring's exceeds it)
         double sum_dt = 0.0, sum_dto = 0.0;
         for (int s = s0; s < s1; ++s) {
           const double rd = ring[RA_R * steps + s] - (s > 0 ? ring[RA_R * steps + s - 1] : 0.0);
-          const double ib = 1.0 / ring[RA_BETA * steps + s];
-          sum_dt += rd * (ib - cosa) / AG_CC;
-          sum_dto += rd * (ib - 1.0) / AG_CC;
+          sum_dt += rd * (ibeta[s] - cosa) / AG_CC;
+          sum_dto += rd * (ibeta[s] - 1.0) / AG_CC;
         }
         double pre_dt = sum_dt, pre_dto = sum_dto;   // inclusive scan over lanes
 #pragma unroll
@@ -445,12 +449,14 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
           const double G = ring[RA_G * steps + s], beta = ring[RA_BETA * steps + s], B = ring[RA_B * steps + s];
           const double R = ring[RA_R * steps + s];
           const double rd = R - (s > 0 ? ring[RA_R * steps + s - 1] : 0.0);
-          const double ib = 1.0 / beta;
-          tobs += rd * (ib - cosa) / AG_CC;
-          tobso += rd * (ib - 1.0) / AG_CC;
+          tobs += rd * (ibeta[s] - cosa) / AG_CC;
+          tobso += rd * (ibeta[s] - 1.0) / AG_CC;
           const double omg = ring[RA_OMG * steps + s];
-          const double Om = expansion ? fmax_nan(Om0, omg) : omg;
-          const double thii = acos(1.0 - Om / rotstep);
+          double Om = omg, cos_thii = costh[s];
+          if (expansion) {
+            Om = fmax_nan(Om0, omg);
+            if (!(Om == omg)) cos_thii = cos_th0;
+          }
           const double NO = Om0 * ring[RA_NE * steps + s] / AG_FOURPI;
           const double dop = 1.0 / (G * (1.0 - beta * cosa));
           const double gc = 6.0 * kPi * AG_ME * AG_CC / (G * a.sigt * B * B * tobso);
@@ -458,7 +464,7 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
           const double num = dop * ring[RA_NUMP * steps + s];
           const double nuc = dop * nucp;
           const double Fmax = NO * ring[RA_PP * steps + s] * dop * dop * dop / (AG_FOURPI * dl2);
-          const double FBB = 2 * Om * cos(thii) * dop * ring[RA_KT * steps + s] * R * R / (AG_C2 * dl2);
+          const double FBB = 2 * Om * cos_thii * dop * ring[RA_KT * steps + s] * R * R / (AG_C2 * dl2);
           my_tobs[s] = tobs;
           for (int h = 0; h < n_nu; ++h)
             my_flux[h * steps + s] = ag_flux(FBB, nuc, num, a.nu_unique[h] * opz, Fmax, p);   // nu = nu0*(1+z) :587
@@ -467,7 +473,8 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
         // ---- calc_lightcurve (:632-640): np.interp(t/(1+z), tobs, Flux[h]) summed over cells ----
         const double x_first = my_tobs[0], x_last = my_tobs[steps - 1];
         for (int e = lane; e < E; e += 32) {
-          const double x = et[e] / opz;
+          const double x = (a.epoch_tab[EP_T * E + e] * kDay) / opz;     // :923  time * day_to_s (the table stays in L1;
+                                                                         // a shared copy would cost the third block per SM)
           const double* fp = my_flux + nuidx[e] * steps;
           double v;
           if (!(x == x)) v = x;

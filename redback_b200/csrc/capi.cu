@@ -990,7 +990,7 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
     h_idx[(size_t)e] = (int)(std::lower_bound(uniq.begin(), uniq.end(), h_freq[(size_t)e]) - uniq.begin());
 
   const int steps = cfg->steps, n_nu = (int)uniq.size();
-  const size_t cell_smem = sizeof(double) * ((size_t)rb::kRingArrays * steps + (size_t)E +
+  const size_t cell_smem = sizeof(double) * ((size_t)(rb::kRingArrays + 2) * steps +
                                              (size_t)rb::kAgWarps * (1 + n_nu) * steps + (size_t)rb::kAgWarps * E +
                                              rb::kAgScalars) + sizeof(int) * (size_t)E;
   if (cell_smem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_ag_eval: steps / epochs exceed shared memory");
