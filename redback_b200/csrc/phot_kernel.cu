@@ -572,14 +572,10 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
 #pragma unroll
         for (int u = 0; u < kGather; ++u) {
           const int q = min(lane + 32 * u, span - 1);
-#ifdef RB_PHOT_NOGATHER
-          g0[u] = g1[u] = g2[u] = g3[u] = (double)q;
-#else
           g0[u] = Sx[q];
           g1[u] = Sx[NL + q];
           g2[u] = Sx[2 * NL + q];
           g3[u] = Sx[3 * NL + q];
-#endif
         }
       };
       gather(warp);
