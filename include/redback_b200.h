@@ -9,7 +9,14 @@
  *   - plain pointers + sizes, no torch / numpy types;
  *   - `*_f64` entry points take DEVICE pointers and are stream-ordered (`stream` is a cudaStream_t
  *     passed as void*; NULL = default stream); they never synchronise;
- *   - `*_host` entry points take HOST pointers, do H2D, launch, D2H and synchronise;
+ *   - `*_host` entry points take ordinary (pageable) HOST pointers and return when the outputs are complete.  Inside,
+ *     samples stream through a per-device two-slot pipeline (pinned staging block -> one H2D copy per chunk -> kernels
+ *     -> D2H into pinned memory -> caller's buffer) on two private streams, so copies overlap compute; the pipeline's
+ *     streams and buffers are created once per device and reused (no cudaMalloc / cudaDeviceSynchronize per call).
+ *     Pointers INSIDE the config (cfg->t0, cfg->f_nickel: [N]; cfg->upper_limits.sigma_level: [E]) are HOST pointers
+ *     for `*_host` calls and device pointers for `*_f64` calls.  One host call at a time per device (internally locked);
+ *   - `*_host_rows` is the same with the parameter block given as RB_*_NPARAM separate row pointers (a redback
+ *     `params_batch` dict of arrays is exactly that): rows[r] = [N] host array, or NULL for the constant fill[r];
  *   - per-sample parameters are struct-of-arrays: params[row * N + sample];
  *   - return 0 on success or a negative rb_status; rb_last_error() gives a message;
  *   - there is no CPU fallback: without a usable CUDA device every compute call fails with
@@ -180,11 +187,17 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
                    const double* sigma, const double* sigma_param, double* out_model, double* out_logl,
                    void* stream);
 
-/* Same computation with HOST buffers (H2D + kernel + D2H + sync inside the call). */
+/* Same computation with HOST buffers: chunked, double-buffered H2D -> kernels -> D2H inside the call (see the
+ * conventions at the top).  This is what a non-Python caller binds; redback_b200.likelihoods reaches it through
+ * GaussianLikelihood.log_likelihood_batch when the batch is host-resident. */
 int rb_sn_eval_f64_host(const rb_sn_config* cfg, int64_t N, int64_t E, const double* params,
                         const double* t_obs, const double* freq_obs, const double* dl_cm,
                         const double* y, const double* sigma, const double* sigma_param,
                         double* out_model, double* out_logl);
+int rb_sn_eval_f64_host_rows(const rb_sn_config* cfg, int64_t N, int64_t E, const double* const* rows,
+                             const double* fill, const double* t_obs, const double* freq_obs,
+                             const double* dl_cm, const double* y, const double* sigma,
+                             const double* sigma_param, double* out_model, double* out_logl);
 
 /* ---- kilonova path ----------------------------------------------------------------------------------
  * one_component_kilonova_model   redback/transient_models/kilonova_models.py:1537-1603 (+ :1853-1893)
@@ -228,6 +241,10 @@ int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, const double* 
 int rb_kn_eval_f64_host(const rb_kn_config* cfg, int64_t N, int64_t E, const double* params,
                         const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
                         const double* sigma, const double* sigma_param, double* out_model, double* out_logl);
+int rb_kn_eval_f64_host_rows(const rb_kn_config* cfg, int64_t N, int64_t E, const double* const* rows,
+                             const double* fill, const double* t_obs, const double* freq_obs,
+                             const double* dl_cm, const double* y, const double* sigma,
+                             const double* sigma_param, double* out_model, double* out_logl);
 
 /* ---- redback-native afterglow path --------------------------------------------------------------------
  * tophat_redback    redback/transient_models/afterglow_models/base_models.py:885-946
@@ -272,6 +289,10 @@ int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, const double* 
 int rb_ag_eval_f64_host(const rb_ag_config* cfg, int64_t N, int64_t E, const double* params,
                         const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
                         const double* sigma, const double* sigma_param, double* out_model, double* out_logl);
+int rb_ag_eval_f64_host_rows(const rb_ag_config* cfg, int64_t N, int64_t E, const double* const* rows,
+                             const double* fill, const double* t_obs, const double* freq_obs,
+                             const double* dl_cm, const double* y, const double* sigma,
+                             const double* sigma_param, double* out_model, double* out_logl);
 
 /* ---- magnetar-driven relativistic ejecta ("mergernova") path ---------------------------------------------
  * basic_mergernova / general_mergernova / general_mergernova_thermalisation
@@ -348,6 +369,10 @@ int rb_mn_eval_f64(const rb_mn_config* cfg, int64_t N, int64_t E, const double* 
 int rb_mn_eval_f64_host(const rb_mn_config* cfg, int64_t N, int64_t E, const double* params,
                         const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
                         const double* sigma, const double* sigma_param, double* out_model, double* out_logl);
+int rb_mn_eval_f64_host_rows(const rb_mn_config* cfg, int64_t N, int64_t E, const double* const* rows,
+                             const double* fill, const double* t_obs, const double* freq_obs,
+                             const double* dl_cm, const double* y, const double* sigma,
+                             const double* sigma_param, double* out_model, double* out_logl);
 
 /* utils.get_optimal_time_array(t_min, t_max, resolution) without user times (utils.py:79-93), HOST function:
  * writes at most `resolution` ascending points to out (host memory) and their count to *n_out. */
@@ -399,6 +424,10 @@ int rb_mk_eval_f64(const rb_mk_config* cfg, int64_t N, int64_t E, const double* 
 int rb_mk_eval_f64_host(const rb_mk_config* cfg, int64_t N, int64_t E, const double* params,
                         const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y,
                         const double* sigma, const double* sigma_param, double* out_model, double* out_logl);
+int rb_mk_eval_f64_host_rows(const rb_mk_config* cfg, int64_t N, int64_t E, const double* const* rows,
+                             const double* fill, const double* t_obs, const double* freq_obs,
+                             const double* dl_cm, const double* y, const double* sigma,
+                             const double* sigma_param, double* out_model, double* out_logl);
 
 /* ---- magnitude / bandpass branch (output_format = 'magnitude' | 'flux') ---------------------------------
  * get_correct_output_format_from_spectra -> RedbackTimeSeriesSource.bandmag -> _bandflux_single_redback
@@ -500,6 +529,8 @@ int64_t rb_launch_count(void);
 
 const char* rb_last_error(void);
 const char* rb_version(void);
+/* digest of the sources the library was built from (bindings compare it with the tree they ship with) */
+const char* rb_source_hash(void);
 
 #ifdef __cplusplus
 }

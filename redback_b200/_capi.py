@@ -114,6 +114,7 @@ _dp = C.c_void_p  # device or host pointer to double
 EXPORTS = {
     "rb_last_error": (C.c_char_p, []),
     "rb_version": (C.c_char_p, []),
+    "rb_source_hash": (C.c_char_p, []),
     "rb_launch_count": (C.c_int64, []),
     "rb_cosmology_flat_lcdm": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.POINTER(C.c_double), C.POINTER(Cosmology)]),
@@ -121,19 +122,29 @@ EXPORTS = {
     "rb_sn_config_default": (C.c_int, [C.POINTER(SnConfig)]),
     "rb_sn_eval_f64": (C.c_int, [C.POINTER(SnConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
     "rb_sn_eval_f64_host": (C.c_int, [C.POINTER(SnConfig), C.c_int64, C.c_int64] + [_dp] * 9),
+    "rb_sn_eval_f64_host_rows": (C.c_int, [C.POINTER(SnConfig), C.c_int64, C.c_int64, C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_double)] + [_dp] * 8),
     "rb_kn_config_default": (C.c_int, [C.POINTER(KnConfig)]),
     "rb_kn_eval_f64": (C.c_int, [C.POINTER(KnConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
     "rb_kn_eval_f64_host": (C.c_int, [C.POINTER(KnConfig), C.c_int64, C.c_int64] + [_dp] * 9),
+    "rb_kn_eval_f64_host_rows": (C.c_int, [C.POINTER(KnConfig), C.c_int64, C.c_int64, C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_double)] + [_dp] * 8),
     "rb_ag_config_default": (C.c_int, [C.POINTER(AgConfig)]),
     "rb_ag_eval_f64": (C.c_int, [C.POINTER(AgConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
     "rb_ag_eval_f64_host": (C.c_int, [C.POINTER(AgConfig), C.c_int64, C.c_int64] + [_dp] * 9),
+    "rb_ag_eval_f64_host_rows": (C.c_int, [C.POINTER(AgConfig), C.c_int64, C.c_int64, C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_double)] + [_dp] * 8),
     "rb_mn_config_default": (C.c_int, [C.POINTER(MnConfig)]),
     "rb_mn_eval_f64": (C.c_int, [C.POINTER(MnConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
     "rb_mn_eval_f64_host": (C.c_int, [C.POINTER(MnConfig), C.c_int64, C.c_int64] + [_dp] * 9),
+    "rb_mn_eval_f64_host_rows": (C.c_int, [C.POINTER(MnConfig), C.c_int64, C.c_int64, C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_double)] + [_dp] * 8),
     "rb_optimal_time_array": (C.c_int, [C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "rb_mk_config_default": (C.c_int, [C.POINTER(MkConfig)]),
     "rb_mk_eval_f64": (C.c_int, [C.POINTER(MkConfig), C.c_int64, C.c_int64] + [_dp] * 9 + [C.c_void_p]),
     "rb_mk_eval_f64_host": (C.c_int, [C.POINTER(MkConfig), C.c_int64, C.c_int64] + [_dp] * 9),
+    "rb_mk_eval_f64_host_rows": (C.c_int, [C.POINTER(MkConfig), C.c_int64, C.c_int64, C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_double)] + [_dp] * 8),
     "rb_sn_mag_eval_f64": (C.c_int, [C.POINTER(SnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_kn_mag_eval_f64": (C.c_int, [C.POINTER(KnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_kn_multi_mag_eval_f64": (C.c_int, [C.POINTER(KnConfig), C.c_void_p, C.c_int, C.c_int64, C.c_int64] + [_dp] * 8
@@ -158,9 +169,7 @@ def lib():
         return _lib
     path = os.environ.get("REDBACK_B200_LIB")   # alternate build of the same ABI (kernel experiments)
     if not path:
-        path = _build.LIB_PATH
-        if not os.path.exists(path):
-            path = _build.build()
+        path = _build.build()       # no-op when the library's compiled-in source digest matches the sources
     handle = C.CDLL(path)
     for name, (res, args) in EXPORTS.items():
         if not hasattr(handle, name) and os.environ.get("REDBACK_B200_LIB"):
@@ -168,6 +177,16 @@ def lib():
         fn = getattr(handle, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
+    if not os.environ.get("REDBACK_B200_LIB"):
+        got = handle.rb_source_hash().decode().replace("RBHASH:", "")
+        if got != _build.source_hash():
+            raise RedbackB200Error(f"{path} was built from other sources (digest {got}); rebuild with "
+                                   "python -m redback_b200._build --force")
+    # the ctypes mirrors below are passed by reference: a layout mismatch would be silent memory corruption
+    for which, cls in enumerate((Cosmology, UpperLimits, SnConfig, KnConfig, AgConfig, MnConfig, MkConfig)):
+        if handle.rb_sizeof(which) != C.sizeof(cls):
+            raise RedbackB200Error(f"struct layout mismatch for {cls.__name__}: library {handle.rb_sizeof(which)} "
+                                   f"bytes, binding {C.sizeof(cls)} bytes")
     _lib = handle
     return _lib
 

@@ -33,15 +33,24 @@ class FusedSpec:
         return self._build(time, kwargs, y, sigma, sigma_mode)
 
     def cache_key(self, kwargs):
-        items = []
-        for k in sorted(kwargs):
-            v = kwargs[k]
-            if k == "frequency":
-                continue
-            if k == "bands":
-                v = tuple(np.atleast_1d(np.asarray(v)).tolist())
-            items.append((k, v if isinstance(v, (int, float, str, bool, type(None))) else id(v)))
-        return (self.name, tuple(items))
+        """Key of the device-resident path built from `kwargs`: scalars by value, arrays (frequency, bands,
+        lambda_array, ...) by a digest of their CONTENT, so in-place edits and recycled ids cannot alias."""
+        return (self.name, tuple((k, content_key(kwargs[k])) for k in sorted(kwargs)))
+
+
+def content_key(v):
+    """Hashable stand-in for a kwarg / data value: the value itself for scalars, a content digest for arrays."""
+    if isinstance(v, (int, float, str, bool, type(None))):
+        return v
+    if isinstance(v, torch.Tensor):
+        v = v.detach().cpu().numpy()
+    if isinstance(v, (np.ndarray, list, tuple)):
+        arr = np.asarray(v)
+        if arr.dtype == object:
+            return ("obj", tuple(content_key(x) for x in arr.reshape(-1).tolist()))
+        import hashlib
+        return (arr.shape, arr.dtype.str, hashlib.blake2b(np.ascontiguousarray(arr).tobytes(), digest_size=12).digest())
+    return ("id", id(v))
 
 
 def collect(named, kwargs, params_batch, needed, defaults=None):

@@ -41,17 +41,39 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call);    \
   } while (0)
 
+// One-time set-up PER DEVICE: cudaFuncSetAttribute and the memory-pool threshold act on the current device only, so a
+// process that evaluates on cuda:1 after cuda:0 (the public `device=` kwarg, or threads on different devices) must run
+// them again there.  A failed set-up is retried on the next call.
+struct DeviceOnce {
+  std::mutex mu;
+  bool done[64] = {};
+  template <typename F> cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return f();
+    std::lock_guard<std::mutex> g(mu);
+    if (done[dev]) return cudaSuccess;
+    e = f();
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+  }
+};
+
 // Keep the stream-ordered workspace pool resident across synchronisations: by default the driver trims it to zero
 // at every sync, and every call would pay for hundreds of MB of fresh allocations (measured: 2x on the photometry path).
 void keep_workspace_pool() {
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static DeviceOnce once;
+  once.run([] {
     int dev = 0;
     cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e == cudaSuccess) {
       uint64_t keep = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
+    return e;
   });
 }
 
@@ -86,10 +108,10 @@ size_t csm_smem_bytes(int D, int64_t E) {
 // CSM engine (RB_ENGINE_CSM): unique epochs -> per-sample scalars -> one block per sample.  `t_dev` are the E
 // observer-frame epochs (or the model's own time grid in grid mode) that a.epoch_tab was built from.
 int launch_csm(rb::SnArgs a, const double* t_dev, cudaStream_t st, int sms) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::csm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  static DeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    cudaError_t attr_err = cudaFuncSetAttribute(rb::csm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    return attr_err;
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(csm_kernel)");
   const int E = a.E;
@@ -162,7 +184,11 @@ int sn_block_threads(int64_t E) {
 extern "C" {
 
 const char* rb_last_error(void) { return g_err.c_str(); }
-const char* rb_version(void) { return "redback_b200 0.1 (sm_100a)"; }
+const char* rb_version(void) { return "redback_b200 0.2 (sm_100a)"; }
+#ifndef RB_SOURCE_HASH
+#define RB_SOURCE_HASH "unknown"
+#endif
+const char* rb_source_hash(void) { return "RBHASH:" RB_SOURCE_HASH; }
 int64_t rb_launch_count(void) { return launch_counter()->load(); }
 
 int rb_cosmology_flat_lcdm(double H0, double Om0, double Tcmb0, double Neff, const double m_nu[3],
@@ -281,10 +307,10 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   int dev = 0, sms = 0;
   RB_CUDA(cudaGetDevice(&dev));
   RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = sn_kernel_attributes();
+  static DeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    cudaError_t attr_err = sn_kernel_attributes();
+    return attr_err;
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sn_kernel)");
 
@@ -384,43 +410,11 @@ int rb_mixture_logl_f64(int64_t N, int64_t E, const double* model, const double*
   return RB_OK;
 }
 
-namespace {
-struct DevBuf {
-  double* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n * sizeof(double) : sizeof(double)); }
-};
+}  // extern "C"
 
-// Host-buffer variant of a device entry point: upload, launch on the default stream, download, synchronise.
-extern "C++" template <typename Cfg, typename DeviceEval>
-int eval_host(DeviceEval device_eval, const Cfg* cfg, int nparam, int64_t N, int64_t E, const double* params,
-              const double* t_obs, const double* freq_obs, const double* dl_cm, const double* y, const double* sigma,
-              const double* sigma_param, double* out_model, double* out_logl) {
-  DevBuf d_par, d_t, d_f, d_dl, d_y, d_s, d_sp, d_m, d_l;
-  const size_t nN = (size_t)N, nE = (size_t)E;
-  auto up = [&](DevBuf& b, const double* h, size_t n) -> cudaError_t {
-    if (!h) return cudaSuccess;
-    cudaError_t e = b.alloc(n);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice);
-  };
-  RB_CUDA(up(d_par, params, (size_t)nparam * nN));
-  RB_CUDA(up(d_t, t_obs, nE));
-  RB_CUDA(up(d_f, freq_obs, nE));
-  RB_CUDA(up(d_dl, dl_cm, nN));
-  RB_CUDA(up(d_y, y, nE));
-  RB_CUDA(up(d_s, sigma, nE));
-  RB_CUDA(up(d_sp, sigma_param, nN));
-  if (out_model) RB_CUDA(d_m.alloc(nN * nE));
-  if (out_logl) RB_CUDA(d_l.alloc(nN));
-  const int rc = device_eval(cfg, N, E, d_par.p, d_t.p, d_f.p, d_dl.p, d_y.p, d_s.p, d_sp.p, d_m.p, d_l.p, nullptr);
-  if (rc != RB_OK) return rc;
-  if (out_model) RB_CUDA(cudaMemcpy(out_model, d_m.p, nN * nE * sizeof(double), cudaMemcpyDeviceToHost));
-  if (out_logl) RB_CUDA(cudaMemcpy(out_logl, d_l.p, nN * sizeof(double), cudaMemcpyDeviceToHost));
-  RB_CUDA(cudaDeviceSynchronize());
-  return RB_OK;
-}
-}  // namespace
+#include "host_pipe.inc"
+
+extern "C" {
 
 int rb_sn_eval_f64_host(const rb_sn_config* cfg, int64_t N, int64_t E, const double* params,
                         const double* t_obs, const double* freq_obs, const double* dl_cm,
@@ -429,8 +423,19 @@ int rb_sn_eval_f64_host(const rb_sn_config* cfg, int64_t N, int64_t E, const dou
   int rc = sn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
-  return eval_host(rb_sn_eval_f64, cfg, RB_SN_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
-                   out_model, out_logl);
+  return eval_host_std(rb_sn_eval_f64, cfg, rows_block(RB_SN_NPARAM, params), N, E, t_obs, freq_obs, dl_cm, y, sigma,
+                       sigma_param, out_model, out_logl, 524288);
+}
+
+int rb_sn_eval_f64_host_rows(const rb_sn_config* cfg, int64_t N, int64_t E, const double* const* rows,
+                             const double* fill, const double* t_obs, const double* freq_obs,
+                             const double* dl_cm, const double* y, const double* sigma,
+                             const double* sigma_param, double* out_model, double* out_logl) {
+  int rc = sn_check(cfg, N, E, rows, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  return eval_host_std(rb_sn_eval_f64, cfg, rows_list(RB_SN_NPARAM, rows, fill), N, E, t_obs, freq_obs, dl_cm, y, sigma,
+                       sigma_param, out_model, out_logl, 524288);
 }
 
 int64_t rb_sizeof(int which) {
@@ -562,12 +567,12 @@ extern "C" int rb_kn_eval_f64(const rb_kn_config* cfg, int64_t N, int64_t E, con
   int dev = 0, sms = 0;
   RB_CUDA(cudaGetDevice(&dev));
   RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::kn_kernel<RB_KN_ONE_COMPONENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  static DeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    cudaError_t attr_err = cudaFuncSetAttribute(rb::kn_kernel<RB_KN_ONE_COMPONENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(rb::kn_kernel<RB_KN_METZGER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    return attr_err;
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(kn_kernel)");
   const size_t ws_doubles = (size_t)rb::kEpochCols * (size_t)E + (size_t)rb::kKnScalars * (size_t)N + 2;
@@ -626,10 +631,20 @@ extern "C" int rb_kn_eval_f64_host(const rb_kn_config* cfg, int64_t N, int64_t E
                                    double* out_model, double* out_logl) {
   int rc = kn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
-  if (cfg->t0) return fail(RB_ERR_UNSUPPORTED, "rb_kn_eval_f64_host: cfg->t0 is a device pointer; use rb_kn_eval_f64");
   if (N == 0) return RB_OK;
-  return eval_host(rb_kn_eval_f64, cfg, RB_KN_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
-                   out_model, out_logl);
+  return eval_host_std(rb_kn_eval_f64, cfg, rows_block(RB_KN_NPARAM, params), N, E, t_obs, freq_obs, dl_cm, y, sigma,
+                       sigma_param, out_model, out_logl, 262144);
+}
+
+extern "C" int rb_kn_eval_f64_host_rows(const rb_kn_config* cfg, int64_t N, int64_t E, const double* const* rows,
+                                        const double* fill, const double* t_obs, const double* freq_obs,
+                                        const double* dl_cm, const double* y, const double* sigma,
+                                        const double* sigma_param, double* out_model, double* out_logl) {
+  int rc = kn_check(cfg, N, E, rows, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  return eval_host_std(rb_kn_eval_f64, cfg, rows_list(RB_KN_NPARAM, rows, fill), N, E, t_obs, freq_obs, dl_cm, y, sigma,
+                       sigma_param, out_model, out_logl, 262144);
 }
 
 // ---- magnetar-driven ejecta (mergernova) path ---------------------------------------------------------------
@@ -791,9 +806,19 @@ extern "C" int rb_mn_eval_f64_host(const rb_mn_config* cfg, int64_t N, int64_t E
   int rc = mn_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
-  if (cfg->t0) return fail(RB_ERR_UNSUPPORTED, "rb_mn_eval_f64_host: cfg->t0 is a device pointer; use rb_mn_eval_f64");
-  return eval_host(rb_mn_eval_f64, cfg, RB_MN_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
-                   out_model, out_logl);
+  return eval_host_std(rb_mn_eval_f64, cfg, rows_block(RB_MN_NPARAM, params), N, E, t_obs, freq_obs, dl_cm, y, sigma,
+                       sigma_param, out_model, out_logl, 262144);
+}
+
+extern "C" int rb_mn_eval_f64_host_rows(const rb_mn_config* cfg, int64_t N, int64_t E, const double* const* rows,
+                                        const double* fill, const double* t_obs, const double* freq_obs,
+                                        const double* dl_cm, const double* y, const double* sigma,
+                                        const double* sigma_param, double* out_model, double* out_logl) {
+  int rc = mn_check(cfg, N, E, rows, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  return eval_host_std(rb_mn_eval_f64, cfg, rows_list(RB_MN_NPARAM, rows, fill), N, E, t_obs, freq_obs, dl_cm, y, sigma,
+                       sigma_param, out_model, out_logl, 262144);
 }
 
 // ---- magnetar-driven Metzger shell model ----------------------------------------------------------------------
@@ -854,10 +879,10 @@ extern "C" int rb_mk_eval_f64(const rb_mk_config* cfg, int64_t N, int64_t E, con
   int dev = 0, sms = 0;
   RB_CUDA(cudaGetDevice(&dev));
   RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  static DeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    cudaError_t attr_err = cudaFuncSetAttribute(rb::mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    return attr_err;
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(mk_kernel)");
   std::vector<double> tg((size_t)cfg->resolution);
@@ -914,9 +939,19 @@ extern "C" int rb_mk_eval_f64_host(const rb_mk_config* cfg, int64_t N, int64_t E
   int rc = mk_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
-  if (cfg->t0) return fail(RB_ERR_UNSUPPORTED, "rb_mk_eval_f64_host: cfg->t0 is a device pointer; use rb_mk_eval_f64");
-  return eval_host(rb_mk_eval_f64, cfg, RB_MK_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
-                   out_model, out_logl);
+  return eval_host_std(rb_mk_eval_f64, cfg, rows_block(RB_MK_NPARAM, params), N, E, t_obs, freq_obs, dl_cm, y, sigma,
+                       sigma_param, out_model, out_logl, 65536);
+}
+
+extern "C" int rb_mk_eval_f64_host_rows(const rb_mk_config* cfg, int64_t N, int64_t E, const double* const* rows,
+                                        const double* fill, const double* t_obs, const double* freq_obs,
+                                        const double* dl_cm, const double* y, const double* sigma,
+                                        const double* sigma_param, double* out_model, double* out_logl) {
+  int rc = mk_check(cfg, N, E, rows, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  return eval_host_std(rb_mk_eval_f64, cfg, rows_list(RB_MK_NPARAM, rows, fill), N, E, t_obs, freq_obs, dl_cm, y, sigma,
+                       sigma_param, out_model, out_logl, 65536);
 }
 
 // ---- afterglow path ---------------------------------------------------------------------------------------
@@ -969,10 +1004,10 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
   int dev = 0, sms = 0;
   RB_CUDA(cudaGetDevice(&dev));
   RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::ag_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  static DeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    cudaError_t attr_err = cudaFuncSetAttribute(rb::ag_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    return attr_err;
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(ag_cell_kernel)");
 
@@ -1084,8 +1119,19 @@ extern "C" int rb_ag_eval_f64_host(const rb_ag_config* cfg, int64_t N, int64_t E
   int rc = ag_check(cfg, N, E, params, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
-  return eval_host(rb_ag_eval_f64, cfg, RB_AG_NPARAM, N, E, params, t_obs, freq_obs, dl_cm, y, sigma, sigma_param,
-                   out_model, out_logl);
+  return eval_host_std(rb_ag_eval_f64, cfg, rows_block(RB_AG_NPARAM, params), N, E, t_obs, freq_obs, dl_cm, y, sigma,
+                       sigma_param, out_model, out_logl, 32768);
+}
+
+extern "C" int rb_ag_eval_f64_host_rows(const rb_ag_config* cfg, int64_t N, int64_t E, const double* const* rows,
+                                        const double* fill, const double* t_obs, const double* freq_obs,
+                                        const double* dl_cm, const double* y, const double* sigma,
+                                        const double* sigma_param, double* out_model, double* out_logl) {
+  int rc = ag_check(cfg, N, E, rows, t_obs, freq_obs, y, sigma, sigma_param, out_model, out_logl);
+  if (rc != RB_OK) return rc;
+  if (N == 0) return RB_OK;
+  return eval_host_std(rb_ag_eval_f64, cfg, rows_list(RB_AG_NPARAM, rows, fill), N, E, t_obs, freq_obs, dl_cm, y, sigma,
+                       sigma_param, out_model, out_logl, 32768);
 }
 
 // ---- magnitude / bandpass branch ---------------------------------------------------------------------------
@@ -1286,10 +1332,10 @@ struct PhotJob {
 extern "C++" template <typename Fill>
 int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   keep_workspace_pool();
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  static DeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    cudaError_t attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    return attr_err;
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(phot_kernel)");
   const int NT = j.NT, NL = j.phot->n_lambda;
@@ -1422,9 +1468,8 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
   int sms = 0;
   rc = device_and_sms(&sms);
   if (rc != RB_OK) return rc;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = sn_kernel_attributes(); });
+  static DeviceOnce once;
+  const cudaError_t attr_err = once.run([] { return sn_kernel_attributes(); });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(sn_kernel)");
   const int NT = phot->n_tgrid;
   std::vector<double> tg(phot->tgrid, phot->tgrid + NT);
@@ -1504,12 +1549,12 @@ static int kn_mag_eval(const rb_kn_config* cfg, const rb_photometry* phot, int n
   int sms = 0;
   rc = device_and_sms(&sms);
   if (rc != RB_OK) return rc;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::kn_kernel<RB_KN_ONE_COMPONENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  static DeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    cudaError_t attr_err = cudaFuncSetAttribute(rb::kn_kernel<RB_KN_ONE_COMPONENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(rb::kn_kernel<RB_KN_METZGER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    return attr_err;
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(kn_kernel)");
   // epoch range for the adaptive grid (get_optimal_time_array(..., user_times)): one tiny D2H read
@@ -1671,10 +1716,10 @@ extern "C" int rb_mk_mag_eval_f64(const rb_mk_config* cfg, const rb_photometry* 
   int sms = 0;
   rc = device_and_sms(&sms);
   if (rc != RB_OK) return rc;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rb::mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  static DeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    cudaError_t attr_err = cudaFuncSetAttribute(rb::mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    return attr_err;
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(mk_kernel)");
   std::vector<double> tg((size_t)cfg->resolution);

@@ -85,7 +85,9 @@ class _FusedPath:
             raise ValueError("time must be a non-empty 1-D array")
         self._check_time(t)
         self.E = int(t.size)
-        self.time = torch.from_numpy(np.ascontiguousarray(t)).to(self.device)
+        self._h_time = np.ascontiguousarray(t)               # host copies: the *_host entry points take host pointers
+        self._h_freq = self._h_y = self._h_sigma = self._h_ul = None
+        self.time = torch.from_numpy(self._h_time).to(self.device)
         self.frequency = None
         if self.NEEDS_FREQUENCY:
             if frequency is None:
@@ -96,10 +98,12 @@ class _FusedPath:
                 f = np.full(self.E, float(f))
             if f.shape != (self.E,):
                 raise ValueError("frequency must be a single number or the same length as time")
-            self.frequency = torch.from_numpy(np.ascontiguousarray(f)).to(self.device)
+            self._h_freq = np.ascontiguousarray(f)
+            self.frequency = torch.from_numpy(self._h_freq).to(self.device)
         self.y = self.sigma = None
         if y is not None:
             self.y = as_device_f64(y, self.device)
+            self._h_y = self.y.cpu().numpy()
             if self.y.shape != (self.E,):
                 raise ValueError("y must have the same length as time")
             if sigma is not None:
@@ -109,41 +113,108 @@ class _FusedPath:
                 self.sigma = as_device_f64(s, self.device)
                 if self.sigma.shape != (self.E,):
                     raise ValueError('Sigma must be either float or array-like x.')
+                self._h_sigma = self.sigma.cpu().numpy()
 
     def set_upper_limits(self, sigma_level, magnitude_mode=False):
         """Mark epochs with sigma_level[e] > 0 as upper limits at that many sigma
         (GaussianLikelihoodWithUpperLimits, likelihoods.py:234-489); None clears them."""
         if sigma_level is None:
-            self._ul_level = None
+            self._ul_level = self._h_ul = None
             self.cfg.upper_limits.sigma_level = None
             self.cfg.upper_limits.magnitude_mode = 0
             return
         self._ul_level = as_device_f64(sigma_level, self.device)   # kept alive by the path
         if self._ul_level.shape != (self.E,):
             raise ValueError("upper-limit sigma levels must have the same length as time")
+        self._h_ul = self._ul_level.cpu().numpy()
         self.cfg.upper_limits.sigma_level = self._ul_level.data_ptr()
         self.cfg.upper_limits.magnitude_mode = int(bool(magnitude_mode))
 
     def pack(self, params, N):
-        """SoA [RB_SN_NPARAM, N] device tensor from {name: scalar | array[N] | tensor[N]}."""
-        out = torch.zeros((self.NPARAM, N), dtype=_F64, device=self.device)
-        host_rows, host_idx = [], []
+        """SoA [NPARAM, N] device tensor from {name: scalar | array[N] | tensor[N]}.  Host values (scalars and
+        numpy arrays) are written row by row into ONE pinned block that goes up in a single asynchronous copy;
+        device tensors are copied row-wise on the device."""
+        out = torch.empty((self.NPARAM, N), dtype=_F64, device=self.device)
+        stage = torch.zeros((self.NPARAM, N), dtype=_F64, pin_memory=True)
+        view = stage.numpy()
+        dev_rows = []
         for name, val in params.items():
             if name not in self.ROWS:
                 continue
             row = self.ROWS[name]
             if isinstance(val, torch.Tensor):
-                out[row] = val.to(device=self.device, dtype=_F64).reshape(-1).expand(N) if val.numel() == 1 \
-                    else val.to(device=self.device, dtype=_F64).reshape(N)
-            elif np.ndim(val) == 0:
-                out[row].fill_(float(val))
+                if val.is_cuda:
+                    dev_rows.append((row, val))
+                else:
+                    view[row] = val.detach().to(_F64).reshape(-1).numpy()
             else:
-                host_rows.append(np.asarray(val, dtype=np.float64).reshape(N))
-                host_idx.append(row)
-        if host_rows:
-            block = torch.from_numpy(np.ascontiguousarray(np.stack(host_rows)))
-            out[torch.tensor(host_idx, device=self.device)] = block.to(self.device, non_blocking=False)
+                view[row] = np.asarray(val, dtype=np.float64).reshape(-1) if np.ndim(val) else float(val)
+        out.copy_(stage, non_blocking=True)
+        for row, val in dev_rows:
+            v = val.to(device=self.device, dtype=_F64).reshape(-1)
+            out[row] = v.expand(N) if v.numel() == 1 else v
+        # `stage` may be freed by the caching host allocator only after the copy has run (stream-ordered reuse)
         return out
+
+    # ---- host-resident batches: the C ABI's *_host_rows entry (chunked, double-buffered pipeline in the library) ----
+    def _host_rows_fn(self):
+        return None
+
+    def supports_host_rows(self):
+        return self._host_rows_fn() is not None
+
+    def evaluate_host(self, params, N, dl=None, sigma_param=None, t0=None, aux=None, want_model=False, want_logl=True):
+        """{name: scalar | ndarray[N]} -> (model ndarray[N, E] | None, logl ndarray[N] | None) through
+        rb_*_eval_f64_host_rows: the arrays are read where they lie (no packing copy on the Python side)."""
+        fn = self._host_rows_fn()
+        if fn is None:
+            raise NotImplementedError("this path has no host-buffer entry point")
+        if want_logl and self._h_y is None:
+            raise ValueError("log-likelihood requested but no data were given")
+        keep = []
+
+        def host(v, n):
+            arr = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (n,)))
+            keep.append(arr)
+            return arr.ctypes.data_as(C.c_void_p)
+
+        rows = (C.c_void_p * self.NPARAM)()
+        fill = (C.c_double * self.NPARAM)()
+        for name, val in params.items():
+            if name not in self.ROWS:
+                continue
+            row = self.ROWS[name]
+            if np.ndim(val) == 0:
+                rows[row], fill[row] = None, float(val)
+            else:
+                arr = np.ascontiguousarray(np.asarray(val, dtype=np.float64).reshape(-1))
+                if arr.size != N:
+                    raise ValueError(f"parameter '{name}' has {arr.size} values, expected {N}")
+                keep.append(arr)
+                rows[row] = arr.ctypes.data
+        cfg = type(self.cfg).from_buffer_copy(self.cfg)
+        cfg.upper_limits.sigma_level = self._h_ul.ctypes.data if self._h_ul is not None else None
+        if t0 is not None:
+            if not hasattr(cfg, "t0"):
+                raise NotImplementedError("a per-sample t0 is not available on this path")
+            cfg.t0 = host(t0, N)
+        aux_name = getattr(self, "AUX_PARAM", None)
+        if aux_name is not None:
+            if aux is None:
+                raise ValueError(f"this path needs the per-sample parameter '{aux_name}'")
+            setattr(cfg, aux_name, host(aux, N))
+        model = np.empty((N, self.E), dtype=np.float64) if want_model else None
+        logl = np.empty((N,), dtype=np.float64) if want_logl else None
+        if N == 0:
+            return model, logl
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        with torch.cuda.device(self.device):
+            rc = fn(C.byref(cfg), N, self.E, rows, fill, ptr(self._h_time), ptr(self._h_freq),
+                    host(dl, N) if dl is not None else None, ptr(self._h_y) if want_logl else None,
+                    ptr(self._h_sigma) if want_logl else None,
+                    host(sigma_param, N) if (sigma_param is not None and want_logl) else None, ptr(model), ptr(logl))
+        _capi.check(rc)
+        return model, logl
 
     def evaluate(self, params_dev, dl=None, sigma_param=None, want_model=True, want_logl=False, out_logl=None,
                  t0=None, aux=None):
@@ -253,6 +324,9 @@ class SupernovaPath(_FusedPath):
     def _eval_fn(self):
         return _capi.lib().rb_sn_eval_f64
 
+    def _host_rows_fn(self):
+        return _capi.lib().rb_sn_eval_f64_host_rows
+
     def _engine_rows(self, engine):
         if engine == _capi.ENGINE_MAGNETAR_NICKEL:
             # f_nickel and p0 share row 1 of the parameter block: f_nickel travels through cfg.f_nickel instead
@@ -294,6 +368,9 @@ class KilonovaPath(_FusedPath):
     def _eval_fn(self):
         return _capi.lib().rb_kn_eval_f64
 
+    def _host_rows_fn(self):
+        return _capi.lib().rb_kn_eval_f64_host_rows
+
     def _check_time(self, t):
         if np.any(t <= 0):
             raise ValueError("A value in x_new is below the interpolation range.")  # scipy interp1d's error
@@ -323,6 +400,9 @@ class SupernovaMagPath(SupernovaPath):
     def _launch(self, *args):
         return self._launch_mag(_capi.lib().rb_sn_mag_eval_f64, *args)
 
+    def _host_rows_fn(self):
+        return None     # the magnitude branch has device entry points only
+
 
 class KilonovaMagPath(KilonovaPath):
     """Magnitude / bandpass-flux branch of one_component_kilonova_model / metzger_kilonova_model
@@ -341,6 +421,9 @@ class KilonovaMagPath(KilonovaPath):
 
     def _launch(self, *args):
         return self._launch_mag(_capi.lib().rb_kn_mag_eval_f64, *args)
+
+    def _host_rows_fn(self):
+        return None     # the magnitude branch has device entry points only
 
 
 class KilonovaMultiMagPath(KilonovaMagPath):
@@ -382,6 +465,9 @@ class AfterglowPath(_FusedPath):
     def _eval_fn(self):
         return _capi.lib().rb_ag_eval_f64
 
+    def _host_rows_fn(self):
+        return _capi.lib().rb_ag_eval_f64_host_rows
+
 
 class MergernovaPath(_FusedPath):
     """Magnetar-driven relativistic ejecta -> relativistic blackbody -> Gaussian log L
@@ -405,6 +491,9 @@ class MergernovaPath(_FusedPath):
 
     def _eval_fn(self):
         return _capi.lib().rb_mn_eval_f64
+
+    def _host_rows_fn(self):
+        return _capi.lib().rb_mn_eval_f64_host_rows
 
     def _check_time(self, t):
         if np.any(~(t > 0)):
@@ -432,6 +521,9 @@ class MetzgerMagnetarPath(_FusedPath):
 
     def _eval_fn(self):
         return _capi.lib().rb_mk_eval_f64
+
+    def _host_rows_fn(self):
+        return _capi.lib().rb_mk_eval_f64_host_rows
 
     def _check_time(self, t):
         if np.any(~(t > 0)):
@@ -461,6 +553,9 @@ class MetzgerMagnetarMagPath(MetzgerMagnetarPath):
     def _launch(self, *args):
         return self._launch_mag(_capi.lib().rb_mk_mag_eval_f64, *args)
 
+    def _host_rows_fn(self):
+        return None     # the magnitude branch has device entry points only
+
 
 class MergernovaMagPath(MergernovaPath):
     """Magnitude / bandpass-flux branch of the mergernova models (_processing_other_formats,
@@ -488,6 +583,9 @@ class MergernovaMagPath(MergernovaPath):
 
     def _launch(self, *args):
         return self._launch_mag(_capi.lib().rb_mn_mag_eval_f64, *args)
+
+    def _host_rows_fn(self):
+        return None     # the magnitude branch has device entry points only
 
 
 def luminosity_distance(redshift, cosmology=None, device=None):

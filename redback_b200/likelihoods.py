@@ -38,7 +38,16 @@ def infer_parameters_from_function(func):
     return [n for n in names[1:] if n != "params_batch"]
 
 
-class _RedbackLikelihood:
+try:    # the reference's base class (likelihoods.py:22): subclass it whenever bilby is importable, so isinstance checks
+    # in bilby's samplers / result classes hold; without bilby the two inherited members are provided below
+    import bilby as _bilby
+    _LikelihoodBase = _bilby.Likelihood
+except ImportError:
+    _bilby = None
+    _LikelihoodBase = object
+
+
+class _RedbackLikelihood(_LikelihoodBase):
     """redback/likelihoods.py:22-143"""
 
     def __init__(self, x, y, function, kwargs=None, priors=None, fiducial_parameters=None):
@@ -48,8 +57,12 @@ class _RedbackLikelihood:
         self.kwargs = kwargs
         self.priors = priors
         self.fiducial_parameters = fiducial_parameters
-        self.parameters = dict.fromkeys(infer_parameters_from_function(function))
-        self._marginalized_parameters = []
+        parameters = dict.fromkeys(infer_parameters_from_function(function))
+        if _bilby is not None:
+            super().__init__(parameters=parameters)
+        else:
+            self.parameters = parameters
+            self._marginalized_parameters = []
 
     def _update_parameters(self, parameters=None):
         if parameters is not None:
@@ -169,7 +182,9 @@ class GaussianLikelihood(_RedbackLikelihood):
             raise ValueError("params_batch must contain at least one array")
         mode, sp = self._split_sigma_param(merged, N)
         if self.function in FUSED:
-            logl = self._fused(merged, N, mode, sp)
+            logl = self._fused(merged, N, mode, sp, host=not device_output)
+            if isinstance(logl, np.ndarray):
+                return logl
         else:
             kw = dict(self.kwargs)
             kw["device_output"] = True
@@ -194,13 +209,16 @@ class GaussianLikelihood(_RedbackLikelihood):
         """(per-epoch sigma level with 0 = detection, magnitude mode) or (None, False): no upper limits."""
         return None, False
 
-    def _fused(self, merged, N, mode, sp):
+    def _fused(self, merged, N, mode, sp, host=False):
         spec = FUSED[self.function]
         spec = spec.for_kwargs(self.kwargs)      # wrappers / kwargs-selected variants (base_model, interaction_process)
         kw = dict(self.kwargs)
         if self.function is _kn.one_component_kilonova_model:
             kw.setdefault("temperature_floor", 4000)
-        key = (spec.cache_key(kw), mode)
+        # the path holds device copies of x / y / sigma: key it on their content so that editing the likelihood's
+        # attributes (assignment or in place) is honoured on the next call, as in the reference (likelihoods.py:206-231)
+        key = (spec.cache_key(kw), mode, _fused.content_key(self.x), _fused.content_key(self.y),
+               _fused.content_key(self._sigma), _fused.content_key(self._upper_limit_levels()[0]))
         if self._path is None or self._path[0] != key:
             self._path = (key, spec.build(self.x, kw, y=self.y, sigma=self._sigma, sigma_mode=mode))
             level, ul_mag = self._upper_limit_levels()
@@ -209,6 +227,14 @@ class GaussianLikelihood(_RedbackLikelihood):
         path = self._path[1]
         params, _ = _fused.collect(merged, kw, None, spec.needed, spec.defaults)
         params = spec.transform(params)
+        if host and path.supports_host_rows() and not any(
+                isinstance(v, torch.Tensor) for v in list(params.values()) + [sp, kw.get("dl")]):
+            # host-resident batch: the library's chunked, double-buffered H2D -> kernels -> D2H pipeline reads the
+            # caller's arrays where they lie (rb_*_eval_f64_host_rows)
+            _, logl = path.evaluate_host(params, N, dl=kw.get("dl"), sigma_param=sp, t0=params.get("t0"),
+                                         aux=params.get(getattr(path, "AUX_PARAM", None) or ""), want_model=False,
+                                         want_logl=True)
+            return logl
         dev = path.pack(params, N)
         sp_dev = None
         if sp is not None:
