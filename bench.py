@@ -134,10 +134,11 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(args, samples):
+def workload_config(args, samples, total=None):
     return {"workload": f"slsn multiband flux_density (ZTF g/r/i x 100 epochs), TemperatureFloor + "
                         f"{'Blackbody' if args.sed == 'blackbody' else 'CutoffBlackbody'} SED, fused GaussianLikelihood",
-            "samples_per_gpu": samples, "epochs": 300, "bands": ["ztfg", "ztfr", "ztfi"],
+            "samples_per_gpu": samples, "samples_total": total if total is not None else samples, "epochs": 300,
+            "bands": ["ztfg", "ztfr", "ztfi"],
             "priors": "priors/slsn.prior incl. redshift U(1e-6,3); d_L integrated on device",
             "l2": "inputs_exceed_l2" if samples * 80 > 126e6 else "small_inputs", "sharding": "samples"}
 
@@ -185,11 +186,196 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _events(n):
+    import torch
+    return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+
+class L2Flush:
+    """Write a buffer larger than the 126 MB L2 between timed launches (outside the event brackets)."""
+
+    def __init__(self, dev):
+        import torch
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.v = 0
+
+    def __call__(self):
+        self.v = (self.v + 1) & 0xFF
+        self.buf.fill_(self.v)
+
+
+def _allmax(x, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def time_launches(fn, dev, world, flush, min_seconds=1.5, max_steps=50, warmup=3, sampler=None):
+    """Mean milliseconds per call of `fn` (device-timed, one event pair per call, L2 flushed in between), max over
+    ranks; the clock sampler runs during the timed region only."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    probe = _events(1)[0]
+    probe[0].record(); fn(); probe[1].record()
+    torch.cuda.synchronize(dev)
+    est = _allmax(max(probe[0].elapsed_time(probe[1]), 1e-3), dev, world)
+    steps = int(min(max_steps, max(3, np.ceil(min_seconds * 1e3 / est))))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    if sampler is not None:
+        sampler.start()
+    ev = _events(steps)
+    for a, b in ev:
+        flush()
+        a.record(); fn(); b.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop() if sampler is not None else None
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    return _allmax(ms, dev, world), steps, clocks
+
+
+def run_paths(args, dev, rank, world, local, peak_tflops, lib):
+    """Every other BASELINE config (bench_paths.workloads) with its own clock sample, roofline fraction and -- at N = 1
+    -- an in-run parity gate against the CPU oracle on the host cores."""
+    import torch
+    import redback_b200 as rb
+    import bench_paths as bp
+    from redback_b200 import distributed as rd
+    flush = L2Flush(dev)
+    out = []
+    do_parity = world == 1 and rank == 0 and args.parity_samples > 0
+    bandpasses = bp._oracle_bandpasses() if do_parity else None
+    for w in bp.workloads(rb, dev, args.paths_scale):
+        if args.only and args.only not in w["key"]:
+            continue
+        n = w["n"]
+        rng = np.random.default_rng(77)                      # the parity prefix is the same on every rank
+        par_n = min(args.parity_samples, n) if do_parity else 0
+        rng_r = np.random.default_rng(1000 + 17 * rank + w["config"])
+        p = w["prior"](rng_r, n)
+        if par_n:
+            head = w["prior"](rng, par_n)
+            p = {k: np.concatenate([head[k], v[par_n:]]) for k, v in p.items()}
+        # data: the device model at a fixed truth + noise (10 % of the model, 0.1 mag for magnitudes)
+        probe = w["build"](None, None)
+        y_model, _ = probe.evaluate(probe.pack(w["truth"], 1))
+        y_model = y_model[0].cpu().numpy()
+        nrng = np.random.default_rng(4)
+        if w.get("magnitudes"):
+            sigma = np.full(y_model.shape, 0.1)
+            y = y_model + nrng.normal(0, 0.1, y_model.shape)
+        else:
+            sigma = 0.1 * np.abs(y_model) + 1e-300
+            y = y_model + nrng.normal(0, 1, y_model.shape) * sigma
+        y = np.where(np.isfinite(y), y, 0.0)
+        path = w["build"](y, sigma)
+        E = path.E
+        order = None
+        if w["kind"] == "tophat" and world > 1:
+            # cost-balanced partition of the GLOBAL batch (res spans 10..100 => 100x work spread per sample)
+            gp = w["prior"](np.random.default_rng(2024), n * world)
+            cost, _ = rd.afterglow_cost(gp["thv"], gp["thc"], gp["g0"])
+            part = rd.balanced_partition(cost, world) if args.ag_partition == "balanced" else \
+                [np.arange(*rd.shard_bounds(n * world, r, world)) for r in range(world)]
+            order = part[rank]
+            p = {k: v[order] for k, v in gp.items()}
+            n = len(order)
+        params = path.pack(p, n)
+        logl = torch.empty(n, dtype=torch.float64, device=dev)
+        line = {"key": w["key"], "config": w["config"], "workload": w["desc"], "samples_per_gpu": n, "epochs": E,
+                "dtype": "f32-quadrature/f64-epilogue" if w.get("fp32") else "f64", "l2": "flushed between launches"}
+        sampler = ClockSampler(local) if rank == 0 else None
+        if w.get("population"):
+            ctx = w["ctx"]
+            lim = ctx["limiting_mag"]
+
+            def fn():
+                mags, _ = path.evaluate(params, want_model=True, want_logl=False)
+                rb.simulate.add_optical_noise_and_cuts(mags, ctx["bands"], lim, seed=99,
+                                                       outputs=("magnitude", "magnitude_error"))
+        else:
+            def fn():
+                path.evaluate(params, want_model=False, want_logl=True, out_logl=logl)
+        l0 = lib.rb_launch_count()
+        ms, steps, clocks = time_launches(fn, dev, world, flush, args.path_seconds, sampler=sampler)
+        line["gpu_launches_per_step"] = int((lib.rb_launch_count() - l0) // (steps + 4))
+        rate = world * n * E / (ms * 1e-3)
+        line.update(units_per_s=rate, ms_per_step=ms, steps=steps, clocks=clocks)
+        flop_eq = w["flop_eq"]
+        if w["kind"] == "tophat":
+            flop_eq, line["res"] = bp.afterglow_flop_eq(p, E)
+            line["partition"] = args.ag_partition if world > 1 else "single GPU"
+        line["roofline"] = {"bound": "fp64", "flop_eq_per_unit": flop_eq, "achieved": rate / world * flop_eq / 1e12,
+                            "peak": peak_tflops, "unit": "TFLOP/s",
+                            "frac": rate / world * flop_eq / 1e12 / peak_tflops if peak_tflops else None}
+        if w.get("population"):
+            # end to end: host parameter table -> chunks -> magnitudes -> noise + cut -> streamed to pinned host memory
+            host_p = {k: np.ascontiguousarray(v) for k, v in p.items()}
+            seen = [0, 0]
+
+            def sink(lo, hi, arrays):
+                seen[0] += hi - lo
+                seen[1] += int(arrays["detected"].sum())
+            t0 = time.perf_counter()
+            rb.simulate.simulate_population_with_cadence(
+                rb.supernova_models.arnett, host_p, ctx["t"], ctx["bands"], lim, seed=99, sink=sink, chunk=65536,
+                outputs=("magnitude", "magnitude_error"), sample_base=rank * n, device=dev)
+            wall = _allmax(time.perf_counter() - t0, dev, world)
+            line["e2e"] = {"units_per_s": world * n * E / wall, "host_bytes_out_per_sample": E * (8 * 3 + 1),
+                           "transients": seen[0], "detected_observations": seen[1],
+                           "what": "simulate_population_with_cadence(sink=...), 65536-transient chunks, D2H of "
+                                   "magnitude, error, model magnitude, detected flag through a pinned double buffer"}
+        if par_n:
+            ctx = dict(w["ctx"], y=y, sigma=sigma)
+            if "bands" in ctx:
+                ctx["bandpasses"] = bandpasses
+            sub = path.pack({k: v[:par_n] for k, v in p.items()}, par_n)
+            gm, gl = path.evaluate(sub, want_model=True, want_logl=True)
+            gm, gl = gm.cpu().numpy(), gl.cpu().numpy()
+            rm, rl, n_done, core_s, wall = bp.run_oracle(w["kind"], ctx, {k: v[:par_n] for k, v in p.items()}, par_n,
+                                                         budget_s=args.parity_budget)
+            stats = bp.parity_stats(gm[:n_done], gl[:n_done], rm, rl, magnitudes=bool(w.get("magnitudes")))
+            stats["requested"] = par_n
+            if w.get("population"):
+                # noise + cut replayed by the oracle on ITS magnitudes with the device's own variates
+                from oracle import restated as r
+                mags = torch.as_tensor(gm[:n_done], device=dev)
+                dev_out = rb.simulate.add_optical_noise_and_cuts(mags, ctx["bands"], lim, seed=99, return_variates=True)
+                ref = np.array([rb.bands.REFERENCE_FLUX[b] for b in ctx["bands"]])
+                exp = r.optical_noise_and_cuts(rm, ref, lim, dev_out["standard_normal"].cpu().numpy())
+                om = dev_out["magnitude"].cpu().numpy()
+                both = np.isfinite(om) & np.isfinite(exp["magnitude"])
+                stats["noise_stage"] = {
+                    "max_abs_dmag_observed": float(np.max(np.abs(om - exp["magnitude"])[both])) if both.any() else 0.0,
+                    "nan_pattern_mismatches": int(np.sum(np.isnan(om) != np.isnan(exp["magnitude"]))),
+                    "detected_mismatches": int(np.sum(dev_out["detected"].cpu().numpy() != exp["detected"]))}
+            line["parity"] = stats
+            cores = os.cpu_count() or 1
+            line["cpu_port"] = {"units_per_s_all_cores": n_done * E / wall, "units_per_s_per_core": n_done * E / core_s
+                                if core_s else None, "cores": cores, "kind": "port",
+                                "sample": f"{n_done} of the same prior draws x {E} epochs, {wall:.1f} s wall"}
+        out.append(line)
+        del path, params, logl
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import redback_b200 as rb
     from redback_b200 import _capi
+    from redback_b200 import distributed as rd
     from redback_b200.engine import SupernovaPath
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,7 +388,12 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _capi.lib()
-    n = args.samples
+    if args.scaling == "strong":
+        lo, hi = rd.shard_bounds(args.samples, rank, world)     # `--samples` is the TOTAL batch (BASELINE: 10^7)
+        n = hi - lo
+    else:
+        n = args.samples                                        # per GPU
+    n_total = args.samples if args.scaling == "strong" else world * n
     t, nu = epochs()
     E = t.size
     sed_id = _capi.SED_BLACKBODY if args.sed == "blackbody" else _capi.SED_CUTOFF_BLACKBODY
@@ -218,13 +409,21 @@ def run_gpu(args):
                          dtype=args.dtype)
 
     params = prior_rows_torch(n, dev, seed=1000 + rank)     # resident in HBM before the timed region
-    logl = torch.empty(n, dtype=torch.float64, device=dev)
-    gathered = torch.empty(n * world, dtype=torch.float64, device=dev) if world > 1 else None
+    # library-level multi-GPU step (redback_b200.distributed): the local shard in `chunks` pieces, the all-gather of
+    # piece i on a side stream under the kernels of piece i+1
+    chunks = args.gather_chunks if world > 1 else 1
+    sizes = [rd.shard_bounds(n, c, chunks) for c in range(chunks)]
+    ev_probe = rd.ShardedEvaluator(n, lambda a, b, out: None, device=dev, chunks=chunks)
+    csz = ev_probe.chunk
+    blocks = [params[:, a:min(a + csz, n)].contiguous() for a in range(0, n, csz)] if world > 1 else [params]
+    if world > 1:
+        del params
 
-    def step():
-        path.evaluate(params, want_model=False, want_logl=True, out_logl=logl)
-        if world > 1:  # the path's only exchange: all-gather of per-sample log L
-            dist.all_gather_into_tensor(gathered, logl)
+    def evaluate(a, b, out):
+        path.evaluate(blocks[a // csz] if world > 1 else blocks[0], want_model=False, want_logl=True, out_logl=out)
+
+    sharded = rd.ShardedEvaluator(n, evaluate, device=dev, chunks=chunks)
+    del ev_probe, sizes
 
     def barrier():
         if world > 1:
@@ -232,58 +431,78 @@ def run_gpu(args):
         torch.cuda.synchronize(dev)
 
     for _ in range(args.warmup):
-        step()
+        sharded.log_likelihood()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = lib.rb_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev[0].record()
     for i in range(args.steps):
-        kev[i][0].record()
-        path.evaluate(params, want_model=False, want_logl=True, out_logl=logl)
-        kev[i][1].record()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, logl)
+        sharded.log_likelihood()
         ev[i + 1].record()
     barrier()
     launches = lib.rb_launch_count() - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    total_ms = _allmax(ev[0].elapsed_time(ev[-1]), dev, world)
     clocks = sampler.stop() if rank == 0 else None
-    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms = float(tm.item())
     ms_per_step = total_ms / args.steps
-    value = world * n * E / (ms_per_step * 1e-3)
+    value = n_total * E / (ms_per_step * 1e-3)
+    logl = sharded.local[:n].clone()
     finite = bool(torch.isfinite(logl).all().item())
 
-    # ---- end to end through the host-buffer entry: pinned host params -> H2D -> kernel -> D2H log L ----
-    host_params = torch.empty(params.shape, dtype=torch.float64, pin_memory=True)
-    host_params.copy_(params)
-    host_out = torch.empty(n, dtype=torch.float64, pin_memory=True)
-    path.log_likelihood_host(host_params, host_out)  # warm-up
+    # kernel-only duration (no collective) for the roofline: the same launches without the gather, timed per launch
+    kev = _events(max(3, min(args.steps, 5)))
+    tmp = torch.empty(n, dtype=torch.float64, device=dev)
+    for a, b in kev:
+        a.record()
+        for bi, blk in enumerate(blocks):
+            path.evaluate(blk, want_model=False, want_logl=True, out_logl=tmp[bi * csz: bi * csz + blk.shape[1]])
+        b.record()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+
+    # ---- end to end through the public entry points, inputs in ordinary (pageable) host memory ----------------
+    host_rows = torch.cat(blocks, dim=1).cpu().numpy() if world > 1 else blocks[0].cpu().numpy()
+    names = ["redshift", "p0", "bp", "mass_ns", "theta_pb", "mej", "vej", "kappa", "kappa_gamma", "temperature_floor"]
+    batch = {k: np.ascontiguousarray(host_rows[i]) for i, k in enumerate(names)}     # a params_batch dict
+    like = rb.GaussianLikelihood(t, y, sigma, rb.supernova_models.slsn,
+                                 kwargs=dict(frequency=nu, output_format="flux_density", dtype=args.dtype,
+                                             sed="Blackbody" if args.sed == "blackbody" else "CutoffBlackbody",
+                                             device=dev))
+    like.log_likelihood_batch({k: v[:4096] for k, v in batch.items()})               # warm-up (path + pipeline set-up)
+    like.log_likelihood_batch(batch)
     e2e_steps = max(1, min(args.steps, 3))
-    e0.record()
-    for _ in range(e2e_steps):
-        path.log_likelihood_host(host_params, host_out)
-    e1.record()
     barrier()
-    em = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(em, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * E / (float(em.item()) / e2e_steps * 1e-3)
-    same = bool(torch.equal(host_out.to(dev), logl))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_logl = like.log_likelihood_batch(batch)
+    e2e_s = _allmax((time.perf_counter() - t0) / e2e_steps, dev, world)
+    e2e_value = n_total * E / e2e_s
+    same = bool(np.array_equal(host_logl, logl.cpu().numpy()))
+    # the C ABI's host entry as a non-Python caller would bind it (ctypes, plain pointers)
+    cfg = _capi.sn_config(_capi.ENGINE_MAGNETAR, sed_id, precision=1 if args.dtype == "float32" else 0)
+    rows_c = np.ascontiguousarray(host_rows)
+    out_c = np.empty(n)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _capi.check(lib.rb_sn_eval_f64_host(C.byref(cfg), n, E, vp(rows_c), vp(t), vp(nu), None, vp(y), vp(sigma), None,
+                                            None, vp(out_c)))
+    capi_s = _allmax((time.perf_counter() - t0) / e2e_steps, dev, world)
+    same_c = bool(np.array_equal(out_c, host_logl))
+    del like, batch, rows_c, host_rows
+
+    peak, pms = C.c_double(0), C.c_double(0)
+    _capi.check(lib.rb_measure_fp64_peak(1 << 16, C.byref(peak), C.byref(pms)))
+    paths = None
+    if args.paths == "on" or (args.paths == "auto"):
+        del blocks, sharded, tmp
+        torch.cuda.empty_cache()
+        paths = run_paths(args, dev, rank, world, local, peak.value, lib)
 
     if rank == 0:
-        import ctypes as C
-        peak, pms = C.c_double(0), C.c_double(0)
-        _capi.check(lib.rb_measure_fp64_peak(1 << 16, C.byref(peak), C.byref(pms)))
         flop_eq = FLOP_EQ[args.sed]
         achieved = n * E * flop_eq / (kernel_ms * 1e-3) / 1e12
         peaks = {}
@@ -296,10 +515,9 @@ def run_gpu(args):
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
             "frac": achieved / peak.value if peak.value else None,
-            # dram__bytes_read+write of rb::sn_kernel from the committed ncu --set full capture
-            # (profiles/r1_final_sn_kernel_ncu_summary.txt: 27.1 MB for 200000 samples), scaled to this launch
-            "traffic": 135.5 * n, "traffic_source": "ncu capture at 200000 samples, scaled per sample",
-            "limiter": "shared-memory data pipe 88 % of peak, FP64 pipe 50 % (ncu, profiles/r1_final_*)",
+            # dram__bytes_read+write of rb::sn_kernel from the committed ncu --set full capture, scaled to this launch
+            "traffic": 135.5 * n, "traffic_source": "ncu capture at 200000 samples, scaled per sample "
+                                                    "(profiles/r1_final_sn_kernel_ncu_summary.txt)",
             "kernel": "rb::sn_kernel", "kernel_ms": kernel_ms,
             "flop_eq_per_unit": flop_eq,
             "peak_source": "DFMA micro-benchmark measured live in this run (rb_measure_fp64_peak); nominal 37.2",
@@ -314,13 +532,22 @@ def run_gpu(args):
                              f"{wall:.1f} s wall"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64" if args.dtype == "float64" else "f32-quadrature/f64-epilogue", "data": "synthetic",
-            "config": workload_config(args, n), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_params.numel() * 8),
-                    "d2h_bytes_per_step": int(n * 8), "matches_resident_run": same},
+            "config": workload_config(args, n, n_total), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 10 * 8),
+                    "d2h_bytes_per_step": int(n * 8), "matches_resident_run": same,
+                    "entry": "redback_b200.GaussianLikelihood.log_likelihood_batch(params_batch = dict of pageable numpy "
+                             "arrays) -> rb_sn_eval_f64_host_rows (chunked two-stream pipeline, pinned staging in the "
+                             "library)",
+                    "capi_host": {"value": n_total * E / capi_s, "entry": "rb_sn_eval_f64_host via ctypes, pageable "
+                                  "numpy block [10][N]", "matches": same_c}},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "all_logl_finite": finite,
+            "multi_gpu": {"api": "redback_b200.distributed.ShardedEvaluator", "gather_chunks": chunks,
+                          "collective": "all_gather_into_tensor of log L per chunk on a side stream"} if world > 1
+            else None,
+            "paths": paths,
         }
         print(json.dumps(line))
     if world > 1:
@@ -332,7 +559,20 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--samples", type=int, default=10_000_000, help="prior draws per GPU")
+    ap.add_argument("--samples", type=int, default=10_000_000,
+                    help="prior draws per GPU (--scaling weak) or in total (--scaling strong)")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
+    ap.add_argument("--gather-chunks", type=int, default=4, help="pieces of the local shard whose all-gather overlaps "
+                                                                 "the next piece's kernels (N > 1)")
+    ap.add_argument("--paths", choices=["auto", "on", "off"], default="auto",
+                    help="also run every other BASELINE config (bench_paths.py); parity gates at N = 1 only")
+    ap.add_argument("--paths-scale", type=float, default=1.0, help="scale the secondary workloads' sample counts")
+    ap.add_argument("--path-seconds", type=float, default=1.5, help="timed region per secondary workload")
+    ap.add_argument("--parity-samples", type=int, default=10_000, help="prior draws per config checked against the "
+                                                                        "CPU oracle in-run (BASELINE.md section 5.5)")
+    ap.add_argument("--parity-budget", type=float, default=75.0, help="wall-clock cap per config for the oracle [s]")
+    ap.add_argument("--ag-partition", choices=["balanced", "contiguous"], default="balanced")
+    ap.add_argument("--only", default="", help="restrict the secondary workloads to keys containing this string")
     ap.add_argument("--sed", choices=["blackbody", "cutoff"], default="blackbody")
     ap.add_argument("--dtype", choices=["float64", "float32"], default="float64",
                     help="float32: FP32 diffusion quadrature (RB_PREC_F32); the headline number is float64")

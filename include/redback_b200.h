@@ -496,6 +496,17 @@ int rb_optical_noise_f64(int noise_type, int64_t N, int64_t E, const double* mod
                          double* obs_mag, double* mag_err, double* obs_flux, double* flux_err, double* snr,
                          unsigned char* detected, void* stream);
 
+/* The same with the standard-normal variates drawn on device: Philox4x32-10 keyed by `seed`, counter = global element
+ * index (sample_base + n) * E + e, two 53-bit uniforms -> Box-Muller.  The draws therefore do not depend on how a
+ * population is chunked or sharded over GPUs.  Replaces `np.random.normal` / `rng.normal` of
+ * simulate_transients.py:476, 493, 506, 1111 (a different but equally distributed stream; the reference's own stream
+ * cannot be reproduced on device).  obs_flux, flux_err, snr and z_out (the variates, for checkers) may be NULL. */
+int rb_optical_noise_philox_f64(int noise_type, int64_t N, int64_t E, int64_t sample_base, uint64_t seed,
+                                const double* model_mag, const double* ref_flux, const double* limiting_mag,
+                                double snr_threshold, int apply_snr_cut, double* obs_mag, double* mag_err,
+                                double* obs_flux, double* flux_err, double* snr, unsigned char* detected,
+                                double* z_out, void* stream);
+
 /* Luminosity distance [cm] for N redshifts on device (same quadrature the fused kernels use). */
 int rb_luminosity_distance_f64(const rb_cosmology* cosmo, int64_t N, const double* redshift,
                                double* out_dl_cm, void* stream);

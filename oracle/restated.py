@@ -1988,3 +1988,42 @@ def optical_noise_and_cuts(model_mag, ref_flux, limiting_mag, z, noise_type="lim
             raise ValueError(noise_type)
     out.update(magnitude=observed_mag, magnitude_error=mag_error, snr=snr, detected=snr >= snr_threshold)
     return out
+
+
+# ---- counter-based normal variates of the device noise kernel -------------------------------------------------------
+# The reference draws its observation noise from numpy's generators (simulate_transients.py:476, 493, 506, 1111); a GPU
+# batch cannot replay that stream, so csrc/noise_kernel.cu draws from Philox4x32-10 (Salmon et al. 2011, "Parallel random
+# numbers: as easy as 1, 2, 3"; Random123).  This restatement of the published algorithm is pinned to Random123's
+# known-answer vectors in tests/test_oracle_golden.py and lets the checker replay the device's variates exactly.
+def philox4x32_10(counter, key):
+    """counter: 4 arrays of uint32, key: 2 arrays of uint32 -> 4 arrays of uint32."""
+    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c = [np.asarray(x, dtype=np.uint32) for x in counter]
+    k = [np.asarray(x, dtype=np.uint64) for x in key]
+    s32 = np.uint64(32)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = m0 * c[0].astype(np.uint64)
+        p1 = m1 * c[2].astype(np.uint64)
+        k0, k1 = (k[0] & mask).astype(np.uint32), (k[1] & mask).astype(np.uint32)
+        c = [(p1 >> s32).astype(np.uint32) ^ c[1] ^ k0, (p1 & mask).astype(np.uint32),
+             (p0 >> s32).astype(np.uint32) ^ c[3] ^ k1, (p0 & mask).astype(np.uint32)]
+        k = [k[0] + np.uint64(0x9E3779B9), k[1] + np.uint64(0xBB67AE85)]
+    return c
+
+
+def philox_standard_normal(seed, index):
+    """Standard-normal variate of global element `index` (array of non-negative ints) for `seed`: two 53-bit uniforms
+    in (0, 1) from one Philox block, Box-Muller cosine branch (csrc/noise_kernel.cu::philox_normal)."""
+    index = np.asarray(index, dtype=np.uint64)
+    seed = int(seed)
+    zero = np.zeros(index.shape, dtype=np.uint32)
+    r = philox4x32_10([(index & np.uint64(0xFFFFFFFF)).astype(np.uint32), (index >> np.uint64(32)).astype(np.uint32),
+                       zero, zero],
+                      [np.full(index.shape, seed & 0xFFFFFFFF, dtype=np.uint64),
+                       np.full(index.shape, (seed >> 32) & 0xFFFFFFFF, dtype=np.uint64)])
+    def uniform(a, b):
+        bits = ((a >> np.uint32(5)).astype(np.uint64) << np.uint64(26)) | (b >> np.uint32(6)).astype(np.uint64)
+        return (bits.astype(np.float64) + 0.5) / 9007199254740992.0
+    u1, u2 = uniform(r[0], r[1]), uniform(r[2], r[3])
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)

@@ -153,6 +153,8 @@ EXPORTS = {
     "rb_mk_mag_eval_f64": (C.c_int, [C.POINTER(MkConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 8 + [C.c_void_p]),
     "rb_optical_noise_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 4 + [C.c_double, C.c_int] + [_dp] * 6
                              + [C.c_void_p]),
+    "rb_optical_noise_philox_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_uint64] + [_dp] * 3
+                                    + [C.c_double, C.c_int] + [_dp] * 7 + [C.c_void_p]),
     "rb_luminosity_distance_f64": (C.c_int, [C.POINTER(Cosmology), C.c_int64, _dp, _dp, C.c_void_p]),
     "rb_gaussian_logl_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 4 + [C.POINTER(UpperLimits), _dp,
                                        C.c_void_p]),

@@ -1770,23 +1770,43 @@ extern "C" int rb_mk_mag_eval_f64(const rb_mk_config* cfg, const rb_photometry* 
   });
 }
 
-extern "C" int rb_optical_noise_f64(int noise_type, int64_t N, int64_t E, const double* model_mag,
-                                    const double* ref_flux, const double* limiting_mag, const double* z,
-                                    double snr_threshold, int apply_snr_cut, double* obs_mag, double* mag_err,
-                                    double* obs_flux, double* flux_err, double* snr, unsigned char* detected,
-                                    void* stream) {
+namespace {
+int optical_noise(int noise_type, int64_t N, int64_t E, const double* model_mag, const double* ref_flux,
+                  const double* limiting_mag, const double* z, uint64_t seed, int64_t sample_base, double snr_threshold,
+                  int apply_snr_cut, double* obs_mag, double* mag_err, double* obs_flux, double* flux_err, double* snr,
+                  unsigned char* detected, double* z_out, void* stream) {
   if (noise_type < RB_NOISE_LIMITING_MAG || noise_type > RB_NOISE_GAUSSIANMODEL)
     return fail(RB_ERR_INVALID, "rb_optical_noise: unknown noise_type");
-  if (N < 0 || E <= 0 || !model_mag || !z || !obs_mag || !mag_err || !snr || !detected)
+  if (N < 0 || E <= 0 || sample_base < 0 || !model_mag || !obs_mag || !mag_err || !detected)
     return fail(RB_ERR_INVALID, "rb_optical_noise: bad arguments");
   if (noise_type == RB_NOISE_LIMITING_MAG && (!ref_flux || !limiting_mag))
     return fail(RB_ERR_INVALID, "rb_optical_noise: ref_flux and limiting_mag are required for limiting_mag noise");
   if (N == 0) return RB_OK;
   const int64_t total = N * E;
   rb::optical_noise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      noise_type, total, (int)E, model_mag, ref_flux, limiting_mag, z, snr_threshold, apply_snr_cut, obs_mag, mag_err,
-      obs_flux, flux_err, snr, detected);
+      noise_type, total, (int)E, model_mag, ref_flux, limiting_mag, z, seed, sample_base, snr_threshold, apply_snr_cut,
+      obs_mag, mag_err, obs_flux, flux_err, snr, detected, z_out);
   launch_counter()->fetch_add(1);
   RB_CUDA(cudaGetLastError());
   return RB_OK;
+}
+}  // namespace
+
+extern "C" int rb_optical_noise_f64(int noise_type, int64_t N, int64_t E, const double* model_mag,
+                                    const double* ref_flux, const double* limiting_mag, const double* z,
+                                    double snr_threshold, int apply_snr_cut, double* obs_mag, double* mag_err,
+                                    double* obs_flux, double* flux_err, double* snr, unsigned char* detected,
+                                    void* stream) {
+  if (!z || !snr) return fail(RB_ERR_INVALID, "rb_optical_noise: z and snr are required");
+  return optical_noise(noise_type, N, E, model_mag, ref_flux, limiting_mag, z, 0, 0, snr_threshold, apply_snr_cut,
+                       obs_mag, mag_err, obs_flux, flux_err, snr, detected, nullptr, stream);
+}
+
+extern "C" int rb_optical_noise_philox_f64(int noise_type, int64_t N, int64_t E, int64_t sample_base, uint64_t seed,
+                                           const double* model_mag, const double* ref_flux,
+                                           const double* limiting_mag, double snr_threshold, int apply_snr_cut,
+                                           double* obs_mag, double* mag_err, double* obs_flux, double* flux_err,
+                                           double* snr, unsigned char* detected, double* z_out, void* stream) {
+  return optical_noise(noise_type, N, E, model_mag, ref_flux, limiting_mag, nullptr, seed, sample_base, snr_threshold,
+                       apply_snr_cut, obs_mag, mag_err, obs_flux, flux_err, snr, detected, z_out, stream);
 }

@@ -7,17 +7,49 @@
 
 namespace rb {
 
+// Philox4x32-10 (Salmon et al. 2011, Random123): counter-based, so the variate of (transient, observation) depends only
+// on the seed and the GLOBAL element index -- results do not change with chunking or with the number of ranks.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// standard normal from one Philox block: two 53-bit uniforms in (0, 1), Box-Muller (cosine branch)
+__device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t index) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const double u1 = ((double)(((uint64_t)(r[0] >> 5) << 26) | (uint64_t)(r[1] >> 6)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(((uint64_t)(r[2] >> 5) << 26) | (uint64_t)(r[3] >> 6)) + 0.5) * (1.0 / 9007199254740992.0);
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+// z == nullptr: the variates are drawn here (Philox, element index = (sample_base + n) * E + e); z_out (optional)
+// receives them so that a checker can replay the noise model on the host.
 __global__ void optical_noise_kernel(int noise_type, int64_t total, int E, const double* __restrict__ model_mag,
                                      const double* __restrict__ ref_flux, const double* __restrict__ limiting_mag,
-                                     const double* __restrict__ z, double snr_threshold, int apply_cut,
+                                     const double* __restrict__ z, uint64_t seed, int64_t sample_base,
+                                     double snr_threshold, int apply_cut,
                                      double* __restrict__ obs_mag, double* __restrict__ mag_err,
                                      double* __restrict__ obs_flux, double* __restrict__ flux_err,
-                                     double* __restrict__ snr_out, unsigned char* __restrict__ detected) {
+                                     double* __restrict__ snr_out, unsigned char* __restrict__ detected,
+                                     double* __restrict__ z_out) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int e = (int)(idx % E);
   const double mm = model_mag[idx];
-  const double zz = z[idx];
+  const double zz = z ? z[idx] : philox_normal(seed, (uint64_t)(sample_base * E + idx));
+  if (z_out) z_out[idx] = zz;
   double om, me, of = NAN, fe = NAN, snr;
   if (noise_type == RB_NOISE_LIMITING_MAG) {
     const double rf = ref_flux[e];
@@ -42,7 +74,7 @@ __global__ void optical_noise_kernel(int noise_type, int64_t total, int E, const
   mag_err[idx] = me;
   if (obs_flux) obs_flux[idx] = of;
   if (flux_err) flux_err[idx] = fe;
-  snr_out[idx] = snr;
+  if (snr_out) snr_out[idx] = snr;
   detected[idx] = apply_cut ? (unsigned char)(snr >= snr_threshold) : (unsigned char)1;   // :516-523
 }
 

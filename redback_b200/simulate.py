@@ -1,26 +1,46 @@
-"""Batched counterpart of redback.simulate_transients.SimulateTransientWithCadence for optical cadences
-(redback/simulate_transients.py:136-610): ONE call evaluates a population of N transients on a shared cadence
-(times, bands, limiting magnitudes), adds the reference's noise model and applies its SNR cut, all on device.
+"""Batched counterpart of redback.simulate_transients for optical surveys: ONE call evaluates a population of N
+transients, adds the reference's noise model and applies its SNR cut, all on device.
 
-The reference loops over transients in Python (simulate_transients.py:665-667, 1168-1178, 2029-2036); here the
-model is a `params_batch` call and the noise / cut is one elementwise kernel (csrc/noise_kernel.cu).
+* `simulate_population_with_cadence` -- SimulateTransientWithCadence in optical mode
+  (redback/simulate_transients.py:136-610): every transient is observed on the same cadence table.
+* `simulate_survey_observations` -- SimulateOpticalTransient._make_observation_single / _make_observations_for_population
+  (:1096-1178): every transient has its OWN list of pointings (time, filter, 5-sigma depth), given in CSR form.
+* `population_light_curves` -- the light-curve loop of PopulationSynthesizer.simulate_population (:2027-2036).
+
+The reference loops over transients in Python (:665-667, 1168-1178, 2029-2036); here the model is a `params_batch`
+call and the noise / cut is one elementwise kernel (csrc/noise_kernel.cu) whose normal variates come from a
+counter-based Philox generator keyed by (seed, global element index): a population can be processed in chunks, in
+any order and on any number of GPUs with identical results.  Large populations are streamed: outputs of chunk i are
+copied to pinned host memory (or handed to a `sink`) while chunk i+1 is computed, so 10^7 transients never need
+N x E device or host arrays at once.
 """
 import ctypes as C
 
 import numpy as np
 import torch
 
-from . import _capi, bands as _bands
-from .engine import _device, _ptr, as_device_f64
+from . import _capi, _fused, bands as _bands
+from .engine import _device, _ptr, as_device_f64, batch_size
+
+_F64 = torch.float64
+OUTPUT_KEYS = ("magnitude", "magnitude_error", "flux", "flux_error", "snr", "detected")
+
+
+def _reference_flux(name):
+    b = _bands.get_bandpass(name)
+    if b.reference_flux is None:
+        raise KeyError(f"Band {name} is not defined in filters.csv!")   # utils.py:869
+    return b.reference_flux
 
 
 def add_optical_noise_and_cuts(model_magnitude, bands, limiting_mag=None, noise_type="limiting_mag",
-                               snr_threshold=5.0, apply_snr_cut=True, seed=None, standard_normal=None):
+                               snr_threshold=5.0, apply_snr_cut=True, seed=None, standard_normal=None,
+                               sample_base=0, outputs=OUTPUT_KEYS, return_variates=False):
     """_add_optical_noise_and_cuts (simulate_transients.py:457-527) for a (N, E) device tensor of model magnitudes.
 
-    `standard_normal`: optional (N, E) tensor of N(0,1) draws (for reproducibility / parity tests); otherwise drawn
-    on device from a Philox generator seeded with `seed`.  Returns a dict of device tensors:
-    magnitude, magnitude_error, flux, flux_error, snr, detected, model_flux."""
+    The N(0,1) draws come from the device Philox stream (`seed`, element index (sample_base + n) * E + e) unless
+    `standard_normal` (an (N, E) tensor) is given.  `outputs` selects which arrays are materialised.  Returns a dict of
+    device tensors (+ 'standard_normal' when `return_variates`)."""
     if noise_type not in _capi.NOISE_TYPES:
         raise ValueError(f"unknown noise_type {noise_type!r}")
     mm = model_magnitude.contiguous()
@@ -31,50 +51,144 @@ def add_optical_noise_and_cuts(model_magnitude, bands, limiting_mag=None, noise_
     if noise_type == "limiting_mag":
         if limiting_mag is None:
             raise ValueError("limiting_mag is required for noise_type='limiting_mag'")
-        ref_np = np.array([_reference_flux(n) for n in names.tolist()], dtype=np.float64)
-        ref = as_device_f64(ref_np, dev)
+        ref = as_device_f64(np.array([_reference_flux(n) for n in names.tolist()], dtype=np.float64), dev)
         lim = as_device_f64(np.broadcast_to(np.asarray(limiting_mag, dtype=np.float64), (E,)).copy(), dev)
-    if standard_normal is None:
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(0 if seed is None else int(seed))
-        z = torch.randn((N, E), dtype=torch.float64, device=dev, generator=gen)
-    else:
-        z = standard_normal.to(device=dev, dtype=torch.float64).contiguous()
-        if z.shape != (N, E):
-            raise ValueError("standard_normal must have shape (N, E)")
-    out = {k: torch.empty((N, E), dtype=torch.float64, device=dev)
-           for k in ("magnitude", "magnitude_error", "flux", "flux_error", "snr")}
+    want = set(outputs) | {"magnitude", "magnitude_error", "detected"}
+    out = {k: torch.empty((N, E), dtype=_F64, device=dev) for k in OUTPUT_KEYS[:5] if k in want}
     out["detected"] = torch.empty((N, E), dtype=torch.uint8, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     with torch.cuda.device(dev):
-        _capi.check(_capi.lib().rb_optical_noise_f64(
-            _capi.NOISE_TYPES[noise_type], N, E, _ptr(mm), _ptr(ref), _ptr(lim), _ptr(z), float(snr_threshold),
-            1 if apply_snr_cut else 0, _ptr(out["magnitude"]), _ptr(out["magnitude_error"]), _ptr(out["flux"]),
-            _ptr(out["flux_error"]), _ptr(out["snr"]), _ptr(out["detected"]),
-            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        if standard_normal is not None:
+            z = standard_normal.to(device=dev, dtype=_F64).contiguous()
+            if z.shape != (N, E):
+                raise ValueError("standard_normal must have shape (N, E)")
+            if "snr" not in out:
+                out["snr"] = torch.empty((N, E), dtype=_F64, device=dev)
+            _capi.check(_capi.lib().rb_optical_noise_f64(
+                _capi.NOISE_TYPES[noise_type], N, E, _ptr(mm), _ptr(ref), _ptr(lim), _ptr(z), float(snr_threshold),
+                1 if apply_snr_cut else 0, _ptr(out["magnitude"]), _ptr(out["magnitude_error"]), _ptr(out.get("flux")),
+                _ptr(out.get("flux_error")), _ptr(out["snr"]), _ptr(out["detected"]), stream))
+        else:
+            zout = torch.empty((N, E), dtype=_F64, device=dev) if return_variates else None
+            _capi.check(_capi.lib().rb_optical_noise_philox_f64(
+                _capi.NOISE_TYPES[noise_type], N, E, int(sample_base), C.c_uint64(0 if seed is None else int(seed)),
+                _ptr(mm), _ptr(ref), _ptr(lim), float(snr_threshold), 1 if apply_snr_cut else 0,
+                _ptr(out["magnitude"]), _ptr(out["magnitude_error"]), _ptr(out.get("flux")),
+                _ptr(out.get("flux_error")), _ptr(out.get("snr")), _ptr(out["detected"]), _ptr(zout), stream))
+            if return_variates:
+                out["standard_normal"] = zout
     out["detected"] = out["detected"].bool()
     return out
 
 
-def _reference_flux(name):
-    b = _bands.get_bandpass(name)
-    if b.reference_flux is None:
-        raise KeyError(f"Band {name} is not defined in filters.csv!")   # utils.py:869
-    return b.reference_flux
+class _ModelRunner:
+    """A model function bound to fixed epochs / kwargs: the device path is built once, parameter chunks stream through."""
+
+    def __init__(self, model, times, kwargs):
+        from .likelihoods import FUSED
+        if model not in FUSED:
+            raise NotImplementedError(f"{getattr(model, '__name__', model)} has no fused device path")
+        self.kwargs = dict(kwargs)
+        self.spec = FUSED[model].for_kwargs(self.kwargs)
+        self.path = self.spec.build(np.asarray(times, dtype=np.float64), self.kwargs)
+
+    def __call__(self, params_chunk):
+        params, n = _fused.collect({}, self.kwargs, params_chunk, self.spec.needed, self.spec.defaults)
+        params = self.spec.transform(params)
+        dev = self.path.pack(params, n)
+        model, _ = self.path.evaluate(dev, dl=_fused.dl_from_kwargs(self.kwargs, self.path, n),
+                                      t0=_fused.t0_tensor(params, self.path, n),
+                                      aux=_fused.aux_tensor(params, self.path, n))
+        return model
+
+
+def _slice(params_batch, lo, hi, n):
+    return {k: (v[lo:hi] if (isinstance(v, torch.Tensor) and v.dim() > 0 and v.numel() == n) or
+                (not isinstance(v, torch.Tensor) and np.ndim(v) > 0 and len(v) == n) else v)
+            for k, v in params_batch.items()}
+
+
+class HostRing:
+    """Two pinned host buffers per output and two copy streams: chunk i is copied device->host while chunk i+1 is
+    computed; `consume(lo, hi, {name: ndarray view})` is called once a chunk has landed."""
+
+    def __init__(self, device, consume):
+        self.device = device
+        self.consume = consume
+        self.slots = [dict(stream=torch.cuda.Stream(device), event=None, buf={}, span=None, keep=None) for _ in range(2)]
+        self.i = 0
+
+    def _flush(self, slot):
+        if slot["span"] is None:
+            return
+        slot["event"].synchronize()
+        lo, hi = slot["span"]
+        self.consume(lo, hi, {k: b[: hi - lo].numpy() for k, b in slot["buf"].items()})
+        slot["span"] = slot["keep"] = None
+
+    def push(self, lo, hi, tensors):
+        slot = self.slots[self.i % 2]
+        self.i += 1
+        self._flush(slot)
+        cur = torch.cuda.current_stream(self.device)
+        slot["stream"].wait_stream(cur)
+        with torch.cuda.stream(slot["stream"]):
+            for k, t in tensors.items():
+                buf = slot["buf"].get(k)
+                if buf is None or buf.shape[0] < t.shape[0] or buf.shape[1:] != t.shape[1:] or buf.dtype != t.dtype:
+                    buf = slot["buf"][k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                buf[: t.shape[0]].copy_(t, non_blocking=True)
+            slot["event"] = torch.cuda.Event()
+            slot["event"].record(slot["stream"])
+        slot["span"] = (lo, hi)
+        slot["keep"] = tensors          # the device tensors stay alive until the copy has run
+
+    def finish(self):
+        for k in (self.i % 2, (self.i + 1) % 2):
+            self._flush(self.slots[k])
 
 
 def simulate_population_with_cadence(model, params_batch, times, bands, limiting_mag=None, model_kwargs=None,
                                      noise_type="limiting_mag", snr_threshold=5.0, apply_snr_cut=True, seed=1234,
-                                     device=None):
+                                     device=None, chunk=None, sink=None, outputs=OUTPUT_KEYS, sample_base=0):
     """Population version of SimulateTransientWithCadence (optical mode): `model` is a redback_b200 model
     function, `params_batch` {name: array[N]}, (`times`, `bands`, `limiting_mag`) the shared cadence
-    (time_since_t0 in days).  Returns the noise dict plus 'model_magnitude'."""
+    (time_since_t0 in days).
+
+    Without `sink` the result is the noise dict plus 'model_magnitude' as (N, E) device tensors (the population is
+    still evaluated in chunks).  With `sink(lo, hi, {name: ndarray})` every chunk's selected `outputs` (plus
+    'model_magnitude') are streamed to the host through a pinned double buffer and handed over as numpy views that are
+    valid during the call; nothing of size N x E is kept -- this is the 10^7-transient mode.  `sample_base` offsets the
+    Philox element index (rank r of a sharded population passes its first global sample index)."""
     dev = _device(device)
     kw = dict(model_kwargs or {})
-    kw.update(bands=np.asarray(bands), output_format="magnitude", device_output=True, device=dev)
-    mags = model(np.asarray(times, dtype=np.float64), params_batch=params_batch, **kw)
-    out = add_optical_noise_and_cuts(mags, bands, limiting_mag, noise_type, snr_threshold, apply_snr_cut, seed)
-    out["model_magnitude"] = mags
-    return out
+    kw.update(bands=np.asarray(bands), output_format="magnitude", device=dev)
+    times = np.asarray(times, dtype=np.float64)
+    n = batch_size(params_batch)
+    if n is None:
+        raise ValueError("params_batch must contain at least one array")
+    E = times.size
+    if chunk is None:
+        chunk = max(1, min(n, (1 << 28) // (8 * E * (3 + len(outputs)))))
+    runner = _ModelRunner(model, times, kw)
+    ring = HostRing(dev, sink) if sink is not None else None
+    parts = []
+    with torch.cuda.device(dev):
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            mags = runner(_slice(params_batch, lo, hi, n))
+            out = add_optical_noise_and_cuts(mags, bands, limiting_mag, noise_type, snr_threshold, apply_snr_cut, seed,
+                                             sample_base=sample_base + lo, outputs=outputs)
+            out = {k: v for k, v in out.items() if k in outputs or k == "detected"}
+            out["model_magnitude"] = mags
+            if ring is not None:
+                ring.push(lo, hi, {k: (v.to(torch.uint8) if v.dtype == torch.bool else v) for k, v in out.items()})
+            else:
+                parts.append(out)
+        if ring is not None:
+            ring.finish()
+            return None
+    return {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
 
 
 def population_light_curves(model, parameters, times=None, model_kwargs=None, device_output=False):

@@ -161,3 +161,18 @@ def test_upper_limit_likelihood_known_answers():
     want = r.gaussian_log_likelihood((y - model)[:3], 0.1) + np.sum(np.log(r.normal_cdf((y - model)[3:] * 2.0 / y[3:])))
     assert abs(r.gaussian_likelihood_upper_limits(y, model, np.full(5, 0.1), det, 2.0) - want) < 1e-13
     assert r.gaussian_likelihood_upper_limits(y, model, 0.1, np.ones(5, bool)) == r.gaussian_likelihood(y, model, 0.1)
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10: the generator behind the device noise kernel."""
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for counter, key, expect in kats:
+        got = r.philox4x32_10([np.array([c], dtype=np.uint32) for c in counter], [np.array([k]) for k in key])
+        assert tuple(int(g[0]) for g in got) == expect
+    z = r.philox_standard_normal(1234, np.arange(200_000))
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01 and np.isfinite(z).all()
+    assert abs(np.mean(z ** 3)) < 0.03 and abs(np.mean(z ** 4) - 3) < 0.06
+    assert not np.array_equal(z[:1000], r.philox_standard_normal(1235, np.arange(1000)))

@@ -83,3 +83,56 @@ def test_population_light_curves(rb):
         kw = {k: v[i] for k, v in p.items()}
         z = kw.pop("redshift")
         h.assert_close(out["flux"][i], r.arnett(times, z, frequency=np.full(40, 4.7e14), **kw), 1e-9, what=f"event {i}")
+
+
+def test_device_philox_variates_match_restatement(rb):
+    """The kernel's own N(0,1) stream = the oracle's Philox4x32-10 restatement (pinned to Random123's known answers);
+    the noise model replayed on the host with those variates reproduces every output."""
+    rng = np.random.default_rng(6)
+    N, E, base, seed = 37, 60, 12345, 2**40 + 17
+    names = np.array(list(LIMITING)[:6] * 10)
+    lim = np.array([LIMITING[n] for n in names])
+    ref = np.array([rb.bands.REFERENCE_FLUX[n] for n in names])
+    mags = rng.uniform(18, 27, (N, E))
+    out = rb.simulate.add_optical_noise_and_cuts(torch.as_tensor(mags, device="cuda"), names, lim, seed=seed,
+                                                 sample_base=base, return_variates=True)
+    z_dev = out["standard_normal"].cpu().numpy()
+    z_ref = r.philox_standard_normal(seed, (base * E + np.arange(N * E)).reshape(N, E))
+    np.testing.assert_allclose(z_dev, z_ref, rtol=0, atol=4e-15)      # log / cos differ by an ulp between libm and CUDA
+    exp = r.optical_noise_and_cuts(mags, ref, lim, z_dev)
+    np.testing.assert_allclose(out["magnitude"].cpu().numpy(), exp["magnitude"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(out["flux"].cpu().numpy(), exp["flux"], rtol=1e-12)
+    assert np.array_equal(out["detected"].cpu().numpy(), exp["detected"])
+
+
+def test_population_streaming_is_chunk_invariant(rb):
+    """Chunked + streamed-to-host evaluation (the 10^7-transient mode) returns exactly what the one-shot call returns,
+    for any chunk size: the variates are keyed by the global element index."""
+    t = np.arange(2.0, 62.0, 3.0)
+    names = np.array([list(LIMITING)[i % 6] for i in range(t.size)])
+    lim = np.array([LIMITING[n] for n in names])
+    rng = np.random.default_rng(10)
+    N = 333
+    p = h.arnett_prior(rng, N, zmax=0.3)
+    p["temperature_floor"] = h.loguniform(rng, 3e3, 1e4, N)
+    whole = rb.simulate.simulate_population_with_cadence(rb.supernova_models.arnett, p, t, names, lim, seed=8)
+    got = {k: np.full((N, t.size), np.nan) for k in ("magnitude", "magnitude_error", "model_magnitude")}
+    got["detected"] = np.zeros((N, t.size), dtype=np.uint8)
+    seen = []
+
+    def sink(lo, hi, arrays):
+        seen.append((lo, hi))
+        for k in got:
+            got[k][lo:hi] = arrays[k]
+
+    assert rb.simulate.simulate_population_with_cadence(rb.supernova_models.arnett, p, t, names, lim, seed=8, chunk=50,
+                                                        sink=sink, outputs=("magnitude", "magnitude_error")) is None
+    assert sorted(seen) == [(a, min(a + 50, N)) for a in range(0, N, 50)]
+    for k in ("magnitude", "magnitude_error", "model_magnitude"):
+        assert np.array_equal(got[k], whole[k].cpu().numpy(), equal_nan=True), k
+    assert np.array_equal(got["detected"].astype(bool), whole["detected"].cpu().numpy())
+    # a rank that owns samples [100, 200) of the same population reproduces that slice
+    sub = {k: v[100:200] for k, v in p.items()}
+    part = rb.simulate.simulate_population_with_cadence(rb.supernova_models.arnett, sub, t, names, lim, seed=8,
+                                                        sample_base=100)
+    assert np.array_equal(part["magnitude"].cpu().numpy(), whole["magnitude"][100:200].cpu().numpy(), equal_nan=True)
