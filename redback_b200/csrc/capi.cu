@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -1296,14 +1297,47 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
   if (e != cudaSuccess) return cuda_fail(e, "photometry table upload");
   pa.n_lambda = NL;
   pa.output = ph->output;
+  pa.j_store_lo = *std::min_element(jlo.begin(), jlo.end());
+  pa.span_max = *std::max_element(span.begin(), span.end());
   return RB_OK;
 }
 
-size_t phot_smem_bytes(int NT, int NL, int n_comp) {
-  return sizeof(double) * ((size_t)6 * NT + 11 * (size_t)NL + (size_t)rb::phot_tile_elems(NT, NL, n_comp) + 40 +
-                          2 * rb::kPhotTileRows * (rb::kPhotThreads / 32) + rb::kExpTabSize);
-}
+// Launch shape of phot_kernel: W wavelength columns per block and P row segments per column (W * P <= threads), chosen
+// so that two blocks fit on an SM when at least 8 columns then fit, else one block per SM with as many columns as fit.
+struct PhotShape {
+  int W = 0, P = 0, nt_pad = 0, blocks_per_sm = 0;
+  size_t smem = 0;
+};
 
+bool phot_shape(int NT, int NL, int n_comp, bool line, PhotShape* out) {
+  const int threads = 256;
+  const size_t fixed = sizeof(double) * rb::phot_fixed_doubles(NT, NL, n_comp, line, threads);
+  const int ntp = NT | 1;
+  const size_t col = sizeof(double) * (size_t)ntp;
+  const size_t budget2 = 115000, budget1 = 227 * 1024;
+  int w_env = 0, bps_env = 0;
+  if (const char* e = std::getenv("RB_PHOT_W")) w_env = std::atoi(e);                 // kernel experiments
+  if (const char* e = std::getenv("RB_PHOT_BLOCKS_PER_SM")) bps_env = std::atoi(e);
+  int bps = 2;
+  long wmax = fixed < budget2 ? (long)((budget2 - fixed) / col) : 0;
+  if (wmax < 8 || bps_env == 1) {
+    bps = 1;
+    wmax = fixed < budget1 ? (long)((budget1 - fixed) / col) : 0;
+  }
+  if (wmax < 1) return false;
+  if (wmax > NL) wmax = NL;
+  if (wmax > threads) wmax = threads;
+  int best = 1;
+  for (int w = 1; w <= (int)wmax; ++w)                        // most busy threads, then most columns
+    if (w * (threads / w) >= best * (threads / best)) best = w;
+  if (w_env > 0 && w_env <= wmax) best = w_env;
+  out->W = best;
+  out->P = threads / best;
+  out->nt_pad = ntp;
+  out->blocks_per_sm = bps;
+  out->smem = fixed + col * (size_t)best;
+  return true;
+}
 
 // ---- shared driver of the magnitude / bandpass branch -------------------------------------------------------------
 // The model kernels run in grid mode and leave (T, R, L, phase) per grid point in a chunk-sized scratch; phot_kernel
@@ -1341,8 +1375,10 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   const int NT = j.NT, NL = j.phot->n_lambda;
   const int64_t N = j.N, E = j.E;
   const int n_comp = j.n_comp > 0 ? j.n_comp : 1;
-  const size_t psmem = phot_smem_bytes(NT, NL, n_comp);
-  if (psmem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, std::string(j.who) + ": grids exceed shared memory");
+  PhotShape shape;
+  if (!phot_shape(NT, NL, n_comp, j.sed == rb::PH_SED_CUTOFF_LINE, &shape))
+    return fail(RB_ERR_UNSUPPORTED, std::string(j.who) + ": grids exceed shared memory");
+  const size_t psmem = shape.smem;
   PhotDevice pd;
   pd.st = st;
   rb::PhotArgs pa{};
@@ -1364,10 +1400,14 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
 
   const int64_t chunk_max = 32768;
   int occ_ph = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, rb::kPhotThreads, psmem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, 256, psmem);
   if (occ_ph < 1) occ_ph = 1;
+  if (occ_ph > shape.blocks_per_sm) occ_ph = shape.blocks_per_sm;
   const int64_t ph_grid_max = (int64_t)sms * occ_ph;
   const int64_t nc_max = std::min<int64_t>(chunk_max, N);
+  // per-block scratch: the epoch records + the forward-eliminated rows of the wavelength-axis solve (L2-resident)
+  const int e_pad = (int)((E + 31) / 32 * 32);
+  const int64_t scratch_stride = (int64_t)(rb::kEpCols + NL - pa.j_store_lo) * e_pad;
   double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_scratch = nullptr;
   int* d_len = nullptr;
   ce = cudaMallocAsync(&d_grid, (size_t)n_comp * nc_max * 4 * NT * sizeof(double), st);
@@ -1375,7 +1415,7 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dl, (size_t)nc_max * sizeof(double), st);
   if (ce == cudaSuccess && j.with_len) ce = cudaMallocAsync(&d_len, (size_t)nc_max * sizeof(int), st);
   if (ce == cudaSuccess)
-    ce = cudaMallocAsync(&d_scratch, (size_t)std::min<int64_t>(ph_grid_max, nc_max) * NT * NL * sizeof(double), st);
+    ce = cudaMallocAsync(&d_scratch, (size_t)std::min<int64_t>(ph_grid_max, nc_max) * scratch_stride * sizeof(double), st);
   int status = RB_OK;
   if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude workspace");
   for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
@@ -1407,9 +1447,14 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
     pa.t0_s = j.t0 ? j.t0 + n0 : nullptr;
     pa.epoch_tab = d_ep_obs;
     pa.scratch = d_scratch;
+    pa.scratch_stride = scratch_stride;
+    pa.W = shape.W;
+    pa.P = shape.P;
+    pa.nt_pad = shape.nt_pad;
+    pa.e_pad = e_pad;
     pa.out_model = j.out_model;
     pa.out_logl = j.y ? j.out_logl : nullptr;
-    rb::phot_kernel<<<(unsigned)std::min<int64_t>(ph_grid_max, nc), rb::kPhotThreads, psmem, st>>>(pa);
+    rb::phot_kernel<<<(unsigned)std::min<int64_t>(ph_grid_max, nc), 256, psmem, st>>>(pa);
     launch_counter()->fetch_add(1);
     ce = cudaGetLastError();
     if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude kernels");

@@ -8,33 +8,28 @@
 //   _bandflux_single_redback / _bandflux_redback / _bandmag_redback                        redback/sed.py:10-118
 //   bandpass_magnitude_to_flux                                   redback/utils.py:707-718
 //
-// One persistent block per sample works on a private N_t x N_lambda scratch tile in global memory (L2):
-//   1. spectra S[k][j] from the model's (T_k, R_k[, L_k]) on its time grid         (all threads, elementwise)
-//   2. clean: non-finite / zero -> 1e-30 * mean(valid)                              (block reduction)
-//   3. spline coefficients C = A_t^-1 S A_lambda^-T: banded (pentadiagonal) LU of the B-spline collocation
-//      matrices, no pivoting (totally positive); time axis: one thread per wavelength column; wavelength
-//      axis: one thread per time row, staged through shared-memory tiles
-//   4. one thread per epoch: FITPACK fpbspl time basis, contraction over time, then the band's 5-Angstrom
-//      integration grid with host-precomputed wavelength bases; |f| is summed as the reference does
-//   5. magnitude / flux, Gaussian log-likelihood term, block reduction.
+// The spline value at (epoch e, wavelength w) is  b_t(e)^T A_t^-1 S A_lambda^-T b_lambda(w)  with S the N_t x N_lambda
+// spectra, A_t / A_lambda the B-spline collocation matrices and b the four non-zero B-splines.  The two solves commute,
+// so the N_t x N_lambda coefficient matrix is never formed: one persistent block per sample streams S through shared
+// memory in BLOCKS OF W WAVELENGTH COLUMNS,
+//   1. spectra of the block (all N_t rows, W columns; non-finite / zero entries replaced, sed.py:985-992);
+//   2. time-axis solve of the W columns in shared memory: every column is cut into P row segments (W * P = threads),
+//      each segment runs the banded recurrences from a zero state and the exact solution is recovered with the
+//      segment's homogeneous solutions scaled by the boundary state (a short serial pass over the P segments);
+//   3. contraction with the E epochs' time B-splines (E x W values) and, because the blocks come in increasing
+//      wavelength order, the forward elimination of the WAVELENGTH-axis solve on those E rows (state carried per epoch);
+//      the eliminated values go to a per-block scratch of E x (N_lambda - first band column) doubles (L2-resident);
+// then per epoch: wavelength-axis back substitution (thread per epoch), the band's 5-Angstrom integration points split
+// over the lanes of a warp with |f| summed as the reference does (sed.py:36-37), magnitude / flux, likelihood term.
+// The mean needed by the clean-up is taken in a statistics pre-pass over the spectra, skipped when a bound shows that
+// every entry is finite and non-zero; the per-sample banded LU of the time axis (kilonova grids) runs on one thread
+// underneath that pre-pass.
 #include "rb_common.cuh"
 
 namespace rb {
 
-constexpr int kPhotThreads = 256;
 constexpr int kPhotMaxSpan = 96;     // max B-spline coefficients (along wavelength) overlapped by one band
-constexpr int kPhotTileRows = 32;    // rows per shared-memory tile in the wavelength-axis solve
-constexpr int kEpRec = 10;           // doubles per epoch in the hand-over array of the epoch phase
-constexpr int kPhotBatch = 8;        // rows of the scratch tile loaded ahead of the time-axis recurrence
-
-// shared-memory doubles of the tile region: a tile of rows for the wavelength-axis solve, or the 2 (per component) + 2
-// per-epoch and 3
-// per-wavelength factor arrays of the spectra phase, or the per-warp coefficient buffers and per-epoch hand-over arrays
-// of the epoch phase (at least 128 epochs per chunk)
-__host__ __device__ inline int phot_tile_elems(int NT, int NL, int n_comp) {
-  const int t = kPhotTileRows * (NL + 1), f = (2 * n_comp + 2) * NT + 3 * NL, e = (kPhotThreads / 32) * kPhotMaxSpan + kEpRec * 128;
-  return max(max(t, f), e);
-}
+constexpr int kEpCols = 8;           // per-epoch record in the block's scratch: h0..h3, first row, y1, y2, band flux
 
 enum { PH_SED_BLACKBODY = 1, PH_SED_CUTOFF = 2, PH_SED_CUTOFF_LINE = 3 };
 enum { PH_T = 0, PH_R, PH_L, PH_X, kPhotGridCols };   // per-sample model grid: temperature, radius, L_bol, phase
@@ -51,6 +46,13 @@ struct PhotArgs {
   int want_logl;
   int common_time_lu;     // 1: time-axis LU supplied (grid identical up to scaling for all samples)
   int n_comp;             // blackbody components summed into one spectrum (multi-component kilonovae), else 1
+  int W;                  // wavelength columns per block
+  int P;                  // row segments per column (W * P <= blockDim.x)
+  int nt_pad;             // odd leading dimension of the column buffer
+  int j_store_lo;         // first wavelength column kept for the back substitution (= min band_jlo)
+  int span_max;           // max band_span
+  int e_pad;              // leading dimension of the per-block epoch arrays
+  int64_t scratch_stride; // doubles of scratch per block
   int64_t grid_comp_stride;   // doubles between the model grids of consecutive components
   double cutoff_wavelength, absorption_index;
   double line_wavelength, line_width, line_time, line_duration, line_amplitude;   // sed.Line (type_1a)
@@ -74,10 +76,17 @@ struct PhotArgs {
   const int* epoch_order;       // [E] epochs grouped by band
   const double* int_rec;        // [total][6] per integration point: the 4 non-zero wavelength B-splines, wave * trans,
                                 //            index of the first of them relative to the band's first coefficient
-  double* scratch;              // [gridDim][n_t_max][n_lambda]
+  double* scratch;              // [gridDim][scratch_stride]
   double* out_model;
   double* out_logl;
 };
+
+// shared-memory doubles: row factors, time LU + homogeneous solutions, column factors, wavelength LU, column buffer
+// (also the per-epoch coefficient buffer of the last phase), boundary states, reduction scratch, exp table
+__host__ __device__ inline size_t phot_fixed_doubles(int NT, int NL, int n_comp, bool line, int threads) {
+  return (size_t)(2 * n_comp + (line ? 2 : 0)) * NT + 9 * (size_t)NT + 3 * (size_t)NL + 5 * (size_t)NL +
+         2 * (size_t)threads + 64 + kExpTabSize;
+}
 
 // FITPACK fpbspl for k = 3: the four non-zero cubic B-splines at x, t[l] <= x < t[l+1] (0-based l)
 __device__ __forceinline__ void fpbspl3(const double* __restrict__ t, int l, double x, double h[4]) {
@@ -106,9 +115,8 @@ __device__ __forceinline__ double nak_knot(const double* __restrict__ x, int n, 
   return x[i - 2];
 }
 
-// Banded LU rows (l2, l1, d, u1, u2) are kept in shared memory as (l2, l1, 1/d, u1/d, u2/d): a back-substitution step
-// is then x = b/d - (u1/d) x[i+1] - (u2/d) x[i+2] with a single FMA on the serial dependency chain (b/d and the x[i+2]
-// term do not depend on the previous step), instead of two FMAs and a division.
+// Banded LU rows (l2, l1, d, u1, u2) are kept as (l2, l1, 1/d, u1/d, u2/d): a back-substitution step is then
+// x = b/d - (u1/d) x[i+1] - (u2/d) x[i+2] with a single FMA on the serial dependency chain.
 __device__ __forceinline__ void load_lu_row(double* __restrict__ dst, const double* __restrict__ src) {
   const double rd = 1.0 / src[2];
   dst[0] = src[0];
@@ -118,65 +126,114 @@ __device__ __forceinline__ void load_lu_row(double* __restrict__ dst, const doub
   dst[4] = src[4] * rd;
 }
 
+// 1 / d to ~1 ulp without the IEEE division's slow path: hardware seed + two Newton steps.  d = 0 / inf / NaN give a
+// non-finite or zero result, which the caller classifies as an invalid spectrum sample like the reference's inf / 0.
+__device__ __forceinline__ double rcp_fast(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// 1 / expm1(x) of the Planck function.  x > 40: exp(-x) (the two differ by e^-x < 4e-18 relative); the reference's
+// expm1 overflows to inf (-> spectrum value 0 -> replaced) above 709.78, reproduced here; between 700 and there the
+// result is subnormal and libm's exp is used.
+__device__ __forceinline__ double planck_inv(double x, const double* __restrict__ tab) {
+  if (x > 40.0) {
+    if (x > 709.782712893384) return 0.0;
+    if (x > 700.0) return exp(-x);
+    return exp_tab(-x, tab);
+  }
+  if (x >= 0.5) return rcp_fast(exp_tab(x, tab) - 1.0);
+  return rcp_fast(expm1(x));
+}
+
 #ifdef RB_PHOT_PROFILE
 // developer aid (tools/phot_phases.sh): block 0 prints the cycles it spent in each phase of its first samples
-#define PHOT_PROF_BEGIN() long long pt_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; int pn_ = 0; long long pc_ = clock64(), pa_ = pc_;
+#define PHOT_PROF_BEGIN() long long pt_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pa_ = clock64();
 #define PHOT_PROF_ACC(i) { __syncthreads(); const long long c_ = clock64(); pt_[i] += c_ - pa_; pa_ = c_; }
-#define PHOT_PROF(i) { __syncthreads(); const long long c_ = clock64(); pt_[pn_++] = c_ - pc_; pc_ = c_; }
-#define PHOT_PROF_END()                                                                                             \
-  if (blockIdx.x == 0 && tid == 0 && n < 3 * (int64_t)gridDim.x)                                                      \
-    printf("phot phases [cycles] setup %lld spectra %lld cleanup+lu %lld forward %lld back+lambda %lld (back %lld "     \
-           "lambda %lld store %lld) epochs %lld (basis %lld integrate %lld)\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[8], \
-           pt_[9], pt_[10], pt_[5], pt_[6], pt_[7]);
+#define PHOT_PROF_END()                                                                                               \
+  if (blockIdx.x == 0 && tid == 0 && n < 3 * (int64_t)gridDim.x)                                                        \
+    printf("phot phases [cycles] setup %lld stats+lu %lld spectra %lld fwd %lld bwd %lld boundary %lld contract %lld "   \
+           "backsub %lld integrate %lld finish %lld\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[5], pt_[6], pt_[7],  \
+           pt_[8], pt_[9]);
 #else
 #define PHOT_PROF_BEGIN()
-#define PHOT_PROF(i)
 #define PHOT_PROF_ACC(i)
 #define PHOT_PROF_END()
 #endif
 
-__global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a) {
+struct PhotSmem {
+  double *rowA, *rowB, *rowC, *rowD, *lut, *hom, *colA, *colB, *colC, *lul, *bnd, *red, *tab, *buf;
+};
+
+__global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
   extern __shared__ double psm[];
   const int NT = a.n_t_max, NL = a.n_lambda, E = a.E, NC = a.n_comp;
-  double* xk = psm;                       // [NT]      time-axis data sites (observer-frame phase, days)
-  double* lut = xk + NT;                  // [NT][5]   time-axis banded LU
-  double* lul = lut + 5 * NT;             // [NL][5]   wavelength-axis banded LU
-  double* tile = lul + 5 * NL;            // [kPhotTileRows][NL + 1]; holds the row / column factors while the spectra are made
-  double* red = tile + phot_tile_elems(NT, NL, NC);    // [40]
-  double* bst = red + 40;                 // [NL][2]   time-axis back-substitution state per wavelength column
-  double* hom = bst + 2 * NL;             // [NL][4]   homogeneous solutions of the partitioned wavelength-axis solve
-  double* bnd = hom + 4 * NL;             // [nwarps][kPhotTileRows][2] boundary states of that solve
-  double* tab = bnd + 2 * kPhotTileRows * (kPhotThreads / 32);   // [1024]
+  const int T = (int)blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const bool line = a.sed == PH_SED_CUTOFF_LINE;
+  const int W = a.W, P = a.P, NTP = a.nt_pad;
+  double* rowA = psm;                          // [NC][NT]  1 / (k_B T)  or 1 / T
+  double* rowB = rowA + NC * NT;               // [NC][NT]  R^2          or R^2 * cutoff normalisation
+  double* rowC = rowB + NC * NT;               // [NT]  1 - line amplitude           (line SED only)
+  double* rowD = rowC + (line ? NT : 0);       // [NT]  scaled line amplitude        (line SED only)
+  double* lut = rowD + (line ? NT : 0);        // [NT][5]  time-axis banded LU, scaled rows
+  double* hom = lut + 5 * NT;                  // [NT][4]  homogeneous solutions of the segmented time-axis solve
+  double* colA = hom + 4 * NT;                 // [NL]  h nu         or hc / (k_B lambda)
+  double* colB = colA + NL;                    // [NL]  everything else that depends on wavelength only
+  double* colC = colB + NL;                    // [NL]  line profile in output units
+  double* lul = colC + NL;                     // [NL][5]  wavelength-axis banded LU, scaled rows
+  double* bnd = lul + 5 * NL;                  // [W][P][2] boundary states (2 * T doubles)
+  double* red = bnd + 2 * T;                   // [64]
+  double* tab = red + 64;                      // [1024]
+  double* buf = tab + kExpTabSize;             // [W][NTP] column block; later [epochs][span_max] coefficients
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
-  for (int j = tid; j < NL; j += blockDim.x) load_lu_row(lul + 5 * j, a.lu_lambda + 5 * j);
-  double* S = a.scratch + (size_t)blockIdx.x * NT * NL;
-  __syncthreads();
-  // segments of the partitioned wavelength-axis solve (at least 2 columns each) and their homogeneous solutions:
-  // forward  y[j] = -l2 y[j-2] - l1 y[j-1] from (y[m-1], y[m-2]) = (1, 0) and (0, 1) at the segment start m,
-  // backward x[j] = -u2' x[j+2] - u1' x[j+1] from (x[m'+1], x[m'+2]) = (1, 0) and (0, 1) at the segment end m'
-  const int seg_len = max((NL + (int)(blockDim.x >> 5) - 1) / (int)(blockDim.x >> 5), 2);
-  const int nseg = (NL + seg_len - 1) / seg_len;
-  if (tid < 4 * nseg) {
-    const int k = tid >> 2, which = tid & 3;
-    const int j_lo = k * seg_len, j_hi = min(j_lo + seg_len, NL);
-    double p1 = (which & 1) ? 0.0 : 1.0, p2 = (which & 1) ? 1.0 : 0.0;
-    if (which < 2) {
-      for (int j = j_lo; j < j_hi; ++j) {
-        const double y = -lul[5 * j + 0] * p2 - lul[5 * j + 1] * p1;
-        hom[4 * j + which] = y;
-        p2 = p1;
-        p1 = y;
-      }
-    } else {
-      for (int j = j_hi - 1; j >= j_lo; --j) {
-        const double x = -lul[5 * j + 4] * p2 - lul[5 * j + 3] * p1;
-        hom[4 * j + which] = x;
-        p2 = p1;
-        p1 = x;
+  for (int i = tid; i < kExpTabSize; i += T) tab[i] = RB_EXP2_1024[i];
+  for (int j = tid; j < NL; j += T) load_lu_row(lul + 5 * j, a.lu_lambda + 5 * j);
+  double* gs = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
+  double* ept = gs;                                   // [kEpCols][e_pad]
+  double* ys = gs + (size_t)kEpCols * a.e_pad;        // [NL - j_store_lo][e_pad]
+  const int EP = a.e_pad;
+  int L = 0, Pe = 0;                                  // segment length (odd) and number of non-empty segments
+  auto set_segments = [&](int G) {
+    L = (G + P - 1) / P;
+    if (L < 3) L = 3;
+    L |= 1;                                           // odd: conflict-free shared-memory strides
+    Pe = (G + L - 1) / L;
+  };
+  // homogeneous solutions of the segmented solve for the current LU and segmentation:
+  //   forward  y[i] = -l2 y[i-2] - l1 y[i-1]   from (y[m-1], y[m-2]) = (1, 0) and (0, 1) at the segment start m,
+  //   backward x[i] = -u2' x[i+2] - u1' x[i+1] from (x[m'+1], x[m'+2]) = (1, 0) and (0, 1) at the segment end m'
+  auto build_hom = [&](int G) {
+    for (int t4 = tid; t4 < 4 * Pe; t4 += T) {
+      const int s = t4 >> 2, which = t4 & 3;
+      const int i_lo = s * L, i_hi = min(i_lo + L, G);
+      double p1 = (which & 1) ? 0.0 : 1.0, p2 = (which & 1) ? 1.0 : 0.0;
+      if (which < 2) {
+        for (int i = i_lo; i < i_hi; ++i) {
+          const double y = -lut[5 * i + 0] * p2 - lut[5 * i + 1] * p1;
+          hom[4 * i + which] = y;
+          p2 = p1;
+          p1 = y;
+        }
+      } else {
+        for (int i = i_hi - 1; i >= i_lo; --i) {
+          const double x = -lut[5 * i + 4] * p2 - lut[5 * i + 3] * p1;
+          hom[4 * i + which] = x;
+          p2 = p1;
+          p1 = x;
+        }
       }
     }
+  };
+  if (a.common_time_lu) {
+    for (int i = tid; i < NT; i += T) load_lu_row(lut + 5 * i, a.lu_time + 5 * i);
+    set_segments(NT);
+    __syncthreads();
+    build_hom(NT);
   }
   __syncthreads();
 
@@ -189,32 +246,33 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
     const double* gX = a.grid + (size_t)n * kPhotGridCols * NT + PH_X * NT;
     const double opz = a.opz[n], dl = a.dl[n];
     const double lam_c = a.cutoff_wavelength * kAngstrom;
-    // Every spectrum sample factorises into a per-epoch and a per-wavelength part around the Planck denominator:
+    double* xk = buf;                                 // [G] data sites; dead once the set-up is done
+    if (!a.common_time_lu) set_segments(G);
+    // ---- 0. set-up.  Every spectrum sample factorises around the Planck denominator:
     //   v[k][j] = colB[j] * rowB[k] / expm1(colA[j] * rowA[k])   (+ the sed.Line terms for type Ia),
-    // so the divisions, powers and unit conversions are done once per row / column (they live in the tile region,
-    // which is free until the solves) and a sample costs one expm1, one division and three multiplies.
-    double* rowA = tile;             // [NC][NT]  1 / (k_B T)  or 1 / T
-    double* rowB = rowA + NC * NT;   // [NC][NT]  R^2          or R^2 * cutoff normalisation
-    double* rowC = rowB + NC * NT;   // [NT]  1 - line amplitude
-    double* rowD = rowC + NT;        // [NT]  scaled line amplitude
-    double* colA = rowD + NT;        // [NL]  h nu         or hc / (k_B lambda)
-    double* colB = colA + NL;        // [NL]  everything else that depends on wavelength only
-    double* colC = colB + NL;        // [NL]  line profile in output units
-    const bool line = a.sed == PH_SED_CUTOFF_LINE;
-    for (int k = tid; k < G; k += blockDim.x) {
+    // so divisions, powers and unit conversions are done once per row / column.
+    double rmin = INFINITY, rmax = 0.0, amax = 0.0;   // bounds for the all-valid test
+    for (int k = tid; k < G; k += T) {
       xk[k] = gX[k];
-      const double T = gT[k], R = gR[k];
+      const double Tk = gT[k], R = gR[k];
       if (a.sed == PH_SED_BLACKBODY) {
-        rowA[k] = 1.0 / (kKB * T);
-        rowB[k] = R * R;
-        for (int c = 1; c < NC; ++c) {                         // kilonova_models.py:1150-1175, 1278-1300
+        for (int c = 0; c < NC; ++c) {                          // kilonova_models.py:1150-1175, 1278-1300
           const double Tc = gT[c * a.grid_comp_stride + k], Rc = gR[c * a.grid_comp_stride + k];
-          rowA[c * NT + k] = 1.0 / (kKB * Tc);
-          rowB[c * NT + k] = Rc * Rc;
+          const double ra = 1.0 / (kKB * Tc), rb_ = Rc * Rc;
+          rowA[c * NT + k] = ra;
+          rowB[c * NT + k] = rb_;
+          rmin = fmin(rmin, (rb_ > 0.0 && isfinite(rb_)) ? rb_ : 0.0);
+          rmax = fmax(rmax, isfinite(rb_) ? rb_ : INFINITY);
+          amax = fmax(amax, (ra > 0.0 && isfinite(ra)) ? ra : INFINITY);
         }
       } else {
-        rowA[k] = 1.0 / T;
-        rowB[k] = (R * R) * cutoff_norm(gL[k], R, T, lam_c, a.absorption_index);
+        const double ra = 1.0 / Tk;
+        const double rb_ = (R * R) * cutoff_norm(gL[k], R, Tk, lam_c, a.absorption_index);
+        rowA[k] = ra;
+        rowB[k] = rb_;
+        rmin = fmin(rmin, (rb_ > 0.0 && isfinite(rb_)) ? rb_ : 0.0);
+        rmax = fmax(rmax, isfinite(rb_) ? rb_ : INFINITY);
+        amax = fmax(amax, (ra > 0.0 && isfinite(ra)) ? ra : INFINITY);
         if (line) {
           // sed.Line on the (N_lambda, N_t) grid (sed.py:859-909; supernova_models.py:2295-2303); time is source frame
           const double te = gX[k] / opz;
@@ -224,68 +282,86 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
           amp_scaled /= (a.line_width * sqrt(2 * kPi));
           rowC[k] = 1 - amp;
           rowD[k] = amp_scaled;
+          if (!(amp_scaled >= 0.0 && isfinite(amp_scaled) && amp < 1.0)) rmax = INFINITY;   // force the pre-pass
         }
       }
     }
-    for (int j = tid; j < NL; j += blockDim.x) {
+    double cmin = INFINITY, cmax = 0.0, camax = 0.0;
+    for (int j = tid; j < NL; j += T) {
       const double lam_obs = a.lambda_obs[j];
       const double nu = (kCSI / (lam_obs * 1.e-10)) * opz;                       // utils.py:357-362, 383
       const double to_flam = 1e-26 * 2.99792458e18 / (lam_obs * lam_obs);        // mJy -> erg/cm^2/s/Angstrom
+      double ca, cb;
       if (a.sed == PH_SED_BLACKBODY) {
-        colA[j] = kH * nu;
-        colB[j] = 2 * kPi * kH * (nu * nu * nu) / ((dl * dl) * (kC * kC)) * opz * kToMJy * to_flam;   // sed.py:216, 929
+        ca = kH * nu;
+        cb = 2 * kPi * kH * (nu * nu * nu) / ((dl * dl) * (kC * kC)) * opz * kToMJy * to_flam;   // sed.py:216, 929
       } else {
         const double lam_A = 1.e10 * (kCSI / nu);
         const double lam = lam_A * kAngstrom;
         const double l2 = lam * lam, l5 = l2 * l2 * lam;
         const double absorb = (lam < lam_c) ? pow(lam / lam_c, a.absorption_index) : 1.0;
-        colA[j] = kXConst / lam;
+        ca = kXConst / lam;
         double c = kFluxConst * (absorb / l5) / (4 * kPi * (dl * dl)) * lam_A / nu * kToMJy;        // sed.py:362-384
         if (line) {
           const double u = (lam_A - a.line_wavelength) / a.line_width;
           colC[j] = exp(-0.5 * (u * u)) * (lam * lam) / kC * kToMJy * opz * to_flam;
           c = c * 1e-26 * kToMJy;
         }
-        colB[j] = c * opz * to_flam;                                              // supernova_models.py:1611-1612, 2304-2305
+        cb = c * opz * to_flam;                                                   // supernova_models.py:1611-1612, 2304-2305
       }
+      colA[j] = ca;
+      colB[j] = cb;
+      cmin = fmin(cmin, (cb > 0.0 && isfinite(cb)) ? cb : 0.0);
+      cmax = fmax(cmax, isfinite(cb) ? cb : INFINITY);
+      camax = fmax(camax, (ca > 0.0 && isfinite(ca)) ? ca : INFINITY);
     }
-    if (a.common_time_lu)
-      for (int i = tid; i < G; i += blockDim.x) load_lu_row(lut + 5 * i, a.lu_time + 5 * i);
+    // block-wide bounds: red[0..7] min r, [8..15] max r, [16..23] max rowA, [24..31] min c, [32..39] max c, [40..47] max colA
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      rmin = fmin(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+      rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+      amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+      cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+      camax = fmax(camax, __shfl_xor_sync(0xffffffffu, camax, o));
+    }
+    if (lane == 0) {
+      red[warp] = rmin; red[8 + warp] = rmax; red[16 + warp] = amax;
+      red[24 + warp] = cmin; red[32 + warp] = cmax; red[40 + warp] = camax;
+    }
     __syncthreads();
-
-    PHOT_PROF(0);
-    // ---- 1. spectra + statistics for the clean-up -------------------------------------------------------
-    double vsum = 0.0, vcnt = 0.0;
-    {
-      int k = tid / NL, j = tid - k * NL;
-      const int dk = (int)blockDim.x / NL, dj = (int)blockDim.x - dk * NL;
-      for (; k < G; k += dk) {
-        double v = colB[j] * rowB[k] / expm1_fast(colA[j] * rowA[k], tab);
-        for (int c = 1; c < NC; ++c) v += colB[j] * rowB[c * NT + k] / expm1_fast(colA[j] * rowA[c * NT + k], tab);
-        if (line) v = v * rowC[k] + rowD[k] * colC[j];
-        S[k * NL + j] = v;
-        if (isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
-        j += dj;
-        if (j >= NL) { j -= NL; ++k; }
+    // ---- 0b. per-epoch time basis (knot interval + the four non-zero B-splines) and the collocation rows ----------
+    for (int e = tid; e < E; e += T) {
+      double x = a.epoch_tab[EP_T * E + e];
+      double h[4] = {0.0, 0.0, 0.0, 0.0};
+      double first = -1.0;
+      bool live = true;
+      if (a.t0_s != nullptr) {                                                    // phase_models.py:33-58
+        x -= a.t0_s[n];
+        if (x < 0.0) live = false;
       }
+      if (live) {
+        if (x < xk[0]) x = xk[0];                                                 // fpbisp clamps to [tb, te]
+        if (x > xk[G - 1]) x = xk[G - 1];
+        // knot interval: largest l in [3, G-1] with t[l] <= x  (t[l] = x[l-2] for 4 <= l <= G-1)
+        int l = 3;
+        int lo = 4, hi = G - 1;
+        while (lo <= hi) {
+          const int mid = (lo + hi) >> 1;
+          if (xk[mid - 2] <= x) { l = mid; lo = mid + 1; } else hi = mid - 1;
+        }
+        double tl[8];
+        for (int q = 0; q < 8; ++q) tl[q] = nak_knot(xk, G, l - 3 + q);
+        fpbspl3(tl, 3, x, h);
+        first = (double)(l - 3);
+      }
+      ept[0 * EP + e] = h[0]; ept[1 * EP + e] = h[1]; ept[2 * EP + e] = h[2]; ept[3 * EP + e] = h[3];
+      ept[4 * EP + e] = first;
+      ept[5 * EP + e] = 0.0;   // y[j-1] of the wavelength-axis forward elimination
+      ept[6 * EP + e] = 0.0;   // y[j-2]
     }
-    __syncthreads();   // the tile region is reused by the solves below
-    PHOT_PROF(1);
-    // ---- 2. clean-up value (sed.py:985-992) ---------------------------------------------------------------
-    vsum = warp_sum(vsum);
-    vcnt = warp_sum(vcnt);
-    if (lane == 0) { red[warp] = vsum; red[8 + warp] = vcnt; }
-    __syncthreads();
-    if (tid == 0) {
-      double s = 0.0, c = 0.0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s += red[w]; c += red[8 + w]; }
-      double mean = (c > 0) ? s / c : NAN;
-      if (!isfinite(mean) || mean == 0.0) mean = 1.0;
-      red[32] = 1e-30 * mean;
-    }
-    // ---- 3a. time-axis collocation + LU when the grid is per-sample ----------------------------------------
     if (!a.common_time_lu) {
-      for (int i = tid; i < G; i += blockDim.x) {
+      for (int i = tid; i < G; i += T) {
         // row i of B_j(x_i): interval l with t[l] <= x_i < t[l+1]; non-zero columns l-3..l
         double row[5] = {0, 0, 0, 0, 0};   // columns i-2..i+2
         if (i == 0) row[2] = 1.0;
@@ -306,10 +382,37 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
         }
         for (int q = 0; q < 5; ++q) lut[5 * i + q] = row[q];
       }
-      __syncthreads();
-      if (tid == 0) {
-        // banded LU without pivoting, in place, stored in the scaled layout of load_lu_row.  The two previous rows
-        // stay in registers and the next row is loaded ahead, so the serial chain per row is multiply, FMA, reciprocal.
+    }
+    bool all_valid;
+    {
+      double r_lo = INFINITY, r_hi = 0.0, a_hi = 0.0, c_lo = INFINITY, c_hi = 0.0, ca_hi = 0.0;
+      for (int w = 0; w < nwarps; ++w) {
+        r_lo = fmin(r_lo, red[w]); r_hi = fmax(r_hi, red[8 + w]); a_hi = fmax(a_hi, red[16 + w]);
+        c_lo = fmin(c_lo, red[24 + w]); c_hi = fmax(c_hi, red[32 + w]); ca_hi = fmax(ca_hi, red[40 + w]);
+      }
+      // every product colB rowB / expm1(x) is then finite and non-zero: x <= 600, prefactors within [1e-280, 1e280]
+      all_valid = (a_hi * ca_hi < 600.0) && (r_lo * c_lo > 1e-280) && (r_hi * c_hi * (double)NC < 1e280) &&
+                  (a_hi * ca_hi > 0.0);
+      // x -> 0 makes 1 / expm1 large but finite (x >= 1e-300 here since both factors are positive and finite)
+    }
+    __syncthreads();                                  // xk (in buf) is dead from here on
+    PHOT_PROF_ACC(0);
+
+    // one spectrum sample
+    auto spec = [&](int j, int k) -> double {
+      const double ca = colA[j], cb = colB[j];
+      double v = cb * rowB[k] * planck_inv(ca * rowA[k], tab);
+      for (int c = 1; c < NC; ++c) v += cb * rowB[c * NT + k] * planck_inv(ca * rowA[c * NT + k], tab);
+      if (line) v = v * rowC[k] + rowD[k] * colC[j];
+      return v;
+    };
+
+    // ---- 1. statistics pre-pass for the clean-up value (sed.py:985-992), with the serial LU underneath ----------
+    const bool lu_thread = !a.common_time_lu && warp == nwarps - 1;
+    if (lu_thread) {
+      if (lane == 0) {
+        // banded LU without pivoting (totally positive collocation matrix), in place, scaled layout of load_lu_row.
+        // The two previous rows stay in registers; the serial chain per row is multiply, FMA, reciprocal.
         double rd1 = 0.0, u1_1 = 0.0, u2_1 = 0.0, rd2 = 0.0, u1_2 = 0.0, u2_2 = 0.0;
         double n0 = lut[0], n1 = lut[1], n2 = lut[2], n3 = lut[3], n4 = lut[4];
         for (int i = 0; i < G; ++i) {
@@ -322,7 +425,7 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
           const double l1 = am1 * rd1;
           d -= l1 * u1_1;
           u1 -= l1 * u2_1;
-          const double rd = 1.0 / d;
+          const double rd = rcp_fast(d);
           lut[5 * i + 0] = l2;
           lut[5 * i + 1] = l1;
           lut[5 * i + 2] = rd;
@@ -333,268 +436,189 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
         }
       }
     }
-    __syncthreads();
-    const double repl = red[32];
+    double repl = 0.0;
+    if (!all_valid) {
+      double vsum = 0.0, vcnt = 0.0;
+      const int wstat = a.common_time_lu ? nwarps : nwarps - 1;     // the LU warp does not take part
+      if (warp < wstat) {
+        for (int j = warp; j < NL; j += wstat)
+          for (int k = lane; k < G; k += 32) {
+            const double v = spec(j, k);
+            if (isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
+          }
+      }
+      vsum = warp_sum(vsum);
+      vcnt = warp_sum(vcnt);
+      if (lane == 0) { red[48 + warp] = vsum; red[56 + warp] = vcnt; }
+      __syncthreads();
+      double s = 0.0, c = 0.0;
+      for (int w = 0; w < nwarps; ++w) { s += red[48 + w]; c += red[56 + w]; }
+      double mean = (c > 0) ? s / c : NAN;
+      if (!isfinite(mean) || mean == 0.0) mean = 1.0;
+      repl = 1e-30 * mean;
+    } else {
+      __syncthreads();
+    }
+    if (!a.common_time_lu) {
+      build_hom(G);
+      __syncthreads();
+    }
+    PHOT_PROF_ACC(1);
 
-    PHOT_PROF(2);
-    // ---- 3b. time-axis forward elimination: one thread per wavelength column (coalesced across columns).  The scratch tile
-    // lives in global memory / L2: loads are issued kPhotBatch rows ahead of the recurrence to hide latency.
-    for (int j = tid; j < NL; j += blockDim.x) {
-      double y1 = 0.0, y2 = 0.0;   // y[i-1], y[i-2]
-      double nb[kPhotBatch];       // the batch after the one being eliminated: its loads overlap the recurrence
-#pragma unroll
-      for (int u = 0; u < kPhotBatch; ++u) nb[u] = (u < G) ? S[u * NL + j] : 0.0;
-      for (int i0 = 0; i0 < G; i0 += kPhotBatch) {
-        double b[kPhotBatch];
-#pragma unroll
-        for (int u = 0; u < kPhotBatch; ++u) {
-          b[u] = nb[u];
-          nb[u] = (i0 + kPhotBatch + u < G) ? S[(i0 + kPhotBatch + u) * NL + j] : 0.0;
+    // ---- 2. wavelength-column blocks ---------------------------------------------------------------------------
+    for (int j0 = 0; j0 < NL; j0 += W) {
+      const int wc = min(W, NL - j0);
+      // 2a. spectra of the block, cleaned
+      for (int jl = warp; jl < wc; jl += nwarps) {
+        double* col = buf + jl * NTP;
+        for (int k = lane; k < G; k += 32) {
+          double v = spec(j0 + jl, k);
+          if (!(isfinite(v) && v != 0.0)) v = repl;
+          col[k] = v;
         }
-#pragma unroll
-        for (int u = 0; u < kPhotBatch; ++u) {
-          const int i = i0 + u;
-          if (i < G) {
-            double v = b[u];
-            if (!(isfinite(v) && v != 0.0)) v = repl;
-            const double y = (v - lut[5 * i + 0] * y2) - lut[5 * i + 1] * y1;   // y[i-2] term first: one FMA on the chain
-            S[i * NL + j] = y;
+      }
+      __syncthreads();
+      PHOT_PROF_ACC(2);
+      // 2b. time axis, forward elimination: particular solution of every (column, segment) from a zero state
+      const int seg = tid % P, jl = tid / P;
+      const bool active = jl < wc && seg < Pe;
+      const int i_lo = seg * L, i_hi = min(i_lo + L, G);
+      double* col = buf + jl * NTP;
+      if (active) {
+        double y1 = 0.0, y2 = 0.0;
+#pragma unroll 4
+        for (int i = i_lo; i < i_hi; ++i) {
+          const double y = (col[i] - lut[5 * i + 0] * y2) - lut[5 * i + 1] * y1;
+          col[i] = y;
+          y2 = y1;
+          y1 = y;
+        }
+      }
+      __syncthreads();
+      PHOT_PROF_ACC(3);
+      // true (y[m-1], y[m-2]) at the start m of every segment: serial over the segments, one thread per column
+      if (tid < wc) {
+        double* c = buf + tid * NTP;
+        double Y1 = 0.0, Y2 = 0.0;
+        bnd[(tid * P + 0) * 2 + 0] = 0.0;
+        bnd[(tid * P + 0) * 2 + 1] = 0.0;
+        for (int s = 1; s < Pe; ++s) {
+          const int m = s * L;
+          const double e1 = c[m - 1] + hom[4 * (m - 1) + 0] * Y1 + hom[4 * (m - 1) + 1] * Y2;
+          const double e2 = c[m - 2] + hom[4 * (m - 2) + 0] * Y1 + hom[4 * (m - 2) + 1] * Y2;
+          Y1 = e1;
+          Y2 = e2;
+          bnd[(tid * P + s) * 2 + 0] = Y1;
+          bnd[(tid * P + s) * 2 + 1] = Y2;
+        }
+      }
+      __syncthreads();
+      PHOT_PROF_ACC(5);
+      // 2c. time axis, back substitution: particular solution per segment, the forward fix-up folded into the load
+      if (active) {
+        const double Y1 = bnd[(jl * P + seg) * 2 + 0], Y2 = bnd[(jl * P + seg) * 2 + 1];
+        double x1 = 0.0, x2 = 0.0;
+#pragma unroll 4
+        for (int i = i_hi - 1; i >= i_lo; --i) {
+          const double b = (col[i] + hom[4 * i + 0] * Y1 + hom[4 * i + 1] * Y2) * lut[5 * i + 2];
+          const double x = (b - lut[5 * i + 4] * x2) - lut[5 * i + 3] * x1;
+          col[i] = x;
+          x2 = x1;
+          x1 = x;
+        }
+      }
+      __syncthreads();
+      PHOT_PROF_ACC(4);
+      // true (x[m], x[m+1]) just after the end of every segment (m = first row of the next one)
+      if (tid < wc) {
+        double* c = buf + tid * NTP;
+        double X1 = 0.0, X2 = 0.0;
+        bnd[(tid * P + (Pe - 1)) * 2 + 0] = 0.0;
+        bnd[(tid * P + (Pe - 1)) * 2 + 1] = 0.0;
+        for (int s = Pe - 2; s >= 0; --s) {
+          const int m = (s + 1) * L;
+          const double s1 = c[m] + hom[4 * m + 2] * X1 + hom[4 * m + 3] * X2;
+          const double s2 = (m + 1 < G) ? c[m + 1] + hom[4 * (m + 1) + 2] * X1 + hom[4 * (m + 1) + 3] * X2 : 0.0;
+          X1 = s1;
+          X2 = s2;
+          bnd[(tid * P + s) * 2 + 0] = X1;
+          bnd[(tid * P + s) * 2 + 1] = X2;
+        }
+      }
+      __syncthreads();
+      PHOT_PROF_ACC(5);
+      // 2d. contraction with the epochs' time B-splines (backward fix-up folded into the loads) and forward
+      // elimination of the wavelength-axis solve on the E resulting rows
+      for (int e = tid; e < E; e += T) {
+        const double h0 = ept[0 * EP + e], h1 = ept[1 * EP + e], h2 = ept[2 * EP + e], h3 = ept[3 * EP + e];
+        const int l = (int)ept[4 * EP + e];
+        double y1 = ept[5 * EP + e], y2 = ept[6 * EP + e];
+        if (l >= 0) {
+          const int s0 = l / L, s3 = (l + 3) / L;
+          const int split = (s3 != s0) ? s3 * L - l : 4;           // rows l .. l+split-1 lie in segment s0
+          const double hb0 = hom[4 * l + 2], hb1 = hom[4 * l + 3], hb2 = hom[4 * l + 6], hb3 = hom[4 * l + 7],
+                       hb4 = hom[4 * l + 10], hb5 = hom[4 * l + 11], hb6 = hom[4 * l + 14], hb7 = hom[4 * l + 15];
+          for (int q = 0; q < wc; ++q) {
+            const double* c = buf + q * NTP + l;
+            const double* ba = bnd + (q * P + s0) * 2;
+            const double* bb = bnd + (q * P + s3) * 2;
+            const double Xa1 = ba[0], Xa2 = ba[1], Xb1 = bb[0], Xb2 = bb[1];
+            const double x0 = c[0] + hb0 * Xa1 + hb1 * Xa2;
+            const double x1v = c[1] + hb2 * (split > 1 ? Xa1 : Xb1) + hb3 * (split > 1 ? Xa2 : Xb2);
+            const double x2v = c[2] + hb4 * (split > 2 ? Xa1 : Xb1) + hb5 * (split > 2 ? Xa2 : Xb2);
+            const double x3v = c[3] + hb6 * (split > 3 ? Xa1 : Xb1) + hb7 * (split > 3 ? Xa2 : Xb2);
+            const double r = h0 * x0 + h1 * x1v + h2 * x2v + h3 * x3v;
+            const int j = j0 + q;
+            const double y = (r - lul[5 * j + 0] * y2) - lul[5 * j + 1] * y1;
+            if (j >= a.j_store_lo) ys[(size_t)(j - a.j_store_lo) * EP + e] = y;
             y2 = y1;
             y1 = y;
           }
+          ept[5 * EP + e] = y1;
+          ept[6 * EP + e] = y2;
         }
-      }
-    }
-    for (int j = tid; j < NL; j += blockDim.x) bst[2 * j] = bst[2 * j + 1] = 0.0;   // x[i+1], x[i+2] per column
-    __syncthreads();
-    PHOT_PROF(3);
-    // ---- 3c. time-axis back substitution fused with the wavelength-axis solve: the rows come out last-to-first, so
-    // each tile of kPhotTileRows finished rows goes straight into shared memory, is solved along wavelength there and
-    // is written to the scratch once (one read and one write pass fewer than solving the two axes separately)
-    PHOT_PROF_ACC(11);
-    // with one column per thread the first batch of the next tile is loaded before the wavelength-axis solve of the
-    // current one, so no tile starts with an exposed round trip to the scratch
-    const bool one_col = NL <= (int)blockDim.x;
-    double nbx[kPhotBatch];
-#pragma unroll
-    for (int u = 0; u < kPhotBatch; ++u)
-      nbx[u] = (one_col && tid < NL && G - 1 - u >= max(G - kPhotTileRows, 0)) ? S[(G - 1 - u) * NL + tid] : 0.0;
-    for (int r1 = G; r1 > 0; r1 -= kPhotTileRows) {
-      const int r0 = max(r1 - kPhotTileRows, 0), rows = r1 - r0;
-      for (int j = tid; j < NL; j += blockDim.x) {
-        double x1 = bst[2 * j], x2 = bst[2 * j + 1];
-        double nb[kPhotBatch];
-#pragma unroll
-        for (int u = 0; u < kPhotBatch; ++u)
-          nb[u] = one_col ? nbx[u] : ((r1 - 1 - u >= r0) ? S[(r1 - 1 - u) * NL + j] : 0.0);
-        for (int i0 = r1 - 1; i0 >= r0; i0 -= kPhotBatch) {
-          double b[kPhotBatch];
-#pragma unroll
-          for (int u = 0; u < kPhotBatch; ++u) {
-            b[u] = nb[u];
-            nb[u] = (i0 - kPhotBatch - u >= r0) ? S[(i0 - kPhotBatch - u) * NL + j] : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < kPhotBatch; ++u) {
-            const int i = i0 - u;
-            if (i >= r0) {
-              const double x = (b[u] * lut[5 * i + 2] - lut[5 * i + 4] * x2) - lut[5 * i + 3] * x1;
-              tile[(i - r0) * (NL + 1) + j] = x;
-              x2 = x1;
-              x1 = x;
-            }
-          }
-        }
-        bst[2 * j] = x1;
-        bst[2 * j + 1] = x2;
-        if (one_col) {
-          const int q0 = max(r0 - kPhotTileRows, 0);
-#pragma unroll
-          for (int u = 0; u < kPhotBatch; ++u) nbx[u] = (r0 - 1 - u >= q0) ? S[(r0 - 1 - u) * NL + j] : 0.0;
-        }
-      }
-      __syncthreads();
-      PHOT_PROF_ACC(8);
-      // Wavelength-axis solve of the tile, partitioned: each row is cut into one segment per warp (lane = row), every
-      // segment runs the recurrence from a zero state, and the true solution is that particular solution plus the
-      // segment's two homogeneous solutions (hom, set up once per block) scaled by the true state at the segment
-      // boundary.  The boundary states follow from a short serial pass over the segments; the serial chain per tile
-      // drops from 2 NL steps to 2 NL / nwarps.
-      const int seg = warp, row_i = lane;
-      const int j_lo = min(seg * seg_len, NL), j_hi = min(j_lo + seg_len, NL);
-      double* row = tile + row_i * (NL + 1);
-      if (row_i < rows) {                                      // forward elimination, particular solution
-        double y1 = 0.0, y2 = 0.0;
-        for (int j0 = j_lo; j0 < j_hi; j0 += kPhotBatch) {
-          double b[kPhotBatch], c0[kPhotBatch], c1[kPhotBatch];
-#pragma unroll
-          for (int u = 0; u < kPhotBatch; ++u) {
-            const int j = min(j0 + u, NL - 1);
-            b[u] = row[j];
-            c0[u] = lul[5 * j + 0];
-            c1[u] = lul[5 * j + 1];
-          }
-#pragma unroll
-          for (int u = 0; u < kPhotBatch; ++u) {
-            if (j0 + u < j_hi) {
-              const double y = (b[u] - c0[u] * y2) - c1[u] * y1;
-              row[j0 + u] = y;
-              y2 = y1;
-              y1 = y;
-            }
-          }
-        }
-      }
-      __syncthreads();
-      if (warp == 0 && row_i < rows) {                         // true (y[j-1], y[j-2]) at the start of every segment
-        double Y1 = 0.0, Y2 = 0.0;
-        for (int k = 1; k < nseg; ++k) {
-          const int m = k * seg_len;                           // first column of segment k; segment k-1 is [m - seg_len, m)
-          const double e1 = row[m - 1] + hom[4 * (m - 1) + 0] * Y1 + hom[4 * (m - 1) + 1] * Y2;
-          const double e2 = row[m - 2] + hom[4 * (m - 2) + 0] * Y1 + hom[4 * (m - 2) + 1] * Y2;
-          Y1 = e1;
-          Y2 = e2;
-          bnd[(k * kPhotTileRows + row_i) * 2 + 0] = Y1;
-          bnd[(k * kPhotTileRows + row_i) * 2 + 1] = Y2;
-        }
-      }
-      __syncthreads();
-      if (row_i < rows && j_lo < j_hi) {                       // back substitution, particular solution
-        const double Y1 = seg > 0 ? bnd[(seg * kPhotTileRows + row_i) * 2 + 0] : 0.0;
-        const double Y2 = seg > 0 ? bnd[(seg * kPhotTileRows + row_i) * 2 + 1] : 0.0;
-        double x1 = 0.0, x2 = 0.0;
-        for (int j0 = j_hi - 1; j0 >= j_lo; j0 -= kPhotBatch) {
-          double b[kPhotBatch], c3[kPhotBatch], c4[kPhotBatch];
-#pragma unroll
-          for (int u = 0; u < kPhotBatch; ++u) {
-            const int j = max(j0 - u, 0);
-            b[u] = (row[j] + hom[4 * j + 0] * Y1 + hom[4 * j + 1] * Y2) * lul[5 * j + 2];   // forward fix-up folded in
-            c3[u] = lul[5 * j + 3];
-            c4[u] = lul[5 * j + 4];
-          }
-#pragma unroll
-          for (int u = 0; u < kPhotBatch; ++u) {
-            if (j0 - u >= j_lo) {
-              const double x = (b[u] - c4[u] * x2) - c3[u] * x1;
-              row[j0 - u] = x;
-              x2 = x1;
-              x1 = x;
-            }
-          }
-        }
-      }
-      __syncthreads();
-      if (warp == 0 && row_i < rows) {                         // true (x[j+1], x[j+2]) at the end of every segment
-        double X1 = 0.0, X2 = 0.0;
-        for (int k = nseg - 2; k >= 0; --k) {
-          const int m = (k + 1) * seg_len;                     // first column of segment k + 1
-          const double s1 = row[m] + hom[4 * m + 2] * X1 + hom[4 * m + 3] * X2;
-          const double s2 = (m + 1 < NL) ? row[m + 1] + hom[4 * (m + 1) + 2] * X1 + hom[4 * (m + 1) + 3] * X2 : 0.0;
-          X1 = s1;
-          X2 = s2;
-          bnd[(k * kPhotTileRows + row_i) * 2 + 0] = X1;
-          bnd[(k * kPhotTileRows + row_i) * 2 + 1] = X2;
-        }
-      }
-      __syncthreads();
-      PHOT_PROF_ACC(9);
-      for (int j = tid; j < NL; j += blockDim.x) {                // backward fix-up folded into the store
-        const int k = j / seg_len;
-        const double hA = (k < nseg - 1) ? hom[4 * j + 2] : 0.0, hB = (k < nseg - 1) ? hom[4 * j + 3] : 0.0;
-        const double* bk = bnd + (min(k, nseg - 2 >= 0 ? nseg - 2 : 0) * kPhotTileRows) * 2;
-#pragma unroll 4
-        for (int r = 0; r < rows; ++r)
-          S[(r0 + r) * NL + j] = tile[r * (NL + 1) + j] + hA * bk[2 * r] + hB * bk[2 * r + 1];
-      }
-      __syncthreads();
-      PHOT_PROF_ACC(10);
-    }
-
-    PHOT_PROF(5);
-    // ---- 4./5. epochs: bispev at (t_e, band grid), band flux, magnitude, likelihood -------------------------
-    // Three sub-phases per chunk of epochs, each with the thread mapping that suits it (the tile region is free again
-    // and holds the per-epoch hand-over arrays):
-    //   a. one thread per epoch: knot interval and the four non-zero B-splines along time (divisions, a search);
-    //   b. one warp per epoch: gather the band's wavelength coefficients from the scratch with coalesced loads into a
-    //      per-warp buffer and split the band-pass integration points between the lanes;
-    //   c. one thread per epoch: magnitude, likelihood term, coalesced store.
-    double logl_part = 0.0;
-    const int nwarps = (int)(blockDim.x >> 5);
-    double* dw = tile + warp * kPhotMaxSpan;
-    double* eh = tile + nwarps * kPhotMaxSpan;                 // [chunk][kEpRec]: h0..h3, first row (< 0: before t0), band
-                                                               // flux, then the band's jlo, span, first and last point
-    const int chunk = (phot_tile_elems(NT, NL, NC) - nwarps * kPhotMaxSpan) / kEpRec;
-    const double sp = a.sigma_param_s ? a.sigma_param_s[n] : 0.0;
-    PHOT_PROF_ACC(11);
-    for (int e0 = 0; e0 < E; e0 += chunk) {
-      const int ne = min(chunk, E - e0);
-      for (int i = tid; i < ne; i += blockDim.x) {
-        const int e = a.epoch_order[e0 + i];
-        double x = a.epoch_tab[EP_T * E + e];
-        double* o = eh + kEpRec * i;
-        const int b = a.band_of_epoch[e];                      // looked up here so that the warps of sub-phase b do not
-        o[6] = (double)a.band_jlo[b];                          // start each epoch with a chain of dependent global loads
-        o[7] = (double)a.band_span[b];
-        o[8] = (double)a.band_off[b];
-        o[9] = (double)a.band_off[b + 1];
-        if (a.t0_s != nullptr) {                                                  // phase_models.py:33-58
-          x -= a.t0_s[n];
-          if (x < 0.0) { o[0] = o[1] = o[2] = o[3] = 0.0; o[4] = -1.0; continue; }
-        }
-        if (x < xk[0]) x = xk[0];                                                 // fpbisp clamps to [tb, te]
-        if (x > xk[G - 1]) x = xk[G - 1];
-        // knot interval: largest l in [3, G-1] with t[l] <= x  (t[l] = x[l-2] for 4 <= l <= G-1)
-        int l = 3;
-        {
-          int lo = 4, hi = G - 1;   // find count of knots t[4..G-1] = xk[2..G-3] that are <= x
-          while (lo <= hi) {
-            const int mid = (lo + hi) >> 1;
-            if (xk[mid - 2] <= x) { l = mid; lo = mid + 1; } else hi = mid - 1;
-          }
-        }
-        double tl[8], h[4];
-        for (int q = 0; q < 8; ++q) tl[q] = nak_knot(xk, G, l - 3 + q);
-        fpbspl3(tl, 3, x, h);
-        o[0] = h[0]; o[1] = h[1]; o[2] = h[2]; o[3] = h[3];
-        o[4] = (double)(l - 3);
       }
       __syncthreads();
       PHOT_PROF_ACC(6);
-      // The scratch is larger than L2 across the grid, so every gather may be a DRAM round trip: all its loads are
-      // issued together, and those of the warp's next epoch before the current one is integrated.
-      constexpr int kGather = kPhotMaxSpan / 32;
-      double g0[kGather], g1[kGather], g2[kGather], g3[kGather];
-      auto gather = [&](int i) {
-        if (i >= ne) return;
-        const double* o = eh + kEpRec * i;
-        const int span = (int)o[7];
-        const double* Sx = S + (size_t)max((int)o[4], 0) * NL + (int)o[6];
-#pragma unroll
-        for (int u = 0; u < kGather; ++u) {
-          const int q = min(lane + 32 * u, span - 1);
-          g0[u] = Sx[q];
-          g1[u] = Sx[NL + q];
-          g2[u] = Sx[2 * NL + q];
-          g3[u] = Sx[3 * NL + q];
+    }
+
+    // ---- 3. epochs: wavelength-axis back substitution, band integrals, magnitudes, likelihood ------------------
+    // chunks of epochs (grouped by band through epoch_order) sized by the coefficient buffer:
+    //   a. thread per epoch: back substitution from the last column down to the band's first coefficient; the band's
+    //      coefficients go to the shared buffer;
+    //   b. warp per epoch: the band-pass integration points are split between the lanes;
+    //   c. thread per epoch: magnitude / flux, likelihood term, coalesced store.
+    double logl_part = 0.0;
+    const int SM = a.span_max;
+    const int chunk = max(1, min((W * NTP) / SM, 4096));
+    const double sp = a.sigma_param_s ? a.sigma_param_s[n] : 0.0;
+    for (int e0 = 0; e0 < E; e0 += chunk) {
+      const int ne = min(chunk, E - e0);
+      for (int i = tid; i < ne; i += T) {
+        const int e = a.epoch_order[e0 + i];
+        const int b = a.band_of_epoch[e];
+        const int jlo = a.band_jlo[b], span = a.band_span[b];
+        double* cb = buf + (size_t)i * SM;
+        if (ept[4 * EP + e] < 0.0) continue;                    // before t0: nothing to integrate
+        double x1 = 0.0, x2 = 0.0;
+        const double* yp = ys + e;
+        for (int j = NL - 1; j >= jlo; --j) {
+          const double x = (yp[(size_t)(j - a.j_store_lo) * EP] * lul[5 * j + 2] - lul[5 * j + 4] * x2) - lul[5 * j + 3] * x1;
+          if (j < jlo + span) cb[j - jlo] = x;
+          x2 = x1;
+          x1 = x;
         }
-      };
-      gather(warp);
+      }
+      __syncthreads();
+      PHOT_PROF_ACC(7);
       for (int i = warp; i < ne; i += nwarps) {
-        const double* o = eh + kEpRec * i;
-        const int span = (int)o[7];
-        const double h0 = o[0], h1 = o[1], h2 = o[2], h3 = o[3];
-#pragma unroll
-        for (int u = 0; u < kGather; ++u) {
-          const int q = lane + 32 * u;
-          if (q < span) dw[q] = h0 * g0[u] + h1 * g1[u] + h2 * g2[u] + h3 * g3[u];
-        }
-        gather(i + nwarps);
-        if (o[4] < 0.0) continue;                              // before t0: no spectrum to integrate
-        __syncwarp();
+        const int e = a.epoch_order[e0 + i];
+        if (ept[4 * EP + e] < 0.0) continue;
+        const int b = a.band_of_epoch[e];
+        const int w0 = a.band_off[b], w1 = a.band_off[b + 1];
+        const double* dw = buf + (size_t)i * SM;
         double acc = 0.0;
-        // four integration points per lane and trip, indices first, then weights, then coefficients: the loads of a
-        // trip overlap instead of forming one dependent chain per point
-        const int w0 = (int)o[8], w1 = (int)o[9];
+        // four integration points per lane and trip: the loads of a trip overlap instead of forming one chain per point
         constexpr int kPts = 4;
         for (int wb = w0 + lane; wb < w1; wb += 32 * kPts) {
           double2 r0[kPts], r1[kPts], r2[kPts];
@@ -615,19 +639,18 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
           }
         }
         acc = warp_sum(acc);
-        __syncwarp();
-        if (lane == 0) eh[kEpRec * i + 5] = acc;
+        if (lane == 0) ept[7 * EP + e] = acc;
       }
       __syncthreads();
-      PHOT_PROF_ACC(7);
-      for (int i = tid; i < ne; i += blockDim.x) {
+      PHOT_PROF_ACC(8);
+      for (int i = tid; i < ne; i += T) {
         const int e = a.epoch_order[e0 + i];
         double model_v;
-        if (eh[kEpRec * i + 4] < 0.0) {
+        if (ept[4 * EP + e] < 0.0) {
           model_v = (a.output == RB_OUT_FLUX) ? 0.0 : 1000.0;
         } else {
           const int b = a.band_of_epoch[e];
-          const double bandflux = eh[kEpRec * i + 5] * a.band_scale[b];
+          const double bandflux = ept[7 * EP + e] * a.band_scale[b];
           model_v = -2.5 * log10(bandflux / a.band_zp[b]);                        // sed.py:114
           if (a.output == RB_OUT_FLUX) model_v = pow(10.0, model_v / (-2.5)) * a.band_ref[b];   // utils.py:716-718
         }
@@ -640,17 +663,16 @@ __global__ void __launch_bounds__(kPhotThreads, 2) phot_kernel(const PhotArgs a)
     }
     if (a.want_logl) {
       logl_part = warp_sum(logl_part);
-      __syncthreads();
       if (lane == 0) red[warp] = logl_part;
       __syncthreads();
       if (tid == 0) {
         double total = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total += red[w];
+        for (int w = 0; w < nwarps; ++w) total += red[w];
         a.out_logl[a.n_base + n] = nan_to_num(total);
       }
     }
     __syncthreads();
-    PHOT_PROF(6);
+    PHOT_PROF_ACC(9);
     PHOT_PROF_END();
   }
 }
