@@ -32,10 +32,14 @@ constexpr double AG_FOURPI = 4 * kPi;
 // SIGT = (QE*QE/(ME*C2))**2 * (8*pi/3): the square is a Python float pow; value computed on the host
 // with the same operations (see ag_sigt()) and passed in AgConst.
 
-constexpr int kAgMaxNu = 4;      // unique frequencies per call
+constexpr int kAgMaxNu = 16;     // unique frequencies per call (the per-warp spectra buffer grows with them)
 constexpr int kAgWarps = 5;      // warps per block in ag_cell_kernel
-constexpr int kAgRingsPerUnit = 10;  // rings handled by one block of ag_cell_kernel (load balance for res up to 100+)
-enum { RA_BETA = 0, RA_NE, RA_OMG, RA_R, RA_B, RA_NUMP, RA_PP, RA_KT, RA_G, kRingArrays };
+constexpr int kAgCellsPerUnit = 100;  // cells handled by one block of ag_cell_kernel: res = 10 -> 10 rings per unit,
+                                      // res = 100 -> one ring per unit (equal work per block whatever the resolution)
+__host__ __device__ inline int ag_rings_per_unit(int nrot) { return nrot >= kAgCellsPerUnit ? 1 : max(1, kAgCellsPerUnit / max(nrot, 1)); }
+// per ring and step; RA_NUCP is the comoving cooling frequency (:363-364), which depends on the ring only: the on-axis
+// observer time it needs is accumulated in the ring kernel's own sequential loop (= np.cumsum order)
+enum { RA_BETA = 0, RA_NE, RA_OMG, RA_R, RA_NUCP, RA_NUMP, RA_PP, RA_KT, RA_G, kRingArrays };
 
 enum {
   AS_OPZ = 0, AS_DL, AS_THV, AS_N, AS_EB, AS_EE, AS_P, AS_XP, AS_FX, AS_XIN, AS_G0, AS_EK, AS_THC, AS_THJ,
@@ -61,7 +65,7 @@ struct AgArgs {
   int* ring_count;           // [N]
   int64_t* ring_off;         // [N + 1]
   double* ring_scratch;      // [rings][kRingArrays][steps]
-  int* unit_count;           // [N]   work units (groups of <= kAgRingsPerUnit rings) per sample
+  int* unit_count;           // [N]   work units (groups of rings, about kAgCellsPerUnit cells) per sample
   int64_t* unit_off;         // [N + 1]
   double* partial;           // [units][E] per-unit light-curve partial sums
   double sigt;
@@ -142,7 +146,8 @@ __global__ void ag_prep_kernel(const AgArgs a) {
   // p outside (1.2, 3.4) raises ValueError in the reference (:576-577): flagged by zero rings -> NaN output
   const int rings = (p < 1.2 || p > 3.4 || !(p == p)) ? 0 : res;
   a.ring_count[n] = rings;
-  a.unit_count[n] = (rings + kAgRingsPerUnit - 1) / kAgRingsPerUnit;
+  const int rpu = ag_rings_per_unit(nrot);
+  a.unit_count[n] = (rings + rpu - 1) / rpu;
 }
 
 // exclusive scan of ring_count[0..N) -> ring_off[0..N]; single block
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t to
   double* out = a.ring_scratch + (size_t)r * kRingArrays * steps;
 
   double G = Gs, dm = dlogm;
-  double ex0 = 1.0, r_prev_orig = 0.0, r_cum = 0.0;
+  double ex0 = 1.0, r_prev_orig = 0.0, r_cum = 0.0, tobso = 0.0;
   for (int s = 0; s < steps; ++s) {
     const double g2m1 = G * G - 1.0;
     const double root = sqrt(g2m1);
@@ -301,7 +306,10 @@ __global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t to
         r_inc = (r_orig - r_prev_orig) * pow(expo, inv3k);
       }
       r_prev_orig = r_orig;
+      const double r_before = r_cum;
       r_cum = (s == 0) ? r_inc : r_cum + r_inc;
+      const double r_diff = (s == 0) ? r_cum : r_cum - r_before;                       // np.diff(R, prepend=0), :347-350
+      tobso += r_diff * (1.0 / beta - 1.0) / AG_CC;                                    // :353, :356
       const double n0 = n_amb * pow(r_cum, -kk);
       const double B = sqrt(2 * AG_FOURPI * EB * n0 * AG_MP * AG_C2 * ((ghat * G + 1.0) / (ghat - 1.0)) * Gm1);
       double gm;
@@ -316,7 +324,10 @@ __global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t to
       out[RA_NE * steps + s] = Ne;
       out[RA_OMG * steps + s] = omg;
       out[RA_R * steps + s] = r_cum;
-      out[RA_B * steps + s] = B;
+      {
+        const double gc = 6.0 * kPi * AG_ME * AG_CC / (G * sigt * B * B * tobso);        // :360
+        out[RA_NUCP * steps + s] = 0.286 * 3.0 * gc * gc * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);   // :361
+      }
       out[RA_NUMP * steps + s] = 3.0 * xp * gm * gm * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);
       out[RA_PP * steps + s] = xiN * Fx * AG_ME * AG_C2 * sigt * B / (3.0 * AG_QE);
       out[RA_KT * steps + s] = gm * AG_ME * AG_C2;
@@ -348,18 +359,38 @@ __device__ __forceinline__ double ag_flux(double fbb, double nuc, double num, do
   return (f < adj) ? f : adj;  // min(FBB_adj, Fluxt): first argument unless the second is smaller
 }
 
-// ---- one block per work unit (<= kAgRingsPerUnit rings of one sample), one warp per cell -------------------------
+// The same with the power laws evaluated as exp(exponent * (log a - log b)): the logarithms of nu_c and nu_m are shared
+// by all frequencies of a step and log(nu) is a per-sample constant, so a step costs two log and one exp per frequency
+// instead of two to four pow.  Comparisons use the original values; |exponent * log| < 1e3 keeps the result within
+// 1e-13 relative of the pow form.  Callers route non-positive / non-finite nu_c, nu_m to ag_flux.
+__device__ __forceinline__ double ag_flux_log(double fbb, double nuc, double num, double nu1, double lnc, double lnm,
+                                              double ln1, double fmax, double p) {
+  double f = 0.0;
+  if (nuc < num) {
+    if (num < nu1) f = fmax * exp(-0.5 * (lnm - lnc) - 0.5 * p * (ln1 - lnm));
+    else if (nuc < nu1) f = fmax * exp(-0.5 * (ln1 - lnc));
+    else if (nu1 < nuc) f = fmax * exp((ln1 - lnc) * (1.0 / 3.0));
+  } else if (num < nuc) {
+    if (nuc < nu1) f = fmax * exp(-0.5 * (p - 1.0) * (lnc - lnm) - 0.5 * p * (ln1 - lnc));
+    else if (num < nu1) f = fmax * exp(-0.5 * (p - 1.0) * (ln1 - lnm));
+    else if (nu1 < num) f = fmax * exp((ln1 - lnm) * (1.0 / 3.0));
+  }
+  const double adj = fbb * (nu1 * nu1) * fmax_nan(1.0, sqrt(nu1 / num));
+  return (f < adj) ? f : adj;
+}
+
+// ---- one block per work unit (about kAgCellsPerUnit cells: a few rings of one sample), one warp per cell -------------------------
 __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, int64_t total_units) {
   extern __shared__ double asm_[];
   const int steps = a.cfg.steps, E = a.E, n_nu = a.n_nu;
-  const int spl = (steps + 31) / 32;          // steps per lane
   double* ring = asm_;                         // [kRingArrays][steps]
   double* ibeta = ring + kRingArrays * steps;  // [steps] 1 / beta                          } per ring and step, shared by
   double* costh = ibeta + steps;               // [steps] cos(acos(1 - omega / rotstep))    } all cells of the ring
   double* wbuf = costh + steps;                // per warp: tobs[steps] + flux[n_nu][steps]
   double* acc = wbuf + (size_t)kAgWarps * (1 + n_nu) * steps;   // [kAgWarps][E]
   double* sc = acc + (size_t)kAgWarps * E;     // [kAgScalars]
-  int* nuidx = reinterpret_cast<int*>(sc + kAgScalars);         // [E]
+  double* lognu = sc + kAgScalars;             // [kAgMaxNu] log(nu (1 + z))
+  int* nuidx = reinterpret_cast<int*>(lognu + kAgMaxNu);        // [E]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t u = blockIdx.x;
@@ -371,14 +402,16 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
     if (a.unit_off[mid] <= u) lo_n = mid; else hi_n = mid;
   }
   const int64_t n = lo_n;
-  const int ring_begin = (int)(u - a.unit_off[n]) * kAgRingsPerUnit;
-  const int ring_end = min(ring_begin + kAgRingsPerUnit, a.ring_count[n]);
+  const int rpu = ag_rings_per_unit((int)a.scalars[n * kAgScalars + AS_NROT]);
+  const int ring_begin = (int)(u - a.unit_off[n]) * rpu;
+  const int ring_end = min(ring_begin + rpu, a.ring_count[n]);
 
   for (int e = tid; e < E; e += blockDim.x) nuidx[e] = a.nu_index[e];
   double* my_tobs = wbuf + (size_t)warp * (1 + n_nu) * steps;
   double* my_flux = my_tobs + steps;
   double* my_acc = acc + (size_t)warp * E;
   if (tid < kAgScalars) sc[tid] = a.scalars[n * kAgScalars + tid];
+  if (tid < kAgMaxNu) lognu[tid] = (tid < n_nu) ? log(a.nu_unique[tid] * a.scalars[n * kAgScalars + AS_OPZ]) : 0.0;
   for (int e = tid; e < kAgWarps * E; e += blockDim.x) acc[e] = 0.0;
   __syncthreads();
   {
@@ -428,29 +461,27 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
         ang = (ang > 1.0) ? 1.0 : ((ang < -1.0) ? -1.0 : ang);
         const double obsa = acos(ang);
         const double cosa = cos(obsa);
-        // ---- step2 (:325-370): this lane's steps [s0, s1) ----
-        const int s0 = min(lane * spl, steps), s1 = min(s0 + spl, steps);
+        // ---- step2 (:325-370).  Lane l owns steps l, l + 32, ...: consecutive lanes touch consecutive doubles of
+        // every per-step array (no shared-memory bank conflicts); the observer-time cumsum is a warp scan per chunk
+        // of 32 steps with the running total carried between chunks.
         const double cos_th0 = cos(acos(1.0 - Om0 / rotstep));   // the cell's own solid angle (expansion: until the ring's exceeds it)
-        double sum_dt = 0.0, sum_dto = 0.0;
-        for (int s = s0; s < s1; ++s) {
-          const double rd = ring[RA_R * steps + s] - (s > 0 ? ring[RA_R * steps + s - 1] : 0.0);
-          sum_dt += rd * (ibeta[s] - cosa) / AG_CC;
-          sum_dto += rd * (ibeta[s] - 1.0) / AG_CC;
-        }
-        double pre_dt = sum_dt, pre_dto = sum_dto;   // inclusive scan over lanes
+        double carry = 0.0;
+        for (int sb = 0; sb < steps; sb += 32) {
+          const int s = sb + lane;
+          const bool live = s < steps;
+          const int sc_ = live ? s : steps - 1;
+          const double R = ring[RA_R * steps + sc_];
+          const double rd = R - (sc_ > 0 ? ring[RA_R * steps + sc_ - 1] : 0.0);
+          double tobs = live ? rd * (ibeta[sc_] - cosa) / AG_CC : 0.0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const double u = __shfl_up_sync(0xffffffffu, pre_dt, o);
-          const double w = __shfl_up_sync(0xffffffffu, pre_dto, o);
-          if (lane >= o) { pre_dt += u; pre_dto += w; }
-        }
-        double tobs = pre_dt - sum_dt, tobso = pre_dto - sum_dto;   // exclusive prefix
-        for (int s = s0; s < s1; ++s) {
-          const double G = ring[RA_G * steps + s], beta = ring[RA_BETA * steps + s], B = ring[RA_B * steps + s];
-          const double R = ring[RA_R * steps + s];
-          const double rd = R - (s > 0 ? ring[RA_R * steps + s - 1] : 0.0);
-          tobs += rd * (ibeta[s] - cosa) / AG_CC;
-          tobso += rd * (ibeta[s] - 1.0) / AG_CC;
+          for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, tobs, o);
+            if (lane >= o) tobs += up;
+          }
+          tobs += carry;
+          carry = __shfl_sync(0xffffffffu, tobs, 31);
+          if (!live) continue;
+          const double G = ring[RA_G * steps + s], beta = ring[RA_BETA * steps + s];
           const double omg = ring[RA_OMG * steps + s];
           double Om = omg, cos_thii = costh[s];
           if (expansion) {
@@ -459,15 +490,18 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
           }
           const double NO = Om0 * ring[RA_NE * steps + s] / AG_FOURPI;
           const double dop = 1.0 / (G * (1.0 - beta * cosa));
-          const double gc = 6.0 * kPi * AG_ME * AG_CC / (G * a.sigt * B * B * tobso);
-          const double nucp = 0.286 * 3.0 * gc * gc * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);
           const double num = dop * ring[RA_NUMP * steps + s];
-          const double nuc = dop * nucp;
+          const double nuc = dop * ring[RA_NUCP * steps + s];
           const double Fmax = NO * ring[RA_PP * steps + s] * dop * dop * dop / (AG_FOURPI * dl2);
           const double FBB = 2 * Om * cos_thii * dop * ring[RA_KT * steps + s] * R * R / (AG_C2 * dl2);
           my_tobs[s] = tobs;
-          for (int h = 0; h < n_nu; ++h)
-            my_flux[h * steps + s] = ag_flux(FBB, nuc, num, a.nu_unique[h] * opz, Fmax, p);   // nu = nu0*(1+z) :587
+          const bool regular = num > 0.0 && num < INFINITY && nuc > 0.0 && nuc < INFINITY;
+          const double lnm = regular ? log(num) : 0.0, lnc = regular ? log(nuc) : 0.0;
+          for (int h = 0; h < n_nu; ++h) {
+            const double nu1 = a.nu_unique[h] * opz;                                   // nu = nu0*(1+z) :587
+            my_flux[h * steps + s] = regular ? ag_flux_log(FBB, nuc, num, nu1, lnc, lnm, lognu[h], Fmax, p)
+                                             : ag_flux(FBB, nuc, num, nu1, Fmax, p);
+          }
         }
         __syncwarp();
         // ---- calc_lightcurve (:632-640): np.interp(t/(1+z), tobs, Flux[h]) summed over cells ----

@@ -1020,7 +1020,7 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
   std::sort(uniq.begin(), uniq.end());
   uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
   if ((int)uniq.size() > rb::kAgMaxNu)
-    return fail(RB_ERR_UNSUPPORTED, "rb_ag_eval: more than 4 distinct frequencies in one call");
+    return fail(RB_ERR_UNSUPPORTED, "rb_ag_eval: more than 16 distinct frequencies in one call");
   std::vector<int> h_idx((size_t)E);
   for (int64_t e = 0; e < E; ++e)
     h_idx[(size_t)e] = (int)(std::lower_bound(uniq.begin(), uniq.end(), h_freq[(size_t)e]) - uniq.begin());
@@ -1028,7 +1028,7 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
   const int steps = cfg->steps, n_nu = (int)uniq.size();
   const size_t cell_smem = sizeof(double) * ((size_t)(rb::kRingArrays + 2) * steps +
                                              (size_t)rb::kAgWarps * (1 + n_nu) * steps + (size_t)rb::kAgWarps * E +
-                                             rb::kAgScalars) + sizeof(int) * (size_t)E;
+                                             rb::kAgScalars + rb::kAgMaxNu) + sizeof(int) * (size_t)E;
   if (cell_smem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_ag_eval: steps / epochs exceed shared memory");
 
   const int64_t chunk_max = 8192;
