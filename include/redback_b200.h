@@ -507,6 +507,28 @@ int rb_optical_noise_philox_f64(int noise_type, int64_t N, int64_t E, int64_t sa
                                 double* obs_flux, double* flux_err, double* snr, unsigned char* detected,
                                 double* z_out, void* stream);
 
+/* ---- survey simulation with per-transient pointings --------------------------------------------------------
+ * SimulateOpticalTransient._make_observation_single / _make_observations_for_population
+ * (redback/simulate_transients.py:1096-1178): every transient is observed at ITS OWN pointings.  The pointing lists
+ * are a padded device table [N][E_max] (row n has epoch_count[n] valid entries): `phase` = expMJD - t0 in days
+ * (the spline source clamps phases outside the model grid, like sncosmo / FITPACK), `band_index` into the bands of
+ * `phot` (whose band_of_epoch must be 0 .. n_bands-1, one entry per band).  Magnitudes as rb_sn_mag_eval_f64;
+ * padding entries of out_model are left untouched. */
+int rb_sn_mag_eval_ragged_f64(const rb_sn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E_max,
+                              const double* params, const double* phase, const int32_t* band_index,
+                              const int32_t* epoch_count, const double* dl_cm, double* out_model, void* stream);
+/* Noise, magnitude errors and the detection flags of :1100-1134 for that table: five_sigma_depth [N][E_max],
+ * band_ref_flux [n_bands] (filters.csv reference_flux), source_noise_factor = 0 switches the source noise off
+ * (add_source_noise=False).  Variates: the Philox stream of rb_optical_noise_philox_f64 at element index
+ * sample_base + row_start[n] + e, i.e. the pointing's position in the flat (CSR) pointing table, so results do not
+ * depend on padding or chunking.  Padding entries: NaN / not detected. */
+int rb_survey_noise_philox_f64(int64_t N, int64_t E_max, int64_t sample_base, uint64_t seed,
+                               const double* model_mag, const double* phase, const int32_t* band_index,
+                               const int32_t* epoch_count, const int64_t* row_start, const double* five_sigma_depth,
+                               const double* band_ref_flux, double source_noise_factor, double snr_threshold,
+                               double* obs_mag, double* mag_err, double* obs_flux, double* flux_err,
+                               unsigned char* detected, double* z_out, void* stream);
+
 /* Luminosity distance [cm] for N redshifts on device (same quadrature the fused kernels use). */
 int rb_luminosity_distance_f64(const rb_cosmology* cosmo, int64_t N, const double* redshift,
                                double* out_dl_cm, void* stream);

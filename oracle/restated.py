@@ -2027,3 +2027,28 @@ def philox_standard_normal(seed, index):
         return (bits.astype(np.float64) + 0.5) / 9007199254740992.0
     u1, u2 = uniform(r[0], r[1]), uniform(r[2], r[3])
     return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def survey_observation_single(model_magnitude, phase, ref_flux, five_sigma_depth, z, snr_threshold=5.0,
+                              add_source_noise=False, source_noise_factor=0.02):
+    """SimulateOpticalTransient._make_observation_single (simulate_transients.py:1096-1140) for one transient, given the
+    model magnitudes at its pointings (`sncosmo_model.bandmag`, :1105), phase = expMJD - t0, the per-pointing reference
+    flux and 5-sigma depth, and standard-normal draws z (the reference calls np.random.normal(loc=flux, scale=err))."""
+    model_magnitude = np.asarray(model_magnitude, dtype=float)
+    with np.errstate(all="ignore"):
+        flux = bandpass_magnitude_to_flux(model_magnitude, ref_flux)                         # :1106
+        err = ref_flux * np.power(10.0, -0.4 * np.asarray(five_sigma_depth, dtype=float)) / 5.0   # utils.py:517-541
+        if add_source_noise:
+            err = np.sqrt(err ** 2 + source_noise_factor ** 2 * flux ** 2)                   # :1108-1109
+        observed_flux = flux + z * err                                                       # :1111
+        magnitudes = -2.5 * np.log10(observed_flux / ref_flux)                               # utils.py:834-845
+        magnitude_errs = np.abs((2.5 / np.log(10)) * (err / flux))                           # utils.py:808-831
+        magnitude_errs[np.isnan(flux) | (np.abs(flux) <= 1.0e-20)] = np.nan
+        mask = (np.asarray(phase) <= 0.) | np.isnan(magnitudes)                              # :1128
+        snr = observed_flux / err                                                            # :1129
+        detected = np.ones(model_magnitude.shape)
+        detected[mask] = 0
+        detected[snr < snr_threshold] = 0                                                    # :1130-1133
+    return dict(magnitude=magnitudes, e_magnitude=magnitude_errs, flux=observed_flux, flux_error=err,
+                detected=detected.astype(bool), flux_limit=bandpass_magnitude_to_flux(
+                    np.asarray(five_sigma_depth, dtype=float), ref_flux))

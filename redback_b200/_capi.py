@@ -155,6 +155,10 @@ EXPORTS = {
                              + [C.c_void_p]),
     "rb_optical_noise_philox_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_uint64] + [_dp] * 3
                                     + [C.c_double, C.c_int] + [_dp] * 7 + [C.c_void_p]),
+    "rb_sn_mag_eval_ragged_f64": (C.c_int, [C.POINTER(SnConfig), C.c_void_p, C.c_int64, C.c_int64] + [_dp] * 6
+                                  + [C.c_void_p]),
+    "rb_survey_noise_philox_f64": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_uint64] + [_dp] * 7
+                                   + [C.c_double, C.c_double] + [_dp] * 6 + [C.c_void_p]),
     "rb_luminosity_distance_f64": (C.c_int, [C.POINTER(Cosmology), C.c_int64, _dp, _dp, C.c_void_p]),
     "rb_gaussian_logl_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64] + [_dp] * 4 + [C.POINTER(UpperLimits), _dp,
                                        C.c_void_p]),

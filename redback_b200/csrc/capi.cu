@@ -1360,6 +1360,10 @@ struct PhotJob {
   rb_upper_limits upper_limits;
   const double *t_obs, *y, *sigma, *sigma_param, *t0;
   double *out_model, *out_logl;
+  // ragged mode (device pointers, see rb_sn_mag_eval_ragged_f64): per-sample pointings instead of the shared t_obs
+  const double* t_ragged = nullptr;
+  const int* band_ragged = nullptr;
+  const int* epoch_count = nullptr;
 };
 
 // fill(n0, nc, d_grid, d_opz, d_dl, d_len) -> RB_OK or an error code (already recorded with fail())
@@ -1382,7 +1386,8 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   PhotDevice pd;
   pd.st = st;
   rb::PhotArgs pa{};
-  int rc = phot_prepare(j.phot, E, pd, pa);
+  const bool ragged = j.t_ragged != nullptr;
+  int rc = phot_prepare(j.phot, ragged ? j.phot->n_bands : E, pd, pa);   // ragged: band_of_epoch is one entry per band
   if (rc != RB_OK) { pd.release(); return rc; }
   cudaError_t ce = cudaSuccess;
   if (j.lu_grid != nullptr) {
@@ -1394,9 +1399,11 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   double* d_ep_obs = nullptr;
   ce = cudaMallocAsync(&d_ep_obs, (size_t)rb::kEpochCols * E * sizeof(double), st);
   if (ce != cudaSuccess) { pd.release(); return cuda_fail(ce, "epoch table"); }
-  rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, j.sigma_mode, j.t_obs, nullptr, j.y,
-                                                                    j.y ? j.sigma : nullptr, j.upper_limits, d_ep_obs);
-  launch_counter()->fetch_add(1);
+  if (!ragged) {
+    rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, j.sigma_mode, j.t_obs, nullptr, j.y,
+                                                                      j.y ? j.sigma : nullptr, j.upper_limits, d_ep_obs);
+    launch_counter()->fetch_add(1);
+  }
 
   const int64_t chunk_max = 32768;
   int occ_ph = 1;
@@ -1446,6 +1453,9 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
     pa.sigma_param_s = j.sigma_param ? j.sigma_param + n0 : nullptr;
     pa.t0_s = j.t0 ? j.t0 + n0 : nullptr;
     pa.epoch_tab = d_ep_obs;
+    pa.t_ragged = j.t_ragged;
+    pa.band_ragged = j.band_ragged;
+    pa.epoch_count = j.epoch_count;
     pa.scratch = d_scratch;
     pa.scratch_stride = scratch_stride;
     pa.W = shape.W;
@@ -1497,16 +1507,19 @@ int device_and_sms(int* sms) {
 }
 }  // namespace
 
-extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
-                                  const double* params, const double* t_obs, const double* dl_cm, const double* y,
-                                  const double* sigma, const double* sigma_param, double* out_model,
-                                  double* out_logl, void* stream) {
+static int sn_mag_eval(const rb_sn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
+                       const double* params, const double* t_obs, const int* band_ragged, const int* epoch_count,
+                       const double* dl_cm, const double* y, const double* sigma, const double* sigma_param,
+                       double* out_model, double* out_logl, void* stream) {
   static const double dummy = 0.0;
+  const bool ragged = band_ragged != nullptr;
   int rc = sn_check(cfg, N, E, params, t_obs, cfg && cfg->sed != RB_SED_BOLOMETRIC ? &dummy : nullptr, y, sigma,
                     sigma_param, out_model, out_logl);
   if (rc != RB_OK) return rc;
   if (cfg->sed == RB_SED_BOLOMETRIC) return fail(RB_ERR_INVALID, "rb_sn_mag_eval: bolometric models have no magnitude output");
-  rc = phot_check(phot, E, true);
+  if (ragged && (!epoch_count || cfg->t0 != nullptr))
+    return fail(RB_ERR_INVALID, "rb_sn_mag_eval_ragged: epoch_count is required and cfg->t0 must be NULL (pass phases)");
+  rc = phot_check(phot, ragged ? phot->n_bands : E, true);
   if (rc != RB_OK) return rc;
   if (N == 0) return RB_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1550,6 +1563,7 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
   j.t_obs = t_obs; j.y = y; j.sigma = sigma; j.sigma_param = sigma_param;
   j.t0 = (cfg->t0 && cfg->engine != RB_ENGINE_CSM) ? cfg->t0 : nullptr;
   j.out_model = out_model; j.out_logl = out_logl;
+  if (ragged) { j.t_ragged = t_obs; j.band_ragged = band_ragged; j.epoch_count = epoch_count; }
   return run_photometry(j, st, sms, [&](int64_t n0, int64_t nc, double* d_grid, double* d_opz, double* d_dl, int*) {
     rb::SnArgs a{};
     a.cfg = *cfg;
@@ -1575,6 +1589,23 @@ extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* 
     launch_counter()->fetch_add(2);
     return (int)RB_OK;
   });
+}
+
+extern "C" int rb_sn_mag_eval_f64(const rb_sn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E,
+                                  const double* params, const double* t_obs, const double* dl_cm, const double* y,
+                                  const double* sigma, const double* sigma_param, double* out_model,
+                                  double* out_logl, void* stream) {
+  return sn_mag_eval(cfg, phot, N, E, params, t_obs, nullptr, nullptr, dl_cm, y, sigma, sigma_param, out_model, out_logl,
+                     stream);
+}
+
+extern "C" int rb_sn_mag_eval_ragged_f64(const rb_sn_config* cfg, const rb_photometry* phot, int64_t N, int64_t E_max,
+                                         const double* params, const double* phase, const int32_t* band_index,
+                                         const int32_t* epoch_count, const double* dl_cm, double* out_model,
+                                         void* stream) {
+  if (!band_index) return fail(RB_ERR_INVALID, "rb_sn_mag_eval_ragged: band_index is required");
+  return sn_mag_eval(cfg, phot, N, E_max, params, phase, band_index, epoch_count, dl_cm, nullptr, nullptr, nullptr,
+                     out_model, nullptr, stream);
 }
 
 static int kn_mag_eval(const rb_kn_config* cfg, const rb_photometry* phot, int n_comp, int64_t N, int64_t E,
@@ -1854,4 +1885,24 @@ extern "C" int rb_optical_noise_philox_f64(int noise_type, int64_t N, int64_t E,
                                            double* snr, unsigned char* detected, double* z_out, void* stream) {
   return optical_noise(noise_type, N, E, model_mag, ref_flux, limiting_mag, nullptr, seed, sample_base, snr_threshold,
                        apply_snr_cut, obs_mag, mag_err, obs_flux, flux_err, snr, detected, z_out, stream);
+}
+
+extern "C" int rb_survey_noise_philox_f64(int64_t N, int64_t E, int64_t sample_base, uint64_t seed,
+                                          const double* model_mag, const double* phase, const int32_t* band_index,
+                                          const int32_t* epoch_count, const int64_t* row_start,
+                                          const double* five_sigma_depth,
+                                          const double* band_ref_flux, double source_noise_factor, double snr_threshold,
+                                          double* obs_mag, double* mag_err, double* obs_flux, double* flux_err,
+                                          unsigned char* detected, double* z_out, void* stream) {
+  if (N < 0 || E <= 0 || sample_base < 0 || !model_mag || !phase || !band_index || !epoch_count || !row_start || !five_sigma_depth ||
+      !band_ref_flux || !obs_mag || !mag_err || !obs_flux || !flux_err || !detected)
+    return fail(RB_ERR_INVALID, "rb_survey_noise: bad arguments");
+  if (N == 0) return RB_OK;
+  const int64_t total = N * E;
+  rb::survey_noise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      total, (int)E, model_mag, phase, band_index, epoch_count, row_start, five_sigma_depth, band_ref_flux, seed, sample_base,
+      source_noise_factor, snr_threshold, obs_mag, mag_err, obs_flux, flux_err, detected, z_out);
+  launch_counter()->fetch_add(1);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
 }

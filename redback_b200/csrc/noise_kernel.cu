@@ -78,4 +78,50 @@ __global__ void optical_noise_kernel(int noise_type, int64_t total, int E, const
   detected[idx] = apply_cut ? (unsigned char)(snr >= snr_threshold) : (unsigned char)1;   // :516-523
 }
 
+// Survey simulation with per-transient pointings: SimulateOpticalTransient._make_observation_single
+// (simulate_transients.py:1096-1140) for a padded [N][E] table; row n has epoch_count[n] valid entries.
+//   flux = bandpass_magnitude_to_flux(model_mag)                 utils.py:707-718
+//   err  = ref_flux 10^(-0.4 depth) / 5  [+ source noise in quadrature]   utils.py:517-541, :1108-1109
+//   observed_flux ~ N(flux, err)                                 :1111
+//   magnitude = -2.5 log10(observed_flux / ref_flux)             utils.py:834-845
+//   magnitude error from the MODEL flux                          utils.py:808-831, :1113
+//   detected = not (phase <= 0 or isnan(magnitude)) and observed_flux / err >= snr_threshold   :1128-1134
+__global__ void survey_noise_kernel(int64_t total, int E, const double* __restrict__ model_mag,
+                                    const double* __restrict__ phase, const int* __restrict__ band_index,
+                                    const int* __restrict__ epoch_count, const int64_t* __restrict__ row_start,
+                                    const double* __restrict__ depth,
+                                    const double* __restrict__ band_ref_flux, uint64_t seed, int64_t sample_base,
+                                    double source_noise_factor, double snr_threshold, double* __restrict__ obs_mag,
+                                    double* __restrict__ mag_err, double* __restrict__ obs_flux,
+                                    double* __restrict__ flux_err, unsigned char* __restrict__ detected,
+                                    double* __restrict__ z_out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int64_t n = idx / E;
+  const int e = (int)(idx - n * E);
+  if (e >= epoch_count[n]) {                               // padding
+    obs_mag[idx] = NAN; mag_err[idx] = NAN; obs_flux[idx] = NAN; flux_err[idx] = NAN; detected[idx] = 0;
+    if (z_out) z_out[idx] = 0.0;
+    return;
+  }
+  // variate of the pointing's position in the FLAT pointing table: independent of padding and chunking
+  const double zz = philox_normal(seed, (uint64_t)(sample_base + row_start[n] + e));
+  if (z_out) z_out[idx] = zz;
+  const double rf = band_ref_flux[band_index[idx]];
+  const double flux = pow(10.0, model_mag[idx] / (-2.5)) * rf;
+  double err = (rf * pow(10.0, -0.4 * depth[idx])) / 5.0;
+  if (source_noise_factor > 0.0) err = sqrt(err * err + (source_noise_factor * source_noise_factor) * (flux * flux));
+  const double of = flux + zz * err;
+  const double om = -2.5 * log10(of / rf);
+  double me = fabs((2.5 / log(10.0)) * (err / flux));
+  if (isnan(flux) || fabs(flux) <= 1.0e-20) me = NAN;
+  const bool masked = (phase[idx] <= 0.0) || isnan(om);
+  const bool low_snr = (of / err) < snr_threshold;
+  obs_mag[idx] = om;
+  mag_err[idx] = me;
+  obs_flux[idx] = of;
+  flux_err[idx] = err;
+  detected[idx] = (unsigned char)(!masked && !low_snr);
+}
+
 }  // namespace rb

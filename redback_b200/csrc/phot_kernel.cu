@@ -74,6 +74,10 @@ struct PhotArgs {
   const double* band_zp;        // [n_bands]
   const double* band_ref;       // [n_bands] reference flux ('flux' output) or nullptr
   const int* epoch_order;       // [E] epochs grouped by band
+  // ragged mode (survey simulation: every transient has its own pointings), all nullptr otherwise:
+  const double* t_ragged;       // [N_total][E] observer-frame phase of sample n's pointings (days)
+  const int* band_ragged;       // [N_total][E] band index per pointing
+  const int* epoch_count;       // [N_total] pointings of sample n (<= E); the rest of the row is padding
   const double* int_rec;        // [total][6] per integration point: the 4 non-zero wavelength B-splines, wave * trans,
                                 //            index of the first of them relative to the band's first coefficient
   double* scratch;              // [gridDim][scratch_stride]
@@ -246,6 +250,10 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     const double* gX = a.grid + (size_t)n * kPhotGridCols * NT + PH_X * NT;
     const double opz = a.opz[n], dl = a.dl[n];
     const double lam_c = a.cutoff_wavelength * kAngstrom;
+    const bool ragged = a.t_ragged != nullptr;
+    const int En = ragged ? a.epoch_count[a.n_base + n] : E;                       // epochs of this sample
+    const double* t_row = ragged ? a.t_ragged + (size_t)(a.n_base + n) * E : a.epoch_tab + (size_t)EP_T * E;
+    const int* band_row = ragged ? a.band_ragged + (size_t)(a.n_base + n) * E : a.band_of_epoch;
     double* xk = buf;                                 // [G] data sites; dead once the set-up is done
     if (!a.common_time_lu) set_segments(G);
     // ---- 0. set-up.  Every spectrum sample factorises around the Planck denominator:
@@ -331,8 +339,8 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     }
     __syncthreads();
     // ---- 0b. per-epoch time basis (knot interval + the four non-zero B-splines) and the collocation rows ----------
-    for (int e = tid; e < E; e += T) {
-      double x = a.epoch_tab[EP_T * E + e];
+    for (int e = tid; e < En; e += T) {
+      double x = t_row[e];
       double h[4] = {0.0, 0.0, 0.0, 0.0};
       double first = -1.0;
       bool live = true;
@@ -549,7 +557,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       PHOT_PROF_ACC(5);
       // 2d. contraction with the epochs' time B-splines (backward fix-up folded into the loads) and forward
       // elimination of the wavelength-axis solve on the E resulting rows
-      for (int e = tid; e < E; e += T) {
+      for (int e = tid; e < En; e += T) {
         const double h0 = ept[0 * EP + e], h1 = ept[1 * EP + e], h2 = ept[2 * EP + e], h3 = ept[3 * EP + e];
         const int l = (int)ept[4 * EP + e];
         double y1 = ept[5 * EP + e], y2 = ept[6 * EP + e];
@@ -592,11 +600,11 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     const int SM = a.span_max;
     const int chunk = max(1, min((W * NTP) / SM, 4096));
     const double sp = a.sigma_param_s ? a.sigma_param_s[n] : 0.0;
-    for (int e0 = 0; e0 < E; e0 += chunk) {
-      const int ne = min(chunk, E - e0);
+    for (int e0 = 0; e0 < En; e0 += chunk) {
+      const int ne = min(chunk, En - e0);
       for (int i = tid; i < ne; i += T) {
-        const int e = a.epoch_order[e0 + i];
-        const int b = a.band_of_epoch[e];
+        const int e = ragged ? e0 + i : a.epoch_order[e0 + i];
+        const int b = band_row[e];
         const int jlo = a.band_jlo[b], span = a.band_span[b];
         double* cb = buf + (size_t)i * SM;
         if (ept[4 * EP + e] < 0.0) continue;                    // before t0: nothing to integrate
@@ -612,9 +620,9 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       __syncthreads();
       PHOT_PROF_ACC(7);
       for (int i = warp; i < ne; i += nwarps) {
-        const int e = a.epoch_order[e0 + i];
+        const int e = ragged ? e0 + i : a.epoch_order[e0 + i];
         if (ept[4 * EP + e] < 0.0) continue;
-        const int b = a.band_of_epoch[e];
+        const int b = band_row[e];
         const int w0 = a.band_off[b], w1 = a.band_off[b + 1];
         const double* dw = buf + (size_t)i * SM;
         double acc = 0.0;
@@ -644,12 +652,12 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       __syncthreads();
       PHOT_PROF_ACC(8);
       for (int i = tid; i < ne; i += T) {
-        const int e = a.epoch_order[e0 + i];
+        const int e = ragged ? e0 + i : a.epoch_order[e0 + i];
         double model_v;
         if (ept[4 * EP + e] < 0.0) {
           model_v = (a.output == RB_OUT_FLUX) ? 0.0 : 1000.0;
         } else {
-          const int b = a.band_of_epoch[e];
+          const int b = band_row[e];
           const double bandflux = ept[7 * EP + e] * a.band_scale[b];
           model_v = -2.5 * log10(bandflux / a.band_zp[b]);                        // sed.py:114
           if (a.output == RB_OUT_FLUX) model_v = pow(10.0, model_v / (-2.5)) * a.band_ref[b];   // utils.py:716-718

@@ -400,6 +400,27 @@ class SupernovaMagPath(SupernovaPath):
     def _launch(self, *args):
         return self._launch_mag(_capi.lib().rb_sn_mag_eval_f64, *args)
 
+    def evaluate_ragged(self, params_dev, phase, band_index, epoch_count, dl=None):
+        """Magnitudes at per-sample pointings (rb_sn_mag_eval_ragged_f64): `phase` [N, E_max] float64 (days since
+        explosion, observer frame), `band_index` [N, E_max] int32 into this path's sorted band list, `epoch_count` [N]
+        int32; the path must have been built with bands = its sorted unique band names, one epoch per band.
+        Returns [N, E_max] (padding entries NaN)."""
+        N, E = phase.shape
+        if params_dev.shape != (self.NPARAM, N) or band_index.shape != (N, E) or epoch_count.shape != (N,):
+            raise ValueError("params [NPARAM, N], phase / band_index [N, E_max] and epoch_count [N] must agree")
+        if phase.dtype != _F64 or band_index.dtype != torch.int32 or epoch_count.dtype != torch.int32:
+            raise ValueError("phase must be float64, band_index and epoch_count int32")
+        out = torch.full((N, E), float("nan"), dtype=_F64, device=self.device)
+        if N == 0 or E == 0:
+            return out
+        with torch.cuda.device(self.device):
+            rc = _capi.lib().rb_sn_mag_eval_ragged_f64(
+                C.byref(self.cfg), C.addressof(self.phot), N, E, _ptr(params_dev.contiguous()), _ptr(phase.contiguous()),
+                _ptr(band_index.contiguous()), _ptr(epoch_count.contiguous()), _ptr(dl), _ptr(out),
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        _capi.check(rc)
+        return out
+
     def _host_rows_fn(self):
         return None     # the magnitude branch has device entry points only
 

@@ -191,6 +191,84 @@ def simulate_population_with_cadence(model, params_batch, times, bands, limiting
     return {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
 
 
+def simulate_survey_observations(model, params_batch, t0_mjd, pointing_offsets, exp_mjd, filters, five_sigma_depth,
+                                 model_kwargs=None, snr_threshold=5.0, add_source_noise=False, source_noise=0.02,
+                                 seed=1234, device=None, chunk=16384, sample_base=0, return_variates=False):
+    """SimulateOpticalTransient._make_observations_for_population (simulate_transients.py:1096-1178) for N transients
+    in one pass: transient n was pointed at by rows pointing_offsets[n] : pointing_offsets[n + 1] of the flat pointing
+    table (`exp_mjd`, `filters` = band names, `five_sigma_depth`, sorted by time within a transient like the
+    reference's `sort_values(by=['expMJD'])`), and exploded at `t0_mjd[n]`.  The model's spectral grid, the bicubic
+    spline, the band integrals at the transient's own phases, the noise draws and the detection flags are evaluated
+    on device; results come back as flat arrays aligned with the pointing table (the columns of the reference's
+    observation DataFrame).  Supernova-family models (the magnitude branch of arnett, type_1a, slsn, ...)."""
+    dev = _device(device)
+    off = np.asarray(pointing_offsets, dtype=np.int64)
+    n = off.size - 1
+    exp_mjd = np.asarray(exp_mjd, dtype=np.float64)
+    depth = np.asarray(five_sigma_depth, dtype=np.float64)
+    names = np.asarray(filters)
+    uniq = sorted(set(names.tolist()))
+    index = {b: i for i, b in enumerate(uniq)}
+    band_flat = np.array([index[b] for b in names.tolist()], dtype=np.int32)
+    ref = np.array([_reference_flux(b) for b in uniq], dtype=np.float64)
+    t0 = np.broadcast_to(np.asarray(t0_mjd, dtype=np.float64), (n,))
+    kw = dict(model_kwargs or {})
+    kw.update(bands=np.array(uniq), output_format="magnitude", device=dev)
+    runner = _ModelRunner(model, np.arange(1.0, len(uniq) + 1.0), kw)
+    if not hasattr(runner.path, "evaluate_ragged"):
+        raise NotImplementedError("per-transient pointings are available for the supernova-family magnitude paths")
+    total = int(off[-1])
+    cols = {k: np.full(total, np.nan) for k in ("model_magnitude", "magnitude", "e_magnitude", "flux", "flux_error")}
+    cols["detected"] = np.zeros(total, dtype=bool)
+    counts = np.diff(off).astype(np.int32)
+    ref_dev = as_device_f64(ref, dev)
+    lib = _capi.lib()
+    with torch.cuda.device(dev):
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            cnt = counts[lo:hi]
+            emax = max(1, int(cnt.max()) if cnt.size else 1)
+            # padded [nc, emax] tables from the CSR rows
+            col = np.arange(emax)[None, :]
+            valid = col < cnt[:, None]
+            src = np.where(valid, off[lo:hi, None] + col, 0)
+            phase = np.where(valid, exp_mjd[src] - t0[lo:hi, None], 1.0)
+            bidx = np.where(valid, band_flat[src], 0).astype(np.int32)
+            dep = np.where(valid, depth[src], 0.0)
+            nc = hi - lo
+            params, _ = _fused.collect({}, runner.kwargs, _slice(params_batch, lo, hi, n), runner.spec.needed,
+                                       runner.spec.defaults)
+            params = runner.spec.transform(params)
+            pdev = runner.path.pack(params, nc)
+            phase_d = torch.from_numpy(np.ascontiguousarray(phase)).to(dev)
+            bidx_d = torch.from_numpy(np.ascontiguousarray(bidx)).to(dev)
+            cnt_d = torch.from_numpy(np.ascontiguousarray(cnt)).to(dev)
+            dep_d = torch.from_numpy(np.ascontiguousarray(dep)).to(dev)
+            start_d = torch.from_numpy(np.ascontiguousarray(off[lo:hi])).to(dev)
+            mags = runner.path.evaluate_ragged(pdev, phase_d, bidx_d, cnt_d,
+                                               dl=_fused.dl_from_kwargs(runner.kwargs, runner.path, nc))
+            out = {k: torch.empty((nc, emax), dtype=_F64, device=dev) for k in ("magnitude", "e_magnitude", "flux",
+                                                                                "flux_error")}
+            det = torch.empty((nc, emax), dtype=torch.uint8, device=dev)
+            zout = torch.empty((nc, emax), dtype=_F64, device=dev) if return_variates else None
+            _capi.check(lib.rb_survey_noise_philox_f64(
+                nc, emax, int(sample_base), C.c_uint64(int(seed)), _ptr(mags), _ptr(phase_d), _ptr(bidx_d),
+                _ptr(cnt_d), _ptr(start_d), _ptr(dep_d), _ptr(ref_dev), float(source_noise) if add_source_noise else 0.0,
+                float(snr_threshold), _ptr(out["magnitude"]), _ptr(out["e_magnitude"]), _ptr(out["flux"]),
+                _ptr(out["flux_error"]), _ptr(det), _ptr(zout), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            flat = slice(int(off[lo]), int(off[hi]))
+            if return_variates:
+                cols.setdefault("standard_normal", np.full(total, np.nan))[flat] = zout.cpu().numpy()[valid]
+            cols["model_magnitude"][flat] = mags.cpu().numpy()[valid]
+            for k, v in out.items():
+                cols[k][flat] = v.cpu().numpy()[valid]
+            cols["detected"][flat] = det.cpu().numpy()[valid].astype(bool)
+    ref_per_row = ref[band_flat]
+    cols.update(time=exp_mjd, band=names, time_days=exp_mjd - np.repeat(t0, counts), limiting_magnitude=depth,
+                flux_limit=10.0 ** (depth / (-2.5)) * ref_per_row, offsets=off)
+    return cols
+
+
 def population_light_curves(model, parameters, times=None, model_kwargs=None, device_output=False):
     """The light-curve loop of PopulationSynthesizer.simulate_population (simulate_transients.py:2027-2036) as one
     batched call: `parameters` is the population table ({name: array[N]} or a pandas DataFrame as returned by

@@ -155,3 +155,23 @@ def metzger_magnetar_prior(rng, n, kind="basic"):
     else:
         p["thermalisation_efficiency"] = rng.uniform(0.1, 1, n)
     return p
+
+
+def realistic_bandpass_table(lo, hi, seed=0):
+    """A transmission table shaped like a real survey filter file (sncosmo's lsst* / ztf* data are not available
+    offline): NON-UNIFORM wavelength sampling (fine at the edges, coarse on the plateau), exactly-zero wings of
+    several samples on both sides, asymmetric edges, a sloped plateau with ripples and a narrow absorption dip.
+    These are the cases in which sncosmo's `integration_grid` / linear `Bandpass.__call__` differ from a top-hat."""
+    rng = np.random.default_rng(seed)
+    w = np.concatenate([np.arange(lo - 320.0, lo - 60.0, 52.0), np.arange(lo - 60.0, lo + 110.0, 2.5),
+                        np.arange(lo + 110.0, hi - 120.0, 23.0 + 4.0 * rng.uniform()),
+                        np.arange(hi - 120.0, hi + 90.0, 3.3), np.arange(hi + 90.0, hi + 420.0, 41.0)])
+    w = np.unique(np.round(w, 3))
+    rise = 1.0 / (1.0 + np.exp(-(w - lo) / 9.0))
+    fall = 1.0 / (1.0 + np.exp((w - hi) / 17.0))
+    plateau = 0.62 + 0.2 * (w - lo) / (hi - lo) + 0.015 * np.sin((w - lo) / 37.0)
+    dip_at = lo + 0.63 * (hi - lo)
+    dip = 1.0 - 0.35 * np.exp(-0.5 * ((w - dip_at) / 6.0) ** 2)
+    tr = rise * fall * plateau * dip
+    tr[(w < lo - 60.0) | (w > hi + 90.0)] = 0.0          # zero-padded wings
+    return w, tr

@@ -136,3 +136,55 @@ def test_population_streaming_is_chunk_invariant(rb):
     part = rb.simulate.simulate_population_with_cadence(rb.supernova_models.arnett, sub, t, names, lim, seed=8,
                                                         sample_base=100)
     assert np.array_equal(part["magnitude"].cpu().numpy(), whole["magnitude"][100:200].cpu().numpy(), equal_nan=True)
+
+
+def test_survey_observations_with_per_transient_pointings(rb):
+    """SimulateOpticalTransient._make_observation_single (simulate_transients.py:1096-1140) for a small population with
+    ragged pointing lists: empty lists, pointings before the explosion (phase <= 0: clamped by the spline, flagged
+    undetected), unequal counts, optional source noise.  Model magnitudes against the oracle; the noise stage replayed
+    by the oracle with the device's own variates; results independent of the chunk size."""
+    from redback_b200.bands import REFERENCE_FLUX
+    ob = {n: r.Bandpass(n, b.wave, b.trans) for n, b in
+          ((n, rb.bands.get_bandpass(n)) for n in rb.bands.SYNTHETIC_LSST_EDGES)}
+    rng = np.random.default_rng(17)
+    N = 41
+    counts = rng.integers(0, 60, N)
+    counts[3] = 0
+    counts[7] = 1
+    off = np.concatenate([[0], np.cumsum(counts)])
+    t0 = rng.uniform(60000, 60100, N)
+    p = h.arnett_prior(rng, N, zmax=0.3)
+    p["temperature_floor"] = h.loguniform(rng, 3e3, 1e4, N)
+    names_all = list(LIMITING)
+    mjd = np.concatenate([np.sort(t0[i] + rng.uniform(-5.0, 150.0, counts[i])) for i in range(N)])
+    filt = np.array([names_all[k] for k in rng.integers(0, 6, off[-1])])
+    depth = np.array([LIMITING[b] for b in filt]) + rng.normal(0, 0.3, off[-1])
+    for source_noise in (False, True):
+        out = rb.simulate.simulate_survey_observations(rb.supernova_models.arnett, p, t0, off, mjd, filt, depth, seed=21,
+                                                       add_source_noise=source_noise, return_variates=True)
+        small = rb.simulate.simulate_survey_observations(rb.supernova_models.arnett, p, t0, off, mjd, filt, depth,
+                                                         seed=21, add_source_noise=source_noise, chunk=7)
+        for k in ("model_magnitude", "magnitude", "e_magnitude", "flux", "flux_error"):
+            assert np.array_equal(out[k], small[k], equal_nan=True), k
+        assert np.array_equal(out["detected"], small["detected"])
+        zref = r.philox_standard_normal(21, np.arange(off[-1]))
+        np.testing.assert_allclose(out["standard_normal"], zref, rtol=0, atol=4e-15)
+        for i in range(N):
+            sl = slice(off[i], off[i + 1])
+            if counts[i] == 0:
+                continue
+            kw = {k: v[i] for k, v in p.items()}
+            z = kw.pop("redshift")
+            phase = mjd[sl] - t0[i]
+            ref_mag = r.sn_magnitude("arnett", phase, z, bands=filt[sl], bandpasses=ob, **kw)
+            assert np.max(np.abs(out["model_magnitude"][sl] - ref_mag)) < 5e-9, i
+            rf = np.array([REFERENCE_FLUX[b] for b in filt[sl]])
+            exp = r.survey_observation_single(ref_mag, phase, rf, depth[sl], out["standard_normal"][sl],
+                                              add_source_noise=source_noise)
+            np.testing.assert_allclose(out["flux"][sl], exp["flux"], rtol=1e-8)
+            np.testing.assert_allclose(out["flux_error"][sl], exp["flux_error"], rtol=1e-8)
+            np.testing.assert_allclose(out["magnitude"][sl], exp["magnitude"], rtol=0, atol=1e-6, equal_nan=True)
+            np.testing.assert_allclose(out["e_magnitude"][sl], exp["e_magnitude"], rtol=1e-8, equal_nan=True)
+            assert np.array_equal(out["detected"][sl], exp["detected"]), i
+            assert not out["detected"][sl][phase <= 0].any()
+        assert np.array_equal(out["time_days"], mjd - np.repeat(t0, counts))
