@@ -184,13 +184,23 @@ __global__ void sn_prep_kernel(const SnArgs a) {
 }
 
 // ---- CutoffBlackbody --------------------------------------------------------------------------------
-// regularised incomplete gammas for the normalisation (sed.py:386-421); integer order
+// regularised incomplete gammas for the normalisation (sed.py:386-421).  Integer orders are closed forms evaluated in
+// Horner form with reciprocal constants (no FP64 divisions): Q(s, x) = e^-x sum_{k<s} x^k / k!.
 __device__ __forceinline__ double gammaincc_int(int s, double x, double emx) {
-  // Q(s, x) = e^-x sum_{k<s} x^k / k!
-  double term = 1.0, sum = 1.0;
-  for (int k = 1; k < s; ++k) {
-    term *= x / k;
-    sum += term;
+  double sum;
+  switch (s) {
+    case 1: sum = 1.0; break;
+    case 2: sum = 1.0 + x; break;
+    case 3: sum = fma(x, fma(x, 0.5, 1.0), 1.0); break;
+    case 4: sum = fma(x, fma(x, fma(x, 1.0 / 6.0, 0.5), 1.0), 1.0); break;
+    default: {
+      double term = 1.0;
+      sum = 1.0;
+      for (int k = 1; k < s; ++k) {
+        term *= x / k;
+        sum += term;
+      }
+    }
   }
   return emx * sum;
 }
@@ -227,23 +237,40 @@ __device__ double gammaincc_real(double s, double x) {
   return lead * h;
 }
 
+// 24 / (k + 4)!, k = 0 .. 19: P(4, x) = e^-x x^4/24 sum_k x^k 24/(k+4)!  (no cancellation; used below x = 1.5, where the
+// truncation after 20 terms is < 1e-17 relative)
+__device__ const double kP4Series[20] = {
+    1.0, 0.2, 0.03333333333333333, 0.004761904761904762, 0.0005952380952380953, 6.613756613756614e-05,
+    6.613756613756614e-06, 6.012506012506013e-07, 5.010421677088344e-08, 3.854170520837188e-09,
+    2.752978943455134e-10, 1.8353192956367562e-11, 1.1470745597729726e-12, 6.747497410429251e-14,
+    3.748609672460695e-15, 1.9729524591898395e-16, 9.864762295949198e-18, 4.697505855213904e-19,
+    2.135229934188138e-20, 9.283608409513644e-22};
+
 __device__ __forceinline__ double gammainc4(double x, double emx) {
-  // P(4, x); series e^-x sum_{k>=4} x^k/k! below 1.5 (no cancellation), 1 - Q(4, x) above
+  // P(4, x); series below 1.5 (no cancellation), 1 - Q(4, x) above
   if (x < 1.5) {
-    double term = x * x * x * x * (1.0 / 24.0), sum = term;
-    for (int k = 5; k < 30; ++k) {
-      term *= x / k;
-      sum += term;
-    }
-    return emx * sum;
+    double sum = kP4Series[19];
+#pragma unroll
+    for (int k = 18; k >= 0; --k) sum = fma(sum, x, kP4Series[k]);
+    const double x2 = x * x;
+    return emx * (x2 * x2) * (1.0 / 24.0) * sum;
   }
   return 1.0 - gammaincc_int(4, x, emx);
+}
+
+// a^b for the handful of exponents the default configurations use, pow otherwise
+__device__ __forceinline__ double pow_small(double a, double b) {
+  if (b == 1.0) return a;
+  if (b == 0.0) return 1.0;
+  if (b == 2.0) return a * a;
+  if (b == 3.0) return a * a * a;
+  return pow(a, b);
 }
 
 // CutoffBlackbody normalisation for one time (sed.py:386-421): norms = L / (FLUX_CONST/A R^2 T) / ((above+below)/T)
 // with above = (kT/hc)^4 Gamma(4) sum_n P(4, n x_c)/n^4, below = lam_c^-alpha (kT/hc)^s Gamma(s) sum_n Q(s, n x_c)/n^s,
 // s = 4 - alpha.  Integer s uses the closed forms, real s the series / continued fraction.
-__device__ double cutoff_norm(double lbol, double rph, double tph, double lam_c, double alpha) {
+__device__ __forceinline__ double cutoff_norm(double lbol, double rph, double tph, double lam_c, double alpha) {
   const double sr = 4.0 - alpha;
   const int s = (int)(sr + 0.5);
   const bool s_int = (sr == (double)s);
@@ -252,11 +279,14 @@ __device__ double cutoff_norm(double lbol, double rph, double tph, double lam_c,
   const double x_c = 1.0 / (lam_c * kt_hc);
   const double e1 = exp(-x_c);
   double en = 1.0, above = 0.0, below = 0.0;
+  // 1 / i^4 and 1 / i^s as running products of exact small integers (i^4 <= 1e4 is exact; the division is by a
+  // loop-invariant constant after unrolling)
+#pragma unroll
   for (int i = 1; i <= 10; ++i) {
     en *= e1;  // e^{-i x_c}
     const double di = (double)i;
     const double xi = x_c * di;
-    above += gammainc4(xi, en) / (di * di * di * di);
+    above += gammainc4(xi, en) * (1.0 / (di * di * di * di));
     if (s_int) {
       double ns = di;
       for (int q = 1; q < s; ++q) ns *= di;
@@ -276,7 +306,7 @@ __device__ double cutoff_norm(double lbol, double rph, double tph, double lam_c,
     gam = tgamma(sr);
   }
   above = kt2 * kt2 * 6.0 * above;
-  below = (1.0 / pow(lam_c, alpha)) * kts * gam * below;
+  below = (1.0 / pow_small(lam_c, alpha)) * kts * gam * below;
   return norm / ((above + below) / tph);
 }
 
@@ -294,7 +324,7 @@ __device__ __noinline__ double cutoff_blackbody_mjy(const rb_sn_config& cfg, dou
   const double em = expm1(kXConst / lam / tph);
   double sedv;
   if (lam < lam_c)
-    sedv = kFluxConst * ((rph * rph) * pow(lam / lam_c, alpha) / l5) / em;
+    sedv = kFluxConst * ((rph * rph) * pow_small(lam / lam_c, alpha) / l5) / em;
   else
     sedv = kFluxConst * ((rph * rph) / l5) / em;
   sedv *= norm;
