@@ -1273,6 +1273,14 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
     if (span[(size_t)b] > rb::kPhotMaxSpan)
       return fail(RB_ERR_UNSUPPORTED, "rb_*_mag_eval: a band overlaps too many wavelength-grid points");
   }
+  // per-band weights of the spline coefficients for the all-positive case: sum_w wave trans B_j(wave)
+  const int span_max = *std::max_element(span.begin(), span.end());
+  std::vector<double> bw((size_t)ph->n_bands * (size_t)span_max, 0.0);
+  for (int b = 0; b < ph->n_bands; ++b)
+    for (int64_t w = ph->band_off[b]; w < ph->band_off[b + 1]; ++w) {
+      const int rel = ly[(size_t)w] - jlo[(size_t)b];
+      for (int q = 0; q < 4; ++q) bw[(size_t)b * span_max + rel + q] += rec[(size_t)w * 6 + 4] * rec[(size_t)w * 6 + q];
+    }
   std::vector<int> boe(ph->band_of_epoch, ph->band_of_epoch + E);
   // epochs grouped by band: the warps of a block then integrate over the same band at the same time and its table of
   // integration points stays in L1
@@ -1293,12 +1301,13 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
   if (e == cudaSuccess) e = dev.upload(ref, &pa.band_ref);
   if (e == cudaSuccess) e = dev.upload(order, &pa.epoch_order);
   if (e == cudaSuccess) e = dev.upload(rec, &pa.int_rec);
+  if (e == cudaSuccess) e = dev.upload(bw, &pa.band_weight);
   if (e == cudaSuccess) e = cudaStreamSynchronize(dev.st);   // host vectors go out of scope
   if (e != cudaSuccess) return cuda_fail(e, "photometry table upload");
   pa.n_lambda = NL;
   pa.output = ph->output;
   pa.j_store_lo = *std::min_element(jlo.begin(), jlo.end());
-  pa.span_max = *std::max_element(span.begin(), span.end());
+  pa.span_max = span_max;
   return RB_OK;
 }
 
@@ -1306,37 +1315,43 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
 // so that two blocks fit on an SM when at least 8 columns then fit, else one block per SM with as many columns as fit.
 struct PhotShape {
   int W = 0, P = 0, nt_pad = 0, blocks_per_sm = 0;
+  bool tables_global = false;
   size_t smem = 0;
 };
 
+// Launch shape of phot_kernel: P row segments per column (a power of two <= 32, the lanes that exchange boundary
+// states by shuffles) and W = 256 / P wavelength columns per block -- the widest block that fits two blocks per SM,
+// else one block per SM, else with the time-axis tables in global memory (very long grids).
 bool phot_shape(int NT, int NL, int n_comp, bool line, PhotShape* out) {
   const int threads = 256;
-  const size_t fixed = sizeof(double) * rb::phot_fixed_doubles(NT, NL, n_comp, line, threads);
   const int ntp = NT | 1;
   const size_t col = sizeof(double) * (size_t)ntp;
   const size_t budget2 = 115000, budget1 = 227 * 1024;
   int w_env = 0, bps_env = 0;
   if (const char* e = std::getenv("RB_PHOT_W")) w_env = std::atoi(e);                 // kernel experiments
   if (const char* e = std::getenv("RB_PHOT_BLOCKS_PER_SM")) bps_env = std::atoi(e);
-  int bps = 2;
-  long wmax = fixed < budget2 ? (long)((budget2 - fixed) / col) : 0;
-  if (wmax < 8 || bps_env == 1) {
-    bps = 1;
-    wmax = fixed < budget1 ? (long)((budget1 - fixed) / col) : 0;
+  for (int pass = 0; pass < 3; ++pass) {
+    const bool tg = pass == 2;
+    const size_t budget = (pass == 0 && bps_env != 1) ? budget2 : budget1;
+    if (pass == 0 && bps_env == 1) continue;
+    const size_t fixed = sizeof(double) * rb::phot_fixed_doubles(NT, NL, n_comp, line, tg);
+    if (fixed >= budget) continue;
+    int w = 0;
+    for (int P = 1; P <= 32; P <<= 1) {                       // widest first
+      const int cand = threads / P;
+      if (w_env > 0 && cand != w_env) continue;
+      if (fixed + col * (size_t)cand <= budget) { w = cand; break; }
+    }
+    if (w == 0) continue;
+    out->W = w;
+    out->P = threads / w;
+    out->nt_pad = ntp;
+    out->blocks_per_sm = pass == 0 ? 2 : 1;
+    out->tables_global = tg;
+    out->smem = fixed + col * (size_t)w;
+    return true;
   }
-  if (wmax < 1) return false;
-  if (wmax > NL) wmax = NL;
-  if (wmax > threads) wmax = threads;
-  int best = 1;
-  for (int w = 1; w <= (int)wmax; ++w)                        // most busy threads, then most columns
-    if (w * (threads / w) >= best * (threads / best)) best = w;
-  if (w_env > 0 && w_env <= wmax) best = w_env;
-  out->W = best;
-  out->P = threads / best;
-  out->nt_pad = ntp;
-  out->blocks_per_sm = bps;
-  out->smem = fixed + col * (size_t)best;
-  return true;
+  return false;
 }
 
 // ---- shared driver of the magnitude / bandpass branch -------------------------------------------------------------
@@ -1372,7 +1387,9 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   keep_workspace_pool();
   static DeviceOnce once;
   const cudaError_t attr_err = once.run([] {
-    cudaError_t attr_err = cudaFuncSetAttribute(rb::phot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t attr_err = cudaFuncSetAttribute(rb::phot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rb::phot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return attr_err;
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(phot_kernel)");
@@ -1407,14 +1424,18 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
 
   const int64_t chunk_max = 32768;
   int occ_ph = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel, 256, psmem);
+  if (shape.tables_global)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel<true>, 256, psmem);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ph, rb::phot_kernel<false>, 256, psmem);
   if (occ_ph < 1) occ_ph = 1;
   if (occ_ph > shape.blocks_per_sm) occ_ph = shape.blocks_per_sm;
   const int64_t ph_grid_max = (int64_t)sms * occ_ph;
   const int64_t nc_max = std::min<int64_t>(chunk_max, N);
   // per-block scratch: the epoch records + the forward-eliminated rows of the wavelength-axis solve (L2-resident)
   const int e_pad = (int)((E + 31) / 32 * 32);
-  const int64_t scratch_stride = (int64_t)(rb::kEpCols + NL - pa.j_store_lo) * e_pad;
+  const int64_t scratch_stride = (int64_t)(rb::kEpCols + NL - pa.j_store_lo) * e_pad +
+                                 (shape.tables_global ? 9 * (int64_t)NT : 0);
   double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_scratch = nullptr;
   int* d_len = nullptr;
   ce = cudaMallocAsync(&d_grid, (size_t)n_comp * nc_max * 4 * NT * sizeof(double), st);
@@ -1464,7 +1485,10 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
     pa.e_pad = e_pad;
     pa.out_model = j.out_model;
     pa.out_logl = j.y ? j.out_logl : nullptr;
-    rb::phot_kernel<<<(unsigned)std::min<int64_t>(ph_grid_max, nc), 256, psmem, st>>>(pa);
+    if (shape.tables_global)
+      rb::phot_kernel<true><<<(unsigned)std::min<int64_t>(ph_grid_max, nc), 256, psmem, st>>>(pa);
+    else
+      rb::phot_kernel<false><<<(unsigned)std::min<int64_t>(ph_grid_max, nc), 256, psmem, st>>>(pa);
     launch_counter()->fetch_add(1);
     ce = cudaGetLastError();
     if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude kernels");

@@ -13,23 +13,31 @@
 // so the N_t x N_lambda coefficient matrix is never formed: one persistent block per sample streams S through shared
 // memory in BLOCKS OF W WAVELENGTH COLUMNS,
 //   1. spectra of the block (all N_t rows, W columns; non-finite / zero entries replaced, sed.py:985-992);
-//   2. time-axis solve of the W columns in shared memory: every column is cut into P row segments (W * P = threads),
-//      each segment runs the banded recurrences from a zero state and the exact solution is recovered with the
-//      segment's homogeneous solutions scaled by the boundary state (a short serial pass over the P segments);
+//   2. time-axis solve of the W columns in shared memory: every column is cut into P row segments (P a power of two
+//      <= 32, W * P = threads).  ONE thread owns a (column, segment) through the whole solve: forward recurrence from a
+//      zero state, the true incoming boundary from a P-lane warp scan of the segments' affine maps (their 2 x 2 matrices
+//      depend on the LU only and are tabulated per sample), backward recurrence, reverse scan, and the final fix-up with
+//      the segment's homogeneous solutions -- no block barrier inside the solve;
 //   3. contraction with the E epochs' time B-splines (E x W values) and, because the blocks come in increasing
 //      wavelength order, the forward elimination of the WAVELENGTH-axis solve on those E rows (state carried per epoch);
 //      the eliminated values go to a per-block scratch of E x (N_lambda - first band column) doubles (L2-resident);
-// then per epoch: wavelength-axis back substitution (thread per epoch), the band's 5-Angstrom integration points split
-// over the lanes of a warp with |f| summed as the reference does (sed.py:36-37), magnitude / flux, likelihood term.
-// The mean needed by the clean-up is taken in a statistics pre-pass over the spectra, skipped when a bound shows that
-// every entry is finite and non-zero; the per-sample banded LU of the time axis (kilonova grids) runs on one thread
-// underneath that pre-pass.
+// then per epoch: wavelength-axis back substitution (thread per epoch) and the band integral.  The reference sums
+// |f| over the band's 5-Angstrom grid (sed.py:36-37); where all of the band's spline coefficients are non-negative the
+// spline is non-negative (B-splines are), |f| = f, and the integral is the dot product of the coefficients with
+// per-band weights contracted on the host; otherwise the points are evaluated one by one, split over a warp's lanes.
+// Columns more than kBlueMargin below the bluest band are not evaluated: the wavelength-axis solve couples columns
+// with a factor <= 0.27 per column and spectra grow towards the blue by at most lambda^-4, so their contribution to a
+// band coefficient is < 1e-18 relative.  The mean needed by the clean-up is taken in a statistics pre-pass over ALL
+// columns (terms e^-50 below their row's largest are counted, not summed), skipped when a bound shows that every entry
+// is finite and non-zero; the per-sample banded LU of the time axis (kilonova grids) runs on one thread underneath it.
 #include "rb_common.cuh"
 
 namespace rb {
 
 constexpr int kPhotMaxSpan = 96;     // max B-spline coefficients (along wavelength) overlapped by one band
 constexpr int kEpCols = 8;           // per-epoch record in the block's scratch: h0..h3, first row, y1, y2, band flux
+constexpr int kBlueMargin = 40;      // wavelength columns kept below the bluest band's first coefficient
+constexpr int kScanSteps = 5;        // log2(32)
 
 enum { PH_SED_BLACKBODY = 1, PH_SED_CUTOFF = 2, PH_SED_CUTOFF_LINE = 3 };
 enum { PH_T = 0, PH_R, PH_L, PH_X, kPhotGridCols };   // per-sample model grid: temperature, radius, L_bol, phase
@@ -80,16 +88,17 @@ struct PhotArgs {
   const int* epoch_count;       // [N_total] pointings of sample n (<= E); the rest of the row is padding
   const double* int_rec;        // [total][6] per integration point: the 4 non-zero wavelength B-splines, wave * trans,
                                 //            index of the first of them relative to the band's first coefficient
+  const double* band_weight;    // [n_bands][span_max] sum over the band's points of wave * trans * B_j(wave)
   double* scratch;              // [gridDim][scratch_stride]
   double* out_model;
   double* out_logl;
 };
 
-// shared-memory doubles: row factors, time LU + homogeneous solutions, column factors, wavelength LU, column buffer
-// (also the per-epoch coefficient buffer of the last phase), boundary states, reduction scratch, exp table
-__host__ __device__ inline size_t phot_fixed_doubles(int NT, int NL, int n_comp, bool line, int threads) {
-  return (size_t)(2 * n_comp + (line ? 2 : 0)) * NT + 9 * (size_t)NT + 3 * (size_t)NL + 5 * (size_t)NL +
-         2 * (size_t)threads + 64 + kExpTabSize;
+// shared-memory doubles: row factors, time LU + homogeneous solutions, column factors, wavelength LU, scan matrices,
+// reduction scratch, exp table, column buffer (also the per-epoch coefficient buffer of the last phase)
+__host__ __device__ inline size_t phot_fixed_doubles(int NT, int NL, int n_comp, bool line, bool tables_global) {
+  return (size_t)(2 * n_comp + (line ? 2 : 0)) * NT + (tables_global ? 0 : 9 * (size_t)NT) + 4 * (size_t)NL +
+         5 * (size_t)NL + 2 * kScanSteps * 32 * 4 + 64 + kExpTabSize;
 }
 
 // FITPACK fpbspl for k = 3: the four non-zero cubic B-splines at x, t[l] <= x < t[l+1] (0-based l)
@@ -142,17 +151,36 @@ __device__ __forceinline__ double rcp_fast(double d) {
   return r;
 }
 
-// 1 / expm1(x) of the Planck function.  x > 40: exp(-x) (the two differ by e^-x < 4e-18 relative); the reference's
-// expm1 overflows to inf (-> spectrum value 0 -> replaced) above 709.78, reproduced here; between 700 and there the
-// result is subnormal and libm's exp is used.
-__device__ __forceinline__ double planck_inv(double x, const double* __restrict__ tab) {
+// exp(x) for -700 <= x <= 700 with the 1024-entry table and a degree-2 polynomial (truncation 6.5e-12 relative,
+// argument reduction with the high word of ln2/1024 only: |x| 1477 * 2.3e-20 < 3e-14): six FP64 operations.
+__device__ __forceinline__ double exp_lean(double x, const double* __restrict__ tab) {
+  const double v = fma(x, kTabOverLn2, kExpMagic);
+  const int k = __double2loint(v);
+  const double r = fma(v - kExpMagic, -kLn2OverTabHi, x);
+  const double p = r * fma(r, 0.5, 1.0);
+  const double t = tab[k & 1023];
+  const double res = fma(t, p, t);
+  return __hiloint2double(__double2hiint(res) + ((k >> 10) << 20), __double2loint(res));
+}
+
+// General 1 / expm1(x) of the Planck function (any x, per lane).  The reference's expm1 overflows to inf (-> value 0 ->
+// replaced) above 709.78, reproduced here; between 700 and there the result is subnormal and libm's exp is used.
+__device__ __noinline__ double planck_inv_general(double x, const double* __restrict__ tab) {
   if (x > 40.0) {
     if (x > 709.782712893384) return 0.0;
     if (x > 700.0) return exp(-x);
-    return exp_tab(-x, tab);
+    return exp_lean(-x, tab);
   }
-  if (x >= 0.5) return rcp_fast(exp_tab(x, tab) - 1.0);
+  if (x >= 0.5) return rcp_fast(exp_lean(x, tab) - 1.0);
   return rcp_fast(expm1(x));
+}
+
+// 1 / expm1(x) for the 32 rows a warp works on (same column).  The rows are consecutive in time, so x is usually in one
+// regime for the whole warp: the two common regimes are warp-uniform branches without divergence bookkeeping.
+__device__ __forceinline__ double planck_inv_warp(double x, const double* __restrict__ tab) {
+  if (__all_sync(0xffffffffu, x > 40.0 && x <= 700.0)) return exp_lean(-x, tab);     // e^-x: differs by e^-x < 4e-18
+  if (__all_sync(0xffffffffu, x >= 0.5 && x <= 40.0)) return rcp_fast(exp_lean(x, tab) - 1.0);
+  return planck_inv_general(x, tab);
 }
 
 #ifdef RB_PHOT_PROFILE
@@ -161,46 +189,47 @@ __device__ __forceinline__ double planck_inv(double x, const double* __restrict_
 #define PHOT_PROF_ACC(i) { __syncthreads(); const long long c_ = clock64(); pt_[i] += c_ - pa_; pa_ = c_; }
 #define PHOT_PROF_END()                                                                                               \
   if (blockIdx.x == 0 && tid == 0 && n < 3 * (int64_t)gridDim.x)                                                        \
-    printf("phot phases [cycles] setup %lld stats+lu %lld spectra %lld fwd %lld bwd %lld boundary %lld contract %lld "   \
-           "backsub %lld integrate %lld finish %lld\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[5], pt_[6], pt_[7],  \
-           pt_[8], pt_[9]);
+    printf("phot phases [cycles] setup %lld stats+lu %lld spectra %lld solve %lld contract %lld backsub %lld "          \
+           "integrate %lld finish %lld\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[5], pt_[6], pt_[7]);
 #else
 #define PHOT_PROF_BEGIN()
 #define PHOT_PROF_ACC(i)
 #define PHOT_PROF_END()
 #endif
 
-struct PhotSmem {
-  double *rowA, *rowB, *rowC, *rowD, *lut, *hom, *colA, *colB, *colC, *lul, *bnd, *red, *tab, *buf;
-};
-
+// GT: the time-axis LU and its homogeneous solutions live in global memory (grids too long for shared memory)
+template <bool GT>
 __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
   extern __shared__ double psm[];
   const int NT = a.n_t_max, NL = a.n_lambda, E = a.E, NC = a.n_comp;
   const int T = (int)blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const bool line = a.sed == PH_SED_CUTOFF_LINE;
   const int W = a.W, P = a.P, NTP = a.nt_pad;
+  double* gs = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
   double* rowA = psm;                          // [NC][NT]  1 / (k_B T)  or 1 / T
   double* rowB = rowA + NC * NT;               // [NC][NT]  R^2          or R^2 * cutoff normalisation
   double* rowC = rowB + NC * NT;               // [NT]  1 - line amplitude           (line SED only)
   double* rowD = rowC + (line ? NT : 0);       // [NT]  scaled line amplitude        (line SED only)
-  double* lut = rowD + (line ? NT : 0);        // [NT][5]  time-axis banded LU, scaled rows
+  double* after_rows = rowD + (line ? NT : 0);
+  double* lut = GT ? gs : after_rows;          // [NT][5]  time-axis banded LU, scaled rows
   double* hom = lut + 5 * NT;                  // [NT][4]  homogeneous solutions of the segmented time-axis solve
-  double* colA = hom + 4 * NT;                 // [NL]  h nu         or hc / (k_B lambda)
+  double* colA = GT ? after_rows : hom + 4 * NT;   // [NL]  h nu         or hc / (k_B lambda)
   double* colB = colA + NL;                    // [NL]  everything else that depends on wavelength only
   double* colC = colB + NL;                    // [NL]  line profile in output units
-  double* lul = colC + NL;                     // [NL][5]  wavelength-axis banded LU, scaled rows
-  double* bnd = lul + 5 * NL;                  // [W][P][2] boundary states (2 * T doubles)
-  double* red = bnd + 2 * T;                   // [64]
+  double* colD = colC + NL;                    // [NL]  2 pi h nu^3 (the reference's numerator, for its underflow point)
+  double* lul = colD + NL;                     // [NL][5]  wavelength-axis banded LU, scaled rows
+  double* mtab = lul + 5 * NL;                 // [2][kScanSteps][32][4] scan matrices (forward, backward)
+  double* red = mtab + 2 * kScanSteps * 32 * 4;   // [64]
   double* tab = red + 64;                      // [1024]
   double* buf = tab + kExpTabSize;             // [W][NTP] column block; later [epochs][span_max] coefficients
+  double* ept = gs + (GT ? 9 * (size_t)NT : 0);       // [kEpCols][e_pad]
+  double* ys = ept + (size_t)kEpCols * a.e_pad;       // [NL - j_store_lo][e_pad]
+  const int EP = a.e_pad;
+  const int lgP = 31 - __clz(P);
+  const int j_first = max(0, a.j_store_lo - kBlueMargin);
 
   for (int i = tid; i < kExpTabSize; i += T) tab[i] = RB_EXP2_1024[i];
   for (int j = tid; j < NL; j += T) load_lu_row(lul + 5 * j, a.lu_lambda + 5 * j);
-  double* gs = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
-  double* ept = gs;                                   // [kEpCols][e_pad]
-  double* ys = gs + (size_t)kEpCols * a.e_pad;        // [NL - j_store_lo][e_pad]
-  const int EP = a.e_pad;
   int L = 0, Pe = 0;                                  // segment length (odd) and number of non-empty segments
   auto set_segments = [&](int G) {
     L = (G + P - 1) / P;
@@ -208,10 +237,13 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     L |= 1;                                           // odd: conflict-free shared-memory strides
     Pe = (G + L - 1) / L;
   };
-  // homogeneous solutions of the segmented solve for the current LU and segmentation:
-  //   forward  y[i] = -l2 y[i-2] - l1 y[i-1]   from (y[m-1], y[m-2]) = (1, 0) and (0, 1) at the segment start m,
-  //   backward x[i] = -u2' x[i+2] - u1' x[i+1] from (x[m'+1], x[m'+2]) = (1, 0) and (0, 1) at the segment end m'
-  auto build_hom = [&](int G) {
+  // Tables of the segmented solve for the current LU and segmentation.
+  //  hom: forward  y[i] = -l2 y[i-2] - l1 y[i-1]   from (y[m-1], y[m-2]) = (1, 0) and (0, 1) at the segment start m,
+  //       backward x[i] = -u2' x[i+2] - u1' x[i+1] from (x[m'+1], x[m'+2]) = (1, 0) and (0, 1) at the segment end m'.
+  //  mtab: segment s maps its incoming boundary state to its outgoing one, out = p_s + H_s in, with H_s made of hom at
+  //       the segment's last (forward) / first (backward) two rows; step d of the log-step scan needs the product of
+  //       the d matrices ending (forward) / starting (backward) at s -- built here by doubling.
+  auto build_tables = [&](int G) {
     for (int t4 = tid; t4 < 4 * Pe; t4 += T) {
       const int s = t4 >> 2, which = t4 & 3;
       const int i_lo = s * L, i_hi = min(i_lo + L, G);
@@ -232,12 +264,50 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         }
       }
     }
+    __syncthreads();
+    if (tid < 64) {
+      const int dir = tid >> 5, s = tid & 31;
+      double* m0 = mtab + (size_t)dir * kScanSteps * 128 + 4 * s;
+      double h00 = 0.0, h01 = 0.0, h10 = 0.0, h11 = 0.0;
+      if (s < Pe) {
+        const int i_lo = s * L, i_hi = min(i_lo + L, G);
+        if (dir == 0) {          // (y[i_hi-1], y[i_hi-2]) from (y[i_lo-1], y[i_lo-2]); all but the last segment have >= 3 rows
+          h00 = hom[4 * (i_hi - 1) + 0]; h01 = hom[4 * (i_hi - 1) + 1];
+          if (i_hi - 2 >= i_lo) { h10 = hom[4 * (i_hi - 2) + 0]; h11 = hom[4 * (i_hi - 2) + 1]; } else { h10 = 1.0; }
+        } else {                 // (x[i_lo], x[i_lo+1]) from (x[i_hi], x[i_hi+1])
+          h00 = hom[4 * i_lo + 2]; h01 = hom[4 * i_lo + 3];
+          if (i_lo + 1 < i_hi) { h10 = hom[4 * (i_lo + 1) + 2]; h11 = hom[4 * (i_lo + 1) + 3]; } else { h10 = 1.0; }
+        }
+      }
+      m0[0] = h00; m0[1] = h01; m0[2] = h10; m0[3] = h11;
+    }
+    __syncthreads();
+    for (int st = 1; st < kScanSteps; ++st) {
+      const int d = 1 << (st - 1);
+      if (tid < 64) {
+        const int dir = tid >> 5, s = tid & 31;
+        const double* prev = mtab + (size_t)dir * kScanSteps * 128 + (size_t)(st - 1) * 128;
+        double* cur = mtab + (size_t)dir * kScanSteps * 128 + (size_t)st * 128 + 4 * s;
+        const int o = dir == 0 ? s - d : s + d;
+        const double* A = prev + 4 * s;
+        if (o >= 0 && o < 32) {
+          const double* B = prev + 4 * o;
+          cur[0] = A[0] * B[0] + A[1] * B[2];
+          cur[1] = A[0] * B[1] + A[1] * B[3];
+          cur[2] = A[2] * B[0] + A[3] * B[2];
+          cur[3] = A[2] * B[1] + A[3] * B[3];
+        } else {
+          cur[0] = A[0]; cur[1] = A[1]; cur[2] = A[2]; cur[3] = A[3];
+        }
+      }
+      __syncthreads();
+    }
   };
   if (a.common_time_lu) {
     for (int i = tid; i < NT; i += T) load_lu_row(lut + 5 * i, a.lu_time + 5 * i);
     set_segments(NT);
     __syncthreads();
-    build_hom(NT);
+    build_tables(NT);
   }
   __syncthreads();
 
@@ -303,6 +373,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       if (a.sed == PH_SED_BLACKBODY) {
         ca = kH * nu;
         cb = 2 * kPi * kH * (nu * nu * nu) / ((dl * dl) * (kC * kC)) * opz * kToMJy * to_flam;   // sed.py:216, 929
+        colD[j] = 2 * kPi * kH * (nu * nu * nu);                                  // sed.py:217 num without R^2
       } else {
         const double lam_A = 1.e10 * (kCSI / nu);
         const double lam = lam_A * kAngstrom;
@@ -316,6 +387,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
           c = c * 1e-26 * kToMJy;
         }
         cb = c * opz * to_flam;                                                   // supernova_models.py:1611-1612, 2304-2305
+        colD[j] = 0.0;
       }
       colA[j] = ca;
       colB[j] = cb;
@@ -392,25 +464,39 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       }
     }
     bool all_valid;
+    double x_hi;
     {
       double r_lo = INFINITY, r_hi = 0.0, a_hi = 0.0, c_lo = INFINITY, c_hi = 0.0, ca_hi = 0.0;
       for (int w = 0; w < nwarps; ++w) {
         r_lo = fmin(r_lo, red[w]); r_hi = fmax(r_hi, red[8 + w]); a_hi = fmax(a_hi, red[16 + w]);
         c_lo = fmin(c_lo, red[24 + w]); c_hi = fmax(c_hi, red[32 + w]); ca_hi = fmax(ca_hi, red[40 + w]);
       }
-      // every product colB rowB / expm1(x) is then finite and non-zero: x <= 600, prefactors within [1e-280, 1e280]
-      all_valid = (a_hi * ca_hi < 600.0) && (r_lo * c_lo > 1e-280) && (r_hi * c_hi * (double)NC < 1e280) &&
-                  (a_hi * ca_hi > 0.0);
-      // x -> 0 makes 1 / expm1 large but finite (x >= 1e-300 here since both factors are positive and finite)
+      x_hi = a_hi * ca_hi;
+      // every product colB rowB / expm1(x) is then finite and non-zero in the reference's own evaluation order too
+      // (its erg/s/Hz/cm^2 value is ~1e-7 of ours): x <= 600 and prefactors within [1e-20, 1e250]
+      all_valid = (x_hi < 600.0) && (x_hi > 0.0) && (r_lo * c_lo > 1e-20) && (r_hi * c_hi * (double)NC < 1e250);
     }
     __syncthreads();                                  // xk (in buf) is dead from here on
     PHOT_PROF_ACC(0);
 
-    // one spectrum sample
-    auto spec = [&](int j, int k) -> double {
-      const double ca = colA[j], cb = colB[j];
-      double v = cb * rowB[k] * planck_inv(ca * rowA[k], tab);
-      for (int c = 1; c < NC; ++c) v += cb * rowB[c * NT + k] * planck_inv(ca * rowA[c * NT + k], tab);
+    const double inv_den = 1.0 / ((dl * dl) * (kC * kC));                           // sed.py:218
+    const double ca_min = colA[NL - 1];
+    // one spectrum sample of column j (uniform over the warp), row k (lane); `tail` out: far below the row's peak
+    auto spec = [&](double ca, double cb, double cd, int k, int j) -> double {
+      const double x = ca * rowA[k];
+      double v = cb * rowB[k] * planck_inv_warp(x, tab);
+      if (x > 650.0 && a.sed == PH_SED_BLACKBODY) {
+        // the reference evaluates (2 pi h nu^3 R^2 / (dl^2 c^2)) * (1 / expm1(x)) in erg/s/Hz/cm^2 (sed.py:217-221),
+        // which underflows to 0 (-> replaced) ~1e7 earlier than the product in our output units
+        const double vc = ((cd * rowB[k]) * inv_den) * (1.0 / expm1(x));
+        if (vc == 0.0) v = 0.0;
+      }
+      for (int c = 1; c < NC; ++c) {
+        const double xc = ca * rowA[c * NT + k];
+        double vc2 = cb * rowB[c * NT + k] * planck_inv_general(xc, tab);
+        if (xc > 650.0 && ((cd * rowB[c * NT + k]) * inv_den) * (1.0 / expm1(xc)) == 0.0) vc2 = 0.0;
+        v += vc2;
+      }
       if (line) v = v * rowC[k] + rowD[k] * colC[j];
       return v;
     };
@@ -448,12 +534,26 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     if (!all_valid) {
       double vsum = 0.0, vcnt = 0.0;
       const int wstat = a.common_time_lu ? nwarps : nwarps - 1;     // the LU warp does not take part
+      const bool plain = NC == 1 && !line;
       if (warp < wstat) {
-        for (int j = warp; j < NL; j += wstat)
-          for (int k = lane; k < G; k += 32) {
-            const double v = spec(j, k);
-            if (isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
+        for (int j = warp; j < NL; j += wstat) {
+          const double ca = colA[j], cb = colB[j], cd = colD[j];
+          const double dca = ca - ca_min;
+          for (int k0 = 0; k0 < G; k0 += 32) {
+            const int k = min(k0 + lane, G - 1);
+            const bool live = k0 + lane < G;
+            // A term more than e^-50 below its row's largest one (the reddest column's, or the Planck peak) cannot
+            // change the sum at 1e-16: it is counted, not evaluated, when it is certainly finite and non-zero.
+            const double ra = rowA[k], crb = cb * rowB[k];
+            const bool tail = plain && ra * dca > 50.0 && ca * ra <= 650.0 && crb > 1e-20 && crb < 1e250;
+            if (__all_sync(0xffffffffu, tail || !live)) {
+              if (live) vcnt += 1.0;
+              continue;
+            }
+            const double v = spec(ca, cb, cd, k, j);
+            if (live && isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
           }
+        }
       }
       vsum = warp_sum(vsum);
       vcnt = warp_sum(vcnt);
@@ -467,115 +567,103 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     } else {
       __syncthreads();
     }
-    if (!a.common_time_lu) {
-      build_hom(G);
-      __syncthreads();
-    }
+    if (!a.common_time_lu) build_tables(G);
     PHOT_PROF_ACC(1);
 
     // ---- 2. wavelength-column blocks ---------------------------------------------------------------------------
-    for (int j0 = 0; j0 < NL; j0 += W) {
+    const int seg = tid & (P - 1), jl = tid >> lgP;
+    const int i_lo = seg * L, i_hi = min(i_lo + L, G);
+    const double* mF = mtab + 4 * seg;
+    const double* mB = mtab + kScanSteps * 128 + 4 * seg;
+    for (int j0 = j_first; j0 < NL; j0 += W) {
       const int wc = min(W, NL - j0);
       // 2a. spectra of the block, cleaned
-      for (int jl = warp; jl < wc; jl += nwarps) {
-        double* col = buf + jl * NTP;
-        for (int k = lane; k < G; k += 32) {
-          double v = spec(j0 + jl, k);
+      for (int q = warp; q < wc; q += nwarps) {
+        double* col = buf + q * NTP;
+        const double ca = colA[j0 + q], cb = colB[j0 + q], cd = colD[j0 + q];
+        for (int k0 = 0; k0 < G; k0 += 32) {
+          const int k = min(k0 + lane, G - 1);
+          double v = spec(ca, cb, cd, k, j0 + q);
           if (!(isfinite(v) && v != 0.0)) v = repl;
-          col[k] = v;
+          if (k0 + lane < G) col[k] = v;
         }
       }
       __syncthreads();
       PHOT_PROF_ACC(2);
-      // 2b. time axis, forward elimination: particular solution of every (column, segment) from a zero state
-      const int seg = tid % P, jl = tid / P;
-      const bool active = jl < wc && seg < Pe;
-      const int i_lo = seg * L, i_hi = min(i_lo + L, G);
-      double* col = buf + jl * NTP;
-      if (active) {
-        double y1 = 0.0, y2 = 0.0;
+      // 2b. time axis: the thread's (column, segment) through forward recurrence, boundary scan, backward recurrence,
+      // reverse scan and fix-up; the P lanes of a column exchange boundary states by shuffles only
+      {
+        const bool active = jl < wc && i_lo < G;
+        double* col = buf + jl * NTP;
+        double p1 = 0.0, p2 = 0.0;
+        if (active) {
 #pragma unroll 4
-        for (int i = i_lo; i < i_hi; ++i) {
-          const double y = (col[i] - lut[5 * i + 0] * y2) - lut[5 * i + 1] * y1;
-          col[i] = y;
-          y2 = y1;
-          y1 = y;
+          for (int i = i_lo; i < i_hi; ++i) {
+            const double y = (col[i] - lut[5 * i + 0] * p2) - lut[5 * i + 1] * p1;
+            col[i] = y;
+            p2 = p1;
+            p1 = y;
+          }
+          if (i_hi - i_lo < 2) p2 = 0.0;              // one-row segment: y[i_hi-2] belongs to the previous one (H row = [1 0])
+        }
+        // inclusive scan of the segments' affine maps: afterwards (p1, p2) is the TRUE state at the segment's end
+        for (int st = 0; st < lgP; ++st) {
+          const int d = 1 << st;
+          const double q1 = __shfl_up_sync(0xffffffffu, p1, d, P), q2 = __shfl_up_sync(0xffffffffu, p2, d, P);
+          if (seg >= d) {
+            const double* M = mF + st * 128;
+            const double n1 = p1 + M[0] * q1 + M[1] * q2;
+            const double n2 = p2 + M[2] * q1 + M[3] * q2;
+            p1 = n1;
+            p2 = n2;
+          }
+        }
+        double Y1 = __shfl_up_sync(0xffffffffu, p1, 1, P), Y2 = __shfl_up_sync(0xffffffffu, p2, 1, P);
+        if (seg == 0) { Y1 = 0.0; Y2 = 0.0; }
+        p1 = 0.0;
+        p2 = 0.0;
+        if (active) {
+#pragma unroll 4
+          for (int i = i_hi - 1; i >= i_lo; --i) {
+            const double b = (col[i] + hom[4 * i + 0] * Y1 + hom[4 * i + 1] * Y2) * lut[5 * i + 2];
+            const double x = (b - lut[5 * i + 4] * p2) - lut[5 * i + 3] * p1;
+            col[i] = x;
+            p2 = p1;
+            p1 = x;
+          }
+          if (i_hi - i_lo < 2) p2 = 0.0;
+        }
+        for (int st = 0; st < lgP; ++st) {
+          const int d = 1 << st;
+          const double q1 = __shfl_down_sync(0xffffffffu, p1, d, P), q2 = __shfl_down_sync(0xffffffffu, p2, d, P);
+          if (seg + d < P) {
+            const double* M = mB + st * 128;
+            const double n1 = p1 + M[0] * q1 + M[1] * q2;
+            const double n2 = p2 + M[2] * q1 + M[3] * q2;
+            p1 = n1;
+            p2 = n2;
+          }
+        }
+        double X1 = __shfl_down_sync(0xffffffffu, p1, 1, P), X2 = __shfl_down_sync(0xffffffffu, p2, 1, P);
+        if (seg == P - 1) { X1 = 0.0; X2 = 0.0; }
+        if (active && (X1 != 0.0 || X2 != 0.0)) {
+#pragma unroll 4
+          for (int i = i_lo; i < i_hi; ++i) col[i] += hom[4 * i + 2] * X1 + hom[4 * i + 3] * X2;
         }
       }
       __syncthreads();
       PHOT_PROF_ACC(3);
-      // true (y[m-1], y[m-2]) at the start m of every segment: serial over the segments, one thread per column
-      if (tid < wc) {
-        double* c = buf + tid * NTP;
-        double Y1 = 0.0, Y2 = 0.0;
-        bnd[(tid * P + 0) * 2 + 0] = 0.0;
-        bnd[(tid * P + 0) * 2 + 1] = 0.0;
-        for (int s = 1; s < Pe; ++s) {
-          const int m = s * L;
-          const double e1 = c[m - 1] + hom[4 * (m - 1) + 0] * Y1 + hom[4 * (m - 1) + 1] * Y2;
-          const double e2 = c[m - 2] + hom[4 * (m - 2) + 0] * Y1 + hom[4 * (m - 2) + 1] * Y2;
-          Y1 = e1;
-          Y2 = e2;
-          bnd[(tid * P + s) * 2 + 0] = Y1;
-          bnd[(tid * P + s) * 2 + 1] = Y2;
-        }
-      }
-      __syncthreads();
-      PHOT_PROF_ACC(5);
-      // 2c. time axis, back substitution: particular solution per segment, the forward fix-up folded into the load
-      if (active) {
-        const double Y1 = bnd[(jl * P + seg) * 2 + 0], Y2 = bnd[(jl * P + seg) * 2 + 1];
-        double x1 = 0.0, x2 = 0.0;
-#pragma unroll 4
-        for (int i = i_hi - 1; i >= i_lo; --i) {
-          const double b = (col[i] + hom[4 * i + 0] * Y1 + hom[4 * i + 1] * Y2) * lut[5 * i + 2];
-          const double x = (b - lut[5 * i + 4] * x2) - lut[5 * i + 3] * x1;
-          col[i] = x;
-          x2 = x1;
-          x1 = x;
-        }
-      }
-      __syncthreads();
-      PHOT_PROF_ACC(4);
-      // true (x[m], x[m+1]) just after the end of every segment (m = first row of the next one)
-      if (tid < wc) {
-        double* c = buf + tid * NTP;
-        double X1 = 0.0, X2 = 0.0;
-        bnd[(tid * P + (Pe - 1)) * 2 + 0] = 0.0;
-        bnd[(tid * P + (Pe - 1)) * 2 + 1] = 0.0;
-        for (int s = Pe - 2; s >= 0; --s) {
-          const int m = (s + 1) * L;
-          const double s1 = c[m] + hom[4 * m + 2] * X1 + hom[4 * m + 3] * X2;
-          const double s2 = (m + 1 < G) ? c[m + 1] + hom[4 * (m + 1) + 2] * X1 + hom[4 * (m + 1) + 3] * X2 : 0.0;
-          X1 = s1;
-          X2 = s2;
-          bnd[(tid * P + s) * 2 + 0] = X1;
-          bnd[(tid * P + s) * 2 + 1] = X2;
-        }
-      }
-      __syncthreads();
-      PHOT_PROF_ACC(5);
-      // 2d. contraction with the epochs' time B-splines (backward fix-up folded into the loads) and forward
-      // elimination of the wavelength-axis solve on the E resulting rows
+      // 2c. contraction with the epochs' time B-splines and forward elimination of the wavelength-axis solve on the E
+      // resulting rows
       for (int e = tid; e < En; e += T) {
-        const double h0 = ept[0 * EP + e], h1 = ept[1 * EP + e], h2 = ept[2 * EP + e], h3 = ept[3 * EP + e];
         const int l = (int)ept[4 * EP + e];
-        double y1 = ept[5 * EP + e], y2 = ept[6 * EP + e];
         if (l >= 0) {
-          const int s0 = l / L, s3 = (l + 3) / L;
-          const int split = (s3 != s0) ? s3 * L - l : 4;           // rows l .. l+split-1 lie in segment s0
-          const double hb0 = hom[4 * l + 2], hb1 = hom[4 * l + 3], hb2 = hom[4 * l + 6], hb3 = hom[4 * l + 7],
-                       hb4 = hom[4 * l + 10], hb5 = hom[4 * l + 11], hb6 = hom[4 * l + 14], hb7 = hom[4 * l + 15];
-          for (int q = 0; q < wc; ++q) {
-            const double* c = buf + q * NTP + l;
-            const double* ba = bnd + (q * P + s0) * 2;
-            const double* bb = bnd + (q * P + s3) * 2;
-            const double Xa1 = ba[0], Xa2 = ba[1], Xb1 = bb[0], Xb2 = bb[1];
-            const double x0 = c[0] + hb0 * Xa1 + hb1 * Xa2;
-            const double x1v = c[1] + hb2 * (split > 1 ? Xa1 : Xb1) + hb3 * (split > 1 ? Xa2 : Xb2);
-            const double x2v = c[2] + hb4 * (split > 2 ? Xa1 : Xb1) + hb5 * (split > 2 ? Xa2 : Xb2);
-            const double x3v = c[3] + hb6 * (split > 3 ? Xa1 : Xb1) + hb7 * (split > 3 ? Xa2 : Xb2);
-            const double r = h0 * x0 + h1 * x1v + h2 * x2v + h3 * x3v;
+          const double h0 = ept[0 * EP + e], h1 = ept[1 * EP + e], h2 = ept[2 * EP + e], h3 = ept[3 * EP + e];
+          double y1 = ept[5 * EP + e], y2 = ept[6 * EP + e];
+          const double* c = buf + l;
+#pragma unroll 2
+          for (int q = 0; q < wc; ++q, c += NTP) {
+            const double r = h0 * c[0] + h1 * c[1] + h2 * c[2] + h3 * c[3];
             const int j = j0 + q;
             const double y = (r - lul[5 * j + 0] * y2) - lul[5 * j + 1] * y1;
             if (j >= a.j_store_lo) ys[(size_t)(j - a.j_store_lo) * EP + e] = y;
@@ -587,14 +675,15 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         }
       }
       __syncthreads();
-      PHOT_PROF_ACC(6);
+      PHOT_PROF_ACC(4);
     }
 
     // ---- 3. epochs: wavelength-axis back substitution, band integrals, magnitudes, likelihood ------------------
     // chunks of epochs (grouped by band through epoch_order) sized by the coefficient buffer:
     //   a. thread per epoch: back substitution from the last column down to the band's first coefficient; the band's
-    //      coefficients go to the shared buffer;
-    //   b. warp per epoch: the band-pass integration points are split between the lanes;
+    //      coefficients go to the shared buffer; if none of them is negative the band integral is their dot product
+    //      with the band's contracted weights, done on the way;
+    //   b. warp per epoch, only where a coefficient is negative: the integration points split between the lanes, |f|;
     //   c. thread per epoch: magnitude / flux, likelihood term, coalesced store.
     double logl_part = 0.0;
     const int SM = a.span_max;
@@ -608,20 +697,28 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         const int jlo = a.band_jlo[b], span = a.band_span[b];
         double* cb = buf + (size_t)i * SM;
         if (ept[4 * EP + e] < 0.0) continue;                    // before t0: nothing to integrate
-        double x1 = 0.0, x2 = 0.0;
+        double x1 = 0.0, x2 = 0.0, lin = 0.0, cneg = 0.0;
         const double* yp = ys + e;
+        const double* wgt = a.band_weight + (size_t)b * SM;
         for (int j = NL - 1; j >= jlo; --j) {
           const double x = (yp[(size_t)(j - a.j_store_lo) * EP] * lul[5 * j + 2] - lul[5 * j + 4] * x2) - lul[5 * j + 3] * x1;
-          if (j < jlo + span) cb[j - jlo] = x;
+          if (j < jlo + span) {
+            cb[j - jlo] = x;
+            lin = fma(x, __ldg(wgt + (j - jlo)), lin);
+            cneg = fmin(cneg, x);                               // NaN-safe: fmin drops a NaN operand, handled below
+            if (!(x == x)) cneg = -1.0;
+          }
           x2 = x1;
           x1 = x;
         }
+        ept[7 * EP + e] = lin;
+        ept[5 * EP + e] = cneg;                                 // < 0: the point-by-point path is needed
       }
       __syncthreads();
-      PHOT_PROF_ACC(7);
+      PHOT_PROF_ACC(5);
       for (int i = warp; i < ne; i += nwarps) {
         const int e = ragged ? e0 + i : a.epoch_order[e0 + i];
-        if (ept[4 * EP + e] < 0.0) continue;
+        if (ept[4 * EP + e] < 0.0 || !(ept[5 * EP + e] < 0.0)) continue;
         const int b = band_row[e];
         const int w0 = a.band_off[b], w1 = a.band_off[b + 1];
         const double* dw = buf + (size_t)i * SM;
@@ -650,7 +747,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         if (lane == 0) ept[7 * EP + e] = acc;
       }
       __syncthreads();
-      PHOT_PROF_ACC(8);
+      PHOT_PROF_ACC(6);
       for (int i = tid; i < ne; i += T) {
         const int e = ragged ? e0 + i : a.epoch_order[e0 + i];
         double model_v;
@@ -680,7 +777,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       }
     }
     __syncthreads();
-    PHOT_PROF_ACC(9);
+    PHOT_PROF_ACC(7);
     PHOT_PROF_END();
   }
 }
