@@ -180,6 +180,7 @@ __device__ __noinline__ double planck_inv_general(double x, const double* __rest
 __device__ __forceinline__ double planck_inv_warp(double x, const double* __restrict__ tab) {
   if (__all_sync(0xffffffffu, x > 40.0 && x <= 700.0)) return exp_lean(-x, tab);     // e^-x: differs by e^-x < 4e-18
   if (__all_sync(0xffffffffu, x >= 0.5 && x <= 40.0)) return rcp_fast(exp_lean(x, tab) - 1.0);
+  if (__all_sync(0xffffffffu, !(x <= 709.782712893384))) return (x == x) ? 0.0 : x;   // expm1 overflow -> 0; NaN rows
   return planck_inv_general(x, tab);
 }
 
@@ -212,7 +213,8 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
   double* rowD = rowC + (line ? NT : 0);       // [NT]  scaled line amplitude        (line SED only)
   double* after_rows = rowD + (line ? NT : 0);
   double* lut = GT ? gs : after_rows;          // [NT][5]  time-axis banded LU, scaled rows
-  double* hom = lut + 5 * NT;                  // [NT][4]  homogeneous solutions of the segmented time-axis solve
+  double* hom = lut + 5 * NT;                  // [4][NT]  homogeneous solutions of the segmented time-axis solve (one array
+                                               //          per solution: lanes stride an odd segment length, no bank conflicts)
   double* colA = GT ? after_rows : hom + 4 * NT;   // [NL]  h nu         or hc / (k_B lambda)
   double* colB = colA + NL;                    // [NL]  everything else that depends on wavelength only
   double* colC = colB + NL;                    // [NL]  line profile in output units
@@ -251,14 +253,14 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       if (which < 2) {
         for (int i = i_lo; i < i_hi; ++i) {
           const double y = -lut[5 * i + 0] * p2 - lut[5 * i + 1] * p1;
-          hom[4 * i + which] = y;
+          hom[which * NT + i] = y;
           p2 = p1;
           p1 = y;
         }
       } else {
         for (int i = i_hi - 1; i >= i_lo; --i) {
           const double x = -lut[5 * i + 4] * p2 - lut[5 * i + 3] * p1;
-          hom[4 * i + which] = x;
+          hom[which * NT + i] = x;
           p2 = p1;
           p1 = x;
         }
@@ -272,11 +274,11 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       if (s < Pe) {
         const int i_lo = s * L, i_hi = min(i_lo + L, G);
         if (dir == 0) {          // (y[i_hi-1], y[i_hi-2]) from (y[i_lo-1], y[i_lo-2]); all but the last segment have >= 3 rows
-          h00 = hom[4 * (i_hi - 1) + 0]; h01 = hom[4 * (i_hi - 1) + 1];
-          if (i_hi - 2 >= i_lo) { h10 = hom[4 * (i_hi - 2) + 0]; h11 = hom[4 * (i_hi - 2) + 1]; } else { h10 = 1.0; }
+          h00 = hom[0 * NT + i_hi - 1]; h01 = hom[1 * NT + i_hi - 1];
+          if (i_hi - 2 >= i_lo) { h10 = hom[0 * NT + i_hi - 2]; h11 = hom[1 * NT + i_hi - 2]; } else { h10 = 1.0; }
         } else {                 // (x[i_lo], x[i_lo+1]) from (x[i_hi], x[i_hi+1])
-          h00 = hom[4 * i_lo + 2]; h01 = hom[4 * i_lo + 3];
-          if (i_lo + 1 < i_hi) { h10 = hom[4 * (i_lo + 1) + 2]; h11 = hom[4 * (i_lo + 1) + 3]; } else { h10 = 1.0; }
+          h00 = hom[2 * NT + i_lo]; h01 = hom[3 * NT + i_lo];
+          if (i_lo + 1 < i_hi) { h10 = hom[2 * NT + i_lo + 1]; h11 = hom[3 * NT + i_lo + 1]; } else { h10 = 1.0; }
         }
       }
       m0[0] = h00; m0[1] = h01; m0[2] = h10; m0[3] = h11;
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     auto spec = [&](double ca, double cb, double cd, int k, int j) -> double {
       const double x = ca * rowA[k];
       double v = cb * rowB[k] * planck_inv_warp(x, tab);
-      if (x > 650.0 && a.sed == PH_SED_BLACKBODY) {
+      if (x > 650.0 && x <= 709.782712893384 && a.sed == PH_SED_BLACKBODY) {
         // the reference evaluates (2 pi h nu^3 R^2 / (dl^2 c^2)) * (1 / expm1(x)) in erg/s/Hz/cm^2 (sed.py:217-221),
         // which underflows to 0 (-> replaced) ~1e7 earlier than the product in our output units
         const double vc = ((cd * rowB[k]) * inv_den) * (1.0 / expm1(x));
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       for (int c = 1; c < NC; ++c) {
         const double xc = ca * rowA[c * NT + k];
         double vc2 = cb * rowB[c * NT + k] * planck_inv_general(xc, tab);
-        if (xc > 650.0 && ((cd * rowB[c * NT + k]) * inv_den) * (1.0 / expm1(xc)) == 0.0) vc2 = 0.0;
+        if (xc > 650.0 && xc <= 709.782712893384 && ((cd * rowB[c * NT + k]) * inv_den) * (1.0 / expm1(xc)) == 0.0) vc2 = 0.0;
         v += vc2;
       }
       if (line) v = v * rowC[k] + rowD[k] * colC[j];
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         if (active) {
 #pragma unroll 4
           for (int i = i_hi - 1; i >= i_lo; --i) {
-            const double b = (col[i] + hom[4 * i + 0] * Y1 + hom[4 * i + 1] * Y2) * lut[5 * i + 2];
+            const double b = (col[i] + hom[0 * NT + i] * Y1 + hom[1 * NT + i] * Y2) * lut[5 * i + 2];
             const double x = (b - lut[5 * i + 4] * p2) - lut[5 * i + 3] * p1;
             col[i] = x;
             p2 = p1;
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         if (seg == P - 1) { X1 = 0.0; X2 = 0.0; }
         if (active && (X1 != 0.0 || X2 != 0.0)) {
 #pragma unroll 4
-          for (int i = i_lo; i < i_hi; ++i) col[i] += hom[4 * i + 2] * X1 + hom[4 * i + 3] * X2;
+          for (int i = i_lo; i < i_hi; ++i) col[i] += hom[2 * NT + i] * X1 + hom[3 * NT + i] * X2;
         }
       }
       __syncthreads();
