@@ -98,7 +98,7 @@ struct PhotArgs {
 // reduction scratch, exp table, column buffer (also the per-epoch coefficient buffer of the last phase)
 __host__ __device__ inline size_t phot_fixed_doubles(int NT, int NL, int n_comp, bool line, bool tables_global) {
   return (size_t)(2 * n_comp + (line ? 2 : 0)) * NT + (tables_global ? 0 : 9 * (size_t)NT) + 4 * (size_t)NL +
-         5 * (size_t)NL + 2 * kScanSteps * 32 * 4 + 64 + kExpTabSize;
+         5 * (size_t)NL + 2 * kScanSteps * 32 * 4 + 64 + 6 * (size_t)((NT + 31) / 32) + kExpTabSize;
 }
 
 // FITPACK fpbspl for k = 3: the four non-zero cubic B-splines at x, t[l] <= x < t[l+1] (0-based l)
@@ -163,6 +163,22 @@ __device__ __forceinline__ double exp_lean(double x, const double* __restrict__ 
   return __hiloint2double(__double2hiint(res) + ((k >> 10) << 20), __double2loint(res));
 }
 
+// expm1(x) for 0 < x <= 700 from the same table: e^x - 1 = T (1 + p) - 1 with T = 2^m 2^(j/1024) and p = e^r - 1 by a
+// degree-4 polynomial (|r| <= 3.4e-4: truncation 4e-20), evaluated as fma(T, p, T - 1): T - 1 is exact for T in [1, 2),
+// so there is no cancellation for small x (relative error < 3e-16 for x >= 1e-12).
+__device__ __forceinline__ double expm1_tab(double x, const double* __restrict__ tab) {
+  const double v = fma(x, kTabOverLn2, kExpMagic);
+  const int k = __double2loint(v);
+  const double r = fma(v - kExpMagic, -kLn2OverTabHi, x);
+  double q = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+  q = fma(r, q, 0.5);
+  q = fma(r, q, 1.0);
+  const double p = r * q;
+  const double t = tab[k & 1023];
+  const double Ts = __hiloint2double(__double2hiint(t) + ((k >> 10) << 20), __double2loint(t));
+  return fma(Ts, p, Ts - 1.0);
+}
+
 // General 1 / expm1(x) of the Planck function (any x, per lane).  The reference's expm1 overflows to inf (-> value 0 ->
 // replaced) above 709.78, reproduced here; between 700 and there the result is subnormal and libm's exp is used.
 __device__ __noinline__ double planck_inv_general(double x, const double* __restrict__ tab) {
@@ -171,17 +187,8 @@ __device__ __noinline__ double planck_inv_general(double x, const double* __rest
     if (x > 700.0) return exp(-x);
     return exp_lean(-x, tab);
   }
-  if (x >= 0.5) return rcp_fast(exp_lean(x, tab) - 1.0);
+  if (x >= 1e-12) return rcp_fast(expm1_tab(x, tab));
   return rcp_fast(expm1(x));
-}
-
-// 1 / expm1(x) for the 32 rows a warp works on (same column).  The rows are consecutive in time, so x is usually in one
-// regime for the whole warp: the two common regimes are warp-uniform branches without divergence bookkeeping.
-__device__ __forceinline__ double planck_inv_warp(double x, const double* __restrict__ tab) {
-  if (__all_sync(0xffffffffu, x > 40.0 && x <= 700.0)) return exp_lean(-x, tab);     // e^-x: differs by e^-x < 4e-18
-  if (__all_sync(0xffffffffu, x >= 0.5 && x <= 40.0)) return rcp_fast(exp_lean(x, tab) - 1.0);
-  if (__all_sync(0xffffffffu, !(x <= 709.782712893384))) return (x == x) ? 0.0 : x;   // expm1 overflow -> 0; NaN rows
-  return planck_inv_general(x, tab);
 }
 
 #ifdef RB_PHOT_PROFILE
@@ -222,7 +229,8 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
   double* lul = colD + NL;                     // [NL][5]  wavelength-axis banded LU, scaled rows
   double* mtab = lul + 5 * NL;                 // [2][kScanSteps][32][4] scan matrices (forward, backward)
   double* red = mtab + 2 * kScanSteps * 32 * 4;   // [64]
-  double* tab = red + 64;                      // [1024]
+  double* grp = red + 64;                      // [6][ngroups] bounds of rowA / rowB over each group of 32 rows
+  double* tab = grp + 6 * ((NT + 31) / 32);    // [1024]
   double* buf = tab + kExpTabSize;             // [W][NTP] column block; later [epochs][span_max] coefficients
   double* ept = gs + (GT ? 9 * (size_t)NT : 0);       // [kEpCols][e_pad]
   double* ys = ept + (size_t)kEpCols * a.e_pad;       // [NL - j_store_lo][e_pad]
@@ -412,6 +420,30 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       red[24 + warp] = cmin; red[32 + warp] = cmax; red[40 + warp] = camax;
     }
     __syncthreads();
+    // bounds of the row factors over each group of 32 consecutive rows (what one warp handles per column): with the
+    // column's factors they decide the evaluation regime of the whole group by a few scalar multiplies
+    const int ng = (G + 31) >> 5;
+    double* g_ralo = grp;                 // min rowA over the group's VALID rows (finite, > 0, finite R^2 > 0); +inf if none
+    double* g_rahi = grp + ng;            // max rowA                               } over the whole group,
+    double* g_rblo = grp + 2 * ng;        // min rowB                               } meaningful when g_clean
+    double* g_rbhi = grp + 3 * ng;        // max rowB
+    double* g_clean = grp + 4 * ng;       // 1: every row of the group is valid
+    for (int g = warp; g < ng; g += nwarps) {
+      const int k = g * 32 + lane;
+      const bool in = k < G;
+      const double ra = in ? rowA[k] : 0.0, rb = in ? rowB[k] : 0.0;
+      const bool ok = in && ra > 0.0 && ra < INFINITY && rb > 0.0 && rb < INFINITY;
+      double lo_v = ok ? ra : INFINITY, hi = ok ? ra : 0.0, blo = ok ? rb : INFINITY, bhi = ok ? rb : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo_v = fmin(lo_v, __shfl_xor_sync(0xffffffffu, lo_v, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        blo = fmin(blo, __shfl_xor_sync(0xffffffffu, blo, o));
+        bhi = fmax(bhi, __shfl_xor_sync(0xffffffffu, bhi, o));
+      }
+      const bool clean = __all_sync(0xffffffffu, ok || !in);
+      if (lane == 0) { g_ralo[g] = lo_v; g_rahi[g] = hi; g_rblo[g] = blo; g_rbhi[g] = bhi; g_clean[g] = clean ? 1.0 : 0.0; }
+    }
     // ---- 0b. per-epoch time basis (knot interval + the four non-zero B-splines) and the collocation rows ----------
     for (int e = tid; e < En; e += T) {
       double x = t_row[e];
@@ -483,10 +515,10 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
 
     const double inv_den = 1.0 / ((dl * dl) * (kC * kC));                           // sed.py:218
     const double ca_min = colA[NL - 1];
-    // one spectrum sample of column j (uniform over the warp), row k (lane); `tail` out: far below the row's peak
+    // General evaluation of one spectrum sample (column j, row k): any regime, any SED, any number of components.
     auto spec = [&](double ca, double cb, double cd, int k, int j) -> double {
       const double x = ca * rowA[k];
-      double v = cb * rowB[k] * planck_inv_warp(x, tab);
+      double v = cb * rowB[k] * planck_inv_general(x, tab);
       if (x > 650.0 && x <= 709.782712893384 && a.sed == PH_SED_BLACKBODY) {
         // the reference evaluates (2 pi h nu^3 R^2 / (dl^2 c^2)) * (1 / expm1(x)) in erg/s/Hz/cm^2 (sed.py:217-221),
         // which underflows to 0 (-> replaced) ~1e7 earlier than the product in our output units
@@ -501,6 +533,22 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       }
       if (line) v = v * rowC[k] + rowD[k] * colC[j];
       return v;
+    };
+    // Regime of (column, group of 32 rows) from the group's bounds -- all scalar, uniform over the warp:
+    //   0 dead   : every row overflows the Planck denominator or is itself invalid -> every sample is replaced
+    //   1 wien   : 40 < x <= 650, all samples valid: value = cb R^2 e^-x (the two differ by e^-x < 4e-18)
+    //   2 planck : x <= 40, all samples valid: value = cb R^2 / expm1(x)
+    //   3 general: anything else, and every multi-component / line spectrum
+    const bool plain = NC == 1 && !line;
+    auto regime = [&](double ca, double cb, int g) -> int {
+      if (!plain) return 3;
+      if (ca * g_ralo[g] > 709.782712893384) return 0;
+      const double clo = cb * g_rblo[g], chi = cb * g_rbhi[g];
+      if (g_clean[g] == 0.0 || !(clo > 1e-20) || !(chi < 1e250)) return 3;
+      const double xlo = ca * g_ralo[g], xhi = ca * g_rahi[g];
+      if (xlo > 40.0 && xhi <= 650.0) return 1;
+      if (xhi <= 40.0 && xlo > 1e-12) return 2;
+      return 3;
     };
 
     // ---- 1. statistics pre-pass for the clean-up value (sed.py:985-992), with the serial LU underneath ----------
@@ -536,20 +584,25 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     if (!all_valid) {
       double vsum = 0.0, vcnt = 0.0;
       const int wstat = a.common_time_lu ? nwarps : nwarps - 1;     // the LU warp does not take part
-      const bool plain = NC == 1 && !line;
       if (warp < wstat) {
         for (int j = warp; j < NL; j += wstat) {
           const double ca = colA[j], cb = colB[j], cd = colD[j];
           const double dca = ca - ca_min;
-          for (int k0 = 0; k0 < G; k0 += 32) {
-            const int k = min(k0 + lane, G - 1);
-            const bool live = k0 + lane < G;
-            // A term more than e^-50 below its row's largest one (the reddest column's, or the Planck peak) cannot
-            // change the sum at 1e-16: it is counted, not evaluated, when it is certainly finite and non-zero.
-            const double ra = rowA[k], crb = cb * rowB[k];
-            const bool tail = plain && ra * dca > 50.0 && ca * ra <= 650.0 && crb > 1e-20 && crb < 1e250;
-            if (__all_sync(0xffffffffu, tail || !live)) {
-              if (live) vcnt += 1.0;
+          for (int g = 0; g < ng; ++g) {
+            const int k = min(g * 32 + lane, G - 1);
+            const bool live = g * 32 + lane < G;
+            const int rg = regime(ca, cb, g);
+            if (rg == 0) continue;
+            if (rg == 1 || rg == 2) {
+              // A term more than e^-50 below its row's largest one (the reddest column's, or the Planck peak) cannot
+              // change the sum at 1e-16: the group's samples are all valid, they are counted, not evaluated.
+              if (rg == 1 && g_ralo[g] * dca > 50.0) {
+                if (lane == 0) vcnt += (double)min(32, G - g * 32);
+                continue;
+              }
+              const double x = ca * rowA[k];
+              const double pv = (rg == 1) ? exp_lean(-x, tab) : rcp_fast(expm1_tab(x, tab));
+              if (live) { vsum += (cb * rowB[k]) * pv; vcnt += 1.0; }
               continue;
             }
             const double v = spec(ca, cb, cd, k, j);
@@ -583,11 +636,22 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       for (int q = warp; q < wc; q += nwarps) {
         double* col = buf + q * NTP;
         const double ca = colA[j0 + q], cb = colB[j0 + q], cd = colD[j0 + q];
-        for (int k0 = 0; k0 < G; k0 += 32) {
-          const int k = min(k0 + lane, G - 1);
-          double v = spec(ca, cb, cd, k, j0 + q);
-          if (!(isfinite(v) && v != 0.0)) v = repl;
-          if (k0 + lane < G) col[k] = v;
+        for (int g = 0; g < ng; ++g) {
+          const int k = min(g * 32 + lane, G - 1);
+          const bool live = g * 32 + lane < G;
+          const int rg = regime(ca, cb, g);
+          double v;
+          if (rg == 0) {
+            v = repl;
+          } else if (rg == 1) {
+            v = (cb * rowB[k]) * exp_lean(-(ca * rowA[k]), tab);
+          } else if (rg == 2) {
+            v = (cb * rowB[k]) * rcp_fast(expm1_tab(ca * rowA[k], tab));
+          } else {
+            v = spec(ca, cb, cd, k, j0 + q);
+            if (!(isfinite(v) && v != 0.0)) v = repl;
+          }
+          if (live) col[k] = v;
         }
       }
       __syncthreads();
