@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     // ---- 0. set-up.  Every spectrum sample factorises around the Planck denominator:
     //   v[k][j] = colB[j] * rowB[k] / expm1(colA[j] * rowA[k])   (+ the sed.Line terms for type Ia),
     // so divisions, powers and unit conversions are done once per row / column.
-    double rmin = INFINITY, rmax = 0.0, amax = 0.0;   // bounds for the all-valid test
+    double rmin = INFINITY, rmax = 0.0, amax = 0.0, amin = INFINITY;   // bounds for the all-valid test
     for (int k = tid; k < G; k += T) {
       xk[k] = gX[k];
       const double Tk = gT[k], R = gR[k];
@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
           rmin = fmin(rmin, (rb_ > 0.0 && isfinite(rb_)) ? rb_ : 0.0);
           rmax = fmax(rmax, isfinite(rb_) ? rb_ : INFINITY);
           amax = fmax(amax, (ra > 0.0 && isfinite(ra)) ? ra : INFINITY);
+          amin = fmin(amin, (ra > 0.0) ? ra : 0.0);
         }
       } else {
         const double ra = 1.0 / Tk;
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         rmin = fmin(rmin, (rb_ > 0.0 && isfinite(rb_)) ? rb_ : 0.0);
         rmax = fmax(rmax, isfinite(rb_) ? rb_ : INFINITY);
         amax = fmax(amax, (ra > 0.0 && isfinite(ra)) ? ra : INFINITY);
+        amin = fmin(amin, (ra > 0.0) ? ra : 0.0);
         if (line) {
           // sed.Line on the (N_lambda, N_t) grid (sed.py:859-909; supernova_models.py:2295-2303); time is source frame
           const double te = gX[k] / opz;
@@ -411,13 +413,14 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       rmin = fmin(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
       rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
       amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      amin = fmin(amin, __shfl_xor_sync(0xffffffffu, amin, o));
       cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
       cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
       camax = fmax(camax, __shfl_xor_sync(0xffffffffu, camax, o));
     }
     if (lane == 0) {
       red[warp] = rmin; red[8 + warp] = rmax; red[16 + warp] = amax;
-      red[24 + warp] = cmin; red[32 + warp] = cmax; red[40 + warp] = camax;
+      red[24 + warp] = cmin; red[32 + warp] = cmax; red[40 + warp] = camax; red[48 + warp] = amin;
     }
     __syncthreads();
     // bounds of the row factors over each group of 32 consecutive rows (what one warp handles per column): with the
@@ -425,8 +428,8 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     const int ng = (G + 31) >> 5;
     double* g_ralo = grp;                 // min rowA over the group's VALID rows (finite, > 0, finite R^2 > 0); +inf if none
     double* g_rahi = grp + ng;            // max rowA                               } over the whole group,
-    double* g_rblo = grp + 2 * ng;        // min rowB                               } meaningful when g_clean
-    double* g_rbhi = grp + 3 * ng;        // max rowB
+    double* g_rblo = grp + 2 * ng;        // log min rowB                           } meaningful when g_clean
+    double* g_rbhi = grp + 3 * ng;        // log max rowB
     double* g_clean = grp + 4 * ng;       // 1: every row of the group is valid
     for (int g = warp; g < ng; g += nwarps) {
       const int k = g * 32 + lane;
@@ -442,7 +445,11 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         bhi = fmax(bhi, __shfl_xor_sync(0xffffffffu, bhi, o));
       }
       const bool clean = __all_sync(0xffffffffu, ok || !in);
-      if (lane == 0) { g_ralo[g] = lo_v; g_rahi[g] = hi; g_rblo[g] = blo; g_rbhi[g] = bhi; g_clean[g] = clean ? 1.0 : 0.0; }
+      if (lane == 0) {
+        g_ralo[g] = lo_v; g_rahi[g] = hi; g_clean[g] = clean ? 1.0 : 0.0;
+        g_rblo[g] = clean ? log(blo) : -INFINITY;          // logarithms: the validity bounds below are sums
+        g_rbhi[g] = clean ? log(bhi) : INFINITY;
+      }
     }
     // ---- 0b. per-epoch time basis (knot interval + the four non-zero B-splines) and the collocation rows ----------
     for (int e = tid; e < En; e += T) {
@@ -500,15 +507,19 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     bool all_valid;
     double x_hi;
     {
-      double r_lo = INFINITY, r_hi = 0.0, a_hi = 0.0, c_lo = INFINITY, c_hi = 0.0, ca_hi = 0.0;
+      double r_lo = INFINITY, r_hi = 0.0, a_hi = 0.0, a_lo = INFINITY, c_lo = INFINITY, c_hi = 0.0, ca_hi = 0.0;
       for (int w = 0; w < nwarps; ++w) {
         r_lo = fmin(r_lo, red[w]); r_hi = fmax(r_hi, red[8 + w]); a_hi = fmax(a_hi, red[16 + w]);
         c_lo = fmin(c_lo, red[24 + w]); c_hi = fmax(c_hi, red[32 + w]); ca_hi = fmax(ca_hi, red[40 + w]);
+        a_lo = fmin(a_lo, red[48 + w]);
       }
       x_hi = a_hi * ca_hi;
-      // every product colB rowB / expm1(x) is then finite and non-zero in the reference's own evaluation order too
-      // (its erg/s/Hz/cm^2 value is ~1e-7 of ours): x <= 600 and prefactors within [1e-20, 1e250]
-      all_valid = (x_hi < 600.0) && (x_hi > 0.0) && (r_lo * c_lo > 1e-20) && (r_hi * c_hi * (double)NC < 1e250);
+      const double x_lo = a_lo * colA[NL - 1];
+      // every product colB rowB / expm1(x) is then finite and non-zero, in the reference's own evaluation order too (its
+      // erg/s/Hz/cm^2 value is >= 3e-15 of ours): value >= cb R^2 e^-x > 1e-290 and <= cb R^2 / x < 1e250
+      all_valid = (x_hi < 600.0) && (x_lo > 1e-12) && (r_lo > 0.0) && (c_lo > 0.0) &&
+                  (log(r_lo) + log(c_lo) - x_hi > -667.0) &&
+                  (log(r_hi) + log(c_hi) + log((double)NC) - log(fmin(x_lo, 1.0)) < 575.0);
     }
     __syncthreads();                                  // xk (in buf) is dead from here on
     PHOT_PROF_ACC(0);
@@ -540,12 +551,13 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     //   2 planck : x <= 40, all samples valid: value = cb R^2 / expm1(x)
     //   3 general: anything else, and every multi-component / line spectrum
     const bool plain = NC == 1 && !line;
-    auto regime = [&](double ca, double cb, int g) -> int {
+    // every sample of a regime-1/2 group is finite and non-zero, here AND in the reference's own evaluation order (its
+    // erg/s/Hz/cm^2 value is >= 3e-15 of ours): value >= cb R^2 e^-x > 1e-290 and <= cb R^2 / x < 1e250, as sums of logs
+    auto regime = [&](double ca, double lcb, int g) -> int {
       if (!plain) return 3;
       if (ca * g_ralo[g] > 709.782712893384) return 0;
-      const double clo = cb * g_rblo[g], chi = cb * g_rbhi[g];
-      if (g_clean[g] == 0.0 || !(clo > 1e-20) || !(chi < 1e250)) return 3;
       const double xlo = ca * g_ralo[g], xhi = ca * g_rahi[g];
+      if (g_clean[g] == 0.0 || !(lcb + g_rblo[g] - xhi > -667.0) || !(lcb + g_rbhi[g] < 540.0)) return 3;
       if (xlo > 40.0 && xhi <= 650.0) return 1;
       if (xhi <= 40.0 && xlo > 1e-12) return 2;
       return 3;
@@ -587,11 +599,12 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       if (warp < wstat) {
         for (int j = warp; j < NL; j += wstat) {
           const double ca = colA[j], cb = colB[j], cd = colD[j];
+          const double lcb = (cb > 0.0 && cb < INFINITY) ? log(cb) : NAN;
           const double dca = ca - ca_min;
           for (int g = 0; g < ng; ++g) {
             const int k = min(g * 32 + lane, G - 1);
             const bool live = g * 32 + lane < G;
-            const int rg = regime(ca, cb, g);
+            const int rg = regime(ca, lcb, g);
             if (rg == 0) continue;
             if (rg == 1 || rg == 2) {
               // A term more than e^-50 below its row's largest one (the reddest column's, or the Planck peak) cannot
@@ -636,10 +649,11 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       for (int q = warp; q < wc; q += nwarps) {
         double* col = buf + q * NTP;
         const double ca = colA[j0 + q], cb = colB[j0 + q], cd = colD[j0 + q];
+        const double lcb = (cb > 0.0 && cb < INFINITY) ? log(cb) : NAN;
         for (int g = 0; g < ng; ++g) {
           const int k = min(g * 32 + lane, G - 1);
           const bool live = g * 32 + lane < G;
-          const int rg = regime(ca, cb, g);
+          const int rg = regime(ca, lcb, g);
           double v;
           if (rg == 0) {
             v = repl;
