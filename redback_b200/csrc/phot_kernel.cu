@@ -601,25 +601,61 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
           const double ca = colA[j], cb = colB[j], cd = colD[j];
           const double lcb = (cb > 0.0 && cb < INFINITY) ? log(cb) : NAN;
           const double dca = ca - ca_min;
-          for (int g = 0; g < ng; ++g) {
-            const int k = min(g * 32 + lane, G - 1);
-            const bool live = g * 32 + lane < G;
-            const int rg = regime(ca, lcb, g);
-            if (rg == 0) continue;
-            if (rg == 1 || rg == 2) {
+          // four groups of 32 rows per trip: when all of them are in a fast regime the four Planck evaluations of a lane
+          // are independent chains that overlap (the kernel runs at 16 warps per SM: latency is hidden by ILP, not TLP)
+          for (int g0 = 0; g0 < ng; g0 += 4) {
+            int rgs = 0;                                   // four regimes, four bits each
+            bool quad = true, wien = true;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int g = g0 + u;
+              int r = g < ng ? regime(ca, lcb, g) : 0;
               // A term more than e^-50 below its row's largest one (the reddest column's, or the Planck peak) cannot
               // change the sum at 1e-16: the group's samples are all valid, they are counted, not evaluated.
-              if (rg == 1 && g_ralo[g] * dca > 50.0) {
+              if (r == 1 && g_ralo[g] * dca > 50.0) {
                 if (lane == 0) vcnt += (double)min(32, G - g * 32);
-                continue;
+                r = 0;
               }
-              const double x = ca * rowA[k];
-              const double pv = (rg == 1) ? exp_lean(-x, tab) : rcp_fast(expm1_tab(x, tab));
-              if (live) { vsum += (cb * rowB[k]) * pv; vcnt += 1.0; }
+              quad = quad && (r == 1 || r == 2);
+              wien = wien && r == 1;
+              rgs |= r << (4 * u);
+            }
+            if (quad) {
+              double x[4], c[4], pv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int k = min((g0 + u) * 32 + lane, G - 1);
+                x[u] = ca * rowA[k];
+                c[u] = cb * rowB[k];
+              }
+              if (wien) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pv[u] = exp_lean(-x[u], tab);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pv[u] = expm1_tab(x[u], tab);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pv[u] = rcp_fast(pv[u]);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if ((g0 + u) * 32 + lane < G) { vsum += c[u] * pv[u]; vcnt += 1.0; }
               continue;
             }
-            const double v = spec(ca, cb, cd, k, j);
-            if (live && isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
+            for (int u = 0; u < 4; ++u) {
+              const int r = (rgs >> (4 * u)) & 15;
+              if (r == 0) continue;
+              const int k = min((g0 + u) * 32 + lane, G - 1);
+              const bool live = (g0 + u) * 32 + lane < G;
+              if (r == 3) {
+                const double v = spec(ca, cb, cd, k, j);
+                if (live && isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
+              } else {
+                const double x = ca * rowA[k];
+                const double pv = (r == 1) ? exp_lean(-x, tab) : rcp_fast(expm1_tab(x, tab));
+                if (live) { vsum += (cb * rowB[k]) * pv; vcnt += 1.0; }
+              }
+            }
           }
         }
       }
@@ -650,22 +686,58 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         double* col = buf + q * NTP;
         const double ca = colA[j0 + q], cb = colB[j0 + q], cd = colD[j0 + q];
         const double lcb = (cb > 0.0 && cb < INFINITY) ? log(cb) : NAN;
-        for (int g = 0; g < ng; ++g) {
-          const int k = min(g * 32 + lane, G - 1);
-          const bool live = g * 32 + lane < G;
-          const int rg = regime(ca, lcb, g);
-          double v;
-          if (rg == 0) {
-            v = repl;
-          } else if (rg == 1) {
-            v = (cb * rowB[k]) * exp_lean(-(ca * rowA[k]), tab);
-          } else if (rg == 2) {
-            v = (cb * rowB[k]) * rcp_fast(expm1_tab(ca * rowA[k], tab));
-          } else {
-            v = spec(ca, cb, cd, k, j0 + q);
-            if (!(isfinite(v) && v != 0.0)) v = repl;
+        for (int g0 = 0; g0 < ng; g0 += 4) {
+          int rgs = 0;                                     // four regimes, four bits each (15: beyond the last group)
+          bool quad = true, wien = true;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = g0 + u < ng ? regime(ca, lcb, g0 + u) : 15;
+            quad = quad && (r == 1 || r == 2);
+            wien = wien && r == 1;
+            rgs |= r << (4 * u);
           }
-          if (live) col[k] = v;
+          if (quad) {
+            double x[4], c[4], pv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k = min((g0 + u) * 32 + lane, G - 1);
+              x[u] = ca * rowA[k];
+              c[u] = cb * rowB[k];
+            }
+            if (wien) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) pv[u] = exp_lean(-x[u], tab);
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) pv[u] = expm1_tab(x[u], tab);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) pv[u] = rcp_fast(pv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k = (g0 + u) * 32 + lane;
+              if (k < G) col[k] = c[u] * pv[u];
+            }
+            continue;
+          }
+          for (int u = 0; u < 4; ++u) {
+            const int r = (rgs >> (4 * u)) & 15;
+            if (r == 15) continue;
+            const int k = min((g0 + u) * 32 + lane, G - 1);
+            const bool live = (g0 + u) * 32 + lane < G;
+            double v;
+            if (r == 0) {
+              v = repl;
+            } else if (r == 1) {
+              v = (cb * rowB[k]) * exp_lean(-(ca * rowA[k]), tab);
+            } else if (r == 2) {
+              v = (cb * rowB[k]) * rcp_fast(expm1_tab(ca * rowA[k], tab));
+            } else {
+              v = spec(ca, cb, cd, k, j0 + q);
+              if (!(isfinite(v) && v != 0.0)) v = repl;
+            }
+            if (live) col[k] = v;
+          }
         }
       }
       __syncthreads();
@@ -703,10 +775,14 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         p1 = 0.0;
         p2 = 0.0;
         if (active) {
+          // forward fix-up and the division by the pivot first, row by row independent (overlapping latencies); the
+          // recurrence proper then has one FMA per row on its dependency chain
+#pragma unroll 8
+          for (int i = i_lo; i < i_hi; ++i)
+            col[i] = (col[i] + hom[0 * NT + i] * Y1 + hom[1 * NT + i] * Y2) * lut[5 * i + 2];
 #pragma unroll 4
           for (int i = i_hi - 1; i >= i_lo; --i) {
-            const double b = (col[i] + hom[0 * NT + i] * Y1 + hom[1 * NT + i] * Y2) * lut[5 * i + 2];
-            const double x = (b - lut[5 * i + 4] * p2) - lut[5 * i + 3] * p1;
+            const double x = (col[i] - lut[5 * i + 4] * p2) - lut[5 * i + 3] * p1;
             col[i] = x;
             p2 = p1;
             p1 = x;
