@@ -563,6 +563,26 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       return 3;
     };
 
+    // The regimes of all row groups of one column at once: lane = group, the answers travel as ballot masks, so the
+    // loops over groups below test bits instead of re-deriving the regime (which costs more than a fast evaluation).
+    // m[0] dead, m[1] wien, m[2] planck, m[3] wien groups whose terms are all e^-50 below their row's largest (`dca` =
+    // colA - colA of the reddest column); bit g of word g / 32.
+    auto regime_masks = [&](double ca, double lcb, double dca, unsigned long long (&m)[4]) {
+      m[0] = m[1] = m[2] = m[3] = 0ull;
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        if (w == 1 && ng <= 32) break;
+        const int g = w * 32 + lane;
+        const int r = g < ng ? regime(ca, lcb, g) : 15;
+        const bool tail = r == 1 && g_ralo[min(g, ng - 1)] * dca > 50.0;
+        m[0] |= (unsigned long long)__ballot_sync(0xffffffffu, r == 0) << (32 * w);
+        m[1] |= (unsigned long long)__ballot_sync(0xffffffffu, r == 1) << (32 * w);
+        m[2] |= (unsigned long long)__ballot_sync(0xffffffffu, r == 2) << (32 * w);
+        m[3] |= (unsigned long long)__ballot_sync(0xffffffffu, tail) << (32 * w);
+      }
+    };
+    auto quad_bits = [&](unsigned long long mw, int g0) -> unsigned { return (unsigned)(mw >> g0) & 15u; };
+
     // ---- 1. statistics pre-pass for the clean-up value (sed.py:985-992), with the serial LU underneath ----------
     const bool lu_thread = !a.common_time_lu && warp == nwarps - 1;
     if (lu_thread) {
@@ -601,26 +621,23 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
           const double ca = colA[j], cb = colB[j], cd = colD[j];
           const double lcb = (cb > 0.0 && cb < INFINITY) ? log(cb) : NAN;
           const double dca = ca - ca_min;
+          unsigned long long m[4];
+          regime_masks(ca, lcb, dca, m);
+          // A term more than e^-50 below its row's largest one (the reddest column's, or the Planck peak) cannot change
+          // the sum at 1e-16: such groups (all samples valid) are counted, not evaluated.
+          if (lane == 0) {
+            const int nt = __popcll(m[3]);
+            const bool last_tail = (m[3] >> (ng - 1)) & 1ull;
+            vcnt += (double)(32 * nt - (last_tail ? 32 * ng - G : 0));
+          }
           // four groups of 32 rows per trip: when all of them are in a fast regime the four Planck evaluations of a lane
           // are independent chains that overlap (the kernel runs at 16 warps per SM: latency is hidden by ILP, not TLP)
           for (int g0 = 0; g0 < ng; g0 += 4) {
-            int rgs = 0;                                   // four regimes, four bits each
-            bool quad = true, wien = true;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int g = g0 + u;
-              int r = g < ng ? regime(ca, lcb, g) : 0;
-              // A term more than e^-50 below its row's largest one (the reddest column's, or the Planck peak) cannot
-              // change the sum at 1e-16: the group's samples are all valid, they are counted, not evaluated.
-              if (r == 1 && g_ralo[g] * dca > 50.0) {
-                if (lane == 0) vcnt += (double)min(32, G - g * 32);
-                r = 0;
-              }
-              quad = quad && (r == 1 || r == 2);
-              wien = wien && r == 1;
-              rgs |= r << (4 * u);
-            }
-            if (quad) {
+            const unsigned skip = quad_bits(m[0], g0) | quad_bits(m[3], g0);       // dead or counted
+            const unsigned qw = quad_bits(m[1], g0) & ~skip, qp = quad_bits(m[2], g0);
+            const unsigned in4 = ng - g0 >= 4 ? 15u : (1u << (ng - g0)) - 1u;
+            if (skip == in4) continue;
+            if ((qw | qp) == 15u) {
               double x[4], c[4], pv[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
@@ -628,7 +645,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
                 x[u] = ca * rowA[k];
                 c[u] = cb * rowB[k];
               }
-              if (wien) {
+              if (qw == 15u) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) pv[u] = exp_lean(-x[u], tab);
               } else {
@@ -643,17 +660,16 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
               continue;
             }
             for (int u = 0; u < 4; ++u) {
-              const int r = (rgs >> (4 * u)) & 15;
-              if (r == 0) continue;
+              if (((skip | ~in4) >> u) & 1u) continue;
               const int k = min((g0 + u) * 32 + lane, G - 1);
               const bool live = (g0 + u) * 32 + lane < G;
-              if (r == 3) {
+              if (((qw | qp) >> u) & 1u) {
+                const double x = ca * rowA[k];
+                const double pv = ((qw >> u) & 1u) ? exp_lean(-x, tab) : rcp_fast(expm1_tab(x, tab));
+                if (live) { vsum += (cb * rowB[k]) * pv; vcnt += 1.0; }
+              } else {
                 const double v = spec(ca, cb, cd, k, j);
                 if (live && isfinite(v) && v != 0.0) { vsum += v; vcnt += 1.0; }
-              } else {
-                const double x = ca * rowA[k];
-                const double pv = (r == 1) ? exp_lean(-x, tab) : rcp_fast(expm1_tab(x, tab));
-                if (live) { vsum += (cb * rowB[k]) * pv; vcnt += 1.0; }
               }
             }
           }
@@ -686,17 +702,12 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         double* col = buf + q * NTP;
         const double ca = colA[j0 + q], cb = colB[j0 + q], cd = colD[j0 + q];
         const double lcb = (cb > 0.0 && cb < INFINITY) ? log(cb) : NAN;
+        unsigned long long m[4];
+        regime_masks(ca, lcb, 0.0, m);
         for (int g0 = 0; g0 < ng; g0 += 4) {
-          int rgs = 0;                                     // four regimes, four bits each (15: beyond the last group)
-          bool quad = true, wien = true;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int r = g0 + u < ng ? regime(ca, lcb, g0 + u) : 15;
-            quad = quad && (r == 1 || r == 2);
-            wien = wien && r == 1;
-            rgs |= r << (4 * u);
-          }
-          if (quad) {
+          const unsigned qd = quad_bits(m[0], g0), qw = quad_bits(m[1], g0), qp = quad_bits(m[2], g0);
+          const unsigned in4 = ng - g0 >= 4 ? 15u : (1u << (ng - g0)) - 1u;
+          if ((qw | qp) == 15u) {
             double x[4], c[4], pv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -704,7 +715,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
               x[u] = ca * rowA[k];
               c[u] = cb * rowB[k];
             }
-            if (wien) {
+            if (qw == 15u) {
 #pragma unroll
               for (int u = 0; u < 4; ++u) pv[u] = exp_lean(-x[u], tab);
             } else {
@@ -721,16 +732,15 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
             continue;
           }
           for (int u = 0; u < 4; ++u) {
-            const int r = (rgs >> (4 * u)) & 15;
-            if (r == 15) continue;
+            if (!((in4 >> u) & 1u)) continue;
             const int k = min((g0 + u) * 32 + lane, G - 1);
             const bool live = (g0 + u) * 32 + lane < G;
             double v;
-            if (r == 0) {
+            if ((qd >> u) & 1u) {
               v = repl;
-            } else if (r == 1) {
+            } else if ((qw >> u) & 1u) {
               v = (cb * rowB[k]) * exp_lean(-(ca * rowA[k]), tab);
-            } else if (r == 2) {
+            } else if ((qp >> u) & 1u) {
               v = (cb * rowB[k]) * rcp_fast(expm1_tab(ca * rowA[k], tab));
             } else {
               v = spec(ca, cb, cd, k, j0 + q);
