@@ -345,6 +345,14 @@ def run_paths(args, dev, rank, world, local, peak_tflops, lib):
                                                          budget_s=args.parity_budget)
             stats = bp.parity_stats(gm[:n_done], gl[:n_done], rm, rl, magnitudes=bool(w.get("magnitudes")))
             stats["requested"] = par_n
+            # the fused reduction against a host sum over the device's OWN model rows: separates the likelihood
+            # arithmetic from the (for magnitudes: ill-conditioned, see bench_paths.parity_stats) model comparison
+            with np.errstate(all="ignore"):
+                own = np.nan_to_num(np.sum(-0.5 * ((y - gm[:n_done]) / sigma) ** 2 - 0.5 * np.log(2 * np.pi * sigma ** 2),
+                                           axis=1))
+            dd = np.abs(gl[:n_done] - own)
+            stats["fused_logl_vs_host_sum_of_device_model"] = {
+                "max_abs": float(dd.max()), "frac_within_1e-6_or_1e-12_rel": float(np.mean(dd <= 1e-6 + 1e-12 * np.abs(own)))}
             if w.get("population"):
                 # noise + cut replayed by the oracle on ITS magnitudes with the device's own variates
                 from oracle import restated as r

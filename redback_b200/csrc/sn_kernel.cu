@@ -47,7 +47,8 @@ enum {
   SC_SIGMA,      // sampled sigma (RB_SIGMA_SAMPLED / RB_SIGMA_QUADRATURE)
   SC_INV_TAU2,   // 1 / tau_diff^2
   SC_T0,         // explosion epoch t0 (phase_models.t0_base_model) or 0
-  kScalars       // = 16
+  SC_SKIP,       // tau_diff^2 * X: abscissae with te^2 (1 - xm^2) above this are dropped (see sn_prep_kernel)
+  kScalars       // = 17
 };
 
 struct SnArgs {
@@ -168,6 +169,23 @@ __global__ void sn_prep_kernel(const SnArgs a) {
     S[SC_ENG_A] = 2.0 * erot / tp;
     S[SC_ENG_B] = 2.0 * kDay / tp;
   }
+  // Abscissae whose weight exp(-X) cannot matter.  Rigorous bound for the engines that decrease monotonically: the
+  // trapezoid sum is >= L(te) * w_last with w_last = lsp[0] = 10^a0 (the node at xm = 1, exponent 0), the dropped
+  // terms sum to <= L(0) * exp(-X) * sum_i xm_i dw_i <= L(0) exp(-X), so with
+  //   X = ln(L(0)/L(t_end)) - a0 ln 10 + ln(1e13)
+  // they change the result by < 1e-13 relative (gate: 1e-9).  Other engines keep exp(-691) ~ 1e-300.
+  double xskip = -(kExpSkip - 1.0);
+  {
+    double lnr = -1.0;
+    const double lnr_ni = log((6.45e43 + 1.45e43) / (6.45e43 * exp(-t_end / 8.8) + 1.45e43 * exp(-t_end / 111.3)));
+    const double lnr_mag = 2.0 * log1p(S[SC_ENG_B] * t_end);
+    if (a.cfg.engine == RB_ENGINE_NICKEL) lnr = lnr_ni;
+    else if (a.cfg.engine == RB_ENGINE_MAGNETAR) lnr = lnr_mag;
+    else if (a.cfg.engine == RB_ENGINE_MAGNETAR_NICKEL) lnr = fmax(lnr_ni, lnr_mag);   // (A0+B0)/(A1+B1) <= max ratio
+    const double x = lnr - 2.302585092994046 * S[SC_A0] + 29.933606208922594;
+    if (lnr >= 0.0 && x < xskip) xskip = x;     // NaN / inf engines (theta_pb = 0) keep the default
+  }
+  S[SC_SKIP] = xskip * tau2;
   S[SC_RCV] = kRadiusConst * vej;
   double tfloor = 0.0, inv_rec = 0.0;
   if (sed != RB_SED_BOLOMETRIC) {
@@ -617,14 +635,14 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       // first abscissa whose exponent can exceed kExpSkip: te^2 (1 - xm^2) <= -(kExpSkip - 1) tau^2
       int m0 = 0;
       {
-        const double lim = -(kExpSkip - 1.0) * sc[SC_TAU2];
+        const double lim = sc[SC_SKIP];
         if (te2 > lim) {                 // 1 - xm^2 <= 1: nothing to skip otherwise
           int lo = 0, hi = kNodes;       // first m with te2 * omx2[m] <= lim (omx2 decreases with m)
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (te2 * omx2[mid] > lim) lo = mid + 1; else hi = mid;
           }
-          m0 = lo;   // every abscissa kept has exponent >= kExpSkip - 1 > -708 (the table exp's domain)
+          m0 = lo;   // every abscissa kept has exponent >= -691 > -708 (the table exp's domain)
         }
       }
       const int ms = max(m0, 1);  // xm[0] = 1 - lsp[49] = 0 -> integrand 0 there
