@@ -37,9 +37,17 @@ constexpr int kAgWarps = 5;      // warps per block in ag_cell_kernel
 constexpr int kAgCellsPerUnit = 100;  // cells handled by one block of ag_cell_kernel: res = 10 -> 10 rings per unit,
                                       // res = 100 -> one ring per unit (equal work per block whatever the resolution)
 __host__ __device__ inline int ag_rings_per_unit(int nrot) { return nrot >= kAgCellsPerUnit ? 1 : max(1, kAgCellsPerUnit / max(nrot, 1)); }
-// per ring and step; RA_NUCP is the comoving cooling frequency (:363-364), which depends on the ring only: the on-axis
-// observer time it needs is accumulated in the ring kernel's own sequential loop (= np.cumsum order)
-enum { RA_BETA = 0, RA_NE, RA_OMG, RA_R, RA_NUCP, RA_NUMP, RA_PP, RA_KT, RA_G, kRingArrays };
+// per ring and step, everything that does not depend on the cell's azimuth (written by ag_ring_kernel, read by every
+// cell of the ring straight from L1 / L2, lane = step):
+//   RA_RD    R[s] - R[s-1]            (np.diff(R, prepend=0), :347-350)
+//   RA_IBETA 1 / beta                 RA_BETA, RA_G: the Doppler factor needs them separately (:343)
+//   RA_OMG   ring solid angle (:305-306), RA_OMCOS = omega * cos(acos(1 - omega / rotstep)) (:351-352)
+//   RA_FMR   Ne * P'  (F_max without the cell's solid angle, Doppler factor and distance, :365-366)
+//   RA_FBR   2 kT R^2 / c^2           (black-body limit without solid angle, Doppler factor and distance, :367)
+//   RA_NUMP, RA_NUCP comoving nu_m, nu_c and their logarithms RA_LNUMP, RA_LNUCP.  nu_c (:363-364) depends on the ring
+//   only: the on-axis observer time it needs is accumulated in the ring kernel's own sequential loop (= np.cumsum order)
+enum { RA_RD = 0, RA_IBETA, RA_BETA, RA_G, RA_OMG, RA_OMCOS, RA_FMR, RA_FBR, RA_NUMP, RA_NUCP, RA_LNUMP, RA_LNUCP,
+       kRingArrays };
 
 enum {
   AS_OPZ = 0, AS_DL, AS_THV, AS_N, AS_EB, AS_EE, AS_P, AS_XP, AS_FX, AS_XIN, AS_G0, AS_EK, AS_THC, AS_THJ,
@@ -58,7 +66,11 @@ struct AgArgs {
   double* out_model;
   double* out_logl;
   const double* epoch_tab;   // [kEpochCols][E]
-  const int* nu_index;       // [E] index into nu_unique
+  // epochs in time order, `epl` consecutive ones per lane, stored transposed (entry k of lane l at k * 32 + l):
+  const double* ep_t_T;      // [32 * epl] observer time [days]
+  const int* ep_nu_T;        // [32 * epl] index into nu_unique, -1 = padding
+  const int* ep_orig_T;      // [32 * epl] index of the epoch in the caller's order, -1 = padding
+  int epl;
   double nu_unique[kAgMaxNu];
   int n_nu;
   double* scalars;           // [N][kAgScalars]
@@ -320,18 +332,25 @@ __global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t to
         if (p == 2) gm = (1 / log(gmm / ((Ee / xiN) * Gm1 * (AG_MP / AG_ME)))) * (Ee / xiN) * Gm1 * (AG_MP / AG_ME);
         else gm = pow((2 - p) / (p - 1) * (AG_MP / AG_ME) * (Ee / xiN) * Gm1 * pow(gmm, p - 2), 1 / (p - 1));
       }
-      out[RA_BETA * steps + s] = beta;
-      out[RA_NE * steps + s] = Ne;
-      out[RA_OMG * steps + s] = omg;
-      out[RA_R * steps + s] = r_cum;
-      {
+      const double nucp = [&] {
         const double gc = 6.0 * kPi * AG_ME * AG_CC / (G * sigt * B * B * tobso);        // :360
-        out[RA_NUCP * steps + s] = 0.286 * 3.0 * gc * gc * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);   // :361
-      }
-      out[RA_NUMP * steps + s] = 3.0 * xp * gm * gm * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);
-      out[RA_PP * steps + s] = xiN * Fx * AG_ME * AG_C2 * sigt * B / (3.0 * AG_QE);
-      out[RA_KT * steps + s] = gm * AG_ME * AG_C2;
+        return 0.286 * 3.0 * gc * gc * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);          // :361
+      }();
+      const double nump = 3.0 * xp * gm * gm * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);
+      const double pp = xiN * Fx * AG_ME * AG_C2 * sigt * B / (3.0 * AG_QE);
+      const double kt = gm * AG_ME * AG_C2;
+      out[RA_RD * steps + s] = r_diff;
+      out[RA_IBETA * steps + s] = 1.0 / beta;
+      out[RA_BETA * steps + s] = beta;
       out[RA_G * steps + s] = G;
+      out[RA_OMG * steps + s] = omg;
+      out[RA_OMCOS * steps + s] = omg * cos(acos(1.0 - omg / rotstep));
+      out[RA_FMR * steps + s] = Ne * pp;
+      out[RA_FBR * steps + s] = 2.0 * kt * r_cum * r_cum / AG_C2;
+      out[RA_NUMP * steps + s] = nump;
+      out[RA_NUCP * steps + s] = nucp;
+      out[RA_LNUMP * steps + s] = log(nump);
+      out[RA_LNUCP * steps + s] = log(nucp);
     }
     // ---- RK4 (:238-246) ----
     const double F1 = ag_rk4(ghat, dm, G, M, fac, 0.0);
@@ -364,7 +383,7 @@ __device__ __forceinline__ double ag_flux(double fbb, double nuc, double num, do
 // instead of two to four pow.  Comparisons use the original values; |exponent * log| < 1e3 keeps the result within
 // 1e-13 relative of the pow form.  Callers route non-positive / non-finite nu_c, nu_m to ag_flux.
 __device__ __forceinline__ double ag_flux_log(double fbb, double nuc, double num, double nu1, double lnc, double lnm,
-                                              double ln1, double fmax, double p) {
+                                              double ln1, double fmax, double p, double nu1_sq, double sqrt_nu1_over_num) {
   double f = 0.0;
   if (nuc < num) {
     if (num < nu1) f = fmax * exp(-0.5 * (lnm - lnc) - 0.5 * p * (ln1 - lnm));
@@ -375,22 +394,24 @@ __device__ __forceinline__ double ag_flux_log(double fbb, double nuc, double num
     else if (num < nu1) f = fmax * exp(-0.5 * (p - 1.0) * (ln1 - lnm));
     else if (nu1 < num) f = fmax * exp((ln1 - lnm) * (1.0 / 3.0));
   }
-  const double adj = fbb * (nu1 * nu1) * fmax_nan(1.0, sqrt(nu1 / num));
+  const double adj = fbb * nu1_sq * fmax_nan(1.0, sqrt_nu1_over_num);
   return (f < adj) ? f : adj;
 }
 
 // ---- one block per work unit (about kAgCellsPerUnit cells: a few rings of one sample), one warp per cell -------------------------
+// Warps are independent (no block barrier inside the ring loop): the ring arrays are read straight from the scratch
+// buffer (coalesced, lane = step; the ~24 KB of a ring stay in L1 while its cells are processed), only the per-warp
+// observer-time / spectrum arrays and light-curve accumulators live in shared memory.
+// Epochs are handed to the lanes in TIME ORDER, a contiguous run of `epl` epochs per lane (tables built by the host,
+// transposed so that entry k of lane l sits at k * 32 + l): within a run the np.interp interval index only moves
+// forward, so after one binary search per lane the search is a short linear walk.
 __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, int64_t total_units) {
   extern __shared__ double asm_[];
-  const int steps = a.cfg.steps, E = a.E, n_nu = a.n_nu;
-  double* ring = asm_;                         // [kRingArrays][steps]
-  double* ibeta = ring + kRingArrays * steps;  // [steps] 1 / beta                          } per ring and step, shared by
-  double* costh = ibeta + steps;               // [steps] cos(acos(1 - omega / rotstep))    } all cells of the ring
-  double* wbuf = costh + steps;                // per warp: tobs[steps] + flux[n_nu][steps]
-  double* acc = wbuf + (size_t)kAgWarps * (1 + n_nu) * steps;   // [kAgWarps][E]
-  double* sc = acc + (size_t)kAgWarps * E;     // [kAgScalars]
-  double* lognu = sc + kAgScalars;             // [kAgMaxNu] log(nu (1 + z))
-  int* nuidx = reinterpret_cast<int*>(lognu + kAgMaxNu);        // [E]
+  const int steps = a.cfg.steps, E = a.E, n_nu = a.n_nu, epl = a.epl, EP = 32 * a.epl;
+  double* wbuf = asm_;                                           // per warp: tobs[steps] + flux[n_nu][steps]
+  double* acc = wbuf + (size_t)kAgWarps * (1 + n_nu) * steps;    // [kAgWarps][EP]  (position = k * 32 + lane)
+  double* sc = acc + (size_t)kAgWarps * EP;                      // [kAgScalars]
+  double* nutab = sc + kAgScalars;                               // [4][kAgMaxNu]: nu (1+z), its log, sqrt, square
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t u = blockIdx.x;
@@ -406,36 +427,34 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
   const int ring_begin = (int)(u - a.unit_off[n]) * rpu;
   const int ring_end = min(ring_begin + rpu, a.ring_count[n]);
 
-  for (int e = tid; e < E; e += blockDim.x) nuidx[e] = a.nu_index[e];
   double* my_tobs = wbuf + (size_t)warp * (1 + n_nu) * steps;
   double* my_flux = my_tobs + steps;
-  double* my_acc = acc + (size_t)warp * E;
+  double* my_acc = acc + (size_t)warp * EP;
   if (tid < kAgScalars) sc[tid] = a.scalars[n * kAgScalars + tid];
-  if (tid < kAgMaxNu) lognu[tid] = (tid < n_nu) ? log(a.nu_unique[tid] * a.scalars[n * kAgScalars + AS_OPZ]) : 0.0;
-  for (int e = tid; e < kAgWarps * E; e += blockDim.x) acc[e] = 0.0;
+  if (tid < kAgMaxNu) {
+    const double nu1 = (tid < n_nu) ? a.nu_unique[tid] * a.scalars[n * kAgScalars + AS_OPZ] : 1.0;   // nu = nu0*(1+z) :587
+    nutab[tid] = nu1;
+    nutab[kAgMaxNu + tid] = log(nu1);
+    nutab[2 * kAgMaxNu + tid] = sqrt(nu1);
+    nutab[3 * kAgMaxNu + tid] = nu1 * nu1;
+  }
+  for (int e = tid; e < kAgWarps * EP; e += blockDim.x) acc[e] = 0.0;
   __syncthreads();
   {
     const int nrot = (int)sc[AS_NROT];
     const double opz = sc[AS_OPZ], dl = sc[AS_DL], rotstep = sc[AS_ROTSTEP], latstep = sc[AS_LATSTEP];
     const double thv = sc[AS_THV], p = sc[AS_P];
-    const double dl2 = dl * dl;
+    const double inv_dl2 = 1.0 / (dl * dl);
+    const double inv_cc = 1.0 / AG_CC;
     const bool expansion = a.cfg.expansion != 0;
     const double sin_tho = sin(thv), cos_tho = cos(thv);
     const int nlat = (int)sc[AS_RES];
     const double th_lo = latstep - latstep / 2., th_hi = (double)nlat * latstep - latstep / 2.;
     const double ph_lo = rotstep - rotstep / 2., ph_hi = (double)nrot * rotstep - rotstep / 2.;
+    const double day_over_opz = kDay / opz;
 
     for (int i = ring_begin; i < ring_end; ++i) {
-      __syncthreads();  // previous ring's cells are done with `ring`
-      const double* src = a.ring_scratch + (size_t)(a.ring_off[n] + i) * kRingArrays * steps;
-      for (int q = tid; q < kRingArrays * steps; q += blockDim.x) ring[q] = src[q];
-      __syncthreads();
-      // quantities of :343-360 that do not depend on the cell's azimuth, with the reference's own expressions
-      for (int q = tid; q < steps; q += blockDim.x) {
-        ibeta[q] = 1.0 / ring[RA_BETA * steps + q];
-        costh[q] = cos(acos(1.0 - ring[RA_OMG * steps + q] / rotstep));
-      }
-      __syncthreads();
+      const double* __restrict__ ring = a.ring_scratch + (size_t)(a.ring_off[n] + i) * kRingArrays * steps;
       double thi;
       if (nlat == 1) thi = th_lo;
       else if (i == nlat - 1) thi = th_hi;
@@ -461,18 +480,28 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
         ang = (ang > 1.0) ? 1.0 : ((ang < -1.0) ? -1.0 : ang);
         const double obsa = acos(ang);
         const double cosa = cos(obsa);
-        // ---- step2 (:325-370).  Lane l owns steps l, l + 32, ...: consecutive lanes touch consecutive doubles of
-        // every per-step array (no shared-memory bank conflicts); the observer-time cumsum is a warp scan per chunk
+        // the cell's own solid angle (expansion: used until the ring's exceeds it)
+        const double omcos0 = Om0 * cos(acos(1.0 - Om0 / rotstep));
+        const double c_fmax = Om0 / AG_FOURPI / AG_FOURPI * inv_dl2;       // NO * P' * dop^3 / (4 pi dl^2), :365-366
+        // ---- step2 (:325-370).  Lane l owns steps l, l + 32, ...; the observer-time cumsum is a warp scan per chunk
         // of 32 steps with the running total carried between chunks.
-        const double cos_th0 = cos(acos(1.0 - Om0 / rotstep));   // the cell's own solid angle (expansion: until the ring's exceeds it)
         double carry = 0.0;
         for (int sb = 0; sb < steps; sb += 32) {
           const int s = sb + lane;
           const bool live = s < steps;
           const int sc_ = live ? s : steps - 1;
-          const double R = ring[RA_R * steps + sc_];
-          const double rd = R - (sc_ > 0 ? ring[RA_R * steps + sc_ - 1] : 0.0);
-          double tobs = live ? rd * (ibeta[sc_] - cosa) / AG_CC : 0.0;
+          const double beta = __ldg(ring + RA_BETA * steps + sc_), G = __ldg(ring + RA_G * steps + sc_);
+          const double nump = __ldg(ring + RA_NUMP * steps + sc_), nucp = __ldg(ring + RA_NUCP * steps + sc_);
+          const double fmr = __ldg(ring + RA_FMR * steps + sc_), fbr = __ldg(ring + RA_FBR * steps + sc_);
+          const double lnump = __ldg(ring + RA_LNUMP * steps + sc_), lnucp = __ldg(ring + RA_LNUCP * steps + sc_);
+          double omcos = __ldg(ring + RA_OMCOS * steps + sc_);
+          if (expansion) {                                                              // :345-352
+            const double omg = __ldg(ring + RA_OMG * steps + sc_);
+            const double Om = fmax_nan(Om0, omg);
+            if (!(Om == omg)) omcos = omcos0;
+          }
+          double tobs = live ? __ldg(ring + RA_RD * steps + sc_) * (__ldg(ring + RA_IBETA * steps + sc_) - cosa) * inv_cc
+                             : 0.0;                                                     // :353-356
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
             const double up = __shfl_up_sync(0xffffffffu, tobs, o);
@@ -481,58 +510,67 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
           tobs += carry;
           carry = __shfl_sync(0xffffffffu, tobs, 31);
           if (!live) continue;
-          const double G = ring[RA_G * steps + s], beta = ring[RA_BETA * steps + s];
-          const double omg = ring[RA_OMG * steps + s];
-          double Om = omg, cos_thii = costh[s];
-          if (expansion) {
-            Om = fmax_nan(Om0, omg);
-            if (!(Om == omg)) cos_thii = cos_th0;
-          }
-          const double NO = Om0 * ring[RA_NE * steps + s] / AG_FOURPI;
-          const double dop = 1.0 / (G * (1.0 - beta * cosa));
-          const double num = dop * ring[RA_NUMP * steps + s];
-          const double nuc = dop * ring[RA_NUCP * steps + s];
-          const double Fmax = NO * ring[RA_PP * steps + s] * dop * dop * dop / (AG_FOURPI * dl2);
-          const double FBB = 2 * Om * cos_thii * dop * ring[RA_KT * steps + s] * R * R / (AG_C2 * dl2);
+          const double dop = 1.0 / (G * (1.0 - beta * cosa));                           // :343
+          const double num = dop * nump;
+          const double nuc = dop * nucp;
+          const double Fmax = c_fmax * fmr * (dop * dop * dop);
+          const double FBB = omcos * dop * fbr * inv_dl2;                               // :367
           my_tobs[s] = tobs;
           const bool regular = num > 0.0 && num < INFINITY && nuc > 0.0 && nuc < INFINITY;
-          const double lnm = regular ? log(num) : 0.0, lnc = regular ? log(nuc) : 0.0;
-          for (int h = 0; h < n_nu; ++h) {
-            const double nu1 = a.nu_unique[h] * opz;                                   // nu = nu0*(1+z) :587
-            my_flux[h * steps + s] = regular ? ag_flux_log(FBB, nuc, num, nu1, lnc, lnm, lognu[h], Fmax, p)
-                                             : ag_flux(FBB, nuc, num, nu1, Fmax, p);
+          if (regular) {
+            // log(dop * nu') = log(dop) + log(nu'): one logarithm per cell step, the ring's are tabulated
+            const double ld = log(dop);
+            const double lnm = ld + lnump, lnc = ld + lnucp;
+            const double rs = rsqrt(num);
+            for (int h = 0; h < n_nu; ++h)
+              my_flux[h * steps + s] = ag_flux_log(FBB, nuc, num, nutab[h], lnc, lnm, nutab[kAgMaxNu + h], Fmax, p,
+                                                   nutab[3 * kAgMaxNu + h], nutab[2 * kAgMaxNu + h] * rs);
+          } else {
+            for (int h = 0; h < n_nu; ++h) my_flux[h * steps + s] = ag_flux(FBB, nuc, num, nutab[h], Fmax, p);
           }
         }
         __syncwarp();
         // ---- calc_lightcurve (:632-640): np.interp(t/(1+z), tobs, Flux[h]) summed over cells ----
         const double x_first = my_tobs[0], x_last = my_tobs[steps - 1];
-        for (int e = lane; e < E; e += 32) {
-          const double x = (a.epoch_tab[EP_T * E + e] * kDay) / opz;     // :923  time * day_to_s (the table stays in L1;
-                                                                         // a shared copy would cost the third block per SM)
-          const double* fp = my_flux + nuidx[e] * steps;
+        int lo = -1;                     // largest j <= steps - 2 with tobs[j] <= x, carried along the lane's time-ordered run
+        for (int k = 0; k < epl; ++k) {
+          const int pos = k * 32 + lane;
+          const int hh = a.ep_nu_T[pos];
+          if (hh < 0) continue;          // padding
+          const double x = a.ep_t_T[pos] * day_over_opz;                 // :923  time * day_to_s / (1 + z)
+          const double* fp = my_flux + hh * steps;
           double v;
           if (!(x == x)) v = x;
           else if (x <= x_first) v = fp[0];           // numpy: x < xp[0] -> left; x == xp[0] -> fp[0]
           else if (x >= x_last) v = fp[steps - 1];
           else {
-            int lo = 0, hi = steps - 1;   // largest j with tobs[j] <= x
-            while (hi - lo > 1) {
-              const int mid = (lo + hi) >> 1;
-              if (my_tobs[mid] <= x) lo = mid; else hi = mid;
+            int walk = 0;
+            if (lo >= 0)
+              while (walk < 4 && lo < steps - 2 && my_tobs[lo + 1] <= x) { ++lo; ++walk; }
+            if (lo < 0 || walk == 4) {
+              int hi = steps - 1;
+              lo = max(lo, 0);
+              while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (my_tobs[mid] <= x) lo = mid; else hi = mid;
+              }
             }
-            const double slope = (fp[lo + 1] - fp[lo]) / (my_tobs[lo + 1] - my_tobs[lo]);
-            v = slope * (x - my_tobs[lo]) + fp[lo];
+            const double t0 = my_tobs[lo], f0 = fp[lo];
+            const double slope = (fp[lo + 1] - f0) / (my_tobs[lo + 1] - t0);
+            v = slope * (x - t0) + f0;
           }
-          my_acc[e] += v;
+          my_acc[pos] += v;
         }
         __syncwarp();
       }
     }
     __syncthreads();
     // per-unit partial light curve (deterministic: warps summed in order)
-    for (int e = tid; e < E; e += blockDim.x) {
+    for (int q = tid; q < EP; q += blockDim.x) {
+      const int e = a.ep_orig_T[q];
+      if (e < 0) continue;
       double lc = 0.0;
-      for (int w = 0; w < kAgWarps; ++w) lc += acc[w * E + e];
+      for (int w = 0; w < kAgWarps; ++w) lc += acc[w * EP + q];
       a.partial[u * (int64_t)E + e] = lc;
     }
   }

@@ -1012,33 +1012,55 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(ag_cell_kernel)");
 
-  // unique frequencies (np.unique(self.freq), base_models.py:586): E doubles to the host once per call
-  std::vector<double> h_freq((size_t)E);
+  // unique frequencies (np.unique(self.freq), base_models.py:586) and the time order of the epochs: 2 E doubles to the
+  // host once per call
+  std::vector<double> h_freq((size_t)E), h_time((size_t)E);
   RB_CUDA(cudaMemcpyAsync(h_freq.data(), freq_obs, (size_t)E * sizeof(double), cudaMemcpyDeviceToHost, st));
+  RB_CUDA(cudaMemcpyAsync(h_time.data(), t_obs, (size_t)E * sizeof(double), cudaMemcpyDeviceToHost, st));
   RB_CUDA(cudaStreamSynchronize(st));
   std::vector<double> uniq(h_freq);
   std::sort(uniq.begin(), uniq.end());
   uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
   if ((int)uniq.size() > rb::kAgMaxNu)
     return fail(RB_ERR_UNSUPPORTED, "rb_ag_eval: more than 16 distinct frequencies in one call");
-  std::vector<int> h_idx((size_t)E);
-  for (int64_t e = 0; e < E; ++e)
-    h_idx[(size_t)e] = (int)(std::lower_bound(uniq.begin(), uniq.end(), h_freq[(size_t)e]) - uniq.begin());
+  // ag_cell_kernel's epoch tables: epochs in ascending time (NaN last), a run of `epl` consecutive ones per lane,
+  // stored transposed (entry k of lane l at k * 32 + l), padded with -1
+  const int epl = (int)((E + 31) / 32);
+  const size_t EP = (size_t)32 * epl;
+  std::vector<int64_t> order((size_t)E);
+  for (int64_t e = 0; e < E; ++e) order[(size_t)e] = e;
+  std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+    const double tx = h_time[(size_t)x], ty = h_time[(size_t)y];
+    if (tx != tx) return false;
+    if (ty != ty) return true;
+    return tx < ty;
+  });
+  std::vector<double> h_tT(EP, 0.0);
+  std::vector<int> h_nuT(EP, -1), h_origT(EP, -1);
+  for (int64_t r = 0; r < E; ++r) {
+    const int64_t e = order[(size_t)r];
+    const size_t pos = (size_t)(r % epl) * 32 + (size_t)(r / epl);
+    h_tT[pos] = h_time[(size_t)e];
+    h_nuT[pos] = (int)(std::lower_bound(uniq.begin(), uniq.end(), h_freq[(size_t)e]) - uniq.begin());
+    h_origT[pos] = (int)e;
+  }
 
   const int steps = cfg->steps, n_nu = (int)uniq.size();
-  const size_t cell_smem = sizeof(double) * ((size_t)(rb::kRingArrays + 2) * steps +
-                                             (size_t)rb::kAgWarps * (1 + n_nu) * steps + (size_t)rb::kAgWarps * E +
-                                             rb::kAgScalars + rb::kAgMaxNu) + sizeof(int) * (size_t)E;
+  const size_t cell_smem = sizeof(double) * ((size_t)rb::kAgWarps * (1 + n_nu) * steps + (size_t)rb::kAgWarps * EP +
+                                             rb::kAgScalars + 4 * rb::kAgMaxNu);
   if (cell_smem > 220 * 1024) return fail(RB_ERR_UNSUPPORTED, "rb_ag_eval: steps / epochs exceed shared memory");
 
   const int64_t chunk_max = 8192;
-  StreamAlloc b_epoch, b_idx, b_scal, b_cnt, b_off, b_ucnt, b_uoff;
+  StreamAlloc b_epoch, b_tT, b_nuT, b_origT, b_scal, b_cnt, b_off, b_ucnt, b_uoff;
   RB_CUDA(b_epoch.alloc((size_t)rb::kEpochCols * (size_t)E * sizeof(double), st));
-  RB_CUDA(b_idx.alloc((size_t)E * sizeof(int), st));
+  RB_CUDA(b_tT.alloc(EP * sizeof(double), st));
+  RB_CUDA(b_nuT.alloc(EP * sizeof(int), st));
+  RB_CUDA(b_origT.alloc(EP * sizeof(int), st));
   double* d_epoch = b_epoch.as<double>();
-  int* d_idx = b_idx.as<int>();
-  RB_CUDA(cudaMemcpyAsync(d_idx, h_idx.data(), (size_t)E * sizeof(int), cudaMemcpyHostToDevice, st));
-  RB_CUDA(cudaStreamSynchronize(st));  // h_idx is pageable host memory
+  RB_CUDA(cudaMemcpyAsync(b_tT.as<double>(), h_tT.data(), EP * sizeof(double), cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaMemcpyAsync(b_nuT.as<int>(), h_nuT.data(), EP * sizeof(int), cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaMemcpyAsync(b_origT.as<int>(), h_origT.data(), EP * sizeof(int), cudaMemcpyHostToDevice, st));
+  RB_CUDA(cudaStreamSynchronize(st));  // the tables are pageable host memory
   rb::epoch_table_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>((int)E, cfg->sigma_mode, t_obs, freq_obs, y,
                                                                     y ? sigma : nullptr, cfg->upper_limits, d_epoch);
   launch_counter()->fetch_add(1);
@@ -1074,7 +1096,10 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
     a.out_logl = y ? out_logl : nullptr;
     a.want_logl = y ? 1 : 0;
     a.epoch_tab = d_epoch;
-    a.nu_index = d_idx;
+    a.ep_t_T = b_tT.as<double>();
+    a.ep_nu_T = b_nuT.as<int>();
+    a.ep_orig_T = b_origT.as<int>();
+    a.epl = epl;
     for (int h = 0; h < rb::kAgMaxNu; ++h) a.nu_unique[h] = h < n_nu ? uniq[(size_t)h] : 0.0;
     a.n_nu = n_nu;
     a.scalars = b_scal.as<double>();
