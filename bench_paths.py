@@ -175,6 +175,64 @@ def parity_stats(gpu_model, gpu_logl, ref_model, ref_logl, magnitudes=False):
     return out
 
 
+def synthetic_data(w):
+    """Data of a workload: the DEVICE model at the workload's fixed truth + seeded noise (10 % of the model for flux-like
+    outputs, 0.1 mag for magnitudes)."""
+    probe = w["build"](None, None)
+    y_model, _ = probe.evaluate(probe.pack(w["truth"], 1))
+    y_model = y_model[0].cpu().numpy()
+    nrng = np.random.default_rng(4)
+    if w.get("magnitudes"):
+        sigma = np.full(y_model.shape, 0.1)
+        y = y_model + nrng.normal(0, 0.1, y_model.shape)
+    else:
+        sigma = 0.1 * np.abs(y_model) + 1e-300
+        y = y_model + nrng.normal(0, 1, y_model.shape) * sigma
+    return np.where(np.isfinite(y), y, 0.0), sigma
+
+
+def parity_gate(rb, w, path, p, y, sigma, par_n, bandpasses, dev, budget_s=None):
+    """The first `par_n` prior draws of `p` through the device path (model rows and fused log L) and through the CPU
+    oracle on the host cores; returns (parity statistics at the flat north-star tolerances, CPU-port rate)."""
+    import torch
+    ctx = dict(w["ctx"], y=y, sigma=sigma)
+    if "bands" in ctx:
+        ctx["bandpasses"] = bandpasses
+    E = path.E
+    head = {k: v[:par_n] for k, v in p.items()}
+    gm, gl = path.evaluate(path.pack(head, par_n), want_model=True, want_logl=True)
+    gm, gl = gm.cpu().numpy(), gl.cpu().numpy()
+    rm, rl, n_done, core_s, wall = run_oracle(w["kind"], ctx, head, par_n, budget_s=budget_s)
+    stats = parity_stats(gm[:n_done], gl[:n_done], rm, rl, magnitudes=bool(w.get("magnitudes")))
+    stats["requested"] = par_n
+    # the fused reduction against a host sum over the device's OWN model rows: separates the likelihood
+    # arithmetic from the (for magnitudes: ill-conditioned, see parity_stats) model comparison
+    with np.errstate(all="ignore"):
+        own = np.nan_to_num(np.sum(-0.5 * ((y - gm[:n_done]) / sigma) ** 2 - 0.5 * np.log(2 * np.pi * sigma ** 2), axis=1))
+    dd = np.abs(gl[:n_done] - own)
+    stats["fused_logl_vs_host_sum_of_device_model"] = {
+        "max_abs": float(dd.max()), "frac_within_1e-6_or_1e-12_rel": float(np.mean(dd <= 1e-6 + 1e-12 * np.abs(own)))}
+    if w.get("population"):
+        # noise + cut replayed by the oracle on ITS magnitudes with the device's own variates
+        from oracle import restated as r
+        lim = ctx["limiting_mag"]
+        mags = torch.as_tensor(gm[:n_done], device=dev)
+        dev_out = rb.simulate.add_optical_noise_and_cuts(mags, ctx["bands"], lim, seed=99, return_variates=True)
+        ref = np.array([rb.bands.REFERENCE_FLUX[b] for b in ctx["bands"]])
+        exp = r.optical_noise_and_cuts(rm, ref, lim, dev_out["standard_normal"].cpu().numpy())
+        om = dev_out["magnitude"].cpu().numpy()
+        both = np.isfinite(om) & np.isfinite(exp["magnitude"])
+        stats["noise_stage"] = {
+            "max_abs_dmag_observed": float(np.max(np.abs(om - exp["magnitude"])[both])) if both.any() else 0.0,
+            "nan_pattern_mismatches": int(np.sum(np.isnan(om) != np.isnan(exp["magnitude"]))),
+            "detected_mismatches": int(np.sum(dev_out["detected"].cpu().numpy() != exp["detected"]))}
+    cores = os.cpu_count() or 1
+    cpu_port = {"units_per_s_all_cores": n_done * E / wall, "units_per_s_per_core": n_done * E / core_s if core_s else None,
+                "cores": cores, "kind": "port",
+                "sample": f"{n_done} of the same prior draws x {E} epochs, {wall:.1f} s wall"}
+    return stats, cpu_port
+
+
 # ------------------------------------------------------------------------------------------------------------
 # workload table
 # ------------------------------------------------------------------------------------------------------------

@@ -197,10 +197,16 @@ __global__ void ag_scan_kernel(int64_t N, const int* __restrict__ cnt, int64_t* 
   if (threadIdx.x == 0) off[N] = carry;
 }
 
+// x ** (1 / (3 - k)) for the two media the reference allows (k = 0: cube root, k = 2: identity); numpy's pow with the
+// rounded exponent 1/3 differs from the cube root by ln(x) * 1.9e-17 relative
+__device__ __forceinline__ double pow_inv3k(double x, int k, double inv3k) {
+  return (k == 0) ? cbrt(x) : ((k == 2) ? x : pow(x, inv3k));
+}
+
 // RK4_step_numba (:182-192)
 __device__ __forceinline__ double ag_rk4(double ghat, double dm, double g, double m, double fac, double therm) {
   const double ghatm1 = ghat - 1.0;
-  const double dm10 = pow(10.0, dm);
+  const double dm10 = exp10(dm);   // 10**dm
   const double g2 = g * g;
   const double ig = 1.0 / g;
   return fac * dm10 * (ghat * (g2 - 1.0) - ghatm1 * (g - ig)) /
@@ -302,7 +308,7 @@ __global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t to
     {
       const double Gm1 = G - 1.0, G2 = G * G;
       const double beta = sqrt(1 - 1.0 / G2);
-      const double Ne = pow(10.0, dm) / AG_MP;
+      const double Ne = exp10(dm) / AG_MP;
       const double cs = sqrt(AG_C2 * ghat * (ghat - 1) * Gm1 / (1 + ghat * Gm1));
       const double te = asin(cs / (AG_CC * sqrt(G2 - 1.0)));
       double ex = 1.0, omg = omg_noexp;
@@ -311,18 +317,18 @@ __global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t to
         omg = rotstep * (cos_lo - cos(ex / resd + thi + hfac));
       }
       if (s == 0) ex0 = ex;
-      const double r_orig = pow((3.0 - kk) * Ne / (AG_FOURPI * n_amb), inv3k);
+      const double r_orig = pow_inv3k((3.0 - kk) * Ne / (AG_FOURPI * n_amb), a.cfg.k, inv3k);
       double r_inc = r_orig;
       if (s > 0) {
         const double expo = sqrt((1 - cos(latstep + ex0)) / (1 - cos(latstep + ex)));
-        r_inc = (r_orig - r_prev_orig) * pow(expo, inv3k);
+        r_inc = (r_orig - r_prev_orig) * pow_inv3k(expo, a.cfg.k, inv3k);
       }
       r_prev_orig = r_orig;
       const double r_before = r_cum;
       r_cum = (s == 0) ? r_inc : r_cum + r_inc;
       const double r_diff = (s == 0) ? r_cum : r_cum - r_before;                       // np.diff(R, prepend=0), :347-350
       tobso += r_diff * (1.0 / beta - 1.0) / AG_CC;                                    // :353, :356
-      const double n0 = n_amb * pow(r_cum, -kk);
+      const double n0 = (a.cfg.k == 0) ? n_amb : n_amb * pow(r_cum, -kk);             // r**-0.0 == 1
       const double B = sqrt(2 * AG_FOURPI * EB * n0 * AG_MP * AG_C2 * ((ghat * G + 1.0) / (ghat - 1.0)) * Gm1);
       double gm;
       if (p > 2) {
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t to
       out[RA_BETA * steps + s] = beta;
       out[RA_G * steps + s] = G;
       out[RA_OMG * steps + s] = omg;
-      out[RA_OMCOS * steps + s] = omg * cos(acos(1.0 - omg / rotstep));
+      out[RA_OMCOS * steps + s] = omg * (1.0 - omg / rotstep);       // cos(arccos(x)) = x to an ulp (x in [-1, 1], a factor)
       out[RA_FMR * steps + s] = Ne * pp;
       out[RA_FBR * steps + s] = 2.0 * kt * r_cum * r_cum / AG_C2;
       out[RA_NUMP * steps + s] = nump;
@@ -405,7 +411,7 @@ __device__ __forceinline__ double ag_flux_log(double fbb, double nuc, double num
 // Epochs are handed to the lanes in TIME ORDER, a contiguous run of `epl` epochs per lane (tables built by the host,
 // transposed so that entry k of lane l sits at k * 32 + l): within a run the np.interp interval index only moves
 // forward, so after one binary search per lane the search is a short linear walk.
-__global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, int64_t total_units) {
+__global__ void __launch_bounds__(kAgWarps * 32, 4) ag_cell_kernel(const AgArgs a, int64_t total_units) {
   extern __shared__ double asm_[];
   const int steps = a.cfg.steps, E = a.E, n_nu = a.n_nu, epl = a.epl, EP = 32 * a.epl;
   double* wbuf = asm_;                                           // per warp: tobs[steps] + flux[n_nu][steps]
@@ -481,7 +487,7 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
         const double obsa = acos(ang);
         const double cosa = cos(obsa);
         // the cell's own solid angle (expansion: used until the ring's exceeds it)
-        const double omcos0 = Om0 * cos(acos(1.0 - Om0 / rotstep));
+        const double omcos0 = Om0 * (1.0 - Om0 / rotstep);
         const double c_fmax = Om0 / AG_FOURPI / AG_FOURPI * inv_dl2;       // NO * P' * dop^3 / (4 pi dl^2), :365-366
         // ---- step2 (:325-370).  Lane l owns steps l, l + 32, ...; the observer-time cumsum is a warp scan per chunk
         // of 32 steps with the running total carried between chunks.
@@ -533,11 +539,16 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
         // ---- calc_lightcurve (:632-640): np.interp(t/(1+z), tobs, Flux[h]) summed over cells ----
         const double x_first = my_tobs[0], x_last = my_tobs[steps - 1];
         int lo = -1;                     // largest j <= steps - 2 with tobs[j] <= x, carried along the lane's time-ordered run
+        int lo_slope = -1;               // interval whose 1 / (tobs[lo+1] - tobs[lo]) is in `inv_dt`
+        double inv_dt = 0.0;
+        double t_next = a.ep_t_T[lane];
+        int h_next = a.ep_nu_T[lane];
         for (int k = 0; k < epl; ++k) {
           const int pos = k * 32 + lane;
-          const int hh = a.ep_nu_T[pos];
+          const int hh = h_next;
+          const double x = t_next * day_over_opz;                        // :923  time * day_to_s / (1 + z)
+          if (k + 1 < epl) { t_next = a.ep_t_T[pos + 32]; h_next = a.ep_nu_T[pos + 32]; }
           if (hh < 0) continue;          // padding
-          const double x = a.ep_t_T[pos] * day_over_opz;                 // :923  time * day_to_s / (1 + z)
           const double* fp = my_flux + hh * steps;
           double v;
           if (!(x == x)) v = x;
@@ -556,8 +567,8 @@ __global__ void __launch_bounds__(kAgWarps * 32) ag_cell_kernel(const AgArgs a, 
               }
             }
             const double t0 = my_tobs[lo], f0 = fp[lo];
-            const double slope = (fp[lo + 1] - f0) / (my_tobs[lo + 1] - t0);
-            v = slope * (x - t0) + f0;
+            if (lo != lo_slope) { inv_dt = 1.0 / (my_tobs[lo + 1] - t0); lo_slope = lo; }
+            v = fma((fp[lo + 1] - f0) * inv_dt, x - t0, f0);             // slope * (x - xp[lo]) + fp[lo]
           }
           my_acc[pos] += v;
         }
