@@ -560,6 +560,11 @@ int rb_measure_fp64_peak(int iters, double* out_tflops, double* out_ms);
 /* Number of kernel launches issued by this library in the current process. */
 int64_t rb_launch_count(void);
 
+/* Diagnostics of the photometry kernel on the current device: samples processed per clean-up mode since the last reset
+ * (out[0] every spectrum entry valid, [1] single pass, no invalid rows, [2] single pass with the row-mask column,
+ * [3] two passes; [4..7] reasons single-pass mode was refused).  Synchronises the device.  `out` may be null. */
+int rb_phot_mode_counts(uint64_t out[8], int reset);
+
 const char* rb_last_error(void);
 const char* rb_version(void);
 /* digest of the sources the library was built from (bindings compare it with the tree they ship with) */

@@ -116,6 +116,7 @@ EXPORTS = {
     "rb_version": (C.c_char_p, []),
     "rb_source_hash": (C.c_char_p, []),
     "rb_launch_count": (C.c_int64, []),
+    "rb_phot_mode_counts": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "rb_cosmology_flat_lcdm": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.POINTER(C.c_double), C.POINTER(Cosmology)]),
     "rb_cosmology_planck18": (C.c_int, [C.POINTER(Cosmology)]),

@@ -192,6 +192,20 @@ const char* rb_version(void) { return "redback_b200 0.2 (sm_100a)"; }
 const char* rb_source_hash(void) { return "RBHASH:" RB_SOURCE_HASH; }
 int64_t rb_launch_count(void) { return launch_counter()->load(); }
 
+int rb_phot_mode_counts(uint64_t out[8], int reset) {
+  unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (out) {
+    RB_CUDA(cudaDeviceSynchronize());
+    RB_CUDA(cudaMemcpyFromSymbol(h, rb::g_phot_modes, sizeof(h)));
+    for (int i = 0; i < 8; ++i) out[i] = h[i];
+  }
+  if (reset) {
+    const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    RB_CUDA(cudaMemcpyToSymbol(rb::g_phot_modes, z, sizeof(z)));
+  }
+  return RB_OK;
+}
+
 int rb_cosmology_flat_lcdm(double H0, double Om0, double Tcmb0, double Neff, const double m_nu[3],
                            rb_cosmology* out) {
   if (!out || !(H0 > 0)) return fail(RB_ERR_INVALID, "rb_cosmology_flat_lcdm: bad arguments");

@@ -30,17 +30,30 @@
 // band coefficient is < 1e-18 relative.  The mean needed by the clean-up is taken in a statistics pre-pass over ALL
 // columns (terms e^-50 below their row's largest are counted, not summed), skipped when a bound shows that every entry
 // is finite and non-zero; the per-sample banded LU of the time axis (kilonova grids) runs on one thread underneath it.
+// SINGLE-PASS MODE (plain blackbody / cutoff spectra): when a bound shows that every entry of the KEPT columns is valid
+// in every valid row, the only replaced entries are whole rows (NaN / zero / infinite T or R: e.g. the kilonova grid
+// points after exp(t^2 / tau^2) has overflowed).  The replacement value r then enters as  S = S0 + r m 1^T  (m = row
+// mask), and because both solves are linear and B-splines sum to one, every coefficient of epoch e changes by the same
+// r U_e with U_e = b_t(e)^T A_t^-1 m: one extra column through the time-axis solve.  The spectra are then evaluated ONCE
+// (rows of m as zeros), their sum is accumulated on the way, the pre-pass shrinks to the columns below the kept ones
+// (mostly counted, not evaluated), and r U_e is added in the epoch phase.  Without invalid rows nothing is replaced in
+// the kept columns and the pre-pass is skipped altogether.
 #include "rb_common.cuh"
 
 namespace rb {
 
 constexpr int kPhotMaxSpan = 96;     // max B-spline coefficients (along wavelength) overlapped by one band
-constexpr int kEpCols = 8;           // per-epoch record in the block's scratch: h0..h3, first row, y1, y2, band flux
+constexpr int kEpCols = 9;           // per-epoch record in the block's scratch: h0..h3, first row, y1, y2, band flux, U_e
 constexpr int kBlueMargin = 40;      // wavelength columns kept below the bluest band's first coefficient
 constexpr int kScanSteps = 5;        // log2(32)
 
 enum { PH_SED_BLACKBODY = 1, PH_SED_CUTOFF = 2, PH_SED_CUTOFF_LINE = 3 };
 enum { PH_T = 0, PH_R, PH_L, PH_X, kPhotGridCols };   // per-sample model grid: temperature, radius, L_bol, phase
+
+// diagnostics (rb_phot_mode_counts): samples per clean-up mode -- 0 every entry valid, 1 single pass without invalid rows,
+// 2 single pass with the row-mask column, 3 two passes; 4..7 why single-pass mode was refused (negative factors, Planck
+// exponent bound of the kept columns, a zero factor, magnitude bounds)
+__device__ unsigned long long g_phot_modes[8];
 
 struct PhotArgs {
   int64_t N;
@@ -98,7 +111,7 @@ struct PhotArgs {
 // reduction scratch, exp table, column buffer (also the per-epoch coefficient buffer of the last phase)
 __host__ __device__ inline size_t phot_fixed_doubles(int NT, int NL, int n_comp, bool line, bool tables_global) {
   return (size_t)(2 * n_comp + (line ? 2 : 0)) * NT + (tables_global ? 0 : 9 * (size_t)NT) + 4 * (size_t)NL +
-         5 * (size_t)NL + 2 * kScanSteps * 32 * 4 + 64 + 6 * (size_t)((NT + 31) / 32) + kExpTabSize;
+         5 * (size_t)NL + 2 * kScanSteps * 32 * 4 + 128 + 6 * (size_t)((NT + 31) / 32) + kExpTabSize;
 }
 
 // FITPACK fpbspl for k = 3: the four non-zero cubic B-splines at x, t[l] <= x < t[l+1] (0-based l)
@@ -229,7 +242,8 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
   double* lul = colD + NL;                     // [NL][5]  wavelength-axis banded LU, scaled rows
   double* mtab = lul + 5 * NL;                 // [2][kScanSteps][32][4] scan matrices (forward, backward)
   double* red = mtab + 2 * kScanSteps * 32 * 4;   // [64]
-  double* grp = red + 64;                      // [6][ngroups] bounds of rowA / rowB over each group of 32 rows
+  double* red2 = red + 64;                     // [64]
+  double* grp = red2 + 64;                     // [6][ngroups] bounds of rowA / rowB over each group of 32 rows
   double* tab = grp + 6 * ((NT + 31) / 32);    // [1024]
   double* buf = tab + kExpTabSize;             // [W][NTP] column block; later [epochs][span_max] coefficients
   double* ept = gs + (GT ? 9 * (size_t)NT : 0);       // [kEpCols][e_pad]
@@ -340,6 +354,18 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     //   v[k][j] = colB[j] * rowB[k] / expm1(colA[j] * rowA[k])   (+ the sed.Line terms for type Ia),
     // so divisions, powers and unit conversions are done once per row / column.
     double rmin = INFINITY, rmax = 0.0, amax = 0.0, amin = INFINITY;   // bounds for the all-valid test
+    // the same over the VALID rows only (T and R^2 finite and positive), and the rows that are neither valid nor plainly
+    // dead (a negative factor gives finite non-zero entries of the wrong sign: those keep the two-pass path)
+    double v_rmin = INFINITY, v_rmax = 0.0, v_amax = 0.0, v_amin = INFINITY, n_dead = 0.0, n_odd = 0.0;
+    auto row_stats = [&](double ra, double rb_) {
+      const bool ok = ra > 0.0 && ra < INFINITY && rb_ > 0.0 && rb_ < INFINITY;
+      if (ok) {
+        v_rmin = fmin(v_rmin, rb_); v_rmax = fmax(v_rmax, rb_); v_amax = fmax(v_amax, ra); v_amin = fmin(v_amin, ra);
+      } else {
+        n_dead += 1.0;
+        if (ra < 0.0 || rb_ < 0.0) n_odd += 1.0;
+      }
+    };
     for (int k = tid; k < G; k += T) {
       xk[k] = gX[k];
       const double Tk = gT[k], R = gR[k];
@@ -353,6 +379,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
           rmax = fmax(rmax, isfinite(rb_) ? rb_ : INFINITY);
           amax = fmax(amax, (ra > 0.0 && isfinite(ra)) ? ra : INFINITY);
           amin = fmin(amin, (ra > 0.0) ? ra : 0.0);
+          row_stats(ra, rb_);
         }
       } else {
         const double ra = 1.0 / Tk;
@@ -363,6 +390,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         rmax = fmax(rmax, isfinite(rb_) ? rb_ : INFINITY);
         amax = fmax(amax, (ra > 0.0 && isfinite(ra)) ? ra : INFINITY);
         amin = fmin(amin, (ra > 0.0) ? ra : 0.0);
+        row_stats(ra, rb_);
         if (line) {
           // sed.Line on the (N_lambda, N_t) grid (sed.py:859-909; supernova_models.py:2295-2303); time is source frame
           const double te = gX[k] / opz;
@@ -377,6 +405,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       }
     }
     double cmin = INFINITY, cmax = 0.0, camax = 0.0;
+    double k_cmin = INFINITY, k_cmax = 0.0;            // over the kept columns j >= j_first
     for (int j = tid; j < NL; j += T) {
       const double lam_obs = a.lambda_obs[j];
       const double nu = (kCSI / (lam_obs * 1.e-10)) * opz;                       // utils.py:357-362, 383
@@ -406,6 +435,10 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       cmin = fmin(cmin, (cb > 0.0 && isfinite(cb)) ? cb : 0.0);
       cmax = fmax(cmax, isfinite(cb) ? cb : INFINITY);
       camax = fmax(camax, (ca > 0.0 && isfinite(ca)) ? ca : INFINITY);
+      if (j >= j_first) {
+        k_cmin = fmin(k_cmin, (cb > 0.0 && isfinite(cb)) ? cb : 0.0);
+        k_cmax = fmax(k_cmax, isfinite(cb) ? cb : INFINITY);
+      }
     }
     // block-wide bounds: red[0..7] min r, [8..15] max r, [16..23] max rowA, [24..31] min c, [32..39] max c, [40..47] max colA
 #pragma unroll
@@ -417,10 +450,20 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
       cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
       camax = fmax(camax, __shfl_xor_sync(0xffffffffu, camax, o));
+      v_rmin = fmin(v_rmin, __shfl_xor_sync(0xffffffffu, v_rmin, o));
+      v_rmax = fmax(v_rmax, __shfl_xor_sync(0xffffffffu, v_rmax, o));
+      v_amax = fmax(v_amax, __shfl_xor_sync(0xffffffffu, v_amax, o));
+      v_amin = fmin(v_amin, __shfl_xor_sync(0xffffffffu, v_amin, o));
+      n_dead += __shfl_xor_sync(0xffffffffu, n_dead, o);
+      n_odd += __shfl_xor_sync(0xffffffffu, n_odd, o);
+      k_cmin = fmin(k_cmin, __shfl_xor_sync(0xffffffffu, k_cmin, o));
+      k_cmax = fmax(k_cmax, __shfl_xor_sync(0xffffffffu, k_cmax, o));
     }
     if (lane == 0) {
       red[warp] = rmin; red[8 + warp] = rmax; red[16 + warp] = amax;
       red[24 + warp] = cmin; red[32 + warp] = cmax; red[40 + warp] = camax; red[48 + warp] = amin;
+      red2[warp] = v_rmin; red2[8 + warp] = v_rmax; red2[16 + warp] = v_amax; red2[24 + warp] = v_amin;
+      red2[32 + warp] = n_dead; red2[40 + warp] = n_odd; red2[48 + warp] = k_cmin; red2[56 + warp] = k_cmax;
     }
     __syncthreads();
     // bounds of the row factors over each group of 32 consecutive rows (what one warp handles per column): with the
@@ -480,6 +523,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       ept[4 * EP + e] = first;
       ept[5 * EP + e] = 0.0;   // y[j-1] of the wavelength-axis forward elimination
       ept[6 * EP + e] = 0.0;   // y[j-2]
+      ept[8 * EP + e] = 0.0;   // U_e: the row mask's time-axis solution contracted with this epoch's B-splines
     }
     if (!a.common_time_lu) {
       for (int i = tid; i < G; i += T) {
@@ -521,6 +565,28 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
                   (log(r_lo) + log(c_lo) - x_hi > -667.0) &&
                   (log(r_hi) + log(c_hi) + log((double)NC) - log(fmin(x_lo, 1.0)) < 575.0);
     }
+    // single-pass mode: the same bounds over the valid rows and the kept columns only
+    bool single_pass = false;
+    double dead_rows = 0.0;
+    if (NC == 1 && !line && !all_valid) {
+      double r_lo = INFINITY, r_hi = 0.0, a_hi = 0.0, a_lo = INFINITY, c_lo = INFINITY, c_hi = 0.0, odd = 0.0;
+      for (int w = 0; w < nwarps; ++w) {
+        r_lo = fmin(r_lo, red2[w]); r_hi = fmax(r_hi, red2[8 + w]); a_hi = fmax(a_hi, red2[16 + w]);
+        a_lo = fmin(a_lo, red2[24 + w]); dead_rows += red2[32 + w]; odd += red2[40 + w];
+        c_lo = fmin(c_lo, red2[48 + w]); c_hi = fmax(c_hi, red2[56 + w]);
+      }
+      const double xk_hi = a_hi * colA[j_first], xk_lo = a_lo * colA[NL - 1];
+      single_pass = odd == 0.0 && dead_rows < (double)G && (xk_hi < 600.0) && (xk_lo > 1e-12) && (r_lo > 0.0) &&
+                    (c_lo > 0.0) && (log(r_lo) + log(c_lo) - xk_hi > -667.0) &&
+                    (log(r_hi) + log(c_hi) - log(fmin(xk_lo, 1.0)) < 575.0);
+      if (tid == 0 && !single_pass) {
+        const int why = (odd != 0.0) ? 4 : (!(xk_hi < 600.0) || !(xk_lo > 1e-12) || !(dead_rows < (double)G)) ? 5
+                        : (!(r_lo > 0.0) || !(c_lo > 0.0)) ? 6 : 7;
+        atomicAdd(&g_phot_modes[why], 1ull);
+      }
+    }
+    const bool need_mask = single_pass && dead_rows > 0.0;
+    if (tid == 0) atomicAdd(&g_phot_modes[all_valid ? 0 : (single_pass ? (need_mask ? 2 : 1) : 3)], 1ull);
     __syncthreads();                                  // xk (in buf) is dead from here on
     PHOT_PROF_ACC(0);
 
@@ -613,11 +679,13 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       }
     }
     double repl = 0.0;
-    if (!all_valid) {
+    double pre_sum = 0.0, pre_cnt = 0.0;             // single-pass mode: sum / count of the columns below the kept ones
+    if (!all_valid && !(single_pass && !need_mask)) {
       double vsum = 0.0, vcnt = 0.0;
       const int wstat = a.common_time_lu ? nwarps : nwarps - 1;     // the LU warp does not take part
+      const int j_stat_end = single_pass ? j_first : NL;
       if (warp < wstat) {
-        for (int j = warp; j < NL; j += wstat) {
+        for (int j = warp; j < j_stat_end; j += wstat) {
           const double ca = colA[j], cb = colB[j], cd = colD[j];
           const double lcb = (cb > 0.0 && cb < INFINITY) ? log(cb) : NAN;
           const double dca = ca - ca_min;
@@ -681,9 +749,14 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       __syncthreads();
       double s = 0.0, c = 0.0;
       for (int w = 0; w < nwarps; ++w) { s += red[48 + w]; c += red[56 + w]; }
-      double mean = (c > 0) ? s / c : NAN;
-      if (!isfinite(mean) || mean == 0.0) mean = 1.0;
-      repl = 1e-30 * mean;
+      if (single_pass) {
+        pre_sum = s;
+        pre_cnt = c;
+      } else {
+        double mean = (c > 0) ? s / c : NAN;
+        if (!isfinite(mean) || mean == 0.0) mean = 1.0;
+        repl = 1e-30 * mean;
+      }
     } else {
       __syncthreads();
     }
@@ -695,10 +768,21 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     const int i_lo = seg * L, i_hi = min(i_lo + L, G);
     const double* mF = mtab + 4 * seg;
     const double* mB = mtab + kScanSteps * 128 + 4 * seg;
-    for (int j0 = j_first; j0 < NL; j0 += W) {
-      const int wc = min(W, NL - j0);
+    const double fill = single_pass ? 0.0 : repl;     // what a replaced entry holds during the solves
+    double ksum = 0.0;                                // single-pass mode: sum of the kept columns' valid entries
+    for (int it = need_mask ? -1 : 0;; ++it) {
+      const bool mask_it = it < 0;                    // the row mask as an extra column (single-pass mode)
+      const int j0 = j_first + max(it, 0) * W;
+      if (!mask_it && j0 >= NL) break;
+      const int wc = mask_it ? 1 : min(W, NL - j0);
       // 2a. spectra of the block, cleaned
-      for (int q = warp; q < wc; q += nwarps) {
+      if (mask_it) {
+        for (int k = tid; k < G; k += T) {
+          const double ra = rowA[k], rb = rowB[k];
+          buf[k] = (ra > 0.0 && ra < INFINITY && rb > 0.0 && rb < INFINITY) ? 0.0 : 1.0;
+        }
+      }
+      for (int q = warp; q < (mask_it ? 0 : wc); q += nwarps) {
         double* col = buf + q * NTP;
         const double ca = colA[j0 + q], cb = colB[j0 + q], cd = colD[j0 + q];
         const double lcb = (cb > 0.0 && cb < INFINITY) ? log(cb) : NAN;
@@ -727,7 +811,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int k = (g0 + u) * 32 + lane;
-              if (k < G) col[k] = c[u] * pv[u];
+              if (k < G) { const double v = c[u] * pv[u]; col[k] = v; ksum += v; }
             }
             continue;
           }
@@ -736,17 +820,19 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
             const int k = min((g0 + u) * 32 + lane, G - 1);
             const bool live = (g0 + u) * 32 + lane < G;
             double v;
+            bool valid = true;
             if ((qd >> u) & 1u) {
-              v = repl;
+              valid = false;
             } else if ((qw >> u) & 1u) {
               v = (cb * rowB[k]) * exp_lean(-(ca * rowA[k]), tab);
             } else if ((qp >> u) & 1u) {
               v = (cb * rowB[k]) * rcp_fast(expm1_tab(ca * rowA[k], tab));
             } else {
               v = spec(ca, cb, cd, k, j0 + q);
-              if (!(isfinite(v) && v != 0.0)) v = repl;
+              valid = isfinite(v) && v != 0.0;
             }
-            if (live) col[k] = v;
+            if (!valid) v = fill;
+            if (live) { col[k] = v; if (valid) ksum += v; }
           }
         }
       }
@@ -823,7 +909,10 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       // resulting rows
       for (int e = tid; e < En; e += T) {
         const int l = (int)ept[4 * EP + e];
-        if (l >= 0) {
+        if (l >= 0 && mask_it) {
+          const double* c = buf + l;
+          ept[8 * EP + e] = ept[0 * EP + e] * c[0] + ept[1 * EP + e] * c[1] + ept[2 * EP + e] * c[2] + ept[3 * EP + e] * c[3];
+        } else if (l >= 0) {
           const double h0 = ept[0 * EP + e], h1 = ept[1 * EP + e], h2 = ept[2 * EP + e], h3 = ept[3 * EP + e];
           double y1 = ept[5 * EP + e], y2 = ept[6 * EP + e];
           const double* c = buf + l;
@@ -851,6 +940,20 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     //      with the band's contracted weights, done on the way;
     //   b. warp per epoch, only where a coefficient is negative: the integration points split between the lanes, |f|;
     //   c. thread per epoch: magnitude / flux, likelihood term, coalesced store.
+    if (need_mask) {
+      // replacement value (sed.py:985-992) from the sums gathered on the way: kept columns + the columns below them;
+      // every entry of a valid row is valid in the kept columns (single_pass bound), so their count is a product
+      ksum = warp_sum(ksum);
+      if (lane == 0) red[warp] = ksum;
+      __syncthreads();
+      double sacc = pre_sum;
+      for (int w = 0; w < nwarps; ++w) sacc += red[w];
+      const double cacc = pre_cnt + ((double)G - dead_rows) * (double)(NL - j_first);
+      double mean = (cacc > 0) ? sacc / cacc : NAN;
+      if (!isfinite(mean) || mean == 0.0) mean = 1.0;
+      repl = 1e-30 * mean;
+      __syncthreads();
+    }
     double logl_part = 0.0;
     const int SM = a.span_max;
     const int chunk = max(1, min((W * NTP) / SM, 4096));
@@ -866,13 +969,15 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         double x1 = 0.0, x2 = 0.0, lin = 0.0, cneg = 0.0;
         const double* yp = ys + e;
         const double* wgt = a.band_weight + (size_t)b * SM;
+        const double corr = need_mask ? repl * ept[8 * EP + e] : 0.0;   // single-pass mode: r U_e on every coefficient
         for (int j = NL - 1; j >= jlo; --j) {
           const double x = (yp[(size_t)(j - a.j_store_lo) * EP] * lul[5 * j + 2] - lul[5 * j + 4] * x2) - lul[5 * j + 3] * x1;
           if (j < jlo + span) {
-            cb[j - jlo] = x;
-            lin = fma(x, __ldg(wgt + (j - jlo)), lin);
-            cneg = fmin(cneg, x);                               // NaN-safe: fmin drops a NaN operand, handled below
-            if (!(x == x)) cneg = -1.0;
+            const double xc = x + corr;
+            cb[j - jlo] = xc;
+            lin = fma(xc, __ldg(wgt + (j - jlo)), lin);
+            cneg = fmin(cneg, xc);                              // NaN-safe: fmin drops a NaN operand, handled below
+            if (!(xc == xc)) cneg = -1.0;
           }
           x2 = x1;
           x1 = x;
