@@ -205,17 +205,22 @@ __device__ __noinline__ double planck_inv_general(double x, const double* __rest
 }
 
 #ifdef RB_PHOT_PROFILE
-// developer aid (tools/phot_phases.sh): block 0 prints the cycles it spent in each phase of its first samples
-#define PHOT_PROF_BEGIN() long long pt_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pa_ = clock64();
+// developer aid (tools/phot_phases.sh): block 0 prints the cycles it spent in each phase, summed over all its samples
+#define PHOT_PROF_DECL() long long pt_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pa_ = 0; long long pn_ = 0;
+#define PHOT_PROF_BEGIN() pa_ = clock64(); ++pn_;
 #define PHOT_PROF_ACC(i) { __syncthreads(); const long long c_ = clock64(); pt_[i] += c_ - pa_; pa_ = c_; }
-#define PHOT_PROF_END()                                                                                               \
-  if (blockIdx.x == 0 && tid == 0 && n < 3 * (int64_t)gridDim.x)                                                        \
-    printf("phot phases [cycles] setup %lld stats+lu %lld spectra %lld solve %lld contract %lld backsub %lld "          \
-           "integrate %lld finish %lld\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[5], pt_[6], pt_[7]);
+#define PHOT_PROF_END()
+#define PHOT_PROF_REPORT()                                                                                            \
+  if (blockIdx.x == 0 && tid == 0)                                                                                    \
+    printf("phot phases [cycles per sample, %lld samples] setup %lld stats+lu %lld spectra %lld solve %lld contract "  \
+           "%lld backsub %lld integrate %lld finish %lld\n", pn_, pt_[0] / pn_, pt_[1] / pn_, pt_[2] / pn_,            \
+           pt_[3] / pn_, pt_[4] / pn_, pt_[5] / pn_, pt_[6] / pn_, pt_[7] / pn_);
 #else
+#define PHOT_PROF_DECL()
 #define PHOT_PROF_BEGIN()
 #define PHOT_PROF_ACC(i)
 #define PHOT_PROF_END()
+#define PHOT_PROF_REPORT()
 #endif
 
 // GT: the time-axis LU and its homogeneous solutions live in global memory (grids too long for shared memory)
@@ -335,6 +340,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
   }
   __syncthreads();
 
+  PHOT_PROF_DECL();
   for (int64_t n = blockIdx.x; n < a.N; n += gridDim.x) {
     PHOT_PROF_BEGIN();
     const int G = a.grid_len ? a.grid_len[n] : NT;
@@ -650,31 +656,48 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     auto quad_bits = [&](unsigned long long mw, int g0) -> unsigned { return (unsigned)(mw >> g0) & 15u; };
 
     // ---- 1. statistics pre-pass for the clean-up value (sed.py:985-992), with the serial LU underneath ----------
+    // Banded LU of the collocation matrix without pivoting (totally positive), in place, in the scaled layout of
+    // load_lu_row.  The matrix is tridiagonal except for the two not-a-knot rows (1 and G-2), so for rows 3 .. G-3 the
+    // pivots obey d_i = b_i - a_i c_{i-1} / d_{i-1}; with d_i = P_i / P_{i-1} that is the LINEAR recurrence
+    // P_i = b_i P_{i-1} - (a_i c_{i-1}) P_{i-2}: one FMA per row on the serial chain instead of multiply, FMA and a
+    // reciprocal (~200 cycles per row at FP64 latencies).  One thread walks the chain (P in `hom`, which is rebuilt
+    // afterwards) while the other warps run the statistics pre-pass; the reciprocals and row scalings are then done by
+    // all threads in parallel, and the last two rows by one thread again.  |P| shrinks like 0.6^i: no underflow for
+    // any grid that fits.
     const bool lu_thread = !a.common_time_lu && warp == nwarps - 1;
-    if (lu_thread) {
-      if (lane == 0) {
-        // banded LU without pivoting (totally positive collocation matrix), in place, scaled layout of load_lu_row.
-        // The two previous rows stay in registers; the serial chain per row is multiply, FMA, reciprocal.
-        double rd1 = 0.0, u1_1 = 0.0, u2_1 = 0.0, rd2 = 0.0, u1_2 = 0.0, u2_2 = 0.0;
-        double n0 = lut[0], n1 = lut[1], n2 = lut[2], n3 = lut[3], n4 = lut[4];
-        for (int i = 0; i < G; ++i) {
-          const double a0 = n0, a1 = n1, u2 = n4;
-          double d = n2, u1 = n3;
-          if (i + 1 < G) { n0 = lut[5 * i + 5]; n1 = lut[5 * i + 6]; n2 = lut[5 * i + 7]; n3 = lut[5 * i + 8]; n4 = lut[5 * i + 9]; }
-          const double l2 = a0 * rd2;
-          const double am1 = a1 - l2 * u1_2;
-          d -= l2 * u2_2;
-          const double l1 = am1 * rd1;
-          d -= l1 * u1_1;
-          u1 -= l1 * u2_1;
-          const double rd = rcp_fast(d);
-          lut[5 * i + 0] = l2;
-          lut[5 * i + 1] = l1;
-          lut[5 * i + 2] = rd;
-          lut[5 * i + 3] = u1 * rd;
-          lut[5 * i + 4] = u2 * rd;
-          rd2 = rd1; u1_2 = u1_1; u2_2 = u2_1;
-          rd1 = rd; u1_1 = u1; u2_1 = u2;
+    const bool lu_fast = !a.common_time_lu && G >= 10;
+    auto lu_row = [&](int i) {
+      const double a0 = lut[5 * i + 0], a1 = lut[5 * i + 1], a2 = lut[5 * i + 2], a3 = lut[5 * i + 3], a4 = lut[5 * i + 4];
+      double rd1 = 0.0, s1_1 = 0.0, s2_1 = 0.0, rd2 = 0.0, s1_2 = 0.0, s2_2 = 0.0;   // 1/d, u1/d, u2/d of rows i-1, i-2
+      if (i >= 1) { rd1 = lut[5 * i - 3]; s1_1 = lut[5 * i - 2]; s2_1 = lut[5 * i - 1]; }
+      if (i >= 2) { rd2 = lut[5 * i - 8]; s1_2 = lut[5 * i - 7]; s2_2 = lut[5 * i - 6]; }
+      const double am1 = a1 - a0 * s1_2;
+      const double d = (a2 - a0 * s2_2) - am1 * s1_1;
+      const double u1 = a3 - am1 * s2_1;
+      const double rd = rcp_fast(d);
+      lut[5 * i + 0] = a0 * rd2;
+      lut[5 * i + 1] = am1 * rd1;
+      lut[5 * i + 2] = rd;
+      lut[5 * i + 3] = u1 * rd;
+      lut[5 * i + 4] = a4 * rd;
+    };
+    if (lu_thread && lane == 0) {
+      if (!lu_fast) {
+        for (int i = 0; i < G; ++i) lu_row(i);
+      } else {
+        lu_row(0);
+        lu_row(1);
+        lu_row(2);
+        double pm2 = 1.0, pm1 = lut[17] - lut[16] * lut[13];      // P_2 = 1, P_3 = d_3 = b_3 - a_3 (u1/d)_2
+        hom[2] = pm2;
+        hom[3] = pm1;
+#pragma unroll 4
+        for (int i = 4; i <= G - 3; ++i) {
+          const double ac = lut[5 * i + 1] * lut[5 * i - 2];      // a_i c_{i-1} (raw rows)
+          const double pi = fma(lut[5 * i + 2], pm1, -(ac * pm2));
+          hom[i] = pi;
+          pm2 = pm1;
+          pm1 = pi;
         }
       }
     }
@@ -758,6 +781,24 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         repl = 1e-30 * mean;
       }
     } else {
+      __syncthreads();
+    }
+    if (lu_fast) {
+      for (int i = 3 + tid; i <= G - 3; i += T) {
+        const double rd = hom[i - 1] / hom[i];                    // 1 / d_i
+        const double rd_prev = (i == 3) ? lut[12] : hom[i - 2] / hom[i - 1];
+        const double a1 = lut[5 * i + 1], c1 = lut[5 * i + 3], c2 = lut[5 * i + 4];
+        lut[5 * i + 0] = 0.0;
+        lut[5 * i + 1] = a1 * rd_prev;
+        lut[5 * i + 2] = rd;
+        lut[5 * i + 3] = c1 * rd;
+        lut[5 * i + 4] = c2 * rd;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        lu_row(G - 2);
+        lu_row(G - 1);
+      }
       __syncthreads();
     }
     if (!a.common_time_lu) build_tables(G);
@@ -1051,6 +1092,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     PHOT_PROF_ACC(7);
     PHOT_PROF_END();
   }
+  PHOT_PROF_REPORT();
 }
 
 }  // namespace rb
