@@ -156,6 +156,16 @@ typedef struct {
      engines, no t0.  area_ratio = area_projection / area_reference (kwargs, per-call scalars). */
   int aspherical;
   double area_ratio;
+  /* interaction_process=Viscous (interaction_processes.py:229-273; the operator of the TDE fallback models,
+     tde_models.py:1127): L convolved with exp(-(t_e - t) / t_viscous) / t_viscous on 1000 abscissae per epoch instead
+     of Diffusion.  t_viscous [days] travels in the RB_SN_KAPPA row of the parameter block (Viscous takes no opacity;
+     mej / kappa_gamma are unused).  Every engine except RB_ENGINE_CSM; FP64; no t0. */
+  int viscous;
+  /* Epochs before the start of the dense grid (t < 0): Diffusion / Viscous leave them out of `uniq_times` and
+     `np.searchsorted(uniq_times, time)` (interaction_processes.py:63, :271) hands them the luminosity of the FIRST valid
+     epoch, while photosphere and SED see the negative time itself.  The smallest t_obs >= 0 of the call (observer
+     frame, days); only read when some t_obs < 0. */
+  double t_first_valid;
 } rb_sn_config;
 
 /* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */

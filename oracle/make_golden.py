@@ -234,6 +234,43 @@ def dump_aspherical():
     print("aspherical fixtures:", len(doc["draws"]))
 
 
+def dump_viscous():
+    """interaction_processes.Viscous of the reference's own source on seeded draws: nickel-cobalt and magnetar engines on
+    the dense grid of the calling model; includes an epoch before the grid and unsorted epochs."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import warnings
+    warnings.simplefilter("ignore")
+    from oracle import refshim, restated as r
+    ns = refshim.load()
+    rng = np.random.default_rng(2031)
+    t = np.sort(rng.uniform(0.5, 250, 30))
+    t_neg = np.concatenate(([-3.0, -0.5], t[:10][::-1], t[10:]))      # negative and unsorted epochs; time[-1] unchanged
+    doc = {"time": [float(v) for v in t], "time_negative_unsorted": [float(v) for v in t_neg], "draws": []}
+    for i in range(8):
+        prm = dict(mej=float(10 ** rng.uniform(-1, 1.5)), f_nickel=float(10 ** rng.uniform(-2, 0)),
+                   t_viscous=float(10 ** rng.uniform(-2, 2)), p0=float(rng.uniform(1, 10)),
+                   bp=float(10 ** rng.uniform(-1, 1)), mass_ns=float(rng.uniform(1.1, 2.2)),
+                   theta_pb=float(rng.uniform(0.05, 1.57)))
+        dense = np.linspace(0, t[-1] + 100, 1000)
+        lum_ni = r.nickelcobalt_engine(dense, prm["f_nickel"], prm["mej"])
+        lum_mag = r.basic_magnetar(dense * 86400.0, prm["p0"], prm["bp"], prm["mass_ns"], prm["theta_pb"])
+        row = dict(params=prm)
+        for key, lum in (("nickel", lum_ni), ("magnetar", lum_mag)):
+            row[key] = [float(v) for v in ns.interaction_processes.Viscous(t, dense, lum, prm["t_viscous"]).new_luminosity]
+            row[key + "_negative_unsorted"] = [float(v) for v in ns.interaction_processes.Viscous(
+                t_neg, dense, lum, prm["t_viscous"]).new_luminosity]
+        # Diffusion with the same awkward epochs (interaction_processes.py:47, :63)
+        dprm = dict(kappa=float(rng.uniform(0.05, 1)), kappa_gamma=float(10 ** rng.uniform(-2, 2)),
+                    vej=float(10 ** rng.uniform(3.3, 4.5)))
+        row["diffusion_params"] = dprm
+        row["diffusion_negative_unsorted"] = [float(v) for v in ns.interaction_processes.Diffusion(
+            t_neg, dense, lum_ni, dprm["kappa"], dprm["kappa_gamma"], prm["mej"], dprm["vej"]).new_luminosity]
+        doc["draws"].append(row)
+    with open(os.path.join(OUT, "viscous_reference_draws.json"), "w") as fh:
+        json.dump(doc, fh)
+    print("viscous fixtures:", len(doc["draws"]))
+
+
 def dump_csm():
     """_csm_engine + CSMDiffusion (+ TemperatureFloor) of the reference's own sources on seeded prior draws
     (priors/csm_interaction.prior ranges)."""
@@ -382,6 +419,7 @@ if __name__ == "__main__":
     dump_ecsv()
     dump_verbatim()
     dump_aspherical()
+    dump_viscous()
     dump_csm()
     dump_mergernova()
     dump_metzger_magnetar()

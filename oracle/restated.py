@@ -156,6 +156,43 @@ def diffusion(time, dense_times, luminosity, kappa, kappa_gamma, mej, vej):
         return tau_diff, out[np.searchsorted(uniq, time)]                                   # :63
 
 
+def viscous(time, dense_times, luminosity, t_viscous):
+    """interaction_processes.Viscous.convert_input_luminosity (:229-273), step by step.  Returns L_out[E]."""
+    time = np.asarray(time, dtype=float)
+    with np.errstate(all="ignore"):
+        t_end = dense_times[-1]
+        tb = max(0.0, min(dense_times))                                                     # :252-253
+        interp = interp1d(dense_times, luminosity, copy=False, assume_sorted=True)         # :254
+        uniq = np.unique(time[(time >= tb) & (time <= t_end)])                              # :256
+        lu = len(uniq)
+        lsp = np.logspace(np.log10(t_viscous / t_end) - 3, 0, 500)                          # :259-260
+        xm = np.unique(np.concatenate((lsp, 1 - lsp)))                                      # :261
+        nodes = np.clip(tb + (uniq.reshape(lu, 1) - tb) * xm, tb, t_end)                    # :263
+        tes = nodes[:, -1]                                                                  # :265
+        lum = interp(nodes)                                                                 # :266
+        integrand = lum * np.exp((nodes - tes.reshape(lu, 1)) / t_viscous)                  # :267
+        integrand[np.isnan(integrand)] = 0.0                                                # :268
+        out = np.trapezoid(integrand, nodes, axis=1) / t_viscous                            # :270
+        return out[np.searchsorted(uniq, time)]                                             # :272
+
+
+def arnett_bolometric_viscous(time, f_nickel, mej, *, t_viscous, dense_resolution=1000, **_):
+    """supernova_models.arnett_bolometric (:949-969) called with interaction_process=ip.Viscous, t_viscous=..."""
+    time = np.asarray(time, dtype=float)
+    dense_times = np.linspace(0, time[-1] + 100, dense_resolution)
+    return viscous(time, dense_times, nickelcobalt_engine(dense_times, f_nickel, mej), t_viscous)
+
+
+def basic_magnetar_powered_viscous(time, redshift, p0, bp, mass_ns, theta_pb, *, frequency, vej, t_viscous,
+                                   temperature_floor, dl=None, dense_resolution=1000, **_):
+    """supernova_models.basic_magnetar_powered (:1471-1509, flux_density) with interaction_process=ip.Viscous."""
+    def bolometric(t):
+        dense_times = np.linspace(0, t[-1] + 100, dense_resolution)
+        return viscous(t, dense_times, basic_magnetar(dense_times * day_to_s, p0, bp, mass_ns, theta_pb), t_viscous)
+    return _sn_flux_density(time, redshift, bolometric, "blackbody", frequency=frequency, vej=vej,
+                            temperature_floor=temperature_floor, dl=dl)
+
+
 # --------------------------------------------------------------------------------------------------
 # photosphere  (photosphere.py:56-111)
 # --------------------------------------------------------------------------------------------------

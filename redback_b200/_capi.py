@@ -43,7 +43,8 @@ class SnConfig(C.Structure):
                 ("line_duration", C.c_double), ("line_amplitude", C.c_double), ("precision", C.c_int),
                 ("upper_limits", UpperLimits), ("csm_nn", C.c_double), ("csm_delta", C.c_double),
                 ("csm_efficiency", C.c_double), ("t0", C.c_void_p), ("f_nickel", C.c_void_p),
-                ("no_interaction", C.c_int), ("aspherical", C.c_int), ("area_ratio", C.c_double)]
+                ("no_interaction", C.c_int), ("aspherical", C.c_int), ("area_ratio", C.c_double),
+                ("viscous", C.c_int), ("t_first_valid", C.c_double)]
 
 
 KN_ONE_COMPONENT, KN_METZGER = 0, 1
@@ -211,7 +212,7 @@ def check(rc):
 
 def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
               absorption_index=1.0, cosmology=None, line=None, precision=0, csm=None, no_interaction=False,
-              area_ratio=None):
+              area_ratio=None, viscous=False):
     cfg = SnConfig()
     check(lib().rb_sn_config_default(C.byref(cfg)))
     cfg.engine, cfg.sed, cfg.sigma_mode = engine, sed, sigma_mode
@@ -225,6 +226,7 @@ def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff
             setattr(cfg, key, float(val))
     cfg.precision = int(precision)
     cfg.no_interaction = int(bool(no_interaction))
+    cfg.viscous = int(bool(viscous))
     if area_ratio is not None:
         cfg.aspherical, cfg.area_ratio = 1, float(area_ratio)
     if csm is not None:

@@ -12,6 +12,7 @@
 #include "csm_kernel.cu"
 #include "mn_kernel.cu"
 #include "direct_kernel.cu"
+#include "viscous_kernel.cu"
 #include "mk_kernel.cu"
 #include "ag_kernel.cu"
 #include "phot_kernel.cu"
@@ -257,6 +258,19 @@ int rb_sn_config_default(rb_sn_config* cfg) {
   return rb_cosmology_planck18(&cfg->cosmology);
 }
 
+// sn_viscous_kernel: one block per sample (grid-stride), dense grid + 1000 abscissae in shared memory
+static cudaError_t launch_viscous(const rb::SnArgs& a, int64_t n, cudaStream_t st, int sms) {
+  const size_t smem = sizeof(double) * rb::viscous_smem_doubles(a.cfg.dense_resolution);
+  static DeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    return cudaFuncSetAttribute(rb::sn_viscous_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  rb::sn_viscous_kernel<<<(unsigned)std::min<int64_t>(n, (int64_t)sms * 16), 256, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* params, const void* t_obs,
                     const void* freq_obs, const void* y, const void* sigma, const void* sigma_param,
                     const void* out_model, const void* out_logl) {
@@ -269,6 +283,9 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
                                     "without t0");
   if (cfg->engine == RB_ENGINE_MAGNETAR_NICKEL && !cfg->f_nickel)
     return fail(RB_ERR_INVALID, "rb_sn_eval: cfg.f_nickel is required for RB_ENGINE_MAGNETAR_NICKEL");
+  if (cfg->viscous && (cfg->engine == RB_ENGINE_CSM || cfg->t0 != nullptr || cfg->no_interaction || cfg->aspherical ||
+                       cfg->precision != RB_PREC_F64))
+    return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: Viscous is FP64, without t0, for every engine except the CSM shock");
   if (cfg->engine == RB_ENGINE_CSM) {
     // utils.py:304-310: RegularGridInterpolator raises outside the tabulated range of n
     if (!(cfg->csm_nn >= 6.0 && cfg->csm_nn <= 14.0))
@@ -353,6 +370,13 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   if (cfg->engine == RB_ENGINE_CSM) {
     launch_counter()->fetch_add(1);
     return launch_csm(a, t_obs, st, sms);
+  }
+  if (cfg->viscous) {
+    rb::sn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
+    RB_CUDA(launch_viscous(a, N, st, sms));
+    launch_counter()->fetch_add(3);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
   }
   if (cfg->no_interaction || cfg->engine >= RB_ENGINE_FALLBACK) {
     rb::sn_prep_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(a);
@@ -1645,7 +1669,9 @@ static int sn_mag_eval(const rb_sn_config* cfg, const rb_photometry* phot, int64
     a.epochs_in_smem = ep_in_smem;
     if (cfg->engine == RB_ENGINE_CSM) return launch_csm(a, b_tgrid.p, st, sms);
     rb::sn_prep_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, st>>>(a);
-    if (cfg->no_interaction || cfg->engine >= RB_ENGINE_FALLBACK)
+    if (cfg->viscous) {
+      if (launch_viscous(a, nc, st, sms) != cudaSuccess) return fail(RB_ERR_CUDA, "sn_viscous_kernel launch");
+    } else if (cfg->no_interaction || cfg->engine >= RB_ENGINE_FALLBACK)
       rb::sn_direct_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * 32), 256, 0, st>>>(a);
     else
       sn_kern<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * occ_sn * 4), sn_threads, sn_smem, st>>>(a);

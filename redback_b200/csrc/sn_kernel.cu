@@ -630,7 +630,10 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
                                  ep[EP_LOGT * E + e], sc[SC_SIGMA]);
         continue;
       }
-      const double te = a.grid_mode ? (t_in * sc[SC_OPZ]) / sc[SC_OPZ] : t_in / sc[SC_OPZ];   // utils.py:382 (:1012-1014)
+      const double te_real = a.grid_mode ? (t_in * sc[SC_OPZ]) / sc[SC_OPZ] : t_in / sc[SC_OPZ];   // utils.py:382 (:1012-1014)
+      // epochs before the dense grid are left out of uniq_times and np.searchsorted hands them the FIRST valid epoch's
+      // luminosity (interaction_processes.py:47, :63); photosphere and SED below see the negative time itself
+      const double te = (te_real < 0.0) ? a.cfg.t_first_valid / sc[SC_OPZ] : te_real;
       const double te2 = te * te;                                             // interaction_processes.py:55
       // first abscissa whose exponent can exceed kExpSkip: te^2 (1 - xm^2) <= -(kExpSkip - 1) tau^2
       int m0 = 0;
@@ -683,7 +686,7 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
         // ---- photosphere.TemperatureFloor (photosphere.py:87-111) ----
         const double opz = sc[SC_OPZ];
         const double tfloor = sc[SC_TFLOOR];
-        const double rr = sc[SC_RCV] * te;
+        const double rr = sc[SC_RCV] * te_real;
         const double r2 = rr * rr;
         const double rec2 = lbol * sc[SC_INV_REC];
         const bool mask = r2 <= rec2;
@@ -705,7 +708,7 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
           model = num * sc[SC_INV_DEN] / em * kToMJy * opz;                   // supernova_models.py:1007
         } else {
           double mjy = cutoff_blackbody_mjy(a.cfg, lbol, rph, tph, nu, sc[SC_DL]);
-          if (sed == RB_SED_CUTOFF_LINE) mjy = line_sed_mjy(a.cfg, mjy, lbol, te, nu, sc[SC_DL]);   // sed.py:859-909
+          if (sed == RB_SED_CUTOFF_LINE) mjy = line_sed_mjy(a.cfg, mjy, lbol, te_real, nu, sc[SC_DL]);   // sed.py:859-909
           model = mjy * opz;                                                  // supernova_models.py:1597, 2278
         }
       }

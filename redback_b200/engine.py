@@ -313,12 +313,14 @@ class SupernovaPath(_FusedPath):
     def __init__(self, engine, sed, time, frequency=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0,
                  absorption_index=1.0, cosmology=None, device=None, line=None, dtype="float64", csm=None,
-                 no_interaction=False, area_ratio=None):
+                 no_interaction=False, area_ratio=None, viscous=False):
         self.NEEDS_FREQUENCY = sed != _capi.SED_BOLOMETRIC
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength,
                                    absorption_index, cosmology, line, _precision(dtype), csm, no_interaction,
-                                   area_ratio)
+                                   area_ratio, viscous)
         self._engine_rows(engine)
+        if viscous:      # interaction_processes.Viscous takes t_viscous instead of the opacities: it rides in kappa's row
+            self.ROWS = dict(self.ROWS, t_viscous=self.ROWS["kappa"])
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):
@@ -341,11 +343,14 @@ class SupernovaPath(_FusedPath):
             if np.any(~(t > 0)):
                 raise ValueError("Geometric sequence cannot include zero: csm_interaction needs time > 0")
             return
-        if np.any(t < 0):
-            raise NotImplementedError("negative times are not supported on device (the reference maps them "
-                                      "to the first valid epoch)")
         if self.cfg.no_interaction or self.cfg.engine >= _capi.ENGINE_FALLBACK:
-            return
+            return                                   # the engine is evaluated at the epochs themselves, any sign
+        if np.any(t < 0):
+            # interaction_processes.py:47, :63: epochs before the dense grid get the first valid epoch's luminosity
+            valid = t[t >= 0]
+            if valid.size == 0:
+                raise IndexError("index 0 is out of bounds for axis 0 with size 0")      # uniq_lums is empty
+            self.cfg.t_first_valid = float(valid.min())
         if np.max(t) > t[-1] + 100:
             # interaction_processes.py:63 would index past uniq_lums here
             raise IndexError("max(time) exceeds time[-1] + 100: outside the reference's dense grid")
@@ -383,14 +388,17 @@ class SupernovaMagPath(SupernovaPath):
 
     def __init__(self, engine, sed, time, bands, output="magnitude", lambda_array=None, y=None, sigma=None,
                  sigma_mode=_capi.SIGMA_FIXED, dense_resolution=1000, cutoff_wavelength=3000.0, absorption_index=1.0,
-                 cosmology=None, device=None, line=None, csm=None, no_interaction=False, area_ratio=None):
+                 cosmology=None, device=None, line=None, csm=None, no_interaction=False, area_ratio=None,
+                 viscous=False):
         from . import bands as _bands
         if sed == _capi.SED_BOLOMETRIC:
             raise ValueError("bolometric models have no magnitude output")
         self.NEEDS_FREQUENCY = False
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength, absorption_index,
-                                   cosmology, line, 0, csm, no_interaction, area_ratio)
+                                   cosmology, line, 0, csm, no_interaction, area_ratio, viscous)
         self._engine_rows(engine)
+        if viscous:
+            self.ROWS = dict(self.ROWS, t_viscous=self.ROWS["kappa"])
         self._setup(time, None, y, sigma, device)
         lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
         # get_optimal_time_array(0.1, 3000, 300) (utils.py:108); csm_interaction: (0.1, 500, 300) (:2095)

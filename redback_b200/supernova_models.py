@@ -12,7 +12,7 @@ from ._fused import FusedSpec, cosmology_from_kwargs, output_mode, run
 from .engine import SupernovaMagPath, SupernovaPath
 
 _ALLOWED_OPERATORS = {
-    "interaction_process": ("Diffusion", "CSMDiffusion", "AsphericalDiffusion"),
+    "interaction_process": ("Diffusion", "CSMDiffusion", "AsphericalDiffusion", "Viscous"),
     "photosphere": ("TemperatureFloor",),
     "sed": ("Blackbody", "CutoffBlackbody"),
 }
@@ -78,21 +78,30 @@ def _area_ratio(kwargs):
 _USES_MEJ = (_capi.ENGINE_NICKEL, _capi.ENGINE_MAGNETAR_NICKEL, _capi.ENGINE_FALLBACK_NICKEL)
 
 
-def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None, direct=False, _variant=False):
+def _ip_name(kwargs):
+    value = kwargs.get("interaction_process")
+    return value if isinstance(value, str) else getattr(value, "__name__", None)
+
+
+def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None, direct=False, _variant=False,
+          _viscous=False):
     """direct: the model has no interaction process at all (sn_fallback); otherwise `interaction_process=None`
-    selects the direct variant of the same spec (engine luminosity -> photosphere -> SED, :961-968)."""
+    selects the direct variant of the same spec (engine luminosity -> photosphere -> SED, :961-968), and
+    `interaction_process=Viscous` (interaction_processes.py:229-273; kwarg / sampled parameter `t_viscous`) the viscous
+    variant: the opacities are not needed then, `mej` only where the engine itself uses it."""
     is_csm = engine == _capi.ENGINE_CSM
     default_ip = "CSMDiffusion" if is_csm else "Diffusion"
     needed = list(engine_params) + list(_DIFFUSION)
     if is_csm:
         needed = list(engine_params)
-    if direct or _variant:
-        needed = list(engine_params) + (["mej"] if engine in _USES_MEJ and "mej" not in engine_params else []) + ["vej"]
+    if direct or _variant or _viscous:
+        needed = list(engine_params) + (["mej"] if engine in _USES_MEJ and "mej" not in engine_params else []) + \
+            (["vej"] if flux_density or not _viscous else []) + (["t_viscous"] if _viscous else [])
     if flux_density:
         needed = ["redshift"] + needed + ["temperature_floor"]
 
     def validate(kwargs):
-        if not (direct or _variant):
+        if not (direct or _variant or _viscous):
             ip_name = _operator_name("interaction_process", kwargs.get("interaction_process", default_ip), default_ip)
             if ip_name == "AsphericalDiffusion" and not is_csm:
                 _area_ratio(kwargs)
@@ -111,7 +120,7 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
         line = None
         csm = _csm_kwargs(kwargs) if is_csm else None
         no_ip = direct or _variant
-        area_ratio = None if no_ip or is_csm else _area_ratio(kwargs)
+        area_ratio = None if no_ip or is_csm or _viscous else _area_ratio(kwargs)
         if flux_density:
             if fixed_sed is not None:     # type_1a hard-wires CutoffBlackbody + Line (supernova_models.py:2268-2275)
                 sed_id, line = fixed_sed, _line_kwargs(kwargs)
@@ -125,7 +134,8 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
                                         cutoff_wavelength=kwargs.get("cutoff_wavelength", 3000),
                                         absorption_index=kwargs.get("absorption_index", 1.0),
                                         cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"),
-                                        line=line, csm=csm, no_interaction=no_ip, area_ratio=area_ratio)
+                                        line=line, csm=csm, no_interaction=no_ip, area_ratio=area_ratio,
+                                        viscous=_viscous)
         return SupernovaPath(engine, sed_id, time, frequency=kwargs.get("frequency") if flux_density else None,
                              y=y, sigma=sigma, sigma_mode=sigma_mode,
                              dense_resolution=kwargs.get("dense_resolution", 1000),
@@ -133,15 +143,18 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
                              absorption_index=kwargs.get("absorption_index", 1.0),
                              cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"), line=line,
                              dtype=kwargs.get("dtype", "float64"), csm=csm, no_interaction=no_ip,
-                             area_ratio=area_ratio)
+                             area_ratio=area_ratio, viscous=_viscous)
 
     resolver = None
-    if not (direct or _variant or is_csm):
+    if not (direct or _variant or _viscous or is_csm):
         variant = _spec(name + "[no interaction]", engine, engine_params, flux_density, default_sed, fixed_sed,
                         _variant=True)
+        viscous = _spec(name + "[Viscous]", engine, engine_params, flux_density, default_sed, fixed_sed, _viscous=True)
 
         def resolver(kwargs):
-            return variant if "interaction_process" in kwargs and kwargs["interaction_process"] is None else None
+            if "interaction_process" in kwargs and kwargs["interaction_process"] is None:
+                return variant
+            return viscous if _ip_name(kwargs) == "Viscous" else None
     return FusedSpec(name, needed, build, validate, resolver=resolver)
 
 

@@ -380,8 +380,15 @@ def test_edge_shapes(rb):
     assert res.shape == (0, t.size)
     like = rb.GaussianLikelihood(t, out, 0.1 * out, sn.arnett_bolometric)
     assert like.log_likelihood_batch(empty).shape == (0,)
-    with pytest.raises(NotImplementedError):
-        sn.arnett_bolometric(np.array([-1.0, 2.0]), 0.1, 1.0, **kw)
+    # epochs before the dense grid: the reference hands them the first valid epoch's luminosity
+    # (interaction_processes.py:47, :63) and the photosphere / SED the negative time itself
+    tneg = np.array([-1.0, 7.0, 2.0, -0.25, 30.0])
+    h.assert_close(sn.arnett_bolometric(tneg, 0.1, 1.0, **kw), r.arnett_bolometric(tneg, 0.1, 1.0, **kw), RTOL)
+    fkw = dict(kw, temperature_floor=4000.0, frequency=np.full(tneg.size, 5e14))
+    h.assert_close(sn.arnett(tneg, 0.05, 0.1, 1.0, output_format="flux_density", **fkw),
+                   r.arnett(tneg, 0.05, 0.1, 1.0, **fkw), RTOL)
+    with pytest.raises(IndexError):
+        sn.arnett_bolometric(np.array([-1.0, -2.0]), 0.1, 1.0, **kw)   # no valid epoch: uniq_lums is empty
     with pytest.raises(IndexError):
         sn.arnett_bolometric(np.array([500.0, 2.0]), 0.1, 1.0, **kw)   # max(t) > t[-1] + 100
 

@@ -171,3 +171,68 @@ def test_device_reproduces_reference_aspherical_diffusion(asph_fx):
     with pytest.raises(KeyError):
         rb.supernova_models.arnett_bolometric(t, interaction_process="AsphericalDiffusion",
                                               **{k: v for k, v in row["params"].items() if k != "area_reference"})
+
+
+@pytest.fixture(scope="module")
+def visc_fx():
+    with open(os.path.join(ROOT, "tests", "golden", "viscous_reference_draws.json")) as fh:
+        return json.load(fh)
+
+
+def test_oracle_reproduces_reference_viscous(visc_fx):
+    """interaction_processes.Viscous (:229-273) and Diffusion's treatment of negative / unsorted epochs (:47, :63), both
+    against outputs of the reference's own classes (oracle/make_golden.py::dump_viscous)."""
+    t, tn = np.array(visc_fx["time"]), np.array(visc_fx["time_negative_unsorted"])
+    for row in visc_fx["draws"]:
+        p = row["params"]
+        dense = np.linspace(0, t[-1] + 100, 1000)
+        lum_ni = r.nickelcobalt_engine(dense, p["f_nickel"], p["mej"])
+        lum_mag = r.basic_magnetar(dense * 86400.0, p["p0"], p["bp"], p["mass_ns"], p["theta_pb"])
+        for key, lum in (("nickel", lum_ni), ("magnetar", lum_mag)):
+            np.testing.assert_allclose(r.viscous(t, dense, lum, p["t_viscous"]), row[key], rtol=1e-14)
+            np.testing.assert_allclose(r.viscous(tn, dense, lum, p["t_viscous"]), row[key + "_negative_unsorted"],
+                                       rtol=1e-14)
+        d = row["diffusion_params"]
+        np.testing.assert_allclose(r.diffusion(tn, dense, lum_ni, d["kappa"], d["kappa_gamma"], p["mej"], d["vej"])[1],
+                                   row["diffusion_negative_unsorted"], rtol=1e-14)
+
+
+@pytest.mark.gpu
+def test_device_reproduces_reference_viscous(visc_fx):
+    """interaction_process='Viscous' through arnett_bolometric / basic_magnetar_powered_bolometric (scalar calls and a
+    params_batch), epochs before the dense grid and unsorted epochs through Viscous and Diffusion, the flux-density
+    branch and the fused likelihood."""
+    import redback_b200 as rb
+    t, tn = np.array(visc_fx["time"]), np.array(visc_fx["time_negative_unsorted"])
+    rows = visc_fx["draws"]
+    for row in rows:
+        p = row["params"]
+        out = rb.supernova_models.arnett_bolometric(t, p["f_nickel"], p["mej"], interaction_process="Viscous",
+                                                    t_viscous=p["t_viscous"])
+        np.testing.assert_allclose(out, row["nickel"], rtol=1e-9)
+        out = rb.supernova_models.basic_magnetar_powered_bolometric(
+            tn, p["p0"], p["bp"], p["mass_ns"], p["theta_pb"], interaction_process="Viscous", t_viscous=p["t_viscous"])
+        np.testing.assert_allclose(out, row["magnetar_negative_unsorted"], rtol=1e-9)
+        d = row["diffusion_params"]
+        out = rb.supernova_models.arnett_bolometric(tn, p["f_nickel"], p["mej"], **d)
+        np.testing.assert_allclose(out, row["diffusion_negative_unsorted"], rtol=1e-9)
+    batch = {k: np.array([row["params"][k] for row in rows]) for k in ("f_nickel", "mej", "t_viscous")}
+    out = rb.supernova_models.arnett_bolometric(tn, params_batch=batch, interaction_process="Viscous")
+    np.testing.assert_allclose(out, [row["nickel_negative_unsorted"] for row in rows], rtol=1e-9)
+    # flux density + fused likelihood against the oracle restatement (pinned above)
+    nu = np.where(np.arange(t.size) % 2 == 0, 6.272e14, 3.813e14)
+    p = rows[0]["params"]
+    kw = dict(frequency=nu, output_format="flux_density", interaction_process="Viscous", t_viscous=p["t_viscous"],
+              vej=7000.0, temperature_floor=4500.0)
+    out = rb.supernova_models.basic_magnetar_powered(t, 0.07, p["p0"], p["bp"], p["mass_ns"], p["theta_pb"], **kw)
+    ref = r.basic_magnetar_powered_viscous(t, 0.07, p["p0"], p["bp"], p["mass_ns"], p["theta_pb"], frequency=nu,
+                                           vej=7000.0, t_viscous=p["t_viscous"], temperature_floor=4500.0)
+    np.testing.assert_allclose(out, ref, rtol=1e-9)
+    like = rb.GaussianLikelihood(t, ref * 1.02, 0.1 * ref, rb.supernova_models.basic_magnetar_powered, kwargs=kw)
+    pb = dict(redshift=np.array([0.07, 0.07]), p0=np.array([p["p0"], 2 * p["p0"]]), bp=np.full(2, p["bp"]),
+              mass_ns=np.full(2, p["mass_ns"]), theta_pb=np.full(2, p["theta_pb"]))
+    logl = like.log_likelihood_batch(pb)
+    ref_l = r.gaussian_likelihood(ref * 1.02, ref, 0.1 * ref)
+    assert abs(logl[0] - ref_l) <= 1e-6 + 1e-9 * abs(ref_l)
+    with pytest.raises(KeyError):
+        rb.supernova_models.arnett_bolometric(t, 0.1, 1.0, interaction_process="Viscous")      # t_viscous missing
