@@ -166,6 +166,13 @@ typedef struct {
      epoch, while photosphere and SED see the negative time itself.  The smallest t_obs >= 0 of the call (observer
      frame, days); only read when some t_obs < 0. */
   double t_first_valid;
+  /* RB_ENGINE_CSM only.  csm_quadrature != 0: CSMDiffusion's legacy per-epoch integral (kwarg csm_diffusion_method =
+     "quadrature" | "legacy", interaction_processes.py:199-227) on csm_timesteps abscissae (kwarg
+     csm_diffusion_timesteps, default 3000, even, <= 6000) instead of the cumulative recurrence.
+     cfg.f_nickel != NULL with RB_ENGINE_CSM selects csm_nickel (supernova_models.py:2120-2165): the nickel-cobalt engine
+     diffused through mej + mass_csm_threshold on the same grid is added; kappa_gamma is then read from its row. */
+  int csm_quadrature;
+  int csm_timesteps;
 } rb_sn_config;
 
 /* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */

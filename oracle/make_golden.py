@@ -292,7 +292,19 @@ def dump_csm():
         eng = ns._csm_engine(time=tt, **prm)
         tfl = float(10 ** rng.uniform(2, 4))
         ph = ns.photosphere.TemperatureFloor(tt, lbol, prm["vej"], tfl)
-        doc["draws"].append(dict(params=dict(prm, temperature_floor=tfl), skip=0 if i % 4 else 6,
+        extra = {}
+        if i < 6:
+            # the legacy quadrature method and csm_nickel (both methods) on the first draws
+            extra["lbol_quadrature"] = [float(v) for v in ns.csm_interaction_bolometric(
+                tt, csm_diffusion_method="quadrature", **prm)]
+            nprm = dict(f_nickel=float(10 ** rng.uniform(-2, 0)), ek=float(10 ** rng.uniform(50.5, 52)),
+                        kappa_gamma=float(10 ** rng.uniform(-2, 2)))
+            cprm = {k: v for k, v in prm.items() if k != "vej"}
+            extra["nickel_params"] = nprm
+            extra["csm_nickel_lbol"] = [float(v) for v in ns.csm_nickel_bolometric(tt, **cprm, **nprm)]
+            extra["csm_nickel_lbol_quadrature"] = [float(v) for v in ns.csm_nickel_bolometric(
+                tt, csm_diffusion_method="legacy", csm_diffusion_timesteps=1000, **cprm, **nprm)]
+        doc["draws"].append(dict(params=dict(prm, temperature_floor=tfl), skip=0 if i % 4 else 6, **extra,
                                  r_photosphere=float(eng.r_photosphere),
                                  mass_csm_threshold=float(eng.mass_csm_threshold),
                                  engine_lbol=[float(v) for v in eng.lbol], lbol=[float(v) for v in lbol],

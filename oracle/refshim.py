@@ -132,9 +132,10 @@ def load_csm():
                km_cgs=r.km_cgs, day_to_s=r.day_to_s, ip=ns.interaction_processes)
     load_functions("redback/utils.py", ["get_csm_properties", "get_optimal_time_array",
                                          "_get_optimal_time_array_cached"], glb)
-    load_functions("redback/transient_models/supernova_models.py", ["_csm_engine", "csm_interaction_bolometric"], glb)
+    load_functions("redback/transient_models/supernova_models.py", ["_csm_engine", "csm_interaction_bolometric",
+                                                                     "csm_nickel_bolometric", "_nickelcobalt_engine"], glb)
     out = types.SimpleNamespace(**{k: glb[k] for k in ("get_csm_properties", "get_optimal_time_array", "_csm_engine",
-                                                       "csm_interaction_bolometric")})
+                                                       "csm_interaction_bolometric", "csm_nickel_bolometric")})
     out.photosphere = ns.photosphere
     out.interaction_processes = ns.interaction_processes
     return out

@@ -784,12 +784,66 @@ def csm_diffusion(time, dense_times, luminosity, kappa, r_photosphere, mass_csm_
     return np.interp(time, knots, out)
 
 
-def csm_interaction_bolometric(time, mej, csm_mass, vej, eta, rho, kappa, r0, *, dense_resolution=1000, **kw):
+def csm_diffusion_quadrature(time, dense_times, luminosity, kappa, r_photosphere, mass_csm_threshold, timesteps=3000):
+    """CSMDiffusion._convert_input_luminosity_quadrature (interaction_processes.py:199-227; csm_diffusion_method =
+    'quadrature' | 'legacy')."""
+    time = np.asarray(time, dtype=float)
+    dense_times = np.asarray(dense_times, dtype=float)
+    t0 = kappa * mass_csm_threshold / (4. * np.pi ** 3. / 9. * speed_of_light * r_photosphere) / day_to_s   # :171-173
+    with np.errstate(all="ignore"):
+        tb = max(0.0, min(dense_times))                                                             # :205-206
+        uniq = np.unique(time[(time >= tb) & (time <= dense_times[-1])])                            # :207
+        lu = len(uniq)
+        num = int(round(timesteps / 2.0))                                                           # :210
+        log_start = min(np.log10(t0 / dense_times[-1]) + -3, 0.0)                                   # :211
+        lsp = np.logspace(log_start, 0, num)
+        xm = np.unique(np.concatenate((lsp, 1 - lsp)))                                              # :213
+        xm = xm[(xm >= 0.0) & (xm <= 1.0)]
+        xm = np.unique(np.concatenate(([0.0], xm, [1.0])))                                          # :215
+        nodes = tb + (uniq.reshape(lu, 1) - tb) * xm                                                # :217
+        lum = np.interp(nodes.ravel(), dense_times, luminosity).reshape(nodes.shape)                # :220
+        integrand = lum * np.exp((nodes - uniq.reshape(lu, 1)) / t0)                                # :221
+        integrand[np.isnan(integrand)] = 0.0
+        out = np.trapezoid(integrand, nodes, axis=1) / t0                                           # :224-225
+        return out[np.searchsorted(uniq, time)]
+
+
+def csm_interaction_bolometric(time, mej, csm_mass, vej, eta, rho, kappa, r0, *, dense_resolution=1000,
+                               csm_diffusion_method="cumulative", csm_diffusion_timesteps=3000, **kw):
     """supernova_models.py:2001-2050 with the default interaction process."""
     time = np.atleast_1d(np.asarray(time, dtype=float))
     dense = get_optimal_time_array(min(0.1, np.min(time)), np.max(time) + 100, dense_resolution, user_times=time)
     lbol, r_ph, m_th = csm_engine(dense, mej, csm_mass, vej, eta, rho, kappa, r0, **kw)
+    if csm_diffusion_method in ("quadrature", "legacy"):
+        return csm_diffusion_quadrature(time, dense, lbol, kappa, r_ph, m_th, csm_diffusion_timesteps)
     return csm_diffusion(time, dense, lbol, kappa, r_ph, m_th)
+
+
+def csm_nickel_bolometric(time, mej, f_nickel, csm_mass, ek, eta, rho, kappa, r0, *, kappa_gamma, dense_resolution=1000,
+                          csm_diffusion_method="cumulative", csm_diffusion_timesteps=3000, **kw):
+    """supernova_models.csm_nickel_bolometric (:2120-2165): CSM shock + nickel diffused through mej + the optically
+    thick CSM, both on the adaptive grid."""
+    time = np.atleast_1d(np.asarray(time, dtype=float))
+    vej = np.sqrt(2.0 * ek / (mej * solar_mass)) / km_cgs                                           # :2140
+    dense = get_optimal_time_array(min(0.01, np.min(time)), np.max(time) + 100, dense_resolution, user_times=time)
+    lbol, r_ph, m_th = csm_engine(dense, mej, csm_mass, vej, eta, rho, kappa, r0, **kw)
+    mej_eff = mej + m_th / solar_mass                                                               # :2148
+    nickel = diffusion(time, dense, nickelcobalt_engine(dense, f_nickel, mej), kappa, kappa_gamma, mej_eff, vej)[1]
+    if csm_diffusion_method in ("quadrature", "legacy"):
+        csm = csm_diffusion_quadrature(time, dense, lbol, kappa, r_ph, m_th, csm_diffusion_timesteps)
+    else:
+        csm = csm_diffusion(time, dense, lbol, kappa, r_ph, m_th)
+    return nickel + csm                                                                             # :2165
+
+
+def csm_nickel(time, redshift, mej, f_nickel, csm_mass, ek, eta, rho, kappa, r0, *, frequency, temperature_floor,
+               kappa_gamma, dl=None, **kw):
+    """supernova_models.csm_nickel (:2168-2200, flux_density): TemperatureFloor + Blackbody, mJy."""
+    vej = np.sqrt(2.0 * ek / (mej * solar_mass)) / km_cgs
+    return _sn_flux_density(
+        time, redshift,
+        lambda t: csm_nickel_bolometric(t, mej, f_nickel, csm_mass, ek, eta, rho, kappa, r0, kappa_gamma=kappa_gamma, **kw),
+        "blackbody", frequency=frequency, vej=vej, temperature_floor=temperature_floor, dl=dl)
 
 
 def csm_interaction(time, redshift, mej, csm_mass, vej, eta, rho, kappa, r0, *, frequency, temperature_floor,

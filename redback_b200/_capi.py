@@ -44,7 +44,8 @@ class SnConfig(C.Structure):
                 ("upper_limits", UpperLimits), ("csm_nn", C.c_double), ("csm_delta", C.c_double),
                 ("csm_efficiency", C.c_double), ("t0", C.c_void_p), ("f_nickel", C.c_void_p),
                 ("no_interaction", C.c_int), ("aspherical", C.c_int), ("area_ratio", C.c_double),
-                ("viscous", C.c_int), ("t_first_valid", C.c_double)]
+                ("viscous", C.c_int), ("t_first_valid", C.c_double), ("csm_quadrature", C.c_int),
+                ("csm_timesteps", C.c_int)]
 
 
 KN_ONE_COMPONENT, KN_METZGER = 0, 1
@@ -231,6 +232,8 @@ def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff
         cfg.aspherical, cfg.area_ratio = 1, float(area_ratio)
     if csm is not None:
         cfg.csm_nn, cfg.csm_delta, cfg.csm_efficiency = (float(csm[k]) for k in ("nn", "delta", "efficiency"))
+        cfg.csm_quadrature = int(bool(csm.get("quadrature", False)))
+        cfg.csm_timesteps = int(csm.get("timesteps", 3000))
     return cfg
 
 

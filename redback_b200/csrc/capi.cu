@@ -102,9 +102,12 @@ size_t sn_smem_bytes(int D, int64_t E, bool epochs_in_smem, bool fp32 = false) {
   return sizeof(double) * n;
 }
 
-size_t csm_smem_bytes(int D, int64_t E) {
-  const size_t M = (size_t)D + (size_t)E;
-  return sizeof(double) * ((size_t)rb::kExpTabSize + 2 * (size_t)D + 4 * M + (size_t)E + 96) + sizeof(int) * (size_t)E;
+size_t csm_smem_bytes(int D, int64_t E, int quad_timesteps = 0) {
+  size_t M4 = 4 * ((size_t)D + (size_t)E);
+  // quadrature method: the knot arrays hold timesteps / 2 + timesteps abscissae instead
+  if ((size_t)quad_timesteps * 3 / 2 + 4 > M4) M4 = (size_t)quad_timesteps * 3 / 2 + 4;
+  return sizeof(double) * ((size_t)rb::kExpTabSize + 3 * (size_t)D + M4 + 3 * (size_t)E + 160 + 96) +
+         sizeof(int) * (size_t)E;
 }
 
 // CSM engine (RB_ENGINE_CSM): unique epochs -> per-sample scalars -> one block per sample.  `t_dev` are the E
@@ -117,7 +120,7 @@ int launch_csm(rb::SnArgs a, const double* t_dev, cudaStream_t st, int sms) {
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(csm_kernel)");
   const int E = a.E;
-  const size_t smem = csm_smem_bytes(a.cfg.dense_resolution, E);
+  const size_t smem = csm_smem_bytes(a.cfg.dense_resolution, E, a.cfg.csm_quadrature ? a.cfg.csm_timesteps : 0);
   if (smem > 220 * 1024)
     return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval (CSM): dense_resolution + number of epochs exceed shared memory");
   StreamAlloc b_ut, b_ui, b_sc;
@@ -255,6 +258,7 @@ int rb_sn_config_default(rb_sn_config* cfg) {
   cfg->csm_nn = 12.0;
   cfg->csm_delta = 1.0;
   cfg->csm_efficiency = 0.5;
+  cfg->csm_timesteps = 3000;
   return rb_cosmology_planck18(&cfg->cosmology);
 }
 
@@ -293,6 +297,8 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
     if (cfg->precision != RB_PREC_F64) return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: the CSM path is FP64 only");
     if (cfg->dense_resolution < 20) return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution must be >= 20 (CSM)");
     if (cfg->t0 != nullptr) return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: t0 is not available for the CSM engine");
+    if (cfg->csm_quadrature && (cfg->csm_timesteps < 4 || cfg->csm_timesteps > 6000 || (cfg->csm_timesteps & 1)))
+      return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: csm_diffusion_timesteps must be even and in [4, 6000] on device");
   }
   if (cfg->sed < RB_SED_BOLOMETRIC || cfg->sed > RB_SED_CUTOFF_LINE)
     return fail(RB_ERR_INVALID, "rb_sn_eval: unknown sed");

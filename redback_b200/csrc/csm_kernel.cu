@@ -5,6 +5,12 @@
 // The recurrence  new[i+1] = new[i] e^{-dt/t0} + L_i (1 - e^{-dt/t0}) + s_i (dt - t0 (1 - e^{-dt/t0}))  over the merged
 // knots unique(dense ∪ epochs) is a chain of affine maps; it is evaluated as a block-wide scan of (a_i, b_i) pairs
 // (per-thread chunks + warp-shuffle scan), not by the reference's sequential Python loop.
+// Two further options of the same path:
+//  * csm_diffusion_method = "quadrature" | "legacy" (interaction_processes.py:199-227): per unique epoch the convolution
+//    with exp((t - t_e) / t0) / t0 on `csm_diffusion_timesteps` abscissae between the grid start and the epoch, the
+//    luminosity by np.interp on the adaptive grid; one thread per unique epoch, the interval index walks forward;
+//  * csm_nickel (supernova_models.py:2120-2165): the nickel-cobalt engine on the SAME adaptive grid through
+//    Diffusion (:33-65) with mej_eff = mej + mass_csm_threshold / Msun, added to the CSM luminosity.
 // (included by capi.cu after sn_kernel.cu and kn_kernel.cu, whose device helpers it uses)
 
 namespace rb {
@@ -16,7 +22,7 @@ constexpr double kAu = 14959787070000.0;   // constants.au_cgs
 enum CsmScalar {
   CS_OPZ = 0, CS_T0, CS_TFS, CS_TRS, CS_CFS, CS_CRS, CS_ALPHA, CS_EFF,
   CS_RCV, CS_TFLOOR, CS_INV_REC, CS_INV_DEN, CS_DL, CS_SIGMA,
-  CS_TMIN, CS_EMIN, CS_EMAX, CS_TMAX, CS_LTMIN, CS_LEMIN, CS_LEMAX, CS_LTMAX, CS_NB, CS_NU, CS_NA,
+  CS_TMIN, CS_EMIN, CS_EMAX, CS_TMAX, CS_LTMIN, CS_LEMIN, CS_LEMAX, CS_LTMAX, CS_NB, CS_NU, CS_NA, CS_MTH,
   kCsmScalars
 };
 
@@ -147,7 +153,8 @@ __global__ void csm_prep_kernel(const CsmArgs c) {
   const double u0 = c.utime[0], u1 = c.utime[Eu - 1];
   const double umin = a.grid_mode ? (u0 * opz) / opz : u0 / opz;
   const double umax = a.grid_mode ? (u1 * opz) / opz : u1 / opz;
-  const double tmin = fmin(0.1, umin), tmax = umax + 100.0;
+  // dense_time_min: min(0.1, min t) for csm_interaction (:2028), min(0.01, min t) for csm_nickel (:2143)
+  const double tmin = fmin(a.cfg.f_nickel != nullptr ? 0.01 : 0.1, umin), tmax = umax + 100.0;
   const double emin = fmax(tmin, umin * 0.5), emax = fmin(tmax, umax * 2.0);       // utils.py:57-58
   const int D = a.cfg.dense_resolution;
   int nb = (int)((double)D * 0.15), nu = (int)((double)D * 0.70);
@@ -165,6 +172,7 @@ __global__ void csm_prep_kernel(const CsmArgs c) {
   S[CS_NB] = (double)nb;
   S[CS_NU] = (double)nu;
   S[CS_NA] = (double)na;
+  S[CS_MTH] = mth;                                                                  // mass_csm_threshold [g], :1949
 }
 
 // photosphere.TemperatureFloor (photosphere.py:87-111) for one epoch
@@ -208,8 +216,14 @@ __global__ void __launch_bounds__(kCsmThreads, 2) csm_kernel(const CsmArgs c) {
   double* ml = mt + Mmax;              // [Mmax] luminosity at the knots; after the scan: diffused luminosity
   double* ca = ml + Mmax;              // [Mmax] affine map of interval i: new' = ca new + cb
   double* cb = ca + Mmax;              // [Mmax]
-  double* us = cb + Mmax;              // [Eu]   unique source-frame epochs
-  double* sc = us + Eu;                // [32]   per-sample scalars
+  // the four knot arrays also hold the quadrature method's timesteps / 2 + timesteps abscissae (host: csm_smem_bytes)
+  const int M4 = max(4 * Mmax, a.cfg.csm_quadrature ? 3 * ((a.cfg.csm_timesteps + 1) / 2) + 4 : 0);
+  double* us = mt + M4;                // [Eu]   unique source-frame epochs
+  double* ldn = us + Eu;               // [D]    nickel-cobalt luminosity on the dense grid (csm_nickel)
+  double* lq = ldn + D;                // [Eu]   CSM luminosity at the unique epochs, quadrature method
+  double* lni = lq + Eu;               // [Eu]   diffused nickel luminosity at the unique epochs (csm_nickel)
+  double* nk = lni + Eu;               // [160]  Diffusion's 50 + 100 abscissae (csm_nickel)
+  double* sc = nk + 160;               // [32]   per-sample scalars
   double* wsa = sc + 32;               // [32]   warp aggregates
   double* wsb = wsa + 32;              // [32]
   int* upos = reinterpret_cast<int*>(wsb + 32);   // [Eu] position of each unique epoch among the knots
@@ -217,6 +231,12 @@ __global__ void __launch_bounds__(kCsmThreads, 2) csm_kernel(const CsmArgs c) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int sed = a.cfg.sed;
   const bool want_logl = a.want_logl != 0;
+  const bool quad = a.cfg.csm_quadrature != 0;
+  const bool nickel = a.cfg.f_nickel != nullptr;
+  const int nq_half = (a.cfg.csm_timesteps + 1) / 2;     // int(round(timesteps / 2.0)) for the even defaults, :209
+  const int NQ = 2 * nq_half;
+  double* qlsp = mt;                   // quadrature method: [nq_half] and [NQ] abscissae in the (then unused) knot arrays
+  double* qx = mt + nq_half;
   for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
 
   for (int64_t n = blockIdx.x; n < a.N; n += gridDim.x) {
@@ -243,6 +263,9 @@ __global__ void __launch_bounds__(kCsmThreads, 2) csm_kernel(const CsmArgs c) {
         const double lfs = (tfs - ts > 0) ? cfs * pw : 0.0;
         const double lrs = (trs - ts > 0) ? crs * pw : 0.0;
         ld[k] = sc[CS_EFF] * (lfs + lrs);
+        if (nickel)                                                              // supernova_models.py:564-579 at :2152
+          ldn[k] = a.cfg.f_nickel[n] * a.params[RB_SN_MEJ * a.param_stride + n] *
+                   (6.45e43 * exp(-t / 8.8) + 1.45e43 * exp(-t / 111.3));
       }
       for (int j = tid; j < Eu; j += blockDim.x) {
         const double u = c.utime[j];
@@ -250,6 +273,61 @@ __global__ void __launch_bounds__(kCsmThreads, 2) csm_kernel(const CsmArgs c) {
       }
     }
     __syncthreads();
+    if (quad) {
+      // ---- csm_diffusion_method = "quadrature" (interaction_processes.py:199-227) ------------------------------------
+      const double t0 = sc[CS_T0], t_end = tg[G - 1], tb = fmax(0.0, tg[0]);                       // :203-206
+      {
+        const double a0 = fmin(log10(t0 / t_end) - 3.0, 0.0);                                      // :210
+        const double da = (0.0 - a0) / (double)(nq_half - 1);
+        for (int j = tid; j < nq_half; j += blockDim.x)
+          qlsp[j] = pow(10.0, (j == nq_half - 1) ? 0.0 : (double)j * da + a0);                     // :211
+      }
+      __syncthreads();
+      // xm = unique(lsp U 1 - lsp) (+ 0 and 1, which are already members): merge by rank, duplicates kept as
+      // zero-width intervals
+      for (int r = tid; r < NQ; r += blockDim.x) {
+        int rank;
+        double v;
+        if (r < nq_half) {
+          v = qlsp[r];
+          int lo = 0, hi = nq_half;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((1.0 - qlsp[mid]) < v) hi = mid; else lo = mid + 1;
+          }
+          rank = r + (nq_half - lo);
+        } else {
+          const int j0 = r - nq_half;
+          v = 1.0 - qlsp[j0];
+          int lo = 0, hi = nq_half;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (qlsp[mid] <= v) lo = mid + 1; else hi = mid;
+          }
+          rank = (nq_half - 1 - j0) + lo;
+        }
+        qx[rank] = v;
+      }
+      __syncthreads();
+      const double inv_t0 = 1.0 / t0;
+      for (int j = tid; j < Eu; j += blockDim.x) {
+        const double te = us[j], span = te - tb;
+        int idx = 0, idx_slope = -1;
+        double slope = 0.0, acc = 0.0;
+        for (int m = 0; m < NQ; ++m) {
+          const double x = qx[m];
+          const double t = tb + span * x;                                                         // :217
+          while (idx < G - 2 && tg[idx + 1] <= t) ++idx;
+          if (idx != idx_slope) { slope = (ld[idx + 1] - ld[idx]) / (tg[idx + 1] - tg[idx]); idx_slope = idx; }
+          const double lum = slope * (t - tg[idx]) + ld[idx];                                     // np.interp, :220
+          const double arg = (t - te) * inv_t0;
+          double g = lum * ((arg > -700.0) ? exp_tab(arg, tab) : exp(arg));                       // :221
+          if (isnan(g)) g = 0.0;                                                                  // :222
+          acc = fma(g, qx[min(m + 1, NQ - 1)] - qx[max(m - 1, 0)], acc);
+        }
+        lq[j] = (0.5 * span * acc) * inv_t0;                                                      // :224-225
+      }
+    } else {
     // ---- knots = unique(dense ∪ epochs) (interaction_processes.py:181-183): rank = own index + number of elements
     // of the other list sorting before it; an epoch equal to a dense point follows it as a zero-length interval -----
     for (int k = tid; k < G; k += blockDim.x) {
@@ -331,12 +409,77 @@ __global__ void __launch_bounds__(kCsmThreads, 2) csm_kernel(const CsmArgs c) {
         ml[i + 1] = v;
       }
     }
+    }
+    if (nickel) {
+      // ---- csm_nickel: Diffusion (interaction_processes.py:33-65) of the nickel-cobalt engine on the adaptive grid,
+      // ejecta mass mej + mass_csm_threshold (supernova_models.py:2148-2157) ------------------------------------------------
+      const int64_t S = a.param_stride;
+      const double mej_eff = a.params[RB_SN_MEJ * S + n] + sc[CS_MTH] / kMsun;
+      const double vkm = a.params[RB_SN_VEJ * S + n];
+      const double tau = sqrt(kDiffusionConst * a.params[RB_SN_KAPPA * S + n] * mej_eff / vkm) / kDay;            // :39
+      const double trap = (kTrappingConst * a.params[RB_SN_KAPPA_GAMMA * S + n] * mej_eff / (vkm * vkm)) / (kDay * kDay);
+      const double t_end = tg[G - 1], tb = fmax(0.0, tg[0]);
+      double* nlsp = nk;               // [50]
+      double* nx = nk + kNodesHalf;    // [100]
+      if (tid < kNodesHalf) {
+        const double a0 = log10(tau / t_end) - 3.0;                                               // :50
+        const double da = (0.0 - a0) / (double)(kNodesHalf - 1);
+        nlsp[tid] = pow(10.0, (tid == kNodesHalf - 1) ? 0.0 : (double)tid * da + a0);
+      }
+      __syncthreads();
+      if (tid < kNodes) {
+        int rank;
+        double v;
+        if (tid < kNodesHalf) {
+          v = nlsp[tid];
+          int lo = 0, hi = kNodesHalf;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((1.0 - nlsp[mid]) < v) hi = mid; else lo = mid + 1;
+          }
+          rank = tid + (kNodesHalf - lo);
+        } else {
+          const int j0 = tid - kNodesHalf;
+          v = 1.0 - nlsp[j0];
+          int lo = 0, hi = kNodesHalf;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (nlsp[mid] <= v) lo = mid + 1; else hi = mid;
+          }
+          rank = (kNodesHalf - 1 - j0) + lo;
+        }
+        nx[rank] = v;
+      }
+      __syncthreads();
+      const double inv_tau2 = 1.0 / (tau * tau);
+      for (int j = tid; j < Eu; j += blockDim.x) {
+        const double te = us[j], span = te - tb;
+        const double te_n = fmin(fmax(tb + span * nx[kNodes - 1], tb), t_end);                     // int_times[:, -1], :53-55
+        const double te2 = te_n * te_n;
+        int idx = 0, idx_slope = -1;
+        double slope = 0.0, acc = 0.0;
+        for (int m = 0; m < kNodes; ++m) {
+          const double t = fmin(fmax(tb + span * nx[m], tb), t_end);                              // :53
+          while (idx < G - 2 && tg[idx + 1] < t) ++idx;                                           // interp1d: x_lo < t <= x_hi
+          if (idx != idx_slope) { slope = (ldn[idx + 1] - ldn[idx]) / (tg[idx + 1] - tg[idx]); idx_slope = idx; }
+          const double lum = slope * (t - tg[idx]) + ldn[idx];                                    // :56
+          const double arg = (__dmul_rn(t, t) - te2) * inv_tau2;                                  // :57
+          double g = lum * t * ((arg > -700.0) ? exp_tab(arg, tab) : exp(arg));
+          if (isnan(g)) g = 0.0;                                                                  // :58
+          const double tp = fmin(fmax(tb + span * nx[min(m + 1, kNodes - 1)], tb), t_end);
+          const double tm = fmin(fmax(tb + span * nx[max(m - 1, 0)], tb), t_end);
+          acc = fma(g, tp - tm, acc);
+        }
+        lni[j] = (0.5 * acc) * (-2.0 * expm1(-trap / te2) * inv_tau2);                            // :60-61
+      }
+    }
     __syncthreads();
     // ---- per-epoch epilogue -----------------------------------------------------------------------------------------
     double logl_part = 0.0;
     for (int e = tid; e < E; e += blockDim.x) {
       const int j = c.uidx[e];
-      const double lbol = ml[upos[j]];                         // np.interp(time, knots, new_lums) at a knot
+      double lbol = quad ? lq[j] : ml[upos[j]];                // np.interp(time, knots, new_lums) at a knot
+      if (nickel) lbol += lni[j];                              // supernova_models.py:2165
       const double te = us[j];
       double model;
       if (sed == RB_SED_BOLOMETRIC) {

@@ -318,6 +318,7 @@ class SupernovaPath(_FusedPath):
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength,
                                    absorption_index, cosmology, line, _precision(dtype), csm, no_interaction,
                                    area_ratio, viscous)
+        self._csm_nickel = bool(csm and csm.get("nickel"))
         self._engine_rows(engine)
         if viscous:      # interaction_processes.Viscous takes t_viscous instead of the opacities: it rides in kappa's row
             self.ROWS = dict(self.ROWS, t_viscous=self.ROWS["kappa"])
@@ -336,6 +337,10 @@ class SupernovaPath(_FusedPath):
             self.AUX_PARAM = "f_nickel"
         elif engine == _capi.ENGINE_FALLBACK_NICKEL:
             self.ROWS = dict(_capi.SN_ROWS, f_nickel=3)      # rows 1-3 = logl1, tr, f_nickel
+        elif engine == _capi.ENGINE_CSM and getattr(self, "_csm_nickel", False):
+            # csm_nickel: f_nickel shares row 1 with csm_mass, so it travels through cfg.f_nickel
+            self.ROWS = {k: v for k, v in _capi.SN_ROWS.items() if k != "f_nickel"}
+            self.AUX_PARAM = "f_nickel"
 
     def _check_time(self, t):
         if self.cfg.engine == _capi.ENGINE_CSM:
@@ -396,13 +401,14 @@ class SupernovaMagPath(SupernovaPath):
         self.NEEDS_FREQUENCY = False
         self.cfg = _capi.sn_config(engine, sed, sigma_mode, dense_resolution, cutoff_wavelength, absorption_index,
                                    cosmology, line, 0, csm, no_interaction, area_ratio, viscous)
+        self._csm_nickel = bool(csm and csm.get("nickel"))
         self._engine_rows(engine)
         if viscous:
             self.ROWS = dict(self.ROWS, t_viscous=self.ROWS["kappa"])
         self._setup(time, None, y, sigma, device)
         lam = np.geomspace(100, 60000, 100) if lambda_array is None else np.asarray(lambda_array, dtype=np.float64)
         # get_optimal_time_array(0.1, 3000, 300) (utils.py:108); csm_interaction: (0.1, 500, 300) (:2095)
-        tgrid = np.geomspace(0.1, 500 if engine == _capi.ENGINE_CSM else 3000, 300)
+        tgrid = np.geomspace(0.1, 500 if engine == _capi.ENGINE_CSM and not self._csm_nickel else 3000, 300)   # csm_nickel: :2213
         self.phot, self._keep = _bands.build_photometry(bands, self.E, lam, output, tgrid=tgrid)
 
     def _launch(self, *args):

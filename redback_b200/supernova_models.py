@@ -52,13 +52,15 @@ def _line_kwargs(kwargs):
 def _csm_kwargs(kwargs):
     """_csm_engine / CSMDiffusion keyword arguments (supernova_models.py:1934-1936, interaction_processes.py:154-155)."""
     method = kwargs.get("csm_diffusion_method", "cumulative")
-    if method != "cumulative":
-        if method in ("quadrature", "legacy"):
-            raise NotImplementedError("csm_diffusion_method='quadrature' is not fused on device (default: 'cumulative')")
-        raise ValueError("csm_diffusion_method must be 'cumulative' or 'quadrature'")
+    if method not in ("cumulative", "quadrature", "legacy"):
+        raise ValueError("csm_diffusion_method must be 'cumulative' or 'quadrature'")          # interaction_processes.py:168
     if "dense_time_min" in kwargs or "stop_time" in kwargs:
         raise NotImplementedError("dense_time_min / stop_time overrides are not fused on device")
-    return dict(nn=kwargs.get("nn", 12), delta=kwargs.get("delta", 1), efficiency=kwargs.get("efficiency", 0.5))
+    timesteps = kwargs.get("csm_diffusion_timesteps", 3000)
+    if method != "cumulative" and (int(timesteps) != timesteps or int(timesteps) % 2 or not 4 <= timesteps <= 6000):
+        raise NotImplementedError("csm_diffusion_timesteps must be an even integer in [4, 6000] on device")
+    return dict(nn=kwargs.get("nn", 12), delta=kwargs.get("delta", 1), efficiency=kwargs.get("efficiency", 0.5),
+                quadrature=method != "cumulative", timesteps=int(timesteps))
 
 
 def _area_ratio(kwargs):
@@ -84,7 +86,7 @@ def _ip_name(kwargs):
 
 
 def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None, direct=False, _variant=False,
-          _viscous=False):
+          _viscous=False, csm_nickel=False):
     """direct: the model has no interaction process at all (sn_fallback); otherwise `interaction_process=None`
     selects the direct variant of the same spec (engine luminosity -> photosphere -> SED, :961-968), and
     `interaction_process=Viscous` (interaction_processes.py:229-273; kwarg / sampled parameter `t_viscous`) the viscous
@@ -118,7 +120,7 @@ def _spec(name, engine, engine_params, flux_density, default_sed, fixed_sed=None
     def build(time, kwargs, y, sigma, sigma_mode):
         sed_id = _capi.SED_BOLOMETRIC
         line = None
-        csm = _csm_kwargs(kwargs) if is_csm else None
+        csm = dict(_csm_kwargs(kwargs), nickel=csm_nickel) if is_csm else None
         no_ip = direct or _variant
         area_ratio = None if no_ip or is_csm or _viscous else _area_ratio(kwargs)
         if flux_density:
@@ -185,6 +187,34 @@ def csm_interaction(time, redshift=None, mej=None, csm_mass=None, vej=None, eta=
     """redback supernova_models.csm_interaction (:2054-2111); TemperatureFloor + Blackbody by default; mJy / mag."""
     named = dict(redshift=redshift, mej=mej, csm_mass=csm_mass, vej=vej, eta=eta, rho=rho, kappa=kappa, r0=r0)
     return run(_CSM_BB, time, named, kwargs, params_batch)
+
+
+# csm_nickel (supernova_models.py:2120-2232): the CSM shock + the nickel-cobalt engine diffused through the ejecta and the
+# optically thick CSM; vej from the kinetic energy, sqrt(2 ek / mej) (:2140); kappa_gamma feeds Diffusion
+_CSM_NI = ("mej", "f_nickel", "csm_mass", "vej", "eta", "rho", "kappa", "r0", "kappa_gamma")
+_CSM_NI_BOLO = _spec("csm_nickel_bolometric", _capi.ENGINE_CSM, _CSM_NI, False, None, csm_nickel=True)
+_CSM_NI_BB = _spec("csm_nickel", _capi.ENGINE_CSM, _CSM_NI, True, "Blackbody", csm_nickel=True)
+
+
+def _with_ek(spec):
+    needed = tuple(n for n in spec.needed if n != "vej") + ("ek",)
+    return FusedSpec(spec.name, needed, spec._build, spec._validate, transform=lambda p: _velocity_from_ek((2.0, 1.0))(p))
+
+
+def csm_nickel_bolometric(time, mej=None, f_nickel=None, csm_mass=None, ek=None, eta=None, rho=None, kappa=None, r0=None,
+                          params_batch=None, **kwargs):
+    """redback supernova_models.csm_nickel_bolometric (:2120-2165); kwargs kappa_gamma, csm_diffusion_method, nn, delta,
+    efficiency, dense_resolution; returns erg/s."""
+    named = dict(mej=mej, f_nickel=f_nickel, csm_mass=csm_mass, ek=ek, eta=eta, rho=rho, kappa=kappa, r0=r0)
+    return run(_CSM_NI_BOLO_EK, time, named, kwargs, params_batch)
+
+
+def csm_nickel(time, redshift=None, mej=None, f_nickel=None, csm_mass=None, ek=None, eta=None, rho=None, kappa=None,
+               r0=None, params_batch=None, **kwargs):
+    """redback supernova_models.csm_nickel (:2168-2232); TemperatureFloor + Blackbody; mJy / mag."""
+    named = dict(redshift=redshift, mej=mej, f_nickel=f_nickel, csm_mass=csm_mass, ek=ek, eta=eta, rho=rho, kappa=kappa,
+                 r0=r0)
+    return run(_CSM_NI_BB_EK, time, named, kwargs, params_batch)
 
 
 def arnett_bolometric(time, f_nickel=None, mej=None, params_batch=None, **kwargs):
@@ -324,6 +354,8 @@ def type_1a(time, redshift=None, f_nickel=None, mej=None, params_batch=None, **k
 
 # model function -> FusedSpec: lets GaussianLikelihood.log_likelihood_batch route through the fused kernel
 # without materialising the (N, E) model matrix.
+_CSM_NI_BOLO_EK, _CSM_NI_BB_EK = None, None      # bound below, once _velocity_from_ek exists
+
 FUSED = {
     arnett_bolometric: _ARNETT_BOLO, arnett: _ARNETT,
     basic_magnetar_powered_bolometric: _MAGNETAR_BOLO, slsn_bolometric: _MAGNETAR_BOLO,
@@ -358,6 +390,11 @@ def _velocity_from_ek(factor):
                                     / (factor[1] * np.asarray(mej, dtype=np.float64) * _SOLAR_MASS)) / _KM
         return params
     return transform
+
+
+_CSM_NI_BOLO_EK, _CSM_NI_BB_EK = _with_ek(_CSM_NI_BOLO), _with_ek(_CSM_NI_BB)
+FUSED[csm_nickel_bolometric] = _CSM_NI_BOLO_EK
+FUSED[csm_nickel] = _CSM_NI_BB_EK
 
 
 class _EkSpec:

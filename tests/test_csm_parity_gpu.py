@@ -33,6 +33,50 @@ def test_reference_fixture_bolometric(rb):
         h.assert_close(out, np.array(row["lbol"]), RTOL, what="csm_interaction_bolometric vs reference")
 
 
+def test_reference_fixture_quadrature_method_and_csm_nickel(rb):
+    """csm_diffusion_method='quadrature' (interaction_processes.py:199-227) and csm_nickel(_bolometric)
+    (supernova_models.py:2120-2232) against outputs of the reference's own sources; flux density and the fused
+    likelihood of csm_nickel against the oracle restatement (pinned to the same fixture on the CPU)."""
+    with open(os.path.join(ROOT, "tests", "golden", "csm_reference_draws.json")) as fh:
+        fx = json.load(fh)
+    t_all = np.array(fx["time"])
+    rows = [row for row in fx["draws"] if "lbol_quadrature" in row]
+    assert len(rows) >= 4
+    for row in rows:
+        t = t_all[row["skip"]:]
+        p = dict(row["params"])
+        p.pop("temperature_floor")
+        out = rb.supernova_models.csm_interaction_bolometric(t, csm_diffusion_method="quadrature", **p)
+        h.assert_close(out, np.array(row["lbol_quadrature"]), RTOL, what="CSMDiffusion quadrature vs reference")
+        c = {k: v for k, v in p.items() if k != "vej"}
+        out = rb.supernova_models.csm_nickel_bolometric(t, **c, **row["nickel_params"])
+        h.assert_close(out, np.array(row["csm_nickel_lbol"]), RTOL, what="csm_nickel_bolometric vs reference")
+        out = rb.supernova_models.csm_nickel_bolometric(t, csm_diffusion_method="legacy", csm_diffusion_timesteps=1000,
+                                                        **c, **row["nickel_params"])
+        h.assert_close(out, np.array(row["csm_nickel_lbol_quadrature"]), RTOL, what="csm_nickel legacy vs reference")
+    # batched flux density + fused likelihood
+    t = t_all[6:]
+    nu = np.where(np.arange(t.size) % 2 == 0, 6.3e14, 3.9e14)
+    names = ("mej", "csm_mass", "eta", "rho", "kappa", "r0")
+    batch = {k: np.array([row["params"][k] for row in rows]) for k in names}
+    for k in ("f_nickel", "ek", "kappa_gamma"):
+        batch[k] = np.array([row["nickel_params"][k] for row in rows])
+    batch["redshift"] = np.linspace(0.01, 0.3, len(rows))
+    batch["temperature_floor"] = np.array([row["params"]["temperature_floor"] for row in rows])
+    fn = rb.supernova_models.csm_nickel
+    kw = dict(frequency=nu, output_format="flux_density")
+    out = fn(t, params_batch=batch, **kw)
+    y, sigma = out[1] * 1.03, 0.05 * np.abs(out[1]) + 1e-12
+    logl = rb.GaussianLikelihood(t, y, sigma, fn, kwargs=kw).log_likelihood_batch(batch)
+    for i in range(len(rows)):
+        kwi = {k: float(v[i]) for k, v in batch.items()}
+        z = kwi.pop("redshift")
+        ref = r.csm_nickel(t, z, frequency=nu, **kwi)
+        h.assert_close(out[i], ref, RTOL, what=f"csm_nickel sample {i}")
+        ref_l = r.gaussian_likelihood(y, ref, sigma)
+        assert abs(logl[i] - ref_l) <= 1e-6 + 1e-9 * abs(ref_l), (i, logl[i], ref_l)
+
+
 def test_prior_draws_flux_density_and_likelihood(rb):
     rng = np.random.default_rng(81)
     tb = np.sort(rng.uniform(0.5, 250, 40))
@@ -72,7 +116,7 @@ def test_kwargs_and_errors(rb):
         rb.supernova_models.csm_interaction_bolometric(t, nn=15, **base)          # outside the (n, s) table
     with pytest.raises(ValueError):
         rb.supernova_models.csm_interaction_bolometric(np.array([0.0, 1.0]), **base)
-    with pytest.raises(NotImplementedError):
-        rb.supernova_models.csm_interaction_bolometric(t, csm_diffusion_method="quadrature", **base)
+    with pytest.raises(ValueError):
+        rb.supernova_models.csm_interaction_bolometric(t, csm_diffusion_method="simpson", **base)
     bad = rb.supernova_models.csm_interaction_bolometric(t, **dict(base, eta=2.5))  # reference raises; NaN per sample
     assert np.all(np.isnan(bad))

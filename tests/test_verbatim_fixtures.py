@@ -80,6 +80,15 @@ def test_oracle_reproduces_reference_csm(csm_fx):
         np.testing.assert_allclose(eng, row["engine_lbol"], rtol=1e-14)
         assert abs(r_ph / row["r_photosphere"] - 1) < 1e-14 and abs(m_th / row["mass_csm_threshold"] - 1) < 1e-14
         out = r.csm_interaction_bolometric(t, **p)
+        if "lbol_quadrature" in row:      # the legacy quadrature method and csm_nickel (both methods)
+            np.testing.assert_allclose(r.csm_interaction_bolometric(t, csm_diffusion_method="quadrature", **p),
+                                       row["lbol_quadrature"], rtol=1e-13)
+            c = {k: v for k, v in p.items() if k != "vej"}
+            np.testing.assert_allclose(r.csm_nickel_bolometric(t, **c, **row["nickel_params"]), row["csm_nickel_lbol"],
+                                       rtol=1e-13)
+            np.testing.assert_allclose(
+                r.csm_nickel_bolometric(t, csm_diffusion_method="legacy", csm_diffusion_timesteps=1000, **c,
+                                        **row["nickel_params"]), row["csm_nickel_lbol_quadrature"], rtol=1e-13)
         np.testing.assert_allclose(out, row["lbol"], rtol=1e-14)
         T, R = r.temperature_floor(t, out, p["vej"], tfl)
         np.testing.assert_allclose(T, row["temperature"], rtol=1e-13)
