@@ -66,3 +66,25 @@ def test_ctypes_struct_layouts_match_the_library():
     assert (mk.resolution, mk.pair_cascade_fraction, mk.vmax, mk.pair_cascade_switch) == (300, 0.01, 0.7, 1)
     ag = _capi.ag_config(_capi.AG_TOPHAT)
     assert (ag.steps, ag.ab_magnitude) == (250, 0)
+
+
+def test_integration_stub_is_generated_from_the_bindings():
+    """INTEGRATION.md section 2 shows the structures a foreign caller mirrors; the text between the stub markers must be
+    exactly what tools/gen_integration_stub.py produces from redback_b200/_capi.py, and must execute."""
+    import ctypes
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_integration_stub", os.path.join(root, "tools",
+                                                                                       "gen_integration_stub.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    committed = doc[doc.index(gen.BEGIN) + len(gen.BEGIN):doc.index(gen.END)]
+    assert committed == gen.stub()
+    # the class definitions of the stub, executed on their own, have the library's layout
+    code = committed.split("```python\n")[1].split("assert lib.rb_sizeof")[0]
+    code = "\n".join(line for line in code.splitlines() if not line.startswith("lib"))
+    ns = {}
+    exec(code, ns)
+    from redback_b200 import _capi
+    assert ctypes.sizeof(ns["SnConfig"]) == _capi.lib().rb_sizeof(2) == ctypes.sizeof(_capi.SnConfig)
