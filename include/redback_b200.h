@@ -164,7 +164,8 @@ typedef struct {
   /* Epochs before the start of the dense grid (t < 0): Diffusion / Viscous leave them out of `uniq_times` and
      `np.searchsorted(uniq_times, time)` (interaction_processes.py:63, :271) hands them the luminosity of the FIRST valid
      epoch, while photosphere and SED see the negative time itself.  The smallest t_obs >= 0 of the call (observer
-     frame, days); only read when some t_obs < 0. */
+     frame, days); read when negative_epochs != 0 (set by the caller when some t_obs < 0; Diffusion: nickel, magnetar and
+     magnetar_nickel engines without t0 / AsphericalDiffusion; Viscous: every engine). */
   double t_first_valid;
   /* RB_ENGINE_CSM only.  csm_quadrature != 0: CSMDiffusion's legacy per-epoch integral (kwarg csm_diffusion_method =
      "quadrature" | "legacy", interaction_processes.py:199-227) on csm_timesteps abscissae (kwarg
@@ -173,6 +174,7 @@ typedef struct {
      diffused through mej + mass_csm_threshold on the same grid is added; kappa_gamma is then read from its row. */
   int csm_quadrature;
   int csm_timesteps;
+  int negative_epochs;      /* see t_first_valid */
 } rb_sn_config;
 
 /* Defaults: nickel engine, Blackbody, fixed sigma, D = 1000, Planck18. */

@@ -45,7 +45,7 @@ class SnConfig(C.Structure):
                 ("csm_efficiency", C.c_double), ("t0", C.c_void_p), ("f_nickel", C.c_void_p),
                 ("no_interaction", C.c_int), ("aspherical", C.c_int), ("area_ratio", C.c_double),
                 ("viscous", C.c_int), ("t_first_valid", C.c_double), ("csm_quadrature", C.c_int),
-                ("csm_timesteps", C.c_int)]
+                ("csm_timesteps", C.c_int), ("negative_epochs", C.c_int)]
 
 
 KN_ONE_COMPONENT, KN_METZGER = 0, 1

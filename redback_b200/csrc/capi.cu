@@ -148,8 +148,11 @@ int launch_csm(rb::SnArgs a, const double* t_dev, cudaStream_t st, int sms) {
 }
 
 typedef void (*SnKernelFn)(const rb::SnArgs);
-SnKernelFn sn_kernel_fn(int engine, bool has_t0, bool aspherical = false) {
+SnKernelFn sn_kernel_fn(int engine, bool has_t0, bool aspherical = false, bool negative = false) {
   if (aspherical) return rb::sn_kernel<false, 0, true>;
+  if (negative)      // epochs before the dense grid: nickel / magnetar / magnetar_nickel without t0 (checked in sn_check)
+    return engine == RB_ENGINE_MAGNETAR_NICKEL ? rb::sn_kernel<false, RB_ENGINE_MAGNETAR_NICKEL, false, true>
+                                               : rb::sn_kernel<false, 0, false, true>;
   switch (engine) {
     case RB_ENGINE_MAGNETAR_NICKEL:
       return has_t0 ? rb::sn_kernel<true, RB_ENGINE_MAGNETAR_NICKEL> : rb::sn_kernel<false, RB_ENGINE_MAGNETAR_NICKEL>;
@@ -174,6 +177,9 @@ cudaError_t sn_kernel_attributes() {
                                  220 * 1024);
   if (err == cudaSuccess)
     err = cudaFuncSetAttribute(sn_kernel_fn(0, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  for (int e = 0; e < 2 && err == cudaSuccess; ++e)
+    err = cudaFuncSetAttribute(sn_kernel_fn(engines[e], false, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               220 * 1024);
   return err;
 }
 
@@ -287,6 +293,11 @@ static int sn_check(const rb_sn_config* cfg, int64_t N, int64_t E, const void* p
                                     "without t0");
   if (cfg->engine == RB_ENGINE_MAGNETAR_NICKEL && !cfg->f_nickel)
     return fail(RB_ERR_INVALID, "rb_sn_eval: cfg.f_nickel is required for RB_ENGINE_MAGNETAR_NICKEL");
+  if (cfg->negative_epochs && !cfg->viscous && !cfg->no_interaction && cfg->engine < RB_ENGINE_FALLBACK &&
+      (cfg->t0 != nullptr || cfg->aspherical ||
+       !(cfg->engine == RB_ENGINE_NICKEL || cfg->engine == RB_ENGINE_MAGNETAR || cfg->engine == RB_ENGINE_MAGNETAR_NICKEL)))
+    return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: epochs before the dense grid are available for the nickel / magnetar "
+                                    "engines with Diffusion (no t0, not aspherical) and for Viscous");
   if (cfg->viscous && (cfg->engine == RB_ENGINE_CSM || cfg->t0 != nullptr || cfg->no_interaction || cfg->aspherical ||
                        cfg->precision != RB_PREC_F64))
     return fail(RB_ERR_UNSUPPORTED, "rb_sn_eval: Viscous is FP64, without t0, for every engine except the CSM shock");
@@ -398,7 +409,7 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   const size_t smem = sn_smem_bytes(cfg->dense_resolution, E, a.epochs_in_smem != 0, fp32);
   if (smem > 220 * 1024) return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution too large for shared memory");
   int occ = 0;
-  const SnKernelFn kern = sn_kernel_fn(cfg->engine, cfg->t0 != nullptr, cfg->aspherical != 0);
+  const SnKernelFn kern = sn_kernel_fn(cfg->engine, cfg->t0 != nullptr, cfg->aspherical != 0, cfg->negative_epochs != 0);
   RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (occ < 1) occ = 1;
   // persistent blocks, grid-stride over samples; 4 waves' worth of blocks for load balance at mid-size N

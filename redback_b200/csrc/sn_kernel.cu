@@ -447,7 +447,9 @@ __device__ __forceinline__ float diffusion_sum_f32(const float4* __restrict__ no
 // (ptxas' register allocation of the hot loop is sensitive to the surrounding code: adding the third engine to the
 // run-time branch cost 4 %, resolving nickel / magnetar at compile time cost the magnetar variant 30 % more spills.)
 // ASPH: AsphericalDiffusion's viewing-angle factor on the diffused luminosity (interaction_processes.py:124-125).
-template <bool HAS_T0, int ENGINE, bool ASPH = false>
+// NEG: some epochs lie before the dense grid (cfg.negative_epochs); its own instantiation for the same reason (the select
+// in front of the hot loop cost the plain path 2.7 % on the headline and 4.5 % on arnett_bolometric when always compiled in).
+template <bool HAS_T0, int ENGINE, bool ASPH = false, bool NEG = false>
 __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
   extern __shared__ double2 smem2[];
   const int D = a.cfg.dense_resolution;
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       const double te_real = a.grid_mode ? (t_in * sc[SC_OPZ]) / sc[SC_OPZ] : t_in / sc[SC_OPZ];   // utils.py:382 (:1012-1014)
       // epochs before the dense grid are left out of uniq_times and np.searchsorted hands them the FIRST valid epoch's
       // luminosity (interaction_processes.py:47, :63); photosphere and SED below see the negative time itself
-      const double te = (te_real < 0.0) ? a.cfg.t_first_valid / sc[SC_OPZ] : te_real;
+      const double te = (NEG && te_real < 0.0) ? a.cfg.t_first_valid / sc[SC_OPZ] : te_real;
       const double te2 = te * te;                                             // interaction_processes.py:55
       // first abscissa whose exponent can exceed kExpSkip: te^2 (1 - xm^2) <= -(kExpSkip - 1) tau^2
       int m0 = 0;

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) sn_viscous_kernel(const SnArgs a) {
       const double t_in = a.epoch_tab[EP_T * E + e];
       const double te = a.grid_mode ? (t_in * opz) / opz : t_in / opz;          // utils.py:382
       // epochs before the grid take the first valid epoch's luminosity (np.searchsorted of an excluded time, :271)
-      const double td = (te >= 0.0) ? te : a.cfg.t_first_valid / opz;
+      const double td = (te >= 0.0 || !a.cfg.negative_epochs) ? te : a.cfg.t_first_valid / opz;
       // first abscissa whose weight exp((xm - 1) t_e / t_visc) is above exp(-691)
       int m0 = 0;
       {

@@ -355,7 +355,13 @@ class SupernovaPath(_FusedPath):
             valid = t[t >= 0]
             if valid.size == 0:
                 raise IndexError("index 0 is out of bounds for axis 0 with size 0")      # uniq_lums is empty
+            plain = self.cfg.engine in (_capi.ENGINE_NICKEL, _capi.ENGINE_MAGNETAR, _capi.ENGINE_MAGNETAR_NICKEL) and \
+                not self.cfg.aspherical
+            if not (plain or self.cfg.viscous):
+                raise NotImplementedError("negative times are fused for the nickel / magnetar engines with Diffusion and "
+                                          "for Viscous only")
             self.cfg.t_first_valid = float(valid.min())
+            self.cfg.negative_epochs = 1
         if np.max(t) > t[-1] + 100:
             # interaction_processes.py:63 would index past uniq_lums here
             raise IndexError("max(time) exceeds time[-1] + 100: outside the reference's dense grid")
