@@ -71,6 +71,7 @@ struct AgArgs {
   const int* ep_nu_T;        // [32 * epl] index into nu_unique, -1 = padding
   const int* ep_orig_T;      // [32 * epl] index of the epoch in the caller's order, -1 = padding
   int epl;
+  double t_epoch_min, t_epoch_max;   // smallest / largest (non-NaN) observer time of the call [days]
   double nu_unique[kAgMaxNu];
   int n_nu;
   double* scalars;           // [N][kAgScalars]
@@ -458,6 +459,7 @@ __global__ void __launch_bounds__(kAgWarps * 32, 4) ag_cell_kernel(const AgArgs 
     const double th_lo = latstep - latstep / 2., th_hi = (double)nlat * latstep - latstep / 2.;
     const double ph_lo = rotstep - rotstep / 2., ph_hi = (double)nrot * rotstep - rotstep / 2.;
     const double day_over_opz = kDay / opz;
+    const double x_epoch_min = a.t_epoch_min * day_over_opz, x_epoch_max = a.t_epoch_max * day_over_opz;
 
     for (int i = ring_begin; i < ring_end; ++i) {
       const double* __restrict__ ring = a.ring_scratch + (size_t)(a.ring_off[n] + i) * kRingArrays * steps;
@@ -489,23 +491,15 @@ __global__ void __launch_bounds__(kAgWarps * 32, 4) ag_cell_kernel(const AgArgs 
         // the cell's own solid angle (expansion: used until the ring's exceeds it)
         const double omcos0 = Om0 * (1.0 - Om0 / rotstep);
         const double c_fmax = Om0 / AG_FOURPI / AG_FOURPI * inv_dl2;       // NO * P' * dop^3 / (4 pi dl^2), :365-366
-        // ---- step2 (:325-370).  Lane l owns steps l, l + 32, ...; the observer-time cumsum is a warp scan per chunk
-        // of 32 steps with the running total carried between chunks.
+        // ---- step2 (:325-370).  Lane l owns steps l, l + 32, ...
+        // Pass 1: observer times of all steps (cumsum = warp scan per chunk of 32 steps, running total carried between
+        // chunks), and how many of them lie at or below the first / above the last epoch.
         double carry = 0.0;
+        int n_le = 0, n_gt = 0;
         for (int sb = 0; sb < steps; sb += 32) {
           const int s = sb + lane;
           const bool live = s < steps;
           const int sc_ = live ? s : steps - 1;
-          const double beta = __ldg(ring + RA_BETA * steps + sc_), G = __ldg(ring + RA_G * steps + sc_);
-          const double nump = __ldg(ring + RA_NUMP * steps + sc_), nucp = __ldg(ring + RA_NUCP * steps + sc_);
-          const double fmr = __ldg(ring + RA_FMR * steps + sc_), fbr = __ldg(ring + RA_FBR * steps + sc_);
-          const double lnump = __ldg(ring + RA_LNUMP * steps + sc_), lnucp = __ldg(ring + RA_LNUCP * steps + sc_);
-          double omcos = __ldg(ring + RA_OMCOS * steps + sc_);
-          if (expansion) {                                                              // :345-352
-            const double omg = __ldg(ring + RA_OMG * steps + sc_);
-            const double Om = fmax_nan(Om0, omg);
-            if (!(Om == omg)) omcos = omcos0;
-          }
           double tobs = live ? __ldg(ring + RA_RD * steps + sc_) * (__ldg(ring + RA_IBETA * steps + sc_) - cosa) * inv_cc
                              : 0.0;                                                     // :353-356
 #pragma unroll
@@ -515,13 +509,38 @@ __global__ void __launch_bounds__(kAgWarps * 32, 4) ag_cell_kernel(const AgArgs 
           }
           tobs += carry;
           carry = __shfl_sync(0xffffffffu, tobs, 31);
-          if (!live) continue;
+          if (live) my_tobs[s] = tobs;
+          n_le += __popc(__ballot_sync(0xffffffffu, live && tobs <= x_epoch_min));
+          n_gt += __popc(__ballot_sync(0xffffffffu, live && tobs > x_epoch_max));
+        }
+        // np.interp only reads the spectra at the steps bracketing an epoch -- from the last step at or below the first
+        // epoch to the first step above the last one -- and at the two ends (epochs outside the observer-time range).
+        // For typical cells that is a fifth of the 250 steps (the step grid spans 14 decades in radius, the epochs 3.5 in
+        // time): the spectra of the others are never evaluated.  A NaN observer time counts on neither side, which
+        // keeps the whole range.
+        const int s_lo = max(n_le - 1, 0), s_hi = min(steps - n_gt, steps - 1);
+        __syncwarp();
+        // Pass 2: spectra of the needed steps
+        for (int sb = 0; sb < steps; sb += 32) {
+          const int s = sb + lane;
+          const bool need = s < steps && ((s >= s_lo && s <= s_hi) || s == 0 || s == steps - 1);
+          if (!__any_sync(0xffffffffu, need)) continue;
+          if (!need) continue;
+          const double beta = __ldg(ring + RA_BETA * steps + s), G = __ldg(ring + RA_G * steps + s);
+          const double nump = __ldg(ring + RA_NUMP * steps + s), nucp = __ldg(ring + RA_NUCP * steps + s);
+          const double fmr = __ldg(ring + RA_FMR * steps + s), fbr = __ldg(ring + RA_FBR * steps + s);
+          const double lnump = __ldg(ring + RA_LNUMP * steps + s), lnucp = __ldg(ring + RA_LNUCP * steps + s);
+          double omcos = __ldg(ring + RA_OMCOS * steps + s);
+          if (expansion) {                                                              // :345-352
+            const double omg = __ldg(ring + RA_OMG * steps + s);
+            const double Om = fmax_nan(Om0, omg);
+            if (!(Om == omg)) omcos = omcos0;
+          }
           const double dop = 1.0 / (G * (1.0 - beta * cosa));                           // :343
           const double num = dop * nump;
           const double nuc = dop * nucp;
           const double Fmax = c_fmax * fmr * (dop * dop * dop);
           const double FBB = omcos * dop * fbr * inv_dl2;                               // :367
-          my_tobs[s] = tobs;
           const bool regular = num > 0.0 && num < INFINITY && nuc > 0.0 && nuc < INFINITY;
           if (regular) {
             // log(dop * nu') = log(dop) + log(nu'): one logarithm per cell step, the ring's are tabulated

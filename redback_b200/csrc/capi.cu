@@ -1090,6 +1090,11 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
     if (ty != ty) return true;
     return tx < ty;
   });
+  double t_epoch_min = INFINITY, t_epoch_max = -INFINITY;
+  for (int64_t e = 0; e < E; ++e) {
+    const double te = h_time[(size_t)e];
+    if (te == te) { t_epoch_min = std::min(t_epoch_min, te); t_epoch_max = std::max(t_epoch_max, te); }
+  }
   std::vector<double> h_tT(EP, 0.0);
   std::vector<int> h_nuT(EP, -1), h_origT(EP, -1);
   for (int64_t r = 0; r < E; ++r) {
@@ -1155,6 +1160,8 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
     a.ep_nu_T = b_nuT.as<int>();
     a.ep_orig_T = b_origT.as<int>();
     a.epl = epl;
+    a.t_epoch_min = t_epoch_min;
+    a.t_epoch_max = t_epoch_max;
     for (int h = 0; h < rb::kAgMaxNu; ++h) a.nu_unique[h] = h < n_nu ? uniq[(size_t)h] : 0.0;
     a.n_nu = n_nu;
     a.scalars = b_scal.as<double>();
