@@ -214,29 +214,61 @@ __device__ __forceinline__ double ag_rk4(double ghat, double dm, double g, doubl
          (m + dm10 * (therm + (1.0 - therm) * (2.0 * ghat * g - ghatm1 * (1 + 1.0 / g2))));
 }
 
-// ---- one thread per ring: structure, RK4 dynamics, step1 ----------------------------------------------------
-__global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t total_rings) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= total_rings) return;
-  // ring -> sample: last n with ring_off[n] <= r
-  int64_t lo = 0, hi = a.N;
+// ring r -> (sample n, latitude index i, ring centre thi)
+struct AgRing {
+  int64_t n;
+  int i;
+  double thi;
+};
+__device__ __forceinline__ AgRing ag_ring_of(const AgArgs& a, int64_t r) {
+  int64_t lo = 0, hi = a.N;      // last n with ring_off[n] <= r
   while (hi - lo > 1) {
     const int64_t mid = (lo + hi) >> 1;
     if (a.ring_off[mid] <= r) lo = mid; else hi = mid;
   }
-  const int64_t n = lo;
-  const int i = (int)(r - a.ring_off[n]);
-  const double* S = a.scalars + n * kAgScalars;
-  const int steps = a.cfg.steps;
-  const double kk = (double)a.cfg.k;
-  const double latstep = S[AS_LATSTEP], rotstep = S[AS_ROTSTEP], resd = S[AS_RES];
-  const int nlat = (int)resd;
+  AgRing g;
+  g.n = lo;
+  g.i = (int)(r - a.ring_off[lo]);
+  const double* S = a.scalars + lo * kAgScalars;
+  const double latstep = S[AS_LATSTEP];
+  const int nlat = (int)S[AS_RES];
   // thi = linspace(latstep - latstep/2, nlat*latstep - latstep/2, nlat)[i]  (:61)
   const double th_lo = latstep - latstep / 2., th_hi = (double)nlat * latstep - latstep / 2.;
-  double thi;
-  if (nlat == 1) thi = th_lo;
-  else if (i == nlat - 1) thi = th_hi;
-  else thi = (double)i * ((th_hi - th_lo) / (double)(nlat - 1)) + th_lo;
+  if (nlat == 1) g.thi = th_lo;
+  else if (g.i == nlat - 1) g.thi = th_hi;
+  else g.thi = (double)g.i * ((th_hi - th_lo) / (double)(nlat - 1)) + th_lo;
+  return g;
+}
+
+// mass grid of get_gamma_numba (:195-249): log10 of the first swept-up mass, the step in log10 m and -h ln 10
+__device__ __forceinline__ void ag_mass_grid(double n_amb, double kk, int steps, double& dlogm, double& h, double& fac) {
+  const double Nmin = (AG_FOURPI / (3.0 - kk)) * n_amb * pow(1e10, 3.0 - kk);
+  const double Nmax = (AG_FOURPI / (3.0 - kk)) * n_amb * pow(1e24, 3.0 - kk);
+  dlogm = log10(Nmin * AG_MP);
+  h = log10(Nmax / Nmin) / (double)steps;
+  fac = -h * log(10.0);
+}
+
+// adiabatic index fit (:200-206)
+__device__ __forceinline__ double ag_ghat(double G) {
+  const double g2m1 = G * G - 1.0;
+  const double root = sqrt(g2m1);
+  const double theta = root * (root + 1.07 * g2m1) / (3.0 * (1 + root + 1.07 * g2m1));
+  const double zz = theta / (0.24 + theta);
+  return ((((((1.07136 * zz - 2.39332) * zz + 2.32513) * zz - 0.96583) * zz + 0.18203) * zz - 1.21937) * zz + 5.0) / 3.0;
+}
+
+// ---- one THREAD per ring: jet structure and the sequential RK4 march of Gamma(log m) (get_gamma_numba) -----------
+// Writes the Lorentz factor and log10 m BEFORE each update (what step1 sees) into the ring's RA_G / RA_RD slots; the
+// latter is overwritten by ag_ring_kernel.
+__global__ void __launch_bounds__(128) ag_gamma_kernel(const AgArgs a, int64_t total_rings) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= total_rings) return;
+  const AgRing ring = ag_ring_of(a, r);
+  const double* S = a.scalars + ring.n * kAgScalars;
+  const int steps = a.cfg.steps;
+  const double kk = (double)a.cfg.k;
+  const double thi = ring.thi;
   // jet structure (:92-112)
   const double g0 = S[AS_G0], ek = S[AS_EK], thc = S[AS_THC], thj = S[AS_THJ];
   double fac_s;
@@ -278,15 +310,51 @@ __global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t to
     const double temp = ((1.0 - ss) * ec + ss * ej) / ((1.0 - ss / aa) * ec + (ss / aa) * ej);
     Gs = isfinite(temp) ? (g0 - 1.0) * temp + 1.0000000000001 : aa;
   }
-  // get_gamma_numba (:195-249), therm = 0
-  const double n_amb = S[AS_N];
-  const double Nmin = (AG_FOURPI / (3.0 - kk)) * n_amb * pow(1e10, 3.0 - kk);
-  const double Nmax = (AG_FOURPI / (3.0 - kk)) * n_amb * pow(1e24, 3.0 - kk);
-  const double dlogm = log10(Nmin * AG_MP);
-  const double h = log10(Nmax / Nmin) / (double)steps;
-  const double fac = -h * log(10.0);
+  double dlogm, h, fac;
+  ag_mass_grid(S[AS_N], kk, steps, dlogm, h, fac);
   const double M = Ei / (Gs * AG_C2);
-  // step1 constants
+  double* out = a.ring_scratch + (size_t)r * kRingArrays * steps;
+  double G = Gs, dm = dlogm;
+  for (int s = 0; s < steps; ++s) {
+    out[RA_G * steps + s] = G;
+    out[RA_RD * steps + s] = dm;
+    const double ghat = ag_ghat(G);
+    // ---- RK4 (:238-246) ----
+    const double F1 = ag_rk4(ghat, dm, G, M, fac, 0.0);
+    const double F2 = ag_rk4(ghat, dm + 0.5 * h, G + 0.5 * F1, M, fac, 0.0);
+    const double F3 = ag_rk4(ghat, dm + 0.5 * h, G + 0.5 * F2, M, fac, 0.0);
+    const double F4 = ag_rk4(ghat, dm + h, G + F3, M, fac, 0.0);
+    G = G + (F1 + 2.0 * (F2 + F3) + F4) / 6.0 + 1e-15;
+    dm = dm + h;
+  }
+}
+
+// inclusive warp scan of v with the running total `carry` of the previous 32-step chunks
+__device__ __forceinline__ double ag_scan(double v, double& carry, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += up;
+  }
+  v += carry;
+  carry = __shfl_sync(0xffffffffu, v, 31);
+  return v;
+}
+
+// ---- one WARP per ring, lane = step: calc_afterglow_step1 (:252-322) and the azimuth-independent part of step2 --------
+// Everything except the two running sums (radius R = cumsum of the increments, on-axis observer time) is local to a
+// step once Gamma is known; the sums are warp scans per chunk of 32 steps with carried totals (np.cumsum).
+__global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t total_rings) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= total_rings) return;
+  const AgRing ring = ag_ring_of(a, r);
+  const double* S = a.scalars + ring.n * kAgScalars;
+  const int steps = a.cfg.steps;
+  const double kk = (double)a.cfg.k;
+  const double thi = ring.thi;
+  const double latstep = S[AS_LATSTEP], rotstep = S[AS_ROTSTEP], resd = S[AS_RES];
+  const double n_amb = S[AS_N];
   const double p = S[AS_P], xp = S[AS_XP], Fx = S[AS_FX], EB = S[AS_EB], Ee = S[AS_EE], xiN = S[AS_XIN];
   const bool expansion = a.cfg.expansion != 0;
   const double a1 = a.cfg.a1;
@@ -297,75 +365,67 @@ __global__ void __launch_bounds__(128) ag_ring_kernel(const AgArgs a, int64_t to
   const double sigt = a.sigt;
   double* out = a.ring_scratch + (size_t)r * kRingArrays * steps;
 
-  double G = Gs, dm = dlogm;
-  double ex0 = 1.0, r_prev_orig = 0.0, r_cum = 0.0, tobso = 0.0;
-  for (int s = 0; s < steps; ++s) {
-    const double g2m1 = G * G - 1.0;
-    const double root = sqrt(g2m1);
-    const double theta = root * (root + 1.07 * g2m1) / (3.0 * (1 + root + 1.07 * g2m1));
-    const double zz = theta / (0.24 + theta);
-    const double ghat = ((((((1.07136 * zz - 2.39332) * zz + 2.32513) * zz - 0.96583) * zz + 0.18203) * zz - 1.21937) * zz + 5.0) / 3.0;
-    // ---- step1 at this step (uses the state before the RK4 update) ----
-    {
-      const double Gm1 = G - 1.0, G2 = G * G;
-      const double beta = sqrt(1 - 1.0 / G2);
-      const double Ne = exp10(dm) / AG_MP;
-      const double cs = sqrt(AG_C2 * ghat * (ghat - 1) * Gm1 / (1 + ghat * Gm1));
-      const double te = asin(cs / (AG_CC * sqrt(G2 - 1.0)));
-      double ex = 1.0, omg = omg_noexp;
-      if (expansion) {
-        ex = te / pow(G, a1 + 1);
-        omg = rotstep * (cos_lo - cos(ex / resd + thi + hfac));
-      }
-      if (s == 0) ex0 = ex;
-      const double r_orig = pow_inv3k((3.0 - kk) * Ne / (AG_FOURPI * n_amb), a.cfg.k, inv3k);
-      double r_inc = r_orig;
-      if (s > 0) {
-        const double expo = sqrt((1 - cos(latstep + ex0)) / (1 - cos(latstep + ex)));
-        r_inc = (r_orig - r_prev_orig) * pow_inv3k(expo, a.cfg.k, inv3k);
-      }
-      r_prev_orig = r_orig;
-      const double r_before = r_cum;
-      r_cum = (s == 0) ? r_inc : r_cum + r_inc;
-      const double r_diff = (s == 0) ? r_cum : r_cum - r_before;                       // np.diff(R, prepend=0), :347-350
-      tobso += r_diff * (1.0 / beta - 1.0) / AG_CC;                                    // :353, :356
-      const double n0 = (a.cfg.k == 0) ? n_amb : n_amb * pow(r_cum, -kk);             // r**-0.0 == 1
-      const double B = sqrt(2 * AG_FOURPI * EB * n0 * AG_MP * AG_C2 * ((ghat * G + 1.0) / (ghat - 1.0)) * Gm1);
-      double gm;
-      if (p > 2) {
-        gm = ((p - 2) / (p - 1)) * (Ee / xiN) * Gm1 * (AG_MP / AG_ME);
-      } else {
-        const double gmm = sqrt(1.5 * AG_FOURPI * AG_QE / (sigt * B));
-        if (p == 2) gm = (1 / log(gmm / ((Ee / xiN) * Gm1 * (AG_MP / AG_ME)))) * (Ee / xiN) * Gm1 * (AG_MP / AG_ME);
-        else gm = pow((2 - p) / (p - 1) * (AG_MP / AG_ME) * (Ee / xiN) * Gm1 * pow(gmm, p - 2), 1 / (p - 1));
-      }
-      const double nucp = [&] {
-        const double gc = 6.0 * kPi * AG_ME * AG_CC / (G * sigt * B * B * tobso);        // :360
-        return 0.286 * 3.0 * gc * gc * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);          // :361
-      }();
-      const double nump = 3.0 * xp * gm * gm * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);
-      const double pp = xiN * Fx * AG_ME * AG_C2 * sigt * B / (3.0 * AG_QE);
-      const double kt = gm * AG_ME * AG_C2;
-      out[RA_RD * steps + s] = r_diff;
-      out[RA_IBETA * steps + s] = 1.0 / beta;
-      out[RA_BETA * steps + s] = beta;
-      out[RA_G * steps + s] = G;
-      out[RA_OMG * steps + s] = omg;
-      out[RA_OMCOS * steps + s] = omg * (1.0 - omg / rotstep);       // cos(arccos(x)) = x to an ulp (x in [-1, 1], a factor)
-      out[RA_FMR * steps + s] = Ne * pp;
-      out[RA_FBR * steps + s] = 2.0 * kt * r_cum * r_cum / AG_C2;
-      out[RA_NUMP * steps + s] = nump;
-      out[RA_NUCP * steps + s] = nucp;
-      out[RA_LNUMP * steps + s] = log(nump);
-      out[RA_LNUCP * steps + s] = log(nucp);
+  double ex0 = 1.0, r_orig_last = 0.0, r_cum_last = 0.0, carry_r = 0.0, carry_t = 0.0;
+  for (int sb = 0; sb < steps; sb += 32) {
+    const int s = sb + lane;
+    const bool live = s < steps;
+    const int sl = live ? s : steps - 1;
+    const double G = out[RA_G * steps + sl], dm = out[RA_RD * steps + sl];
+    const double ghat = ag_ghat(G);
+    const double Gm1 = G - 1.0, G2 = G * G;
+    const double beta = sqrt(1 - 1.0 / G2);
+    const double Ne = exp10(dm) / AG_MP;
+    const double cs = sqrt(AG_C2 * ghat * (ghat - 1) * Gm1 / (1 + ghat * Gm1));
+    const double te = asin(cs / (AG_CC * sqrt(G2 - 1.0)));
+    double ex = 1.0, omg = omg_noexp;
+    if (expansion) {
+      ex = te / pow(G, a1 + 1);
+      omg = rotstep * (cos_lo - cos(ex / resd + thi + hfac));
     }
-    // ---- RK4 (:238-246) ----
-    const double F1 = ag_rk4(ghat, dm, G, M, fac, 0.0);
-    const double F2 = ag_rk4(ghat, dm + 0.5 * h, G + 0.5 * F1, M, fac, 0.0);
-    const double F3 = ag_rk4(ghat, dm + 0.5 * h, G + 0.5 * F2, M, fac, 0.0);
-    const double F4 = ag_rk4(ghat, dm + h, G + F3, M, fac, 0.0);
-    G = G + (F1 + 2.0 * (F2 + F3) + F4) / 6.0 + 1e-15;
-    dm = dm + h;
+    if (sb == 0) ex0 = __shfl_sync(0xffffffffu, ex, 0);
+    const double r_orig = pow_inv3k((3.0 - kk) * Ne / (AG_FOURPI * n_amb), a.cfg.k, inv3k);
+    double r_prev = __shfl_up_sync(0xffffffffu, r_orig, 1);
+    if (lane == 0) r_prev = r_orig_last;
+    r_orig_last = __shfl_sync(0xffffffffu, r_orig, 31);
+    double r_inc = r_orig;
+    if (s > 0) {
+      const double expo = sqrt((1 - cos(latstep + ex0)) / (1 - cos(latstep + ex)));
+      r_inc = (r_orig - r_prev) * pow_inv3k(expo, a.cfg.k, inv3k);
+    }
+    const double r_cum = ag_scan(live ? r_inc : 0.0, carry_r, lane);
+    double r_before = __shfl_up_sync(0xffffffffu, r_cum, 1);
+    if (lane == 0) r_before = r_cum_last;
+    r_cum_last = __shfl_sync(0xffffffffu, r_cum, 31);
+    const double r_diff = (s == 0) ? r_cum : r_cum - r_before;                       // np.diff(R, prepend=0), :347-350
+    const double ibeta = 1.0 / beta;
+    const double tobso = ag_scan(live ? r_diff * (ibeta - 1.0) / AG_CC : 0.0, carry_t, lane);   // :353, :356
+    if (!live) continue;
+    const double n0 = (a.cfg.k == 0) ? n_amb : n_amb * pow(r_cum, -kk);             // r**-0.0 == 1
+    const double B = sqrt(2 * AG_FOURPI * EB * n0 * AG_MP * AG_C2 * ((ghat * G + 1.0) / (ghat - 1.0)) * Gm1);
+    double gm;
+    if (p > 2) {
+      gm = ((p - 2) / (p - 1)) * (Ee / xiN) * Gm1 * (AG_MP / AG_ME);
+    } else {
+      const double gmm = sqrt(1.5 * AG_FOURPI * AG_QE / (sigt * B));
+      if (p == 2) gm = (1 / log(gmm / ((Ee / xiN) * Gm1 * (AG_MP / AG_ME)))) * (Ee / xiN) * Gm1 * (AG_MP / AG_ME);
+      else gm = pow((2 - p) / (p - 1) * (AG_MP / AG_ME) * (Ee / xiN) * Gm1 * pow(gmm, p - 2), 1 / (p - 1));
+    }
+    const double gc = 6.0 * kPi * AG_ME * AG_CC / (G * sigt * B * B * tobso);        // :360
+    const double nucp = 0.286 * 3.0 * gc * gc * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);          // :361
+    const double nump = 3.0 * xp * gm * gm * AG_QE * B / (AG_FOURPI * AG_ME * AG_CC);
+    const double pp = xiN * Fx * AG_ME * AG_C2 * sigt * B / (3.0 * AG_QE);
+    const double kt = gm * AG_ME * AG_C2;
+    out[RA_RD * steps + s] = r_diff;
+    out[RA_IBETA * steps + s] = ibeta;
+    out[RA_BETA * steps + s] = beta;
+    out[RA_OMG * steps + s] = omg;
+    out[RA_OMCOS * steps + s] = omg * (1.0 - omg / rotstep);       // cos(arccos(x)) = x to an ulp (x in [-1, 1], a factor)
+    out[RA_FMR * steps + s] = Ne * pp;
+    out[RA_FBR * steps + s] = 2.0 * kt * r_cum * r_cum / AG_C2;
+    out[RA_NUMP * steps + s] = nump;
+    out[RA_NUCP * steps + s] = nucp;
+    out[RA_LNUMP * steps + s] = log(nump);
+    out[RA_LNUCP * steps + s] = log(nucp);
   }
 }
 

@@ -1188,9 +1188,10 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
     a.ring_scratch = b_ring.as<double>();
     a.partial = b_part.as<double>();
     if (total > 0) {
-      rb::ag_ring_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, total);
+      rb::ag_gamma_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, total);
+      rb::ag_ring_kernel<<<(unsigned)((total + 3) / 4), 128, 0, st>>>(a, total);
       rb::ag_cell_kernel<<<(unsigned)total_units, rb::kAgWarps * 32, cell_smem, st>>>(a, total_units);
-      launch_counter()->fetch_add(2);
+      launch_counter()->fetch_add(3);
     }
     rb::ag_finish_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * 16), 128, 0, st>>>(a);
     launch_counter()->fetch_add(1);
