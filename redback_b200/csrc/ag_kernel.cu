@@ -531,23 +531,30 @@ __global__ void __launch_bounds__(kAgWarps * 32, 4) ag_cell_kernel(const AgArgs 
       // Omi row factor (:57): (cos(i*latstep) - cos((i+1)*latstep))
       const double dcos = cos((double)i * latstep) - cos((double)(i + 1) * latstep);
 
-      for (int j = warp; j < nrot; j += kAgWarps) {
-        // phi = linspace(rotstep, nrot*rotstep, nrot)[j]; phii = linspace(rotstep/2, ...)[j]   (:53,62)
-        double phi, phii;
-        if (nrot == 1) { phi = rotstep; phii = ph_lo; }
-        else {
-          const double phi_hi = (double)nrot * rotstep;
-          phi = (j == nrot - 1) ? phi_hi : (double)j * ((phi_hi - rotstep) / (double)(nrot - 1)) + rotstep;
-          phii = (j == nrot - 1) ? ph_hi : (double)j * ((ph_hi - ph_lo) / (double)(nrot - 1)) + ph_lo;
+      // geometry of this warp's cells (j = warp, warp + 5, ...), 32 at a time with lane = cell: the trigonometric
+      // functions of get_obsangle_numba run once per cell instead of once per lane of the cell's warp
+      double cosa_l = 0.0, om0_l = 0.0;
+      for (int j = warp, q = 0; j < nrot; j += kAgWarps, ++q) {
+        if ((q & 31) == 0) {
+          const int jl = j + kAgWarps * lane;
+          // phi = linspace(rotstep, nrot*rotstep, nrot)[j]; phii = linspace(rotstep/2, ...)[j]   (:53,62)
+          double phi, phii;
+          if (nrot == 1) { phi = rotstep; phii = ph_lo; }
+          else {
+            const double phi_hi = (double)nrot * rotstep;
+            phi = (jl == nrot - 1) ? phi_hi : (double)jl * ((phi_hi - rotstep) / (double)(nrot - 1)) + rotstep;
+            phii = (jl == nrot - 1) ? ph_hi : (double)jl * ((ph_hi - ph_lo) / (double)(nrot - 1)) + ph_lo;
+          }
+          om0_l = (phi - (phi - rotstep)) * dcos;
+          // get_obsangle_numba (:151-179) with phi = 0
+          const double f1 = 0.0 * sin_tho * sin(phii) * sin_thi;
+          const double f2 = 1.0 * sin_tho * cos(phii) * sin_thi;
+          double ang = cos_tho * cos_thi + f2 + f1;
+          ang = (ang > 1.0) ? 1.0 : ((ang < -1.0) ? -1.0 : ang);
+          cosa_l = cos(acos(ang));
         }
-        const double Om0 = (phi - (phi - rotstep)) * dcos;
-        // get_obsangle_numba (:151-179) with phi = 0
-        const double f1 = 0.0 * sin_tho * sin(phii) * sin_thi;
-        const double f2 = 1.0 * sin_tho * cos(phii) * sin_thi;
-        double ang = cos_tho * cos_thi + f2 + f1;
-        ang = (ang > 1.0) ? 1.0 : ((ang < -1.0) ? -1.0 : ang);
-        const double obsa = acos(ang);
-        const double cosa = cos(obsa);
+        const double Om0 = __shfl_sync(0xffffffffu, om0_l, q & 31);
+        const double cosa = __shfl_sync(0xffffffffu, cosa_l, q & 31);
         // the cell's own solid angle (expansion: used until the ring's exceeds it)
         const double omcos0 = Om0 * (1.0 - Om0 / rotstep);
         const double c_fmax = Om0 / AG_FOURPI / AG_FOURPI * inv_dl2;       // NO * P' * dop^3 / (4 pi dl^2), :365-366
