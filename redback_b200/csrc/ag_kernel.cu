@@ -627,6 +627,11 @@ __global__ void __launch_bounds__(kAgWarps * 32, 4) ag_cell_kernel(const AgArgs 
         int lo = -1;                     // largest j <= steps - 2 with tobs[j] <= x, carried along the lane's time-ordered run
         int lo_slope = -1;               // interval whose 1 / (tobs[lo+1] - tobs[lo]) is in `inv_dt`
         double inv_dt = 0.0;
+        // epochs observed at the same time in several bands sit next to each other in the run: the interval search and
+        // the abscissa part of the interpolation are done once per distinct time (mode 0 interior, 1 / 2 clamped to the
+        // first / last step, 3 NaN)
+        double x_prev = NAN, dx = 0.0;
+        int mode = 3;
         double t_next = a.ep_t_T[lane];
         int h_next = a.ep_nu_T[lane];
         for (int k = 0; k < epl; ++k) {
@@ -636,26 +641,36 @@ __global__ void __launch_bounds__(kAgWarps * 32, 4) ag_cell_kernel(const AgArgs 
           if (k + 1 < epl) { t_next = a.ep_t_T[pos + 32]; h_next = a.ep_nu_T[pos + 32]; }
           if (hh < 0) continue;          // padding
           const double* fp = my_flux + hh * steps;
-          double v;
-          if (!(x == x)) v = x;
-          else if (x <= x_first) v = fp[0];           // numpy: x < xp[0] -> left; x == xp[0] -> fp[0]
-          else if (x >= x_last) v = fp[steps - 1];
-          else {
-            int walk = 0;
-            if (lo >= 0)
-              while (walk < 4 && lo < steps - 2 && my_tobs[lo + 1] <= x) { ++lo; ++walk; }
-            if (lo < 0 || walk == 4) {
-              int hi = steps - 1;
-              lo = max(lo, 0);
-              while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (my_tobs[mid] <= x) lo = mid; else hi = mid;
+          if (!(x == x_prev)) {
+            x_prev = x;
+            if (!(x == x)) mode = 3;
+            else if (x <= x_first) mode = 1;        // numpy: x < xp[0] -> left; x == xp[0] -> fp[0]
+            else if (x >= x_last) mode = 2;
+            else {
+              mode = 0;
+              int walk = 0;
+              if (lo >= 0)
+                while (walk < 4 && lo < steps - 2 && my_tobs[lo + 1] <= x) { ++lo; ++walk; }
+              if (lo < 0 || walk == 4) {
+                int hi = steps - 1;
+                lo = max(lo, 0);
+                while (hi - lo > 1) {
+                  const int mid = (lo + hi) >> 1;
+                  if (my_tobs[mid] <= x) lo = mid; else hi = mid;
+                }
               }
+              const double t0 = my_tobs[lo];
+              if (lo != lo_slope) { inv_dt = 1.0 / (my_tobs[lo + 1] - t0); lo_slope = lo; }
+              dx = x - t0;
             }
-            const double t0 = my_tobs[lo], f0 = fp[lo];
-            if (lo != lo_slope) { inv_dt = 1.0 / (my_tobs[lo + 1] - t0); lo_slope = lo; }
-            v = fma((fp[lo + 1] - f0) * inv_dt, x - t0, f0);             // slope * (x - xp[lo]) + fp[lo]
           }
+          double v;
+          if (mode == 0) {
+            const double f0 = fp[lo];
+            v = fma((fp[lo + 1] - f0) * inv_dt, dx, f0);                 // slope * (x - xp[lo]) + fp[lo]
+          } else if (mode == 1) v = fp[0];
+          else if (mode == 2) v = fp[steps - 1];
+          else v = x;
           my_acc[pos] += v;
         }
         __syncwarp();
