@@ -200,12 +200,8 @@ __global__ void __launch_bounds__(kMkThreads) mk_kernel(const MkArgs a) {
         if (isnan(dist)) dist = -INFINITY;                                      // np.argmin returns the first NaN
         int idx = s;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          lo += __shfl_xor_sync(0xffffffffu, lo, o);
-          const double od = __shfl_xor_sync(0xffffffffu, dist, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-          if (od < dist || (od == dist && oi < idx)) { dist = od; idx = oi; }
-        }
+        for (int o = 16; o > 0; o >>= 1) lo += __shfl_xor_sync(0xffffffffu, lo, o);
+        warp_argmin_first(dist, idx);
         if (lane == 0) {
           lpart[warp * G + ii] = lo;
           tpart[warp * G + ii] = dist;

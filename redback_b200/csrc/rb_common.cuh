@@ -82,6 +82,22 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
   return scratch[32];
 }
 
+// np.argmin over the warp's lanes for values that are >= 0, +inf, or -inf (the caller's stand-in for NaN, which np.argmin
+// returns first): the smallest value and, among equals, the smallest index, left in every lane.  Non-negative doubles
+// order like their bit patterns, so three integer warp reductions (REDUX.MIN on the high word, the low word among the
+// lanes that tie on it, the index among those that tie on both) replace five shuffle stages of (value, index) pairs.
+__device__ __forceinline__ void warp_argmin_first(double& dist, int& idx) {
+  const unsigned long long key = (dist < 0.0) ? 0ull : (unsigned long long)__double_as_longlong(dist) + 1ull;
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned m_hi = __reduce_min_sync(0xffffffffu, hi);
+  const bool c1 = hi == m_hi;
+  const unsigned m_lo = __reduce_min_sync(0xffffffffu, c1 ? lo : 0xffffffffu);
+  const bool c2 = c1 && lo == m_lo;
+  idx = (int)__reduce_min_sync(0xffffffffu, c2 ? (unsigned)idx : 0xffffffffu);
+  const unsigned long long kmin = ((unsigned long long)m_hi << 32) | m_lo;
+  dist = (kmin == 0ull) ? -INFINITY : __longlong_as_double((long long)(kmin - 1ull));
+}
+
 // np.maximum / Python max(a, b) on floats: NaN-propagating maximum
 __device__ __forceinline__ double fmax_nan(double a, double b) {
   if (a != a) return a;
