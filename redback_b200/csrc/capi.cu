@@ -1523,7 +1523,7 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   // per-block scratch: the epoch records + the forward-eliminated rows of the wavelength-axis solve (L2-resident)
   const int e_pad = (int)((E + 31) / 32 * 32);
   const int64_t scratch_stride = (int64_t)(rb::kEpCols + NL - pa.j_store_lo) * e_pad +
-                                 (shape.tables_global ? 9 * (int64_t)NT : 0);
+                                 (shape.tables_global ? 9 * (int64_t)NT + 2 : 0);
   double *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr, *d_scratch = nullptr;
   int* d_len = nullptr;
   ce = cudaMallocAsync(&d_grid, (size_t)n_comp * nc_max * 4 * NT * sizeof(double), st);

@@ -111,7 +111,7 @@ struct PhotArgs {
 // reduction scratch, exp table, column buffer (also the per-epoch coefficient buffer of the last phase)
 __host__ __device__ inline size_t phot_fixed_doubles(int NT, int NL, int n_comp, bool line, bool tables_global) {
   return (size_t)(2 * n_comp + (line ? 2 : 0)) * NT + (tables_global ? 0 : 9 * (size_t)NT) + 4 * (size_t)NL +
-         5 * (size_t)NL + 2 * kScanSteps * 32 * 4 + 128 + 6 * (size_t)((NT + 31) / 32) + kExpTabSize;
+         5 * (size_t)NL + 2 * kScanSteps * 32 * 4 + 128 + 6 * (size_t)((NT + 31) / 32) + kExpTabSize + 4;
 }
 
 // FITPACK fpbspl for k = 3: the four non-zero cubic B-splines at x, t[l] <= x < t[l+1] (0-based l)
@@ -223,10 +223,17 @@ __device__ __noinline__ double planck_inv_general(double x, const double* __rest
 #define PHOT_PROF_REPORT()
 #endif
 
+// two adjacent doubles: one 16-byte load where the base is known to be 16-byte aligned (shared-memory tables)
+template <bool SCALAR>
+__device__ __forceinline__ double2 ld_pair(const double* __restrict__ p) {
+  if (SCALAR) return make_double2(p[0], p[1]);
+  return *reinterpret_cast<const double2*>(p);
+}
+
 // GT: the time-axis LU and its homogeneous solutions live in global memory (grids too long for shared memory)
 template <bool GT>
 __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
-  extern __shared__ double psm[];
+  extern __shared__ __align__(16) double psm[];
   const int NT = a.n_t_max, NL = a.n_lambda, E = a.E, NC = a.n_comp;
   const int T = (int)blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const bool line = a.sed == PH_SED_CUTOFF_LINE;
@@ -237,9 +244,20 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
   double* rowC = rowB + NC * NT;               // [NT]  1 - line amplitude           (line SED only)
   double* rowD = rowC + (line ? NT : 0);       // [NT]  scaled line amplitude        (line SED only)
   double* after_rows = rowD + (line ? NT : 0);
-  double* lut = GT ? gs : after_rows;          // [NT][5]  time-axis banded LU, scaled rows
-  double* hom = lut + 5 * NT;                  // [4][NT]  homogeneous solutions of the segmented time-axis solve (one array
-                                               //          per solution: lanes stride an odd segment length, no bank conflicts)
+  // time-axis banded LU, scaled rows (l2, l1, 1/d, u1/d, u2/d), stored as THREE arrays so that a sweep of the segmented
+  // solve fetches its two coefficients with one 16-byte load: [NT] pairs (l2, l1), [NT] pairs (u1/d, u2/d), [NT] 1/d;
+  // the homogeneous solutions of the segmented solve likewise as [NT] pairs (forward 0, 1) and [NT] pairs (backward 0, 1).
+  // Both bases are 16-byte aligned in shared memory; with the tables in global memory (GT) the loads stay scalar.
+  double* lut = GT ? gs : after_rows + ((after_rows - psm) & 1);    // (no pointer <-> integer round trip: it would
+                                                                     // turn every access into a generic load)
+  double* hom = lut + 5 * NT + (NT & 1);
+#define LUT0(i) lut[2 * (i)]
+#define LUT1(i) lut[2 * (i) + 1]
+#define LUT2(i) lut[4 * NT + (i)]
+#define LUT3(i) lut[2 * NT + 2 * (i)]
+#define LUT4(i) lut[2 * NT + 2 * (i) + 1]
+#define HOMF(w, i) hom[2 * (i) + (w)]
+#define HOMB(w, i) hom[2 * NT + 2 * (i) + (w)]
   double* colA = GT ? after_rows : hom + 4 * NT;   // [NL]  h nu         or hc / (k_B lambda)
   double* colB = colA + NL;                    // [NL]  everything else that depends on wavelength only
   double* colC = colB + NL;                    // [NL]  line profile in output units
@@ -251,7 +269,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
   double* grp = red2 + 64;                     // [6][ngroups] bounds of rowA / rowB over each group of 32 rows
   double* tab = grp + 6 * ((NT + 31) / 32);    // [1024]
   double* buf = tab + kExpTabSize;             // [W][NTP] column block; later [epochs][span_max] coefficients
-  double* ept = gs + (GT ? 9 * (size_t)NT : 0);       // [kEpCols][e_pad]
+  double* ept = gs + (GT ? 9 * (size_t)NT + 2 : 0);   // [kEpCols][e_pad]
   double* ys = ept + (size_t)kEpCols * a.e_pad;       // [NL - j_store_lo][e_pad]
   const int EP = a.e_pad;
   const int lgP = 31 - __clz(P);
@@ -279,15 +297,15 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       double p1 = (which & 1) ? 0.0 : 1.0, p2 = (which & 1) ? 1.0 : 0.0;
       if (which < 2) {
         for (int i = i_lo; i < i_hi; ++i) {
-          const double y = -lut[5 * i + 0] * p2 - lut[5 * i + 1] * p1;
-          hom[which * NT + i] = y;
+          const double y = -LUT0(i) * p2 - LUT1(i) * p1;
+          HOMF(which, i) = y;
           p2 = p1;
           p1 = y;
         }
       } else {
         for (int i = i_hi - 1; i >= i_lo; --i) {
-          const double x = -lut[5 * i + 4] * p2 - lut[5 * i + 3] * p1;
-          hom[which * NT + i] = x;
+          const double x = -LUT4(i) * p2 - LUT3(i) * p1;
+          HOMB(which - 2, i) = x;
           p2 = p1;
           p1 = x;
         }
@@ -301,11 +319,11 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       if (s < Pe) {
         const int i_lo = s * L, i_hi = min(i_lo + L, G);
         if (dir == 0) {          // (y[i_hi-1], y[i_hi-2]) from (y[i_lo-1], y[i_lo-2]); all but the last segment have >= 3 rows
-          h00 = hom[0 * NT + i_hi - 1]; h01 = hom[1 * NT + i_hi - 1];
-          if (i_hi - 2 >= i_lo) { h10 = hom[0 * NT + i_hi - 2]; h11 = hom[1 * NT + i_hi - 2]; } else { h10 = 1.0; }
+          h00 = HOMF(0, i_hi - 1); h01 = HOMF(1, i_hi - 1);
+          if (i_hi - 2 >= i_lo) { h10 = HOMF(0, i_hi - 2); h11 = HOMF(1, i_hi - 2); } else { h10 = 1.0; }
         } else {                 // (x[i_lo], x[i_lo+1]) from (x[i_hi], x[i_hi+1])
-          h00 = hom[2 * NT + i_lo]; h01 = hom[3 * NT + i_lo];
-          if (i_lo + 1 < i_hi) { h10 = hom[2 * NT + i_lo + 1]; h11 = hom[3 * NT + i_lo + 1]; } else { h10 = 1.0; }
+          h00 = HOMB(0, i_lo); h01 = HOMB(1, i_lo);
+          if (i_lo + 1 < i_hi) { h10 = HOMB(0, i_lo + 1); h11 = HOMB(1, i_lo + 1); } else { h10 = 1.0; }
         }
       }
       m0[0] = h00; m0[1] = h01; m0[2] = h10; m0[3] = h11;
@@ -333,7 +351,11 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     }
   };
   if (a.common_time_lu) {
-    for (int i = tid; i < NT; i += T) load_lu_row(lut + 5 * i, a.lu_time + 5 * i);
+    for (int i = tid; i < NT; i += T) {
+      double row[5];
+      load_lu_row(row, a.lu_time + 5 * i);
+      LUT0(i) = row[0]; LUT1(i) = row[1]; LUT2(i) = row[2]; LUT3(i) = row[3]; LUT4(i) = row[4];
+    }
     set_segments(NT);
     __syncthreads();
     build_tables(NT);
@@ -551,7 +573,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
             if (off >= 0 && off < 5) row[off] = h[q];
           }
         }
-        for (int q = 0; q < 5; ++q) lut[5 * i + q] = row[q];
+        LUT0(i) = row[0]; LUT1(i) = row[1]; LUT2(i) = row[2]; LUT3(i) = row[3]; LUT4(i) = row[4];
       }
     }
     bool all_valid;
@@ -667,19 +689,19 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     const bool lu_thread = !a.common_time_lu && warp == nwarps - 1;
     const bool lu_fast = !a.common_time_lu && G >= 10;
     auto lu_row = [&](int i) {
-      const double a0 = lut[5 * i + 0], a1 = lut[5 * i + 1], a2 = lut[5 * i + 2], a3 = lut[5 * i + 3], a4 = lut[5 * i + 4];
+      const double a0 = LUT0(i), a1 = LUT1(i), a2 = LUT2(i), a3 = LUT3(i), a4 = LUT4(i);
       double rd1 = 0.0, s1_1 = 0.0, s2_1 = 0.0, rd2 = 0.0, s1_2 = 0.0, s2_2 = 0.0;   // 1/d, u1/d, u2/d of rows i-1, i-2
-      if (i >= 1) { rd1 = lut[5 * i - 3]; s1_1 = lut[5 * i - 2]; s2_1 = lut[5 * i - 1]; }
-      if (i >= 2) { rd2 = lut[5 * i - 8]; s1_2 = lut[5 * i - 7]; s2_2 = lut[5 * i - 6]; }
+      if (i >= 1) { rd1 = LUT2(i - 1); s1_1 = LUT3(i - 1); s2_1 = LUT4(i - 1); }
+      if (i >= 2) { rd2 = LUT2(i - 2); s1_2 = LUT3(i - 2); s2_2 = LUT4(i - 2); }
       const double am1 = a1 - a0 * s1_2;
       const double d = (a2 - a0 * s2_2) - am1 * s1_1;
       const double u1 = a3 - am1 * s2_1;
       const double rd = rcp_fast(d);
-      lut[5 * i + 0] = a0 * rd2;
-      lut[5 * i + 1] = am1 * rd1;
-      lut[5 * i + 2] = rd;
-      lut[5 * i + 3] = u1 * rd;
-      lut[5 * i + 4] = a4 * rd;
+      LUT0(i) = a0 * rd2;
+      LUT1(i) = am1 * rd1;
+      LUT2(i) = rd;
+      LUT3(i) = u1 * rd;
+      LUT4(i) = a4 * rd;
     };
     if (lu_thread && lane == 0) {
       if (!lu_fast) {
@@ -688,13 +710,13 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         lu_row(0);
         lu_row(1);
         lu_row(2);
-        double pm2 = 1.0, pm1 = lut[17] - lut[16] * lut[13];      // P_2 = 1, P_3 = d_3 = b_3 - a_3 (u1/d)_2
+        double pm2 = 1.0, pm1 = LUT2(3) - LUT1(3) * LUT3(2);      // P_2 = 1, P_3 = d_3 = b_3 - a_3 (u1/d)_2
         hom[2] = pm2;
         hom[3] = pm1;
 #pragma unroll 4
         for (int i = 4; i <= G - 3; ++i) {
-          const double ac = lut[5 * i + 1] * lut[5 * i - 2];      // a_i c_{i-1} (raw rows)
-          const double pi = fma(lut[5 * i + 2], pm1, -(ac * pm2));
+          const double ac = LUT1(i) * LUT3(i - 1);                // a_i c_{i-1} (raw rows)
+          const double pi = fma(LUT2(i), pm1, -(ac * pm2));
           hom[i] = pi;
           pm2 = pm1;
           pm1 = pi;
@@ -786,13 +808,13 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     if (lu_fast) {
       for (int i = 3 + tid; i <= G - 3; i += T) {
         const double rd = hom[i - 1] / hom[i];                    // 1 / d_i
-        const double rd_prev = (i == 3) ? lut[12] : hom[i - 2] / hom[i - 1];
-        const double a1 = lut[5 * i + 1], c1 = lut[5 * i + 3], c2 = lut[5 * i + 4];
-        lut[5 * i + 0] = 0.0;
-        lut[5 * i + 1] = a1 * rd_prev;
-        lut[5 * i + 2] = rd;
-        lut[5 * i + 3] = c1 * rd;
-        lut[5 * i + 4] = c2 * rd;
+        const double rd_prev = (i == 3) ? LUT2(2) : hom[i - 2] / hom[i - 1];
+        const double a1 = LUT1(i), c1 = LUT3(i), c2 = LUT4(i);
+        LUT0(i) = 0.0;
+        LUT1(i) = a1 * rd_prev;
+        LUT2(i) = rd;
+        LUT3(i) = c1 * rd;
+        LUT4(i) = c2 * rd;
       }
       __syncthreads();
       if (tid == 0) {
@@ -888,7 +910,8 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         if (active) {
 #pragma unroll 4
           for (int i = i_lo; i < i_hi; ++i) {
-            const double y = (col[i] - lut[5 * i + 0] * p2) - lut[5 * i + 1] * p1;
+            const double2 f = ld_pair<GT>(lut + 2 * i);                       // (l2, l1)
+            const double y = (col[i] - f.x * p2) - f.y * p1;
             col[i] = y;
             p2 = p1;
             p1 = y;
@@ -916,10 +939,14 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
           // recurrence proper then has one FMA per row on its dependency chain
 #pragma unroll 8
           for (int i = i_lo; i < i_hi; ++i)
-            col[i] = (col[i] + hom[0 * NT + i] * Y1 + hom[1 * NT + i] * Y2) * lut[5 * i + 2];
+{
+            const double2 hf = ld_pair<GT>(hom + 2 * i);
+            col[i] = (col[i] + hf.x * Y1 + hf.y * Y2) * LUT2(i);
+          }
 #pragma unroll 4
           for (int i = i_hi - 1; i >= i_lo; --i) {
-            const double x = (col[i] - lut[5 * i + 4] * p2) - lut[5 * i + 3] * p1;
+            const double2 ub = ld_pair<GT>(lut + 2 * NT + 2 * i);             // (u1/d, u2/d)
+            const double x = (col[i] - ub.y * p2) - ub.x * p1;
             col[i] = x;
             p2 = p1;
             p1 = x;
@@ -941,7 +968,10 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         if (seg == P - 1) { X1 = 0.0; X2 = 0.0; }
         if (active && (X1 != 0.0 || X2 != 0.0)) {
 #pragma unroll 4
-          for (int i = i_lo; i < i_hi; ++i) col[i] += hom[2 * NT + i] * X1 + hom[3 * NT + i] * X2;
+          for (int i = i_lo; i < i_hi; ++i) {
+            const double2 hb = ld_pair<GT>(hom + 2 * NT + 2 * i);
+            col[i] += hb.x * X1 + hb.y * X2;
+          }
         }
       }
       __syncthreads();
