@@ -455,6 +455,25 @@ int rb_mk_eval_f64_host_rows(const rb_mk_config* cfg, int64_t N, int64_t E, cons
  * The caller prepares, per band b (what sncosmo does on the host in the reference):
  *   - the integration grid  wave = arange(minwave + d/2, maxwave, d), d = range / ceil(range / 5 A)
  *   - int_wt = wave * transmission(wave), band_scale = d / HC_ERG_AA, band_zp = AB zero-point band flux. */
+/* ---- dust extinction (redback/transient_models/extinction_models.py:77-170, _perform_extinction) ---------------
+ * Host-galaxy extinction at lambda / (1 + z) with (host_law, av_host, rv_host) and Milky-Way extinction at lambda with
+ * (mw_law, av_mw, rv_mw); flux * 10^(-0.4 A); A is zeroed where it exceeds 10 mag while A_V < 10.  The laws are the
+ * `extinction` package's (third party, absent here: parity unpinned, see csrc/ext_kernel.cu).  For
+ * RB_EXT_FITZPATRICK99 the caller supplies the cubic spline through Fitzpatrick's nine anchor points as 9 breakpoints
+ * [1/micron] followed by 8 x 4 piecewise-cubic coefficients (highest power first, in x - breakpoint). */
+enum { RB_EXT_CCM89 = 1, RB_EXT_ODONNELL94 = 2, RB_EXT_CALZETTI00 = 3, RB_EXT_FITZPATRICK99 = 4 };
+typedef struct {
+  int host_law, mw_law;         /* RB_EXT_*                                                          */
+  double rv_host, rv_mw;        /* 3.1; calzetti00: 4.05 (the package default, redback passes none)  */
+  double av_mw;                 /* 0: no Milky-Way extinction                                        */
+  double f99_host[41], f99_mw[41];
+} rb_extinction;
+
+/* Flux-density branch of _evaluate_extinction_model (:194-221): model[n][e] *= 10^(-0.4 A), in place, with the observed
+ * wavelength c / freq_obs[e].  Device pointers: freq_obs [E], redshift [N], av_host [N], model [N][E]. */
+int rb_extinction_apply_f64(const rb_extinction* ext, int64_t N, int64_t E, const double* freq_obs,
+                            const double* redshift, const double* av_host, double* model, void* stream);
+
 enum { RB_OUT_MAGNITUDE = 0, RB_OUT_FLUX = 1 };
 typedef struct {
   int output;                   /* RB_OUT_*                                                         */
@@ -470,6 +489,11 @@ typedef struct {
   const double* band_scale;     /* [n_bands]                                                         */
   const double* band_zp;        /* [n_bands]                                                         */
   const double* band_ref_flux;  /* [n_bands] tables/filters.csv reference_flux (RB_OUT_FLUX) or NULL */
+  /* magnitude / flux branch of _evaluate_extinction_model (:223-251): the spectra are attenuated per observer-frame
+     wavelength before the spline fit.  `extinction` HOST pointer or NULL; `ext_av_host` DEVICE pointer [N] (the
+     per-sample host-galaxy A_V), required when `extinction` is given. */
+  const rb_extinction* extinction;
+  const double* ext_av_host;
 } rb_photometry;
 
 /* Magnitude-branch twins of rb_sn_eval_f64 / rb_kn_eval_f64: same device arguments minus freq_obs

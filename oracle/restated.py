@@ -1885,7 +1885,8 @@ def bandpass_magnitude_to_flux(magnitude, reference_flux):
     return 10.0 ** (magnitude / (-2.5)) * reference_flux
 
 
-def sn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, **params):
+def sn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, spectra_transform=None,
+                 **params):
     """Magnitude branch of arnett / basic_magnetar_powered / slsn (supernova_models.py:1008-1028, 1510-1530,
     1599-1624; csm_interaction :2093-2111).  `model` in {'arnett', 'basic_magnetar_powered', 'slsn', 'type_1a',
     'csm_interaction'}."""
@@ -1919,6 +1920,8 @@ def sn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None,
         else:
             fd = blackbody_to_flux_density(temp, rad, dl, frequency[:, None]).T
             spectra = flux_density_to_spectrum(fd, redshift, lam)
+        if spectra_transform is not None:                                        # extinction_models.py:236-251
+            spectra = spectra_transform(spectra, lam)
     return bandmag_from_spectra(time_obs, time_observer_frame, spectra, lam, bands, bandpasses)
 
 
@@ -2002,7 +2005,7 @@ def metzger_magnetar_magnitude(model, time, redshift, *, bands, bandpasses, lamb
 
 
 def kn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, dense_resolution=500,
-                 **params):
+                 spectra_transform=None, **params):
     """Magnitude branch of one_component_kilonova_model / metzger_kilonova_model
     (kilonova_models.py:1579-1603, 1937-1962)."""
     time_obs = np.asarray(time, dtype=float)
@@ -2023,6 +2026,8 @@ def kn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None,
     with np.errstate(all="ignore"):
         fd = blackbody_to_flux_density(temp, rad, dl, frequency[:, None]).T
         spectra = flux_density_to_spectrum(fd, redshift, lam)
+        if spectra_transform is not None:                                        # extinction_models.py:236-251
+            spectra = spectra_transform(spectra, lam)
     return bandmag_from_spectra(time_obs, time_observer_frame / day_to_s, spectra, lam, bands, bandpasses)
 
 
@@ -2143,3 +2148,115 @@ def survey_observation_single(model_magnitude, phase, ref_flux, five_sigma_depth
     return dict(magnitude=magnitudes, e_magnitude=magnitude_errs, flux=observed_flux, flux_error=err,
                 detected=detected.astype(bool), flux_limit=bandpass_magnitude_to_flux(
                     np.asarray(five_sigma_depth, dtype=float), ref_flux))
+
+
+# --------------------------------------------------------------------------------------------------
+# dust extinction (transient_models/extinction_models.py:77-170).  The laws live in the third-party `extinction`
+# package (kbarbary/extinction; redback's setup.py / optional_requirements.txt pin no version; not vendored, not
+# installable here).  Pinned only to the package's documented example values (README / API docs, as known-answer
+# tests in tests/test_extinction.py: ccm89([2000, 4000, 8000] A, 1.0, 3.1) = [2.84252644, 1.4645557, 0.59748901],
+# fitzpatrick99(same) = [2.76225609, 1.42325373, 0.55333671]); otherwise PARITY UNPINNED (odonnell94, calzetti00 have
+# no vector).  Restated from the papers the package cites -- Cardelli, Clayton & Mathis 1989
+# (eqs. 2-5), O'Donnell 1994 (optical coefficients), Calzetti et al. 2000 (eq. 4), Fitzpatrick 1999 (Fitzpatrick &
+# Massa 1990 UV curve with the 1999 parameters, cubic spline through nine anchors at longer wavelengths) -- and
+# anchored on what test/extinction_test.py:92-141 checks (zero A_V is the identity, extinction dims, host + MW
+# dims more, input not mutated) plus the papers' own fixed points (A(V) = A_V at x = 1.82 / micron).
+# --------------------------------------------------------------------------------------------------
+_CCM_A_OPT = [1.0, 0.17699, -0.50447, -0.02427, 0.72085, 0.01979, -0.77530, 0.32999]          # CCM89 eq. 3a, ascending in y
+_CCM_B_OPT = [0.0, 1.41338, 2.28305, 1.07233, -5.38434, -0.62251, 5.30260, -2.09002]          # eq. 3b
+_OD94_A_OPT = [1.0, 0.104, -0.609, 0.701, 1.137, -1.718, -0.827, 1.647, -0.505]               # O'Donnell 1994
+_OD94_B_OPT = [0.0, 1.952, 2.908, -3.989, -7.985, 11.102, 5.491, -10.805, 3.347]
+
+
+def _ccm89_like(wave, a_v, r_v, a_opt, b_opt):
+    x = 1e4 / np.asarray(wave, dtype=float)
+    a, b = np.empty_like(x), np.empty_like(x)
+    ir, opt, uv, fuv = x < 1.1, (x >= 1.1) & (x < 3.3), (x >= 3.3) & (x < 8.0), x >= 8.0
+    a[ir], b[ir] = 0.574 * x[ir] ** 1.61, -0.527 * x[ir] ** 1.61                                # eq. 2
+    y = x[opt] - 1.82
+    a[opt] = np.polynomial.polynomial.polyval(y, a_opt)
+    b[opt] = np.polynomial.polynomial.polyval(y, b_opt)
+    xu = x[uv]
+    yf = np.where(xu >= 5.9, xu - 5.9, 0.0)
+    a[uv] = 1.752 - 0.316 * xu - 0.104 / ((xu - 4.67) ** 2 + 0.341) - 0.04473 * yf ** 2 - 0.009779 * yf ** 3   # eq. 4
+    b[uv] = -3.090 + 1.825 * xu + 1.206 / ((xu - 4.62) ** 2 + 0.263) + 0.2130 * yf ** 2 + 0.1207 * yf ** 3
+    y = x[fuv] - 8.0
+    a[fuv] = -1.073 - 0.628 * y + 0.137 * y ** 2 - 0.070 * y ** 3                                # eq. 5
+    b[fuv] = 13.670 + 4.257 * y - 0.420 * y ** 2 + 0.374 * y ** 3
+    return a_v * (a + b / r_v)
+
+
+def extinction_ccm89(wave, a_v, r_v):
+    return _ccm89_like(wave, a_v, r_v, _CCM_A_OPT, _CCM_B_OPT)
+
+
+def extinction_odonnell94(wave, a_v, r_v):
+    return _ccm89_like(wave, a_v, r_v, _OD94_A_OPT, _OD94_B_OPT)
+
+
+def extinction_calzetti00(wave, a_v, r_v=4.05):
+    """Calzetti et al. 2000 eq. 4: k(lambda) over 0.12-0.63 and 0.63-2.2 micron, A = A_V k / R_V with k = k' + R_V.
+    The reference calls the package without R_V (:131-133, 'Calzetti law doesn't use R_V'): 4.05, the paper's value."""
+    x = 1e4 / np.asarray(wave, dtype=float)
+    k = np.where(x > 1.0 / 0.63, 2.659 * (-2.156 + 1.509 * x - 0.198 * x ** 2 + 0.011 * x ** 3),
+                 2.659 * (-1.857 + 1.040 * x))
+    return a_v * (1.0 + k / r_v)
+
+
+_F99_ANCHORS_AA = np.array([np.inf, 26500.0, 12200.0, 6000.0, 5470.0, 4670.0, 4110.0, 2700.0, 2600.0])
+
+
+def _fm90_k(x, r_v):
+    """Fitzpatrick & Massa 1990 with Fitzpatrick 1999's x0 = 4.596, gamma = 0.99, c3 = 3.23, c4 = 0.41 and the R_V
+    dependent c2 = -0.824 + 4.717 / R_V, c1 = 2.030 - 3.007 c2: E(lambda - V) / E(B - V)."""
+    x = np.asarray(x, dtype=float)
+    c2 = -0.824 + 4.717 / r_v
+    c1 = 2.030 - 3.007 * c2
+    drude = x ** 2 / ((x ** 2 - 4.596 ** 2) ** 2 + (x * 0.99) ** 2)
+    y = np.where(x >= 5.9, x - 5.9, 0.0)
+    return c1 + c2 * x + 3.23 * drude + 0.41 * (0.5392 * y ** 2 + 0.05644 * y ** 3)
+
+
+def extinction_fitzpatrick99(wave, a_v, r_v=3.1):
+    """Fitzpatrick 1999: FM90 below 2700 A, NATURAL cubic spline through the nine anchors of the IDL fm_unred routine at
+    longer wavelengths.  The natural end condition reproduces the package's documented example
+    fitzpatrick99([2000, 4000, 8000], 1.0, 3.1) = [2.76225609, 1.42325373, 0.55333671] to every printed digit
+    (not-a-knot gives 1.42339332, 0.55307718)."""
+    from scipy.interpolate import CubicSpline
+    x = 1e4 / np.asarray(wave, dtype=float)
+    xk = 1e4 / _F99_ANCHORS_AA
+    kk = np.array([0.0, 0.26469 * r_v / 3.1, 0.82925 * r_v / 3.1,
+                   -0.422809 + 1.00270 * r_v + 2.13572e-04 * r_v ** 2,
+                   -5.13540e-02 + 1.00216 * r_v - 7.35778e-05 * r_v ** 2,
+                   0.700127 + 1.00184 * r_v - 3.32598e-05 * r_v ** 2,
+                   1.19456 + 1.01707 * r_v - 5.46959e-03 * r_v ** 2 + 7.97809e-04 * r_v ** 3 - 4.45636e-05 * r_v ** 4,
+                   0.0, 0.0]) - r_v
+    kk[7:] = _fm90_k(xk[7:], r_v)
+    spline = CubicSpline(xk, kk, bc_type="natural")
+    uv = x >= 1e4 / 2700.0
+    k = np.where(uv, _fm90_k(x, r_v), spline(np.where(uv, xk[7], x)))
+    return a_v / r_v * (k + r_v)
+
+
+EXTINCTION_LAWS = dict(fitzpatrick99=extinction_fitzpatrick99, calzetti00=extinction_calzetti00,
+                       odonnell94=extinction_odonnell94, ccm89=extinction_ccm89)
+
+
+def perform_extinction(flux_density, angstroms, av_host, rv_host, av_mw=0.0, rv_mw=3.1, host_law="fitzpatrick99",
+                       mw_law="fitzpatrick99", *, redshift):
+    """extinction_models._perform_extinction (:77-170); `flux_density` [..., len(angstroms)]."""
+    for law, who in ((host_law, "host"), (mw_law, "MW")):
+        if law not in ("fitzpatrick99", "fm07", "calzetti00", "odonnell94", "ccm89"):              # :112-117
+            raise ValueError(f"Unknown {who} extinction law: {law}")
+    angstroms = np.atleast_1d(np.asarray(angstroms, dtype=float))
+    out = np.array(flux_density, dtype=float, copy=True)                                           # :119
+    for a_v, r_v, law, wave in ((av_host, rv_host, host_law, angstroms / (1 + redshift)),          # :122-142
+                                (av_mw, rv_mw, mw_law, angstroms)):                                # :145-165
+        if not a_v > 0:
+            continue
+        fn = EXTINCTION_LAWS[law]
+        mag = fn(wave, a_v) if law == "calzetti00" else fn(wave, a_v, r_v)
+        if a_v < 10:
+            mag = np.where(mag > 10, 0.0, mag)                                                     # :137-139
+        out = out * 10.0 ** (-0.4 * mag)                                                           # extinction.apply
+    return out

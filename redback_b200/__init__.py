@@ -2,7 +2,7 @@
 likelihood API.  The CUDA library is the only compute path; importing the package does
 not need a GPU, calling it does."""
 from . import ejecta_relations  # noqa: F401
-from . import (_capi, afterglow_models, bands, engine, kilonova_models, likelihoods,  # noqa: F401
+from . import (_capi, afterglow_models, bands, engine, extinction_models, kilonova_models, likelihoods,  # noqa: F401
                magnetar_driven_ejecta_models, phase_models, simulate, supernova_models, tde_models)
 from .likelihoods import (GaussianLikelihood, GaussianLikelihoodQuadratureNoise,  # noqa: F401
                           GaussianLikelihoodWithFractionalNoise, GaussianLikelihoodWithSystematicNoise,
@@ -31,3 +31,4 @@ all_models_dict.update({fn.__name__: fn for fn in afterglow_models.FUSED})
 all_models_dict.update({fn.__name__: fn for fn in magnetar_driven_ejecta_models.FUSED})
 all_models_dict.update({fn.__name__: fn for fn in tde_models.FUSED})
 all_models_dict["t0_base_model"] = phase_models.t0_base_model
+all_models_dict.update({fn.__name__: fn for fn in extinction_models.MODELS})

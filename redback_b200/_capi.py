@@ -48,6 +48,15 @@ class SnConfig(C.Structure):
                 ("csm_timesteps", C.c_int), ("negative_epochs", C.c_int)]
 
 
+EXT_CCM89, EXT_ODONNELL94, EXT_CALZETTI00, EXT_FITZPATRICK99 = 1, 2, 3, 4
+
+
+class Extinction(C.Structure):
+    """rb_extinction (include/redback_b200.h)"""
+    _fields_ = [("host_law", C.c_int), ("mw_law", C.c_int), ("rv_host", C.c_double), ("rv_mw", C.c_double),
+                ("av_mw", C.c_double), ("f99_host", C.c_double * 41), ("f99_mw", C.c_double * 41)]
+
+
 KN_ONE_COMPONENT, KN_METZGER = 0, 1
 KN_ROWS = dict(redshift=0, mej=1, vej=2, kappa=3, temperature_floor=4, beta=4)
 KN_NPARAM = 5
@@ -167,6 +176,7 @@ EXPORTS = {
                                        C.c_void_p]),
     "rb_mixture_logl_f64": (C.c_int, [C.c_int64, C.c_int64] + [_dp] * 6 + [C.c_void_p]),
     "rb_sizeof": (C.c_int64, [C.c_int]),
+    "rb_extinction_apply_f64": (C.c_int, [C.POINTER(Extinction), C.c_int64, C.c_int64, _dp, _dp, _dp, _dp, C.c_void_p]),
     "rb_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
@@ -192,7 +202,8 @@ def lib():
             raise RedbackB200Error(f"{path} was built from other sources (digest {got}); rebuild with "
                                    "python -m redback_b200._build --force")
     # the ctypes mirrors below are passed by reference: a layout mismatch would be silent memory corruption
-    for which, cls in enumerate((Cosmology, UpperLimits, SnConfig, KnConfig, AgConfig, MnConfig, MkConfig)):
+    for which, cls in ((0, Cosmology), (1, UpperLimits), (2, SnConfig), (3, KnConfig), (4, AgConfig), (5, MnConfig),
+                       (6, MkConfig), (8, Extinction)):
         if handle.rb_sizeof(which) != C.sizeof(cls):
             raise RedbackB200Error(f"struct layout mismatch for {cls.__name__}: library {handle.rb_sizeof(which)} "
                                    f"bytes, binding {C.sizeof(cls)} bytes")

@@ -153,6 +153,15 @@ def run(spec, time, named, kwargs, params_batch):
     params = spec.transform(params)
     path = spec.build(time, kwargs)
     dev = path.pack(params, N if N is not None else 1)
-    model, _ = path.evaluate(dev, dl=dl_from_kwargs(kwargs, path, N), t0=t0_tensor(params, path, N),
-                             aux=aux_tensor(params, path, N))
+    ext = kwargs.get("_extinction")
+    if ext is not None:
+        # extinction_models: the magnitude / flux branch attenuates the spectra inside the photometry kernel
+        path.set_extinction(ext["struct"], t0_tensor({"t0": ext["av_host"]}, path, N))
+        ext["applied"] = True
+    try:
+        model, _ = path.evaluate(dev, dl=dl_from_kwargs(kwargs, path, N), t0=t0_tensor(params, path, N),
+                                 aux=aux_tensor(params, path, N))
+    finally:
+        if ext is not None:
+            path.set_extinction(None, None)
     return finish(model, N, kwargs)

@@ -102,7 +102,7 @@ class Photometry(C.Structure):
     _fields_ = [("output", C.c_int), ("n_lambda", C.c_int), ("lambda_obs", C.c_void_p), ("n_tgrid", C.c_int),
                 ("tgrid", C.c_void_p), ("n_bands", C.c_int), ("band_of_epoch", C.c_void_p), ("band_off", C.c_void_p),
                 ("int_wave", C.c_void_p), ("int_wt", C.c_void_p), ("band_scale", C.c_void_p), ("band_zp", C.c_void_p),
-                ("band_ref_flux", C.c_void_p)]
+                ("band_ref_flux", C.c_void_p), ("extinction", C.c_void_p), ("ext_av_host", C.c_void_p)]
 
 
 def build_photometry(bands, n_epochs, lambda_array, output, tgrid=None):
@@ -143,6 +143,7 @@ def build_photometry(bands, n_epochs, lambda_array, output, tgrid=None):
     ph.int_wave, ph.int_wt = int_wave.ctypes.data, int_wt.ctypes.data
     ph.band_scale, ph.band_zp = scale.ctypes.data, zp.ctypes.data
     ph.band_ref_flux = None
+    ph.extinction = ph.ext_av_host = None
     if output == "flux":
         missing = [b.name for b in bps if b.reference_flux is None]
         if missing:

@@ -15,6 +15,7 @@
 #include "viscous_kernel.cu"
 #include "mk_kernel.cu"
 #include "ag_kernel.cu"
+#include "ext_kernel.cu"
 #include "phot_kernel.cu"
 #include "noise_kernel.cu"
 #include <algorithm>
@@ -494,6 +495,21 @@ int rb_sn_eval_f64_host_rows(const rb_sn_config* cfg, int64_t N, int64_t E, cons
                        sigma_param, out_model, out_logl, 524288);
 }
 
+int rb_extinction_apply_f64(const rb_extinction* ext, int64_t N, int64_t E, const double* freq_obs,
+                            const double* redshift, const double* av_host, double* model, void* stream) {
+  if (!ext || !freq_obs || !redshift || !av_host || !model || N < 0 || E <= 0)
+    return fail(RB_ERR_INVALID, "rb_extinction_apply: bad arguments");
+  for (int law : {ext->host_law, ext->mw_law})
+    if (law < RB_EXT_CCM89 || law > RB_EXT_FITZPATRICK99) return fail(RB_ERR_INVALID, "rb_extinction_apply: unknown law");
+  if (N == 0) return RB_OK;
+  const int64_t total = N * E;
+  rb::ext_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*ext, N, (int)E, freq_obs,
+                                                                                        redshift, av_host, model);
+  launch_counter()->fetch_add(1);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
 int64_t rb_sizeof(int which) {
   switch (which) {
     case 0: return (int64_t)sizeof(rb_cosmology);
@@ -504,6 +520,7 @@ int64_t rb_sizeof(int which) {
     case 5: return (int64_t)sizeof(rb_mn_config);
     case 6: return (int64_t)sizeof(rb_mk_config);
     case 7: return (int64_t)sizeof(rb_photometry);
+    case 8: return (int64_t)sizeof(rb_extinction);
     default: return -1;
   }
 }
@@ -1484,6 +1501,12 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   const int NT = j.NT, NL = j.phot->n_lambda;
   const int64_t N = j.N, E = j.E;
   const int n_comp = j.n_comp > 0 ? j.n_comp : 1;
+  if (j.phot->extinction != nullptr) {
+    if (!j.phot->ext_av_host) return fail(RB_ERR_INVALID, std::string(j.who) + ": extinction needs ext_av_host");
+    for (int law : {j.phot->extinction->host_law, j.phot->extinction->mw_law})
+      if (law < RB_EXT_CCM89 || law > RB_EXT_FITZPATRICK99)
+        return fail(RB_ERR_INVALID, std::string(j.who) + ": unknown extinction law");
+  }
   PhotShape shape;
   if (!phot_shape(NT, NL, n_comp, j.sed == rb::PH_SED_CUTOFF_LINE, &shape))
     return fail(RB_ERR_UNSUPPORTED, std::string(j.who) + ": grids exceed shared memory");
@@ -1532,6 +1555,12 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   if (ce == cudaSuccess && j.with_len) ce = cudaMallocAsync(&d_len, (size_t)nc_max * sizeof(int), st);
   if (ce == cudaSuccess)
     ce = cudaMallocAsync(&d_scratch, (size_t)std::min<int64_t>(ph_grid_max, nc_max) * scratch_stride * sizeof(double), st);
+  rb_extinction* d_ext = nullptr;
+  if (ce == cudaSuccess && j.phot->extinction != nullptr) {
+    ce = cudaMallocAsync(&d_ext, sizeof(rb_extinction), st);
+    if (ce == cudaSuccess)   // pageable source: the copy is staged before the call returns
+      ce = cudaMemcpyAsync(d_ext, j.phot->extinction, sizeof(rb_extinction), cudaMemcpyHostToDevice, st);
+  }
   int status = RB_OK;
   if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude workspace");
   for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
@@ -1561,6 +1590,8 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
     pa.dl = d_dl;
     pa.sigma_param_s = j.sigma_param ? j.sigma_param + n0 : nullptr;
     pa.t0_s = j.t0 ? j.t0 + n0 : nullptr;
+    pa.ext = d_ext;
+    pa.ext_av_host_s = d_ext ? j.phot->ext_av_host + n0 : nullptr;
     pa.epoch_tab = d_ep_obs;
     pa.t_ragged = j.t_ragged;
     pa.band_ragged = j.band_ragged;
@@ -1581,6 +1612,7 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
     ce = cudaGetLastError();
     if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude kernels");
   }
+  if (d_ext) cudaFreeAsync(d_ext, st);
   cudaFreeAsync(d_scratch, st);
   if (d_len) cudaFreeAsync(d_len, st);
   cudaFreeAsync(d_dl, st);

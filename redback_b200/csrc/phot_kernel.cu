@@ -103,6 +103,9 @@ struct PhotArgs {
                                 //            index of the first of them relative to the band's first coefficient
   const double* band_weight;    // [n_bands][span_max] sum over the band's points of wave * trans * B_j(wave)
   double* scratch;              // [gridDim][scratch_stride]
+  // extinction of the spectra per observer-frame wavelength (extinction_models.py:223-251), see ext_kernel.cu
+  const rb_extinction* ext;     // device copy of the laws, or nullptr
+  const double* ext_av_host_s;  // [N] host-galaxy A_V (sliced to the chunk)
   double* out_model;
   double* out_logl;
 };
@@ -457,6 +460,12 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         }
         cb = c * opz * to_flam;                                                   // supernova_models.py:1611-1612, 2304-2305
         colD[j] = 0.0;
+      }
+      if (a.ext != nullptr) {
+        // spectra * 10^(-0.4 A(lambda_obs)): a factor per wavelength column (the line term of type Ia carries it too)
+        const double att = ext_factor(*a.ext, lam_obs, opz, a.ext_av_host_s[n]);
+        cb *= att;
+        if (line) colC[j] *= att;
       }
       colA[j] = ca;
       colB[j] = cb;

@@ -115,6 +115,16 @@ class _FusedPath:
                     raise ValueError('Sigma must be either float or array-like x.')
                 self._h_sigma = self.sigma.cpu().numpy()
 
+    def set_extinction(self, ext, av_host):
+        """Attenuate the spectra of a magnitude / flux path per observer-frame wavelength before the spline fit
+        (extinction_models.py:223-251): `ext` a _capi.Extinction, `av_host` a contiguous float64 device tensor [N] that
+        must match the next evaluate(); None clears it."""
+        if not hasattr(self, "phot"):
+            raise NotImplementedError("extinction of the spectra needs a magnitude / flux path")
+        self._ext_keep = (ext, av_host)
+        self.phot.extinction = C.addressof(ext) if ext is not None else None
+        self.phot.ext_av_host = av_host.data_ptr() if av_host is not None else None
+
     def set_upper_limits(self, sigma_level, magnitude_mode=False):
         """Mark epochs with sigma_level[e] > 0 as upper limits at that many sigma
         (GaussianLikelihoodWithUpperLimits, likelihoods.py:234-489); None clears them."""

@@ -52,7 +52,7 @@ def test_ctypes_struct_layouts_match_the_library():
     from redback_b200 import bands
     lib = _capi.lib()
     mirrors = [_capi.Cosmology, _capi.UpperLimits, _capi.SnConfig, _capi.KnConfig, _capi.AgConfig, _capi.MnConfig,
-               _capi.MkConfig, bands.Photometry]
+               _capi.MkConfig, bands.Photometry, _capi.Extinction]
     for which, cls in enumerate(mirrors):
         assert lib.rb_sizeof(which) == ctypes.sizeof(cls), (cls.__name__, lib.rb_sizeof(which), ctypes.sizeof(cls))
     assert lib.rb_sizeof(99) == -1
