@@ -31,4 +31,4 @@ all_models_dict.update({fn.__name__: fn for fn in afterglow_models.FUSED})
 all_models_dict.update({fn.__name__: fn for fn in magnetar_driven_ejecta_models.FUSED})
 all_models_dict.update({fn.__name__: fn for fn in tde_models.FUSED})
 all_models_dict["t0_base_model"] = phase_models.t0_base_model
-all_models_dict.update({fn.__name__: fn for fn in extinction_models.MODELS})
+all_models_dict.update({fn.__name__: fn for fn in extinction_models.MODELS + phase_models.EXTINCTION_MODELS})

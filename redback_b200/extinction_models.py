@@ -144,7 +144,7 @@ def _evaluate_extinction_model(time, av_host, av_mw=0.0, model_type=None, params
         raise KeyError("av_host")
     z = batch["redshift"] if "redshift" in batch else kwargs["redshift"]                  # KeyError like the reference (:100)
     N = batch_size(dict(batch, av_host=av))
-    function = _get_correct_function(base_model=base_model, model_type=model_type)
+    function = kwargs.pop("_function", None) or _get_correct_function(base_model=base_model, model_type=model_type)
     device_output = kwargs.pop("device_output", False)
     if N is not None and not batch:
         # only av_host is sampled: the base model still has to produce N rows

@@ -67,3 +67,73 @@ def t0_base_model(time, t0=None, params_batch=None, **kwargs):
 
 
 FUSED = {t0_base_model: _SPEC}
+
+
+def _t0_with_extinction(time, t0, av_host, model_type, params_batch=None, **kwargs):
+    """phase_models._t0_with_extinction (:57-86): the extinction wrapper of `model_type` evaluated at time - t0, epochs
+    before t0 -> 0 (5000 for magnitudes, where t0_base_model uses 1000).  Base models with a fused explosion epoch
+    (see t0_base_model) take a sampled t0 per sample; the others (afterglows) a scalar t0, shifted on the host."""
+    from . import extinction_models as _em
+    import torch
+    base = _em._get_correct_function(kwargs["base_model"], model_type)
+    name = getattr(base, "__name__", None)
+    magnitude = kwargs["output_format"] == "magnitude"
+    batch = dict(params_batch) if params_batch is not None else {}
+    t0 = batch.pop("t0", t0)
+    if t0 is None:
+        raise KeyError("t0")
+    if _BASE.get(name) is base:
+        def shifted(time, **kw):
+            return t0_base_model(time, base_model=name, **kw)
+        if np.ndim(t0):
+            batch["t0"] = t0
+        else:
+            kwargs["t0"] = float(t0)
+        out = _em._evaluate_extinction_model(time, av_host, model_type=model_type, params_batch=batch or None,
+                                             _function=shifted, **kwargs)
+        if magnitude:       # exactly 1000.0 is t0_base_model's placeholder (phase_models.py:54 vs :81)
+            out = torch.where(out == 1000.0, 5000.0, out) if isinstance(out, torch.Tensor) else \
+                np.where(out == 1000.0, 5000.0, out)
+        return out
+    if np.ndim(t0):
+        raise NotImplementedError(f"t0 per sample is not fused for base_model={name!r}; pass a scalar t0")
+    t = _check_sorted(time) - float(t0)
+    good = t >= 0.0
+    kw = dict(kwargs)
+    for key in ("frequency", "bands"):        # the reference passes them unsliced, which only works when no epoch is cut
+        if isinstance(kw.get(key), np.ndarray):
+            kw[key] = kw[key][good]
+    real = _em._evaluate_extinction_model(t[good], av_host, model_type=model_type, params_batch=batch or None, **kw)
+    pad = 5000.0 if magnitude else 0.0
+    if isinstance(real, torch.Tensor):
+        return torch.cat((real.new_full(real.shape[:-1] + (int((~good).sum()),), pad), real), dim=-1)
+    return np.concatenate((np.full(real.shape[:-1] + (int((~good).sum()),), pad), real), axis=-1)
+
+
+def t0_afterglow_extinction(time, t0=None, av_host=None, params_batch=None, **kwargs):
+    """redback phase_models.t0_afterglow_extinction (:89-107)."""
+    return _t0_with_extinction(time, t0, av_host, "afterglow", params_batch=params_batch, **kwargs)
+
+
+def t0_supernova_extinction(time, t0=None, av_host=None, params_batch=None, **kwargs):
+    """redback phase_models.t0_supernova_extinction (:110-128)."""
+    return _t0_with_extinction(time, t0, av_host, "supernova", params_batch=params_batch, **kwargs)
+
+
+def t0_kilonova_extinction(time, t0=None, av_host=None, params_batch=None, **kwargs):
+    """redback phase_models.t0_kilonova_extinction (:131-149)."""
+    return _t0_with_extinction(time, t0, av_host, "kilonova", params_batch=params_batch, **kwargs)
+
+
+def t0_tde_extinction(time, t0=None, av_host=None, params_batch=None, **kwargs):
+    """redback phase_models.t0_tde_extinction (:152-173)."""
+    return _t0_with_extinction(time, t0, av_host, "tde", params_batch=params_batch, **kwargs)
+
+
+def t0_magnetar_driven_extinction(time, t0=None, av_host=None, params_batch=None, **kwargs):
+    """redback phase_models.t0_magnetar_driven_extinction (:176-194)."""
+    return _t0_with_extinction(time, t0, av_host, "magnetar_driven", params_batch=params_batch, **kwargs)
+
+
+EXTINCTION_MODELS = (t0_afterglow_extinction, t0_supernova_extinction, t0_kilonova_extinction, t0_tde_extinction,
+                     t0_magnetar_driven_extinction)

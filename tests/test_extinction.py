@@ -205,3 +205,50 @@ def test_kilonova_and_afterglow_wrappers():
     base = rb.afterglow_models.tophat_redback(ta, **{k: v for k, v in akw.items() if k != "base_model"})
     ref = r.perform_extinction(base, r.nu_to_lambda(fa), 10 ** 21.3 / 2.21e21, 3.1, redshift=0.5)
     np.testing.assert_allclose(got, ref, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_t0_with_extinction():
+    """phase_models._t0_with_extinction (:57-86): a sampled explosion epoch inside the supernova kernel, a scalar one
+    shifted on the host for the afterglow; epochs before t0 -> 0 (5000 mag)."""
+    import redback_b200 as rb
+    rng = np.random.default_rng(11)
+    N, E = 30, 40
+    mjd = np.sort(rng.uniform(59000, 59120, E))
+    freq = 2.99792458e18 / rng.uniform(3500, 9000, E)
+    p = h.arnett_prior(rng, N, zmax=0.8)
+    p["t0"] = rng.uniform(58990, 59030, N)
+    p["av_host"] = rng.uniform(0, 2, N)
+    out = rb.phase_models.t0_supernova_extinction(mjd, base_model="arnett", params_batch=p, frequency=freq,
+                                                  output_format="flux_density", av_mw=0.1, mw_law="ccm89")
+    plain = rb.phase_models.t0_base_model(mjd, base_model="arnett", frequency=freq, output_format="flux_density",
+                                          params_batch={k: v for k, v in p.items() if k != "av_host"})
+    for i in range(N):
+        ref = r.perform_extinction(plain[i], r.nu_to_lambda(freq), p["av_host"][i], 3.1, av_mw=0.1, mw_law="ccm89",
+                                   redshift=p["redshift"][i])
+        h.assert_close(out[i], ref, 1e-12, what=f"sample {i}")
+        assert np.all(out[i][mjd < p["t0"][i]] == 0.0)
+    # magnitudes: the placeholder is 5000 (phase_models.py:81)
+    rb.bands.register_synthetic_lsst()
+    names = np.array(list(h.LSST_NU)[:6] * 7)[:E]
+    mag = rb.phase_models.t0_supernova_extinction(mjd, base_model="arnett", params_batch=p, bands=names,
+                                                  output_format="magnitude")
+    ext = rb.extinction_models.extinction_with_supernova_base_model
+    for i in range(0, N, 7):
+        before = mjd < p["t0"][i]
+        assert np.all(mag[i][before] == 5000.0)
+        kw = {k: v[i] for k, v in p.items() if k not in ("t0",)}
+        ref = ext(mjd[~before] - p["t0"][i], base_model="arnett", bands=names[~before], output_format="magnitude", **kw)
+        ok = np.isfinite(ref) & (ref < np.nanmin(ref) + 25)
+        assert np.max(np.abs(mag[i][~before][ok] - ref[ok])) < 1e-8
+    # afterglow: scalar t0 on the host
+    ta = 59000.0 + np.geomspace(0.1, 50, 12) - 0.5
+    fa = np.where(np.arange(12) % 2 == 0, 4.6e14, 2.4e17)
+    akw = dict(redshift=0.5, thv=0.1, loge0=52.0, thc=0.08, logn0=0.0, p=2.3, logepse=-1.0, logepsb=-2.0, g0=300.0,
+               xiN=1.0, output_format="flux_density", base_model="tophat_redback")
+    got = rb.phase_models.t0_afterglow_extinction(ta, t0=59000.0, av_host=0.7, frequency=fa, **akw)
+    good = ta - 59000.0 >= 0
+    assert np.all(got[~good] == 0) and (~good).sum() > 0
+    ref = rb.extinction_models.extinction_with_afterglow_base_model(ta[good] - 59000.0, av_host=0.7, frequency=fa[good],
+                                                                    **akw)
+    np.testing.assert_array_equal(got[good], ref)
