@@ -474,7 +474,7 @@ typedef struct {
 int rb_extinction_apply_f64(const rb_extinction* ext, int64_t N, int64_t E, const double* freq_obs,
                             const double* redshift, const double* av_host, double* model, void* stream);
 
-enum { RB_OUT_MAGNITUDE = 0, RB_OUT_FLUX = 1 };
+enum { RB_OUT_MAGNITUDE = 0, RB_OUT_FLUX = 1, RB_OUT_SPECTRA = 2 };
 typedef struct {
   int output;                   /* RB_OUT_*                                                         */
   int n_lambda;
@@ -494,6 +494,14 @@ typedef struct {
      per-sample host-galaxy A_V), required when `extinction` is given. */
   const rb_extinction* extinction;
   const double* ext_av_host;
+  /* output == RB_OUT_SPECTRA: output_format='spectra' (supernova_models.py:1019-1023 and its twins) -- the namedtuple
+     (time, lambdas, spectra) per sample, before the clean-up of sed.py:985-992.  DEVICE pointers: spectra_out
+     [N][n_t][n_lambda] erg/cm^2/s/Angstrom, spectra_time_out [N][n_t] observer-frame days, spectra_len_out [N] valid
+     grid points of sample n (rows beyond are NaN); n_t = n_tgrid (supernova family), dense_resolution (kilonovae) or the
+     model's fixed grid (magnetar-driven models).  The band tables, out_model and out_logl are ignored. */
+  double* spectra_out;
+  double* spectra_time_out;
+  int32_t* spectra_len_out;
 } rb_photometry;
 
 /* Magnitude-branch twins of rb_sn_eval_f64 / rb_kn_eval_f64: same device arguments minus freq_obs

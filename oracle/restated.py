@@ -1885,8 +1885,8 @@ def bandpass_magnitude_to_flux(magnitude, reference_flux):
     return 10.0 ** (magnitude / (-2.5)) * reference_flux
 
 
-def sn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, spectra_transform=None,
-                 **params):
+def sn_magnitude(model, time, redshift, *, bands=None, bandpasses=None, lambda_array=None, dl=None,
+                 spectra_transform=None, spectra_only=False, **params):
     """Magnitude branch of arnett / basic_magnetar_powered / slsn (supernova_models.py:1008-1028, 1510-1530,
     1599-1624; csm_interaction :2093-2111).  `model` in {'arnett', 'basic_magnetar_powered', 'slsn', 'type_1a',
     'csm_interaction'}."""
@@ -1922,6 +1922,8 @@ def sn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None,
             spectra = flux_density_to_spectrum(fd, redshift, lam)
         if spectra_transform is not None:                                        # extinction_models.py:236-251
             spectra = spectra_transform(spectra, lam)
+    if spectra_only:                                                             # output_format='spectra' (:1019-1023)
+        return time_observer_frame, lam, spectra
     return bandmag_from_spectra(time_obs, time_observer_frame, spectra, lam, bands, bandpasses)
 
 
@@ -2004,8 +2006,8 @@ def metzger_magnetar_magnitude(model, time, redshift, *, bands, bandpasses, lamb
     return bandmag_from_spectra(time_obs, time_observer_frame / day_to_s, spectra, lam, bands, bandpasses)
 
 
-def kn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None, dl=None, dense_resolution=500,
-                 spectra_transform=None, **params):
+def kn_magnitude(model, time, redshift, *, bands=None, bandpasses=None, lambda_array=None, dl=None,
+                 dense_resolution=500, spectra_transform=None, spectra_only=False, **params):
     """Magnitude branch of one_component_kilonova_model / metzger_kilonova_model
     (kilonova_models.py:1579-1603, 1937-1962)."""
     time_obs = np.asarray(time, dtype=float)
@@ -2028,6 +2030,8 @@ def kn_magnitude(model, time, redshift, *, bands, bandpasses, lambda_array=None,
         spectra = flux_density_to_spectrum(fd, redshift, lam)
         if spectra_transform is not None:                                        # extinction_models.py:236-251
             spectra = spectra_transform(spectra, lam)
+    if spectra_only:                                          # output_format='spectra' (kilonova_models.py:1596-1599)
+        return time_observer_frame, lam, spectra
     return bandmag_from_spectra(time_obs, time_observer_frame / day_to_s, spectra, lam, bands, bandpasses)
 
 

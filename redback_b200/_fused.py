@@ -106,8 +106,9 @@ def dl_from_kwargs(kwargs, path, N):
 
 
 def output_mode(kwargs, name, photometric=True):
-    """kwargs['output_format'] -> 'flux_density' | 'magnitude' | 'flux' (sed.py:971-1009).  'spectra' and
-    'sncosmo_source' return Python objects in the reference and are not fused on device."""
+    """kwargs['output_format'] -> 'flux_density' | 'magnitude' | 'flux' | 'spectra' (sed.py:971-1009).  'spectra' is the
+    namedtuple (time, lambdas, spectra) evaluated on device (run -> engine.evaluate_spectra, no bands needed);
+    'sncosmo_source' returns an sncosmo object in the reference and is not available."""
     fmt = kwargs.get("output_format")
     if fmt is None:
         raise KeyError("output_format")
@@ -118,6 +119,8 @@ def output_mode(kwargs, name, photometric=True):
             raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device")
         if "bands" not in kwargs:
             raise KeyError("bands")
+        return fmt
+    if fmt == "spectra" and photometric:
         return fmt
     if fmt in ("spectra", "sncosmo_source"):
         raise NotImplementedError(f"{name}: output_format='{fmt}' is not fused on device")
@@ -147,13 +150,43 @@ def aux_tensor(params, path, N):
     return t0_tensor({"t0": params[name]}, path, N)
 
 
+def run_spectra(path, dev, params, N, kwargs, ext):
+    """output_format='spectra': namedtuple('output', ['time', 'lambdas', 'spectra']) as in the reference
+    (supernova_models.py:1019-1023).  Batched calls return time [N, n_t] and spectra [N, n_t, n_lambda]; where a sample's
+    grid is shorter than n_t (kilonova grids, np.unique) the remaining rows are NaN; a scalar call is trimmed to its grid."""
+    from collections import namedtuple
+    if not hasattr(path, "phot") or "t0" in params:
+        raise NotImplementedError("output_format='spectra' is not fused for this model")
+    if ext is not None:
+        path.set_extinction(ext["struct"], t0_tensor({"t0": ext["av_host"]}, path, N))
+        ext["applied"] = True
+    try:
+        tt, spec, count = path.evaluate_spectra(dev, dl=dl_from_kwargs(kwargs, path, N), aux=aux_tensor(params, path, N))
+    finally:
+        if ext is not None:
+            path.set_extinction(None, None)
+    lam = np.array(path._keep[0])
+    output = namedtuple("output", ["time", "lambdas", "spectra"])
+    if N is None:
+        g = int(count[0])
+        tt, spec = tt[0, :g], spec[0, :g]
+    if kwargs.get("device_output", False):
+        return output(time=tt, lambdas=lam, spectra=spec)
+    return output(time=tt.cpu().numpy(), lambdas=lam, spectra=spec.cpu().numpy())
+
+
 def run(spec, time, named, kwargs, params_batch):
     spec = spec.for_kwargs(kwargs)
     params, N = collect(named, kwargs, params_batch, spec.needed, spec.defaults)
     params = spec.transform(params)
+    spectra = kwargs.get("output_format") == "spectra"
+    if spectra:
+        kwargs = dict(kwargs, bands=None)              # the reference reads no bands on this branch
     path = spec.build(time, kwargs)
     dev = path.pack(params, N if N is not None else 1)
     ext = kwargs.get("_extinction")
+    if spectra:
+        return run_spectra(path, dev, params, N, kwargs, ext)
     if ext is not None:
         # extinction_models: the magnitude / flux branch attenuates the spectra inside the photometry kernel
         path.set_extinction(ext["struct"], t0_tensor({"t0": ext["av_host"]}, path, N))

@@ -102,11 +102,25 @@ class Photometry(C.Structure):
     _fields_ = [("output", C.c_int), ("n_lambda", C.c_int), ("lambda_obs", C.c_void_p), ("n_tgrid", C.c_int),
                 ("tgrid", C.c_void_p), ("n_bands", C.c_int), ("band_of_epoch", C.c_void_p), ("band_off", C.c_void_p),
                 ("int_wave", C.c_void_p), ("int_wt", C.c_void_p), ("band_scale", C.c_void_p), ("band_zp", C.c_void_p),
-                ("band_ref_flux", C.c_void_p), ("extinction", C.c_void_p), ("ext_av_host", C.c_void_p)]
+                ("band_ref_flux", C.c_void_p), ("extinction", C.c_void_p), ("ext_av_host", C.c_void_p),
+                ("spectra_out", C.c_void_p), ("spectra_time_out", C.c_void_p), ("spectra_len_out", C.c_void_p)]
 
 
 def build_photometry(bands, n_epochs, lambda_array, output, tgrid=None):
-    """Return (Photometry struct, keepalive list).  `bands`: band name or array of names (one per epoch)."""
+    """Return (Photometry struct, keepalive list).  `bands`: band name or array of names (one per epoch); ignored for
+    output='spectra' (no band tables: the spectra themselves are the output, engine.evaluate_spectra)."""
+    if output == "spectra":
+        lam = np.ascontiguousarray(lambda_array, dtype=np.float64)
+        ph = Photometry()
+        ph.output = 2
+        ph.n_lambda, ph.lambda_obs = lam.size, lam.ctypes.data
+        keep = [lam]
+        ph.n_tgrid, ph.tgrid = 0, None
+        if tgrid is not None:
+            tg = np.ascontiguousarray(tgrid, dtype=np.float64)
+            keep.append(tg)
+            ph.n_tgrid, ph.tgrid = tg.size, tg.ctypes.data
+        return ph, keep
     names = np.broadcast_to(np.asarray(bands), (n_epochs,))
     uniq = sorted(set(names.tolist()))
     bps = [get_bandpass(n) for n in uniq]

@@ -17,6 +17,7 @@
 #include "ag_kernel.cu"
 #include "ext_kernel.cu"
 #include "phot_kernel.cu"
+#include "spectra_kernel.cu"
 #include "noise_kernel.cu"
 #include <algorithm>
 #include <vector>
@@ -1322,12 +1323,20 @@ struct PhotDevice {
 
 int phot_check(const rb_photometry* ph, int64_t E, bool need_tgrid) {
   if (!ph) return fail(RB_ERR_INVALID, "rb_*_mag_eval: null photometry");
-  if (ph->output != RB_OUT_MAGNITUDE && ph->output != RB_OUT_FLUX)
+  if (ph->output != RB_OUT_MAGNITUDE && ph->output != RB_OUT_FLUX && ph->output != RB_OUT_SPECTRA)
     return fail(RB_ERR_INVALID, "Output format must be 'flux', 'magnitude', 'sncosmo_source', or 'flux_density'");
   if (ph->n_lambda < 8 || ph->n_lambda > 1024 || !ph->lambda_obs)
     return fail(RB_ERR_INVALID, "rb_*_mag_eval: lambda_array needs 8..1024 points");
   if (need_tgrid && (ph->n_tgrid < 8 || ph->n_tgrid > 2000 || !ph->tgrid))
     return fail(RB_ERR_INVALID, "rb_sn_mag_eval: time grid needs 8..2000 points");
+  if (ph->output == RB_OUT_SPECTRA) {
+    if (!ph->spectra_out || !ph->spectra_time_out || !ph->spectra_len_out)
+      return fail(RB_ERR_INVALID, "rb_*_mag_eval: spectra output needs spectra_out, spectra_time_out and spectra_len_out");
+    for (int i = 1; i < ph->n_lambda; ++i)
+      if (!(ph->lambda_obs[i] > ph->lambda_obs[i - 1]))
+        return fail(RB_ERR_INVALID, "rb_*_mag_eval: lambda_array must be strictly increasing");
+    return RB_OK;
+  }
   if (ph->n_bands < 1 || !ph->band_of_epoch || !ph->band_off || !ph->int_wave || !ph->int_wt || !ph->band_scale ||
       !ph->band_zp)
     return fail(RB_ERR_INVALID, "rb_*_mag_eval: incomplete band tables");
@@ -1486,6 +1495,67 @@ struct PhotJob {
   const int* epoch_count = nullptr;
 };
 
+// output_format='spectra': the same grid-mode fill, then spectra_kernel writes the N_t x N_lambda tile per sample
+extern "C++" template <typename Fill>
+int run_spectra(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
+  static DeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    return cudaFuncSetAttribute(rb::spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(spectra_kernel)");
+  const int NT = j.NT, NL = j.phot->n_lambda;
+  const int n_comp = j.n_comp > 0 ? j.n_comp : 1;
+  const bool line = j.sed == rb::PH_SED_CUTOFF_LINE;
+  const size_t smem = ((size_t)(2 * n_comp + (line ? 2 : 0)) * NT + 4 * (size_t)NL) * sizeof(double);
+  if (smem > 227 * 1024) return fail(RB_ERR_UNSUPPORTED, std::string(j.who) + ": grids exceed shared memory");
+  const int64_t N = j.N, chunk_max = 32768, nc_max = std::min<int64_t>(chunk_max, N);
+  double *d_lam = nullptr, *d_grid = nullptr, *d_opz = nullptr, *d_dl = nullptr;
+  int* d_len = nullptr;
+  rb_extinction* d_ext = nullptr;
+  cudaError_t ce = cudaMallocAsync(&d_lam, (size_t)NL * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_lam, j.phot->lambda_obs, (size_t)NL * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_grid, (size_t)n_comp * nc_max * 4 * NT * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_opz, (size_t)nc_max * sizeof(double), st);
+  if (ce == cudaSuccess) ce = cudaMallocAsync(&d_dl, (size_t)nc_max * sizeof(double), st);
+  if (ce == cudaSuccess && j.with_len) ce = cudaMallocAsync(&d_len, (size_t)nc_max * sizeof(int), st);
+  if (ce == cudaSuccess && j.phot->extinction != nullptr) {
+    ce = cudaMallocAsync(&d_ext, sizeof(rb_extinction), st);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync(d_ext, j.phot->extinction, sizeof(rb_extinction), cudaMemcpyHostToDevice, st);
+  }
+  int status = ce == cudaSuccess ? RB_OK : cuda_fail(ce, "spectra workspace");
+  for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
+    const int64_t nc = std::min<int64_t>(chunk_max, N - n0);
+    status = fill(n0, nc, d_grid, d_opz, d_dl, d_len);
+    if (status != RB_OK) break;
+    rb::SpectraArgs sa{};
+    sa.N = nc;
+    sa.n_t_max = NT; sa.n_lambda = NL; sa.sed = j.sed; sa.n_comp = n_comp;
+    sa.grid_comp_stride = (int64_t)nc_max * 4 * NT;
+    sa.cutoff_wavelength = j.cutoff_wavelength; sa.absorption_index = j.absorption_index;
+    sa.line_wavelength = j.line_wavelength; sa.line_width = j.line_width; sa.line_time = j.line_time;
+    sa.line_duration = j.line_duration; sa.line_amplitude = j.line_amplitude;
+    sa.grid = d_grid; sa.grid_len = d_len; sa.opz = d_opz; sa.dl = d_dl; sa.lambda_obs = d_lam;
+    sa.ext = d_ext;
+    sa.ext_av_host_s = d_ext ? j.phot->ext_av_host + n0 : nullptr;
+    sa.spectra_out = j.phot->spectra_out + (size_t)n0 * NT * NL;
+    sa.time_out = j.phot->spectra_time_out + (size_t)n0 * NT;
+    sa.len_out = j.phot->spectra_len_out + n0;
+    rb::spectra_kernel<<<(unsigned)std::min<int64_t>((int64_t)sms * 4, nc), 256, smem, st>>>(sa);
+    launch_counter()->fetch_add(1);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) status = cuda_fail(ce, "spectra kernel");
+  }
+  if (ce == cudaSuccess && status == RB_OK) ce = cudaStreamSynchronize(st);   // lambda_obs / extinction are host memory
+  if (d_ext) cudaFreeAsync(d_ext, st);
+  if (d_len) cudaFreeAsync(d_len, st);
+  if (d_dl) cudaFreeAsync(d_dl, st);
+  if (d_opz) cudaFreeAsync(d_opz, st);
+  if (d_grid) cudaFreeAsync(d_grid, st);
+  if (d_lam) cudaFreeAsync(d_lam, st);
+  return status;
+}
+
 // fill(n0, nc, d_grid, d_opz, d_dl, d_len) -> RB_OK or an error code (already recorded with fail())
 extern "C++" template <typename Fill>
 int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
@@ -1507,6 +1577,7 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
       if (law < RB_EXT_CCM89 || law > RB_EXT_FITZPATRICK99)
         return fail(RB_ERR_INVALID, std::string(j.who) + ": unknown extinction law");
   }
+  if (j.phot->output == RB_OUT_SPECTRA) return run_spectra(j, st, sms, fill);
   PhotShape shape;
   if (!phot_shape(NT, NL, n_comp, j.sed == rb::PH_SED_CUTOFF_LINE, &shape))
     return fail(RB_ERR_UNSUPPORTED, std::string(j.who) + ": grids exceed shared memory");

@@ -125,6 +125,31 @@ class _FusedPath:
         self.phot.extinction = C.addressof(ext) if ext is not None else None
         self.phot.ext_av_host = av_host.data_ptr() if av_host is not None else None
 
+    SPECTRA_TIME_SCALE = 1.0      # observer-frame days of the model grid -> the unit of the reference's `time` field
+
+    def _spectra_grid_points(self):
+        raise NotImplementedError("output_format='spectra' needs a magnitude / flux path")
+
+    def evaluate_spectra(self, params_dev, dl=None, aux=None):
+        """output_format='spectra' (supernova_models.py:1019-1023 and its twins): (time [N, n_t], spectra [N, n_t, n_lambda]
+        erg/cm^2/s/Angstrom, grid_points [N]) on the model's own time grid, before any clean-up; rows beyond
+        grid_points[n] are NaN.  The path must have been built with output='spectra'."""
+        if getattr(self, "phot", None) is None or self.phot.output != 2:
+            raise ValueError("the path was not built with output='spectra'")
+        N, n_t, n_l = params_dev.shape[1], self._spectra_grid_points(), self.phot.n_lambda
+        spectra = torch.empty((N, n_t, n_l), dtype=_F64, device=self.device)
+        tt = torch.empty((N, n_t), dtype=_F64, device=self.device)
+        count = torch.empty((N,), dtype=torch.int32, device=self.device)
+        self.phot.spectra_out, self.phot.spectra_time_out = spectra.data_ptr(), tt.data_ptr()
+        self.phot.spectra_len_out = count.data_ptr()
+        try:
+            self.evaluate(params_dev, dl=dl, aux=aux)
+        finally:
+            self.phot.spectra_out = self.phot.spectra_time_out = self.phot.spectra_len_out = None
+        if self.SPECTRA_TIME_SCALE != 1.0:
+            tt *= self.SPECTRA_TIME_SCALE
+        return tt, spectra, count
+
     def set_upper_limits(self, sigma_level, magnitude_mode=False):
         """Mark epochs with sigma_level[e] > 0 as upper limits at that many sigma
         (GaussianLikelihoodWithUpperLimits, likelihoods.py:234-489); None clears them."""
@@ -430,6 +455,9 @@ class SupernovaMagPath(SupernovaPath):
     def _launch(self, *args):
         return self._launch_mag(_capi.lib().rb_sn_mag_eval_f64, *args)
 
+    def _spectra_grid_points(self):
+        return int(self.phot.n_tgrid)
+
     def evaluate_ragged(self, params_dev, phase, band_index, epoch_count, dl=None):
         """Magnitudes at per-sample pointings (rb_sn_mag_eval_ragged_f64): `phase` [N, E_max] float64 (days since
         explosion, observer frame), `band_index` [N, E_max] int32 into this path's sorted band list, `epoch_count` [N]
@@ -472,6 +500,11 @@ class KilonovaMagPath(KilonovaPath):
 
     def _launch(self, *args):
         return self._launch_mag(_capi.lib().rb_kn_mag_eval_f64, *args)
+
+    SPECTRA_TIME_SCALE = 86400.0        # time_observer_frame in seconds (kilonova_models.py:1594-1600)
+
+    def _spectra_grid_points(self):
+        return int(self.cfg.dense_resolution)
 
     def _host_rows_fn(self):
         return None     # the magnitude branch has device entry points only
@@ -604,6 +637,11 @@ class MetzgerMagnetarMagPath(MetzgerMagnetarPath):
     def _launch(self, *args):
         return self._launch_mag(_capi.lib().rb_mk_mag_eval_f64, *args)
 
+    SPECTRA_TIME_SCALE = 86400.0        # time_observer_frame in seconds (magnetar_driven_ejecta_models.py:212, :232)
+
+    def _spectra_grid_points(self):
+        return _optimal_grid_points(1e-4, 1e7, int(self.cfg.resolution))
+
     def _host_rows_fn(self):
         return None     # the magnitude branch has device entry points only
 
@@ -635,8 +673,21 @@ class MergernovaMagPath(MergernovaPath):
     def _launch(self, *args):
         return self._launch_mag(_capi.lib().rb_mn_mag_eval_f64, *args)
 
+    SPECTRA_TIME_SCALE = 86400.0        # time_observer_frame in seconds (magnetar_driven_ejecta_models.py:212, :232)
+
+    def _spectra_grid_points(self):
+        return _optimal_grid_points(self.cfg.grid_t_min, self.cfg.grid_t_max, int(self.cfg.resolution))
+
     def _host_rows_fn(self):
         return None     # the magnitude branch has device entry points only
+
+
+def _optimal_grid_points(t_min, t_max, resolution):
+    """Length of get_optimal_time_array(t_min, t_max, resolution) without user times (host logic of the library)."""
+    buf = (C.c_double * int(resolution))()
+    count = C.c_int(0)
+    _capi.check(_capi.lib().rb_optimal_time_array(float(t_min), float(t_max), int(resolution), buf, C.byref(count)))
+    return int(count.value)
 
 
 def luminosity_distance(redshift, cosmology=None, device=None):

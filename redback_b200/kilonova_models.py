@@ -64,7 +64,8 @@ def _multi_component(name, time, redshift, components, params_batch, kwargs, den
     params, N = collect(named, kwargs, params_batch, names)
     if mode != "flux_density":
         # kilonova_models.py:1166-1211, 1277-1323: the components' spectra are summed before the band integration
-        path = KilonovaMultiMagPath(len(components), time, kwargs["bands"], grid_t_max, output=mode,
+        path = KilonovaMultiMagPath(len(components), time, kwargs.get("bands") if mode == "spectra" else kwargs["bands"],
+                                    grid_t_max, output=mode,
                                     lambda_array=kwargs.get("lambda_array"),
                                     dense_resolution=kwargs.get("dense_resolution", dense_resolution),
                                     cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"))
@@ -74,6 +75,9 @@ def _multi_component(name, time, redshift, components, params_batch, kwargs, den
             for k in ("mej", "vej", "kappa", "temperature_floor"):
                 rows[f"{k}_{c}"] = params[f"{k}_{c}"]
         n = N if N is not None else 1
+        if mode == "spectra":                                                    # :1190-1194, :1301-1305
+            from ._fused import run_spectra
+            return run_spectra(path, path.pack(rows, n), {}, N, kwargs, None)
         model, _ = path.evaluate(path.pack(rows, n), dl=dl_from_kwargs(kwargs, path, N))
         return finish(model, N, kwargs)
     path = KilonovaPath(_capi.KN_ONE_COMPONENT, time, frequency=kwargs.get("frequency"),
