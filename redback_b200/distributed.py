@@ -43,7 +43,7 @@ def shard_params(params_batch, rank, world, index=None):
 
 def balanced_partition(cost, world, lpt_rounds=2048):
     """Deal samples to `world` ranks so that the per-rank cost sums are nearly equal and the counts differ by at most
-    one.  Returns a list of index arrays (rank r evaluates samples parts[r], in that order).  Samples are sorted by
+    one.  Returns a list of index arrays (rank r evaluates samples parts[r], in that order: ascending cost).  Samples are sorted by
     descending cost; the heavy head (`lpt_rounds` rounds of `world` samples) is dealt round by round with the largest
     sample of the round going to the currently lightest rank (longest-processing-time greedy with equal counts), the
     light tail in snake order (0..w-1, w-1..0, ...)."""
@@ -64,7 +64,9 @@ def balanced_partition(cost, world, lpt_rounds=2048):
         pos = np.arange(n - head)
         rnd, k = np.divmod(pos, world)
         owner[head:] = rot[np.where(rnd % 2 == 0, k, world - 1 - k)]
-    return [order[owner == r] for r in range(world)]
+    # ascending cost inside a rank: measured on the afterglow path (tools/ag_order_probe.py, 4e5 samples), the same
+    # shard runs 7 % slower with its heavy samples first and 2.6 % faster with them last than in random order
+    return [order[owner == r][::-1].copy() for r in range(world)]
 
 
 def unpermute(gathered_parts, parts, n_total):
