@@ -266,15 +266,22 @@ __device__ const double kP4Series[20] = {
 
 __device__ __forceinline__ double gammainc4(double x, double emx) {
   // P(4, x); series below 1.5 (no cancellation), 1 - Q(4, x) above
-  if (x < 1.5) {
-    double sum = kP4Series[19];
+  if (x < 0.25) {
+    double sum = kP4Series[11];
 #pragma unroll
-    for (int k = 18; k >= 0; --k) sum = fma(sum, x, kP4Series[k]);
+    for (int k = 10; k >= 0; --k) sum = fma(sum, x, kP4Series[k]);
     const double x2 = x * x;
     return emx * (x2 * x2) * (1.0 / 24.0) * sum;
   }
   return 1.0 - gammaincc_int(4, x, emx);
 }
+
+// 1 / i^S, i = 1 .. 10 (row S - 1)
+__device__ const double kInvPow[4][10] = {
+    {1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10},
+    {1.0, 1.0 / 4, 1.0 / 9, 1.0 / 16, 1.0 / 25, 1.0 / 36, 1.0 / 49, 1.0 / 64, 1.0 / 81, 1.0 / 100},
+    {1.0, 1.0 / 8, 1.0 / 27, 1.0 / 64, 1.0 / 125, 1.0 / 216, 1.0 / 343, 1.0 / 512, 1.0 / 729, 1.0 / 1000},
+    {1.0, 1.0 / 16, 1.0 / 81, 1.0 / 256, 1.0 / 625, 1.0 / 1296, 1.0 / 2401, 1.0 / 4096, 1.0 / 6561, 1.0 / 10000}};
 
 // a^b for the handful of exponents the default configurations use, pow otherwise
 __device__ __forceinline__ double pow_small(double a, double b) {
@@ -292,7 +299,6 @@ __device__ __forceinline__ double cutoff_norm(double lbol, double rph, double tp
   const double sr = 4.0 - alpha;
   const int s = (int)(sr + 0.5);
   const bool s_int = (sr == (double)s);
-  double norm = lbol / (kFluxConst / kAngstrom * (rph * rph) * tph);
   const double kt_hc = tph / kXConst;
   const double x_c = 1.0 / (lam_c * kt_hc);
   const double e1 = exp(-x_c);
@@ -305,7 +311,9 @@ __device__ __forceinline__ double cutoff_norm(double lbol, double rph, double tp
     const double di = (double)i;
     const double xi = x_c * di;
     above += gammainc4(xi, en) * (1.0 / (di * di * di * di));
-    if (s_int) {
+    if (s_int && s <= 4) {
+      below += gammaincc_int(s, xi, en) * kInvPow[s - 1][i - 1];
+    } else if (s_int) {
       double ns = di;
       for (int q = 1; q < s; ++q) ns *= di;
       below += gammaincc_int(s, xi, en) / ns;
@@ -325,7 +333,8 @@ __device__ __forceinline__ double cutoff_norm(double lbol, double rph, double tp
   }
   above = kt2 * kt2 * 6.0 * above;
   below = (1.0 / pow_small(lam_c, alpha)) * kts * gam * below;
-  return norm / ((above + below) / tph);
+  // norms = L / (FLUX_CONST/A R^2 T) / ((above + below) / T): the temperature cancels, one division instead of three
+  return lbol / ((kFluxConst / kAngstrom * (rph * rph)) * (above + below));
 }
 
 // sed.CutoffBlackbody (sed.py:301-426) + _SED.flux_density (sed.py:239-251) for one (epoch, frequency);
@@ -339,17 +348,13 @@ __device__ __noinline__ double cutoff_blackbody_mjy(const rb_sn_config& cfg, dou
   const double lam = lam_A * kAngstrom;
   const double l2 = lam * lam;
   const double l5 = l2 * l2 * lam;
-  const double em = expm1(kXConst / lam / tph);
-  double sedv;
-  if (lam < lam_c)
-    sedv = kFluxConst * ((rph * rph) * pow_small(lam / lam_c, alpha) / l5) / em;
-  else
-    sedv = kFluxConst * ((rph * rph) / l5) / em;
-  sedv *= norm;
-  double fd = sedv / (4 * kPi * (dl * dl));                                   // sed.py:239-251
-  fd *= lam_A;
-  fd /= nu;
-  return fd * kToMJy;
+  const double em = expm1(kXConst / (lam * tph));
+  // FLUX_CONST R^2 (lam / lam_c)^alpha / lam^5 / expm1(x) * norm / (4 pi dl^2) * lam_A / nu (sed.py:362-384, 239-251):
+  // the factors that cannot overflow are gathered into one quotient, the Planck denominator (up to 1e308) divides last
+  double num = (kFluxConst * kToMJy) * (rph * rph) * norm * lam_A;
+  if (lam < lam_c) num *= pow_small(lam / lam_c, alpha);
+  const double den = l5 * (4 * kPi * (dl * dl)) * nu;
+  return (num / den) / em;
 }
 
 // sed.Line._set_sed (sed.py:859-909) for one (time, frequency): attenuate the base SED by the time-dependent line

@@ -2,8 +2,8 @@
 
     python tools/bench_variants.py lib_a.so lib_b.so ...
 
-Each library is timed in its own subprocess (REDBACK_B200_LIB) on the headline workload (slsn + Blackbody, E = 300)
-and on arnett_bolometric (E = 100); prints one line per library."""
+Each library is timed in its own subprocess (REDBACK_B200_LIB) on the headline workload (slsn + Blackbody, E = 300),
+the same with the CutoffBlackbody SED and on arnett_bolometric (E = 100); prints one line per library."""
 import json
 import os
 import subprocess
@@ -33,6 +33,8 @@ t2, nu2 = h.config2_epochs(np.random.default_rng(0))
 p = SupernovaPath(_capi.ENGINE_MAGNETAR, _capi.SED_BLACKBODY, t2, frequency=nu2, y=np.full(300, 1e-3), sigma=1e-4)
 n = 2_000_000
 out["slsn_bb_E300"] = n * 300 / timed(p, p.pack(h.slsn_prior(rng, n), n)) / 1e6
+p = SupernovaPath(_capi.ENGINE_MAGNETAR, _capi.SED_CUTOFF_BLACKBODY, t2, frequency=nu2, y=np.full(300, 1e-3), sigma=1e-4)
+out["slsn_cutoff_E300"] = n * 300 / timed(p, p.pack(h.slsn_prior(rng, n), n)) / 1e6
 t1 = h.config1_time()
 p = SupernovaPath(_capi.ENGINE_NICKEL, _capi.SED_BOLOMETRIC, t1, y=np.full(100, 1e42), sigma=1e41)
 out["arnett_bol_E100"] = n * 100 / timed(p, p.pack(h.arnett_bolometric_prior(rng, n), n)) / 1e6
