@@ -259,8 +259,15 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
 #define LUT2(i) lut[4 * NT + (i)]
 #define LUT3(i) lut[2 * NT + 2 * (i)]
 #define LUT4(i) lut[2 * NT + 2 * (i) + 1]
-#define HOMF(w, i) hom[2 * (i) + (w)]
-#define HOMB(w, i) hom[2 * NT + 2 * (i) + (w)]
+  // The LU is first order away from the two not-a-knot rows (l2 != 0 only in row G-2, u2 != 0 only in row 1), and
+  // set_segments keeps row G-2 off the start of its segment: one boundary value per direction crosses a segment border,
+  // so there is ONE homogeneous solution per direction and the sweeps read l1 / u1 from dense copies (8-byte loads at the
+  // conflict-free odd stride L; the 16-byte pair loads cost twice the shared-memory wavefronts, and the solve is bound by
+  // that pipe: ~34 wavefronts per row and column before, 22 now).
+#define HOMF(i) hom[(i)]
+#define HOMB(i) hom[NT + (i)]
+#define L1D(i) hom[2 * NT + (i)]
+#define U1D(i) hom[3 * NT + (i)]
   double* colA = GT ? after_rows : hom + 4 * NT;   // [NL]  h nu         or hc / (k_B lambda)
   double* colB = colA + NL;                    // [NL]  everything else that depends on wavelength only
   double* colC = colB + NL;                    // [NL]  line profile in output units
@@ -285,34 +292,40 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     L = (G + P - 1) / P;
     if (L < 3) L = 3;
     L |= 1;                                           // odd: conflict-free shared-memory strides
+    while (G % L == 2) L += 2;                        // row G-2 (the only one with l2 != 0) never starts a segment
     Pe = (G + L - 1) / L;
   };
   // Tables of the segmented solve for the current LU and segmentation.
-  //  hom: forward  y[i] = -l2 y[i-2] - l1 y[i-1]   from (y[m-1], y[m-2]) = (1, 0) and (0, 1) at the segment start m,
-  //       backward x[i] = -u2' x[i+2] - u1' x[i+1] from (x[m'+1], x[m'+2]) = (1, 0) and (0, 1) at the segment end m'.
+  //  hom: forward  y[i] = -l2 y[i-2] - l1 y[i-1]   from (y[m-1], y[m-2]) = (1, 0) at the segment start m,
+  //       backward x[i] = -u2' x[i+2] - u1' x[i+1] from (x[m'+1], x[m'+2]) = (1, 0) at the segment end m'
+  //       (the responses to the second boundary value vanish, see HOMF above).
   //  mtab: segment s maps its incoming boundary state to its outgoing one, out = p_s + H_s in, with H_s made of hom at
   //       the segment's last (forward) / first (backward) two rows; step d of the log-step scan needs the product of
   //       the d matrices ending (forward) / starting (backward) at s -- built here by doubling.
   auto build_tables = [&](int G) {
-    for (int t4 = tid; t4 < 4 * Pe; t4 += T) {
-      const int s = t4 >> 2, which = t4 & 3;
+    for (int t2 = tid; t2 < 2 * Pe; t2 += T) {
+      const int s = t2 >> 1, which = t2 & 1;
       const int i_lo = s * L, i_hi = min(i_lo + L, G);
-      double p1 = (which & 1) ? 0.0 : 1.0, p2 = (which & 1) ? 1.0 : 0.0;
-      if (which < 2) {
+      double p1 = 1.0, p2 = 0.0;
+      if (which == 0) {
         for (int i = i_lo; i < i_hi; ++i) {
           const double y = -LUT0(i) * p2 - LUT1(i) * p1;
-          HOMF(which, i) = y;
+          HOMF(i) = y;
           p2 = p1;
           p1 = y;
         }
       } else {
         for (int i = i_hi - 1; i >= i_lo; --i) {
           const double x = -LUT4(i) * p2 - LUT3(i) * p1;
-          HOMB(which - 2, i) = x;
+          HOMB(i) = x;
           p2 = p1;
           p1 = x;
         }
       }
+    }
+    for (int i = tid; i < G; i += T) {
+      L1D(i) = LUT1(i);
+      U1D(i) = LUT3(i);
     }
     __syncthreads();
     if (tid < 64) {
@@ -322,11 +335,11 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       if (s < Pe) {
         const int i_lo = s * L, i_hi = min(i_lo + L, G);
         if (dir == 0) {          // (y[i_hi-1], y[i_hi-2]) from (y[i_lo-1], y[i_lo-2]); all but the last segment have >= 3 rows
-          h00 = HOMF(0, i_hi - 1); h01 = HOMF(1, i_hi - 1);
-          if (i_hi - 2 >= i_lo) { h10 = HOMF(0, i_hi - 2); h11 = HOMF(1, i_hi - 2); } else { h10 = 1.0; }
+          h00 = HOMF(i_hi - 1);
+          if (i_hi - 2 >= i_lo) { h10 = HOMF(i_hi - 2); } else { h10 = 1.0; }
         } else {                 // (x[i_lo], x[i_lo+1]) from (x[i_hi], x[i_hi+1])
-          h00 = HOMB(0, i_lo); h01 = HOMB(1, i_lo);
-          if (i_lo + 1 < i_hi) { h10 = HOMB(0, i_lo + 1); h11 = HOMB(1, i_lo + 1); } else { h10 = 1.0; }
+          h00 = HOMB(i_lo);
+          if (i_lo + 1 < i_hi) { h10 = HOMB(i_lo + 1); } else { h10 = 1.0; }
         }
       }
       m0[0] = h00; m0[1] = h01; m0[2] = h10; m0[3] = h11;
@@ -919,11 +932,16 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         if (active) {
 #pragma unroll 4
           for (int i = i_lo; i < i_hi; ++i) {
-            const double2 f = ld_pair<GT>(lut + 2 * i);                       // (l2, l1)
-            const double y = (col[i] - f.x * p2) - f.y * p1;
+            const double y = col[i] - L1D(i) * p1;
             col[i] = y;
             p2 = p1;
             p1 = y;
+          }
+          const int g2 = G - 2;                       // the not-a-knot row with l2 != 0; nothing after it depends on it
+          if (g2 >= i_lo && g2 < i_hi && g2 - 2 >= i_lo) {     // (l1 of row G-1 is zero); y[G-4] outside: in HOMF
+            const double y = col[g2] - LUT0(g2) * col[g2 - 2];
+            col[g2] = y;
+            if (g2 == i_hi - 1) p1 = y; else p2 = y;
           }
           if (i_hi - i_lo < 2) p2 = 0.0;              // one-row segment: y[i_hi-2] belongs to the previous one (H row = [1 0])
         }
@@ -944,21 +962,20 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         p1 = 0.0;
         p2 = 0.0;
         if (active) {
-          // forward fix-up and the division by the pivot first, row by row independent (overlapping latencies); the
-          // recurrence proper then has one FMA per row on its dependency chain
-#pragma unroll 8
-          for (int i = i_lo; i < i_hi; ++i)
-{
-            const double2 hf = ld_pair<GT>(hom + 2 * i);
-            col[i] = (col[i] + hf.x * Y1 + hf.y * Y2) * LUT2(i);
-          }
+          // forward fix-up, division by the pivot and the backward recurrence in one sweep (one read and one write of the
+          // column less than as separate passes); the fix-up and the scaling are off the recurrence's dependency chain
 #pragma unroll 4
           for (int i = i_hi - 1; i >= i_lo; --i) {
-            const double2 ub = ld_pair<GT>(lut + 2 * NT + 2 * i);             // (u1/d, u2/d)
-            const double x = (col[i] - ub.y * p2) - ub.x * p1;
+            const double yv = (col[i] + HOMF(i) * Y1) * LUT2(i);
+            const double x = yv - U1D(i) * p1;
             col[i] = x;
             p2 = p1;
             p1 = x;
+          }
+          if (i_lo == 0 && 3 < i_hi) {                // row 1, the not-a-knot row with u2 != 0 (u1 of row 0 is zero);
+            const double x = col[1] - LUT4(1) * col[3];   // x[3] outside the segment: in HOMB
+            col[1] = x;
+            if (i_hi - i_lo >= 2) p2 = x;
           }
           if (i_hi - i_lo < 2) p2 = 0.0;
         }
@@ -975,12 +992,9 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         }
         double X1 = __shfl_down_sync(0xffffffffu, p1, 1, P), X2 = __shfl_down_sync(0xffffffffu, p2, 1, P);
         if (seg == P - 1) { X1 = 0.0; X2 = 0.0; }
-        if (active && (X1 != 0.0 || X2 != 0.0)) {
+        if (active && X1 != 0.0) {
 #pragma unroll 4
-          for (int i = i_lo; i < i_hi; ++i) {
-            const double2 hb = ld_pair<GT>(hom + 2 * NT + 2 * i);
-            col[i] += hb.x * X1 + hb.y * X2;
-          }
+          for (int i = i_lo; i < i_hi; ++i) col[i] += HOMB(i) * X1;
         }
       }
       __syncthreads();
