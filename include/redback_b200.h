@@ -474,6 +474,13 @@ typedef struct {
 int rb_extinction_apply_f64(const rb_extinction* ext, int64_t N, int64_t E, const double* freq_obs,
                             const double* redshift, const double* av_host, double* model, void* stream);
 
+/* type_1c (supernova_models.py:2317-2352): add the epoch-independent sed.Synchrotron flux density (sed.py:703-751) times
+ * (1 + z) to a device-resident (N, E) flux-density matrix, in place.  Device pointers: freq_obs [E], redshift / pp /
+ * dl_cm [N], model [N][E]; the reference's source radius is 1e13 cm. */
+int rb_synchrotron_add_f64(int64_t N, int64_t E, const double* freq_obs, const double* redshift, const double* pp,
+                           const double* dl_cm, double nu_max, double f0, double source_radius, double* model,
+                           void* stream);
+
 enum { RB_OUT_MAGNITUDE = 0, RB_OUT_FLUX = 1, RB_OUT_SPECTRA = 2 };
 typedef struct {
   int output;                   /* RB_OUT_*                                                         */

@@ -177,6 +177,8 @@ EXPORTS = {
     "rb_mixture_logl_f64": (C.c_int, [C.c_int64, C.c_int64] + [_dp] * 6 + [C.c_void_p]),
     "rb_sizeof": (C.c_int64, [C.c_int]),
     "rb_extinction_apply_f64": (C.c_int, [C.POINTER(Extinction), C.c_int64, C.c_int64, _dp, _dp, _dp, _dp, C.c_void_p]),
+    "rb_synchrotron_add_f64": (C.c_int, [C.c_int64, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, _dp,
+                                         C.c_void_p]),
     "rb_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

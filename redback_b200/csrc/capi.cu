@@ -511,6 +511,20 @@ int rb_extinction_apply_f64(const rb_extinction* ext, int64_t N, int64_t E, cons
   return RB_OK;
 }
 
+int rb_synchrotron_add_f64(int64_t N, int64_t E, const double* freq_obs, const double* redshift, const double* pp,
+                           const double* dl_cm, double nu_max, double f0, double source_radius, double* model,
+                           void* stream) {
+  if (!freq_obs || !redshift || !pp || !dl_cm || !model || N < 0 || E <= 0)
+    return fail(RB_ERR_INVALID, "rb_synchrotron_add: bad arguments");
+  if (N == 0) return RB_OK;
+  const int64_t total = N * E;
+  rb::synchrotron_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      N, (int)E, freq_obs, redshift, pp, dl_cm, nu_max, f0, source_radius, model);
+  launch_counter()->fetch_add(1);
+  RB_CUDA(cudaGetLastError());
+  return RB_OK;
+}
+
 int64_t rb_sizeof(int which) {
   switch (which) {
     case 0: return (int64_t)sizeof(rb_cosmology);

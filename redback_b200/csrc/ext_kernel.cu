@@ -115,4 +115,25 @@ __global__ void ext_apply_kernel(const rb_extinction e, int64_t N, int E, const 
   model[i] *= ext_factor_inline(e, wave, 1.0 + redshift[n], av_host[n]);
 }
 
+// sed.Synchrotron (sed.py:703-751) + _SED.flux_density (sed.py:239-251) as type_1c adds it to the arnett flux density
+// (supernova_models.py:2343-2352): model[n][e] += mJy(nu_e (1 + z_n), pp_n, dl_n) (1 + z_n), in place.  Epoch-independent.
+__global__ void synchrotron_add_kernel(int64_t N, int E, const double* __restrict__ freq_obs,
+                                       const double* __restrict__ redshift, const double* __restrict__ pp,
+                                       const double* __restrict__ dl, double nu_max, double f0, double source_radius,
+                                       double* __restrict__ model) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * (int64_t)E) return;
+  const int64_t n = i / E;
+  const int ep = (int)(i - n * E);
+  const double opz = 1.0 + redshift[n];
+  const double nu = freq_obs[ep] * opz;                                        // utils.py:357-384
+  const double r2 = source_radius * source_radius;
+  double sed;
+  if (nu < nu_max) sed = f0 * r2 * pow(nu / nu_max, 2.5) * kAngstrom / kC * (nu * nu);                         // :742-744
+  else sed = (f0 * r2 * pow(nu_max, 2.5)) * pow(nu / nu_max, -(pp[n] - 1.) / 2.) * kAngstrom / kC * (nu * nu);  // :745-747
+  const double d = dl[n];
+  const double mjy = sed / (4 * kPi * (d * d)) * (1.e10 * (kCSI / nu)) / nu * kToMJy;
+  model[i] += mjy * opz;                                                       // :2351-2352
+}
+
 }  // namespace rb

@@ -230,8 +230,8 @@ def arnett(time, redshift=None, f_nickel=None, mej=None, params_batch=None, **kw
 def type_1c(time, redshift=None, f_nickel=None, mej=None, pp=None, params_batch=None, **kwargs):
     """redback supernova_models.type_1c (:2317-2352), output_format='flux_density': arnett with the Blackbody SED plus
     the epoch-independent Synchrotron SED (sed.py:703-751; kwargs nu_max = 1e9 Hz, f0 = 1e-26, source radius 1e13 cm
-    as in the reference's call).  The synchrotron term is a closed form per (sample, epoch) added to the fused arnett
-    output on device; the likelihood of this model goes through the stand-alone reduction."""
+    as in the reference's call).  The synchrotron term is a closed form per (sample, epoch) added in place to the fused arnett
+    output by `rb_synchrotron_add_f64`; the likelihood of this model goes through the stand-alone reduction."""
     import numpy as np
     import torch
     from . import engine
@@ -254,14 +254,16 @@ def type_1c(time, redshift=None, f_nickel=None, mej=None, pp=None, params_batch=
     dl = kwargs.get("dl")
     dl = engine.luminosity_distance(z.reshape(-1), cosmology_from_kwargs(kwargs), device=dev).reshape(-1, 1) \
         if dl is None else as_col(dl)
-    nu = torch.as_tensor(np.broadcast_to(np.asarray(kwargs["frequency"], dtype=np.float64), (fd.shape[-1],)).copy(),
-                         device=dev).reshape(1, -1) * (1 + z)                         # utils.py:357-384
+    out = fd.reshape(-1, fd.shape[-1]).contiguous()
+    n, e = out.shape
+    nu = torch.as_tensor(np.broadcast_to(np.asarray(kwargs["frequency"], dtype=np.float64), (e,)).copy(), device=dev)
+    col = lambda v: v.reshape(-1).expand(n).contiguous()
+    z, p, dl = col(z), col(p), col(dl)
     nu_max, f0, radius = float(kwargs.get("nu_max", 1e9)), float(kwargs.get("f0", 1e-26)), 1e13
-    low = f0 * radius ** 2 * (nu / nu_max) ** 2.5 * 1e-8 / 29979245800.0 * nu ** 2                          # sed.py:742-744
-    high = (f0 * radius ** 2 * nu_max ** 2.5) * (nu / nu_max) ** (-(p - 1.) / 2.) * 1e-8 / 29979245800.0 * nu ** 2   # :745-747
-    sed_2 = torch.where(nu < nu_max, low, high)
-    synch = sed_2 / (4 * np.pi * dl ** 2) * (1.e10 * (299792458.0 / nu)) / nu * 1e26  # sed.py:239-251, mJy
-    out = fd.reshape(-1, fd.shape[-1]) + synch * (1 + z)                              # :2351-2352
+    with torch.cuda.device(dev):                                                      # sed.py:703-751, :2343-2352
+        _capi.check(_capi.lib().rb_synchrotron_add_f64(
+            n, e, nu.data_ptr(), z.data_ptr(), p.data_ptr(), dl.data_ptr(), nu_max, f0, radius, out.data_ptr(),
+            _capi.C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
     out = out if params_batch is not None else out[0]
     return out if want_device else out.cpu().numpy()
 
