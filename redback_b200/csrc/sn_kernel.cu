@@ -303,8 +303,8 @@ __device__ __forceinline__ double cutoff_norm(double lbol, double rph, double tp
   const double x_c = 1.0 / (lam_c * kt_hc);
   const double e1 = exp(-x_c);
   double en = 1.0, above = 0.0, below = 0.0;
-  // 1 / i^4 and 1 / i^s as running products of exact small integers (i^4 <= 1e4 is exact; the division is by a
-  // loop-invariant constant after unrolling)
+  // 1 / i^4 and 1 / i^s: compile-time constants after unrolling, a table for the run-time s (a rolled loop was measured
+  // neutral for this SED and raised sn_kernel's spills around the call)
 #pragma unroll
   for (int i = 1; i <= 10; ++i) {
     en *= e1;  // e^{-i x_c}
@@ -454,7 +454,10 @@ __device__ __forceinline__ float diffusion_sum_f32(const float4* __restrict__ no
 // ASPH: AsphericalDiffusion's viewing-angle factor on the diffused luminosity (interaction_processes.py:124-125).
 // NEG: some epochs lie before the dense grid (cfg.negative_epochs); its own instantiation for the same reason (the select
 // in front of the hot loop cost the plain path 2.7 % on the headline and 4.5 % on arnett_bolometric when always compiled in).
-template <bool HAS_T0, int ENGINE, bool ASPH = false, bool NEG = false>
+// NOCUT: the SED is bolometric or the plain Blackbody: the instantiation carries no CutoffBlackbody / Line code at all, so
+// the out-of-line SED's register footprint and code size cannot touch the headline path (the rolled ten-term loop of
+// cutoff_norm raised this kernel's spills around the call from 96 to 156 B when both lived in one instantiation).
+template <bool HAS_T0, int ENGINE, bool ASPH = false, bool NEG = false, bool NOCUT = false>
 __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
   extern __shared__ double2 smem2[];
   const int D = a.cfg.dense_resolution;
@@ -713,6 +716,8 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
           const double num = 2 * kPi * kH * (nu * nu * nu) * (rph * rph);
           const double em = expm1_fast((kH * nu) / (kKB * tph), tab);
           model = num * sc[SC_INV_DEN] / em * kToMJy * opz;                   // supernova_models.py:1007
+        } else if (NOCUT) {
+          model = NAN;                                                        // not reachable (sn_kernel_fn)
         } else {
           double mjy = cutoff_blackbody_mjy(a.cfg, lbol, rph, tph, nu, sc[SC_DL]);
           if (sed == RB_SED_CUTOFF_LINE) mjy = line_sed_mjy(a.cfg, mjy, lbol, te_real, nu, sc[SC_DL]);   // sed.py:859-909
