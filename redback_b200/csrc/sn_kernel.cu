@@ -392,12 +392,12 @@ constexpr double kA2 = 2.2909784980688164e-07;
 // FUSED: evaluate t_i^2 - t_e^2 with one FMA instead of the reference's rounded square + subtraction.  The two
 //        differ by the rounding of t_i^2, i.e. by eps/2 * (t_e/tau_d)^2 relative in the integrand -- the
 //        reference's own noise floor.  Selected per sample only where that is < 2e-11.
-template <bool GUARD, bool FUSED>
+template <bool GUARD, bool FUSED, int UNROLL>
 __device__ __forceinline__ double diffusion_sum(const double2* __restrict__ nodes, const double2* __restrict__ seg,
                                                 const double* __restrict__ tab, int ms, int Dm1, double te,
                                                 double te2, double te_is, double c1) {
   double acc = 0.0;
-#pragma unroll 6   // A/B-measured (tools/bench_variants.py): 2: -1.1 %, 3: +0.1 %, 4: base, 6: +0.6 %, 8: +0.2 %
+#pragma unroll UNROLL   // A/B-measured (tools/bench_variants.py): 2: -1.1 %, 3: +0.1 %, 4: base, 6: +0.6 %, 8: +0.2 %
   for (int m = ms; m < kNodes; ++m) {
     const double2 nd = nodes[m];                                            // (xm, xm * dw)
     const double t = te * nd.x;                                             // interaction_processes.py:53
@@ -459,6 +459,12 @@ __device__ __forceinline__ float diffusion_sum_f32(const float4* __restrict__ no
 // cutoff_norm raised this kernel's spills around the call from 96 to 156 B when both lived in one instantiation).
 template <bool HAS_T0, int ENGINE, bool ASPH = false, bool NEG = false, bool NOCUT = false>
 __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
+#ifndef RB_SN_UNROLL_NOCUT
+#define RB_SN_UNROLL_NOCUT 12
+#endif
+  // unroll factor of the quadrature loop, A/B-measured per instantiation (tools/bench_variants.py): the spill-free
+  // Blackbody instantiation gains from a deeper unroll, the generic one loses
+  constexpr int kUnroll = NOCUT ? RB_SN_UNROLL_NOCUT : 6;
   extern __shared__ double2 smem2[];
   const int D = a.cfg.dense_resolution;
   double2* seg = smem2;                                  // [D]      (a_k, b_k)
@@ -679,9 +685,9 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
         const float accf = diffusion_sum_f32(nodesf, segf, mf, D - 1, (float)te, (float)te_is, (float)step,
                                              (float)(-te2 * sc[SC_INV_TAU2]));
         acc = (double)accf * l0;
-      } else if (any_bad) acc = diffusion_sum<true, false>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
-      else if (fused_ok) acc = diffusion_sum<false, true>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
-      else acc = diffusion_sum<false, false>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
+      } else if (any_bad) acc = diffusion_sum<true, false, kUnroll>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
+      else if (fused_ok) acc = diffusion_sum<false, true, kUnroll>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
+      else acc = diffusion_sum<false, false, kUnroll>(nodes, seg, tab, ms, D - 1, te, te2, te_is, c1);
       double lbol = (0.5 * (te2 * acc)) *
                     (-2.0 * expm1_fast(-sc[SC_TRAP] / te2, tab) * sc[SC_INV_TAU2]);             // :60-61
       if (ASPH) {                                                                               // :124-125
