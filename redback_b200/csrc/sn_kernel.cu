@@ -397,7 +397,8 @@ __device__ __forceinline__ double diffusion_sum(const double2* __restrict__ node
                                                 const double* __restrict__ tab, int ms, int Dm1, double te,
                                                 double te2, double te_is, double c1) {
   double acc = 0.0;
-#pragma unroll UNROLL   // A/B-measured (tools/bench_variants.py): 2: -1.1 %, 3: +0.1 %, 4: base, 6: +0.6 %, 8: +0.2 %
+#pragma unroll UNROLL   // generic instantiations, A/B-measured (tools/bench_variants.py): 2: -1.1 %, 3: +0.1 %, 4: base, 6: +0.6 %,
+                        // 8: +0.2 %; the spill-free Blackbody instantiation: 6: base, 10: +0.1 %, 12: +0.9 %, 16: +1.7 %, 25: -3.5 %
   for (int m = ms; m < kNodes; ++m) {
     const double2 nd = nodes[m];                                            // (xm, xm * dw)
     const double t = te * nd.x;                                             // interaction_processes.py:53
@@ -460,7 +461,7 @@ __device__ __forceinline__ float diffusion_sum_f32(const float4* __restrict__ no
 template <bool HAS_T0, int ENGINE, bool ASPH = false, bool NEG = false, bool NOCUT = false>
 __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
 #ifndef RB_SN_UNROLL_NOCUT
-#define RB_SN_UNROLL_NOCUT 12
+#define RB_SN_UNROLL_NOCUT 16
 #endif
   // unroll factor of the quadrature loop, A/B-measured per instantiation (tools/bench_variants.py): the spill-free
   // Blackbody instantiation gains from a deeper unroll, the generic one loses
