@@ -415,13 +415,21 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   const int threads = sn_block_threads(E);
   const bool fp32 = cfg->precision == RB_PREC_F32;
   a.epochs_in_smem = (sn_smem_bytes(cfg->dense_resolution, E, true, true) <= 64 * 1024) ? 1 : 0;
-  const size_t smem = sn_smem_bytes(cfg->dense_resolution, E, a.epochs_in_smem != 0, fp32);
+  size_t smem = sn_smem_bytes(cfg->dense_resolution, E, a.epochs_in_smem != 0, fp32);
   if (smem > 220 * 1024) return fail(RB_ERR_INVALID, "rb_sn_eval: dense_resolution too large for shared memory");
   int occ = 0;
   const bool nocut = cfg->sed == RB_SED_BLACKBODY;   // (bolometric, E = 100: measured 1.4 % slower in that instantiation)
   const SnKernelFn kern = sn_kernel_fn(cfg->engine, cfg->t0 != nullptr, cfg->aspherical != 0, cfg->negative_epochs != 0,
                                        nocut);
   RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+  if (a.epochs_in_smem) {
+    // the epoch table stays in global memory (L1) where that buys another resident block: E = 100 -> 6 blocks of 128
+    // threads per SM instead of 5, arnett_bolometric 4.58e9 -> 4.82e9 unit/s; E = 300 is limited by registers either way
+    const size_t smem_g = sn_smem_bytes(cfg->dense_resolution, E, false, fp32);
+    int occ_g = 0;
+    RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, kern, threads, smem_g));
+    if (occ_g > occ) { a.epochs_in_smem = 0; smem = smem_g; occ = occ_g; }
+  }
   if (occ < 1) occ = 1;
   // persistent blocks, grid-stride over samples; 4 waves' worth of blocks for load balance at mid-size N
   int64_t grid = (int64_t)sms * occ * 4;
