@@ -97,9 +97,11 @@ class ShardedEvaluator:
 
     evaluate(lo, hi, out) must write the results of local samples [lo, hi) into `out` (a view of length hi - lo) and
     be stream-ordered on the current CUDA stream (any redback_b200 path's `evaluate(..., out_logl=out)` is).
+    `width`: None for one value per sample (log L); E for a row of E values per sample (light curves / magnitudes on
+    every rank) -- `out` is then a [hi - lo, E] view.
     """
 
-    def __init__(self, n_local, evaluate, device=None, group=None, chunks=4, dtype=torch.float64):
+    def __init__(self, n_local, evaluate, device=None, group=None, chunks=4, dtype=torch.float64, width=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -114,9 +116,11 @@ class ShardedEvaluator:
             dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=group)
         self.n_pad = int(n_max.item())
         self.chunk = -(-self.n_pad // self.chunks) if self.n_pad else 0
-        self.local = torch.zeros(self.chunk * self.chunks, dtype=dtype, device=self.device)
-        self.stage = [torch.empty(self.world * self.chunk, dtype=dtype, device=self.device) for _ in range(2)]
-        self.gathered = torch.empty((self.world, self.chunk * self.chunks), dtype=dtype, device=self.device)
+        tail = () if width is None else (int(width),)
+        self.tail = tail
+        self.local = torch.zeros((self.chunk * self.chunks,) + tail, dtype=dtype, device=self.device)
+        self.stage = [torch.empty((self.world * self.chunk,) + tail, dtype=dtype, device=self.device) for _ in range(2)]
+        self.gathered = torch.empty((self.world, self.chunk * self.chunks) + tail, dtype=dtype, device=self.device)
         self.comm = torch.cuda.Stream(self.device) if self.cuda else None
         if self.world > 1:
             sizes = torch.zeros(self.world, dtype=torch.int64, device=self.device)
@@ -147,7 +151,7 @@ class ShardedEvaluator:
                 self.comm.wait_stream(cur)
                 with torch.cuda.stream(self.comm):
                     dist.all_gather_into_tensor(stage, src, group=self.group)
-                    self.gathered[:, lo: lo + self.chunk].copy_(stage.view(self.world, self.chunk))
+                    self.gathered[:, lo: lo + self.chunk].copy_(stage.view((self.world, self.chunk) + self.tail))
             else:
                 parts = [torch.empty_like(src) for _ in range(self.world)]
                 works.append(dist.all_gather(parts, src, group=self.group))

@@ -60,6 +60,16 @@ def _worker(rank, world, port, n_total, out_dir):
 
     ev2 = rd.ShardedEvaluator(len(idx), evaluate2, chunks=2)
     restored = rd.unpermute(ev2.log_likelihood(), parts, n_total).numpy()
+    # --- rows of E values per sample (light curves on every rank) ---------------------
+    width = 7
+
+    def evaluate3(a, b, out):
+        out.copy_(torch.from_numpy(_value(mine["a"][a:b])[:, None] + np.arange(width)[None, :] * 0.5))
+
+    ev3 = rd.ShardedEvaluator(hi - lo, evaluate3, chunks=3, width=width)
+    curves = ev3.concatenated().numpy()
+    assert curves.shape == (n_total, width)
+    assert np.array_equal(curves, _value(np.arange(n_total, dtype=np.float64))[:, None] + np.arange(width)[None, :] * 0.5)
     np.save(os.path.join(out_dir, f"r{rank}.npy"), np.stack([got, restored]))
     np.save(os.path.join(out_dir, f"c{rank}.npy"), np.array([cost[p].sum() for p in parts]))
     dist.destroy_process_group()
