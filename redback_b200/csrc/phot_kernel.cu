@@ -43,7 +43,8 @@
 namespace rb {
 
 constexpr int kPhotMaxSpan = 96;     // max B-spline coefficients (along wavelength) overlapped by one band
-constexpr int kEpCols = 9;           // per-epoch record in the block's scratch: h0..h3, first row, y1, y2, band flux, U_e
+constexpr int kEpCols = 12;          // per-epoch record in the block's scratch: h0..h3, first row, y1, y2, band flux, U_e,
+                                     // Ga, Gb, s0 (the backward fix-up folded into the contraction, see 2b)
 constexpr int kBlueMargin = 40;      // wavelength columns kept below the bluest band's first coefficient
 constexpr int kScanSteps = 5;        // log2(32)
 
@@ -114,7 +115,7 @@ struct PhotArgs {
 // reduction scratch, exp table, column buffer (also the per-epoch coefficient buffer of the last phase)
 __host__ __device__ inline size_t phot_fixed_doubles(int NT, int NL, int n_comp, bool line, bool tables_global) {
   return (size_t)(2 * n_comp + (line ? 2 : 0)) * NT + (tables_global ? 0 : 9 * (size_t)NT) + 4 * (size_t)NL +
-         5 * (size_t)NL + 2 * kScanSteps * 32 * 4 + 128 + 6 * (size_t)((NT + 31) / 32) + kExpTabSize + 4;
+         5 * (size_t)NL + 2 * kScanSteps * 32 * 4 + 128 + 256 + 6 * (size_t)((NT + 31) / 32) + kExpTabSize + 4;
 }
 
 // FITPACK fpbspl for k = 3: the four non-zero cubic B-splines at x, t[l] <= x < t[l+1] (0-based l)
@@ -276,7 +277,8 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
   double* mtab = lul + 5 * NL;                 // [2][kScanSteps][32][4] scan matrices (forward, backward)
   double* red = mtab + 2 * kScanSteps * 32 * 4;   // [64]
   double* red2 = red + 64;                     // [64]
-  double* grp = red2 + 64;                     // [6][ngroups] bounds of rowA / rowB over each group of 32 rows
+  double* xfix = red2 + 64;                    // [256] per (column, segment) thread: the backward boundary value X1
+  double* grp = xfix + 256;                    // [6][ngroups] bounds of rowA / rowB over each group of 32 rows
   double* tab = grp + 6 * ((NT + 31) / 32);    // [1024]
   double* buf = tab + kExpTabSize;             // [W][NTP] column block; later [epochs][span_max] coefficients
   double* ept = gs + (GT ? 9 * (size_t)NT + 2 : 0);   // [kEpCols][e_pad]
@@ -846,6 +848,23 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       __syncthreads();
     }
     if (!a.common_time_lu) build_tables(G);
+    // per epoch: the weights of the two boundary values that the rows l .. l+3 of its B-splines respond to (2b)
+    for (int e = tid; e < En; e += T) {
+      const int l = (int)ept[4 * EP + e];
+      if (l < 0) continue;
+      const int s0 = l / L;
+      const int cnt = min(4, (s0 + 1) * L - l);
+      double ga = 0.0, gb = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double g = ept[q * EP + e] * HOMB(l + q);
+        if (q < cnt) ga += g; else gb += g;
+      }
+      ept[9 * EP + e] = ga;
+      ept[10 * EP + e] = gb;
+      ept[11 * EP + e] = (double)s0;
+    }
+    __syncthreads();
     PHOT_PROF_ACC(1);
 
     // ---- 2. wavelength-column blocks ---------------------------------------------------------------------------
@@ -992,10 +1011,10 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         }
         double X1 = __shfl_down_sync(0xffffffffu, p1, 1, P), X2 = __shfl_down_sync(0xffffffffu, p2, 1, P);
         if (seg == P - 1) { X1 = 0.0; X2 = 0.0; }
-        if (active && X1 != 0.0) {
-#pragma unroll 4
-          for (int i = i_lo; i < i_hi; ++i) col[i] += HOMB(i) * X1;
-        }
+        // The backward fix-up x[i] += HOMB(i) X1 is NOT swept over the column (a read and a write of every row): the
+        // only consumer is the contraction below, r_e = sum_q h_q x[l+q], so it takes the local solution and adds
+        // Ga_e X1[seg(l)] + Gb_e X1[seg(l)+1] with Ga / Gb = sum of h_q HOMB(l+q) over the rows of either segment.
+        xfix[tid] = active ? X1 : 0.0;
       }
       __syncthreads();
       PHOT_PROF_ACC(3);
@@ -1005,14 +1024,18 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
         const int l = (int)ept[4 * EP + e];
         if (l >= 0 && mask_it) {
           const double* c = buf + l;
-          ept[8 * EP + e] = ept[0 * EP + e] * c[0] + ept[1 * EP + e] * c[1] + ept[2 * EP + e] * c[2] + ept[3 * EP + e] * c[3];
+          const int s0 = (int)ept[11 * EP + e];
+          ept[8 * EP + e] = ept[0 * EP + e] * c[0] + ept[1 * EP + e] * c[1] + ept[2 * EP + e] * c[2] + ept[3 * EP + e] * c[3] +
+                            ept[9 * EP + e] * xfix[s0] + ept[10 * EP + e] * xfix[min(s0 + 1, P - 1)];
         } else if (l >= 0) {
           const double h0 = ept[0 * EP + e], h1 = ept[1 * EP + e], h2 = ept[2 * EP + e], h3 = ept[3 * EP + e];
+          const double ga = ept[9 * EP + e], gb = ept[10 * EP + e];
+          const int s0 = (int)ept[11 * EP + e], s1 = min(s0 + 1, P - 1);
           double y1 = ept[5 * EP + e], y2 = ept[6 * EP + e];
           const double* c = buf + l;
 #pragma unroll 2
           for (int q = 0; q < wc; ++q, c += NTP) {
-            const double r = h0 * c[0] + h1 * c[1] + h2 * c[2] + h3 * c[3];
+            const double r = h0 * c[0] + h1 * c[1] + h2 * c[2] + h3 * c[3] + ga * xfix[q * P + s0] + gb * xfix[q * P + s1];
             const int j = j0 + q;
             const double y = (r - lul[5 * j + 0] * y2) - lul[5 * j + 1] * y1;
             if (j >= a.j_store_lo) ys[(size_t)(j - a.j_store_lo) * EP + e] = y;
