@@ -61,8 +61,41 @@ class _T0Spec:
 _SPEC = _T0Spec()
 
 
+def _host_shift(time, t0, function, pad, params_batch, kwargs):
+    """Scalar explosion epoch for a base model without a fused t0: time - t0 on the host, epochs before t0 -> `pad`
+    (phase_models.py:36-58; frequency / bands sliced like :44-49)."""
+    import torch
+    t = _check_sorted(time) - float(t0)
+    good = t >= 0.0
+    kw = dict(kwargs)
+    for key in ("frequency", "bands"):
+        if isinstance(kw.get(key), np.ndarray):
+            kw[key] = kw[key][good]
+    if params_batch is not None:
+        kw["params_batch"] = params_batch
+    real = function(t[good], **kw)
+    n_bad = int((~good).sum())
+    if isinstance(real, torch.Tensor):
+        return torch.cat((real.new_full(real.shape[:-1] + (n_bad,), pad), real), dim=-1)
+    return np.concatenate((np.full(np.shape(real)[:-1] + (n_bad,), pad), real), axis=-1)
+
+
 def t0_base_model(time, t0=None, params_batch=None, **kwargs):
-    """redback phase_models.t0_base_model (:19-59); kwargs base_model + everything the base model needs."""
+    """redback phase_models.t0_base_model (:19-59); kwargs base_model + everything the base model needs.  Base models
+    with a fused explosion epoch (module docstring) take `t0` per sample; any other fused model (afterglows, CSM
+    interaction, ...) a scalar `t0`, shifted on the host."""
+    base_model = kwargs["base_model"]                            # KeyError like the reference (:28)
+    name = base_model if isinstance(base_model, str) else getattr(base_model, "__name__", None)
+    if name not in _BASE:
+        import redback_b200 as rb
+        batch = dict(params_batch) if params_batch is not None else {}
+        t0 = batch.pop("t0", t0)
+        function = rb.all_models_dict.get(name)
+        if function is None or function is t0_base_model or t0 is None or np.ndim(t0):
+            raise NotImplementedError(f"t0_base_model: base_model={base_model!r} is not fused on device with a sampled "
+                                      f"t0 (per-sample t0: {sorted(_BASE)}; scalar t0: every fused model)")
+        kw = {k: v for k, v in kwargs.items() if k != "base_model"}
+        return _host_shift(time, t0, function, 1000.0 if kwargs["output_format"] == "magnitude" else 0.0, batch or None, kw)
     return run(_SPEC.for_kwargs(kwargs), time, dict(t0=t0), kwargs, params_batch)
 
 
@@ -97,17 +130,10 @@ def _t0_with_extinction(time, t0, av_host, model_type, params_batch=None, **kwar
         return out
     if np.ndim(t0):
         raise NotImplementedError(f"t0 per sample is not fused for base_model={name!r}; pass a scalar t0")
-    t = _check_sorted(time) - float(t0)
-    good = t >= 0.0
-    kw = dict(kwargs)
-    for key in ("frequency", "bands"):        # the reference passes them unsliced, which only works when no epoch is cut
-        if isinstance(kw.get(key), np.ndarray):
-            kw[key] = kw[key][good]
-    real = _em._evaluate_extinction_model(t[good], av_host, model_type=model_type, params_batch=batch or None, **kw)
-    pad = 5000.0 if magnitude else 0.0
-    if isinstance(real, torch.Tensor):
-        return torch.cat((real.new_full(real.shape[:-1] + (int((~good).sum()),), pad), real), dim=-1)
-    return np.concatenate((np.full(real.shape[:-1] + (int((~good).sum()),), pad), real), axis=-1)
+    def extinguished(t, **kw):
+        return _em._evaluate_extinction_model(t, av_host, model_type=model_type, **kw)
+    # (the reference passes frequency / bands unsliced, which only works when no epoch is cut)
+    return _host_shift(time, t0, extinguished, 5000.0 if magnitude else 0.0, batch or None, kwargs)
 
 
 def t0_afterglow_extinction(time, t0=None, av_host=None, params_batch=None, **kwargs):

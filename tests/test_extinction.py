@@ -252,3 +252,28 @@ def test_t0_with_extinction():
     ref = rb.extinction_models.extinction_with_afterglow_base_model(ta[good] - 59000.0, av_host=0.7, frequency=fa[good],
                                                                     **akw)
     np.testing.assert_array_equal(got[good], ref)
+
+
+@pytest.mark.gpu
+def test_t0_base_model_scalar_t0_for_models_without_a_fused_epoch():
+    """phase_models.t0_base_model (:19-59) around an afterglow and the CSM model: a scalar t0 is shifted on the host
+    (epochs before t0 -> 0), a sampled t0 is refused for these base models."""
+    import redback_b200 as rb
+    ta = 59000.0 + np.geomspace(0.1, 50, 12) - 0.5
+    fa = np.where(np.arange(12) % 2 == 0, 4.6e14, 2.4e17)
+    akw = dict(redshift=0.5, thv=0.1, loge0=52.0, thc=0.08, logn0=0.0, p=2.3, logepse=-1.0, logepsb=-2.0, g0=300.0,
+               xiN=1.0, output_format="flux_density")
+    got = rb.phase_models.t0_base_model(ta, t0=59000.0, base_model="tophat_redback", frequency=fa, **akw)
+    good = ta - 59000.0 >= 0
+    assert (~good).sum() > 0 and np.all(got[~good] == 0)
+    ref = rb.afterglow_models.tophat_redback(ta[good] - 59000.0, frequency=fa[good], **akw)
+    np.testing.assert_array_equal(got[good], ref)
+    rng = np.random.default_rng(9)
+    p = h.csm_prior(rng, 5, zmax=0.3)
+    tc = 58000.0 + np.linspace(-3, 60, 10)
+    out = rb.phase_models.t0_base_model(tc, t0=58000.0, base_model="csm_interaction", params_batch=p,
+                                        frequency=np.full(10, 5e14), output_format="flux_density", temperature_floor=5000.0)
+    assert out.shape == (5, 10) and np.all(out[:, tc < 58000.0] == 0)
+    with pytest.raises(NotImplementedError):
+        rb.phase_models.t0_base_model(tc, base_model="csm_interaction", params_batch=dict(p, t0=np.full(5, 58000.0)),
+                                      frequency=np.full(10, 5e14), output_format="flux_density", temperature_floor=5000.0)

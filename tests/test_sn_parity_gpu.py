@@ -630,8 +630,9 @@ def test_t0_base_model(rb):
     with pytest.raises(NotImplementedError):
         fn(t[::-1], mjd0, base_model="arnett", frequency=nu, output_format="flux_density",
            **{k: float(v[0]) for k, v in p.items() if k != "t0"})
-    with pytest.raises(NotImplementedError):
-        fn(t, mjd0, base_model="tophat_redback", frequency=nu, output_format="flux_density")
+    with pytest.raises(NotImplementedError):      # a SAMPLED t0 needs a fused explosion epoch (a scalar one is shifted on the host)
+        fn(t, base_model="tophat_redback", frequency=nu, output_format="flux_density",
+           params_batch=dict(t0=np.full(3, mjd0)))
 
 
 @pytest.mark.gpu
