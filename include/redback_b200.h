@@ -247,6 +247,11 @@ typedef struct {
   const double* t0;             /* device [N] or NULL: phase_models.t0_base_model (phase_models.py:19-59) — epochs are
                                    t_obs - t0[n] (ascending t_obs), those before t0 return 0 (1000 mag), and the
                                    sample's model grid follows ITS valid epochs                   */
+  int precision;                /* RB_PREC_F64 (default, memset 0) | RB_PREC_F32: one_component_kilonova_model only -- the
+                                   smooth per-grid-point factors (thermalisation efficiency and the r-process heating
+                                   shape: exp, log1p, atan, three pow) are evaluated in FP32, the exp(+-t^2/tau^2) pair,
+                                   the cumulative trapezoid, photosphere, SED and likelihood stay FP64.  Target: rtol
+                                   1e-5 on model outputs (north_star).  Inputs / outputs remain float64.             */
 } rb_kn_config;
 
 int rb_kn_config_default(rb_kn_config* cfg);

@@ -65,7 +65,7 @@ KN_NPARAM = 5
 class KnConfig(C.Structure):
     _fields_ = [("model", C.c_int), ("sigma_mode", C.c_int), ("dense_resolution", C.c_int),
                 ("neutron_precursor_switch", C.c_int), ("vmax", C.c_double), ("cosmology", Cosmology),
-                ("upper_limits", UpperLimits), ("grid_t_max", C.c_double), ("t0", C.c_void_p)]
+                ("upper_limits", UpperLimits), ("grid_t_max", C.c_double), ("t0", C.c_void_p), ("precision", C.c_int)]
 
 
 AG_TOPHAT, AG_GAUSSIAN, AG_POWERLAW, AG_POWERLAW_ALT, AG_TWO_COMPONENT, AG_DOUBLE_GAUSSIAN = 1, 2, 3, 4, 5, 6
@@ -251,7 +251,7 @@ def sn_config(engine, sed, sigma_mode=SIGMA_FIXED, dense_resolution=1000, cutoff
 
 
 def kn_config(model, sigma_mode=SIGMA_FIXED, dense_resolution=500, neutron_precursor_switch=True, vmax=0.7,
-              cosmology=None, grid_t_max=7e6):
+              cosmology=None, grid_t_max=7e6, precision=0):
     cfg = KnConfig()
     check(lib().rb_kn_config_default(C.byref(cfg)))
     cfg.model, cfg.sigma_mode = model, sigma_mode
@@ -259,6 +259,7 @@ def kn_config(model, sigma_mode=SIGMA_FIXED, dense_resolution=500, neutron_precu
     cfg.neutron_precursor_switch = 1 if neutron_precursor_switch else 0
     cfg.vmax = float(vmax)
     cfg.grid_t_max = float(grid_t_max)
+    cfg.precision = int(precision)
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg

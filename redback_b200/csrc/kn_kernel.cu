@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
   constexpr int model = MODEL;
   const int sigma_mode = a.cfg.sigma_mode;
   const bool want_logl = a.want_logl != 0;
+  const bool fp32 = a.cfg.precision == RB_PREC_F32;
   const double grid_t_max = a.cfg.grid_t_max, log_grid_t_max = log10(a.cfg.grid_t_max);
   for (int i = tid; i < kExpTabSize; i += blockDim.x) tab[i] = RB_EXP2_1024[i];
   for (int i = tid; i < kEpochCols * E; i += blockDim.x) ep[i] = a.epoch_tab[i];
@@ -270,6 +271,20 @@ __global__ void __launch_bounds__(512, 1) kn_kernel(const KnArgs a) {
       if (nb == 1 && k == 0) t = 1e-2;
       tg[k] = t;
       const double tdays = t / kDay;
+      if (model == KN_ONE_COMPONENT && fp32) {
+        // RB_PREC_F32: the smooth O(1) factors in single precision (six of the grid point's nine transcendentals); the
+        // shape 0.5 - atan(u) / pi is taken as atan(1 / u) / pi for u > 1, where the subtraction would cancel in FP32
+        // (down to 5e-9 at the end of the grid).  Everything that needs the FP64 range stays FP64.
+        const float tdf = (float)tdays;
+        const float xxf = 2.0f * (float)bv * powf(tdf, (float)dv);
+        const float ethf = 0.36f * (expf(-(float)av * tdf) + log1pf(xxf) / xxf);
+        const float u = (float)((t - 1.3) * (1.0 / 0.11));
+        const float shape = (u > 1.0f) ? atanf(1.0f / u) * 0.31830988618379067f
+                                       : 0.5f - atanf(u) * 0.31830988618379067f;
+        const double smooth = (double)(powf(shape, 1.3f) * ethf);
+        w1[k] = (4.0e18 * m0) * smooth * (t / tdiff) * exp((t * t) / (tdiff * tdiff));
+        continue;
+      }
       const double xx = 2.0 * bv * pow(tdays, dv);
       const double e_th = 0.36 * (exp(-av * tdays) + log1p(xx) / xx);          // :1867
       if (model == KN_ONE_COMPONENT) {

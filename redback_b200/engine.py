@@ -411,9 +411,12 @@ class KilonovaPath(_FusedPath):
 
     def __init__(self, model, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED,
                  dense_resolution=500, neutron_precursor_switch=True, vmax=0.7, cosmology=None, device=None,
-                 grid_t_max=7e6):
+                 grid_t_max=7e6, dtype="float64"):
+        precision = _precision(dtype)
+        if precision != _capi.PREC_F64 and model != _capi.KN_ONE_COMPONENT:
+            raise NotImplementedError("dtype='float32' is available for one_component_kilonova_model only")
         self.cfg = _capi.kn_config(model, sigma_mode, dense_resolution, neutron_precursor_switch, vmax, cosmology,
-                                   grid_t_max)
+                                   grid_t_max, precision)
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):

@@ -23,7 +23,7 @@ def _spec(name, model, needed):
                             dense_resolution=kwargs.get("dense_resolution", 500),
                             neutron_precursor_switch=kwargs.get("neutron_precursor_switch", True),
                             vmax=kwargs.get("vmax", 0.7), cosmology=cosmology_from_kwargs(kwargs),
-                            device=kwargs.get("device"))
+                            device=kwargs.get("device"), dtype=kwargs.get("dtype", "float64"))
 
     return FusedSpec(name, needed, build, validate)
 

@@ -160,6 +160,39 @@ def test_config3_one_component_flux_density(rb):
         assert abs(logl[i] - ref_l) <= 1e-6 + 1e-8 * abs(ref_l), (i, logl[i], ref_l)
 
 
+def test_one_component_fp32_variant(rb):
+    """dtype='float32' (rb_kn_config.precision = RB_PREC_F32): the smooth per-grid-point factors in FP32.  North-star
+    tolerance of the FP32 path: 1e-5 relative on the model (0.001 mag); NaN pattern as in FP64."""
+    t, nu = h.config3_epochs()
+    rng = np.random.default_rng(31)
+    N = 2000
+    p = h.one_component_prior(rng, N)
+    fn = rb.kilonova_models.one_component_kilonova_model
+    f64 = fn(t, params_batch=p, frequency=nu, output_format="flux_density")
+    f32 = fn(t, params_batch=p, frequency=nu, output_format="flux_density", dtype="float32")
+    assert np.array_equal(np.isnan(f32), np.isnan(f64))
+    # The FP32 factors carry ~3e-7 into L_bol, i.e. ~1e-7 into T; the blackbody amplifies a temperature error by
+    # x = h nu / k T, which is O(1) around the peak of a light curve and > 100 deep in its Wien tail.  So: 1e-5 within a
+    # factor 1e4 of each sample's peak flux (10 mag), and the north star's 0.001 mag (9.2e-4) on every finite epoch.
+    ok = np.isfinite(f64) & (f64 > 0)
+    with np.errstate(all="ignore"):
+        rel = np.where(ok, np.abs(f32 - f64) / f64, 0.0)
+        peak = np.nanmax(np.where(ok, f64, 0.0), axis=1, keepdims=True)
+    bright = ok & (f64 >= 1e-4 * peak)
+    assert rel[bright].max() < 1e-5, rel[bright].max()
+    assert rel.max() < 9.2e-4, rel.max()
+    assert rel.max() > 1e-9                       # the variant really ran (not the FP64 path under another name)
+    for i in range(0, N, 200):                    # and against the oracle directly
+        kw = {k: v[i] for k, v in p.items()}
+        z = kw.pop("redshift")
+        ref = r.one_component_kilonova_model(t, z, frequency=nu, **kw)
+        good = np.isfinite(ref) & (ref >= 1e-4 * np.nanmax(ref))
+        assert np.max(np.abs(f32[i][good] - ref[good]) / ref[good]) < 1e-5
+    with pytest.raises(NotImplementedError):
+        rb.kilonova_models.metzger_kilonova_model(t, params_batch=h.metzger_prior(rng, 4), frequency=nu,
+                                                  output_format="flux_density", dtype="float32")
+
+
 def test_metzger_flux_density(rb):
     t, nu = h.config3_epochs(60)
     rng = np.random.default_rng(4)

@@ -61,6 +61,10 @@ def main():
     jobs.append(("one_component_kilonova_model flux_density E=200 (config 3 epochs)", int(1_000_000 * scale),
                  lambda n: KilonovaPath(_capi.KN_ONE_COMPONENT, t3, frequency=nu3, y=np.full(200, 1e-3), sigma=1e-4),
                  lambda n: h.one_component_prior(rng, n), None))
+    jobs.append(("one_component_kilonova_model flux_density E=200, FP32 smooth factors", int(1_000_000 * scale),
+                 lambda n: KilonovaPath(_capi.KN_ONE_COMPONENT, t3, frequency=nu3, y=np.full(200, 1e-3), sigma=1e-4,
+                                        dtype="float32"),
+                 lambda n: h.one_component_prior(rng, n), None))
     jobs.append(("metzger_kilonova_model flux_density E=200", int(200_000 * scale),
                  lambda n: KilonovaPath(_capi.KN_METZGER, t3, frequency=nu3, y=np.full(200, 1e-3), sigma=1e-4),
                  lambda n: h.metzger_prior(rng, n), None))
