@@ -300,6 +300,10 @@ typedef struct {
   rb_upper_limits upper_limits;
   int ab_magnitude;   /* output_format='magnitude': monochromatic AB magnitude of the mJy flux density
                          (utils.calc_ABmag_from_flux_density, utils.py:481-488; base_models.py:944-946) */
+  int precision;      /* RB_PREC_F64 (default, memset 0) | RB_PREC_F32: the synchrotron spectrum of a cell step (one log, one
+                         exp per frequency) through single-precision hardware transcendentals on FP64-reduced arguments
+                         (relative error ~2e-7 per term); dynamics, observer times, interpolation and sums stay FP64.
+                         Target: rtol 1e-5 on model outputs (north_star) */
 } rb_ag_config;
 
 int rb_ag_config_default(rb_ag_config* cfg);

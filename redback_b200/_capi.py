@@ -76,7 +76,7 @@ AG_NPARAM = 11
 class AgConfig(C.Structure):
     _fields_ = [("jet", C.c_int), ("sigma_mode", C.c_int), ("steps", C.c_int), ("res", C.c_int), ("k", C.c_int),
                 ("expansion", C.c_int), ("a1", C.c_double), ("cosmology", Cosmology), ("ss", C.c_double),
-                ("aa", C.c_double), ("upper_limits", UpperLimits), ("ab_magnitude", C.c_int)]
+                ("aa", C.c_double), ("upper_limits", UpperLimits), ("ab_magnitude", C.c_int), ("precision", C.c_int)]
 
 
 MN_BASIC_MAGNETAR, MN_MAGNETAR_ONLY, MN_EVOLVING = 0, 1, 2
@@ -266,7 +266,7 @@ def kn_config(model, sigma_mode=SIGMA_FIXED, dense_resolution=500, neutron_precu
 
 
 def ag_config(jet, sigma_mode=SIGMA_FIXED, steps=250, res=0, k=0, expansion=1, a1=1.0, cosmology=None, ss=0.01,
-              aa=0.5, ab_magnitude=False):
+              aa=0.5, ab_magnitude=False, precision=0):
     cfg = AgConfig()
     check(lib().rb_ag_config_default(C.byref(cfg)))
     cfg.jet, cfg.sigma_mode = jet, sigma_mode
@@ -275,6 +275,7 @@ def ag_config(jet, sigma_mode=SIGMA_FIXED, steps=250, res=0, k=0, expansion=1, a
     cfg.a1 = float(a1)
     cfg.ss, cfg.aa = float(ss), float(aa)
     cfg.ab_magnitude = int(bool(ab_magnitude))
+    cfg.precision = int(precision)
     if cosmology is not None:
         cfg.cosmology = cosmology
     return cfg

@@ -23,7 +23,7 @@ def _spec(name, jet, needed, ss=0.01, aa=0.5):
                              expansion=kwargs.get("expansion", 1), a1=kwargs.get("a1", 1),
                              cosmology=cosmology_from_kwargs(kwargs), device=kwargs.get("device"),
                              ss=kwargs.get("ss", ss), aa=kwargs.get("aa", aa),
-                             ab_magnitude=kwargs["output_format"] == "magnitude")
+                             ab_magnitude=kwargs["output_format"] == "magnitude", dtype=kwargs.get("dtype", "float64"))
 
     return FusedSpec(name, needed, build, validate)
 

@@ -465,6 +465,36 @@ __device__ __forceinline__ double ag_flux_log(double fbb, double nuc, double num
   return (f < adj) ? f : adj;
 }
 
+// RB_PREC_F32: exp(x) through the single-precision hardware exponential on an FP64-reduced argument: x = k ln2 + r with
+// |r| <= 0.35 in FP64, e^r in FP32 (relative error ~2e-7), 2^k into the exponent field.
+__device__ __forceinline__ double exp_sp(double x) {
+  if (!(x > -708.0)) return (x == x) ? 0.0 : x;
+  if (x > 708.0) return INFINITY;
+  const double v = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const int k = __double2loint(v);
+  const double r = fma(v - 6755399441055744.0, -0.6931471805599453, x);
+  const double res = (double)expf((float)r);
+  return __hiloint2double(__double2hiint(res) + (k << 20), __double2loint(res));
+}
+
+// ag_flux_log with exp_sp (RB_PREC_F32)
+__device__ __forceinline__ double ag_flux_log_sp(double fbb, double nuc, double num, double nu1, double lnc, double lnm,
+                                                 double ln1, double fmax, double p, double nu1_sq,
+                                                 double sqrt_nu1_over_num) {
+  double f = 0.0;
+  if (nuc < num) {
+    if (num < nu1) f = fmax * exp_sp(-0.5 * (lnm - lnc) - 0.5 * p * (ln1 - lnm));
+    else if (nuc < nu1) f = fmax * exp_sp(-0.5 * (ln1 - lnc));
+    else if (nu1 < nuc) f = fmax * exp_sp((ln1 - lnc) * (1.0 / 3.0));
+  } else if (num < nuc) {
+    if (nuc < nu1) f = fmax * exp_sp(-0.5 * (p - 1.0) * (lnc - lnm) - 0.5 * p * (ln1 - lnc));
+    else if (num < nu1) f = fmax * exp_sp(-0.5 * (p - 1.0) * (ln1 - lnm));
+    else if (nu1 < num) f = fmax * exp_sp((ln1 - lnm) * (1.0 / 3.0));
+  }
+  const double adj = fbb * nu1_sq * fmax_nan(1.0, sqrt_nu1_over_num);
+  return (f < adj) ? f : adj;
+}
+
 // ---- one block per work unit (about kAgCellsPerUnit cells: a few rings of one sample), one warp per cell -------------------------
 // Warps are independent (no block barrier inside the ring loop): the ring arrays are read straight from the scratch
 // buffer (coalesced, lane = step; the ~24 KB of a ring stay in L1 while its cells are processed), only the per-warp
@@ -475,6 +505,7 @@ __device__ __forceinline__ double ag_flux_log(double fbb, double nuc, double num
 __global__ void __launch_bounds__(kAgWarps * 32, 4) ag_cell_kernel(const AgArgs a, int64_t total_units) {
   extern __shared__ double asm_[];
   const int steps = a.cfg.steps, E = a.E, n_nu = a.n_nu, epl = a.epl, EP = 32 * a.epl;
+  const bool fp32 = a.cfg.precision == RB_PREC_F32;
   double* wbuf = asm_;                                           // per warp: tobs[steps] + flux[n_nu][steps]
   double* acc = wbuf + (size_t)kAgWarps * (1 + n_nu) * steps;    // [kAgWarps][EP]  (position = k * 32 + lane)
   double* sc = acc + (size_t)kAgWarps * EP;                      // [kAgScalars]
@@ -611,12 +642,18 @@ __global__ void __launch_bounds__(kAgWarps * 32, 4) ag_cell_kernel(const AgArgs 
           const bool regular = num > 0.0 && num < INFINITY && nuc > 0.0 && nuc < INFINITY;
           if (regular) {
             // log(dop * nu') = log(dop) + log(nu'): one logarithm per cell step, the ring's are tabulated
-            const double ld = log(dop);
+            const double ld = fp32 ? (double)logf((float)dop) : log(dop);
             const double lnm = ld + lnump, lnc = ld + lnucp;
             const double rs = rsqrt(num);
-            for (int h = 0; h < n_nu; ++h)
-              my_flux[h * steps + s] = ag_flux_log(FBB, nuc, num, nutab[h], lnc, lnm, nutab[kAgMaxNu + h], Fmax, p,
-                                                   nutab[3 * kAgMaxNu + h], nutab[2 * kAgMaxNu + h] * rs);
+            if (fp32) {
+              for (int h = 0; h < n_nu; ++h)
+                my_flux[h * steps + s] = ag_flux_log_sp(FBB, nuc, num, nutab[h], lnc, lnm, nutab[kAgMaxNu + h], Fmax, p,
+                                                        nutab[3 * kAgMaxNu + h], nutab[2 * kAgMaxNu + h] * rs);
+            } else {
+              for (int h = 0; h < n_nu; ++h)
+                my_flux[h * steps + s] = ag_flux_log(FBB, nuc, num, nutab[h], lnc, lnm, nutab[kAgMaxNu + h], Fmax, p,
+                                                     nutab[3 * kAgMaxNu + h], nutab[2 * kAgMaxNu + h] * rs);
+            }
           } else {
             for (int h = 0; h < n_nu; ++h) my_flux[h * steps + s] = ag_flux(FBB, nuc, num, nutab[h], Fmax, p);
           }

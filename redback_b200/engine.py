@@ -542,11 +542,11 @@ class AfterglowPath(_FusedPath):
 
     def __init__(self, jet, time, frequency=None, y=None, sigma=None, sigma_mode=_capi.SIGMA_FIXED, steps=250,
                  res=None, k=0, expansion=1, a1=1, cosmology=None, device=None, ss=0.01, aa=0.5,
-                 ab_magnitude=False):
+                 ab_magnitude=False, dtype="float64"):
         if k not in (0, 2):
             raise ValueError("k must either be 0 or 2")
         self.cfg = _capi.ag_config(jet, sigma_mode, steps, 0 if res is None else int(res), k, expansion, a1, cosmology,
-                                   ss, aa, ab_magnitude)
+                                   ss, aa, ab_magnitude, _precision(dtype))
         self._setup(time, frequency, y, sigma, device)
 
     def _eval_fn(self):

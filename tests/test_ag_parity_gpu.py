@@ -129,3 +129,26 @@ def test_errors(rb):
         rb.afterglow_models.tophat_redback(t, 0.5, frequency=1e9, output_format="flux_density", k=1, **kw)
     out = rb.afterglow_models.tophat_redback(t, 0.5, frequency=1e9, output_format="flux_density", **dict(kw, p=3.6))
     assert np.all(np.isnan(out))  # the reference raises ValueError("p is out of range"); flagged as NaN per sample
+
+
+def test_tophat_fp32_variant():
+    """dtype='float32' (rb_ag_config.precision = RB_PREC_F32): the cell-step synchrotron spectrum through single-precision
+    hardware transcendentals on FP64-reduced arguments.  North-star tolerance of the FP32 path: 1e-5 on the model."""
+    import redback_b200 as rb
+    rng = np.random.default_rng(41)
+    t, nu = h.config4_epochs(40)
+    N = 400
+    p = h.tophat_prior(rng, N)
+    fn = rb.afterglow_models.tophat_redback
+    f64 = fn(t, params_batch=p, frequency=nu, output_format="flux_density")
+    f32 = fn(t, params_batch=p, frequency=nu, output_format="flux_density", dtype="float32")
+    assert np.array_equal(np.isnan(f32), np.isnan(f64))
+    ok = np.isfinite(f64) & (f64 > 0)
+    rel = np.abs(f32[ok] - f64[ok]) / f64[ok]
+    assert rel.max() < 1e-5, rel.max()
+    assert rel.max() > 1e-12                      # the variant really ran
+    y = f64[0] * 1.02
+    kw = dict(frequency=nu, output_format="flux_density")
+    l64 = rb.GaussianLikelihood(t, y, 0.1 * np.abs(y) + 1e-12, fn, kwargs=kw).log_likelihood_batch(p)
+    l32 = rb.GaussianLikelihood(t, y, 0.1 * np.abs(y) + 1e-12, fn, kwargs=dict(kw, dtype="float32")).log_likelihood_batch(p)
+    assert np.all(np.abs(l32 - l64) <= 1e-4 + 1e-4 * np.abs(l64))

@@ -80,6 +80,10 @@ def main():
     jobs.append(("tophat_redback radio+X-ray E=500 (config 4 shape)", int(200_000 * scale),
                  lambda n: AfterglowPath(_capi.AG_TOPHAT, t4, frequency=nu4, y=np.full(500, 1e-3), sigma=1e-4),
                  lambda n: h.tophat_prior(rng, n), None))
+    jobs.append(("tophat_redback radio+X-ray E=500 (config 4 shape), FP32 spectrum transcendentals", int(200_000 * scale),
+                 lambda n: AfterglowPath(_capi.AG_TOPHAT, t4, frequency=nu4, y=np.full(500, 1e-3), sigma=1e-4,
+                                         dtype="float32"),
+                 lambda n: h.tophat_prior(rng, n), None))
     rb_bands.register_synthetic_lsst()
     names6 = list(h.LSST_NU)
     b3 = np.array([names6[i % 6] for i in range(200)])
