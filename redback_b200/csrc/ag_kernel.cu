@@ -502,10 +502,12 @@ __device__ __forceinline__ double ag_flux_log_sp(double fbb, double nuc, double 
 // Epochs are handed to the lanes in TIME ORDER, a contiguous run of `epl` epochs per lane (tables built by the host,
 // transposed so that entry k of lane l sits at k * 32 + l): within a run the np.interp interval index only moves
 // forward, so after one binary search per lane the search is a short linear walk.
+// SP: RB_PREC_F32 (its own instantiation: the FP64 path carries none of it)
+template <bool SP>
 __global__ void __launch_bounds__(kAgWarps * 32, 4) ag_cell_kernel(const AgArgs a, int64_t total_units) {
   extern __shared__ double asm_[];
   const int steps = a.cfg.steps, E = a.E, n_nu = a.n_nu, epl = a.epl, EP = 32 * a.epl;
-  const bool fp32 = a.cfg.precision == RB_PREC_F32;
+  constexpr bool fp32 = SP;
   double* wbuf = asm_;                                           // per warp: tobs[steps] + flux[n_nu][steps]
   double* acc = wbuf + (size_t)kAgWarps * (1 + n_nu) * steps;    // [kAgWarps][EP]  (position = k * 32 + lane)
   double* sc = acc + (size_t)kAgWarps * EP;                      // [kAgScalars]

@@ -1111,7 +1111,9 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
   RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   static DeviceOnce once;
   const cudaError_t attr_err = once.run([] {
-    cudaError_t attr_err = cudaFuncSetAttribute(rb::ag_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t attr_err = cudaFuncSetAttribute(rb::ag_cell_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rb::ag_cell_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     return attr_err;
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(ag_cell_kernel)");
@@ -1239,7 +1241,10 @@ extern "C" int rb_ag_eval_f64(const rb_ag_config* cfg, int64_t N, int64_t E, con
     if (total > 0) {
       rb::ag_gamma_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, total);
       rb::ag_ring_kernel<<<(unsigned)((total + 3) / 4), 128, 0, st>>>(a, total);
-      rb::ag_cell_kernel<<<(unsigned)total_units, rb::kAgWarps * 32, cell_smem, st>>>(a, total_units);
+      if (cfg->precision == RB_PREC_F32)
+        rb::ag_cell_kernel<true><<<(unsigned)total_units, rb::kAgWarps * 32, cell_smem, st>>>(a, total_units);
+      else
+        rb::ag_cell_kernel<false><<<(unsigned)total_units, rb::kAgWarps * 32, cell_smem, st>>>(a, total_units);
       launch_counter()->fetch_add(3);
     }
     rb::ag_finish_kernel<<<(unsigned)std::min<int64_t>(nc, (int64_t)sms * 16), 128, 0, st>>>(a);
