@@ -1458,6 +1458,18 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
   pa.output = ph->output;
   pa.j_store_lo = *std::min_element(jlo.begin(), jlo.end());
   pa.span_max = span_max;
+  // columns kept below the bluest band (phot_kernel.cu header): smallest M with 2.5 x^M / (1 - x) < 1e-11, x = 0.268 q^6
+  {
+    double q = 1.0;
+    for (int j = 1; j <= pa.j_store_lo && j < NL; ++j) q = std::max(q, lam[(size_t)j] / lam[(size_t)j - 1]);
+    const double x = 0.268 * std::pow(q, 6.0);
+    // with dust extinction the 10-mag cap of _perform_extinction (extinction_models.py:137-139) can leave far-UV columns
+    // up to 1e4 times LESS attenuated than the band: that factor comes off the target
+    const double target = ph->extinction != nullptr ? 1e-15 : 1e-11;
+    int margin = NL;                                   // very coarse grids: keep every column
+    if (x < 0.8) margin = (int)std::ceil(std::log(target * (1.0 - x) / 2.5) / std::log(x));
+    pa.blue_margin = std::max(8, margin);
+  }
   return RB_OK;
 }
 

@@ -25,9 +25,13 @@
 // |f| over the band's 5-Angstrom grid (sed.py:36-37); where all of the band's spline coefficients are non-negative the
 // spline is non-negative (B-splines are), |f| = f, and the integral is the dot product of the coefficients with
 // per-band weights contracted on the host; otherwise the points are evaluated one by one, split over a warp's lanes.
-// Columns more than kBlueMargin below the bluest band are not evaluated: the wavelength-axis solve couples columns
-// with a factor <= 0.27 per column and spectra grow towards the blue by at most lambda^-4, so their contribution to a
-// band coefficient is < 1e-18 relative.  The mean needed by the clean-up is taken in a statistics pre-pass over ALL
+// Columns more than `blue_margin` below the bluest band are not evaluated: the inverse of the wavelength-axis collocation
+// matrix decays like rho^|i-j| (rho = 2 - sqrt(3) = 0.268 on a uniform grid, <= 0.268 q^2 on a grid whose neighbouring
+// wavelengths differ by at most a factor q; prefactor < 2.5) and spectra grow towards the blue by at most lambda^-4 =
+// q^4 per column, so the dropped columns change a band coefficient by < 2.5 x^M / (1 - x) relative to the spectrum at
+// the band's blue edge, x = 0.268 q^6.  The host picks the smallest M with that bound below 1e-11 (29 columns on the
+// default 100-point grid, 24 on the kilonova models' 200 points; a fixed 40 until late in round 2 cost 12-14 %), below
+// 1e-15 with dust extinction (its 10-mag cap can leave far-UV columns 1e4 times less attenuated than the band).  The mean needed by the clean-up is taken in a statistics pre-pass over ALL
 // columns (terms e^-50 below their row's largest are counted, not summed), skipped when a bound shows that every entry
 // is finite and non-zero; the per-sample banded LU of the time axis (kilonova grids) runs on one thread underneath it.
 // SINGLE-PASS MODE (plain blackbody / cutoff spectra): when a bound shows that every entry of the KEPT columns is valid
@@ -45,7 +49,6 @@ namespace rb {
 constexpr int kPhotMaxSpan = 96;     // max B-spline coefficients (along wavelength) overlapped by one band
 constexpr int kEpCols = 12;          // per-epoch record in the block's scratch: h0..h3, first row, y1, y2, band flux, U_e,
                                      // Ga, Gb, s0 (the backward fix-up folded into the contraction, see 2b)
-constexpr int kBlueMargin = 40;      // wavelength columns kept below the bluest band's first coefficient
 constexpr int kScanSteps = 5;        // log2(32)
 
 enum { PH_SED_BLACKBODY = 1, PH_SED_CUTOFF = 2, PH_SED_CUTOFF_LINE = 3 };
@@ -72,6 +75,7 @@ struct PhotArgs {
   int P;                  // row segments per column (W * P <= blockDim.x)
   int nt_pad;             // odd leading dimension of the column buffer
   int j_store_lo;         // first wavelength column kept for the back substitution (= min band_jlo)
+  int blue_margin;        // columns evaluated below j_store_lo (see the header comment)
   int span_max;           // max band_span
   int e_pad;              // leading dimension of the per-block epoch arrays
   int64_t scratch_stride; // doubles of scratch per block
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
   double* ys = ept + (size_t)kEpCols * a.e_pad;       // [NL - j_store_lo][e_pad]
   const int EP = a.e_pad;
   const int lgP = 31 - __clz(P);
-  const int j_first = max(0, a.j_store_lo - kBlueMargin);
+  const int j_first = max(0, a.j_store_lo - a.blue_margin);
 
   for (int i = tid; i < kExpTabSize; i += T) tab[i] = RB_EXP2_1024[i];
   for (int j = tid; j < NL; j += T) load_lu_row(lul + 5 * j, a.lu_lambda + 5 * j);
