@@ -1469,6 +1469,13 @@ int phot_prepare(const rb_photometry* ph, int64_t E, PhotDevice& dev, rb::PhotAr
     int margin = NL;                                   // very coarse grids: keep every column
     if (x < 0.8) margin = (int)std::ceil(std::log(target * (1.0 - x) / 2.5) / std::log(x));
     pa.blue_margin = std::max(8, margin);
+    // red side (phot_kernel.cu, 0c): last coefficient any band uses and the grid's neighbour ratio beyond it
+    int jhi = 0;
+    for (int b = 0; b < ph->n_bands; ++b) jhi = std::max(jhi, jlo[(size_t)b] + span[(size_t)b] - 1);
+    pa.j_store_hi = std::min(jhi, NL - 1);
+    double qr = 1.0;
+    for (int j = pa.j_store_hi + 1; j < NL; ++j) qr = std::max(qr, lam[(size_t)j] / lam[(size_t)j - 1]);
+    pa.q_red = qr;
   }
   return RB_OK;
 }
@@ -1612,6 +1619,8 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   const cudaError_t attr_err = once.run([] {
     cudaError_t attr_err = cudaFuncSetAttribute(rb::phot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rb::phot_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(rb::phot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return attr_err;
   });
@@ -1682,6 +1691,15 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
   }
   int status = RB_OK;
   if (ce != cudaSuccess) status = cuda_fail(ce, "magnitude workspace");
+  // red-side cut (phot_kernel.cu, 0c): worth its instantiation only if at least 8 columns can go for the hottest samples
+  bool red_cut = false;
+  {
+    const double xr0 = 0.268 * pa.q_red * pa.q_red;
+    if (xr0 < 0.8) {
+      const int m0 = std::max(8, (int)std::ceil(std::log(1e-11 * (1.0 - xr0) / 2.5) / std::log(xr0)));
+      red_cut = NL - 1 - pa.j_store_hi >= m0 + 8;
+    }
+  }
   for (int64_t n0 = 0; n0 < N && status == RB_OK; n0 += chunk_max) {
     const int64_t nc = std::min<int64_t>(chunk_max, N - n0);
     status = fill(n0, nc, d_grid, d_opz, d_dl, d_len);
@@ -1725,6 +1743,8 @@ int run_photometry(const PhotJob& j, cudaStream_t st, int sms, Fill fill) {
     pa.out_logl = j.y ? j.out_logl : nullptr;
     if (shape.tables_global)
       rb::phot_kernel<true><<<(unsigned)std::min<int64_t>(ph_grid_max, nc), 256, psmem, st>>>(pa);
+    else if (red_cut)   // the red-side cut where the grid extends well beyond the reddest band
+      rb::phot_kernel<false, true><<<(unsigned)std::min<int64_t>(ph_grid_max, nc), 256, psmem, st>>>(pa);
     else
       rb::phot_kernel<false><<<(unsigned)std::min<int64_t>(ph_grid_max, nc), 256, psmem, st>>>(pa);
     launch_counter()->fetch_add(1);

@@ -76,6 +76,8 @@ struct PhotArgs {
   int nt_pad;             // odd leading dimension of the column buffer
   int j_store_lo;         // first wavelength column kept for the back substitution (= min band_jlo)
   int blue_margin;        // columns evaluated below j_store_lo (see the header comment)
+  int j_store_hi;         // last wavelength coefficient used by any band (= max band_jlo + band_span - 1)
+  double q_red;           // largest ratio of neighbouring wavelengths above j_store_hi (red-side cut, section 0c)
   int span_max;           // max band_span
   int e_pad;              // leading dimension of the per-block epoch arrays
   int64_t scratch_stride; // doubles of scratch per block
@@ -212,6 +214,14 @@ __device__ __noinline__ double planck_inv_general(double x, const double* __rest
   return rcp_fast(expm1(x));
 }
 
+// Columns to keep beyond the reddest band's last coefficient (phot_kernel, section 0c); out of line: pow / log / ceil
+// once per sample must not weigh on the kernel's register allocation.
+__device__ __noinline__ int red_margin(double xe, double q, int NL) {
+  const double xr = 0.268 * (q * q) * pow(q, fmax(xe - 4.0, 0.0));
+  if (!(xr < 0.8)) return NL;
+  return max(8, (int)ceil(log(1e-11 * (1.0 - xr) / 2.5) / log(xr)));
+}
+
 #ifdef RB_PHOT_PROFILE
 // developer aid (tools/phot_phases.sh): block 0 prints the cycles it spent in each phase, summed over all its samples
 #define PHOT_PROF_DECL() long long pt_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pa_ = 0; long long pn_ = 0;
@@ -239,7 +249,10 @@ __device__ __forceinline__ double2 ld_pair(const double* __restrict__ p) {
 }
 
 // GT: the time-axis LU and its homogeneous solutions live in global memory (grids too long for shared memory)
-template <bool GT>
+// RED: the red-side column cut (section 0c) is compiled in; the host picks it where the grid extends well beyond the
+// reddest band (the kilonova models' 200-point default), the other instantiation is the same code without it (the cut's
+// few lines cost the 100-point Arnett case 2 % through the register allocation of the hot loops).
+template <bool GT, bool RED = false>
 __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
   extern __shared__ __align__(16) double psm[];
   const int NT = a.n_t_max, NL = a.n_lambda, E = a.E, NC = a.n_comp;
@@ -642,6 +655,22 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       }
     }
     const bool need_mask = single_pass && dead_rows > 0.0;
+    // ---- 0c. red-side column cut (plain blackbody / cutoff spectra without extinction).  Towards the red a valid entry
+    // grows by at most lambda^(x - 4) with x = h nu / k T <= x_e at the reddest band's last coefficient for the coolest
+    // valid row (d ln B_lambda / d ln lambda = -5 + x e^x / (e^x - 1) <= x - 4), i.e. by g = q^max(x_e - 4, 0) per column,
+    // and the collocation inverse decays like 0.268 q^2 per column: columns more than M beyond that coefficient change a
+    // band coefficient by < 2.5 xr^M / (1 - xr), xr = 0.268 q^2 g.  M from the same 1e-11 target as the blue side; no
+    // cut for samples with xr >= 0.8 (very cool rows) or with rows of the wrong sign.
+    int j_last = NL - 1;
+    if (RED && NC == 1 && !line && a.ext == nullptr && a.q_red > 0.0) {
+      double ah = 0.0, odd = 0.0;
+      if (all_valid) {
+        for (int w = 0; w < nwarps; ++w) ah = fmax(ah, red[16 + w]);
+      } else {
+        for (int w = 0; w < nwarps; ++w) { ah = fmax(ah, red2[16 + w]); odd += red2[40 + w]; }
+      }
+      if (odd == 0.0 && ah > 0.0) j_last = min(NL - 1, a.j_store_hi + red_margin(ah * colA[a.j_store_hi], a.q_red, NL));
+    }
     if (tid == 0) atomicAdd(&g_phot_modes[all_valid ? 0 : (single_pass ? (need_mask ? 2 : 1) : 3)], 1ull);
     __syncthreads();                                  // xk (in buf) is dead from here on
     PHOT_PROF_ACC(0);
@@ -756,9 +785,11 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     if (!all_valid && !(single_pass && !need_mask)) {
       double vsum = 0.0, vcnt = 0.0;
       const int wstat = a.common_time_lu ? nwarps : nwarps - 1;     // the LU warp does not take part
-      const int j_stat_end = single_pass ? j_first : NL;
+      // single-pass mode: the columns outside the kept range [j_first, j_last]; otherwise all of them
+      const int j_stat_end = single_pass ? j_first + (NL - 1 - j_last) : NL;
       if (warp < wstat) {
-        for (int j = warp; j < j_stat_end; j += wstat) {
+        for (int jj = warp; jj < j_stat_end; jj += wstat) {
+          const int j = (single_pass && jj >= j_first) ? j_last + 1 + (jj - j_first) : jj;
           const double ca = colA[j], cb = colB[j], cd = colD[j];
           const double lcb = (cb > 0.0 && cb < INFINITY) ? log(cb) : NAN;
           const double dca = ca - ca_min;
@@ -881,8 +912,8 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
     for (int it = need_mask ? -1 : 0;; ++it) {
       const bool mask_it = it < 0;                    // the row mask as an extra column (single-pass mode)
       const int j0 = j_first + max(it, 0) * W;
-      if (!mask_it && j0 >= NL) break;
-      const int wc = mask_it ? 1 : min(W, NL - j0);
+      if (!mask_it && j0 > j_last) break;
+      const int wc = mask_it ? 1 : min(W, j_last + 1 - j0);
       // 2a. spectra of the block, cleaned
       if (mask_it) {
         for (int k = tid; k < G; k += T) {
@@ -1053,6 +1084,20 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       __syncthreads();
       PHOT_PROF_ACC(4);
     }
+    if (RED && j_last < NL - 1) {
+      // the columns beyond j_last count as zero spectra: the wavelength-axis forward elimination just runs on
+      for (int e = tid; e < En; e += T) {
+        if ((int)ept[4 * EP + e] < 0) continue;
+        double y1 = ept[5 * EP + e], y2 = ept[6 * EP + e];
+        for (int j = j_last + 1; j < NL; ++j) {
+          const double y = -(lul[5 * j + 0] * y2) - lul[5 * j + 1] * y1;
+          if (j >= a.j_store_lo) ys[(size_t)(j - a.j_store_lo) * EP + e] = y;
+          y2 = y1;
+          y1 = y;
+        }
+      }
+      __syncthreads();
+    }
 
     // ---- 3. epochs: wavelength-axis back substitution, band integrals, magnitudes, likelihood ------------------
     // chunks of epochs (grouped by band through epoch_order) sized by the coefficient buffer:
@@ -1069,7 +1114,7 @@ __global__ void __launch_bounds__(256, 2) phot_kernel(const PhotArgs a) {
       __syncthreads();
       double sacc = pre_sum;
       for (int w = 0; w < nwarps; ++w) sacc += red[w];
-      const double cacc = pre_cnt + ((double)G - dead_rows) * (double)(NL - j_first);
+      const double cacc = pre_cnt + ((double)G - dead_rows) * (double)(j_last + 1 - j_first);
       double mean = (cacc > 0) ? sacc / cacc : NAN;
       if (!isfinite(mean) || mean == 0.0) mean = 1.0;
       repl = 1e-30 * mean;
