@@ -34,7 +34,7 @@ def rate(index, label):
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / 3
     print(f"{label:34s} {len(index)} samples, cost {cost[index].sum():.4e}, {ms:8.2f} ms, "
-          f"{len(index) * path.E / ms / 1e3:.4e} unit/s", flush=True)
+          f"{len(index) * path.E / (ms * 1e-3):.4e} unit/s", flush=True)
 
 
 rng = np.random.default_rng(0)
