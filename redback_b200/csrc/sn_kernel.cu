@@ -458,14 +458,19 @@ __device__ __forceinline__ float diffusion_sum_f32(const float4* __restrict__ no
 // NOCUT: the SED is bolometric or the plain Blackbody: the instantiation carries no CutoffBlackbody / Line code at all, so
 // the out-of-line SED's register footprint and code size cannot touch the headline path (the rolled ten-term loop of
 // cutoff_norm raised this kernel's spills around the call from 96 to 156 B when both lived in one instantiation).
-template <bool HAS_T0, int ENGINE, bool ASPH = false, bool NEG = false, bool NOCUT = false>
+// BOLO: bolometric output at the epochs (arnett_bolometric & co., BASELINE config 1): no photosphere / SED code at all;
+// E = 100: 4.83e9 -> 5.08e9 unit/s against the generic instantiation (gpurun A/B, tools/bench_variants.py).
+template <bool HAS_T0, int ENGINE, bool ASPH = false, bool NEG = false, bool NOCUT = false, bool BOLO = false>
 __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
 #ifndef RB_SN_UNROLL_NOCUT
 #define RB_SN_UNROLL_NOCUT 16
 #endif
   // unroll factor of the quadrature loop, A/B-measured per instantiation (tools/bench_variants.py): the spill-free
   // Blackbody instantiation gains from a deeper unroll, the generic one loses
-  constexpr int kUnroll = NOCUT ? RB_SN_UNROLL_NOCUT : 6;
+#ifndef RB_SN_UNROLL_BOLO
+#define RB_SN_UNROLL_BOLO 10
+#endif
+  constexpr int kUnroll = BOLO ? RB_SN_UNROLL_BOLO : (NOCUT ? RB_SN_UNROLL_NOCUT : 6);
   extern __shared__ double2 smem2[];
   const int D = a.cfg.dense_resolution;
   double2* seg = smem2;                                  // [D]      (a_k, b_k)
@@ -697,7 +702,7 @@ __global__ void __launch_bounds__(512, 2) sn_kernel(const SnArgs a) {
       }
 
       double model;
-      if (sed == RB_SED_BOLOMETRIC) {
+      if (BOLO || sed == RB_SED_BOLOMETRIC) {
         model = lbol;
       } else {
         // ---- photosphere.TemperatureFloor (photosphere.py:87-111) ----
