@@ -426,7 +426,7 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   int occ = 0;
   const bool nocut = cfg->sed == RB_SED_BLACKBODY;   // (bolometric, E = 100: measured 1.4 % slower in that instantiation)
   const SnKernelFn kern = sn_kernel_fn(cfg->engine, cfg->t0 != nullptr, cfg->aspherical != 0, cfg->negative_epochs != 0,
-                                       nocut, cfg->sed == RB_SED_BOLOMETRIC && !a.grid_mode);
+                                       nocut, cfg->sed == RB_SED_BOLOMETRIC && !a.grid_mode && threads <= RB_SN_BOLO_MAXT);
   RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (a.epochs_in_smem) {
     // the epoch table stays in global memory (L1) where that buys another resident block: E = 100 -> 6 blocks of 128
