@@ -151,9 +151,10 @@ int launch_csm(rb::SnArgs a, const double* t_dev, cudaStream_t st, int sms) {
 
 typedef void (*SnKernelFn)(const rb::SnArgs);
 SnKernelFn sn_kernel_fn(int engine, bool has_t0, bool aspherical = false, bool negative = false, bool nocut = false,
-                        bool bolo = false) {
+                        int bolo = 0) {
+  // bolometric output: 1 = blocks of at most 256 threads (higher register cap), 2 = larger blocks
   if (bolo && !aspherical && !negative && !has_t0 && (engine == RB_ENGINE_NICKEL || engine == RB_ENGINE_MAGNETAR))
-    return rb::sn_kernel<false, 0, false, false, false, true>;
+    return bolo == 1 ? rb::sn_kernel<false, 0, false, false, false, 1> : rb::sn_kernel<false, 0, false, false, false, 2>;
   // the headline path (nickel / magnetar engine, bolometric or Blackbody SED, no t0): its own instantiation without
   // the CutoffBlackbody / Line code
   if (nocut && !aspherical && !negative && !has_t0 && (engine == RB_ENGINE_NICKEL || engine == RB_ENGINE_MAGNETAR))
@@ -190,7 +191,10 @@ cudaError_t sn_kernel_attributes() {
     err = cudaFuncSetAttribute(sn_kernel_fn(RB_ENGINE_NICKEL, false, false, false, true),
                                cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (err == cudaSuccess)
-    err = cudaFuncSetAttribute(sn_kernel_fn(RB_ENGINE_NICKEL, false, false, false, false, true),
+    err = cudaFuncSetAttribute(sn_kernel_fn(RB_ENGINE_NICKEL, false, false, false, false, 1),
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(sn_kernel_fn(RB_ENGINE_NICKEL, false, false, false, false, 2),
                                cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   for (int e = 0; e < 2 && err == cudaSuccess; ++e)
     err = cudaFuncSetAttribute(sn_kernel_fn(engines[e], false, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -426,7 +430,7 @@ int rb_sn_eval_f64(const rb_sn_config* cfg, int64_t N, int64_t E, const double* 
   int occ = 0;
   const bool nocut = cfg->sed == RB_SED_BLACKBODY;   // (bolometric, E = 100: measured 1.4 % slower in that instantiation)
   const SnKernelFn kern = sn_kernel_fn(cfg->engine, cfg->t0 != nullptr, cfg->aspherical != 0, cfg->negative_epochs != 0,
-                                       nocut, cfg->sed == RB_SED_BOLOMETRIC && !a.grid_mode && threads <= RB_SN_BOLO_MAXT);
+                                       nocut, (cfg->sed == RB_SED_BOLOMETRIC && !a.grid_mode) ? (threads <= 256 ? 1 : 2) : 0);
   RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (a.epochs_in_smem) {
     // the epoch table stays in global memory (L1) where that buys another resident block: E = 100 -> 6 blocks of 128

@@ -460,14 +460,10 @@ __device__ __forceinline__ float diffusion_sum_f32(const float4* __restrict__ no
 // cutoff_norm raised this kernel's spills around the call from 96 to 156 B when both lived in one instantiation).
 // BOLO: bolometric output at the epochs (arnett_bolometric & co., BASELINE config 1): no photosphere / SED code at all;
 // E = 100: 4.83e9 -> 5.08e9 unit/s against the generic instantiation (gpurun A/B, tools/bench_variants.py).
-// Its blocks are small (the host picks it for at most RB_SN_BOLO_MAXT threads), so its register cap follows from the
-// blocks that are resident at that size rather than from the generic 2 x 512 threads.
-#ifndef RB_SN_BOLO_MAXT
-#define RB_SN_BOLO_MAXT 512
-#define RB_SN_BOLO_MINB 2
-#endif
-template <bool HAS_T0, int ENGINE, bool ASPH = false, bool NEG = false, bool NOCUT = false, bool BOLO = false>
-__global__ void __launch_bounds__(BOLO ? RB_SN_BOLO_MAXT : 512, BOLO ? RB_SN_BOLO_MINB : 2) sn_kernel(const SnArgs a) {
+// BOLO = 1: blocks of at most 256 threads (E <= 256), three of which (six of 128) are resident per SM: the register cap
+// follows from that (80 instead of 64: 5.08e9 -> 5.21e9 unit/s at E = 100); BOLO = 2: larger blocks, generic cap.
+template <bool HAS_T0, int ENGINE, bool ASPH = false, bool NEG = false, bool NOCUT = false, int BOLO = 0>
+__global__ void __launch_bounds__(BOLO == 1 ? 256 : 512, BOLO == 1 ? 3 : 2) sn_kernel(const SnArgs a) {
 #ifndef RB_SN_UNROLL_NOCUT
 #define RB_SN_UNROLL_NOCUT 16
 #endif
