@@ -503,8 +503,11 @@ __device__ __forceinline__ double ag_flux_log_sp(double fbb, double nuc, double 
 // transposed so that entry k of lane l sits at k * 32 + l): within a run the np.interp interval index only moves
 // forward, so after one binary search per lane the search is a short linear walk.
 // SP: RB_PREC_F32 (its own instantiation: the FP64 path carries none of it)
+#ifndef RB_AG_CELL_MINB
+#define RB_AG_CELL_MINB 4   // resident blocks per SM the register cap is derived from (A/B switch)
+#endif
 template <bool SP>
-__global__ void __launch_bounds__(kAgWarps * 32, 4) ag_cell_kernel(const AgArgs a, int64_t total_units) {
+__global__ void __launch_bounds__(kAgWarps * 32, RB_AG_CELL_MINB) ag_cell_kernel(const AgArgs a, int64_t total_units) {
   extern __shared__ double asm_[];
   const int steps = a.cfg.steps, E = a.E, n_nu = a.n_nu, epl = a.epl, EP = 32 * a.epl;
   constexpr bool fp32 = SP;
