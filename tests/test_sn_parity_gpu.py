@@ -337,6 +337,20 @@ def test_full_size_properties(rb):
     np.testing.assert_allclose(b, 2.0 * a, rtol=1e-14)
 
 
+@pytest.mark.parametrize("E", [100, 200, 300])
+def test_bolometric_block_sizes(rb, E):
+    """Bolometric output has its own kernel instantiations by block size (E <= 256: higher register cap, larger blocks:
+    generic cap; csrc/capi.cu sn_kernel_fn): arnett_bolometric at E epochs against the oracle."""
+    t = np.sort(np.random.default_rng(E).uniform(0.5, 400.0, E))
+    N = 64
+    p = h.arnett_bolometric_prior(np.random.default_rng(7), N)
+    out = rb.supernova_models.arnett_bolometric(t, params_batch=p)
+    assert out.shape == (N, E)
+    for i in range(N):
+        ref = r.arnett_bolometric(t, **{k: v[i] for k, v in p.items()})
+        h.assert_close(out[i], ref, RTOL, h.diffusion_condition(t, _tau(p, i)), what=f"E {E} sample {i}")
+
+
 def test_baseline_full_size(rb):
     """BASELINE configs[1] at its full size (N = 1e7 prior draws x 300 epochs) through the host-buffer entry point:
     duplication invariance (the second half of the batch repeats the first), a checksum of checksums against chunked
