@@ -484,8 +484,8 @@ def run_gpu(args):
             "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
             "frac": achieved / peak.value if peak.value else None,
             # dram__bytes_read+write of rb::sn_kernel from the committed ncu --set full capture, scaled to this launch
-            "traffic": 135.5 * n, "traffic_source": "ncu capture at 200000 samples, scaled per sample "
-                                                    "(profiles/r1_final_sn_kernel_ncu_summary.txt)",
+            "traffic": 136.5 * n, "traffic_source": "ncu capture at 200000 samples, scaled per sample "
+                                                    "(profiles/r2l_sn_headline_ncu_summary.txt: 27.3 MB read, writes absorbed by L2)",
             "kernel": "rb::sn_kernel", "kernel_ms": kernel_ms,
             "flop_eq_per_unit": flop_eq,
             "peak_source": "DFMA micro-benchmark measured live in this run (rb_measure_fp64_peak); nominal 37.2",
